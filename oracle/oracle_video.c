@@ -1,0 +1,704 @@
+/* oracle/oracle_video.c — CPU ORACLE (TEST INFRASTRUCTURE, NOT PRODUCT CODE).
+ *
+ * Restatement of the videoconvertscale hot path for 4:2:0 semi-planar YUV -> packed
+ * 8-bit RGB with scaling, as whole-frame passes in the exact stage order and
+ * integer arithmetic of the reference's pull chain:
+ *
+ *   unpack (nearest chroma)          video-format.c:1593-1641 (NV12), :1679+ (NV21)
+ *   chroma upsample h then v         video-converter.c:2991-3021, video-chroma.c:309-327, :687-699
+ *   [downscale h/v]  -> matrix -> [upscale h/v]     video-converter.c:1685-1718, :2509-2539
+ *   h scale                          video-scaler.c:596-618 (2-tap), :621-760 (n-tap), :462-580 (nearest)
+ *   v scale                          video-scaler.c:846-879 (2-tap), :923-1072 (4/n-tap), :828-844 (nearest)
+ *   AYUV->ARGB matrix                video-converter.c:1209-1216; video-orc.orc:1634-1688
+ *   pack                             video-format.c:1445-1452 (+ :1473-1520 siblings)
+ *
+ * Defined for n-threads=1 (the element default, gstvideoconvertscale.c:144).
+ * Pinned byte-for-byte against oracle/_ref (the reference's own sources) by
+ * tests/test_oracle_vs_ref.py.
+ */
+#include "oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define CLAMPI(x,lo,hi) ((x) > (hi) ? (hi) : ((x) < (lo) ? (lo) : (x)))
+#define ROUND_UP_4(n) (((n) + 3) & ~3)
+#define ROUND_UP_2(n) (((n) + 1) & ~1)
+
+/* ======================================================================= taps */
+
+/* video-resampler.c:142-202 */
+static double
+sinc_ (double x)
+{
+  if (x == 0)
+    return 1;
+  return sin (M_PI * x) / (M_PI * x);
+}
+
+static double
+envelope_ (double x)
+{
+  if (x <= -1 || x >= 1)
+    return 0;
+  return sinc_ (x);
+}
+
+typedef struct
+{
+  int method;
+  double fx, ex, b, c, sharpen;
+} TapParams;
+
+static double
+get_tap (const TapParams * p, int l, int xi, double x)
+{
+  int xl = xi + l;
+  switch (p->method) {
+    case ORC_RS_NEAREST:       /* video-resampler.c:156-160 */
+      return 1.0;
+    case ORC_RS_LINEAR:{       /* :162-176 */
+      double a = fabs (x - xl) * p->fx;
+      return a < 1.0 ? 1.0 - a : 0.0;
+    }
+    case ORC_RS_CUBIC:{        /* :178-201 */
+      double a = fabs (x - xl) * p->fx, a2 = a * a, a3 = a2 * a, b = p->b, c = p->c;
+      if (a <= 1.0)
+        return ((12.0 - 9.0 * b - 6.0 * c) * a3 + (-18.0 + 12.0 * b + 6.0 * c) * a2 +
+            (6.0 - 2.0 * b)) / 6.0;
+      else if (a <= 2.0)
+        return ((-b - 6.0 * c) * a3 + (6.0 * b + 30.0 * c) * a2 + (-12.0 * b - 48.0 * c) * a +
+            (8.0 * b + 24.0 * c)) / 6.0;
+      return 0.0;
+    }
+    case ORC_RS_SINC:          /* :203-208 */
+      return sinc_ ((x - xl) * p->fx);
+    case ORC_RS_LANCZOS:       /* :210-216 */
+    default:
+      return (sinc_ ((x - xl) * p->fx) - p->sharpen) * envelope_ ((x - xl) * p->ex);
+  }
+}
+
+int
+oracle_resampler_taps (const OracleResamplerOpts * o, int in_size, int out_size,
+    uint32_t * offset, double *taps)
+{
+  /* gst_video_resampler_init, video-resampler.c:343-429 */
+  TapParams p;
+  int max_taps = o->max_taps_opt > 0 ? o->max_taps_opt : 128;
+  int n_taps = o->n_taps_req;
+  double envelope = 2.0, scale_factor, dx, corr;
+  int j, l, tap_offs;
+
+  if (in_size <= 0 || out_size <= 0)
+    return -1;
+  p.method = o->method;
+  p.sharpen = o->sharpen;
+  p.b = o->cubic_b;
+  p.c = o->cubic_c;
+  scale_factor = in_size / (double) out_size;
+  if (scale_factor > 1.0)
+    p.fx = (1.0 / scale_factor) * o->sharpness;
+  else
+    p.fx = 1.0 * o->sharpness;
+
+  if (n_taps > max_taps)
+    n_taps = max_taps;
+  switch (o->method) {
+    case ORC_RS_NEAREST:
+      envelope = o->envelope;
+      if (n_taps == 0)
+        n_taps = 1;
+      break;
+    case ORC_RS_LINEAR:
+      envelope = 1.0;
+      break;
+    case ORC_RS_CUBIC:
+      envelope = 2.0;
+      break;
+    default:
+      envelope = o->envelope;
+      break;
+  }
+  if (n_taps == 0) {
+    dx = ceil (2.0 * envelope / p.fx);
+    n_taps = (int) CLAMPI (dx, 0, max_taps);
+  }
+  p.fx = 2.0 * envelope / n_taps;
+  p.ex = 2.0 / n_taps;
+  if (n_taps > in_size)
+    n_taps = in_size;
+
+  /* resampler_calculate_taps, video-resampler.c:204-288 */
+  tap_offs = (n_taps - 1) / 2;
+  corr = (n_taps == 1 ? 0.0 : 0.5);
+  for (j = 0; j < out_size; j++) {
+    double ox, x, weight = 0, *t = taps + (size_t) j * n_taps;
+    int xi;
+    ox = (0.5 + (double) j - 0.0) / out_size;
+    x = ox * (double) in_size - corr;
+    x = CLAMPI (x, 0, in_size - 1);
+    xi = (int) floor (x - tap_offs);
+    offset[j] = (uint32_t) xi;
+    for (l = 0; l < n_taps; l++) {
+      t[l] = get_tap (&p, l, xi, x);
+      weight += t[l];
+    }
+    for (l = 0; l < n_taps; l++)
+      t[l] /= weight;
+    if (xi < 0) {
+      int sh = -xi;
+      for (l = 0; l < sh; l++)
+        t[sh] += t[l];
+      for (l = 0; l < n_taps - sh; l++)
+        t[l] = t[sh + l];
+      for (; l < n_taps; l++)
+        t[l] = 0;
+      offset[j] += sh;
+    }
+    if (xi > in_size - n_taps) {
+      int sh = xi - (in_size - n_taps);
+      for (l = 0; l < sh; l++)
+        t[n_taps - sh - 1] += t[n_taps - sh + l];
+      for (l = 0; l < n_taps - sh; l++)
+        t[n_taps - 1 - l] = t[n_taps - 1 - sh - l];
+      for (l = 0; l < sh; l++)
+        t[l] = 0;
+      offset[j] -= sh;
+    }
+  }
+  return n_taps;
+}
+
+int
+oracle_quantize_taps (const double *src, int16_t * dst, int n, int precision)
+{
+  /* resampler_convert_coeff, video-scaler.c:338-388: bisection on the rounding
+   * bias until the integer taps sum to 1<<precision (may fail -> keeps last try) */
+  double multiplier = (double) (1 << precision);
+  double l_offset = 0.0, h_offset = 1.0, offset = 0.5;
+  int i, j, exact = 0;
+  for (i = 0; i < 64; i++) {
+    int sum = 0;
+    for (j = 0; j < n; j++) {
+      int16_t tap = (int16_t) floor (offset + src[j] * multiplier);
+      dst[j] = tap;
+      sum += tap;
+    }
+    if (sum == (1 << precision)) {
+      exact = 1;
+      break;
+    }
+    if (l_offset == h_offset)
+      break;
+    if (sum < (1 << precision)) {
+      if (offset > l_offset)
+        l_offset = offset;
+      offset += (h_offset - l_offset) / 2;
+    } else {
+      if (offset < h_offset)
+        h_offset = offset;
+      offset -= (h_offset - l_offset) / 2;
+    }
+  }
+  return exact;
+}
+
+/* ===================================================================== layout */
+
+int
+oracle_vcs_default_desc (OracleVcsDesc * d, int in_format, int in_w, int in_h,
+    int out_format, int out_w, int out_h, int method, int max_taps_opt)
+{
+  memset (d, 0, sizeof (*d));
+  if (in_format != ORC_FMT_NV12 && in_format != ORC_FMT_NV21)
+    return -1;
+  d->in_format = in_format;
+  d->in_width = in_w;
+  d->in_height = in_h;
+  /* video-info.c:1053-1063 */
+  d->in_stride[0] = ROUND_UP_4 (in_w);
+  d->in_stride[1] = d->in_stride[0];
+  d->in_offset[0] = 0;
+  d->in_offset[1] = (size_t) d->in_stride[0] * ROUND_UP_2 (in_h);
+  /* video-info.c:165-185, :211-225 */
+  d->in_matrix = in_h > 576 ? ORC_CM_BT709 : ORC_CM_BT601;
+  d->in_range = ORC_RANGE_16_235;
+  d->in_chroma_site = in_h > 576 ? ORC_SITE_H_COSITED : ORC_SITE_NONE;
+  d->out_format = out_format;
+  d->out_width = out_w;
+  d->out_height = out_h;
+  d->out_stride[0] = out_w * 4;         /* video-info.c:890-894 */
+  d->rs.method = method;
+  d->rs.max_taps_opt = max_taps_opt;
+  d->rs.envelope = 2.0;
+  d->rs.sharpness = 1.0;
+  d->rs.sharpen = 0.0;
+  d->rs.cubic_b = 1.0 / 3.0;
+  d->rs.cubic_c = 1.0 / 3.0;
+  return 0;
+}
+
+size_t
+oracle_vcs_in_size (const OracleVcsDesc * d)
+{
+  return d->in_offset[1] + (size_t) d->in_stride[1] * (ROUND_UP_2 (d->in_height) / 2);
+}
+
+size_t
+oracle_vcs_out_size (const OracleVcsDesc * d)
+{
+  return d->out_offset[0] + (size_t) d->out_stride[0] * d->out_height;
+}
+
+/* ===================================================================== matrix */
+
+typedef struct
+{
+  double dm[4][4];
+} Mat;
+
+static void
+mat_identity (Mat * m)
+{
+  int i, j;
+  for (i = 0; i < 4; i++)
+    for (j = 0; j < 4; j++)
+      m->dm[i][j] = (i == j);
+}
+
+/* dst = a * b (video-converter.c:925-941) */
+static void
+mat_mul (Mat * dst, const Mat * a, const Mat * b)
+{
+  Mat t;
+  int i, j, k;
+  for (i = 0; i < 4; i++)
+    for (j = 0; j < 4; j++) {
+      double x = 0;
+      for (k = 0; k < 4; k++)
+        x += a->dm[i][k] * b->dm[k][j];
+      t.dm[i][j] = x;
+    }
+  *dst = t;
+}
+
+static void
+mat_offset (Mat * m, double a1, double a2, double a3)
+{
+  Mat a;
+  mat_identity (&a);
+  a.dm[0][3] = a1;
+  a.dm[1][3] = a2;
+  a.dm[2][3] = a3;
+  mat_mul (m, &a, m);
+}
+
+static void
+mat_scale (Mat * m, double a1, double a2, double a3)
+{
+  Mat a;
+  mat_identity (&a);
+  a.dm[0][0] = a1;
+  a.dm[1][1] = a2;
+  a.dm[2][2] = a3;
+  mat_mul (m, &a, m);
+}
+
+int
+oracle_vcs_matrix (const OracleVcsDesc * d, int p[5], int im[4][4])
+{
+  /* chain_convert (video-converter.c:1720-1868) for 8-bit YUV in, 8-bit RGB out,
+   * gamma/primaries modes NONE: identity -> compute_matrix_to_RGB (:1373-1404)
+   * -> compute_matrix_to_YUV (:1406-1442, RGB out: range scaling only)
+   * -> prepare_matrix (:1324-1370): x256, rint. */
+  Mat m;
+  double Kr, Kb, Kg;
+  int offset[3], scale[3], i, j;
+  mat_identity (&m);
+  /* gst_video_color_range_offsets for AYUV 8 bit (video-color.c:204-252) */
+  if (d->in_range == ORC_RANGE_16_235) {
+    offset[0] = 16; scale[0] = 219;
+    offset[1] = offset[2] = 128; scale[1] = scale[2] = 224;
+  } else {
+    offset[0] = 0; scale[0] = 255;
+    offset[1] = offset[2] = 128; scale[1] = scale[2] = 255;
+  }
+  mat_offset (&m, -offset[0], -offset[1], -offset[2]);
+  mat_scale (&m, 1 / ((float) scale[0]), 1 / ((float) scale[1]), 1 / ((float) scale[2]));
+  switch (d->in_matrix) {      /* video-color.c:423-459 */
+    case ORC_CM_FCC: Kr = 0.30; Kb = 0.11; break;
+    case ORC_CM_BT709: Kr = 0.2126; Kb = 0.0722; break;
+    case ORC_CM_BT601: Kr = 0.2990; Kb = 0.1140; break;
+    case ORC_CM_SMPTE240M: Kr = 0.212; Kb = 0.087; break;
+    case ORC_CM_BT2020: Kr = 0.2627; Kb = 0.0593; break;
+    default: return -1;
+  }
+  Kg = 1.0 - Kr - Kb;
+  {                             /* color_matrix_YCbCr_to_RGB, :1027-1040 */
+    Mat k = { {{1., 0., 2 * (1 - Kr), 0.},
+        {1., -2 * Kb * (1 - Kb) / Kg, -2 * Kr * (1 - Kr) / Kg, 0.},
+        {1., 2 * (1 - Kb), 0., 0.},
+        {0., 0., 0., 1.}} };
+    mat_mul (&m, &k, &m);
+  }
+  /* out: ARGB 0-255 full range */
+  mat_scale (&m, (float) 255, (float) 255, (float) 255);
+  mat_offset (&m, 0, 0, 0);
+  mat_scale (&m, 256.0f, 256.0f, 256.0f);
+  for (i = 0; i < 4; i++)
+    for (j = 0; j < 4; j++)
+      im[i][j] = (int) rint (m.dm[i][j]);
+  /* is_ayuv_to_rgb_matrix (:1218-1228) must hold for the fast path */
+  if (im[0][0] != im[1][0] || im[1][0] != im[2][0] || im[0][1] != 0 || im[2][2] != 0)
+    return -2;
+  p[0] = im[0][0];
+  p[1] = im[0][2];
+  p[2] = im[2][1];
+  p[3] = im[1][1];
+  p[4] = im[1][2];
+  return 0;
+}
+
+/* video_orc_convert_AYUV_ARGB, video-orc.orc:1634-1688, in place on one line */
+static inline int16_t
+splatbw (uint8_t b)
+{
+  return (int16_t) (uint16_t) ((b << 8) | b);
+}
+
+static inline int
+sat_s8 (int v)
+{
+  return CLAMPI (v, -128, 127);
+}
+
+static void
+matrix_line (uint8_t * px, int n, const int p[5])
+{
+  int i;
+  int16_t p1 = (int16_t) p[0], p2 = (int16_t) p[1], p3 = (int16_t) p[2], p4 = (int16_t) p[3],
+      p5 = (int16_t) p[4];
+  for (i = 0; i < n; i++, px += 4) {
+    uint8_t a = (uint8_t) (px[0] - 128), y = (uint8_t) (px[1] - 128);
+    uint8_t u = (uint8_t) (px[2] - 128), v = (uint8_t) (px[3] - 128);
+    int16_t wy = (int16_t) ((splatbw (y) * p1) >> 16);
+    int16_t r = (int16_t) (wy + (int16_t) ((splatbw (v) * p2) >> 16));
+    int16_t b = (int16_t) (wy + (int16_t) ((splatbw (u) * p3) >> 16));
+    int16_t g = (int16_t) (wy + (int16_t) ((splatbw (u) * p4) >> 16));
+    g = (int16_t) (g + (int16_t) ((splatbw (v) * p5) >> 16));
+    px[0] = (uint8_t) (a + 128);
+    px[1] = (uint8_t) (sat_s8 (r) + 128);
+    px[2] = (uint8_t) (sat_s8 (g) + 128);
+    px[3] = (uint8_t) (sat_s8 (b) + 128);
+  }
+}
+
+/* ===================================================================== stages */
+
+/* unpack one line to AYUV, chroma replicated (video-format.c:1595-1641) */
+static void
+unpack_line (const OracleVcsDesc * d, const uint8_t * in, int y, uint8_t * dst)
+{
+  const uint8_t *sy = in + d->in_offset[0] + (size_t) d->in_stride[0] * y;
+  const uint8_t *suv = in + d->in_offset[1] + (size_t) d->in_stride[1] * (y >> 1);
+  int x, ui = d->in_format == ORC_FMT_NV21 ? 1 : 0;
+  for (x = 0; x < d->in_width; x++) {
+    dst[x * 4 + 0] = 0xff;
+    dst[x * 4 + 1] = sy[x];
+    dst[x * 4 + 2] = suv[(x & ~1) + ui];
+    dst[x * 4 + 3] = suv[(x & ~1) + (ui ^ 1)];
+  }
+}
+
+/* video_chroma_up_h2_cs_u8 (video-chroma.c:687-699) / video_chroma_up_h2_u8 (:277-296) */
+static void
+chroma_h_line (uint8_t * p, int width, int cosited)
+{
+  int i;
+  if (cosited) {
+    for (i = 1; i < width - 1; i += 2) {
+      p[2 + 4 * i] = (uint8_t) ((p[2 + 4 * (i - 1)] + p[2 + 4 * (i + 1)] + 1) >> 1);
+      p[3 + 4 * i] = (uint8_t) ((p[3 + 4 * (i - 1)] + p[3 + 4 * (i + 1)] + 1) >> 1);
+    }
+  } else {
+    int tr0, tr1 = p[2], tb0, tb1 = p[3];
+    for (i = 1; i < width - 1; i += 2) {
+      tr0 = tr1, tr1 = p[2 + 4 * (i + 1)];
+      tb0 = tb1, tb1 = p[3 + 4 * (i + 1)];
+      p[2 + 4 * i] = (uint8_t) ((3 * tr0 + tr1 + 2) >> 2);
+      p[3 + 4 * i] = (uint8_t) ((3 * tb0 + tb1 + 2) >> 2);
+      p[2 + 4 * (i + 1)] = (uint8_t) ((tr0 + 3 * tr1 + 2) >> 2);
+      p[3 + 4 * (i + 1)] = (uint8_t) ((tb0 + 3 * tb1 + 2) >> 2);
+    }
+  }
+}
+
+typedef struct
+{
+  int n_taps;
+  uint32_t *offset;
+  double *taps;
+  int16_t *taps_s16;            /* out_size * n_taps, lazily quantised */
+  int in_size, out_size, inc;
+} Scaler;
+
+static int
+scaler_init (Scaler * s, const OracleResamplerOpts * o, int in_size, int out_size)
+{
+  memset (s, 0, sizeof (*s));
+  s->offset = malloc (sizeof (uint32_t) * out_size);
+  s->taps = malloc (sizeof (double) * out_size * ORACLE_MAX_TAPS);
+  s->n_taps = oracle_resampler_taps (o, in_size, out_size, s->offset, s->taps);
+  s->in_size = in_size;
+  s->out_size = out_size;
+  /* video-scaler.c:254-257 */
+  s->inc = out_size == 1 ? 0 : ((in_size - 1) << 16) / (out_size - 1) - 1;
+  return s->n_taps > 0 ? 0 : -1;
+}
+
+static void
+scaler_quantize (Scaler * s, int precision)
+{
+  int i;
+  s->taps_s16 = malloc (sizeof (int16_t) * s->out_size * s->n_taps);
+  for (i = 0; i < s->out_size; i++)
+    oracle_quantize_taps (s->taps + (size_t) i * s->n_taps, s->taps_s16 + (size_t) i * s->n_taps,
+        s->n_taps, precision);
+}
+
+static void
+scaler_clear (Scaler * s)
+{
+  free (s->offset);
+  free (s->taps);
+  free (s->taps_s16);
+}
+
+static inline uint8_t
+scale_round_u8 (int acc)
+{
+  /* addw 32; shrsw 6; convsuswb  (video-orc.orc:2474-2481): 16-bit wrap-around */
+  int16_t w = (int16_t) (acc + 32);
+  int v = w >> 6;
+  return (uint8_t) CLAMPI (v, 0, 255);
+}
+
+/* horizontal pass over a packed 4x8-bit image: src (sw x h) -> dst (dw x h) */
+static void
+hscale_image (Scaler * s, const uint8_t * src, int sw, uint8_t * dst, int dw, int h)
+{
+  int x, y, c, k;
+  if (s->n_taps > 2 && !s->taps_s16)
+    scaler_quantize (s, 6);     /* SCALE_U8_LQ, video-scaler.c:632-637 */
+  for (y = 0; y < h; y++) {
+    const uint8_t *sl = src + (size_t) y * sw * 4;
+    uint8_t *dl = dst + (size_t) y * dw * 4;
+    for (x = 0; x < dw; x++) {
+      if (s->n_taps == 1) {     /* video_scale_h_near_u32, :558-590 */
+        memcpy (dl + 4 * x, sl + 4 * s->offset[x], 4);
+      } else if (s->n_taps == 2) {      /* video_scale_h_2tap_4u8 -> ldreslinl, :609-618 */
+        int tmp = x * s->inc, i0 = tmp >> 16, f = (tmp >> 8) & 0xff;
+        int i1 = (i0 + 1 < sw) ? i0 + 1 : i0;   /* f==0 whenever i0+1 leaves the line */
+        for (c = 0; c < 4; c++)
+          dl[4 * x + c] = (uint8_t) ((sl[4 * i0 + c] * (256 - f) + sl[4 * i1 + c] * f) >> 8);
+      } else {                  /* video_scale_h_ntap_u8, :621-760 */
+        const int16_t *t = s->taps_s16 + (size_t) x * s->n_taps;
+        for (c = 0; c < 4; c++) {
+          int acc = 0;
+          for (k = 0; k < s->n_taps; k++)
+            acc += (int16_t) (sl[4 * (s->offset[x] + k) + c] * t[k]);
+          dl[4 * x + c] = scale_round_u8 (acc);
+        }
+      }
+    }
+  }
+}
+
+/* vertical pass: src (w x sh) -> dst (w x dh) */
+static void
+vscale_image (Scaler * s, const uint8_t * src, int sh, uint8_t * dst, int dh, int w)
+{
+  int x, y, k, n = w * 4;
+  (void) sh;
+  if (s->n_taps >= 2 && !s->taps_s16)
+    scaler_quantize (s, s->n_taps == 2 ? 8 : 6);       /* video-scaler.c:857, :937, :998 */
+  for (y = 0; y < dh; y++) {
+    uint8_t *dl = dst + (size_t) y * n;
+    const uint8_t *s0 = src + (size_t) s->offset[y] * n;
+    if (s->n_taps == 1) {       /* video_scale_v_near_u8, :828-835 */
+      memcpy (dl, s0, n);
+    } else if (s->n_taps == 2) {        /* video_orc_resample_v_2tap_u8_lq, video-orc.orc:2212-2228 */
+      int16_t p1 = s->taps_s16[(size_t) y * 2 + 1];
+      const uint8_t *s1 = s0 + n;
+      for (x = 0; x < n; x++) {
+        int16_t w2 = (int16_t) (s1[x] - s0[x]);
+        w2 = (int16_t) (w2 * p1);
+        w2 = (int16_t) (w2 + 128);
+        dl[x] = (uint8_t) (((uint16_t) w2 >> 8) + s0[x]);
+      }
+    } else {                    /* video_scale_v_4tap_u8 / _ntap_u8, :923-1072 */
+      const int16_t *t = s->taps_s16 + (size_t) y * s->n_taps;
+      for (x = 0; x < n; x++) {
+        int acc = 0;
+        for (k = 0; k < s->n_taps; k++)
+          acc += (int16_t) (s0[(size_t) k * n + x] * t[k]);
+        dl[x] = scale_round_u8 (acc);
+      }
+    }
+  }
+}
+
+static void
+pack_line (int fmt, const uint8_t * argb, uint8_t * d, int n)
+{
+  /* video-format.c pack_BGRA :1445, pack_ABGR :1473, pack_RGBA :1505, pack_copy4 (ARGB),
+   * RGBx/BGRx/xRGB/xBGR share the 4-byte shuffles of their alpha siblings */
+  int i;
+  for (i = 0; i < n; i++, argb += 4, d += 4) {
+    uint8_t a = argb[0], r = argb[1], g = argb[2], b = argb[3];
+    switch (fmt) {
+      case ORC_FMT_BGRA: case ORC_FMT_BGRx: d[0] = b; d[1] = g; d[2] = r; d[3] = a; break;
+      case ORC_FMT_RGBA: case ORC_FMT_RGBx: d[0] = r; d[1] = g; d[2] = b; d[3] = a; break;
+      case ORC_FMT_ABGR: case ORC_FMT_xBGR: d[0] = a; d[1] = b; d[2] = g; d[3] = r; break;
+      default: d[0] = a; d[1] = r; d[2] = g; d[3] = b; break;
+    }
+  }
+}
+
+/* Which input lines does the chain pull through the chroma upsampler, and how is each
+ * paired?  The upsample cache hands out lines in PAIRS (n_lines=2, offset=-1,
+ * video-chroma.c:997) starting at whichever line is requested first after a gap
+ * (gst_line_cache_get_lines skip-ahead, video-converter.c:571-617; do_upsample_lines
+ * :2991-3021).  Requests are monotonic, so: a requested line y that directly follows a
+ * requested "first of pair" y-1 is the pair's second line; otherwise y opens a new
+ * pair (y, y+1) - except y==0, which is the second line of the clamped pair (-1,0).
+ * mode: 0 = keep own chroma row, 1 = first of pair, 2 = second of pair. */
+static void
+chroma_plan (const OracleVcsDesc * d, const Scaler * vs, uint8_t * mode)
+{
+  int ih = d->in_height, y, r, k;
+  uint8_t *req = calloc (ih, 1);
+  int prev_first = -2;
+  if (vs) {
+    for (r = 0; r < vs->out_size; r++)
+      for (k = 0; k < vs->n_taps; k++)
+        req[vs->offset[r] + k] = 1;
+  } else
+    memset (req, 1, ih);
+  for (y = 0; y < ih; y++) {
+    mode[y] = 0;
+    if (!req[y])
+      continue;
+    if (y == 0)
+      mode[y] = 0;              /* pair (-1,0): both lines carry chroma row 0 */
+    else if (prev_first == y - 1)
+      mode[y] = 2;
+    else {
+      mode[y] = 1;
+      prev_first = y;
+    }
+  }
+  free (req);
+}
+
+int
+oracle_vcs_convert (const OracleVcsDesc * d, const uint8_t * in, uint8_t * out)
+{
+  int iw = d->in_width, ih = d->in_height, ow = d->out_width, oh = d->out_height;
+  int p[5], im[4][4], y, cw, ch;
+  uint8_t *cur, *tmp, *mode;
+  Scaler hs, vs;
+  int have_h = iw != ow, have_v = ih != oh, pass;
+  long s0, s3;
+
+  if (oracle_vcs_matrix (d, p, im) != 0)
+    return -1;
+  /* chain_hscale / chain_vscale always build in_width->out_width and
+   * in_height->out_height scalers (video-converter.c:1625-1683) */
+  if (have_h && scaler_init (&hs, &d->rs, iw, ow))
+    return -1;
+  if (have_v && scaler_init (&vs, &d->rs, ih, oh))
+    return -1;
+
+  /* unpack + chroma upsample, whole frame: h filter on every line, then the v filter
+   * on the pairs the pull chain forms.  V_COSITED selects the "IMPLEMENT ME"
+   * resampler (video-chroma.c:1000): h filter only, n_lines=1. */
+  cur = malloc ((size_t) iw * ih * 4);
+  mode = malloc (ih);
+  chroma_plan (d, have_v ? &vs : NULL, mode);
+  for (y = 0; y < ih; y++) {
+    unpack_line (d, in, y, cur + (size_t) y * iw * 4);
+    chroma_h_line (cur + (size_t) y * iw * 4, iw, (d->in_chroma_site & ORC_SITE_H_COSITED) != 0);
+  }
+  if (!(d->in_chroma_site & ORC_SITE_V_COSITED)) {
+    /* both lines of a pair are filtered from the ORIGINAL (h-filtered) values, so
+     * work from a copy of the chroma of the partner line */
+    uint8_t *orig = malloc ((size_t) iw * ih * 4);
+    memcpy (orig, cur, (size_t) iw * ih * 4);
+    for (y = 0; y < ih; y++) {
+      int x, c, yo = -1;
+      uint8_t *l = cur + (size_t) y * iw * 4;
+      if (mode[y] == 1)
+        yo = y + 1 < ih ? y + 1 : ih - 1;       /* do_unpack_lines clamp, :2973 */
+      else if (mode[y] == 2)
+        yo = y - 1;
+      if (yo < 0)
+        continue;
+      for (x = 0; x < iw; x++)
+        for (c = 2; c < 4; c++) {
+          int own = orig[((size_t) y * iw + x) * 4 + c], oth = orig[((size_t) yo * iw + x) * 4 + c];
+          l[4 * x + c] = (uint8_t) ((3 * own + oth + 2) >> 2);  /* FILT_3_1 / FILT_1_3 */
+        }
+    }
+    free (orig);
+  }
+  free (mode);
+
+  cw = iw;
+  ch = ih;
+  s0 = (long) iw * ih;
+  s3 = (long) ow * oh;
+  /* pass 0 = chain_scale(force=FALSE) before the matrix, pass 1 = chain_scale(force=TRUE)
+   * after it (video-converter.c:2517-2531, :1685-1718) */
+  for (pass = 0; pass < 2; pass++) {
+    if (pass == 1) {
+      for (y = 0; y < ch; y++)
+        matrix_line (cur + (size_t) y * cw * 4, cw, p);
+    }
+    if (pass == 0 && !(s3 <= s0))
+      continue;
+    if (cw == ow && ch == oh)
+      continue;
+    {
+      long s1 = (long) ow * ch, s2 = (long) cw * oh;
+      int h_first = s1 <= s2, step;
+      for (step = 0; step < 2; step++) {
+        int do_h = (step == 0) == (h_first != 0);
+        if (do_h && cw != ow) {
+          tmp = malloc ((size_t) ow * ch * 4);
+          hscale_image (&hs, cur, cw, tmp, ow, ch);
+          free (cur);
+          cur = tmp;
+          cw = ow;
+        } else if (!do_h && ch != oh) {
+          tmp = malloc ((size_t) cw * oh * 4);
+          vscale_image (&vs, cur, ch, tmp, oh, cw);
+          free (cur);
+          cur = tmp;
+          ch = oh;
+        }
+      }
+    }
+  }
+  for (y = 0; y < oh; y++)
+    pack_line (d->out_format, cur + (size_t) y * ow * 4,
+        out + d->out_offset[0] + (size_t) d->out_stride[0] * y, ow);
+  free (cur);
+  if (have_h)
+    scaler_clear (&hs);
+  if (have_v)
+    scaler_clear (&vs);
+  return 0;
+}
