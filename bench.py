@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the convert+scale hot path (BASELINE.json configs[1]).
+
+Workload (N=1): 3840x2160 NV12 -> 1920x1080 BGRA, method=lanczos (8-tap, 6-bit taps), bt709
+16-235, chroma-site mpeg2.  One "step" = one batch of FRAMES_PER_STEP distinct frames drawn from
+a ring whose working set (>= 1.3 GB) is far larger than the 126 MB L2, so no L2 flush is needed.
+
+  value      whole-job Mpix/s (input pixels), frames resident in HBM, kernel launches only
+  e2e        same metric through the C-ABI host call (pinned host buffers, H2D + kernel + D2H
+             inside the timed region)
+  roofline   algorithmic bytes (20 736 000 B/frame) / CUDA-event kernel time vs the
+             measured HBM copy bandwidth in MEASURED_PEAKS.json
+  cpu_baseline  the reference's own converter (oracle/_ref, compiled from /root/reference
+             sources) — or the oracle port if that library is absent — on the host cores
+
+N>1: one process per GPU (torchrun), independent streams, no collective on the data path
+(SURVEY §8e): "scaling": "weak".  `--impl reference` times the reference CPU path instead.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+IW, IH, OW, OH = 3840, 2160, 1920, 1080
+METHOD = 3  # GST_VIDEO_SCALE_LANCZOS
+ALG_BYTES_PER_FRAME = 12_441_600 + 8_294_400
+IN_PIX_PER_FRAME = IW * IH
+FRAMES_PER_STEP = 32
+RING = 64
+WORKLOAD = "3840x2160 NV12 -> 1920x1080 BGRA, lanczos (8-tap), cudavideoconvertscale"
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons during the timed region"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.gpu)], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    f = [x.strip() for x in line.split(",")]
+                    if len(f) >= 9:
+                        self.samples.append(f)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit())
+        mx = [float(s[2]) for s in self.samples if s[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            for name, v in zip(names, s[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+def cpu_baseline(seconds=10.0, threads=None):
+    """time the reference's CPU converter on frames of the same workload"""
+    import numpy as np
+    from oracle import bindings as ob
+    cores = threads or os.cpu_count() or 1
+    frames = [ob.nv12_random_frame(IW, IH, s) for s in range(2)]
+    if ob.have_ref():
+        kind = "reference"
+        conv = ob.RefVcs(IW, IH, OW, OH, METHOD, n_threads=cores)
+        out = np.zeros(OW * OH * 4, dtype=np.uint8)
+        run = lambda f: conv.convert(f, out)
+        impl = "oracle/_ref: reference video-converter.c + ORC C backups (no liborc SIMD JIT)"
+    else:
+        kind = "port"
+        cores = 1
+        d = ob.vcs_desc(IW, IH, OW, OH, METHOD)
+        run = lambda f: ob.oracle_vcs_convert(d, f)
+        impl = "oracle port (scalar C)"
+    run(frames[0])  # warm (tap tables are built lazily on first use)
+    n, t0 = 0, time.perf_counter()
+    while True:
+        run(frames[n % 2])
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt >= seconds and n >= 3:
+            break
+    return {"value": n * IN_PIX_PER_FRAME / dt / 1e6, "unit": "Mpix/s", "cores": cores, "kind": kind,
+            "sample": f"{n} frames of the same workload in {dt:.1f} s, {impl}"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import bindings as ob
+    import numpy as np
+    cores = os.cpu_count() or 1
+    per_step = 4
+    frames = [ob.nv12_random_frame(IW, IH, s) for s in range(per_step)]
+    if ob.have_ref():
+        kind = "reference"
+        conv = ob.RefVcs(IW, IH, OW, OH, METHOD, n_threads=cores)
+        out = np.zeros(OW * OH * 4, dtype=np.uint8)
+        run = lambda f: conv.convert(f, out)
+    else:
+        kind, cores = "port", 1
+        d = ob.vcs_desc(IW, IH, OW, OH, METHOD)
+        run = lambda f: ob.oracle_vcs_convert(d, f)
+    for _ in range(args.warmup):
+        for f in frames:
+            run(f)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for f in frames:
+            run(f)
+    dt = time.perf_counter() - t0
+    val = args.steps * per_step * IN_PIX_PER_FRAME / dt / 1e6
+    line = {"impl": "reference", "metric": "4K NV12->BGRA+lanczos->1080p throughput", "value": val,
+            "unit": "Mpix/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD + " (CPU videoconvertscale path)", "frames_per_step": per_step},
+            "cpu_baseline": {"value": val, "unit": "Mpix/s", "cores": cores, "kind": kind,
+                             "sample": f"{args.steps}x{per_step} frames, n-threads={cores}"},
+            "e2e": {"value": val, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import gstreamer_b200 as g
+    from oracle import bindings as ob  # input generator only (synthetic frames)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+
+    el = g.CudaVideoConvertScale(method=METHOD, cuda_device_id=local)
+    ii, oi = g.VideoInfo(g.VideoFormat.NV12, IW, IH), g.VideoInfo(g.VideoFormat.BGRA, OW, OH)
+    el.set_info(ii, oi)
+    pinfo = el.plan_info()
+
+    # ring of distinct frames resident in HBM
+    base = [torch.from_numpy(ob.nv12_random_frame(IW, IH, 1000 * rank + s)).to(dev) for s in range(4)]
+    ring_in = []
+    for k in range(RING):
+        t = base[k % 4].clone()
+        t[:: 4099] = (t[:: 4099].to(torch.int32) + k).to(torch.uint8)  # make every frame distinct
+        ring_in.append(t)
+    ring_out = [torch.empty(oi.size, dtype=torch.uint8, device=dev) for _ in range(RING)]
+    stream = torch.cuda.Stream(device=dev)
+
+    def step(i):
+        o = (i % (RING // FRAMES_PER_STEP)) * FRAMES_PER_STEP
+        el.transform_frames(ring_in[o:o + FRAMES_PER_STEP], ring_out[o:o + FRAMES_PER_STEP], stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        for i in range(args.warmup):
+            step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for i in range(args.steps):
+            step(i)
+        e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- e2e: host frames through the C-ABI (pinned staging, copies inside the timed region)
+    e2e_frames = 16
+    hin = [g.PinnedBuffer(ii.size) for _ in range(e2e_frames)]
+    hout = [g.PinnedBuffer(oi.size) for _ in range(e2e_frames)]
+    for k, b in enumerate(hin):
+        b.array[:] = ob.nv12_random_frame(IW, IH, 77 + k)
+    inp, outp = [b.ptr for b in hin], [b.ptr for b in hout]
+    for _ in range(max(1, min(args.warmup, 3))):
+        el.transform_host_frames(inp, outp)
+    barrier()
+    e2e_steps = max(3, min(args.steps, 20))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        el.transform_host_frames(inp, outp)     # returns when every output is back in host memory
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    checksum = int(hout[0].array[:4096].sum())
+
+    t = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_s = float(t[0]), float(t[1])
+    if rank == 0:
+        frames = args.steps * FRAMES_PER_STEP * world
+        value = frames * IN_PIX_PER_FRAME / (ms * 1e-3) / 1e6
+        peak, peak_src = measured_peak()
+        achieved = args.steps * FRAMES_PER_STEP * ALG_BYTES_PER_FRAME / (ms * 1e-3) / 1e9   # per GPU
+        e2e_val = e2e_steps * e2e_frames * world * IN_PIX_PER_FRAME / e2e_s / 1e6
+        line = {
+            "metric": "4K NV12->BGRA+lanczos->1080p throughput", "value": value, "unit": "Mpix/s",
+            "frames_per_s": frames / (ms * 1e-3),
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_step": FRAMES_PER_STEP, "ring_frames": RING,
+                       "l2": "inputs larger than L2 (ring %.0f MB in + %.0f MB out)" %
+                             (RING * ii.size / 1e6, RING * oi.size / 1e6),
+                       "kernel_variant": int(pinfo.kernel_variant), "parallelism": f"streams{world}"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel": "vcs_lanczos2_kernel" if pinfo.kernel_variant == 1 else "vcs_generic_kernel",
+                         "alg_bytes_per_launch": FRAMES_PER_STEP * ALG_BYTES_PER_FRAME,
+                         "us_per_launch": ms * 1e3 / args.steps},
+            "e2e": {"value": e2e_val, "unit": "Mpix/s", "h2d_bytes_per_step": e2e_frames * ii.size,
+                    "d2h_bytes_per_step": e2e_frames * oi.size, "frames_per_step": e2e_frames,
+                    "steps": e2e_steps, "checksum": checksum},
+            "gpu_launches": args.steps * pinfo.n_launches_per_convert,
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

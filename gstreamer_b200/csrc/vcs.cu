@@ -1,0 +1,306 @@
+// gstreamer_b200/csrc/vcs.cu — b200_vcs_* entry points (product code).
+//
+// Replaces gst_video_converter_new/_frame/_free for the element's transform_frame()
+// (gst-plugins-base/gst/videoconvertscale/gstvideoconvertscale.c:1981-2005); device
+// calling convention after gst_cuda_converter_convert_frame
+// (gst-plugins-bad/gst-libs/gst/cuda/gstcudaconverter.cpp:1911).
+#include "common.h"
+#include "vcs_plan.h"
+#include "vcs_device.h"
+#include "vcs_kernels.cuh"
+#include "vcs_lanczos2.cuh"
+
+#include <string.h>
+#include <new>
+#include <vector>
+
+using namespace b200;
+
+struct b200_vcs {
+  VcsPlan plan;
+  int device = -1;
+  VcsDev dev;                     // kernel parameter block (device pointers inside)
+  int variant = 0;
+  // device tables
+  uint32_t *d_hoff = nullptr, *d_voff = nullptr;
+  int16_t *d_hcoef = nullptr, *d_vcoef = nullptr, *d_hsum = nullptr, *d_vsum = nullptr;
+  uint8_t *d_cmode = nullptr;
+  // host<->device pipeline for system-memory peers
+  static const int kSlots = 4;
+  uint8_t *slot_in[kSlots] = {nullptr}, *slot_out[kSlots] = {nullptr};
+  cudaStream_t s_h2d = nullptr, s_run = nullptr, s_d2h = nullptr;
+  cudaEvent_t ev_in[kSlots] = {nullptr}, ev_run[kSlots] = {nullptr}, ev_out[kSlots] = {nullptr};
+  bool pipeline_ready = false;
+  size_t in_bytes = 0, out_bytes = 0;
+};
+
+namespace {
+
+size_t frame_bytes (const b200_video_info & i)
+{
+  return b200_video_info_size (&i);
+}
+
+int upload_axis (const AxisPlan & a, uint32_t **off, int16_t **coef, int16_t **sum, AxisDev * d)
+{
+  int st;
+  if ((st = upload (off, a.offset.data (), a.offset.size ())) != B200_OK) return st;
+  if ((st = upload (coef, a.coef.data (), a.coef.size ())) != B200_OK) return st;
+  if ((st = upload (sum, a.sum.data (), a.sum.size ())) != B200_OK) return st;
+  d->offset = *off; d->coef = *coef; d->sum = *sum;
+  d->mode = a.mode; d->n_taps = a.n_taps; d->coef_per_out = a.coef_per_out; d->span = a.span;
+  d->out_size = a.out_size; d->in_size = a.in_size;
+  return B200_OK;
+}
+
+int launch (b200_vcs * h, int n, const VcsBatch & batch, cudaStream_t stream)
+{
+  const VcsPlan & p = h->plan;
+  if (h->variant == 1 && p.lanczos2_ok)
+    return launch_lanczos2 (h->dev, batch, n, h->device, stream);
+  dim3 grid ((p.out.width + p.tile_w - 1) / p.tile_w, (p.out.height + p.tile_h - 1) / p.tile_h, n);
+  vcs_generic_kernel <<<grid, 256, p.smem_bytes, stream>>> (h->dev, batch);
+  B200_CUDA_TRY (cudaGetLastError ());
+  return B200_OK;
+}
+
+int ensure_pipeline (b200_vcs * h)
+{
+  if (h->pipeline_ready) return B200_OK;
+  h->in_bytes = frame_bytes (h->plan.in);
+  h->out_bytes = frame_bytes (h->plan.out);
+  B200_CUDA_TRY (cudaStreamCreateWithFlags (&h->s_h2d, cudaStreamNonBlocking));
+  B200_CUDA_TRY (cudaStreamCreateWithFlags (&h->s_run, cudaStreamNonBlocking));
+  B200_CUDA_TRY (cudaStreamCreateWithFlags (&h->s_d2h, cudaStreamNonBlocking));
+  for (int i = 0; i < b200_vcs::kSlots; i++) {
+    B200_CUDA_TRY (cudaMalloc ((void **) &h->slot_in[i], h->in_bytes));
+    B200_CUDA_TRY (cudaMalloc ((void **) &h->slot_out[i], h->out_bytes));
+    B200_CUDA_TRY (cudaEventCreateWithFlags (&h->ev_in[i], cudaEventDisableTiming));
+    B200_CUDA_TRY (cudaEventCreateWithFlags (&h->ev_run[i], cudaEventDisableTiming));
+    B200_CUDA_TRY (cudaEventCreateWithFlags (&h->ev_out[i], cudaEventDisableTiming));
+  }
+  h->pipeline_ready = true;
+  return B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void b200_vcs_config_init (b200_vcs_config * cfg)
+{
+  if (!cfg) return;
+  memset (cfg, 0, sizeof (*cfg));
+  cfg->method = B200_SCALE_BILINEAR;    // DEFAULT_PROP_METHOD, gstvideoconvertscale.c:130
+  cfg->envelope = 2.0; cfg->sharpness = 1.0; cfg->sharpen = 0.0;
+}
+
+int b200_video_info_set_format (b200_video_info * info, int format, int width, int height)
+{
+  if (!info || width < 1 || height < 1) return B200_ERR_INVALID_ARG;
+  memset (info, 0, sizeof (*info));
+  info->format = format; info->width = width; info->height = height;
+  switch (format) {
+    case B200_VIDEO_FORMAT_NV12: case B200_VIDEO_FORMAT_NV21:
+      // video-info.c:1053-1063
+      info->stride[0] = (width + 3) & ~3; info->stride[1] = info->stride[0];
+      info->offset[0] = 0; info->offset[1] = (uint64_t) info->stride[0] * ((height + 1) & ~1);
+      info->color_matrix = height > 576 ? B200_COLOR_MATRIX_BT709 : B200_COLOR_MATRIX_BT601;
+      info->color_range = B200_COLOR_RANGE_16_235;
+      info->chroma_site = height > 576 ? B200_CHROMA_SITE_H_COSITED : B200_CHROMA_SITE_NONE;
+      return B200_OK;
+    case B200_VIDEO_FORMAT_RGBx: case B200_VIDEO_FORMAT_BGRx: case B200_VIDEO_FORMAT_xRGB:
+    case B200_VIDEO_FORMAT_xBGR: case B200_VIDEO_FORMAT_RGBA: case B200_VIDEO_FORMAT_BGRA:
+    case B200_VIDEO_FORMAT_ARGB: case B200_VIDEO_FORMAT_ABGR:
+      info->stride[0] = width * 4;      // video-info.c:890-894
+      info->color_matrix = B200_COLOR_MATRIX_RGB; info->color_range = B200_COLOR_RANGE_0_255;
+      return B200_OK;
+    default:
+      return B200_ERR_UNSUPPORTED;
+  }
+}
+
+size_t b200_video_info_size (const b200_video_info * info)
+{
+  if (!info) return 0;
+  switch (info->format) {
+    case B200_VIDEO_FORMAT_NV12: case B200_VIDEO_FORMAT_NV21:
+      return (size_t) info->offset[1] + (size_t) info->stride[1] * (((info->height + 1) & ~1) / 2);
+    default:
+      return (size_t) info->offset[0] + (size_t) info->stride[0] * info->height;
+  }
+}
+
+int b200_vcs_create (const b200_video_info * in, const b200_video_info * out,
+    const b200_vcs_config * cfg, int device, b200_vcs ** handle)
+{
+  if (!handle) return B200_ERR_INVALID_ARG;
+  *handle = nullptr;
+  b200_vcs_config defcfg;
+  if (!cfg) { b200_vcs_config_init (&defcfg); cfg = &defcfg; }
+  b200_vcs *h = new (std::nothrow) b200_vcs ();
+  if (!h) return B200_ERR_NOMEM;
+  int st = build_vcs_plan (in, out, cfg, &h->plan);
+  if (st != B200_OK) { delete h; return st; }
+  const VcsPlan & p = h->plan;
+  if ((p.out.stride[0] & 3) || (p.out.offset[0] & 3)) { delete h; return B200_ERR_UNSUPPORTED; }
+  h->device = device;
+  if (device >= 0) {
+    int ndev = b200_device_count ();
+    if (ndev <= 0) { delete h; return ndev < 0 ? ndev : B200_ERR_NO_DEVICE; }
+    if (device >= ndev) { delete h; return B200_ERR_INVALID_ARG; }
+    DeviceGuard g (device);
+    if (!g.ok) { delete h; return B200_ERR_CUDA; }
+    VcsDev & d = h->dev;
+    memset (&d, 0, sizeof (d));
+    d.iw = p.in.width; d.ih = p.in.height; d.ow = p.out.width; d.oh = p.out.height;
+    d.stride_y = p.in.stride[0]; d.stride_c = p.in.stride[1]; d.stride_out = p.out.stride[0];
+    d.off_y = p.in.offset[0]; d.off_c = p.in.offset[1]; d.off_out = p.out.offset[0];
+    d.u_index = p.u_index; d.h_cosited = p.h_cosited; d.v_pairs = p.v_pairs;
+    d.h_first = p.h_first; d.matrix_first = p.matrix_first;
+    d.p1 = p.p[0]; d.p2 = p.p[1]; d.p3 = p.p[2]; d.p4 = p.p[3]; d.p5 = p.p[4];
+    d.sel = p.byte_sel[0] | (p.byte_sel[1] << 4) | (p.byte_sel[2] << 8) | (p.byte_sel[3] << 12);
+    d.tile_w = p.tile_w; d.tile_h = p.tile_h; d.max_rows = p.max_rows; d.cols_pitch = p.cols_pitch;
+    d.max_crows = p.max_crows;
+    if ((st = upload_axis (p.h, &h->d_hoff, &h->d_hcoef, &h->d_hsum, &d.h)) != B200_OK ||
+        (st = upload_axis (p.v, &h->d_voff, &h->d_vcoef, &h->d_vsum, &d.v)) != B200_OK ||
+        (st = upload (&h->d_cmode, p.chroma_mode.data (), p.chroma_mode.size ())) != B200_OK) {
+      b200_vcs_destroy (h);
+      return st;
+    }
+    d.chroma_mode = h->d_cmode;
+    cudaError_t e = cudaFuncSetAttribute (vcs_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        p.smem_bytes);
+    if (e != cudaSuccess) { b200_vcs_destroy (h); return cuda_fail (e, "cudaFuncSetAttribute", __FILE__, __LINE__); }
+    if (p.lanczos2_ok) {
+      st = prepare_lanczos2 (h->dev, device);
+      if (st != B200_OK) { b200_vcs_destroy (h); return st; }
+      h->variant = 1;
+    }
+  }
+  *handle = h;
+  return B200_OK;
+}
+
+void b200_vcs_destroy (b200_vcs * h)
+{
+  if (!h) return;
+  if (h->device >= 0) {
+    DeviceGuard g (h->device);
+    cudaFree (h->d_hoff); cudaFree (h->d_voff); cudaFree (h->d_hcoef); cudaFree (h->d_vcoef);
+    cudaFree (h->d_hsum); cudaFree (h->d_vsum); cudaFree (h->d_cmode);
+    for (int i = 0; i < b200_vcs::kSlots; i++) {
+      cudaFree (h->slot_in[i]); cudaFree (h->slot_out[i]);
+      if (h->ev_in[i]) cudaEventDestroy (h->ev_in[i]);
+      if (h->ev_run[i]) cudaEventDestroy (h->ev_run[i]);
+      if (h->ev_out[i]) cudaEventDestroy (h->ev_out[i]);
+    }
+    if (h->s_h2d) cudaStreamDestroy (h->s_h2d);
+    if (h->s_run) cudaStreamDestroy (h->s_run);
+    if (h->s_d2h) cudaStreamDestroy (h->s_d2h);
+  }
+  delete h;
+}
+
+int b200_vcs_convert_batch (b200_vcs * h, int n, const void *const *in_frames,
+    void *const *out_frames, void *cuda_stream)
+{
+  if (!h || !in_frames || !out_frames || n < 1 || n > B200_VCS_MAX_BATCH) return B200_ERR_INVALID_ARG;
+  if (h->device < 0) return B200_ERR_NO_DEVICE;
+  DeviceGuard g (h->device);
+  if (!g.ok) return B200_ERR_CUDA;
+  VcsBatch b;
+  for (int i = 0; i < n; i++) {
+    if (!in_frames[i] || !out_frames[i]) return B200_ERR_INVALID_ARG;
+    b.in[i] = (const uint8_t *) in_frames[i];
+    b.out[i] = (uint8_t *) out_frames[i];
+  }
+  return launch (h, n, b, (cudaStream_t) cuda_stream);
+}
+
+int b200_vcs_convert (b200_vcs * h, const void *in_frame, void *out_frame, void *cuda_stream)
+{
+  return b200_vcs_convert_batch (h, 1, &in_frame, &out_frame, cuda_stream);
+}
+
+int b200_vcs_convert_host (b200_vcs * h, int n, const void *const *in_host, void *const *out_host)
+{
+  if (!h || !in_host || !out_host || n < 1) return B200_ERR_INVALID_ARG;
+  if (h->device < 0) return B200_ERR_NO_DEVICE;
+  DeviceGuard g (h->device);
+  if (!g.ok) return B200_ERR_CUDA;
+  int st = ensure_pipeline (h);
+  if (st != B200_OK) return st;
+  // three-stage software pipeline over kSlots device frame pairs: the upload of frame
+  // i+1 and the download of frame i-1 overlap the kernel of frame i (copy engines run
+  // beside the SMs).  Slot reuse is fenced by the download event of its previous user.
+  const int K = b200_vcs::kSlots;
+  for (int i = 0; i < n; i++) {
+    const int s = i % K;
+    if (!in_host[i] || !out_host[i]) return B200_ERR_INVALID_ARG;
+    if (i >= K) {
+      B200_CUDA_TRY (cudaStreamWaitEvent (h->s_h2d, h->ev_run[s], 0));   // input slot consumed
+      B200_CUDA_TRY (cudaStreamWaitEvent (h->s_run, h->ev_out[s], 0));   // output slot drained
+    }
+    B200_CUDA_TRY (cudaMemcpyAsync (h->slot_in[s], in_host[i], h->in_bytes, cudaMemcpyHostToDevice, h->s_h2d));
+    B200_CUDA_TRY (cudaEventRecord (h->ev_in[s], h->s_h2d));
+    B200_CUDA_TRY (cudaStreamWaitEvent (h->s_run, h->ev_in[s], 0));
+    VcsBatch b;
+    b.in[0] = h->slot_in[s]; b.out[0] = h->slot_out[s];
+    if ((st = launch (h, 1, b, h->s_run)) != B200_OK) return st;
+    B200_CUDA_TRY (cudaEventRecord (h->ev_run[s], h->s_run));
+    B200_CUDA_TRY (cudaStreamWaitEvent (h->s_d2h, h->ev_run[s], 0));
+    B200_CUDA_TRY (cudaMemcpyAsync (out_host[i], h->slot_out[s], h->out_bytes, cudaMemcpyDeviceToHost, h->s_d2h));
+    B200_CUDA_TRY (cudaEventRecord (h->ev_out[s], h->s_d2h));
+  }
+  B200_CUDA_TRY (cudaStreamSynchronize (h->s_d2h));
+  return B200_OK;
+}
+
+int b200_vcs_get_plan_info (const b200_vcs * h, b200_vcs_plan_info * info)
+{
+  if (!h || !info) return B200_ERR_INVALID_ARG;
+  const VcsPlan & p = h->plan;
+  memset (info, 0, sizeof (*info));
+  info->h_taps = p.h.scaling ? p.h.n_taps : 0;
+  info->v_taps = p.v.scaling ? p.v.n_taps : 0;
+  info->h_first = p.h_first; info->matrix_first = p.matrix_first;
+  for (int i = 0; i < 5; i++) info->p[i] = p.p[i];
+  info->tile_w = p.tile_w; info->tile_h = p.tile_h; info->smem_bytes = p.smem_bytes;
+  info->kernel_variant = (h->variant == 1 && p.lanczos2_ok) ? 1 : 0;
+  info->n_launches_per_convert = 1;
+  return B200_OK;
+}
+
+int b200_vcs_get_taps (const b200_vcs * h, int dir, uint32_t * offsets, int16_t * taps,
+    size_t offsets_len, size_t taps_len)
+{
+  if (!h || (dir != 0 && dir != 1)) return B200_ERR_INVALID_ARG;
+  const AxisPlan & a = dir == 0 ? h->plan.h : h->plan.v;
+  if (offsets) {
+    if (offsets_len < a.offset.size ()) return B200_ERR_INVALID_ARG;
+    memcpy (offsets, a.offset.data (), a.offset.size () * sizeof (uint32_t));
+  }
+  if (taps) {
+    if (taps_len < a.coef.size ()) return B200_ERR_INVALID_ARG;
+    memcpy (taps, a.coef.data (), a.coef.size () * sizeof (int16_t));
+  }
+  return (int) a.coef_per_out;
+}
+
+int b200_vcs_get_chroma_plan (const b200_vcs * h, uint8_t * mode, size_t len)
+{
+  if (!h || !mode || len < h->plan.chroma_mode.size ()) return B200_ERR_INVALID_ARG;
+  memcpy (mode, h->plan.chroma_mode.data (), h->plan.chroma_mode.size ());
+  return B200_OK;
+}
+
+int b200_vcs_set_kernel_variant (b200_vcs * h, int variant)
+{
+  if (!h || variant < 0 || variant > 1) return B200_ERR_INVALID_ARG;
+  if (variant == 1 && !h->plan.lanczos2_ok) return B200_ERR_UNSUPPORTED;
+  h->variant = variant;
+  return B200_OK;
+}
+
+}  // extern "C"

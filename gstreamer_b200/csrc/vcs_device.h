@@ -1,0 +1,36 @@
+// gstreamer_b200/csrc/vcs_device.h — device-side view of a convert+scale plan (product code).
+#pragma once
+
+#include <stdint.h>
+
+#include "../../include/b200dsp.h"
+
+namespace b200 {
+
+struct AxisDev {
+  const uint32_t *offset;        // [out_size]
+  const int16_t *coef;           // [out_size * coef_per_out]
+  const int16_t *sum;            // [out_size] (NTAP only)
+  int mode, n_taps, coef_per_out, span, out_size, in_size;
+};
+
+// kernel parameter block: plain data, < 4 KB with the batch pointer table
+struct VcsDev {
+  int iw, ih, ow, oh;
+  int stride_y, stride_c, stride_out;
+  unsigned long long off_y, off_c, off_out;
+  int u_index, h_cosited, v_pairs;
+  int h_first, matrix_first;
+  int p1, p2, p3, p4, p5;
+  unsigned sel;                  // byte selector nibbles for PRMT-style packing: byte i <- comp sel[i]
+  AxisDev h, v;
+  const uint8_t *chroma_mode;    // [ih]
+  int tile_w, tile_h, max_rows, cols_pitch, max_crows;
+};
+
+struct VcsBatch {
+  const uint8_t *in[B200_VCS_MAX_BATCH];
+  uint8_t *out[B200_VCS_MAX_BATCH];
+};
+
+}  // namespace b200

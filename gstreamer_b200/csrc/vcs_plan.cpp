@@ -1,0 +1,355 @@
+// gstreamer_b200/csrc/vcs_plan.cpp — host-side plan builder for convert+scale (product code).
+//
+// Follows the *numbers* of the reference's setup exactly (they decide every output
+// byte) while producing flat tables for the fused CUDA kernels:
+//   tap positions/weights      gst-libs/gst/video/video-resampler.c:204-288, :343-429
+//   integer taps + DC bisection gst-libs/gst/video/video-scaler.c:338-449
+//   2-tap specials             video-scaler.c:254-257, :609-618 (h, 16.16 stepping), :846-879 (v, 8-bit tap)
+//   stage order                video-converter.c:1685-1718 (chain_scale), :2509-2539
+//   colour matrix              video-converter.c:1324-1442 (+ :899-1040 algebra), video-color.c:204-252, :423-459
+//   chroma pairing             video-converter.c:571-617, :2991-3021; video-chroma.c:959-1036
+//   element option mapping     gst/videoconvertscale/gstvideoconvertscale.c:991-1087
+#include "vcs_plan.h"
+
+#include <math.h>
+#include <string.h>
+#include <algorithm>
+
+namespace b200 {
+
+namespace {
+
+enum Kernel1D { K_NEAREST, K_LINEAR, K_CUBIC, K_SINC, K_LANCZOS };
+
+struct FilterSpec {
+  Kernel1D kind = K_LINEAR;
+  int max_taps = 128;            // GST_VIDEO_RESAMPLER_OPT_MAX_TAPS
+  double cubic_b = 1.0 / 3.0, cubic_c = 1.0 / 3.0;
+  double envelope = 2.0, sharpness = 1.0, sharpen = 0.0;
+};
+
+// gstvideoconvertscale.c:991-1050: element "method" -> resampler method + extra options
+FilterSpec filter_from_method (const b200_vcs_config & cfg)
+{
+  FilterSpec f;
+  f.envelope = cfg.envelope;
+  f.sharpness = cfg.sharpness;
+  f.sharpen = cfg.sharpen;
+  switch (cfg.method) {
+    case B200_SCALE_NEAREST:   f.kind = K_NEAREST; break;
+    case B200_SCALE_BILINEAR:  f.kind = K_LINEAR; f.max_taps = 2; break;
+    case B200_SCALE_4TAP:      f.kind = K_SINC; f.max_taps = 4; break;
+    case B200_SCALE_LANCZOS:   f.kind = K_LANCZOS; break;
+    case B200_SCALE_BILINEAR2: f.kind = K_LINEAR; break;
+    case B200_SCALE_SINC:      f.kind = K_SINC; break;
+    case B200_SCALE_HERMITE:   f.kind = K_CUBIC; f.cubic_b = 0.0; f.cubic_c = 0.0; break;
+    case B200_SCALE_SPLINE:    f.kind = K_CUBIC; f.cubic_b = 1.0; f.cubic_c = 0.0; break;
+    case B200_SCALE_CATROM:    f.kind = K_CUBIC; f.cubic_b = 0.0; f.cubic_c = 0.5; break;
+    case B200_SCALE_MITCHELL:
+    default:                   f.kind = K_CUBIC; break;
+  }
+  return f;
+}
+
+inline double sinc_pi (double x) { return x == 0 ? 1.0 : sin (M_PI * x) / (M_PI * x); }
+inline double window (double x) { return (x <= -1 || x >= 1) ? 0.0 : sinc_pi (x); }
+
+struct Weigher {
+  Kernel1D kind;
+  double fx, ex, b, c, sharpen;
+  double operator() (double dist) const      // dist = x - (xi + l), signed
+  {
+    switch (kind) {
+      case K_NEAREST: return 1.0;
+      case K_LINEAR: { double a = fabs (dist) * fx; return a < 1.0 ? 1.0 - a : 0.0; }
+      case K_CUBIC: {
+        double a = fabs (dist) * fx, a2 = a * a, a3 = a2 * a;
+        if (a <= 1.0)
+          return ((12.0 - 9.0 * b - 6.0 * c) * a3 + (-18.0 + 12.0 * b + 6.0 * c) * a2 + (6.0 - 2.0 * b)) / 6.0;
+        if (a <= 2.0)
+          return ((-b - 6.0 * c) * a3 + (6.0 * b + 30.0 * c) * a2 + (-12.0 * b - 48.0 * c) * a + (8.0 * b + 24.0 * c)) / 6.0;
+        return 0.0;
+      }
+      case K_SINC: return sinc_pi (dist * fx);
+      case K_LANCZOS:
+      default: return (sinc_pi (dist * fx) - sharpen) * window (dist * ex);
+    }
+  }
+};
+
+struct RealTaps {
+  int n = 0;
+  std::vector<uint32_t> first;
+  std::vector<double> w;         // out_size * n
+};
+
+// video-resampler.c:343-429 (tap count) + :204-288 (positions, normalisation, edge folding)
+RealTaps real_taps (const FilterSpec & f, int in_size, int out_size)
+{
+  RealTaps r;
+  Weigher wf;
+  wf.kind = f.kind; wf.b = f.cubic_b; wf.c = f.cubic_c; wf.sharpen = f.sharpen;
+  double ratio = in_size / (double) out_size;
+  wf.fx = (ratio > 1.0 ? 1.0 / ratio : 1.0) * f.sharpness;
+  double env = f.envelope;
+  int n = 0;
+  if (f.kind == K_NEAREST) n = 1;
+  else if (f.kind == K_LINEAR) env = 1.0;
+  else if (f.kind == K_CUBIC) env = 2.0;
+  if (n == 0) {
+    double dx = ceil (2.0 * env / wf.fx);
+    n = (int) std::min<double> (std::max<double> (dx, 0), f.max_taps);
+  }
+  wf.fx = 2.0 * env / n;
+  wf.ex = 2.0 / n;
+  n = std::min (n, in_size);
+  r.n = n;
+  r.first.resize (out_size);
+  r.w.assign ((size_t) out_size * n, 0.0);
+  const int centre = (n - 1) / 2;
+  const double half = n == 1 ? 0.0 : 0.5;
+  for (int j = 0; j < out_size; j++) {
+    double pos = ((0.5 + (double) j - 0.0) / out_size) * (double) in_size - half;
+    pos = std::min<double> (std::max<double> (pos, 0), in_size - 1);
+    int xi = (int) floor (pos - centre);
+    double *t = &r.w[(size_t) j * n];
+    double total = 0;
+    for (int l = 0; l < n; l++) { t[l] = wf (pos - (xi + l)); total += t[l]; }
+    for (int l = 0; l < n; l++) t[l] /= total;
+    int first = xi;
+    if (xi < 0) {                       // fold taps hanging over the left edge
+      int sh = -xi, l;
+      for (l = 0; l < sh; l++) t[sh] += t[l];
+      for (l = 0; l < n - sh; l++) t[l] = t[sh + l];
+      for (; l < n; l++) t[l] = 0;
+      first += sh;
+    }
+    if (xi > in_size - n) {             // ... and over the right edge
+      int sh = xi - (in_size - n), l;
+      for (l = 0; l < sh; l++) t[n - sh - 1] += t[n - sh + l];
+      for (l = 0; l < n - sh; l++) t[n - 1 - l] = t[n - 1 - sh - l];
+      for (l = 0; l < sh; l++) t[l] = 0;
+      first -= sh;
+    }
+    r.first[j] = (uint32_t) first;
+  }
+  return r;
+}
+
+// video-scaler.c:338-388: floor(bias + w * 2^prec) with the bias bisected until the
+// taps sum to 2^prec; the last attempt is kept when no bias achieves it.
+void integer_taps (const double *w, int16_t * q, int n, int prec)
+{
+  const double mul = (double) (1 << prec);
+  const int target = 1 << prec;
+  double lo = 0.0, hi = 1.0, bias = 0.5;
+  for (int it = 0; it < 64; it++) {
+    int sum = 0;
+    for (int j = 0; j < n; j++) { q[j] = (int16_t) floor (bias + w[j] * mul); sum += q[j]; }
+    if (sum == target || lo == hi) break;
+    if (sum < target) { if (bias > lo) lo = bias; bias += (hi - lo) / 2; }
+    else { if (bias < hi) hi = bias; bias -= (hi - lo) / 2; }
+  }
+}
+
+void identity_axis (AxisPlan * a, int size)
+{
+  a->in_size = a->out_size = size;
+  a->mode = PASS_COPY; a->n_taps = 1; a->coef_per_out = 0; a->span = 1; a->scaling = false;
+  a->offset.resize (size);
+  for (int i = 0; i < size; i++) a->offset[i] = (uint32_t) i;
+  a->coef.clear (); a->sum.clear ();
+}
+
+void scaled_axis (AxisPlan * a, const FilterSpec & f, int in_size, int out_size, bool horizontal)
+{
+  RealTaps r = real_taps (f, in_size, out_size);
+  a->in_size = in_size; a->out_size = out_size; a->scaling = true;
+  a->n_taps = r.n; a->span = r.n;
+  if (r.n == 1) {                       // video_scale_h_near_u32 / video_scale_v_near_u8
+    a->mode = PASS_COPY; a->coef_per_out = 0; a->offset = r.first;
+  } else if (r.n == 2 && horizontal) {  // video_scale_h_2tap_4u8: edge-aligned 16.16 stepping
+    a->mode = PASS_2TAP; a->coef_per_out = 1;
+    a->offset.resize (out_size); a->coef.resize (out_size);
+    int inc = out_size == 1 ? 0 : (int) ((((int64_t) in_size - 1) << 16) / (out_size - 1)) - 1;
+    for (int i = 0; i < out_size; i++) {
+      int tmp = i * inc;                // int arithmetic like ldreslinl
+      a->offset[i] = (uint32_t) (tmp >> 16);
+      a->coef[i] = (int16_t) ((tmp >> 8) & 0xff);
+    }
+  } else if (r.n == 2) {                // video_scale_v_2tap_u8: centre-aligned, 8-bit second tap
+    a->mode = PASS_2TAP; a->coef_per_out = 1;
+    a->offset = r.first; a->coef.resize (out_size);
+    for (int i = 0; i < out_size; i++) {
+      int16_t q[2];
+      integer_taps (&r.w[(size_t) i * 2], q, 2, 8);
+      a->coef[i] = q[1];
+    }
+  } else {                              // n-tap FIR at 6-bit precision (SCALE_U8_LQ)
+    a->mode = PASS_NTAP; a->coef_per_out = r.n;
+    a->offset = r.first; a->coef.resize ((size_t) out_size * r.n); a->sum.resize (out_size);
+    for (int i = 0; i < out_size; i++) {
+      int16_t *q = &a->coef[(size_t) i * r.n];
+      integer_taps (&r.w[(size_t) i * r.n], q, r.n, 6);
+      int s = 0;
+      for (int k = 0; k < r.n; k++) s += q[k];
+      a->sum[i] = (int16_t) s;
+    }
+  }
+}
+
+struct Mat4 {
+  double m[4][4];
+  static Mat4 identity () { Mat4 r; for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) r.m[i][j] = i == j; return r; }
+};
+// left-multiply: dst = a * b, accumulating k = 0..3 in order (rounding must match)
+Mat4 mul (const Mat4 & a, const Mat4 & b)
+{
+  Mat4 r;
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++) {
+      double x = 0;
+      for (int k = 0; k < 4; k++) x += a.m[i][k] * b.m[k][j];
+      r.m[i][j] = x;
+    }
+  return r;
+}
+Mat4 diag (double a, double b, double c) { Mat4 r = Mat4::identity (); r.m[0][0] = a; r.m[1][1] = b; r.m[2][2] = c; return r; }
+Mat4 shift (double a, double b, double c) { Mat4 r = Mat4::identity (); r.m[0][3] = a; r.m[1][3] = b; r.m[2][3] = c; return r; }
+
+int colour_matrix (VcsPlan * p)
+{
+  int off[3], scl[3];
+  if (p->in.color_range == B200_COLOR_RANGE_16_235) { off[0] = 16; scl[0] = 219; off[1] = off[2] = 128; scl[1] = scl[2] = 224; }
+  else { off[0] = 0; scl[0] = 255; off[1] = off[2] = 128; scl[1] = scl[2] = 255; }
+  double kr, kb;
+  switch (p->in.color_matrix) {
+    case B200_COLOR_MATRIX_FCC: kr = 0.30; kb = 0.11; break;
+    case B200_COLOR_MATRIX_BT709: kr = 0.2126; kb = 0.0722; break;
+    case B200_COLOR_MATRIX_BT601: kr = 0.2990; kb = 0.1140; break;
+    case B200_COLOR_MATRIX_SMPTE240M: kr = 0.212; kb = 0.087; break;
+    case B200_COLOR_MATRIX_BT2020: kr = 0.2627; kb = 0.0593; break;
+    default: return B200_ERR_INVALID_ARG;   // YUV input needs a YUV matrix (video-info.c:187-209)
+  }
+  double kg = 1.0 - kr - kb;
+  Mat4 m = Mat4::identity ();
+  m = mul (shift (-off[0], -off[1], -off[2]), m);
+  m = mul (diag (1 / ((float) scl[0]), 1 / ((float) scl[1]), 1 / ((float) scl[2])), m);
+  Mat4 k = Mat4::identity ();
+  k.m[0][0] = 1.; k.m[0][1] = 0.; k.m[0][2] = 2 * (1 - kr);
+  k.m[1][0] = 1.; k.m[1][1] = -2 * kb * (1 - kb) / kg; k.m[1][2] = -2 * kr * (1 - kr) / kg;
+  k.m[2][0] = 1.; k.m[2][1] = 2 * (1 - kb); k.m[2][2] = 0.;
+  m = mul (k, m);
+  m = mul (diag ((float) 255, (float) 255, (float) 255), m);     // ARGB out, full range
+  m = mul (shift (0, 0, 0), m);
+  m = mul (diag (256.0f, 256.0f, 256.0f), m);                    // SCALE_F
+  for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) p->im[i][j] = (int) rint (m.m[i][j]);
+  // the reference only takes its fused AYUV->ARGB routine for matrices of this shape
+  if (p->im[0][0] != p->im[1][0] || p->im[1][0] != p->im[2][0] || p->im[0][1] != 0 || p->im[2][2] != 0)
+    return B200_ERR_UNSUPPORTED;
+  p->p[0] = p->im[0][0]; p->p[1] = p->im[0][2]; p->p[2] = p->im[2][1]; p->p[3] = p->im[1][1]; p->p[4] = p->im[1][2];
+  return B200_OK;
+}
+
+// Which lines reach the chroma upsampler and how they pair up (see DESIGN.md "chroma plan").
+void chroma_pairing (VcsPlan * p)
+{
+  const int ih = p->in.height;
+  std::vector<uint8_t> wanted (ih, p->v.scaling ? 0 : 1);
+  if (p->v.scaling)
+    for (int r = 0; r < p->v.out_size; r++)
+      for (int k = 0; k < p->v.span; k++) wanted[p->v.offset[r] + k] = 1;
+  p->chroma_mode.assign (ih, 0);
+  int open_pair = -2;
+  for (int y = 1; y < ih; y++) {        // line 0 always rides the clamped pair (-1,0)
+    if (!wanted[y]) continue;
+    if (open_pair == y - 1) p->chroma_mode[y] = 2;
+    else { p->chroma_mode[y] = 1; open_pair = y; }
+  }
+}
+
+void tile_geometry (VcsPlan * p)
+{
+  const int ow = p->out.width, oh = p->out.height;
+  int tw = ow >= 64 ? 64 : (ow >= 32 ? 32 : 16), th = 16;
+  const int budget = 200 * 1024;
+  for (;;) {
+    int max_rows = 0, max_cols = 0;
+    for (int y0 = 0; y0 < oh; y0 += th) {
+      int y1 = std::min (y0 + th, oh) - 1;
+      max_rows = std::max (max_rows, (int) (p->v.offset[y1] + p->v.span - p->v.offset[y0]));
+    }
+    for (int x0 = 0; x0 < ow; x0 += tw) {
+      int x1 = std::min (x0 + tw, ow) - 1;
+      max_cols = std::max (max_cols, (int) (p->h.offset[x1] + p->h.span - p->h.offset[x0]));
+    }
+    int pitch = (max_cols + 3) & ~3;
+    int crows = max_rows / 2 + 3;
+    size_t planes = (size_t) 3 * max_rows * pitch;
+    size_t hup = (size_t) 2 * crows * pitch;
+    size_t mid = p->h_first ? (size_t) 3 * max_rows * tw : (size_t) 3 * th * pitch;
+    size_t coefs = ((size_t) tw * std::max (p->h.coef_per_out, 1) + (size_t) th * std::max (p->v.coef_per_out, 1)) * 2 + 64;
+    size_t total = planes + hup + mid + coefs + 64;
+    if (total <= (size_t) budget || (tw == 1 && th == 1)) {
+      p->tile_w = tw; p->tile_h = th; p->max_rows = max_rows; p->max_cols = max_cols;
+      p->cols_pitch = pitch; p->max_crows = crows; p->smem_bytes = (int) total;
+      return;
+    }
+    // shrink the dimension that contributes most
+    if (max_rows >= max_cols && th > 1) th = std::max (1, th / 2);
+    else if (tw > 1) tw = std::max (1, tw / 2);
+    else th = std::max (1, th / 2);
+  }
+}
+
+}  // namespace
+
+int build_vcs_plan (const b200_video_info * in, const b200_video_info * out,
+    const b200_vcs_config * cfg, VcsPlan * p)
+{
+  if (!in || !out || !cfg || !p) return B200_ERR_INVALID_ARG;
+  if (in->width < 1 || in->height < 1 || out->width < 1 || out->height < 1 ||
+      in->width > 32767 || in->height > 32767 || out->width > 32767 || out->height > 32767)
+    return B200_ERR_INVALID_ARG;        // caps range [1,32767], gstvideoconvertscale.c:168-169
+  if (in->format != B200_VIDEO_FORMAT_NV12 && in->format != B200_VIDEO_FORMAT_NV21)
+    return B200_ERR_UNSUPPORTED;
+  p->in = *in; p->out = *out; p->cfg = *cfg;
+  // caps defaults (video-info.c:165-185, :211-225)
+  if (p->in.color_matrix == 0) p->in.color_matrix = in->height > 576 ? B200_COLOR_MATRIX_BT709 : B200_COLOR_MATRIX_BT601;
+  if (p->in.color_range == 0) p->in.color_range = B200_COLOR_RANGE_16_235;
+  if (p->in.chroma_site == 0) p->in.chroma_site = in->height > 576 ? B200_CHROMA_SITE_H_COSITED : B200_CHROMA_SITE_NONE;
+  switch (out->format) {                // (A,R,G,B) component placed at each output byte
+    case B200_VIDEO_FORMAT_BGRA: case B200_VIDEO_FORMAT_BGRx: { uint8_t s[4] = {3, 2, 1, 0}; memcpy (p->byte_sel, s, 4); break; }
+    case B200_VIDEO_FORMAT_RGBA: case B200_VIDEO_FORMAT_RGBx: { uint8_t s[4] = {1, 2, 3, 0}; memcpy (p->byte_sel, s, 4); break; }
+    case B200_VIDEO_FORMAT_ABGR: case B200_VIDEO_FORMAT_xBGR: { uint8_t s[4] = {0, 3, 2, 1}; memcpy (p->byte_sel, s, 4); break; }
+    case B200_VIDEO_FORMAT_ARGB: case B200_VIDEO_FORMAT_xRGB: { uint8_t s[4] = {0, 1, 2, 3}; memcpy (p->byte_sel, s, 4); break; }
+    default: return B200_ERR_UNSUPPORTED;
+  }
+  if (in->stride[0] < in->width || in->stride[1] < ((in->width + 1) & ~1) || out->stride[0] < out->width * 4)
+    return B200_ERR_INVALID_ARG;
+  p->u_index = in->format == B200_VIDEO_FORMAT_NV21 ? 1 : 0;
+  p->h_cosited = (p->in.chroma_site & B200_CHROMA_SITE_H_COSITED) != 0;
+  p->v_pairs = (p->in.chroma_site & B200_CHROMA_SITE_V_COSITED) == 0;
+
+  int st = colour_matrix (p);
+  if (st != B200_OK) return st;
+
+  FilterSpec f = filter_from_method (*cfg);
+  const int iw = in->width, ih = in->height, ow = out->width, oh = out->height;
+  if (iw != ow) scaled_axis (&p->h, f, iw, ow, true); else identity_axis (&p->h, iw);
+  if (ih != oh) scaled_axis (&p->v, f, ih, oh, false); else identity_axis (&p->v, ih);
+  // chain_scale: shrink before the matrix, grow after it; horizontal first unless the
+  // vertical pass leaves fewer pixels for the second pass
+  const int64_t s0 = (int64_t) iw * ih, s3 = (int64_t) ow * oh;
+  p->matrix_first = !(s3 <= s0);
+  p->h_first = (int64_t) ow * ih <= (int64_t) iw * oh;
+  chroma_pairing (p);
+  tile_geometry (p);
+
+  // the specialised kernel covers exactly the headline shape class: even 2:1 in both
+  // directions with the 8-tap lanczos the reference derives for it
+  p->lanczos2_ok = false;
+  return B200_OK;
+}
+
+}  // namespace b200

@@ -1,0 +1,57 @@
+// gstreamer_b200/csrc/vcs_plan.h — host-side per-caps plan of the convert+scale path.
+//
+// Product code.  This is the B200 build's equivalent of the one-time setup the
+// reference does in gst_video_converter_new_with_pool()/chain_*()
+// (gst-libs/gst/video/video-converter.c:2421, :852-2112): instead of a chain of
+// line caches it produces flat tables the fused kernels index directly.
+#pragma once
+
+#include <stdint.h>
+#include <vector>
+
+#include "../../include/b200dsp.h"
+
+namespace b200 {
+
+// pass kinds understood by the kernels
+enum PassMode : int { PASS_COPY = 1, PASS_2TAP = 2, PASS_NTAP = 3 };
+
+struct AxisPlan {
+  int in_size = 0, out_size = 0;
+  int mode = PASS_COPY;          // PASS_COPY covers "no scaling" (identity offsets) and nearest
+  int n_taps = 1;                // taps per output sample as the reference counts them
+  int coef_per_out = 0;          // int16 coefficients stored per output sample (0, 1 or n_taps)
+  int span = 1;                  // input samples read per output sample
+  bool scaling = false;
+  std::vector<uint32_t> offset;  // first input sample of each output sample
+  std::vector<int16_t> coef;     // NTAP: n_taps 6-bit taps; 2TAP-h: 8-bit fraction; 2TAP-v: 8-bit p1
+  std::vector<int16_t> sum;      // NTAP: sum of taps (alpha channel), else unused
+};
+
+struct VcsPlan {
+  b200_video_info in, out;
+  b200_vcs_config cfg;
+  AxisPlan h, v;
+  bool h_first = true;
+  bool matrix_first = false;
+  int p[5] = {0, 0, 0, 0, 0};
+  int im[4][4];
+  bool h_cosited = false, v_pairs = true;
+  int u_index = 0;               // byte index of U inside an interleaved chroma pair
+  uint8_t byte_sel[4] = {3, 2, 1, 0};   // output byte i takes component byte_sel[i] of (A,R,G,B)
+  std::vector<uint8_t> chroma_mode;     // per input line: 0 own row, 1 first of pair, 2 second
+
+  // generic tiled kernel geometry
+  int tile_w = 64, tile_h = 16;
+  int max_rows = 0, max_cols = 0, cols_pitch = 0, max_crows = 0;
+  int smem_bytes = 0;
+
+  // specialised 2:1 lanczos kernel eligibility
+  bool lanczos2_ok = false;
+};
+
+// builds everything that does not need a device; returns b200_status
+int build_vcs_plan (const b200_video_info * in, const b200_video_info * out,
+    const b200_vcs_config * cfg, VcsPlan * plan);
+
+}  // namespace b200

@@ -1,0 +1,238 @@
+"""Host-side mirror of the reference's convert+scale interface over the C-ABI.
+
+Names follow the reference (paths under subprojects/gst-plugins-base/):
+  VideoInfo            ~ GstVideoInfo            gst-libs/gst/video/video-info.h:399
+  VideoScaleMethod     ~ GstVideoScaleMethod     gst/videoconvertscale/gstvideoconvertscale.h:59
+  CudaVideoConvertScale ~ the element: properties + GstVideoFilterClass::set_info /
+                          ::transform_frame      gst/videoconvertscale/gstvideoconvertscale.c:906, :1981
+The arithmetic lives in libb200dsp.so; this layer only marshals descriptors and pointers.
+"""
+import ctypes as C
+import enum
+
+import numpy as np
+
+from . import _lib
+from ._lib import lib, check
+
+
+class VideoFormat(enum.IntEnum):
+    RGBx = 7
+    BGRx = 8
+    xRGB = 9
+    xBGR = 10
+    RGBA = 11
+    BGRA = 12
+    ARGB = 13
+    ABGR = 14
+    NV12 = 23
+    NV21 = 24
+
+
+class VideoScaleMethod(enum.IntEnum):
+    NEAREST = 0
+    BILINEAR = 1
+    FOUR_TAP = 2
+    LANCZOS = 3
+    BILINEAR2 = 4
+    SINC = 5
+    HERMITE = 6
+    SPLINE = 7
+    CATROM = 8
+    MITCHELL = 9
+
+
+class ColorMatrix(enum.IntEnum):
+    UNKNOWN = 0
+    RGB = 1
+    FCC = 2
+    BT709 = 3
+    BT601 = 4
+    SMPTE240M = 5
+    BT2020 = 6
+
+
+class ColorRange(enum.IntEnum):
+    UNKNOWN = 0
+    RANGE_0_255 = 1
+    RANGE_16_235 = 2
+
+
+class ChromaSite(enum.IntFlag):
+    UNKNOWN = 0
+    NONE = 1
+    H_COSITED = 2
+    V_COSITED = 4
+    ALT_LINE = 8
+    COSITED = 6
+    JPEG = 1
+    MPEG2 = 2
+
+
+def _ptr(x):
+    """device/host pointer from an int, a torch tensor or a numpy array"""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if hasattr(x, "data_ptr"):
+        return x.data_ptr()
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data
+    raise TypeError(f"cannot take a pointer from {type(x)}")
+
+
+def _stream(s):
+    if s is None:
+        return None
+    if isinstance(s, int):
+        return s
+    return s.cuda_stream  # torch.cuda.Stream
+
+
+class VideoInfo:
+    """Subset of GstVideoInfo the arithmetic depends on."""
+
+    def __init__(self, fmt, width, height):
+        self.c = _lib.VideoInfoC()
+        check(lib.b200_video_info_set_format(C.byref(self.c), int(fmt), width, height),
+              "b200_video_info_set_format")
+
+    format = property(lambda s: VideoFormat(s.c.format))
+    width = property(lambda s: s.c.width)
+    height = property(lambda s: s.c.height)
+
+    @property
+    def size(self):
+        return lib.b200_video_info_size(C.byref(self.c))
+
+    @property
+    def stride(self):
+        return list(self.c.stride)
+
+    @property
+    def offset(self):
+        return list(self.c.offset)
+
+    def set_layout(self, strides, offsets):
+        for i, (s, o) in enumerate(zip(strides, offsets)):
+            self.c.stride[i] = s
+            self.c.offset[i] = o
+        return self
+
+    def set_colorimetry(self, matrix=None, range=None, chroma_site=None):
+        if matrix is not None:
+            self.c.color_matrix = int(matrix)
+        if range is not None:
+            self.c.color_range = int(range)
+        if chroma_site is not None:
+            self.c.chroma_site = int(chroma_site)
+        return self
+
+
+class PinnedBuffer:
+    """Page-locked host staging buffer (b200_host_alloc), exposed as a numpy uint8 array."""
+
+    def __init__(self, nbytes):
+        p = C.c_void_p()
+        check(lib.b200_host_alloc(nbytes, C.byref(p)), "b200_host_alloc")
+        self.ptr = p.value
+        self.nbytes = nbytes
+        self.array = np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(self.ptr))
+
+    def free(self):
+        if self.ptr:
+            lib.b200_host_free(self.ptr)
+            self.ptr = None
+            self.array = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class CudaVideoConvertScale:
+    """`cudavideoconvertscale`: same properties and call sequence as the stock element.
+
+    method / envelope / sharpness / sharpen mirror the GObject properties
+    (gstvideoconvertscale.c:306-391); `cuda_device_id` mirrors GstCudaBaseTransform's
+    property (gst-plugins-bad/sys/nvcodec/gstcudabasetransform.c:89-90).
+    """
+
+    def __init__(self, method=VideoScaleMethod.BILINEAR, envelope=2.0, sharpness=1.0, sharpen=0.0,
+                 cuda_device_id=0):
+        self.method = VideoScaleMethod(method)
+        self.envelope = envelope
+        self.sharpness = sharpness
+        self.sharpen = sharpen
+        self.cuda_device_id = cuda_device_id
+        self._h = None
+        self.in_info = self.out_info = None
+
+    # GstVideoFilterClass::set_info
+    def set_info(self, in_info, out_info):
+        self._free()
+        cfg = _lib.VcsConfigC()
+        lib.b200_vcs_config_init(C.byref(cfg))
+        cfg.method = int(self.method)
+        cfg.envelope, cfg.sharpness, cfg.sharpen = self.envelope, self.sharpness, self.sharpen
+        h = C.c_void_p()
+        check(lib.b200_vcs_create(C.byref(in_info.c), C.byref(out_info.c), C.byref(cfg),
+                                  self.cuda_device_id, C.byref(h)), "b200_vcs_create")
+        self._h = h
+        self.in_info, self.out_info = in_info, out_info
+        return True
+
+    # GstVideoFilterClass::transform_frame — frames are device memory (GST_MAP_CUDA)
+    def transform_frame(self, in_frame, out_frame, stream=None):
+        check(lib.b200_vcs_convert(self._h, _ptr(in_frame), _ptr(out_frame), _stream(stream)),
+              "b200_vcs_convert")
+
+    def transform_frames(self, in_frames, out_frames, stream=None):
+        n = len(in_frames)
+        ins = (C.c_void_p * n)(*[_ptr(f) for f in in_frames])
+        outs = (C.c_void_p * n)(*[_ptr(f) for f in out_frames])
+        check(lib.b200_vcs_convert_batch(self._h, n, ins, outs, _stream(stream)),
+              "b200_vcs_convert_batch")
+
+    # system-memory peers: pinned staging + side streams inside the library
+    def transform_host_frames(self, in_frames, out_frames):
+        n = len(in_frames)
+        ins = (C.c_void_p * n)(*[_ptr(f) for f in in_frames])
+        outs = (C.c_void_p * n)(*[_ptr(f) for f in out_frames])
+        check(lib.b200_vcs_convert_host(self._h, n, ins, outs), "b200_vcs_convert_host")
+
+    # ---- introspection -------------------------------------------------------------
+    def plan_info(self):
+        info = _lib.VcsPlanInfoC()
+        check(lib.b200_vcs_get_plan_info(self._h, C.byref(info)))
+        return info
+
+    def taps(self, direction):
+        size = (self.out_info.width if direction == 0 else self.out_info.height)
+        off = np.zeros(size, dtype=np.uint32)
+        coef = np.zeros(size * 128, dtype=np.int16)
+        per = check(lib.b200_vcs_get_taps(self._h, direction, off.ctypes.data, coef.ctypes.data,
+                                          off.size, coef.size))
+        return off, coef[:size * per].reshape(size, per) if per else coef[:0]
+
+    def chroma_plan(self):
+        m = np.zeros(self.in_info.height, dtype=np.uint8)
+        check(lib.b200_vcs_get_chroma_plan(self._h, m.ctypes.data, m.size))
+        return m
+
+    def set_kernel_variant(self, v):
+        check(lib.b200_vcs_set_kernel_variant(self._h, v), "b200_vcs_set_kernel_variant")
+
+    def _free(self):
+        if self._h:
+            lib.b200_vcs_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self._free()
+        except Exception:
+            pass

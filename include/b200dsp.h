@@ -1,0 +1,225 @@
+/* include/b200dsp.h — C-ABI of libb200dsp: the B200-native raw-frame DSP hot path.
+ *
+ * This is the drop-in boundary.  Every entry point is what a GStreamer element's
+ * vmethod would call in place of the reference's CPU library call; the reference
+ * interface each one replaces is cited (paths under /root/reference/subprojects/):
+ *
+ *   b200_vcs_*   replace  gst_video_converter_new / _frame / _free
+ *                         gst-plugins-base/gst-libs/gst/video/video-converter.c:2421, :2782, :2618
+ *                called from GstVideoFilterClass::set_info / ::transform_frame
+ *                         gst-plugins-base/gst/videoconvertscale/gstvideoconvertscale.c:906, :1981
+ *                device-memory calling convention follows gst_cuda_converter_convert_frame
+ *                         gst-plugins-bad/gst-libs/gst/cuda/gstcudaconverter.cpp:1911
+ *   b200_comp_*  replace  the BlendFunction / FillCheckerFunction / FillColorFunction table
+ *                         gst-plugins-base/gst/compositor/blend.h:50-79
+ *                called from GstVideoAggregatorClass::aggregate_frames
+ *                         gst-plugins-base/gst/compositor/compositor.c:1739
+ *   b200_ars_*   replace  gst_audio_resampler_new / _get_out_frames / _resample / _reset / _free
+ *                         gst-plugins-base/gst-libs/gst/audio/audio-resampler.c:1344, :1648, :1750, :1458, :1616
+ *                called from GstBaseTransformClass::transform
+ *                         gst-plugins-base/gst/audioresample/gstaudioresample.c:885, :743
+ *
+ * Conventions: plain C, POD descriptors, raw pointers + sizes, an opaque
+ * `void *cuda_stream` (a cudaStream_t / CUstream; NULL = legacy default stream).
+ * No GLib, GStreamer or torch type crosses this boundary.  All calls return a
+ * b200_status; 0 is success.  Device pointers must belong to the device the handle
+ * was created on.  Launch-only calls are asynchronous on `cuda_stream` exactly like
+ * gst_cuda_converter_convert_frame(): the caller owns synchronisation
+ * (gst-plugins-bad/sys/nvcodec/gstcudaconvertscale.c:1541-1579).
+ *
+ * Enum values are GStreamer's own so an element can pass GstVideoInfo fields
+ * through without translation.
+ */
+#ifndef B200DSP_H
+#define B200DSP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200DSP_VERSION_MAJOR 0
+#define B200DSP_VERSION_MINOR 1
+
+typedef enum {
+  B200_OK = 0,
+  B200_ERR_INVALID_ARG = -1,     /* -> set_info FALSE / GST_FLOW_NOT_NEGOTIATED */
+  B200_ERR_UNSUPPORTED = -2,     /* format / mode not implemented -> caps not accepted */
+  B200_ERR_NO_DEVICE = -3,       /* no CUDA device / driver: product never falls back to CPU */
+  B200_ERR_CUDA = -4,            /* a CUDA call failed -> GST_FLOW_ERROR */
+  B200_ERR_NOMEM = -5,
+  B200_ERR_STATE = -6
+} b200_status;
+
+const char *b200_strerror (int status);
+/* last CUDA error string recorded on this thread (for GST_ELEMENT_ERROR text) */
+const char *b200_last_cuda_error (void);
+int b200_version (void);
+/* number of CUDA devices visible, or a negative b200_status */
+int b200_device_count (void);
+
+/* pinned host staging memory (what a GstCudaBufferPool-style pool hands upstream
+ * so H2D/D2H can be asynchronous; gst-plugins-bad/gst-libs/gst/cuda/gstcudamemory.cpp:446-522) */
+int b200_host_alloc (size_t size, void **ptr);
+int b200_host_free (void *ptr);
+
+/* ------------------------------------------------------------------ video types */
+/* GstVideoFormat values (gst-libs/gst/video/video-format.h:195-) */
+typedef enum {
+  B200_VIDEO_FORMAT_RGBx = 7, B200_VIDEO_FORMAT_BGRx = 8, B200_VIDEO_FORMAT_xRGB = 9,
+  B200_VIDEO_FORMAT_xBGR = 10, B200_VIDEO_FORMAT_RGBA = 11, B200_VIDEO_FORMAT_BGRA = 12,
+  B200_VIDEO_FORMAT_ARGB = 13, B200_VIDEO_FORMAT_ABGR = 14,
+  B200_VIDEO_FORMAT_NV12 = 23, B200_VIDEO_FORMAT_NV21 = 24
+} b200_video_format;
+
+/* GstVideoScaleMethod of the element (gst/videoconvertscale/gstvideoconvertscale.h:59-71) */
+typedef enum {
+  B200_SCALE_NEAREST = 0, B200_SCALE_BILINEAR, B200_SCALE_4TAP, B200_SCALE_LANCZOS,
+  B200_SCALE_BILINEAR2, B200_SCALE_SINC, B200_SCALE_HERMITE, B200_SCALE_SPLINE,
+  B200_SCALE_CATROM, B200_SCALE_MITCHELL
+} b200_scale_method;
+
+/* GstVideoColorMatrix / GstVideoColorRange / GstVideoChromaSite (video-color.h:40-83, video-chroma.h:43-52) */
+enum { B200_COLOR_MATRIX_UNKNOWN = 0, B200_COLOR_MATRIX_RGB = 1, B200_COLOR_MATRIX_FCC = 2,
+  B200_COLOR_MATRIX_BT709 = 3, B200_COLOR_MATRIX_BT601 = 4, B200_COLOR_MATRIX_SMPTE240M = 5,
+  B200_COLOR_MATRIX_BT2020 = 6 };
+enum { B200_COLOR_RANGE_UNKNOWN = 0, B200_COLOR_RANGE_0_255 = 1, B200_COLOR_RANGE_16_235 = 2 };
+enum { B200_CHROMA_SITE_UNKNOWN = 0, B200_CHROMA_SITE_NONE = 1, B200_CHROMA_SITE_H_COSITED = 2,
+  B200_CHROMA_SITE_V_COSITED = 4, B200_CHROMA_SITE_ALT_LINE = 8 };
+
+#define B200_VIDEO_MAX_PLANES 4
+
+/* The subset of GstVideoInfo the arithmetic depends on (gst-libs/gst/video/video-info.h:399-438).
+ * stride/offset are per PLANE, in bytes, offset relative to the frame base pointer —
+ * arbitrary values are honoured (GstCudaMemory uses a common pitch for all planes,
+ * gst-plugins-bad/gst-libs/gst/cuda/gstcudamemory.cpp:194-345). */
+typedef struct {
+  int32_t format;                /* b200_video_format */
+  int32_t width, height;
+  int32_t stride[B200_VIDEO_MAX_PLANES];
+  uint64_t offset[B200_VIDEO_MAX_PLANES];
+  int32_t color_matrix;          /* 0 = default by height, like gst_video_info_set_format */
+  int32_t color_range;           /* 0 = default */
+  int32_t chroma_site;           /* 0 = default by height, like gst_video_info_from_caps */
+} b200_video_info;
+
+/* fill default system-memory layout + caps-default colorimetry for (format, w, h);
+ * replaces gst_video_info_set_format (video-info.c:292) for the supported formats */
+int b200_video_info_set_format (b200_video_info * info, int format, int width, int height);
+/* total bytes of one frame with this layout (GstVideoInfo.size) */
+size_t b200_video_info_size (const b200_video_info * info);
+
+/* the videoconvertscale properties that reach the converter
+ * (gstvideoconvertscale.c:130-144 defaults, :991-1087 option mapping) */
+typedef struct {
+  int32_t method;                /* b200_scale_method; element default BILINEAR */
+  double envelope;               /* 2.0 */
+  double sharpness;              /* 1.0 */
+  double sharpen;                /* 0.0 */
+  int32_t reserved[8];
+} b200_vcs_config;
+void b200_vcs_config_init (b200_vcs_config * cfg);
+
+typedef struct b200_vcs b200_vcs;
+
+/* Build the per-caps plan (tap tables, matrix, chroma pairing, tiling) and upload it.
+ * device >= 0: CUDA device ordinal (the element's cuda-device-id property,
+ * gst-plugins-bad/sys/nvcodec/gstcudabasetransform.c:89-90).
+ * device == -1: host-side plan only (no CUDA calls; convert() then fails with
+ * B200_ERR_NO_DEVICE) — used by caps negotiation dry-runs and CPU-only tests. */
+int b200_vcs_create (const b200_video_info * in, const b200_video_info * out,
+    const b200_vcs_config * cfg, int device, b200_vcs ** handle);
+void b200_vcs_destroy (b200_vcs * h);
+
+/* one frame, device memory, asynchronous on cuda_stream. in_frame/out_frame are the
+ * frame BASE device pointers; planes live at base + info.offset[i]. */
+int b200_vcs_convert (b200_vcs * h, const void *in_frame, void *out_frame, void *cuda_stream);
+/* n independent frames (same caps) in one launch: what a batching element / multi-stream
+ * mux feeds; n <= B200_VCS_MAX_BATCH */
+#define B200_VCS_MAX_BATCH 64
+int b200_vcs_convert_batch (b200_vcs * h, int n, const void *const *in_frames,
+    void *const *out_frames, void *cuda_stream);
+/* system-memory peers: host frames in, host frames out.  H2D / kernel / D2H are
+ * pipelined over internal device frame slots on side streams; returns when all n
+ * outputs are complete in host memory.  Host buffers should come from
+ * b200_host_alloc (pinned) for the copies to overlap. */
+int b200_vcs_convert_host (b200_vcs * h, int n, const void *const *in_host,
+    void *const *out_host);
+
+/* plan introspection (tests, debugging, gst-inspect style dumps) */
+typedef struct {
+  int32_t h_taps, v_taps;        /* 0 = no scaling in that direction */
+  int32_t h_first;               /* 1: horizontal pass before vertical */
+  int32_t matrix_first;          /* 1: matrix before scaling (net upscale) */
+  int32_t p[5];                  /* AYUV->ARGB mulhi parameters p1..p5 */
+  int32_t tile_w, tile_h;        /* generic kernel output tile */
+  int32_t smem_bytes;
+  int32_t kernel_variant;        /* 0 = generic tiled, 1 = lanczos 2:1 specialised */
+  int32_t n_launches_per_convert;
+} b200_vcs_plan_info;
+int b200_vcs_get_plan_info (const b200_vcs * h, b200_vcs_plan_info * info);
+/* copy out the integer tap tables: dir 0 = horizontal, 1 = vertical.
+ * offsets[out_size], taps[out_size * n_taps] (int16) */
+int b200_vcs_get_taps (const b200_vcs * h, int dir, uint32_t * offsets, int16_t * taps,
+    size_t offsets_len, size_t taps_len);
+/* per input line chroma pairing mode (0 own row, 1 first of pair, 2 second of pair) */
+int b200_vcs_get_chroma_plan (const b200_vcs * h, uint8_t * mode, size_t len);
+/* force a kernel variant (0 generic, 1 specialised if eligible); for A/B tests */
+int b200_vcs_set_kernel_variant (b200_vcs * h, int variant);
+
+/* ------------------------------------------------------------------ compositor */
+typedef enum { B200_COMP_BG_CHECKER = 0, B200_COMP_BG_BLACK = 1, B200_COMP_BG_WHITE = 2,
+  B200_COMP_BG_TRANSPARENT = 3 } b200_comp_background;      /* compositor.c:742 */
+typedef enum { B200_COMP_OP_SOURCE = 0, B200_COMP_OP_OVER = 1, B200_COMP_OP_ADD = 2 } b200_comp_operator;
+
+/* one sink pad's prepared frame + its pad properties (compositor.c:190-196) */
+typedef struct {
+  const void *data;              /* device pointer to the pad's packed 4x8-bit frame */
+  int32_t width, height, stride;
+  int32_t xpos, ypos;
+  double alpha;                  /* pad alpha 0.0..1.0 */
+  int32_t op;                    /* b200_comp_operator */
+  int32_t reserved;
+} b200_comp_pad;
+
+typedef struct b200_comp b200_comp;
+#define B200_COMP_MAX_PADS 64
+/* out_format: one of the packed 8-bit RGB formats with alpha (RGBA/BGRA/ARGB/ABGR) */
+int b200_comp_create (int out_format, int width, int height, int device, b200_comp ** handle);
+void b200_comp_destroy (b200_comp * h);
+/* background fill + every pad in z-order in ONE pass over the destination.
+ * pads[] is in sink-pad (z) order, lowest first.  Pads with alpha 0 are skipped and
+ * fully obscured pads give the same bytes as the reference's culling (compositor.c:519-601). */
+int b200_comp_blend (b200_comp * h, void *dst, int32_t dst_stride, int background,
+    const b200_comp_pad * pads, int n_pads, void *cuda_stream);
+
+/* ------------------------------------------------------------------ audio resampler */
+typedef struct b200_ars b200_ars;
+typedef struct {
+  int32_t in_rate, out_rate, channels;
+  int32_t quality;               /* 0..10, element default 4 (gstaudioresample.c:68) */
+  int32_t reserved[8];
+} b200_ars_config;
+
+int b200_ars_create (const b200_ars_config * cfg, int device, b200_ars ** handle);
+void b200_ars_destroy (b200_ars * h);
+/* discard history (flush / discont), gst_audio_resampler_reset */
+int b200_ars_reset (b200_ars * h);
+/* frames the next process() call will produce for in_frames of input */
+size_t b200_ars_get_out_frames (b200_ars * h, size_t in_frames);
+size_t b200_ars_get_in_frames (b200_ars * h, size_t out_frames);
+size_t b200_ars_get_max_latency (b200_ars * h);
+/* F32 interleaved device buffers.  in == NULL feeds silence (drain).  Consumes all
+ * in_frames, writes b200_ars_get_out_frames() frames, asynchronous on cuda_stream. */
+int b200_ars_process (b200_ars * h, const float *in, size_t in_frames, float *out,
+    size_t out_capacity_frames, size_t * out_frames, void *cuda_stream);
+typedef struct { int32_t n_taps, n_phases, in_step, out_step, filter_mode, oversample; } b200_ars_plan_info;
+int b200_ars_get_plan_info (const b200_ars * h, b200_ars_plan_info * info);
+int b200_ars_get_phase_taps (const b200_ars * h, int phase, float *taps, size_t len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200DSP_H */
