@@ -209,12 +209,17 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    profiling = os.environ.get("B200_PROFILE") == "1"      # ncu --profile-from-start off
+    if profiling:
+        torch.cuda.cudart().cudaProfilerStart()
     with torch.cuda.stream(stream):
         e0.record(stream)
         for i in range(args.steps):
             step(i)
         e1.record(stream)
     barrier()
+    if profiling:
+        torch.cuda.cudart().cudaProfilerStop()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
 

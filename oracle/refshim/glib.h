@@ -204,6 +204,9 @@ static inline gpointer g_realloc (gpointer p, gsize n) { if (!n) { free (p); ret
 static inline void g_free (gpointer p) { free (p); }
 static inline gpointer g_memdup2 (gconstpointer p, gsize n) { gpointer r; if (!p || !n) return NULL; r = malloc (n); memcpy (r, p, n); return r; }
 #define g_memdup(p,n) g_memdup2 (p, n)
+static inline gpointer g_realloc_n (gpointer p, gsize n, gsize sz) { return g_realloc (p, n * sz); }
+static inline gpointer g_malloc_n (gsize n, gsize sz) { return g_malloc (n * sz); }
+static inline gpointer g_malloc0_n (gsize n, gsize sz) { return g_malloc0 (n * sz); }
 #define g_new(t,n) ((t *) g_malloc (sizeof (t) * (gsize) (n)))
 #define g_new0(t,n) ((t *) g_malloc0 (sizeof (t) * (gsize) (n)))
 #define g_renew(t,p,n) ((t *) g_realloc (p, sizeof (t) * (gsize) (n)))

@@ -44,6 +44,7 @@ typedef struct _GstDebugCategory GstDebugCategory;
 #define GST_CAT_LOG(...) do { } while (0)
 #define GST_CAT_DEBUG_OBJECT(...) do { } while (0)
 #define GST_PTR_FORMAT "p"
+#define GST_DEBUG_FUNCPTR(f) (f)
 
 /* ---- misc scalar helpers ------------------------------------------------------ */
 typedef guint64 GstClockTime;

@@ -1,0 +1,82 @@
+/* oracle/refshim/refdrv_comp.c — TEST INFRASTRUCTURE ONLY.
+ *
+ * Drives the reference's own blend kernels (gst/compositor/blend.c + the ORC C backups in
+ * compositororc-dist.c, compiled in place) in the call sequence of
+ * blend_pads()/_draw_background() (gst/compositor/compositor.c:1619-1697): background
+ * fill over [0,height), then every pad in z-order through the `blend` family (opaque
+ * backgrounds) or the `overlay` family (transparent background).
+ */
+#include <gst/video/video.h>
+#include "blend.h"
+
+typedef struct
+{
+  const guint8 *data; int width, height, stride;
+  int xpos, ypos; double alpha; int op;
+} RefPad;
+
+static void
+fill_frame (GstVideoFrame * f, int format, guint8 * data, int width, int height, int stride)
+{
+  memset (f, 0, sizeof (*f));
+  gst_video_info_set_format (&f->info, (GstVideoFormat) format, width, height);
+  f->info.stride[0] = stride;
+  f->data[0] = data;
+}
+
+int
+ref_compositor (int out_format, guint8 * dst, int width, int height, int stride, int background,
+    const RefPad * pads, int n_pads)
+{
+  static gsize inited = 0;
+  GstVideoFrame out;
+  BlendFunction blend, overlay, composite;
+  FillCheckerFunction fill_checker;
+  FillColorFunction fill_color;
+  int i;
+  if (!inited) {
+    gst_compositor_init_blend ();
+    inited = 1;
+  }
+  switch (out_format) {         /* compositor.c:844-867 */
+    case GST_VIDEO_FORMAT_ARGB:
+      blend = gst_compositor_blend_argb; overlay = gst_compositor_overlay_argb;
+      fill_checker = gst_compositor_fill_checker_argb; fill_color = gst_compositor_fill_color_argb;
+      break;
+    case GST_VIDEO_FORMAT_BGRA:
+      blend = gst_compositor_blend_bgra; overlay = gst_compositor_overlay_bgra;
+      fill_checker = gst_compositor_fill_checker_bgra; fill_color = gst_compositor_fill_color_bgra;
+      break;
+    case GST_VIDEO_FORMAT_ABGR:
+      blend = gst_compositor_blend_abgr; overlay = gst_compositor_overlay_abgr;
+      fill_checker = gst_compositor_fill_checker_abgr; fill_color = gst_compositor_fill_color_abgr;
+      break;
+    case GST_VIDEO_FORMAT_RGBA:
+      blend = gst_compositor_blend_rgba; overlay = gst_compositor_overlay_rgba;
+      fill_checker = gst_compositor_fill_checker_rgba; fill_color = gst_compositor_fill_color_rgba;
+      break;
+    default:
+      return -1;
+  }
+  fill_frame (&out, out_format, dst, width, height, stride);
+  composite = blend;
+  switch (background) {         /* compositor.c:1619-1675; RGB 0-255: black 0,0,0 white 255,255,255 (:1131-1149) */
+    case 0: fill_checker (&out, 0, height); break;
+    case 1: fill_color (&out, 0, height, 0, 0, 0); break;
+    case 2: fill_color (&out, 0, height, 255, 255, 255); break;
+    default:
+      for (i = 0; i < height; i++)
+        memset (dst + (gsize) i * stride, 0, (gsize) width * 4);
+      composite = overlay;
+      break;
+  }
+  for (i = 0; i < n_pads; i++) {
+    GstVideoFrame src;
+    fill_frame (&src, out_format, (guint8 *) pads[i].data, pads[i].width, pads[i].height,
+        pads[i].stride);
+    /* COMPOSITOR_BLEND_MODE_* share the operator's numbering (blend.h, compositor.c:1800-1813) */
+    composite (&src, pads[i].xpos, pads[i].ypos, pads[i].alpha, &out, 0, height,
+        (GstCompositorBlendMode) pads[i].op);
+  }
+  return 0;
+}
