@@ -31,6 +31,8 @@ struct b200_vcs {
   cudaStream_t s_h2d = nullptr, s_run = nullptr, s_d2h = nullptr;
   cudaEvent_t ev_in[kSlots] = {nullptr}, ev_run[kSlots] = {nullptr}, ev_out[kSlots] = {nullptr};
   bool pipeline_ready = false;
+  Lanczos2Tables l2_tables;
+  Lanczos2State l2;
   size_t in_bytes = 0, out_bytes = 0;
 };
 
@@ -57,7 +59,7 @@ int launch (b200_vcs * h, int n, const VcsBatch & batch, cudaStream_t stream)
 {
   const VcsPlan & p = h->plan;
   if (h->variant == 1 && p.lanczos2_ok)
-    return launch_lanczos2 (h->dev, batch, n, h->device, stream);
+    return launch_lanczos2 (h->dev, h->l2, batch, n, stream);
   dim3 grid ((p.out.width + p.tile_w - 1) / p.tile_w, (p.out.height + p.tile_h - 1) / p.tile_h, n);
   vcs_generic_kernel <<<grid, 256, p.smem_bytes, stream>>> (h->dev, batch);
   B200_CUDA_TRY (cudaGetLastError ());
@@ -142,6 +144,8 @@ int b200_vcs_create (const b200_video_info * in, const b200_video_info * out,
   if (!h) return B200_ERR_NOMEM;
   int st = build_vcs_plan (in, out, cfg, &h->plan);
   if (st != B200_OK) { delete h; return st; }
+  h->l2_tables = build_lanczos2_tables (h->plan);
+  h->plan.lanczos2_ok = h->l2_tables.ok;
   const VcsPlan & p = h->plan;
   if ((p.out.stride[0] & 3) || (p.out.offset[0] & 3)) { delete h; return B200_ERR_UNSUPPORTED; }
   h->device = device;
@@ -173,7 +177,7 @@ int b200_vcs_create (const b200_video_info * in, const b200_video_info * out,
         p.smem_bytes);
     if (e != cudaSuccess) { b200_vcs_destroy (h); return cuda_fail (e, "cudaFuncSetAttribute", __FILE__, __LINE__); }
     if (p.lanczos2_ok) {
-      st = prepare_lanczos2 (h->dev, device);
+      st = prepare_lanczos2 (h->l2_tables, h->dev, &h->l2);
       if (st != B200_OK) { b200_vcs_destroy (h); return st; }
       h->variant = 1;
     }
@@ -189,6 +193,7 @@ void b200_vcs_destroy (b200_vcs * h)
     DeviceGuard g (h->device);
     cudaFree (h->d_hoff); cudaFree (h->d_voff); cudaFree (h->d_hcoef); cudaFree (h->d_vcoef);
     cudaFree (h->d_hsum); cudaFree (h->d_vsum); cudaFree (h->d_cmode);
+    cudaFree (h->l2.d_htab); cudaFree (h->l2.d_vtab);
     for (int i = 0; i < b200_vcs::kSlots; i++) {
       cudaFree (h->slot_in[i]); cudaFree (h->slot_out[i]);
       if (h->ev_in[i]) cudaEventDestroy (h->ev_in[i]);

@@ -1,9 +1,327 @@
-// gstreamer_b200/csrc/vcs_lanczos2.cuh — specialised 2:1 lanczos NV12->RGB kernel (product).
-// Placeholder until the specialised path lands; the generic kernel covers every plan.
+// gstreamer_b200/csrc/vcs_lanczos2.cuh — specialised fused kernel for the headline shape class
+// (product code, sm_100a): 4:2:0 semi-planar -> packed RGB, exact 2:1 reduction in both
+// directions with the 8-tap filters the reference derives for it (lanczos and every other
+// 8-tap/2:1 method), h-cosited chroma, all input lines consumed in order.
+//
+// Same arithmetic as vcs_generic_kernel (and therefore as the reference chain
+// unpack -> chroma up h,v -> h scale -> v scale -> AYUV->ARGB -> pack, see vcs_kernels.cuh),
+// organised for instruction count instead of generality:
+//
+//  * byte-SIMD everywhere: 4 pixels per 32-bit register; chroma up-sampling is done with
+//    packed byte averages ((a+b+1)>>1 and (3a+b+2)>>2 == avg_ceil(a, avg_floor(a,b))), the FIRs
+//    with IDP.4A.U8.S8 on aligned words and zero-padded tap words (no funnel shifts)
+//  * H phase: a warp owns 4 input lines x 128 input-aligned output columns straight from global
+//    memory (LDG.64 per lane, halo words by warp shuffle, lanes 0/31 are halo providers), and
+//    writes the h-scaled bytes TRANSPOSED (4 consecutive lines of one column per word) with one
+//    STS.128 per channel
+//  * V phase: a thread owns 4 output rows of one column: 4 LDS.32 per channel give the 16 lines
+//    it needs, IDP.4A again, I2IP saturating packs, PRMT sign-splat for the mulhi matrix,
+//    coalesced 4-byte stores
+//  * the per-column / per-row tap words (12 registers each) come from host-built tables, so the
+//    folded, non-uniform taps at the frame edges need no special code path.
 #pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <vector>
+
 #include "common.h"
 #include "vcs_device.h"
+#include "vcs_plan.h"
+
 namespace b200 {
-inline int prepare_lanczos2 (const VcsDev &, int) { return B200_ERR_UNSUPPORTED; }
-inline int launch_lanczos2 (const VcsDev &, const VcsBatch &, int, int, cudaStream_t) { return B200_ERR_UNSUPPORTED; }
+
+constexpr int L2_TH = 32;              // output rows per tile
+constexpr int L2_NG = 18;              // 4-line groups per tile: 2*32 + 6 = 70 lines -> 72
+constexpr int L2_WCOLS = 120;          // useful output columns per warp-column (30 lanes x 4)
+constexpr int L2_NWC = 2;              // warp-columns per tile
+constexpr int L2_TW = L2_WCOLS * L2_NWC;
+constexpr int L2_TWP = 128 * L2_NWC;   // smem columns incl. the halo lanes' slots
+constexpr int L2_THREADS = 256;
+constexpr int L2_SMEM = 3 * L2_NG * L2_TWP * 4;
+
+struct Lanczos2Dev {
+  const int4 *htab;                    // [ow/4][3] : 12 packed s8x4 tap words per 4-column group
+  const int4 *vtab;                    // [oh/4][3]
+  const short *hsum, *vsum;            // tap sums (alpha channel)
+  int alpha_opaque;                    // every tap sum >= 64: alpha is 255 everywhere
+};
+
+// ---- packed byte helpers -----------------------------------------------------------------
+__device__ __forceinline__ unsigned avg_floor4 (unsigned a, unsigned b)
+{
+  return (a & b) + (((a ^ b) & 0xfefefefeu) >> 1);
 }
+__device__ __forceinline__ unsigned avg_ceil4 (unsigned a, unsigned b)
+{
+  return (a | b) - (((a ^ b) & 0xfefefefeu) >> 1);
+}
+__device__ __forceinline__ int dp4a_u8s8 (unsigned px, int taps, int acc)
+{
+  int d;
+  asm ("dp4a.u32.s32 %0, %1, %2, %3;" : "=r" (d) : "r" (px), "r" (taps), "r" (acc));
+  return d;
+}
+__device__ __forceinline__ int prmt_s (unsigned a, unsigned sel)      // prmt.b32: selector msb replicates the sign
+{
+  int d;
+  asm ("prmt.b32 %0, %1, 0, %2;" : "=r" (d) : "r" (a), "r" (sel));
+  return d;
+}
+// d = { c[15:0], sat_u8(a), sat_u8(b) }  (b in the lowest byte)
+__device__ __forceinline__ unsigned pack_sat2 (int a, int b, unsigned c)
+{
+  unsigned d;
+  asm ("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r" (d) : "r" (a), "r" (b), "r" (c));
+  return d;
+}
+
+// 4 outputs from 16 aligned bytes w0..w3: outputs 0,1 read words 0..2, outputs 2,3 words 1..3
+#define L2_FIR4(o0, o1, o2, o3, w0, w1, w2, w3, T)                                             \
+  do {                                                                                         \
+    o0 = dp4a_u8s8 (w2, T[0].z, dp4a_u8s8 (w1, T[0].y, dp4a_u8s8 (w0, T[0].x, 32)));           \
+    o1 = dp4a_u8s8 (w2, T[1].y, dp4a_u8s8 (w1, T[1].x, dp4a_u8s8 (w0, T[0].w, 32)));           \
+    o2 = dp4a_u8s8 (w3, T[2].x, dp4a_u8s8 (w2, T[1].w, dp4a_u8s8 (w1, T[1].z, 32)));           \
+    o3 = dp4a_u8s8 (w3, T[2].w, dp4a_u8s8 (w2, T[2].z, dp4a_u8s8 (w1, T[2].y, 32)));           \
+  } while (0)
+
+template <bool ALPHA_OPAQUE>
+__global__ void __launch_bounds__ (L2_THREADS, 3)
+vcs_lanczos2_kernel (const VcsDev P, const Lanczos2Dev L, const VcsBatch frames)
+{
+  extern __shared__ __align__ (16) unsigned hs[];                // [3][L2_NG][L2_TWP] words
+  const int lane = threadIdx.x & 31;
+  const int warp = __shfl_sync (0xffffffffu, (int) (threadIdx.x >> 5), 0);   // warp-uniform for the compiler
+  const uint8_t *__restrict__ in = frames.in[blockIdx.z];
+  uint8_t *__restrict__ out = frames.out[blockIdx.z];
+  const uint8_t *__restrict__ plane_y = in + P.off_y;
+  const uint8_t *__restrict__ plane_c = in + P.off_c;
+  const int x0 = blockIdx.x * L2_TW, oy0 = blockIdx.y * L2_TH;
+  const int R0 = 2 * oy0 - 3;                                    // first input line of the tile
+  const int crows = P.ih >> 1;
+  const unsigned selU = P.u_index ? 0x7531u : 0x6420u, selV = P.u_index ? 0x6420u : 0x7531u;
+
+  // ---------------------------------------------------------------- H phase
+  for (int item = warp; item < L2_NG * L2_NWC; item += L2_THREADS / 32) {
+    const int g = item >> 1, wc = item & 1;
+    const int col0 = x0 + wc * L2_WCOLS + (lane - 1) * 4;        // first of this lane's 4 output columns
+    int4 T[3];
+    {
+      const int grp = min (max (col0 >> 2, 0), (P.ow >> 2) - 1);
+      T[0] = __ldg (L.htab + grp * 3 + 0);
+      T[1] = __ldg (L.htab + grp * 3 + 1);
+      T[2] = __ldg (L.htab + grp * 3 + 2);
+    }
+    const int xb = min (max (2 * col0, 0), P.iw - 8);            // byte column of the lane's 8 input pixels
+    const bool right_edge = 2 * col0 + 8 >= P.iw;                // no chroma sample to the right
+    const int y0 = R0 + 4 * g;                                   // lines y0..y0+3, y0 % 4 == 1
+    const int m2 = (y0 - 1) >> 1;                                // chroma rows m2, m2+1, m2+2
+
+    // chroma: three rows, de-interleave, cosited h up-sample (video-chroma.c:687-699)
+    unsigned ulo[3], uhi[3], vlo[3], vhi[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const int cr = min (max (m2 + k, 0), crows - 1);
+      const uint2 c = __ldg ((const uint2 *) (plane_c + (size_t) cr * P.stride_c + xb));
+      const unsigned ue = __byte_perm (c.x, c.y, selU), ve = __byte_perm (c.x, c.y, selV);
+      unsigned un = __shfl_down_sync (0xffffffffu, ue, 1), vn = __shfl_down_sync (0xffffffffu, ve, 1);
+      un = right_edge ? __byte_perm (ue, ue, 0x3321) : __byte_perm (ue, un, 0x4321);
+      vn = right_edge ? __byte_perm (ve, ve, 0x3321) : __byte_perm (ve, vn, 0x4321);
+      const unsigned uo = avg_ceil4 (ue, un), vo = avg_ceil4 (ve, vn);
+      ulo[k] = __byte_perm (ue, uo, 0x5140); uhi[k] = __byte_perm (ue, uo, 0x7362);
+      vlo[k] = __byte_perm (ve, vo, 0x5140); vhi[k] = __byte_perm (ve, vo, 0x7362);
+    }
+    // vertical pairs (4m+1,4m+2) on rows (a,b) and (4m+3,4m+4) on rows (b,c):
+    // (3x+y+2)>>2 == avg_ceil (x, avg_floor (x,y))   (video-orc.orc:2705-2735)
+    unsigned U[4][2], V[4][2];
+    {
+      unsigned f;
+      f = avg_floor4 (ulo[0], ulo[1]); U[0][0] = avg_ceil4 (ulo[0], f); U[1][0] = avg_ceil4 (ulo[1], f);
+      f = avg_floor4 (uhi[0], uhi[1]); U[0][1] = avg_ceil4 (uhi[0], f); U[1][1] = avg_ceil4 (uhi[1], f);
+      f = avg_floor4 (ulo[1], ulo[2]); U[2][0] = avg_ceil4 (ulo[1], f); U[3][0] = avg_ceil4 (ulo[2], f);
+      f = avg_floor4 (uhi[1], uhi[2]); U[2][1] = avg_ceil4 (uhi[1], f); U[3][1] = avg_ceil4 (uhi[2], f);
+      f = avg_floor4 (vlo[0], vlo[1]); V[0][0] = avg_ceil4 (vlo[0], f); V[1][0] = avg_ceil4 (vlo[1], f);
+      f = avg_floor4 (vhi[0], vhi[1]); V[0][1] = avg_ceil4 (vhi[0], f); V[1][1] = avg_ceil4 (vhi[1], f);
+      f = avg_floor4 (vlo[1], vlo[2]); V[2][0] = avg_ceil4 (vlo[1], f); V[3][0] = avg_ceil4 (vlo[2], f);
+      f = avg_floor4 (vhi[1], vhi[2]); V[2][1] = avg_ceil4 (vhi[1], f); V[3][1] = avg_ceil4 (vhi[2], f);
+    }
+
+    // (acc+32)>>6 saturated to u8 (video-orc.orc:2474-2481); four lines of a column go into
+    // one word so that the V phase finds its 16 lines in 4 aligned words
+#define L2_STORE(ch, A)                                                                        \
+    do {                                                                                       \
+      uint4 o;                                                                                 \
+      o.x = pack_sat2 (A[1][0] >> 6, A[0][0] >> 6, pack_sat2 (A[3][0] >> 6, A[2][0] >> 6, 0u)); \
+      o.y = pack_sat2 (A[1][1] >> 6, A[0][1] >> 6, pack_sat2 (A[3][1] >> 6, A[2][1] >> 6, 0u)); \
+      o.z = pack_sat2 (A[1][2] >> 6, A[0][2] >> 6, pack_sat2 (A[3][2] >> 6, A[2][2] >> 6, 0u)); \
+      o.w = pack_sat2 (A[1][3] >> 6, A[0][3] >> 6, pack_sat2 (A[3][3] >> 6, A[2][3] >> 6, 0u)); \
+      *(uint4 *) (hs + ((ch) * L2_NG + g) * L2_TWP + wc * 128 + lane * 4) = o;                 \
+    } while (0)
+
+    int acc[4][4];                                               // [line][column]
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const unsigned w0 = __shfl_up_sync (0xffffffffu, U[r][1], 1), w3 = __shfl_down_sync (0xffffffffu, U[r][0], 1);
+      L2_FIR4 (acc[r][0], acc[r][1], acc[r][2], acc[r][3], w0, U[r][0], U[r][1], w3, T);
+    }
+    L2_STORE (1, acc);
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const unsigned w0 = __shfl_up_sync (0xffffffffu, V[r][1], 1), w3 = __shfl_down_sync (0xffffffffu, V[r][0], 1);
+      L2_FIR4 (acc[r][0], acc[r][1], acc[r][2], acc[r][3], w0, V[r][0], V[r][1], w3, T);
+    }
+    L2_STORE (2, acc);
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const int y = min (max (y0 + r, 0), P.ih - 1);
+      const uint2 yy = __ldg ((const uint2 *) (plane_y + (size_t) y * P.stride_y + xb));
+      const unsigned w0 = __shfl_up_sync (0xffffffffu, yy.y, 1), w3 = __shfl_down_sync (0xffffffffu, yy.x, 1);
+      L2_FIR4 (acc[r][0], acc[r][1], acc[r][2], acc[r][3], w0, yy.x, yy.y, w3, T);
+    }
+    L2_STORE (0, acc);
+  }
+  __syncthreads ();
+
+  // ---------------------------------------------------------------- V phase
+  // warp q owns output rows oy0+4q .. +3 for all 240 columns of the tile
+  {
+    const int q = warp, oy = oy0 + 4 * q;
+    if (oy < P.oh) {
+      int4 T[3];
+      T[0] = __ldg (L.vtab + (oy >> 2) * 3 + 0);
+      T[1] = __ldg (L.vtab + (oy >> 2) * 3 + 1);
+      T[2] = __ldg (L.vtab + (oy >> 2) * 3 + 2);
+      int vs[4] = {64, 64, 64, 64};
+      if (!ALPHA_OPAQUE) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) vs[i] = L.vsum[min (oy + i, P.oh - 1)];
+      }
+      for (int c = lane; c < L2_TW; c += 32) {
+        const int ox = x0 + c;
+        if (ox >= P.ow) break;
+        const int sc = (c >= L2_WCOLS ? 128 + 4 - L2_WCOLS : 4) + c;        // smem column of this output column
+        int a[3][4];
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+          const unsigned *p = hs + (ch * L2_NG + 2 * q) * L2_TWP + sc;
+          const unsigned w0 = p[0], w1 = p[L2_TWP], w2 = p[2 * L2_TWP], w3 = p[3 * L2_TWP];
+          L2_FIR4 (a[ch][0], a[ch][1], a[ch][2], a[ch][3], w0, w1, w2, w3, T);
+        }
+        int ah = 255;
+        if (!ALPHA_OPAQUE) ah = fir_round_u8 ((int) (short) (255 * (int) L.hsum[ox]));
+        uint8_t *dst = out + P.off_out + (size_t) oy * P.stride_out + (size_t) ox * 4;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          if (oy + i >= P.oh) break;
+          // saturate the three channels at once, bias by 128 and sign-splat each byte to s16
+          unsigned yuv = pack_sat2 (a[1][i] >> 6, a[0][i] >> 6, pack_sat2 (0, a[2][i] >> 6, 0u));
+          yuv ^= 0x00808080u;
+          const int wy = prmt_s (yuv, 0x8800u), wu = prmt_s (yuv, 0x9911u), wv = prmt_s (yuv, 0xaa22u);
+          const int ty = ((wy * P.p1) >> 16) + 128;
+          const int r = ty + ((wv * P.p2) >> 16);
+          const int b = ty + ((wu * P.p3) >> 16);
+          const int gg = ty + ((wu * P.p4) >> 16) + ((wv * P.p5) >> 16);
+          int al = 255;
+          if (!ALPHA_OPAQUE) al = fir_round_u8 ((int) (short) (ah * vs[i]));
+          // ARGB bytes in one word, then the output format's byte order
+          const unsigned argb = pack_sat2 (r, al, pack_sat2 (b, gg, 0u));
+          *(unsigned *) (dst + (size_t) i * P.stride_out) = __byte_perm (argb, 0, P.sel);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ host side
+struct Lanczos2Tables {
+  std::vector<int> htab, vtab;          // 12 words per group
+  bool ok = false;
+  bool alpha_opaque = false;
+};
+
+// Place the taps of 4 consecutive outputs into their 16-sample aligned frame; outputs 0,1 may
+// only touch samples 0..11 and outputs 2,3 samples 4..15.
+inline bool pack_axis_lanczos2 (const AxisPlan & a, int frame_bias, std::vector<int> * tab)
+{
+  if (a.mode != PASS_NTAP || a.n_taps != 8 || a.in_size != 2 * a.out_size || (a.out_size & 3))
+    return false;
+  const int groups = a.out_size / 4;
+  tab->assign ((size_t) groups * 12, 0);
+  for (int gidx = 0; gidx < groups; gidx++) {
+    const int base = 8 * gidx - frame_bias;
+    for (int i = 0; i < 4; i++) {
+      const int j = 4 * gidx + i;
+      int8_t frame[16] = {0};
+      for (int k = 0; k < 8; k++) {
+        const int tap = a.coef[(size_t) j * 8 + k];
+        if (tap == 0) continue;
+        const int pos = (int) a.offset[j] + k - base;
+        const int lo = i < 2 ? 0 : 4, hi = i < 2 ? 12 : 16;
+        if (pos < lo || pos >= hi || tap < -128 || tap > 127) return false;
+        frame[pos] = (int8_t) tap;
+      }
+      // 255 * sum(|taps|) + 32 must stay inside the reference's 16-bit accumulator
+      int mag = 0;
+      for (int k = 0; k < 8; k++) mag += abs ((int) a.coef[(size_t) j * 8 + k]);
+      if (255 * mag + 32 > 32767) return false;
+      const int first = i < 2 ? 0 : 1;
+      for (int w = 0; w < 3; w++) {
+        uint32_t word = 0;
+        for (int b = 0; b < 4; b++) word |= (uint32_t) (uint8_t) frame[4 * (first + w) + b] << (8 * b);
+        (*tab)[(size_t) gidx * 12 + i * 3 + w] = (int) word;
+      }
+    }
+  }
+  return true;
+}
+
+inline Lanczos2Tables build_lanczos2_tables (const VcsPlan & p)
+{
+  Lanczos2Tables t;
+  if (!p.h_first || p.matrix_first || !p.h_cosited || !p.v_pairs) return t;
+  if ((p.in.stride[0] & 7) || (p.in.stride[1] & 7) || (p.in.offset[0] & 7) || (p.in.offset[1] & 7)) return t;
+  if ((p.in.width & 7) || (p.in.height & 1)) return t;
+  for (int y = 0; y < p.in.height; y++)       // every line consumed in order: standard pairing
+    if (p.chroma_mode[y] != (y == 0 ? 0 : ((y & 1) ? 1 : 2))) return t;
+  if (!pack_axis_lanczos2 (p.h, 4, &t.htab)) return t;
+  if (!pack_axis_lanczos2 (p.v, 3, &t.vtab)) return t;
+  t.alpha_opaque = true;
+  for (int16_t s : p.h.sum) if (s < 64 || s > 128) t.alpha_opaque = false;
+  for (int16_t s : p.v.sum) if (s < 64 || s > 128) t.alpha_opaque = false;
+  t.ok = true;
+  return t;
+}
+
+struct Lanczos2State {
+  int4 *d_htab = nullptr, *d_vtab = nullptr;
+  Lanczos2Dev dev;
+};
+
+inline int prepare_lanczos2 (const Lanczos2Tables & t, const VcsDev & d, Lanczos2State * st)
+{
+  int rc;
+  int *h = nullptr, *v = nullptr;
+  if ((rc = upload (&h, t.htab.data (), t.htab.size ())) != B200_OK) return rc;
+  if ((rc = upload (&v, t.vtab.data (), t.vtab.size ())) != B200_OK) return rc;
+  st->d_htab = (int4 *) h; st->d_vtab = (int4 *) v;
+  st->dev.htab = st->d_htab; st->dev.vtab = st->d_vtab;
+  st->dev.hsum = d.h.sum; st->dev.vsum = d.v.sum;
+  st->dev.alpha_opaque = t.alpha_opaque;
+  B200_CUDA_TRY (cudaFuncSetAttribute (vcs_lanczos2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L2_SMEM));
+  B200_CUDA_TRY (cudaFuncSetAttribute (vcs_lanczos2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L2_SMEM));
+  return B200_OK;
+}
+
+inline int launch_lanczos2 (const VcsDev & d, const Lanczos2State & st, const VcsBatch & batch, int n,
+    cudaStream_t stream)
+{
+  dim3 grid ((d.ow + L2_TW - 1) / L2_TW, (d.oh + L2_TH - 1) / L2_TH, n);
+  if (st.dev.alpha_opaque)
+    vcs_lanczos2_kernel<true> <<<grid, L2_THREADS, L2_SMEM, stream>>> (d, st.dev, batch);
+  else
+    vcs_lanczos2_kernel<false> <<<grid, L2_THREADS, L2_SMEM, stream>>> (d, st.dev, batch);
+  B200_CUDA_TRY (cudaGetLastError ());
+  return B200_OK;
+}
+
+}  // namespace b200

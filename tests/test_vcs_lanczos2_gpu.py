@@ -1,0 +1,89 @@
+"""The specialised 2:1 / 8-tap kernel must produce the same bytes as the oracle (and as the
+generic kernel) on every shape it declares itself eligible for."""
+import numpy as np
+import pytest
+
+from oracle import bindings as ob
+
+pytestmark = pytest.mark.gpu
+
+SIZES = [(16, 16), (64, 48), (256, 144), (480, 272), (488, 264), (1920, 1080), (1928, 1096), (3840, 2160)]
+METHODS = [3, 5, 6, 7, 8, 9]          # every element method that yields 8 taps at 2:1
+
+
+def _convert(iw, ih, method, frame, variant, in_fmt=23, out_fmt=12, matrix=None, rng=None):
+    import torch
+    import gstreamer_b200 as g
+    el = g.CudaVideoConvertScale(method=method)
+    ii = g.VideoInfo(in_fmt, iw, ih).set_colorimetry(chroma_site=2, matrix=matrix, range=rng)
+    oi = g.VideoInfo(out_fmt, iw // 2, ih // 2)
+    el.set_info(ii, oi)
+    assert el.plan_info().kernel_variant == 1, "shape should be eligible for the specialised kernel"
+    el.set_kernel_variant(variant)
+    src = torch.from_numpy(frame).cuda()
+    dst = torch.full((oi.size,), 0x5A, dtype=torch.uint8, device="cuda")
+    el.transform_frame(src, dst)
+    torch.cuda.synchronize()
+    return dst.cpu().numpy()
+
+
+def _explain(got, want, ow):
+    bad = np.nonzero(got != want)[0]
+    if bad.size == 0:
+        return ""
+    px = bad // 4
+    rows, cols = np.unique(px // ow), np.unique(px % ow)
+    return (f"{bad.size} bytes differ; rows {rows[:12]}.. ({rows.size}), cols {cols[:12]}.. ({cols.size}), "
+            f"channels {np.unique(bad % 4)}, first got {got[bad[:6]]} want {want[bad[:6]]}")
+
+
+@pytest.mark.parametrize("size", SIZES, ids=lambda s: "%dx%d" % s)
+@pytest.mark.parametrize("method", METHODS)
+def test_specialised_matches_oracle(cuda_device, size, method):
+    iw, ih = size
+    if method != 3 and iw > 2000:
+        pytest.skip("full-size run only for the headline method")
+    d = ob.vcs_desc(iw, ih, iw // 2, ih // 2, method, site=2)
+    frame = ob.nv12_random_frame(iw, ih, seed=iw + method)
+    want = ob.oracle_vcs_convert(d, frame)
+    got = _convert(iw, ih, method, frame, 1)
+    assert np.array_equal(got, want), _explain(got, want, iw // 2)
+
+
+@pytest.mark.parametrize("in_fmt", ["NV12", "NV21"])
+@pytest.mark.parametrize("out_fmt", ["BGRA", "RGBA", "ARGB", "ABGR"])
+def test_specialised_formats(cuda_device, in_fmt, out_fmt):
+    iw, ih = 496, 280
+    d = ob.vcs_desc(iw, ih, iw // 2, ih // 2, 3, in_fmt=ob.FMT[in_fmt], out_fmt=ob.FMT[out_fmt], site=2,
+                    matrix=4, rng=1)
+    frame = ob.nv12_random_frame(iw, ih, seed=3)
+    want = ob.oracle_vcs_convert(d, frame)
+    got = _convert(iw, ih, 3, frame, 1, in_fmt=ob.FMT[in_fmt], out_fmt=ob.FMT[out_fmt], matrix=4, rng=1)
+    assert np.array_equal(got, want), _explain(got, want, iw // 2)
+
+
+def test_specialised_equals_generic_on_structured_content(cuda_device):
+    iw, ih = 3840, 2160
+    frame = ob.nv12_smpte_like_frame(iw, ih, 4)
+    a = _convert(iw, ih, 3, frame, 0)
+    b = _convert(iw, ih, 3, frame, 1)
+    assert np.array_equal(a, b), _explain(b, a, iw // 2)
+
+
+def test_extreme_values(cuda_device):
+    """all-0 / all-255 / checkerboard inputs drive the FIR overshoot into both saturations"""
+    iw, ih = 512, 288
+    st = iw
+    for pat in range(3):
+        frame = np.zeros(st * ih * 3 // 2, dtype=np.uint8)
+        if pat == 1:
+            frame[:] = 255
+        elif pat == 2:
+            y = frame[: st * ih].reshape(ih, st)
+            y[::2, ::2] = 255
+            y[1::2, 1::2] = 255
+            frame[st * ih:] = np.tile(np.array([0, 255, 255, 0], dtype=np.uint8), st * ih // 8)
+        d = ob.vcs_desc(iw, ih, iw // 2, ih // 2, 3, site=2)
+        want = ob.oracle_vcs_convert(d, frame)
+        got = _convert(iw, ih, 3, frame, 1)
+        assert np.array_equal(got, want), f"pattern {pat}: " + _explain(got, want, iw // 2)
