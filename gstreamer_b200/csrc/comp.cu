@@ -1,0 +1,224 @@
+// gstreamer_b200/csrc/comp.cu — b200_comp_* : single-pass compositor (product code, sm_100a).
+//
+// Replaces the per-pad read-modify-write passes of the reference
+//   blend_pads()/_draw_background()      gst-plugins-base/gst/compositor/compositor.c:1619-1697
+//   BLEND_A32 clip + _blend_loop/_overlay_loop   gst/compositor/blend.c:42-159
+//   compositor_orc_{blend,source,overlay,overlay_*_addition}_{argb,bgra}   compositororc.orc:163-560
+// with ONE kernel: every output pixel starts from the background value, walks the pads that
+// cover it in z-order entirely in registers, and is written once.  Bytes are identical to the
+// sequential reference because each pad's operator only reads the destination pixel it writes.
+//
+// HBM traffic per frame = every covered source pixel once + the destination once
+// (the reference moves bg write + per pad src read + dst read + dst write).
+#include "common.h"
+
+#include <string.h>
+#include <new>
+
+namespace b200 {
+
+enum CompMode : int { CM_COPY = 0, CM_SOURCE = 1, CM_BLEND = 2, CM_OVERLAY = 3, CM_OVERLAY_ADD = 4 };
+
+struct CompPadDev {
+  const uint8_t *data;           // already offset so that data + y*stride + x*4 addresses DEST pixel (x,y)
+  long long stride;
+  int x0, y0, x1, y1;            // clipped destination rectangle
+  int s_alpha, mode;
+};
+
+constexpr int COMP_CHUNK = 32;
+
+struct CompParams {
+  uint8_t *dst;
+  int width, height, stride;
+  int background;                // b200_comp_background, or -1: continue from the current dst contents
+  int alpha_shift;               // bit position of the alpha byte in a little-endian pixel word (0 or 24)
+  int n_pads;
+  CompPadDev pads[COMP_CHUNK];
+};
+
+// floor(x/255) on two 16-bit lanes, x <= 65025 per lane (== div255w: (x*0x8081)>>23, compositororc.orc)
+__device__ __forceinline__ unsigned div255_x2 (unsigned t)
+{
+  return ((t + 0x00010001u + ((t >> 8) & 0x00ff00ffu)) >> 8) & 0x00ff00ffu;
+}
+__device__ __forceinline__ unsigned div255_1 (unsigned x) { return (x * 0x8081u) >> 23; }
+
+// compositor_orc_blend_*: d = div255 (s*a + d*(255-a)) on all four bytes, then alpha := 0xff
+__device__ __forceinline__ unsigned px_blend (unsigned d, unsigned s, unsigned a, unsigned alpha_mask)
+{
+  const unsigned ia = 255u - a;
+  const unsigned lo = (s & 0x00ff00ffu) * a + (d & 0x00ff00ffu) * ia;
+  const unsigned hi = ((s >> 8) & 0x00ff00ffu) * a + ((d >> 8) & 0x00ff00ffu) * ia;
+  return (div255_x2 (lo) | (div255_x2 (hi) << 8)) | alpha_mask;
+}
+
+// compositor_orc_overlay_* (+ _addition): colour = (s*as + d*ad) / (as+ad) with divluw semantics
+__device__ __forceinline__ unsigned px_overlay (unsigned d, unsigned s, unsigned as, int shift, bool addition,
+    const unsigned *recip)
+{
+  const unsigned dalpha = (d >> shift) & 0xffu;
+  const unsigned ad = div255_1 (dalpha * (255u - as));
+  const unsigned asum = as + ad;                                   // <= 255
+  const unsigned lo = (s & 0x00ff00ffu) * as + (d & 0x00ff00ffu) * ad;       // lanes <= 65025
+  const unsigned hi = ((s >> 8) & 0x00ff00ffu) * as + ((d >> 8) & 0x00ff00ffu) * ad;
+  unsigned c[4] = {lo & 0xffffu, hi & 0xffffu, lo >> 16, hi >> 16};
+  unsigned out = 0;
+  if ((asum & 0xffu) == 0) {
+    out = 0xffffffffu;                                             // divluw: divide by zero -> 255
+  } else {
+    const unsigned r = recip[asum & 0xffu];                        // ceil (2^24 / asum): exact for v < 2^16
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const unsigned q = __umulhi (c[k] << 8, r);
+      out |= min (q, 255u) << (8 * k);
+    }
+  }
+  const unsigned na = (addition ? dalpha + as : asum) & 0xffu;
+  return (out & ~(0xffu << shift)) | (na << shift);
+}
+
+__global__ void __launch_bounds__ (256)
+comp_kernel (const CompParams P)
+{
+  __shared__ unsigned s_mask;
+  __shared__ unsigned s_recip[256];
+  // tile: 64 x 4 pixels, one pixel per thread (coalesced 256 B rows)
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const int x = blockIdx.x * 64 + tx, y = blockIdx.y * 4 + ty;
+  s_recip[threadIdx.x] = threadIdx.x ? (0x1000000u + threadIdx.x - 1) / threadIdx.x : 0u;
+  if (threadIdx.x < 32) {
+    // which pads touch this tile?  (the reference culls whole pads, compositor.c:519-601;
+    // here the cull is per tile and costs one ballot)
+    bool hit = false;
+    if ((int) threadIdx.x < P.n_pads) {
+      const CompPadDev & p = P.pads[threadIdx.x];
+      const int bx = blockIdx.x * 64, by = blockIdx.y * 4;
+      hit = p.x0 < bx + 64 && p.x1 > bx && p.y0 < by + 4 && p.y1 > by;
+    }
+    const unsigned m = __ballot_sync (0xffffffffu, hit);
+    if (threadIdx.x == 0) s_mask = m;
+  }
+  __syncthreads ();
+  if (x >= P.width || y >= P.height) return;
+  unsigned *dp = (unsigned *) (P.dst + (size_t) y * P.stride) + x;
+  const unsigned alpha_mask = 0xffu << P.alpha_shift;
+  unsigned d;
+  switch (P.background) {
+    case B200_COMP_BG_CHECKER: {                                   // fill_checker_*_c, blend.c:178-215
+      const unsigned v = (((y >> 3) ^ (x >> 3)) & 1) ? 160u : 80u;
+      d = (v * 0x01010101u) | alpha_mask;
+      break;
+    }
+    case B200_COMP_BG_BLACK: d = alpha_mask; break;                // fill_color_*, blend.c:222-237
+    case B200_COMP_BG_WHITE: d = 0xffffffffu; break;
+    case B200_COMP_BG_TRANSPARENT: d = 0u; break;                  // memset 0, compositor.c:1641-1672
+    default: d = *dp; break;                                       // continuation chunk
+  }
+  unsigned mask = s_mask;
+  while (mask) {
+    const int i = __ffs (mask) - 1;
+    mask &= mask - 1;
+    const CompPadDev & p = P.pads[i];
+    if (x < p.x0 || x >= p.x1 || y < p.y0 || y >= p.y1) continue;
+    const unsigned s = __ldg ((const unsigned *) (p.data + (long long) y * p.stride) + x);
+    if (p.mode == CM_COPY) { d = s; continue; }
+    const unsigned a = div255_1 (((s >> P.alpha_shift) & 0xffu) * (unsigned) p.s_alpha);
+    switch (p.mode) {
+      case CM_SOURCE: d = (s & ~alpha_mask) | (a << P.alpha_shift); break;
+      case CM_BLEND: d = px_blend (d, s, a, alpha_mask); break;
+      case CM_OVERLAY: d = px_overlay (d, s, a, P.alpha_shift, false, s_recip); break;
+      default: d = px_overlay (d, s, a, P.alpha_shift, true, s_recip); break;
+    }
+  }
+  *dp = d;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+struct b200_comp {
+  int format, width, height, device;
+  int alpha_shift;
+};
+
+extern "C" {
+
+int b200_comp_create (int out_format, int width, int height, int device, b200_comp ** handle)
+{
+  if (!handle) return B200_ERR_INVALID_ARG;
+  *handle = nullptr;
+  if (width < 1 || height < 1 || width > 32767 || height > 32767) return B200_ERR_INVALID_ARG;
+  int shift;
+  switch (out_format) {          // blend.h:55-66: rgba uses the bgra kernels, abgr the argb ones
+    case B200_VIDEO_FORMAT_BGRA: case B200_VIDEO_FORMAT_RGBA: shift = 24; break;
+    case B200_VIDEO_FORMAT_ARGB: case B200_VIDEO_FORMAT_ABGR: shift = 0; break;
+    default: return B200_ERR_UNSUPPORTED;
+  }
+  if (device >= 0) {
+    int n = b200_device_count ();
+    if (n <= 0) return n < 0 ? n : B200_ERR_NO_DEVICE;
+    if (device >= n) return B200_ERR_INVALID_ARG;
+  }
+  b200_comp *h = new (std::nothrow) b200_comp ();
+  if (!h) return B200_ERR_NOMEM;
+  h->format = out_format; h->width = width; h->height = height; h->device = device; h->alpha_shift = shift;
+  *handle = h;
+  return B200_OK;
+}
+
+void b200_comp_destroy (b200_comp * h) { delete h; }
+
+int b200_comp_blend (b200_comp * h, void *dst, int32_t dst_stride, int background,
+    const b200_comp_pad * pads, int n_pads, void *cuda_stream)
+{
+  if (!h || !dst || n_pads < 0 || n_pads > B200_COMP_MAX_PADS || (n_pads && !pads)) return B200_ERR_INVALID_ARG;
+  if (background < 0 || background > 3) return B200_ERR_INVALID_ARG;
+  if (dst_stride < h->width * 4 || (dst_stride & 3)) return B200_ERR_INVALID_ARG;
+  if (h->device < 0) return B200_ERR_NO_DEVICE;
+  DeviceGuard g (h->device);
+  if (!g.ok) return B200_ERR_CUDA;
+  CompParams P;
+  memset (&P, 0, sizeof (P));
+  P.dst = (uint8_t *) dst; P.width = h->width; P.height = h->height; P.stride = dst_stride;
+  P.alpha_shift = h->alpha_shift; P.background = background;
+  const dim3 grid ((h->width + 63) / 64, (h->height + 3) / 4);
+  int launched = 0;
+  auto flush = [&] () -> int {
+    comp_kernel <<<grid, 256, 0, (cudaStream_t) cuda_stream>>> (P);
+    B200_CUDA_TRY (cudaGetLastError ());
+    launched++;
+    P.n_pads = 0; P.background = -1;
+    return B200_OK;
+  };
+  for (int i = 0; i < n_pads; i++) {
+    const b200_comp_pad & pad = pads[i];
+    if (!pad.data || pad.width < 1 || pad.height < 1 || pad.stride < pad.width * 4 || (pad.stride & 3))
+      return B200_ERR_INVALID_ARG;
+    // s_alpha = CLAMP ((gint) (alpha * 255), 0, 255); fully transparent pads are skipped (blend.c:63-67)
+    int s_alpha = (int) (pad.alpha * 255);
+    s_alpha = s_alpha < 0 ? 0 : (s_alpha > 255 ? 255 : s_alpha);
+    if (s_alpha == 0) continue;
+    CompPadDev d;
+    d.x0 = pad.xpos < 0 ? 0 : pad.xpos; d.y0 = pad.ypos < 0 ? 0 : pad.ypos;
+    d.x1 = pad.xpos + pad.width > h->width ? h->width : pad.xpos + pad.width;
+    d.y1 = pad.ypos + pad.height > h->height ? h->height : pad.ypos + pad.height;
+    if (d.x1 <= d.x0 || d.y1 <= d.y0) continue;
+    d.stride = pad.stride;
+    d.data = (const uint8_t *) pad.data - (long long) pad.ypos * pad.stride - (long long) pad.xpos * 4;
+    d.s_alpha = s_alpha;
+    switch (pad.op) {            // blend.c:99-159 with compositor.c:1622-1674 choosing the family
+      case B200_COMP_OP_SOURCE: d.mode = s_alpha == 255 ? CM_COPY : CM_SOURCE; break;
+      case B200_COMP_OP_OVER: d.mode = background == B200_COMP_BG_TRANSPARENT ? CM_OVERLAY : CM_BLEND; break;
+      case B200_COMP_OP_ADD: d.mode = background == B200_COMP_BG_TRANSPARENT ? CM_OVERLAY_ADD : CM_BLEND; break;
+      default: return B200_ERR_INVALID_ARG;
+    }
+    P.pads[P.n_pads++] = d;
+    if (P.n_pads == COMP_CHUNK) { int st = flush (); if (st != B200_OK) return st; }
+  }
+  if (P.n_pads > 0 || launched == 0) { int st = flush (); if (st != B200_OK) return st; }
+  return B200_OK;
+}
+
+}  // extern "C"

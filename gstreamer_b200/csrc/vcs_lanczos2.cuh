@@ -23,6 +23,7 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <vector>
 
 #include "common.h"
@@ -68,6 +69,8 @@ __device__ __forceinline__ int prmt_s (unsigned a, unsigned sel)      // prmt.b3
   asm ("prmt.b32 %0, %1, 0, %2;" : "=r" (d) : "r" (a), "r" (sel));
   return d;
 }
+// acc >> 6 (arithmetic) issued on the FMA pipe (IMAD.HI) - the ALU pipe is this kernel's bottleneck
+__device__ __forceinline__ int sra6 (int acc) { return __mulhi (acc, 1 << 26); }
 // d = { c[15:0], sat_u8(a), sat_u8(b) }  (b in the lowest byte)
 __device__ __forceinline__ unsigned pack_sat2 (int a, int b, unsigned c)
 {
@@ -85,8 +88,8 @@ __device__ __forceinline__ unsigned pack_sat2 (int a, int b, unsigned c)
     o3 = dp4a_u8s8 (w3, T[2].w, dp4a_u8s8 (w2, T[2].z, dp4a_u8s8 (w1, T[2].y, 32)));           \
   } while (0)
 
-template <bool ALPHA_OPAQUE>
-__global__ void __launch_bounds__ (L2_THREADS, 3)
+template <bool ALPHA_OPAQUE, int MINB>
+__global__ void __launch_bounds__ (L2_THREADS, MINB)
 vcs_lanczos2_kernel (const VcsDev P, const Lanczos2Dev L, const VcsBatch frames)
 {
   extern __shared__ __align__ (16) unsigned hs[];                // [3][L2_NG][L2_TWP] words
@@ -151,10 +154,10 @@ vcs_lanczos2_kernel (const VcsDev P, const Lanczos2Dev L, const VcsBatch frames)
 #define L2_STORE(ch, A)                                                                        \
     do {                                                                                       \
       uint4 o;                                                                                 \
-      o.x = pack_sat2 (A[1][0] >> 6, A[0][0] >> 6, pack_sat2 (A[3][0] >> 6, A[2][0] >> 6, 0u)); \
-      o.y = pack_sat2 (A[1][1] >> 6, A[0][1] >> 6, pack_sat2 (A[3][1] >> 6, A[2][1] >> 6, 0u)); \
-      o.z = pack_sat2 (A[1][2] >> 6, A[0][2] >> 6, pack_sat2 (A[3][2] >> 6, A[2][2] >> 6, 0u)); \
-      o.w = pack_sat2 (A[1][3] >> 6, A[0][3] >> 6, pack_sat2 (A[3][3] >> 6, A[2][3] >> 6, 0u)); \
+      o.x = pack_sat2 (sra6 (A[1][0]), sra6 (A[0][0]), pack_sat2 (sra6 (A[3][0]), sra6 (A[2][0]), 0u)); \
+      o.y = pack_sat2 (sra6 (A[1][1]), sra6 (A[0][1]), pack_sat2 (sra6 (A[3][1]), sra6 (A[2][1]), 0u)); \
+      o.z = pack_sat2 (sra6 (A[1][2]), sra6 (A[0][2]), pack_sat2 (sra6 (A[3][2]), sra6 (A[2][2]), 0u)); \
+      o.w = pack_sat2 (sra6 (A[1][3]), sra6 (A[0][3]), pack_sat2 (sra6 (A[3][3]), sra6 (A[2][3]), 0u)); \
       *(uint4 *) (hs + ((ch) * L2_NG + g) * L2_TWP + wc * 128 + lane * 4) = o;                 \
     } while (0)
 
@@ -295,6 +298,7 @@ inline Lanczos2Tables build_lanczos2_tables (const VcsPlan & p)
 struct Lanczos2State {
   int4 *d_htab = nullptr, *d_vtab = nullptr;
   Lanczos2Dev dev;
+  int minb = 3;
 };
 
 inline int prepare_lanczos2 (const Lanczos2Tables & t, const VcsDev & d, Lanczos2State * st)
@@ -307,8 +311,13 @@ inline int prepare_lanczos2 (const Lanczos2Tables & t, const VcsDev & d, Lanczos
   st->dev.htab = st->d_htab; st->dev.vtab = st->d_vtab;
   st->dev.hsum = d.h.sum; st->dev.vsum = d.v.sum;
   st->dev.alpha_opaque = t.alpha_opaque;
-  B200_CUDA_TRY (cudaFuncSetAttribute (vcs_lanczos2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L2_SMEM));
-  B200_CUDA_TRY (cudaFuncSetAttribute (vcs_lanczos2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L2_SMEM));
+  B200_CUDA_TRY (cudaFuncSetAttribute (vcs_lanczos2_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, L2_SMEM));
+  B200_CUDA_TRY (cudaFuncSetAttribute (vcs_lanczos2_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, L2_SMEM));
+  B200_CUDA_TRY (cudaFuncSetAttribute (vcs_lanczos2_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, L2_SMEM));
+  {
+    const char *e = getenv ("B200_L2_MINB");        // tuning knob: resident CTAs per SM the kernel is compiled for
+    st->minb = (e && atoi (e) == 4) ? 4 : 3;
+  }
   return B200_OK;
 }
 
@@ -316,10 +325,12 @@ inline int launch_lanczos2 (const VcsDev & d, const Lanczos2State & st, const Vc
     cudaStream_t stream)
 {
   dim3 grid ((d.ow + L2_TW - 1) / L2_TW, (d.oh + L2_TH - 1) / L2_TH, n);
-  if (st.dev.alpha_opaque)
-    vcs_lanczos2_kernel<true> <<<grid, L2_THREADS, L2_SMEM, stream>>> (d, st.dev, batch);
+  if (st.dev.alpha_opaque && st.minb == 4)
+    vcs_lanczos2_kernel<true, 4> <<<grid, L2_THREADS, L2_SMEM, stream>>> (d, st.dev, batch);
+  else if (st.dev.alpha_opaque)
+    vcs_lanczos2_kernel<true, 3> <<<grid, L2_THREADS, L2_SMEM, stream>>> (d, st.dev, batch);
   else
-    vcs_lanczos2_kernel<false> <<<grid, L2_THREADS, L2_SMEM, stream>>> (d, st.dev, batch);
+    vcs_lanczos2_kernel<false, 3> <<<grid, L2_THREADS, L2_SMEM, stream>>> (d, st.dev, batch);
   B200_CUDA_TRY (cudaGetLastError ());
   return B200_OK;
 }
