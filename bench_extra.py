@@ -1,0 +1,147 @@
+#!/usr/bin/env python
+"""bench_extra.py — secondary BASELINE configs on one B200 (kernel-resident numbers):
+  C4  cudacompositor: 16 x 1080p RGBA pads -> 3840x2160 RGBA   (configs[3])
+  C5  cudaaudioresample: 48k -> 44.1k F32, 256 channels          (configs[4], shortened buffer)
+Prints one JSON line per config with achieved GB/s against the measured HBM peak and, for C5,
+achieved non-FMA FP32 GFLOP/s (the binding resource)."""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+def bench_c4(args):
+    import numpy as np
+    import torch
+    from gstreamer_b200.compositor import CudaCompositor
+    from oracle import bindings as ob
+    W, H = 3840, 2160
+    rng = np.random.default_rng(0)
+    out_ring = [torch.empty(W * H * 4, dtype=torch.uint8, device="cuda") for _ in range(6)]
+    rings = []
+    for ring in range(3):            # 3 sets of 16 pads = 398 MB of sources, > L2
+        comp = CudaCompositor(11, W, H, args.background)
+        for k in range(16):
+            src = torch.randint(0, 256, (1080 * 1920 * 4,), dtype=torch.uint8, device="cuda")
+            comp.request_pad(1920, 1080, xpos=(k % 4) * 640, ypos=(k // 4) * 360,
+                             alpha=0.5 if k % 2 else 1.0).set_frame(src)
+        rings.append(comp)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        for i in range(5):
+            rings[i % 3].aggregate_frames(out_ring[i % 6], stream=s)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(s)
+        for i in range(args.steps):
+            rings[i % 3].aggregate_frames(out_ring[i % 6], stream=s)
+        e1.record(s)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    alg = 16 * 1920 * 1080 * 4 + W * H * 4
+    # CPU baseline: the reference's blend.c on one frame
+    cpu = None
+    if ob.have_ref() and not args.no_cpu:
+        r = ob.ref()
+        pads = (ob.OraclePad * 16)()
+        keep = []
+        for k in range(16):
+            a = rng.integers(0, 256, (1080, 1920, 4), dtype=np.uint8)
+            keep.append(a)
+            pads[k].data, pads[k].width, pads[k].height, pads[k].stride = a.ctypes.data, 1920, 1080, 7680
+            pads[k].xpos, pads[k].ypos, pads[k].alpha, pads[k].op = (k % 4) * 640, (k // 4) * 360, 0.5 if k % 2 else 1.0, 1
+        dst = np.zeros((H, W, 4), dtype=np.uint8)
+        r.ref_compositor(11, dst.ctypes.data, W, H, W * 4, args.background, pads, 16)
+        t0 = time.perf_counter()
+        n = 0
+        while time.perf_counter() - t0 < 5:
+            r.ref_compositor(11, dst.ctypes.data, W, H, W * 4, args.background, pads, 16)
+            n += 1
+        cpu = {"value": n / (time.perf_counter() - t0), "unit": "frames/s", "cores": 1, "kind": "reference",
+               "sample": f"{n} frames, blend.c + ORC C backups, single thread"}
+    print(json.dumps({"config": "C4 cudacompositor 16x1080p RGBA -> 4K RGBA", "background": args.background,
+                      "frames_per_s": 1e3 / ms, "us_per_frame": ms * 1e3,
+                      "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak(), "unit": "GB/s",
+                                   "frac": alg / (ms * 1e-3) / 1e9 / peak(), "alg_bytes_per_launch": alg},
+                      "cpu_baseline": cpu}), flush=True)
+
+
+def bench_c5(args):
+    import numpy as np
+    import torch
+    from gstreamer_b200.audio import CudaAudioResample
+    from oracle import bindings as ob
+    ch, in_rate, out_rate = 256, 48000, 44100
+    frames = in_rate * args.seconds
+    rs = CudaAudioResample(quality=4)
+    rs.set_caps(in_rate, out_rate, ch)
+    x = torch.randn(frames * ch, dtype=torch.float32, device="cuda") * 0.25
+    cap = int(frames * out_rate / in_rate) + 64
+    out = torch.empty(cap * ch, dtype=torch.float32, device="cuda")
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        for _ in range(2):
+            rs.reset()
+            rs.transform(x, frames, out, cap, stream=s)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_out = 0
+        e0.record(s)
+        for _ in range(args.steps):
+            n_out = rs.transform(x, frames, out, cap, stream=s)
+        e1.record(s)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    taps = rs.plan_info().n_taps
+    alg = (frames + n_out) * ch * 4
+    flops = 2.0 * taps * n_out * ch
+    cpu = None
+    if ob.have_ref() and not args.no_cpu:
+        r = ob.ref()
+        h = r.ref_ars_new(in_rate, out_rate, ch, 4)
+        n = in_rate // 2
+        xi = (np.random.default_rng(0).standard_normal((n, ch)) * 0.25).astype(np.float32)
+        o = np.zeros((n, ch), dtype=np.float32)
+        r.ref_ars_process(h, xi.ctypes.data, n, o.ctypes.data, n)
+        t0 = time.perf_counter()
+        k = 0
+        while time.perf_counter() - t0 < 5:
+            r.ref_ars_process(h, xi.ctypes.data, n, o.ctypes.data, n)
+            k += 1
+        dt = time.perf_counter() - t0
+        cpu = {"value": k * n * ch / dt / 1e6, "unit": "Msamples/s (input)", "cores": 1, "kind": "reference",
+               "sample": f"{k} x 0.5 s buffers, audio-resampler.c SSE inner product, single thread"}
+        r.ref_ars_free(h)
+    print(json.dumps({"config": f"C5 cudaaudioresample 48k->44.1k F32 256ch, {args.seconds} s buffer",
+                      "msamples_per_s_in": frames * ch / (ms * 1e-3) / 1e6, "ms_per_buffer": ms,
+                      "realtime_factor": args.seconds / (ms * 1e-3),
+                      "roofline": {"bound": "fp32-issue (no FMA allowed for bit-exactness), then hbm",
+                                   "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak(), "unit": "GB/s",
+                                   "frac": alg / (ms * 1e-3) / 1e9 / peak(),
+                                   "achieved_gflops": flops / (ms * 1e-3) / 1e9, "alg_bytes_per_launch": alg},
+                      "cpu_baseline": cpu}), flush=True)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--seconds", type=int, default=20)
+    ap.add_argument("--background", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--only", default="")
+    a = ap.parse_args()
+    if a.only in ("", "c4"):
+        bench_c4(a)
+    if a.only in ("", "c5"):
+        bench_c5(a)

@@ -1,0 +1,466 @@
+// gstreamer_b200/csrc/ars.cu — b200_ars_* : polyphase FIR audio resampler (product code, sm_100a).
+//
+// Replaces, for F32 interleaved audio with the audioresample element's defaults
+// (kaiser, filter-mode auto, cubic filter interpolation; gst/audioresample/gstaudioresample.c:68-72):
+//   gst_audio_resampler_new / update / calculate_taps   gst-libs/gst/audio/audio-resampler.c:1344, :1502, :1062
+//   get_taps_gfloat_full (phase cache)                  audio-resampler.c:503-561
+//   resample_gfloat_full_1_sse + inner product          audio-resampler-macros.h:62-100, audio-resampler-x86-sse.c:27-46
+//   framing: get_out_frames / resample                  audio-resampler.c:1648-1678, :1750-1805
+//
+// Device side: one thread = one channel (lanes = 32 adjacent channels, so every load/store of
+// the interleaved stream is a fully coalesced 128 B row) x RQ consecutive output frames whose
+// input windows overlap by >90 %, so each input sample is loaded once per thread and feeds RQ
+// accumulator sets.  Bit-exactness with the reference's SSE kernel comes from keeping its lane
+// structure: four partial sums by (tap index mod 4), separate multiply and add (no FMA), final
+// (l0+l2)+(l1+l3).  Indexing the partial sums by the ABSOLUTE input index mod 4 instead of the
+// tap index only rotates the lanes, and the final reduction is invariant under rotation.
+// Tap rows are staged per CTA in shared memory pre-shifted to the window alignment of each
+// output so that all tap loads are aligned 128-bit broadcasts.
+#include "common.h"
+
+#include <math.h>
+#include <string.h>
+#include <new>
+#include <vector>
+
+#include "besi0_coeffs.inc"
+
+namespace b200 {
+
+// ------------------------------------------------------------------------------ host: filter design
+static double bessel_i0 (double x)
+{
+  const double w = fabs (x);
+  double t, y;
+  if (w < 8.5) {
+    t = w * w * 0.0625;
+    const double *p = B200_I0_LOW + 13 * (int) t;
+    y = p[0];
+    for (int i = 1; i < 13; i++) y = y * t + p[i];
+  } else if (w < 12.5) {
+    const int k = (int) w;
+    t = w - k;
+    const double *p = B200_I0_MID + 14 * (k - 8);
+    y = p[0];
+    for (int i = 1; i < 14; i++) y = y * t + p[i];
+  } else {
+    t = 60 / w;
+    const double *p = B200_I0_HIGH + 9 * (int) t;
+    y = p[0];
+    for (int i = 1; i < 9; i++) y = y * t + p[i];
+    y = y * sqrt (t) * exp (w);
+  }
+  return y;
+}
+
+struct ArsPlan {
+  int channels = 0, in_step = 0, out_step = 0;   // rates / gcd
+  int samp_inc = 0, samp_frac = 0;
+  int n_taps = 0, oversample = 0, n_phases = 0;
+  bool full = false;
+  double cutoff = 0, beta = 0;
+  std::vector<float> proto;      // (oversample + 4) x n_taps oversampled prototype
+  std::vector<float> phases;     // n_phases x n_taps (FULL mode), all phases precomputed
+};
+
+static const struct { double cutoff, down, atten, trbw; } kKaiser[11] = {
+  {0.860, 0.96511, 60, 0.7}, {0.880, 0.96591, 65, 0.29}, {0.910, 0.96923, 70, 0.145},
+  {0.920, 0.97600, 80, 0.105}, {0.940, 0.97979, 85, 0.087}, {0.940, 0.98085, 95, 0.077},
+  {0.945, 0.99471, 100, 0.068}, {0.950, 1.0, 105, 0.055}, {0.960, 1.0, 110, 0.045},
+  {0.968, 1.0, 115, 0.039}, {0.975, 1.0, 120, 0.0305}
+};
+static const int kOversample[11] = {4, 4, 4, 8, 8, 16, 16, 16, 16, 32, 32};
+
+static void cubic_coeff (int num, int denom, float ic[4])
+{
+  // make_coeff_gfloat_cubic (audio-resampler.c:360-373): float arithmetic, these literals
+  const float x = (float) num / denom, x2 = x * x, x3 = x2 * x;
+  ic[0] = 0.16667f * (x3 - x);
+  ic[1] = x + 0.5f * (x2 - x3);
+  ic[3] = -0.33333f * x + 0.5f * x2 - 0.16667f * x3;
+  ic[2] = (float) 1.0 - ic[0] - ic[1] - ic[3];
+}
+
+static int build_ars_plan (const b200_ars_config & cfg, ArsPlan * p)
+{
+  if (cfg.in_rate <= 0 || cfg.out_rate <= 0 || cfg.channels <= 0 || cfg.quality < 0 || cfg.quality > 10)
+    return B200_ERR_INVALID_ARG;
+  p->channels = cfg.channels;
+  int a = cfg.in_rate, b = cfg.out_rate;
+  while (b) { int t = a; a = b; b = t % b; }
+  p->in_step = cfg.in_rate / a;
+  p->out_step = cfg.out_rate / a;
+  p->samp_inc = p->in_step / p->out_step;
+  p->samp_frac = p->in_step % p->out_step;
+  const auto & q = kKaiser[cfg.quality];
+  double fc = q.cutoff;
+  if (cfg.out_rate < cfg.in_rate) fc *= q.down;
+  const double A = q.atten;
+  p->beta = A > 50 ? 0.1102 * (A - 8.7) : (A >= 21 ? 0.5842 * pow (A - 21, 0.4) + 0.07886 * (A - 21) : 0.0);
+  const double dw = 2 * M_PI * q.trbw;
+  p->n_taps = (int) ((A - 8.0) / (2.285 * dw)) + 1;
+  p->cutoff = fc;
+  if (p->out_step < p->in_step) {
+    p->cutoff = p->cutoff * p->out_step / p->in_step;
+    p->n_taps = (int) (((unsigned long long) p->n_taps * p->in_step) / p->out_step);
+  }
+  p->n_taps = (p->n_taps + 7) & ~7;
+  int over = kOversample[cfg.quality];
+  for (int mult = 2; over > 1 && mult * p->out_step < p->in_step; mult *= 2) over >>= 1;
+  p->oversample = over;
+  // filter-mode auto with the element's VARIABLE_RATE flag: FULL when the whole phase table is
+  // below the (effectively fixed) 1 MiB threshold (audio-resampler.c:1147-1166)
+  p->full = (long long) 4 * p->n_taps * p->out_step < 1048576;
+  p->n_phases = p->full ? p->out_step : 0;
+
+  const int n = p->n_taps;
+  p->proto.assign ((size_t) (over + 4) * n, 0.f);
+  std::vector<double> tmp (n);
+  for (int row = 0; row < over + 4; row++) {
+    const double x0 = -(n / 2) + row / (double) over;
+    double weight = 0.0;
+    for (int i = 0; i < n; i++) {          // get_kaiser_tap, audio-resampler.c:205-215
+      const double x = x0 + i, y = M_PI * x;
+      const double s = (y == 0.0 ? p->cutoff : sin (y * p->cutoff) / y);
+      const double w = 2.0 * x / n;
+      tmp[i] = s * bessel_i0 (p->beta * sqrt (fmax (1 - w * w, 0)));
+      weight += tmp[i];
+    }
+    for (int i = 0; i < n; i++) p->proto[(size_t) row * n + i] = (float) (tmp[i] / weight);
+  }
+  if (p->full) {
+    // every phase, built exactly as the reference builds it lazily (get_taps_gfloat_full +
+    // interpolate_gfloat_cubic_sse: (c0*f0 + c1*f1) + (c2*f2 + c3*f3))
+    p->phases.assign ((size_t) p->n_phases * n, 0.f);
+    for (int ph = 0; ph < p->n_phases; ph++) {
+      const int pos = ph * over, offset = (over - 1) - pos / p->n_phases, frac = pos % p->n_phases;
+      float ic[4];
+      cubic_coeff (frac, p->n_phases, ic);
+      const float *c0 = &p->proto[(size_t) offset * n], *c1 = c0 + n, *c2 = c1 + n, *c3 = c2 + n;
+      float *res = &p->phases[(size_t) ph * n];
+      for (int i = 0; i < n; i++) {
+        volatile float t0 = c0[i] * ic[0], t1 = c1[i] * ic[1], t2 = c2[i] * ic[2], t3 = c3[i] * ic[3];
+        volatile float u0 = t0 + t1, u2 = t2 + t3;
+        res[i] = u0 + u2;
+      }
+    }
+  }
+  return B200_OK;
+}
+
+// ------------------------------------------------------------------------------ device
+constexpr int ARS_RQ = 4;        // output frames per thread pass
+constexpr int ARS_THREADS = 256;
+
+struct ArsLaunch {
+  const float *hist;             // [hist_frames][channels] retained input
+  const float *in;               // [in_frames][channels] or nullptr (silence)
+  float *out;
+  const float *phases;           // [n_phases][n_taps]
+  long long hist_frames, avail;  // avail = hist_frames + in_frames
+  long long out_frames;
+  int channels, n_taps, out_step, samp_inc, samp_frac;
+  int samp_index, samp_phase;    // state at the start of this call
+  int no;                        // output frames per CTA (multiple of ARS_RQ)
+  int wcn;                       // warps across channels
+  int row_pitch;                 // floats per staged tap row (multiple of 4)
+};
+
+__device__ __forceinline__ void ars_position (const ArsLaunch & L, long long o, long long &idx, int &phase)
+{
+  // closed form of the per-sample stepping in get_taps_* (audio-resampler.c:554-559)
+  const long long t = (long long) L.samp_phase + o * L.samp_frac;
+  idx = (long long) L.samp_index + o * L.samp_inc + t / L.out_step;
+  phase = (int) (t % L.out_step);
+}
+
+__global__ void __launch_bounds__ (ARS_THREADS)
+ars_full_kernel (const ArsLaunch L)
+{
+  extern __shared__ __align__ (16) float rows[];                // [no][row_pitch]
+  __shared__ long long s_idx[64];
+  const int lane = threadIdx.x & 31;
+  const int warp = __shfl_sync (0xffffffffu, (int) (threadIdx.x >> 5), 0);
+  const long long o0 = (long long) blockIdx.x * L.no;
+  const int n_out = (int) min ((long long) L.no, L.out_frames - o0);
+
+  // stage this CTA's tap rows, each shifted by (window start & 3) and zero padded
+  for (int j = warp; j < n_out; j += ARS_THREADS / 32) {
+    long long idx; int phase;
+    ars_position (L, o0 + j, idx, phase);
+    if (lane == 0) s_idx[j] = idx;
+    const int delta = (int) (idx & 3);
+    const float *src = L.phases + (size_t) phase * L.n_taps;
+    float *dst = rows + (size_t) j * L.row_pitch;
+    for (int m = lane; m < L.row_pitch; m += 32) {
+      const int k = m - delta;
+      dst[m] = (k >= 0 && k < L.n_taps) ? __ldg (src + k) : 0.f;
+    }
+  }
+  __syncthreads ();
+
+  const int cg = warp % L.wcn, og = warp / L.wcn, nog = (ARS_THREADS / 32) / L.wcn;
+  const int c = (blockIdx.y * L.wcn + cg) * 32 + lane;
+  const bool c_ok = c < L.channels;
+  const int cc = c_ok ? c : L.channels - 1;
+  for (int q = og * ARS_RQ; q < n_out; q += nog * ARS_RQ) {
+    long long idx[ARS_RQ];
+    float acc[ARS_RQ][4];
+#pragma unroll
+    for (int r = 0; r < ARS_RQ; r++) {
+      idx[r] = s_idx[min (q + r, n_out - 1)];
+#pragma unroll
+      for (int j = 0; j < 4; j++) acc[r][j] = 0.f;
+    }
+    const long long s_begin = idx[0] & ~3LL;
+    const long long s_end = idx[ARS_RQ - 1] + L.n_taps;
+    for (long long s4 = s_begin; s4 < s_end; s4 += 4) {
+      float x[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const long long f = s4 + j;
+        float v = 0.f;
+        if (f < L.hist_frames) v = __ldg (L.hist + f * L.channels + cc);
+        else if (f < L.avail && L.in) v = __ldg (L.in + (f - L.hist_frames) * L.channels + cc);
+        x[j] = v;
+      }
+#pragma unroll
+      for (int r = 0; r < ARS_RQ; r++) {
+        const long long k0 = s4 - idx[r];                        // tap index of x[0]
+        if (k0 <= -4 || k0 >= L.n_taps) continue;                // warp-uniform
+        const int m0 = (int) (s4 - (idx[r] & ~3LL));             // aligned column in the shifted row
+        const float4 t = *(const float4 *) (rows + (size_t) min (q + r, n_out - 1) * L.row_pitch + m0);
+        if (k0 >= 0 && k0 + 3 < L.n_taps) {
+          acc[r][0] = __fadd_rn (acc[r][0], __fmul_rn (x[0], t.x));
+          acc[r][1] = __fadd_rn (acc[r][1], __fmul_rn (x[1], t.y));
+          acc[r][2] = __fadd_rn (acc[r][2], __fmul_rn (x[2], t.z));
+          acc[r][3] = __fadd_rn (acc[r][3], __fmul_rn (x[3], t.w));
+        } else {                                                 // window edge: skip taps outside [0, n_taps)
+          if (k0 + 0 >= 0 && k0 + 0 < L.n_taps) acc[r][0] = __fadd_rn (acc[r][0], __fmul_rn (x[0], t.x));
+          if (k0 + 1 >= 0 && k0 + 1 < L.n_taps) acc[r][1] = __fadd_rn (acc[r][1], __fmul_rn (x[1], t.y));
+          if (k0 + 2 >= 0 && k0 + 2 < L.n_taps) acc[r][2] = __fadd_rn (acc[r][2], __fmul_rn (x[2], t.z));
+          if (k0 + 3 >= 0 && k0 + 3 < L.n_taps) acc[r][3] = __fadd_rn (acc[r][3], __fmul_rn (x[3], t.w));
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < ARS_RQ; r++) {
+      if (q + r < n_out && c_ok) {
+        // (l0 + l2) + (l1 + l3), audio-resampler-x86-sse.c:43-45
+        const float v = __fadd_rn (__fadd_rn (acc[r][0], acc[r][2]), __fadd_rn (acc[r][1], acc[r][3]));
+        L.out[(size_t) (o0 + q + r) * L.channels + c] = v;
+      }
+    }
+  }
+}
+
+// new history = frames [first, first+keep) of the (old history ++ input) stream
+__global__ void ars_history_kernel (float *dst, const float *hist, const float *in, long long hist_frames,
+    long long first, long long keep, int channels)
+{
+  const long long n = keep * channels;
+  for (long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x; i < n; i += (long long) gridDim.x * blockDim.x) {
+    const long long f = first + i / channels;
+    const int c = (int) (i % channels);
+    float v = 0.f;
+    if (f < hist_frames) v = hist[f * channels + c];
+    else if (in) v = in[(f - hist_frames) * channels + c];
+    dst[i] = v;
+  }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+struct b200_ars {
+  ArsPlan plan;
+  int device = -1;
+  float *d_phases = nullptr;
+  float *d_hist[2] = {nullptr, nullptr};
+  size_t hist_cap[2] = {0, 0};   // frames
+  int cur = 0;
+  // reference state (audio-resampler-private.h:103-112)
+  int samp_index = 0, samp_phase = 0, skip = 0;
+  size_t samples_avail = 0;
+};
+
+static int ars_reset_state (b200_ars * h, cudaStream_t stream)
+{
+  h->samp_index = 0;
+  h->samples_avail = h->plan.n_taps / 2 - 1;                    // gst_audio_resampler_reset, :1465-1484
+  if (h->device >= 0 && h->d_hist[h->cur])
+    B200_CUDA_TRY (cudaMemsetAsync (h->d_hist[h->cur], 0, (size_t) (h->plan.n_taps / 2) * h->plan.channels * sizeof (float), stream));
+  return B200_OK;
+}
+
+static int ars_ensure_hist (b200_ars * h, int which, size_t frames)
+{
+  if (h->hist_cap[which] >= frames) return B200_OK;
+  size_t cap = frames + (size_t) h->plan.n_taps;
+  float *n = nullptr;
+  B200_CUDA_TRY (cudaMalloc ((void **) &n, cap * h->plan.channels * sizeof (float)));
+  B200_CUDA_TRY (cudaMemset (n, 0, cap * h->plan.channels * sizeof (float)));
+  if (h->d_hist[which]) {
+    if (which == h->cur && h->samples_avail)
+      B200_CUDA_TRY (cudaMemcpy (n, h->d_hist[which], h->samples_avail * h->plan.channels * sizeof (float), cudaMemcpyDeviceToDevice));
+    cudaFree (h->d_hist[which]);
+  }
+  h->d_hist[which] = n;
+  h->hist_cap[which] = cap;
+  return B200_OK;
+}
+
+extern "C" {
+
+int b200_ars_create (const b200_ars_config * cfg, int device, b200_ars ** handle)
+{
+  if (!cfg || !handle) return B200_ERR_INVALID_ARG;
+  *handle = nullptr;
+  b200_ars *h = new (std::nothrow) b200_ars ();
+  if (!h) return B200_ERR_NOMEM;
+  int st = build_ars_plan (*cfg, &h->plan);
+  if (st != B200_OK) { delete h; return st; }
+  h->device = device;
+  h->samples_avail = h->plan.n_taps / 2 - 1;
+  if (device >= 0) {
+    if (!h->plan.full) { delete h; return B200_ERR_UNSUPPORTED; }   // interpolated filter mode: not yet on device
+    int n = b200_device_count ();
+    if (n <= 0) { delete h; return n < 0 ? n : B200_ERR_NO_DEVICE; }
+    if (device >= n) { delete h; return B200_ERR_INVALID_ARG; }
+    DeviceGuard g (device);
+    if ((st = upload (&h->d_phases, h->plan.phases.data (), h->plan.phases.size ())) != B200_OK ||
+        (st = ars_ensure_hist (h, 0, (size_t) h->plan.n_taps)) != B200_OK ||
+        (st = ars_ensure_hist (h, 1, (size_t) h->plan.n_taps)) != B200_OK) {
+      b200_ars_destroy (h);
+      return st;
+    }
+    cudaFuncSetAttribute (ars_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  }
+  *handle = h;
+  return B200_OK;
+}
+
+void b200_ars_destroy (b200_ars * h)
+{
+  if (!h) return;
+  if (h->device >= 0) {
+    DeviceGuard g (h->device);
+    cudaFree (h->d_phases); cudaFree (h->d_hist[0]); cudaFree (h->d_hist[1]);
+  }
+  delete h;
+}
+
+int b200_ars_reset (b200_ars * h)
+{
+  if (!h) return B200_ERR_INVALID_ARG;
+  if (h->device >= 0) {
+    DeviceGuard g (h->device);
+    B200_CUDA_TRY (cudaDeviceSynchronize ());
+    return ars_reset_state (h, nullptr);
+  }
+  return ars_reset_state (h, nullptr);
+}
+
+size_t b200_ars_get_out_frames (b200_ars * h, size_t in_frames)
+{
+  if (!h) return 0;
+  const ArsPlan & p = h->plan;
+  const size_t need = (size_t) p.n_taps + h->samp_index + h->skip, avail = h->samples_avail + in_frames;
+  if (avail < need) return 0;
+  size_t out = (avail - need) * p.out_step;
+  if (out < (size_t) h->samp_phase) return 0;
+  return (out - h->samp_phase) / p.in_step + 1;
+}
+
+size_t b200_ars_get_in_frames (b200_ars * h, size_t out_frames)
+{
+  if (!h) return 0;
+  const ArsPlan & p = h->plan;
+  return (h->samp_phase + out_frames * p.samp_frac) / p.out_step + out_frames * p.samp_inc;
+}
+
+size_t b200_ars_get_max_latency (b200_ars * h) { return h ? h->plan.n_taps / 2 : 0; }
+
+int b200_ars_process (b200_ars * h, const float *in, size_t in_frames, float *out,
+    size_t out_capacity_frames, size_t * out_frames_ret, void *cuda_stream)
+{
+  if (!h || (!out && out_capacity_frames)) return B200_ERR_INVALID_ARG;
+  if (h->device < 0) return B200_ERR_NO_DEVICE;
+  DeviceGuard g (h->device);
+  if (!g.ok) return B200_ERR_CUDA;
+  cudaStream_t stream = (cudaStream_t) cuda_stream;
+  const ArsPlan & p = h->plan;
+  size_t out_frames = b200_ars_get_out_frames (h, in_frames);
+  if (out_frames > out_capacity_frames) out_frames = out_capacity_frames;
+  if (out_frames_ret) *out_frames_ret = out_frames;
+  // gst_audio_resampler_resample (audio-resampler.c:1750-1805)
+  if ((size_t) h->skip >= in_frames) { h->skip -= (int) in_frames; return B200_OK; }
+  h->samp_index += h->skip;
+  const size_t hist = h->samples_avail, avail = hist + in_frames;
+  const size_t need = (size_t) p.n_taps + h->samp_index;
+  size_t consumed = 0;
+  int new_phase = h->samp_phase;
+  if (avail >= need && out_frames > 0) {
+    ArsLaunch L;
+    L.hist = h->d_hist[h->cur]; L.in = in; L.out = out; L.phases = h->d_phases;
+    L.hist_frames = (long long) hist; L.avail = (long long) avail; L.out_frames = (long long) out_frames;
+    L.channels = p.channels; L.n_taps = p.n_taps; L.out_step = p.out_step;
+    L.samp_inc = p.samp_inc; L.samp_frac = p.samp_frac;
+    L.samp_index = h->samp_index; L.samp_phase = h->samp_phase;
+    L.row_pitch = (p.n_taps + 4 + 3) & ~3;
+    L.wcn = (p.channels + 31) / 32; if (L.wcn > 8) L.wcn = 8;
+    while (8 % L.wcn) L.wcn++;                                   // 1, 2, 4 or 8 warps across channels
+    int no = 32;
+    while (no > ARS_RQ && (size_t) no * L.row_pitch * sizeof (float) > 96 * 1024) no >>= 1;
+    if ((size_t) no * L.row_pitch * sizeof (float) > 160 * 1024) return B200_ERR_UNSUPPORTED;
+    L.no = no;
+    const dim3 grid ((unsigned) ((out_frames + no - 1) / no), (unsigned) ((p.channels + 32 * L.wcn - 1) / (32 * L.wcn)));
+    ars_full_kernel <<<grid, ARS_THREADS, (size_t) no * L.row_pitch * sizeof (float), stream>>> (L);
+    B200_CUDA_TRY (cudaGetLastError ());
+    // state after out_frames outputs (closed form of the stepping loop)
+    const long long t = (long long) h->samp_phase + (long long) out_frames * p.samp_frac;
+    const long long end_index = (long long) h->samp_index + (long long) out_frames * p.samp_inc + t / p.out_step;
+    new_phase = (int) (t % p.out_step);
+    consumed = (size_t) (end_index - h->samp_index);
+    h->samp_index = 0;
+    h->samp_phase = new_phase;
+  }
+  // history: what the reference keeps in its per-channel buffers (macros.h:91-93, :1790-1804)
+  size_t first = 0, keep = avail;
+  if (consumed > 0) {
+    if (avail > consumed) { first = consumed; keep = avail - consumed; }
+    else { first = avail; keep = 0; h->skip = (int) (consumed - avail); }
+  }
+  const int nxt = h->cur ^ 1;
+  int st = ars_ensure_hist (h, nxt, keep);
+  if (st != B200_OK) return st;
+  if (keep) {
+    const long long n = (long long) keep * p.channels;
+    const int blocks = (int) ((n + 255) / 256 > 1184 ? 1184 : (n + 255) / 256);
+    ars_history_kernel <<<blocks, 256, 0, stream>>> (h->d_hist[nxt], h->d_hist[h->cur], in, (long long) hist,
+        (long long) first, (long long) keep, p.channels);
+    B200_CUDA_TRY (cudaGetLastError ());
+  }
+  h->cur = nxt;
+  h->samples_avail = keep;
+  return B200_OK;
+}
+
+int b200_ars_get_plan_info (const b200_ars * h, b200_ars_plan_info * info)
+{
+  if (!h || !info) return B200_ERR_INVALID_ARG;
+  info->n_taps = h->plan.n_taps; info->n_phases = h->plan.n_phases; info->in_step = h->plan.in_step;
+  info->out_step = h->plan.out_step; info->filter_mode = h->plan.full ? 1 : 0; info->oversample = h->plan.oversample;
+  return B200_OK;
+}
+
+int b200_ars_get_phase_taps (const b200_ars * h, int phase, float *taps, size_t len)
+{
+  if (!h || !taps || !h->plan.full || phase < 0 || phase >= h->plan.n_phases || len < (size_t) h->plan.n_taps)
+    return B200_ERR_INVALID_ARG;
+  memcpy (taps, &h->plan.phases[(size_t) phase * h->plan.n_taps], sizeof (float) * h->plan.n_taps);
+  return h->plan.n_taps;
+}
+
+}  // extern "C"
