@@ -1,0 +1,110 @@
+#!/usr/bin/env python
+"""Generates tests/golden/*.npz from the reference's OWN code (oracle/_ref/libgstref.so, built by
+oracle/Makefile from /root/reference sources).  Run in the build container only:
+
+    python tests/golden/make_golden.py
+
+Inputs are regenerated from seeds by oracle.bindings.nv12_random_frame (deterministic LCG), so
+only seeds, parameters and the reference's output bytes (or their SHA-256 for large cases) are
+stored.  The reference's tests hold no value-level vectors for these paths, hence
+fixtures produced by running the reference itself.
+"""
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import bindings as ob  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def video():
+    cases = []
+    small = [(16, 16, 8, 8), (64, 48, 32, 24), (32, 24, 64, 48), (33, 17, 20, 11), (20, 11, 33, 17),
+             (64, 48, 64, 48), (1, 1, 1, 1), (2, 2, 1, 1), (1, 1, 2, 2), (90, 40, 31, 40), (40, 90, 40, 31)]
+    arrays = {}
+    for (iw, ih, ow, oh) in small:
+        for m in range(10):
+            r = ob.RefVcs(iw, ih, ow, oh, m)
+            frame = ob.nv12_random_frame(iw, ih, seed=iw * 131 + ih * 7 + m)
+            out = r.convert(frame)
+            key = f"v_{iw}x{ih}_{ow}x{oh}_m{m}"
+            arrays[key] = out
+            cases.append({"key": key, "in": [iw, ih], "out": [ow, oh], "method": m, "seed": iw * 131 + ih * 7 + m})
+            r.close()
+    big = []
+    for (iw, ih, ow, oh, m) in [(1920, 1080, 1280, 720, 1), (3840, 2160, 1920, 1080, 3), (640, 480, 320, 240, 0),
+                                (641, 481, 111, 30, 1), (320, 240, 640, 480, 3)]:
+        r = ob.RefVcs(iw, ih, ow, oh, m)
+        frame = ob.nv12_random_frame(iw, ih, seed=99)
+        out = r.convert(frame)
+        big.append({"in": [iw, ih], "out": [ow, oh], "method": m, "seed": 99,
+                    "sha256": hashlib.sha256(out.tobytes()).hexdigest(), "first16": out[:16].tolist()})
+        r.close()
+    np.savez_compressed(os.path.join(HERE, "video_small.npz"), **arrays)
+    json.dump({"small": cases, "big": big}, open(os.path.join(HERE, "video_cases.json"), "w"), indent=1)
+
+
+def compositor():
+    import ctypes as C
+    rng = np.random.default_rng(2024)
+    arrays, cases = {}, []
+    for t in range(24):
+        W, H = int(rng.integers(4, 80)), int(rng.integers(4, 60))
+        fmt, bg = int(rng.choice([11, 12, 13, 14])), int(rng.integers(0, 4))
+        n = int(rng.integers(1, 5))
+        pads = (ob.OraclePad * n)()
+        spec, keep = [], []
+        for i in range(n):
+            w, h = int(rng.integers(1, 50)), int(rng.integers(1, 40))
+            seed = int(rng.integers(0, 1 << 30))
+            a = np.random.default_rng(seed).integers(0, 256, (h, w, 4), dtype=np.uint8)
+            keep.append(a)
+            x, y = int(rng.integers(-20, W)), int(rng.integers(-20, H))
+            al, op = float(rng.choice([0.25, 0.5, 1.0, 0.9])), int(rng.integers(0, 3))
+            pads[i].data, pads[i].width, pads[i].height, pads[i].stride = a.ctypes.data, w, h, w * 4
+            pads[i].xpos, pads[i].ypos, pads[i].alpha, pads[i].op = x, y, al, op
+            spec.append([w, h, x, y, al, op, seed])
+        dst = np.zeros((H, W, 4), dtype=np.uint8)
+        ob.ref().ref_compositor(fmt, dst.ctypes.data, W, H, W * 4, bg, pads, n)
+        arrays[f"c_{t}"] = dst
+        cases.append({"key": f"c_{t}", "W": W, "H": H, "fmt": fmt, "bg": bg, "pads": spec})
+    np.savez_compressed(os.path.join(HERE, "comp.npz"), **arrays)
+    json.dump(cases, open(os.path.join(HERE, "comp_cases.json"), "w"), indent=1)
+
+
+def audio():
+    r = ob.ref()
+    arrays, cases = {}, []
+    for t, (a, b, ch, q, bufs) in enumerate([(48000, 44100, 2, 4, [480, 480, 480]), (44100, 48000, 1, 4, [441, 441]),
+                                             (8000, 16000, 1, 4, [160, 160, 160, 160]), (48000, 44100, 4, 10, [1024, 512]),
+                                             (12345, 54321, 2, 4, [600]), (96000, 8000, 1, 2, [4000, 4000])]):
+        h = r.ref_ars_new(a, b, ch, q)
+        rng = np.random.default_rng(500 + t)
+        outs, counts = [], []
+        for n in bufs:
+            x = (rng.standard_normal((n, ch)) * 0.5).astype(np.float32)
+            cap = int(n * b / a) + 64
+            o = np.zeros((cap, ch), dtype=np.float32)
+            k = r.ref_ars_process(h, x.ctypes.data, n, o.ctypes.data, cap)
+            outs.append(o[:k].copy())
+            counts.append(int(k))
+        r.ref_ars_free(h)
+        arrays[f"a_{t}"] = np.concatenate(outs) if outs else np.zeros((0, ch), np.float32)
+        cases.append({"key": f"a_{t}", "in_rate": a, "out_rate": b, "ch": ch, "quality": q, "bufs": bufs,
+                      "counts": counts, "seed": 500 + t})
+    np.savez_compressed(os.path.join(HERE, "audio.npz"), **arrays)
+    json.dump(cases, open(os.path.join(HERE, "audio_cases.json"), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    assert ob.have_ref(), "needs oracle/_ref/libgstref.so (make -C oracle ref)"
+    video()
+    compositor()
+    audio()
+    print("golden fixtures written to", HERE)

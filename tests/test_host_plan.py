@@ -1,0 +1,152 @@
+"""Host-side plan builders of the product (C++, no device needed: device=-1) against the oracle:
+tap tables, stage order, matrix, chroma pairing, specialised-kernel eligibility, audio filter."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import bindings as ob
+
+SIZES = [(3840, 2160, 1920, 1080), (1920, 1080, 1280, 720), (641, 481, 111, 30), (111, 30, 641, 481),
+         (100, 100, 150, 50), (640, 480, 320, 240), (17, 33, 64, 7), (64, 48, 64, 48), (40, 90, 40, 31)]
+
+
+def _oracle_taps(method, insz, outsz, prec):
+    o = ob.oracle()
+    m, mt, bc = ob.ELEMENT_METHODS[method]
+    rs = ob.RS(m, mt, 0, 2.0, 1.0, 0.0, 1 / 3, 1 / 3)
+    if bc:
+        rs.cubic_b, rs.cubic_c = bc
+    off = np.zeros(outsz, dtype=np.uint32)
+    t = np.zeros(outsz * 128)
+    n = o.oracle_resampler_taps(C.byref(rs), insz, outsz, off.ctypes.data, t.ctypes.data)
+    t = t[: outsz * n].reshape(outsz, n)
+    q = np.zeros((outsz, n), dtype=np.int16)
+    for i in range(outsz):
+        row = np.ascontiguousarray(t[i])
+        qq = np.zeros(n, dtype=np.int16)
+        o.oracle_quantize_taps(row.ctypes.data, qq.ctypes.data, n, prec)
+        q[i] = qq
+    return n, off, q
+
+
+@pytest.mark.parametrize("size", SIZES, ids=lambda s: "%dx%d-%dx%d" % s)
+@pytest.mark.parametrize("method", range(10))
+def test_tap_tables_and_order(size, method):
+    import gstreamer_b200 as g
+    iw, ih, ow, oh = size
+    el = g.CudaVideoConvertScale(method=method, cuda_device_id=-1)
+    el.set_info(g.VideoInfo(23, iw, ih), g.VideoInfo(12, ow, oh))
+    pi = el.plan_info()
+    for d, (a, b) in enumerate([(iw, ow), (ih, oh)]):
+        off, coef = el.taps(d)
+        if a == b:
+            assert (off == np.arange(b)).all()
+            continue
+        n, ooff, oq = _oracle_taps(method, a, b, 6)
+        assert (pi.h_taps, pi.v_taps)[d] == n
+        if n >= 3:
+            assert (off == ooff).all() and (coef == oq).all()
+        elif n == 1:
+            assert (off == ooff).all()
+        elif d == 1:                      # vertical 2-tap: centre aligned, 8-bit second tap
+            n, ooff, oq = _oracle_taps(method, a, b, 8)
+            assert (off == ooff).all() and (coef[:, 0] == oq[:, 1]).all()
+        else:                             # horizontal 2-tap: edge aligned 16.16 stepping
+            inc = 0 if b == 1 else ((a - 1) << 16) // (b - 1) - 1
+            x = np.arange(b, dtype=np.int64) * inc
+            assert (off == (x >> 16)).all() and (coef[:, 0] == ((x >> 8) & 0xff)).all()
+    # chain_scale ordering (video-converter.c:1685-1718)
+    assert pi.matrix_first == int(ow * oh > iw * ih)
+    assert pi.h_first == int(ow * ih <= iw * oh)
+    d = ob.vcs_desc(iw, ih, ow, oh, method)
+    p = (C.c_int * 5)()
+    im = (C.c_int * 16)()
+    assert ob.oracle().oracle_vcs_matrix(C.byref(d), p, im) == 0
+    assert list(pi.p) == list(p)
+
+
+@pytest.mark.parametrize("matrix,rng", [(2, 1), (2, 2), (3, 1), (3, 2), (4, 1), (4, 2), (5, 2), (6, 1), (6, 2)])
+def test_matrix_all_colorimetries(matrix, rng):
+    import gstreamer_b200 as g
+    el = g.CudaVideoConvertScale(method=3, cuda_device_id=-1)
+    el.set_info(g.VideoInfo(23, 64, 48).set_colorimetry(matrix=matrix, range=rng), g.VideoInfo(12, 32, 24))
+    d = ob.vcs_desc(64, 48, 32, 24, 3, matrix=matrix, rng=rng)
+    p = (C.c_int * 5)()
+    im = (C.c_int * 16)()
+    assert ob.oracle().oracle_vcs_matrix(C.byref(d), p, im) == 0
+    assert list(el.plan_info().p) == list(p)
+
+
+def test_chroma_plan_standard_and_skipping():
+    import gstreamer_b200 as g
+    el = g.CudaVideoConvertScale(method=3, cuda_device_id=-1)
+    el.set_info(g.VideoInfo(23, 64, 48), g.VideoInfo(12, 32, 24))
+    m = el.chroma_plan()
+    assert m[0] == 0 and (m[1::2] == 1).all() and (m[2::2] == 2).all()
+    # nearest 2:1 skips lines: a requested even line opens its own pair
+    el = g.CudaVideoConvertScale(method=0, cuda_device_id=-1)
+    el.set_info(g.VideoInfo(23, 640, 480), g.VideoInfo(12, 320, 240))
+    off, _ = el.taps(1)
+    m = el.chroma_plan()
+    assert off[122] == 244 and off[123] == 246          # the floating point floor lands on even lines here
+    assert m[244] == 2 and m[246] == 1 and m[245] == 0 and m[1] == 1
+
+
+def test_specialised_kernel_eligibility():
+    import gstreamer_b200 as g
+
+    def eligible(iw, ih, ow, oh, method, site=2, **kw):
+        el = g.CudaVideoConvertScale(method=method, cuda_device_id=-1)
+        ii = g.VideoInfo(23, iw, ih).set_colorimetry(chroma_site=site)
+        if "stride" in kw:
+            ii.set_layout([kw["stride"], kw["stride"]], [0, kw["stride"] * ih])
+        el.set_info(ii, g.VideoInfo(12, ow, oh))
+        try:
+            el.set_kernel_variant(1)
+            return True
+        except g.B200Error:
+            return False
+
+    assert eligible(3840, 2160, 1920, 1080, 3)
+    assert eligible(1920, 1080, 960, 540, 9)
+    assert not eligible(3840, 2160, 1920, 1080, 1)            # bilinear: 2 taps
+    assert not eligible(3840, 2160, 1280, 720, 3)             # 3:1
+    assert not eligible(3840, 2160, 1920, 1080, 3, site=1)    # not h-cosited
+    assert not eligible(644, 480, 322, 240, 3)                # width not a multiple of 8
+    assert not eligible(640, 480, 320, 240, 3, stride=644)    # rows not 8-byte aligned
+    assert not eligible(640, 480, 320, 240, 0)                # nearest
+
+
+@pytest.mark.parametrize("cfg", [(48000, 44100, 4), (44100, 48000, 4), (8000, 16000, 0), (22050, 48000, 9),
+                                 (96000, 8000, 7), (48000, 24000, 10), (101, 99, 4)])
+def test_audio_filter_design(cfg):
+    from gstreamer_b200.audio import CudaAudioResample
+    a, b, q = cfg
+    o = ob.oracle()
+    rs = CudaAudioResample(quality=q, cuda_device_id=-1)
+    rs.set_caps(a, b, 2)
+    pi = rs.plan_info()
+    ho = o.oracle_ars_new(a, b, 2, q)
+    v = [C.c_int() for _ in range(6)]
+    o.oracle_ars_info(ho, *[C.byref(x) for x in v])
+    assert [pi.n_taps, pi.n_phases, pi.in_step, pi.out_step, pi.filter_mode, pi.oversample] == [x.value for x in v]
+    for ph in range(pi.n_phases):
+        t = np.zeros(pi.n_taps, dtype=np.float32)
+        o.oracle_ars_phase_taps(ho, ph, t.ctypes.data)
+        assert np.array_equal(t.view(np.uint32), rs.phase_taps(ph).view(np.uint32)), f"phase {ph}"
+    # framing arithmetic before any data: get_out_frames for a few sizes
+    for n in (1, 100, 480, 4800):
+        assert rs.get_out_frames(n) == o.oracle_ars_get_out_frames(ho, n)
+        assert rs.get_in_frames(n) == o.oracle_ars_get_in_frames(ho, n)
+    assert rs.max_latency == o.oracle_ars_max_latency(ho)
+    o.oracle_ars_free(ho)
+
+
+def test_c5_filter_numbers_from_the_survey():
+    """48k -> 44.1k at quality 4: steps 160/147, 72 taps, 147 phases, FULL mode"""
+    from gstreamer_b200.audio import CudaAudioResample
+    rs = CudaAudioResample(quality=4, cuda_device_id=-1)
+    rs.set_caps(48000, 44100, 256)
+    pi = rs.plan_info()
+    assert (pi.in_step, pi.out_step, pi.n_taps, pi.n_phases, pi.filter_mode, pi.oversample) == (160, 147, 72, 147, 1, 8)

@@ -1,0 +1,152 @@
+"""Pins the oracle (oracle/*.c, our restatement) against the reference's own sources compiled in
+place (oracle/_ref/libgstref.so).  Needs that library: present in the build container and shipped
+prebuilt to the GPU box; skipped elsewhere (tests/test_golden.py covers that case)."""
+import numpy as np
+import pytest
+
+from oracle import bindings as ob
+
+pytestmark = pytest.mark.ref
+
+# the reference element test's size matrix (tests/check/elements/videoscale.c:451-492) and more
+SIZES = [(640, 480, 320, 240), (320, 240, 640, 480), (641, 481, 111, 30), (111, 30, 641, 481),
+         (641, 481, 30, 111), (30, 111, 641, 481), (1, 1, 1, 1), (2, 2, 1, 1), (1, 1, 2, 2), (16, 16, 16, 16),
+         (100, 100, 50, 150), (3, 5, 7, 2), (17, 33, 64, 7), (640, 480, 641, 481), (1920, 1080, 1280, 720)]
+
+
+def _vfirst(iw, ih, ow, oh):
+    return ih != oh and (iw == ow or ow * ih > iw * oh)
+
+
+@pytest.mark.parametrize("size", SIZES, ids=lambda s: "%dx%d-%dx%d" % s)
+@pytest.mark.parametrize("method", range(10))
+def test_video_matches_reference(size, method):
+    iw, ih, ow, oh = size
+    frame = ob.nv12_random_frame(iw, ih, seed=iw + 3 * oh + method)
+    r = ob.RefVcs(iw, ih, ow, oh, method)
+    want = r.convert(frame)
+    r.close()
+    got = ob.oracle_vcs_convert(ob.vcs_desc(iw, ih, ow, oh, method), frame)
+    if _vfirst(iw, ih, ow, oh) and not np.array_equal(got, want):
+        pytest.xfail("reference ring aliasing (vertical-first chain); see test_vertical_first_two_step")
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("size", [(100, 100, 150, 50), (641, 481, 640, 480), (720, 480, 640, 360), (17, 33, 64, 7), (40, 90, 40, 31),
+                          (64, 64, 64, 32)],
+                         ids=lambda s: "%dx%d-%dx%d" % s)
+@pytest.mark.parametrize("method", [3, 4, 5, 6, 9])
+def test_vertical_first_two_step(size, method):
+    """On vertical-first chains the reference's unpack ring is one line short and a tap reads a
+    recycled line.  Its INTENDED arithmetic is pinned by composing two reference runs that
+    cannot alias: NV12 -> AYUV at the same size (chroma up-sampling only), then AYUV -> BGRA with
+    scaling (identity unpack, no temp-line ring in front of the vertical scaler)."""
+    iw, ih, ow, oh = size
+    assert _vfirst(iw, ih, ow, oh)
+    d = ob.vcs_desc(iw, ih, ow, oh, method)
+    frame = ob.nv12_random_frame(iw, ih, seed=7)
+    r1 = ob.RefVcs(iw, ih, iw, ih, method, out_fmt=ob.FMT["AYUV"], matrix=d.in_matrix, rng=d.in_range,
+                   site=d.in_chroma_site, out_matrix=d.in_matrix, out_rng=d.in_range, out_site=0)
+    ayuv = r1.convert(frame)
+    r1.close()
+    r2 = ob.RefVcs(iw, ih, ow, oh, method, in_fmt=ob.FMT["AYUV"], matrix=d.in_matrix, rng=d.in_range, site=0)
+    want = r2.convert(ayuv)
+    r2.close()
+    got = ob.oracle_vcs_convert(d, frame)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("in_fmt", ["NV12", "NV21"])
+@pytest.mark.parametrize("out_fmt", ["RGBx", "BGRx", "xRGB", "xBGR", "RGBA", "BGRA", "ARGB", "ABGR"])
+def test_video_formats(in_fmt, out_fmt):
+    iw, ih, ow, oh = 98, 66, 45, 37
+    frame = ob.nv12_random_frame(iw, ih, 5)
+    r = ob.RefVcs(iw, ih, ow, oh, 3, in_fmt=ob.FMT[in_fmt], out_fmt=ob.FMT[out_fmt])
+    want = r.convert(frame)
+    r.close()
+    got = ob.oracle_vcs_convert(ob.vcs_desc(iw, ih, ow, oh, 3, in_fmt=ob.FMT[in_fmt], out_fmt=ob.FMT[out_fmt]), frame)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("site", [1, 2, 4, 6])
+@pytest.mark.parametrize("matrix,rng", [(3, 2), (4, 2), (4, 1), (6, 2), (2, 1), (5, 2)])
+def test_video_colorimetry_and_siting(site, matrix, rng):
+    iw, ih, ow, oh = 130, 74, 65, 37
+    frame = ob.nv12_random_frame(iw, ih, site + matrix)
+    r = ob.RefVcs(iw, ih, ow, oh, 3, site=site, matrix=matrix, rng=rng)
+    want = r.convert(frame)
+    r.close()
+    got = ob.oracle_vcs_convert(ob.vcs_desc(iw, ih, ow, oh, 3, site=site, matrix=matrix, rng=rng), frame)
+    assert np.array_equal(got, want)
+
+
+def test_reference_threads_equal_single_thread():
+    """the reference's own invariant (tests/check/libs/video.c:3189-3260) holds for our build of it
+    on the headline shape: n-threads=4 output == n-threads=1 output"""
+    iw, ih, ow, oh = 1920, 1080, 960, 540
+    frame = ob.nv12_random_frame(iw, ih, 1)
+    a = ob.RefVcs(iw, ih, ow, oh, 3, n_threads=1).convert(frame)
+    b = ob.RefVcs(iw, ih, ow, oh, 3, n_threads=4).convert(frame)
+    assert np.array_equal(a, b)
+
+
+def test_compositor_matches_reference():
+    rng = np.random.default_rng(7)
+    o, r = ob.oracle(), ob.ref()
+    for trial in range(150):
+        W, H = int(rng.integers(1, 90)), int(rng.integers(1, 70))
+        fmt, bg = int(rng.choice([11, 12, 13, 14])), int(rng.integers(0, 4))
+        n = int(rng.integers(0, 6))
+        pads = (ob.OraclePad * max(n, 1))()
+        keep = []
+        for i in range(n):
+            w, h = int(rng.integers(1, 60)), int(rng.integers(1, 50))
+            a = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+            keep.append(a)
+            pads[i].data, pads[i].width, pads[i].height, pads[i].stride = a.ctypes.data, w, h, w * 4
+            pads[i].xpos, pads[i].ypos = int(rng.integers(-30, W + 5)), int(rng.integers(-30, H + 5))
+            pads[i].alpha, pads[i].op = float(rng.choice([0.0, 0.3, 0.5, 0.999, 1.0, 0.004])), int(rng.integers(0, 3))
+        d1 = np.full((H, W, 4), 0x77, dtype=np.uint8)
+        d2 = d1.copy()
+        r.ref_compositor(fmt, d1.ctypes.data, W, H, W * 4, bg, pads, n)
+        o.oracle_compositor(fmt, d2.ctypes.data, W, H, W * 4, bg, pads, n)
+        assert np.array_equal(d1, d2), f"trial {trial}"
+
+
+@pytest.mark.parametrize("cfg", [(48000, 44100, 2, 4), (44100, 48000, 3, 4), (8000, 16000, 1, 4), (48000, 24000, 2, 4),
+                                 (12345, 54321, 2, 4), (101, 99, 1, 4), (44100, 8000, 2, 10), (48000, 96000, 2, 0),
+                                 (96000, 8000, 1, 7), (22050, 48000, 2, 9), (48000, 44100, 256, 4)],
+                         ids=lambda c: "%d-%d-%dch-q%d" % c)
+def test_audio_matches_reference(cfg):
+    import ctypes as C
+    a, b, ch, q = cfg
+    o, r = ob.oracle(), ob.ref()
+    ho, hr = o.oracle_ars_new(a, b, ch, q), r.ref_ars_new(a, b, ch, q)
+    io = [C.c_int() for _ in range(6)]
+    ir = [C.c_int() for _ in range(6)]
+    o.oracle_ars_info(ho, *[C.byref(v) for v in io])
+    r.ref_ars_info(hr, *[C.byref(v) for v in ir])
+    assert [v.value for v in io] == [v.value for v in ir]
+    if io[4].value == 1:
+        for ph in sorted({0, 1, io[1].value // 2, io[1].value - 1}):
+            t1 = np.zeros(io[0].value, dtype=np.float32)
+            t2 = t1.copy()
+            o.oracle_ars_phase_taps(ho, ph, t1.ctypes.data)
+            r.ref_ars_phase_taps(hr, ph, t2.ctypes.data)
+            assert np.array_equal(t1.view(np.uint32), t2.view(np.uint32))
+    rng = np.random.default_rng(a + b)
+    for n in [480, 480, 100, 1, 2000, None]:
+        x = None
+        if n is None:
+            n = io[0].value // 2        # drain: push silence like the element (gstaudioresample.c:590-662)
+        else:
+            x = rng.standard_normal((n, ch)).astype(np.float32)
+        cap = int(n * b / a) + 64
+        o1 = np.zeros((cap, ch), dtype=np.float32)
+        o2 = o1.copy()
+        n1 = o.oracle_ars_process(ho, x.ctypes.data if x is not None else None, n, o1.ctypes.data, cap)
+        n2 = r.ref_ars_process(hr, x.ctypes.data if x is not None else None, n, o2.ctypes.data, cap)
+        assert n1 == n2
+        assert np.array_equal(o1[:n1].view(np.uint32), o2[:n2].view(np.uint32))
+    o.oracle_ars_free(ho)
+    r.ref_ars_free(hr)
