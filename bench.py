@@ -166,15 +166,11 @@ def run_ours(args):
     import gstreamer_b200 as g
     from oracle import bindings as ob  # input generator only (synthetic frames)
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    from gstreamer_b200 import multi
+    rank, world, local = multi.rank_info()
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
+    dist = multi.init("nccl", device=dev)
 
     el = g.CudaVideoConvertScale(method=METHOD, cuda_device_id=local)
     ii, oi = g.VideoInfo(g.VideoFormat.NV12, IW, IH), g.VideoInfo(g.VideoFormat.BGRA, OW, OH)
@@ -182,7 +178,7 @@ def run_ours(args):
     pinfo = el.plan_info()
 
     # ring of distinct frames resident in HBM
-    base = [torch.from_numpy(ob.nv12_random_frame(IW, IH, 1000 * rank + s)).to(dev) for s in range(4)]
+    base = [torch.from_numpy(ob.nv12_random_frame(IW, IH, multi.stream_seed(rank, s))).to(dev) for s in range(4)]
     ring_in = []
     for k in range(RING):
         t = base[k % 4].clone()
@@ -241,10 +237,7 @@ def run_ours(args):
     e2e_s = time.perf_counter() - t0
     checksum = int(hout[0].array[:4096].sum())
 
-    t = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_s = float(t[0]), float(t[1])
+    ms, e2e_s = multi.reduce_max(dist, [ms, e2e_s], device=dev)    # slowest rank defines the job
     if rank == 0:
         frames = args.steps * FRAMES_PER_STEP * world
         value = frames * IN_PIX_PER_FRAME / (ms * 1e-3) / 1e6

@@ -34,6 +34,7 @@ struct CompParams {
   int background;                // b200_comp_background, or -1: continue from the current dst contents
   int alpha_shift;               // bit position of the alpha byte in a little-endian pixel word (0 or 24)
   int n_pads;
+  int need_recip;                // some pad uses the overlay family (needs the reciprocal table)
   CompPadDev pads[COMP_CHUNK];
 };
 
@@ -78,60 +79,106 @@ __device__ __forceinline__ unsigned px_overlay (unsigned d, unsigned s, unsigned
   return (out & ~(0xffu << shift)) | (na << shift);
 }
 
+// one pad applied to one pixel value held in a register
+__device__ __forceinline__ unsigned apply_pad (unsigned d, unsigned s, int mode, unsigned s_alpha, int shift,
+    unsigned alpha_mask, const unsigned *recip)
+{
+  if (mode == CM_COPY) return s;
+  const unsigned a = div255_1 (((s >> shift) & 0xffu) * s_alpha);
+  switch (mode) {
+    case CM_SOURCE: return (s & ~alpha_mask) | (a << shift);
+    case CM_BLEND: return px_blend (d, s, a, alpha_mask);
+    case CM_OVERLAY: return px_overlay (d, s, a, shift, false, recip);
+    default: return px_overlay (d, s, a, shift, true, recip);
+  }
+}
+
+__device__ __forceinline__ unsigned background_px (int bg, int x, int y, unsigned alpha_mask)
+{
+  switch (bg) {
+    case B200_COMP_BG_CHECKER:                                     // fill_checker_*_c, blend.c:178-215
+      return (((((y >> 3) ^ (x >> 3)) & 1) ? 160u : 80u) * 0x01010101u) | alpha_mask;
+    case B200_COMP_BG_BLACK: return alpha_mask;                    // fill_color_*, blend.c:222-237
+    case B200_COMP_BG_WHITE: return 0xffffffffu;
+    default: return 0u;                                            // transparent: memset 0, compositor.c:1641-1672
+  }
+}
+
+// tile: 128 x 8 pixels, 4 horizontally adjacent pixels per thread (16 B: one STG.128 per thread,
+// LDG.128 per covering pad when the pad's x offset keeps 16 B alignment)
+constexpr int CT_W = 128, CT_H = 8;
+
 __global__ void __launch_bounds__ (256)
 comp_kernel (const CompParams P)
 {
   __shared__ unsigned s_mask;
   __shared__ unsigned s_recip[256];
-  // tile: 64 x 4 pixels, one pixel per thread (coalesced 256 B rows)
-  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
-  const int x = blockIdx.x * 64 + tx, y = blockIdx.y * 4 + ty;
-  s_recip[threadIdx.x] = threadIdx.x ? (0x1000000u + threadIdx.x - 1) / threadIdx.x : 0u;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int x0 = blockIdx.x * CT_W + tx * 4, y = blockIdx.y * CT_H + ty;
+  if (P.need_recip)                                                // only the overlay family divides
+    s_recip[threadIdx.x] = threadIdx.x ? (0x1000000u + threadIdx.x - 1) / threadIdx.x : 0u;
   if (threadIdx.x < 32) {
     // which pads touch this tile?  (the reference culls whole pads, compositor.c:519-601;
     // here the cull is per tile and costs one ballot)
     bool hit = false;
     if ((int) threadIdx.x < P.n_pads) {
       const CompPadDev & p = P.pads[threadIdx.x];
-      const int bx = blockIdx.x * 64, by = blockIdx.y * 4;
-      hit = p.x0 < bx + 64 && p.x1 > bx && p.y0 < by + 4 && p.y1 > by;
+      const int bx = blockIdx.x * CT_W, by = blockIdx.y * CT_H;
+      hit = p.x0 < bx + CT_W && p.x1 > bx && p.y0 < by + CT_H && p.y1 > by;
     }
     const unsigned m = __ballot_sync (0xffffffffu, hit);
     if (threadIdx.x == 0) s_mask = m;
   }
   __syncthreads ();
-  if (x >= P.width || y >= P.height) return;
-  unsigned *dp = (unsigned *) (P.dst + (size_t) y * P.stride) + x;
+  if (x0 >= P.width || y >= P.height) return;
+  const int n = min (4, P.width - x0);
+  unsigned *dp = (unsigned *) (P.dst + (size_t) y * P.stride) + x0;
+  const bool vec = n == 4 && ((((size_t) dp) & 15) == 0);
   const unsigned alpha_mask = 0xffu << P.alpha_shift;
-  unsigned d;
-  switch (P.background) {
-    case B200_COMP_BG_CHECKER: {                                   // fill_checker_*_c, blend.c:178-215
-      const unsigned v = (((y >> 3) ^ (x >> 3)) & 1) ? 160u : 80u;
-      d = (v * 0x01010101u) | alpha_mask;
-      break;
-    }
-    case B200_COMP_BG_BLACK: d = alpha_mask; break;                // fill_color_*, blend.c:222-237
-    case B200_COMP_BG_WHITE: d = 0xffffffffu; break;
-    case B200_COMP_BG_TRANSPARENT: d = 0u; break;                  // memset 0, compositor.c:1641-1672
-    default: d = *dp; break;                                       // continuation chunk
+  unsigned d[4];
+  if (P.background >= 0) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) d[i] = background_px (P.background, x0 + i, y, alpha_mask);
+  } else if (vec) {                                                // continuation chunk: start from dst
+    const uint4 v = *(const uint4 *) dp;
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; i++) d[i] = i < n ? dp[i] : 0u;
   }
   unsigned mask = s_mask;
   while (mask) {
-    const int i = __ffs (mask) - 1;
+    const int pi = __ffs (mask) - 1;
     mask &= mask - 1;
-    const CompPadDev & p = P.pads[i];
-    if (x < p.x0 || x >= p.x1 || y < p.y0 || y >= p.y1) continue;
-    const unsigned s = __ldg ((const unsigned *) (p.data + (long long) y * p.stride) + x);
-    if (p.mode == CM_COPY) { d = s; continue; }
-    const unsigned a = div255_1 (((s >> P.alpha_shift) & 0xffu) * (unsigned) p.s_alpha);
-    switch (p.mode) {
-      case CM_SOURCE: d = (s & ~alpha_mask) | (a << P.alpha_shift); break;
-      case CM_BLEND: d = px_blend (d, s, a, alpha_mask); break;
-      case CM_OVERLAY: d = px_overlay (d, s, a, P.alpha_shift, false, s_recip); break;
-      default: d = px_overlay (d, s, a, P.alpha_shift, true, s_recip); break;
+    const CompPadDev & p = P.pads[pi];
+    if (y < p.y0 || y >= p.y1 || x0 >= p.x1 || x0 + n <= p.x0) continue;
+    const unsigned *sp = (const unsigned *) (p.data + (long long) y * p.stride) + x0;
+    const int mode = p.mode, shift = P.alpha_shift;
+    const unsigned s_alpha = (unsigned) p.s_alpha;
+    if (x0 >= p.x0 && x0 + 4 <= p.x1 && n == 4) {                  // whole group inside the pad
+      unsigned s[4];
+      if ((((size_t) sp) & 15) == 0) {
+        const uint4 v = __ldg ((const uint4 *) sp);
+        s[0] = v.x; s[1] = v.y; s[2] = v.z; s[3] = v.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; i++) s[i] = __ldg (sp + i);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; i++) d[i] = apply_pad (d[i], s[i], mode, s_alpha, shift, alpha_mask, s_recip);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+        if (i < n && x0 + i >= p.x0 && x0 + i < p.x1)
+          d[i] = apply_pad (d[i], __ldg (sp + i), mode, s_alpha, shift, alpha_mask, s_recip);
     }
   }
-  *dp = d;
+  if (vec) {
+    *(uint4 *) dp = make_uint4 (d[0], d[1], d[2], d[3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; i++) if (i < n) dp[i] = d[i];
+  }
 }
 
 }  // namespace b200
@@ -183,13 +230,13 @@ int b200_comp_blend (b200_comp * h, void *dst, int32_t dst_stride, int backgroun
   memset (&P, 0, sizeof (P));
   P.dst = (uint8_t *) dst; P.width = h->width; P.height = h->height; P.stride = dst_stride;
   P.alpha_shift = h->alpha_shift; P.background = background;
-  const dim3 grid ((h->width + 63) / 64, (h->height + 3) / 4);
+  const dim3 grid ((h->width + CT_W - 1) / CT_W, (h->height + CT_H - 1) / CT_H);
   int launched = 0;
   auto flush = [&] () -> int {
     comp_kernel <<<grid, 256, 0, (cudaStream_t) cuda_stream>>> (P);
     B200_CUDA_TRY (cudaGetLastError ());
     launched++;
-    P.n_pads = 0; P.background = -1;
+    P.n_pads = 0; P.background = -1; P.need_recip = 0;
     return B200_OK;
   };
   for (int i = 0; i < n_pads; i++) {
@@ -214,6 +261,7 @@ int b200_comp_blend (b200_comp * h, void *dst, int32_t dst_stride, int backgroun
       case B200_COMP_OP_ADD: d.mode = background == B200_COMP_BG_TRANSPARENT ? CM_OVERLAY_ADD : CM_BLEND; break;
       default: return B200_ERR_INVALID_ARG;
     }
+    if (d.mode == CM_OVERLAY || d.mode == CM_OVERLAY_ADD) P.need_recip = 1;
     P.pads[P.n_pads++] = d;
     if (P.n_pads == COMP_CHUNK) { int st = flush (); if (st != B200_OK) return st; }
   }

@@ -69,8 +69,9 @@ __device__ __forceinline__ int prmt_s (unsigned a, unsigned sel)      // prmt.b3
   asm ("prmt.b32 %0, %1, 0, %2;" : "=r" (d) : "r" (a), "r" (sel));
   return d;
 }
-// acc >> 6 (arithmetic) issued on the FMA pipe (IMAD.HI) - the ALU pipe is this kernel's bottleneck
-__device__ __forceinline__ int sra6 (int acc) { return __mulhi (acc, 1 << 26); }
+// acc >> 6 (arithmetic).  SHF runs at half rate on the ALU pipe; IMAD.HI would be a quarter-rate
+// alternative on sm_100a (profiles/r01_ubench_sm100a.txt), so the plain shift stays.
+__device__ __forceinline__ int sra6 (int acc) { return acc >> 6; }
 // d = { c[15:0], sat_u8(a), sat_u8(b) }  (b in the lowest byte)
 __device__ __forceinline__ unsigned pack_sat2 (int a, int b, unsigned c)
 {
@@ -199,6 +200,7 @@ vcs_lanczos2_kernel (const VcsDev P, const Lanczos2Dev L, const VcsBatch frames)
 #pragma unroll
         for (int i = 0; i < 4; i++) vs[i] = L.vsum[min (oy + i, P.oh - 1)];
       }
+      uint8_t *row0 = out + P.off_out + (size_t) oy * P.stride_out;   // oh % 4 == 0: all 4 rows exist
       for (int c = lane; c < L2_TW; c += 32) {
         const int ox = x0 + c;
         if (ox >= P.ow) break;
@@ -212,10 +214,9 @@ vcs_lanczos2_kernel (const VcsDev P, const Lanczos2Dev L, const VcsBatch frames)
         }
         int ah = 255;
         if (!ALPHA_OPAQUE) ah = fir_round_u8 ((int) (short) (255 * (int) L.hsum[ox]));
-        uint8_t *dst = out + P.off_out + (size_t) oy * P.stride_out + (size_t) ox * 4;
+        uint8_t *dst = row0 + (unsigned) ox * 4u;
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-          if (oy + i >= P.oh) break;
           // saturate the three channels at once, bias by 128 and sign-splat each byte to s16
           unsigned yuv = pack_sat2 (a[1][i] >> 6, a[0][i] >> 6, pack_sat2 (0, a[2][i] >> 6, 0u));
           yuv ^= 0x00808080u;
