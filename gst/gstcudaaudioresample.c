@@ -1,0 +1,312 @@
+/* gst/gstcudaaudioresample.c — `cudaaudioresample`
+ *
+ * Drop-in for `audioresample` for F32 interleaved audio: same `quality` property
+ * (gst-plugins-base/gst/audioresample/gstaudioresample.c:68, :144-228), same framing rules —
+ * output length from the resampler before processing (:763-769), zero-length outputs dropped
+ * (:879-882), reset on flush/discont (:462, :907-915), drain with silence on EOS (:590-662),
+ * timestamps from running sample counters (:846-866).  The FIR runs on the GPU through
+ * b200_ars_process(); audio buffers are system memory, so the element stages them through
+ * pinned buffers and one CUDA stream.
+ *
+ * NOT compiled in the development image (no GLib/GStreamer there); see INTEGRATION.md.
+ */
+#include <gst/base/gstbasetransform.h>
+#include <gst/audio/audio.h>
+#include <cuda_runtime_api.h>
+
+#include "gstb200elements.h"
+
+GST_DEBUG_CATEGORY_STATIC (cuda_ars_debug);
+#define GST_CAT_DEFAULT cuda_ars_debug
+
+#define ARS_CAPS "audio/x-raw, format = (string) " GST_AUDIO_NE (F32) ", layout = (string) interleaved, " \
+    "rate = (int) [ 1, MAX ], channels = (int) [ 1, MAX ]"
+static GstStaticPadTemplate ars_sink = GST_STATIC_PAD_TEMPLATE ("sink", GST_PAD_SINK, GST_PAD_ALWAYS, GST_STATIC_CAPS (ARS_CAPS));
+static GstStaticPadTemplate ars_src = GST_STATIC_PAD_TEMPLATE ("src", GST_PAD_SRC, GST_PAD_ALWAYS, GST_STATIC_CAPS (ARS_CAPS));
+
+enum { PROP_0, PROP_QUALITY, PROP_DEVICE_ID };
+
+typedef struct
+{
+  GstBaseTransform parent;
+  gint quality, device_id;
+  GstAudioInfo in, out;
+  b200_ars *ars;
+  cudaStream_t stream;
+  float *d_in, *d_out;           /* device staging */
+  gsize d_in_frames, d_out_frames;
+  /* running position (gstaudioresample.c:846-866) */
+  GstClockTime t0;
+  guint64 in_offset0, out_offset0, samples_in, samples_out;
+  gboolean need_discont;
+} GstCudaAudioResample;
+typedef struct { GstBaseTransformClass parent_class; } GstCudaAudioResampleClass;
+G_DEFINE_TYPE (GstCudaAudioResample, gst_cuda_audio_resample, GST_TYPE_BASE_TRANSFORM);
+
+static void
+ars_reset_position (GstCudaAudioResample * self)
+{
+  self->t0 = GST_CLOCK_TIME_NONE;
+  self->samples_in = self->samples_out = 0;
+  self->need_discont = TRUE;
+  if (self->ars)
+    b200_ars_reset (self->ars);
+}
+
+static gboolean
+ars_ensure_staging (GstCudaAudioResample * self, gsize in_frames, gsize out_frames)
+{
+  const gsize ch = GST_AUDIO_INFO_CHANNELS (&self->in);
+  if (in_frames > self->d_in_frames) {
+    cudaFree (self->d_in);
+    if (cudaMalloc ((void **) &self->d_in, in_frames * ch * sizeof (float)) != cudaSuccess)
+      return FALSE;
+    self->d_in_frames = in_frames;
+  }
+  if (out_frames > self->d_out_frames) {
+    cudaFree (self->d_out);
+    if (cudaMalloc ((void **) &self->d_out, out_frames * ch * sizeof (float)) != cudaSuccess)
+      return FALSE;
+    self->d_out_frames = out_frames;
+  }
+  return TRUE;
+}
+
+static gboolean
+ars_set_caps (GstBaseTransform * trans, GstCaps * incaps, GstCaps * outcaps)
+{
+  GstCudaAudioResample *self = (GstCudaAudioResample *) trans;
+  b200_ars_config cfg = { 0, };
+  if (!gst_audio_info_from_caps (&self->in, incaps) || !gst_audio_info_from_caps (&self->out, outcaps))
+    return FALSE;
+  g_clear_pointer (&self->ars, b200_ars_destroy);
+  cfg.in_rate = GST_AUDIO_INFO_RATE (&self->in);
+  cfg.out_rate = GST_AUDIO_INFO_RATE (&self->out);
+  cfg.channels = GST_AUDIO_INFO_CHANNELS (&self->in);
+  cfg.quality = self->quality;
+  if (b200_ars_create (&cfg, self->device_id, &self->ars) != B200_OK)
+    return FALSE;
+  gst_base_transform_set_passthrough (trans, cfg.in_rate == cfg.out_rate);
+  ars_reset_position (self);
+  return TRUE;
+}
+
+static gboolean
+ars_get_unit_size (GstBaseTransform * trans, GstCaps * caps, gsize * size)
+{
+  GstAudioInfo info;
+  if (!gst_audio_info_from_caps (&info, caps))
+    return FALSE;
+  *size = GST_AUDIO_INFO_BPF (&info);
+  return TRUE;
+}
+
+static gboolean
+ars_transform_size (GstBaseTransform * trans, GstPadDirection direction, GstCaps * caps, gsize size,
+    GstCaps * othercaps, gsize * othersize)
+{
+  GstCudaAudioResample *self = (GstCudaAudioResample *) trans;
+  const gsize bpf = GST_AUDIO_INFO_BPF (&self->in);
+  gsize frames = size / bpf;
+  if (!self->ars)
+    return FALSE;
+  frames = direction == GST_PAD_SINK ? b200_ars_get_out_frames (self->ars, frames)
+      : b200_ars_get_in_frames (self->ars, frames);
+  *othersize = frames * bpf;
+  return TRUE;
+}
+
+static GstFlowReturn
+ars_transform (GstBaseTransform * trans, GstBuffer * inbuf, GstBuffer * outbuf)
+{
+  GstCudaAudioResample *self = (GstCudaAudioResample *) trans;
+  const gsize bpf = GST_AUDIO_INFO_BPF (&self->in);
+  GstMapInfo imap, omap;
+  gsize in_frames, out_frames, got = 0;
+  int st;
+
+  if (GST_BUFFER_IS_DISCONT (inbuf))
+    ars_reset_position (self);                         /* gstaudioresample.c:907-915 */
+  if (!GST_CLOCK_TIME_IS_VALID (self->t0)) {
+    self->t0 = GST_BUFFER_PTS (inbuf);
+    self->in_offset0 = GST_BUFFER_OFFSET (inbuf);
+    self->out_offset0 = gst_util_uint64_scale_int_round (self->in_offset0, GST_AUDIO_INFO_RATE (&self->out),
+        GST_AUDIO_INFO_RATE (&self->in));
+  }
+  gst_buffer_map (inbuf, &imap, GST_MAP_READ);
+  in_frames = imap.size / bpf;
+  out_frames = b200_ars_get_out_frames (self->ars, in_frames);
+  if (!ars_ensure_staging (self, in_frames, MAX (out_frames, 1))) {
+    gst_buffer_unmap (inbuf, &imap);
+    return GST_FLOW_ERROR;
+  }
+  gst_buffer_map (outbuf, &omap, GST_MAP_WRITE);
+  cudaMemcpyAsync (self->d_in, imap.data, in_frames * bpf, cudaMemcpyHostToDevice, self->stream);
+  st = b200_ars_process (self->ars, GST_BUFFER_FLAG_IS_SET (inbuf, GST_BUFFER_FLAG_GAP) ? NULL : self->d_in,
+      in_frames, self->d_out, out_frames, &got, self->stream);
+  if (st == B200_OK && got)
+    cudaMemcpyAsync (omap.data, self->d_out, got * bpf, cudaMemcpyDeviceToHost, self->stream);
+  cudaStreamSynchronize (self->stream);
+  gst_buffer_unmap (outbuf, &omap);
+  gst_buffer_unmap (inbuf, &imap);
+  GST_B200_FLOW_FROM_STATUS (self, st, "b200_ars_process");
+
+  gst_buffer_set_size (outbuf, got * bpf);             /* :763-769 */
+  GST_BUFFER_PTS (outbuf) = self->t0 + gst_util_uint64_scale_int_round (self->samples_out, GST_SECOND,
+      GST_AUDIO_INFO_RATE (&self->out));
+  GST_BUFFER_OFFSET (outbuf) = self->out_offset0 + self->samples_out;
+  self->samples_in += in_frames;
+  self->samples_out += got;
+  GST_BUFFER_OFFSET_END (outbuf) = self->out_offset0 + self->samples_out;
+  GST_BUFFER_DURATION (outbuf) = self->t0 + gst_util_uint64_scale_int_round (self->samples_out, GST_SECOND,
+      GST_AUDIO_INFO_RATE (&self->out)) - GST_BUFFER_PTS (outbuf);
+  if (self->need_discont) {
+    GST_BUFFER_FLAG_SET (outbuf, GST_BUFFER_FLAG_DISCONT);
+    self->need_discont = FALSE;
+  }
+  return got ? GST_FLOW_OK : GST_BASE_TRANSFORM_FLOW_DROPPED;     /* :879-882 */
+}
+
+/* drain: feed get_max_latency() frames of silence and push what comes out (gstaudioresample.c:590-662) */
+static void
+ars_push_drain (GstCudaAudioResample * self)
+{
+  GstBaseTransform *trans = GST_BASE_TRANSFORM (self);
+  const gsize bpf = GST_AUDIO_INFO_BPF (&self->in);
+  gsize in_frames, out_frames, got = 0;
+  GstBuffer *outbuf;
+  GstMapInfo omap;
+  if (!self->ars || gst_base_transform_is_passthrough (trans))
+    return;
+  in_frames = b200_ars_get_max_latency (self->ars);
+  out_frames = b200_ars_get_out_frames (self->ars, in_frames);
+  if (out_frames == 0 || !ars_ensure_staging (self, 1, out_frames))
+    return;
+  outbuf = gst_buffer_new_and_alloc (out_frames * bpf);
+  if (b200_ars_process (self->ars, NULL, in_frames, self->d_out, out_frames, &got, self->stream) != B200_OK || !got) {
+    gst_buffer_unref (outbuf);
+    return;
+  }
+  gst_buffer_map (outbuf, &omap, GST_MAP_WRITE);
+  cudaMemcpyAsync (omap.data, self->d_out, got * bpf, cudaMemcpyDeviceToHost, self->stream);
+  cudaStreamSynchronize (self->stream);
+  gst_buffer_unmap (outbuf, &omap);
+  gst_buffer_set_size (outbuf, got * bpf);
+  GST_BUFFER_PTS (outbuf) = self->t0 + gst_util_uint64_scale_int_round (self->samples_out, GST_SECOND,
+      GST_AUDIO_INFO_RATE (&self->out));
+  self->samples_out += got;
+  gst_pad_push (GST_BASE_TRANSFORM_SRC_PAD (trans), outbuf);
+}
+
+static gboolean
+ars_sink_event (GstBaseTransform * trans, GstEvent * event)
+{
+  GstCudaAudioResample *self = (GstCudaAudioResample *) trans;
+  switch (GST_EVENT_TYPE (event)) {
+    case GST_EVENT_FLUSH_STOP: ars_reset_position (self); break;
+    case GST_EVENT_SEGMENT: ars_push_drain (self); ars_reset_position (self); break;
+    case GST_EVENT_EOS: ars_push_drain (self); break;
+    default: break;
+  }
+  return GST_BASE_TRANSFORM_CLASS (gst_cuda_audio_resample_parent_class)->sink_event (trans, event);
+}
+
+static gboolean
+ars_start (GstBaseTransform * trans)
+{
+  GstCudaAudioResample *self = (GstCudaAudioResample *) trans;
+  if (b200_device_count () <= 0)
+    return FALSE;
+  cudaSetDevice (self->device_id);
+  return cudaStreamCreateWithFlags (&self->stream, cudaStreamNonBlocking) == cudaSuccess;
+}
+
+static gboolean
+ars_stop (GstBaseTransform * trans)
+{
+  GstCudaAudioResample *self = (GstCudaAudioResample *) trans;
+  g_clear_pointer (&self->ars, b200_ars_destroy);
+  cudaFree (self->d_in);
+  cudaFree (self->d_out);
+  self->d_in = self->d_out = NULL;
+  self->d_in_frames = self->d_out_frames = 0;
+  if (self->stream)
+    cudaStreamDestroy (self->stream);
+  self->stream = NULL;
+  return TRUE;
+}
+
+static GstCaps *
+ars_transform_caps (GstBaseTransform * trans, GstPadDirection direction, GstCaps * caps, GstCaps * filter)
+{
+  /* everything but the rate passes through (gstaudioresample.c:296-330) */
+  GstCaps *res = gst_caps_copy (caps);
+  guint i;
+  for (i = 0; i < gst_caps_get_size (res); i++)
+    gst_structure_set (gst_caps_get_structure (res, i), "rate", GST_TYPE_INT_RANGE, 1, G_MAXINT, NULL);
+  if (filter) {
+    GstCaps *t = gst_caps_intersect_full (filter, res, GST_CAPS_INTERSECT_FIRST);
+    gst_caps_unref (res);
+    res = t;
+  }
+  return res;
+}
+
+static void
+ars_set_property (GObject * obj, guint id, const GValue * value, GParamSpec * pspec)
+{
+  GstCudaAudioResample *self = (GstCudaAudioResample *) obj;
+  switch (id) {
+    case PROP_QUALITY: self->quality = g_value_get_int (value); break;
+    case PROP_DEVICE_ID: self->device_id = g_value_get_int (value); break;
+    default: G_OBJECT_WARN_INVALID_PROPERTY_ID (obj, id, pspec); break;
+  }
+}
+
+static void
+ars_get_property (GObject * obj, guint id, GValue * value, GParamSpec * pspec)
+{
+  GstCudaAudioResample *self = (GstCudaAudioResample *) obj;
+  switch (id) {
+    case PROP_QUALITY: g_value_set_int (value, self->quality); break;
+    case PROP_DEVICE_ID: g_value_set_int (value, self->device_id); break;
+    default: G_OBJECT_WARN_INVALID_PROPERTY_ID (obj, id, pspec); break;
+  }
+}
+
+static void
+gst_cuda_audio_resample_class_init (GstCudaAudioResampleClass * klass)
+{
+  GObjectClass *gobject = G_OBJECT_CLASS (klass);
+  GstElementClass *element = GST_ELEMENT_CLASS (klass);
+  GstBaseTransformClass *trans = GST_BASE_TRANSFORM_CLASS (klass);
+  gobject->set_property = ars_set_property;
+  gobject->get_property = ars_get_property;
+  g_object_class_install_property (gobject, PROP_QUALITY, g_param_spec_int ("quality", "Quality",
+          "Resample quality with 0 being the lowest and 10 being the best", 0, 10, 4,
+          G_PARAM_READWRITE | G_PARAM_STATIC_STRINGS));
+  g_object_class_install_property (gobject, PROP_DEVICE_ID, g_param_spec_int ("cuda-device-id", "Cuda Device ID",
+          "GPU device to use", 0, G_MAXINT, 0, G_PARAM_READWRITE | GST_PARAM_MUTABLE_READY | G_PARAM_STATIC_STRINGS));
+  gst_element_class_add_static_pad_template (element, &ars_sink);
+  gst_element_class_add_static_pad_template (element, &ars_src);
+  gst_element_class_set_static_metadata (element, "B200 audio resampler", "Filter/Converter/Audio/Hardware",
+      "Bit-exact audioresample (F32, kaiser) polyphase FIR on sm_100a (libb200dsp)", "b200-gst-dsp");
+  trans->start = ars_start;
+  trans->stop = ars_stop;
+  trans->get_unit_size = ars_get_unit_size;
+  trans->transform_caps = ars_transform_caps;
+  trans->transform_size = ars_transform_size;
+  trans->set_caps = ars_set_caps;
+  trans->transform = ars_transform;
+  trans->sink_event = ars_sink_event;
+  GST_DEBUG_CATEGORY_INIT (cuda_ars_debug, "cudaaudioresample", 0, "B200 audio resampler");
+}
+
+static void
+gst_cuda_audio_resample_init (GstCudaAudioResample * self)
+{
+  self->quality = 4;
+  self->device_id = 0;
+  self->t0 = GST_CLOCK_TIME_NONE;
+  self->need_discont = TRUE;
+}

@@ -1,0 +1,333 @@
+/* gst/gstcudavideoconvertscale.c — `cudavideoconvertscale`
+ *
+ * Drop-in for `videoconvertscale` on CUDA memory: same properties (method, envelope, sharpness,
+ * sharpen; gst-plugins-base/gst/videoconvertscale/gstvideoconvertscale.c:306-391), same caps
+ * transform rules (:703-748, restricted to the formats libb200dsp implements), and a
+ * transform() that hands the mapped device frames to b200_vcs_convert() where the stock
+ * element calls gst_video_converter_frame() (:1981-2005).  Device-memory plumbing (context
+ * sharing, stream selection, allocation queries) follows the stock CUDA converter
+ * gst-plugins-bad/sys/nvcodec/gstcudaconvertscale.c:1483-1587 and gstcudabasetransform.c.
+ *
+ * NOT compiled in the development image (no GLib/GStreamer there); see INTEGRATION.md.
+ */
+#include <gst/base/gstbasetransform.h>
+#include <gst/cuda/gstcuda.h>
+
+#include "gstb200elements.h"
+
+GST_DEBUG_CATEGORY_STATIC (cuda_vcs_debug);
+#define GST_CAT_DEFAULT cuda_vcs_debug
+
+#define SINK_FORMATS "{ NV12, NV21 }"
+#define SRC_FORMATS "{ BGRA, RGBA, ARGB, ABGR, BGRx, RGBx, xRGB, xBGR }"
+#define CUDA_CAPS(f) "video/x-raw(" GST_CAPS_FEATURE_MEMORY_CUDA_MEMORY "), format = (string) " f \
+    ", width = (int) [ 1, 32767 ], height = (int) [ 1, 32767 ], framerate = (fraction) [ 0/1, max ]"
+
+static GstStaticPadTemplate sink_tmpl = GST_STATIC_PAD_TEMPLATE ("sink", GST_PAD_SINK, GST_PAD_ALWAYS,
+    GST_STATIC_CAPS (CUDA_CAPS (SINK_FORMATS)));
+static GstStaticPadTemplate src_tmpl = GST_STATIC_PAD_TEMPLATE ("src", GST_PAD_SRC, GST_PAD_ALWAYS,
+    GST_STATIC_CAPS (CUDA_CAPS (SRC_FORMATS)));
+
+enum { PROP_0, PROP_METHOD, PROP_ENVELOPE, PROP_SHARPNESS, PROP_SHARPEN, PROP_DEVICE_ID };
+
+typedef struct
+{
+  GstBaseTransform parent;
+  /* properties (defaults: gstvideoconvertscale.c:130-144) */
+  gint method;
+  gdouble envelope, sharpness, sharpen;
+  gint device_id;
+  gboolean config_changed;
+  /* negotiated state */
+  GstVideoInfo in_info, out_info;
+  GstCudaContext *context;
+  GstCudaStream *stream;
+  b200_vcs *vcs;
+} GstCudaVideoConvertScale;
+
+typedef struct { GstBaseTransformClass parent_class; } GstCudaVideoConvertScaleClass;
+
+G_DEFINE_TYPE (GstCudaVideoConvertScale, gst_cuda_video_convert_scale, GST_TYPE_BASE_TRANSFORM);
+
+#define GST_TYPE_B200_SCALE_METHOD (gst_b200_scale_method_get_type ())
+static GType
+gst_b200_scale_method_get_type (void)
+{
+  static GType t = 0;
+  /* nicks and values of GstVideoScaleMethod (gstvideoconvertscale.h:59-71) */
+  static const GEnumValue v[] = {
+    {B200_SCALE_NEAREST, "Nearest Neighbour", "nearest-neighbour"},
+    {B200_SCALE_BILINEAR, "Bilinear (2-tap)", "bilinear"},
+    {B200_SCALE_4TAP, "4-tap Sinc", "4-tap"},
+    {B200_SCALE_LANCZOS, "Lanczos", "lanczos"},
+    {B200_SCALE_BILINEAR2, "Bilinear (multi-tap)", "bilinear2"},
+    {B200_SCALE_SINC, "Sinc (multi-tap)", "sinc"},
+    {B200_SCALE_HERMITE, "Hermite (multi-tap)", "hermite"},
+    {B200_SCALE_SPLINE, "Spline (multi-tap)", "spline"},
+    {B200_SCALE_CATROM, "Catmull-Rom (multi-tap)", "catrom"},
+    {B200_SCALE_MITCHELL, "Mitchell (multi-tap)", "mitchell"},
+    {0, NULL, NULL}
+  };
+  if (g_once_init_enter (&t))
+    g_once_init_leave (&t, g_enum_register_static ("GstB200VideoScaleMethod", v));
+  return t;
+}
+
+static void
+vcs_set_property (GObject * obj, guint id, const GValue * value, GParamSpec * pspec)
+{
+  GstCudaVideoConvertScale *self = (GstCudaVideoConvertScale *) obj;
+  GST_OBJECT_LOCK (self);
+  switch (id) {
+    case PROP_METHOD: self->method = g_value_get_enum (value); break;
+    case PROP_ENVELOPE: self->envelope = g_value_get_double (value); break;
+    case PROP_SHARPNESS: self->sharpness = g_value_get_double (value); break;
+    case PROP_SHARPEN: self->sharpen = g_value_get_double (value); break;
+    case PROP_DEVICE_ID: self->device_id = g_value_get_int (value); break;
+    default: G_OBJECT_WARN_INVALID_PROPERTY_ID (obj, id, pspec); break;
+  }
+  /* like the stock element, the converter is rebuilt lazily on the streaming thread
+   * (gstvideoconvertscale.c:1989-2000) */
+  self->config_changed = TRUE;
+  GST_OBJECT_UNLOCK (self);
+}
+
+static void
+vcs_get_property (GObject * obj, guint id, GValue * value, GParamSpec * pspec)
+{
+  GstCudaVideoConvertScale *self = (GstCudaVideoConvertScale *) obj;
+  GST_OBJECT_LOCK (self);
+  switch (id) {
+    case PROP_METHOD: g_value_set_enum (value, self->method); break;
+    case PROP_ENVELOPE: g_value_set_double (value, self->envelope); break;
+    case PROP_SHARPNESS: g_value_set_double (value, self->sharpness); break;
+    case PROP_SHARPEN: g_value_set_double (value, self->sharpen); break;
+    case PROP_DEVICE_ID: g_value_set_int (value, self->device_id); break;
+    default: G_OBJECT_WARN_INVALID_PROPERTY_ID (obj, id, pspec); break;
+  }
+  GST_OBJECT_UNLOCK (self);
+}
+
+static void
+vcs_set_context (GstElement * element, GstContext * context)
+{
+  GstCudaVideoConvertScale *self = (GstCudaVideoConvertScale *) element;
+  gst_cuda_handle_set_context (element, context, self->device_id, &self->context);
+  GST_ELEMENT_CLASS (gst_cuda_video_convert_scale_parent_class)->set_context (element, context);
+}
+
+static gboolean
+vcs_start (GstBaseTransform * trans)
+{
+  GstCudaVideoConvertScale *self = (GstCudaVideoConvertScale *) trans;
+  if (!gst_cuda_ensure_element_context (GST_ELEMENT (self), self->device_id, &self->context)) {
+    GST_ERROR_OBJECT (self, "no CUDA context (libb200dsp has no CPU fallback)");
+    return FALSE;
+  }
+  self->stream = gst_cuda_stream_new (self->context);
+  return TRUE;
+}
+
+static gboolean
+vcs_stop (GstBaseTransform * trans)
+{
+  GstCudaVideoConvertScale *self = (GstCudaVideoConvertScale *) trans;
+  g_clear_pointer (&self->vcs, b200_vcs_destroy);
+  gst_clear_cuda_stream (&self->stream);
+  gst_clear_object (&self->context);
+  return TRUE;
+}
+
+static gboolean
+vcs_query (GstBaseTransform * trans, GstPadDirection direction, GstQuery * query)
+{
+  GstCudaVideoConvertScale *self = (GstCudaVideoConvertScale *) trans;
+  if (GST_QUERY_TYPE (query) == GST_QUERY_CONTEXT &&
+      gst_cuda_handle_context_query (GST_ELEMENT (self), query, self->context))
+    return TRUE;
+  return GST_BASE_TRANSFORM_CLASS (gst_cuda_video_convert_scale_parent_class)->query (trans, direction, query);
+}
+
+/* caps on the other pad: any supported format of the other direction, any size in range,
+ * colorimetry/chroma-site dropped (gstvideoconvertscale.c:703-748) */
+static GstCaps *
+vcs_transform_caps (GstBaseTransform * trans, GstPadDirection direction, GstCaps * caps, GstCaps * filter)
+{
+  GstCaps *tmpl, *res;
+  guint i, n;
+  tmpl = gst_static_pad_template_get_caps (direction == GST_PAD_SINK ? &src_tmpl : &sink_tmpl);
+  res = gst_caps_new_empty ();
+  n = gst_caps_get_size (caps);
+  for (i = 0; i < n; i++) {
+    GstStructure *in = gst_caps_get_structure (caps, i);
+    GstCaps *one = gst_caps_copy (tmpl);
+    const GValue *fr = gst_structure_get_value (in, "framerate");
+    if (fr)
+      gst_caps_set_value (one, "framerate", fr);       /* framerate and interlace-mode pass through */
+    gst_caps_append (res, one);
+  }
+  gst_caps_unref (tmpl);
+  if (filter) {
+    GstCaps *t = gst_caps_intersect_full (filter, res, GST_CAPS_INTERSECT_FIRST);
+    gst_caps_unref (res);
+    res = t;
+  }
+  return res;
+}
+
+static gboolean
+vcs_rebuild (GstCudaVideoConvertScale * self)
+{
+  b200_video_info in, out;
+  b200_vcs_config cfg;
+  int st;
+  b200_vcs_config_init (&cfg);
+  GST_OBJECT_LOCK (self);
+  cfg.method = self->method;
+  cfg.envelope = self->envelope;
+  cfg.sharpness = self->sharpness;
+  cfg.sharpen = self->sharpen;
+  self->config_changed = FALSE;
+  GST_OBJECT_UNLOCK (self);
+  gst_b200_video_info_from_gst (&in, &self->in_info);
+  gst_b200_video_info_from_gst (&out, &self->out_info);
+  g_clear_pointer (&self->vcs, b200_vcs_destroy);
+  st = b200_vcs_create (&in, &out, &cfg, self->device_id, &self->vcs);
+  if (st != B200_OK) {
+    GST_ERROR_OBJECT (self, "b200_vcs_create: %s", b200_strerror (st));
+    return FALSE;                                      /* -> not negotiated */
+  }
+  return TRUE;
+}
+
+static gboolean
+vcs_set_caps (GstBaseTransform * trans, GstCaps * incaps, GstCaps * outcaps)
+{
+  GstCudaVideoConvertScale *self = (GstCudaVideoConvertScale *) trans;
+  if (!gst_video_info_from_caps (&self->in_info, incaps) || !gst_video_info_from_caps (&self->out_info, outcaps))
+    return FALSE;
+  if (self->in_info.interlace_mode != self->out_info.interlace_mode)
+    return FALSE;                                      /* gstvideoconvertscale.c:958-960 */
+  return vcs_rebuild (self);
+}
+
+static GstFlowReturn
+vcs_transform (GstBaseTransform * trans, GstBuffer * inbuf, GstBuffer * outbuf)
+{
+  GstCudaVideoConvertScale *self = (GstCudaVideoConvertScale *) trans;
+  GstVideoFrame in_frame, out_frame;
+  GstMemory *in_mem = gst_buffer_peek_memory (inbuf, 0), *out_mem = gst_buffer_peek_memory (outbuf, 0);
+  GstCudaStream *in_stream, *out_stream, *use;
+  int st;
+
+  if (!gst_is_cuda_memory (in_mem) || !gst_is_cuda_memory (out_mem)) {
+    GST_ERROR_OBJECT (self, "buffers are not CUDA memory");
+    return GST_FLOW_ERROR;
+  }
+  if (self->config_changed && !vcs_rebuild (self))
+    return GST_FLOW_NOT_NEGOTIATED;
+
+  in_stream = gst_cuda_memory_get_stream (GST_CUDA_MEMORY_CAST (in_mem));
+  out_stream = gst_cuda_memory_get_stream (GST_CUDA_MEMORY_CAST (out_mem));
+  /* stream choice as gstcudaconvertscale.c:1549-1565: downstream's, else upstream's, else ours */
+  use = out_stream ? out_stream : (in_stream ? in_stream : self->stream);
+  if (out_stream && in_stream && in_stream != out_stream)
+    gst_cuda_memory_sync (GST_CUDA_MEMORY_CAST (in_mem));
+
+  if (!gst_video_frame_map (&in_frame, &self->in_info, inbuf, GST_MAP_READ | GST_MAP_CUDA))
+    return GST_FLOW_ERROR;
+  if (!gst_video_frame_map (&out_frame, &self->out_info, outbuf, GST_MAP_WRITE | GST_MAP_CUDA)) {
+    gst_video_frame_unmap (&in_frame);
+    return GST_FLOW_ERROR;
+  }
+  gst_cuda_context_push (self->context);
+  /* plane 0 is the frame base; the library adds the per-plane offsets it was created with */
+  st = b200_vcs_convert (self->vcs, GST_VIDEO_FRAME_PLANE_DATA (&in_frame, 0),
+      GST_VIDEO_FRAME_PLANE_DATA (&out_frame, 0), gst_cuda_stream_get_handle (use));
+  if (st == B200_OK && use != out_stream) {
+    /* downstream is not stream aware: finish before the buffer leaves (gstcudaconvertscale.c:1573-1579) */
+    GST_MEMORY_FLAG_UNSET (out_mem, GST_CUDA_MEMORY_TRANSFER_NEED_SYNC);
+    CuStreamSynchronize (gst_cuda_stream_get_handle (use));
+  }
+  gst_cuda_context_pop (NULL);
+  gst_video_frame_unmap (&out_frame);
+  gst_video_frame_unmap (&in_frame);
+  GST_B200_FLOW_FROM_STATUS (self, st, "b200_vcs_convert");
+  return GST_FLOW_OK;
+}
+
+static gboolean
+vcs_decide_allocation (GstBaseTransform * trans, GstQuery * query)
+{
+  GstCudaVideoConvertScale *self = (GstCudaVideoConvertScale *) trans;
+  GstCaps *caps;
+  GstBufferPool *pool = NULL;
+  GstStructure *config;
+  guint size = GST_VIDEO_INFO_SIZE (&self->out_info), min = 0, max = 0;
+  gst_query_parse_allocation (query, &caps, NULL);
+  if (gst_query_get_n_allocation_pools (query) > 0)
+    gst_query_parse_nth_allocation_pool (query, 0, &pool, &size, &min, &max);
+  if (pool && !GST_IS_CUDA_BUFFER_POOL (pool))
+    gst_clear_object (&pool);
+  if (!pool)
+    pool = gst_cuda_buffer_pool_new (self->context);
+  config = gst_buffer_pool_get_config (pool);
+  gst_buffer_pool_config_set_params (config, caps, size, min, max);
+  gst_buffer_pool_config_add_option (config, GST_BUFFER_POOL_OPTION_VIDEO_META);
+  gst_buffer_pool_set_config (pool, config);
+  if (gst_query_get_n_allocation_pools (query) > 0)
+    gst_query_set_nth_allocation_pool (query, 0, pool, size, min, max);
+  else
+    gst_query_add_allocation_pool (query, pool, size, min, max);
+  gst_object_unref (pool);
+  return TRUE;
+}
+
+static void
+gst_cuda_video_convert_scale_class_init (GstCudaVideoConvertScaleClass * klass)
+{
+  GObjectClass *gobject = G_OBJECT_CLASS (klass);
+  GstElementClass *element = GST_ELEMENT_CLASS (klass);
+  GstBaseTransformClass *trans = GST_BASE_TRANSFORM_CLASS (klass);
+
+  gobject->set_property = vcs_set_property;
+  gobject->get_property = vcs_get_property;
+  g_object_class_install_property (gobject, PROP_METHOD, g_param_spec_enum ("method", "method", "scaling method",
+          GST_TYPE_B200_SCALE_METHOD, B200_SCALE_BILINEAR, G_PARAM_READWRITE | G_PARAM_STATIC_STRINGS));
+  g_object_class_install_property (gobject, PROP_ENVELOPE, g_param_spec_double ("envelope", "Envelope",
+          "Size of filter envelope", 1.0, 5.0, 2.0, G_PARAM_READWRITE | G_PARAM_STATIC_STRINGS));
+  g_object_class_install_property (gobject, PROP_SHARPNESS, g_param_spec_double ("sharpness", "Sharpness",
+          "Sharpness of filter", 0.5, 1.5, 1.0, G_PARAM_READWRITE | G_PARAM_STATIC_STRINGS));
+  g_object_class_install_property (gobject, PROP_SHARPEN, g_param_spec_double ("sharpen", "Sharpen",
+          "Sharpening", 0.0, 1.0, 0.0, G_PARAM_READWRITE | G_PARAM_STATIC_STRINGS));
+  g_object_class_install_property (gobject, PROP_DEVICE_ID, g_param_spec_int ("cuda-device-id", "Cuda Device ID",
+          "Set the GPU device to use for operations (-1 = auto)", -1, G_MAXINT, 0,
+          G_PARAM_READWRITE | GST_PARAM_MUTABLE_READY | G_PARAM_STATIC_STRINGS));
+
+  gst_element_class_add_static_pad_template (element, &sink_tmpl);
+  gst_element_class_add_static_pad_template (element, &src_tmpl);
+  gst_element_class_set_static_metadata (element, "B200 colourspace converter and scaler",
+      "Filter/Converter/Video/Scaler/Colorspace/Hardware",
+      "Bit-exact videoconvertscale on sm_100a (libb200dsp)", "b200-gst-dsp");
+  element->set_context = vcs_set_context;
+
+  trans->passthrough_on_same_caps = TRUE;
+  trans->start = vcs_start;
+  trans->stop = vcs_stop;
+  trans->query = vcs_query;
+  trans->transform_caps = vcs_transform_caps;
+  trans->set_caps = vcs_set_caps;
+  trans->transform = vcs_transform;
+  trans->decide_allocation = vcs_decide_allocation;
+  GST_DEBUG_CATEGORY_INIT (cuda_vcs_debug, "cudavideoconvertscale", 0, "B200 convert + scale");
+}
+
+static void
+gst_cuda_video_convert_scale_init (GstCudaVideoConvertScale * self)
+{
+  self->method = B200_SCALE_BILINEAR;
+  self->envelope = 2.0;
+  self->sharpness = 1.0;
+  self->sharpen = 0.0;
+  self->device_id = 0;
+}
