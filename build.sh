@@ -6,7 +6,7 @@ cd "$(dirname "$0")"
 SRC=gstreamer_b200/csrc
 OUT=gstreamer_b200/libb200dsp.so
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --use_fast_math -Xcompiler -fPIC,-O3,-Wall,-ffp-contract=off -Xptxas -v"
+FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-O3,-Wall,-ffp-contract=off -Xptxas -v"
 mkdir -p build
 OBJS=""
 for f in $SRC/*.cu $SRC/*.cpp; do

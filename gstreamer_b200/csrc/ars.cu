@@ -256,121 +256,101 @@ ars_full_kernel (const ArsLaunch L)
 }
 
 // Fast path: the CTA's whole input window is staged in shared memory once (frames x channel
-// block), so the inner loop touches only shared memory with 32-bit pointer bumps:
-// per 4-frame chunk 4 LDS (inputs) + per output 1 LDS.128 (taps) + 4 FMUL + 4 FADD.
+// block) and the taps of each group of RQ consecutive outputs are laid out chunk-major
+// ([chunk][output] float4, zero outside each output's window), so the inner loop is branch free:
+// per 4-frame chunk 4 LDS (inputs, immediate offsets) + RQ LDS.128 (broadcast taps) + 4*RQ FMUL
+// + 4*RQ FADD and two pointer bumps.  A zero tap contributes x*0 = +-0, which leaves the
+// partial sums unchanged for finite input (the sums start at +0 and can never become -0).
 struct ArsTile {
-  int cb;                        // channels per CTA (multiple of 32)
   int win;                       // staged frames per CTA (multiple of 4)
+  int nch;                       // chunks per output group (upper bound, fixed stride of the tap table)
 };
 
+template <int CB>
 __global__ void __launch_bounds__ (ARS_THREADS)
 ars_tile_kernel (const ArsLaunch L, const ArsTile Tl)
 {
   extern __shared__ __align__ (16) float sm[];
-  float *rows = sm;                                              // [no][row_pitch]
-  float *xin = sm + (size_t) L.no * L.row_pitch;                 // [win][cb]
-  __shared__ int s_rel[64];                                      // window start of each output, relative to f0
+  constexpr int RQ = ARS_RQ;
+  const int nq_max = L.no / RQ;
+  float4 *qt = (float4 *) sm;                                    // [nq][nch][RQ]
+  float *xin = sm + (size_t) nq_max * Tl.nch * RQ * 4;           // [win][CB]
+  __shared__ int s_rel[64], s_phase[64];
   const int lane = threadIdx.x & 31;
   const int warp = __shfl_sync (0xffffffffu, (int) (threadIdx.x >> 5), 0);
   const long long o0 = (long long) blockIdx.x * L.no;
   const int n_out = (int) min ((long long) L.no, L.out_frames - o0);
+  const int nq = (n_out + RQ - 1) / RQ;
   long long f0; int ph0;
   ars_position (L, o0, f0, ph0);
   f0 &= ~3LL;                                                    // chunk aligned window origin
 
-  for (int j = warp; j < n_out; j += ARS_THREADS / 32) {
+  if (threadIdx.x < L.no) {
     long long idx; int phase;
-    ars_position (L, o0 + j, idx, phase);
-    if (lane == 0) s_rel[j] = (int) (idx - f0);
-    const int delta = (int) (idx & 3);
-    const float *src = L.phases + (size_t) phase * L.n_taps;
-    float *dst = rows + (size_t) j * L.row_pitch;
-    for (int m = lane; m < L.row_pitch; m += 32) {
-      const int k = m - delta;
-      dst[m] = (k >= 0 && k < L.n_taps) ? __ldg (src + k) : 0.f;
-    }
+    ars_position (L, o0 + min ((int) threadIdx.x, n_out - 1), idx, phase);
+    s_rel[threadIdx.x] = (int) (idx - f0);
+    s_phase[threadIdx.x] = phase;
   }
-  // stage the input window: rows of cb channels, coalesced
-  const int c_base = blockIdx.y * Tl.cb;
-  for (int i = threadIdx.x; i < Tl.win * Tl.cb; i += ARS_THREADS) {
-    const int fr = i / Tl.cb, c = c_base + (i - fr * Tl.cb);
+  // stage the input window row by row (one warp per frame, coalesced)
+  const int c_base = blockIdx.y * CB;
+  for (int fr = warp; fr < Tl.win; fr += ARS_THREADS / 32) {
     const long long f = f0 + fr;
-    float v = 0.f;
-    if (c < L.channels) {
-      if (f < L.hist_frames) v = __ldg (L.hist + f * L.channels + c);
-      else if (f < L.avail && L.in) v = __ldg (L.in + (f - L.hist_frames) * L.channels + c);
-    }
-    xin[i] = v;
+    const float *src = nullptr;
+    if (f < L.hist_frames) src = L.hist + f * L.channels;
+    else if (f < L.avail && L.in) src = L.in + (f - L.hist_frames) * L.channels;
+#pragma unroll
+    for (int c = lane; c < CB; c += 32)
+      xin[fr * CB + c] = (src && c_base + c < L.channels) ? __ldg (src + c_base + c) : 0.f;
+  }
+  __syncthreads ();
+  // chunk-major tap table
+  for (int i = threadIdx.x; i < nq * Tl.nch * RQ; i += ARS_THREADS) {
+    const int r = i % RQ, chunk = (i / RQ) % Tl.nch, q = i / (RQ * Tl.nch);
+    const int j = q * RQ + r;
+    const int s_min = s_rel[q * RQ] & ~3;
+    const int k0 = s_min + 4 * chunk - s_rel[j];
+    const float *src = L.phases + (size_t) s_phase[j] * L.n_taps;
+    float4 t;
+    t.x = (k0 + 0 >= 0 && k0 + 0 < L.n_taps) ? __ldg (src + k0 + 0) : 0.f;
+    t.y = (k0 + 1 >= 0 && k0 + 1 < L.n_taps) ? __ldg (src + k0 + 1) : 0.f;
+    t.z = (k0 + 2 >= 0 && k0 + 2 < L.n_taps) ? __ldg (src + k0 + 2) : 0.f;
+    t.w = (k0 + 3 >= 0 && k0 + 3 < L.n_taps) ? __ldg (src + k0 + 3) : 0.f;
+    qt[i] = t;
   }
   __syncthreads ();
 
-  const int wcn = Tl.cb / 32;
-  const int cg = warp % wcn, og = warp / wcn, nog = (ARS_THREADS / 32) / wcn;
+  constexpr int WCN = CB / 32;
+  const int cg = warp % WCN, og = warp / WCN;
+  constexpr int NOG = (ARS_THREADS / 32) / WCN;
   const int cl = cg * 32 + lane, c = c_base + cl;
-  for (int q = og * ARS_RQ; q < n_out; q += nog * ARS_RQ) {
-    int rel[ARS_RQ];
-    float acc[ARS_RQ][4];
-    const float *trow[ARS_RQ];
+  for (int q = og; q < nq; q += NOG) {
+    float acc[RQ][4];
 #pragma unroll
-    for (int r = 0; r < ARS_RQ; r++) {
-      const int j = min (q + r, n_out - 1);
-      rel[r] = s_rel[j];
-      trow[r] = rows + (size_t) j * L.row_pitch - (rel[r] & ~3);      // trow[r] + s = taps for chunk at frame s
+    for (int r = 0; r < RQ; r++)
 #pragma unroll
       for (int k = 0; k < 4; k++) acc[r][k] = 0.f;
-    }
-    // chunk ranges (frames relative to f0, multiples of 4)
-    int s_min = rel[0] & ~3, s_max = (rel[ARS_RQ - 1] + L.n_taps + 3) & ~3;       // all chunks touched
-    int s_lo = (rel[ARS_RQ - 1] + 3) & ~3, s_hi = (rel[0] + L.n_taps) & ~3;       // chunks full for every output
-    if (s_hi < s_lo) s_hi = s_lo;
-    const float *xp = xin + (size_t) s_min * Tl.cb + cl;
-    int s = s_min;
-    // leading partial chunks
-    for (; s < s_lo; s += 4, xp += 4 * Tl.cb) {
-      const float x0 = xp[0], x1 = xp[Tl.cb], x2 = xp[2 * Tl.cb], x3 = xp[3 * Tl.cb];
-#pragma unroll
-      for (int r = 0; r < ARS_RQ; r++) {
-        const int k0 = s - rel[r];
-        if (k0 <= -4 || k0 >= L.n_taps) continue;
-        const float4 t = *(const float4 *) (trow[r] + s);
-        if (k0 + 0 >= 0 && k0 + 0 < L.n_taps) acc[r][0] = __fadd_rn (acc[r][0], __fmul_rn (x0, t.x));
-        if (k0 + 1 >= 0 && k0 + 1 < L.n_taps) acc[r][1] = __fadd_rn (acc[r][1], __fmul_rn (x1, t.y));
-        if (k0 + 2 >= 0 && k0 + 2 < L.n_taps) acc[r][2] = __fadd_rn (acc[r][2], __fmul_rn (x2, t.z));
-        if (k0 + 3 >= 0 && k0 + 3 < L.n_taps) acc[r][3] = __fadd_rn (acc[r][3], __fmul_rn (x3, t.w));
-      }
-    }
-    // interior: every output's window covers the whole chunk - no tests
+    const int s_min = s_rel[q * RQ] & ~3;
+    const int s_max = (s_rel[min (q * RQ + RQ - 1, n_out - 1)] + L.n_taps + 3) & ~3;
+    const int nch = (s_max - s_min) >> 2;
+    const float *xp = xin + s_min * CB + cl;
+    const float4 *tp = qt + (size_t) q * Tl.nch * RQ;
 #pragma unroll 2
-    for (; s < s_hi; s += 4, xp += 4 * Tl.cb) {
-      const float x0 = xp[0], x1 = xp[Tl.cb], x2 = xp[2 * Tl.cb], x3 = xp[3 * Tl.cb];
+    for (int ch = 0; ch < nch; ch++, xp += 4 * CB, tp += RQ) {
+      const float x0 = xp[0], x1 = xp[CB], x2 = xp[2 * CB], x3 = xp[3 * CB];
 #pragma unroll
-      for (int r = 0; r < ARS_RQ; r++) {
-        const float4 t = *(const float4 *) (trow[r] + s);
+      for (int r = 0; r < RQ; r++) {
+        const float4 t = tp[r];
         acc[r][0] = __fadd_rn (acc[r][0], __fmul_rn (x0, t.x));
         acc[r][1] = __fadd_rn (acc[r][1], __fmul_rn (x1, t.y));
         acc[r][2] = __fadd_rn (acc[r][2], __fmul_rn (x2, t.z));
         acc[r][3] = __fadd_rn (acc[r][3], __fmul_rn (x3, t.w));
       }
     }
-    // trailing partial chunks
-    for (; s < s_max; s += 4, xp += 4 * Tl.cb) {
-      const float x0 = xp[0], x1 = xp[Tl.cb], x2 = xp[2 * Tl.cb], x3 = xp[3 * Tl.cb];
 #pragma unroll
-      for (int r = 0; r < ARS_RQ; r++) {
-        const int k0 = s - rel[r];
-        if (k0 <= -4 || k0 >= L.n_taps) continue;
-        const float4 t = *(const float4 *) (trow[r] + s);
-        if (k0 + 0 >= 0 && k0 + 0 < L.n_taps) acc[r][0] = __fadd_rn (acc[r][0], __fmul_rn (x0, t.x));
-        if (k0 + 1 >= 0 && k0 + 1 < L.n_taps) acc[r][1] = __fadd_rn (acc[r][1], __fmul_rn (x1, t.y));
-        if (k0 + 2 >= 0 && k0 + 2 < L.n_taps) acc[r][2] = __fadd_rn (acc[r][2], __fmul_rn (x2, t.z));
-        if (k0 + 3 >= 0 && k0 + 3 < L.n_taps) acc[r][3] = __fadd_rn (acc[r][3], __fmul_rn (x3, t.w));
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < ARS_RQ; r++) {
-      if (q + r < n_out && c < L.channels) {
+    for (int r = 0; r < RQ; r++) {
+      if (q * RQ + r < n_out && c < L.channels) {
         const float v = __fadd_rn (__fadd_rn (acc[r][0], acc[r][2]), __fadd_rn (acc[r][1], acc[r][3]));
-        L.out[(size_t) (o0 + q + r) * L.channels + c] = v;
+        L.out[(size_t) (o0 + q * RQ + r) * L.channels + c] = v;
       }
     }
   }
@@ -458,7 +438,9 @@ int b200_ars_create (const b200_ars_config * cfg, int device, b200_ars ** handle
       return st;
     }
     cudaFuncSetAttribute (ars_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    cudaFuncSetAttribute (ars_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
+    cudaFuncSetAttribute (ars_tile_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
+    cudaFuncSetAttribute (ars_tile_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
+    cudaFuncSetAttribute (ars_tile_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
   }
   *handle = h;
   return B200_OK;
@@ -538,18 +520,22 @@ int b200_ars_process (b200_ars * h, const float *in, size_t in_frames, float *ou
     while (no > ARS_RQ && (size_t) no * L.row_pitch * sizeof (float) > 96 * 1024) no >>= 1;
     if ((size_t) no * L.row_pitch * sizeof (float) > 160 * 1024) return B200_ERR_UNSUPPORTED;
     L.no = no;
-    // fast path when the CTA's input window fits in shared memory next to the tap rows
+    // fast path when the CTA's input window fits in shared memory next to the chunk-major taps
     ArsTile tl;
-    tl.cb = 32 * (L.wcn > 4 ? 4 : L.wcn);
+    const int cb = 32 * (L.wcn > 4 ? 4 : L.wcn);
     {
       // frames spanned by `no` outputs: ceil (no * in_step / out_step) + alignment + taps
       const long long span = ((long long) no * p.in_step + p.out_step - 1) / p.out_step + 8 + p.n_taps;
       tl.win = (int) ((span + 3) & ~3LL);
+      const long long spread = ((long long) (ARS_RQ - 1) * p.in_step + p.out_step - 1) / p.out_step + 1;
+      tl.nch = (int) ((spread + p.n_taps + 3 + 3) / 4 + 1);
     }
-    const size_t smem_tile = ((size_t) no * L.row_pitch + (size_t) tl.win * tl.cb) * sizeof (float);
+    const size_t smem_tile = ((size_t) (no / ARS_RQ) * tl.nch * ARS_RQ * 4 + (size_t) tl.win * cb) * sizeof (float);
     if (smem_tile <= 72 * 1024 && !getenv ("B200_ARS_GENERIC")) {
-      const dim3 grid ((unsigned) ((out_frames + no - 1) / no), (unsigned) ((p.channels + tl.cb - 1) / tl.cb));
-      ars_tile_kernel <<<grid, ARS_THREADS, smem_tile, stream>>> (L, tl);
+      const dim3 grid ((unsigned) ((out_frames + no - 1) / no), (unsigned) ((p.channels + cb - 1) / cb));
+      if (cb == 128) ars_tile_kernel<128> <<<grid, ARS_THREADS, smem_tile, stream>>> (L, tl);
+      else if (cb == 64) ars_tile_kernel<64> <<<grid, ARS_THREADS, smem_tile, stream>>> (L, tl);
+      else ars_tile_kernel<32> <<<grid, ARS_THREADS, smem_tile, stream>>> (L, tl);
     } else {
       const dim3 grid ((unsigned) ((out_frames + no - 1) / no), (unsigned) ((p.channels + 32 * L.wcn - 1) / (32 * L.wcn)));
       ars_full_kernel <<<grid, ARS_THREADS, (size_t) no * L.row_pitch * sizeof (float), stream>>> (L);

@@ -32,14 +32,16 @@
 
 namespace b200 {
 
-constexpr int L2_TH = 32;              // output rows per tile
-constexpr int L2_NG = 18;              // 4-line groups per tile: 2*32 + 6 = 70 lines -> 72
-constexpr int L2_WCOLS = 120;          // useful output columns per warp-column (30 lanes x 4)
-constexpr int L2_NWC = 2;              // warp-columns per tile
-constexpr int L2_TW = L2_WCOLS * L2_NWC;
-constexpr int L2_TWP = 128 * L2_NWC;   // smem columns incl. the halo lanes' slots
+// tile shape: TH output rows x NWC warp-columns of 120 useful output columns (30 lanes x 4; lanes
+// 0 and 31 only provide halo words).  A tile needs 2*TH + 6 input lines = NG groups of 4.
+constexpr int L2_WCOLS = 120;
 constexpr int L2_THREADS = 256;
-constexpr int L2_SMEM = 3 * L2_NG * L2_TWP * 4;
+template <int TH, int NWC> struct L2Shape {
+  static constexpr int NG = (2 * TH + 6 + 3) / 4;
+  static constexpr int TW = L2_WCOLS * NWC;
+  static constexpr int TWP = 128 * NWC;       // smem columns incl. the halo lanes' slots
+  static constexpr int SMEM = 3 * NG * TWP * 4;
+};
 
 struct Lanczos2Dev {
   const int4 *htab;                    // [ow/4][3] : 12 packed s8x4 tap words per 4-column group
@@ -89,10 +91,12 @@ __device__ __forceinline__ unsigned pack_sat2 (int a, int b, unsigned c)
     o3 = dp4a_u8s8 (w3, T[2].w, dp4a_u8s8 (w2, T[2].z, dp4a_u8s8 (w1, T[2].y, 32)));           \
   } while (0)
 
-template <bool ALPHA_OPAQUE, int MINB>
+template <bool ALPHA_OPAQUE, int MINB, int TH, int NWC>
 __global__ void __launch_bounds__ (L2_THREADS, MINB)
 vcs_lanczos2_kernel (const VcsDev P, const Lanczos2Dev L, const VcsBatch frames)
 {
+  constexpr int L2_TH = TH, L2_NWC = NWC, L2_NG = L2Shape<TH, NWC>::NG, L2_TW = L2Shape<TH, NWC>::TW,
+      L2_TWP = L2Shape<TH, NWC>::TWP;
   extern __shared__ __align__ (16) unsigned hs[];                // [3][L2_NG][L2_TWP] words
   const int lane = threadIdx.x & 31;
   const int warp = __shfl_sync (0xffffffffu, (int) (threadIdx.x >> 5), 0);   // warp-uniform for the compiler
@@ -107,7 +111,7 @@ vcs_lanczos2_kernel (const VcsDev P, const Lanczos2Dev L, const VcsBatch frames)
 
   // ---------------------------------------------------------------- H phase
   for (int item = warp; item < L2_NG * L2_NWC; item += L2_THREADS / 32) {
-    const int g = item >> 1, wc = item & 1;
+    const int g = item / L2_NWC, wc = item - g * L2_NWC;
     const int col0 = x0 + wc * L2_WCOLS + (lane - 1) * 4;        // first of this lane's 4 output columns
     int4 T[3];
     {
@@ -187,9 +191,9 @@ vcs_lanczos2_kernel (const VcsDev P, const Lanczos2Dev L, const VcsBatch frames)
   __syncthreads ();
 
   // ---------------------------------------------------------------- V phase
-  // warp q owns output rows oy0+4q .. +3 for all 240 columns of the tile
-  {
-    const int q = warp, oy = oy0 + 4 * q;
+  // a warp owns output rows oy0+4q .. +3 for all columns of the tile
+  for (int q = warp; q < L2_TH / 4; q += L2_THREADS / 32) {
+    const int oy = oy0 + 4 * q;
     if (oy < P.oh) {
       int4 T[3];
       T[0] = __ldg (L.vtab + (oy >> 2) * 3 + 0);
@@ -204,7 +208,7 @@ vcs_lanczos2_kernel (const VcsDev P, const Lanczos2Dev L, const VcsBatch frames)
       for (int c = lane; c < L2_TW; c += 32) {
         const int ox = x0 + c;
         if (ox >= P.ow) break;
-        const int sc = (c >= L2_WCOLS ? 128 + 4 - L2_WCOLS : 4) + c;        // smem column of this output column
+        const int sc = c + 4 + (c / L2_WCOLS) * (128 - L2_WCOLS);           // smem column of this output column
         int a[3][4];
 #pragma unroll
         for (int ch = 0; ch < 3; ch++) {
@@ -299,7 +303,7 @@ inline Lanczos2Tables build_lanczos2_tables (const VcsPlan & p)
 struct Lanczos2State {
   int4 *d_htab = nullptr, *d_vtab = nullptr;
   Lanczos2Dev dev;
-  int minb = 3;
+  int variant = 0;
 };
 
 inline int prepare_lanczos2 (const Lanczos2Tables & t, const VcsDev & d, Lanczos2State * st)
@@ -312,12 +316,9 @@ inline int prepare_lanczos2 (const Lanczos2Tables & t, const VcsDev & d, Lanczos
   st->dev.htab = st->d_htab; st->dev.vtab = st->d_vtab;
   st->dev.hsum = d.h.sum; st->dev.vsum = d.v.sum;
   st->dev.alpha_opaque = t.alpha_opaque;
-  B200_CUDA_TRY (cudaFuncSetAttribute (vcs_lanczos2_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, L2_SMEM));
-  B200_CUDA_TRY (cudaFuncSetAttribute (vcs_lanczos2_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, L2_SMEM));
-  B200_CUDA_TRY (cudaFuncSetAttribute (vcs_lanczos2_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, L2_SMEM));
   {
-    const char *e = getenv ("B200_L2_MINB");        // tuning knob: resident CTAs per SM the kernel is compiled for
-    st->minb = (e && atoi (e) == 4) ? 4 : 3;
+    const char *e = getenv ("B200_L2_VARIANT");      // tuning knob (0..3), see launch_lanczos2
+    st->variant = e ? atoi (e) : 0;
   }
   return B200_OK;
 }
@@ -325,13 +326,27 @@ inline int prepare_lanczos2 (const Lanczos2Tables & t, const VcsDev & d, Lanczos
 inline int launch_lanczos2 (const VcsDev & d, const Lanczos2State & st, const VcsBatch & batch, int n,
     cudaStream_t stream)
 {
-  dim3 grid ((d.ow + L2_TW - 1) / L2_TW, (d.oh + L2_TH - 1) / L2_TH, n);
-  if (st.dev.alpha_opaque && st.minb == 4)
-    vcs_lanczos2_kernel<true, 4> <<<grid, L2_THREADS, L2_SMEM, stream>>> (d, st.dev, batch);
-  else if (st.dev.alpha_opaque)
-    vcs_lanczos2_kernel<true, 3> <<<grid, L2_THREADS, L2_SMEM, stream>>> (d, st.dev, batch);
-  else
-    vcs_lanczos2_kernel<false, 3> <<<grid, L2_THREADS, L2_SMEM, stream>>> (d, st.dev, batch);
+#define L2_LAUNCH(ALPHA, MINB, TH, NWC)                                                        \
+  do {                                                                                         \
+    auto kern = vcs_lanczos2_kernel<ALPHA, MINB, TH, NWC>;                                     \
+    static bool attr_done[16] = {false};                                                       \
+    int dev = 0; cudaGetDevice (&dev);                                                         \
+    if (!attr_done[dev & 15]) {                                                                \
+      B200_CUDA_TRY (cudaFuncSetAttribute (kern, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+              L2Shape<TH, NWC>::SMEM));                                                        \
+      attr_done[dev & 15] = true;                                                              \
+    }                                                                                          \
+    dim3 grid ((d.ow + L2Shape<TH, NWC>::TW - 1) / L2Shape<TH, NWC>::TW, (d.oh + TH - 1) / TH, n); \
+    kern <<<grid, L2_THREADS, L2Shape<TH, NWC>::SMEM, stream>>> (d, st.dev, batch);            \
+  } while (0)
+  if (!st.dev.alpha_opaque) L2_LAUNCH (false, 3, 32, 2);
+  else switch (st.variant) {
+    case 1: L2_LAUNCH (true, 4, 32, 2); break;
+    case 2: L2_LAUNCH (true, 3, 60, 1); break;
+    case 3: L2_LAUNCH (true, 4, 60, 1); break;
+    default: L2_LAUNCH (true, 3, 32, 2); break;
+  }
+#undef L2_LAUNCH
   B200_CUDA_TRY (cudaGetLastError ());
   return B200_OK;
 }

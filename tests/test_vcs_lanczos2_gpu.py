@@ -87,3 +87,16 @@ def test_extreme_values(cuda_device):
         want = ob.oracle_vcs_convert(d, frame)
         got = _convert(iw, ih, 3, frame, 1)
         assert np.array_equal(got, want), f"pattern {pat}: " + _explain(got, want, iw // 2)
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("size", [(488, 264), (1928, 1096), (3840, 2160)], ids=lambda s: "%dx%d" % s)
+def test_tile_shape_variants(cuda_device, monkeypatch, variant, size):
+    """the tuning knob B200_L2_VARIANT picks tile shape / residency; every variant must be exact"""
+    monkeypatch.setenv("B200_L2_VARIANT", str(variant))
+    iw, ih = size
+    d = ob.vcs_desc(iw, ih, iw // 2, ih // 2, 3, site=2)
+    frame = ob.nv12_random_frame(iw, ih, seed=variant + iw)
+    want = ob.oracle_vcs_convert(d, frame)
+    got = _convert(iw, ih, 3, frame, 1)
+    assert np.array_equal(got, want), _explain(got, want, iw // 2)
