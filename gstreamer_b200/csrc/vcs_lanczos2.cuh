@@ -24,6 +24,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <type_traits>
 #include <vector>
 
 #include "common.h"
@@ -110,18 +111,23 @@ vcs_lanczos2_kernel (const VcsDev P, const Lanczos2Dev L, const VcsBatch frames)
   const unsigned selU = P.u_index ? 0x7531u : 0x6420u, selV = P.u_index ? 0x6420u : 0x7531u;
 
   // ---------------------------------------------------------------- H phase
+  // Tiles that touch no frame border skip every clamp (line / chroma-row / column indices and the
+  // "no chroma sample to the right" fix-up): warp-uniform choice between two instantiations.
+  const bool edge_tile = R0 < 0 || R0 + 4 * L2_NG > P.ih || x0 == 0 || x0 + L2_TW + 4 >= P.ow;
+  auto h_phase = [&] (auto edge_tag) {
+    constexpr bool EDGE = decltype (edge_tag)::value;
   for (int item = warp; item < L2_NG * L2_NWC; item += L2_THREADS / 32) {
     const int g = item / L2_NWC, wc = item - g * L2_NWC;
     const int col0 = x0 + wc * L2_WCOLS + (lane - 1) * 4;        // first of this lane's 4 output columns
     int4 T[3];
     {
-      const int grp = min (max (col0 >> 2, 0), (P.ow >> 2) - 1);
+      const int grp = EDGE ? min (max (col0 >> 2, 0), (P.ow >> 2) - 1) : (col0 >> 2);
       T[0] = __ldg (L.htab + grp * 3 + 0);
       T[1] = __ldg (L.htab + grp * 3 + 1);
       T[2] = __ldg (L.htab + grp * 3 + 2);
     }
-    const int xb = min (max (2 * col0, 0), P.iw - 8);            // byte column of the lane's 8 input pixels
-    const bool right_edge = 2 * col0 + 8 >= P.iw;                // no chroma sample to the right
+    const int xb = EDGE ? min (max (2 * col0, 0), P.iw - 8) : 2 * col0;   // byte column of the lane's 8 input pixels
+    const bool right_edge = EDGE && 2 * col0 + 8 >= P.iw;        // no chroma sample to the right
     const int y0 = R0 + 4 * g;                                   // lines y0..y0+3, y0 % 4 == 1
     const int m2 = (y0 - 1) >> 1;                                // chroma rows m2, m2+1, m2+2
 
@@ -129,12 +135,17 @@ vcs_lanczos2_kernel (const VcsDev P, const Lanczos2Dev L, const VcsBatch frames)
     unsigned ulo[3], uhi[3], vlo[3], vhi[3];
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-      const int cr = min (max (m2 + k, 0), crows - 1);
+      const int cr = EDGE ? min (max (m2 + k, 0), crows - 1) : m2 + k;
       const uint2 c = __ldg ((const uint2 *) (plane_c + (size_t) cr * P.stride_c + xb));
       const unsigned ue = __byte_perm (c.x, c.y, selU), ve = __byte_perm (c.x, c.y, selV);
       unsigned un = __shfl_down_sync (0xffffffffu, ue, 1), vn = __shfl_down_sync (0xffffffffu, ve, 1);
-      un = right_edge ? __byte_perm (ue, ue, 0x3321) : __byte_perm (ue, un, 0x4321);
-      vn = right_edge ? __byte_perm (ve, ve, 0x3321) : __byte_perm (ve, vn, 0x4321);
+      if (EDGE) {
+        un = right_edge ? __byte_perm (ue, ue, 0x3321) : __byte_perm (ue, un, 0x4321);
+        vn = right_edge ? __byte_perm (ve, ve, 0x3321) : __byte_perm (ve, vn, 0x4321);
+      } else {
+        un = __byte_perm (ue, un, 0x4321);
+        vn = __byte_perm (ve, vn, 0x4321);
+      }
       const unsigned uo = avg_ceil4 (ue, un), vo = avg_ceil4 (ve, vn);
       ulo[k] = __byte_perm (ue, uo, 0x5140); uhi[k] = __byte_perm (ue, uo, 0x7362);
       vlo[k] = __byte_perm (ve, vo, 0x5140); vhi[k] = __byte_perm (ve, vo, 0x7362);
@@ -181,13 +192,15 @@ vcs_lanczos2_kernel (const VcsDev P, const Lanczos2Dev L, const VcsBatch frames)
     L2_STORE (2, acc);
 #pragma unroll
     for (int r = 0; r < 4; r++) {
-      const int y = min (max (y0 + r, 0), P.ih - 1);
+      const int y = EDGE ? min (max (y0 + r, 0), P.ih - 1) : y0 + r;
       const uint2 yy = __ldg ((const uint2 *) (plane_y + (size_t) y * P.stride_y + xb));
       const unsigned w0 = __shfl_up_sync (0xffffffffu, yy.y, 1), w3 = __shfl_down_sync (0xffffffffu, yy.x, 1);
       L2_FIR4 (acc[r][0], acc[r][1], acc[r][2], acc[r][3], w0, yy.x, yy.y, w3, T);
     }
     L2_STORE (0, acc);
   }
+  };
+  if (edge_tile) h_phase (std::true_type {}); else h_phase (std::false_type {});
   __syncthreads ();
 
   // ---------------------------------------------------------------- V phase
@@ -318,7 +331,7 @@ inline int prepare_lanczos2 (const Lanczos2Tables & t, const VcsDev & d, Lanczos
   st->dev.alpha_opaque = t.alpha_opaque;
   {
     const char *e = getenv ("B200_L2_VARIANT");      // tuning knob (0..3), see launch_lanczos2
-    st->variant = e ? atoi (e) : 0;
+    st->variant = e ? atoi (e) : 3;        // 120x60 tiles, 4 CTAs/SM measured fastest (profiles/)
   }
   return B200_OK;
 }

@@ -101,3 +101,32 @@ def test_reset_discards_history(cuda_device):
     assert n2 == nw and n1 > 0
     assert np.array_equal(out2.cpu().numpy()[: n2 * 2].view(np.uint32), w[:nw].reshape(-1).view(np.uint32))
     o.oracle_ars_free(ho)
+
+
+def test_denormals_are_not_flushed(cuda_device):
+    """products of tiny samples with taps are subnormal; the reference (SSE, no FTZ/DAZ set by the
+    element) keeps them, so the kernel must be compiled without flush-to-zero"""
+    import torch
+    from gstreamer_b200.audio import CudaAudioResample
+    o = ob.oracle()
+    ch, n = 4, 960
+    x = (np.random.default_rng(3).standard_normal((n, ch)) * 1e-38).astype(np.float32)
+    ho = o.oracle_ars_new(48000, 44100, ch, 4)
+    want = np.zeros((n, ch), dtype=np.float32)
+    nw = o.oracle_ars_process(ho, x.ctypes.data, n, want.ctypes.data, n)
+    o.oracle_ars_free(ho)
+    w = np.abs(want[:nw])
+    assert ((w > 0) & (w < 1.1754944e-38)).mean() > 0.5            # mostly subnormal results
+    rs = CudaAudioResample()
+    rs.set_caps(48000, 44100, ch)
+    out = torch.zeros(n * ch, dtype=torch.float32, device="cuda")
+    ng = rs.transform(torch.from_numpy(x).cuda(), n, out, n)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy().reshape(n, ch)
+    assert ng == nw and np.array_equal(got[:ng].view(np.uint32), want[:nw].view(np.uint32))
+
+
+def test_large_tap_count_falls_back_to_generic_kernel(cuda_device):
+    """96k -> 8k at quality 7 needs 1480 taps: the shared-memory tile does not fit, the global-memory
+    kernel must give the same bits"""
+    _stream_through(96000, 8000, 2, 7, [4096, 4096, 1000], seed=5)
