@@ -58,6 +58,8 @@ class ClockSampler:
         self._t = None
 
     def _run(self):
+        if self._run_nvml():
+            return
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
@@ -69,6 +71,37 @@ class ClockSampler:
             except Exception:
                 pass
             self._stop.wait(0.1)
+
+    def _run_nvml(self):
+        """NVML (the library nvidia-smi itself queries) polled every millisecond: the timed region is tens of ms"""
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = self.gpu
+            if vis:
+                ids = [v for v in vis.split(",") if v.strip()]
+                if self.gpu < len(ids) and ids[self.gpu].strip().isdigit():
+                    idx = int(ids[self.gpu])
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+        except Exception:
+            return False
+        while not self._stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                r = get_reasons(h)
+                self.samples.append([str(self.gpu), str(sm), str(mx), "", hex(r)] +
+                                    ["Active" if r & bits[k] else "Not Active" for k in
+                                     ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")])
+            except Exception:
+                pass
+            self._stop.wait(0.001)
+        return True
 
     def start(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -275,7 +308,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=10.0)

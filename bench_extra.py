@@ -1,5 +1,6 @@
 #!/usr/bin/env python
 """bench_extra.py — secondary BASELINE configs on one B200 (kernel-resident numbers):
+  C1  cudavideoconvertscale: 1080p NV12 -> 720p BGRA, bilinear (configs[0], the element default)
   C4  cudacompositor: 16 x 1080p RGBA pads -> 3840x2160 RGBA   (configs[3])
   C5  cudaaudioresample: 48k -> 44.1k F32, 256 channels          (configs[4], shortened buffer)
 Prints one JSON line per config with achieved GB/s against the measured HBM peak and, for C5,
@@ -19,6 +20,65 @@ def peak():
         return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
     except Exception:
         return 6650.0
+
+
+def bench_c1(args):
+    import numpy as np
+    import torch
+    import gstreamer_b200 as g
+    from oracle import bindings as ob
+    IW, IH, OW, OH = 1920, 1080, 1280, 720
+    el = g.CudaVideoConvertScale(method=1)
+    ii, oi = g.VideoInfo(g.VideoFormat.NV12, IW, IH), g.VideoInfo(g.VideoFormat.BGRA, OW, OH)
+    el.set_info(ii, oi)
+    if args.variant >= 0:
+        el.set_kernel_variant(args.variant)
+    ring, per = 128, 64                       # 128 x (3.1 + 3.7) MB = 870 MB >> L2
+    base = [torch.from_numpy(ob.nv12_random_frame(IW, IH, s)).cuda() for s in range(4)]
+    rin = []
+    for k in range(ring):
+        t = base[k % 4].clone()
+        t[::4099] = (t[::4099].to(torch.int32) + k).to(torch.uint8)
+        rin.append(t)
+    rout = [torch.empty(oi.size, dtype=torch.uint8, device="cuda") for _ in range(ring)]
+    s = torch.cuda.Stream()
+    step = lambda i: el.transform_frames(rin[(i % 2) * per:(i % 2 + 1) * per], rout[(i % 2) * per:(i % 2 + 1) * per], s)
+    with torch.cuda.stream(s):
+        for i in range(4):
+            step(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(s)
+        for i in range(args.steps):
+            step(i)
+        e1.record(s)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    alg = per * (ii.size + oi.size)
+    cpu = None
+    if ob.have_ref() and not args.no_cpu:
+        for threads in (1, os.cpu_count() or 1):
+            conv = ob.RefVcs(IW, IH, OW, OH, 1, n_threads=threads)
+            f = ob.nv12_smpte_like_frame(IW, IH) if hasattr(ob, "nv12_smpte_like_frame") else ob.nv12_random_frame(IW, IH, 0)
+            out = np.zeros(oi.size, dtype=np.uint8)
+            conv.convert(f, out)
+            n, t0 = 0, time.perf_counter()
+            while time.perf_counter() - t0 < 4:
+                conv.convert(f, out)
+                n += 1
+            fps = n / (time.perf_counter() - t0)
+            if threads == 1:
+                cpu = {"value": fps, "unit": "frames/s", "cores": 1, "kind": "reference",
+                       "sample": f"{n} frames, video-converter.c + ORC C backups, n-threads=1 (element default)"}
+            else:
+                cpu["all_cores"] = {"value": fps, "cores": threads}
+    print(json.dumps({"config": "C1 cudavideoconvertscale 1920x1080 NV12 -> 1280x720 BGRA bilinear",
+                      "kernel_variant": int(el.plan_info().kernel_variant),
+                      "frames_per_s": per * 1e3 / ms, "us_per_frame": ms * 1e3 / per,
+                      "mpix_per_s_in": per * IW * IH / (ms * 1e-3) / 1e6,
+                      "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak(), "unit": "GB/s",
+                                   "frac": alg / (ms * 1e-3) / 1e9 / peak(), "alg_bytes_per_launch": alg},
+                      "cpu_baseline": cpu}), flush=True)
 
 
 def bench_c4(args):
@@ -140,7 +200,10 @@ if __name__ == "__main__":
     ap.add_argument("--background", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--only", default="")
+    ap.add_argument("--variant", type=int, default=-1, help="C1: force a convert+scale kernel variant")
     a = ap.parse_args()
+    if a.only in ("", "c1"):
+        bench_c1(a)
     if a.only in ("", "c4"):
         bench_c4(a)
     if a.only in ("", "c5"):

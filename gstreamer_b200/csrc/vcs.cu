@@ -9,6 +9,7 @@
 #include "vcs_device.h"
 #include "vcs_kernels.cuh"
 #include "vcs_lanczos2.cuh"
+#include "vcs_light.cuh"
 
 #include <string.h>
 #include <new>
@@ -60,6 +61,12 @@ int launch (b200_vcs * h, int n, const VcsBatch & batch, cudaStream_t stream)
   const VcsPlan & p = h->plan;
   if (h->variant == 1 && p.lanczos2_ok)
     return launch_lanczos2 (h->dev, h->l2, batch, n, stream);
+  if (h->variant == 2 && p.light_ok) {
+    // 32-bit plane loads: the frame itself must be word aligned (device allocations always are)
+    bool aligned = true;
+    for (int i = 0; i < n; i++) aligned = aligned && (((uintptr_t) batch.in[i]) & 3) == 0;
+    if (aligned) return launch_light (h->dev, p, batch, n, stream);
+  }
   dim3 grid ((p.out.width + p.tile_w - 1) / p.tile_w, (p.out.height + p.tile_h - 1) / p.tile_h, n);
   vcs_generic_kernel <<<grid, 256, p.smem_bytes, stream>>> (h->dev, batch);
   B200_CUDA_TRY (cudaGetLastError ());
@@ -180,6 +187,10 @@ int b200_vcs_create (const b200_video_info * in, const b200_video_info * out,
       st = prepare_lanczos2 (h->l2_tables, h->dev, &h->l2);
       if (st != B200_OK) { b200_vcs_destroy (h); return st; }
       h->variant = 1;
+    } else if (p.light_ok) {
+      e = cudaFuncSetAttribute (light_kernel_for (p), cudaFuncAttributeMaxDynamicSharedMemorySize, p.light_smem);
+      if (e != cudaSuccess) { b200_vcs_destroy (h); return cuda_fail (e, "cudaFuncSetAttribute", __FILE__, __LINE__); }
+      h->variant = 2;
     }
   }
   *handle = h;
@@ -272,7 +283,7 @@ int b200_vcs_get_plan_info (const b200_vcs * h, b200_vcs_plan_info * info)
   info->h_first = p.h_first; info->matrix_first = p.matrix_first;
   for (int i = 0; i < 5; i++) info->p[i] = p.p[i];
   info->tile_w = p.tile_w; info->tile_h = p.tile_h; info->smem_bytes = p.smem_bytes;
-  info->kernel_variant = (h->variant == 1 && p.lanczos2_ok) ? 1 : 0;
+  info->kernel_variant = (h->variant == 1 && p.lanczos2_ok) ? 1 : (h->variant == 2 && p.light_ok) ? 2 : 0;
   info->n_launches_per_convert = 1;
   return B200_OK;
 }
@@ -302,8 +313,9 @@ int b200_vcs_get_chroma_plan (const b200_vcs * h, uint8_t * mode, size_t len)
 
 int b200_vcs_set_kernel_variant (b200_vcs * h, int variant)
 {
-  if (!h || variant < 0 || variant > 1) return B200_ERR_INVALID_ARG;
+  if (!h || variant < 0 || variant > 2) return B200_ERR_INVALID_ARG;
   if (variant == 1 && !h->plan.lanczos2_ok) return B200_ERR_UNSUPPORTED;
+  if (variant == 2 && !h->plan.light_ok) return B200_ERR_UNSUPPORTED;
   h->variant = variant;
   return B200_OK;
 }

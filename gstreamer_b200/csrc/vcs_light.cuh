@@ -1,0 +1,253 @@
+// gstreamer_b200/csrc/vcs_light.cuh — fused kernel for the element's DEFAULT configuration class
+// (product code, sm_100a): 4:2:0 semi-planar -> packed RGB where each axis is either untouched /
+// nearest (PASS_COPY) or bilinear (PASS_2TAP), horizontal pass first.  BASELINE config C1
+// (1920x1080 NV12 -> 1280x720 BGRA, method=bilinear) lands here.
+//
+// Same arithmetic as vcs_generic_kernel, stage by stage (reference chain: unpack_NV12 -> chroma up
+// h,v -> video_orc_resample_h_2tap_4u8_lq -> video_orc_resample_v_2tap_u8_lq ->
+// video_orc_convert_AYUV_ARGB -> pack; see vcs_kernels.cuh for the per-stage citations), organised
+// around packed 4-byte pixels:
+//
+//  A  a thread owns 4 consecutive pixels of one input line, or of the two lines of a chroma pair:
+//     one LDG.32 of luma per line, the chroma words of the two chroma rows involved, byte-SIMD
+//     up-sampling shared by the pair, then four pixels per line leave as one STS.128 of {Y,U,V,-}
+//     words (or {A,R,G,B} when the matrix runs first)
+//  B  horizontal pass: both taps are whole pixels (2 LDS.32); the lerp runs on two 16-bit lanes per
+//     register, so 4 IMAD cover all channels:  (a*(256-f) + b*f) >> 8  never exceeds 16 bits
+//  C  vertical pass on the same lane trick:  bits 8..15 of s0*(256-p) + s1*p + 128  is exactly the
+//     reference's wrapping 16-bit  s0 + (((s1-s0)*p + 128) >> 8)  for p in [0,256];
+//     then the mulhi matrix, byte order, one coalesced 4-byte store per thread.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.h"
+#include "vcs_device.h"
+#include "vcs_kernels.cuh"
+#include "vcs_lanczos2.cuh"      // packed-byte helpers
+
+namespace b200 {
+
+struct LightDev {
+  int tw, th, max_rows, cp;      // tile size, shared-memory rows, words per staged input row
+};
+
+constexpr int LIGHT_THREADS = 256;
+
+// {Y,U,V,-} -> {A,R,G,B} word (A = 255): video_orc_convert_AYUV_ARGB on one pixel
+__device__ __forceinline__ unsigned light_matrix (unsigned yuv, const VcsDev & P)
+{
+  yuv ^= 0x00808080u;
+  const int wy = prmt_s (yuv, 0x8800u), wu = prmt_s (yuv, 0x9911u), wv = prmt_s (yuv, 0xaa22u);
+  const int ty = ((wy * P.p1) >> 16) + 128;
+  const int r = ty + ((wv * P.p2) >> 16);
+  const int b = ty + ((wu * P.p3) >> 16);
+  const int g = ty + ((wu * P.p4) >> 16) + ((wv * P.p5) >> 16);
+  return pack_sat2 (r, 255, pack_sat2 (b, g, 0u));
+}
+
+// 4 h-upsampled samples of one chroma component for luma columns x..x+3 (x % 4 == 0).
+// e = that component's samples {c[k], c[k+1], c[k+2], -} (k = x/2), p = c[k-1] in byte 0.
+template <bool COSITED>
+__device__ __forceinline__ unsigned light_hup4 (unsigned e, unsigned p)
+{
+  const unsigned a = __byte_perm (e, 0, 0x1100);                 // c[k] c[k] c[k+1] c[k+1]
+  if (COSITED)                                                   // video_chroma_up_h2_cs_u8: odd px = (l + r + 1) >> 1
+    return avg_ceil4 (a, __byte_perm (e, 0, 0x2110));
+  // video_chroma_up_h2_u8: even px (c[k-1] + 3c[k] + 2) >> 2, odd px (3c[k] + c[k+1] + 2) >> 2
+  const unsigned b = __byte_perm (e, p, 0x2014);                 // c[k-1] c[k+1] c[k] c[k+2]
+  return avg_ceil4 (a, avg_floor4 (a, b));
+}
+
+// lerp of two packed pixels on 16-bit lanes: every byte = (a*wa + b*wb + rnd) >> 8
+__device__ __forceinline__ unsigned light_lerp (unsigned a, unsigned b, unsigned wa, unsigned wb, unsigned rnd)
+{
+  const unsigned ae = a & 0x00ff00ffu, ao = __byte_perm (a, 0, 0x4341);
+  const unsigned be = b & 0x00ff00ffu, bo = __byte_perm (b, 0, 0x4341);
+  const unsigned re = ae * wa + (be * wb + rnd), ro = ao * wa + (bo * wb + rnd);
+  return __byte_perm (re, ro, 0x7351);
+}
+
+template <int HM, int VM, bool MFIRST, bool COSITED>
+__global__ void __launch_bounds__ (LIGHT_THREADS, 2)
+vcs_light_kernel (const VcsDev P, const LightDev G, const VcsBatch frames)
+{
+  extern __shared__ __align__ (16) unsigned lsm[];
+  unsigned *S = lsm;                                             // [max_rows][cp]   staged input pixels
+  unsigned *T = lsm + G.max_rows * G.cp;                         // [max_rows][tw]   after the h pass
+  const int tid = threadIdx.x;
+  const uint8_t *__restrict__ in = frames.in[blockIdx.z];
+  uint8_t *__restrict__ out = frames.out[blockIdx.z];
+  const uint8_t *__restrict__ plane_y = in + P.off_y;
+  const uint8_t *__restrict__ plane_c = in + P.off_c;
+
+  const int ox0 = blockIdx.x * G.tw, oy0 = blockIdx.y * G.th;
+  const int tw = min (G.tw, P.ow - ox0), th = min (G.th, P.oh - oy0);
+  const int cx0 = P.h.offset[ox0], cx1 = P.h.offset[ox0 + tw - 1] + P.h.span;
+  const int ry0 = P.v.offset[oy0], ry1 = P.v.offset[oy0 + th - 1] + P.v.span;
+  const int cxa = cx0 & ~3, R = ry1 - ry0, ng = (cx1 - cxa + 3) >> 2;
+  const int cw2 = ((P.iw + 1) >> 1) * 2;                         // bytes of chroma per row
+  const unsigned selU = P.u_index ? 0x7531u : 0x6420u, selV = P.u_index ? 0x6420u : 0x7531u;
+
+  // ---------------------------------------------------------------- A: unpack + chroma up-sample
+  // Work list: one entry per input line, or per PAIR of lines (2k+1, 2k+2) that share their two
+  // chroma rows with swapped 3:1 weights (video_chroma_up_v2_u8) — the h up-sampling of both rows
+  // and the floor average are then computed once for the two lines.
+  unsigned *ent = T + G.max_rows * G.tw;                         // [max_rows] entries, then the count
+  if (tid < 32) {
+    int count = 0;
+    for (int b0 = 0; b0 < R; b0 += 32) {
+      const int r = b0 + tid, y = ry0 + r;
+      int m = 0, mprev = 0, mnext = 0;
+      if (r < R && P.v_pairs) {
+        m = P.chroma_mode[y];
+        if (r > 0) mprev = P.chroma_mode[y - 1];
+        if (r + 1 < R) mnext = P.chroma_mode[y + 1];
+      }
+      const bool second = m == 2 && mprev == 1 && r > 0;         // handled by the entry of line y-1
+      const bool pair = m == 1 && mnext == 2;
+      const bool keep = r < R && !second;
+      const unsigned mask = __ballot_sync (0xffffffffu, keep);
+      if (keep) ent[count + __popc (mask & ((1u << tid) - 1u))] = (unsigned) r | (unsigned) m << 16 | (pair ? 1u << 20 : 0u);
+      count += __popc (mask);
+    }
+    if (tid == 0) ent[G.max_rows] = (unsigned) count;
+  }
+  __syncthreads ();
+  {
+    const int nitems = (int) ent[G.max_rows] * ng;
+    const unsigned magic = 0xffffffffu / (unsigned) ng + 1u;     // item / ng == umulhi (item, magic) for item < 65536, ng > 1
+    for (int item = tid; item < nitems; item += LIGHT_THREADS) {
+      const int e = ng > 1 ? (int) __umulhi ((unsigned) item, magic) : item, j = item - e * ng;
+      const unsigned en = ent[e];
+      const int r = (int) (en & 0xffffu), m = (int) (en >> 16) & 3;
+      const bool pair = (en >> 20) != 0;
+      const int y = ry0 + r, x = cxa + 4 * j;
+      const int oth = (m == 1 ? min (y + 1, P.ih - 1) : y - 1) >> 1;
+      const uint8_t *rowc = plane_c + (unsigned) ((y >> 1) * P.stride_c + x);
+      const uint8_t *rowo = plane_c + (unsigned) ((m ? oth : (y >> 1)) * P.stride_c + x);
+      const uint8_t *rowy = plane_y + (unsigned) (y * P.stride_y + x);
+      unsigned u, v, ub = 0, vb = 0;
+      if (x + 8 <= cw2 && (COSITED || x >= 4)) {
+        const unsigned w0 = __ldg ((const unsigned *) rowc), w1 = __ldg ((const unsigned *) (rowc + 4));
+        unsigned wp = 0;
+        if (!COSITED) wp = __ldg ((const unsigned *) (rowc - 4)) >> 16;            // {U,V}[k-1] in bytes 0,1
+        u = light_hup4<COSITED> (__byte_perm (w0, w1, selU), __byte_perm (wp, 0, selU));
+        v = light_hup4<COSITED> (__byte_perm (w0, w1, selV), __byte_perm (wp, 0, selV));
+        if (m) {                                                 // FILT_3_1 / FILT_1_3 against the paired row
+          const unsigned o0 = __ldg ((const unsigned *) rowo), o1 = __ldg ((const unsigned *) (rowo + 4));
+          unsigned op = 0;
+          if (!COSITED) op = __ldg ((const unsigned *) (rowo - 4)) >> 16;
+          const unsigned uo = light_hup4<COSITED> (__byte_perm (o0, o1, selU), __byte_perm (op, 0, selU));
+          const unsigned vo = light_hup4<COSITED> (__byte_perm (o0, o1, selV), __byte_perm (op, 0, selV));
+          const unsigned fu = avg_floor4 (u, uo), fv = avg_floor4 (v, vo);
+          u = avg_ceil4 (u, fu); v = avg_ceil4 (v, fv);
+          ub = avg_ceil4 (uo, fu); vb = avg_ceil4 (vo, fv);      // the pair's second line: weights swapped
+        }
+      } else {                                                   // frame edges: scalar, clamps inside chroma_hup
+        u = v = 0;
+        const uint8_t *rc = rowc - x, *ro = rowo - x;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          if (x + i < P.iw) {
+            const int u0 = chroma_hup (rc + P.u_index, x + i, P.iw, COSITED);
+            const int v0 = chroma_hup (rc + (P.u_index ^ 1), x + i, P.iw, COSITED);
+            int uu = u0, vv = v0;
+            if (m) {
+              const int u1 = chroma_hup (ro + P.u_index, x + i, P.iw, COSITED);
+              const int v1 = chroma_hup (ro + (P.u_index ^ 1), x + i, P.iw, COSITED);
+              uu = (3 * u0 + u1 + 2) >> 2; vv = (3 * v0 + v1 + 2) >> 2;
+              ub |= (unsigned) ((3 * u1 + u0 + 2) >> 2) << (8 * i);
+              vb |= (unsigned) ((3 * v1 + v0 + 2) >> 2) << (8 * i);
+            }
+            u |= (unsigned) uu << (8 * i);
+            v |= (unsigned) vv << (8 * i);
+          }
+        }
+      }
+#pragma unroll
+      for (int l = 0; l < 2; l++) {
+        if (l == 1) {
+          if (!pair) break;
+          u = ub; v = vb;
+        }
+        const unsigned yw = __ldg ((const unsigned *) (rowy + l * P.stride_y));
+        // {Y,U,V,-} per pixel
+        const unsigned yu01 = __byte_perm (yw, u, 0x5140), yu23 = __byte_perm (yw, u, 0x7362);   // Y0 U0 Y1 U1
+        uint4 px;
+        px.x = __byte_perm (yu01, v, 0x4410);
+        px.y = __byte_perm (yu01, v, 0x5532);
+        px.z = __byte_perm (yu23, v, 0x6610);
+        px.w = __byte_perm (yu23, v, 0x7732);
+        if (MFIRST) {
+          px.x = light_matrix (px.x, P); px.y = light_matrix (px.y, P);
+          px.z = light_matrix (px.z, P); px.w = light_matrix (px.w, P);
+        }
+        *(uint4 *) (S + (r + l) * G.cp + 4 * j) = px;
+      }
+    }
+  }
+  __syncthreads ();
+
+  // ---------------------------------------------------------------- B: horizontal pass
+  // a thread keeps one output column: its source column and fraction live in registers
+  const int tx = tid & 127, rph = tid >> 7;                      // tw <= 128, two row phases
+  if (tx < tw) {
+    const int base = (int) P.h.offset[ox0 + tx] - cxa;
+    unsigned f = 0;
+    if (HM == 2) f = (unsigned) (int) P.h.coef[ox0 + tx];
+    for (int r = rph; r < R; r += LIGHT_THREADS / 128) {
+      const unsigned a = S[r * G.cp + base];
+      unsigned d = a;
+      if (HM == 2) d = light_lerp (a, S[r * G.cp + base + 1], 256u - f, f, 0u);
+      T[r * G.tw + tx] = d;
+    }
+  }
+  __syncthreads ();
+
+  // ---------------------------------------------------------------- C: vertical pass, matrix, pack
+  if (tx < tw) {
+    const int ox = ox0 + tx;
+    for (int ty = rph; ty < th; ty += LIGHT_THREADS / 128) {
+      const int oy = oy0 + ty;
+      const int base = (int) P.v.offset[oy] - ry0;
+      unsigned d = T[base * G.tw + tx];
+      if (VM == 2) {
+        const unsigned p = (unsigned) (int) P.v.coef[oy];
+        d = light_lerp (d, T[(base + 1) * G.tw + tx], 256u - p, p, 0x00800080u);
+      }
+      if (!MFIRST) d = light_matrix (d, P);
+      else d |= 0x000000ffu;                                      // alpha passes every 2-tap/copy stage as 255
+      *(unsigned *) (out + P.off_out + (size_t) oy * P.stride_out + (size_t) ox * 4u) = __byte_perm (d, 0, P.sel);
+    }
+  }
+}
+
+typedef void (*light_kernel_fn) (const VcsDev, const LightDev, const VcsBatch);
+
+inline light_kernel_fn light_kernel_for (const VcsPlan & p)
+{
+#define LIGHT_PICK(HM, VM)                                                                            \
+  if (p.h.mode == HM && p.v.mode == VM) {                                                             \
+    if (p.matrix_first) return p.h_cosited ? vcs_light_kernel<HM, VM, true, true> : vcs_light_kernel<HM, VM, true, false>;   \
+    return p.h_cosited ? vcs_light_kernel<HM, VM, false, true> : vcs_light_kernel<HM, VM, false, false>;                     \
+  }
+  LIGHT_PICK (1, 1) LIGHT_PICK (1, 2) LIGHT_PICK (2, 1) LIGHT_PICK (2, 2)
+#undef LIGHT_PICK
+  return nullptr;
+}
+
+inline int launch_light (const VcsDev & dev, const VcsPlan & p, const VcsBatch & batch, int n, cudaStream_t stream)
+{
+  light_kernel_fn fn = light_kernel_for (p);
+  if (!fn) return B200_ERR_STATE;
+  LightDev g;
+  g.tw = p.light_tw; g.th = p.light_th; g.max_rows = p.light_rows; g.cp = p.light_cp;
+  dim3 grid ((p.out.width + g.tw - 1) / g.tw, (p.out.height + g.th - 1) / g.th, n);
+  fn <<<grid, LIGHT_THREADS, p.light_smem, stream>>> (dev, g, batch);
+  B200_CUDA_TRY (cudaGetLastError ());
+  return B200_OK;
+}
+
+}  // namespace b200

@@ -302,6 +302,45 @@ void tile_geometry (VcsPlan * p)
   }
 }
 
+// Geometry of the light kernel (vcs_light.cuh): packed 4-byte pixels in shared memory, input
+// columns taken from a 4-aligned start, 128 output columns per tile.
+void light_geometry (VcsPlan * p)
+{
+  p->light_ok = false;
+  if (!(p->h.mode == PASS_COPY || p->h.mode == PASS_2TAP) || !(p->v.mode == PASS_COPY || p->v.mode == PASS_2TAP))
+    return;
+  if (!p->h_first) return;
+  // 32-bit row loads: every plane row starts 4-aligned and holds whole words up to the width
+  const int iw = p->in.width;
+  if ((p->in.stride[0] & 3) || (p->in.stride[1] & 3) || (p->in.offset[0] & 3) || (p->in.offset[1] & 3)) return;
+  if (p->in.stride[0] < ((iw + 3) & ~3) || p->in.stride[1] < ((iw + 3) & ~3)) return;
+  if ((int64_t) p->in.stride[0] * p->in.height >= (1ll << 31) || (int64_t) p->in.stride[1] * p->in.height >= (1ll << 31))
+    return;                                                       // 32-bit row offsets inside a plane
+  // the packed 16-bit-lane lerps need fractions in [0,255] (h) and weights in [0,256] (v)
+  if (p->h.mode == PASS_2TAP) for (int16_t c : p->h.coef) if (c < 0 || c > 255) return;
+  if (p->v.mode == PASS_2TAP) for (int16_t c : p->v.coef) if (c < 0 || c > 256) return;
+  const int ow = p->out.width, oh = p->out.height, tw = 128;
+  for (int th = 16; th >= 1; th /= 2) {
+    int max_rows = 0, max_cols = 0;
+    for (int y0 = 0; y0 < oh; y0 += th) {
+      int y1 = std::min (y0 + th, oh) - 1;
+      max_rows = std::max (max_rows, (int) (p->v.offset[y1] + p->v.span - p->v.offset[y0]));
+    }
+    for (int x0 = 0; x0 < ow; x0 += tw) {
+      int x1 = std::min (x0 + tw, ow) - 1;
+      int c0 = (int) p->h.offset[x0] & ~3, c1 = ((int) (p->h.offset[x1] + p->h.span) + 3) & ~3;
+      max_cols = std::max (max_cols, c1 - c0);
+    }
+    const int cp = max_cols + 4;                                  // +4 words: rows start on distinct banks
+    const size_t total = ((size_t) max_rows * cp + (size_t) max_rows * tw + max_rows + 4) * 4;   // S, T, work list
+    if (total <= 96 * 1024) {
+      p->light_ok = true; p->light_tw = tw; p->light_th = th; p->light_rows = max_rows; p->light_cp = cp;
+      p->light_smem = (int) total;
+      return;
+    }
+  }
+}
+
 }  // namespace
 
 int build_vcs_plan (const b200_video_info * in, const b200_video_info * out,
@@ -345,6 +384,7 @@ int build_vcs_plan (const b200_video_info * in, const b200_video_info * out,
   p->h_first = (int64_t) ow * ih <= (int64_t) iw * oh;
   chroma_pairing (p);
   tile_geometry (p);
+  light_geometry (p);
 
   // the specialised kernel covers exactly the headline shape class: even 2:1 in both
   // directions with the 8-tap lanczos the reference derives for it

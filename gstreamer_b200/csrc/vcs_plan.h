@@ -48,6 +48,10 @@ struct VcsPlan {
 
   // specialised 2:1 lanczos kernel eligibility
   bool lanczos2_ok = false;
+
+  // "light" kernel (both axes copy or 2-tap, horizontal first): tile geometry
+  bool light_ok = false;
+  int light_tw = 128, light_th = 16, light_rows = 0, light_cp = 0, light_smem = 0;
 };
 
 // builds everything that does not need a device; returns b200_status
