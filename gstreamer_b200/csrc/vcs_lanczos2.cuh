@@ -52,13 +52,21 @@ struct Lanczos2Dev {
 };
 
 // ---- packed byte helpers -----------------------------------------------------------------
+// ((a ^ b) & 0xfefefefe) as ONE LOP3 (lut 0x28); written in PTX because the compiler otherwise
+// re-associates the mask behind the shift and spends a second LOP3 on it
+__device__ __forceinline__ unsigned xor_and_fe (unsigned a, unsigned b)
+{
+  unsigned d;
+  asm ("lop3.b32 %0, %1, %2, 0xfefefefe, 0x28;" : "=r" (d) : "r" (a), "r" (b));
+  return d;
+}
 __device__ __forceinline__ unsigned avg_floor4 (unsigned a, unsigned b)
 {
-  return (a & b) + (((a ^ b) & 0xfefefefeu) >> 1);
+  return (a & b) + (xor_and_fe (a, b) >> 1);
 }
 __device__ __forceinline__ unsigned avg_ceil4 (unsigned a, unsigned b)
 {
-  return (a | b) - (((a ^ b) & 0xfefefefeu) >> 1);
+  return (a | b) - (xor_and_fe (a, b) >> 1);
 }
 __device__ __forceinline__ int dp4a_u8s8 (unsigned px, int taps, int acc)
 {

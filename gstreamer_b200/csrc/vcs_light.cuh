@@ -95,6 +95,11 @@ vcs_light_kernel (const VcsDev P, const LightDev G, const VcsBatch frames)
   // chroma rows with swapped 3:1 weights (video_chroma_up_v2_u8) — the h up-sampling of both rows
   // and the floor average are then computed once for the two lines.
   unsigned *ent = T + G.max_rows * G.tw;                         // [max_rows] entries, then the count
+  unsigned *vtab = ent + G.max_rows + 1;                         // [th] vertical source row and weight of each output row
+  if (tid >= 32 && tid < 32 + th) {
+    const int oy = oy0 + tid - 32;
+    vtab[tid - 32] = (P.v.offset[oy] - (unsigned) ry0) | (VM == 2 ? (unsigned) (int) P.v.coef[oy] << 16 : 0u);
+  }
   if (tid < 32) {
     int count = 0;
     for (int b0 = 0; b0 < R; b0 += 32) {
@@ -208,18 +213,19 @@ vcs_light_kernel (const VcsDev P, const LightDev G, const VcsBatch frames)
 
   // ---------------------------------------------------------------- C: vertical pass, matrix, pack
   if (tx < tw) {
-    const int ox = ox0 + tx;
-    for (int ty = rph; ty < th; ty += LIGHT_THREADS / 128) {
-      const int oy = oy0 + ty;
-      const int base = (int) P.v.offset[oy] - ry0;
-      unsigned d = T[base * G.tw + tx];
+    uint8_t *dst = out + P.off_out + (size_t) (oy0 + rph) * P.stride_out + (size_t) (ox0 + tx) * 4u;
+    const size_t dstep = (size_t) P.stride_out * (LIGHT_THREADS / 128);
+    for (int ty = rph; ty < th; ty += LIGHT_THREADS / 128, dst += dstep) {
+      const unsigned vo = vtab[ty];                               // row offset inside the tile | weight << 16
+      const unsigned *t = T + (vo & 0xffffu) * G.tw + tx;
+      unsigned d = t[0];
       if (VM == 2) {
-        const unsigned p = (unsigned) (int) P.v.coef[oy];
-        d = light_lerp (d, T[(base + 1) * G.tw + tx], 256u - p, p, 0x00800080u);
+        const unsigned p = vo >> 16;
+        d = light_lerp (d, t[G.tw], 256u - p, p, 0x00800080u);
       }
       if (!MFIRST) d = light_matrix (d, P);
       else d |= 0x000000ffu;                                      // alpha passes every 2-tap/copy stage as 255
-      *(unsigned *) (out + P.off_out + (size_t) oy * P.stride_out + (size_t) ox * 4u) = __byte_perm (d, 0, P.sel);
+      *(unsigned *) dst = __byte_perm (d, 0, P.sel);
     }
   }
 }

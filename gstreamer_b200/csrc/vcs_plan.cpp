@@ -332,7 +332,7 @@ void light_geometry (VcsPlan * p)
       max_cols = std::max (max_cols, c1 - c0);
     }
     const int cp = max_cols + 4;                                  // +4 words: rows start on distinct banks
-    const size_t total = ((size_t) max_rows * cp + (size_t) max_rows * tw + max_rows + 4) * 4;   // S, T, work list
+    const size_t total = ((size_t) max_rows * cp + (size_t) max_rows * tw + max_rows + 4 + th) * 4;   // S, T, work list, v table
     if (total <= 96 * 1024) {
       p->light_ok = true; p->light_tw = tw; p->light_th = th; p->light_rows = max_rows; p->light_cp = cp;
       p->light_smem = (int) total;
