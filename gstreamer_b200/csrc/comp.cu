@@ -45,38 +45,48 @@ __device__ __forceinline__ unsigned div255_x2 (unsigned t)
 }
 __device__ __forceinline__ unsigned div255_1 (unsigned x) { return (x * 0x8081u) >> 23; }
 
-// compositor_orc_blend_*: d = div255 (s*a + d*(255-a)) on all four bytes, then alpha := 0xff
+// compositor_orc_blend_*: d = div255 (s*a + d*(255-a)) on all four bytes, then alpha := 0xff.
+// Two 16-bit lanes per register; floor(x/255) == (x + 1 + (x >> 8)) >> 8 for x <= 65025, and the
+// final ">> 8" of both registers plus their interleave is a single PRMT.
 __device__ __forceinline__ unsigned px_blend (unsigned d, unsigned s, unsigned a, unsigned alpha_mask)
 {
-  const unsigned ia = 255u - a;
-  const unsigned lo = (s & 0x00ff00ffu) * a + (d & 0x00ff00ffu) * ia;
-  const unsigned hi = ((s >> 8) & 0x00ff00ffu) * a + ((d >> 8) & 0x00ff00ffu) * ia;
-  return (div255_x2 (lo) | (div255_x2 (hi) << 8)) | alpha_mask;
+  const unsigned ia = a ^ 0xffu;
+  const unsigned se = s & 0x00ff00ffu, so = __byte_perm (s, 0, 0x4341);      // bytes 0,2 / bytes 1,3
+  const unsigned de = d & 0x00ff00ffu, dd = __byte_perm (d, 0, 0x4341);
+  const unsigned lo = se * a + de * ia, hi = so * a + dd * ia;               // lanes <= 65025
+  const unsigned lo2 = lo + 0x00010001u + __byte_perm (lo, 0, 0x4341);
+  const unsigned hi2 = hi + 0x00010001u + __byte_perm (hi, 0, 0x4341);
+  return __byte_perm (lo2, hi2, 0x7351) | alpha_mask;
+}
+
+// d = { c[15:0], sat_u8(a), sat_u8(b) }  (b in the lowest byte): I2IP
+__device__ __forceinline__ unsigned sat_pack2 (unsigned a, unsigned b, unsigned c)
+{
+  unsigned d;
+  asm ("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r" (d) : "r" (a), "r" (b), "r" (c));
+  return d;
 }
 
 // compositor_orc_overlay_* (+ _addition): colour = (s*as + d*ad) / (as+ad) with divluw semantics
+// (quotient clamped to 255, x/0 = 255); the alpha byte becomes as+ad (or dalpha+as, wrapping).
 __device__ __forceinline__ unsigned px_overlay (unsigned d, unsigned s, unsigned as, int shift, bool addition,
     const unsigned *recip)
 {
-  const unsigned dalpha = (d >> shift) & 0xffu;
-  const unsigned ad = div255_1 (dalpha * (255u - as));
+  const unsigned asel = 0x4440u | ((unsigned) shift >> 3);
+  const unsigned dalpha = __byte_perm (d, 0, asel);
+  const unsigned ad = div255_1 (dalpha * (as ^ 0xffu));
   const unsigned asum = as + ad;                                   // <= 255
-  const unsigned lo = (s & 0x00ff00ffu) * as + (d & 0x00ff00ffu) * ad;       // lanes <= 65025
-  const unsigned hi = ((s >> 8) & 0x00ff00ffu) * as + ((d >> 8) & 0x00ff00ffu) * ad;
-  unsigned c[4] = {lo & 0xffffu, hi & 0xffffu, lo >> 16, hi >> 16};
-  unsigned out = 0;
-  if ((asum & 0xffu) == 0) {
-    out = 0xffffffffu;                                             // divluw: divide by zero -> 255
-  } else {
-    const unsigned r = recip[asum & 0xffu];                        // ceil (2^24 / asum): exact for v < 2^16
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const unsigned q = __umulhi (c[k] << 8, r);
-      out |= min (q, 255u) << (8 * k);
-    }
-  }
-  const unsigned na = (addition ? dalpha + as : asum) & 0xffu;
-  return (out & ~(0xffu << shift)) | (na << shift);
+  const unsigned se = s & 0x00ff00ffu, so = __byte_perm (s, 0, 0x4341);
+  const unsigned de = d & 0x00ff00ffu, dd = __byte_perm (d, 0, 0x4341);
+  const unsigned lo = se * as + de * ad, hi = so * as + dd * ad;   // lanes <= 65025: bytes (0,2) and (1,3)
+  const unsigned r = recip[asum];                                  // ceil (2^24 / asum): exact floor for v < 2^16
+  // umulhi (v << 8, r) == v / asum; the four "v << 8" come straight out of the lanes by PRMT
+  const unsigned q0 = __umulhi (__byte_perm (lo, 0, 0x4104), r), q2 = __umulhi (__byte_perm (lo, 0, 0x4324), r);
+  const unsigned q1 = __umulhi (__byte_perm (hi, 0, 0x4104), r), q3 = __umulhi (__byte_perm (hi, 0, 0x4324), r);
+  unsigned out = sat_pack2 (q1, q0, sat_pack2 (q3, q2, 0u));
+  if (asum == 0) out = 0xffffffffu;                                // divluw: divide by zero -> 255
+  const unsigned na = addition ? dalpha + as : asum;
+  return __byte_perm (out, na, shift ? 0x4210u : 0x3214u);         // alpha byte := low byte of na
 }
 
 // one pad applied to one pixel value held in a register
@@ -84,12 +94,36 @@ __device__ __forceinline__ unsigned apply_pad (unsigned d, unsigned s, int mode,
     unsigned alpha_mask, const unsigned *recip)
 {
   if (mode == CM_COPY) return s;
-  const unsigned a = div255_1 (((s >> shift) & 0xffu) * s_alpha);
+  unsigned a = (s >> shift) & 0xffu;
+  if (s_alpha != 255u) a = div255_1 (a * s_alpha);                 // div255 (A * 255) == A
   switch (mode) {
     case CM_SOURCE: return (s & ~alpha_mask) | (a << shift);
     case CM_BLEND: return px_blend (d, s, a, alpha_mask);
     case CM_OVERLAY: return px_overlay (d, s, a, shift, false, recip);
     default: return px_overlay (d, s, a, shift, true, recip);
+  }
+}
+
+// the same for a thread's four pixels: the (warp-uniform) operator and pad-alpha tests are taken
+// once, the common blend operator gets a straight-line body
+__device__ __forceinline__ void apply_pad4 (unsigned (&d)[4], const unsigned (&s)[4], int mode, unsigned s_alpha,
+    int shift, unsigned alpha_mask, const unsigned *recip)
+{
+  if (mode == CM_BLEND) {
+    const unsigned asel = 0x4440u | ((unsigned) shift >> 3);        // PRMT selector: alpha byte, zero-extended
+    if (s_alpha == 255u) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) d[i] = px_blend (d[i], s[i], __byte_perm (s[i], 0, asel), alpha_mask);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; i++) d[i] = px_blend (d[i], s[i], div255_1 (__byte_perm (s[i], 0, asel) * s_alpha), alpha_mask);
+    }
+  } else if (mode == CM_COPY) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) d[i] = s[i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; i++) d[i] = apply_pad (d[i], s[i], mode, s_alpha, shift, alpha_mask, recip);
   }
 }
 
@@ -164,8 +198,7 @@ comp_kernel (const CompParams P)
 #pragma unroll
         for (int i = 0; i < 4; i++) s[i] = __ldg (sp + i);
       }
-#pragma unroll
-      for (int i = 0; i < 4; i++) d[i] = apply_pad (d[i], s[i], mode, s_alpha, shift, alpha_mask, s_recip);
+      apply_pad4 (d, s, mode, s_alpha, shift, alpha_mask, s_recip);
     } else {
 #pragma unroll
       for (int i = 0; i < 4; i++)
