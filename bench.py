@@ -125,6 +125,15 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(self.samples)}
 
 
+def ncu_traffic(kernel, frames_per_launch):
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/)"""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[kernel]
+        return (t["dram_bytes_read"] + t["dram_bytes_write"]) * frames_per_launch / t["frames_per_launch"]
+    except Exception:
+        return None
+
+
 def cpu_baseline(seconds=10.0, threads=None):
     """time the reference's CPU converter on frames of the same workload"""
     import numpy as np
@@ -288,7 +297,9 @@ def run_ours(args):
                              (RING * ii.size / 1e6, RING * oi.size / 1e6),
                        "kernel_variant": int(pinfo.kernel_variant), "parallelism": f"streams{world}"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak,
+                         "traffic": ncu_traffic("vcs_lanczos2_kernel", FRAMES_PER_STEP) if pinfo.kernel_variant == 1 else None,
+                         "peak_source": peak_src,
                          "kernel": "vcs_lanczos2_kernel" if pinfo.kernel_variant == 1 else "vcs_generic_kernel",
                          "alg_bytes_per_launch": FRAMES_PER_STEP * ALG_BYTES_PER_FRAME,
                          "us_per_launch": ms * 1e3 / args.steps},
