@@ -152,6 +152,7 @@ static int build_ars_plan (const b200_ars_config & cfg, ArsPlan * p)
 // ------------------------------------------------------------------------------ device
 constexpr int ARS_RQ = 4;        // output frames per thread pass
 constexpr int ARS_THREADS = 256;
+constexpr int ARS_TILE_SMEM = 110 * 1024;   // dynamic shared memory the tile kernel may ask for (2 CTAs/SM)
 
 struct ArsLaunch {
   const float *hist;             // [hist_frames][channels] retained input
@@ -266,7 +267,7 @@ struct ArsTile {
   int nch;                       // chunks per output group (upper bound, fixed stride of the tap table)
 };
 
-template <int CB>
+template <int CB, int CPT>
 __global__ void __launch_bounds__ (ARS_THREADS)
 ars_tile_kernel (const ArsLaunch L, const ArsTile Tl)
 {
@@ -319,16 +320,20 @@ ars_tile_kernel (const ArsLaunch L, const ArsTile Tl)
   }
   __syncthreads ();
 
-  constexpr int WCN = CB / 32;
+  // a thread owns CPT adjacent channels x RQ consecutive outputs: every broadcast tap quad (LDS.128)
+  // then feeds CPT channels, which halves the shared-memory traffic per multiply for CPT = 2
+  constexpr int WCN = CB / (32 * CPT);
   const int cg = warp % WCN, og = warp / WCN;
   constexpr int NOG = (ARS_THREADS / 32) / WCN;
-  const int cl = cg * 32 + lane, c = c_base + cl;
+  const int cl = (cg * 32 + lane) * CPT, c = c_base + cl;
   for (int q = og; q < nq; q += NOG) {
-    float acc[RQ][4];
+    float acc[CPT][RQ][4];
 #pragma unroll
-    for (int r = 0; r < RQ; r++)
+    for (int u = 0; u < CPT; u++)
 #pragma unroll
-      for (int k = 0; k < 4; k++) acc[r][k] = 0.f;
+      for (int r = 0; r < RQ; r++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) acc[u][r][k] = 0.f;
     const int s_min = s_rel[q * RQ] & ~3;
     const int s_max = (s_rel[min (q * RQ + RQ - 1, n_out - 1)] + L.n_taps + 3) & ~3;
     const int nch = (s_max - s_min) >> 2;
@@ -336,21 +341,43 @@ ars_tile_kernel (const ArsLaunch L, const ArsTile Tl)
     const float4 *tp = qt + (size_t) q * Tl.nch * RQ;
 #pragma unroll 2
     for (int ch = 0; ch < nch; ch++, xp += 4 * CB, tp += RQ) {
-      const float x0 = xp[0], x1 = xp[CB], x2 = xp[2 * CB], x3 = xp[3 * CB];
+      float x[CPT][4];
+      if (CPT == 4) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const float4 v = *(const float4 *) (xp + k * CB);
+          x[0][k] = v.x; x[1 % CPT][k] = v.y; x[2 % CPT][k] = v.z; x[3 % CPT][k] = v.w;
+        }
+      } else if (CPT == 2) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const float2 v = *(const float2 *) (xp + k * CB);
+          x[0][k] = v.x; x[CPT - 1][k] = v.y;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++) x[0][k] = xp[k * CB];
+      }
 #pragma unroll
       for (int r = 0; r < RQ; r++) {
         const float4 t = tp[r];
-        acc[r][0] = __fadd_rn (acc[r][0], __fmul_rn (x0, t.x));
-        acc[r][1] = __fadd_rn (acc[r][1], __fmul_rn (x1, t.y));
-        acc[r][2] = __fadd_rn (acc[r][2], __fmul_rn (x2, t.z));
-        acc[r][3] = __fadd_rn (acc[r][3], __fmul_rn (x3, t.w));
+#pragma unroll
+        for (int u = 0; u < CPT; u++) {
+          acc[u][r][0] = __fadd_rn (acc[u][r][0], __fmul_rn (x[u][0], t.x));
+          acc[u][r][1] = __fadd_rn (acc[u][r][1], __fmul_rn (x[u][1], t.y));
+          acc[u][r][2] = __fadd_rn (acc[u][r][2], __fmul_rn (x[u][2], t.z));
+          acc[u][r][3] = __fadd_rn (acc[u][r][3], __fmul_rn (x[u][3], t.w));
+        }
       }
     }
 #pragma unroll
     for (int r = 0; r < RQ; r++) {
-      if (q * RQ + r < n_out && c < L.channels) {
-        const float v = __fadd_rn (__fadd_rn (acc[r][0], acc[r][2]), __fadd_rn (acc[r][1], acc[r][3]));
-        L.out[(size_t) (o0 + q * RQ + r) * L.channels + c] = v;
+#pragma unroll
+      for (int u = 0; u < CPT; u++) {
+        if (q * RQ + r < n_out && c + u < L.channels) {
+          const float v = __fadd_rn (__fadd_rn (acc[u][r][0], acc[u][r][2]), __fadd_rn (acc[u][r][1], acc[u][r][3]));
+          L.out[(size_t) (o0 + q * RQ + r) * L.channels + c + u] = v;
+        }
       }
     }
   }
@@ -438,9 +465,12 @@ int b200_ars_create (const b200_ars_config * cfg, int device, b200_ars ** handle
       return st;
     }
     cudaFuncSetAttribute (ars_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-    cudaFuncSetAttribute (ars_tile_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
-    cudaFuncSetAttribute (ars_tile_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
-    cudaFuncSetAttribute (ars_tile_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024);
+    cudaFuncSetAttribute (ars_tile_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ARS_TILE_SMEM);
+    cudaFuncSetAttribute (ars_tile_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ARS_TILE_SMEM);
+    cudaFuncSetAttribute (ars_tile_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ARS_TILE_SMEM);
+    cudaFuncSetAttribute (ars_tile_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ARS_TILE_SMEM);
+    cudaFuncSetAttribute (ars_tile_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ARS_TILE_SMEM);
+    cudaFuncSetAttribute (ars_tile_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ARS_TILE_SMEM);
   }
   *handle = h;
   return B200_OK;
@@ -516,13 +546,18 @@ int b200_ars_process (b200_ars * h, const float *in, size_t in_frames, float *ou
     L.row_pitch = (p.n_taps + 4 + 3) & ~3;
     L.wcn = (p.channels + 31) / 32; if (L.wcn > 8) L.wcn = 8;
     while (8 % L.wcn) L.wcn++;                                   // 1, 2, 4 or 8 warps across channels
-    int no = 32;
+    const char *env_no = getenv ("B200_ARS_NO"), *env_cpt = getenv ("B200_ARS_CPT");
+    int no = env_no ? atoi (env_no) : 32;
+    if (no < ARS_RQ || no > 64 || (no & (no - 1))) no = 32;      // s_rel/s_phase hold 64 outputs
     while (no > ARS_RQ && (size_t) no * L.row_pitch * sizeof (float) > 96 * 1024) no >>= 1;
     if ((size_t) no * L.row_pitch * sizeof (float) > 160 * 1024) return B200_ERR_UNSUPPORTED;
     L.no = no;
     // fast path when the CTA's input window fits in shared memory next to the chunk-major taps
     ArsTile tl;
     const int cb = 32 * (L.wcn > 4 ? 4 : L.wcn);
+    // channels per thread: 2 measured best on B200 (C5: 2.01 ms vs 2.44 ms for 1 and 2.57 ms for 4)
+    int cpt = cb >= 64 ? 2 : 1;
+    if (env_cpt && (atoi (env_cpt) == 1 || (atoi (env_cpt) == 4 && cb >= 128))) cpt = atoi (env_cpt);
     {
       // frames spanned by `no` outputs: ceil (no * in_step / out_step) + alignment + taps
       const long long span = ((long long) no * p.in_step + p.out_step - 1) / p.out_step + 8 + p.n_taps;
@@ -531,11 +566,14 @@ int b200_ars_process (b200_ars * h, const float *in, size_t in_frames, float *ou
       tl.nch = (int) ((spread + p.n_taps + 3 + 3) / 4 + 1);
     }
     const size_t smem_tile = ((size_t) (no / ARS_RQ) * tl.nch * ARS_RQ * 4 + (size_t) tl.win * cb) * sizeof (float);
-    if (smem_tile <= 72 * 1024 && !getenv ("B200_ARS_GENERIC")) {
+    if (smem_tile <= (size_t) ARS_TILE_SMEM && !getenv ("B200_ARS_GENERIC")) {
       const dim3 grid ((unsigned) ((out_frames + no - 1) / no), (unsigned) ((p.channels + cb - 1) / cb));
-      if (cb == 128) ars_tile_kernel<128> <<<grid, ARS_THREADS, smem_tile, stream>>> (L, tl);
-      else if (cb == 64) ars_tile_kernel<64> <<<grid, ARS_THREADS, smem_tile, stream>>> (L, tl);
-      else ars_tile_kernel<32> <<<grid, ARS_THREADS, smem_tile, stream>>> (L, tl);
+      if (cb == 128 && cpt == 4) ars_tile_kernel<128, 4> <<<grid, ARS_THREADS, smem_tile, stream>>> (L, tl);
+      else if (cb == 128 && cpt == 2) ars_tile_kernel<128, 2> <<<grid, ARS_THREADS, smem_tile, stream>>> (L, tl);
+      else if (cb == 128) ars_tile_kernel<128, 1> <<<grid, ARS_THREADS, smem_tile, stream>>> (L, tl);
+      else if (cb == 64 && cpt == 2) ars_tile_kernel<64, 2> <<<grid, ARS_THREADS, smem_tile, stream>>> (L, tl);
+      else if (cb == 64) ars_tile_kernel<64, 1> <<<grid, ARS_THREADS, smem_tile, stream>>> (L, tl);
+      else ars_tile_kernel<32, 1> <<<grid, ARS_THREADS, smem_tile, stream>>> (L, tl);
     } else {
       const dim3 grid ((unsigned) ((out_frames + no - 1) / no), (unsigned) ((p.channels + 32 * L.wcn - 1) / (32 * L.wcn)));
       ars_full_kernel <<<grid, ARS_THREADS, (size_t) no * L.row_pitch * sizeof (float), stream>>> (L);
