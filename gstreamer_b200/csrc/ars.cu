@@ -383,6 +383,69 @@ ars_tile_kernel (const ArsLaunch L, const ArsTile Tl)
   }
 }
 
+// Interpolated filter mode (audio-resampler.c:567-600 get_taps_gfloat_cubic +
+// inner_product_gfloat_cubic_1_sse, audio-resampler-x86-sse.c:82-120): too many phases to cache, so
+// every output takes four inner products against adjacent rows of the oversampled prototype and
+// blends the four lane sums with the cubic coefficients of its own fractional position.
+// Warp = one output frame x 32 channels; the prototype rows are warp-uniform LDG.128.
+// Lane sums follow the tap index mod 4 as in the reference; (c0*f0 + c1*f1) + (c2*f2 + c3*f3)
+// per lane, then (l0 + l2) + (l1 + l3).  No FMA anywhere.
+__global__ void __launch_bounds__ (ARS_THREADS)
+ars_interp_kernel (const ArsLaunch L, const float *__restrict__ table, int oversample)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long o = (long long) blockIdx.x * (ARS_THREADS / 32) + warp;
+  if (o >= L.out_frames) return;
+  const int c = blockIdx.y * 32 + lane;
+  long long idx; int phase;
+  ars_position (L, o, idx, phase);
+  const long long pos = (long long) phase * oversample;
+  const int offset = (oversample - 1) - (int) (pos / L.out_step), frac = (int) (pos % L.out_step);
+  // make_coeff_gfloat_cubic (audio-resampler.c:360-373), evaluated in float like the reference
+  const float x = __fdiv_rn (__int2float_rn (frac), __int2float_rn (L.out_step));
+  const float x2 = __fmul_rn (x, x), x3 = __fmul_rn (x2, x);
+  const float ic0 = __fmul_rn (0.16667f, __fsub_rn (x3, x));
+  const float ic1 = __fadd_rn (x, __fmul_rn (0.5f, __fsub_rn (x2, x3)));
+  const float ic3 = __fsub_rn (__fadd_rn (__fmul_rn (-0.33333f, x), __fmul_rn (0.5f, x2)), __fmul_rn (0.16667f, x3));
+  const float ic2 = __fsub_rn (__fsub_rn (__fsub_rn (1.0f, ic0), ic1), ic3);
+  const float4 *row = (const float4 *) (table + (size_t) offset * L.n_taps);
+  const int rstride = L.n_taps >> 2;
+  float acc[4][4];
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+#pragma unroll
+    for (int l = 0; l < 4; l++) acc[k][l] = 0.f;
+  const bool live = c < L.channels;
+  for (int i = 0; i < L.n_taps; i += 4) {
+    float xs[4];
+#pragma unroll
+    for (int l = 0; l < 4; l++) {
+      const long long f = idx + i + l;
+      float v = 0.f;
+      if (live) {
+        if (f < L.hist_frames) v = __ldg (L.hist + f * L.channels + c);
+        else if (L.in) v = __ldg (L.in + (f - L.hist_frames) * L.channels + c);
+      }
+      xs[l] = v;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const float4 t = __ldg (row + k * rstride + (i >> 2));
+      acc[k][0] = __fadd_rn (acc[k][0], __fmul_rn (xs[0], t.x));
+      acc[k][1] = __fadd_rn (acc[k][1], __fmul_rn (xs[1], t.y));
+      acc[k][2] = __fadd_rn (acc[k][2], __fmul_rn (xs[2], t.z));
+      acc[k][3] = __fadd_rn (acc[k][3], __fmul_rn (xs[3], t.w));
+    }
+  }
+  float t[4];
+#pragma unroll
+  for (int l = 0; l < 4; l++)
+    t[l] = __fadd_rn (__fadd_rn (__fmul_rn (acc[0][l], ic0), __fmul_rn (acc[1][l], ic1)),
+        __fadd_rn (__fmul_rn (acc[2][l], ic2), __fmul_rn (acc[3][l], ic3)));
+  if (live)
+    L.out[(size_t) o * L.channels + c] = __fadd_rn (__fadd_rn (t[0], t[2]), __fadd_rn (t[1], t[3]));
+}
+
 // new history = frames [first, first+keep) of the (old history ++ input) stream
 __global__ void ars_history_kernel (float *dst, const float *hist, const float *in, long long hist_frames,
     long long first, long long keep, int channels)
@@ -406,6 +469,7 @@ struct b200_ars {
   ArsPlan plan;
   int device = -1;
   float *d_phases = nullptr;
+  float *d_proto = nullptr;      // interpolated mode: the oversampled prototype rows
   float *d_hist[2] = {nullptr, nullptr};
   size_t hist_cap[2] = {0, 0};   // frames
   int cur = 0;
@@ -453,12 +517,12 @@ int b200_ars_create (const b200_ars_config * cfg, int device, b200_ars ** handle
   h->device = device;
   h->samples_avail = h->plan.n_taps / 2 - 1;
   if (device >= 0) {
-    if (!h->plan.full) { delete h; return B200_ERR_UNSUPPORTED; }   // interpolated filter mode: not yet on device
     int n = b200_device_count ();
     if (n <= 0) { delete h; return n < 0 ? n : B200_ERR_NO_DEVICE; }
     if (device >= n) { delete h; return B200_ERR_INVALID_ARG; }
     DeviceGuard g (device);
-    if ((st = upload (&h->d_phases, h->plan.phases.data (), h->plan.phases.size ())) != B200_OK ||
+    if ((st = h->plan.full ? upload (&h->d_phases, h->plan.phases.data (), h->plan.phases.size ())
+                           : upload (&h->d_proto, h->plan.proto.data (), h->plan.proto.size ())) != B200_OK ||
         (st = ars_ensure_hist (h, 0, (size_t) h->plan.n_taps)) != B200_OK ||
         (st = ars_ensure_hist (h, 1, (size_t) h->plan.n_taps)) != B200_OK) {
       b200_ars_destroy (h);
@@ -481,7 +545,7 @@ void b200_ars_destroy (b200_ars * h)
   if (!h) return;
   if (h->device >= 0) {
     DeviceGuard g (h->device);
-    cudaFree (h->d_phases); cudaFree (h->d_hist[0]); cudaFree (h->d_hist[1]);
+    cudaFree (h->d_phases); cudaFree (h->d_proto); cudaFree (h->d_hist[0]); cudaFree (h->d_hist[1]);
   }
   delete h;
 }
@@ -546,6 +610,11 @@ int b200_ars_process (b200_ars * h, const float *in, size_t in_frames, float *ou
     L.row_pitch = (p.n_taps + 4 + 3) & ~3;
     L.wcn = (p.channels + 31) / 32; if (L.wcn > 8) L.wcn = 8;
     while (8 % L.wcn) L.wcn++;                                   // 1, 2, 4 or 8 warps across channels
+    if (!p.full) {
+      L.no = 0; L.row_pitch = 0; L.wcn = 1;
+      const dim3 grid ((unsigned) ((out_frames + ARS_THREADS / 32 - 1) / (ARS_THREADS / 32)), (unsigned) ((p.channels + 31) / 32));
+      ars_interp_kernel <<<grid, ARS_THREADS, 0, stream>>> (L, h->d_proto, p.oversample);
+    } else {
     const char *env_no = getenv ("B200_ARS_NO"), *env_cpt = getenv ("B200_ARS_CPT");
     int no = env_no ? atoi (env_no) : 32;
     if (no < ARS_RQ || no > 64 || (no & (no - 1))) no = 32;      // s_rel/s_phase hold 64 outputs
@@ -577,6 +646,7 @@ int b200_ars_process (b200_ars * h, const float *in, size_t in_frames, float *ou
     } else {
       const dim3 grid ((unsigned) ((out_frames + no - 1) / no), (unsigned) ((p.channels + 32 * L.wcn - 1) / (32 * L.wcn)));
       ars_full_kernel <<<grid, ARS_THREADS, (size_t) no * L.row_pitch * sizeof (float), stream>>> (L);
+    }
     }
     B200_CUDA_TRY (cudaGetLastError ());
     // state after out_frames outputs (closed form of the stepping loop)

@@ -130,3 +130,17 @@ def test_large_tap_count_falls_back_to_generic_kernel(cuda_device):
     """96k -> 8k at quality 7 needs 1480 taps: the shared-memory tile does not fit, the global-memory
     kernel must give the same bits"""
     _stream_through(96000, 8000, 2, 7, [4096, 4096, 1000], seed=5)
+
+
+# interpolated filter mode: n_taps * out_step too large to cache every phase (audio-resampler.c:1147-1166);
+# each output blends four inner products with its own cubic coefficients
+@pytest.mark.parametrize("cfg", [(12345, 54321, 2, 4), (44100, 48001, 2, 4), (48000, 44101, 1, 6), (96000, 8001, 2, 3),
+                                 (7999, 48000, 3, 10), (44100, 48001, 40, 4)],
+                         ids=lambda c: "%d-%d-%dch-q%d" % c)
+def test_interpolated_filter_mode(cuda_device, cfg):
+    from gstreamer_b200.audio import CudaAudioResample
+    a, b, ch, q = cfg
+    rs = CudaAudioResample(quality=q)
+    rs.set_caps(a, b, ch)
+    assert rs.plan_info().filter_mode == 0          # GST_AUDIO_RESAMPLER_FILTER_MODE_INTERPOLATED
+    _stream_through(a, b, ch, q, [480, 480, 100, 1, 2000, 37], seed=ch)

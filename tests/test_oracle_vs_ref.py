@@ -115,7 +115,9 @@ def test_compositor_matches_reference():
 
 @pytest.mark.parametrize("cfg", [(48000, 44100, 2, 4), (44100, 48000, 3, 4), (8000, 16000, 1, 4), (48000, 24000, 2, 4),
                                  (12345, 54321, 2, 4), (101, 99, 1, 4), (44100, 8000, 2, 10), (48000, 96000, 2, 0),
-                                 (96000, 8000, 1, 7), (22050, 48000, 2, 9), (48000, 44100, 256, 4)],
+                                 (96000, 8000, 1, 7), (22050, 48000, 2, 9), (48000, 44100, 256, 4),
+                                 # interpolated filter mode (phase table would exceed 1 MiB)
+                                 (44100, 48001, 2, 4), (48000, 44101, 1, 6), (96000, 8001, 2, 3), (7999, 48000, 3, 10)],
                          ids=lambda c: "%d-%d-%dch-q%d" % c)
 def test_audio_matches_reference(cfg):
     import ctypes as C
