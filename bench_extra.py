@@ -81,6 +81,41 @@ def bench_c1(args):
                       "cpu_baseline": cpu}), flush=True)
 
 
+def bench_ntap(args):
+    """not a BASELINE config: lanczos at ratios the 2:1 kernel does not take (n-tap kernel vs generic)"""
+    import torch
+    import gstreamer_b200 as g
+    from oracle import bindings as ob
+    for (IW, IH, OW, OH) in [(1920, 1080, 1280, 720), (3840, 2160, 1280, 720), (1280, 720, 1920, 1080)]:
+        el = g.CudaVideoConvertScale(method=3)
+        ii, oi = g.VideoInfo(g.VideoFormat.NV12, IW, IH), g.VideoInfo(g.VideoFormat.BGRA, OW, OH)
+        el.set_info(ii, oi)
+        if args.variant >= 0:
+            el.set_kernel_variant(args.variant)
+        per = 32
+        base = [torch.from_numpy(ob.nv12_random_frame(IW, IH, s)).cuda() for s in range(2)]
+        rin = [base[k % 2].clone() for k in range(2 * per)]
+        rout = [torch.empty(oi.size, dtype=torch.uint8, device="cuda") for _ in range(2 * per)]
+        s = torch.cuda.Stream()
+        step = lambda i: el.transform_frames(rin[(i % 2) * per:(i % 2 + 1) * per], rout[(i % 2) * per:(i % 2 + 1) * per], s)
+        with torch.cuda.stream(s):
+            for i in range(3):
+                step(i)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(s)
+            for i in range(args.steps):
+                step(i)
+            e1.record(s)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        alg = per * (ii.size + oi.size)
+        print(json.dumps({"config": f"lanczos {IW}x{IH} NV12 -> {OW}x{OH} BGRA", "kernel_variant": int(el.plan_info().kernel_variant),
+                          "us_per_frame": ms * 1e3 / per, "frames_per_s": per * 1e3 / ms,
+                          "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak(), "unit": "GB/s",
+                                       "frac": alg / (ms * 1e-3) / 1e9 / peak()}}), flush=True)
+
+
 def bench_c4(args):
     import numpy as np
     import torch
@@ -204,6 +239,8 @@ if __name__ == "__main__":
     a = ap.parse_args()
     if a.only in ("", "c1"):
         bench_c1(a)
+    if a.only == "ntap":
+        bench_ntap(a)
     if a.only in ("", "c4"):
         bench_c4(a)
     if a.only in ("", "c5"):

@@ -10,6 +10,7 @@
 #include "vcs_kernels.cuh"
 #include "vcs_lanczos2.cuh"
 #include "vcs_light.cuh"
+#include "vcs_ntap.cuh"
 
 #include <string.h>
 #include <new>
@@ -34,6 +35,7 @@ struct b200_vcs {
   bool pipeline_ready = false;
   Lanczos2Tables l2_tables;
   Lanczos2State l2;
+  NtapState ntap;
   size_t in_bytes = 0, out_bytes = 0;
 };
 
@@ -66,6 +68,11 @@ int launch (b200_vcs * h, int n, const VcsBatch & batch, cudaStream_t stream)
     bool aligned = true;
     for (int i = 0; i < n; i++) aligned = aligned && (((uintptr_t) batch.in[i]) & 3) == 0;
     if (aligned) return launch_light (h->dev, p, batch, n, stream);
+  }
+  if (h->variant == 3 && p.ntap_ok) {
+    bool aligned = true;
+    for (int i = 0; i < n; i++) aligned = aligned && (((uintptr_t) batch.in[i]) & 3) == 0;
+    if (aligned) return launch_ntap (h->dev, p, h->ntap, batch, n, stream);
   }
   dim3 grid ((p.out.width + p.tile_w - 1) / p.tile_w, (p.out.height + p.tile_h - 1) / p.tile_h, n);
   vcs_generic_kernel <<<grid, 256, p.smem_bytes, stream>>> (h->dev, batch);
@@ -191,6 +198,10 @@ int b200_vcs_create (const b200_video_info * in, const b200_video_info * out,
       e = cudaFuncSetAttribute (light_kernel_for (p), cudaFuncAttributeMaxDynamicSharedMemorySize, p.light_smem);
       if (e != cudaSuccess) { b200_vcs_destroy (h); return cuda_fail (e, "cudaFuncSetAttribute", __FILE__, __LINE__); }
       h->variant = 2;
+    } else if (p.ntap_ok) {
+      st = prepare_ntap (p, &h->ntap);
+      if (st != B200_OK) { b200_vcs_destroy (h); return st; }
+      h->variant = 3;
     }
   }
   *handle = h;
@@ -204,7 +215,7 @@ void b200_vcs_destroy (b200_vcs * h)
     DeviceGuard g (h->device);
     cudaFree (h->d_hoff); cudaFree (h->d_voff); cudaFree (h->d_hcoef); cudaFree (h->d_vcoef);
     cudaFree (h->d_hsum); cudaFree (h->d_vsum); cudaFree (h->d_cmode);
-    cudaFree (h->l2.d_htab); cudaFree (h->l2.d_vtab);
+    cudaFree (h->l2.d_htab); cudaFree (h->l2.d_vtab); cudaFree (h->ntap.d_h); cudaFree (h->ntap.d_v);
     for (int i = 0; i < b200_vcs::kSlots; i++) {
       cudaFree (h->slot_in[i]); cudaFree (h->slot_out[i]);
       if (h->ev_in[i]) cudaEventDestroy (h->ev_in[i]);
@@ -283,7 +294,7 @@ int b200_vcs_get_plan_info (const b200_vcs * h, b200_vcs_plan_info * info)
   info->h_first = p.h_first; info->matrix_first = p.matrix_first;
   for (int i = 0; i < 5; i++) info->p[i] = p.p[i];
   info->tile_w = p.tile_w; info->tile_h = p.tile_h; info->smem_bytes = p.smem_bytes;
-  info->kernel_variant = (h->variant == 1 && p.lanczos2_ok) ? 1 : (h->variant == 2 && p.light_ok) ? 2 : 0;
+  info->kernel_variant = (h->variant == 1 && p.lanczos2_ok) ? 1 : (h->variant == 2 && p.light_ok) ? 2 : (h->variant == 3 && p.ntap_ok) ? 3 : 0;
   info->n_launches_per_convert = 1;
   return B200_OK;
 }
@@ -313,7 +324,8 @@ int b200_vcs_get_chroma_plan (const b200_vcs * h, uint8_t * mode, size_t len)
 
 int b200_vcs_set_kernel_variant (b200_vcs * h, int variant)
 {
-  if (!h || variant < 0 || variant > 2) return B200_ERR_INVALID_ARG;
+  if (!h || variant < 0 || variant > 3) return B200_ERR_INVALID_ARG;
+  if (variant == 3 && !(h->plan.ntap_ok && h->ntap.ready)) return B200_ERR_UNSUPPORTED;
   if (variant == 1 && !h->plan.lanczos2_ok) return B200_ERR_UNSUPPORTED;
   if (variant == 2 && !h->plan.light_ok) return B200_ERR_UNSUPPORTED;
   h->variant = variant;

@@ -69,6 +69,137 @@ __device__ __forceinline__ unsigned light_lerp (unsigned a, unsigned b, unsigned
   return __byte_perm (re, ro, 0x7351);
 }
 
+// ---- stage A, shared by the light and n-tap kernels ---------------------------------------
+// Work list: one entry per input line, or per PAIR of lines (2k+1, 2k+2) that share their two
+// chroma rows with swapped 3:1 weights (video_chroma_up_v2_u8) — the h up-sampling of both rows
+// and the floor average are then computed once for the two lines.
+// entry = row | chroma_mode << 16 | pair << 20; ent[cap] receives the count.  Call with the whole
+// CTA; only warp 0 works.
+__device__ __forceinline__ void vcs_unpack_worklist (const VcsDev & P, int ry0, int R, unsigned *ent, int cap)
+{
+  const int tid = threadIdx.x;
+  if (tid < 32) {
+    int count = 0;
+    for (int b0 = 0; b0 < R; b0 += 32) {
+      const int r = b0 + tid, y = ry0 + r;
+      int m = 0, mprev = 0, mnext = 0;
+      if (r < R && P.v_pairs) {
+        m = P.chroma_mode[y];
+        if (r > 0) mprev = P.chroma_mode[y - 1];
+        if (r + 1 < R) mnext = P.chroma_mode[y + 1];
+      }
+      const bool second = m == 2 && mprev == 1 && r > 0;         // handled by the entry of line y-1
+      const bool pair = m == 1 && mnext == 2;
+      const bool keep = r < R && !second;
+      const unsigned mask = __ballot_sync (0xffffffffu, keep);
+      if (keep) ent[count + __popc (mask & ((1u << tid) - 1u))] = (unsigned) r | (unsigned) m << 16 | (pair ? 1u << 20 : 0u);
+      count += __popc (mask);
+    }
+    if (tid == 0) ent[cap] = (unsigned) count;
+  }
+}
+
+// Unpack + chroma up-sample the tile's input region: a thread owns 4 consecutive pixels (columns
+// cxa + 4j ..) of one work-list entry.
+// LAYOUT 0: packed pixels {Y,U,V,-} (or {A,R,G,B} when MFIRST) at S[row * pitch + column] (pitch in words).
+// LAYOUT 1: three byte planes (Y,U,V or R,G,B) of plane_words words, rows of `pitch` words, 4 pixels per word.
+// LAYOUT 2: byte planes in groups of 4 rows, the 4 rows of a word column adjacent:
+//           word (row r, column word j, channel ch) at (((r >> 2) * 3 + ch) * pitch + j) * 4 + (r & 3).
+template <bool MFIRST, bool COSITED, int LAYOUT>
+__device__ __forceinline__ void vcs_unpack_stage (const VcsDev & P, const uint8_t *__restrict__ plane_y,
+    const uint8_t *__restrict__ plane_c, int ry0, int cxa, int ng, const unsigned *ent, int n_ent,
+    unsigned *S, int pitch, int plane_words)
+{
+  const int cw2 = ((P.iw + 1) >> 1) * 2;                         // bytes of chroma per row
+  const unsigned selU = P.u_index ? 0x7531u : 0x6420u, selV = P.u_index ? 0x6420u : 0x7531u;
+  const int nitems = n_ent * ng;
+  const unsigned magic = 0xffffffffu / (unsigned) ng + 1u;       // item / ng == umulhi (item, magic) for item < 65536, ng > 1
+  for (int item = threadIdx.x; item < nitems; item += blockDim.x) {
+    const int e = ng > 1 ? (int) __umulhi ((unsigned) item, magic) : item, j = item - e * ng;
+    const unsigned en = ent[e];
+    const int r = (int) (en & 0xffffu), m = (int) (en >> 16) & 3;
+    const bool pair = (en >> 20) != 0;
+    const int y = ry0 + r, x = cxa + 4 * j;
+    const int oth = (m == 1 ? min (y + 1, P.ih - 1) : y - 1) >> 1;
+    const uint8_t *rowc = plane_c + (unsigned) ((y >> 1) * P.stride_c + x);
+    const uint8_t *rowo = plane_c + (unsigned) ((m ? oth : (y >> 1)) * P.stride_c + x);
+    const uint8_t *rowy = plane_y + (unsigned) (y * P.stride_y + x);
+    unsigned u, v, ub = 0, vb = 0;
+    if (x + 8 <= cw2 && (COSITED || x >= 4)) {
+      const unsigned w0 = __ldg ((const unsigned *) rowc), w1 = __ldg ((const unsigned *) (rowc + 4));
+      unsigned wp = 0;
+      if (!COSITED) wp = __ldg ((const unsigned *) (rowc - 4)) >> 16;              // {U,V}[k-1] in bytes 0,1
+      u = light_hup4<COSITED> (__byte_perm (w0, w1, selU), __byte_perm (wp, 0, selU));
+      v = light_hup4<COSITED> (__byte_perm (w0, w1, selV), __byte_perm (wp, 0, selV));
+      if (m) {                                                   // FILT_3_1 / FILT_1_3 against the paired row
+        const unsigned o0 = __ldg ((const unsigned *) rowo), o1 = __ldg ((const unsigned *) (rowo + 4));
+        unsigned op = 0;
+        if (!COSITED) op = __ldg ((const unsigned *) (rowo - 4)) >> 16;
+        const unsigned uo = light_hup4<COSITED> (__byte_perm (o0, o1, selU), __byte_perm (op, 0, selU));
+        const unsigned vo = light_hup4<COSITED> (__byte_perm (o0, o1, selV), __byte_perm (op, 0, selV));
+        const unsigned fu = avg_floor4 (u, uo), fv = avg_floor4 (v, vo);
+        u = avg_ceil4 (u, fu); v = avg_ceil4 (v, fv);
+        ub = avg_ceil4 (uo, fu); vb = avg_ceil4 (vo, fv);        // the pair's second line: weights swapped
+      }
+    } else {                                                     // frame edges: scalar, clamps inside chroma_hup
+      u = v = 0;
+      const uint8_t *rc = rowc - x, *ro = rowo - x;
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        if (x + i < P.iw) {
+          const int u0 = chroma_hup (rc + P.u_index, x + i, P.iw, COSITED);
+          const int v0 = chroma_hup (rc + (P.u_index ^ 1), x + i, P.iw, COSITED);
+          int uu = u0, vv = v0;
+          if (m) {
+            const int u1 = chroma_hup (ro + P.u_index, x + i, P.iw, COSITED);
+            const int v1 = chroma_hup (ro + (P.u_index ^ 1), x + i, P.iw, COSITED);
+            uu = (3 * u0 + u1 + 2) >> 2; vv = (3 * v0 + v1 + 2) >> 2;
+            ub |= (unsigned) ((3 * u1 + u0 + 2) >> 2) << (8 * i);
+            vb |= (unsigned) ((3 * v1 + v0 + 2) >> 2) << (8 * i);
+          }
+          u |= (unsigned) uu << (8 * i);
+          v |= (unsigned) vv << (8 * i);
+        }
+      }
+    }
+#pragma unroll
+    for (int l = 0; l < 2; l++) {
+      if (l == 1) {
+        if (!pair) break;
+        u = ub; v = vb;
+      }
+      const unsigned yw = __ldg ((const unsigned *) (rowy + l * P.stride_y));
+      const int rr = r + l;
+      unsigned *d = LAYOUT == 2 ? S + ((rr >> 2) * 3 * pitch + j) * 4 + (rr & 3) : S + rr * pitch + j;
+      const int cstep = LAYOUT == 2 ? pitch * 4 : plane_words;    // distance between channels
+      if (LAYOUT != 0 && !MFIRST) {
+        d[0] = yw; d[cstep] = u; d[2 * cstep] = v;
+        continue;
+      }
+      // {Y,U,V,-} per pixel
+      const unsigned yu01 = __byte_perm (yw, u, 0x5140), yu23 = __byte_perm (yw, u, 0x7362);     // Y0 U0 Y1 U1
+      uint4 px;
+      px.x = __byte_perm (yu01, v, 0x4410);
+      px.y = __byte_perm (yu01, v, 0x5532);
+      px.z = __byte_perm (yu23, v, 0x6610);
+      px.w = __byte_perm (yu23, v, 0x7732);
+      if (MFIRST) {
+        px.x = light_matrix (px.x, P); px.y = light_matrix (px.y, P);
+        px.z = light_matrix (px.z, P); px.w = light_matrix (px.w, P);
+      }
+      if (LAYOUT != 0) {                                         // {A,R,G,B} x 4 -> R, G, B words
+        const unsigned rg01 = __byte_perm (px.x, px.y, 0x6251), rg23 = __byte_perm (px.z, px.w, 0x6251);
+        const unsigned b01 = __byte_perm (px.x, px.y, 0x0073), b23 = __byte_perm (px.z, px.w, 0x0073);
+        d[0] = __byte_perm (rg01, rg23, 0x5410);
+        d[cstep] = __byte_perm (rg01, rg23, 0x7632);
+        d[2 * cstep] = __byte_perm (b01, b23, 0x5410);
+      } else {
+        *(uint4 *) (S + rr * pitch + 4 * j) = px;
+      }
+    }
+  }
+}
+
 template <int HM, int VM, bool MFIRST, bool COSITED>
 __global__ void __launch_bounds__ (LIGHT_THREADS, 2)
 vcs_light_kernel (const VcsDev P, const LightDev G, const VcsBatch frames)
@@ -87,112 +218,17 @@ vcs_light_kernel (const VcsDev P, const LightDev G, const VcsBatch frames)
   const int cx0 = P.h.offset[ox0], cx1 = P.h.offset[ox0 + tw - 1] + P.h.span;
   const int ry0 = P.v.offset[oy0], ry1 = P.v.offset[oy0 + th - 1] + P.v.span;
   const int cxa = cx0 & ~3, R = ry1 - ry0, ng = (cx1 - cxa + 3) >> 2;
-  const int cw2 = ((P.iw + 1) >> 1) * 2;                         // bytes of chroma per row
-  const unsigned selU = P.u_index ? 0x7531u : 0x6420u, selV = P.u_index ? 0x6420u : 0x7531u;
 
   // ---------------------------------------------------------------- A: unpack + chroma up-sample
-  // Work list: one entry per input line, or per PAIR of lines (2k+1, 2k+2) that share their two
-  // chroma rows with swapped 3:1 weights (video_chroma_up_v2_u8) — the h up-sampling of both rows
-  // and the floor average are then computed once for the two lines.
   unsigned *ent = T + G.max_rows * G.tw;                         // [max_rows] entries, then the count
   unsigned *vtab = ent + G.max_rows + 1;                         // [th] vertical source row and weight of each output row
   if (tid >= 32 && tid < 32 + th) {
     const int oy = oy0 + tid - 32;
     vtab[tid - 32] = (P.v.offset[oy] - (unsigned) ry0) | (VM == 2 ? (unsigned) (int) P.v.coef[oy] << 16 : 0u);
   }
-  if (tid < 32) {
-    int count = 0;
-    for (int b0 = 0; b0 < R; b0 += 32) {
-      const int r = b0 + tid, y = ry0 + r;
-      int m = 0, mprev = 0, mnext = 0;
-      if (r < R && P.v_pairs) {
-        m = P.chroma_mode[y];
-        if (r > 0) mprev = P.chroma_mode[y - 1];
-        if (r + 1 < R) mnext = P.chroma_mode[y + 1];
-      }
-      const bool second = m == 2 && mprev == 1 && r > 0;         // handled by the entry of line y-1
-      const bool pair = m == 1 && mnext == 2;
-      const bool keep = r < R && !second;
-      const unsigned mask = __ballot_sync (0xffffffffu, keep);
-      if (keep) ent[count + __popc (mask & ((1u << tid) - 1u))] = (unsigned) r | (unsigned) m << 16 | (pair ? 1u << 20 : 0u);
-      count += __popc (mask);
-    }
-    if (tid == 0) ent[G.max_rows] = (unsigned) count;
-  }
+  vcs_unpack_worklist (P, ry0, R, ent, G.max_rows);
   __syncthreads ();
-  {
-    const int nitems = (int) ent[G.max_rows] * ng;
-    const unsigned magic = 0xffffffffu / (unsigned) ng + 1u;     // item / ng == umulhi (item, magic) for item < 65536, ng > 1
-    for (int item = tid; item < nitems; item += LIGHT_THREADS) {
-      const int e = ng > 1 ? (int) __umulhi ((unsigned) item, magic) : item, j = item - e * ng;
-      const unsigned en = ent[e];
-      const int r = (int) (en & 0xffffu), m = (int) (en >> 16) & 3;
-      const bool pair = (en >> 20) != 0;
-      const int y = ry0 + r, x = cxa + 4 * j;
-      const int oth = (m == 1 ? min (y + 1, P.ih - 1) : y - 1) >> 1;
-      const uint8_t *rowc = plane_c + (unsigned) ((y >> 1) * P.stride_c + x);
-      const uint8_t *rowo = plane_c + (unsigned) ((m ? oth : (y >> 1)) * P.stride_c + x);
-      const uint8_t *rowy = plane_y + (unsigned) (y * P.stride_y + x);
-      unsigned u, v, ub = 0, vb = 0;
-      if (x + 8 <= cw2 && (COSITED || x >= 4)) {
-        const unsigned w0 = __ldg ((const unsigned *) rowc), w1 = __ldg ((const unsigned *) (rowc + 4));
-        unsigned wp = 0;
-        if (!COSITED) wp = __ldg ((const unsigned *) (rowc - 4)) >> 16;            // {U,V}[k-1] in bytes 0,1
-        u = light_hup4<COSITED> (__byte_perm (w0, w1, selU), __byte_perm (wp, 0, selU));
-        v = light_hup4<COSITED> (__byte_perm (w0, w1, selV), __byte_perm (wp, 0, selV));
-        if (m) {                                                 // FILT_3_1 / FILT_1_3 against the paired row
-          const unsigned o0 = __ldg ((const unsigned *) rowo), o1 = __ldg ((const unsigned *) (rowo + 4));
-          unsigned op = 0;
-          if (!COSITED) op = __ldg ((const unsigned *) (rowo - 4)) >> 16;
-          const unsigned uo = light_hup4<COSITED> (__byte_perm (o0, o1, selU), __byte_perm (op, 0, selU));
-          const unsigned vo = light_hup4<COSITED> (__byte_perm (o0, o1, selV), __byte_perm (op, 0, selV));
-          const unsigned fu = avg_floor4 (u, uo), fv = avg_floor4 (v, vo);
-          u = avg_ceil4 (u, fu); v = avg_ceil4 (v, fv);
-          ub = avg_ceil4 (uo, fu); vb = avg_ceil4 (vo, fv);      // the pair's second line: weights swapped
-        }
-      } else {                                                   // frame edges: scalar, clamps inside chroma_hup
-        u = v = 0;
-        const uint8_t *rc = rowc - x, *ro = rowo - x;
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          if (x + i < P.iw) {
-            const int u0 = chroma_hup (rc + P.u_index, x + i, P.iw, COSITED);
-            const int v0 = chroma_hup (rc + (P.u_index ^ 1), x + i, P.iw, COSITED);
-            int uu = u0, vv = v0;
-            if (m) {
-              const int u1 = chroma_hup (ro + P.u_index, x + i, P.iw, COSITED);
-              const int v1 = chroma_hup (ro + (P.u_index ^ 1), x + i, P.iw, COSITED);
-              uu = (3 * u0 + u1 + 2) >> 2; vv = (3 * v0 + v1 + 2) >> 2;
-              ub |= (unsigned) ((3 * u1 + u0 + 2) >> 2) << (8 * i);
-              vb |= (unsigned) ((3 * v1 + v0 + 2) >> 2) << (8 * i);
-            }
-            u |= (unsigned) uu << (8 * i);
-            v |= (unsigned) vv << (8 * i);
-          }
-        }
-      }
-#pragma unroll
-      for (int l = 0; l < 2; l++) {
-        if (l == 1) {
-          if (!pair) break;
-          u = ub; v = vb;
-        }
-        const unsigned yw = __ldg ((const unsigned *) (rowy + l * P.stride_y));
-        // {Y,U,V,-} per pixel
-        const unsigned yu01 = __byte_perm (yw, u, 0x5140), yu23 = __byte_perm (yw, u, 0x7362);   // Y0 U0 Y1 U1
-        uint4 px;
-        px.x = __byte_perm (yu01, v, 0x4410);
-        px.y = __byte_perm (yu01, v, 0x5532);
-        px.z = __byte_perm (yu23, v, 0x6610);
-        px.w = __byte_perm (yu23, v, 0x7732);
-        if (MFIRST) {
-          px.x = light_matrix (px.x, P); px.y = light_matrix (px.y, P);
-          px.z = light_matrix (px.z, P); px.w = light_matrix (px.w, P);
-        }
-        *(uint4 *) (S + (r + l) * G.cp + 4 * j) = px;
-      }
-    }
-  }
+  vcs_unpack_stage<MFIRST, COSITED, 0> (P, plane_y, plane_c, ry0, cxa, ng, ent, (int) ent[G.max_rows], S, G.cp, 0);
   __syncthreads ();
 
   // ---------------------------------------------------------------- B: horizontal pass

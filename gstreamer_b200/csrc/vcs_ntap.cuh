@@ -1,0 +1,219 @@
+// gstreamer_b200/csrc/vcs_ntap.cuh — fused kernel for n-tap filters at ANY ratio (product code,
+// sm_100a): 4:2:0 semi-planar -> packed RGB where at least one axis runs the reference's n-tap FIR
+// (lanczos / cubic / sinc / linear-as-n-tap, video_scale_h_ntap_u8 + video_scale_v_ntap_u8) and the
+// other one too or is untouched; horizontal pass first.  The exact-2:1 8-tap case has its own
+// kernel (vcs_lanczos2.cuh); this one takes every other size, e.g. 1080p -> 720p or 4K -> 720p.
+//
+// Same arithmetic as vcs_generic_kernel stage by stage (see vcs_kernels.cuh for the citations):
+//
+//  A  shared with the light kernel (vcs_unpack_stage): byte-SIMD unpack + chroma up-sampling of
+//     the tile's input region into three byte planes, 4 pixels per word
+//  B  horizontal FIR: a thread owns one output column x 4 consecutive input lines x 3 channels.
+//     Its taps are 8-bit and packed 4 per word (host table); the source bytes start at an arbitrary
+//     column, so each tap word meets its 4 pixels through one funnel shift of two aligned words
+//     (SHF.R.W) and one IDP.4A.U8.S8 — 3 instructions per 4 taps.  (acc+32)>>6 with saturation
+//     packs the 4 lines of the column into ONE word (transposed), so that
+//  C  the vertical FIR is the same loop over words of 4 lines: funnel shift by the window's line
+//     offset, IDP.4A; then matrix (or not, when it ran first), alpha, byte order, coalesced store.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.h"
+#include "vcs_device.h"
+#include "vcs_kernels.cuh"
+#include "vcs_lanczos2.cuh"      // packed-byte helpers
+#include "vcs_light.cuh"         // stage A
+
+namespace b200 {
+
+struct NtapDev {
+  int tw, th, rows, pitch;       // tile, staged rows (multiple of 4), words per staged row
+  int ntw_h, ntw_v;              // packed tap words per output column / row
+  const int *h_packed, *v_packed;
+  int alpha_opaque;
+};
+
+constexpr int NTAP_THREADS = 256;
+
+template <int HM, int VM, bool MFIRST, bool COSITED>
+__global__ void __launch_bounds__ (NTAP_THREADS, 2)
+vcs_ntap_kernel (const VcsDev P, const NtapDev G, const VcsBatch frames)
+{
+  extern __shared__ __align__ (16) unsigned nsm[];
+  const int ngr = G.rows / 4;                                    // staged groups of 4 input lines
+  const int groups = ngr + 1 + G.ntw_v;                          // groups of the h-scaled tile (+ slack for padded taps)
+  // S: [group][channel][word column][4 lines]  — the 4 lines of one word column are one uint4
+  // T: [group][output column][channel (4)]     — one uint4 = the 3 channels' words (4 lines each)
+  uint4 *S4 = (uint4 *) nsm;
+  uint4 *T4 = S4 + ngr * 3 * G.pitch + 2;
+  int *TH = (int *) (T4 + groups * G.tw);                        // [tw][ntw_h]
+  int *TV = TH + G.tw * max (G.ntw_h, 1);                        // [th][ntw_v]
+  unsigned *vrow = (unsigned *) (TV + G.th * max (G.ntw_v, 1));  // [th] first source line of each output row
+  unsigned *ent = vrow + G.th;                                   // [rows] entries + count
+  const int tid = threadIdx.x;
+  const uint8_t *__restrict__ in = frames.in[blockIdx.z];
+  uint8_t *__restrict__ out = frames.out[blockIdx.z];
+  const uint8_t *__restrict__ plane_y = in + P.off_y;
+  const uint8_t *__restrict__ plane_c = in + P.off_c;
+
+  const int ox0 = blockIdx.x * G.tw, oy0 = blockIdx.y * G.th;
+  const int tw = min (G.tw, P.ow - ox0), th = min (G.th, P.oh - oy0);
+  const int cx0 = P.h.offset[ox0], cx1 = P.h.offset[ox0 + tw - 1] + P.h.span;
+  const int ry0 = P.v.offset[oy0], ry1 = P.v.offset[oy0 + th - 1] + P.v.span;
+  const int cxa = cx0 & ~3, R = ry1 - ry0, ng = (cx1 - cxa + 3) >> 2;
+
+  // tap words and source lines of this tile's columns and rows
+  if (HM == 3)
+    for (int i = tid; i < tw * G.ntw_h; i += NTAP_THREADS) TH[i] = __ldg (G.h_packed + (size_t) ox0 * G.ntw_h + i);
+  if (VM == 3)
+    for (int i = tid; i < th * G.ntw_v; i += NTAP_THREADS) TV[i] = __ldg (G.v_packed + (size_t) oy0 * G.ntw_v + i);
+  if (tid < th) vrow[tid] = P.v.offset[oy0 + tid] - (unsigned) ry0;
+
+  // ---------------------------------------------------------------- A: unpack + chroma up-sample
+  vcs_unpack_worklist (P, ry0, R, ent, G.rows);
+  __syncthreads ();
+  vcs_unpack_stage<MFIRST, COSITED, 2> (P, plane_y, plane_c, ry0, cxa, ng, ent, (int) ent[G.rows], (unsigned *) S4,
+      G.pitch, 0);
+  __syncthreads ();
+
+  // ---------------------------------------------------------------- B: horizontal pass
+  const int tx = tid % G.tw, ph = tid / G.tw, nph = NTAP_THREADS / G.tw;   // tw is 32, 64 or 128
+  if (tx < tw) {
+    const int base = (int) P.h.offset[ox0 + tx] - cxa;
+    const int wi = base >> 2, sh = (base & 3) * 8;
+    const int RG = (R + 3) >> 2;
+    const int *th_taps = TH + tx * G.ntw_h;
+    for (int g = ph; g < RG; g += nph) {
+      const uint4 *sp = S4 + g * 3 * G.pitch + wi;               // channel ch at sp + ch * pitch
+      uint4 o;
+      if (HM == 3) {
+        int acc[3][4];
+        uint4 lo[3];
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+          lo[ch] = sp[ch * G.pitch];
+#pragma unroll
+          for (int i = 0; i < 4; i++) acc[ch][i] = 32;
+        }
+        for (int w = 0; w < G.ntw_h; w++) {
+          const int t = th_taps[w];
+          sp++;
+#pragma unroll
+          for (int ch = 0; ch < 3; ch++) {
+            const uint4 hi = sp[ch * G.pitch];
+            acc[ch][0] = dp4a_u8s8 (__funnelshift_r (lo[ch].x, hi.x, sh), t, acc[ch][0]);
+            acc[ch][1] = dp4a_u8s8 (__funnelshift_r (lo[ch].y, hi.y, sh), t, acc[ch][1]);
+            acc[ch][2] = dp4a_u8s8 (__funnelshift_r (lo[ch].z, hi.z, sh), t, acc[ch][2]);
+            acc[ch][3] = dp4a_u8s8 (__funnelshift_r (lo[ch].w, hi.w, sh), t, acc[ch][3]);
+            lo[ch] = hi;
+          }
+        }
+        // (acc+32)>>6 saturated to u8 (video-orc.orc:2474-2481); 4 lines of the column in one word
+        o.x = pack_sat2 (acc[0][1] >> 6, acc[0][0] >> 6, pack_sat2 (acc[0][3] >> 6, acc[0][2] >> 6, 0u));
+        o.y = pack_sat2 (acc[1][1] >> 6, acc[1][0] >> 6, pack_sat2 (acc[1][3] >> 6, acc[1][2] >> 6, 0u));
+        o.z = pack_sat2 (acc[2][1] >> 6, acc[2][0] >> 6, pack_sat2 (acc[2][3] >> 6, acc[2][2] >> 6, 0u));
+      } else {
+        const unsigned s01 = (unsigned) (base & 3) | (unsigned) (4 + (base & 3)) << 4;
+        const uint4 a = sp[0], b = sp[G.pitch], c = sp[2 * G.pitch];
+        o.x = __byte_perm (__byte_perm (a.x, a.y, s01), __byte_perm (a.z, a.w, s01), 0x5410);
+        o.y = __byte_perm (__byte_perm (b.x, b.y, s01), __byte_perm (b.z, b.w, s01), 0x5410);
+        o.z = __byte_perm (__byte_perm (c.x, c.y, s01), __byte_perm (c.z, c.w, s01), 0x5410);
+      }
+      o.w = 0u;
+      T4[g * G.tw + tx] = o;
+    }
+  }
+  __syncthreads ();
+
+  // ---------------------------------------------------------------- C: vertical pass, matrix, pack
+  if (tx < tw) {
+    const int ox = ox0 + tx;
+    int ah = 255;
+    if (!G.alpha_opaque) ah = alpha_pass (255, P.h, ox);
+    uint8_t *dst = out + P.off_out + (size_t) (oy0 + ph) * P.stride_out + (size_t) ox * 4u;
+    const size_t dstep = (size_t) P.stride_out * nph;
+    for (int ty = ph; ty < th; ty += nph, dst += dstep) {
+      const int rb = (int) vrow[ty];
+      const uint4 *tp = T4 + (rb >> 2) * G.tw + tx;
+      const int sh = (rb & 3) * 8;
+      int c0, c1, c2;
+      if (VM == 3) {
+        c0 = c1 = c2 = 32;
+        uint4 lo = *tp;
+        const int *tv_taps = TV + ty * G.ntw_v;
+        for (int w = 0; w < G.ntw_v; w++) {
+          const int t = tv_taps[w];
+          tp += G.tw;
+          const uint4 hi = *tp;
+          c0 = dp4a_u8s8 (__funnelshift_r (lo.x, hi.x, sh), t, c0);
+          c1 = dp4a_u8s8 (__funnelshift_r (lo.y, hi.y, sh), t, c1);
+          c2 = dp4a_u8s8 (__funnelshift_r (lo.z, hi.z, sh), t, c2);
+          lo = hi;
+        }
+        c0 >>= 6; c1 >>= 6; c2 >>= 6;
+      } else {
+        const uint4 w = *tp;
+        const unsigned sel = 0x4440u | (unsigned) (rb & 3);
+        c0 = (int) __byte_perm (w.x, 0, sel); c1 = (int) __byte_perm (w.y, 0, sel); c2 = (int) __byte_perm (w.z, 0, sel);
+      }
+      int al = 255;
+      if (!G.alpha_opaque) al = alpha_pass (ah, P.v, oy0 + ty);
+      unsigned argb;
+      if (MFIRST) {
+        argb = pack_sat2 (c0, al, pack_sat2 (c2, c1, 0u));
+      } else {
+        argb = light_matrix (pack_sat2 (c1, c0, pack_sat2 (0, c2, 0u)), P);
+        if (!G.alpha_opaque) argb = (argb & 0xffffff00u) | (unsigned) al;
+      }
+      *(unsigned *) dst = __byte_perm (argb, 0, P.sel);
+    }
+  }
+}
+
+typedef void (*ntap_kernel_fn) (const VcsDev, const NtapDev, const VcsBatch);
+
+inline ntap_kernel_fn ntap_kernel_for (const VcsPlan & p)
+{
+#define NTAP_PICK(HM, VM)                                                                             \
+  if (p.h.mode == HM && p.v.mode == VM) {                                                             \
+    if (p.matrix_first) return p.h_cosited ? vcs_ntap_kernel<HM, VM, true, true> : vcs_ntap_kernel<HM, VM, true, false>;     \
+    return p.h_cosited ? vcs_ntap_kernel<HM, VM, false, true> : vcs_ntap_kernel<HM, VM, false, false>;                       \
+  }
+  NTAP_PICK (3, 3) NTAP_PICK (3, 1) NTAP_PICK (1, 3)
+#undef NTAP_PICK
+  return nullptr;
+}
+
+struct NtapState {
+  int *d_h = nullptr, *d_v = nullptr;
+  bool ready = false;
+};
+
+inline int prepare_ntap (const VcsPlan & p, NtapState * st)
+{
+  int s;
+  if ((s = upload (&st->d_h, p.h_packed.data (), p.h_packed.size ())) != B200_OK) return s;
+  if ((s = upload (&st->d_v, p.v_packed.data (), p.v_packed.size ())) != B200_OK) return s;
+  B200_CUDA_TRY (cudaFuncSetAttribute (ntap_kernel_for (p), cudaFuncAttributeMaxDynamicSharedMemorySize, p.ntap_smem));
+  st->ready = true;
+  return B200_OK;
+}
+
+inline int launch_ntap (const VcsDev & dev, const VcsPlan & p, const NtapState & st, const VcsBatch & batch, int n,
+    cudaStream_t stream)
+{
+  ntap_kernel_fn fn = ntap_kernel_for (p);
+  if (!fn) return B200_ERR_STATE;
+  NtapDev g;
+  g.tw = p.ntap_tw; g.th = p.ntap_th; g.rows = p.ntap_rows; g.pitch = p.ntap_pitch;
+  g.ntw_h = p.ntw_h; g.ntw_v = p.ntw_v; g.h_packed = st.d_h; g.v_packed = st.d_v;
+  g.alpha_opaque = p.ntap_alpha_opaque ? 1 : 0;
+  dim3 grid ((p.out.width + g.tw - 1) / g.tw, (p.out.height + g.th - 1) / g.th, n);
+  fn <<<grid, NTAP_THREADS, p.ntap_smem, stream>>> (dev, g, batch);
+  B200_CUDA_TRY (cudaGetLastError ());
+  return B200_OK;
+}
+
+}  // namespace b200

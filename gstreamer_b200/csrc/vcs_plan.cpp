@@ -341,6 +341,74 @@ void light_geometry (VcsPlan * p)
   }
 }
 
+// 4 signed 8-bit taps per word, zero padded to a whole number of words; false when a tap does not
+// fit or the 16-bit accumulator of the reference could wrap (the kernel accumulates in 32 bits)
+bool pack_taps_s8 (const AxisPlan & a, int *ntw, std::vector<int32_t> * out)
+{
+  *ntw = 0; out->clear ();
+  if (a.mode != PASS_NTAP) return true;
+  const int n = a.n_taps, w = (n + 3) / 4;
+  out->assign ((size_t) a.out_size * w, 0);
+  for (int j = 0; j < a.out_size; j++) {
+    int mag = 0;
+    for (int k = 0; k < n; k++) {
+      const int t = a.coef[(size_t) j * n + k];
+      if (t < -128 || t > 127) return false;
+      mag += abs (t);
+      (*out)[(size_t) j * w + k / 4] |= (int32_t) ((uint32_t) (uint8_t) (int8_t) t << (8 * (k & 3)));
+    }
+    if (255 * mag + 32 > 32767) return false;
+  }
+  *ntw = w;
+  return true;
+}
+
+// Geometry of the n-tap kernel (vcs_ntap.cuh)
+void ntap_geometry (VcsPlan * p)
+{
+  p->ntap_ok = false;
+  const bool hn = p->h.mode == PASS_NTAP, vn = p->v.mode == PASS_NTAP;
+  if (!(hn || vn) || p->h.mode == PASS_2TAP || p->v.mode == PASS_2TAP || !p->h_first) return;
+  const int iw = p->in.width;
+  if ((p->in.stride[0] & 3) || (p->in.stride[1] & 3) || (p->in.offset[0] & 3) || (p->in.offset[1] & 3)) return;
+  if (p->in.stride[0] < ((iw + 3) & ~3) || p->in.stride[1] < ((iw + 3) & ~3)) return;
+  if ((int64_t) p->in.stride[0] * p->in.height >= (1ll << 31) || (int64_t) p->in.stride[1] * p->in.height >= (1ll << 31))
+    return;
+  if (!pack_taps_s8 (p->h, &p->ntw_h, &p->h_packed) || !pack_taps_s8 (p->v, &p->ntw_v, &p->v_packed)) return;
+  p->ntap_alpha_opaque = true;
+  if (hn) for (int16_t s : p->h.sum) if (s < 64 || s > 128) p->ntap_alpha_opaque = false;
+  if (vn) for (int16_t s : p->v.sum) if (s < 64 || s > 128) p->ntap_alpha_opaque = false;
+  const int ow = p->out.width, oh = p->out.height;
+  static const int shapes[][2] = {{128, 16}, {128, 8}, {64, 8}, {64, 4}, {32, 4}, {32, 2}, {32, 1}};
+  for (auto & sh : shapes) {
+    const int tw = sh[0], th = sh[1];
+    int max_rows = 0, max_cols = 0;
+    for (int y0 = 0; y0 < oh; y0 += th) {
+      int y1 = std::min (y0 + th, oh) - 1;
+      max_rows = std::max (max_rows, (int) (p->v.offset[y1] + p->v.span - p->v.offset[y0]));
+    }
+    for (int x0 = 0; x0 < ow; x0 += tw) {
+      int x1 = std::min (x0 + tw, ow) - 1;
+      int c0 = (int) p->h.offset[x0] & ~3, c1 = ((int) (p->h.offset[x1] + p->h.span) + 3) & ~3;
+      max_cols = std::max (max_cols, c1 - c0);
+    }
+    // rows: whole groups of 4; pitch (word columns per line): the zero-padded horizontal taps may
+    // read up to ntw_h + 1 words past the window start; the h-scaled tile keeps 1 + ntw_v groups of
+    // slack for the zero-padded vertical taps
+    const int rows = ((max_rows + 3) & ~3), ngr = rows / 4, groups = ngr + 1 + p->ntw_v;
+    const int pitch = max_cols / 4 + 2 + p->ntw_h;
+    const size_t s_words = ((size_t) ngr * 3 * pitch + 2) * 4;
+    const size_t t_words = (size_t) groups * tw * 4;
+    const size_t tap_words = (size_t) tw * std::max (p->ntw_h, 1) + (size_t) th * std::max (p->ntw_v, 1) + th;
+    const size_t total = (s_words + t_words + tap_words + rows + 8) * 4;
+    if (total <= 100 * 1024) {
+      p->ntap_ok = true; p->ntap_tw = tw; p->ntap_th = th; p->ntap_rows = rows; p->ntap_pitch = pitch;
+      p->ntap_smem = (int) total;
+      return;
+    }
+  }
+}
+
 }  // namespace
 
 int build_vcs_plan (const b200_video_info * in, const b200_video_info * out,
@@ -385,6 +453,7 @@ int build_vcs_plan (const b200_video_info * in, const b200_video_info * out,
   chroma_pairing (p);
   tile_geometry (p);
   light_geometry (p);
+  ntap_geometry (p);
 
   // the specialised kernel covers exactly the headline shape class: even 2:1 in both
   // directions with the 8-tap lanczos the reference derives for it

@@ -49,6 +49,13 @@ struct VcsPlan {
   // specialised 2:1 lanczos kernel eligibility
   bool lanczos2_ok = false;
 
+  // n-tap kernel (vcs_ntap.cuh): dp4a FIRs on planar tiles, any ratio, horizontal first
+  bool ntap_ok = false;
+  int ntap_tw = 128, ntap_th = 16, ntap_rows = 0, ntap_pitch = 0, ntap_smem = 0;   // rows: multiple of 4; pitch in words
+  int ntw_h = 0, ntw_v = 0;              // packed tap words per output (0 for a copy axis)
+  std::vector<int32_t> h_packed, v_packed;
+  bool ntap_alpha_opaque = true;
+
   // "light" kernel (both axes copy or 2-tap, horizontal first): tile geometry
   bool light_ok = false;
   int light_tw = 128, light_th = 16, light_rows = 0, light_cp = 0, light_smem = 0;
