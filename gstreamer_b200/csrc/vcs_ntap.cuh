@@ -37,7 +37,8 @@ struct NtapDev {
 
 constexpr int NTAP_THREADS = 256;
 
-template <int HM, int VM, bool MFIRST, bool COSITED>
+// NTW > 0: both n-tap axes use exactly NTW packed tap words (straight-line FIRs); NTW == 0: run-time loops
+template <int HM, int VM, bool MFIRST, bool COSITED, int NTW>
 __global__ void __launch_bounds__ (NTAP_THREADS, 2)
 vcs_ntap_kernel (const VcsDev P, const NtapDev G, const VcsBatch frames)
 {
@@ -97,19 +98,27 @@ vcs_ntap_kernel (const VcsDev P, const NtapDev G, const VcsBatch frames)
 #pragma unroll
           for (int i = 0; i < 4; i++) acc[ch][i] = 32;
         }
-        for (int w = 0; w < G.ntw_h; w++) {
-          const int t = th_taps[w];
-          sp++;
+#define NTAP_H_STEP(W)                                                                          \
+        do {                                                                                   \
+          const int t = th_taps[W];                                                            \
+          sp++;                                                                                \
+          _Pragma ("unroll") for (int ch = 0; ch < 3; ch++) {                                  \
+            const uint4 hi = sp[ch * G.pitch];                                                 \
+            acc[ch][0] = dp4a_u8s8 (__funnelshift_r (lo[ch].x, hi.x, sh), t, acc[ch][0]);      \
+            acc[ch][1] = dp4a_u8s8 (__funnelshift_r (lo[ch].y, hi.y, sh), t, acc[ch][1]);      \
+            acc[ch][2] = dp4a_u8s8 (__funnelshift_r (lo[ch].z, hi.z, sh), t, acc[ch][2]);      \
+            acc[ch][3] = dp4a_u8s8 (__funnelshift_r (lo[ch].w, hi.w, sh), t, acc[ch][3]);      \
+            lo[ch] = hi;                                                                       \
+          }                                                                                    \
+        } while (0)
+        if (NTW > 0) {
 #pragma unroll
-          for (int ch = 0; ch < 3; ch++) {
-            const uint4 hi = sp[ch * G.pitch];
-            acc[ch][0] = dp4a_u8s8 (__funnelshift_r (lo[ch].x, hi.x, sh), t, acc[ch][0]);
-            acc[ch][1] = dp4a_u8s8 (__funnelshift_r (lo[ch].y, hi.y, sh), t, acc[ch][1]);
-            acc[ch][2] = dp4a_u8s8 (__funnelshift_r (lo[ch].z, hi.z, sh), t, acc[ch][2]);
-            acc[ch][3] = dp4a_u8s8 (__funnelshift_r (lo[ch].w, hi.w, sh), t, acc[ch][3]);
-            lo[ch] = hi;
-          }
+          for (int w = 0; w < NTW; w++) NTAP_H_STEP (w);
+        } else {
+#pragma unroll 1
+          for (int w = 0; w < G.ntw_h; w++) NTAP_H_STEP (w);
         }
+#undef NTAP_H_STEP
         // (acc+32)>>6 saturated to u8 (video-orc.orc:2474-2481); 4 lines of the column in one word
         o.x = pack_sat2 (acc[0][1] >> 6, acc[0][0] >> 6, pack_sat2 (acc[0][3] >> 6, acc[0][2] >> 6, 0u));
         o.y = pack_sat2 (acc[1][1] >> 6, acc[1][0] >> 6, pack_sat2 (acc[1][3] >> 6, acc[1][2] >> 6, 0u));
@@ -143,15 +152,24 @@ vcs_ntap_kernel (const VcsDev P, const NtapDev G, const VcsBatch frames)
         c0 = c1 = c2 = 32;
         uint4 lo = *tp;
         const int *tv_taps = TV + ty * G.ntw_v;
-        for (int w = 0; w < G.ntw_v; w++) {
-          const int t = tv_taps[w];
-          tp += G.tw;
-          const uint4 hi = *tp;
-          c0 = dp4a_u8s8 (__funnelshift_r (lo.x, hi.x, sh), t, c0);
-          c1 = dp4a_u8s8 (__funnelshift_r (lo.y, hi.y, sh), t, c1);
-          c2 = dp4a_u8s8 (__funnelshift_r (lo.z, hi.z, sh), t, c2);
-          lo = hi;
+#define NTAP_V_STEP(W)                                                                          \
+        do {                                                                                   \
+          const int t = tv_taps[W];                                                            \
+          tp += G.tw;                                                                          \
+          const uint4 hi = *tp;                                                                \
+          c0 = dp4a_u8s8 (__funnelshift_r (lo.x, hi.x, sh), t, c0);                            \
+          c1 = dp4a_u8s8 (__funnelshift_r (lo.y, hi.y, sh), t, c1);                            \
+          c2 = dp4a_u8s8 (__funnelshift_r (lo.z, hi.z, sh), t, c2);                            \
+          lo = hi;                                                                             \
+        } while (0)
+        if (NTW > 0) {
+#pragma unroll
+          for (int w = 0; w < NTW; w++) NTAP_V_STEP (w);
+        } else {
+#pragma unroll 1
+          for (int w = 0; w < G.ntw_v; w++) NTAP_V_STEP (w);
         }
+#undef NTAP_V_STEP
         c0 >>= 6; c1 >>= 6; c2 >>= 6;
       } else {
         const uint4 w = *tp;
@@ -174,15 +192,31 @@ vcs_ntap_kernel (const VcsDev P, const NtapDev G, const VcsBatch frames)
 
 typedef void (*ntap_kernel_fn) (const VcsDev, const NtapDev, const VcsBatch);
 
+template <int HM, int VM, int NTW>
+inline ntap_kernel_fn ntap_kernel_pick (const VcsPlan & p)
+{
+  if (p.matrix_first) return p.h_cosited ? vcs_ntap_kernel<HM, VM, true, true, NTW> : vcs_ntap_kernel<HM, VM, true, false, NTW>;
+  return p.h_cosited ? vcs_ntap_kernel<HM, VM, false, true, NTW> : vcs_ntap_kernel<HM, VM, false, false, NTW>;
+}
+
+template <int HM, int VM>
+inline ntap_kernel_fn ntap_kernel_pick_ntw (const VcsPlan & p)
+{
+  int ntw = HM == 3 && VM == 3 ? (p.ntw_h == p.ntw_v ? p.ntw_h : 0) : (HM == 3 ? p.ntw_h : p.ntw_v);
+  switch (ntw) {
+    case 1: return ntap_kernel_pick<HM, VM, 1> (p);
+    case 2: return ntap_kernel_pick<HM, VM, 2> (p);
+    case 3: return ntap_kernel_pick<HM, VM, 3> (p);
+    case 4: return ntap_kernel_pick<HM, VM, 4> (p);
+    default: return ntap_kernel_pick<HM, VM, 0> (p);
+  }
+}
+
 inline ntap_kernel_fn ntap_kernel_for (const VcsPlan & p)
 {
-#define NTAP_PICK(HM, VM)                                                                             \
-  if (p.h.mode == HM && p.v.mode == VM) {                                                             \
-    if (p.matrix_first) return p.h_cosited ? vcs_ntap_kernel<HM, VM, true, true> : vcs_ntap_kernel<HM, VM, true, false>;     \
-    return p.h_cosited ? vcs_ntap_kernel<HM, VM, false, true> : vcs_ntap_kernel<HM, VM, false, false>;                       \
-  }
-  NTAP_PICK (3, 3) NTAP_PICK (3, 1) NTAP_PICK (1, 3)
-#undef NTAP_PICK
+  if (p.h.mode == 3 && p.v.mode == 3) return ntap_kernel_pick_ntw<3, 3> (p);
+  if (p.h.mode == 3 && p.v.mode == 1) return ntap_kernel_pick_ntw<3, 1> (p);
+  if (p.h.mode == 1 && p.v.mode == 3) return ntap_kernel_pick_ntw<1, 3> (p);
   return nullptr;
 }
 

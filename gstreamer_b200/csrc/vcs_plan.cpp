@@ -379,9 +379,14 @@ void ntap_geometry (VcsPlan * p)
   if (hn) for (int16_t s : p->h.sum) if (s < 64 || s > 128) p->ntap_alpha_opaque = false;
   if (vn) for (int16_t s : p->v.sum) if (s < 64 || s > 128) p->ntap_alpha_opaque = false;
   const int ow = p->out.width, oh = p->out.height;
-  static const int shapes[][2] = {{128, 16}, {128, 8}, {64, 8}, {64, 4}, {32, 4}, {32, 2}, {32, 1}};
+  // tile shape: the one that stages the fewest input pixels per output pixel (filter halos shrink
+  // with the tile) among those whose shared memory lets at least two CTAs share an SM
+  static const int shapes[][2] = {{128, 32}, {128, 16}, {64, 32}, {128, 8}, {64, 16}, {32, 32}, {64, 8}, {32, 16},
+                                  {64, 4}, {32, 8}, {32, 4}, {32, 2}, {32, 1}};
+  double best = 0;
   for (auto & sh : shapes) {
     const int tw = sh[0], th = sh[1];
+    if (th > 16 && oh < 2 * th) continue;
     int max_rows = 0, max_cols = 0;
     for (int y0 = 0; y0 < oh; y0 += th) {
       int y1 = std::min (y0 + th, oh) - 1;
@@ -401,10 +406,14 @@ void ntap_geometry (VcsPlan * p)
     const size_t t_words = (size_t) groups * tw * 4;
     const size_t tap_words = (size_t) tw * std::max (p->ntw_h, 1) + (size_t) th * std::max (p->ntw_v, 1) + th;
     const size_t total = (s_words + t_words + tap_words + rows + 8) * 4;
-    if (total <= 100 * 1024) {
+    if (total > 100 * 1024) continue;
+    // staged input pixels + h-scaled pixels per output pixel; small tiles pay extra per-tile overhead
+    const double cost = ((double) rows * max_cols + (double) rows * tw) / ((double) std::min (tw, ow) * std::min (th, oh))
+        + 64.0 / th + 256.0 / tw;
+    if (!p->ntap_ok || cost < best) {
+      best = cost;
       p->ntap_ok = true; p->ntap_tw = tw; p->ntap_th = th; p->ntap_rows = rows; p->ntap_pitch = pitch;
       p->ntap_smem = (int) total;
-      return;
     }
   }
 }
