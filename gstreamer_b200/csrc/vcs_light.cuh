@@ -114,88 +114,128 @@ __device__ __forceinline__ void vcs_unpack_stage (const VcsDev & P, const uint8_
   const unsigned selU = P.u_index ? 0x7531u : 0x6420u, selV = P.u_index ? 0x6420u : 0x7531u;
   const int nitems = n_ent * ng;
   const unsigned magic = 0xffffffffu / (unsigned) ng + 1u;       // item / ng == umulhi (item, magic) for item < 65536, ng > 1
-  for (int item = threadIdx.x; item < nitems; item += blockDim.x) {
-    const int e = ng > 1 ? (int) __umulhi ((unsigned) item, magic) : item, j = item - e * ng;
+
+  struct Item {                                                  // one work item: 4 pixels of a line or of a line pair
+    int r, m, j, x;
+    bool pair, fast;
+    const uint8_t *rowc, *rowo, *rowy;
+  };
+  struct Raw { unsigned w0, w1, wp, o0, o1, op, y0, y1; };       // everything the fast path reads from HBM
+
+  auto decode = [&] (int item) {
+    Item it;
+    const int e = ng > 1 ? (int) __umulhi ((unsigned) item, magic) : item;
+    it.j = item - e * ng;
     const unsigned en = ent[e];
-    const int r = (int) (en & 0xffffu), m = (int) (en >> 16) & 3;
-    const bool pair = (en >> 20) != 0;
-    const int y = ry0 + r, x = cxa + 4 * j;
-    const int oth = (m == 1 ? min (y + 1, P.ih - 1) : y - 1) >> 1;
-    const uint8_t *rowc = plane_c + (unsigned) ((y >> 1) * P.stride_c + x);
-    const uint8_t *rowo = plane_c + (unsigned) ((m ? oth : (y >> 1)) * P.stride_c + x);
-    const uint8_t *rowy = plane_y + (unsigned) (y * P.stride_y + x);
-    unsigned u, v, ub = 0, vb = 0;
-    if (x + 8 <= cw2 && (COSITED || x >= 4)) {
-      const unsigned w0 = __ldg ((const unsigned *) rowc), w1 = __ldg ((const unsigned *) (rowc + 4));
-      unsigned wp = 0;
-      if (!COSITED) wp = __ldg ((const unsigned *) (rowc - 4)) >> 16;              // {U,V}[k-1] in bytes 0,1
-      u = light_hup4<COSITED> (__byte_perm (w0, w1, selU), __byte_perm (wp, 0, selU));
-      v = light_hup4<COSITED> (__byte_perm (w0, w1, selV), __byte_perm (wp, 0, selV));
-      if (m) {                                                   // FILT_3_1 / FILT_1_3 against the paired row
-        const unsigned o0 = __ldg ((const unsigned *) rowo), o1 = __ldg ((const unsigned *) (rowo + 4));
-        unsigned op = 0;
-        if (!COSITED) op = __ldg ((const unsigned *) (rowo - 4)) >> 16;
-        const unsigned uo = light_hup4<COSITED> (__byte_perm (o0, o1, selU), __byte_perm (op, 0, selU));
-        const unsigned vo = light_hup4<COSITED> (__byte_perm (o0, o1, selV), __byte_perm (op, 0, selV));
-        const unsigned fu = avg_floor4 (u, uo), fv = avg_floor4 (v, vo);
-        u = avg_ceil4 (u, fu); v = avg_ceil4 (v, fv);
-        ub = avg_ceil4 (uo, fu); vb = avg_ceil4 (vo, fv);        // the pair's second line: weights swapped
-      }
-    } else {                                                     // frame edges: scalar, clamps inside chroma_hup
-      u = v = 0;
-      const uint8_t *rc = rowc - x, *ro = rowo - x;
+    it.r = (int) (en & 0xffffu); it.m = (int) (en >> 16) & 3; it.pair = (en >> 20) != 0;
+    const int y = ry0 + it.r;
+    it.x = cxa + 4 * it.j;
+    const int oth = (it.m == 1 ? min (y + 1, P.ih - 1) : y - 1) >> 1;
+    it.rowc = plane_c + (unsigned) ((y >> 1) * P.stride_c + it.x);
+    it.rowo = plane_c + (unsigned) ((it.m ? oth : (y >> 1)) * P.stride_c + it.x);
+    it.rowy = plane_y + (unsigned) (y * P.stride_y + it.x);
+    it.fast = it.x + 8 <= cw2 && (COSITED || it.x >= 4);
+    return it;
+  };
+  auto load_raw = [&] (const Item & it) {                        // loads only: issued back to back for two items
+    Raw q;
+    q.w0 = __ldg ((const unsigned *) it.rowc); q.w1 = __ldg ((const unsigned *) (it.rowc + 4));
+    q.o0 = __ldg ((const unsigned *) it.rowo); q.o1 = __ldg ((const unsigned *) (it.rowo + 4));
+    q.wp = q.op = 0;
+    if (!COSITED) {
+      q.wp = __ldg ((const unsigned *) (it.rowc - 4)); q.op = __ldg ((const unsigned *) (it.rowo - 4));
+    }
+    q.y0 = __ldg ((const unsigned *) it.rowy);
+    q.y1 = it.pair ? __ldg ((const unsigned *) (it.rowy + P.stride_y)) : 0u;
+    return q;
+  };
+  auto store_line = [&] (int rr, int j, unsigned yw, unsigned u, unsigned v) {
+    unsigned *d = LAYOUT == 2 ? S + ((rr >> 2) * 3 * pitch + j) * 4 + (rr & 3) : S + rr * pitch + j;
+    const int cstep = LAYOUT == 2 ? pitch * 4 : plane_words;      // distance between channels
+    if (LAYOUT != 0 && !MFIRST) {
+      d[0] = yw; d[cstep] = u; d[2 * cstep] = v;
+      return;
+    }
+    // {Y,U,V,-} per pixel
+    const unsigned yu01 = __byte_perm (yw, u, 0x5140), yu23 = __byte_perm (yw, u, 0x7362);       // Y0 U0 Y1 U1
+    uint4 px;
+    px.x = __byte_perm (yu01, v, 0x4410);
+    px.y = __byte_perm (yu01, v, 0x5532);
+    px.z = __byte_perm (yu23, v, 0x6610);
+    px.w = __byte_perm (yu23, v, 0x7732);
+    if (MFIRST) {
+      px.x = light_matrix (px.x, P); px.y = light_matrix (px.y, P);
+      px.z = light_matrix (px.z, P); px.w = light_matrix (px.w, P);
+    }
+    if (LAYOUT != 0) {                                           // {A,R,G,B} x 4 -> R, G, B words
+      const unsigned rg01 = __byte_perm (px.x, px.y, 0x6251), rg23 = __byte_perm (px.z, px.w, 0x6251);
+      const unsigned b01 = __byte_perm (px.x, px.y, 0x0073), b23 = __byte_perm (px.z, px.w, 0x0073);
+      d[0] = __byte_perm (rg01, rg23, 0x5410);
+      d[cstep] = __byte_perm (rg01, rg23, 0x7632);
+      d[2 * cstep] = __byte_perm (b01, b23, 0x5410);
+    } else {
+      *(uint4 *) (S + rr * pitch + 4 * j) = px;
+    }
+  };
+  auto finish_fast = [&] (const Item & it, const Raw & q) {
+    const unsigned wp = q.wp >> 16, op = q.op >> 16;             // {U,V}[k-1] in bytes 0,1
+    unsigned u = light_hup4<COSITED> (__byte_perm (q.w0, q.w1, selU), __byte_perm (wp, 0, selU));
+    unsigned v = light_hup4<COSITED> (__byte_perm (q.w0, q.w1, selV), __byte_perm (wp, 0, selV));
+    unsigned ub = 0, vb = 0;
+    if (it.m) {                                                  // FILT_3_1 / FILT_1_3 against the paired row
+      const unsigned uo = light_hup4<COSITED> (__byte_perm (q.o0, q.o1, selU), __byte_perm (op, 0, selU));
+      const unsigned vo = light_hup4<COSITED> (__byte_perm (q.o0, q.o1, selV), __byte_perm (op, 0, selV));
+      const unsigned fu = avg_floor4 (u, uo), fv = avg_floor4 (v, vo);
+      u = avg_ceil4 (u, fu); v = avg_ceil4 (v, fv);
+      ub = avg_ceil4 (uo, fu); vb = avg_ceil4 (vo, fv);          // the pair's second line: weights swapped
+    }
+    store_line (it.r, it.j, q.y0, u, v);
+    if (it.pair) store_line (it.r + 1, it.j, q.y1, ub, vb);
+  };
+  auto slow = [&] (const Item & it) {                            // frame edges: scalar, clamps inside chroma_hup
+    unsigned u = 0, v = 0, ub = 0, vb = 0;
+    const uint8_t *rc = it.rowc - it.x, *ro = it.rowo - it.x;
 #pragma unroll
-      for (int i = 0; i < 4; i++) {
-        if (x + i < P.iw) {
-          const int u0 = chroma_hup (rc + P.u_index, x + i, P.iw, COSITED);
-          const int v0 = chroma_hup (rc + (P.u_index ^ 1), x + i, P.iw, COSITED);
-          int uu = u0, vv = v0;
-          if (m) {
-            const int u1 = chroma_hup (ro + P.u_index, x + i, P.iw, COSITED);
-            const int v1 = chroma_hup (ro + (P.u_index ^ 1), x + i, P.iw, COSITED);
-            uu = (3 * u0 + u1 + 2) >> 2; vv = (3 * v0 + v1 + 2) >> 2;
-            ub |= (unsigned) ((3 * u1 + u0 + 2) >> 2) << (8 * i);
-            vb |= (unsigned) ((3 * v1 + v0 + 2) >> 2) << (8 * i);
-          }
-          u |= (unsigned) uu << (8 * i);
-          v |= (unsigned) vv << (8 * i);
+    for (int i = 0; i < 4; i++) {
+      if (it.x + i < P.iw) {
+        const int u0 = chroma_hup (rc + P.u_index, it.x + i, P.iw, COSITED);
+        const int v0 = chroma_hup (rc + (P.u_index ^ 1), it.x + i, P.iw, COSITED);
+        int uu = u0, vv = v0;
+        if (it.m) {
+          const int u1 = chroma_hup (ro + P.u_index, it.x + i, P.iw, COSITED);
+          const int v1 = chroma_hup (ro + (P.u_index ^ 1), it.x + i, P.iw, COSITED);
+          uu = (3 * u0 + u1 + 2) >> 2; vv = (3 * v0 + v1 + 2) >> 2;
+          ub |= (unsigned) ((3 * u1 + u0 + 2) >> 2) << (8 * i);
+          vb |= (unsigned) ((3 * v1 + v0 + 2) >> 2) << (8 * i);
         }
+        u |= (unsigned) uu << (8 * i);
+        v |= (unsigned) vv << (8 * i);
       }
     }
-#pragma unroll
-    for (int l = 0; l < 2; l++) {
-      if (l == 1) {
-        if (!pair) break;
-        u = ub; v = vb;
-      }
-      const unsigned yw = __ldg ((const unsigned *) (rowy + l * P.stride_y));
-      const int rr = r + l;
-      unsigned *d = LAYOUT == 2 ? S + ((rr >> 2) * 3 * pitch + j) * 4 + (rr & 3) : S + rr * pitch + j;
-      const int cstep = LAYOUT == 2 ? pitch * 4 : plane_words;    // distance between channels
-      if (LAYOUT != 0 && !MFIRST) {
-        d[0] = yw; d[cstep] = u; d[2 * cstep] = v;
-        continue;
-      }
-      // {Y,U,V,-} per pixel
-      const unsigned yu01 = __byte_perm (yw, u, 0x5140), yu23 = __byte_perm (yw, u, 0x7362);     // Y0 U0 Y1 U1
-      uint4 px;
-      px.x = __byte_perm (yu01, v, 0x4410);
-      px.y = __byte_perm (yu01, v, 0x5532);
-      px.z = __byte_perm (yu23, v, 0x6610);
-      px.w = __byte_perm (yu23, v, 0x7732);
-      if (MFIRST) {
-        px.x = light_matrix (px.x, P); px.y = light_matrix (px.y, P);
-        px.z = light_matrix (px.z, P); px.w = light_matrix (px.w, P);
-      }
-      if (LAYOUT != 0) {                                         // {A,R,G,B} x 4 -> R, G, B words
-        const unsigned rg01 = __byte_perm (px.x, px.y, 0x6251), rg23 = __byte_perm (px.z, px.w, 0x6251);
-        const unsigned b01 = __byte_perm (px.x, px.y, 0x0073), b23 = __byte_perm (px.z, px.w, 0x0073);
-        d[0] = __byte_perm (rg01, rg23, 0x5410);
-        d[cstep] = __byte_perm (rg01, rg23, 0x7632);
-        d[2 * cstep] = __byte_perm (b01, b23, 0x5410);
+    store_line (it.r, it.j, __ldg ((const unsigned *) it.rowy), u, v);
+    if (it.pair) store_line (it.r + 1, it.j, __ldg ((const unsigned *) (it.rowy + P.stride_y)), ub, vb);
+  };
+
+  // two items per trip: when both take the fast path all their loads are in flight before the first
+  // byte-SIMD instruction needs one (the stage is latency bound otherwise)
+  // (not when the matrix runs here: its registers cost more occupancy than the overlap returns)
+  constexpr bool DUAL = !MFIRST;
+  const int stride = (int) blockDim.x;
+  for (int item = threadIdx.x; item < nitems; item += (DUAL ? 2 : 1) * stride) {
+    const Item a = decode (item);
+    const bool has_b = DUAL && item + stride < nitems;
+    if (has_b) {
+      const Item b = decode (item + stride);
+      if (a.fast && b.fast) {
+        const Raw qa = load_raw (a), qb = load_raw (b);
+        finish_fast (a, qa);
+        finish_fast (b, qb);
       } else {
-        *(uint4 *) (S + rr * pitch + 4 * j) = px;
+        if (a.fast) finish_fast (a, load_raw (a)); else slow (a);
+        if (b.fast) finish_fast (b, load_raw (b)); else slow (b);
       }
+    } else {
+      if (a.fast) finish_fast (a, load_raw (a)); else slow (a);
     }
   }
 }
