@@ -31,6 +31,8 @@ namespace b200 {
 
 struct LightDev {
   int tw, th, max_rows, cp;      // tile size, shared-memory rows, words per staged input row
+  int t_words;                   // words of the intermediate tile (max_rows x tw, or th x cp when vertical runs first)
+  int h_first;
 };
 
 constexpr int LIGHT_THREADS = 256;
@@ -260,7 +262,7 @@ vcs_light_kernel (const VcsDev P, const LightDev G, const VcsBatch frames)
   const int cxa = cx0 & ~3, R = ry1 - ry0, ng = (cx1 - cxa + 3) >> 2;
 
   // ---------------------------------------------------------------- A: unpack + chroma up-sample
-  unsigned *ent = T + G.max_rows * G.tw;                         // [max_rows] entries, then the count
+  unsigned *ent = T + G.t_words;                                 // [max_rows] entries, then the count
   unsigned *vtab = ent + G.max_rows + 1;                         // [th] vertical source row and weight of each output row
   if (tid >= 32 && tid < 32 + th) {
     const int oy = oy0 + tid - 32;
@@ -271,37 +273,68 @@ vcs_light_kernel (const VcsDev P, const LightDev G, const VcsBatch frames)
   vcs_unpack_stage<MFIRST, COSITED, 0> (P, plane_y, plane_c, ry0, cxa, ng, ent, (int) ent[G.max_rows], S, G.cp, 0);
   __syncthreads ();
 
-  // ---------------------------------------------------------------- B: horizontal pass
-  // a thread keeps one output column: its source column and fraction live in registers
   const int tx = tid & 127, rph = tid >> 7;                      // tw <= 128, two row phases
-  if (tx < tw) {
-    const int base = (int) P.h.offset[ox0 + tx] - cxa;
-    unsigned f = 0;
-    if (HM == 2) f = (unsigned) (int) P.h.coef[ox0 + tx];
-    for (int r = rph; r < R; r += LIGHT_THREADS / 128) {
-      const unsigned a = S[r * G.cp + base];
-      unsigned d = a;
-      if (HM == 2) d = light_lerp (a, S[r * G.cp + base + 1], 256u - f, f, 0u);
-      T[r * G.tw + tx] = d;
-    }
-  }
-  __syncthreads ();
-
-  // ---------------------------------------------------------------- C: vertical pass, matrix, pack
-  if (tx < tw) {
-    uint8_t *dst = out + P.off_out + (size_t) (oy0 + rph) * P.stride_out + (size_t) (ox0 + tx) * 4u;
-    const size_t dstep = (size_t) P.stride_out * (LIGHT_THREADS / 128);
-    for (int ty = rph; ty < th; ty += LIGHT_THREADS / 128, dst += dstep) {
-      const unsigned vo = vtab[ty];                               // row offset inside the tile | weight << 16
-      const unsigned *t = T + (vo & 0xffffu) * G.tw + tx;
-      unsigned d = t[0];
-      if (VM == 2) {
-        const unsigned p = vo >> 16;
-        d = light_lerp (d, t[G.tw], 256u - p, p, 0x00800080u);
+  if (G.h_first) {
+    // -------------------------------------------------------------- B: horizontal pass
+    // a thread keeps one output column: its source column and fraction live in registers
+    if (tx < tw) {
+      const int base = (int) P.h.offset[ox0 + tx] - cxa;
+      unsigned f = 0;
+      if (HM == 2) f = (unsigned) (int) P.h.coef[ox0 + tx];
+      for (int r = rph; r < R; r += LIGHT_THREADS / 128) {
+        const unsigned a = S[r * G.cp + base];
+        unsigned d = a;
+        if (HM == 2) d = light_lerp (a, S[r * G.cp + base + 1], 256u - f, f, 0u);
+        T[r * G.tw + tx] = d;
       }
-      if (!MFIRST) d = light_matrix (d, P);
-      else d |= 0x000000ffu;                                      // alpha passes every 2-tap/copy stage as 255
-      *(unsigned *) dst = __byte_perm (d, 0, P.sel);
+    }
+    __syncthreads ();
+
+    // -------------------------------------------------------------- C: vertical pass, matrix, pack
+    if (tx < tw) {
+      uint8_t *dst = out + P.off_out + (size_t) (oy0 + rph) * P.stride_out + (size_t) (ox0 + tx) * 4u;
+      const size_t dstep = (size_t) P.stride_out * (LIGHT_THREADS / 128);
+      for (int ty = rph; ty < th; ty += LIGHT_THREADS / 128, dst += dstep) {
+        const unsigned vo = vtab[ty];                             // row offset inside the tile | weight << 16
+        const unsigned *t = T + (vo & 0xffffu) * G.tw + tx;
+        unsigned d = t[0];
+        if (VM == 2) {
+          const unsigned p = vo >> 16;
+          d = light_lerp (d, t[G.tw], 256u - p, p, 0x00800080u);
+        }
+        if (!MFIRST) d = light_matrix (d, P);
+        else d |= 0x000000ffu;                                    // alpha passes every 2-tap/copy stage as 255
+        *(unsigned *) dst = __byte_perm (d, 0, P.sel);
+      }
+    }
+  } else {
+    // vertical pass first (chain_scale when out_w * in_h > in_w * out_h): same two lerps, other order
+    const int C = cx1 - cxa, lane = tid & 31;
+    for (int ty = tid >> 5; ty < th; ty += LIGHT_THREADS / 32) {
+      const unsigned vo = vtab[ty];
+      const unsigned *s0 = S + (vo & 0xffffu) * G.cp;
+      const unsigned p = vo >> 16;
+      for (int c = lane; c < C; c += 32) {
+        unsigned d = s0[c];
+        if (VM == 2) d = light_lerp (d, s0[G.cp + c], 256u - p, p, 0x00800080u);
+        T[ty * G.cp + c] = d;
+      }
+    }
+    __syncthreads ();
+    if (tx < tw) {
+      const int base = (int) P.h.offset[ox0 + tx] - cxa;
+      unsigned f = 0;
+      if (HM == 2) f = (unsigned) (int) P.h.coef[ox0 + tx];
+      uint8_t *dst = out + P.off_out + (size_t) (oy0 + rph) * P.stride_out + (size_t) (ox0 + tx) * 4u;
+      const size_t dstep = (size_t) P.stride_out * (LIGHT_THREADS / 128);
+      for (int ty = rph; ty < th; ty += LIGHT_THREADS / 128, dst += dstep) {
+        const unsigned *t = T + ty * G.cp + base;
+        unsigned d = t[0];
+        if (HM == 2) d = light_lerp (d, t[1], 256u - f, f, 0u);
+        if (!MFIRST) d = light_matrix (d, P);
+        else d |= 0x000000ffu;
+        *(unsigned *) dst = __byte_perm (d, 0, P.sel);
+      }
     }
   }
 }
@@ -326,6 +359,8 @@ inline int launch_light (const VcsDev & dev, const VcsPlan & p, const VcsBatch &
   if (!fn) return B200_ERR_STATE;
   LightDev g;
   g.tw = p.light_tw; g.th = p.light_th; g.max_rows = p.light_rows; g.cp = p.light_cp;
+  g.h_first = p.h_first ? 1 : 0;
+  g.t_words = p.h_first ? p.light_rows * p.light_tw : p.light_th * p.light_cp;
   dim3 grid ((p.out.width + g.tw - 1) / g.tw, (p.out.height + g.th - 1) / g.th, n);
   fn <<<grid, LIGHT_THREADS, p.light_smem, stream>>> (dev, g, batch);
   B200_CUDA_TRY (cudaGetLastError ());

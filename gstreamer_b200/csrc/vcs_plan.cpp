@@ -309,7 +309,6 @@ void light_geometry (VcsPlan * p)
   p->light_ok = false;
   if (!(p->h.mode == PASS_COPY || p->h.mode == PASS_2TAP) || !(p->v.mode == PASS_COPY || p->v.mode == PASS_2TAP))
     return;
-  if (!p->h_first) return;
   // 32-bit row loads: every plane row starts 4-aligned and holds whole words up to the width
   const int iw = p->in.width;
   if ((p->in.stride[0] & 3) || (p->in.stride[1] & 3) || (p->in.offset[0] & 3) || (p->in.offset[1] & 3)) return;
@@ -332,7 +331,8 @@ void light_geometry (VcsPlan * p)
       max_cols = std::max (max_cols, c1 - c0);
     }
     const int cp = max_cols + 4;                                  // +4 words: rows start on distinct banks
-    const size_t total = ((size_t) max_rows * cp + (size_t) max_rows * tw + max_rows + 4 + th) * 4;   // S, T, work list, v table
+    const size_t t_words = p->h_first ? (size_t) max_rows * tw : (size_t) th * cp;
+    const size_t total = ((size_t) max_rows * cp + t_words + max_rows + 4 + th) * 4;   // S, T, work list, v table
     if (total <= 96 * 1024) {
       p->light_ok = true; p->light_tw = tw; p->light_th = th; p->light_rows = max_rows; p->light_cp = cp;
       p->light_smem = (int) total;
