@@ -190,6 +190,128 @@ vcs_ntap_kernel (const VcsDev P, const NtapDev G, const VcsBatch frames)
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Vertical pass first (chain_scale picks it when out_w * in_h > in_w * out_h).
+//  A   as above, into plain byte planes S[ch][line][word column]
+//  B'  vertical FIR on two 16-bit lanes per register: acc += tap * (bytes 0,2) and tap * (bytes 1,3) with
+//      32-bit IMAD — the low lane is exact modulo 2^16, the high lane is off by the low lane's borrow, which
+//      bit 15 of the low lane gives back (|sums| < 2^15 is an eligibility condition).  One word = 4 columns.
+//  C'  horizontal FIR per output pixel with funnel shift + IDP.4A on the v-scaled rows, matrix, pack.
+template <int HM, int VM, bool MFIRST, bool COSITED>
+__global__ void __launch_bounds__ (NTAP_THREADS, 2)
+vcs_ntap_vfirst_kernel (const VcsDev P, const NtapDev G, const VcsBatch frames)
+{
+  extern __shared__ __align__ (16) unsigned nsm[];
+  const int plane_words = G.rows * G.pitch, tplane = G.th * G.pitch;
+  unsigned *S = nsm;                                             // [3][rows][pitch]
+  unsigned *T = S + 3 * plane_words + 4;                         // [3][th][pitch]
+  int *TH = (int *) (T + 3 * tplane + 4);                        // [tw][ntw_h]
+  int *TV = TH + G.tw * max (G.ntw_h, 1);                        // [th][n_taps_v]  (16-bit taps, one per word)
+  unsigned *vrow = (unsigned *) (TV + G.th * max (P.v.n_taps, 1));
+  unsigned *ent = vrow + G.th;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const uint8_t *__restrict__ in = frames.in[blockIdx.z];
+  uint8_t *__restrict__ out = frames.out[blockIdx.z];
+  const uint8_t *__restrict__ plane_y = in + P.off_y;
+  const uint8_t *__restrict__ plane_c = in + P.off_c;
+
+  const int ox0 = blockIdx.x * G.tw, oy0 = blockIdx.y * G.th;
+  const int tw = min (G.tw, P.ow - ox0), th = min (G.th, P.oh - oy0);
+  const int cx0 = P.h.offset[ox0], cx1 = P.h.offset[ox0 + tw - 1] + P.h.span;
+  const int ry0 = P.v.offset[oy0], ry1 = P.v.offset[oy0 + th - 1] + P.v.span;
+  const int cxa = cx0 & ~3, R = ry1 - ry0, ng = (cx1 - cxa + 3) >> 2;
+
+  if (HM == 3)
+    for (int i = tid; i < tw * G.ntw_h; i += NTAP_THREADS) TH[i] = __ldg (G.h_packed + (size_t) ox0 * G.ntw_h + i);
+  if (VM == 3)
+    for (int i = tid; i < th * P.v.n_taps; i += NTAP_THREADS) TV[i] = (int) P.v.coef[(size_t) oy0 * P.v.n_taps + i];
+  if (tid < th) vrow[tid] = P.v.offset[oy0 + tid] - (unsigned) ry0;
+
+  vcs_unpack_worklist (P, ry0, R, ent, G.rows);
+  __syncthreads ();
+  vcs_unpack_stage<MFIRST, COSITED, 1> (P, plane_y, plane_c, ry0, cxa, ng, ent, (int) ent[G.rows], S, G.pitch, plane_words);
+  __syncthreads ();
+
+  // ---------------------------------------------------------------- B': vertical pass
+  if (VM == 3) {
+    const int nv = P.v.n_taps;
+    for (int ty = tid >> 5; ty < th; ty += NTAP_THREADS / 32) {
+      const int rb = (int) vrow[ty];
+      const int *tv = TV + ty * nv;
+      for (int j = lane; j < ng; j += 32) {
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+          const unsigned *sp = S + ch * plane_words + rb * G.pitch + j;
+          unsigned ae = 0x00200020u, ao = 0x00200020u;           // +32 in every lane
+#pragma unroll 2
+          for (int k = 0; k < nv; k++) {
+            const unsigned w = sp[k * G.pitch];
+            const unsigned t = (unsigned) tv[k];
+            ae += t * (w & 0x00ff00ffu);
+            ao += t * __byte_perm (w, 0, 0x4341);
+          }
+          // lanes -> four signed sums (the high lane takes back the low lane's borrow), >> 6, saturate
+          const int e0 = (int) (short) ae, e1 = ((int) ae >> 16) + (int) ((ae >> 15) & 1u);
+          const int o0 = (int) (short) ao, o1 = ((int) ao >> 16) + (int) ((ao >> 15) & 1u);
+          T[ch * tplane + ty * G.pitch + j] = pack_sat2 (o0 >> 6, e0 >> 6, pack_sat2 (o1 >> 6, e1 >> 6, 0u));
+        }
+      }
+    }
+    __syncthreads ();
+  }
+
+  // ---------------------------------------------------------------- C': horizontal pass, matrix, pack
+  const int tx = tid % G.tw, ph = tid / G.tw, nph = NTAP_THREADS / G.tw;
+  if (tx < tw) {
+    const int ox = ox0 + tx;
+    const int base = (int) P.h.offset[ox] - cxa;
+    const int wi = base >> 2, sh = (base & 3) * 8;
+    const int *th_taps = TH + tx * G.ntw_h;
+    uint8_t *dst = out + P.off_out + (size_t) (oy0 + ph) * P.stride_out + (size_t) ox * 4u;
+    const size_t dstep = (size_t) P.stride_out * nph;
+    for (int ty = ph; ty < th; ty += nph, dst += dstep) {
+      // the row this output line reads: v-scaled, or straight from the staged input when the vertical axis is a copy
+      const unsigned *row = VM == 3 ? T + ty * G.pitch + wi : S + (int) vrow[ty] * G.pitch + wi;
+      const int cstep = VM == 3 ? tplane : plane_words;
+      int c[3];
+      if (HM == 3) {
+        unsigned lo[3];
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) { c[ch] = 32; lo[ch] = row[ch * cstep]; }
+#pragma unroll 1
+        for (int w = 0; w < G.ntw_h; w++) {
+          const int t = th_taps[w];
+#pragma unroll
+          for (int ch = 0; ch < 3; ch++) {
+            const unsigned hi = row[ch * cstep + w + 1];
+            c[ch] = dp4a_u8s8 (__funnelshift_r (lo[ch], hi, sh), t, c[ch]);
+            lo[ch] = hi;
+          }
+        }
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) c[ch] >>= 6;
+      } else {
+        const unsigned sel = 0x4440u | (unsigned) (base & 3);
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) c[ch] = (int) __byte_perm (row[ch * cstep], 0, sel);
+      }
+      int al = 255;
+      if (!G.alpha_opaque) {                                     // alpha follows the passes in their order: v, then h
+        al = alpha_pass (255, P.v, oy0 + ty);
+        al = alpha_pass (al, P.h, ox);
+      }
+      unsigned argb;
+      if (MFIRST) {
+        argb = pack_sat2 (c[0], al, pack_sat2 (c[2], c[1], 0u));
+      } else {
+        argb = light_matrix (pack_sat2 (c[1], c[0], pack_sat2 (0, c[2], 0u)), P);
+        if (!G.alpha_opaque) argb = (argb & 0xffffff00u) | (unsigned) al;
+      }
+      *(unsigned *) dst = __byte_perm (argb, 0, P.sel);
+    }
+  }
+}
+
 typedef void (*ntap_kernel_fn) (const VcsDev, const NtapDev, const VcsBatch);
 
 template <int HM, int VM, int NTW>
@@ -212,8 +334,21 @@ inline ntap_kernel_fn ntap_kernel_pick_ntw (const VcsPlan & p)
   }
 }
 
+template <int HM, int VM>
+inline ntap_kernel_fn ntap_vfirst_pick (const VcsPlan & p)
+{
+  if (p.matrix_first) return p.h_cosited ? vcs_ntap_vfirst_kernel<HM, VM, true, true> : vcs_ntap_vfirst_kernel<HM, VM, true, false>;
+  return p.h_cosited ? vcs_ntap_vfirst_kernel<HM, VM, false, true> : vcs_ntap_vfirst_kernel<HM, VM, false, false>;
+}
+
 inline ntap_kernel_fn ntap_kernel_for (const VcsPlan & p)
 {
+  if (!p.h_first) {
+    if (p.h.mode == 3 && p.v.mode == 3) return ntap_vfirst_pick<3, 3> (p);
+    if (p.h.mode == 3 && p.v.mode == 1) return ntap_vfirst_pick<3, 1> (p);
+    if (p.h.mode == 1 && p.v.mode == 3) return ntap_vfirst_pick<1, 3> (p);
+    return nullptr;
+  }
   if (p.h.mode == 3 && p.v.mode == 3) return ntap_kernel_pick_ntw<3, 3> (p);
   if (p.h.mode == 3 && p.v.mode == 1) return ntap_kernel_pick_ntw<3, 1> (p);
   if (p.h.mode == 1 && p.v.mode == 3) return ntap_kernel_pick_ntw<1, 3> (p);

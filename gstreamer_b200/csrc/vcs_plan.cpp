@@ -368,7 +368,7 @@ void ntap_geometry (VcsPlan * p)
 {
   p->ntap_ok = false;
   const bool hn = p->h.mode == PASS_NTAP, vn = p->v.mode == PASS_NTAP;
-  if (!(hn || vn) || p->h.mode == PASS_2TAP || p->v.mode == PASS_2TAP || !p->h_first) return;
+  if (!(hn || vn) || p->h.mode == PASS_2TAP || p->v.mode == PASS_2TAP) return;
   const int iw = p->in.width;
   if ((p->in.stride[0] & 3) || (p->in.stride[1] & 3) || (p->in.offset[0] & 3) || (p->in.offset[1] & 3)) return;
   if (p->in.stride[0] < ((iw + 3) & ~3) || p->in.stride[1] < ((iw + 3) & ~3)) return;
@@ -405,7 +405,12 @@ void ntap_geometry (VcsPlan * p)
     const size_t s_words = ((size_t) ngr * 3 * pitch + 2) * 4;
     const size_t t_words = (size_t) groups * tw * 4;
     const size_t tap_words = (size_t) tw * std::max (p->ntw_h, 1) + (size_t) th * std::max (p->ntw_v, 1) + th;
-    const size_t total = (s_words + t_words + tap_words + rows + 8) * 4;
+    size_t total = (s_words + t_words + tap_words + rows + 8) * 4;
+    if (!p->h_first) {
+      // vertical first: plain planes S[3][rows][pitch], v-scaled rows T[3][th][pitch], 16-bit v taps one per word
+      total = ((size_t) 3 * rows * pitch + 4 + (size_t) 3 * th * pitch + 4 + (size_t) tw * std::max (p->ntw_h, 1) +
+          (size_t) th * std::max (p->v.n_taps, 1) + th + rows + 8) * 4;
+    }
     if (total > 100 * 1024) continue;
     // staged input pixels + h-scaled pixels per output pixel; small tiles pay extra per-tile overhead
     const double cost = ((double) rows * max_cols + (double) rows * tw) / ((double) std::min (tw, ow) * std::min (th, oh))

@@ -11,6 +11,7 @@ SIZES = [
     (720, 480, 1280, 720), (642, 362, 320, 180), (322, 242, 1000, 730), (131, 77, 130, 76),
     (64, 64, 640, 640), (2048, 64, 256, 8), (9, 7, 8, 6), (4, 4, 8, 8), (8, 8, 4, 4), (254, 100, 127, 50),
     (1000, 600, 100, 60), (640, 480, 640, 360), (640, 360, 320, 360), (1920, 1080, 480, 270),
+    (1920, 1080, 854, 480), (1280, 720, 854, 480), (100, 300, 250, 310), (3840, 2160, 3840, 1000),   # vertical pass first
 ]
 METHODS = [2, 3, 4, 5, 6, 7, 8, 9]      # every n-tap method of GstVideoScaleMethod
 
@@ -39,6 +40,7 @@ def test_ntap_matches_oracle(cuda_device, size, method):
     frame = ob.nv12_random_frame(iw, ih, seed=iw + 3 * oh + method)
     want = ob.oracle_vcs_convert(ob.vcs_desc(iw, ih, ow, oh, method), frame)
     got, variant = _convert(iw, ih, ow, oh, method, frame)
+    assert variant in (1, 3)                     # 1: the exact-2:1 kernel takes (254,100)->(127,50)-like shapes
     bad = np.nonzero(got != want)[0]
     assert bad.size == 0, f"variant {variant}: {bad.size} bytes differ, first at {bad[:8]}: got {got[bad[:8]]} want {want[bad[:8]]}"
 
@@ -65,8 +67,7 @@ def test_ntap_formats_and_siting(cuda_device, site, in_fmt, out_fmt, size):
     d = ob.vcs_desc(iw, ih, ow, oh, 3, in_fmt=ob.FMT[in_fmt], out_fmt=ob.FMT[out_fmt], site=site)
     want = ob.oracle_vcs_convert(d, frame)
     got, variant = _convert(iw, ih, ow, oh, 3, frame, in_fmt=ob.FMT[in_fmt], out_fmt=ob.FMT[out_fmt], site=site)
-    if ow * ih <= iw * oh:
-        assert variant == 3
+    assert variant == 3                          # either pass order
     assert np.array_equal(got, want)
 
 
