@@ -125,6 +125,16 @@ int b200_video_info_set_format (b200_video_info * info, int format, int width, i
       info->color_range = B200_COLOR_RANGE_16_235;
       info->chroma_site = height > 576 ? B200_CHROMA_SITE_H_COSITED : B200_CHROMA_SITE_NONE;
       return B200_OK;
+    case B200_VIDEO_FORMAT_I420: case B200_VIDEO_FORMAT_YV12:
+      // video-info.c:997-1009 (YV12: same layout, the format description swaps planes 1 and 2)
+      info->stride[0] = (width + 3) & ~3;
+      info->stride[1] = info->stride[2] = ((((width + 1) & ~1) / 2) + 3) & ~3;
+      info->offset[0] = 0; info->offset[1] = (uint64_t) info->stride[0] * ((height + 1) & ~1);
+      info->offset[2] = info->offset[1] + (uint64_t) info->stride[1] * (((height + 1) & ~1) / 2);
+      info->color_matrix = height > 576 ? B200_COLOR_MATRIX_BT709 : B200_COLOR_MATRIX_BT601;
+      info->color_range = B200_COLOR_RANGE_16_235;
+      info->chroma_site = height > 576 ? B200_CHROMA_SITE_H_COSITED : B200_CHROMA_SITE_NONE;
+      return B200_OK;
     case B200_VIDEO_FORMAT_RGBx: case B200_VIDEO_FORMAT_BGRx: case B200_VIDEO_FORMAT_xRGB:
     case B200_VIDEO_FORMAT_xBGR: case B200_VIDEO_FORMAT_RGBA: case B200_VIDEO_FORMAT_BGRA:
     case B200_VIDEO_FORMAT_ARGB: case B200_VIDEO_FORMAT_ABGR:
@@ -142,6 +152,12 @@ size_t b200_video_info_size (const b200_video_info * info)
   switch (info->format) {
     case B200_VIDEO_FORMAT_NV12: case B200_VIDEO_FORMAT_NV21:
       return (size_t) info->offset[1] + (size_t) info->stride[1] * (((info->height + 1) & ~1) / 2);
+    case B200_VIDEO_FORMAT_I420: case B200_VIDEO_FORMAT_YV12: {
+      const size_t ch = (size_t) (((info->height + 1) & ~1) / 2);
+      const size_t e1 = (size_t) info->offset[1] + (size_t) info->stride[1] * ch;
+      const size_t e2 = (size_t) info->offset[2] + (size_t) info->stride[2] * ch;
+      return e1 > e2 ? e1 : e2;
+    }
     default:
       return (size_t) info->offset[0] + (size_t) info->stride[0] * info->height;
   }
@@ -175,6 +191,15 @@ int b200_vcs_create (const b200_video_info * in, const b200_video_info * out,
     d.stride_y = p.in.stride[0]; d.stride_c = p.in.stride[1]; d.stride_out = p.out.stride[0];
     d.off_y = p.in.offset[0]; d.off_c = p.in.offset[1]; d.off_out = p.out.offset[0];
     d.u_index = p.u_index; d.h_cosited = p.h_cosited; d.v_pairs = p.v_pairs;
+    d.planar = p.planar ? 1 : 0; d.chroma_nearest = p.chroma_nearest ? 1 : 0;
+    if (p.planar) {
+      d.off_u = p.in.offset[p.plane_u]; d.off_v = p.in.offset[p.plane_v];
+      d.stride_u = p.in.stride[p.plane_u]; d.stride_v = p.in.stride[p.plane_v];
+    } else {                                                      // interleaved pairs: both components walk the same rows
+      d.off_u = p.in.offset[1] + p.u_index; d.off_v = p.in.offset[1] + (p.u_index ^ 1);
+      d.stride_u = d.stride_v = p.in.stride[1];
+    }
+    d.cstep = p.planar ? 1 : 2;
     d.h_first = p.h_first; d.matrix_first = p.matrix_first;
     d.p1 = p.p[0]; d.p2 = p.p[1]; d.p3 = p.p[2]; d.p4 = p.p[3]; d.p5 = p.p[4];
     d.sel = p.byte_sel[0] | (p.byte_sel[1] << 4) | (p.byte_sel[2] << 8) | (p.byte_sel[3] << 12);

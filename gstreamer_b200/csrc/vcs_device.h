@@ -20,6 +20,12 @@ struct VcsDev {
   int stride_y, stride_c, stride_out;
   unsigned long long off_y, off_c, off_out;
   int u_index, h_cosited, v_pairs;
+  // chroma components as two strided byte streams: U sample k of chroma row r at in[off_u + r * stride_u + k * cstep]
+  // (cstep 2 for the interleaved NV12/NV21 plane, 1 for the I420/YV12 planes)
+  unsigned long long off_u, off_v;
+  int stride_u, stride_v, cstep;
+  int planar;                    // I420 / YV12
+  int chroma_nearest;            // unchanged-size I420/YV12: the reference's fast path replicates chroma (no filter)
   int h_first, matrix_first;
   int p1, p2, p3, p4, p5;
   unsigned sel;                  // byte selector nibbles for PRMT-style packing: byte i <- comp sel[i]

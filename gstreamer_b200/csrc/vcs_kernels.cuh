@@ -37,20 +37,24 @@ __device__ __forceinline__ int lerp_h_u8 (int a, int b, int f)
 // One chroma component of one chroma row, horizontally upsampled to luma column x.
 // cosited:      video_chroma_up_h2_cs_u8, video-chroma.c:687-699
 // non-cosited:  video_chroma_up_h2_u8,    video-chroma.c:277-296
-// c points at the first byte of that component in an interleaved UV row (stride 2).
-__device__ __forceinline__ int chroma_hup (const uint8_t * __restrict__ c, int x, int iw, int cosited)
+// mode 2 (nearest): no filter at all — unpack's replication (loadupdb), what the I420 fast path keeps
+// c points at sample 0 of that component in its chroma row; consecutive samples are `step` bytes apart
+// (2 in an interleaved UV row, 1 in a planar one).
+__device__ __forceinline__ int chroma_hup (const uint8_t * __restrict__ c, int x, int iw, int mode, int step = 2)
 {
   const int k = x >> 1;
-  if (cosited) {
+  if (mode == 2)
+    return c[step * k];
+  if (mode == 1) {
     if ((x & 1) && x < iw - 1)
-      return (c[2 * k] + c[2 * k + 2] + 1) >> 1;
-    return c[2 * k];
+      return (c[step * k] + c[step * k + step] + 1) >> 1;
+    return c[step * k];
   }
   if (x == 0 || ((x & 1) && x >= iw - 1))
-    return c[2 * k];
+    return c[step * k];
   if (x & 1)
-    return (3 * c[2 * k] + c[2 * k + 2] + 2) >> 2;
-  return (c[2 * k - 2] + 3 * c[2 * k] + 2) >> 2;
+    return (3 * c[step * k] + c[step * k + step] + 2) >> 2;
+  return (c[step * k - step] + 3 * c[step * k] + 2) >> 2;
 }
 
 // video_orc_convert_AYUV_ARGB, video-orc.orc:1634-1688:
@@ -108,7 +112,6 @@ vcs_generic_kernel (const VcsDev P, const VcsBatch frames)
   const uint8_t *__restrict__ in = frames.in[blockIdx.z];
   uint8_t *__restrict__ out = frames.out[blockIdx.z];
   const uint8_t *__restrict__ plane_y = in + P.off_y;
-  const uint8_t *__restrict__ plane_c = in + P.off_c;
 
   const int ox0 = blockIdx.x * P.tile_w, oy0 = blockIdx.y * P.tile_h;
   const int tw = min (P.tile_w, P.ow - ox0), th = min (P.tile_h, P.oh - oy0);
@@ -137,10 +140,10 @@ vcs_generic_kernel (const VcsDev P, const VcsBatch frames)
   const int ncr = cr1 - cr0 + 1;
   for (int i = tid; i < ncr * C; i += nthr) {
     const int r = i / C, c = i - r * C;
-    const uint8_t *row = plane_c + (size_t) (cr0 + r) * P.stride_c;
     const int x = cx0 + c;
-    HU[r * Cp + c] = (uint8_t) chroma_hup (row + P.u_index, x, P.iw, P.h_cosited);
-    HU[hup_sz + r * Cp + c] = (uint8_t) chroma_hup (row + (P.u_index ^ 1), x, P.iw, P.h_cosited);
+    const int hmode = P.chroma_nearest ? 2 : P.h_cosited;
+    HU[r * Cp + c] = (uint8_t) chroma_hup (in + P.off_u + (size_t) (cr0 + r) * P.stride_u, x, P.iw, hmode, P.cstep);
+    HU[hup_sz + r * Cp + c] = (uint8_t) chroma_hup (in + P.off_v + (size_t) (cr0 + r) * P.stride_v, x, P.iw, hmode, P.cstep);
   }
   __syncthreads ();
 

