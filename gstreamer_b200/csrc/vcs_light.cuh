@@ -75,9 +75,9 @@ __device__ __forceinline__ unsigned light_lerp (unsigned a, unsigned b, unsigned
 // Work list: one entry per input line, or per PAIR of lines (2k+1, 2k+2) that share their two
 // chroma rows with swapped 3:1 weights (video_chroma_up_v2_u8) — the h up-sampling of both rows
 // and the floor average are then computed once for the two lines.
-// entry = row | chroma_mode << 16 | pair << 20; ent[cap] receives the count.  Call with the whole
-// CTA; only warp 0 works.
-__device__ __forceinline__ void vcs_unpack_worklist (const VcsDev & P, int ry0, int R, unsigned *ent, int cap)
+// entry (uint4) = { row | chroma_mode << 16 | pair << 20, byte offset of the luma line, of its own chroma row, of
+// the paired chroma row }; ent[cap].x receives the count.  Call with the whole CTA; only warp 0 works.
+__device__ __forceinline__ void vcs_unpack_worklist (const VcsDev & P, int ry0, int R, uint4 *ent, int cap)
 {
   const int tid = threadIdx.x;
   if (tid < 32) {
@@ -94,10 +94,14 @@ __device__ __forceinline__ void vcs_unpack_worklist (const VcsDev & P, int ry0, 
       const bool pair = m == 1 && mnext == 2;
       const bool keep = r < R && !second;
       const unsigned mask = __ballot_sync (0xffffffffu, keep);
-      if (keep) ent[count + __popc (mask & ((1u << tid) - 1u))] = (unsigned) r | (unsigned) m << 16 | (pair ? 1u << 20 : 0u);
+      if (keep) {
+        const int oth = m ? ((m == 1 ? min (y + 1, P.ih - 1) : y - 1) >> 1) : (y >> 1);
+        ent[count + __popc (mask & ((1u << tid) - 1u))] = make_uint4 ((unsigned) r | (unsigned) m << 16 | (pair ? 1u << 20 : 0u),
+            (unsigned) (y * P.stride_y), (unsigned) ((y >> 1) * P.stride_u), (unsigned) (oth * P.stride_u));
+      }
       count += __popc (mask);
     }
-    if (tid == 0) ent[cap] = (unsigned) count;
+    if (tid == 0) ent[cap].x = (unsigned) count;
   }
 }
 
@@ -109,7 +113,7 @@ __device__ __forceinline__ void vcs_unpack_worklist (const VcsDev & P, int ry0, 
 //           word (row r, column word j, channel ch) at (((r >> 2) * 3 + ch) * pitch + j) * 4 + (r & 3).
 template <bool MFIRST, bool COSITED, int LAYOUT>
 __device__ __forceinline__ void vcs_unpack_stage (const VcsDev & P, const uint8_t *__restrict__ plane_y,
-    const uint8_t *__restrict__ in, int ry0, int cxa, int ng, const unsigned *ent, int n_ent,
+    const uint8_t *__restrict__ in, int cxa, int ng, const uint4 *ent, int n_ent,
     unsigned *S, int pitch, int plane_words)
 {
   const int cw2 = ((P.iw + 1) >> 1) * 2;                         // luma columns covered by whole chroma samples
@@ -119,6 +123,10 @@ __device__ __forceinline__ void vcs_unpack_stage (const VcsDev & P, const uint8_
   const int nitems = n_ent * ng;
   const unsigned magic = 0xffffffffu / (unsigned) ng + 1u;       // item / ng == umulhi (item, magic) for item < 65536, ng > 1
 
+  // the chroma fetch differs between interleaved and planar inputs: two instantiations of the loop, one
+  // warp-uniform branch (no predicated-off twin of every address computation)
+  auto run = [&] (auto planar_tag) {
+    constexpr bool PLANAR = decltype (planar_tag)::value;
   struct Item {                                                  // one work item: 4 pixels of a line or of a line pair
     int r, m, j, x;
     bool pair, fast;
@@ -133,21 +141,19 @@ __device__ __forceinline__ void vcs_unpack_stage (const VcsDev & P, const uint8_
     Item it;
     const int e = ng > 1 ? (int) __umulhi ((unsigned) item, magic) : item;
     it.j = item - e * ng;
-    const unsigned en = ent[e];
-    it.r = (int) (en & 0xffffu); it.m = (int) (en >> 16) & 3; it.pair = (en >> 20) != 0;
-    const int y = ry0 + it.r;
+    const uint4 en = ent[e];
+    it.r = (int) (en.x & 0xffffu); it.m = (int) (en.x >> 16) & 3; it.pair = (en.x >> 20) != 0;
     it.x = cxa + 4 * it.j;
-    const int oth = (it.m == 1 ? min (y + 1, P.ih - 1) : y - 1) >> 1;
-    const unsigned kb = (unsigned) ((it.x >> 1) * P.cstep);       // stride_u == stride_v on this path
-    it.co = (unsigned) ((y >> 1) * P.stride_u) + kb;
-    it.oo = (unsigned) ((it.m ? oth : (y >> 1)) * P.stride_u) + kb;
-    it.rowy = plane_y + (unsigned) (y * P.stride_y + it.x);
+    const unsigned kb = (unsigned) (it.x >> 1) * (PLANAR ? 1u : 2u);      // stride_u == stride_v on this path
+    it.co = en.z + kb;
+    it.oo = en.w + kb;
+    it.rowy = plane_y + (en.y + (unsigned) it.x);
     it.fast = it.x + 8 <= cw2 && (COSITED || it.x >= 4 || P.chroma_nearest);
     return it;
   };
   auto load_row = [&] (unsigned off, unsigned & ue, unsigned & ve, unsigned & up, unsigned & vp) {
     up = vp = 0;
-    if (P.planar) {                                               // two aligned 16-bit loads per component
+    if (PLANAR) {                                                 // two aligned 16-bit loads per component
       const unsigned short *pu = (const unsigned short *) (plane_u + off), *pv = (const unsigned short *) (plane_v + off);
       ue = (unsigned) __ldg (pu) | (unsigned) __ldg (pu + 1) << 16;
       ve = (unsigned) __ldg (pv) | (unsigned) __ldg (pv + 1) << 16;
@@ -217,7 +223,7 @@ __device__ __forceinline__ void vcs_unpack_stage (const VcsDev & P, const uint8_
   };
   auto slow = [&] (const Item & it) {                            // frame edges: scalar, clamps inside chroma_hup
     unsigned u = 0, v = 0, ub = 0, vb = 0;
-    const unsigned kb = (unsigned) ((it.x >> 1) * P.cstep);
+    const unsigned kb = (unsigned) (it.x >> 1) * (PLANAR ? 1u : 2u);
     const uint8_t *cu = plane_u + (it.co - kb), *cv = plane_v + (it.co - kb);
     const uint8_t *ou = plane_u + (it.oo - kb), *ov = plane_v + (it.oo - kb);
 #pragma unroll
@@ -263,10 +269,12 @@ __device__ __forceinline__ void vcs_unpack_stage (const VcsDev & P, const uint8_
       if (a.fast) finish_fast (a, load_raw (a)); else slow (a);
     }
   }
+  };
+  if (P.planar) run (std::true_type {}); else run (std::false_type {});
 }
 
 template <int HM, int VM, bool MFIRST, bool COSITED>
-__global__ void __launch_bounds__ (LIGHT_THREADS, 2)
+__global__ void __launch_bounds__ (LIGHT_THREADS, 3)
 vcs_light_kernel (const VcsDev P, const LightDev G, const VcsBatch frames)
 {
   extern __shared__ __align__ (16) unsigned lsm[];
@@ -284,15 +292,15 @@ vcs_light_kernel (const VcsDev P, const LightDev G, const VcsBatch frames)
   const int cxa = cx0 & ~3, R = ry1 - ry0, ng = (cx1 - cxa + 3) >> 2;
 
   // ---------------------------------------------------------------- A: unpack + chroma up-sample
-  unsigned *ent = T + G.t_words;                                 // [max_rows] entries, then the count
-  unsigned *vtab = ent + G.max_rows + 1;                         // [th] vertical source row and weight of each output row
+  uint4 *ent = (uint4 *) (T + G.t_words);                        // [max_rows] entries, then the count
+  unsigned *vtab = (unsigned *) (ent + G.max_rows + 1);          // [th] vertical source row and weight of each output row
   if (tid >= 32 && tid < 32 + th) {
     const int oy = oy0 + tid - 32;
     vtab[tid - 32] = (P.v.offset[oy] - (unsigned) ry0) | (VM == 2 ? (unsigned) (int) P.v.coef[oy] << 16 : 0u);
   }
   vcs_unpack_worklist (P, ry0, R, ent, G.max_rows);
   __syncthreads ();
-  vcs_unpack_stage<MFIRST, COSITED, 0> (P, plane_y, in, ry0, cxa, ng, ent, (int) ent[G.max_rows], S, G.cp, 0);
+  vcs_unpack_stage<MFIRST, COSITED, 0> (P, plane_y, in, cxa, ng, ent, (int) ent[G.max_rows].x, S, G.cp, 0);
   __syncthreads ();
 
   const int tx = tid & 127, rph = tid >> 7;                      // tw <= 128, two row phases

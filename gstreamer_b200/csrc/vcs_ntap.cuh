@@ -52,7 +52,7 @@ vcs_ntap_kernel (const VcsDev P, const NtapDev G, const VcsBatch frames)
   int *TH = (int *) (T4 + groups * G.tw);                        // [tw][ntw_h]
   int *TV = TH + G.tw * max (G.ntw_h, 1);                        // [th][ntw_v]
   unsigned *vrow = (unsigned *) (TV + G.th * max (G.ntw_v, 1));  // [th] first source line of each output row
-  unsigned *ent = vrow + G.th;                                   // [rows] entries + count
+  uint4 *ent = (uint4 *) (((uintptr_t) (vrow + G.th) + 15) & ~(uintptr_t) 15);   // [rows] entries + count
   const int tid = threadIdx.x;
   const uint8_t *__restrict__ in = frames.in[blockIdx.z];
   uint8_t *__restrict__ out = frames.out[blockIdx.z];
@@ -74,7 +74,7 @@ vcs_ntap_kernel (const VcsDev P, const NtapDev G, const VcsBatch frames)
   // ---------------------------------------------------------------- A: unpack + chroma up-sample
   vcs_unpack_worklist (P, ry0, R, ent, G.rows);
   __syncthreads ();
-  vcs_unpack_stage<MFIRST, COSITED, 2> (P, plane_y, in, ry0, cxa, ng, ent, (int) ent[G.rows], (unsigned *) S4,
+  vcs_unpack_stage<MFIRST, COSITED, 2> (P, plane_y, in, cxa, ng, ent, (int) ent[G.rows].x, (unsigned *) S4,
       G.pitch, 0);
   __syncthreads ();
 
@@ -207,7 +207,7 @@ vcs_ntap_vfirst_kernel (const VcsDev P, const NtapDev G, const VcsBatch frames)
   int *TH = (int *) (T + 3 * tplane + 4);                        // [tw][ntw_h]
   int *TV = TH + G.tw * max (G.ntw_h, 1);                        // [th][n_taps_v]  (16-bit taps, one per word)
   unsigned *vrow = (unsigned *) (TV + G.th * max (P.v.n_taps, 1));
-  unsigned *ent = vrow + G.th;
+  uint4 *ent = (uint4 *) (((uintptr_t) (vrow + G.th) + 15) & ~(uintptr_t) 15);
   const int tid = threadIdx.x, lane = tid & 31;
   const uint8_t *__restrict__ in = frames.in[blockIdx.z];
   uint8_t *__restrict__ out = frames.out[blockIdx.z];
@@ -227,7 +227,7 @@ vcs_ntap_vfirst_kernel (const VcsDev P, const NtapDev G, const VcsBatch frames)
 
   vcs_unpack_worklist (P, ry0, R, ent, G.rows);
   __syncthreads ();
-  vcs_unpack_stage<MFIRST, COSITED, 1> (P, plane_y, in, ry0, cxa, ng, ent, (int) ent[G.rows], S, G.pitch, plane_words);
+  vcs_unpack_stage<MFIRST, COSITED, 1> (P, plane_y, in, cxa, ng, ent, (int) ent[G.rows].x, S, G.pitch, plane_words);
   __syncthreads ();
 
   // ---------------------------------------------------------------- B': vertical pass

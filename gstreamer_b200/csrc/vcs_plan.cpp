@@ -346,7 +346,7 @@ void light_geometry (VcsPlan * p)
     }
     const int cp = max_cols + 4;                                  // +4 words: rows start on distinct banks
     const size_t t_words = p->h_first ? (size_t) max_rows * tw : (size_t) th * cp;
-    const size_t total = ((size_t) max_rows * cp + t_words + max_rows + 4 + th) * 4;   // S, T, work list, v table
+    const size_t total = ((size_t) max_rows * cp + t_words + 4 * (size_t) max_rows + 4 + th) * 4;   // S, T, work list, v table
     if (total <= 96 * 1024) {
       p->light_ok = true; p->light_tw = tw; p->light_th = th; p->light_rows = max_rows; p->light_cp = cp;
       p->light_smem = (int) total;
@@ -415,11 +415,11 @@ void ntap_geometry (VcsPlan * p)
     const size_t s_words = ((size_t) ngr * 3 * pitch + 2) * 4;
     const size_t t_words = (size_t) groups * tw * 4;
     const size_t tap_words = (size_t) tw * std::max (p->ntw_h, 1) + (size_t) th * std::max (p->ntw_v, 1) + th;
-    size_t total = (s_words + t_words + tap_words + rows + 8) * 4;
+    size_t total = (s_words + t_words + tap_words + 4 * (size_t) rows + 12) * 4;
     if (!p->h_first) {
       // vertical first: plain planes S[3][rows][pitch], v-scaled rows T[3][th][pitch], 16-bit v taps one per word
       total = ((size_t) 3 * rows * pitch + 4 + (size_t) 3 * th * pitch + 4 + (size_t) tw * std::max (p->ntw_h, 1) +
-          (size_t) th * std::max (p->v.n_taps, 1) + th + rows + 8) * 4;
+          (size_t) th * std::max (p->v.n_taps, 1) + th + 4 * (size_t) rows + 12) * 4;
     }
     if (total > 100 * 1024) continue;
     // staged input pixels + h-scaled pixels per output pixel; small tiles pay extra per-tile overhead
