@@ -26,15 +26,39 @@ class Operator(enum.IntEnum):
 
 
 class CudaCompositorPad:
-    def __init__(self, width, height, stride=None, xpos=0, ypos=0, alpha=1.0, operator=Operator.OVER):
+    """GstCompositorPad.  `width`/`height` are the pad properties (compositor.c:190-196): the size the
+    pad's picture takes in the output.  With `in_info` the pad is a GstVideoAggregatorConvertPad: its
+    input frames (NV12/NV21/I420/YV12 of any size) are converted to the aggregator's format and scaled to
+    width x height in prepare_frame (gstvideoaggregator.c:479-570, :782-830) by a GstVideoConverter with
+    DEFAULT options — cubic b = c = 1/3 (video-converter.c:791, video-resampler.c:63-64), i.e. exactly
+    cudavideoconvertscale method=mitchell — before blending."""
+
+    def __init__(self, width, height, stride=None, xpos=0, ypos=0, alpha=1.0, operator=Operator.OVER, in_info=None):
         self.width, self.height = width, height
         self.stride = stride or width * 4
         self.xpos, self.ypos, self.alpha, self.operator = xpos, ypos, alpha, Operator(operator)
         self.frame = None          # the pad's prepared frame (device memory)
+        self.in_info = in_info
+        self._conv = self._converted = None
 
     def set_frame(self, frame):
         self.frame = frame
         return self
+
+    def _prepare_frame(self, out_format, device, stream):
+        """prepare_frame of a convert pad: returns the frame to blend"""
+        if self.in_info is None or self.frame is None:
+            return self.frame
+        import torch
+        from .video import CudaVideoConvertScale, VideoInfo, VideoScaleMethod
+        if self._conv is None:
+            self._conv = CudaVideoConvertScale(method=VideoScaleMethod.MITCHELL, cuda_device_id=device)
+            self._out_info = VideoInfo(out_format, self.width, self.height)
+            self._conv.set_info(self.in_info, self._out_info)
+            self._converted = torch.empty(self._out_info.size, dtype=torch.uint8, device=f"cuda:{device}")
+            self.stride = self._out_info.stride[0]
+        self._conv.transform_frame(self.frame, self._converted, stream)
+        return self._converted
 
 
 class CudaCompositor:
@@ -42,6 +66,7 @@ class CudaCompositor:
         self.background = Background(background)
         self.width, self.height, self.format = width, height, VideoFormat(out_format)
         self.sinkpads = []
+        self.device = cuda_device_id
         h = C.c_void_p()
         check(lib.b200_comp_create(int(out_format), width, height, cuda_device_id, C.byref(h)),
               "b200_comp_create")
@@ -57,7 +82,7 @@ class CudaCompositor:
         pads = [p for p in self.sinkpads if p.frame is not None]
         arr = (_lib.CompPadC * max(len(pads), 1))()
         for i, p in enumerate(pads):
-            arr[i].data = _ptr(p.frame)
+            arr[i].data = _ptr(p._prepare_frame(self.format, self.device, stream))
             arr[i].width, arr[i].height, arr[i].stride = p.width, p.height, p.stride
             arr[i].xpos, arr[i].ypos, arr[i].alpha, arr[i].op = p.xpos, p.ypos, p.alpha, int(p.operator)
         check(lib.b200_comp_blend(self._h, _ptr(outbuf), out_stride or self.width * 4, int(self.background),

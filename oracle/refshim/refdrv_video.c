@@ -177,6 +177,12 @@ ref_vcs_new (int in_format, int in_w, int in_h, const int *in_stride,
       GST_VIDEO_PRIMARIES_MODE_NONE,
       GST_VIDEO_CONVERTER_OPT_THREADS, G_TYPE_UINT, (guint) n_threads, NULL);
 
+  if (method < 0) {
+    /* GstVideoAggregatorConvertPad without a converter-config: gst_video_converter_new (..., NULL)
+     * (gstvideoaggregator.c:508-513) — every option at its default */
+    gst_structure_free (options);
+    options = NULL;
+  }
   r->convert = gst_video_converter_new (&r->in_info, &r->out_info, options);
   if (!r->convert) {
     g_free (r);

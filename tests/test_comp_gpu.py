@@ -77,3 +77,31 @@ def test_zorder_and_obscuring(cuda_device):
     specs = [(64, 48, 0, 0, 1.0, 1), (64, 48, 0, 0, 1.0, 1)]
     got, want = _run(12, 64, 48, 0, specs, seed=1, opaque_some=False)
     assert np.array_equal(got, want)
+
+
+def test_convert_pads(cuda_device):
+    """GstVideoAggregatorConvertPad: NV12 / I420 inputs of other sizes are converted (default converter =
+    mitchell cubic) to the output format at the pad's width x height, then blended"""
+    import torch
+    import gstreamer_b200 as g
+    from gstreamer_b200.compositor import CudaCompositor, Background
+    W, H = 320, 200
+    comp = CudaCompositor(g.VideoFormat.BGRA, W, H, Background.CHECKER)
+    specs = [("NV12", 23, 160, 90, 200, 120, -20, 10, 1.0), ("I420", 2, 352, 288, 176, 144, 100, 40, 0.6),
+             ("NV12", 23, 128, 72, 128, 72, 180, 120, 0.9)]
+    opads = (ob.OraclePad * len(specs))()
+    keep = []
+    for k, (name, fmt, iw, ih, pw, ph, x, y, a) in enumerate(specs):
+        frame = ob.i420_random_frame(iw, ih, k) if name == "I420" else ob.nv12_random_frame(iw, ih, k)
+        pad = comp.request_pad(pw, ph, xpos=x, ypos=y, alpha=a, in_info=g.VideoInfo(fmt, iw, ih))
+        pad.set_frame(torch.from_numpy(frame).cuda())
+        conv = ob.oracle_vcs_convert(ob.vcs_desc(iw, ih, pw, ph, 9, in_fmt=fmt, out_fmt=12), frame)
+        keep.append(conv)
+        opads[k].data, opads[k].width, opads[k].height, opads[k].stride = conv.ctypes.data, pw, ph, pw * 4
+        opads[k].xpos, opads[k].ypos, opads[k].alpha, opads[k].op = x, y, a, 1
+    want = np.zeros((H, W, 4), dtype=np.uint8)
+    ob.oracle().oracle_compositor(12, want.ctypes.data, W, H, W * 4, 0, opads, len(specs))
+    out = torch.zeros(H * W * 4, dtype=torch.uint8, device="cuda")
+    comp.aggregate_frames(out)
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy().reshape(H, W, 4), want)

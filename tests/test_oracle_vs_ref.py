@@ -116,6 +116,20 @@ def test_video_colorimetry_and_siting(site, matrix, rng):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("size", [(64, 48, 40, 30), (64, 48, 100, 70), (64, 48, 64, 48), (130, 74, 65, 37)],
+                         ids=lambda s: "%dx%d-%dx%d" % s)
+@pytest.mark.parametrize("in_fmt", ["NV12", "I420"])
+def test_default_converter_is_mitchell(size, in_fmt):
+    """a GstVideoAggregatorConvertPad builds its converter with NO options (gstvideoaggregator.c:508-513):
+    cubic b = c = 1/3, exactly what the element's method=mitchell sets"""
+    iw, ih, ow, oh = size
+    frame = ob.i420_random_frame(iw, ih, 3) if in_fmt == "I420" else ob.nv12_random_frame(iw, ih, 3)
+    a = ob.RefVcs(iw, ih, ow, oh, -1, in_fmt=ob.FMT[in_fmt])
+    b = ob.RefVcs(iw, ih, ow, oh, 9, in_fmt=ob.FMT[in_fmt])
+    assert np.array_equal(a.convert(frame), b.convert(frame))
+    a.close(); b.close()
+
+
 def test_reference_threads_equal_single_thread():
     """the reference's own invariant (tests/check/libs/video.c:3189-3260) holds for our build of it
     on the headline shape: n-threads=4 output == n-threads=1 output"""
