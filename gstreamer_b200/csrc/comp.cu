@@ -142,26 +142,48 @@ __device__ __forceinline__ unsigned background_px (int bg, int x, int y, unsigne
 // LDG.128 per covering pad when the pad's x offset keeps 16 B alignment)
 constexpr int CT_W = 128, CT_H = 8;
 
+// what a thread needs of a pad that touches its tile, staged once per CTA (warp-uniform LDS.128 x 2
+// instead of indexed constant-bank loads per thread)
+struct __align__ (16) CompTilePad {
+  const uint8_t *data;           // as CompPadDev::data
+  long long stride;
+  int x0, x1;                    // clipped destination rectangle
+  int y0, y1;
+  int s_alpha, mode;
+  int full;                      // the whole tile lies inside the rectangle: no per-thread clipping
+  int pad_;
+};
+
 __global__ void __launch_bounds__ (256)
 comp_kernel (const CompParams P)
 {
-  __shared__ unsigned s_mask;
+  __shared__ int s_count;
   __shared__ unsigned s_recip[256];
+  __shared__ CompTilePad s_pads[COMP_CHUNK];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int x0 = blockIdx.x * CT_W + tx * 4, y = blockIdx.y * CT_H + ty;
   if (P.need_recip)                                                // only the overlay family divides
     s_recip[threadIdx.x] = threadIdx.x ? (0x1000000u + threadIdx.x - 1) / threadIdx.x : 0u;
   if (threadIdx.x < 32) {
     // which pads touch this tile?  (the reference culls whole pads, compositor.c:519-601;
-    // here the cull is per tile and costs one ballot)
+    // here the cull is per tile and costs one ballot); the hits are compacted in z-order
     bool hit = false;
+    const int bx = blockIdx.x * CT_W, by = blockIdx.y * CT_H;
     if ((int) threadIdx.x < P.n_pads) {
       const CompPadDev & p = P.pads[threadIdx.x];
-      const int bx = blockIdx.x * CT_W, by = blockIdx.y * CT_H;
       hit = p.x0 < bx + CT_W && p.x1 > bx && p.y0 < by + CT_H && p.y1 > by;
     }
     const unsigned m = __ballot_sync (0xffffffffu, hit);
-    if (threadIdx.x == 0) s_mask = m;
+    if (hit) {
+      const CompPadDev & p = P.pads[threadIdx.x];
+      CompTilePad t;
+      t.data = p.data; t.stride = p.stride; t.x0 = p.x0; t.x1 = p.x1; t.y0 = p.y0; t.y1 = p.y1;
+      t.s_alpha = p.s_alpha; t.mode = p.mode;
+      t.full = p.x0 <= bx && p.x1 >= min (bx + CT_W, P.width) && p.y0 <= by && p.y1 >= min (by + CT_H, P.height);
+      t.pad_ = 0;
+      s_pads[__popc (m & ((1u << threadIdx.x) - 1u))] = t;
+    }
+    if (threadIdx.x == 0) s_count = __popc (m);
   }
   __syncthreads ();
   if (x0 >= P.width || y >= P.height) return;
@@ -169,6 +191,7 @@ comp_kernel (const CompParams P)
   unsigned *dp = (unsigned *) (P.dst + (size_t) y * P.stride) + x0;
   const bool vec = n == 4 && ((((size_t) dp) & 15) == 0);
   const unsigned alpha_mask = 0xffu << P.alpha_shift;
+  const int shift = P.alpha_shift;
   unsigned d[4];
   if (P.background >= 0) {
 #pragma unroll
@@ -180,16 +203,15 @@ comp_kernel (const CompParams P)
 #pragma unroll
     for (int i = 0; i < 4; i++) d[i] = i < n ? dp[i] : 0u;
   }
-  unsigned mask = s_mask;
-  while (mask) {
-    const int pi = __ffs (mask) - 1;
-    mask &= mask - 1;
-    const CompPadDev & p = P.pads[pi];
-    if (y < p.y0 || y >= p.y1 || x0 >= p.x1 || x0 + n <= p.x0) continue;
+  const int count = s_count;
+  for (int k = 0; k < count; k++) {
+    const CompTilePad & p = s_pads[k];
+    const int full = p.full;
+    if (!full && (y < p.y0 || y >= p.y1 || x0 >= p.x1 || x0 + n <= p.x0)) continue;
     const unsigned *sp = (const unsigned *) (p.data + (long long) y * p.stride) + x0;
-    const int mode = p.mode, shift = P.alpha_shift;
+    const int mode = p.mode;
     const unsigned s_alpha = (unsigned) p.s_alpha;
-    if (x0 >= p.x0 && x0 + 4 <= p.x1 && n == 4) {                  // whole group inside the pad
+    if (n == 4 && (full || (x0 >= p.x0 && x0 + 4 <= p.x1))) {     // whole group inside the pad
       unsigned s[4];
       if ((((size_t) sp) & 15) == 0) {
         const uint4 v = __ldg ((const uint4 *) sp);
