@@ -19,7 +19,8 @@
 GST_DEBUG_CATEGORY_STATIC (cuda_ars_debug);
 #define GST_CAT_DEFAULT cuda_ars_debug
 
-#define ARS_CAPS "audio/x-raw, format = (string) " GST_AUDIO_NE (F32) ", layout = (string) interleaved, " \
+#define ARS_CAPS "audio/x-raw, format = (string) { " GST_AUDIO_NE (F32) ", " GST_AUDIO_NE (S16) ", " GST_AUDIO_NE (S32) ", " \
+    GST_AUDIO_NE (F64) " }, layout = (string) interleaved, " \
     "rate = (int) [ 1, MAX ], channels = (int) [ 1, MAX ]"
 static GstStaticPadTemplate ars_sink = GST_STATIC_PAD_TEMPLATE ("sink", GST_PAD_SINK, GST_PAD_ALWAYS, GST_STATIC_CAPS (ARS_CAPS));
 static GstStaticPadTemplate ars_src = GST_STATIC_PAD_TEMPLATE ("src", GST_PAD_SRC, GST_PAD_ALWAYS, GST_STATIC_CAPS (ARS_CAPS));
@@ -84,6 +85,7 @@ ars_set_caps (GstBaseTransform * trans, GstCaps * incaps, GstCaps * outcaps)
   cfg.out_rate = GST_AUDIO_INFO_RATE (&self->out);
   cfg.channels = GST_AUDIO_INFO_CHANNELS (&self->in);
   cfg.quality = self->quality;
+  cfg.format = GST_AUDIO_INFO_FORMAT (&self->in);       /* B200_AUDIO_FORMAT_* are GstAudioFormat values */
   if (b200_ars_create (&cfg, self->device_id, &self->ars) != B200_OK)
     return FALSE;
   gst_base_transform_set_passthrough (trans, cfg.in_rate == cfg.out_rate);

@@ -49,7 +49,7 @@ class CompPadC(C.Structure):
 
 class ArsConfigC(C.Structure):
     _fields_ = [("in_rate", C.c_int32), ("out_rate", C.c_int32), ("channels", C.c_int32),
-                ("quality", C.c_int32), ("reserved", C.c_int32 * 8)]
+                ("quality", C.c_int32), ("format", C.c_int32), ("reserved", C.c_int32 * 7)]
 
 
 class ArsPlanInfoC(C.Structure):

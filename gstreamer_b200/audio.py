@@ -14,18 +14,26 @@ from ._lib import lib, check
 from .video import _ptr, _stream
 
 
+class AudioFormat:
+    """GstAudioFormat values of the sample formats the element resamples natively (audio-converter.c:700-727)"""
+    S16LE, S32LE, F32LE, F64LE = 4, 12, 28, 30
+    DTYPE = {4: np.int16, 12: np.int32, 28: np.float32, 30: np.float64}
+
+
 class CudaAudioResample:
-    def __init__(self, quality=4, cuda_device_id=0):
+    def __init__(self, quality=4, cuda_device_id=0, format=AudioFormat.F32LE):
         self.quality = quality
+        self.format = format
         self.cuda_device_id = cuda_device_id
         self._h = None
         self.in_rate = self.out_rate = self.channels = None
 
-    # GstBaseTransformClass::set_caps (F32 interleaved)
+    # GstBaseTransformClass::set_caps (interleaved samples of self.format)
     def set_caps(self, in_rate, out_rate, channels):
         self._free()
         cfg = _lib.ArsConfigC()
         cfg.in_rate, cfg.out_rate, cfg.channels, cfg.quality = in_rate, out_rate, channels, self.quality
+        cfg.format = int(self.format)
         h = C.c_void_p()
         check(lib.b200_ars_create(C.byref(cfg), self.cuda_device_id, C.byref(h)), "b200_ars_create")
         self._h = h

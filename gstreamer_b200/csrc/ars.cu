@@ -62,7 +62,64 @@ struct ArsPlan {
   double cutoff = 0, beta = 0;
   std::vector<float> proto;      // (oversample + 4) x n_taps oversampled prototype
   std::vector<float> phases;     // n_phases x n_taps (FULL mode), all phases precomputed
+  // other sample formats: the same two tables in the samples' own type
+  int fmt = 0, bps = 4;          // ArsFmt, bytes per sample
+  std::vector<uint8_t> proto_x, phases_x;
 };
+
+enum ArsFmt : int { ARS_F32 = 0, ARS_S16 = 1, ARS_S32 = 2, ARS_F64 = 3 };
+
+// convert_taps_gint16_c / _gint32_c (audio-resampler.c:217-258): round with a bias found by bisection so that
+// the integer taps sum to (1 << precision) - 1
+template <typename T>
+static void convert_taps_int (const double *tmp, T *taps, double weight, int n, int precision)
+{
+  const long long one = (1LL << precision) - 1;
+  const double multiplier = (double) one;
+  double offset = 0.5, l_offset = 0.0, h_offset = 1.0;
+  for (int i = 0; i < 32; i++) {
+    long long sum = 0;
+    for (int j = 0; j < n; j++) sum += (long long) floor (offset + tmp[j] * multiplier / weight);
+    if (sum == one || l_offset == h_offset) break;
+    if (sum < one) { if (offset > l_offset) l_offset = offset; offset += (h_offset - l_offset) / 2; }
+    else { if (offset < h_offset) h_offset = offset; offset -= (h_offset - l_offset) / 2; }
+  }
+  for (int j = 0; j < n; j++) taps[j] = (T) floor (offset + tmp[j] * multiplier / weight);
+}
+
+// make_coeff_gint16_cubic / make_coeff_gint32_cubic (audio-resampler.c:350-372); host and device
+__host__ __device__ inline void cubic_coeff_s16 (int num, int denom, int ic[4])
+{
+  const int x = (int) (((long long) num << 15) / denom);
+  const int x2 = (int) ((unsigned) x * (unsigned) x) >> 15, x3 = (int) ((unsigned) x2 * (unsigned) x) >> 15;
+  const short c0 = (short) ((((x3 - x) << 15) / 6) >> 15);
+  const short c1 = (short) (x + ((x2 - x3) >> 1));
+  const short c3 = (short) (-(((x << 15) / 3) >> 15) + (x2 >> 1) - (((x3 << 15) / 6) >> 15));
+  ic[0] = c0; ic[1] = c1; ic[3] = c3;
+  ic[2] = (short) (32767 - c0 - c1 - c3);
+}
+__host__ __device__ inline void cubic_coeff_s32 (int num, int denom, int ic[4])
+{
+  const long long one = (1LL << 31) - 1;
+  const long long x = ((long long) num << 31) / denom, x2 = (x * x) >> 31, x3 = (x2 * x) >> 31;
+  ic[0] = (int) ((((x3 - x) << 31) / 6) >> 31);
+  ic[1] = (int) (x + ((x2 - x3) >> 1));
+  ic[3] = (int) (-(((x << 31) / 3) >> 31) + (x2 >> 1) - (((x3 << 31) / 6) >> 31));
+  ic[2] = (int) (one - ic[0] - ic[1] - ic[3]);
+}
+// make_coeff_gdouble_cubic: float literals promoted to double; no FMA may be formed
+static void cubic_coeff_f64_host (int num, int denom, double ic[4])
+{
+  volatile double x = (double) num / denom, x2 = x * x, x3 = x2 * x;
+  volatile double a = x3 - x, b = x2 - x3, c = 0.5f * b;
+  ic[0] = 0.16667f * a;
+  ic[1] = x + c;
+  volatile double d = -0.33333f * x, e = 0.5f * x2, f = 0.16667f * x3, g = d + e;
+  ic[3] = g - f;
+  volatile double h = (double) 1.0 - ic[0], k = h - ic[1];
+  ic[2] = k - ic[3];
+}
+
 
 static const struct { double cutoff, down, atten, trbw; } kKaiser[11] = {
   {0.860, 0.96511, 60, 0.7}, {0.880, 0.96591, 65, 0.29}, {0.910, 0.96923, 70, 0.145},
@@ -86,6 +143,13 @@ static int build_ars_plan (const b200_ars_config & cfg, ArsPlan * p)
 {
   if (cfg.in_rate <= 0 || cfg.out_rate <= 0 || cfg.channels <= 0 || cfg.quality < 0 || cfg.quality > 10)
     return B200_ERR_INVALID_ARG;
+  switch (cfg.format) {          // GstAudioFormat values, native endianness (audio-format.h:97-140)
+    case 0: case B200_AUDIO_FORMAT_F32LE: p->fmt = ARS_F32; p->bps = 4; break;
+    case B200_AUDIO_FORMAT_S16LE: p->fmt = ARS_S16; p->bps = 2; break;
+    case B200_AUDIO_FORMAT_S32LE: p->fmt = ARS_S32; p->bps = 4; break;
+    case B200_AUDIO_FORMAT_F64LE: p->fmt = ARS_F64; p->bps = 8; break;
+    default: return B200_ERR_UNSUPPORTED;
+  }
   p->channels = cfg.channels;
   int a = cfg.in_rate, b = cfg.out_rate;
   while (b) { int t = a; a = b; b = t % b; }
@@ -111,11 +175,12 @@ static int build_ars_plan (const b200_ars_config & cfg, ArsPlan * p)
   p->oversample = over;
   // filter-mode auto with the element's VARIABLE_RATE flag: FULL when the whole phase table is
   // below the (effectively fixed) 1 MiB threshold (audio-resampler.c:1147-1166)
-  p->full = (long long) 4 * p->n_taps * p->out_step < 1048576;
+  p->full = (long long) p->bps * p->n_taps * p->out_step < 1048576;       // bps * n_taps * out_rate, :1153
   p->n_phases = p->full ? p->out_step : 0;
 
   const int n = p->n_taps;
   p->proto.assign ((size_t) (over + 4) * n, 0.f);
+  if (p->fmt != ARS_F32) p->proto_x.assign ((size_t) (over + 4) * n * p->bps, 0);
   std::vector<double> tmp (n);
   for (int row = 0; row < over + 4; row++) {
     const double x0 = -(n / 2) + row / (double) over;
@@ -128,7 +193,50 @@ static int build_ars_plan (const b200_ars_config & cfg, ArsPlan * p)
       weight += tmp[i];
     }
     for (int i = 0; i < n; i++) p->proto[(size_t) row * n + i] = (float) (tmp[i] / weight);
+    uint8_t *px = p->proto_x.data () + (size_t) row * n * p->bps;
+    if (p->fmt == ARS_S16) convert_taps_int (tmp.data (), (int16_t *) px, weight, n, 15);
+    else if (p->fmt == ARS_S32) convert_taps_int (tmp.data (), (int32_t *) px, weight, n, 31);
+    else if (p->fmt == ARS_F64) for (int i = 0; i < n; i++) ((double *) px)[i] = tmp[i] / weight;
   }
+  if (p->full && p->fmt != ARS_F32) {
+    // every phase (get_taps_<type>_full): interpolate_gint16_cubic_sse2 / interpolate_gint32_cubic_c /
+    // interpolate_gdouble_cubic_sse2 between four prototype rows
+    p->phases_x.assign ((size_t) p->n_phases * n * p->bps, 0);
+    for (int ph = 0; ph < p->n_phases; ph++) {
+      const int pos = ph * over, offset = (over - 1) - pos / p->n_phases, frac = pos % p->n_phases;
+      const uint8_t *c0 = p->proto_x.data () + (size_t) offset * n * p->bps;
+      uint8_t *res = p->phases_x.data () + (size_t) ph * n * p->bps;
+      if (p->fmt == ARS_S16) {
+        int ic[4];
+        cubic_coeff_s16 (frac, p->n_phases, ic);
+        const int16_t *a = (const int16_t *) c0, *b = a + n, *c = b + n, *d = c + n;
+        for (int i = 0; i < n; i++) {
+          const int t = (int) ((unsigned) (a[i] * ic[0]) + (unsigned) (b[i] * ic[1]) + (unsigned) (c[i] * ic[2]) +
+              (unsigned) (d[i] * ic[3]) + (1u << 14)) >> 15;
+          ((int16_t *) res)[i] = (int16_t) (t < -32768 ? -32768 : (t > 32767 ? 32767 : t));
+        }
+      } else if (p->fmt == ARS_S32) {
+        int ic[4];
+        cubic_coeff_s32 (frac, p->n_phases, ic);
+        const int32_t *a = (const int32_t *) c0, *b = a + n, *c = b + n, *d = c + n;
+        for (int i = 0; i < n; i++) {
+          long long t = (long long) a[i] * ic[0] + (long long) b[i] * ic[1] + (long long) c[i] * ic[2] + (long long) d[i] * ic[3];
+          t = (t + (1LL << 30)) >> 31;
+          ((int32_t *) res)[i] = (int32_t) (t < -(1LL << 31) ? -(1LL << 31) : (t > (1LL << 31) - 1 ? (1LL << 31) - 1 : t));
+        }
+      } else {
+        double ic[4];
+        cubic_coeff_f64_host (frac, p->n_phases, ic);
+        const double *a = (const double *) c0, *b = a + n, *c = b + n, *d = c + n;
+        for (int i = 0; i < n; i++) {
+          volatile double t0 = a[i] * ic[0], t1 = b[i] * ic[1], t2 = c[i] * ic[2], t3 = d[i] * ic[3];
+          volatile double u0 = t0 + t1, u2 = t2 + t3;
+          ((double *) res)[i] = u0 + u2;
+        }
+      }
+    }
+  }
+  if (p->fmt != ARS_F32) return B200_OK;
   if (p->full) {
     // every phase, built exactly as the reference builds it lazily (get_taps_gfloat_full +
     // interpolate_gfloat_cubic_sse: (c0*f0 + c1*f1) + (c2*f2 + c3*f3))
@@ -446,6 +554,151 @@ ars_interp_kernel (const ArsLaunch L, const float *__restrict__ table, int overs
     L.out[(size_t) o * L.channels + c] = __fadd_rn (__fadd_rn (t[0], t[2]), __fadd_rn (t[1], t[3]));
 }
 
+// ------------------------------------------------------------------------------------------
+// S16 / S32 / F64 samples (audio-resampler.c macros, audio-resampler-x86-sse2.c, -sse41.c — the
+// implementations an x86 build of the reference selects).  Integer sums are exact, so only the
+// rounding points matter; F64 keeps the SSE2 two-lane order (lanes by tap parity, mul then add).
+// Warp = one output frame x 32 channels; taps / prototype rows are warp-uniform loads.
+struct ArsLaunchX {
+  const void *hist, *in;
+  void *out;
+  const void *table;             // FULL: [n_phases][n_taps] taps; interpolated: [oversample + 4][n_taps] prototype
+  long long hist_frames, avail, out_frames;
+  int channels, n_taps, out_step, samp_inc, samp_frac, samp_index, samp_phase;
+  int full, oversample;
+};
+
+template <typename T>
+__device__ __forceinline__ T ars_sample (const ArsLaunchX & L, long long f, int c)
+{
+  if (f < L.hist_frames) return __ldg ((const T *) L.hist + f * L.channels + c);
+  if (L.in) return __ldg ((const T *) L.in + (f - L.hist_frames) * L.channels + c);
+  return (T) 0;
+}
+
+__device__ __forceinline__ int sat_s16 (int v) { return min (max (v, -32768), 32767); }
+__device__ __forceinline__ long long sat_s32 (long long v) { return v < -2147483648LL ? -2147483648LL : (v > 2147483647LL ? 2147483647LL : v); }
+
+template <int FMT>
+__global__ void __launch_bounds__ (ARS_THREADS)
+ars_direct_kernel (const ArsLaunchX L)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long o = (long long) blockIdx.x * (ARS_THREADS / 32) + warp;
+  if (o >= L.out_frames) return;
+  const int c = blockIdx.y * 32 + lane;
+  if (c >= L.channels) return;
+  const long long t0 = (long long) L.samp_phase + o * L.samp_frac;
+  const long long idx = (long long) L.samp_index + o * L.samp_inc + t0 / L.out_step;
+  const int phase = (int) (t0 % L.out_step), n = L.n_taps;
+  // interpolated mode: first of the four prototype rows and the fractional position (get_taps_<type>_cubic)
+  const long long pos = (long long) phase * L.oversample;
+  const int offset = (L.oversample - 1) - (int) (pos / L.out_step), frac = (int) (pos % L.out_step);
+  const size_t row0 = L.full ? (size_t) phase * n : (size_t) offset * n;
+
+  if (FMT == ARS_S16) {
+    const short *tab = (const short *) L.table + row0;
+    if (L.full) {                 // inner_product_gint16_full_1_sse2
+      unsigned sum = 0;
+      for (int i = 0; i < n; i++) sum += (unsigned) ((int) ars_sample<short> (L, idx + i, c) * (int) __ldg (tab + i));
+      ((short *) L.out)[(size_t) o * L.channels + c] = (short) sat_s16 ((int) (sum + (1u << 14)) >> 15);
+    } else {                      // inner_product_gint16_cubic_1_sse2
+      unsigned s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+      for (int i = 0; i < n; i++) {
+        const int x = ars_sample<short> (L, idx + i, c);
+        s0 += (unsigned) (x * (int) __ldg (tab + i));
+        s1 += (unsigned) (x * (int) __ldg (tab + n + i));
+        s2 += (unsigned) (x * (int) __ldg (tab + 2 * n + i));
+        s3 += (unsigned) (x * (int) __ldg (tab + 3 * n + i));
+      }
+      int ic[4];
+      cubic_coeff_s16 (frac, L.out_step, ic);
+      const unsigned acc = (unsigned) ((int) (short) ((int) s0 >> 15) * ic[0]) + (unsigned) ((int) (short) ((int) s1 >> 15) * ic[1]) +
+          (unsigned) ((int) (short) ((int) s2 >> 15) * ic[2]) + (unsigned) ((int) (short) ((int) s3 >> 15) * ic[3]);
+      ((short *) L.out)[(size_t) o * L.channels + c] = (short) sat_s16 ((int) (acc + (1u << 14)) >> 15);
+    }
+  } else if (FMT == ARS_S32) {
+    const int *tab = (const int *) L.table + row0;
+    if (L.full) {                 // inner_product_gint32_full_1_sse41
+      unsigned long long sum = 0;
+      for (int i = 0; i < n; i++) sum += (unsigned long long) ((long long) ars_sample<int> (L, idx + i, c) * __ldg (tab + i));
+      ((int *) L.out)[(size_t) o * L.channels + c] = (int) sat_s32 (((long long) sum + (1 << 30)) >> 31);
+    } else {                      // inner_product_gint32_cubic_1_sse41: each 64-bit LANE (even / odd taps) is
+      unsigned long long s[4][2]; // shifted and multiplied before the lanes are added
+#pragma unroll
+      for (int k = 0; k < 4; k++) s[k][0] = s[k][1] = 0;
+      for (int i = 0; i < n; i += 2) {
+        const long long x0 = ars_sample<int> (L, idx + i, c), x1 = ars_sample<int> (L, idx + i + 1, c);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          s[k][0] += (unsigned long long) (x0 * __ldg (tab + k * n + i));
+          s[k][1] += (unsigned long long) (x1 * __ldg (tab + k * n + i + 1));
+        }
+      }
+      int ic[4];
+      cubic_coeff_s32 (frac, L.out_step, ic);
+      unsigned long long acc = 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+#pragma unroll
+        for (int l = 0; l < 2; l++)
+          acc += (unsigned long long) ((long long) (int) (unsigned) (s[k][l] >> 31) * (long long) ic[k]);
+      ((int *) L.out)[(size_t) o * L.channels + c] = (int) sat_s32 (((long long) acc + (1 << 30)) >> 31);
+    }
+  } else {
+    const double *tab = (const double *) L.table + row0;
+    if (L.full) {                 // inner_product_gdouble_full_1_sse2
+      double s0 = 0.0, s1 = 0.0;
+      for (int i = 0; i < n; i += 2) {
+        s0 = __dadd_rn (s0, __dmul_rn (ars_sample<double> (L, idx + i, c), __ldg (tab + i)));
+        s1 = __dadd_rn (s1, __dmul_rn (ars_sample<double> (L, idx + i + 1, c), __ldg (tab + i + 1)));
+      }
+      ((double *) L.out)[(size_t) o * L.channels + c] = __dadd_rn (s0, s1);
+    } else {                      // inner_product_gdouble_cubic_1_sse2
+      double s[4][2];
+#pragma unroll
+      for (int k = 0; k < 4; k++) s[k][0] = s[k][1] = 0.0;
+      for (int i = 0; i < n; i += 2) {
+        const double x0 = ars_sample<double> (L, idx + i, c), x1 = ars_sample<double> (L, idx + i + 1, c);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          s[k][0] = __dadd_rn (s[k][0], __dmul_rn (x0, __ldg (tab + k * n + i)));
+          s[k][1] = __dadd_rn (s[k][1], __dmul_rn (x1, __ldg (tab + k * n + i + 1)));
+        }
+      }
+      // make_coeff_gdouble_cubic: float literals promoted to double
+      const double x = __ddiv_rn ((double) frac, (double) L.out_step), x2 = __dmul_rn (x, x), x3 = __dmul_rn (x2, x);
+      const double ic0 = __dmul_rn ((double) 0.16667f, __dsub_rn (x3, x));
+      const double ic1 = __dadd_rn (x, __dmul_rn ((double) 0.5f, __dsub_rn (x2, x3)));
+      const double ic3 = __dsub_rn (__dadd_rn (__dmul_rn ((double) -0.33333f, x), __dmul_rn ((double) 0.5f, x2)),
+          __dmul_rn ((double) 0.16667f, x3));
+      const double ic2 = __dsub_rn (__dsub_rn (__dsub_rn (1.0, ic0), ic1), ic3);
+      double l[2];
+#pragma unroll
+      for (int j = 0; j < 2; j++)
+        l[j] = __dadd_rn (__dadd_rn (__dmul_rn (s[0][j], ic0), __dmul_rn (s[1][j], ic1)),
+            __dadd_rn (__dmul_rn (s[2][j], ic2), __dmul_rn (s[3][j], ic3)));
+      ((double *) L.out)[(size_t) o * L.channels + c] = __dadd_rn (l[0], l[1]);
+    }
+  }
+}
+
+// new history = frames [first, first+keep) of the (old history ++ input) stream, any sample width
+template <typename T>
+__global__ void ars_history_kernel_x (T *dst, const T *hist, const T *in, long long hist_frames,
+    long long first, long long keep, int channels)
+{
+  const long long n = keep * channels;
+  for (long long i = blockIdx.x * (long long) blockDim.x + threadIdx.x; i < n; i += (long long) gridDim.x * blockDim.x) {
+    const long long f = first + i / channels;
+    const int c = (int) (i % channels);
+    T v = 0;
+    if (f < hist_frames) v = hist[f * channels + c];
+    else if (in) v = in[(f - hist_frames) * channels + c];
+    dst[i] = v;
+  }
+}
+
 // new history = frames [first, first+keep) of the (old history ++ input) stream
 __global__ void ars_history_kernel (float *dst, const float *hist, const float *in, long long hist_frames,
     long long first, long long keep, int channels)
@@ -470,6 +723,7 @@ struct b200_ars {
   int device = -1;
   float *d_phases = nullptr;
   float *d_proto = nullptr;      // interpolated mode: the oversampled prototype rows
+  void *d_table_x = nullptr;     // other sample formats: phase taps (FULL) or prototype rows, in the samples' type
   float *d_hist[2] = {nullptr, nullptr};
   size_t hist_cap[2] = {0, 0};   // frames
   int cur = 0;
@@ -483,7 +737,7 @@ static int ars_reset_state (b200_ars * h, cudaStream_t stream)
   h->samp_index = 0;
   h->samples_avail = h->plan.n_taps / 2 - 1;                    // gst_audio_resampler_reset, :1465-1484
   if (h->device >= 0 && h->d_hist[h->cur])
-    B200_CUDA_TRY (cudaMemsetAsync (h->d_hist[h->cur], 0, (size_t) (h->plan.n_taps / 2) * h->plan.channels * sizeof (float), stream));
+    B200_CUDA_TRY (cudaMemsetAsync (h->d_hist[h->cur], 0, (size_t) (h->plan.n_taps / 2) * h->plan.channels * h->plan.bps, stream));
   return B200_OK;
 }
 
@@ -492,11 +746,12 @@ static int ars_ensure_hist (b200_ars * h, int which, size_t frames)
   if (h->hist_cap[which] >= frames) return B200_OK;
   size_t cap = frames + (size_t) h->plan.n_taps;
   float *n = nullptr;
-  B200_CUDA_TRY (cudaMalloc ((void **) &n, cap * h->plan.channels * sizeof (float)));
-  B200_CUDA_TRY (cudaMemset (n, 0, cap * h->plan.channels * sizeof (float)));
+  const size_t bps = (size_t) h->plan.bps;                        // the buffers hold samples of the plan's format
+  B200_CUDA_TRY (cudaMalloc ((void **) &n, cap * h->plan.channels * bps));
+  B200_CUDA_TRY (cudaMemset (n, 0, cap * h->plan.channels * bps));
   if (h->d_hist[which]) {
     if (which == h->cur && h->samples_avail)
-      B200_CUDA_TRY (cudaMemcpy (n, h->d_hist[which], h->samples_avail * h->plan.channels * sizeof (float), cudaMemcpyDeviceToDevice));
+      B200_CUDA_TRY (cudaMemcpy (n, h->d_hist[which], h->samples_avail * h->plan.channels * bps, cudaMemcpyDeviceToDevice));
     cudaFree (h->d_hist[which]);
   }
   h->d_hist[which] = n;
@@ -521,8 +776,15 @@ int b200_ars_create (const b200_ars_config * cfg, int device, b200_ars ** handle
     if (n <= 0) { delete h; return n < 0 ? n : B200_ERR_NO_DEVICE; }
     if (device >= n) { delete h; return B200_ERR_INVALID_ARG; }
     DeviceGuard g (device);
-    if ((st = h->plan.full ? upload (&h->d_phases, h->plan.phases.data (), h->plan.phases.size ())
-                           : upload (&h->d_proto, h->plan.proto.data (), h->plan.proto.size ())) != B200_OK ||
+    if (h->plan.fmt != ARS_F32) {
+      const std::vector<uint8_t> & t = h->plan.full ? h->plan.phases_x : h->plan.proto_x;
+      uint8_t *d = nullptr;
+      st = upload (&d, t.data (), t.size ());
+      h->d_table_x = d;
+    } else
+      st = h->plan.full ? upload (&h->d_phases, h->plan.phases.data (), h->plan.phases.size ())
+                        : upload (&h->d_proto, h->plan.proto.data (), h->plan.proto.size ());
+    if (st != B200_OK ||
         (st = ars_ensure_hist (h, 0, (size_t) h->plan.n_taps)) != B200_OK ||
         (st = ars_ensure_hist (h, 1, (size_t) h->plan.n_taps)) != B200_OK) {
       b200_ars_destroy (h);
@@ -545,7 +807,7 @@ void b200_ars_destroy (b200_ars * h)
   if (!h) return;
   if (h->device >= 0) {
     DeviceGuard g (h->device);
-    cudaFree (h->d_phases); cudaFree (h->d_proto); cudaFree (h->d_hist[0]); cudaFree (h->d_hist[1]);
+    cudaFree (h->d_phases); cudaFree (h->d_proto); cudaFree (h->d_table_x); cudaFree (h->d_hist[0]); cudaFree (h->d_hist[1]);
   }
   delete h;
 }
@@ -581,9 +843,11 @@ size_t b200_ars_get_in_frames (b200_ars * h, size_t out_frames)
 
 size_t b200_ars_get_max_latency (b200_ars * h) { return h ? h->plan.n_taps / 2 : 0; }
 
-int b200_ars_process (b200_ars * h, const float *in, size_t in_frames, float *out,
+int b200_ars_process (b200_ars * h, const void *in_v, size_t in_frames, void *out_v,
     size_t out_capacity_frames, size_t * out_frames_ret, void *cuda_stream)
 {
+  const float *in = (const float *) in_v;
+  float *out = (float *) out_v;
   if (!h || (!out && out_capacity_frames)) return B200_ERR_INVALID_ARG;
   if (h->device < 0) return B200_ERR_NO_DEVICE;
   DeviceGuard g (h->device);
@@ -610,7 +874,18 @@ int b200_ars_process (b200_ars * h, const float *in, size_t in_frames, float *ou
     L.row_pitch = (p.n_taps + 4 + 3) & ~3;
     L.wcn = (p.channels + 31) / 32; if (L.wcn > 8) L.wcn = 8;
     while (8 % L.wcn) L.wcn++;                                   // 1, 2, 4 or 8 warps across channels
-    if (!p.full) {
+    if (p.fmt != ARS_F32) {
+      ArsLaunchX X;
+      X.hist = h->d_hist[h->cur]; X.in = in_v; X.out = out_v; X.table = h->d_table_x;
+      X.hist_frames = (long long) hist; X.avail = (long long) avail; X.out_frames = (long long) out_frames;
+      X.channels = p.channels; X.n_taps = p.n_taps; X.out_step = p.out_step;
+      X.samp_inc = p.samp_inc; X.samp_frac = p.samp_frac; X.samp_index = h->samp_index; X.samp_phase = h->samp_phase;
+      X.full = p.full ? 1 : 0; X.oversample = p.oversample;
+      const dim3 grid ((unsigned) ((out_frames + ARS_THREADS / 32 - 1) / (ARS_THREADS / 32)), (unsigned) ((p.channels + 31) / 32));
+      if (p.fmt == ARS_S16) ars_direct_kernel<ARS_S16> <<<grid, ARS_THREADS, 0, stream>>> (X);
+      else if (p.fmt == ARS_S32) ars_direct_kernel<ARS_S32> <<<grid, ARS_THREADS, 0, stream>>> (X);
+      else ars_direct_kernel<ARS_F64> <<<grid, ARS_THREADS, 0, stream>>> (X);
+    } else if (!p.full) {
       L.no = 0; L.row_pitch = 0; L.wcn = 1;
       const dim3 grid ((unsigned) ((out_frames + ARS_THREADS / 32 - 1) / (ARS_THREADS / 32)), (unsigned) ((p.channels + 31) / 32));
       ars_interp_kernel <<<grid, ARS_THREADS, 0, stream>>> (L, h->d_proto, p.oversample);
@@ -669,8 +944,17 @@ int b200_ars_process (b200_ars * h, const float *in, size_t in_frames, float *ou
   if (keep) {
     const long long n = (long long) keep * p.channels;
     const int blocks = (int) ((n + 255) / 256 > 1184 ? 1184 : (n + 255) / 256);
-    ars_history_kernel <<<blocks, 256, 0, stream>>> (h->d_hist[nxt], h->d_hist[h->cur], in, (long long) hist,
-        (long long) first, (long long) keep, p.channels);
+    if (p.bps == 2)
+      ars_history_kernel_x<unsigned short> <<<blocks, 256, 0, stream>>> ((unsigned short *) h->d_hist[nxt],
+          (const unsigned short *) h->d_hist[h->cur], (const unsigned short *) in_v, (long long) hist, (long long) first,
+          (long long) keep, p.channels);
+    else if (p.bps == 8)
+      ars_history_kernel_x<unsigned long long> <<<blocks, 256, 0, stream>>> ((unsigned long long *) h->d_hist[nxt],
+          (const unsigned long long *) h->d_hist[h->cur], (const unsigned long long *) in_v, (long long) hist,
+          (long long) first, (long long) keep, p.channels);
+    else
+      ars_history_kernel <<<blocks, 256, 0, stream>>> (h->d_hist[nxt], h->d_hist[h->cur], in, (long long) hist,
+          (long long) first, (long long) keep, p.channels);
     B200_CUDA_TRY (cudaGetLastError ());
   }
   h->cur = nxt;
@@ -688,7 +972,7 @@ int b200_ars_get_plan_info (const b200_ars * h, b200_ars_plan_info * info)
 
 int b200_ars_get_phase_taps (const b200_ars * h, int phase, float *taps, size_t len)
 {
-  if (!h || !taps || !h->plan.full || phase < 0 || phase >= h->plan.n_phases || len < (size_t) h->plan.n_taps)
+  if (!h || !taps || !h->plan.full || h->plan.fmt != ARS_F32 || phase < 0 || phase >= h->plan.n_phases || len < (size_t) h->plan.n_taps)
     return B200_ERR_INVALID_ARG;
   memcpy (taps, &h->plan.phases[(size_t) phase * h->plan.n_taps], sizeof (float) * h->plan.n_taps);
   return h->plan.n_taps;

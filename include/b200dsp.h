@@ -198,10 +198,15 @@ int b200_comp_blend (b200_comp * h, void *dst, int32_t dst_stride, int backgroun
 
 /* ------------------------------------------------------------------ audio resampler */
 typedef struct b200_ars b200_ars;
+/* GstAudioFormat values (gst-libs/gst/audio/audio-format.h:97-140) of the sample formats audioresample hands to
+ * its resampler unconverted (audio-converter.c:700-727), native (little) endian */
+enum { B200_AUDIO_FORMAT_S16LE = 4, B200_AUDIO_FORMAT_S32LE = 12, B200_AUDIO_FORMAT_F32LE = 28,
+  B200_AUDIO_FORMAT_F64LE = 30 };
 typedef struct {
   int32_t in_rate, out_rate, channels;
   int32_t quality;               /* 0..10, element default 4 (gstaudioresample.c:68) */
-  int32_t reserved[8];
+  int32_t format;                /* B200_AUDIO_FORMAT_*; 0 = F32LE */
+  int32_t reserved[7];
 } b200_ars_config;
 
 int b200_ars_create (const b200_ars_config * cfg, int device, b200_ars ** handle);
@@ -212,9 +217,9 @@ int b200_ars_reset (b200_ars * h);
 size_t b200_ars_get_out_frames (b200_ars * h, size_t in_frames);
 size_t b200_ars_get_in_frames (b200_ars * h, size_t out_frames);
 size_t b200_ars_get_max_latency (b200_ars * h);
-/* F32 interleaved device buffers.  in == NULL feeds silence (drain).  Consumes all
- * in_frames, writes b200_ars_get_out_frames() frames, asynchronous on cuda_stream. */
-int b200_ars_process (b200_ars * h, const float *in, size_t in_frames, float *out,
+/* Interleaved device buffers of the configured sample format.  in == NULL feeds silence (drain).
+ * Consumes all in_frames, writes b200_ars_get_out_frames() frames, asynchronous on cuda_stream. */
+int b200_ars_process (b200_ars * h, const void *in, size_t in_frames, void *out,
     size_t out_capacity_frames, size_t * out_frames, void *cuda_stream);
 typedef struct { int32_t n_taps, n_phases, in_step, out_step, filter_mode, oversample; } b200_ars_plan_info;
 int b200_ars_get_plan_info (const b200_ars * h, b200_ars_plan_info * info);

@@ -78,6 +78,10 @@ def oracle():
         if hasattr(o, "oracle_ars_new"):
             o.oracle_ars_new.restype = P
             o.oracle_ars_new.argtypes = [C.c_int] * 4
+            o.oracle_ars_new_fmt.restype = P
+            o.oracle_ars_new_fmt.argtypes = [C.c_int] * 5
+            o.oracle_ars_process_any.restype = C.c_size_t
+            o.oracle_ars_process_any.argtypes = [P, P, C.c_size_t, P, C.c_size_t]
             o.oracle_ars_free.argtypes = [P]
             o.oracle_ars_reset.argtypes = [P]
             for n in ("oracle_ars_get_out_frames", "oracle_ars_get_in_frames"):
@@ -113,6 +117,9 @@ def ref():
         if hasattr(r, "ref_ars_new"):
             r.ref_ars_new.restype = P
             r.ref_ars_new.argtypes = [C.c_int] * 4
+            if hasattr(r, "ref_ars_new_fmt"):
+                r.ref_ars_new_fmt.restype = P
+                r.ref_ars_new_fmt.argtypes = [C.c_int] * 5
             r.ref_ars_free.argtypes = [P]
             r.ref_ars_reset.argtypes = [P]
             for n in ("ref_ars_get_out_frames", "ref_ars_get_in_frames"):
@@ -229,6 +236,19 @@ def nv12_random_frame(w, h, seed):
     stride = (w + 3) & ~3
     rows = ((h + 1) & ~1) + ((h + 1) & ~1) // 2
     return lcg_bytes(stride * rows, seed + 1)
+
+
+# audio sample formats: (oracle enum, GstAudioFormat value, numpy dtype, amplitude for test signals)
+AUDIO_FORMATS = {"F32": (0, 28, np.float32, 0.5), "S16": (1, 4, np.int16, 9000.0), "S32": (2, 12, np.int32, 6e8),
+                 "F64": (3, 30, np.float64, 0.5)}
+
+
+def audio_test_signal(rng, n, ch, fmt):
+    _, _, dt, amp = AUDIO_FORMATS[fmt]
+    x = rng.standard_normal((n, ch)) * amp
+    if np.issubdtype(dt, np.integer):
+        x = np.clip(x, np.iinfo(dt).min, np.iinfo(dt).max)
+    return x.astype(dt)
 
 
 def i420_random_frame(w, h, seed):

@@ -91,6 +91,12 @@ typedef struct OracleArs OracleArs;
 /* gstaudioresample.c:374-396 (element option plumbing) + audio-resampler.c:1344-1424.
  * quality 0..10, F32 interleaved, kaiser method, filter-mode auto, cubic interpolation. */
 OracleArs *oracle_ars_new (int in_rate, int out_rate, int channels, int quality);
+/* sample formats the element hands to the resampler unconverted (audio-converter.c:700-727):
+ * F32 (default), S16, S32, F64, native endianness */
+enum { ORACLE_AFMT_F32 = 0, ORACLE_AFMT_S16 = 1, ORACLE_AFMT_S32 = 2, ORACLE_AFMT_F64 = 3 };
+OracleArs *oracle_ars_new_fmt (int in_rate, int out_rate, int channels, int quality, int fmt);
+/* like oracle_ars_process for any format: in/out are interleaved samples of the handle's format */
+size_t oracle_ars_process_any (OracleArs * r, const void *in, size_t in_frames, void *out, size_t out_capacity);
 void oracle_ars_free (OracleArs * r);
 void oracle_ars_reset (OracleArs * r);
 size_t oracle_ars_get_out_frames (OracleArs * r, size_t in_frames);

@@ -61,10 +61,11 @@ struct OracleArs
   int samp_inc, samp_frac, samp_index, samp_phase, skip;
   int n_taps, oversample, n_phases, full;
   double cutoff, beta;
-  float *table;                 /* (oversample + 4) rows of n_taps, the oversampled prototype */
-  float *cache;                 /* n_phases rows of n_taps (FULL mode) */
+  int fmt, bps;                 /* ORACLE_AFMT_*, bytes per sample */
+  float *table;                 /* (oversample + 4) rows of n_taps, the oversampled prototype (typed by fmt) */
+  float *cache;                 /* n_phases rows of n_taps (FULL mode) (typed by fmt) */
   unsigned char *have;
-  float **sbuf;                 /* per channel history + input */
+  float **sbuf;                 /* per channel history + input (typed by fmt) */
   size_t samples_len, samples_avail;
 };
 
@@ -83,9 +84,45 @@ gcd_ (int a, int b)
   return a < 0 ? -a : a;
 }
 
-/* one prototype row: n_taps kaiser-windowed sinc values at offset x, normalised, as float */
+/* convert_taps_gint16_c / _gint32_c (audio-resampler.c:217-258): round with an adjustable bias found by
+ * bisection so that the integer taps sum to (1 << precision) - 1 */
 static void
-make_row (const OracleArs * r, float *res, double x)
+convert_taps_int (const double *tmp, void *taps, double weight, int n, int precision, int is16)
+{
+  long long one = (1LL << precision) - 1;
+  double multiplier = (double) one, offset = 0.5, l_offset = 0.0, h_offset = 1.0;
+  int i, j;
+  for (i = 0; i < 32; i++) {
+    long long sum = 0;
+    for (j = 0; j < n; j++)
+      sum += (long long) floor (offset + tmp[j] * multiplier / weight);
+    if (sum == one)
+      break;
+    if (l_offset == h_offset)
+      break;
+    if (sum < one) {
+      if (offset > l_offset)
+        l_offset = offset;
+      offset += (h_offset - l_offset) / 2;
+    } else {
+      if (offset < h_offset)
+        h_offset = offset;
+      offset -= (h_offset - l_offset) / 2;
+    }
+  }
+  for (j = 0; j < n; j++) {
+    double v = floor (offset + tmp[j] * multiplier / weight);
+    if (is16)
+      ((int16_t *) taps)[j] = (int16_t) v;
+    else
+      ((int32_t *) taps)[j] = (int32_t) v;
+  }
+}
+
+/* one prototype row: n_taps kaiser-windowed sinc values at offset x, normalised, in the sample format
+ * (make_taps + convert_taps_<type>, audio-resampler.c:287-323, :217-268) */
+static void
+make_row (const OracleArs * r, void *res, double x)
 {
   int i, n = r->n_taps;
   double weight = 0.0, *tmp = malloc (sizeof (double) * n);
@@ -96,21 +133,40 @@ make_row (const OracleArs * r, float *res, double x)
     tmp[i] = s * bessel_i0 (r->beta * sqrt (fmax (1 - w * w, 0)));
     weight += tmp[i];
   }
-  for (i = 0; i < n; i++)
-    res[i] = (float) (tmp[i] / weight);
+  switch (r->fmt) {
+    case ORACLE_AFMT_S16: convert_taps_int (tmp, res, weight, n, 15, 1); break;
+    case ORACLE_AFMT_S32: convert_taps_int (tmp, res, weight, n, 31, 0); break;
+    case ORACLE_AFMT_F64:
+      for (i = 0; i < n; i++)
+        ((double *) res)[i] = tmp[i] / weight;
+      break;
+    default:
+      for (i = 0; i < n; i++)
+        ((float *) res)[i] = (float) (tmp[i] / weight);
+  }
   free (tmp);
 }
 
 OracleArs *
 oracle_ars_new (int in_rate, int out_rate, int channels, int quality)
 {
+  return oracle_ars_new_fmt (in_rate, out_rate, channels, quality, ORACLE_AFMT_F32);
+}
+
+OracleArs *
+oracle_ars_new_fmt (int in_rate, int out_rate, int channels, int quality, int fmt)
+{
   OracleArs *r;
   double Fc, A, tr_bw, B, dw;
   int g, n, oversample, i;
   if (in_rate <= 0 || out_rate <= 0 || channels <= 0 || quality < 0 || quality > 10)
     return NULL;
+  if (fmt < 0 || fmt > ORACLE_AFMT_F64)
+    return NULL;
   r = calloc (1, sizeof (*r));
   r->channels = channels;
+  r->fmt = fmt;
+  r->bps = fmt == ORACLE_AFMT_S16 ? 2 : (fmt == ORACLE_AFMT_F64 ? 8 : 4);
   /* update(): first call runs with options == NULL: max_error 0.1, samp_phase 0 -> plain gcd */
   g = gcd_ (in_rate, out_rate);
   r->in_rate = in_rate / g;
@@ -157,14 +213,14 @@ oracle_ars_new (int in_rate, int out_rate, int channels, int quality)
   /* filter-mode auto; the element stores the threshold as UINT, the resampler reads it as INT,
    * so the default 1048576 always applies; VARIABLE_RATE is set by the
    * element so the first clause never selects FULL */
-  if (4 * r->n_taps * r->out_rate < 1048576)
+  if (r->bps * r->n_taps * r->out_rate < 1048576)       /* bps * n_taps * out_rate, :1153 */
     r->full = 1;
   r->n_phases = r->out_rate;
-  r->table = calloc ((size_t) (oversample + 4) * r->n_taps, sizeof (float));
+  r->table = calloc ((size_t) (oversample + 4) * r->n_taps, r->bps);
   for (i = 0; i < oversample + 4; i++)
-    make_row (r, r->table + (size_t) i * r->n_taps, -(r->n_taps / 2) + i / (double) oversample);
+    make_row (r, (char *) r->table + (size_t) i * r->n_taps * r->bps, -(r->n_taps / 2) + i / (double) oversample);
   if (r->full) {
-    r->cache = calloc ((size_t) r->n_phases * r->n_taps, sizeof (float));
+    r->cache = calloc ((size_t) r->n_phases * r->n_taps, r->bps);
     r->have = calloc (r->n_phases, 1);
   }
   r->sbuf = calloc (channels, sizeof (float *));
@@ -193,7 +249,7 @@ oracle_ars_reset (OracleArs * r)
   int c;
   for (c = 0; c < r->channels; c++)
     if (r->sbuf[c])
-      memset (r->sbuf[c], 0, sizeof (float) * (r->n_taps / 2));
+      memset (r->sbuf[c], 0, (size_t) r->bps * (r->n_taps / 2));
   r->samp_index = 0;
   r->samples_avail = r->n_taps / 2 - 1;
   /* note: samp_phase and skip are left alone, exactly like gst_audio_resampler_reset() */
@@ -314,6 +370,250 @@ dot_cubic (const float *a, const float *c0, int stride, int len, const float ic[
     s[0][l] = t0 + t2;
   }
   return (s[0][0] + s[0][2]) + (s[0][1] + s[0][3]);
+}
+
+/* ---- S16 / S32 / F64 (audio-resampler.c macros + audio-resampler-x86-sse2.c / -sse41.c, the
+ * implementations an x86 build selects, audio-resampler-x86.h:29-70) --------------------------- */
+
+static int64_t
+sat64 (int64_t v, int64_t lo, int64_t hi)
+{
+  return v < lo ? lo : (v > hi ? hi : v);
+}
+
+/* make_coeff_gint16_cubic / _gint32_cubic (audio-resampler.c:350-372) */
+static void
+cubic_coeff_int (int num, int denom, int prec, int64_t ic[4])
+{
+  int64_t one = ((int64_t) 1 << prec) - 1;
+  int64_t x = ((int64_t) num << prec) / denom, x2, x3;
+  if (prec == 15) {             /* type2 = gint32: products wrap in 32 bits */
+    int32_t x32 = (int32_t) x, x2_32 = (int32_t) ((int32_t) (x32 * x32) >> 15), x3_32 = (int32_t) ((int32_t) (x2_32 * x32) >> 15);
+    int16_t c0 = (int16_t) ((((x3_32 - x32) << 15) / 6) >> 15);
+    int16_t c1 = (int16_t) (x32 + ((x2_32 - x3_32) >> 1));
+    int16_t c3 = (int16_t) (-(((x32 << 15) / 3) >> 15) + (x2_32 >> 1) - (((x3_32 << 15) / 6) >> 15));
+    int16_t c2 = (int16_t) ((int32_t) one - c0 - c1 - c3);
+    ic[0] = c0; ic[1] = c1; ic[2] = c2; ic[3] = c3;
+    return;
+  }
+  x2 = (x * x) >> prec;
+  x3 = (x2 * x) >> prec;
+  ic[0] = (int32_t) ((((x3 - x) << prec) / 6) >> prec);
+  ic[1] = (int32_t) (x + ((x2 - x3) >> 1));
+  ic[3] = (int32_t) (-(((x << prec) / 3) >> prec) + (x2 >> 1) - (((x3 << prec) / 6) >> prec));
+  ic[2] = (int32_t) (one - ic[0] - ic[1] - ic[3]);
+}
+
+/* make_coeff_gdouble_cubic: the literals are float constants promoted to double */
+static void
+cubic_coeff_f64 (int num, int denom, double ic[4])
+{
+  double x = (double) num / denom, x2 = x * x, x3 = x2 * x;
+  ic[0] = 0.16667f * (x3 - x);
+  ic[1] = x + 0.5f * (x2 - x3);
+  ic[3] = -0.33333f * x + 0.5f * x2 - 0.16667f * x3;
+  ic[2] = (double) 1.0 - ic[0] - ic[1] - ic[3];
+}
+
+/* FULL-mode taps of one phase in the handle's format (get_taps_<type>_full + interpolate_<type>_cubic) */
+static const void *
+phase_taps_any (OracleArs * r, int phase)
+{
+  size_t n = r->n_taps;
+  char *res = (char *) r->cache + (size_t) phase * n * r->bps;
+  if (!r->have[phase]) {
+    int pos = phase * r->oversample, offset = (r->oversample - 1) - pos / r->n_phases;
+    int frac = pos % r->n_phases;
+    size_t i;
+    const char *c0 = (const char *) r->table + (size_t) offset * n * r->bps;
+    if (r->fmt == ORACLE_AFMT_S16) {    /* interpolate_gint16_cubic_sse2: 32-bit sums, +2^14, >>15, packs */
+      const int16_t *a = (const int16_t *) c0, *b = a + n, *c = b + n, *d = c + n;
+      int64_t ic[4];
+      cubic_coeff_int (frac, r->n_phases, 15, ic);
+      for (i = 0; i < n; i++) {
+        int32_t t = (int32_t) ((uint32_t) (a[i] * (int32_t) ic[0]) + (uint32_t) (b[i] * (int32_t) ic[1]) +
+            (uint32_t) (c[i] * (int32_t) ic[2]) + (uint32_t) (d[i] * (int32_t) ic[3]) + (1u << 14));
+        ((int16_t *) res)[i] = (int16_t) sat64 (t >> 15, -32768, 32767);
+      }
+    } else if (r->fmt == ORACLE_AFMT_S32) {     /* interpolate_gint32_cubic_c */
+      const int32_t *a = (const int32_t *) c0, *b = a + n, *c = b + n, *d = c + n;
+      int64_t ic[4];
+      cubic_coeff_int (frac, r->n_phases, 31, ic);
+      for (i = 0; i < n; i++) {
+        int64_t t = (int64_t) a[i] * ic[0] + (int64_t) b[i] * ic[1] + (int64_t) c[i] * ic[2] + (int64_t) d[i] * ic[3];
+        t = (t + ((int64_t) 1 << 30)) >> 31;
+        ((int32_t *) res)[i] = (int32_t) sat64 (t, -((int64_t) 1 << 31), ((int64_t) 1 << 31) - 1);
+      }
+    } else {                    /* interpolate_gdouble_cubic_sse2: (c0*f0 + c1*f1) + (c2*f2 + c3*f3) */
+      const double *a = (const double *) c0, *b = a + n, *c = b + n, *d = c + n;
+      double ic[4];
+      cubic_coeff_f64 (frac, r->n_phases, ic);
+      for (i = 0; i < n; i++) {
+        double t0 = a[i] * ic[0], t1 = b[i] * ic[1], t2 = c[i] * ic[2], t3 = d[i] * ic[3];
+        t0 = t0 + t1;
+        t2 = t2 + t3;
+        ((double *) res)[i] = t0 + t2;
+      }
+    }
+    r->have[phase] = 1;
+  }
+  return res;
+}
+
+/* one output sample at window `a`, phase `phase`, written to *o (type by format) */
+static void
+resample_one_any (OracleArs * r, const void *a, int phase, void *o)
+{
+  int n = r->n_taps, i, k;
+  if (r->fmt == ORACLE_AFMT_S16) {
+    const int16_t *x = a;
+    if (r->full) {              /* inner_product_gint16_full_1_sse2 */
+      const int16_t *t = phase_taps_any (r, phase);
+      uint32_t sum = 0;
+      for (i = 0; i < n; i++)
+        sum += (uint32_t) (x[i] * (int32_t) t[i]);
+      *(int16_t *) o = (int16_t) sat64 ((int32_t) (sum + (1u << 14)) >> 15, -32768, 32767);
+    } else {                    /* get_taps_gint16_cubic + inner_product_gint16_cubic_1_sse2 */
+      int pos = phase * r->oversample, offset = (r->oversample - 1) - pos / r->out_rate;
+      const int16_t *c = (const int16_t *) r->table + (size_t) offset * n;
+      int64_t ic[4];
+      uint32_t s[4] = { 0, 0, 0, 0 }, acc = 0;
+      cubic_coeff_int (pos % r->out_rate, r->out_rate, 15, ic);
+      for (k = 0; k < 4; k++)
+        for (i = 0; i < n; i++)
+          s[k] += (uint32_t) (x[i] * (int32_t) c[(size_t) k * n + i]);
+      for (k = 0; k < 4; k++)   /* srai 15, then pmaddwd with the low 16 bits */
+        acc += (uint32_t) ((int32_t) (int16_t) ((int32_t) s[k] >> 15) * (int32_t) ic[k]);
+      *(int16_t *) o = (int16_t) sat64 ((int32_t) (acc + (1u << 14)) >> 15, -32768, 32767);
+    }
+  } else if (r->fmt == ORACLE_AFMT_S32) {
+    const int32_t *x = a;
+    const int64_t lo = -((int64_t) 1 << 31), hi = ((int64_t) 1 << 31) - 1;
+    if (r->full) {              /* inner_product_gint32_full_1_sse41 */
+      const int32_t *t = phase_taps_any (r, phase);
+      uint64_t sum = 0;
+      for (i = 0; i < n; i++)
+        sum += (uint64_t) ((int64_t) x[i] * t[i]);
+      *(int32_t *) o = (int32_t) sat64 (((int64_t) sum + (1 << 30)) >> 31, lo, hi);
+    } else {                    /* inner_product_gint32_cubic_1_sse41 */
+      int pos = phase * r->oversample, offset = (r->oversample - 1) - pos / r->out_rate;
+      const int32_t *c = (const int32_t *) r->table + (size_t) offset * n;
+      int64_t ic[4];
+      uint64_t s[4][2], acc = 0;
+      int l;
+      cubic_coeff_int (pos % r->out_rate, r->out_rate, 31, ic);
+      memset (s, 0, sizeof (s));
+      /* two 64-bit lanes per row: pmuldq of (a0,a1 | a2,a3) pairs puts even taps in lane 0, odd taps in lane 1 */
+      for (k = 0; k < 4; k++)
+        for (i = 0; i < n; i++)
+          s[k][i & 1] += (uint64_t) ((int64_t) x[i] * c[(size_t) k * n + i]);
+      /* each LANE is shifted (srli 31) and multiplied (pmuldq: low 32 bits, signed) before the lanes meet */
+      for (k = 0; k < 4; k++)
+        for (l = 0; l < 2; l++)
+          acc += (uint64_t) ((int64_t) (int32_t) (uint32_t) (s[k][l] >> 31) * (int64_t) (int32_t) ic[k]);
+      *(int32_t *) o = (int32_t) sat64 (((int64_t) acc + (1 << 30)) >> 31, lo, hi);
+    }
+  } else {
+    const double *x = a;
+    if (r->full) {              /* inner_product_gdouble_full_1_sse2: two lanes by tap parity */
+      const double *t = phase_taps_any (r, phase);
+      double s0 = 0, s1 = 0;
+      for (i = 0; i < n; i += 2) {
+        double p0 = x[i] * t[i], p1 = x[i + 1] * t[i + 1];
+        s0 = s0 + p0;
+        s1 = s1 + p1;
+      }
+      *(double *) o = s0 + s1;
+    } else {                    /* inner_product_gdouble_cubic_1_sse2 */
+      int pos = phase * r->oversample, offset = (r->oversample - 1) - pos / r->out_rate;
+      const double *c = (const double *) r->table + (size_t) offset * n;
+      double ic[4], s[4][2], l[2];
+      cubic_coeff_f64 (pos % r->out_rate, r->out_rate, ic);
+      memset (s, 0, sizeof (s));
+      for (i = 0; i < n; i += 2)
+        for (k = 0; k < 4; k++) {
+          double p0 = x[i] * c[(size_t) k * n + i], p1 = x[i + 1] * c[(size_t) k * n + i + 1];
+          s[k][0] = s[k][0] + p0;
+          s[k][1] = s[k][1] + p1;
+        }
+      for (i = 0; i < 2; i++) {
+        double t0 = s[0][i] * ic[0], t1 = s[1][i] * ic[1], t2 = s[2][i] * ic[2], t3 = s[3][i] * ic[3];
+        t0 = t0 + t1;
+        t2 = t2 + t3;
+        l[i] = t0 + t2;
+      }
+      *(double *) o = l[0] + l[1];
+    }
+  }
+}
+
+size_t
+oracle_ars_process_any (OracleArs * r, const void *in, size_t in_frames, void *out, size_t out_capacity)
+{
+  size_t out_frames = oracle_ars_get_out_frames (r, in_frames), avail, need, di, consumed;
+  int c, ch = r->channels, samp_index = 0, samp_phase = 0, bps = r->bps;
+  if (r->fmt == ORACLE_AFMT_F32)
+    return oracle_ars_process (r, in, in_frames, out, out_capacity);
+  if (out_frames > out_capacity)
+    out_frames = out_capacity;
+  if ((size_t) r->skip >= in_frames) {
+    r->skip -= (int) in_frames;
+    return out_frames;
+  }
+  r->samp_index += r->skip;
+  avail = r->samples_avail;
+  if (r->samples_len < in_frames + avail) {
+    for (c = 0; c < ch; c++) {
+      char *n = calloc (in_frames + avail, bps);
+      if (r->sbuf[c])
+        memcpy (n, r->sbuf[c], avail * bps);
+      free (r->sbuf[c]);
+      r->sbuf[c] = (float *) n;
+    }
+    r->samples_len = in_frames + avail;
+  }
+  for (c = 0; c < ch; c++) {    /* deinterleave_<type> */
+    char *s = (char *) r->sbuf[c] + avail * bps;
+    size_t i;
+    for (i = 0; i < in_frames; i++) {
+      if (in)
+        memcpy (s + i * bps, (const char *) in + (i * ch + c) * bps, bps);
+      else
+        memset (s + i * bps, 0, bps);
+    }
+  }
+  r->samples_avail = avail += in_frames;
+  need = r->n_taps + r->samp_index;
+  if (avail < need || out_frames == 0)
+    return out_frames;
+  for (c = 0; c < ch; c++) {
+    char *ip = (char *) r->sbuf[c];
+    samp_index = r->samp_index;
+    samp_phase = r->samp_phase;
+    for (di = 0; di < out_frames; di++) {
+      resample_one_any (r, ip + (size_t) samp_index * bps, samp_phase, (char *) out + (di * ch + c) * bps);
+      samp_index += r->samp_inc;
+      samp_phase += r->samp_frac;
+      if (samp_phase >= r->out_rate) {
+        samp_phase -= r->out_rate;
+        samp_index += 1;
+      }
+    }
+    if (avail > (size_t) samp_index)
+      memmove (ip, ip + (size_t) samp_index * bps, (avail - samp_index) * bps);
+  }
+  consumed = samp_index - r->samp_index;
+  r->samp_index = 0;
+  r->samp_phase = samp_phase;
+  if (consumed > 0) {
+    if (avail > consumed) {
+      r->samples_avail = avail - consumed;
+    } else {
+      r->samples_avail = 0;
+      r->skip = (int) (consumed - avail);
+    }
+  }
+  return out_frames;
 }
 
 size_t

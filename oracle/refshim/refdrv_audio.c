@@ -12,8 +12,18 @@
 
 #define OPT_METHOD "GstAudioConverter.resampler-method"
 
+GstAudioResampler *ref_ars_new_fmt (int in_rate, int out_rate, int channels, int quality, int format);
+
 GstAudioResampler *
 ref_ars_new (int in_rate, int out_rate, int channels, int quality)
+{
+  return ref_ars_new_fmt (in_rate, out_rate, channels, quality, GST_AUDIO_FORMAT_F32);
+}
+
+/* format: GstAudioFormat of the samples the resampler works on — S16, S32, F32 or F64 in native
+ * endianness, the formats audioresample hands over unconverted (audio-converter.c:700-727) */
+GstAudioResampler *
+ref_ars_new_fmt (int in_rate, int out_rate, int channels, int quality, int format)
 {
   GstStructure *options = gst_structure_new_static_str_empty ("resampler-options");
   GstAudioResampler *r;
@@ -27,7 +37,7 @@ ref_ars_new (int in_rate, int out_rate, int channels, int quality)
       GST_AUDIO_RESAMPLER_OPT_FILTER_INTERPOLATION, GST_TYPE_AUDIO_RESAMPLER_FILTER_INTERPOLATION,
       GST_AUDIO_RESAMPLER_FILTER_INTERPOLATION_CUBIC, NULL);
   r = gst_audio_resampler_new (GST_AUDIO_RESAMPLER_METHOD_KAISER,
-      GST_AUDIO_RESAMPLER_FLAG_VARIABLE_RATE, GST_AUDIO_FORMAT_F32, channels, in_rate, out_rate,
+      GST_AUDIO_RESAMPLER_FLAG_VARIABLE_RATE, (GstAudioFormat) format, channels, in_rate, out_rate,
       options);
   gst_structure_free (options);
   return r;
@@ -41,7 +51,7 @@ size_t ref_ars_max_latency (GstAudioResampler * r) { return gst_audio_resampler_
 
 /* like gst_audio_resample_process() (gstaudioresample.c:743-883): compute out length, resample */
 size_t
-ref_ars_process (GstAudioResampler * r, const float *in, size_t in_frames, float *out,
+ref_ars_process (GstAudioResampler * r, const void *in, size_t in_frames, void *out,
     size_t out_capacity)
 {
   size_t n = gst_audio_resampler_get_out_frames (r, in_frames);

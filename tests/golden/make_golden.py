@@ -144,11 +144,39 @@ def audio_interpolated():
     json.dump(cases, open(os.path.join(HERE, "audio_interp_cases.json"), "w"), indent=1)
 
 
+def audio_formats():
+    """S16 / S32 / F64 sample formats, FULL and interpolated filter modes"""
+    r = ob.ref()
+    arrays, cases = {}, []
+    t = 0
+    for fmt in ("S16", "S32", "F64"):
+        _, gfmt, dt, _ = ob.AUDIO_FORMATS[fmt]
+        for (a, b, ch, q, bufs) in [(48000, 44100, 2, 4, [480, 480]), (8000, 16000, 1, 4, [160, 160, 160]),
+                                    (44100, 48001, 2, 4, [441, 100]), (96000, 8000, 1, 7, [4000])]:
+            h = r.ref_ars_new_fmt(a, b, ch, q, gfmt)
+            rng = np.random.default_rng(1200 + t)
+            outs, counts = [], []
+            for n in bufs:
+                x = ob.audio_test_signal(rng, n, ch, fmt)
+                cap = int(n * b / a) + 64
+                o = np.zeros((cap, ch), dtype=dt)
+                k = r.ref_ars_process(h, x.ctypes.data, n, o.ctypes.data, cap)
+                outs.append(o[:k].copy())
+                counts.append(int(k))
+            r.ref_ars_free(h)
+            arrays[f"af_{t}"] = np.concatenate(outs)
+            cases.append({"key": f"af_{t}", "fmt": fmt, "in_rate": a, "out_rate": b, "ch": ch, "quality": q, "bufs": bufs,
+                          "counts": counts, "seed": 1200 + t})
+            t += 1
+    np.savez_compressed(os.path.join(HERE, "audio_formats.npz"), **arrays)
+    json.dump(cases, open(os.path.join(HERE, "audio_formats_cases.json"), "w"), indent=1)
+
+
 if __name__ == "__main__":
     assert ob.have_ref(), "needs oracle/_ref/libgstref.so (make -C oracle ref)"
     only = set(sys.argv[1:])
     for name, fn in [("video", video), ("compositor", compositor), ("audio", audio), ("video_planar", video_planar),
-                     ("audio_interpolated", audio_interpolated)]:
+                     ("audio_interpolated", audio_interpolated), ("audio_formats", audio_formats)]:
         if not only or name in only:
             fn()
     print("golden fixtures written to", HERE)

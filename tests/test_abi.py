@@ -63,7 +63,8 @@ def test_argument_validation_matches_caps_ranges():
     from gstreamer_b200 import _lib
     ii, oi = _lib.VideoInfoC(), _lib.VideoInfoC()
     assert lib.b200_video_info_set_format(C.byref(ii), 23, 0, 10) == -1
-    assert lib.b200_video_info_set_format(C.byref(ii), 2, 64, 48) == -2       # I420: not on this path yet
+    assert lib.b200_video_info_set_format(C.byref(ii), 2, 64, 48) == 0        # I420 is supported
+    assert lib.b200_video_info_set_format(C.byref(ii), 16, 64, 48) == -2      # Y444: not on this path yet
     assert lib.b200_video_info_set_format(C.byref(ii), 23, 64, 48) == 0
     assert lib.b200_video_info_set_format(C.byref(oi), 12, 32, 24) == 0
     h = C.c_void_p()

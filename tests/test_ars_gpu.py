@@ -144,3 +144,39 @@ def test_interpolated_filter_mode(cuda_device, cfg):
     rs.set_caps(a, b, ch)
     assert rs.plan_info().filter_mode == 0          # GST_AUDIO_RESAMPLER_FILTER_MODE_INTERPOLATED
     _stream_through(a, b, ch, q, [480, 480, 100, 1, 2000, 37], seed=ch)
+
+
+@pytest.mark.parametrize("cfg", [(48000, 44100, 2, 4), (44100, 48000, 3, 4), (8000, 16000, 1, 4), (48000, 24000, 40, 4),
+                                 (101, 99, 1, 4), (44100, 8000, 2, 10), (96000, 8000, 1, 7), (12345, 54321, 2, 4),
+                                 (44100, 48001, 2, 4), (48000, 44101, 1, 6), (7999, 48000, 3, 10)],
+                         ids=lambda c: "%d-%d-%dch-q%d" % c)
+@pytest.mark.parametrize("fmt", ["S16", "S32", "F64"])
+def test_sample_formats(cuda_device, fmt, cfg):
+    """S16 / S32 / F64 sample formats, FULL and interpolated filter modes: byte-identical to the oracle"""
+    import torch
+    from gstreamer_b200.audio import CudaAudioResample
+    a, b, ch, q = cfg
+    ofmt, gfmt, dt, _ = ob.AUDIO_FORMATS[fmt]
+    o = ob.oracle()
+    ho = o.oracle_ars_new_fmt(a, b, ch, q, ofmt)
+    rs = CudaAudioResample(quality=q, format=gfmt)
+    rs.set_caps(a, b, ch)
+    rng = np.random.default_rng(ch + a)
+    tdt = {np.int16: torch.int16, np.int32: torch.int32, np.float64: torch.float64}[dt]
+    for n in [480, 480, 100, 1, 2000, 37, None]:
+        x = None
+        if n is None:
+            n = rs.max_latency
+        else:
+            x = ob.audio_test_signal(rng, n, ch, fmt)
+        cap = int(n * b / a) + 64
+        want = np.zeros((cap, ch), dtype=dt)
+        assert rs.get_out_frames(n) == o.oracle_ars_get_out_frames(ho, n)
+        nw = o.oracle_ars_process_any(ho, x.ctypes.data if x is not None else None, n, want.ctypes.data, cap)
+        out = torch.full((cap * ch,), 7, dtype=tdt, device="cuda")
+        ng = rs.transform(torch.from_numpy(x).cuda() if x is not None else None, n, out, cap)
+        torch.cuda.synchronize()
+        got = out.cpu().numpy().reshape(cap, ch)
+        assert ng == nw and got[:ng].tobytes() == want[:nw].tobytes()
+        assert (got[ng:] == 7).all()
+    o.oracle_ars_free(ho)

@@ -130,3 +130,23 @@ def test_audio_interpolated(case):
     o.oracle_ars_free(h)
     assert counts == case["counts"]
     assert np.array_equal(np.concatenate(outs).view(np.uint32), gold.view(np.uint32))
+
+
+@pytest.mark.parametrize("case", json.load(open(os.path.join(G, "audio_formats_cases.json"))), ids=lambda c: c["key"] + "_" + c["fmt"])
+def test_audio_formats(case):
+    gold = np.load(os.path.join(G, "audio_formats.npz"))[case["key"]]
+    ofmt, _, dt, _ = ob.AUDIO_FORMATS[case["fmt"]]
+    o = ob.oracle()
+    h = o.oracle_ars_new_fmt(case["in_rate"], case["out_rate"], case["ch"], case["quality"], ofmt)
+    rng = np.random.default_rng(case["seed"])
+    outs, counts = [], []
+    for n in case["bufs"]:
+        x = ob.audio_test_signal(rng, n, case["ch"], case["fmt"])
+        cap = int(n * case["out_rate"] / case["in_rate"]) + 64
+        out = np.zeros((cap, case["ch"]), dtype=dt)
+        k = o.oracle_ars_process_any(h, x.ctypes.data, n, out.ctypes.data, cap)
+        outs.append(out[:k].copy())
+        counts.append(int(k))
+    o.oracle_ars_free(h)
+    assert counts == case["counts"]
+    assert np.concatenate(outs).tobytes() == gold.tobytes()
