@@ -12,6 +12,8 @@
 #include "vcs_plan.h"
 
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 
@@ -333,7 +335,10 @@ void light_geometry (VcsPlan * p)
   if (p->h.mode == PASS_2TAP) for (int16_t c : p->h.coef) if (c < 0 || c > 255) return;
   if (p->v.mode == PASS_2TAP) for (int16_t c : p->v.coef) if (c < 0 || c > 256) return;
   const int ow = p->out.width, oh = p->out.height, tw = 128;
-  for (int th = 16; th >= 1; th /= 2) {
+  const char *env_th = getenv ("B200_LIGHT_TH");              // tuning aid
+  static const int heights[] = {32, 16, 8, 4, 2, 1};              // 32 rows measured best on C1 (4.77 us vs 5.67 at 16)
+  for (int hi = 0; hi < 6; hi++) {
+    const int th = (env_th && hi == 0) ? atoi (env_th) : heights[hi];
     int max_rows = 0, max_cols = 0;
     for (int y0 = 0; y0 < oh; y0 += th) {
       int y1 = std::min (y0 + th, oh) - 1;
@@ -347,7 +352,7 @@ void light_geometry (VcsPlan * p)
     const int cp = max_cols + 4;                                  // +4 words: rows start on distinct banks
     const size_t t_words = p->h_first ? (size_t) max_rows * tw : (size_t) th * cp;
     const size_t total = ((size_t) max_rows * cp + t_words + 4 * (size_t) max_rows + 4 + th) * 4;   // S, T, work list, v table
-    if (total <= 96 * 1024) {
+    if (total <= (env_th ? 200 : 96) * 1024) {
       p->light_ok = true; p->light_tw = tw; p->light_th = th; p->light_rows = max_rows; p->light_cp = cp;
       p->light_smem = (int) total;
       return;
@@ -394,8 +399,12 @@ void ntap_geometry (VcsPlan * p)
   static const int shapes[][2] = {{128, 32}, {128, 16}, {64, 32}, {128, 8}, {64, 16}, {32, 32}, {64, 8}, {32, 16},
                                   {64, 4}, {32, 8}, {32, 4}, {32, 2}, {32, 1}};
   double best = 0;
+  const char *env_shape = getenv ("B200_NTAP_SHAPE");             // tuning aid: "tw,th"
+  int etw = 0, eth = 0;
+  if (env_shape && sscanf (env_shape, "%d,%d", &etw, &eth) != 2) etw = eth = 0;
   for (auto & sh : shapes) {
     const int tw = sh[0], th = sh[1];
+    if (etw && (tw != etw || th != eth)) continue;
     if (th > 16 && oh < 2 * th) continue;
     int max_rows = 0, max_cols = 0;
     for (int y0 = 0; y0 < oh; y0 += th) {
