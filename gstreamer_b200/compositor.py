@@ -77,8 +77,29 @@ class CudaCompositor:
         self.sinkpads.append(pad)
         return pad
 
+    YUV_FORMATS = (VideoFormat.I420, VideoFormat.YV12, VideoFormat.NV12, VideoFormat.NV21)
+
+    def _aggregate_yuv(self, outbuf, out_info, stream):
+        """4:2:0 output: every pad frame has the output's format (blend.c PLANAR_YUV_BLEND / NV_YUV_BLEND);
+        a pad's plane layout comes from pad.in_info, default layout otherwise"""
+        from .video import VideoInfo
+        out_info = out_info or VideoInfo(self.format, self.width, self.height)
+        pads = [p for p in self.sinkpads if p.frame is not None]
+        arr = (_lib.CompPadYuvC * max(len(pads), 1))()
+        keep = []
+        for i, p in enumerate(pads):
+            info = p.in_info or VideoInfo(self.format, p.width, p.height)
+            keep.append(info)
+            arr[i].data = _ptr(p.frame)
+            arr[i].info = info.c
+            arr[i].xpos, arr[i].ypos, arr[i].alpha, arr[i].op = p.xpos, p.ypos, p.alpha, int(p.operator)
+        check(lib.b200_comp_blend_yuv(self._h, _ptr(outbuf), C.byref(out_info.c), int(self.background), arr, len(pads),
+                                      _stream(stream)), "b200_comp_blend_yuv")
+
     # GstVideoAggregatorClass::aggregate_frames (outbuf is device memory)
-    def aggregate_frames(self, outbuf, out_stride=None, stream=None):
+    def aggregate_frames(self, outbuf, out_stride=None, stream=None, out_info=None):
+        if self.format in self.YUV_FORMATS:
+            return self._aggregate_yuv(outbuf, out_info, stream)
         pads = [p for p in self.sinkpads if p.frame is not None]
         arr = (_lib.CompPadC * max(len(pads), 1))()
         for i, p in enumerate(pads):

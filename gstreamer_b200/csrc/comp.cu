@@ -13,6 +13,7 @@
 #include "common.h"
 
 #include <string.h>
+#include <algorithm>
 #include <new>
 
 namespace b200 {
@@ -240,6 +241,78 @@ comp_kernel (const CompParams P)
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// 4:2:0 output (I420 / YV12 / NV12 / NV21): blend.c PLANAR_YUV_BLEND (:246-401) and NV_YUV_BLEND
+// (:1386-1500).  Per plane the reference runs compositor_orc_blend_u8 (compositororc.orc:20-36) —
+// d = (d*256 + (s-d)*alpha) >> 8 on bytes, or a row copy for alpha 1.0 / SOURCE — over a byte
+// rectangle; the interleaved UV plane is blended as 2*width bytes.  The host reproduces the
+// reference's rectangle arithmetic (ROUND_UP_2 of the position, ceil-halved chroma extents); the
+// kernel is the same single pass as comp_kernel: background, every pad in z-order in registers,
+// one store, 4 bytes per thread, one launch for all planes (blockIdx.z).
+constexpr int CY_MAX_PADS = 24;
+
+struct CompYuvRect {
+  const uint8_t *src;            // offset so that src + y*stride + x is the source byte of PLANE byte (x,y)
+  int stride;
+  int x0, x1, y0, y1;            // plane-byte rectangle
+  int alpha;                     // 0..255 blend, 256 = copy
+};
+
+struct CompYuvParams {
+  uint8_t *dst[3];
+  int stride[3], wbytes[3], rows[3];
+  int bg_mode[3];                // 0 checker (luma), 1 constant, -1 keep destination (continuation chunk)
+  int bg_value[3];
+  int n_planes, n_pads;
+  CompYuvRect pads[CY_MAX_PADS][3];
+};
+
+__global__ void __launch_bounds__ (256)
+comp_yuv_kernel (const CompYuvParams P)
+{
+  const int z = blockIdx.z;
+  const int x = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4, y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (x >= P.wbytes[z] || y >= P.rows[z]) return;
+  uint8_t *dp = P.dst[z] + (size_t) y * P.stride[z] + x;
+  const int n = min (4, P.wbytes[z] - x);
+  const bool vec = n == 4 && (((size_t) dp) & 3) == 0;
+  unsigned d;
+  if (P.bg_mode[z] == 0) {                                         // fill_checker_*: 8x8 squares of 80 / 160
+    const unsigned v = ((y >> 3) ^ (x >> 3)) & 1 ? 160u : 80u;     // x % 4 == 0: the 4 bytes share a square
+    d = v * 0x01010101u;
+  } else if (P.bg_mode[z] == 1) {
+    d = (unsigned) P.bg_value[z] * 0x01010101u;
+  } else if (vec) {
+    d = *(const unsigned *) dp;
+  } else {
+    d = 0;
+    for (int i = 0; i < n; i++) d |= (unsigned) dp[i] << (8 * i);
+  }
+  for (int k = 0; k < P.n_pads; k++) {
+    const CompYuvRect & r = P.pads[k][z];
+    if (y < r.y0 || y >= r.y1 || x >= r.x1 || x + 4 <= r.x0) continue;
+    const uint8_t *sp = r.src + (size_t) y * r.stride + x;
+    unsigned s = 0, m = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+      if (x + i >= r.x0 && x + i < r.x1) {
+        s |= (unsigned) __ldg (sp + i) << (8 * i);
+        m |= 0xffu << (8 * i);
+      }
+    unsigned v = s;
+    if (r.alpha < 256) {                                           // (d*(256-a) + s*a) >> 8 on two 16-bit lanes
+      const unsigned a = (unsigned) r.alpha, ia = 256u - a;
+      const unsigned lo = (d & 0x00ff00ffu) * ia + (s & 0x00ff00ffu) * a;
+      const unsigned hi = __byte_perm (d, 0, 0x4341) * ia + __byte_perm (s, 0, 0x4341) * a;
+      v = __byte_perm (lo, hi, 0x7351);
+    }
+    d = (v & m) | (d & ~m);
+  }
+  if (vec) *(unsigned *) dp = d;
+  else
+    for (int i = 0; i < n; i++) dp[i] = (uint8_t) (d >> (8 * i));
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -260,6 +333,8 @@ int b200_comp_create (int out_format, int width, int height, int device, b200_co
   switch (out_format) {          // blend.h:55-66: rgba uses the bgra kernels, abgr the argb ones
     case B200_VIDEO_FORMAT_BGRA: case B200_VIDEO_FORMAT_RGBA: shift = 24; break;
     case B200_VIDEO_FORMAT_ARGB: case B200_VIDEO_FORMAT_ABGR: shift = 0; break;
+    case B200_VIDEO_FORMAT_I420: case B200_VIDEO_FORMAT_YV12: case B200_VIDEO_FORMAT_NV12: case B200_VIDEO_FORMAT_NV21:
+      shift = -1; break;                                           // 4:2:0 output: b200_comp_blend_yuv
     default: return B200_ERR_UNSUPPORTED;
   }
   if (device >= 0) {
@@ -281,6 +356,7 @@ int b200_comp_blend (b200_comp * h, void *dst, int32_t dst_stride, int backgroun
 {
   if (!h || !dst || n_pads < 0 || n_pads > B200_COMP_MAX_PADS || (n_pads && !pads)) return B200_ERR_INVALID_ARG;
   if (background < 0 || background > 3) return B200_ERR_INVALID_ARG;
+  if (h->alpha_shift < 0) return B200_ERR_STATE;                   // created for a 4:2:0 format
   if (dst_stride < h->width * 4 || (dst_stride & 3)) return B200_ERR_INVALID_ARG;
   if (h->device < 0) return B200_ERR_NO_DEVICE;
   DeviceGuard g (h->device);
@@ -323,6 +399,88 @@ int b200_comp_blend (b200_comp * h, void *dst, int32_t dst_stride, int backgroun
     if (d.mode == CM_OVERLAY || d.mode == CM_OVERLAY_ADD) P.need_recip = 1;
     P.pads[P.n_pads++] = d;
     if (P.n_pads == COMP_CHUNK) { int st = flush (); if (st != B200_OK) return st; }
+  }
+  if (P.n_pads > 0 || launched == 0) { int st = flush (); if (st != B200_OK) return st; }
+  return B200_OK;
+}
+
+int b200_comp_blend_yuv (b200_comp * h, void *dst, const b200_video_info * di, int background,
+    const b200_comp_pad_yuv * pads, int n_pads, void *cuda_stream)
+{
+  if (!h || !dst || !di || n_pads < 0 || n_pads > B200_COMP_MAX_PADS || (n_pads && !pads)) return B200_ERR_INVALID_ARG;
+  if (background < 0 || background > 3) return B200_ERR_INVALID_ARG;
+  if (h->alpha_shift >= 0) return B200_ERR_STATE;                  // created for a packed RGB format
+  if (di->format != h->format || di->width != h->width || di->height != h->height) return B200_ERR_INVALID_ARG;
+  if (h->device < 0) return B200_ERR_NO_DEVICE;
+  DeviceGuard g (h->device);
+  if (!g.ok) return B200_ERR_CUDA;
+  const bool semi = h->format == B200_VIDEO_FORMAT_NV12 || h->format == B200_VIDEO_FORMAT_NV21;
+  const int W = h->width, H = h->height, n_planes = semi ? 2 : 3;
+  auto half_up = [] (int v) { return -((-v) >> 1); };              // GST_VIDEO_FORMAT_INFO_SCALE_WIDTH / _HEIGHT, 2x sub-sampling
+  CompYuvParams P;
+  memset (&P, 0, sizeof (P));
+  P.n_planes = n_planes;
+  for (int p = 0; p < n_planes; p++) {
+    P.dst[p] = (uint8_t *) dst + di->offset[p];
+    P.stride[p] = di->stride[p];
+    P.wbytes[p] = p == 0 ? W : (semi ? 2 * half_up (W) : half_up (W));
+    P.rows[p] = p == 0 ? H : half_up (H);
+    if (P.stride[p] < P.wbytes[p]) return B200_ERR_INVALID_ARG;
+    // _draw_background (compositor.c:1619-1675): checker = luma squares + 0x80 chroma; black / white from the
+    // range offsets (compositor.c:1131-1149); transparent = zeroed planes (and overlay == blend)
+    const bool full_range = di->color_range == B200_COLOR_RANGE_0_255;
+    if (background == B200_COMP_BG_CHECKER) { P.bg_mode[p] = p == 0 ? 0 : 1; P.bg_value[p] = 0x80; }
+    else if (background == B200_COMP_BG_TRANSPARENT) { P.bg_mode[p] = 1; P.bg_value[p] = 0; }
+    else {
+      P.bg_mode[p] = 1;
+      P.bg_value[p] = p ? 128 : (background == B200_COMP_BG_BLACK ? (full_range ? 0 : 16) : (full_range ? 255 : 235));
+    }
+  }
+  unsigned gx = 0, gy = 0;
+  for (int p = 0; p < n_planes; p++) {
+    gx = std::max (gx, (unsigned) ((P.wbytes[p] + 127) / 128));
+    gy = std::max (gy, (unsigned) ((P.rows[p] + 7) / 8));
+  }
+  const dim3 grid (gx, gy, n_planes);
+  int launched = 0;
+  auto flush = [&] () -> int {
+    comp_yuv_kernel <<<grid, 256, 0, (cudaStream_t) cuda_stream>>> (P);
+    B200_CUDA_TRY (cudaGetLastError ());
+    launched++;
+    P.n_pads = 0;
+    for (int p = 0; p < n_planes; p++) P.bg_mode[p] = -1;           // later chunks continue from the destination
+    return B200_OK;
+  };
+  for (int i = 0; i < n_pads; i++) {
+    const b200_comp_pad_yuv & pad = pads[i];
+    if (pad.info.format != h->format || pad.info.width < 1 || pad.info.height < 1 || !pad.data) return B200_ERR_INVALID_ARG;
+    double alpha = pad.alpha;
+    if (pad.op == B200_COMP_OP_SOURCE) alpha = 1.0;                // _blend_*: source mode copies
+    if (alpha == 0.0) continue;
+    // blend_<format> (blend.c:284-340 / :1418-1470): position rounded up to even, clip against the frame
+    int xpos = (pad.xpos + 1) & ~1, ypos = (pad.ypos + 1) & ~1, xoffset = 0, yoffset = 0;
+    int bw = pad.info.width, bh = pad.info.height;
+    if (xpos < 0) { xoffset = -xpos; bw -= -xpos; xpos = 0; }
+    if (ypos < 0) { yoffset = -ypos; bh -= -ypos; ypos = 0; }
+    if (xoffset >= pad.info.width || yoffset >= pad.info.height) continue;
+    if (xpos + bw > W) bw = W - xpos;
+    if (ypos + bh > H) bh = H - ypos;
+    if (bw <= 0 || bh <= 0) continue;
+    int b_alpha = 256;
+    if (alpha != 1.0) { b_alpha = (int) (alpha * 255); b_alpha = b_alpha < 0 ? 0 : (b_alpha > 255 ? 255 : b_alpha); }
+    if (P.n_pads == CY_MAX_PADS) { int st = flush (); if (st != B200_OK) return st; }
+    const int cw = half_up (bw), ch = half_up (bh);
+    const int cxpos = xpos ? half_up (xpos) : 0, cypos = ypos >> 1, cxoff = xoffset ? half_up (xoffset) : 0, cyoff = yoffset >> 1;
+    for (int p = 0; p < n_planes; p++) {
+      CompYuvRect & r = P.pads[P.n_pads][p];
+      const int mul = (p && semi) ? 2 : 1;
+      const int px = p ? mul * cxpos : xpos, py = p ? cypos : ypos, sx = p ? mul * cxoff : xoffset, sy = p ? cyoff : yoffset;
+      const int w = p ? mul * cw : bw, hgt = p ? ch : bh;
+      r.stride = pad.info.stride[p];
+      r.x0 = px; r.x1 = px + w; r.y0 = py; r.y1 = py + hgt; r.alpha = b_alpha;
+      r.src = (const uint8_t *) pad.data + pad.info.offset[p] + (long long) (sy - py) * r.stride + (sx - px);
+    }
+    P.n_pads++;
   }
   if (P.n_pads > 0 || launched == 0) { int st = flush (); if (st != B200_OK) return st; }
   return B200_OK;

@@ -187,7 +187,8 @@ typedef struct {
 
 typedef struct b200_comp b200_comp;
 #define B200_COMP_MAX_PADS 64
-/* out_format: one of the packed 8-bit RGB formats with alpha (RGBA/BGRA/ARGB/ABGR) */
+/* out_format: a packed 8-bit RGB format with alpha (RGBA/BGRA/ARGB/ABGR; b200_comp_blend) or a 4:2:0 YUV format
+ * (I420/YV12/NV12/NV21; b200_comp_blend_yuv) */
 int b200_comp_create (int out_format, int width, int height, int device, b200_comp ** handle);
 void b200_comp_destroy (b200_comp * h);
 /* background fill + every pad in z-order in ONE pass over the destination.
@@ -195,6 +196,21 @@ void b200_comp_destroy (b200_comp * h);
  * fully obscured pads give the same bytes as the reference's culling (compositor.c:519-601). */
 int b200_comp_blend (b200_comp * h, void *dst, int32_t dst_stride, int background,
     const b200_comp_pad * pads, int n_pads, void *cuda_stream);
+
+/* 4:2:0 output (I420, YV12, NV12, NV21 given to b200_comp_create): blend.c PLANAR_YUV_BLEND / NV_YUV_BLEND.
+ * Every pad frame has the OUTPUT's format (the aggregator converts pads that differ);
+ * plane strides / offsets of the destination and of every pad come from their b200_video_info. */
+typedef struct {
+  const void *data;              /* device pointer to the pad's frame */
+  b200_video_info info;          /* format (== output format), width, height, plane layout */
+  int32_t xpos, ypos;
+  double alpha;
+  int32_t op;                    /* b200_comp_operator: SOURCE copies, OVER and ADD blend with the pad alpha */
+  int32_t reserved;
+} b200_comp_pad_yuv;
+/* dst_info->color_range picks the black / white background levels (16..235 unless B200_COLOR_RANGE_0_255) */
+int b200_comp_blend_yuv (b200_comp * h, void *dst, const b200_video_info * dst_info, int background,
+    const b200_comp_pad_yuv * pads, int n_pads, void *cuda_stream);
 
 /* ------------------------------------------------------------------ audio resampler */
 typedef struct b200_ars b200_ars;

@@ -75,6 +75,10 @@ def oracle():
         if hasattr(o, "oracle_compositor"):
             o.oracle_compositor.argtypes = [C.c_int, P, C.c_int, C.c_int, C.c_int, C.c_int,
                                             C.POINTER(OraclePad), C.c_int]
+        if hasattr(o, "oracle_compositor_yuv"):
+            o.oracle_compositor_yuv_size.restype = C.c_size_t
+            o.oracle_compositor_yuv_size.argtypes = [C.c_int] * 3
+            o.oracle_compositor_yuv.argtypes = [C.c_int, P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(OraclePad), C.c_int]
         if hasattr(o, "oracle_ars_new"):
             o.oracle_ars_new.restype = P
             o.oracle_ars_new.argtypes = [C.c_int] * 4
@@ -114,6 +118,8 @@ def ref():
         if hasattr(r, "ref_compositor"):
             r.ref_compositor.argtypes = [C.c_int, P, C.c_int, C.c_int, C.c_int, C.c_int,
                                          C.POINTER(OraclePad), C.c_int]
+        if hasattr(r, "ref_compositor_yuv"):
+            r.ref_compositor_yuv.argtypes = [C.c_int, P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(OraclePad), C.c_int]
         if hasattr(r, "ref_ars_new"):
             r.ref_ars_new.restype = P
             r.ref_ars_new.argtypes = [C.c_int] * 4

@@ -86,6 +86,11 @@ typedef struct {
 int oracle_compositor (int out_format, uint8_t * dst, int width, int height, int stride,
     int background, const OraclePad * pads, int n_pads);
 
+/* 4:2:0 output and pads (I420, YV12, NV12, NV21; default plane layouts): blend.c PLANAR_YUV_BLEND / NV_YUV_BLEND */
+size_t oracle_compositor_yuv_size (int format, int width, int height);
+int oracle_compositor_yuv (int format, uint8_t * dst, int width, int height, int background, int range_16_235,
+    const OraclePad * pads, int n_pads);
+
 /* ---------------- audio resampler -------------------------------------------- */
 typedef struct OracleArs OracleArs;
 /* gstaudioresample.c:374-396 (element option plumbing) + audio-resampler.c:1344-1424.

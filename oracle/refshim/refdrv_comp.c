@@ -80,3 +80,60 @@ ref_compositor (int out_format, guint8 * dst, int width, int height, int stride,
   }
   return 0;
 }
+
+
+/* 4:2:0 formats (I420, YV12, NV12, NV21): every pad frame has the output's format, default plane
+ * layouts (gst_video_info_set_format); range_16_235 selects the black/white levels the way
+ * gst_video_color_range_offsets does (compositor.c:1131-1149). */
+int
+ref_compositor_yuv (int format, guint8 * dst, int width, int height, int background, int range_16_235,
+    const RefPad * pads, int n_pads)
+{
+  static gsize inited = 0;
+  GstVideoFrame out;
+  BlendFunction blend;
+  FillCheckerFunction fill_checker;
+  FillColorFunction fill_color;
+  int i, p;
+  if (!inited) {
+    gst_compositor_init_blend ();
+    inited = 1;
+  }
+  switch (format) {             /* compositor.c:982-1005 */
+    case GST_VIDEO_FORMAT_I420:
+      blend = gst_compositor_blend_i420; fill_checker = gst_compositor_fill_checker_i420; fill_color = gst_compositor_fill_color_i420;
+      break;
+    case GST_VIDEO_FORMAT_YV12:
+      blend = gst_compositor_blend_yv12; fill_checker = gst_compositor_fill_checker_yv12; fill_color = gst_compositor_fill_color_yv12;
+      break;
+    case GST_VIDEO_FORMAT_NV12:
+      blend = gst_compositor_blend_nv12; fill_checker = gst_compositor_fill_checker_nv12; fill_color = gst_compositor_fill_color_nv12;
+      break;
+    case GST_VIDEO_FORMAT_NV21:
+      blend = gst_compositor_blend_nv21; fill_checker = gst_compositor_fill_checker_nv21; fill_color = gst_compositor_fill_color_nv21;
+      break;
+    default:
+      return -1;
+  }
+  memset (&out, 0, sizeof (out));
+  gst_video_info_set_format (&out.info, (GstVideoFormat) format, width, height);
+  for (p = 0; p < (int) GST_VIDEO_INFO_N_PLANES (&out.info); p++)
+    out.data[p] = dst + out.info.offset[p];
+  switch (background) {
+    case 0: fill_checker (&out, 0, height); break;
+    case 1: fill_color (&out, 0, height, range_16_235 ? 16 : 0, 128, 128); break;
+    case 2: fill_color (&out, 0, height, range_16_235 ? 235 : 255, 128, 128); break;
+    default:
+      memset (dst, 0, out.info.size);   /* every plane row zeroed; overlay == blend for these formats */
+      break;
+  }
+  for (i = 0; i < n_pads; i++) {
+    GstVideoFrame src;
+    memset (&src, 0, sizeof (src));
+    gst_video_info_set_format (&src.info, (GstVideoFormat) format, pads[i].width, pads[i].height);
+    for (p = 0; p < (int) GST_VIDEO_INFO_N_PLANES (&src.info); p++)
+      src.data[p] = (guint8 *) pads[i].data + src.info.offset[p];
+    blend (&src, pads[i].xpos, pads[i].ypos, pads[i].alpha, &out, 0, height, (GstCompositorBlendMode) pads[i].op);
+  }
+  return 0;
+}

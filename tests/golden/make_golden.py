@@ -172,11 +172,40 @@ def audio_formats():
     json.dump(cases, open(os.path.join(HERE, "audio_formats_cases.json"), "w"), indent=1)
 
 
+def compositor_420():
+    """I420 / YV12 / NV12 / NV21 output"""
+    o, r = ob.oracle(), ob.ref()
+    rng = np.random.default_rng(4242)
+    arrays, cases = {}, []
+    for t in range(24):
+        fmt = [2, 3, 23, 24][t % 4]
+        W, H, bg, rg = int(rng.integers(2, 80)), int(rng.integers(2, 60)), int(rng.integers(0, 4)), int(rng.integers(0, 2))
+        n = int(rng.integers(1, 5))
+        pads = (ob.OraclePad * n)()
+        spec, keep = [], []
+        for i in range(n):
+            w, h = int(rng.integers(1, 50)), int(rng.integers(1, 40))
+            seed = int(rng.integers(0, 1 << 30))
+            a = np.random.default_rng(seed).integers(0, 256, o.oracle_compositor_yuv_size(fmt, w, h), dtype=np.uint8)
+            keep.append(a)
+            x, y = int(rng.integers(-20, W)), int(rng.integers(-20, H))
+            al, op = float(rng.choice([0.25, 0.5, 1.0, 0.9])), int(rng.integers(0, 3))
+            pads[i].data, pads[i].width, pads[i].height, pads[i].stride = a.ctypes.data, w, h, 0
+            pads[i].xpos, pads[i].ypos, pads[i].alpha, pads[i].op = x, y, al, op
+            spec.append([w, h, x, y, al, op, seed])
+        dst = np.zeros(o.oracle_compositor_yuv_size(fmt, W, H), dtype=np.uint8)
+        r.ref_compositor_yuv(fmt, dst.ctypes.data, W, H, bg, rg, pads, n)
+        arrays[f"cy_{t}"] = dst
+        cases.append({"key": f"cy_{t}", "W": W, "H": H, "fmt": fmt, "bg": bg, "range": rg, "pads": spec})
+    np.savez_compressed(os.path.join(HERE, "comp_420.npz"), **arrays)
+    json.dump(cases, open(os.path.join(HERE, "comp_420_cases.json"), "w"), indent=1)
+
+
 if __name__ == "__main__":
     assert ob.have_ref(), "needs oracle/_ref/libgstref.so (make -C oracle ref)"
     only = set(sys.argv[1:])
     for name, fn in [("video", video), ("compositor", compositor), ("audio", audio), ("video_planar", video_planar),
-                     ("audio_interpolated", audio_interpolated), ("audio_formats", audio_formats)]:
+                     ("audio_interpolated", audio_interpolated), ("audio_formats", audio_formats), ("compositor_420", compositor_420)]:
         if not only or name in only:
             fn()
     print("golden fixtures written to", HERE)

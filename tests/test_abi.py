@@ -78,7 +78,9 @@ def test_argument_validation_matches_caps_ranges():
     assert lib.b200_vcs_create(C.byref(ii), C.byref(oi), None, -1, C.byref(h)) == -1
     # compositor / resampler argument checks
     hc = C.c_void_p()
-    assert lib.b200_comp_create(23, 64, 48, -1, C.byref(hc)) == -2
+    assert lib.b200_comp_create(23, 64, 48, -1, C.byref(hc)) == 0          # NV12 output: b200_comp_blend_yuv
+    lib.b200_comp_destroy(hc)
+    assert lib.b200_comp_create(7, 64, 48, -1, C.byref(hc)) == -2           # RGBx: no alpha, unsupported
     assert lib.b200_comp_create(11, 0, 48, -1, C.byref(hc)) == -1
     cfg = _lib.ArsConfigC()
     cfg.in_rate, cfg.out_rate, cfg.channels, cfg.quality = 48000, 44100, 2, 11

@@ -105,3 +105,73 @@ def test_convert_pads(cuda_device):
     comp.aggregate_frames(out)
     torch.cuda.synchronize()
     assert np.array_equal(out.cpu().numpy().reshape(H, W, 4), want)
+
+
+@pytest.mark.parametrize("fmt", [2, 3, 23, 24], ids=["I420", "YV12", "NV12", "NV21"])
+def test_420_output_random_layouts(cuda_device, fmt):
+    """4:2:0 output and pads: every plane byte equals the oracle's (random sizes, positions, alphas, operators,
+    backgrounds, both ranges; more pads than one launch chunk in some trials)"""
+    import torch
+    import gstreamer_b200 as g
+    from gstreamer_b200.compositor import CudaCompositor
+    o = ob.oracle()
+    rng = np.random.default_rng(fmt)
+    for trial in range(25):
+        W, H, bg, rg = int(rng.integers(1, 200)), int(rng.integers(1, 150)), int(rng.integers(0, 4)), int(rng.integers(0, 2))
+        n = int(rng.integers(0, 6)) if trial % 5 else 30
+        comp = CudaCompositor(fmt, W, H, bg)
+        out_info = g.VideoInfo(fmt, W, H)
+        out_info.set_colorimetry(range=2 if rg else 1)
+        pads = (ob.OraclePad * max(n, 1))()
+        keep = []
+        for i in range(n):
+            w, h = int(rng.integers(1, 120)), int(rng.integers(1, 90))
+            a = rng.integers(0, 256, o.oracle_compositor_yuv_size(fmt, w, h), dtype=np.uint8)
+            keep.append(a)
+            x, y = int(rng.integers(-40, W + 5)), int(rng.integers(-40, H + 5))
+            al, op = float(rng.choice([0.0, 0.3, 0.5, 0.999, 1.0, 0.004])), int(rng.integers(0, 3))
+            pads[i].data, pads[i].width, pads[i].height, pads[i].stride = a.ctypes.data, w, h, 0
+            pads[i].xpos, pads[i].ypos, pads[i].alpha, pads[i].op = x, y, al, op
+            comp.request_pad(w, h, xpos=x, ypos=y, alpha=al, operator=op).set_frame(torch.from_numpy(a).cuda())
+        sz = o.oracle_compositor_yuv_size(fmt, W, H)
+        assert sz == out_info.size
+        want = np.zeros(sz, dtype=np.uint8)
+        assert o.oracle_compositor_yuv(fmt, want.ctypes.data, W, H, bg, rg, pads, n) == 0
+        out = torch.zeros(sz, dtype=torch.uint8, device="cuda")
+        comp.aggregate_frames(out, out_info=out_info)
+        torch.cuda.synchronize()
+        got = out.cpu().numpy()
+        bad = np.nonzero(got != want)[0]
+        assert bad.size == 0, f"trial {trial}: {bad.size} bytes differ, first at {bad[:6]}: got {got[bad[:6]]} want {want[bad[:6]]}"
+
+
+def test_420_pitched_planes(cuda_device):
+    """common-pitch GstCudaMemory layout for the destination and a pad"""
+    import torch
+    import gstreamer_b200 as g
+    from gstreamer_b200.compositor import CudaCompositor
+    o = ob.oracle()
+    W, H, w, h = 100, 60, 64, 40
+    rng = np.random.default_rng(3)
+    src = rng.integers(0, 256, o.oracle_compositor_yuv_size(23, w, h), dtype=np.uint8)
+    pads = (ob.OraclePad * 1)()
+    pads[0].data, pads[0].width, pads[0].height, pads[0].stride = src.ctypes.data, w, h, 0
+    pads[0].xpos, pads[0].ypos, pads[0].alpha, pads[0].op = 21, 9, 0.5, 1
+    want = np.zeros(o.oracle_compositor_yuv_size(23, W, H), dtype=np.uint8)
+    o.oracle_compositor_yuv(23, want.ctypes.data, W, H, 0, 1, pads, 1)
+    # destination: pitch 256, UV plane after 64 rows; pad: pitch 128
+    dpitch, spitch = 256, 128
+    di = g.VideoInfo(23, W, H).set_layout([dpitch, dpitch], [0, dpitch * 64])
+    si = g.VideoInfo(23, w, h).set_layout([spitch, spitch], [0, spitch * 40])
+    sbuf = np.zeros(spitch * 60, dtype=np.uint8)
+    sbuf[: spitch * 40].reshape(40, spitch)[:, :64] = src[: 64 * 40].reshape(40, 64)
+    sbuf[spitch * 40:].reshape(20, spitch)[:, :64] = src[64 * 40:].reshape(20, 64)
+    comp = CudaCompositor(23, W, H, 0)
+    comp.request_pad(w, h, xpos=21, ypos=9, alpha=0.5, in_info=si).set_frame(torch.from_numpy(sbuf).cuda())
+    out = torch.full((dpitch * 96,), 0x55, dtype=torch.uint8, device="cuda")
+    comp.aggregate_frames(out, out_info=di)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    assert np.array_equal(got[: dpitch * 60].reshape(60, dpitch)[:, :100], want[: 100 * 60].reshape(60, 100))
+    assert np.array_equal(got[dpitch * 64: dpitch * 94].reshape(30, dpitch)[:, :100], want[100 * 60:].reshape(30, 100))
+    assert (got[: dpitch * 60].reshape(60, dpitch)[:, 100:] == 0x55).all()

@@ -150,3 +150,20 @@ def test_audio_formats(case):
     o.oracle_ars_free(h)
     assert counts == case["counts"]
     assert np.concatenate(outs).tobytes() == gold.tobytes()
+
+
+@pytest.mark.parametrize("case", json.load(open(os.path.join(G, "comp_420_cases.json"))), ids=lambda c: c["key"])
+def test_compositor_420(case):
+    gold = np.load(os.path.join(G, "comp_420.npz"))[case["key"]]
+    o = ob.oracle()
+    pads = (ob.OraclePad * len(case["pads"]))()
+    keep = []
+    for i, (w, h, x, y, al, op, seed) in enumerate(case["pads"]):
+        a = np.random.default_rng(seed).integers(0, 256, o.oracle_compositor_yuv_size(case["fmt"], w, h), dtype=np.uint8)
+        keep.append(a)
+        pads[i].data, pads[i].width, pads[i].height, pads[i].stride = a.ctypes.data, w, h, 0
+        pads[i].xpos, pads[i].ypos, pads[i].alpha, pads[i].op = x, y, al, op
+    dst = np.zeros(o.oracle_compositor_yuv_size(case["fmt"], case["W"], case["H"]), dtype=np.uint8)
+    assert o.oracle_compositor_yuv(case["fmt"], dst.ctypes.data, case["W"], case["H"], case["bg"], case["range"], pads,
+                                   len(case["pads"])) == 0
+    assert np.array_equal(dst, gold)
