@@ -16,7 +16,7 @@
 GST_DEBUG_CATEGORY_STATIC (cuda_comp_debug);
 #define GST_CAT_DEFAULT cuda_comp_debug
 
-#define COMP_FORMATS "{ RGBA, BGRA, ARGB, ABGR }"
+#define COMP_FORMATS "{ RGBA, BGRA, ARGB, ABGR, I420, YV12, NV12, NV21 }"
 #define COMP_CAPS "video/x-raw(" GST_CAPS_FEATURE_MEMORY_CUDA_MEMORY "), format = (string) " COMP_FORMATS \
     ", width = (int) [ 1, 32767 ], height = (int) [ 1, 32767 ], framerate = (fraction) [ 0/1, max ]"
 
@@ -191,6 +191,21 @@ comp_aggregate_frames (GstVideoAggregator * vagg, GstBuffer * outbuf)
   GST_OBJECT_UNLOCK (vagg);
 
   gst_cuda_context_push (self->context);
+  if (GST_VIDEO_INFO_IS_YUV (oinfo)) {
+    /* 4:2:0 output: plane layouts travel as b200_video_info, offsets relative to plane 0 */
+    b200_comp_pad_yuv ypads[B200_COMP_MAX_PADS];
+    b200_video_info di;
+    gint i;
+    gst_b200_video_info_from_gst (&di, &out_frame.info);
+    for (i = 0; i < n; i++) {
+      ypads[i].data = GST_VIDEO_FRAME_PLANE_DATA (mapped[i], 0);
+      gst_b200_video_info_from_gst (&ypads[i].info, &mapped[i]->info);
+      ypads[i].xpos = pads[i].xpos; ypads[i].ypos = pads[i].ypos;
+      ypads[i].alpha = pads[i].alpha; ypads[i].op = pads[i].op; ypads[i].reserved = 0;
+    }
+    st = b200_comp_blend_yuv (self->comp, GST_VIDEO_FRAME_PLANE_DATA (&out_frame, 0), &di, self->background, ypads, n,
+        gst_cuda_stream_get_handle (self->stream));
+  } else
   st = b200_comp_blend (self->comp, GST_VIDEO_FRAME_PLANE_DATA (&out_frame, 0),
       GST_VIDEO_FRAME_PLANE_STRIDE (&out_frame, 0), self->background, pads, n,
       gst_cuda_stream_get_handle (self->stream));
