@@ -179,6 +179,8 @@ int b200_vcs_create (const b200_video_info * in, const b200_video_info * out,
   const VcsPlan & p = h->plan;
   if ((p.out.stride[0] & 3) || (p.out.offset[0] & 3)) { delete h; return B200_ERR_UNSUPPORTED; }
   h->device = device;
+  // the kernel this plan will run (also reported for host-only handles: caps negotiation dry-runs, CPU tests)
+  h->variant = h->plan.lanczos2_ok ? 1 : (h->plan.light_ok ? 2 : (h->plan.ntap_ok ? 3 : 0));
   if (device >= 0) {
     int ndev = b200_device_count ();
     if (ndev <= 0) { delete h; return ndev < 0 ? ndev : B200_ERR_NO_DEVICE; }

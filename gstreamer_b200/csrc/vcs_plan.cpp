@@ -442,6 +442,50 @@ void ntap_geometry (VcsPlan * p)
   }
 }
 
+// Walk every tile the fast kernels will run and check each shared-memory index range against the
+// geometry chosen above; a violation (none is known) downgrades the plan to the generic kernel instead
+// of risking an out-of-bounds access.  tests/test_host_plan.py sweeps random sizes over this.
+void validate_fast_geometry (VcsPlan * p)
+{
+  const int ow = p->out.width, oh = p->out.height;
+  auto tile_ok = [&] (int tw, int th, int rows_cap, int words_cap, int ntw_h, int extra_words) {
+    for (int y0 = 0; y0 < oh; y0 += th) {
+      const int y1 = std::min (y0 + th, oh) - 1;
+      const int R = (int) (p->v.offset[y1] + p->v.span - p->v.offset[y0]);
+      if (R > rows_cap || R < 1) return false;
+      for (int y = y0; y <= y1; y++) {                            // every output row's window inside the staged rows
+        const int rb = (int) p->v.offset[y] - (int) p->v.offset[y0];
+        if (rb < 0 || rb + p->v.span > R) return false;
+      }
+    }
+    for (int x0 = 0; x0 < ow; x0 += tw) {
+      const int x1 = std::min (x0 + tw, ow) - 1;
+      const int cxa = (int) p->h.offset[x0] & ~3, cx1 = (int) (p->h.offset[x1] + p->h.span);
+      const int ng = (cx1 - cxa + 3) >> 2;
+      if (ng + extra_words > words_cap) return false;
+      for (int x = x0; x <= x1; x++) {
+        const int base = (int) p->h.offset[x] - cxa;
+        if (base < 0 || base + p->h.span > cx1 - cxa) return false;
+        if ((base >> 2) + ntw_h + 1 > words_cap) return false;    // funnel-shift FIR reads words wi .. wi + ntw_h
+      }
+    }
+    return true;
+  };
+  if (p->light_ok && !tile_ok (p->light_tw, p->light_th, p->light_rows, p->light_cp / 4, 0, 0)) p->light_ok = false;
+  if (p->ntap_ok) {
+    bool ok = tile_ok (p->ntap_tw, p->ntap_th, p->ntap_rows, p->ntap_pitch, p->ntw_h, 0);
+    if (ok && p->h_first) {                                       // vertical FIR over 4-line groups: g0 + ntw_v < groups
+      const int groups = p->ntap_rows / 4 + 1 + p->ntw_v;
+      for (int y0 = 0; y0 < oh && ok; y0 += p->ntap_th)
+        for (int y = y0; y < std::min (y0 + p->ntap_th, oh); y++) {
+          const int rb = (int) p->v.offset[y] - (int) p->v.offset[y0];
+          if ((rb >> 2) + p->ntw_v >= groups) { ok = false; break; }
+        }
+    }
+    if (!ok) p->ntap_ok = false;
+  }
+}
+
 }  // namespace
 
 int build_vcs_plan (const b200_video_info * in, const b200_video_info * out,
@@ -503,6 +547,7 @@ int build_vcs_plan (const b200_video_info * in, const b200_video_info * out,
   tile_geometry (p);
   light_geometry (p);
   ntap_geometry (p);
+  validate_fast_geometry (p);
 
   // the specialised kernel covers exactly the headline shape class: even 2:1 in both
   // directions with the 8-tap lanczos the reference derives for it

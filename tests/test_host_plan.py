@@ -150,3 +150,34 @@ def test_c5_filter_numbers_from_the_survey():
     rs.set_caps(48000, 44100, 256)
     pi = rs.plan_info()
     assert (pi.in_step, pi.out_step, pi.n_taps, pi.n_phases, pi.filter_mode, pi.oversample) == (160, 147, 72, 147, 1, 8)
+
+
+def test_fast_kernel_selection_sweep():
+    """host-only plans over random sizes, methods and input formats: the plan builder validates every
+    shared-memory index range of the fast kernels tile by tile (validate_fast_geometry) and would fall back
+    to the generic kernel on a violation — for default layouts that must never happen for the common
+    methods at moderate ratios, and every plan must build"""
+    import gstreamer_b200 as g
+    rng = np.random.default_rng(0)
+    counts = {}
+    for t in range(1500):
+        iw, ih = int(rng.integers(1, 2000)), int(rng.integers(1, 1200))
+        uniform = rng.random() < 0.6
+        if uniform:
+            f = rng.uniform(0.25, 4.0)
+            ow, oh = max(1, int(iw * f)), max(1, int(ih * f))
+        else:
+            ow, oh = int(rng.integers(1, 2000)), int(rng.integers(1, 1200))
+        m = int(rng.integers(0, 10))
+        fmt = int(rng.choice([23, 24, 2, 3]))
+        el = g.CudaVideoConvertScale(method=m, cuda_device_id=-1)
+        el.set_info(g.VideoInfo(fmt, iw, ih), g.VideoInfo(12, ow, oh))
+        v = int(el.plan_info().kernel_variant)
+        counts[v] = counts.get(v, 0) + 1
+        if m in (0, 1):
+            assert v == 2, (iw, ih, ow, oh, m, fmt)          # nearest / bilinear: light kernel, either order
+        elif uniform and m in (3, 9) and min(iw, ih) >= 16:
+            assert v in (1, 3), (iw, ih, ow, oh, m, fmt)     # lanczos / mitchell at moderate ratios
+        if v == 1:
+            assert fmt in (23, 24) and iw == 2 * ow and ih == 2 * oh
+    assert counts.get(0, 0) < 0.08 * 1500                    # mixed 2-tap / n-tap axes and extreme ratios only
