@@ -11,6 +11,7 @@
 #include "vcs_lanczos2.cuh"
 #include "vcs_light.cuh"
 #include "vcs_ntap.cuh"
+#include "vcs_planes.cuh"
 
 #include <string.h>
 #include <new>
@@ -36,6 +37,7 @@ struct b200_vcs {
   Lanczos2Tables l2_tables;
   Lanczos2State l2;
   NtapState ntap;
+  PlanesState planes;
   size_t in_bytes = 0, out_bytes = 0;
 };
 
@@ -61,6 +63,7 @@ int upload_axis (const AxisPlan & a, uint32_t **off, int16_t **coef, int16_t **s
 int launch (b200_vcs * h, int n, const VcsBatch & batch, cudaStream_t stream)
 {
   const VcsPlan & p = h->plan;
+  if (p.planes_mode) return launch_planes (h->planes, batch, n, stream);
   if (h->variant == 1 && p.lanczos2_ok)
     return launch_lanczos2 (h->dev, h->l2, batch, n, stream);
   if (h->variant == 2 && p.light_ok) {
@@ -174,6 +177,21 @@ int b200_vcs_create (const b200_video_info * in, const b200_video_info * out,
   if (!h) return B200_ERR_NOMEM;
   int st = build_vcs_plan (in, out, cfg, &h->plan);
   if (st != B200_OK) { delete h; return st; }
+  if (h->plan.planes_mode) {                                       // YUV -> same YUV family: plane scaling
+    h->device = device;
+    h->variant = 4;
+    h->in_bytes = frame_bytes (h->plan.in); h->out_bytes = frame_bytes (h->plan.out);
+    if (device >= 0) {
+      int ndev = b200_device_count ();
+      if (ndev <= 0) { delete h; return ndev < 0 ? ndev : B200_ERR_NO_DEVICE; }
+      if (device >= ndev) { delete h; return B200_ERR_INVALID_ARG; }
+      DeviceGuard g (device);
+      if (!g.ok) { delete h; return B200_ERR_CUDA; }
+      if ((st = prepare_planes (h->plan, &h->planes)) != B200_OK) { b200_vcs_destroy (h); return st; }
+    }
+    *handle = h;
+    return B200_OK;
+  }
   h->l2_tables = build_lanczos2_tables (h->plan);
   h->plan.lanczos2_ok = h->l2_tables.ok;
   const VcsPlan & p = h->plan;
@@ -243,6 +261,7 @@ void b200_vcs_destroy (b200_vcs * h)
     cudaFree (h->d_hoff); cudaFree (h->d_voff); cudaFree (h->d_hcoef); cudaFree (h->d_vcoef);
     cudaFree (h->d_hsum); cudaFree (h->d_vsum); cudaFree (h->d_cmode);
     cudaFree (h->l2.d_htab); cudaFree (h->l2.d_vtab); cudaFree (h->ntap.d_h); cudaFree (h->ntap.d_v);
+    free_planes (&h->planes);
     for (int i = 0; i < b200_vcs::kSlots; i++) {
       cudaFree (h->slot_in[i]); cudaFree (h->slot_out[i]);
       if (h->ev_in[i]) cudaEventDestroy (h->ev_in[i]);
@@ -321,7 +340,7 @@ int b200_vcs_get_plan_info (const b200_vcs * h, b200_vcs_plan_info * info)
   info->h_first = p.h_first; info->matrix_first = p.matrix_first;
   for (int i = 0; i < 5; i++) info->p[i] = p.p[i];
   info->tile_w = p.tile_w; info->tile_h = p.tile_h; info->smem_bytes = p.smem_bytes;
-  info->kernel_variant = (h->variant == 1 && p.lanczos2_ok) ? 1 : (h->variant == 2 && p.light_ok) ? 2 : (h->variant == 3 && p.ntap_ok) ? 3 : 0;
+  info->kernel_variant = p.planes_mode ? 4 : (h->variant == 1 && p.lanczos2_ok) ? 1 : (h->variant == 2 && p.light_ok) ? 2 : (h->variant == 3 && p.ntap_ok) ? 3 : 0;
   info->n_launches_per_convert = 1;
   return B200_OK;
 }
@@ -352,6 +371,7 @@ int b200_vcs_get_chroma_plan (const b200_vcs * h, uint8_t * mode, size_t len)
 int b200_vcs_set_kernel_variant (b200_vcs * h, int variant)
 {
   if (!h || variant < 0 || variant > 3) return B200_ERR_INVALID_ARG;
+  if (h->plan.planes_mode) return B200_ERR_UNSUPPORTED;            // one kernel only
   if (variant == 3 && !(h->plan.ntap_ok && h->ntap.ready)) return B200_ERR_UNSUPPORTED;
   if (variant == 1 && !h->plan.lanczos2_ok) return B200_ERR_UNSUPPORTED;
   if (variant == 2 && !h->plan.light_ok) return B200_ERR_UNSUPPORTED;

@@ -163,14 +163,15 @@ void identity_axis (AxisPlan * a, int size)
   a->coef.clear (); a->sum.clear ();
 }
 
-void scaled_axis (AxisPlan * a, const FilterSpec & f, int in_size, int out_size, bool horizontal)
+void scaled_axis (AxisPlan * a, const FilterSpec & f, int in_size, int out_size, bool horizontal,
+    bool two_tap_stepping = true)
 {
   RealTaps r = real_taps (f, in_size, out_size);
   a->in_size = in_size; a->out_size = out_size; a->scaling = true;
   a->n_taps = r.n; a->span = r.n;
   if (r.n == 1) {                       // video_scale_h_near_u32 / video_scale_v_near_u8
     a->mode = PASS_COPY; a->coef_per_out = 0; a->offset = r.first;
-  } else if (r.n == 2 && horizontal) {  // video_scale_h_2tap_4u8: edge-aligned 16.16 stepping
+  } else if (r.n == 2 && horizontal && two_tap_stepping) {  // video_scale_h_2tap_4u8 / _1u8: edge-aligned 16.16 stepping
     a->mode = PASS_2TAP; a->coef_per_out = 1;
     a->offset.resize (out_size); a->coef.resize (out_size);
     int inc = out_size == 1 ? 0 : (int) ((((int64_t) in_size - 1) << 16) / (out_size - 1)) - 1;
@@ -179,7 +180,7 @@ void scaled_axis (AxisPlan * a, const FilterSpec & f, int in_size, int out_size,
       a->offset[i] = (uint32_t) (tmp >> 16);
       a->coef[i] = (int16_t) ((tmp >> 8) & 0xff);
     }
-  } else if (r.n == 2) {                // video_scale_v_2tap_u8: centre-aligned, 8-bit second tap
+  } else if (r.n == 2 && !horizontal) { // video_scale_v_2tap_u8: centre-aligned, 8-bit second tap
     a->mode = PASS_2TAP; a->coef_per_out = 1;
     a->offset = r.first; a->coef.resize (out_size);
     for (int i = 0; i < out_size; i++) {
@@ -486,6 +487,46 @@ void validate_fast_geometry (VcsPlan * p)
   }
 }
 
+// setup_scale (video-converter.c:8092-8245) for same-family 4:2:0 in/out: what each output plane does
+int build_planes (VcsPlan * p, const FilterSpec & f)
+{
+  const bool semi = p->out.format == B200_VIDEO_FORMAT_NV12 || p->out.format == B200_VIDEO_FORMAT_NV21;
+  const int iw = p->in.width, ih = p->in.height, ow = p->out.width, oh = p->out.height;
+  p->planes_mode = true;
+  p->n_planes = semi ? 2 : 3;
+  for (int i = 0; i < p->n_planes; i++) {
+    PlanePlan & q = p->planes[i];
+    q = PlanePlan ();
+    q.src_plane = (!semi && i > 0 && p->in.format != p->out.format) ? 3 - i : i;   // I420 <-> YV12 swap U and V
+    q.iw = i ? (iw + 1) / 2 : iw; q.ih = i ? (ih + 1) / 2 : ih;
+    q.ow = i ? (ow + 1) / 2 : ow; q.oh = i ? (oh + 1) / 2 : oh;
+    q.ne = (semi && i == 1) ? 2 : 1;
+    if (p->in.stride[q.src_plane] < q.iw * q.ne || p->out.stride[i] < q.ow * q.ne) return B200_ERR_INVALID_ARG;
+    FilterSpec fs = f;
+    if (i > 0 && fs.kind != K_NEAREST) fs.kind = K_LINEAR;         // chroma resampler (cr_method), :7981-7986
+    const bool same_w = q.iw == q.ow, same_h = q.ih == q.oh;
+    if (same_w && same_h) { q.mode = PM_COPY; continue; }
+    if (q.ne == 1 && fs.kind == K_LINEAR) {                        // convert_plane_{v,h,hv}_halve
+      if (same_w && q.ih == 2 * q.oh) { q.mode = PM_HALVE_V; continue; }
+      if (same_h && q.iw == 2 * q.ow) { q.mode = PM_HALVE_H; continue; }
+      if (q.iw == 2 * q.ow && q.ih == 2 * q.oh) { q.mode = PM_HALVE_HV; continue; }
+    }
+    if (q.ne == 1 && fs.kind == K_NEAREST) {                       // convert_plane_{v,h,hv}_double
+      if ((same_w && 2 * q.ih == q.oh) || (same_h && 2 * q.iw == q.ow) || (2 * q.iw == q.ow && 2 * q.ih == q.oh)) {
+        q.mode = PM_DOUBLE; continue;
+      }
+    }
+    q.mode = PM_SCALE;
+    q.have_h = !same_w; q.have_v = !same_h;
+    // get_functions (video-scaler.c:1283-1420): only the single-byte plane has the stepping 2-tap h scaler
+    if (q.have_h) scaled_axis (&q.h, fs, q.iw, q.ow, true, q.ne == 1); else identity_axis (&q.h, q.iw);
+    if (q.have_v) scaled_axis (&q.v, fs, q.ih, q.oh, false); else identity_axis (&q.v, q.ih);
+    // gst_video_scaler_2d (:1542-1545): horizontal first when width * v.offset[last] <= width * height
+    q.h_first = !(q.have_h && q.have_v) || (int64_t) q.v.offset[q.oh - 1] <= (int64_t) q.oh;
+  }
+  return B200_OK;
+}
+
 }  // namespace
 
 int build_vcs_plan (const b200_video_info * in, const b200_video_info * out,
@@ -503,6 +544,19 @@ int build_vcs_plan (const b200_video_info * in, const b200_video_info * out,
   if (p->in.color_matrix == 0) p->in.color_matrix = in->height > 576 ? B200_COLOR_MATRIX_BT709 : B200_COLOR_MATRIX_BT601;
   if (p->in.color_range == 0) p->in.color_range = B200_COLOR_RANGE_16_235;
   if (p->in.chroma_site == 0) p->in.chroma_site = in->height > 576 ? B200_CHROMA_SITE_H_COSITED : B200_CHROMA_SITE_NONE;
+  {
+    const bool in_pl = in->format == B200_VIDEO_FORMAT_I420 || in->format == B200_VIDEO_FORMAT_YV12;
+    const bool out_pl = out->format == B200_VIDEO_FORMAT_I420 || out->format == B200_VIDEO_FORMAT_YV12;
+    const bool out_semi = out->format == B200_VIDEO_FORMAT_NV12 || out->format == B200_VIDEO_FORMAT_NV21;
+    if (out_pl || out_semi) {
+      // the reference has plane-scaling fast paths for NV12->NV12, NV21->NV21, I420/YV12 -> I420/YV12
+      // (video-converter.c:8722-8760); the other YUV pairs run the chain with chroma down-sampling: not built
+      if (!((in_pl && out_pl) || (out_semi && in->format == out->format))) return B200_ERR_UNSUPPORTED;
+      if (in->stride[0] < in->width || out->stride[0] < out->width) return B200_ERR_INVALID_ARG;
+      if (p->in.color_matrix == 0) p->in.color_matrix = in->height > 576 ? B200_COLOR_MATRIX_BT709 : B200_COLOR_MATRIX_BT601;
+      return build_planes (p, filter_from_method (*cfg));
+    }
+  }
   switch (out->format) {                // (A,R,G,B) component placed at each output byte
     case B200_VIDEO_FORMAT_BGRA: case B200_VIDEO_FORMAT_BGRx: { uint8_t s[4] = {3, 2, 1, 0}; memcpy (p->byte_sel, s, 4); break; }
     case B200_VIDEO_FORMAT_RGBA: case B200_VIDEO_FORMAT_RGBx: { uint8_t s[4] = {1, 2, 3, 0}; memcpy (p->byte_sel, s, 4); break; }

@@ -28,6 +28,17 @@ struct AxisPlan {
   std::vector<int16_t> sum;      // NTAP: sum of taps (alpha channel), else unused
 };
 
+// YUV -> same YUV family (convert_scale_planes, video-converter.c:7757-7769): one of these per output plane
+enum PlaneMode : int { PM_COPY = 0, PM_HALVE_V = 1, PM_HALVE_H = 2, PM_HALVE_HV = 3, PM_DOUBLE = 4, PM_SCALE = 5 };
+struct PlanePlan {
+  int src_plane = 0;             // plane of the input that feeds this output plane
+  int iw = 0, ih = 0, ow = 0, oh = 0;    // in pixels of this plane
+  int ne = 1;                    // bytes per pixel (2 for the interleaved UV plane)
+  int mode = PM_COPY;
+  bool have_h = false, have_v = false, h_first = true;
+  AxisPlan h, v;
+};
+
 struct VcsPlan {
   b200_video_info in, out;
   b200_vcs_config cfg;
@@ -48,6 +59,11 @@ struct VcsPlan {
   int tile_w = 64, tile_h = 16;
   int max_rows = 0, max_cols = 0, cols_pitch = 0, max_crows = 0;
   int smem_bytes = 0;
+
+  // 4:2:0 output: per-plane scaling instead of the unpack -> ... -> pack chain
+  bool planes_mode = false;
+  int n_planes = 0;
+  PlanePlan planes[3];
 
   // specialised 2:1 lanczos kernel eligibility
   bool lanczos2_ok = false;

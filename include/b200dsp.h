@@ -157,7 +157,7 @@ typedef struct {
   int32_t p[5];                  /* AYUV->ARGB mulhi parameters p1..p5 */
   int32_t tile_w, tile_h;        /* generic kernel output tile */
   int32_t smem_bytes;
-  int32_t kernel_variant;        /* 0 = generic tiled, 1 = lanczos 2:1 specialised, 2 = light (copy / 2-tap axes), 3 = n-tap any ratio */
+  int32_t kernel_variant;        /* 0 = generic tiled, 1 = lanczos 2:1 specialised, 2 = light (copy / 2-tap axes), 3 = n-tap any ratio, 4 = YUV plane scaling */
   int32_t n_launches_per_convert;
 } b200_vcs_plan_info;
 int b200_vcs_get_plan_info (const b200_vcs * h, b200_vcs_plan_info * info);

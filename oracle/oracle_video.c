@@ -238,6 +238,15 @@ oracle_vcs_default_desc (OracleVcsDesc * d, int in_format, int in_w, int in_h,
   d->out_width = out_w;
   d->out_height = out_h;
   d->out_stride[0] = out_w * 4;         /* video-info.c:890-894 */
+  if (out_format == ORC_FMT_I420 || out_format == ORC_FMT_YV12) {
+    d->out_stride[0] = ROUND_UP_4 (out_w);
+    d->out_stride[1] = d->out_stride[2] = ROUND_UP_4 (ROUND_UP_2 (out_w) / 2);
+    d->out_offset[1] = (size_t) d->out_stride[0] * ROUND_UP_2 (out_h);
+    d->out_offset[2] = d->out_offset[1] + (size_t) d->out_stride[1] * (ROUND_UP_2 (out_h) / 2);
+  } else if (out_format == ORC_FMT_NV12 || out_format == ORC_FMT_NV21) {
+    d->out_stride[0] = d->out_stride[1] = ROUND_UP_4 (out_w);
+    d->out_offset[1] = (size_t) d->out_stride[0] * ROUND_UP_2 (out_h);
+  }
   d->rs.method = method;
   d->rs.max_taps_opt = max_taps_opt;
   d->rs.envelope = 2.0;
@@ -259,6 +268,10 @@ oracle_vcs_in_size (const OracleVcsDesc * d)
 size_t
 oracle_vcs_out_size (const OracleVcsDesc * d)
 {
+  if (d->out_format == ORC_FMT_I420 || d->out_format == ORC_FMT_YV12)
+    return d->out_offset[2] + (size_t) d->out_stride[2] * (ROUND_UP_2 (d->out_height) / 2);
+  if (d->out_format == ORC_FMT_NV12 || d->out_format == ORC_FMT_NV21)
+    return d->out_offset[1] + (size_t) d->out_stride[1] * (ROUND_UP_2 (d->out_height) / 2);
   return d->out_offset[0] + (size_t) d->out_stride[0] * d->out_height;
 }
 
@@ -628,6 +641,197 @@ chroma_plan (const OracleVcsDesc * d, const Scaler * vs, uint8_t * mode)
   free (req);
 }
 
+/* ============================================================== YUV -> same YUV family: plane scaling
+ * Fast path convert_scale_planes (video-converter.c:7757-7769, table rows NV12->NV12, I420->I420, I420<->YV12 with
+ * keeps_size = FALSE): every plane is scaled on its own by setup_scale's choice (:8092-8245) —
+ * luma with the element's method, chroma with the chroma resampler (LINEAR unless the method is NEAREST),
+ * exact 2:1 / 1:2 steps of single-byte planes by the planar_chroma averaging / doubling kernels, everything
+ * else by gst_video_scaler_2d (video-scaler.c:1451-1640). */
+
+/* one line through the horizontal scaler, n_elems bytes per pixel (1 or 2): video_scale_h_near_u8/_u16,
+ * video_scale_h_2tap_1u8 (ldreslinb stepping), video_scale_h_ntap_u8 */
+static void
+hscale_line_n (Scaler * s, const uint8_t * sl, uint8_t * dl, int dw, int ne)
+{
+  int x, c, k;
+  if (s->n_taps >= 2 && !(s->n_taps == 2 && ne == 1) && !s->taps_s16)
+    scaler_quantize (s, 6);
+  for (x = 0; x < dw; x++) {
+    if (s->n_taps == 1) {
+      memcpy (dl + ne * x, sl + ne * s->offset[x], ne);
+    } else if (s->n_taps == 2 && ne == 1) {
+      int tmp = x * s->inc, i0 = tmp >> 16, f = (tmp >> 8) & 0xff;
+      int i1 = (i0 + 1 < s->in_size) ? i0 + 1 : i0;
+      dl[x] = (uint8_t) ((sl[i0] * (256 - f) + sl[i1] * f) >> 8);
+    } else {
+      const int16_t *t = s->taps_s16 + (size_t) x * s->n_taps;
+      for (c = 0; c < ne; c++) {
+        int acc = 0;
+        for (k = 0; k < s->n_taps; k++)
+          acc += (int16_t) (sl[ne * (s->offset[x] + k) + c] * t[k]);
+        dl[ne * x + c] = scale_round_u8 (acc);
+      }
+    }
+  }
+}
+
+/* one output line of the vertical scaler from `lines[]` (n bytes each): v_near / v_2tap / v_4tap / v_ntap */
+static void
+vscale_line_n (Scaler * s, const uint8_t ** lines, uint8_t * dl, int y, int n)
+{
+  int x, k;
+  if (s->n_taps >= 2 && !s->taps_s16)
+    scaler_quantize (s, s->n_taps == 2 ? 8 : 6);
+  if (s->n_taps == 1) {
+    memcpy (dl, lines[0], n);
+  } else if (s->n_taps == 2) {
+    int16_t p1 = s->taps_s16[(size_t) y * 2 + 1];
+    for (x = 0; x < n; x++) {
+      int16_t w2 = (int16_t) (lines[1][x] - lines[0][x]);
+      w2 = (int16_t) (w2 * p1);
+      w2 = (int16_t) (w2 + 128);
+      dl[x] = (uint8_t) (((uint16_t) w2 >> 8) + lines[0][x]);
+    }
+  } else {
+    const int16_t *t = s->taps_s16 + (size_t) y * s->n_taps;
+    for (x = 0; x < n; x++) {
+      int acc = 0;
+      for (k = 0; k < s->n_taps; k++)
+        acc += (int16_t) (lines[k][x] * t[k]);
+      dl[x] = scale_round_u8 (acc);
+    }
+  }
+}
+
+/* gst_video_scaler_2d for a whole plane */
+static void
+scale_plane_2d (Scaler * hs, Scaler * vs, const uint8_t * src, int sstride, int iw, uint8_t * dst, int dstride,
+    int ow, int oh, int ne)
+{
+  int y, j;
+  const uint8_t *lines[ORACLE_MAX_TAPS];
+  if (!vs) {
+    for (y = 0; y < oh; y++) {
+      if (hs)
+        hscale_line_n (hs, src + (size_t) y * sstride, dst + (size_t) y * dstride, ow, ne);
+      else
+        memcpy (dst + (size_t) y * dstride, src + (size_t) y * sstride, (size_t) ow * ne);
+    }
+    return;
+  }
+  if (!hs) {
+    for (y = 0; y < oh; y++) {
+      for (j = 0; j < vs->n_taps; j++)
+        lines[j] = src + (size_t) (vs->offset[y] + j) * sstride;
+      vscale_line_n (vs, lines, dst + (size_t) y * dstride, y, ow * ne);
+    }
+    return;
+  }
+  if ((long) ow * vs->offset[oh - 1] <= (long) ow * oh) {
+    /* horizontal first: every needed input line is h-scaled (the reference caches them in a ring; same values) */
+    uint8_t *tmp = malloc ((size_t) vs->in_size * ow * ne);
+    uint8_t *have = calloc (vs->in_size, 1);
+    for (y = 0; y < oh; y++) {
+      for (j = 0; j < vs->n_taps; j++) {
+        int l = vs->offset[y] + j;
+        if (!have[l]) {
+          hscale_line_n (hs, src + (size_t) l * sstride, tmp + (size_t) l * ow * ne, ow, ne);
+          have[l] = 1;
+        }
+        lines[j] = tmp + (size_t) l * ow * ne;
+      }
+      vscale_line_n (vs, lines, dst + (size_t) y * dstride, y, ow * ne);
+    }
+    free (tmp);
+    free (have);
+  } else {
+    /* vertical first into a temp line of input width, then horizontal */
+    uint8_t *tmp = malloc ((size_t) iw * ne + 16);
+    for (y = 0; y < oh; y++) {
+      for (j = 0; j < vs->n_taps; j++)
+        lines[j] = src + (size_t) (vs->offset[y] + j) * sstride;
+      vscale_line_n (vs, lines, tmp, y, iw * ne);
+      hscale_line_n (hs, tmp, dst + (size_t) y * dstride, ow, ne);
+    }
+    free (tmp);
+  }
+}
+
+#define AVGUB(a, b) ((uint8_t) (((a) + (b) + 1) >> 1))
+
+static int
+convert_planes (const OracleVcsDesc * d, const uint8_t * in, uint8_t * out)
+{
+  int semi = d->out_format == ORC_FMT_NV12 || d->out_format == ORC_FMT_NV21;
+  int n_planes = semi ? 2 : 3, i;
+  int iw = d->in_width, ih = d->in_height, ow = d->out_width, oh = d->out_height;
+  for (i = 0; i < n_planes; i++) {
+    /* plane i of the output holds component i (Y,U,V) for I420 and (Y,V,U) for YV12; the source plane is the
+     * one holding the same component (fsplane) */
+    int sp = i;
+    int pw, ph, qw, qh, ne = (semi && i == 1) ? 2 : 1, x, y;
+    const uint8_t *s;
+    uint8_t *dp;
+    int ss, ds, method;
+    OracleResamplerOpts rs = d->rs;
+    Scaler hs, vs;
+    int need_h = 0, need_v = 0;
+    if (!semi && i > 0 && d->in_format != d->out_format)
+      sp = 3 - i;               /* I420 <-> YV12: U and V planes swap */
+    pw = i ? (iw + 1) / 2 : iw; ph = i ? (ih + 1) / 2 : ih;
+    qw = i ? (ow + 1) / 2 : ow; qh = i ? (oh + 1) / 2 : oh;
+    s = in + d->in_offset[sp]; ss = d->in_stride[sp];
+    dp = out + d->out_offset[i]; ds = d->out_stride[i];
+    /* resample_method = (i == 0 ? method : cr_method), cr_method = LINEAR unless method == NEAREST (:7981-7986) */
+    method = rs.method;
+    if (i > 0 && method != ORC_RS_NEAREST)
+      method = ORC_RS_LINEAR;
+    rs.method = method;
+    if (pw == qw && ph == qh) {
+      for (y = 0; y < qh; y++)
+        memcpy (dp + (size_t) y * ds, s + (size_t) y * ss, (size_t) qw * ne);
+      continue;
+    }
+    if (ne == 1 && method == ORC_RS_LINEAR && ((pw == qw && ph == 2 * qh) || (ph == qh && pw == 2 * qw) ||
+            (pw == 2 * qw && ph == 2 * qh))) {
+      /* convert_plane_v_halve / _h_halve / _hv_halve: video_orc_planar_chroma_422_420 / _444_422 / _444_420 */
+      for (y = 0; y < qh; y++)
+        for (x = 0; x < qw; x++) {
+          if (pw == qw)
+            dp[(size_t) y * ds + x] = AVGUB (s[(size_t) (2 * y) * ss + x], s[(size_t) (2 * y + 1) * ss + x]);
+          else if (ph == qh)
+            dp[(size_t) y * ds + x] = AVGUB (s[(size_t) y * ss + 2 * x], s[(size_t) y * ss + 2 * x + 1]);
+          else {
+            uint8_t t1 = AVGUB (s[(size_t) (2 * y) * ss + 2 * x], s[(size_t) (2 * y + 1) * ss + 2 * x]);
+            uint8_t t2 = AVGUB (s[(size_t) (2 * y) * ss + 2 * x + 1], s[(size_t) (2 * y + 1) * ss + 2 * x + 1]);
+            dp[(size_t) y * ds + x] = AVGUB (t1, t2);
+          }
+        }
+      continue;
+    }
+    if (ne == 1 && method == ORC_RS_NEAREST && ((pw == qw && 2 * ph == qh) || (ph == qh && 2 * pw == qw) ||
+            (2 * pw == qw && 2 * ph == qh))) {
+      /* convert_plane_v_double / _h_double / _hv_double: plain replication */
+      for (y = 0; y < qh; y++)
+        for (x = 0; x < qw; x++)
+          dp[(size_t) y * ds + x] = s[(size_t) (ph == qh ? y : y / 2) * ss + (pw == qw ? x : x / 2)];
+      continue;
+    }
+    need_h = pw != qw;
+    need_v = ph != qh;
+    if (need_h && scaler_init (&hs, &rs, pw, qw))
+      return -1;
+    if (need_v && scaler_init (&vs, &rs, ph, qh))
+      return -1;
+    scale_plane_2d (need_h ? &hs : NULL, need_v ? &vs : NULL, s, ss, pw, dp, ds, qw, qh, ne);
+    if (need_h)
+      scaler_clear (&hs);
+    if (need_v)
+      scaler_clear (&vs);
+  }
+  return 0;
+}
+
 int
 oracle_vcs_convert (const OracleVcsDesc * d, const uint8_t * in, uint8_t * out)
 {
@@ -638,6 +842,15 @@ oracle_vcs_convert (const OracleVcsDesc * d, const uint8_t * in, uint8_t * out)
   int have_h = iw != ow, have_v = ih != oh, pass;
   long s0, s3;
 
+  {
+    int in_planar = d->in_format == ORC_FMT_I420 || d->in_format == ORC_FMT_YV12;
+    int out_planar = d->out_format == ORC_FMT_I420 || d->out_format == ORC_FMT_YV12;
+    if ((in_planar && out_planar) || ((d->out_format == ORC_FMT_NV12 || d->out_format == ORC_FMT_NV21) &&
+            d->in_format == d->out_format))
+      return convert_planes (d, in, out);
+    if (out_planar || d->out_format == ORC_FMT_NV12 || d->out_format == ORC_FMT_NV21)
+      return -1;                /* other YUV -> YUV pairs run the generic chain with chroma down-sampling: not restated */
+  }
   if (oracle_vcs_matrix (d, p, im) != 0)
     return -1;
   if ((d->in_format == ORC_FMT_I420 || d->in_format == ORC_FMT_YV12) && iw == ow && ih == oh) {

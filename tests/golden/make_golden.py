@@ -172,6 +172,26 @@ def audio_formats():
     json.dump(cases, open(os.path.join(HERE, "audio_formats_cases.json"), "w"), indent=1)
 
 
+def video_yuv():
+    """YUV -> same YUV family plane scaling"""
+    arrays, cases = {}, []
+    for fi, fo in [("NV12", "NV12"), ("I420", "I420"), ("I420", "YV12"), ("NV21", "NV21")]:
+        for (iw, ih, ow, oh) in [(64, 48, 32, 24), (64, 48, 100, 70), (65, 49, 33, 25), (64, 48, 64, 24), (32, 24, 64, 48),
+                                 (33, 17, 20, 9)]:
+            for m in (0, 1, 3, 9):
+                frame = ob.i420_random_frame(iw, ih, m + iw) if fi in ("I420", "YV12") else ob.nv12_random_frame(iw, ih, m + iw)
+                d = ob.vcs_desc(iw, ih, ow, oh, m, in_fmt=ob.FMT[fi], out_fmt=ob.FMT[fo])
+                size = ob.vcs_sizes(d)[1]
+                r = ob.RefVcs(iw, ih, ow, oh, m, in_fmt=ob.FMT[fi], out_fmt=ob.FMT[fo])
+                out = r.convert(frame, np.zeros(size, dtype=np.uint8))
+                r.close()
+                key = f"y_{fi}_{fo}_{iw}x{ih}_{ow}x{oh}_m{m}"
+                arrays[key] = out
+                cases.append({"key": key, "in_fmt": fi, "out_fmt": fo, "in": [iw, ih], "out": [ow, oh], "method": m, "seed": m + iw})
+    np.savez_compressed(os.path.join(HERE, "video_yuv.npz"), **arrays)
+    json.dump(cases, open(os.path.join(HERE, "video_yuv_cases.json"), "w"), indent=1)
+
+
 def compositor_420():
     """I420 / YV12 / NV12 / NV21 output"""
     o, r = ob.oracle(), ob.ref()
@@ -205,7 +225,7 @@ if __name__ == "__main__":
     assert ob.have_ref(), "needs oracle/_ref/libgstref.so (make -C oracle ref)"
     only = set(sys.argv[1:])
     for name, fn in [("video", video), ("compositor", compositor), ("audio", audio), ("video_planar", video_planar),
-                     ("audio_interpolated", audio_interpolated), ("audio_formats", audio_formats), ("compositor_420", compositor_420)]:
+                     ("audio_interpolated", audio_interpolated), ("audio_formats", audio_formats), ("compositor_420", compositor_420), ("video_yuv", video_yuv)]:
         if not only or name in only:
             fn()
     print("golden fixtures written to", HERE)

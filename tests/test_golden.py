@@ -167,3 +167,12 @@ def test_compositor_420(case):
     assert o.oracle_compositor_yuv(case["fmt"], dst.ctypes.data, case["W"], case["H"], case["bg"], case["range"], pads,
                                    len(case["pads"])) == 0
     assert np.array_equal(dst, gold)
+
+
+@pytest.mark.parametrize("case", json.load(open(os.path.join(G, "video_yuv_cases.json"))), ids=lambda c: c["key"])
+def test_video_yuv_plane_scaling(case):
+    gold = np.load(os.path.join(G, "video_yuv.npz"))[case["key"]]
+    (iw, ih), (ow, oh), m = case["in"], case["out"], case["method"]
+    frame = (ob.i420_random_frame if case["in_fmt"] in ("I420", "YV12") else ob.nv12_random_frame)(iw, ih, case["seed"])
+    d = ob.vcs_desc(iw, ih, ow, oh, m, in_fmt=ob.FMT[case["in_fmt"]], out_fmt=ob.FMT[case["out_fmt"]])
+    assert np.array_equal(ob.oracle_vcs_convert(d, frame), gold)

@@ -264,3 +264,26 @@ def test_compositor_420_matches_reference():
         assert r.ref_compositor_yuv(fmt, d1.ctypes.data, W, H, bg, rg, pads, n) == 0
         assert o.oracle_compositor_yuv(fmt, d2.ctypes.data, W, H, bg, rg, pads, n) == 0
         assert np.array_equal(d1, d2), f"trial {trial}"
+
+
+YUV_PAIRS = [("NV12", "NV12"), ("NV21", "NV21"), ("I420", "I420"), ("YV12", "YV12"), ("I420", "YV12"), ("YV12", "I420")]
+YUV_SIZES = [(64, 48, 32, 24), (64, 48, 128, 96), (64, 48, 40, 30), (64, 48, 100, 70), (65, 49, 33, 25), (33, 17, 20, 9),
+             (64, 48, 64, 24), (64, 48, 32, 48), (64, 48, 64, 96), (64, 48, 128, 48), (640, 480, 320, 240), (320, 240, 640, 480),
+             (1920, 1080, 1280, 720), (100, 100, 50, 150), (3, 5, 7, 2), (2, 2, 1, 1), (1, 1, 2, 2), (16, 16, 16, 16)]
+
+
+@pytest.mark.parametrize("size", YUV_SIZES, ids=lambda s: "%dx%d-%dx%d" % s)
+@pytest.mark.parametrize("pair", YUV_PAIRS, ids=lambda p: "%s-%s" % p)
+def test_yuv_plane_scaling_matches_reference(pair, size):
+    """convert_scale_planes (video-converter.c:7757-7769, setup_scale :7958-8245, gst_video_scaler_2d
+    video-scaler.c:1451-1640): per-plane scalers, linear chroma resampler, halve / double kernels, both 2-D
+    pass orders, all ten element methods"""
+    iw, ih, ow, oh = size
+    fi, fo = ob.FMT[pair[0]], ob.FMT[pair[1]]
+    frame = ob.i420_random_frame(iw, ih, 5) if pair[0] in ("I420", "YV12") else ob.nv12_random_frame(iw, ih, 5)
+    for m in range(10):
+        got = ob.oracle_vcs_convert(ob.vcs_desc(iw, ih, ow, oh, m, in_fmt=fi, out_fmt=fo), frame)
+        r = ob.RefVcs(iw, ih, ow, oh, m, in_fmt=fi, out_fmt=fo)
+        want = r.convert(frame, np.zeros(got.size, dtype=np.uint8))
+        r.close()
+        assert np.array_equal(got, want), f"method {m}"
