@@ -19,7 +19,9 @@ GST_DEBUG_CATEGORY_STATIC (cuda_vcs_debug);
 #define GST_CAT_DEFAULT cuda_vcs_debug
 
 #define SINK_FORMATS "{ NV12, NV21, I420, YV12 }"
-#define SRC_FORMATS "{ BGRA, RGBA, ARGB, ABGR, BGRx, RGBx, xRGB, xBGR }"
+/* YUV outputs only from the same family (NV12->NV12, NV21->NV21, I420/YV12 -> I420/YV12): transform_caps drops the
+ * other pairs, b200_vcs_create refuses them with B200_ERR_UNSUPPORTED */
+#define SRC_FORMATS "{ BGRA, RGBA, ARGB, ABGR, BGRx, RGBx, xRGB, xBGR, NV12, NV21, I420, YV12 }"
 #define CUDA_CAPS(f) "video/x-raw(" GST_CAPS_FEATURE_MEMORY_CUDA_MEMORY "), format = (string) " f \
     ", width = (int) [ 1, 32767 ], height = (int) [ 1, 32767 ], framerate = (fraction) [ 0/1, max ]"
 
