@@ -116,6 +116,42 @@ def bench_ntap(args):
                                        "frac": alg / (ms * 1e-3) / 1e9 / peak()}}), flush=True)
 
 
+def bench_planes(args):
+    """not a BASELINE config: YUV -> YUV plane scaling (the transcoding-ladder case)"""
+    import torch
+    import gstreamer_b200 as g
+    from oracle import bindings as ob
+    for (fmt, IW, IH, OW, OH, m) in [(23, 3840, 2160, 1920, 1080, 1), (23, 3840, 2160, 1920, 1080, 3),
+                                     (2, 1920, 1080, 1280, 720, 3), (23, 1920, 1080, 1280, 720, 1)]:
+        el = g.CudaVideoConvertScale(method=m)
+        ii, oi = g.VideoInfo(fmt, IW, IH), g.VideoInfo(fmt, OW, OH)
+        el.set_info(ii, oi)
+        per = 32
+        gen = ob.i420_random_frame if fmt in (2, 3) else ob.nv12_random_frame
+        base = [torch.from_numpy(gen(IW, IH, s)).cuda() for s in range(2)]
+        rin = [base[k % 2].clone() for k in range(2 * per)]
+        rout = [torch.empty(oi.size, dtype=torch.uint8, device="cuda") for _ in range(2 * per)]
+        s = torch.cuda.Stream()
+        step = lambda i: el.transform_frames(rin[(i % 2) * per:(i % 2 + 1) * per], rout[(i % 2) * per:(i % 2 + 1) * per], s)
+        with torch.cuda.stream(s):
+            for i in range(3):
+                step(i)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(s)
+            for i in range(args.steps):
+                step(i)
+            e1.record(s)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        alg = per * (ii.size + oi.size)
+        print(json.dumps({"config": f"{g.VideoFormat(fmt).name} {IW}x{IH} -> {g.VideoFormat(fmt).name} {OW}x{OH} method {m}",
+                          "kernel_variant": int(el.plan_info().kernel_variant), "us_per_frame": ms * 1e3 / per,
+                          "frames_per_s": per * 1e3 / ms,
+                          "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak(), "unit": "GB/s",
+                                       "frac": alg / (ms * 1e-3) / 1e9 / peak()}}), flush=True)
+
+
 def bench_c4(args):
     import numpy as np
     import torch
@@ -239,6 +275,8 @@ if __name__ == "__main__":
     a = ap.parse_args()
     if a.only in ("", "c1"):
         bench_c1(a)
+    if a.only == "planes":
+        bench_planes(a)
     if a.only == "ntap":
         bench_ntap(a)
     if a.only in ("", "c4"):

@@ -63,7 +63,11 @@ int upload_axis (const AxisPlan & a, uint32_t **off, int16_t **coef, int16_t **s
 int launch (b200_vcs * h, int n, const VcsBatch & batch, cudaStream_t stream)
 {
   const VcsPlan & p = h->plan;
-  if (p.planes_mode) return launch_planes (h->planes, batch, n, stream);
+  if (p.planes_mode) {
+    bool aligned = true;                                            // the word-wide halve / copy path needs 8-byte aligned frames
+    for (int i = 0; i < n; i++) aligned = aligned && ((((uintptr_t) batch.in[i]) | ((uintptr_t) batch.out[i])) & 7) == 0;
+    return launch_planes (h->planes, batch, n, stream, aligned);
+  }
   if (h->variant == 1 && p.lanczos2_ok)
     return launch_lanczos2 (h->dev, h->l2, batch, n, stream);
   if (h->variant == 2 && p.light_ok) {
