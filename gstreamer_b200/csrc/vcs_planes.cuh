@@ -107,7 +107,8 @@ vcs_planes_kernel (const PlanesParams P, const VcsBatch frames)
   const bool live = xb < wbytes && y < Q.oh;
   const uint8_t *__restrict__ src = frames.in[frame] + Q.src_off;
   uint8_t *__restrict__ dst = frames.out[frame] + Q.dst_off;
-  const int x = min (xb, wbytes - 1) / Q.ne, c = min (xb, wbytes - 1) - x * Q.ne;
+  const int nes = Q.ne >> 1;                                        // ne is 1 or 2: divide by shifting
+  const int x = min (xb, wbytes - 1) >> nes, c = min (xb, wbytes - 1) - (x << nes);
   int v = 0;
   if (Q.mode != PM_SCALE) {
     if (!live) return;
@@ -138,7 +139,7 @@ vcs_planes_kernel (const PlanesParams P, const VcsBatch frames)
   const PlaneAxisDev & V = Q.v, & H = Q.h;
   const int rows = min (PL_TH, Q.oh - y0);
   const int xl = min (xb0 + PL_TW, wbytes) - 1;                     // last output byte of the tile
-  const int px0 = xb0 / Q.ne, px1 = xl / Q.ne;                      // first / last output pixel
+  const int px0 = xb0 >> nes, px1 = xl >> nes;                      // first / last output pixel
   const int hspan = H.mode == PASS_NTAP ? H.n_taps : (H.mode == PASS_2TAP ? 2 : 1);
   const int vspan = V.mode == PASS_NTAP ? V.n_taps : (V.mode == PASS_2TAP ? 2 : 1);
   auto vfilter = [&] (const uint8_t *s, int oy) -> int {            // s: first source line of output row oy, one byte column
@@ -155,9 +156,10 @@ vcs_planes_kernel (const PlanesParams P, const VcsBatch frames)
     const int nb = (c1 - c0) * Q.ne;
     const bool staged = nb <= PL_STAGE_COLS;
     if (staged) {
-      for (int i = threadIdx.x; i < rows * nb; i += 256) {
-        const int r = i / nb, col = i - r * nb;
-        stage[r * PL_STAGE_COLS + col] = (uint8_t) vfilter (src + (size_t) V.offset[y0 + r] * Q.sstride + c0 * Q.ne + col, y0 + r);
+      for (int r = 0; r < rows; r++) {
+        const uint8_t *s0 = src + (size_t) V.offset[y0 + r] * Q.sstride + c0 * Q.ne;
+        for (int col = threadIdx.x; col < nb; col += 256)
+          stage[r * PL_STAGE_COLS + col] = (uint8_t) vfilter (s0 + col, y0 + r);
       }
     }
     __syncthreads ();
@@ -181,11 +183,10 @@ vcs_planes_kernel (const PlanesParams P, const VcsBatch frames)
     const int nr = r1 - r0, tw = xl - xb0 + 1;
     const bool staged = nr <= PL_STAGE_ROWS;
     if (staged) {
-      for (int i = threadIdx.x; i < nr * tw; i += 256) {
-        const int r = i / tw, col = i - r * tw;
-        const int ob = xb0 + col, ox = ob / Q.ne;
-        stage[r * PL_TW + col] = (uint8_t) plane_h (Q, src + (size_t) (r0 + r) * Q.sstride, ox, ob - ox * Q.ne);
-      }
+      // thread (tx, ty) fills column tx of source lines ty, ty + 4, ...
+      if (tx < tw)
+        for (int r = ty; r < nr; r += PL_TH)
+          stage[r * PL_TW + tx] = (uint8_t) plane_h (Q, src + (size_t) (r0 + r) * Q.sstride, x, c);
     }
     __syncthreads ();
     if (!live) return;
