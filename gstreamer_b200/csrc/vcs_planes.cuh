@@ -156,10 +156,9 @@ vcs_planes_kernel (const PlanesParams P, const VcsBatch frames)
     const int nb = (c1 - c0) * Q.ne;
     const bool staged = nb <= PL_STAGE_COLS;
     if (staged) {
-      for (int r = 0; r < rows; r++) {
-        const uint8_t *s0 = src + (size_t) V.offset[y0 + r] * Q.sstride + c0 * Q.ne;
-        for (int col = threadIdx.x; col < nb; col += 256)
-          stage[r * PL_STAGE_COLS + col] = (uint8_t) vfilter (s0 + col, y0 + r);
+      for (int i = threadIdx.x; i < rows * nb; i += 256) {
+        const int r = (i >= nb) + (i >= 2 * nb) + (i >= 3 * nb), col = i - r * nb;      // rows <= 4: no division
+        stage[r * PL_STAGE_COLS + col] = (uint8_t) vfilter (src + (size_t) V.offset[y0 + r] * Q.sstride + c0 * Q.ne + col, y0 + r);
       }
     }
     __syncthreads ();
