@@ -152,6 +152,38 @@ def bench_planes(args):
                                        "frac": alg / (ms * 1e-3) / 1e9 / peak()}}), flush=True)
 
 
+def bench_audio_formats(args):
+    """C5 shape (48k -> 44.1k, 256 channels, 20 s buffer) in the other sample formats (correctness-first kernels)"""
+    import torch
+    from gstreamer_b200.audio import CudaAudioResample, AudioFormat
+    ch, in_rate, out_rate, seconds = 256, 48000, 44100, 5
+    frames = in_rate * seconds
+    for name, fmt, tdt in [("S16", AudioFormat.S16LE, torch.int16), ("S32", AudioFormat.S32LE, torch.int32),
+                           ("F64", AudioFormat.F64LE, torch.float64)]:
+        rs = CudaAudioResample(quality=4, format=fmt)
+        rs.set_caps(in_rate, out_rate, ch)
+        if tdt.is_floating_point:
+            x = torch.randn(frames * ch, dtype=tdt, device="cuda") * 0.25
+        else:
+            x = torch.randint(-20000, 20000, (frames * ch,), dtype=tdt, device="cuda")
+        cap = int(frames * out_rate / in_rate) + 64
+        out = torch.empty(cap * ch, dtype=tdt, device="cuda")
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            rs.transform(x, frames, out, cap, stream=s)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(s)
+            for _ in range(3):
+                rs.reset()
+                rs.transform(x, frames, out, cap, stream=s)
+            e1.record(s)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        print(json.dumps({"config": f"cudaaudioresample 48k->44.1k {name} 256ch, {seconds} s buffer", "ms_per_buffer": ms,
+                          "realtime_factor": seconds / (ms * 1e-3)}), flush=True)
+
+
 def bench_c4(args):
     import numpy as np
     import torch
@@ -275,6 +307,8 @@ if __name__ == "__main__":
     a = ap.parse_args()
     if a.only in ("", "c1"):
         bench_c1(a)
+    if a.only == "audiofmt":
+        bench_audio_formats(a)
     if a.only == "planes":
         bench_planes(a)
     if a.only == "ntap":
