@@ -491,6 +491,104 @@ ars_tile_kernel (const ArsLaunch L, const ArsTile Tl)
   }
 }
 
+__device__ __forceinline__ int sat_s16 (int v) { return min (max (v, -32768), 32767); }
+__device__ __forceinline__ long long sat_s32 (long long v) { return v < -2147483648LL ? -2147483648LL : (v > 2147483647LL ? 2147483647LL : v); }
+
+// S16 samples through the same tiling: the window is staged widened to 32 bits, taps likewise; the sums are
+// integers (wrapping 32 bit like the SSE2 pmaddwd path), so no lane structure has to be kept —
+// inner_product_gint16_full_1_sse2 (audio-resampler-x86-sse2.c:29-56): sum, + 2^14, >> 15, saturate.
+template <int CB>
+__global__ void __launch_bounds__ (ARS_THREADS)
+ars_tile_kernel_s16 (const ArsLaunch L, const ArsTile Tl)
+{
+  extern __shared__ __align__ (16) float sm[];
+  constexpr int RQ = ARS_RQ, CPT = 2;
+  const int nq_max = L.no / RQ;
+  int4 *qt = (int4 *) sm;                                        // [nq][nch][RQ]
+  int *xin = (int *) sm + (size_t) nq_max * Tl.nch * RQ * 4;      // [win][CB]
+  __shared__ int s_rel[64], s_phase[64];
+  const short *hist = (const short *) L.hist, *in = (const short *) L.in, *phases = (const short *) L.phases;
+  short *out = (short *) L.out;
+  const int lane = threadIdx.x & 31;
+  const int warp = __shfl_sync (0xffffffffu, (int) (threadIdx.x >> 5), 0);
+  const long long o0 = (long long) blockIdx.x * L.no;
+  const int n_out = (int) min ((long long) L.no, L.out_frames - o0);
+  const int nq = (n_out + RQ - 1) / RQ;
+  long long f0; int ph0;
+  ars_position (L, o0, f0, ph0);
+  f0 &= ~3LL;
+  if (threadIdx.x < L.no) {
+    long long idx; int phase;
+    ars_position (L, o0 + min ((int) threadIdx.x, n_out - 1), idx, phase);
+    s_rel[threadIdx.x] = (int) (idx - f0);
+    s_phase[threadIdx.x] = phase;
+  }
+  const int c_base = blockIdx.y * CB;
+  for (int fr = warp; fr < Tl.win; fr += ARS_THREADS / 32) {
+    const long long f = f0 + fr;
+    const short *src = nullptr;
+    if (f < L.hist_frames) src = hist + f * L.channels;
+    else if (f < L.avail && in) src = in + (f - L.hist_frames) * L.channels;
+#pragma unroll
+    for (int c = lane; c < CB; c += 32)
+      xin[fr * CB + c] = (src && c_base + c < L.channels) ? (int) __ldg (src + c_base + c) : 0;
+  }
+  __syncthreads ();
+  for (int i = threadIdx.x; i < nq * Tl.nch * RQ; i += ARS_THREADS) {
+    const int r = i % RQ, chunk = (i / RQ) % Tl.nch, q = i / (RQ * Tl.nch);
+    const int j = q * RQ + r;
+    const int s_min = s_rel[q * RQ] & ~3;
+    const int k0 = s_min + 4 * chunk - s_rel[j];
+    const short *src = phases + (size_t) s_phase[j] * L.n_taps;
+    int4 t;
+    t.x = (k0 + 0 >= 0 && k0 + 0 < L.n_taps) ? (int) __ldg (src + k0 + 0) : 0;
+    t.y = (k0 + 1 >= 0 && k0 + 1 < L.n_taps) ? (int) __ldg (src + k0 + 1) : 0;
+    t.z = (k0 + 2 >= 0 && k0 + 2 < L.n_taps) ? (int) __ldg (src + k0 + 2) : 0;
+    t.w = (k0 + 3 >= 0 && k0 + 3 < L.n_taps) ? (int) __ldg (src + k0 + 3) : 0;
+    qt[i] = t;
+  }
+  __syncthreads ();
+
+  constexpr int WCN = CB / (32 * CPT);
+  const int cg = warp % WCN, og = warp / WCN;
+  constexpr int NOG = (ARS_THREADS / 32) / WCN;
+  const int cl = (cg * 32 + lane) * CPT, c = c_base + cl;
+  for (int q = og; q < nq; q += NOG) {
+    unsigned acc[CPT][RQ];
+#pragma unroll
+    for (int u = 0; u < CPT; u++)
+#pragma unroll
+      for (int r = 0; r < RQ; r++) acc[u][r] = 0u;
+    const int s_min = s_rel[q * RQ] & ~3;
+    const int s_max = (s_rel[min (q * RQ + RQ - 1, n_out - 1)] + L.n_taps + 3) & ~3;
+    const int nch = (s_max - s_min) >> 2;
+    const int *xp = xin + s_min * CB + cl;
+    const int4 *tp = qt + (size_t) q * Tl.nch * RQ;
+#pragma unroll 2
+    for (int ch = 0; ch < nch; ch++, xp += 4 * CB, tp += RQ) {
+      int x[CPT][4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int2 v = *(const int2 *) (xp + k * CB);
+        x[0][k] = v.x; x[1][k] = v.y;
+      }
+#pragma unroll
+      for (int r = 0; r < RQ; r++) {
+        const int4 t = tp[r];
+#pragma unroll
+        for (int u = 0; u < CPT; u++)
+          acc[u][r] += (unsigned) (x[u][0] * t.x) + (unsigned) (x[u][1] * t.y) + (unsigned) (x[u][2] * t.z) + (unsigned) (x[u][3] * t.w);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < RQ; r++)
+#pragma unroll
+      for (int u = 0; u < CPT; u++)
+        if (q * RQ + r < n_out && c + u < L.channels)
+          out[(size_t) (o0 + q * RQ + r) * L.channels + c + u] = (short) sat_s16 ((int) (acc[u][r] + (1u << 14)) >> 15);
+  }
+}
+
 // Interpolated filter mode (audio-resampler.c:567-600 get_taps_gfloat_cubic +
 // inner_product_gfloat_cubic_1_sse, audio-resampler-x86-sse.c:82-120): too many phases to cache, so
 // every output takes four inner products against adjacent rows of the oversampled prototype and
@@ -576,8 +674,6 @@ __device__ __forceinline__ T ars_sample (const ArsLaunchX & L, long long f, int 
   return (T) 0;
 }
 
-__device__ __forceinline__ int sat_s16 (int v) { return min (max (v, -32768), 32767); }
-__device__ __forceinline__ long long sat_s32 (long long v) { return v < -2147483648LL ? -2147483648LL : (v > 2147483647LL ? 2147483647LL : v); }
 
 template <int FMT>
 __global__ void __launch_bounds__ (ARS_THREADS)
@@ -797,6 +893,8 @@ int b200_ars_create (const b200_ars_config * cfg, int device, b200_ars ** handle
     cudaFuncSetAttribute (ars_tile_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ARS_TILE_SMEM);
     cudaFuncSetAttribute (ars_tile_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ARS_TILE_SMEM);
     cudaFuncSetAttribute (ars_tile_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ARS_TILE_SMEM);
+    cudaFuncSetAttribute (ars_tile_kernel_s16<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, ARS_TILE_SMEM);
+    cudaFuncSetAttribute (ars_tile_kernel_s16<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ARS_TILE_SMEM);
   }
   *handle = h;
   return B200_OK;
@@ -874,7 +972,27 @@ int b200_ars_process (b200_ars * h, const void *in_v, size_t in_frames, void *ou
     L.row_pitch = (p.n_taps + 4 + 3) & ~3;
     L.wcn = (p.channels + 31) / 32; if (L.wcn > 8) L.wcn = 8;
     while (8 % L.wcn) L.wcn++;                                   // 1, 2, 4 or 8 warps across channels
-    if (p.fmt != ARS_F32) {
+    bool s16_tiled = false;
+    if (p.fmt == ARS_S16 && p.full && p.channels >= 64 && !getenv ("B200_ARS_GENERIC")) {
+      // tiled S16 kernel: same tile geometry as the F32 one (4-byte staged samples and taps)
+      const int cb = p.channels >= 128 ? 128 : 64, no = 32;
+      ArsTile tl;
+      const long long span = ((long long) no * p.in_step + p.out_step - 1) / p.out_step + 8 + p.n_taps;
+      tl.win = (int) ((span + 3) & ~3LL);
+      const long long spread = ((long long) (ARS_RQ - 1) * p.in_step + p.out_step - 1) / p.out_step + 1;
+      tl.nch = (int) ((spread + p.n_taps + 3 + 3) / 4 + 1);
+      const size_t smem_tile = ((size_t) (no / ARS_RQ) * tl.nch * ARS_RQ * 4 + (size_t) tl.win * cb) * sizeof (float);
+      if (smem_tile <= (size_t) ARS_TILE_SMEM) {
+        L.no = no; L.row_pitch = 0; L.wcn = 1;
+        L.phases = (const float *) h->d_table_x;
+        const dim3 grid ((unsigned) ((out_frames + no - 1) / no), (unsigned) ((p.channels + cb - 1) / cb));
+        if (cb == 128) ars_tile_kernel_s16<128> <<<grid, ARS_THREADS, smem_tile, stream>>> (L, tl);
+        else ars_tile_kernel_s16<64> <<<grid, ARS_THREADS, smem_tile, stream>>> (L, tl);
+        s16_tiled = true;
+      }
+    }
+    if (s16_tiled) {
+    } else if (p.fmt != ARS_F32) {
       ArsLaunchX X;
       X.hist = h->d_hist[h->cur]; X.in = in_v; X.out = out_v; X.table = h->d_table_x;
       X.hist_frames = (long long) hist; X.avail = (long long) avail; X.out_frames = (long long) out_frames;

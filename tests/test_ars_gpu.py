@@ -148,7 +148,9 @@ def test_interpolated_filter_mode(cuda_device, cfg):
 
 @pytest.mark.parametrize("cfg", [(48000, 44100, 2, 4), (44100, 48000, 3, 4), (8000, 16000, 1, 4), (48000, 24000, 40, 4),
                                  (101, 99, 1, 4), (44100, 8000, 2, 10), (96000, 8000, 1, 7), (12345, 54321, 2, 4),
-                                 (44100, 48001, 2, 4), (48000, 44101, 1, 6), (7999, 48000, 3, 10)],
+                                 (44100, 48001, 2, 4), (48000, 44101, 1, 6), (7999, 48000, 3, 10),
+                                 # >= 64 channels: S16 takes the tiled kernel
+                                 (48000, 44100, 130, 4), (44100, 48000, 64, 4), (8000, 16000, 256, 2), (96000, 8000, 70, 7)],
                          ids=lambda c: "%d-%d-%dch-q%d" % c)
 @pytest.mark.parametrize("fmt", ["S16", "S32", "F64"])
 def test_sample_formats(cuda_device, fmt, cfg):
