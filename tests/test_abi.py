@@ -71,9 +71,12 @@ def test_argument_validation_matches_caps_ranges():
     oi.width = 40000
     assert lib.b200_vcs_create(C.byref(ii), C.byref(oi), None, -1, C.byref(h)) == -1
     oi.width = 32
-    oi.format = 23                                                            # NV12 output: unsupported
+    assert lib.b200_video_info_set_format(C.byref(oi), 2, 32, 24) == 0        # NV12 -> I420: a YUV pair the path does not build
     assert lib.b200_vcs_create(C.byref(ii), C.byref(oi), None, -1, C.byref(h)) == -2
-    oi.format = 12
+    assert lib.b200_video_info_set_format(C.byref(oi), 23, 32, 24) == 0       # NV12 -> NV12: plane scaling, accepted
+    assert lib.b200_vcs_create(C.byref(ii), C.byref(oi), None, -1, C.byref(h)) == 0
+    lib.b200_vcs_destroy(h)
+    assert lib.b200_video_info_set_format(C.byref(oi), 12, 32, 24) == 0
     ii.stride[0] = 10                                                         # stride < width
     assert lib.b200_vcs_create(C.byref(ii), C.byref(oi), None, -1, C.byref(h)) == -1
     # compositor / resampler argument checks
