@@ -287,3 +287,51 @@ def test_yuv_plane_scaling_matches_reference(pair, size):
         want = r.convert(frame, np.zeros(got.size, dtype=np.uint8))
         r.close()
         assert np.array_equal(got, want), f"method {m}"
+
+
+def _one_tap_vertical_repeat(iw, ih, ow, oh, method):
+    """1-tap vertical pass (nearest, or a 1-line input) that repeats source lines, with the matrix after the scalers"""
+    return (method == 0 or ih == 1) and oh > ih and ow * oh <= iw * ih
+
+
+@pytest.mark.parametrize("size", [(64, 2, 16, 3), (64, 8, 16, 9), (202, 12, 40, 51), (128, 5, 40, 6)],
+                         ids=lambda s: "%dx%d-%dx%d" % s)
+def test_one_tap_vertical_repeat_defect_is_double_conversion(size):
+    """Second reference defect we do NOT reproduce: with a 1-tap vertical pass the reference hands the cached h-scaled
+    line itself downstream, and the in-place AYUV->ARGB matrix then converts that cached line; every later output row
+    that repeats the same source line is converted AGAIN (ARGB output, where pack is the identity).  Pinned here: each
+    row where the reference differs is exactly matrix(our row) — i.e. our row is the reference's own single conversion."""
+    import ctypes as C
+    iw, ih, ow, oh = size
+    assert _one_tap_vertical_repeat(iw, ih, ow, oh, 0)
+    frame = ob.nv12_random_frame(iw, ih, 1)
+    d = ob.vcs_desc(iw, ih, ow, oh, 0, in_fmt=23, out_fmt=13)
+    ours = ob.oracle_vcs_convert(d, frame).reshape(oh, ow, 4)
+    r = ob.RefVcs(iw, ih, ow, oh, 0, in_fmt=23, out_fmt=13)
+    ref = r.convert(frame).reshape(oh, ow, 4)
+    r.close()
+    p = (C.c_int * 5)()
+    im = ((C.c_int * 4) * 4)()
+    ob.oracle().oracle_vcs_matrix(C.byref(d), p, im)
+    p = list(p)
+
+    def splat(v):
+        sb = (v - 128) & 0xff
+        w = (sb << 8) | sb
+        return w - 65536 if w >= 32768 else w
+
+    def matrix(px):                      # video_orc_convert_AYUV_ARGB on one pixel held as (A, Y, U, V)
+        a, y, u, v = (int(t) for t in px)
+        wy = (splat(y) * p[0]) >> 16
+        rr = wy + ((splat(v) * p[1]) >> 16)
+        bb = wy + ((splat(u) * p[2]) >> 16)
+        gg = wy + ((splat(u) * p[3]) >> 16) + ((splat(v) * p[4]) >> 16)
+        cl = lambda t: max(-128, min(127, t)) + 128
+        return [a, cl(rr), cl(gg), cl(bb)]
+
+    bad_rows = [y for y in range(oh) if np.any(ours[y] != ref[y])]
+    assert bad_rows, "the defect should show on this shape"
+    for y in bad_rows:
+        assert y > 0 and np.array_equal(np.array([matrix(px) for px in ours[y]], dtype=np.uint8), ref[y])
+    # the first output row of every source line is converted once by both
+    assert np.array_equal(ours[0], ref[0])
