@@ -44,7 +44,8 @@ class VcsDesc(C.Structure):
                 ("in_stride", C.c_int * 4), ("in_offset", C.c_size_t * 4), ("in_matrix", C.c_int),
                 ("in_range", C.c_int), ("in_chroma_site", C.c_int), ("out_format", C.c_int),
                 ("out_width", C.c_int), ("out_height", C.c_int), ("out_stride", C.c_int * 4),
-                ("out_offset", C.c_size_t * 4), ("rs", RS)]
+                ("out_offset", C.c_size_t * 4), ("rs", RS),
+                ("out_matrix", C.c_int), ("out_chroma_site", C.c_int)]
 
 
 class OraclePad(C.Structure):

@@ -61,6 +61,9 @@ typedef struct {
   int out_stride[4];
   size_t out_offset[4];
   OracleResamplerOpts rs;
+  /* YUV output only; 0 = carried over from the input the way the element's caps fixation does when the
+   * input caps hold them (gstvideoconvertscale.c:1335-1427) */
+  int out_matrix, out_chroma_site;
 } OracleVcsDesc;
 
 /* fills the default system-memory layout (video-info.c fill_planes :1053-1063, :890-894)

@@ -605,6 +605,62 @@ pack_line (int fmt, const uint8_t * argb, uint8_t * d, int n)
   }
 }
 
+/* chroma down-sampling, horizontal, in place on one AYUV line: video_chroma_down_h2_u8 -> video_orc_chroma_down_h2_u8
+ * (video-chroma.c:398-409, video-orc.orc:2657-2671) averages each pixel pair into its first pixel; the co-sited
+ * variant video_chroma_down_h2_cs_u8 (:742-764) filters 3-1 / 1-2-1 / 1-3 around every even pixel.  Only the even
+ * pixels are read by the 4:2:0 pack functions. */
+static void
+chroma_down_h_line (uint8_t * p, int width, int cosited)
+{
+  int i, c;
+  if (!cosited) {
+    for (i = 0; i + 1 < width; i += 2)
+      for (c = 2; c < 4; c++)
+        p[c + 4 * i] = (uint8_t) ((p[c + 4 * i] + p[c + 4 * (i + 1)] + 1) >> 1);
+    return;
+  }
+  if (width < 2)
+    return;
+  for (c = 2; c < 4; c++)
+    p[c] = (uint8_t) ((3 * p[c] + p[c + 4] + 2) >> 2);
+  for (i = 2; i < width - 2; i += 2)
+    for (c = 2; c < 4; c++)
+      p[c + 4 * i] = (uint8_t) ((p[c + 4 * (i - 1)] + 2 * p[c + 4 * i] + p[c + 4 * (i + 1)] + 2) >> 2);
+  if (i < width)
+    for (c = 2; c < 4; c++)
+      p[c + 4 * i] = (uint8_t) ((p[c + 4 * (i - 1)] + 3 * p[c + 4 * i] + 2) >> 2);
+}
+
+/* pack one AYUV line into a 4:2:0 frame: pack_planar_420 (video-format.c:117-148), pack_NV12 (:1642-1672),
+ * pack_NV21 (:1818-1848): Y of every line; chroma only from even lines (IS_CHROMA_LINE_420), taken from the even
+ * pixel of each pair, plus the last pixel of an odd width */
+static void
+pack_line_420 (const OracleVcsDesc * d, const uint8_t * ayuv, uint8_t * out, int y)
+{
+  int w = d->out_width, i;
+  uint8_t *dy = out + d->out_offset[0] + (size_t) d->out_stride[0] * y;
+  for (i = 0; i < w; i++)
+    dy[i] = ayuv[4 * i + 1];
+  if (y & 1)
+    return;
+  if (d->out_format == ORC_FMT_I420 || d->out_format == ORC_FMT_YV12) {
+    const int pu = d->out_format == ORC_FMT_YV12 ? 2 : 1, pv = 3 - pu;
+    uint8_t *du = out + d->out_offset[pu] + (size_t) d->out_stride[pu] * (y >> 1);
+    uint8_t *dv = out + d->out_offset[pv] + (size_t) d->out_stride[pv] * (y >> 1);
+    for (i = 0; i < w; i += 2) {
+      du[i >> 1] = ayuv[4 * i + 2];
+      dv[i >> 1] = ayuv[4 * i + 3];
+    }
+  } else {
+    const int ui = d->out_format == ORC_FMT_NV21 ? 1 : 0;
+    uint8_t *duv = out + d->out_offset[1] + (size_t) d->out_stride[1] * (y >> 1);
+    for (i = 0; i < w; i += 2) {
+      duv[i + ui] = ayuv[4 * i + 2];
+      duv[i + (ui ^ 1)] = ayuv[4 * i + 3];
+    }
+  }
+}
+
 /* Which input lines does the chain pull through the chroma upsampler, and how is each
  * paired?  The upsample cache hands out lines in PAIRS (n_lines=2, offset=-1,
  * video-chroma.c:997) starting at whichever line is requested first after a gap
@@ -840,6 +896,7 @@ oracle_vcs_convert (const OracleVcsDesc * d, const uint8_t * in, uint8_t * out)
   uint8_t *cur, *tmp, *mode;
   Scaler hs, vs;
   int have_h = iw != ow, have_v = ih != oh, pass;
+  int yuv_out = 0, out_site = 0;
   long s0, s3;
 
   {
@@ -848,12 +905,32 @@ oracle_vcs_convert (const OracleVcsDesc * d, const uint8_t * in, uint8_t * out)
     if ((in_planar && out_planar) || ((d->out_format == ORC_FMT_NV12 || d->out_format == ORC_FMT_NV21) &&
             d->in_format == d->out_format))
       return convert_planes (d, in, out);
-    if (out_planar || d->out_format == ORC_FMT_NV12 || d->out_format == ORC_FMT_NV21)
-      return -1;                /* other YUV -> YUV pairs run the generic chain with chroma down-sampling: not restated */
+    if (out_planar || d->out_format == ORC_FMT_NV12 || d->out_format == ORC_FMT_NV21) {
+      /* the other 4:2:0 pairs (NV12 <-> I420, NV12 <-> NV21 ...) have no table row: generic chain, with
+       * chain_downsample (video-converter.c:2018-2032) and the 4:2:0 pack functions at its end.  chain_convert
+       * (:1720-1868) adds no matrix stage when both sides name the same colour matrix (the range is not
+       * compared); a differing matrix selects video_orc_matrix8, whose SIMD program and C backup disagree
+       * (video-orc.orc:2079-2133 vs video-converter.c:1136-1176): not restated */
+      if (d->out_matrix && d->out_matrix != d->in_matrix)
+        return -1;
+      yuv_out = 1;
+      out_site = d->out_chroma_site ? d->out_chroma_site : d->in_chroma_site;
+    }
   }
-  if (oracle_vcs_matrix (d, p, im) != 0)
+  if (yuv_out && iw == ow && ih == oh && out_site == d->in_chroma_site) {
+    /* video_converter_compute_resample (:2850-2895): same sub-sampling, site and size -> no chroma resampler
+     * on either side; unpack replicates every chroma sample and pack reads it back */
+    uint8_t *line = malloc ((size_t) iw * 4);
+    for (y = 0; y < ih; y++) {
+      unpack_line (d, in, y, line);
+      pack_line_420 (d, line, out, y);
+    }
+    free (line);
+    return 0;
+  }
+  if (!yuv_out && oracle_vcs_matrix (d, p, im) != 0)
     return -1;
-  if ((d->in_format == ORC_FMT_I420 || d->in_format == ORC_FMT_YV12) && iw == ow && ih == oh) {
+  if (!yuv_out && (d->in_format == ORC_FMT_I420 || d->in_format == ORC_FMT_YV12) && iw == ow && ih == oh) {
     /* fast path (video-converter.c:8766-8800 table rows, keeps_size): convert_I420_BGRA / _ARGB /
      * _pack_ARGB (:6772-6988) -> video_orc_convert_I420_BGRA (video-orc.orc:1859-1911): the chroma
      * sample of row y>>1 is used as is for both of its pixels (no up-sampling filter), same mulhi
@@ -915,7 +992,7 @@ oracle_vcs_convert (const OracleVcsDesc * d, const uint8_t * in, uint8_t * out)
   /* pass 0 = chain_scale(force=FALSE) before the matrix, pass 1 = chain_scale(force=TRUE)
    * after it (video-converter.c:2517-2531, :1685-1718) */
   for (pass = 0; pass < 2; pass++) {
-    if (pass == 1) {
+    if (pass == 1 && !yuv_out) {
       for (y = 0; y < ch; y++)
         matrix_line (cur + (size_t) y * cw * 4, cw, p);
     }
@@ -944,9 +1021,44 @@ oracle_vcs_convert (const OracleVcsDesc * d, const uint8_t * in, uint8_t * out)
       }
     }
   }
-  for (y = 0; y < oh; y++)
-    pack_line (d->out_format, cur + (size_t) y * ow * 4,
-        out + d->out_offset[0] + (size_t) d->out_stride[0] * y, ow);
+  if (yuv_out) {
+    /* do_downsample_lines (:3194-3222): the pack stage pulls line after line; every even line 2k makes the
+     * down-sampler fetch the pair (2k, 2k+1) and filter it IN PLACE: vertical average of the chroma into line 2k
+     * (video_chroma_down_v2_u8, video-chroma.c:434-442; the V_COSITED resampler is the unimplemented one that only
+     * runs the horizontal filter, :774-785), then the horizontal filter on line 2k.  For an odd height the pair's
+     * second line is line `oh`: the vertical scaler clamps it back to oh-1 (:3070-3080), but without a vertical
+     * scaler the request reaches do_unpack_lines' clamp (:2973) through a fresh up-sampler pair (oh, oh+1), i.e.
+     * the last source line with its chroma row NOT vertically filtered. */
+    uint8_t *extra = NULL;
+    if ((oh & 1) && !have_v && !(out_site & ORC_SITE_V_COSITED)) {
+      uint8_t *one = malloc ((size_t) iw * 4);
+      unpack_line (d, in, ih - 1, one);
+      chroma_h_line (one, iw, (d->in_chroma_site & ORC_SITE_H_COSITED) != 0);
+      if (have_h) {
+        extra = malloc ((size_t) ow * 4);
+        hscale_image (&hs, one, iw, extra, ow, 1);
+        free (one);
+      } else
+        extra = one;
+    }
+    for (y = 0; y < oh; y += 2) {
+      uint8_t *l0 = cur + (size_t) y * ow * 4;
+      if (!(out_site & ORC_SITE_V_COSITED)) {
+        const uint8_t *l1 = y + 1 < oh ? l0 + (size_t) ow * 4 : (extra ? extra : l0);
+        int x, c;
+        for (x = 0; x < ow; x++)
+          for (c = 2; c < 4; c++)
+            l0[4 * x + c] = (uint8_t) ((l0[4 * x + c] + l1[4 * x + c] + 1) >> 1);
+      }
+      chroma_down_h_line (l0, ow, (out_site & ORC_SITE_H_COSITED) != 0);
+    }
+    free (extra);
+    for (y = 0; y < oh; y++)
+      pack_line_420 (d, cur + (size_t) y * ow * 4, out, y);
+  } else
+    for (y = 0; y < oh; y++)
+      pack_line (d->out_format, cur + (size_t) y * ow * 4,
+          out + d->out_offset[0] + (size_t) d->out_stride[0] * y, ow);
   free (cur);
   if (have_h)
     scaler_clear (&hs);

@@ -192,6 +192,31 @@ def video_yuv():
     json.dump(cases, open(os.path.join(HERE, "video_yuv_cases.json"), "w"), indent=1)
 
 
+def video_cross():
+    """4:2:0 -> the other 4:2:0 family: generic chain with chroma down-sampling (horizontal-first geometries, where the
+    reference's temp-line ring does not alias)"""
+    arrays, cases = {}, []
+    for fi, fo in [("NV12", "I420"), ("I420", "NV12"), ("NV12", "NV21"), ("YV12", "NV21")]:
+        for (iw, ih, ow, oh) in [(64, 48, 32, 24), (64, 48, 96, 72), (65, 49, 33, 25), (33, 17, 20, 31), (50, 21, 50, 21),
+                                 (57, 35, 29, 35)]:
+            for m, site, osite in ((1, 2, 2), (3, 1, 1), (9, 2, 1), (0, 1, 2)):
+                if m == 0 and oh > ih:
+                    continue    # nearest vertical repeats + in-place down-sampling: reference defect class
+                frame = ob.i420_random_frame(iw, ih, m + iw) if fi in ("I420", "YV12") else ob.nv12_random_frame(iw, ih, m + iw)
+                d = ob.vcs_desc(iw, ih, ow, oh, m, in_fmt=ob.FMT[fi], out_fmt=ob.FMT[fo], site=site)
+                size = ob.vcs_sizes(d)[1]
+                r = ob.RefVcs(iw, ih, ow, oh, m, in_fmt=ob.FMT[fi], out_fmt=ob.FMT[fo], site=site, matrix=d.in_matrix,
+                              out_matrix=d.in_matrix, out_site=osite)
+                out = r.convert(frame, np.zeros(size, dtype=np.uint8))
+                r.close()
+                key = f"x_{fi}_{fo}_{iw}x{ih}_{ow}x{oh}_m{m}_s{site}{osite}"
+                arrays[key] = out
+                cases.append({"key": key, "in_fmt": fi, "out_fmt": fo, "in": [iw, ih], "out": [ow, oh], "method": m,
+                              "site": site, "out_site": osite, "seed": m + iw})
+    np.savez_compressed(os.path.join(HERE, "video_cross.npz"), **arrays)
+    json.dump(cases, open(os.path.join(HERE, "video_cross_cases.json"), "w"), indent=1)
+
+
 def compositor_420():
     """I420 / YV12 / NV12 / NV21 output"""
     o, r = ob.oracle(), ob.ref()
@@ -225,7 +250,8 @@ if __name__ == "__main__":
     assert ob.have_ref(), "needs oracle/_ref/libgstref.so (make -C oracle ref)"
     only = set(sys.argv[1:])
     for name, fn in [("video", video), ("compositor", compositor), ("audio", audio), ("video_planar", video_planar),
-                     ("audio_interpolated", audio_interpolated), ("audio_formats", audio_formats), ("compositor_420", compositor_420), ("video_yuv", video_yuv)]:
+                     ("audio_interpolated", audio_interpolated), ("audio_formats", audio_formats), ("compositor_420", compositor_420), ("video_yuv", video_yuv),
+                     ("video_cross", video_cross)]:
         if not only or name in only:
             fn()
     print("golden fixtures written to", HERE)

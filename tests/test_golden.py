@@ -176,3 +176,13 @@ def test_video_yuv_plane_scaling(case):
     frame = (ob.i420_random_frame if case["in_fmt"] in ("I420", "YV12") else ob.nv12_random_frame)(iw, ih, case["seed"])
     d = ob.vcs_desc(iw, ih, ow, oh, m, in_fmt=ob.FMT[case["in_fmt"]], out_fmt=ob.FMT[case["out_fmt"]])
     assert np.array_equal(ob.oracle_vcs_convert(d, frame), gold)
+
+
+@pytest.mark.parametrize("case", json.load(open(os.path.join(G, "video_cross_cases.json"))), ids=lambda c: c["key"])
+def test_video_cross_family_420(case):
+    gold = np.load(os.path.join(G, "video_cross.npz"))[case["key"]]
+    (iw, ih), (ow, oh), m = case["in"], case["out"], case["method"]
+    frame = (ob.i420_random_frame if case["in_fmt"] in ("I420", "YV12") else ob.nv12_random_frame)(iw, ih, case["seed"])
+    d = ob.vcs_desc(iw, ih, ow, oh, m, in_fmt=ob.FMT[case["in_fmt"]], out_fmt=ob.FMT[case["out_fmt"]], site=case["site"])
+    d.out_chroma_site = case["out_site"]
+    assert np.array_equal(ob.oracle_vcs_convert(d, frame), gold)

@@ -335,3 +335,91 @@ def test_one_tap_vertical_repeat_defect_is_double_conversion(size):
         assert y > 0 and np.array_equal(np.array([matrix(px) for px in ours[y]], dtype=np.uint8), ref[y])
     # the first output row of every source line is converted once by both
     assert np.array_equal(ours[0], ref[0])
+
+
+# ------------------------------------------------------------------- 4:2:0 -> the other 4:2:0 family (generic chain)
+CROSS_PAIRS = [("NV12", "I420"), ("I420", "NV12"), ("NV12", "NV21"), ("NV21", "YV12"), ("YV12", "NV21"), ("I420", "NV21")]
+CROSS_SIZES = [(64, 48, 32, 24), (64, 48, 96, 72), (33, 17, 20, 31), (50, 21, 50, 21), (57, 35, 29, 35), (40, 33, 57, 33),
+               (320, 240, 213, 120), (17, 9, 64, 31), (2, 2, 1, 1), (1, 1, 5, 4)]
+
+
+def _cross(pair, size, method, site, out_site=None, seed=3):
+    iw, ih, ow, oh = size
+    fi, fo = ob.FMT[pair[0]], ob.FMT[pair[1]]
+    frame = ob.i420_random_frame(iw, ih, seed) if pair[0] in ("I420", "YV12") else ob.nv12_random_frame(iw, ih, seed)
+    d = ob.vcs_desc(iw, ih, ow, oh, method, in_fmt=fi, out_fmt=fo, site=site)
+    if out_site is not None:
+        d.out_chroma_site = out_site
+    got = ob.oracle_vcs_convert(d, frame)
+    # the element's caps fixation carries colorimetry (and, for an unchanged sub-sampling, the chroma site) over from
+    # the input caps (gstvideoconvertscale.c:1335-1427): same matrix on both sides -> no matrix stage in the chain
+    r = ob.RefVcs(iw, ih, ow, oh, method, in_fmt=fi, out_fmt=fo, site=site, matrix=d.in_matrix, out_matrix=d.in_matrix,
+                  out_site=site if out_site is None else out_site)
+    want = r.convert(frame, np.zeros(got.size, dtype=np.uint8))
+    r.close()
+    return got, want, d, frame
+
+
+def _one_tap_vertical_inplace(ih, oh, method):
+    """the chroma down-sampler filters IN PLACE the line the 1-tap vertical pass handed through, so a repeated source
+    line is filtered once per repeat (same defect class as the in-place matrix above)"""
+    return (method == 0 or ih == 1) and oh > ih
+
+
+@pytest.mark.parametrize("pair", CROSS_PAIRS, ids=lambda p: "%s-%s" % p)
+@pytest.mark.parametrize("size", CROSS_SIZES, ids=lambda s: "%dx%d-%dx%d" % s)
+def test_cross_family_420_matches_reference(pair, size):
+    """unpack -> chroma up -> scalers -> chroma DOWN (video-converter.c:2018-2032, :3194-3222; video-chroma.c:398-442,
+    :742-785) -> pack_planar_420 / pack_NV12 / pack_NV21, all ten element methods, both default chroma sites"""
+    iw, ih, ow, oh = size
+    for method in range(10):
+        for site in (1, 2):
+            got, want, _, _ = _cross(pair, size, method, site)
+            if not np.array_equal(got, want):
+                if _vfirst(iw, ih, ow, oh) or _one_tap_vertical_inplace(ih, oh, method):
+                    continue            # the two reference defect classes; intended arithmetic pinned below
+                assert False, f"method {method} site {site}"
+
+
+@pytest.mark.parametrize("site,out_site", [(1, 2), (2, 1), (6, 2), (2, 4), (4, 6), (1, 6)])
+@pytest.mark.parametrize("size", [(64, 48, 32, 24), (33, 17, 20, 31), (50, 21, 50, 21), (57, 35, 29, 35), (40, 33, 57, 33)],
+                         ids=lambda s: "%dx%d-%dx%d" % s)
+def test_cross_family_420_output_chroma_site(size, site, out_site):
+    """a different output site picks the other down filters (co-sited horizontal 3-1 / 1-2-1 / 1-3; the vertical
+    co-sited one is the reference's unimplemented resampler) and turns on both resamplers even at the same size"""
+    iw, ih, ow, oh = size
+    for method in (1, 3, 9):
+        got, want, _, _ = _cross(("NV12", "I420"), size, method, site, out_site)
+        if _vfirst(iw, ih, ow, oh) and not np.array_equal(got, want):
+            continue
+        assert np.array_equal(got, want), f"method {method}"
+
+
+@pytest.mark.parametrize("size", [(100, 100, 150, 50), (64, 66, 64, 31), (40, 90, 40, 31), (48, 68, 36, 12)],
+                         ids=lambda s: "%dx%d-%dx%d" % s)
+@pytest.mark.parametrize("method", [3, 4, 5, 9])
+def test_cross_family_420_vertical_first_two_step(size, method):
+    """vertical-first chains: the intended arithmetic, pinned by two reference runs that cannot alias
+    (NV12 -> AYUV at the same size, then AYUV -> I420 with scaling and chroma down-sampling).  Filters whose
+    vertical windows skip source lines are left out: the first run would pair chroma rows in a different pull order."""
+    iw, ih, ow, oh = size
+    assert _vfirst(iw, ih, ow, oh)
+    d = ob.vcs_desc(iw, ih, ow, oh, method, out_fmt=ob.FMT["I420"])
+    frame = ob.nv12_random_frame(iw, ih, seed=11)
+    r1 = ob.RefVcs(iw, ih, iw, ih, method, out_fmt=ob.FMT["AYUV"], matrix=d.in_matrix, rng=d.in_range,
+                   site=d.in_chroma_site, out_matrix=d.in_matrix, out_rng=d.in_range, out_site=0)
+    ayuv = r1.convert(frame)
+    r1.close()
+    r2 = ob.RefVcs(iw, ih, ow, oh, method, in_fmt=ob.FMT["AYUV"], out_fmt=ob.FMT["I420"], matrix=d.in_matrix, rng=d.in_range,
+                   site=0, out_matrix=d.in_matrix, out_rng=d.in_range, out_site=d.in_chroma_site)
+    got = ob.oracle_vcs_convert(d, frame)
+    want = r2.convert(ayuv, np.zeros(got.size, dtype=np.uint8))
+    r2.close()
+    assert np.array_equal(got, want)
+
+
+def test_cross_family_420_differing_matrix_is_refused():
+    d = ob.vcs_desc(64, 48, 32, 24, 1, out_fmt=ob.FMT["I420"])
+    d.out_matrix = 4 if d.in_matrix == 3 else 3
+    with pytest.raises(RuntimeError):
+        ob.oracle_vcs_convert(d, ob.nv12_random_frame(64, 48, 1))
