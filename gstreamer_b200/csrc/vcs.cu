@@ -12,6 +12,7 @@
 #include "vcs_light.cuh"
 #include "vcs_ntap.cuh"
 #include "vcs_planes.cuh"
+#include "vcs_down420.cuh"
 
 #include <string.h>
 #include <new>
@@ -38,6 +39,10 @@ struct b200_vcs {
   Lanczos2State l2;
   NtapState ntap;
   PlanesState planes;
+  // 4:2:0 -> other 4:2:0 family: scaled A,Y,U,V scratch images between the two launches
+  Down420Dev down;
+  uint8_t *d_scratch = nullptr;
+  int scratch_frames = 0;
   size_t in_bytes = 0, out_bytes = 0;
 };
 
@@ -82,6 +87,29 @@ int launch (b200_vcs * h, int n, const VcsBatch & batch, cudaStream_t stream)
     if (aligned) return launch_ntap (h->dev, p, h->ntap, batch, n, stream);
   }
   dim3 grid ((p.out.width + p.tile_w - 1) / p.tile_w, (p.out.height + p.tile_h - 1) / p.tile_h, n);
+  if (p.yuv_out) {
+    // launch 1 writes the scaled pixels of every frame to its scratch image, launch 2 down-samples and packs
+    const size_t frame = (size_t) h->down.stride_s * p.out.height;
+    if (n > h->scratch_frames) {
+      B200_CUDA_TRY (cudaFree (h->d_scratch));                      // synchronises with launches still reading it
+      h->d_scratch = nullptr; h->scratch_frames = 0;
+      B200_CUDA_TRY (cudaMalloc ((void **) &h->d_scratch, frame * n));
+      h->scratch_frames = n;
+    }
+    VcsBatch mid;
+    Down420Batch fin;
+    for (int i = 0; i < n; i++) {
+      mid.in[i] = batch.in[i]; mid.out[i] = h->d_scratch + frame * i;
+      fin.scratch[i] = mid.out[i]; fin.out[i] = batch.out[i];
+    }
+    vcs_generic_kernel <<<grid, 256, p.smem_bytes, stream>>> (h->dev, mid);
+    B200_CUDA_TRY (cudaGetLastError ());
+    const int cw = (p.out.width + 1) / 2, chh = (p.out.height + 1) / 2;
+    dim3 blk (32, 8), g2 ((cw + 31) / 32, (chh + 7) / 8, n);
+    vcs_down420_kernel <<<g2, blk, 0, stream>>> (h->down, fin);
+    B200_CUDA_TRY (cudaGetLastError ());
+    return B200_OK;
+  }
   vcs_generic_kernel <<<grid, 256, p.smem_bytes, stream>>> (h->dev, batch);
   B200_CUDA_TRY (cudaGetLastError ());
   return B200_OK;
@@ -196,10 +224,12 @@ int b200_vcs_create (const b200_video_info * in, const b200_video_info * out,
     *handle = h;
     return B200_OK;
   }
-  h->l2_tables = build_lanczos2_tables (h->plan);
-  h->plan.lanczos2_ok = h->l2_tables.ok;
+  if (!h->plan.yuv_out) {
+    h->l2_tables = build_lanczos2_tables (h->plan);
+    h->plan.lanczos2_ok = h->l2_tables.ok;
+  }
   const VcsPlan & p = h->plan;
-  if ((p.out.stride[0] & 3) || (p.out.offset[0] & 3)) { delete h; return B200_ERR_UNSUPPORTED; }
+  if (!p.yuv_out && ((p.out.stride[0] & 3) || (p.out.offset[0] & 3))) { delete h; return B200_ERR_UNSUPPORTED; }
   h->device = device;
   // the kernel this plan will run (also reported for host-only handles: caps negotiation dry-runs, CPU tests)
   h->variant = h->plan.lanczos2_ok ? 1 : (h->plan.light_ok ? 2 : (h->plan.ntap_ok ? 3 : 0));
@@ -225,6 +255,19 @@ int b200_vcs_create (const b200_video_info * in, const b200_video_info * out,
     }
     d.cstep = p.planar ? 1 : 2;
     d.h_first = p.h_first; d.matrix_first = p.matrix_first;
+    d.yuv_out = p.yuv_out ? 1 : 0;
+    if (p.yuv_out) {                                              // the chain's output is the scratch image
+      d.stride_out = p.out.width * 4; d.off_out = 0;
+      Down420Dev & q = h->down;
+      memset (&q, 0, sizeof (q));
+      q.ow = p.out.width; q.oh = p.out.height; q.stride_s = d.stride_out;
+      q.hmode = p.down_h; q.vavg = p.down_v ? 1 : 0;
+      q.stride_y = p.out.stride[0]; q.off_y = p.out.offset[0];
+      q.stride_u = p.out.stride[p.out_plane_u]; q.stride_v = p.out.stride[p.out_plane_v];
+      q.cstep = p.out_cstep;
+      q.off_u = p.out.offset[p.out_plane_u] + (p.out_cstep == 2 ? p.out_u_index : 0);
+      q.off_v = p.out.offset[p.out_plane_v] + (p.out_cstep == 2 ? (p.out_u_index ^ 1) : 0);
+    }
     d.p1 = p.p[0]; d.p2 = p.p[1]; d.p3 = p.p[2]; d.p4 = p.p[3]; d.p5 = p.p[4];
     d.sel = p.byte_sel[0] | (p.byte_sel[1] << 4) | (p.byte_sel[2] << 8) | (p.byte_sel[3] << 12);
     d.tile_w = p.tile_w; d.tile_h = p.tile_h; d.max_rows = p.max_rows; d.cols_pitch = p.cols_pitch;
@@ -266,6 +309,7 @@ void b200_vcs_destroy (b200_vcs * h)
     cudaFree (h->d_hsum); cudaFree (h->d_vsum); cudaFree (h->d_cmode);
     cudaFree (h->l2.d_htab); cudaFree (h->l2.d_vtab); cudaFree (h->ntap.d_h); cudaFree (h->ntap.d_v);
     free_planes (&h->planes);
+    cudaFree (h->d_scratch);
     for (int i = 0; i < b200_vcs::kSlots; i++) {
       cudaFree (h->slot_in[i]); cudaFree (h->slot_out[i]);
       if (h->ev_in[i]) cudaEventDestroy (h->ev_in[i]);
@@ -344,8 +388,8 @@ int b200_vcs_get_plan_info (const b200_vcs * h, b200_vcs_plan_info * info)
   info->h_first = p.h_first; info->matrix_first = p.matrix_first;
   for (int i = 0; i < 5; i++) info->p[i] = p.p[i];
   info->tile_w = p.tile_w; info->tile_h = p.tile_h; info->smem_bytes = p.smem_bytes;
-  info->kernel_variant = p.planes_mode ? 4 : (h->variant == 1 && p.lanczos2_ok) ? 1 : (h->variant == 2 && p.light_ok) ? 2 : (h->variant == 3 && p.ntap_ok) ? 3 : 0;
-  info->n_launches_per_convert = 1;
+  info->kernel_variant = p.yuv_out ? 5 : p.planes_mode ? 4 : (h->variant == 1 && p.lanczos2_ok) ? 1 : (h->variant == 2 && p.light_ok) ? 2 : (h->variant == 3 && p.ntap_ok) ? 3 : 0;
+  info->n_launches_per_convert = p.yuv_out ? 2 : 1;
   return B200_OK;
 }
 
@@ -375,7 +419,7 @@ int b200_vcs_get_chroma_plan (const b200_vcs * h, uint8_t * mode, size_t len)
 int b200_vcs_set_kernel_variant (b200_vcs * h, int variant)
 {
   if (!h || variant < 0 || variant > 3) return B200_ERR_INVALID_ARG;
-  if (h->plan.planes_mode) return B200_ERR_UNSUPPORTED;            // one kernel only
+  if (h->plan.planes_mode || h->plan.yuv_out) return B200_ERR_UNSUPPORTED;   // one kernel only
   if (variant == 3 && !(h->plan.ntap_ok && h->ntap.ready)) return B200_ERR_UNSUPPORTED;
   if (variant == 1 && !h->plan.lanczos2_ok) return B200_ERR_UNSUPPORTED;
   if (variant == 2 && !h->plan.light_ok) return B200_ERR_UNSUPPORTED;

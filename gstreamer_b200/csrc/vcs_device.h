@@ -27,6 +27,7 @@ struct VcsDev {
   int planar;                    // I420 / YV12
   int chroma_nearest;            // unchanged-size I420/YV12: the reference's fast path replicates chroma (no filter)
   int h_first, matrix_first;
+  int yuv_out;                   // 4:2:0 output through the chain: no matrix stage, scaled A,Y,U,V pixels go to a scratch image
   int p1, p2, p3, p4, p5;
   unsigned sel;                  // byte selector nibbles for PRMT-style packing: byte i <- comp sel[i]
   AxisDev h, v;

@@ -248,7 +248,7 @@ vcs_generic_kernel (const VcsDev P, const VcsBatch frames)
       }
     }
     int r, g, b;
-    if (P.matrix_first) { r = comp[0]; g = comp[1]; b = comp[2]; }
+    if (P.matrix_first || P.yuv_out) { r = comp[0]; g = comp[1]; b = comp[2]; }
     else yuv_to_rgb (comp[0], comp[1], comp[2], P.p1, P.p2, P.p3, P.p4, P.p5, r, g, b);
     int a = 255;
     if (P.h_first) { a = alpha_pass (a, P.h, ox); a = alpha_pass (a, P.v, oy); }

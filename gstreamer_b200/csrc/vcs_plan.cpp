@@ -551,12 +551,40 @@ int build_vcs_plan (const b200_video_info * in, const b200_video_info * out,
     if (out_pl || out_semi) {
       // the reference has plane-scaling fast paths for NV12->NV12, NV21->NV21, I420/YV12 -> I420/YV12
       // (video-converter.c:8722-8760); the other YUV pairs run the chain with chroma down-sampling: not built
-      if (!((in_pl && out_pl) || (out_semi && in->format == out->format))) return B200_ERR_UNSUPPORTED;
-      if (in->stride[0] < in->width || out->stride[0] < out->width) return B200_ERR_INVALID_ARG;
-      if (p->in.color_matrix == 0) p->in.color_matrix = in->height > 576 ? B200_COLOR_MATRIX_BT709 : B200_COLOR_MATRIX_BT601;
-      return build_planes (p, filter_from_method (*cfg));
+      if (!((in_pl && out_pl) || (out_semi && in->format == out->format))) {
+        // the remaining 4:2:0 pairs have no table row: the generic chain, closed by chain_downsample
+        // (video-converter.c:2018-2032) and the 4:2:0 pack functions.  Not yet confirmed on a device: opt-in.
+        if (!getenv ("B200_VCS_EXPERIMENTAL")) return B200_ERR_UNSUPPORTED;
+        p->yuv_out = true;
+      } else {
+        if (in->stride[0] < in->width || out->stride[0] < out->width) return B200_ERR_INVALID_ARG;
+        if (p->in.color_matrix == 0) p->in.color_matrix = in->height > 576 ? B200_COLOR_MATRIX_BT709 : B200_COLOR_MATRIX_BT601;
+        return build_planes (p, filter_from_method (*cfg));
+      }
     }
   }
+  if (p->yuv_out) {
+    const bool out_pl = out->format == B200_VIDEO_FORMAT_I420 || out->format == B200_VIDEO_FORMAT_YV12;
+    const int ocw = (out->width + 1) / 2;
+    // chain_convert (video-converter.c:1720-1868) compares the two colour matrices only (not the range): equal ->
+    // no matrix stage.  A differing one would run video_orc_matrix8, whose SIMD program and C backup disagree
+    // (video-orc.orc:2079-2133 vs video-converter.c:1136-1176): refused.  The element's caps fixation carries the
+    // input colorimetry over to a YUV output (gstvideoconvertscale.c:1335-1427), so equal is the negotiated case.
+    if (p->out.color_matrix != 0 && p->out.color_matrix != p->in.color_matrix) return B200_ERR_UNSUPPORTED;
+    if (p->out.chroma_site == 0) p->out.chroma_site = p->in.chroma_site;
+    if (out->stride[0] < out->width) return B200_ERR_INVALID_ARG;
+    if (out_pl) {
+      if (out->stride[1] < ocw || out->stride[2] < ocw) return B200_ERR_INVALID_ARG;
+      p->out_plane_u = out->format == B200_VIDEO_FORMAT_YV12 ? 2 : 1;
+      p->out_plane_v = 3 - p->out_plane_u;
+      p->out_cstep = 1; p->out_u_index = 0;
+    } else {
+      if (out->stride[1] < 2 * ocw) return B200_ERR_INVALID_ARG;
+      p->out_plane_u = p->out_plane_v = 1;
+      p->out_cstep = 2; p->out_u_index = out->format == B200_VIDEO_FORMAT_NV21 ? 1 : 0;
+    }
+    { uint8_t s[4] = {0, 1, 2, 3}; memcpy (p->byte_sel, s, 4); }   // scratch pixels stay A,Y,U,V
+  } else
   switch (out->format) {                // (A,R,G,B) component placed at each output byte
     case B200_VIDEO_FORMAT_BGRA: case B200_VIDEO_FORMAT_BGRx: { uint8_t s[4] = {3, 2, 1, 0}; memcpy (p->byte_sel, s, 4); break; }
     case B200_VIDEO_FORMAT_RGBA: case B200_VIDEO_FORMAT_RGBx: { uint8_t s[4] = {1, 2, 3, 0}; memcpy (p->byte_sel, s, 4); break; }
@@ -565,20 +593,23 @@ int build_vcs_plan (const b200_video_info * in, const b200_video_info * out,
     default: return B200_ERR_UNSUPPORTED;
   }
   p->planar = in->format == B200_VIDEO_FORMAT_I420 || in->format == B200_VIDEO_FORMAT_YV12;
+  const int min_out_stride = p->yuv_out ? out->width : out->width * 4;
   if (p->planar) {
     const int cw = (in->width + 1) / 2;
-    if (in->stride[0] < in->width || in->stride[1] < cw || in->stride[2] < cw || out->stride[0] < out->width * 4)
+    if (in->stride[0] < in->width || in->stride[1] < cw || in->stride[2] < cw || out->stride[0] < min_out_stride)
       return B200_ERR_INVALID_ARG;
     p->plane_u = in->format == B200_VIDEO_FORMAT_YV12 ? 2 : 1;   // YV12 keeps V in plane 1
     p->plane_v = 3 - p->plane_u;
-  } else if (in->stride[0] < in->width || in->stride[1] < ((in->width + 1) & ~1) || out->stride[0] < out->width * 4)
+  } else if (in->stride[0] < in->width || in->stride[1] < ((in->width + 1) & ~1) || out->stride[0] < min_out_stride)
     return B200_ERR_INVALID_ARG;
   p->u_index = in->format == B200_VIDEO_FORMAT_NV21 ? 1 : 0;
   p->h_cosited = (p->in.chroma_site & B200_CHROMA_SITE_H_COSITED) != 0;
   p->v_pairs = (p->in.chroma_site & B200_CHROMA_SITE_V_COSITED) == 0;
 
-  int st = colour_matrix (p);
-  if (st != B200_OK) return st;
+  if (!p->yuv_out) {
+    int st = colour_matrix (p);
+    if (st != B200_OK) return st;
+  }
 
   FilterSpec f = filter_from_method (*cfg);
   const int iw = in->width, ih = in->height, ow = out->width, oh = out->height;
@@ -587,16 +618,36 @@ int build_vcs_plan (const b200_video_info * in, const b200_video_info * out,
   // chain_scale: shrink before the matrix, grow after it; horizontal first unless the
   // vertical pass leaves fewer pixels for the second pass
   const int64_t s0 = (int64_t) iw * ih, s3 = (int64_t) ow * oh;
-  p->matrix_first = !(s3 <= s0);
+  p->matrix_first = !p->yuv_out && !(s3 <= s0);
   p->h_first = (int64_t) ow * ih <= (int64_t) iw * oh;
   chroma_pairing (p);
   // unchanged size, planar 4:2:0 in, packed RGB out: the reference never builds the chain, its fast path
   // (convert_I420_BGRA / _ARGB / _pack_ARGB, video-converter.c:6772-6988, table :8766-8800) feeds each
   // chroma sample to its 2x2 pixels unfiltered
-  p->chroma_nearest = p->planar && iw == ow && ih == oh;
+  p->chroma_nearest = !p->yuv_out && p->planar && iw == ow && ih == oh;
   if (p->chroma_nearest) {
     p->v_pairs = false;
     std::fill (p->chroma_mode.begin (), p->chroma_mode.end (), 0);
+  }
+  if (p->yuv_out) {
+    // video_converter_compute_resample (video-converter.c:2850-2895): chroma resamplers exist on BOTH sides as soon
+    // as the size or the site differs (the sub-sampling is 4:2:0 on both), on neither otherwise
+    const bool resample = iw != ow || ih != oh || p->out.chroma_site != p->in.chroma_site;
+    if (!resample) {
+      p->chroma_nearest = true; p->v_pairs = false;
+      std::fill (p->chroma_mode.begin (), p->chroma_mode.end (), 0);
+      p->down_h = 0; p->down_v = false;
+    } else {
+      p->down_h = (p->out.chroma_site & B200_CHROMA_SITE_H_COSITED) ? 2 : 1;
+      p->down_v = (p->out.chroma_site & B200_CHROMA_SITE_V_COSITED) == 0;
+      // odd height and no vertical scaler: the down-sampler's second line of the last pair is line `oh`, which
+      // reaches do_unpack_lines' clamp through a fresh up-sampler pair, i.e. the last source line with its chroma
+      // row not vertically filtered (see oracle_vcs_convert).  Not built.
+      if ((oh & 1) && ih == oh && p->down_v && p->v_pairs && p->chroma_mode[ih - 1] != 0) return B200_ERR_UNSUPPORTED;
+    }
+    tile_geometry (p);
+    p->light_ok = p->ntap_ok = p->lanczos2_ok = false;
+    return B200_OK;
   }
   tile_geometry (p);
   light_geometry (p);

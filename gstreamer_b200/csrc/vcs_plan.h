@@ -65,6 +65,13 @@ struct VcsPlan {
   int n_planes = 0;
   PlanePlan planes[3];
 
+  // 4:2:0 -> the other 4:2:0 family (NV12 <-> I420, NV12 <-> NV21 ...): the chain without a matrix stage, then
+  // chroma down-sampling + pack (vcs_down420.cuh)
+  bool yuv_out = false;
+  int down_h = 0;                // Down420H: none / pair average / co-sited 3-1, 1-2-1, 1-3
+  bool down_v = false;           // average the line pair (out site not V_COSITED)
+  int out_plane_u = 1, out_plane_v = 1, out_cstep = 1, out_u_index = 0;
+
   // specialised 2:1 lanczos kernel eligibility
   bool lanczos2_ok = false;
 

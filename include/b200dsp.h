@@ -135,7 +135,9 @@ int b200_vcs_create (const b200_video_info * in, const b200_video_info * out,
 void b200_vcs_destroy (b200_vcs * h);
 
 /* one frame, device memory, asynchronous on cuda_stream. in_frame/out_frame are the
- * frame BASE device pointers; planes live at base + info.offset[i]. */
+ * frame BASE device pointers; planes live at base + info.offset[i].
+ * A handle serves one stream at a time (the element's streaming thread): kernel_variant 5 keeps per-handle
+ * scratch images between its two launches. */
 int b200_vcs_convert (b200_vcs * h, const void *in_frame, void *out_frame, void *cuda_stream);
 /* n independent frames (same caps) in one launch: what a batching element / multi-stream
  * mux feeds; n <= B200_VCS_MAX_BATCH */
@@ -157,7 +159,8 @@ typedef struct {
   int32_t p[5];                  /* AYUV->ARGB mulhi parameters p1..p5 */
   int32_t tile_w, tile_h;        /* generic kernel output tile */
   int32_t smem_bytes;
-  int32_t kernel_variant;        /* 0 = generic tiled, 1 = lanczos 2:1 specialised, 2 = light (copy / 2-tap axes), 3 = n-tap any ratio, 4 = YUV plane scaling */
+  int32_t kernel_variant;        /* 0 = generic tiled, 1 = lanczos 2:1 specialised, 2 = light (copy / 2-tap axes), 3 = n-tap any ratio, 4 = YUV plane scaling,
+                                  * 5 = chain + chroma down-sampling (4:2:0 -> the other 4:2:0 family; 2 launches, opt-in) */
   int32_t n_launches_per_convert;
 } b200_vcs_plan_info;
 int b200_vcs_get_plan_info (const b200_vcs * h, b200_vcs_plan_info * info);

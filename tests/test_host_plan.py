@@ -181,3 +181,42 @@ def test_fast_kernel_selection_sweep():
         if v == 1:
             assert fmt in (23, 24) and iw == 2 * ow and ih == 2 * oh
     assert counts.get(0, 0) < 0.08 * 1500                    # mixed 2-tap / n-tap axes and extreme ratios only
+
+
+def test_cross_family_420_plan_is_opt_in(monkeypatch):
+    """NV12 <-> I420 etc.: the chain + chroma down-sampling plan (kernel_variant 5, two launches) is refused unless
+    B200_VCS_EXPERIMENTAL is set; with it, the host plan builds for every method and both pass orders, a differing
+    colour matrix (a matrix stage) is refused, and so is the odd-height / no-vertical-scaler corner"""
+    import gstreamer_b200 as g
+
+    def build(fi, fo, iw, ih, ow, oh, m=1, matrix=None, site=None, out_site=None):
+        el = g.CudaVideoConvertScale(method=m, cuda_device_id=-1)
+        ii, oi = g.VideoInfo(fi, iw, ih), g.VideoInfo(fo, ow, oh)
+        if site is not None:
+            ii.set_colorimetry(chroma_site=site)
+        oi.set_colorimetry(matrix=ii.c.color_matrix if matrix is None else matrix,
+                           chroma_site=ii.c.chroma_site if out_site is None else out_site)
+        el.set_info(ii, oi)
+        return el.plan_info()
+
+    monkeypatch.delenv("B200_VCS_EXPERIMENTAL", raising=False)
+    with pytest.raises(g.B200Error) as e:
+        build(23, 2, 64, 48, 32, 24)
+    assert e.value.status == -2
+    monkeypatch.setenv("B200_VCS_EXPERIMENTAL", "1")
+    for fi, fo in [(23, 2), (2, 23), (23, 24), (24, 3), (3, 24)]:
+        for size in [(64, 48, 32, 24), (64, 48, 96, 72), (1920, 1080, 1280, 720), (100, 100, 150, 50), (33, 17, 33, 17)]:
+            for m in range(10):
+                pi = build(fi, fo, *size, m=m)
+                assert (int(pi.kernel_variant), int(pi.n_launches_per_convert), int(pi.matrix_first)) == (5, 2, 0)
+                assert int(pi.h_first) == int(size[2] * size[1] <= size[0] * size[3])
+    with pytest.raises(g.B200Error):
+        build(23, 2, 64, 48, 32, 24, matrix=3)                 # 64x48 defaults to bt601: a matrix stage would be needed
+    with pytest.raises(g.B200Error):
+        build(23, 2, 64, 49, 32, 49)                           # odd height, horizontal scaling only
+    build(23, 2, 64, 49, 32, 49, site=4, out_site=4)           # ... fine when the input chroma is vertically co-sited
+    build(23, 2, 64, 49, 64, 49)                               # same size and site: no resamplers at all
+    with pytest.raises(g.B200Error):
+        build(23, 2, 64, 49, 64, 49, out_site=2)               # same size, other site: both resamplers, odd height
+    # the same-family pairs keep their plane-scaling plan
+    assert int(build(23, 23, 64, 48, 32, 24).kernel_variant) == 4
