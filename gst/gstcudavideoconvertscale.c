@@ -19,8 +19,10 @@ GST_DEBUG_CATEGORY_STATIC (cuda_vcs_debug);
 #define GST_CAT_DEFAULT cuda_vcs_debug
 
 #define SINK_FORMATS "{ NV12, NV21, I420, YV12 }"
-/* YUV outputs only from the same family (NV12->NV12, NV21->NV21, I420/YV12 -> I420/YV12): transform_caps drops the
- * other pairs, b200_vcs_create refuses them with B200_ERR_UNSUPPORTED */
+/* YUV outputs: the same family (NV12->NV12, NV21->NV21, I420/YV12 -> I420/YV12) scales plane by plane, the other
+ * 4:2:0 pairs run the chain with chroma down-sampling; fixate_caps must carry the input colorimetry over
+ * (transfer_colorimetry_from_input, gstvideoconvertscale.c:1335-1427) - b200_vcs_create refuses a YUV -> YUV
+ * matrix change with B200_ERR_UNSUPPORTED */
 #define SRC_FORMATS "{ BGRA, RGBA, ARGB, ABGR, BGRx, RGBx, xRGB, xBGR, NV12, NV21, I420, YV12 }"
 #define CUDA_CAPS(f) "video/x-raw(" GST_CAPS_FEATURE_MEMORY_CUDA_MEMORY "), format = (string) " f \
     ", width = (int) [ 1, 32767 ], height = (int) [ 1, 32767 ], framerate = (fraction) [ 0/1, max ]"

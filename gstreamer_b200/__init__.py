@@ -6,7 +6,7 @@ C-ABI, include/b200dsp.h).  Importing this package without the built library fai
 """
 from ._lib import lib, LIB_PATH, B200Error, EXPORTED_SYMBOLS, MISSING_SYMBOLS  # noqa: F401
 from .video import (VideoFormat, VideoScaleMethod, ColorMatrix, ColorRange, ChromaSite,  # noqa: F401
-                    VideoInfo, PinnedBuffer, CudaVideoConvertScale)
+                    VideoInfo, PinnedBuffer, CudaVideoConvertScale, transfer_colorimetry_from_input)
 
 __all__ = ["lib", "LIB_PATH", "B200Error", "VideoFormat", "VideoScaleMethod", "ColorMatrix",
-           "ColorRange", "ChromaSite", "VideoInfo", "PinnedBuffer", "CudaVideoConvertScale"]
+           "ColorRange", "ChromaSite", "VideoInfo", "PinnedBuffer", "CudaVideoConvertScale", "transfer_colorimetry_from_input"]

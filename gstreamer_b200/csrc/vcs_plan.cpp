@@ -550,11 +550,10 @@ int build_vcs_plan (const b200_video_info * in, const b200_video_info * out,
     const bool out_semi = out->format == B200_VIDEO_FORMAT_NV12 || out->format == B200_VIDEO_FORMAT_NV21;
     if (out_pl || out_semi) {
       // the reference has plane-scaling fast paths for NV12->NV12, NV21->NV21, I420/YV12 -> I420/YV12
-      // (video-converter.c:8722-8760); the other YUV pairs run the chain with chroma down-sampling: not built
+      // (video-converter.c:8722-8760); the other 4:2:0 pairs run the chain with chroma down-sampling
       if (!((in_pl && out_pl) || (out_semi && in->format == out->format))) {
         // the remaining 4:2:0 pairs have no table row: the generic chain, closed by chain_downsample
-        // (video-converter.c:2018-2032) and the 4:2:0 pack functions.  Not yet confirmed on a device: opt-in.
-        if (!getenv ("B200_VCS_EXPERIMENTAL")) return B200_ERR_UNSUPPORTED;
+        // (video-converter.c:2018-2032) and the 4:2:0 pack functions
         p->yuv_out = true;
       } else {
         if (in->stride[0] < in->width || out->stride[0] < out->width) return B200_ERR_INVALID_ARG;

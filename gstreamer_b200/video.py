@@ -132,6 +132,21 @@ class VideoInfo:
         return self
 
 
+_YUV_420 = (VideoFormat.I420, VideoFormat.YV12, VideoFormat.NV12, VideoFormat.NV21)
+
+
+def transfer_colorimetry_from_input(in_info, out_info):
+    """What the element's caps fixation does when the output caps leave colorimetry / chroma-site open
+    (transfer_colorimetry_from_input, gstvideoconvertscale.c:1335-1427): a YUV output of a YUV input takes the input's
+    colorimetry intact, and its chroma site too when the sub-sampling is unchanged (every format here is 4:2:0).
+    RGB outputs keep their own defaults.  Returns out_info."""
+    if in_info.format in _YUV_420 and out_info.format in _YUV_420:
+        out_info.c.color_matrix = in_info.c.color_matrix
+        out_info.c.color_range = in_info.c.color_range
+        out_info.c.chroma_site = in_info.c.chroma_site
+    return out_info
+
+
 class PinnedBuffer:
     """Page-locked host staging buffer (b200_host_alloc), exposed as a numpy uint8 array."""
 

@@ -160,7 +160,7 @@ typedef struct {
   int32_t tile_w, tile_h;        /* generic kernel output tile */
   int32_t smem_bytes;
   int32_t kernel_variant;        /* 0 = generic tiled, 1 = lanczos 2:1 specialised, 2 = light (copy / 2-tap axes), 3 = n-tap any ratio, 4 = YUV plane scaling,
-                                  * 5 = chain + chroma down-sampling (4:2:0 -> the other 4:2:0 family; 2 launches, opt-in) */
+                                  * 5 = chain + chroma down-sampling (4:2:0 -> the other 4:2:0 family; 2 launches) */
   int32_t n_launches_per_convert;
 } b200_vcs_plan_info;
 int b200_vcs_get_plan_info (const b200_vcs * h, b200_vcs_plan_info * info);

@@ -71,7 +71,10 @@ def test_argument_validation_matches_caps_ranges():
     oi.width = 40000
     assert lib.b200_vcs_create(C.byref(ii), C.byref(oi), None, -1, C.byref(h)) == -1
     oi.width = 32
-    assert lib.b200_video_info_set_format(C.byref(oi), 2, 32, 24) == 0        # NV12 -> I420: a YUV pair the path does not build
+    assert lib.b200_video_info_set_format(C.byref(oi), 2, 32, 24) == 0        # NV12 -> I420: chain + chroma down-sampling
+    assert lib.b200_vcs_create(C.byref(ii), C.byref(oi), None, -1, C.byref(h)) == 0
+    lib.b200_vcs_destroy(h)
+    oi.color_matrix = 3                                                       # ... but not with a matrix stage (bt601 -> bt709)
     assert lib.b200_vcs_create(C.byref(ii), C.byref(oi), None, -1, C.byref(h)) == -2
     assert lib.b200_video_info_set_format(C.byref(oi), 23, 32, 24) == 0       # NV12 -> NV12: plane scaling, accepted
     assert lib.b200_vcs_create(C.byref(ii), C.byref(oi), None, -1, C.byref(h)) == 0

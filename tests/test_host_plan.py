@@ -183,10 +183,10 @@ def test_fast_kernel_selection_sweep():
     assert counts.get(0, 0) < 0.08 * 1500                    # mixed 2-tap / n-tap axes and extreme ratios only
 
 
-def test_cross_family_420_plan_is_opt_in(monkeypatch):
-    """NV12 <-> I420 etc.: the chain + chroma down-sampling plan (kernel_variant 5, two launches) is refused unless
-    B200_VCS_EXPERIMENTAL is set; with it, the host plan builds for every method and both pass orders, a differing
-    colour matrix (a matrix stage) is refused, and so is the odd-height / no-vertical-scaler corner"""
+def test_cross_family_420_plan():
+    """NV12 <-> I420 etc.: the chain + chroma down-sampling plan (kernel_variant 5, two launches) builds for every
+    method and both pass orders; a differing colour matrix (a matrix stage) is refused, and so is the odd-height /
+    no-vertical-scaler corner"""
     import gstreamer_b200 as g
 
     def build(fi, fo, iw, ih, ow, oh, m=1, matrix=None, site=None, out_site=None):
@@ -199,11 +199,6 @@ def test_cross_family_420_plan_is_opt_in(monkeypatch):
         el.set_info(ii, oi)
         return el.plan_info()
 
-    monkeypatch.delenv("B200_VCS_EXPERIMENTAL", raising=False)
-    with pytest.raises(g.B200Error) as e:
-        build(23, 2, 64, 48, 32, 24)
-    assert e.value.status == -2
-    monkeypatch.setenv("B200_VCS_EXPERIMENTAL", "1")
     for fi, fo in [(23, 2), (2, 23), (23, 24), (24, 3), (3, 24)]:
         for size in [(64, 48, 32, 24), (64, 48, 96, 72), (1920, 1080, 1280, 720), (100, 100, 150, 50), (33, 17, 33, 17)]:
             for m in range(10):
@@ -220,3 +215,21 @@ def test_cross_family_420_plan_is_opt_in(monkeypatch):
         build(23, 2, 64, 49, 64, 49, out_site=2)               # same size, other site: both resamplers, odd height
     # the same-family pairs keep their plane-scaling plan
     assert int(build(23, 23, 64, 48, 32, 24).kernel_variant) == 4
+
+
+def test_transfer_colorimetry_from_input():
+    """1080p (bt709, mpeg2 site) -> 480p I420: the caps defaults of the small size would be bt601 / site none; the
+    element's fixation carries the input's over, which is what makes the chain matrix-free"""
+    import gstreamer_b200 as g
+    ii, oi = g.VideoInfo(23, 1920, 1080), g.VideoInfo(2, 854, 480)
+    assert (oi.c.color_matrix, oi.c.chroma_site) == (4, 1)
+    el = g.CudaVideoConvertScale(method=1, cuda_device_id=-1)
+    with pytest.raises(g.B200Error):
+        el.set_info(ii, oi)
+    g.transfer_colorimetry_from_input(ii, oi)
+    assert (oi.c.color_matrix, oi.c.color_range, oi.c.chroma_site) == (3, 2, 2)
+    el.set_info(ii, oi)
+    assert int(el.plan_info().kernel_variant) == 5
+    rgb = g.VideoInfo(12, 854, 480)
+    g.transfer_colorimetry_from_input(ii, rgb)
+    assert rgb.c.color_matrix == 1

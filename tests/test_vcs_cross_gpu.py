@@ -1,28 +1,18 @@
 """4:2:0 -> the other 4:2:0 family (NV12 <-> I420, NV12 <-> NV21, ...): the reference's generic chain closed by chroma
 down-sampling and the 4:2:0 pack functions (video-converter.c:2018-2032, :3194-3222; video-chroma.c:398-442, :742-785).
 Product: vcs_generic_kernel (no matrix stage) into scratch A,Y,U,V images, then vcs_down420_kernel.
-
-The path is opt-in (B200_VCS_EXPERIMENTAL) until these tests have run green on a device; they are skipped unless
-B200_TEST_EXPERIMENTAL=1 so that an unconfirmed kernel cannot take the suite down."""
-import os
-
+"""
 import numpy as np
 import pytest
 
 from oracle import bindings as ob
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("B200_TEST_EXPERIMENTAL") != "1", reason="opt-in: B200_TEST_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 
 PAIRS = [("NV12", "I420"), ("I420", "NV12"), ("NV12", "NV21"), ("NV21", "YV12"), ("YV12", "NV21"), ("I420", "NV21")]
 SIZES = [(64, 48, 32, 24), (64, 48, 96, 72), (65, 49, 33, 26), (33, 17, 20, 31), (50, 21, 50, 21), (57, 35, 29, 35),
          (40, 34, 57, 34), (100, 100, 150, 50), (64, 66, 64, 30), (320, 240, 213, 120), (17, 9, 64, 31), (2, 2, 1, 1),
          (1, 1, 5, 4), (640, 480, 320, 240), (1920, 1080, 1280, 720), (1280, 720, 1920, 1080)]
-
-
-@pytest.fixture(autouse=True)
-def _opt_in(monkeypatch):
-    monkeypatch.setenv("B200_VCS_EXPERIMENTAL", "1")
 
 
 def planes_equal(got, want, oi, ow, oh, semi, fill=0x5A):

@@ -66,11 +66,3 @@ def test_plane_scaling_batch(cuda_device):
     st = oi.stride[0]
     for o in outs:
         assert np.array_equal(o[: st * oh].reshape(oh, st)[:, :ow], want[: st * oh].reshape(oh, st)[:, :ow])
-
-
-def test_unsupported_yuv_pairs_are_refused(cuda_device):
-    """NV12 -> I420 etc. run the reference's generic chain with chroma down-sampling: not built, refused at caps time"""
-    import gstreamer_b200 as g
-    el = g.CudaVideoConvertScale(method=1)
-    with pytest.raises(Exception):
-        el.set_info(g.VideoInfo(23, 64, 48), g.VideoInfo(2, 32, 24))

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""One-shot device check of the opt-in 4:2:0 -> other-4:2:0-family path (kernel_variant 5) against the oracle.
+"""Device check of the 4:2:0 -> other-4:2:0-family path (kernel_variant 5) against the oracle.
 Runs every case of tests/test_vcs_cross_gpu.py plus a random sweep, records EVERY outcome (it does not stop at the
 first mismatch) in gpurun_out/cross_check.json, and times one 1080p -> 720p NV12 -> I420 conversion."""
 import json
@@ -10,8 +10,6 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-os.environ["B200_VCS_EXPERIMENTAL"] = "1"
-os.environ["B200_TEST_EXPERIMENTAL"] = "1"
 
 import numpy as np   # noqa: E402
 
