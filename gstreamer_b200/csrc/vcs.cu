@@ -89,7 +89,7 @@ int launch (b200_vcs * h, int n, const VcsBatch & batch, cudaStream_t stream)
   dim3 grid ((p.out.width + p.tile_w - 1) / p.tile_w, (p.out.height + p.tile_h - 1) / p.tile_h, n);
   if (p.yuv_out) {
     // launch 1 writes the scaled pixels of every frame to its scratch image, launch 2 down-samples and packs
-    const size_t frame = (size_t) h->down.stride_s * p.out.height;
+    const size_t frame = (size_t) h->down.stride_s * (p.out.height + (p.extra_row ? 1 : 0));
     if (n > h->scratch_frames) {
       B200_CUDA_TRY (cudaFree (h->d_scratch));                      // synchronises with launches still reading it
       h->d_scratch = nullptr; h->scratch_frames = 0;
@@ -104,6 +104,18 @@ int launch (b200_vcs * h, int n, const VcsBatch & batch, cudaStream_t stream)
     }
     vcs_generic_kernel <<<grid, 256, p.smem_bytes, stream>>> (h->dev, mid);
     B200_CUDA_TRY (cudaGetLastError ());
+    if (p.extra_row) {
+      // scratch row `oh`: the chain over a one-line view of the frame (its last line, chroma row unfiltered vertically)
+      VcsDev x = h->dev;
+      x.off_y += (unsigned long long) (p.in.height - 1) * x.stride_y;
+      x.off_u += (unsigned long long) ((p.in.height - 1) >> 1) * x.stride_u;
+      x.off_v += (unsigned long long) ((p.in.height - 1) >> 1) * x.stride_v;
+      x.ih = 1; x.oh = 1; x.v.in_size = x.v.out_size = 1;
+      x.off_out = (unsigned long long) p.out.height * x.stride_out;
+      dim3 gx (grid.x, 1, n);
+      vcs_generic_kernel <<<gx, 256, p.smem_bytes, stream>>> (x, mid);
+      B200_CUDA_TRY (cudaGetLastError ());
+    }
     const int cw = (p.out.width + 1) / 2, chh = (p.out.height + 1) / 2;
     dim3 blk (32, 8), g2 ((cw + 31) / 32, (chh + 7) / 8, n);
     vcs_down420_kernel <<<g2, blk, 0, stream>>> (h->down, fin);
@@ -261,7 +273,7 @@ int b200_vcs_create (const b200_video_info * in, const b200_video_info * out,
       Down420Dev & q = h->down;
       memset (&q, 0, sizeof (q));
       q.ow = p.out.width; q.oh = p.out.height; q.stride_s = d.stride_out;
-      q.hmode = p.down_h; q.vavg = p.down_v ? 1 : 0;
+      q.hmode = p.down_h; q.vavg = p.down_v ? 1 : 0; q.extra_row = p.extra_row ? 1 : 0;
       q.stride_y = p.out.stride[0]; q.off_y = p.out.offset[0];
       q.stride_u = p.out.stride[p.out_plane_u]; q.stride_v = p.out.stride[p.out_plane_v];
       q.cstep = p.out_cstep;
@@ -389,7 +401,7 @@ int b200_vcs_get_plan_info (const b200_vcs * h, b200_vcs_plan_info * info)
   for (int i = 0; i < 5; i++) info->p[i] = p.p[i];
   info->tile_w = p.tile_w; info->tile_h = p.tile_h; info->smem_bytes = p.smem_bytes;
   info->kernel_variant = p.yuv_out ? 5 : p.planes_mode ? 4 : (h->variant == 1 && p.lanczos2_ok) ? 1 : (h->variant == 2 && p.light_ok) ? 2 : (h->variant == 3 && p.ntap_ok) ? 3 : 0;
-  info->n_launches_per_convert = p.yuv_out ? 2 : 1;
+  info->n_launches_per_convert = p.yuv_out ? (p.extra_row ? 3 : 2) : 1;
   return B200_OK;
 }
 

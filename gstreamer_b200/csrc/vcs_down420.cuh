@@ -27,6 +27,7 @@ struct Down420Dev {
   int ow, oh;                    // luma size of the output frame
   int stride_s;                  // scratch row pitch in bytes (4 bytes per pixel: A,Y,U,V)
   int hmode, vavg;               // Down420H; 1 = average the line pair
+  int extra_row;                 // odd height: the last pair's second line is scratch row `oh` instead of the last line itself
   int stride_y, stride_u, stride_v, cstep;
   unsigned long long off_y, off_u, off_v;
 };
@@ -54,7 +55,7 @@ vcs_down420_kernel (const Down420Dev P, const Down420Batch frames)
   const int x0 = 2 * j, y0 = 2 * k;
   const bool two_cols = x0 + 1 < P.ow, two_rows = y0 + 1 < P.oh;
   const unsigned *r0 = (const unsigned *) (s + (size_t) y0 * P.stride_s);
-  const unsigned *r1 = two_rows ? (const unsigned *) (s + (size_t) (y0 + 1) * P.stride_s) : r0;
+  const unsigned *r1 = (two_rows || P.extra_row) ? (const unsigned *) (s + (size_t) (y0 + 1) * P.stride_s) : r0;
 
   // the pixels of the pair's two lines this sample reads: x0-1 (co-sited filter only), x0, x0+1
   const unsigned a0 = r0[x0], b0 = r1[x0];
@@ -70,7 +71,8 @@ vcs_down420_kernel (const Down420Dev P, const Down420Batch frames)
   }
 
   // vertical filter first (it rewrites the whole of line 2k before the horizontal filter runs on it); for an odd
-  // height the pair's second line is the vertical scaler's clamped repeat of the last line: avg(a, a) = a
+  // height the pair's second line is the vertical scaler's clamped repeat of the last line: avg(a, a) = a — or, with
+  // no vertical scaler in the chain, the rebuilt line the first launches left in scratch row `oh` (extra_row)
   const bool vavg = P.vavg != 0;
   const unsigned c0 = vavg ? down_avg_uv (a0, b0) : a0;
   const unsigned c1 = vavg ? down_avg_uv (a1, b1) : a1;

@@ -639,10 +639,13 @@ int build_vcs_plan (const b200_video_info * in, const b200_video_info * out,
     } else {
       p->down_h = (p->out.chroma_site & B200_CHROMA_SITE_H_COSITED) ? 2 : 1;
       p->down_v = (p->out.chroma_site & B200_CHROMA_SITE_V_COSITED) == 0;
-      // odd height and no vertical scaler: the down-sampler's second line of the last pair is line `oh`, which
-      // reaches do_unpack_lines' clamp through a fresh up-sampler pair, i.e. the last source line with its chroma
-      // row not vertically filtered (see oracle_vcs_convert).  Not built.
-      if ((oh & 1) && ih == oh && p->down_v && p->v_pairs && p->chroma_mode[ih - 1] != 0) return B200_ERR_UNSUPPORTED;
+      // odd height and no vertical scaler: the down-sampler's second line of the last pair is line `oh`.  A vertical
+      // scaler would clamp that request to its last line (video-converter.c:3070-3080: the pair averages a line
+      // with itself); without one it reaches do_unpack_lines' clamp (:2973) through a fresh up-sampler pair
+      // (oh, oh+1), i.e. the LAST SOURCE LINE WITH ITS CHROMA ROW NOT VERTICALLY FILTERED, pushed through the
+      // horizontal stages.  The device code rebuilds that line as row `oh` of the scratch image by running the chain
+      // on a one-line view of the frame (line ih-1 with chroma row (ih-1)>>1: a 1-line frame has no vertical filter).
+      p->extra_row = (oh & 1) && ih == oh && p->down_v && p->v_pairs && p->chroma_mode[ih - 1] != 0;
     }
     tile_geometry (p);
     p->light_ok = p->ntap_ok = p->lanczos2_ok = false;

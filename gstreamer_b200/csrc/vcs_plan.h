@@ -70,6 +70,7 @@ struct VcsPlan {
   bool yuv_out = false;
   int down_h = 0;                // Down420H: none / pair average / co-sited 3-1, 1-2-1, 1-3
   bool down_v = false;           // average the line pair (out site not V_COSITED)
+  bool extra_row = false;        // odd height, no vertical scaler: the last pair's second line is rebuilt (see build_vcs_plan)
   int out_plane_u = 1, out_plane_v = 1, out_cstep = 1, out_u_index = 0;
 
   // specialised 2:1 lanczos kernel eligibility

@@ -42,7 +42,7 @@ def convert(size, method, frame, pair, site, out_site, batch=1):
     oi.set_colorimetry(matrix=ii.c.color_matrix, chroma_site=out_site)      # what the element's caps fixation does
     el.set_info(ii, oi)
     info = el.plan_info()
-    assert int(info.kernel_variant) == 5 and int(info.n_launches_per_convert) == 2
+    assert int(info.kernel_variant) == 5 and int(info.n_launches_per_convert) in (2, 3)
     src = [torch.from_numpy(frame).cuda() for _ in range(batch)]
     dst = [torch.full((oi.size,), 0x5A, dtype=torch.uint8, device="cuda") for _ in range(batch)]
     if batch == 1:
@@ -60,14 +60,6 @@ def expected(size, method, frame, pair, site, out_site):
     return ob.oracle_vcs_convert(d, frame)
 
 
-def refused(size, site, out_site):
-    """odd height without a vertical scaler, both sites vertically non-co-sited: the down-sampler's last pair reads a
-    line past the frame that the reference rebuilds with an unfiltered chroma row — not built, refused at caps time"""
-    iw, ih, ow, oh = size
-    resample = (iw, ih) != (ow, oh) or site != out_site
-    return bool((oh & 1) and ih == oh and ih >= 3 and resample and not (out_site & 4) and not (site & 4))
-
-
 def random_frame(pair, iw, ih, seed):
     return ob.i420_random_frame(iw, ih, seed) if pair[0] in ("I420", "YV12") else ob.nv12_random_frame(iw, ih, seed)
 
@@ -80,12 +72,7 @@ def test_cross_family_matches_oracle(cuda_device, pair, size, method):
     if iw * ih > 500_000 and (pair != ("NV12", "I420") or method not in (1, 3)):
         pytest.skip("large shapes: NV12 -> I420, bilinear / lanczos only")
     frame = random_frame(pair, iw, ih, 5)
-    import gstreamer_b200 as g
     for site, out_site in ((2, 2), (1, 1), (2, 1), (6, 4)):
-        if refused(size, site, out_site):
-            with pytest.raises(g.B200Error):
-                convert(size, method, frame, pair, site, out_site)
-            continue
         want = expected(size, method, frame, pair, site, out_site)
         (got,), oi = convert(size, method, frame, pair, site, out_site)
         assert got.size == want.size
@@ -114,7 +101,26 @@ def test_cross_family_refusals(cuda_device):
     oi.set_colorimetry(matrix=3 if ii.c.color_matrix == 4 else 4)           # a matrix stage: not built
     with pytest.raises(g.B200Error):
         el.set_info(ii, oi)
-    ii, oi = g.VideoInfo(23, 64, 49), g.VideoInfo(2, 32, 49)                # odd height, no vertical scaler
-    oi.set_colorimetry(matrix=ii.c.color_matrix, chroma_site=ii.c.chroma_site)
-    with pytest.raises(g.B200Error):
-        el.set_info(ii, oi)
+
+
+@pytest.mark.parametrize("size", [(64, 49, 32, 49), (50, 21, 50, 21), (33, 5, 70, 5), (1920, 1081, 1280, 1081), (7, 3, 7, 3)],
+                         ids=lambda s: "%dx%d-%dx%d" % s)
+def test_cross_family_odd_height_without_vertical_scaler(cuda_device, size):
+    """the down-sampler's last pair reads line `oh`; with no vertical scaler to clamp it the reference rebuilds it from
+    the last source line with a vertically unfiltered chroma row — a third launch over a one-line view of the frame"""
+    import gstreamer_b200 as g
+    iw, ih, ow, oh = size
+    pair = ("NV12", "I420")
+    frame = random_frame(pair, iw, ih, 3)
+    for method in (1, 3):
+        for site, out_site in ((1, 1), (2, 2), (2, 1), (1, 6), (4, 1)):
+            if (iw, ih) == (ow, oh) and site == out_site:
+                continue
+            want = expected(size, method, frame, pair, site, out_site)
+            (got,), oi = convert(size, method, frame, pair, site, out_site)
+            assert not planes_equal(got, want, oi, ow, oh, False), (method, site, out_site)
+    el = g.CudaVideoConvertScale(method=1)
+    ii, oi = g.VideoInfo(23, 64, 49), g.VideoInfo(2, 32, 49)
+    g.transfer_colorimetry_from_input(ii, oi)
+    el.set_info(ii, oi)
+    assert int(el.plan_info().n_launches_per_convert) == 3

@@ -21,7 +21,7 @@ def main():
     import gstreamer_b200 as g
     import test_vcs_cross_gpu as T
     from oracle import bindings as ob
-    out = {"cases": 0, "ok": 0, "refused_as_expected": 0, "failures": [], "errors": []}
+    out = {"cases": 0, "ok": 0, "odd_height_cases": 0, "failures": [], "errors": []}
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 
     def flush():
@@ -34,13 +34,9 @@ def main():
         out["cases"] += 1
         try:
             frame = T.random_frame(pair, iw, ih, seed)
-            if T.refused(size, site, out_site):
-                try:
-                    T.convert(size, method, frame, pair, site, out_site)
-                    out["failures"].append(tag + ": expected a refusal")
-                except g.B200Error:
-                    out["refused_as_expected"] += 1
-                return
+            odd = (oh & 1) and ih == oh and ((iw, ih) != (ow, oh) or site != out_site) and not (site & 4) and not (out_site & 4)
+            if odd and ih >= 3:
+                out["odd_height_cases"] += 1
             want = T.expected(size, method, frame, pair, site, out_site)
             (got,), oi = T.convert(size, method, frame, pair, site, out_site)
             bad = T.planes_equal(got, want, oi, ow, oh, pair[1] in ("NV12", "NV21"))
@@ -51,8 +47,9 @@ def main():
         except Exception as e:                                   # noqa: BLE001 - record and go on
             out["errors"].append(tag + ": " + repr(e)[:300])
 
+    odd_only = len(sys.argv) > 2 and sys.argv[2] == "odd"
     # 1. the pytest matrix (small shapes first)
-    for size in sorted(T.SIZES, key=lambda s: s[0] * s[1]):
+    for size in [] if odd_only else sorted(T.SIZES, key=lambda s: s[0] * s[1]):
         for pair in T.PAIRS:
             for method in (0, 1, 3, 4, 9):
                 if size[0] * size[1] > 500_000 and (pair != ("NV12", "I420") or method not in (1, 3)):
@@ -68,12 +65,15 @@ def main():
         iw, ih, ow, oh = (int(v) for v in rng.integers(1, 200, 4))
         if rng.random() < 0.2:
             ow = iw
-        if rng.random() < 0.2:
-            oh = ih
+        if rng.random() < 0.2 or odd_only:
+            oh = ih = ih | 1
         pair = T.PAIRS[int(rng.integers(0, len(T.PAIRS)))]
         one(pair, (iw, ih, ow, oh), int(rng.integers(0, 10)), int(rng.choice([1, 2, 4, 6])), int(rng.choice([1, 2, 4, 6])),
             seed=int(rng.integers(0, 1000)))
     flush()
+    if odd_only:
+        print(json.dumps({k: (v if not isinstance(v, list) else v[:8]) for k, v in out.items()}, indent=1))
+        return 0 if not out["failures"] and not out["errors"] else 1
     # 3. timing: 1080p -> 720p NV12 -> I420 lanczos, 16 frames per launch pair
     try:
         size, pair = (1920, 1080, 1280, 720), ("NV12", "I420")

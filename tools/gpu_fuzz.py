@@ -26,18 +26,25 @@ def main():
             ow, oh = max(1, int(iw * f)), max(1, int(ih * f))
         m = int(rng.integers(0, 10))
         fi = int(rng.choice([23, 24, 2, 3]))
-        if rng.random() < 0.3:
+        r = rng.random()
+        if r < 0.2:
             fo = {23: 23, 24: 24, 2: int(rng.choice([2, 3])), 3: int(rng.choice([2, 3]))}[fi]
+        elif r < 0.35:
+            fo = int(rng.choice([23, 24, 2, 3]))            # includes the cross-family pairs (chain + chroma down-sampling)
         else:
             fo = int(rng.choice([7, 8, 9, 10, 11, 12, 13, 14]))
         site, mat, rg = int(rng.choice([1, 2, 4, 6])), int(rng.choice([3, 4, 6, 2, 5])), int(rng.choice([1, 2]))
         frame = ob.i420_random_frame(iw, ih, n) if fi in (2, 3) else ob.nv12_random_frame(iw, ih, n)
+        out_site = int(rng.choice([1, 2, 4, 6]))
         d = ob.vcs_desc(iw, ih, ow, oh, m, in_fmt=fi, out_fmt=fo, site=site, matrix=mat, rng=rg)
+        d.out_chroma_site = out_site
         want = ob.oracle_vcs_convert(d, frame)
         el = g.CudaVideoConvertScale(method=m)
         ii = g.VideoInfo(fi, iw, ih)
         ii.set_colorimetry(matrix=mat, range=rg, chroma_site=site)
         oi = g.VideoInfo(fo, ow, oh)
+        if fo in (23, 24, 2, 3):
+            oi.set_colorimetry(matrix=mat, range=rg, chroma_site=out_site)   # caps fixation carries the input colorimetry over
         el.set_info(ii, oi)
         v = int(el.plan_info().kernel_variant)
         variants[v] = variants.get(v, 0) + 1
