@@ -45,7 +45,7 @@ class VcsDesc(C.Structure):
                 ("in_range", C.c_int), ("in_chroma_site", C.c_int), ("out_format", C.c_int),
                 ("out_width", C.c_int), ("out_height", C.c_int), ("out_stride", C.c_int * 4),
                 ("out_offset", C.c_size_t * 4), ("rs", RS),
-                ("out_matrix", C.c_int), ("out_chroma_site", C.c_int)]
+                ("out_matrix", C.c_int), ("out_chroma_site", C.c_int), ("out_range", C.c_int)]
 
 
 class OraclePad(C.Structure):
@@ -73,6 +73,7 @@ def oracle():
         o.oracle_vcs_out_size.argtypes = [C.POINTER(VcsDesc)]
         o.oracle_vcs_matrix.argtypes = [C.POINTER(VcsDesc), P, P]
         o.oracle_vcs_convert.argtypes = [C.POINTER(VcsDesc), P, P]
+        o.oracle_vcs_matrix_rgb2yuv.argtypes = [C.POINTER(VcsDesc), P]
         if hasattr(o, "oracle_compositor"):
             o.oracle_compositor.argtypes = [C.c_int, P, C.c_int, C.c_int, C.c_int, C.c_int,
                                             C.POINTER(OraclePad), C.c_int]

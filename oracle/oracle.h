@@ -64,6 +64,9 @@ typedef struct {
   /* YUV output only; 0 = carried over from the input the way the element's caps fixation does when the
    * input caps hold them (gstvideoconvertscale.c:1335-1427) */
   int out_matrix, out_chroma_site;
+  /* packed RGB input -> 4:2:0 output: 0 = caps default of the output size (the fixation forwards only primaries and
+   * transfer across a YUV/RGB change, gstvideoconvertscale.c:1394-1408); out_range 0 = 16-235 */
+  int out_range;
 } OracleVcsDesc;
 
 /* fills the default system-memory layout (video-info.c fill_planes :1053-1063, :890-894)
@@ -72,6 +75,9 @@ int oracle_vcs_default_desc (OracleVcsDesc * d, int in_format, int in_w, int in_
     int out_format, int out_w, int out_h, int method, int max_taps_opt);
 size_t oracle_vcs_in_size (const OracleVcsDesc * d);
 size_t oracle_vcs_out_size (const OracleVcsDesc * d);
+/* packed RGB in, YUV out: the x256 integer matrix of chain_convert (rows Y,U,V; columns R,G,B,offset); 0 when the
+ * reference would take its table path (is_no_clip_matrix, video-converter.c:1262-1300), -2 otherwise */
+int oracle_vcs_matrix_rgb2yuv (const OracleVcsDesc * d, int im[4][4]);
 /* the fast AYUV->ARGB matrix parameters p1..p5 (video-converter.c:1209-1216, :1324-1442) */
 int oracle_vcs_matrix (const OracleVcsDesc * d, int p[5], int im[4][4]);
 /* whole-frame conversion; 0 on success */

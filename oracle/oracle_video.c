@@ -207,20 +207,28 @@ oracle_quantize_taps (const double *src, int16_t * dst, int n, int precision)
 
 /* ===================================================================== layout */
 
+static int
+fmt_is_rgb (int f)
+{
+  return f >= ORC_FMT_RGBx && f <= ORC_FMT_ABGR;
+}
+
 int
 oracle_vcs_default_desc (OracleVcsDesc * d, int in_format, int in_w, int in_h,
     int out_format, int out_w, int out_h, int method, int max_taps_opt)
 {
   memset (d, 0, sizeof (*d));
   if (in_format != ORC_FMT_NV12 && in_format != ORC_FMT_NV21 && in_format != ORC_FMT_I420 &&
-      in_format != ORC_FMT_YV12)
+      in_format != ORC_FMT_YV12 && !fmt_is_rgb (in_format))
     return -1;
   d->in_format = in_format;
   d->in_width = in_w;
   d->in_height = in_h;
   d->in_stride[0] = ROUND_UP_4 (in_w);
   d->in_offset[0] = 0;
-  if (in_format == ORC_FMT_I420 || in_format == ORC_FMT_YV12) {
+  if (fmt_is_rgb (in_format)) {
+    d->in_stride[0] = in_w * 4;         /* video-info.c:890-894 */
+  } else if (in_format == ORC_FMT_I420 || in_format == ORC_FMT_YV12) {
     /* video-info.c:997-1009 (YV12: same planes, 1 and 2 swapped in the format description) */
     d->in_stride[1] = d->in_stride[2] = ROUND_UP_4 (ROUND_UP_2 (in_w) / 2);
     d->in_offset[1] = (size_t) d->in_stride[0] * ROUND_UP_2 (in_h);
@@ -234,6 +242,11 @@ oracle_vcs_default_desc (OracleVcsDesc * d, int in_format, int in_w, int in_h,
   d->in_matrix = in_h > 576 ? ORC_CM_BT709 : ORC_CM_BT601;
   d->in_range = ORC_RANGE_16_235;
   d->in_chroma_site = in_h > 576 ? ORC_SITE_H_COSITED : ORC_SITE_NONE;
+  if (fmt_is_rgb (in_format)) {
+    d->in_matrix = ORC_CM_RGB;
+    d->in_range = ORC_RANGE_0_255;
+    d->in_chroma_site = 0;
+  }
   d->out_format = out_format;
   d->out_width = out_w;
   d->out_height = out_h;
@@ -260,6 +273,8 @@ oracle_vcs_default_desc (OracleVcsDesc * d, int in_format, int in_w, int in_h,
 size_t
 oracle_vcs_in_size (const OracleVcsDesc * d)
 {
+  if (fmt_is_rgb (d->in_format))
+    return d->in_offset[0] + (size_t) d->in_stride[0] * d->in_height;
   if (d->in_format == ORC_FMT_I420 || d->in_format == ORC_FMT_YV12)
     return d->in_offset[2] + (size_t) d->in_stride[2] * (ROUND_UP_2 (d->in_height) / 2);
   return d->in_offset[1] + (size_t) d->in_stride[1] * (ROUND_UP_2 (d->in_height) / 2);
@@ -384,6 +399,98 @@ oracle_vcs_matrix (const OracleVcsDesc * d, int p[5], int im[4][4])
   return 0;
 }
 
+static int
+kr_kb (int matrix, double *Kr, double *Kb)
+{
+  switch (matrix) {             /* video-color.c:423-459 */
+    case ORC_CM_FCC: *Kr = 0.30; *Kb = 0.11; return 0;
+    case ORC_CM_BT709: *Kr = 0.2126; *Kb = 0.0722; return 0;
+    case ORC_CM_BT601: *Kr = 0.2990; *Kb = 0.1140; return 0;
+    case ORC_CM_SMPTE240M: *Kr = 0.212; *Kb = 0.087; return 0;
+    case ORC_CM_BT2020: *Kr = 0.2627; *Kb = 0.0593; return 0;
+    default: return -1;
+  }
+}
+
+/* colorimetry of a 4:2:0 output fed by packed RGB: explicit, else the caps defaults of the output size */
+static void
+rgb_in_out_colorimetry (const OracleVcsDesc * d, int *matrix, int *range, int *site)
+{
+  *matrix = d->out_matrix ? d->out_matrix : (d->out_height > 576 ? ORC_CM_BT709 : ORC_CM_BT601);
+  *range = d->out_range ? d->out_range : ORC_RANGE_16_235;
+  *site = d->out_chroma_site ? d->out_chroma_site : (d->out_height > 576 ? ORC_SITE_H_COSITED : ORC_SITE_NONE);
+}
+
+int
+oracle_vcs_matrix_rgb2yuv (const OracleVcsDesc * d, int im[4][4])
+{
+  /* chain_convert (video-converter.c:1720-1868), 8-bit ARGB in, 8-bit AYUV out, no gamma / primaries remap:
+   * identity -> compute_matrix_to_RGB (:1373-1404; RGB input: only the range normalisation of the unpack format,
+   * gst_video_color_range_offsets video-color.c:204-252) -> compute_matrix_to_YUV (:1406-1442): color_matrix_RGB_to_YCbCr
+   * (:1037-1066) with the OUTPUT matrix, output range scale + offset -> prepare_matrix (:1324-1370): x256, rint */
+  Mat m;
+  double Kr, Kb, Kg, x;
+  int i, j, matrix, range, site, t;
+  static const uint8_t corner[8][3] = { {0, 0, 0}, {0, 0, 255}, {0, 255, 0}, {0, 255, 255}, {255, 0, 0}, {255, 0, 255},
+    {255, 255, 0}, {255, 255, 255} };
+  rgb_in_out_colorimetry (d, &matrix, &range, &site);
+  mat_identity (&m);
+  if (d->in_range == ORC_RANGE_16_235) {
+    mat_offset (&m, -16, -16, -16);
+    mat_scale (&m, 1 / ((float) 219), 1 / ((float) 219), 1 / ((float) 219));
+  } else {
+    mat_offset (&m, 0, 0, 0);
+    mat_scale (&m, 1 / ((float) 255), 1 / ((float) 255), 1 / ((float) 255));
+  }
+  if (kr_kb (matrix, &Kr, &Kb))
+    return -1;
+  Kg = 1.0 - Kr - Kb;
+  {
+    Mat k;
+    mat_identity (&k);
+    k.dm[0][0] = Kr; k.dm[0][1] = Kg; k.dm[0][2] = Kb;
+    x = 1 / (2 * (1 - Kb));
+    k.dm[1][0] = -x * Kr; k.dm[1][1] = -x * Kg; k.dm[1][2] = x * (1 - Kb);
+    x = 1 / (2 * (1 - Kr));
+    k.dm[2][0] = x * (1 - Kr); k.dm[2][1] = -x * Kg; k.dm[2][2] = -x * Kb;
+    mat_mul (&m, &k, &m);
+  }
+  if (range == ORC_RANGE_16_235) {
+    mat_scale (&m, (float) 219, (float) 224, (float) 224);
+    mat_offset (&m, 16, 128, 128);
+  } else {
+    mat_scale (&m, (float) 255, (float) 255, (float) 255);
+    mat_offset (&m, 0, 128, 128);
+  }
+  mat_scale (&m, 256.0f, 256.0f, 256.0f);
+  for (i = 0; i < 4; i++)
+    for (j = 0; j < 4; j++)
+      im[i][j] = (int) rint (m.dm[i][j]);
+  /* is_no_clip_matrix (:1262-1300) -> video_converter_matrix8_table; a clipping matrix would run video_orc_matrix8,
+   * whose SIMD program and C backup disagree: not restated */
+  for (t = 0; t < 8; t++)
+    for (i = 0; i < 3; i++) {
+      int v = (im[i][0] * corner[t][0] + im[i][1] * corner[t][1] + im[i][2] * corner[t][2] + im[i][3]) >> 8;
+      if (v < 0 || v > 255)
+        return -2;
+    }
+  return 0;
+}
+
+/* video_converter_matrix8_table (:1178-1200) with the tables of videoconvert_convert_init_tables (:1110-1134): the
+ * three 16-bit fields of the packed 64-bit sums never borrow from each other for a no-clip matrix, so every component
+ * is (row . (r,g,b) + offset) >> 8 */
+static void
+matrix_line_rgb2yuv (uint8_t * px, int n, int im[4][4])
+{
+  int i, c;
+  for (i = 0; i < n; i++, px += 4) {
+    const int r = px[1], g = px[2], b = px[3];
+    for (c = 0; c < 3; c++)
+      px[1 + c] = (uint8_t) ((im[c][0] * r + im[c][1] * g + im[c][2] * b + im[c][3]) >> 8);
+  }
+}
+
 /* video_orc_convert_AYUV_ARGB, video-orc.orc:1634-1688, in place on one line */
 static inline int16_t
 splatbw (uint8_t b)
@@ -447,6 +554,23 @@ unpack_line (const OracleVcsDesc * d, const uint8_t * in, int y, uint8_t * dst)
     dst[x * 4 + 1] = sy[x];
     dst[x * 4 + 2] = suv[(x & ~1) + ui];
     dst[x * 4 + 3] = suv[(x & ~1) + (ui ^ 1)];
+  }
+}
+
+/* packed RGB line -> ARGB: unpack_copy4 / unpack_BGRA / unpack_ABGR / unpack_RGBA (video-format.c:536-547, :1433-1443,
+ * :1457-1470, :1489-1502); the x formats share them, their padding byte travels as alpha */
+static void
+unpack_line_rgb (const OracleVcsDesc * d, const uint8_t * in, int y, uint8_t * dst)
+{
+  const uint8_t *s = in + d->in_offset[0] + (size_t) d->in_stride[0] * y;
+  int i;
+  for (i = 0; i < d->in_width; i++, s += 4, dst += 4) {
+    switch (d->in_format) {
+      case ORC_FMT_BGRA: case ORC_FMT_BGRx: dst[0] = s[3]; dst[1] = s[2]; dst[2] = s[1]; dst[3] = s[0]; break;
+      case ORC_FMT_RGBA: case ORC_FMT_RGBx: dst[0] = s[3]; dst[1] = s[0]; dst[2] = s[1]; dst[3] = s[2]; break;
+      case ORC_FMT_ABGR: case ORC_FMT_xBGR: dst[0] = s[0]; dst[1] = s[3]; dst[2] = s[2]; dst[3] = s[1]; break;
+      default: dst[0] = s[0]; dst[1] = s[1]; dst[2] = s[2]; dst[3] = s[3]; break;
+    }
   }
 }
 
@@ -896,10 +1020,22 @@ oracle_vcs_convert (const OracleVcsDesc * d, const uint8_t * in, uint8_t * out)
   uint8_t *cur, *tmp, *mode;
   Scaler hs, vs;
   int have_h = iw != ow, have_v = ih != oh, pass;
-  int yuv_out = 0, out_site = 0;
+  int yuv_out = 0, out_site = 0, rgb_in = 0;
   long s0, s3;
 
-  {
+  if (fmt_is_rgb (d->in_format)) {
+    /* packed RGB -> 4:2:0 (the encoder-feeding direction): no table row, generic chain: unpack to ARGB, the scalers
+     * that shrink, the RGB -> YUV matrix (chain_convert :1720-1868 -> video_converter_matrix8_table), the scalers
+     * that grow, chroma down-sampling (RGB has no sub-sampling: only the down side exists, :2850-2895), 4:2:0 pack */
+    int m_, r_;
+    if (!(d->out_format == ORC_FMT_I420 || d->out_format == ORC_FMT_YV12 || d->out_format == ORC_FMT_NV12 ||
+            d->out_format == ORC_FMT_NV21))
+      return -1;                /* RGB -> RGB: not restated */
+    if (oracle_vcs_matrix_rgb2yuv (d, im) != 0)
+      return -1;
+    rgb_in = yuv_out = 1;
+    rgb_in_out_colorimetry (d, &m_, &r_, &out_site);
+  } else {
     int in_planar = d->in_format == ORC_FMT_I420 || d->in_format == ORC_FMT_YV12;
     int out_planar = d->out_format == ORC_FMT_I420 || d->out_format == ORC_FMT_YV12;
     if ((in_planar && out_planar) || ((d->out_format == ORC_FMT_NV12 || d->out_format == ORC_FMT_NV21) &&
@@ -917,7 +1053,7 @@ oracle_vcs_convert (const OracleVcsDesc * d, const uint8_t * in, uint8_t * out)
       out_site = d->out_chroma_site ? d->out_chroma_site : d->in_chroma_site;
     }
   }
-  if (yuv_out && iw == ow && ih == oh && out_site == d->in_chroma_site) {
+  if (yuv_out && !rgb_in && iw == ow && ih == oh && out_site == d->in_chroma_site) {
     /* video_converter_compute_resample (:2850-2895): same sub-sampling, site and size -> no chroma resampler
      * on either side; unpack replicates every chroma sample and pack reads it back */
     uint8_t *line = malloc ((size_t) iw * 4);
@@ -930,6 +1066,16 @@ oracle_vcs_convert (const OracleVcsDesc * d, const uint8_t * in, uint8_t * out)
   }
   if (!yuv_out && oracle_vcs_matrix (d, p, im) != 0)
     return -1;
+  if (rgb_in) {
+    if (have_h && scaler_init (&hs, &d->rs, iw, ow))
+      return -1;
+    if (have_v && scaler_init (&vs, &d->rs, ih, oh))
+      return -1;
+    cur = malloc ((size_t) iw * ih * 4);
+    for (y = 0; y < ih; y++)
+      unpack_line_rgb (d, in, y, cur + (size_t) y * iw * 4);
+    goto scale_passes;
+  }
   if (!yuv_out && (d->in_format == ORC_FMT_I420 || d->in_format == ORC_FMT_YV12) && iw == ow && ih == oh) {
     /* fast path (video-converter.c:8766-8800 table rows, keeps_size): convert_I420_BGRA / _ARGB /
      * _pack_ARGB (:6772-6988) -> video_orc_convert_I420_BGRA (video-orc.orc:1859-1911): the chroma
@@ -985,6 +1131,7 @@ oracle_vcs_convert (const OracleVcsDesc * d, const uint8_t * in, uint8_t * out)
   }
   free (mode);
 
+scale_passes:
   cw = iw;
   ch = ih;
   s0 = (long) iw * ih;
@@ -995,6 +1142,10 @@ oracle_vcs_convert (const OracleVcsDesc * d, const uint8_t * in, uint8_t * out)
     if (pass == 1 && !yuv_out) {
       for (y = 0; y < ch; y++)
         matrix_line (cur + (size_t) y * cw * 4, cw, p);
+    }
+    if (pass == 1 && rgb_in) {
+      for (y = 0; y < ch; y++)
+        matrix_line_rgb2yuv (cur + (size_t) y * cw * 4, cw, im);
     }
     if (pass == 0 && !(s3 <= s0))
       continue;
@@ -1030,7 +1181,7 @@ oracle_vcs_convert (const OracleVcsDesc * d, const uint8_t * in, uint8_t * out)
      * scaler the request reaches do_unpack_lines' clamp (:2973) through a fresh up-sampler pair (oh, oh+1), i.e.
      * the last source line with its chroma row NOT vertically filtered. */
     uint8_t *extra = NULL;
-    if ((oh & 1) && !have_v && !(out_site & ORC_SITE_V_COSITED)) {
+    if ((oh & 1) && !have_v && !(out_site & ORC_SITE_V_COSITED) && !rgb_in) {   /* RGB: the clamped line IS the last line */
       uint8_t *one = malloc ((size_t) iw * 4);
       unpack_line (d, in, ih - 1, one);
       chroma_h_line (one, iw, (d->in_chroma_site & ORC_SITE_H_COSITED) != 0);

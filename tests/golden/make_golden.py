@@ -217,6 +217,30 @@ def video_cross():
     json.dump(cases, open(os.path.join(HERE, "video_cross_cases.json"), "w"), indent=1)
 
 
+def video_rgb_in():
+    """packed RGB -> 4:2:0: unpack, scalers, RGB -> YUV table matrix, chroma down-sampling, pack"""
+    arrays, cases = {}, []
+    for fi, fo in [("BGRA", "NV12"), ("RGBA", "I420"), ("ARGB", "NV21"), ("xBGR", "YV12")]:
+        for (iw, ih, ow, oh) in [(64, 48, 32, 24), (64, 48, 96, 72), (65, 49, 33, 25), (33, 17, 20, 31), (50, 21, 50, 21),
+                                 (40, 90, 40, 31)]:
+            for m, omat, orng, osite in ((1, 0, 0, 0), (3, 3, 2, 2), (9, 4, 1, 1), (0, 6, 2, 6)):
+                if m == 0 and oh > ih:
+                    continue    # nearest vertical repeats + in-place stages: reference defect class
+                frame = np.random.default_rng(m + iw).integers(0, 256, iw * ih * 4, dtype=np.uint8)
+                d = ob.vcs_desc(iw, ih, ow, oh, m, in_fmt=ob.FMT[fi], out_fmt=ob.FMT[fo])
+                size = ob.vcs_sizes(d)[1]
+                r = ob.RefVcs(iw, ih, ow, oh, m, in_fmt=ob.FMT[fi], out_fmt=ob.FMT[fo], out_matrix=omat or -1,
+                              out_rng=orng or -1, out_site=osite or -1)
+                out = r.convert(frame, np.zeros(size, dtype=np.uint8))
+                r.close()
+                key = f"r_{fi}_{fo}_{iw}x{ih}_{ow}x{oh}_m{m}"
+                arrays[key] = out
+                cases.append({"key": key, "in_fmt": fi, "out_fmt": fo, "in": [iw, ih], "out": [ow, oh], "method": m,
+                              "out_matrix": omat, "out_range": orng, "out_site": osite, "seed": m + iw})
+    np.savez_compressed(os.path.join(HERE, "video_rgb_in.npz"), **arrays)
+    json.dump(cases, open(os.path.join(HERE, "video_rgb_in_cases.json"), "w"), indent=1)
+
+
 def compositor_420():
     """I420 / YV12 / NV12 / NV21 output"""
     o, r = ob.oracle(), ob.ref()
@@ -251,7 +275,7 @@ if __name__ == "__main__":
     only = set(sys.argv[1:])
     for name, fn in [("video", video), ("compositor", compositor), ("audio", audio), ("video_planar", video_planar),
                      ("audio_interpolated", audio_interpolated), ("audio_formats", audio_formats), ("compositor_420", compositor_420), ("video_yuv", video_yuv),
-                     ("video_cross", video_cross)]:
+                     ("video_cross", video_cross), ("video_rgb_in", video_rgb_in)]:
         if not only or name in only:
             fn()
     print("golden fixtures written to", HERE)

@@ -423,3 +423,59 @@ def test_cross_family_420_differing_matrix_is_refused():
     d.out_matrix = 4 if d.in_matrix == 3 else 3
     with pytest.raises(RuntimeError):
         ob.oracle_vcs_convert(d, ob.nv12_random_frame(64, 48, 1))
+
+
+# ------------------------------------------------------------------- packed RGB -> 4:2:0 (the encoder-feeding direction)
+RGB_IN = ["BGRA", "RGBA", "ARGB", "ABGR", "BGRx", "RGBx", "xRGB", "xBGR"]
+
+
+def _rgb_frame(iw, ih, seed):
+    return np.random.default_rng(seed).integers(0, 256, iw * ih * 4, dtype=np.uint8)
+
+
+@pytest.mark.parametrize("fi", RGB_IN)
+@pytest.mark.parametrize("fo", ["I420", "YV12", "NV12", "NV21"])
+@pytest.mark.parametrize("size", [(64, 48, 32, 24), (64, 48, 96, 72), (33, 17, 20, 31), (50, 21, 50, 21), (57, 35, 29, 35),
+                                  (100, 100, 150, 50), (40, 90, 40, 31), (1, 1, 5, 4), (2, 3, 1, 1)],
+                         ids=lambda s: "%dx%d-%dx%d" % s)
+def test_rgb_to_420_matches_reference(fi, fo, size):
+    """unpack to ARGB -> scalers that shrink -> RGB->YUV matrix (video_converter_matrix8_table) -> scalers that grow ->
+    chroma down-sampling -> 4:2:0 pack; output colorimetry = the caps defaults of the output size.  No chroma
+    up-sampler in this chain, so vertical-first geometries are compared directly too."""
+    iw, ih, ow, oh = size
+    frame = _rgb_frame(iw, ih, 3)
+    for method in range(10):
+        got = ob.oracle_vcs_convert(ob.vcs_desc(iw, ih, ow, oh, method, in_fmt=ob.FMT[fi], out_fmt=ob.FMT[fo]), frame)
+        r = ob.RefVcs(iw, ih, ow, oh, method, in_fmt=ob.FMT[fi], out_fmt=ob.FMT[fo])
+        want = r.convert(frame, np.zeros(got.size, dtype=np.uint8))
+        r.close()
+        if _one_tap_vertical_inplace(ih, oh, method) and not np.array_equal(got, want):
+            continue
+        assert np.array_equal(got, want), f"method {method}"
+
+
+@pytest.mark.parametrize("matrix", [2, 3, 4, 5, 6])
+@pytest.mark.parametrize("rng", [1, 2])
+@pytest.mark.parametrize("site", [1, 2, 4, 6])
+def test_rgb_to_420_colorimetry(matrix, rng, site):
+    for (iw, ih, ow, oh) in [(64, 48, 40, 30), (40, 30, 64, 48), (33, 33, 33, 33)]:
+        frame = _rgb_frame(iw, ih, 5)
+        d = ob.vcs_desc(iw, ih, ow, oh, 3, in_fmt=ob.FMT["BGRA"], out_fmt=ob.FMT["NV12"])
+        d.out_matrix, d.out_range, d.out_chroma_site = matrix, rng, site
+        got = ob.oracle_vcs_convert(d, frame)
+        r = ob.RefVcs(iw, ih, ow, oh, 3, in_fmt=ob.FMT["BGRA"], out_fmt=ob.FMT["NV12"], out_matrix=matrix, out_rng=rng, out_site=site)
+        want = r.convert(frame, np.zeros(got.size, dtype=np.uint8))
+        r.close()
+        assert np.array_equal(got, want)
+
+
+def test_rgb_to_yuv_matrix_known_answers():
+    """bt709 and bt601, full-range RGB -> 16-235: the x256 integer matrices the reference derives (rows Y, U, V)"""
+    import ctypes as C
+    im = (C.c_int * 16)()
+    d = ob.vcs_desc(1920, 1080, 1920, 1080, 1, in_fmt=ob.FMT["BGRA"], out_fmt=ob.FMT["NV12"])
+    assert ob.oracle().oracle_vcs_matrix_rgb2yuv(C.byref(d), im) == 0
+    assert list(im)[:12] == [47, 157, 16, 4096, -26, -87, 112, 32768, 112, -102, -10, 32768]
+    d = ob.vcs_desc(640, 480, 640, 480, 1, in_fmt=ob.FMT["BGRA"], out_fmt=ob.FMT["NV12"])
+    assert ob.oracle().oracle_vcs_matrix_rgb2yuv(C.byref(d), im) == 0
+    assert list(im)[:12] == [66, 129, 25, 4096, -38, -74, 112, 32768, 112, -94, -18, 32768]
