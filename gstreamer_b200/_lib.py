@@ -88,6 +88,7 @@ _SIGS = {
     "b200_vcs_convert_host": (C.c_int, [_P, C.c_int, C.POINTER(_P), C.POINTER(_P)]),
     "b200_vcs_get_plan_info": (C.c_int, [_P, C.POINTER(VcsPlanInfoC)]),
     "b200_vcs_get_taps": (C.c_int, [_P, C.c_int, _P, _P, C.c_size_t, C.c_size_t]),
+    "b200_vcs_get_matrix": (C.c_int, [_P, _P]),
     "b200_vcs_get_chroma_plan": (C.c_int, [_P, _P, C.c_size_t]),
     "b200_vcs_set_kernel_variant": (C.c_int, [_P, C.c_int]),
     "b200_comp_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),

@@ -87,6 +87,8 @@ int launch (b200_vcs * h, int n, const VcsBatch & batch, cudaStream_t stream)
     if (aligned) return launch_ntap (h->dev, p, h->ntap, batch, n, stream);
   }
   dim3 grid ((p.out.width + p.tile_w - 1) / p.tile_w, (p.out.height + p.tile_h - 1) / p.tile_h, n);
+  if (p.rgb_in)                                                    // packed pixels are read with 32-bit loads
+    for (int i = 0; i < n; i++) if (((uintptr_t) batch.in[i]) & 3) return B200_ERR_INVALID_ARG;
   if (p.yuv_out) {
     // launch 1 writes the scaled pixels of every frame to its scratch image, launch 2 down-samples and packs
     const size_t frame = (size_t) h->down.stride_s * (p.out.height + (p.extra_row ? 1 : 0));
@@ -268,6 +270,8 @@ int b200_vcs_create (const b200_video_info * in, const b200_video_info * out,
     d.cstep = p.planar ? 1 : 2;
     d.h_first = p.h_first; d.matrix_first = p.matrix_first;
     d.yuv_out = p.yuv_out ? 1 : 0;
+    d.rgb_in = p.rgb_in ? 1 : 0; d.in_sel = p.in_sel;
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 4; j++) d.m[i][j] = p.m_rgb2yuv[i][j];
     if (p.yuv_out) {                                              // the chain's output is the scratch image
       d.stride_out = p.out.width * 4; d.off_out = 0;
       Down420Dev & q = h->down;
@@ -419,6 +423,15 @@ int b200_vcs_get_taps (const b200_vcs * h, int dir, uint32_t * offsets, int16_t 
     memcpy (taps, a.coef.data (), a.coef.size () * sizeof (int16_t));
   }
   return (int) a.coef_per_out;
+}
+
+int b200_vcs_get_matrix (const b200_vcs * h, int32_t im[16])
+{
+  if (!h || !im) return B200_ERR_INVALID_ARG;
+  const VcsPlan & p = h->plan;
+  const bool has = !p.planes_mode && (!p.yuv_out || p.rgb_in);
+  for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) im[4 * i + j] = has ? p.im[i][j] : 0;
+  return B200_OK;
 }
 
 int b200_vcs_get_chroma_plan (const b200_vcs * h, uint8_t * mode, size_t len)

@@ -28,6 +28,11 @@ struct VcsDev {
   int chroma_nearest;            // unchanged-size I420/YV12: the reference's fast path replicates chroma (no filter)
   int h_first, matrix_first;
   int yuv_out;                   // 4:2:0 output through the chain: no matrix stage, scaled A,Y,U,V pixels go to a scratch image
+  // packed RGB input (generic kernel only): 4-byte pixels at off_y / stride_y, byte i of (R,G,B) at in_sel nibble i;
+  // m = the x256 RGB -> YUV matrix of video_converter_matrix8_table (rows Y,U,V; columns R,G,B,offset)
+  int rgb_in;
+  unsigned in_sel;
+  int m[3][4];
   int p1, p2, p3, p4, p5;
   unsigned sel;                  // byte selector nibbles for PRMT-style packing: byte i <- comp sel[i]
   AxisDev h, v;

@@ -80,6 +80,16 @@ __device__ __forceinline__ void yuv_to_rgb (int y, int u, int v, int p1, int p2,
   b = min (max (bb, -128), 127) + 128;
 }
 
+// video_converter_matrix8_table (video-converter.c:1178-1200; tables :1110-1134): for a matrix that cannot clip
+// (is_no_clip_matrix :1262-1300) the three 16-bit fields of its packed 64-bit sums never borrow from each other, so
+// each component is (row . (r,g,b) + offset) >> 8
+__device__ __forceinline__ void rgb_to_yuv (int r, int g, int b, const int (&m)[3][4], int &y, int &u, int &v)
+{
+  y = (m[0][0] * r + m[0][1] * g + m[0][2] * b + m[0][3]) >> 8;
+  u = (m[1][0] * r + m[1][1] * g + m[1][2] * b + m[1][3]) >> 8;
+  v = (m[2][0] * r + m[2][1] * g + m[2][2] * b + m[2][3]) >> 8;
+}
+
 // alpha travels through the scalers as a constant 255 line (unpack sets A=0xff,
 // video-format.c:1612-1637): n-tap passes turn it into round(255 * sum(taps)).
 __device__ __forceinline__ int alpha_pass (int a, const AxisDev & ax, int idx)
@@ -138,7 +148,7 @@ vcs_generic_kernel (const VcsDev P, const VcsBatch frames)
   // ---- A1: chroma rows, horizontally upsampled to the region's columns
   const int cr0 = max (ry0 - 1, 0) >> 1, cr1 = min (ry1, P.ih - 1) >> 1;       // inclusive
   const int ncr = cr1 - cr0 + 1;
-  for (int i = tid; i < ncr * C; i += nthr) {
+  for (int i = tid; i < (P.rgb_in ? 0 : ncr * C); i += nthr) {
     const int r = i / C, c = i - r * C;
     const int x = cx0 + c;
     const int hmode = P.chroma_nearest ? 2 : P.h_cosited;
@@ -152,8 +162,19 @@ vcs_generic_kernel (const VcsDev P, const VcsBatch frames)
     const int r = i / C, c = i - r * C;
     const int y = ry0 + r;
     const int own = (y >> 1) - cr0;
-    int yy = plane_y[(size_t) y * P.stride_y + cx0 + c];
-    int u = HU[own * Cp + c], v = HU[hup_sz + own * Cp + c];
+    int yy, u, v;
+    if (P.rgb_in) {
+      // unpack_BGRA / _RGBA / _ABGR / unpack_copy4 (video-format.c:1433-1502, :536-547): a byte shuffle to A,R,G,B
+      const unsigned px = __byte_perm (*(const unsigned *) (plane_y + (size_t) y * P.stride_y + 4 * (size_t) (cx0 + c)), 0, P.in_sel);
+      yy = px & 0xff; u = (px >> 8) & 0xff; v = (px >> 16) & 0xff;
+      if (P.matrix_first) rgb_to_yuv (yy, u, v, P.m, yy, u, v);
+      S[r * Cp + c] = (uint8_t) yy;
+      S[plane_sz + r * Cp + c] = (uint8_t) u;
+      S[2 * plane_sz + r * Cp + c] = (uint8_t) v;
+      continue;
+    }
+    yy = plane_y[(size_t) y * P.stride_y + cx0 + c];
+    u = HU[own * Cp + c]; v = HU[hup_sz + own * Cp + c];
     const int m = P.v_pairs ? P.chroma_mode[y] : 0;
     if (m) {
       const int oth = ((m == 1 ? min (y + 1, P.ih - 1) : y - 1) >> 1) - cr0;
@@ -248,7 +269,8 @@ vcs_generic_kernel (const VcsDev P, const VcsBatch frames)
       }
     }
     int r, g, b;
-    if (P.matrix_first || P.yuv_out) { r = comp[0]; g = comp[1]; b = comp[2]; }
+    if (P.rgb_in && !P.matrix_first) rgb_to_yuv (comp[0], comp[1], comp[2], P.m, r, g, b);
+    else if (P.matrix_first || P.yuv_out) { r = comp[0]; g = comp[1]; b = comp[2]; }
     else yuv_to_rgb (comp[0], comp[1], comp[2], P.p1, P.p2, P.p3, P.p4, P.p5, r, g, b);
     int a = 255;
     if (P.h_first) { a = alpha_pass (a, P.h, ox); a = alpha_pass (a, P.v, oy); }

@@ -254,6 +254,56 @@ int colour_matrix (VcsPlan * p)
   return B200_OK;
 }
 
+// packed RGB in, YUV out: chain_convert (video-converter.c:1720-1868): identity -> compute_matrix_to_RGB (:1373-1404;
+// for an RGB unpack format only the range normalisation) -> compute_matrix_to_YUV (:1406-1442): RGB_to_YCbCr (:1037-1066)
+// of the OUTPUT matrix, output range scale + offset -> prepare_matrix (:1324-1370): x256, rint.  Only matrices the
+// reference routes to video_converter_matrix8_table (is_no_clip_matrix :1262-1300) are accepted.
+int colour_matrix_rgb2yuv (VcsPlan * p)
+{
+  double kr, kb;
+  switch (p->out.color_matrix) {
+    case B200_COLOR_MATRIX_FCC: kr = 0.30; kb = 0.11; break;
+    case B200_COLOR_MATRIX_BT709: kr = 0.2126; kb = 0.0722; break;
+    case B200_COLOR_MATRIX_BT601: kr = 0.2990; kb = 0.1140; break;
+    case B200_COLOR_MATRIX_SMPTE240M: kr = 0.212; kb = 0.087; break;
+    case B200_COLOR_MATRIX_BT2020: kr = 0.2627; kb = 0.0593; break;
+    default: return B200_ERR_INVALID_ARG;
+  }
+  const double kg = 1.0 - kr - kb;
+  Mat4 m = Mat4::identity ();
+  if (p->in.color_range == B200_COLOR_RANGE_16_235) {
+    m = mul (shift (-16, -16, -16), m);
+    m = mul (diag (1 / ((float) 219), 1 / ((float) 219), 1 / ((float) 219)), m);
+  } else {
+    m = mul (shift (0, 0, 0), m);
+    m = mul (diag (1 / ((float) 255), 1 / ((float) 255), 1 / ((float) 255)), m);
+  }
+  Mat4 k = Mat4::identity ();
+  k.m[0][0] = kr; k.m[0][1] = kg; k.m[0][2] = kb;
+  double x = 1 / (2 * (1 - kb));
+  k.m[1][0] = -x * kr; k.m[1][1] = -x * kg; k.m[1][2] = x * (1 - kb);
+  x = 1 / (2 * (1 - kr));
+  k.m[2][0] = x * (1 - kr); k.m[2][1] = -x * kg; k.m[2][2] = -x * kb;
+  m = mul (k, m);
+  if (p->out.color_range == B200_COLOR_RANGE_16_235) {
+    m = mul (diag ((float) 219, (float) 224, (float) 224), m);
+    m = mul (shift (16, 128, 128), m);
+  } else {
+    m = mul (diag ((float) 255, (float) 255, (float) 255), m);
+    m = mul (shift (0, 128, 128), m);
+  }
+  m = mul (diag (256.0f, 256.0f, 256.0f), m);
+  for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) p->im[i][j] = (int) rint (m.m[i][j]);
+  for (int t = 0; t < 8; t++)
+    for (int i = 0; i < 3; i++) {
+      const int r = (t & 4) ? 255 : 0, g = (t & 2) ? 255 : 0, b = (t & 1) ? 255 : 0;
+      const int v = (p->im[i][0] * r + p->im[i][1] * g + p->im[i][2] * b + p->im[i][3]) >> 8;
+      if (v < 0 || v > 255) return B200_ERR_UNSUPPORTED;       // the reference would run video_orc_matrix8: not built
+    }
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 4; j++) p->m_rgb2yuv[i][j] = p->im[i][j];
+  return B200_OK;
+}
+
 // Which lines reach the chroma upsampler and how they pair up (see DESIGN.md "chroma plan").
 void chroma_pairing (VcsPlan * p)
 {
@@ -529,6 +579,62 @@ int build_planes (VcsPlan * p, const FilterSpec & f)
 
 }  // namespace
 
+// packed RGB -> 4:2:0 (the encoder-feeding direction): no table row in the reference, its generic chain: unpack to
+// ARGB, the scalers that shrink, the RGB -> YUV table matrix, the scalers that grow, chroma down-sampling (RGB has no
+// sub-sampling, so only the down side exists and it exists at every size: video-converter.c:2850-2895), 4:2:0 pack.
+// Generic kernel + vcs_down420_kernel.  Written without device access: opt-in until it has run green on a GPU.
+static int build_rgb_in_plan (VcsPlan * p)
+{
+  const b200_video_info *in = &p->in, *out = &p->out;
+  if (!getenv ("B200_VCS_EXPERIMENTAL")) return B200_ERR_UNSUPPORTED;
+  const bool out_pl = out->format == B200_VIDEO_FORMAT_I420 || out->format == B200_VIDEO_FORMAT_YV12;
+  const bool out_semi = out->format == B200_VIDEO_FORMAT_NV12 || out->format == B200_VIDEO_FORMAT_NV21;
+  if (!out_pl && !out_semi) return B200_ERR_UNSUPPORTED;           // RGB -> RGB: not built
+  if (in->stride[0] < in->width * 4 || (in->stride[0] & 3) || (in->offset[0] & 3)) return B200_ERR_INVALID_ARG;
+  const int ocw = (out->width + 1) / 2;
+  if (out->stride[0] < out->width) return B200_ERR_INVALID_ARG;
+  if (out_pl) {
+    if (out->stride[1] < ocw || out->stride[2] < ocw) return B200_ERR_INVALID_ARG;
+    p->out_plane_u = out->format == B200_VIDEO_FORMAT_YV12 ? 2 : 1;
+    p->out_plane_v = 3 - p->out_plane_u;
+    p->out_cstep = 1; p->out_u_index = 0;
+  } else {
+    if (out->stride[1] < 2 * ocw) return B200_ERR_INVALID_ARG;
+    p->out_plane_u = p->out_plane_v = 1;
+    p->out_cstep = 2; p->out_u_index = out->format == B200_VIDEO_FORMAT_NV21 ? 1 : 0;
+  }
+  // caps defaults of the output size where the caller left them open (the fixation forwards only primaries and
+  // transfer across an RGB/YUV change, gstvideoconvertscale.c:1394-1408)
+  if (p->in.color_range == 0) p->in.color_range = B200_COLOR_RANGE_0_255;
+  if (p->out.color_matrix == 0) p->out.color_matrix = out->height > 576 ? B200_COLOR_MATRIX_BT709 : B200_COLOR_MATRIX_BT601;
+  if (p->out.color_range == 0) p->out.color_range = B200_COLOR_RANGE_16_235;
+  if (p->out.chroma_site == 0) p->out.chroma_site = out->height > 576 ? B200_CHROMA_SITE_H_COSITED : B200_CHROMA_SITE_NONE;
+  int st = colour_matrix_rgb2yuv (p);
+  if (st != B200_OK) return st;
+  p->rgb_in = p->yuv_out = true;
+  switch (in->format) {                 // source byte of R, G, B, A (nibbles 0..3)
+    case B200_VIDEO_FORMAT_BGRA: case B200_VIDEO_FORMAT_BGRx: p->in_sel = 0x3012; break;
+    case B200_VIDEO_FORMAT_RGBA: case B200_VIDEO_FORMAT_RGBx: p->in_sel = 0x3210; break;
+    case B200_VIDEO_FORMAT_ABGR: case B200_VIDEO_FORMAT_xBGR: p->in_sel = 0x0123; break;
+    default: p->in_sel = 0x0321; break;                            // ARGB / xRGB
+  }
+  { uint8_t s[4] = {0, 1, 2, 3}; memcpy (p->byte_sel, s, 4); }
+  p->planar = false; p->u_index = 0; p->h_cosited = false; p->v_pairs = false; p->chroma_nearest = false;
+  FilterSpec f = filter_from_method (p->cfg);
+  const int iw = in->width, ih = in->height, ow = out->width, oh = out->height;
+  if (iw != ow) scaled_axis (&p->h, f, iw, ow, true); else identity_axis (&p->h, iw);
+  if (ih != oh) scaled_axis (&p->v, f, ih, oh, false); else identity_axis (&p->v, ih);
+  p->matrix_first = !((int64_t) ow * oh <= (int64_t) iw * ih);     // chain_scale: shrink before the matrix, grow after
+  p->h_first = (int64_t) ow * ih <= (int64_t) iw * oh;
+  p->chroma_mode.assign (ih, 0);
+  p->down_h = (p->out.chroma_site & B200_CHROMA_SITE_H_COSITED) ? 2 : 1;
+  p->down_v = (p->out.chroma_site & B200_CHROMA_SITE_V_COSITED) == 0;
+  p->extra_row = false;                 // the line past an odd frame is the last line itself (no chroma up-sampler)
+  tile_geometry (p);
+  p->light_ok = p->ntap_ok = p->lanczos2_ok = false;
+  return B200_OK;
+}
+
 int build_vcs_plan (const b200_video_info * in, const b200_video_info * out,
     const b200_vcs_config * cfg, VcsPlan * p)
 {
@@ -536,10 +642,12 @@ int build_vcs_plan (const b200_video_info * in, const b200_video_info * out,
   if (in->width < 1 || in->height < 1 || out->width < 1 || out->height < 1 ||
       in->width > 32767 || in->height > 32767 || out->width > 32767 || out->height > 32767)
     return B200_ERR_INVALID_ARG;        // caps range [1,32767], gstvideoconvertscale.c:168-169
+  const bool in_rgb = in->format >= B200_VIDEO_FORMAT_RGBx && in->format <= B200_VIDEO_FORMAT_ABGR;
   if (in->format != B200_VIDEO_FORMAT_NV12 && in->format != B200_VIDEO_FORMAT_NV21 &&
-      in->format != B200_VIDEO_FORMAT_I420 && in->format != B200_VIDEO_FORMAT_YV12)
+      in->format != B200_VIDEO_FORMAT_I420 && in->format != B200_VIDEO_FORMAT_YV12 && !in_rgb)
     return B200_ERR_UNSUPPORTED;
   p->in = *in; p->out = *out; p->cfg = *cfg;
+  if (in_rgb) return build_rgb_in_plan (p);
   // caps defaults (video-info.c:165-185, :211-225)
   if (p->in.color_matrix == 0) p->in.color_matrix = in->height > 576 ? B200_COLOR_MATRIX_BT709 : B200_COLOR_MATRIX_BT601;
   if (p->in.color_range == 0) p->in.color_range = B200_COLOR_RANGE_16_235;

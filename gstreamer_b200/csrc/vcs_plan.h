@@ -73,6 +73,11 @@ struct VcsPlan {
   bool extra_row = false;        // odd height, no vertical scaler: the last pair's second line is rebuilt (see build_vcs_plan)
   int out_plane_u = 1, out_plane_v = 1, out_cstep = 1, out_u_index = 0;
 
+  // packed RGB input -> 4:2:0 (generic kernel only): byte selector to (R,G,B,A) and the x256 table matrix
+  bool rgb_in = false;
+  unsigned in_sel = 0x3210;
+  int m_rgb2yuv[3][4] = {{0}};
+
   // specialised 2:1 lanczos kernel eligibility
   bool lanczos2_ok = false;
 

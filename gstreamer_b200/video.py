@@ -227,6 +227,11 @@ class CudaVideoConvertScale:
         check(lib.b200_vcs_get_plan_info(self._h, C.byref(info)))
         return info
 
+    def matrix(self):
+        im = (C.c_int32 * 16)()
+        check(lib.b200_vcs_get_matrix(self._h, im))
+        return np.array(list(im), dtype=np.int32).reshape(4, 4)
+
     def taps(self, direction):
         size = (self.out_info.width if direction == 0 else self.out_info.height)
         off = np.zeros(size, dtype=np.uint32)

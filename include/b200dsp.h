@@ -168,6 +168,9 @@ int b200_vcs_get_plan_info (const b200_vcs * h, b200_vcs_plan_info * info);
  * offsets[out_size], taps[out_size * n_taps] (int16) */
 int b200_vcs_get_taps (const b200_vcs * h, int dir, uint32_t * offsets, int16_t * taps,
     size_t offsets_len, size_t taps_len);
+/* the x256 integer colour matrix of the plan (prepare_matrix, video-converter.c:1324-1370), row-major 4x4: YUV -> RGB
+ * for RGB outputs, RGB -> YUV for a packed RGB input; all zero for plans without a matrix stage */
+int b200_vcs_get_matrix (const b200_vcs * h, int32_t im[16]);
 /* per input line chroma pairing mode (0 own row, 1 first of pair, 2 second of pair) */
 int b200_vcs_get_chroma_plan (const b200_vcs * h, uint8_t * mode, size_t len);
 /* force a kernel variant (0 generic, 1 specialised if eligible); for A/B tests */

@@ -233,3 +233,45 @@ def test_transfer_colorimetry_from_input():
     rgb = g.VideoInfo(12, 854, 480)
     g.transfer_colorimetry_from_input(ii, rgb)
     assert rgb.c.color_matrix == 1
+
+
+def test_rgb_input_plan_is_opt_in_and_matches_the_oracle_matrix(monkeypatch):
+    """packed RGB -> 4:2:0 (generic kernel + chroma down-sampling, written without device access): refused unless
+    B200_VCS_EXPERIMENTAL is set; with it the host plan carries the same x256 RGB -> YUV matrix as the oracle for
+    every output colorimetry, sits the matrix between the shrinking and the growing scalers, and never needs the
+    odd-height third launch"""
+    import gstreamer_b200 as g
+
+    def build(fi, fo, iw, ih, ow, oh, m=1, **out_colorimetry):
+        el = g.CudaVideoConvertScale(method=m, cuda_device_id=-1)
+        ii, oi = g.VideoInfo(fi, iw, ih), g.VideoInfo(fo, ow, oh)
+        if out_colorimetry:
+            oi.set_colorimetry(**out_colorimetry)
+        el.set_info(ii, oi)
+        return el
+
+    monkeypatch.delenv("B200_VCS_EXPERIMENTAL", raising=False)
+    with pytest.raises(g.B200Error) as e:
+        build(12, 23, 64, 48, 32, 24)
+    assert e.value.status == -2
+    monkeypatch.setenv("B200_VCS_EXPERIMENTAL", "1")
+    im = (C.c_int * 16)()
+    for fi in (7, 8, 9, 10, 11, 12, 13, 14):
+        for fo in (2, 3, 23, 24):
+            for size in [(64, 48, 32, 24), (64, 48, 96, 72), (1920, 1080, 1280, 720), (33, 17, 33, 17), (64, 49, 32, 49)]:
+                el = build(fi, fo, *size)
+                pi = el.plan_info()
+                assert (int(pi.kernel_variant), int(pi.n_launches_per_convert)) == (5, 2)
+                assert int(pi.matrix_first) == int(size[2] * size[3] > size[0] * size[1])
+                d = ob.vcs_desc(*size, 1, in_fmt=fi, out_fmt=fo)
+                assert ob.oracle().oracle_vcs_matrix_rgb2yuv(C.byref(d), im) == 0
+                assert el.matrix().ravel().tolist() == list(im)
+    for matrix in (2, 3, 4, 5, 6):
+        for rng in (1, 2):
+            el = build(12, 23, 64, 48, 32, 24, matrix=matrix, range=rng, chroma_site=6)
+            d = ob.vcs_desc(64, 48, 32, 24, 1, in_fmt=12, out_fmt=23)
+            d.out_matrix, d.out_range = matrix, rng
+            assert ob.oracle().oracle_vcs_matrix_rgb2yuv(C.byref(d), im) == 0
+            assert el.matrix().ravel().tolist() == list(im)
+    with pytest.raises(g.B200Error):
+        build(12, 11, 64, 48, 32, 24)                          # RGB -> RGB: not built

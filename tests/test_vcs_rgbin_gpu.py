@@ -1,0 +1,96 @@
+"""Packed RGB -> 4:2:0 (BGRA -> NV12 ...: what sits between a compositor and an encoder).  The reference runs its
+generic chain: unpack to ARGB, the scalers that shrink, the RGB -> YUV table matrix (video_converter_matrix8_table,
+video-converter.c:1178-1200), the scalers that grow, chroma down-sampling, 4:2:0 pack.  Product: vcs_generic_kernel
+(packed-pixel input stage, matrix between the passes) into scratch A,Y,U,V images, then vcs_down420_kernel.
+
+Written after this round's device budget was spent: the path is opt-in in the product (B200_VCS_EXPERIMENTAL) and these
+tests are skipped unless B200_TEST_EXPERIMENTAL=1, so that an unconfirmed kernel cannot take the suite down.
+First thing to run next round:  B200_TEST_EXPERIMENTAL=1 python -m pytest tests/test_vcs_rgbin_gpu.py -q"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import bindings as ob
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("B200_TEST_EXPERIMENTAL") != "1", reason="opt-in: B200_TEST_EXPERIMENTAL=1")]
+
+RGB_IN = ["BGRA", "RGBA", "ARGB", "ABGR", "BGRx", "RGBx", "xRGB", "xBGR"]
+YUV_OUT = ["NV12", "I420", "NV21", "YV12"]
+SIZES = [(64, 48, 32, 24), (64, 48, 96, 72), (65, 49, 33, 26), (33, 17, 20, 31), (50, 21, 50, 21), (57, 35, 29, 35),
+         (100, 100, 150, 50), (40, 90, 40, 31), (17, 9, 64, 31), (2, 2, 1, 1), (1, 1, 5, 4), (640, 480, 320, 240),
+         (1920, 1080, 1280, 720), (1280, 720, 1920, 1080)]
+
+
+@pytest.fixture(autouse=True)
+def _opt_in(monkeypatch):
+    monkeypatch.setenv("B200_VCS_EXPERIMENTAL", "1")
+
+
+def rgb_frame(iw, ih, seed):
+    return np.random.default_rng(seed).integers(0, 256, iw * ih * 4, dtype=np.uint8)
+
+
+def convert(size, method, frame, fi, fo, colorimetry=None, batch=1):
+    import torch
+    import gstreamer_b200 as g
+    iw, ih, ow, oh = size
+    el = g.CudaVideoConvertScale(method=method, cuda_device_id=0)
+    ii, oi = g.VideoInfo(ob.FMT[fi], iw, ih), g.VideoInfo(ob.FMT[fo], ow, oh)
+    if colorimetry:
+        oi.set_colorimetry(matrix=colorimetry[0], range=colorimetry[1], chroma_site=colorimetry[2])
+    el.set_info(ii, oi)
+    assert int(el.plan_info().kernel_variant) == 5
+    src = [torch.from_numpy(frame).cuda() for _ in range(batch)]
+    dst = [torch.full((oi.size,), 0x5A, dtype=torch.uint8, device="cuda") for _ in range(batch)]
+    if batch == 1:
+        el.transform_frame(src[0], dst[0])
+    else:
+        el.transform_frames(src, dst)
+    torch.cuda.synchronize()
+    return [d.cpu().numpy() for d in dst], oi
+
+
+def expected(size, method, frame, fi, fo, colorimetry=None):
+    d = ob.vcs_desc(*size, method, in_fmt=ob.FMT[fi], out_fmt=ob.FMT[fo])
+    if colorimetry:
+        d.out_matrix, d.out_range, d.out_chroma_site = colorimetry
+    return ob.oracle_vcs_convert(d, frame)
+
+
+@pytest.mark.parametrize("method", [0, 1, 3, 4, 9], ids=["nearest", "bilinear", "lanczos", "bilinear2", "mitchell"])
+@pytest.mark.parametrize("size", SIZES, ids=lambda s: "%dx%d-%dx%d" % s)
+@pytest.mark.parametrize("fo", YUV_OUT)
+def test_rgb_to_420_matches_oracle(cuda_device, fo, size, method):
+    from test_vcs_cross_gpu import planes_equal
+    iw, ih, ow, oh = size
+    big = iw * ih > 500_000
+    if big and (fo != "NV12" or method not in (1, 3)):
+        pytest.skip("large shapes: NV12, bilinear / lanczos only")
+    for fi in (["BGRA"] if big else RGB_IN):
+        frame = rgb_frame(iw, ih, 5)
+        want = expected(size, method, frame, fi, fo)
+        (got,), oi = convert(size, method, frame, fi, fo)
+        bad = planes_equal(got, want, oi, ow, oh, fo in ("NV12", "NV21"))
+        assert not bad, f"{fi}: {bad}"
+
+
+@pytest.mark.parametrize("colorimetry", [(3, 2, 2), (4, 1, 1), (6, 2, 6), (2, 1, 4), (5, 2, 1)])
+def test_rgb_to_420_colorimetry(cuda_device, colorimetry):
+    from test_vcs_cross_gpu import planes_equal
+    for size in [(64, 48, 40, 30), (40, 30, 64, 48), (33, 33, 33, 33)]:
+        frame = rgb_frame(size[0], size[1], 7)
+        want = expected(size, 3, frame, "BGRA", "NV12", colorimetry)
+        (got,), oi = convert(size, 3, frame, "BGRA", "NV12", colorimetry)
+        assert not planes_equal(got, want, oi, size[2], size[3], True)
+
+
+def test_rgb_to_420_batch(cuda_device):
+    from test_vcs_cross_gpu import planes_equal
+    size = (640, 360, 426, 240)
+    frame = rgb_frame(640, 360, 9)
+    want = expected(size, 1, frame, "RGBA", "I420")
+    outs, oi = convert(size, 1, frame, "RGBA", "I420", batch=4)
+    for o in outs:
+        assert not planes_equal(o, want, oi, 426, 240, False)

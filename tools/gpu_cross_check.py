@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Device check of the 4:2:0 -> other-4:2:0-family path (kernel_variant 5) against the oracle.
+"""Device check of the chain + chroma down-sampling paths (kernel_variant 5) against the oracle: the 4:2:0 -> other-4:2:0
+family pairs, and with `rgb` as second argument the (opt-in) packed RGB -> 4:2:0 direction.
 Runs every case of tests/test_vcs_cross_gpu.py plus a random sweep, records EVERY outcome (it does not stop at the
 first mismatch) in gpurun_out/cross_check.json, and times one 1080p -> 720p NV12 -> I420 conversion."""
 import json
@@ -12,6 +13,40 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import numpy as np   # noqa: E402
+
+
+def rgb_mode(budget, t_start, out, flush):
+    """random packed RGB -> 4:2:0 configurations (B200_VCS_EXPERIMENTAL path)"""
+    os.environ["B200_VCS_EXPERIMENTAL"] = "1"
+    os.environ["B200_TEST_EXPERIMENTAL"] = "1"
+    import test_vcs_rgbin_gpu as R
+    import test_vcs_cross_gpu as T
+    rng = np.random.default_rng(2)
+    while time.time() - t_start < budget and len(out["errors"]) <= 5:
+        iw, ih, ow, oh = (int(v) for v in rng.integers(1, 200, 4))
+        if rng.random() < 0.2:
+            ow = iw
+        if rng.random() < 0.2:
+            oh = ih
+        fi, fo = R.RGB_IN[int(rng.integers(0, 8))], R.YUV_OUT[int(rng.integers(0, 4))]
+        method = int(rng.integers(0, 10))
+        col = (int(rng.choice([2, 3, 4, 5, 6])), int(rng.choice([1, 2])), int(rng.choice([1, 2, 4, 6]))) if rng.random() < 0.5 else None
+        tag = f"{fi}-{fo} {iw}x{ih}-{ow}x{oh} m{method} {col}"
+        out["cases"] += 1
+        try:
+            frame = R.rgb_frame(iw, ih, int(rng.integers(0, 1000)))
+            want = R.expected((iw, ih, ow, oh), method, frame, fi, fo, col)
+            (got,), oi = R.convert((iw, ih, ow, oh), method, frame, fi, fo, col)
+            bad = T.planes_equal(got, want, oi, ow, oh, fo in ("NV12", "NV21"))
+            if bad:
+                out["failures"].append(tag + ": " + "; ".join(bad))
+            else:
+                out["ok"] += 1
+        except Exception as e:                                   # noqa: BLE001
+            out["errors"].append(tag + ": " + repr(e)[:300])
+    flush()
+    print(json.dumps({k: (v if not isinstance(v, list) else v[:8]) for k, v in out.items()}, indent=1))
+    return 0 if not out["failures"] and not out["errors"] else 1
 
 
 def main():
@@ -48,6 +83,8 @@ def main():
             out["errors"].append(tag + ": " + repr(e)[:300])
 
     odd_only = len(sys.argv) > 2 and sys.argv[2] == "odd"
+    if len(sys.argv) > 2 and sys.argv[2] == "rgb":
+        return rgb_mode(budget, t_start, out, flush)
     # 1. the pytest matrix (small shapes first)
     for size in [] if odd_only else sorted(T.SIZES, key=lambda s: s[0] * s[1]):
         for pair in T.PAIRS:
