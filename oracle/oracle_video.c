@@ -834,15 +834,18 @@ static void
 hscale_line_n (Scaler * s, const uint8_t * sl, uint8_t * dl, int dw, int ne)
 {
   int x, c, k;
-  if (s->n_taps >= 2 && !(s->n_taps == 2 && ne == 1) && !s->taps_s16)
+  if (s->n_taps >= 2 && !(s->n_taps == 2 && (ne == 1 || ne == 4)) && !s->taps_s16)
     scaler_quantize (s, 6);
   for (x = 0; x < dw; x++) {
     if (s->n_taps == 1) {
       memcpy (dl + ne * x, sl + ne * s->offset[x], ne);
-    } else if (s->n_taps == 2 && ne == 1) {
+    } else if (s->n_taps == 2 && (ne == 1 || ne == 4)) {
+      /* video_scale_h_2tap_1u8 (mono planes) / video_scale_h_2tap_4u8 (4-byte pixels): edge-aligned 16.16 stepping;
+       * 2-byte pixels (the interleaved UV plane) take the n-tap routine (video-scaler.c:1286-1292) */
       int tmp = x * s->inc, i0 = tmp >> 16, f = (tmp >> 8) & 0xff;
       int i1 = (i0 + 1 < s->in_size) ? i0 + 1 : i0;
-      dl[x] = (uint8_t) ((sl[i0] * (256 - f) + sl[i1] * f) >> 8);
+      for (c = 0; c < ne; c++)
+        dl[ne * x + c] = (uint8_t) ((sl[ne * i0 + c] * (256 - f) + sl[ne * i1 + c] * f) >> 8);
     } else {
       const int16_t *t = s->taps_s16 + (size_t) x * s->n_taps;
       for (c = 0; c < ne; c++) {
@@ -944,6 +947,30 @@ convert_planes (const OracleVcsDesc * d, const uint8_t * in, uint8_t * out)
 {
   int semi = d->out_format == ORC_FMT_NV12 || d->out_format == ORC_FMT_NV21;
   int n_planes = semi ? 2 : 3, i;
+  if (fmt_is_rgb (d->out_format)) {
+    /* table rows ARGB->ARGB ... BGRx->BGRx (video-converter.c:8879-8896): one plane of 4-byte pixels through
+     * gst_video_scaler_2d with the element's method; every byte, the alpha / padding one included, is a channel */
+    OracleResamplerOpts rs = d->rs;
+    Scaler hs, vs;
+    int need_h = d->in_width != d->out_width, need_v = d->in_height != d->out_height, y;
+    if (!need_h && !need_v) {
+      for (y = 0; y < d->out_height; y++)
+        memcpy (out + d->out_offset[0] + (size_t) y * d->out_stride[0], in + d->in_offset[0] + (size_t) y * d->in_stride[0],
+            (size_t) d->out_width * 4);
+      return 0;
+    }
+    if (need_h && scaler_init (&hs, &rs, d->in_width, d->out_width))
+      return -1;
+    if (need_v && scaler_init (&vs, &rs, d->in_height, d->out_height))
+      return -1;
+    scale_plane_2d (need_h ? &hs : NULL, need_v ? &vs : NULL, in + d->in_offset[0], d->in_stride[0], d->in_width,
+        out + d->out_offset[0], d->out_stride[0], d->out_width, d->out_height, 4);
+    if (need_h)
+      scaler_clear (&hs);
+    if (need_v)
+      scaler_clear (&vs);
+    return 0;
+  }
   int iw = d->in_width, ih = d->in_height, ow = d->out_width, oh = d->out_height;
   for (i = 0; i < n_planes; i++) {
     /* plane i of the output holds component i (Y,U,V) for I420 and (Y,V,U) for YV12; the source plane is the
@@ -1020,7 +1047,7 @@ oracle_vcs_convert (const OracleVcsDesc * d, const uint8_t * in, uint8_t * out)
   uint8_t *cur, *tmp, *mode;
   Scaler hs, vs;
   int have_h = iw != ow, have_v = ih != oh, pass;
-  int yuv_out = 0, out_site = 0, rgb_in = 0;
+  int yuv_out = 0, out_site = 0, rgb_in = 0, rgb_out = 0;
   long s0, s3;
 
   if (fmt_is_rgb (d->in_format)) {
@@ -1028,13 +1055,21 @@ oracle_vcs_convert (const OracleVcsDesc * d, const uint8_t * in, uint8_t * out)
      * that shrink, the RGB -> YUV matrix (chain_convert :1720-1868 -> video_converter_matrix8_table), the scalers
      * that grow, chroma down-sampling (RGB has no sub-sampling: only the down side exists, :2850-2895), 4:2:0 pack */
     int m_, r_;
-    if (!(d->out_format == ORC_FMT_I420 || d->out_format == ORC_FMT_YV12 || d->out_format == ORC_FMT_NV12 ||
-            d->out_format == ORC_FMT_NV21))
-      return -1;                /* RGB -> RGB: not restated */
-    if (oracle_vcs_matrix_rgb2yuv (d, im) != 0)
-      return -1;
-    rgb_in = yuv_out = 1;
-    rgb_in_out_colorimetry (d, &m_, &r_, &out_site);
+    if (d->out_format == d->in_format)
+      return convert_planes (d, in, out);
+    if (fmt_is_rgb (d->out_format)) {
+      /* another byte order: the chain with no matrix stage (both sides name the RGB matrix) and, at the default
+       * alpha value 1.0, no alpha stage either (convert_get_alpha_mode :2263-2294): unpack, scalers, pack */
+      rgb_in = rgb_out = 1;
+    } else {
+      if (!(d->out_format == ORC_FMT_I420 || d->out_format == ORC_FMT_YV12 || d->out_format == ORC_FMT_NV12 ||
+              d->out_format == ORC_FMT_NV21))
+        return -1;
+      if (oracle_vcs_matrix_rgb2yuv (d, im) != 0)
+        return -1;
+      rgb_in = yuv_out = 1;
+      rgb_in_out_colorimetry (d, &m_, &r_, &out_site);
+    }
   } else {
     int in_planar = d->in_format == ORC_FMT_I420 || d->in_format == ORC_FMT_YV12;
     int out_planar = d->out_format == ORC_FMT_I420 || d->out_format == ORC_FMT_YV12;
@@ -1064,7 +1099,7 @@ oracle_vcs_convert (const OracleVcsDesc * d, const uint8_t * in, uint8_t * out)
     free (line);
     return 0;
   }
-  if (!yuv_out && oracle_vcs_matrix (d, p, im) != 0)
+  if (!yuv_out && !rgb_out && oracle_vcs_matrix (d, p, im) != 0)
     return -1;
   if (rgb_in) {
     if (have_h && scaler_init (&hs, &d->rs, iw, ow))
@@ -1076,7 +1111,7 @@ oracle_vcs_convert (const OracleVcsDesc * d, const uint8_t * in, uint8_t * out)
       unpack_line_rgb (d, in, y, cur + (size_t) y * iw * 4);
     goto scale_passes;
   }
-  if (!yuv_out && (d->in_format == ORC_FMT_I420 || d->in_format == ORC_FMT_YV12) && iw == ow && ih == oh) {
+  if (!yuv_out && !rgb_in && (d->in_format == ORC_FMT_I420 || d->in_format == ORC_FMT_YV12) && iw == ow && ih == oh) {
     /* fast path (video-converter.c:8766-8800 table rows, keeps_size): convert_I420_BGRA / _ARGB /
      * _pack_ARGB (:6772-6988) -> video_orc_convert_I420_BGRA (video-orc.orc:1859-1911): the chroma
      * sample of row y>>1 is used as is for both of its pixels (no up-sampling filter), same mulhi
@@ -1139,11 +1174,11 @@ scale_passes:
   /* pass 0 = chain_scale(force=FALSE) before the matrix, pass 1 = chain_scale(force=TRUE)
    * after it (video-converter.c:2517-2531, :1685-1718) */
   for (pass = 0; pass < 2; pass++) {
-    if (pass == 1 && !yuv_out) {
+    if (pass == 1 && !yuv_out && !rgb_out) {
       for (y = 0; y < ch; y++)
         matrix_line (cur + (size_t) y * cw * 4, cw, p);
     }
-    if (pass == 1 && rgb_in) {
+    if (pass == 1 && rgb_in && yuv_out) {
       for (y = 0; y < ch; y++)
         matrix_line_rgb2yuv (cur + (size_t) y * cw * 4, cw, im);
     }

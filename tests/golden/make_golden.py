@@ -241,6 +241,23 @@ def video_rgb_in():
     json.dump(cases, open(os.path.join(HERE, "video_rgb_in_cases.json"), "w"), indent=1)
 
 
+def video_rgb_rgb():
+    """packed RGB -> packed RGB: same format (one-plane scaling) and another byte order (chain without matrix)"""
+    arrays, cases = {}, []
+    for fi, fo in [("BGRA", "BGRA"), ("RGBA", "RGBA"), ("xRGB", "xRGB"), ("BGRA", "RGBA"), ("ARGB", "BGRx"), ("RGBx", "ABGR")]:
+        for (iw, ih, ow, oh) in [(64, 48, 32, 24), (40, 30, 64, 48), (65, 49, 33, 25), (33, 17, 20, 31), (40, 90, 40, 31)]:
+            for m in (0, 1, 3, 9):
+                frame = np.random.default_rng(m + iw).integers(0, 256, iw * ih * 4, dtype=np.uint8)
+                r = ob.RefVcs(iw, ih, ow, oh, m, in_fmt=ob.FMT[fi], out_fmt=ob.FMT[fo])
+                out = r.convert(frame, np.zeros(ow * oh * 4, dtype=np.uint8))
+                r.close()
+                key = f"q_{fi}_{fo}_{iw}x{ih}_{ow}x{oh}_m{m}"
+                arrays[key] = out
+                cases.append({"key": key, "in_fmt": fi, "out_fmt": fo, "in": [iw, ih], "out": [ow, oh], "method": m, "seed": m + iw})
+    np.savez_compressed(os.path.join(HERE, "video_rgb_rgb.npz"), **arrays)
+    json.dump(cases, open(os.path.join(HERE, "video_rgb_rgb_cases.json"), "w"), indent=1)
+
+
 def compositor_420():
     """I420 / YV12 / NV12 / NV21 output"""
     o, r = ob.oracle(), ob.ref()
@@ -275,7 +292,7 @@ if __name__ == "__main__":
     only = set(sys.argv[1:])
     for name, fn in [("video", video), ("compositor", compositor), ("audio", audio), ("video_planar", video_planar),
                      ("audio_interpolated", audio_interpolated), ("audio_formats", audio_formats), ("compositor_420", compositor_420), ("video_yuv", video_yuv),
-                     ("video_cross", video_cross), ("video_rgb_in", video_rgb_in)]:
+                     ("video_cross", video_cross), ("video_rgb_in", video_rgb_in), ("video_rgb_rgb", video_rgb_rgb)]:
         if not only or name in only:
             fn()
     print("golden fixtures written to", HERE)

@@ -196,3 +196,12 @@ def test_video_rgb_to_420(case):
     d = ob.vcs_desc(iw, ih, ow, oh, m, in_fmt=ob.FMT[case["in_fmt"]], out_fmt=ob.FMT[case["out_fmt"]])
     d.out_matrix, d.out_range, d.out_chroma_site = case["out_matrix"], case["out_range"], case["out_site"]
     assert np.array_equal(ob.oracle_vcs_convert(d, frame), gold)
+
+
+@pytest.mark.parametrize("case", json.load(open(os.path.join(G, "video_rgb_rgb_cases.json"))), ids=lambda c: c["key"])
+def test_video_rgb_to_rgb(case):
+    gold = np.load(os.path.join(G, "video_rgb_rgb.npz"))[case["key"]]
+    (iw, ih), (ow, oh), m = case["in"], case["out"], case["method"]
+    frame = np.random.default_rng(case["seed"]).integers(0, 256, iw * ih * 4, dtype=np.uint8)
+    d = ob.vcs_desc(iw, ih, ow, oh, m, in_fmt=ob.FMT[case["in_fmt"]], out_fmt=ob.FMT[case["out_fmt"]])
+    assert np.array_equal(ob.oracle_vcs_convert(d, frame), gold)

@@ -479,3 +479,20 @@ def test_rgb_to_yuv_matrix_known_answers():
     d = ob.vcs_desc(640, 480, 640, 480, 1, in_fmt=ob.FMT["BGRA"], out_fmt=ob.FMT["NV12"])
     assert ob.oracle().oracle_vcs_matrix_rgb2yuv(C.byref(d), im) == 0
     assert list(im)[:12] == [66, 129, 25, 4096, -38, -74, 112, 32768, 112, -94, -18, 32768]
+
+
+@pytest.mark.parametrize("fi", RGB_IN)
+@pytest.mark.parametrize("fo", RGB_IN)
+def test_rgb_to_rgb_matches_reference(fi, fo):
+    """same format: the one-plane convert_scale_planes rows (video-converter.c:8879-8896; 4-byte pixels through
+    gst_video_scaler_2d, stepping 2-tap horizontal, every byte a channel) — the compositor's scaled RGBA pads; another
+    byte order: the chain without matrix or alpha stage"""
+    for (iw, ih, ow, oh) in [(64, 48, 32, 24), (40, 30, 64, 48), (33, 17, 20, 31), (100, 100, 150, 50), (40, 90, 40, 31),
+                             (50, 21, 50, 21), (3, 5, 7, 2)]:
+        frame = _rgb_frame(iw, ih, 4)
+        for method in (0, 1, 3, 4, 9):
+            got = ob.oracle_vcs_convert(ob.vcs_desc(iw, ih, ow, oh, method, in_fmt=ob.FMT[fi], out_fmt=ob.FMT[fo]), frame)
+            r = ob.RefVcs(iw, ih, ow, oh, method, in_fmt=ob.FMT[fi], out_fmt=ob.FMT[fo])
+            want = r.convert(frame, np.zeros(got.size, dtype=np.uint8))
+            r.close()
+            assert np.array_equal(got, want), f"{iw}x{ih}->{ow}x{oh} method {method}"
