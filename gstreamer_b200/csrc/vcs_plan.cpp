@@ -583,13 +583,38 @@ int build_planes (VcsPlan * p, const FilterSpec & f)
 // ARGB, the scalers that shrink, the RGB -> YUV table matrix, the scalers that grow, chroma down-sampling (RGB has no
 // sub-sampling, so only the down side exists and it exists at every size: video-converter.c:2850-2895), 4:2:0 pack.
 // Generic kernel + vcs_down420_kernel.  Written without device access: opt-in until it has run green on a GPU.
+// packed RGB -> the same packed RGB format at another size (a compositor's scaled RGBA pads): the reference's one-plane
+// convert_scale_planes rows (video-converter.c:8879-8896): 4-byte pixels through gst_video_scaler_2d with the element's
+// method, the stepping 2-tap horizontal scaler (video_scale_h_2tap_4u8), every byte - alpha or padding included - a
+// channel.  vcs_planes_kernel with ne = 4.
+static int build_rgb_same_plan (VcsPlan * p)
+{
+  const b200_video_info *in = &p->in, *out = &p->out;
+  const int iw = in->width, ih = in->height, ow = out->width, oh = out->height;
+  if (in->stride[0] < iw * 4 || out->stride[0] < ow * 4) return B200_ERR_INVALID_ARG;
+  const FilterSpec f = filter_from_method (p->cfg);
+  p->planes_mode = true;
+  p->n_planes = 1;
+  PlanePlan & q = p->planes[0];
+  q = PlanePlan ();
+  q.src_plane = 0; q.iw = iw; q.ih = ih; q.ow = ow; q.oh = oh; q.ne = 4;
+  if (iw == ow && ih == oh) { q.mode = PM_COPY; return B200_OK; }
+  q.mode = PM_SCALE;
+  q.have_h = iw != ow; q.have_v = ih != oh;
+  if (q.have_h) scaled_axis (&q.h, f, iw, ow, true, true); else identity_axis (&q.h, iw);
+  if (q.have_v) scaled_axis (&q.v, f, ih, oh, false); else identity_axis (&q.v, ih);
+  q.h_first = !(q.have_h && q.have_v) || (int64_t) q.v.offset[oh - 1] <= (int64_t) oh;
+  return B200_OK;
+}
+
 static int build_rgb_in_plan (VcsPlan * p)
 {
   const b200_video_info *in = &p->in, *out = &p->out;
   if (!getenv ("B200_VCS_EXPERIMENTAL")) return B200_ERR_UNSUPPORTED;
+  if (out->format == in->format) return build_rgb_same_plan (p);
   const bool out_pl = out->format == B200_VIDEO_FORMAT_I420 || out->format == B200_VIDEO_FORMAT_YV12;
   const bool out_semi = out->format == B200_VIDEO_FORMAT_NV12 || out->format == B200_VIDEO_FORMAT_NV21;
-  if (!out_pl && !out_semi) return B200_ERR_UNSUPPORTED;           // RGB -> RGB: not built
+  if (!out_pl && !out_semi) return B200_ERR_UNSUPPORTED;           // RGB -> another RGB byte order: not built
   if (in->stride[0] < in->width * 4 || (in->stride[0] & 3) || (in->offset[0] & 3)) return B200_ERR_INVALID_ARG;
   const int ocw = (out->width + 1) / 2;
   if (out->stride[0] < out->width) return B200_ERR_INVALID_ARG;

@@ -1,5 +1,6 @@
 // gstreamer_b200/csrc/vcs_planes.cuh — YUV -> same YUV family (NV12->NV12, NV21->NV21, I420/YV12 ->
-// I420/YV12): the reference's plane-scaling fast path (product code, sm_100a).
+// I420/YV12) and packed RGB -> the same packed RGB (one plane of 4-byte pixels, opt-in): the reference's
+// plane-scaling fast path (product code, sm_100a).
 //
 //   convert_scale_planes            gst-libs/gst/video/video-converter.c:7757-7769
 //   setup_scale                     :7958-8245  (which kernel each plane gets; built on the host, vcs_plan.cpp)
@@ -107,7 +108,7 @@ vcs_planes_kernel (const PlanesParams P, const VcsBatch frames)
   const bool live = xb < wbytes && y < Q.oh;
   const uint8_t *__restrict__ src = frames.in[frame] + Q.src_off;
   uint8_t *__restrict__ dst = frames.out[frame] + Q.dst_off;
-  const int nes = Q.ne >> 1;                                        // ne is 1 or 2: divide by shifting
+  const int nes = Q.ne >> 1;                                        // ne is 1, 2 or 4 (shift 0, 1, 2): divide by shifting
   const int x = min (xb, wbytes - 1) >> nes, c = min (xb, wbytes - 1) - (x << nes);
   int v = 0;
   if (Q.mode != PM_SCALE) {
