@@ -179,6 +179,50 @@ vcs_transform_caps (GstBaseTransform * trans, GstPadDirection direction, GstCaps
   return res;
 }
 
+/* what transfer_colorimetry_from_input does in the stock element (gstvideoconvertscale.c:1335-1427): a YUV output of
+ * a YUV input takes the input's colorimetry intact and - the sub-sampling is 4:2:0 on both sides here - its
+ * chroma-site; that is what keeps the NV12 <-> I420 chain free of a matrix stage (b200_vcs_create refuses one).
+ * Across an RGB <-> YUV change the output keeps the defaults of its own size. */
+static void
+vcs_transfer_colorimetry (GstCaps * in_caps, GstCaps * out_caps)
+{
+  GstStructure *in = gst_caps_get_structure (in_caps, 0), *out = gst_caps_get_structure (out_caps, 0);
+  const gchar *fi = gst_structure_get_string (in, "format"), *fo = gst_structure_get_string (out, "format");
+  const GValue *v;
+  if (!fi || !fo)
+    return;
+  if (!GST_VIDEO_FORMAT_INFO_IS_YUV (gst_video_format_get_info (gst_video_format_from_string (fi))) ||
+      !GST_VIDEO_FORMAT_INFO_IS_YUV (gst_video_format_get_info (gst_video_format_from_string (fo))))
+    return;
+  if (!gst_structure_has_field (out, "colorimetry") && (v = gst_structure_get_value (in, "colorimetry")))
+    gst_structure_set_value (out, "colorimetry", v);
+  if (!gst_structure_has_field (out, "chroma-site") && (v = gst_structure_get_value (in, "chroma-site")))
+    gst_structure_set_value (out, "chroma-site", v);
+}
+
+/* fixate_caps (gstvideoconvertscale.c:1431-1960, reduced to what this element negotiates): prefer the input format
+ * and size when the peer allows them, carry the colorimetry over, let the default fixation settle the rest */
+static GstCaps *
+vcs_fixate_caps (GstBaseTransform * trans, GstPadDirection direction, GstCaps * caps, GstCaps * othercaps)
+{
+  GstStructure *in = gst_caps_get_structure (caps, 0), *out;
+  const gchar *fmt = gst_structure_get_string (in, "format");
+  gint w = 0, h = 0;
+  (void) trans;
+  othercaps = gst_caps_truncate (gst_caps_make_writable (othercaps));
+  out = gst_caps_get_structure (othercaps, 0);
+  if (fmt && gst_structure_has_field (out, "format"))
+    gst_structure_fixate_field_string (out, "format", fmt);
+  if (gst_structure_get_int (in, "width", &w))
+    gst_structure_fixate_field_nearest_int (out, "width", w);
+  if (gst_structure_get_int (in, "height", &h))
+    gst_structure_fixate_field_nearest_int (out, "height", h);
+  othercaps = gst_caps_fixate (othercaps);
+  if (direction == GST_PAD_SINK)
+    vcs_transfer_colorimetry (caps, othercaps);
+  return othercaps;
+}
+
 static gboolean
 vcs_rebuild (GstCudaVideoConvertScale * self)
 {
@@ -320,6 +364,7 @@ gst_cuda_video_convert_scale_class_init (GstCudaVideoConvertScaleClass * klass)
   trans->stop = vcs_stop;
   trans->query = vcs_query;
   trans->transform_caps = vcs_transform_caps;
+  trans->fixate_caps = vcs_fixate_caps;
   trans->set_caps = vcs_set_caps;
   trans->transform = vcs_transform;
   trans->decide_allocation = vcs_decide_allocation;
