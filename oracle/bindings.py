@@ -45,7 +45,7 @@ class VcsDesc(C.Structure):
                 ("in_range", C.c_int), ("in_chroma_site", C.c_int), ("out_format", C.c_int),
                 ("out_width", C.c_int), ("out_height", C.c_int), ("out_stride", C.c_int * 4),
                 ("out_offset", C.c_size_t * 4), ("rs", RS),
-                ("out_matrix", C.c_int), ("out_chroma_site", C.c_int), ("out_range", C.c_int)]
+                ("out_matrix", C.c_int), ("out_chroma_site", C.c_int), ("out_range", C.c_int), ("force_resample", C.c_int)]
 
 
 class OraclePad(C.Structure):
@@ -74,6 +74,9 @@ def oracle():
         o.oracle_vcs_matrix.argtypes = [C.POINTER(VcsDesc), P, P]
         o.oracle_vcs_convert.argtypes = [C.POINTER(VcsDesc), P, P]
         o.oracle_vcs_matrix_rgb2yuv.argtypes = [C.POINTER(VcsDesc), P]
+        o.oracle_vcs_borders.argtypes = [C.c_int] * 4 + [P]
+        o.oracle_vcs_borders.restype = None
+        o.oracle_vcs_convert_dest.argtypes = [C.POINTER(VcsDesc)] + [C.c_int] * 4 + [C.c_uint32, P, P]
         if hasattr(o, "oracle_compositor"):
             o.oracle_compositor.argtypes = [C.c_int, P, C.c_int, C.c_int, C.c_int, C.c_int,
                                             C.POINTER(OraclePad), C.c_int]
@@ -113,6 +116,11 @@ def ref():
         r = C.CDLL(REF_SO)
         P = C.c_void_p
         r.ref_vcs_new.restype = P
+        if hasattr(r, 'ref_vcs_next_dest'):
+            r.ref_vcs_next_dest.argtypes = [C.c_int] * 4
+            r.ref_vcs_next_dest.restype = None
+            r.ref_vcs_next_border_argb.argtypes = [C.c_uint]
+            r.ref_vcs_next_border_argb.restype = None
         r.ref_vcs_new.argtypes = ([C.c_int] * 3 + [P] * 2 + [C.c_int] * 3) * 2 + [C.c_int] * 3 + [C.c_double] * 3
         r.ref_vcs_convert.argtypes = [P, P, P]
         r.ref_vcs_free.argtypes = [P]
@@ -180,7 +188,11 @@ class RefVcs:
     """The reference's own GstVideoConverter (compiled in place), element option mapping."""
 
     def __init__(self, iw, ih, ow, oh, method, in_fmt=23, out_fmt=12, site=-1, matrix=-1, rng=-1,
-                 n_threads=1, out_matrix=-1, out_rng=-1, out_site=-1):
+                 n_threads=1, out_matrix=-1, out_rng=-1, out_site=-1, dest=None, border_argb=None):
+        if border_argb is not None:
+            ref().ref_vcs_next_border_argb(int(border_argb))
+        if dest is not None:
+            ref().ref_vcs_next_dest(*[int(v) for v in dest])
         self.h = ref().ref_vcs_new(in_fmt, iw, ih, None, None, matrix, rng, site,
                                    out_fmt, ow, oh, None, None, out_matrix, out_rng, out_site,
                                    int(method), n_threads, 4, 2.0, 1.0, 0.0)
@@ -205,6 +217,23 @@ class RefVcs:
             self.close()
         except Exception:
             pass
+
+
+def vcs_borders(iw, ih, ow, oh):
+    """the element's add-borders rectangle (x, y, w, h) for pixel aspect ratio 1/1 on both sides"""
+    d = (C.c_int * 4)()
+    oracle().oracle_vcs_borders(iw, ih, ow, oh, d)
+    return tuple(d)
+
+
+def oracle_vcs_convert_dest(d, frame, dest, border_argb=0xff000000, fill=0):
+    frame = np.ascontiguousarray(frame, dtype=np.uint8)
+    out = np.full(vcs_sizes(d)[1], fill, dtype=np.uint8)
+    st = oracle().oracle_vcs_convert_dest(C.byref(d), dest[0], dest[1], dest[2], dest[3], border_argb, frame.ctypes.data,
+                                          out.ctypes.data)
+    if st != 0:
+        raise RuntimeError(f"oracle_vcs_convert_dest -> {st}")
+    return out
 
 
 # ------------------------------------------------------------------- synthetic inputs

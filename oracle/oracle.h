@@ -67,6 +67,9 @@ typedef struct {
   /* packed RGB input -> 4:2:0 output: 0 = caps default of the output size (the fixation forwards only primaries and
    * transfer across a YUV/RGB change, gstvideoconvertscale.c:1394-1408); out_range 0 = 16-235 */
   int out_range;
+  /* set by oracle_vcs_convert_dest: the chroma resamplers of a 4:2:0 -> other 4:2:0 chain exist because the input
+   * size differs from the size of the whole OUTPUT FRAME, even if it equals the destination rectangle's */
+  int force_resample;
 } OracleVcsDesc;
 
 /* fills the default system-memory layout (video-info.c fill_planes :1053-1063, :890-894)
@@ -82,6 +85,15 @@ int oracle_vcs_matrix_rgb2yuv (const OracleVcsDesc * d, int im[4][4]);
 int oracle_vcs_matrix (const OracleVcsDesc * d, int p[5], int im[4][4]);
 /* whole-frame conversion; 0 on success */
 int oracle_vcs_convert (const OracleVcsDesc * d, const uint8_t * in, uint8_t * out);
+
+/* the element's add-borders geometry (gstvideoconvertscale.c:926-952): borders that keep the display aspect ratio
+ * when both pixel aspect ratios are 1/1.  Returns dest x, y, width, height inside the out_w x out_h frame. */
+void oracle_vcs_borders (int in_w, int in_h, int out_w, int out_h, int dest[4]);
+/* whole-frame conversion into the destination rectangle of the output frame, the rest filled with the border colour
+ * (GST_VIDEO_CONVERTER_OPT_DEST_*, fill-border, border-argb default 0xff000000: video-converter.c:2333-2366,
+ * setup_borderline :2189-2258, convert_fill_border :7190-7300).  d describes the WHOLE output frame. */
+int oracle_vcs_convert_dest (const OracleVcsDesc * d, int dest_x, int dest_y, int dest_w, int dest_h,
+    uint32_t border_argb, const uint8_t * in, uint8_t * out);
 
 /* ---------------- compositor ------------------------------------------------- */
 enum { ORC_BG_CHECKER = 0, ORC_BG_BLACK = 1, ORC_BG_WHITE = 2, ORC_BG_TRANSPARENT = 3 };

@@ -1088,7 +1088,7 @@ oracle_vcs_convert (const OracleVcsDesc * d, const uint8_t * in, uint8_t * out)
       out_site = d->out_chroma_site ? d->out_chroma_site : d->in_chroma_site;
     }
   }
-  if (yuv_out && !rgb_in && iw == ow && ih == oh && out_site == d->in_chroma_site) {
+  if (yuv_out && !rgb_in && iw == ow && ih == oh && out_site == d->in_chroma_site && !d->force_resample) {
     /* video_converter_compute_resample (:2850-2895): same sub-sampling, site and size -> no chroma resampler
      * on either side; unpack replicates every chroma sample and pack reads it back */
     uint8_t *line = malloc ((size_t) iw * 4);
@@ -1250,5 +1250,175 @@ scale_passes:
     scaler_clear (&hs);
   if (have_v)
     scaler_clear (&vs);
+  return 0;
+}
+
+
+/* ===================================================================== borders */
+
+static unsigned long long
+gcd_u64 (unsigned long long a, unsigned long long b)
+{
+  while (b) {
+    unsigned long long t = a % b;
+    a = b;
+    b = t;
+  }
+  return a;
+}
+
+void
+oracle_vcs_borders (int in_w, int in_h, int out_w, int out_h, int dest[4])
+{
+  /* gst_video_convert_scale_set_info (gstvideoconvertscale.c:920-952) with par 1/1 on both sides:
+   * from_dar = in_w/in_h and to_dar = out_w/out_h reduced (gst_util_fraction_multiply); different ->
+   * to_h = out_w * d / n (gst_util_uint64_scale_int: floor); fits -> bars above/below, else to_w = out_h * n / d */
+  unsigned long long g1 = gcd_u64 (in_w, in_h), g2 = gcd_u64 (out_w, out_h);
+  int n = (int) (in_w / g1), dd = (int) (in_h / g1);
+  int borders_w = 0, borders_h = 0;
+  if (n != (int) (out_w / g2) || dd != (int) (out_h / g2)) {
+    int to_h = (int) (((unsigned long long) out_w * dd) / n);
+    if (to_h <= out_h)
+      borders_h = out_h - to_h;
+    else
+      borders_w = out_w - (int) (((unsigned long long) out_h * n) / dd);
+  }
+  dest[0] = borders_w / 2;
+  dest[1] = borders_h / 2;
+  dest[2] = out_w - borders_w;
+  dest[3] = out_h - borders_h;
+}
+
+int
+oracle_vcs_convert_dest (const OracleVcsDesc * d, int dest_x, int dest_y, int dest_w, int dest_h, uint32_t border_argb,
+    const uint8_t * in, uint8_t * out)
+{
+  OracleVcsDesc q = *d;
+  const int W = d->out_width, H = d->out_height;
+  const int yuv = !fmt_is_rgb (d->out_format);
+  const int planar = d->out_format == ORC_FMT_I420 || d->out_format == ORC_FMT_YV12;
+  int x, y, c, st;
+  uint8_t argb[4] = { (uint8_t) (border_argb >> 24), (uint8_t) (border_argb >> 16), (uint8_t) (border_argb >> 8),
+    (uint8_t) border_argb };
+  uint8_t px[4];
+  if (yuv) {                    /* out_x / out_y are rounded down to the chroma grid (video-converter.c:2335-2336) */
+    dest_x &= ~1;
+    dest_y &= ~1;
+  }
+  /* :2338-2362 */
+  if (dest_w > W - dest_x)
+    dest_w = W - dest_x;
+  dest_w = CLAMPI (dest_w, 0, W);
+  if (dest_h > H - dest_y)
+    dest_h = H - dest_y;
+  dest_h = CLAMPI (dest_h, 0, H);
+  if (dest_w < 1 || dest_h < 1)
+    return -1;                  /* an empty rectangle: no chain is built (:2509-2510) and the rows of the rectangle are
+                                 * never touched - degenerate, not restated */
+  /* the chain runs on the rectangle: same layout, shifted plane origins; colorimetry defaults stay those of the
+   * whole frame */
+  q.out_width = dest_w;
+  q.out_height = dest_h;
+  /* video_converter_compute_resample (:2850-2895) compares the input with the whole output frame */
+  q.force_resample = d->in_width != W || d->in_height != H;
+  if (!yuv) {
+    q.out_offset[0] += (size_t) dest_y * d->out_stride[0] + (size_t) dest_x * 4;
+  } else {
+    q.out_offset[0] += (size_t) dest_y * d->out_stride[0] + dest_x;
+    if (planar) {
+      q.out_offset[1] += (size_t) (dest_y / 2) * d->out_stride[1] + dest_x / 2;
+      q.out_offset[2] += (size_t) (dest_y / 2) * d->out_stride[2] + dest_x / 2;
+    } else
+      q.out_offset[1] += (size_t) (dest_y / 2) * d->out_stride[1] + dest_x;
+    if (fmt_is_rgb (d->in_format)) {
+      int m_, r_, s_;
+      rgb_in_out_colorimetry (d, &m_, &r_, &s_);
+      q.out_matrix = m_;
+      q.out_range = r_;
+      q.out_chroma_site = s_;
+    }
+  }
+  st = oracle_vcs_convert (&q, in, out);
+  if (st != 0)
+    return st;
+  if (dest_w == W && dest_h == H)
+    return 0;
+  /* border pixel: setup_borderline (:2189-2258) */
+  if (!yuv) {
+    switch (d->out_format) {
+      case ORC_FMT_BGRA: case ORC_FMT_BGRx: px[0] = argb[3]; px[1] = argb[2]; px[2] = argb[1]; px[3] = argb[0]; break;
+      case ORC_FMT_RGBA: case ORC_FMT_RGBx: px[0] = argb[1]; px[1] = argb[2]; px[2] = argb[3]; px[3] = argb[0]; break;
+      case ORC_FMT_ABGR: case ORC_FMT_xBGR: px[0] = argb[0]; px[1] = argb[3]; px[2] = argb[2]; px[3] = argb[1]; break;
+      default: memcpy (px, argb, 4); break;
+    }
+    for (y = 0; y < H; y++)
+      for (x = 0; x < W; x++)
+        if (y < dest_y || y >= dest_y + dest_h || x < dest_x || x >= dest_x + dest_w)
+          memcpy (out + d->out_offset[0] + (size_t) y * d->out_stride[0] + 4 * (size_t) x, px, 4);
+  } else {
+    /* identity -> compute_matrix_to_YUV (force) with the OUTPUT colorimetry -> rint (no x256 here: the matrix maps
+     * [0,1] RGB... it is applied to 8-bit r,g,b and shifted by 8, offsets added by hand: :2207-2226) */
+    Mat m;
+    double Kr, Kb, Kg, xk;
+    int im[3][3], matrix, range, site, yv, uv, vv, cx0, cy0, cw, chh, CW, CH;
+    if (fmt_is_rgb (d->in_format))
+      rgb_in_out_colorimetry (d, &matrix, &range, &site);
+    else {
+      matrix = d->out_matrix ? d->out_matrix : d->in_matrix;
+      range = d->out_range ? d->out_range : d->in_range;
+    }
+    mat_identity (&m);
+    if (kr_kb (matrix, &Kr, &Kb))
+      return -1;
+    Kg = 1.0 - Kr - Kb;
+    {
+      Mat k;
+      mat_identity (&k);
+      k.dm[0][0] = Kr; k.dm[0][1] = Kg; k.dm[0][2] = Kb;
+      xk = 1 / (2 * (1 - Kb));
+      k.dm[1][0] = -xk * Kr; k.dm[1][1] = -xk * Kg; k.dm[1][2] = xk * (1 - Kb);
+      xk = 1 / (2 * (1 - Kr));
+      k.dm[2][0] = xk * (1 - Kr); k.dm[2][1] = -xk * Kg; k.dm[2][2] = -xk * Kb;
+      mat_mul (&m, &k, &m);
+    }
+    if (range == ORC_RANGE_16_235) {
+      mat_scale (&m, (float) 219, (float) 224, (float) 224);
+      mat_offset (&m, 16, 128, 128);
+    } else {
+      mat_scale (&m, (float) 255, (float) 255, (float) 255);
+      mat_offset (&m, 0, 128, 128);
+    }
+    for (y = 0; y < 3; y++)
+      for (x = 0; x < 3; x++)
+        im[y][x] = (int) rint (m.dm[y][x]);
+    yv = 16 + ((argb[1] * im[0][0] + argb[2] * im[0][1] + argb[3] * im[0][2]) >> 8);
+    uv = 128 + ((argb[1] * im[1][0] + argb[2] * im[1][1] + argb[3] * im[1][2]) >> 8);
+    vv = 128 + ((argb[1] * im[2][0] + argb[2] * im[2][1] + argb[3] * im[2][2]) >> 8);
+    yv = CLAMPI (yv, 0, 255);
+    uv = CLAMPI (uv, 0, 255);
+    vv = CLAMPI (vv, 0, 255);
+    for (y = 0; y < H; y++)
+      for (x = 0; x < W; x++)
+        if (y < dest_y || y >= dest_y + dest_h || x < dest_x || x >= dest_x + dest_w)
+          out[d->out_offset[0] + (size_t) y * d->out_stride[0] + x] = (uint8_t) yv;
+    /* chroma planes: GST_VIDEO_FORMAT_INFO_SCALE_WIDTH / _HEIGHT round up (convert_fill_border :7209-7221) */
+    cx0 = (dest_x + 1) / 2; cy0 = (dest_y + 1) / 2; cw = (dest_w + 1) / 2; chh = (dest_h + 1) / 2;
+    CW = (W + 1) / 2; CH = (H + 1) / 2;
+    for (y = 0; y < CH; y++)
+      for (x = 0; x < CW; x++) {
+        if (!(y < cy0 || y >= cy0 + chh || x < cx0 || x >= cx0 + cw))
+          continue;
+        if (planar) {
+          const int pu = d->out_format == ORC_FMT_YV12 ? 2 : 1, pv = 3 - pu;
+          out[d->out_offset[pu] + (size_t) y * d->out_stride[pu] + x] = (uint8_t) uv;
+          out[d->out_offset[pv] + (size_t) y * d->out_stride[pv] + x] = (uint8_t) vv;
+        } else {
+          const int ui = d->out_format == ORC_FMT_NV21 ? 1 : 0;
+          out[d->out_offset[1] + (size_t) y * d->out_stride[1] + 2 * x + ui] = (uint8_t) uv;
+          out[d->out_offset[1] + (size_t) y * d->out_stride[1] + 2 * x + (ui ^ 1)] = (uint8_t) vv;
+        }
+      }
+    (void) c;
+  }
   return 0;
 }

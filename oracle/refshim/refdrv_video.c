@@ -70,6 +70,26 @@ ref_video_format_from_string (const char *s)
   return (int) gst_video_format_from_string (s);
 }
 
+/* the element's DAR-preserving borders (gstvideoconvertscale.c:926-952 -> GST_VIDEO_CONVERTER_OPT_DEST_*, :1068-1072):
+ * the destination rectangle of the NEXT ref_vcs_new() call; w < 0 = the whole output frame */
+static int next_dest[4] = { 0, 0, -1, -1 };
+static unsigned next_border = 0xff000000u;      /* DEFAULT_OPT_BORDER_ARGB, video-converter.c:778 */
+
+void
+ref_vcs_next_border_argb (unsigned argb)
+{
+  next_border = argb;
+}
+
+void
+ref_vcs_next_dest (int x, int y, int w, int h)
+{
+  next_dest[0] = x;
+  next_dest[1] = y;
+  next_dest[2] = w;
+  next_dest[3] = h;
+}
+
 /* in_cm / in_range / in_site: -1 = caps default.  strides NULL = default layout. */
 RefVcs *
 ref_vcs_new (int in_format, int in_w, int in_h, const int *in_stride,
@@ -160,10 +180,10 @@ ref_vcs_new (int in_format, int in_w, int in_h, const int *in_stride,
       GST_VIDEO_RESAMPLER_OPT_ENVELOPE, G_TYPE_DOUBLE, envelope,
       GST_VIDEO_RESAMPLER_OPT_SHARPNESS, G_TYPE_DOUBLE, sharpness,
       GST_VIDEO_RESAMPLER_OPT_SHARPEN, G_TYPE_DOUBLE, sharpen,
-      GST_VIDEO_CONVERTER_OPT_DEST_X, G_TYPE_INT, 0,
-      GST_VIDEO_CONVERTER_OPT_DEST_Y, G_TYPE_INT, 0,
-      GST_VIDEO_CONVERTER_OPT_DEST_WIDTH, G_TYPE_INT, out_w,
-      GST_VIDEO_CONVERTER_OPT_DEST_HEIGHT, G_TYPE_INT, out_h,
+      GST_VIDEO_CONVERTER_OPT_DEST_X, G_TYPE_INT, next_dest[2] < 0 ? 0 : next_dest[0],
+      GST_VIDEO_CONVERTER_OPT_DEST_Y, G_TYPE_INT, next_dest[2] < 0 ? 0 : next_dest[1],
+      GST_VIDEO_CONVERTER_OPT_DEST_WIDTH, G_TYPE_INT, next_dest[2] < 0 ? out_w : next_dest[2],
+      GST_VIDEO_CONVERTER_OPT_DEST_HEIGHT, G_TYPE_INT, next_dest[2] < 0 ? out_h : next_dest[3],
       GST_VIDEO_CONVERTER_OPT_DITHER_METHOD, GST_TYPE_VIDEO_DITHER_METHOD, dither,
       GST_VIDEO_CONVERTER_OPT_DITHER_QUANTIZATION, G_TYPE_UINT, 1u,
       GST_VIDEO_CONVERTER_OPT_CHROMA_RESAMPLER_METHOD, GST_TYPE_VIDEO_RESAMPLER_METHOD,
@@ -176,7 +196,11 @@ ref_vcs_new (int in_format, int in_w, int in_h, const int *in_stride,
       GST_VIDEO_CONVERTER_OPT_PRIMARIES_MODE, GST_TYPE_VIDEO_PRIMARIES_MODE,
       GST_VIDEO_PRIMARIES_MODE_NONE,
       GST_VIDEO_CONVERTER_OPT_THREADS, G_TYPE_UINT, (guint) n_threads, NULL);
+  if (next_border != 0xff000000u)
+    gst_structure_set_static_str (options, GST_VIDEO_CONVERTER_OPT_BORDER_ARGB, G_TYPE_UINT, (guint) next_border, NULL);
+  next_border = 0xff000000u;
 
+  next_dest[2] = next_dest[3] = -1;
   if (method < 0) {
     /* GstVideoAggregatorConvertPad without a converter-config: gst_video_converter_new (..., NULL)
      * (gstvideoaggregator.c:508-513) — every option at its default */

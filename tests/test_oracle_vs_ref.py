@@ -496,3 +496,53 @@ def test_rgb_to_rgb_matches_reference(fi, fo):
             want = r.convert(frame, np.zeros(got.size, dtype=np.uint8))
             r.close()
             assert np.array_equal(got, want), f"{iw}x{ih}->{ow}x{oh} method {method}"
+
+
+# ------------------------------------------------------------------- destination rectangle + borders (add-borders)
+def test_add_borders_geometry():
+    """gst_video_convert_scale_set_info (gstvideoconvertscale.c:920-952), pixel aspect ratio 1/1 on both sides"""
+    assert ob.vcs_borders(1920, 1080, 1280, 720) == (0, 0, 1280, 720)          # same display aspect ratio: none
+    assert ob.vcs_borders(1920, 1080, 1280, 1024) == (0, 152, 1280, 720)       # bars above / below
+    assert ob.vcs_borders(640, 480, 1920, 1080) == (240, 0, 1440, 1080)        # pillar box
+    assert ob.vcs_borders(100, 100, 150, 50) == (50, 0, 50, 50)
+    assert ob.vcs_borders(7, 3, 10, 10) == (0, 3, 10, 4)                       # 10*3/7 = 4 (floor), borders 6 -> y = 3
+
+
+@pytest.mark.parametrize("pair", [("NV12", "BGRA"), ("I420", "RGBA"), ("NV12", "NV12"), ("I420", "YV12"), ("NV12", "I420"),
+                                  ("YV12", "NV21"), ("BGRA", "NV12"), ("RGBA", "I420"), ("BGRA", "BGRA")],
+                         ids=lambda p: "%s-%s" % p)
+def test_destination_rectangle_and_borders_match_reference(pair):
+    """GST_VIDEO_CONVERTER_OPT_DEST_X/Y/WIDTH/HEIGHT as the element sets them for add-borders, and arbitrary rectangles;
+    border colour: the default opaque black and two others (setup_borderline's RGB -> YUV of the border pixel)"""
+    rnd = np.random.default_rng(17)
+    fi, fo = pair
+    rgb_in = fi in RGB_IN
+    checked = 0
+    for t in range(40):
+        iw, ih, W, H = (int(v) for v in rnd.integers(2, 70, 4))
+        method = int(rnd.choice([0, 1, 3, 4, 9]))
+        if t % 2:
+            dest = ob.vcs_borders(iw, ih, W, H)
+        else:
+            dw, dh = int(rnd.integers(1, W + 1)), int(rnd.integers(1, H + 1))
+            dest = (int(rnd.integers(0, W - dw + 1)), int(rnd.integers(0, H - dh + 1)), dw, dh)
+        border = [0xff000000, 0x80ff4020, 0xff10c0f0][t % 3]
+        if dest[2] < 1 or dest[3] < 1:
+            continue                # extreme aspect ratios leave an empty rectangle: degenerate in the reference too
+        frame = _rgb_frame(iw, ih, t) if rgb_in else (ob.i420_random_frame(iw, ih, t) if fi in ("I420", "YV12") else ob.nv12_random_frame(iw, ih, t))
+        d = ob.vcs_desc(iw, ih, W, H, method, in_fmt=ob.FMT[fi], out_fmt=ob.FMT[fo])
+        kw = {}
+        if not rgb_in and fo not in RGB_IN:
+            kw = dict(matrix=d.in_matrix, out_matrix=d.in_matrix, site=d.in_chroma_site, out_site=d.in_chroma_site)
+        got = ob.oracle_vcs_convert_dest(d, frame, dest, border)
+        r = ob.RefVcs(iw, ih, W, H, method, in_fmt=ob.FMT[fi], out_fmt=ob.FMT[fo], dest=dest, border_argb=border, **kw)
+        want = r.convert(frame, np.zeros(got.size, dtype=np.uint8))
+        r.close()
+        if not np.array_equal(got, want):
+            dw, dh = dest[2], dest[3]
+            if fo not in RGB_IN or fi not in RGB_IN:            # the two reference defect classes, on the rectangle's size
+                if _vfirst(iw, ih, dw, dh) or (method == 0 or ih == 1) and dh > ih:
+                    continue
+            assert False, (iw, ih, W, H, dest, method)
+        checked += 1
+    assert checked >= 25
