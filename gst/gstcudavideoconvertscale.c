@@ -32,7 +32,7 @@ static GstStaticPadTemplate sink_tmpl = GST_STATIC_PAD_TEMPLATE ("sink", GST_PAD
 static GstStaticPadTemplate src_tmpl = GST_STATIC_PAD_TEMPLATE ("src", GST_PAD_SRC, GST_PAD_ALWAYS,
     GST_STATIC_CAPS (CUDA_CAPS (SRC_FORMATS)));
 
-enum { PROP_0, PROP_METHOD, PROP_ENVELOPE, PROP_SHARPNESS, PROP_SHARPEN, PROP_DEVICE_ID };
+enum { PROP_0, PROP_METHOD, PROP_ENVELOPE, PROP_SHARPNESS, PROP_SHARPEN, PROP_ADD_BORDERS, PROP_DEVICE_ID };
 
 typedef struct
 {
@@ -40,6 +40,7 @@ typedef struct
   /* properties (defaults: gstvideoconvertscale.c:130-144) */
   gint method;
   gdouble envelope, sharpness, sharpen;
+  gboolean add_borders;           /* DEFAULT_PROP_ADD_BORDERS TRUE, gstvideoconvertscale.c:131 */
   gint device_id;
   gboolean config_changed;
   /* negotiated state */
@@ -87,6 +88,7 @@ vcs_set_property (GObject * obj, guint id, const GValue * value, GParamSpec * ps
     case PROP_ENVELOPE: self->envelope = g_value_get_double (value); break;
     case PROP_SHARPNESS: self->sharpness = g_value_get_double (value); break;
     case PROP_SHARPEN: self->sharpen = g_value_get_double (value); break;
+    case PROP_ADD_BORDERS: self->add_borders = g_value_get_boolean (value); break;
     case PROP_DEVICE_ID: self->device_id = g_value_get_int (value); break;
     default: G_OBJECT_WARN_INVALID_PROPERTY_ID (obj, id, pspec); break;
   }
@@ -106,6 +108,7 @@ vcs_get_property (GObject * obj, guint id, GValue * value, GParamSpec * pspec)
     case PROP_ENVELOPE: g_value_set_double (value, self->envelope); break;
     case PROP_SHARPNESS: g_value_set_double (value, self->sharpness); break;
     case PROP_SHARPEN: g_value_set_double (value, self->sharpen); break;
+    case PROP_ADD_BORDERS: g_value_set_boolean (value, self->add_borders); break;
     case PROP_DEVICE_ID: g_value_set_int (value, self->device_id); break;
     default: G_OBJECT_WARN_INVALID_PROPERTY_ID (obj, id, pspec); break;
   }
@@ -235,6 +238,25 @@ vcs_rebuild (GstCudaVideoConvertScale * self)
   cfg.envelope = self->envelope;
   cfg.sharpness = self->sharpness;
   cfg.sharpen = self->sharpen;
+  if (self->add_borders) {
+    /* gst_video_convert_scale_set_info (gstvideoconvertscale.c:920-952): when the display aspect ratio changes, scale
+     * into a centred rectangle that keeps it and let the converter fill the rest with opaque black */
+    const GstVideoInfo *ii = &self->in_info, *oi = &self->out_info;
+    gint fn, fd, tn, td, n, d, bw = 0, bh = 0;
+    if (gst_util_fraction_multiply (ii->width, ii->height, ii->par_n, ii->par_d, &fn, &fd) &&
+        gst_util_fraction_multiply (oi->width, oi->height, oi->par_n, oi->par_d, &tn, &td) &&
+        (fn != tn || fd != td) && gst_util_fraction_multiply (fn, fd, oi->par_d, oi->par_n, &n, &d)) {
+      gint to_h = (gint) gst_util_uint64_scale_int (oi->width, d, n);
+      if (to_h <= oi->height)
+        bh = oi->height - to_h;
+      else
+        bw = oi->width - (gint) gst_util_uint64_scale_int (oi->height, n, d);
+    }
+    cfg.dest_x = bw / 2;
+    cfg.dest_y = bh / 2;
+    cfg.dest_width = oi->width - bw;
+    cfg.dest_height = oi->height - bh;
+  }
   self->config_changed = FALSE;
   GST_OBJECT_UNLOCK (self);
   gst_b200_video_info_from_gst (&in, &self->in_info);
@@ -348,6 +370,9 @@ gst_cuda_video_convert_scale_class_init (GstCudaVideoConvertScaleClass * klass)
           "Sharpness of filter", 0.5, 1.5, 1.0, G_PARAM_READWRITE | G_PARAM_STATIC_STRINGS));
   g_object_class_install_property (gobject, PROP_SHARPEN, g_param_spec_double ("sharpen", "Sharpen",
           "Sharpening", 0.0, 1.0, 0.0, G_PARAM_READWRITE | G_PARAM_STATIC_STRINGS));
+  g_object_class_install_property (gobject, PROP_ADD_BORDERS, g_param_spec_boolean ("add-borders", "Add Borders",
+          "Add black borders if necessary to keep the display aspect ratio", TRUE,
+          G_PARAM_READWRITE | G_PARAM_STATIC_STRINGS));
   g_object_class_install_property (gobject, PROP_DEVICE_ID, g_param_spec_int ("cuda-device-id", "Cuda Device ID",
           "Set the GPU device to use for operations (-1 = auto)", -1, G_MAXINT, 0,
           G_PARAM_READWRITE | GST_PARAM_MUTABLE_READY | G_PARAM_STATIC_STRINGS));
@@ -378,5 +403,6 @@ gst_cuda_video_convert_scale_init (GstCudaVideoConvertScale * self)
   self->envelope = 2.0;
   self->sharpness = 1.0;
   self->sharpen = 0.0;
+  self->add_borders = TRUE;
   self->device_id = 0;
 }

@@ -31,7 +31,9 @@ class VideoInfoC(C.Structure):
 
 class VcsConfigC(C.Structure):
     _fields_ = [("method", C.c_int32), ("envelope", C.c_double), ("sharpness", C.c_double),
-                ("sharpen", C.c_double), ("reserved", C.c_int32 * 8)]
+                ("sharpen", C.c_double), ("dest_x", C.c_int32), ("dest_y", C.c_int32), ("dest_width", C.c_int32),
+                ("dest_height", C.c_int32), ("border_argb", C.c_uint32), ("fill_border", C.c_int32),
+                ("reserved", C.c_int32 * 2)]
 
 
 class VcsPlanInfoC(C.Structure):

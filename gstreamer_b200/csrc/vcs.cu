@@ -41,6 +41,7 @@ struct b200_vcs {
   PlanesState planes;
   // 4:2:0 -> other 4:2:0 family: scaled A,Y,U,V scratch images between the two launches
   Down420Dev down;
+  BorderDev border;               // destination rectangle: what to fill around it
   uint8_t *d_scratch = nullptr;
   int scratch_frames = 0;
   size_t in_bytes = 0, out_bytes = 0;
@@ -65,7 +66,27 @@ int upload_axis (const AxisPlan & a, uint32_t **off, int16_t **coef, int16_t **s
   return B200_OK;
 }
 
+int launch_convert (b200_vcs * h, int n, const VcsBatch & batch, cudaStream_t stream);
+
 int launch (b200_vcs * h, int n, const VcsBatch & batch, cudaStream_t stream)
+{
+  const VcsPlan & p = h->plan;
+  if (p.has_dest && p.fill_border) {
+    // border and rectangle are disjoint byte sets: the fill simply goes first on the same stream
+    BorderBatch b;
+    int wmax = 0, hmax = 0;
+    for (int i = 0; i < n; i++) b.out[i] = batch.out[i];
+    for (int i = 0; i < h->border.n_planes; i++) {
+      wmax = max (wmax, h->border.pl[i].pw); hmax = max (hmax, h->border.pl[i].ph);
+    }
+    dim3 grid ((wmax + 255) / 256, hmax, h->border.n_planes * n);
+    vcs_border_kernel <<<grid, 256, 0, stream>>> (h->border, b);
+    B200_CUDA_TRY (cudaGetLastError ());
+  }
+  return launch_convert (h, n, batch, stream);
+}
+
+int launch_convert (b200_vcs * h, int n, const VcsBatch & batch, cudaStream_t stream)
 {
   const VcsPlan & p = h->plan;
   if (p.planes_mode) {
@@ -133,7 +154,7 @@ int ensure_pipeline (b200_vcs * h)
 {
   if (h->pipeline_ready) return B200_OK;
   h->in_bytes = frame_bytes (h->plan.in);
-  h->out_bytes = frame_bytes (h->plan.out);
+  h->out_bytes = frame_bytes (h->plan.frame_out);
   B200_CUDA_TRY (cudaStreamCreateWithFlags (&h->s_h2d, cudaStreamNonBlocking));
   B200_CUDA_TRY (cudaStreamCreateWithFlags (&h->s_run, cudaStreamNonBlocking));
   B200_CUDA_TRY (cudaStreamCreateWithFlags (&h->s_d2h, cudaStreamNonBlocking));
@@ -158,6 +179,7 @@ void b200_vcs_config_init (b200_vcs_config * cfg)
   memset (cfg, 0, sizeof (*cfg));
   cfg->method = B200_SCALE_BILINEAR;    // DEFAULT_PROP_METHOD, gstvideoconvertscale.c:130
   cfg->envelope = 2.0; cfg->sharpness = 1.0; cfg->sharpen = 0.0;
+  cfg->border_argb = 0xff000000u; cfg->fill_border = 1;   // DEFAULT_OPT_FILL_BORDER / _BORDER_ARGB, video-converter.c:778, :782
 }
 
 int b200_video_info_set_format (b200_video_info * info, int format, int width, int height)
@@ -223,10 +245,38 @@ int b200_vcs_create (const b200_video_info * in, const b200_video_info * out,
   if (!h) return B200_ERR_NOMEM;
   int st = build_vcs_plan (in, out, cfg, &h->plan);
   if (st != B200_OK) { delete h; return st; }
+  if (h->plan.has_dest) {
+    // per-plane rectangles: chroma planes use GST_VIDEO_FORMAT_INFO_SCALE_WIDTH / _HEIGHT (round up), :7209-7221
+    const VcsPlan & q = h->plan;
+    const b200_video_info & f = q.frame_out;
+    BorderDev & b = h->border;
+    memset (&b, 0, sizeof (b));
+    const bool rgb = f.format >= B200_VIDEO_FORMAT_RGBx && f.format <= B200_VIDEO_FORMAT_ABGR;
+    const bool planar = f.format == B200_VIDEO_FORMAT_I420 || f.format == B200_VIDEO_FORMAT_YV12;
+    if (rgb) {
+      b.n_planes = 1;
+      b.pl[0] = BorderPlane {f.offset[0], f.stride[0], f.width, f.height, 4, q.dest[0], q.dest[1], q.dest[2], q.dest[3],
+        (unsigned) q.border_px[0] | ((unsigned) q.border_px[1] << 8) | ((unsigned) q.border_px[2] << 16) | ((unsigned) q.border_px[3] << 24)};
+    } else {
+      const int cx = (q.dest[0] + 1) / 2, cy = (q.dest[1] + 1) / 2, cw = (q.dest[2] + 1) / 2, chh = (q.dest[3] + 1) / 2;
+      const int CW = (f.width + 1) / 2, CH = (f.height + 1) / 2;
+      b.pl[0] = BorderPlane {f.offset[0], f.stride[0], f.width, f.height, 1, q.dest[0], q.dest[1], q.dest[2], q.dest[3], (unsigned) q.border_yuv[0]};
+      if (planar) {
+        const int pu = f.format == B200_VIDEO_FORMAT_YV12 ? 2 : 1, pv = 3 - pu;
+        b.n_planes = 3;
+        b.pl[1] = BorderPlane {f.offset[pu], f.stride[pu], CW, CH, 1, cx, cy, cw, chh, (unsigned) q.border_yuv[1]};
+        b.pl[2] = BorderPlane {f.offset[pv], f.stride[pv], CW, CH, 1, cx, cy, cw, chh, (unsigned) q.border_yuv[2]};
+      } else {
+        const unsigned u = (unsigned) q.border_yuv[1], v = (unsigned) q.border_yuv[2];
+        b.n_planes = 2;
+        b.pl[1] = BorderPlane {f.offset[1], f.stride[1], CW, CH, 2, cx, cy, cw, chh, f.format == B200_VIDEO_FORMAT_NV21 ? (v | (u << 8)) : (u | (v << 8))};
+      }
+    }
+  }
   if (h->plan.planes_mode) {                                       // YUV -> same YUV family: plane scaling
     h->device = device;
     h->variant = 4;
-    h->in_bytes = frame_bytes (h->plan.in); h->out_bytes = frame_bytes (h->plan.out);
+    h->in_bytes = frame_bytes (h->plan.in); h->out_bytes = frame_bytes (h->plan.frame_out);
     if (device >= 0) {
       int ndev = b200_device_count ();
       if (ndev <= 0) { delete h; return ndev < 0 ? ndev : B200_ERR_NO_DEVICE; }
@@ -405,7 +455,7 @@ int b200_vcs_get_plan_info (const b200_vcs * h, b200_vcs_plan_info * info)
   for (int i = 0; i < 5; i++) info->p[i] = p.p[i];
   info->tile_w = p.tile_w; info->tile_h = p.tile_h; info->smem_bytes = p.smem_bytes;
   info->kernel_variant = p.yuv_out ? 5 : p.planes_mode ? 4 : (h->variant == 1 && p.lanczos2_ok) ? 1 : (h->variant == 2 && p.light_ok) ? 2 : (h->variant == 3 && p.ntap_ok) ? 3 : 0;
-  info->n_launches_per_convert = p.yuv_out ? (p.extra_row ? 3 : 2) : 1;
+  info->n_launches_per_convert = (p.yuv_out ? (p.extra_row ? 3 : 2) : 1) + (p.has_dest && p.fill_border ? 1 : 0);
   return B200_OK;
 }
 

@@ -104,4 +104,37 @@ vcs_down420_kernel (const Down420Dev P, const Down420Batch frames)
   out[P.off_v + (size_t) k * P.stride_v + (size_t) j * P.cstep] = (uint8_t) v;
 }
 
+// ---- border fill (the element's add-borders): every pixel of every plane outside the destination rectangle takes the
+// border value (setup_borderline / convert_fill_border, video-converter.c:2189-2258, :7190-7300)
+struct BorderPlane {
+  unsigned long long off;
+  int stride, pw, ph, bpp;       // plane size in pixels, bytes per pixel (1, 2: interleaved chroma pair, 4: packed RGB)
+  int x0, y0, w, h;              // the rectangle in this plane's pixels
+  unsigned value;                // pixel bytes, lowest byte first
+};
+struct BorderDev {
+  BorderPlane pl[3];
+  int n_planes;
+};
+struct BorderBatch {
+  uint8_t *out[B200_VCS_MAX_BATCH];
+};
+
+__global__ void __launch_bounds__ (256)
+vcs_border_kernel (const BorderDev P, const BorderBatch frames)
+{
+  const int plane = blockIdx.z % P.n_planes, frame = blockIdx.z / P.n_planes;
+  const BorderPlane & Q = P.pl[plane];
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= Q.pw || y >= Q.ph) return;
+  if (y >= Q.y0 && y < Q.y0 + Q.h && x >= Q.x0 && x < Q.x0 + Q.w) return;
+  uint8_t *d = frames.out[frame] + Q.off + (size_t) y * Q.stride + (size_t) x * Q.bpp;
+  if (Q.bpp == 4) {
+    d[0] = (uint8_t) Q.value; d[1] = (uint8_t) (Q.value >> 8); d[2] = (uint8_t) (Q.value >> 16); d[3] = (uint8_t) (Q.value >> 24);
+  } else if (Q.bpp == 2) {
+    d[0] = (uint8_t) Q.value; d[1] = (uint8_t) (Q.value >> 8);
+  } else
+    d[0] = (uint8_t) Q.value;
+}
+
 }  // namespace b200

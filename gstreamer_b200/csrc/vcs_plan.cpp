@@ -660,8 +660,114 @@ static int build_rgb_in_plan (VcsPlan * p)
   return B200_OK;
 }
 
+static int build_inner_plan (const b200_video_info * in, const b200_video_info * out,
+    const b200_vcs_config * cfg, VcsPlan * p, bool resample_forced);
+
+// border pixel of setup_borderline (video-converter.c:2189-2258): packed RGB outputs take border_argb's bytes in the
+// format's order; YUV outputs convert it with the un-scaled (no x256) rint'ed RGB -> YCbCr matrix of the OUTPUT
+// colorimetry and hand-added 16 / 128 / 128 offsets
+static int border_colour (VcsPlan * p, const b200_video_info & fo, uint32_t argb_word)
+{
+  const int a = argb_word >> 24, r = (argb_word >> 16) & 0xff, g = (argb_word >> 8) & 0xff, b = argb_word & 0xff;
+  const bool rgb = fo.format >= B200_VIDEO_FORMAT_RGBx && fo.format <= B200_VIDEO_FORMAT_ABGR;
+  if (rgb) {
+    const uint8_t comp[4] = {(uint8_t) a, (uint8_t) r, (uint8_t) g, (uint8_t) b};
+    uint8_t sel[4];
+    switch (fo.format) {
+      case B200_VIDEO_FORMAT_BGRA: case B200_VIDEO_FORMAT_BGRx: { uint8_t s_[4] = {3, 2, 1, 0}; memcpy (sel, s_, 4); break; }
+      case B200_VIDEO_FORMAT_RGBA: case B200_VIDEO_FORMAT_RGBx: { uint8_t s_[4] = {1, 2, 3, 0}; memcpy (sel, s_, 4); break; }
+      case B200_VIDEO_FORMAT_ABGR: case B200_VIDEO_FORMAT_xBGR: { uint8_t s_[4] = {0, 3, 2, 1}; memcpy (sel, s_, 4); break; }
+      default: { uint8_t s_[4] = {0, 1, 2, 3}; memcpy (sel, s_, 4); break; }
+    }
+    for (int i = 0; i < 4; i++) p->border_px[i] = comp[sel[i]];
+    return B200_OK;
+  }
+  // the plan's `out` carries the resolved output colorimetry (the input's for 4:2:0 -> 4:2:0, the caps defaults of
+  // the frame for packed RGB input)
+  int matrix = p->out.color_matrix ? p->out.color_matrix : p->in.color_matrix;
+  int range = p->out.color_range ? p->out.color_range : p->in.color_range;
+  double kr, kb;
+  switch (matrix) {
+    case B200_COLOR_MATRIX_FCC: kr = 0.30; kb = 0.11; break;
+    case B200_COLOR_MATRIX_BT709: kr = 0.2126; kb = 0.0722; break;
+    case B200_COLOR_MATRIX_BT601: kr = 0.2990; kb = 0.1140; break;
+    case B200_COLOR_MATRIX_SMPTE240M: kr = 0.212; kb = 0.087; break;
+    case B200_COLOR_MATRIX_BT2020: kr = 0.2627; kb = 0.0593; break;
+    default: return B200_ERR_INVALID_ARG;
+  }
+  const double kg = 1.0 - kr - kb;
+  Mat4 k = Mat4::identity ();
+  k.m[0][0] = kr; k.m[0][1] = kg; k.m[0][2] = kb;
+  double x = 1 / (2 * (1 - kb));
+  k.m[1][0] = -x * kr; k.m[1][1] = -x * kg; k.m[1][2] = x * (1 - kb);
+  x = 1 / (2 * (1 - kr));
+  k.m[2][0] = x * (1 - kr); k.m[2][1] = -x * kg; k.m[2][2] = -x * kb;
+  Mat4 m = mul (k, Mat4::identity ());
+  if (range == B200_COLOR_RANGE_16_235) { m = mul (diag ((float) 219, (float) 224, (float) 224), m); m = mul (shift (16, 128, 128), m); }
+  else { m = mul (diag ((float) 255, (float) 255, (float) 255), m); m = mul (shift (0, 128, 128), m); }
+  int im[3][3];
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) im[i][j] = (int) rint (m.m[i][j]);
+  const int yy = 16 + ((r * im[0][0] + g * im[0][1] + b * im[0][2]) >> 8);
+  const int uu = 128 + ((r * im[1][0] + g * im[1][1] + b * im[1][2]) >> 8);
+  const int vv = 128 + ((r * im[2][0] + g * im[2][1] + b * im[2][2]) >> 8);
+  p->border_yuv[0] = std::min (std::max (yy, 0), 255);
+  p->border_yuv[1] = std::min (std::max (uu, 0), 255);
+  p->border_yuv[2] = std::min (std::max (vv, 0), 255);
+  return B200_OK;
+}
+
 int build_vcs_plan (const b200_video_info * in, const b200_video_info * out,
     const b200_vcs_config * cfg, VcsPlan * p)
+{
+  if (!in || !out || !cfg || !p) return B200_ERR_INVALID_ARG;
+  if (cfg->dest_width == 0 || cfg->dest_height == 0 ||
+      (cfg->dest_x == 0 && cfg->dest_y == 0 && cfg->dest_width == out->width && cfg->dest_height == out->height)) {
+    int st = build_inner_plan (in, out, cfg, p, false);
+    if (st == B200_OK) p->frame_out = p->out;
+    return st;
+  }
+  // GST_VIDEO_CONVERTER_OPT_DEST_* (video-converter.c:2333-2362): the chain scales into the rectangle; for sub-sampled
+  // outputs its origin is rounded down to the chroma grid; it is clipped to the frame
+  if (out->width < 1 || out->height < 1 || out->width > 32767 || out->height > 32767) return B200_ERR_INVALID_ARG;
+  const bool yuv = out->format == B200_VIDEO_FORMAT_I420 || out->format == B200_VIDEO_FORMAT_YV12 ||
+      out->format == B200_VIDEO_FORMAT_NV12 || out->format == B200_VIDEO_FORMAT_NV21;
+  const bool planar = out->format == B200_VIDEO_FORMAT_I420 || out->format == B200_VIDEO_FORMAT_YV12;
+  int dx = cfg->dest_x, dy = cfg->dest_y, dw = cfg->dest_width, dh = cfg->dest_height;
+  if (yuv) { dx &= ~1; dy &= ~1; }
+  if (dx < 0 || dy < 0 || dw < 0 || dh < 0) return B200_ERR_INVALID_ARG;
+  if (dw > out->width - dx) dw = out->width - dx;
+  if (dh > out->height - dy) dh = out->height - dy;
+  if (dw < 1 || dh < 1) return B200_ERR_INVALID_ARG;               // an empty rectangle: degenerate in the reference too
+  b200_video_info inner = *out;
+  inner.width = dw; inner.height = dh;
+  if (!yuv) inner.offset[0] += (uint64_t) dy * out->stride[0] + (uint64_t) dx * 4;
+  else {
+    inner.offset[0] += (uint64_t) dy * out->stride[0] + (uint64_t) dx;
+    if (planar) {
+      inner.offset[1] += (uint64_t) (dy / 2) * out->stride[1] + (uint64_t) (dx / 2);
+      inner.offset[2] += (uint64_t) (dy / 2) * out->stride[2] + (uint64_t) (dx / 2);
+    } else inner.offset[1] += (uint64_t) (dy / 2) * out->stride[1] + (uint64_t) dx;
+  }
+  // colorimetry defaults belong to the whole frame, not to the rectangle
+  const bool in_rgb = in->format >= B200_VIDEO_FORMAT_RGBx && in->format <= B200_VIDEO_FORMAT_ABGR;
+  if (yuv && in_rgb) {
+    if (inner.color_matrix == 0) inner.color_matrix = out->height > 576 ? B200_COLOR_MATRIX_BT709 : B200_COLOR_MATRIX_BT601;
+    if (inner.color_range == 0) inner.color_range = B200_COLOR_RANGE_16_235;
+    if (inner.chroma_site == 0) inner.chroma_site = out->height > 576 ? B200_CHROMA_SITE_H_COSITED : B200_CHROMA_SITE_NONE;
+  }
+  // video_converter_compute_resample (:2850-2895) compares the input with the whole output frame
+  const bool forced = in->width != out->width || in->height != out->height;
+  int st = build_inner_plan (in, &inner, cfg, p, forced);
+  if (st != B200_OK) return st;
+  p->has_dest = true;
+  p->frame_out = *out;
+  p->dest[0] = dx; p->dest[1] = dy; p->dest[2] = dw; p->dest[3] = dh;
+  p->fill_border = cfg->fill_border != 0;
+  return border_colour (p, *out, cfg->border_argb);
+}
+
+static int build_inner_plan (const b200_video_info * in, const b200_video_info * out,
+    const b200_vcs_config * cfg, VcsPlan * p, bool resample_forced)
 {
   if (!in || !out || !cfg || !p) return B200_ERR_INVALID_ARG;
   if (in->width < 1 || in->height < 1 || out->width < 1 || out->height < 1 ||
@@ -764,7 +870,7 @@ int build_vcs_plan (const b200_video_info * in, const b200_video_info * out,
   if (p->yuv_out) {
     // video_converter_compute_resample (video-converter.c:2850-2895): chroma resamplers exist on BOTH sides as soon
     // as the size or the site differs (the sub-sampling is 4:2:0 on both), on neither otherwise
-    const bool resample = iw != ow || ih != oh || p->out.chroma_site != p->in.chroma_site;
+    const bool resample = iw != ow || ih != oh || p->out.chroma_site != p->in.chroma_site || resample_forced;
     if (!resample) {
       p->chroma_nearest = true; p->v_pairs = false;
       std::fill (p->chroma_mode.begin (), p->chroma_mode.end (), 0);

@@ -78,6 +78,15 @@ struct VcsPlan {
   unsigned in_sel = 0x3210;
   int m_rgb2yuv[3][4] = {{0}};
 
+  // destination rectangle (the element's add-borders): `out` above describes the RECTANGLE (same strides, plane
+  // origins shifted to its first pixel) so that every kernel runs unchanged; frame_out is the whole output frame
+  bool has_dest = false;
+  b200_video_info frame_out;
+  int dest[4] = {0, 0, 0, 0};     // x, y, width, height in luma pixels
+  bool fill_border = true;
+  uint8_t border_px[4] = {0, 0, 0, 0};   // packed RGB outputs: the border pixel in memory order
+  int border_yuv[3] = {16, 128, 128};    // 4:2:0 outputs
+
   // specialised 2:1 lanczos kernel eligibility
   bool lanczos2_ok = false;
 

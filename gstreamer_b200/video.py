@@ -179,7 +179,11 @@ class CudaVideoConvertScale:
     """
 
     def __init__(self, method=VideoScaleMethod.BILINEAR, envelope=2.0, sharpness=1.0, sharpen=0.0,
-                 cuda_device_id=0):
+                 cuda_device_id=0, add_borders=False):
+        # add-borders: TRUE in the stock element (DEFAULT_PROP_ADD_BORDERS, gstvideoconvertscale.c:131); this mirror keeps
+        # it FALSE until the border path has run on a device, so the converter-level parity tests stay border-free
+        self.add_borders = add_borders
+        self.borders_w = self.borders_h = 0
         self.method = VideoScaleMethod(method)
         self.envelope = envelope
         self.sharpness = sharpness
@@ -195,6 +199,22 @@ class CudaVideoConvertScale:
         lib.b200_vcs_config_init(C.byref(cfg))
         cfg.method = int(self.method)
         cfg.envelope, cfg.sharpness, cfg.sharpen = self.envelope, self.sharpness, self.sharpen
+        # gst_video_convert_scale_set_info (gstvideoconvertscale.c:920-952): when the display aspect ratio changes (pixel
+        # aspect ratio 1/1 on both sides here) and add-borders is set, scale into a centred rectangle that keeps it
+        self.borders_w = self.borders_h = 0
+        if self.add_borders:
+            from math import gcd
+            iw, ih, ow, oh = in_info.width, in_info.height, out_info.width, out_info.height
+            g1, g2 = gcd(iw, ih), gcd(ow, oh)
+            n, d = iw // g1, ih // g1
+            if (n, d) != (ow // g2, oh // g2):
+                to_h = ow * d // n
+                if to_h <= oh:
+                    self.borders_h = oh - to_h
+                else:
+                    self.borders_w = ow - oh * n // d
+            cfg.dest_x, cfg.dest_y = self.borders_w // 2, self.borders_h // 2
+            cfg.dest_width, cfg.dest_height = ow - self.borders_w, oh - self.borders_h
         h = C.c_void_p()
         check(lib.b200_vcs_create(C.byref(in_info.c), C.byref(out_info.c), C.byref(cfg),
                                   self.cuda_device_id, C.byref(h)), "b200_vcs_create")

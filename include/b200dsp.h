@@ -119,7 +119,14 @@ typedef struct {
   double envelope;               /* 2.0 */
   double sharpness;              /* 1.0 */
   double sharpen;                /* 0.0 */
-  int32_t reserved[8];
+  /* GST_VIDEO_CONVERTER_OPT_DEST_X/Y/WIDTH/HEIGHT as the element sets them for add-borders
+   * (gstvideoconvertscale.c:926-952, :1068-1072): the input is scaled into this rectangle of the output frame and
+   * the rest is filled with border_argb.  dest_width == 0 or dest_height == 0: the whole frame, no border.
+   * For 4:2:0 outputs dest_x / dest_y are rounded down to even (video-converter.c:2335-2336). */
+  int32_t dest_x, dest_y, dest_width, dest_height;
+  uint32_t border_argb;          /* GST_VIDEO_CONVERTER_OPT_BORDER_ARGB, default 0xff000000 */
+  int32_t fill_border;           /* GST_VIDEO_CONVERTER_OPT_FILL_BORDER, default 1 */
+  int32_t reserved[2];
 } b200_vcs_config;
 void b200_vcs_config_init (b200_vcs_config * cfg);
 

@@ -279,3 +279,38 @@ def test_rgb_input_plan_is_opt_in_and_matches_the_oracle_matrix(monkeypatch):
     for m in range(10):
         for size in [(64, 48, 32, 24), (40, 30, 64, 48), (100, 100, 150, 50), (64, 48, 64, 48)]:
             assert int(build(11, 11, *size, m=m).plan_info().kernel_variant) == 4
+
+
+def test_add_borders_rectangle_and_plan():
+    """the mirror's add-borders geometry equals the oracle's (both restate gstvideoconvertscale.c:920-952), the plan then
+    describes the rectangle (tap tables of the rectangle's size) and one more launch for the border fill"""
+    import gstreamer_b200 as g
+    rng = np.random.default_rng(3)
+    for t in range(200):
+        iw, ih, ow, oh = (int(v) for v in rng.integers(2, 400, 4))
+        el = g.CudaVideoConvertScale(method=3, cuda_device_id=-1, add_borders=True)
+        x, y, w, h = ob.vcs_borders(iw, ih, ow, oh)
+        if w < 1 or h < 1:
+            continue
+        el.set_info(g.VideoInfo(23, iw, ih), g.VideoInfo(12, ow, oh))
+        assert (el.borders_w // 2, el.borders_h // 2, ow - el.borders_w, oh - el.borders_h) == (x, y, w, h)
+        pi = el.plan_info()
+        bordered = (w, h) != (ow, oh)
+        assert int(pi.n_launches_per_convert) == (2 if bordered else 1)
+        n, off, q = _oracle_taps(3, iw, w, 6) if iw != w else (0, None, None)
+        assert int(pi.h_taps) == n
+    # explicit rectangle through the C-ABI config; 4:2:0 outputs round the origin down to even
+    from gstreamer_b200 import _lib
+    cfg = _lib.VcsConfigC()
+    g.lib.b200_vcs_config_init(C.byref(cfg))
+    assert (cfg.border_argb, cfg.fill_border) == (0xff000000, 1)
+    cfg.dest_x, cfg.dest_y, cfg.dest_width, cfg.dest_height = 5, 3, 20, 10
+    h = C.c_void_p()
+    ii, oi = g.VideoInfo(23, 64, 48), g.VideoInfo(23, 40, 30)
+    assert g.lib.b200_vcs_create(C.byref(ii.c), C.byref(oi.c), C.byref(cfg), -1, C.byref(h)) == 0
+    g.lib.b200_vcs_destroy(h)
+    cfg.dest_x = 39                                            # clipped to the frame: 1 column left
+    assert g.lib.b200_vcs_create(C.byref(ii.c), C.byref(oi.c), C.byref(cfg), -1, C.byref(h)) == 0
+    g.lib.b200_vcs_destroy(h)
+    cfg.dest_x = 41                                            # rounds down to 40 = outside: empty rectangle
+    assert g.lib.b200_vcs_create(C.byref(ii.c), C.byref(oi.c), C.byref(cfg), -1, C.byref(h)) == -1
