@@ -1,0 +1,17 @@
+#!/bin/bash
+# First device run of the next round: everything that was written after the round-1 GPU budget was spent.
+#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/next_round_first.sh'
+# Each step has its own timeout and writes under gpurun_out/; a red step does not stop the later ones.
+set -u
+mkdir -p gpurun_out
+export B200_TEST_EXPERIMENTAL=1
+run() { local name=$1; shift; echo "== $name"; timeout "$1" "${@:2}" > "gpurun_out/nr_$name.log" 2>&1; echo "rc=$? ($name)"; tail -4 "gpurun_out/nr_$name.log"; }
+# 1. packed RGB -> 4:2:0 and same-format RGB scaling (opt-in product paths: B200_VCS_EXPERIMENTAL is set by the tests)
+run rgbin 240 python -m pytest tests/test_vcs_rgbin_gpu.py -q -p no:cacheprovider
+# 2. destination rectangle + borders (new vcs_border_kernel around the existing kernels)
+run borders 180 python -m pytest tests/test_vcs_borders_gpu.py -q -p no:cacheprovider
+# 3. random sweep of the RGB -> 4:2:0 path, every outcome recorded in gpurun_out/cross_check.json
+run rgbsweep 90 python tools/gpu_cross_check.py 60 rgb
+# 4. the regular device suite (the generic kernel and the plan builder changed underneath it)
+unset B200_TEST_EXPERIMENTAL
+run suite 600 python -m pytest tests -q -m gpu -x -p no:cacheprovider
