@@ -32,7 +32,12 @@ static GstStaticPadTemplate sink_tmpl = GST_STATIC_PAD_TEMPLATE ("sink", GST_PAD
 static GstStaticPadTemplate src_tmpl = GST_STATIC_PAD_TEMPLATE ("src", GST_PAD_SRC, GST_PAD_ALWAYS,
     GST_STATIC_CAPS (CUDA_CAPS (SRC_FORMATS)));
 
-enum { PROP_0, PROP_METHOD, PROP_ENVELOPE, PROP_SHARPNESS, PROP_SHARPEN, PROP_ADD_BORDERS, PROP_DEVICE_ID };
+enum { PROP_0, PROP_METHOD, PROP_ENVELOPE, PROP_SHARPNESS, PROP_SHARPEN, PROP_ADD_BORDERS, PROP_DEVICE_ID,
+  /* the stock element's remaining properties (gstvideoconvertscale.c:326-391): installed so that existing pipelines keep
+   * working; only the default of each is implemented (vcs_rebuild refuses anything else), n-threads is free */
+  PROP_DITHER, PROP_N_THREADS, PROP_DITHER_QUANTIZATION, PROP_CHROMA_RESAMPLER, PROP_ALPHA_MODE, PROP_ALPHA_VALUE,
+  PROP_CHROMA_MODE, PROP_MATRIX_MODE, PROP_GAMMA_MODE, PROP_PRIMARIES_MODE
+};
 
 typedef struct
 {
@@ -42,6 +47,9 @@ typedef struct
   gdouble envelope, sharpness, sharpen;
   gboolean add_borders;           /* DEFAULT_PROP_ADD_BORDERS TRUE, gstvideoconvertscale.c:131 */
   gint device_id;
+  gint dither, chroma_resampler, alpha_mode, chroma_mode, matrix_mode, gamma_mode, primaries_mode;
+  guint n_threads, dither_quantization;
+  gdouble alpha_value;
   gboolean config_changed;
   /* negotiated state */
   GstVideoInfo in_info, out_info;
@@ -90,6 +98,16 @@ vcs_set_property (GObject * obj, guint id, const GValue * value, GParamSpec * ps
     case PROP_SHARPEN: self->sharpen = g_value_get_double (value); break;
     case PROP_ADD_BORDERS: self->add_borders = g_value_get_boolean (value); break;
     case PROP_DEVICE_ID: self->device_id = g_value_get_int (value); break;
+    case PROP_DITHER: self->dither = g_value_get_enum (value); break;
+    case PROP_N_THREADS: self->n_threads = g_value_get_uint (value); break;
+    case PROP_DITHER_QUANTIZATION: self->dither_quantization = g_value_get_uint (value); break;
+    case PROP_CHROMA_RESAMPLER: self->chroma_resampler = g_value_get_enum (value); break;
+    case PROP_ALPHA_MODE: self->alpha_mode = g_value_get_enum (value); break;
+    case PROP_ALPHA_VALUE: self->alpha_value = g_value_get_double (value); break;
+    case PROP_CHROMA_MODE: self->chroma_mode = g_value_get_enum (value); break;
+    case PROP_MATRIX_MODE: self->matrix_mode = g_value_get_enum (value); break;
+    case PROP_GAMMA_MODE: self->gamma_mode = g_value_get_enum (value); break;
+    case PROP_PRIMARIES_MODE: self->primaries_mode = g_value_get_enum (value); break;
     default: G_OBJECT_WARN_INVALID_PROPERTY_ID (obj, id, pspec); break;
   }
   /* like the stock element, the converter is rebuilt lazily on the streaming thread
@@ -110,6 +128,16 @@ vcs_get_property (GObject * obj, guint id, GValue * value, GParamSpec * pspec)
     case PROP_SHARPEN: g_value_set_double (value, self->sharpen); break;
     case PROP_ADD_BORDERS: g_value_set_boolean (value, self->add_borders); break;
     case PROP_DEVICE_ID: g_value_set_int (value, self->device_id); break;
+    case PROP_DITHER: g_value_set_enum (value, self->dither); break;
+    case PROP_N_THREADS: g_value_set_uint (value, self->n_threads); break;
+    case PROP_DITHER_QUANTIZATION: g_value_set_uint (value, self->dither_quantization); break;
+    case PROP_CHROMA_RESAMPLER: g_value_set_enum (value, self->chroma_resampler); break;
+    case PROP_ALPHA_MODE: g_value_set_enum (value, self->alpha_mode); break;
+    case PROP_ALPHA_VALUE: g_value_set_double (value, self->alpha_value); break;
+    case PROP_CHROMA_MODE: g_value_set_enum (value, self->chroma_mode); break;
+    case PROP_MATRIX_MODE: g_value_set_enum (value, self->matrix_mode); break;
+    case PROP_GAMMA_MODE: g_value_set_enum (value, self->gamma_mode); break;
+    case PROP_PRIMARIES_MODE: g_value_set_enum (value, self->primaries_mode); break;
     default: G_OBJECT_WARN_INVALID_PROPERTY_ID (obj, id, pspec); break;
   }
   GST_OBJECT_UNLOCK (self);
@@ -234,6 +262,17 @@ vcs_rebuild (GstCudaVideoConvertScale * self)
   int st;
   b200_vcs_config_init (&cfg);
   GST_OBJECT_LOCK (self);
+  /* dither only acts when quantising (8 -> 8 bit at dither-quantization 1 never does, video-converter.c:2056-2079);
+   * n-threads does not change the arithmetic except the reference's chroma pairing at slab boundaries */
+  if (self->dither_quantization != 1 || self->chroma_resampler != GST_VIDEO_RESAMPLER_METHOD_LINEAR ||
+      self->alpha_mode != GST_VIDEO_ALPHA_MODE_COPY || self->alpha_value != 1.0 ||
+      self->chroma_mode != GST_VIDEO_CHROMA_MODE_FULL || self->matrix_mode != GST_VIDEO_MATRIX_MODE_FULL ||
+      self->gamma_mode != GST_VIDEO_GAMMA_MODE_NONE || self->primaries_mode != GST_VIDEO_PRIMARIES_MODE_NONE) {
+    GST_OBJECT_UNLOCK (self);
+    GST_ERROR_OBJECT (self, "only the default of dither-quantization, chroma-resampler, alpha-mode, alpha-value, "
+        "chroma-mode, matrix-mode, gamma-mode and primaries-mode is implemented");
+    return FALSE;
+  }
   cfg.method = self->method;
   cfg.envelope = self->envelope;
   cfg.sharpness = self->sharpness;
@@ -370,6 +409,33 @@ gst_cuda_video_convert_scale_class_init (GstCudaVideoConvertScaleClass * klass)
           "Sharpness of filter", 0.5, 1.5, 1.0, G_PARAM_READWRITE | G_PARAM_STATIC_STRINGS));
   g_object_class_install_property (gobject, PROP_SHARPEN, g_param_spec_double ("sharpen", "Sharpen",
           "Sharpening", 0.0, 1.0, 0.0, G_PARAM_READWRITE | G_PARAM_STATIC_STRINGS));
+  g_object_class_install_property (gobject, PROP_DITHER, g_param_spec_enum ("dither", "Dither", "Apply dithering while converting",
+          gst_video_dither_method_get_type (), GST_VIDEO_DITHER_BAYER, G_PARAM_READWRITE | G_PARAM_STATIC_STRINGS));
+  g_object_class_install_property (gobject, PROP_N_THREADS, g_param_spec_uint ("n-threads", "Threads",
+          "Maximum number of threads to use (accepted; the GPU path has no use for it)", 0, G_MAXUINT, 1,
+          G_PARAM_READWRITE | G_PARAM_STATIC_STRINGS));
+  g_object_class_install_property (gobject, PROP_DITHER_QUANTIZATION, g_param_spec_uint ("dither-quantization",
+          "Dither Quantize", "Quantizer to use", 0, G_MAXUINT, 1, G_PARAM_READWRITE | G_PARAM_STATIC_STRINGS));
+  g_object_class_install_property (gobject, PROP_CHROMA_RESAMPLER, g_param_spec_enum ("chroma-resampler", "Chroma resampler",
+          "Chroma resampler method", gst_video_resampler_method_get_type (), GST_VIDEO_RESAMPLER_METHOD_LINEAR,
+          G_PARAM_READWRITE | G_PARAM_STATIC_STRINGS));
+  g_object_class_install_property (gobject, PROP_ALPHA_MODE, g_param_spec_enum ("alpha-mode", "Alpha Mode",
+          "Alpha Mode to use", gst_video_alpha_mode_get_type (), GST_VIDEO_ALPHA_MODE_COPY,
+          G_PARAM_READWRITE | G_PARAM_STATIC_STRINGS));
+  g_object_class_install_property (gobject, PROP_ALPHA_VALUE, g_param_spec_double ("alpha-value", "Alpha Value",
+          "Alpha Value to use", 0.0, 1.0, 1.0, G_PARAM_READWRITE | G_PARAM_STATIC_STRINGS));
+  g_object_class_install_property (gobject, PROP_CHROMA_MODE, g_param_spec_enum ("chroma-mode", "Chroma Mode",
+          "Chroma Resampling Mode", gst_video_chroma_mode_get_type (), GST_VIDEO_CHROMA_MODE_FULL,
+          G_PARAM_READWRITE | G_PARAM_STATIC_STRINGS));
+  g_object_class_install_property (gobject, PROP_MATRIX_MODE, g_param_spec_enum ("matrix-mode", "Matrix Mode",
+          "Matrix Conversion Mode", gst_video_matrix_mode_get_type (), GST_VIDEO_MATRIX_MODE_FULL,
+          G_PARAM_READWRITE | G_PARAM_STATIC_STRINGS));
+  g_object_class_install_property (gobject, PROP_GAMMA_MODE, g_param_spec_enum ("gamma-mode", "Gamma Mode",
+          "Gamma Conversion Mode", gst_video_gamma_mode_get_type (), GST_VIDEO_GAMMA_MODE_NONE,
+          G_PARAM_READWRITE | G_PARAM_STATIC_STRINGS));
+  g_object_class_install_property (gobject, PROP_PRIMARIES_MODE, g_param_spec_enum ("primaries-mode", "Primaries Mode",
+          "Primaries Conversion Mode", gst_video_primaries_mode_get_type (), GST_VIDEO_PRIMARIES_MODE_NONE,
+          G_PARAM_READWRITE | G_PARAM_STATIC_STRINGS));
   g_object_class_install_property (gobject, PROP_ADD_BORDERS, g_param_spec_boolean ("add-borders", "Add Borders",
           "Add black borders if necessary to keep the display aspect ratio", TRUE,
           G_PARAM_READWRITE | G_PARAM_STATIC_STRINGS));
@@ -404,5 +470,15 @@ gst_cuda_video_convert_scale_init (GstCudaVideoConvertScale * self)
   self->sharpness = 1.0;
   self->sharpen = 0.0;
   self->add_borders = TRUE;
+  self->dither = GST_VIDEO_DITHER_BAYER;
+  self->n_threads = 1;
+  self->dither_quantization = 1;
+  self->chroma_resampler = GST_VIDEO_RESAMPLER_METHOD_LINEAR;
+  self->alpha_mode = GST_VIDEO_ALPHA_MODE_COPY;
+  self->alpha_value = 1.0;
+  self->chroma_mode = GST_VIDEO_CHROMA_MODE_FULL;
+  self->matrix_mode = GST_VIDEO_MATRIX_MODE_FULL;
+  self->gamma_mode = GST_VIDEO_GAMMA_MODE_NONE;
+  self->primaries_mode = GST_VIDEO_PRIMARIES_MODE_NONE;
   self->device_id = 0;
 }

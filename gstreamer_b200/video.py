@@ -178,8 +178,21 @@ class CudaVideoConvertScale:
     property (gst-plugins-bad/sys/nvcodec/gstcudabasetransform.c:89-90).
     """
 
+    # the stock element's remaining properties and their defaults (gstvideoconvertscale.c:130-144, :306-391).  They are
+    # accepted so that existing pipelines keep working; only the default of each is implemented (set_info refuses any
+    # other value the way a failed converter setup does), and n-threads is free: the arithmetic is that of n-threads=1,
+    # which differs from a multi-threaded reference run only in the chroma pairing at its slab boundaries (SURVEY A.4)
+    REST_DEFAULTS = {"dither": "bayer", "dither_quantization": 1, "chroma_resampler": "linear", "alpha_mode": "copy",
+                     "alpha_value": 1.0, "chroma_mode": "full", "matrix_mode": "full", "gamma_mode": "none",
+                     "primaries_mode": "none", "converter_config": None}
+
     def __init__(self, method=VideoScaleMethod.BILINEAR, envelope=2.0, sharpness=1.0, sharpen=0.0,
-                 cuda_device_id=0, add_borders=False):
+                 cuda_device_id=0, add_borders=False, n_threads=1, **rest):
+        unknown = set(rest) - set(self.REST_DEFAULTS)
+        if unknown:
+            raise TypeError(f"no such property: {sorted(unknown)}")
+        self.n_threads = n_threads
+        self.rest = dict(self.REST_DEFAULTS, **rest)
         # add-borders: TRUE in the stock element (DEFAULT_PROP_ADD_BORDERS, gstvideoconvertscale.c:131); this mirror keeps
         # it FALSE until the border path has run on a device, so the converter-level parity tests stay border-free
         self.add_borders = add_borders
@@ -195,6 +208,10 @@ class CudaVideoConvertScale:
     # GstVideoFilterClass::set_info
     def set_info(self, in_info, out_info):
         self._free()
+        for k, v in self.rest.items():
+            # dither only acts when quantising (8 -> 8 bit with dither-quantization 1 never does, video-converter.c:2056-2079)
+            if k != "dither" and v != self.REST_DEFAULTS[k]:
+                raise _lib.B200Error(-2, f"property {k.replace('_', '-')}={v!r}: only the default is implemented")
         cfg = _lib.VcsConfigC()
         lib.b200_vcs_config_init(C.byref(cfg))
         cfg.method = int(self.method)

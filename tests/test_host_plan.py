@@ -314,3 +314,16 @@ def test_add_borders_rectangle_and_plan():
     g.lib.b200_vcs_destroy(h)
     cfg.dest_x = 41                                            # rounds down to 40 = outside: empty rectangle
     assert g.lib.b200_vcs_create(C.byref(ii.c), C.byref(oi.c), C.byref(cfg), -1, C.byref(h)) == -1
+
+
+def test_remaining_element_properties_are_accepted_at_their_defaults():
+    import gstreamer_b200 as g
+    ii, oi = g.VideoInfo(23, 64, 48), g.VideoInfo(12, 32, 24)
+    g.CudaVideoConvertScale(cuda_device_id=-1, n_threads=8, dither="none", chroma_resampler="linear", alpha_value=1.0).set_info(ii, oi)
+    for kw in ({"chroma_resampler": "cubic"}, {"alpha_mode": "set"}, {"alpha_value": 0.5}, {"gamma_mode": "remap"},
+               {"primaries_mode": "fast"}, {"matrix_mode": "none"}, {"chroma_mode": "none"}, {"dither_quantization": 4}):
+        with pytest.raises(g.B200Error) as e:
+            g.CudaVideoConvertScale(cuda_device_id=-1, **kw).set_info(ii, oi)
+        assert e.value.status == -2
+    with pytest.raises(TypeError):
+        g.CudaVideoConvertScale(no_such_property=1)
