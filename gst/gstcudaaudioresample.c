@@ -25,12 +25,18 @@ GST_DEBUG_CATEGORY_STATIC (cuda_ars_debug);
 static GstStaticPadTemplate ars_sink = GST_STATIC_PAD_TEMPLATE ("sink", GST_PAD_SINK, GST_PAD_ALWAYS, GST_STATIC_CAPS (ARS_CAPS));
 static GstStaticPadTemplate ars_src = GST_STATIC_PAD_TEMPLATE ("src", GST_PAD_SRC, GST_PAD_ALWAYS, GST_STATIC_CAPS (ARS_CAPS));
 
-enum { PROP_0, PROP_QUALITY, PROP_DEVICE_ID };
+enum { PROP_0, PROP_QUALITY, PROP_DEVICE_ID,
+  /* the stock element's remaining properties (gstaudioresample.c:160-186): installed with the stock defaults so that
+   * existing pipelines load; only the default of each is implemented (set_caps refuses anything else) */
+  PROP_RESAMPLE_METHOD, PROP_SINC_FILTER_MODE, PROP_SINC_FILTER_AUTO_THRESHOLD, PROP_SINC_FILTER_INTERPOLATION
+};
 
 typedef struct
 {
   GstBaseTransform parent;
   gint quality, device_id;
+  gint method, sinc_filter_mode, sinc_filter_interpolation;
+  guint sinc_filter_auto_threshold;
   GstAudioInfo in, out;
   b200_ars *ars;
   cudaStream_t stream;
@@ -81,6 +87,11 @@ ars_set_caps (GstBaseTransform * trans, GstCaps * incaps, GstCaps * outcaps)
   if (!gst_audio_info_from_caps (&self->in, incaps) || !gst_audio_info_from_caps (&self->out, outcaps))
     return FALSE;
   g_clear_pointer (&self->ars, b200_ars_destroy);
+  if (self->method != GST_AUDIO_RESAMPLER_METHOD_KAISER || self->sinc_filter_mode != GST_AUDIO_RESAMPLER_FILTER_MODE_AUTO ||
+      self->sinc_filter_interpolation != GST_AUDIO_RESAMPLER_FILTER_INTERPOLATION_CUBIC) {
+    GST_ERROR_OBJECT (self, "only resample-method=kaiser, sinc-filter-mode=auto, sinc-filter-interpolation=cubic are implemented");
+    return FALSE;
+  }
   cfg.in_rate = GST_AUDIO_INFO_RATE (&self->in);
   cfg.out_rate = GST_AUDIO_INFO_RATE (&self->out);
   cfg.channels = GST_AUDIO_INFO_CHANNELS (&self->in);
@@ -261,6 +272,10 @@ ars_set_property (GObject * obj, guint id, const GValue * value, GParamSpec * ps
   switch (id) {
     case PROP_QUALITY: self->quality = g_value_get_int (value); break;
     case PROP_DEVICE_ID: self->device_id = g_value_get_int (value); break;
+    case PROP_RESAMPLE_METHOD: self->method = g_value_get_enum (value); break;
+    case PROP_SINC_FILTER_MODE: self->sinc_filter_mode = g_value_get_enum (value); break;
+    case PROP_SINC_FILTER_AUTO_THRESHOLD: self->sinc_filter_auto_threshold = g_value_get_uint (value); break;
+    case PROP_SINC_FILTER_INTERPOLATION: self->sinc_filter_interpolation = g_value_get_enum (value); break;
     default: G_OBJECT_WARN_INVALID_PROPERTY_ID (obj, id, pspec); break;
   }
 }
@@ -272,6 +287,10 @@ ars_get_property (GObject * obj, guint id, GValue * value, GParamSpec * pspec)
   switch (id) {
     case PROP_QUALITY: g_value_set_int (value, self->quality); break;
     case PROP_DEVICE_ID: g_value_set_int (value, self->device_id); break;
+    case PROP_RESAMPLE_METHOD: g_value_set_enum (value, self->method); break;
+    case PROP_SINC_FILTER_MODE: g_value_set_enum (value, self->sinc_filter_mode); break;
+    case PROP_SINC_FILTER_AUTO_THRESHOLD: g_value_set_uint (value, self->sinc_filter_auto_threshold); break;
+    case PROP_SINC_FILTER_INTERPOLATION: g_value_set_enum (value, self->sinc_filter_interpolation); break;
     default: G_OBJECT_WARN_INVALID_PROPERTY_ID (obj, id, pspec); break;
   }
 }
@@ -289,6 +308,18 @@ gst_cuda_audio_resample_class_init (GstCudaAudioResampleClass * klass)
           G_PARAM_READWRITE | G_PARAM_STATIC_STRINGS));
   g_object_class_install_property (gobject, PROP_DEVICE_ID, g_param_spec_int ("cuda-device-id", "Cuda Device ID",
           "GPU device to use", 0, G_MAXINT, 0, G_PARAM_READWRITE | GST_PARAM_MUTABLE_READY | G_PARAM_STATIC_STRINGS));
+  g_object_class_install_property (gobject, PROP_RESAMPLE_METHOD, g_param_spec_enum ("resample-method", "Resample method to use",
+          "What resample method to use", GST_TYPE_AUDIO_RESAMPLER_METHOD, GST_AUDIO_RESAMPLER_METHOD_KAISER,
+          G_PARAM_READWRITE | G_PARAM_STATIC_STRINGS));
+  g_object_class_install_property (gobject, PROP_SINC_FILTER_MODE, g_param_spec_enum ("sinc-filter-mode", "Sinc filter table mode",
+          "What sinc filter table mode to use", GST_TYPE_AUDIO_RESAMPLER_FILTER_MODE, GST_AUDIO_RESAMPLER_FILTER_MODE_AUTO,
+          G_PARAM_READWRITE | G_PARAM_STATIC_STRINGS));
+  g_object_class_install_property (gobject, PROP_SINC_FILTER_AUTO_THRESHOLD, g_param_spec_uint ("sinc-filter-auto-threshold",
+          "Sinc filter auto mode threshold", "Memory usage threshold to use if sinc filter mode is AUTO, given in bytes "
+          "(the stock resampler never sees it: SURVEY A.10)", 0, G_MAXUINT, 1 * 1048576, G_PARAM_READWRITE | G_PARAM_STATIC_STRINGS));
+  g_object_class_install_property (gobject, PROP_SINC_FILTER_INTERPOLATION, g_param_spec_enum ("sinc-filter-interpolation",
+          "Sinc filter interpolation", "How to interpolate the sinc filter table", GST_TYPE_AUDIO_RESAMPLER_FILTER_INTERPOLATION,
+          GST_AUDIO_RESAMPLER_FILTER_INTERPOLATION_CUBIC, G_PARAM_READWRITE | G_PARAM_STATIC_STRINGS));
   gst_element_class_add_static_pad_template (element, &ars_sink);
   gst_element_class_add_static_pad_template (element, &ars_src);
   gst_element_class_set_static_metadata (element, "B200 audio resampler", "Filter/Converter/Audio/Hardware",
@@ -309,6 +340,10 @@ gst_cuda_audio_resample_init (GstCudaAudioResample * self)
 {
   self->quality = 4;
   self->device_id = 0;
+  self->method = GST_AUDIO_RESAMPLER_METHOD_KAISER;
+  self->sinc_filter_mode = GST_AUDIO_RESAMPLER_FILTER_MODE_AUTO;
+  self->sinc_filter_auto_threshold = 1 * 1048576;
+  self->sinc_filter_interpolation = GST_AUDIO_RESAMPLER_FILTER_INTERPOLATION_CUBIC;
   self->t0 = GST_CLOCK_TIME_NONE;
   self->need_discont = TRUE;
 }

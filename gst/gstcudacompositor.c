@@ -30,13 +30,18 @@ typedef struct
 {
   GstVideoAggregatorPad parent;
   gint xpos, ypos;
+  gint width, height;            /* pad properties (compositor.c:686-692): the size of the picture in the output, <= 0 unscaled */
+  gint sizing_policy;            /* 0 none, 1 keep-aspect-ratio (compositor.c:714) */
+  gint x_offset, y_offset;       /* centring offsets of keep-aspect-ratio, from pad_output_size() */
   gdouble alpha;
   gint op;                       /* b200_comp_operator == GstCompositorOperator numbering */
+  b200_vcs *conv;                /* convert pad: input caps differ from the aggregator's in format or size */
 } GstB200CompositorPad;
 typedef struct { GstVideoAggregatorPadClass parent_class; } GstB200CompositorPadClass;
 G_DEFINE_TYPE (GstB200CompositorPad, gst_b200_compositor_pad, GST_TYPE_VIDEO_AGGREGATOR_PAD);
 
-enum { PAD_PROP_0, PAD_PROP_XPOS, PAD_PROP_YPOS, PAD_PROP_ALPHA, PAD_PROP_OPERATOR };
+enum { PAD_PROP_0, PAD_PROP_XPOS, PAD_PROP_YPOS, PAD_PROP_WIDTH, PAD_PROP_HEIGHT, PAD_PROP_ALPHA, PAD_PROP_OPERATOR,
+  PAD_PROP_SIZING_POLICY };
 
 static void
 pad_set_property (GObject * obj, guint id, const GValue * value, GParamSpec * pspec)
@@ -45,6 +50,9 @@ pad_set_property (GObject * obj, guint id, const GValue * value, GParamSpec * ps
   switch (id) {
     case PAD_PROP_XPOS: pad->xpos = g_value_get_int (value); break;
     case PAD_PROP_YPOS: pad->ypos = g_value_get_int (value); break;
+    case PAD_PROP_WIDTH: pad->width = g_value_get_int (value); break;
+    case PAD_PROP_HEIGHT: pad->height = g_value_get_int (value); break;
+    case PAD_PROP_SIZING_POLICY: pad->sizing_policy = g_value_get_int (value); break;
     case PAD_PROP_ALPHA: pad->alpha = g_value_get_double (value); break;
     case PAD_PROP_OPERATOR: pad->op = g_value_get_int (value); break;
     default: G_OBJECT_WARN_INVALID_PROPERTY_ID (obj, id, pspec); break;
@@ -58,6 +66,9 @@ pad_get_property (GObject * obj, guint id, GValue * value, GParamSpec * pspec)
   switch (id) {
     case PAD_PROP_XPOS: g_value_set_int (value, pad->xpos); break;
     case PAD_PROP_YPOS: g_value_set_int (value, pad->ypos); break;
+    case PAD_PROP_WIDTH: g_value_set_int (value, pad->width); break;
+    case PAD_PROP_HEIGHT: g_value_set_int (value, pad->height); break;
+    case PAD_PROP_SIZING_POLICY: g_value_set_int (value, pad->sizing_policy); break;
     case PAD_PROP_ALPHA: g_value_set_double (value, pad->alpha); break;
     case PAD_PROP_OPERATOR: g_value_set_int (value, pad->op); break;
     default: G_OBJECT_WARN_INVALID_PROPERTY_ID (obj, id, pspec); break;
@@ -74,6 +85,12 @@ gst_b200_compositor_pad_class_init (GstB200CompositorPadClass * klass)
           "X Position of the picture", G_MININT, G_MAXINT, 0, G_PARAM_READWRITE | GST_PARAM_CONTROLLABLE));
   g_object_class_install_property (gobject, PAD_PROP_YPOS, g_param_spec_int ("ypos", "Y Position",
           "Y Position of the picture", G_MININT, G_MAXINT, 0, G_PARAM_READWRITE | GST_PARAM_CONTROLLABLE));
+  g_object_class_install_property (gobject, PAD_PROP_WIDTH, g_param_spec_int ("width", "Width",
+          "Width of the picture", G_MININT, G_MAXINT, 0, G_PARAM_READWRITE | GST_PARAM_CONTROLLABLE));
+  g_object_class_install_property (gobject, PAD_PROP_HEIGHT, g_param_spec_int ("height", "Height",
+          "Height of the picture", G_MININT, G_MAXINT, 0, G_PARAM_READWRITE | GST_PARAM_CONTROLLABLE));
+  g_object_class_install_property (gobject, PAD_PROP_SIZING_POLICY, g_param_spec_int ("sizing-policy", "Sizing policy",
+          "0 none, 1 keep-aspect-ratio (GstCompositorSizingPolicy)", 0, 1, 0, G_PARAM_READWRITE | GST_PARAM_CONTROLLABLE));
   g_object_class_install_property (gobject, PAD_PROP_ALPHA, g_param_spec_double ("alpha", "Alpha",
           "Alpha of the picture", 0.0, 1.0, 1.0, G_PARAM_READWRITE | GST_PARAM_CONTROLLABLE));
   g_object_class_install_property (gobject, PAD_PROP_OPERATOR, g_param_spec_int ("operator", "Operator",
@@ -87,11 +104,51 @@ gst_b200_compositor_pad_init (GstB200CompositorPad * pad)
   pad->op = B200_COMP_OP_OVER;
 }
 
+/* _mixer_pad_get_output_size (compositor.c:289-417) for pixel aspect ratio 1/1: the size the pad's picture takes in the
+ * output and the offsets that centre it under sizing-policy=keep-aspect-ratio (gst_video_center_rect,
+ * gstvideosink.c:122-164).  The pad's converter (b200_vcs, method mitchell = the option-less GstVideoConverter of a
+ * GstVideoAggregatorConvertPad) scales to this size; blending happens at xpos + x_offset, ypos + y_offset. */
+static void
+pad_output_size (GstB200CompositorPad * pad, gboolean zero_size_is_unscaled, gint * width, gint * height)
+{
+  const GstVideoInfo *info = &GST_VIDEO_AGGREGATOR_PAD (pad)->info;
+  gint sw = GST_VIDEO_INFO_WIDTH (info), sh = GST_VIDEO_INFO_HEIGHT (info);
+  gint pw = (zero_size_is_unscaled ? pad->width <= 0 : pad->width < 0) ? sw : pad->width;
+  gint ph = (zero_size_is_unscaled ? pad->height <= 0 : pad->height < 0) ? sh : pad->height;
+  gint fn, fd, tn, td;
+  pad->x_offset = pad->y_offset = 0;
+  *width = *height = 0;
+  if (pw == 0 || ph == 0)
+    return;
+  if (pad->sizing_policy == 1 && gst_util_fraction_multiply (sw, sh, 1, 1, &fn, &fd) &&
+      gst_util_fraction_multiply (pw, ph, 1, 1, &tn, &td) && (fn != tn || fd != td)) {
+    gint rh = (gint) gst_util_uint64_scale_int (pw, fd, fn);
+    gdouble src_ratio, dst_ratio;
+    if (rh == 0)
+      return;
+    src_ratio = (gdouble) pw / rh;
+    dst_ratio = (gdouble) pw / ph;
+    if (src_ratio > dst_ratio) {
+      gint h = (gint) (pw / src_ratio);
+      pad->y_offset = (ph - h) / 2;
+      ph = h;
+    } else if (src_ratio < dst_ratio) {
+      gint w = (gint) (ph * src_ratio);
+      pad->x_offset = (pw - w) / 2;
+      pw = w;
+    }
+  }
+  *width = pw;
+  *height = ph;
+}
+
 /* ------------------------------------------------------------------ element */
 typedef struct
 {
   GstVideoAggregator parent;
   gint background, device_id;
+  gboolean zero_size_is_unscaled, ignore_inactive_pads;      /* compositor.c:2117, :2162; defaults TRUE / FALSE */
+  guint max_threads;             /* accepted; the single-pass GPU blend has no use for it */
   GstCudaContext *context;
   GstCudaStream *stream;
   b200_comp *comp;
@@ -100,7 +157,7 @@ typedef struct
 typedef struct { GstVideoAggregatorClass parent_class; } GstB200CudaCompositorClass;
 G_DEFINE_TYPE (GstB200CudaCompositor, gst_b200_cuda_compositor, GST_TYPE_VIDEO_AGGREGATOR);
 
-enum { PROP_0, PROP_BACKGROUND, PROP_DEVICE_ID };
+enum { PROP_0, PROP_BACKGROUND, PROP_DEVICE_ID, PROP_ZERO_SIZE_IS_UNSCALED, PROP_MAX_THREADS, PROP_IGNORE_INACTIVE_PADS };
 
 static void
 comp_set_property (GObject * obj, guint id, const GValue * value, GParamSpec * pspec)
@@ -109,6 +166,9 @@ comp_set_property (GObject * obj, guint id, const GValue * value, GParamSpec * p
   switch (id) {
     case PROP_BACKGROUND: self->background = g_value_get_int (value); break;
     case PROP_DEVICE_ID: self->device_id = g_value_get_int (value); break;
+    case PROP_ZERO_SIZE_IS_UNSCALED: self->zero_size_is_unscaled = g_value_get_boolean (value); break;
+    case PROP_MAX_THREADS: self->max_threads = g_value_get_uint (value); break;
+    case PROP_IGNORE_INACTIVE_PADS: self->ignore_inactive_pads = g_value_get_boolean (value); break;
     default: G_OBJECT_WARN_INVALID_PROPERTY_ID (obj, id, pspec); break;
   }
 }
@@ -120,6 +180,9 @@ comp_get_property (GObject * obj, guint id, GValue * value, GParamSpec * pspec)
   switch (id) {
     case PROP_BACKGROUND: g_value_set_int (value, self->background); break;
     case PROP_DEVICE_ID: g_value_set_int (value, self->device_id); break;
+    case PROP_ZERO_SIZE_IS_UNSCALED: g_value_set_boolean (value, self->zero_size_is_unscaled); break;
+    case PROP_MAX_THREADS: g_value_set_uint (value, self->max_threads); break;
+    case PROP_IGNORE_INACTIVE_PADS: g_value_set_boolean (value, self->ignore_inactive_pads); break;
     default: G_OBJECT_WARN_INVALID_PROPERTY_ID (obj, id, pspec); break;
   }
 }
@@ -176,13 +239,20 @@ comp_aggregate_frames (GstVideoAggregator * vagg, GstBuffer * outbuf)
     GstVideoFrame *f = gst_video_aggregator_pad_get_prepared_frame (GST_VIDEO_AGGREGATOR_PAD (cpad));
     if (!f)
       continue;
+    {
+      /* refreshes x_offset / y_offset; the prepared frame (the pad's own b200_vcs) already has this size */
+      gint pw, ph;
+      pad_output_size (cpad, self->zero_size_is_unscaled, &pw, &ph);
+      if (pw == 0 || ph == 0)
+        continue;                /* compositor.c:547-550: nothing to draw */
+    }
     mapped[n] = f;
     pads[n].data = GST_VIDEO_FRAME_PLANE_DATA (f, 0);
     pads[n].width = GST_VIDEO_FRAME_WIDTH (f);
     pads[n].height = GST_VIDEO_FRAME_HEIGHT (f);
     pads[n].stride = GST_VIDEO_FRAME_PLANE_STRIDE (f, 0);
-    pads[n].xpos = cpad->xpos;
-    pads[n].ypos = cpad->ypos;
+    pads[n].xpos = cpad->xpos + cpad->x_offset;      /* compositor.c:1692-1693 */
+    pads[n].ypos = cpad->ypos + cpad->y_offset;
     pads[n].alpha = cpad->alpha;
     pads[n].op = cpad->op;
     pads[n].reserved = 0;
@@ -231,6 +301,15 @@ gst_b200_cuda_compositor_class_init (GstB200CudaCompositorClass * klass)
   g_object_class_install_property (gobject, PROP_BACKGROUND, g_param_spec_int ("background", "Background",
           "0 checker, 1 black, 2 white, 3 transparent (GstCompositorBackground)", 0, 3, 0,
           G_PARAM_READWRITE | G_PARAM_STATIC_STRINGS));
+  g_object_class_install_property (gobject, PROP_ZERO_SIZE_IS_UNSCALED, g_param_spec_boolean ("zero-size-is-unscaled",
+          "Zero size is unscaled", "If TRUE, then input video is unscaled in that dimension if width or height is 0",
+          TRUE, G_PARAM_READWRITE | G_PARAM_STATIC_STRINGS));
+  g_object_class_install_property (gobject, PROP_MAX_THREADS, g_param_spec_uint ("max-threads", "Max Threads",
+          "Maximum number of blending/rendering worker threads (accepted; the GPU blend is one pass)", 0, G_MAXINT, 0,
+          G_PARAM_READWRITE | G_PARAM_STATIC_STRINGS));
+  g_object_class_install_property (gobject, PROP_IGNORE_INACTIVE_PADS, g_param_spec_boolean ("ignore-inactive-pads",
+          "Ignore inactive pads", "Avoid timing out waiting for inactive pads", FALSE,
+          G_PARAM_READWRITE | G_PARAM_STATIC_STRINGS));
   g_object_class_install_property (gobject, PROP_DEVICE_ID, g_param_spec_int ("cuda-device-id", "Cuda Device ID",
           "GPU device to use", -1, G_MAXINT, 0, G_PARAM_READWRITE | GST_PARAM_MUTABLE_READY | G_PARAM_STATIC_STRINGS));
   gst_element_class_add_static_pad_template_with_gtype (element, &comp_src, GST_TYPE_AGGREGATOR_PAD);
@@ -248,4 +327,5 @@ gst_b200_cuda_compositor_init (GstB200CudaCompositor * self)
 {
   self->background = B200_COMP_BG_CHECKER;
   self->device_id = 0;
+  self->zero_size_is_unscaled = TRUE;
 }

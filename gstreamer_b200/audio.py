@@ -21,7 +21,17 @@ class AudioFormat:
 
 
 class CudaAudioResample:
-    def __init__(self, quality=4, cuda_device_id=0, format=AudioFormat.F32LE):
+    # the stock element's remaining properties (gstaudioresample.c:153-186) and their defaults: accepted so that existing
+    # pipelines keep working, only the default of each is implemented (set_caps refuses anything else).
+    # sinc-filter-auto-threshold never reaches the reference's resampler anyway (UINT stored, INT read: SURVEY A.10)
+    REST_DEFAULTS = {"resample_method": "kaiser", "sinc_filter_mode": "auto", "sinc_filter_interpolation": "cubic"}
+
+    def __init__(self, quality=4, cuda_device_id=0, format=AudioFormat.F32LE, sinc_filter_auto_threshold=1048576, **rest):
+        unknown = set(rest) - set(self.REST_DEFAULTS)
+        if unknown:
+            raise TypeError(f"no such property: {sorted(unknown)}")
+        self.rest = dict(self.REST_DEFAULTS, **rest)
+        self.sinc_filter_auto_threshold = sinc_filter_auto_threshold
         self.quality = quality
         self.format = format
         self.cuda_device_id = cuda_device_id
@@ -31,6 +41,9 @@ class CudaAudioResample:
     # GstBaseTransformClass::set_caps (interleaved samples of self.format)
     def set_caps(self, in_rate, out_rate, channels):
         self._free()
+        for k, v in self.rest.items():
+            if v != self.REST_DEFAULTS[k]:
+                raise _lib.B200Error(-2, f"property {k.replace('_', '-')}={v!r}: only the default is implemented")
         cfg = _lib.ArsConfigC()
         cfg.in_rate, cfg.out_rate, cfg.channels, cfg.quality = in_rate, out_rate, channels, self.quality
         cfg.format = int(self.format)

@@ -2,7 +2,8 @@
 
   CudaCompositor          ~ the `compositor` element: `background` property (compositor.c:742),
                             request sink pads, GstVideoAggregatorClass::aggregate_frames (:1739)
-  CudaCompositorPad       ~ GstCompositorPad: xpos / ypos / alpha / operator (compositor.c:190-196)
+  CudaCompositorPad       ~ GstCompositorPad: xpos / ypos / width / height / alpha / operator / sizing-policy
+                            (compositor.c:190-196, :678-716)
 """
 import ctypes as C
 import enum
@@ -25,6 +26,40 @@ class Operator(enum.IntEnum):
     ADD = 2
 
 
+def pad_output_size(src_w, src_h, pad_w, pad_h, sizing_policy="none", zero_size_is_unscaled=True):
+    """_mixer_pad_get_output_size (compositor.c:289-417) for pixel aspect ratio 1/1 everywhere: the size a pad's picture
+    takes in the output and the offset that centres it.  pad_w / pad_h are the pad's width / height properties (unset:
+    the source size), sizing_policy "none" or "keep-aspect-ratio".  Returns (width, height, x_offset, y_offset)."""
+    from math import gcd
+    if zero_size_is_unscaled:
+        pad_w = src_w if pad_w <= 0 else pad_w
+        pad_h = src_h if pad_h <= 0 else pad_h
+    else:
+        pad_w = src_w if pad_w < 0 else pad_w
+        pad_h = src_h if pad_h < 0 else pad_h
+    if pad_w == 0 or pad_h == 0:
+        return 0, 0, 0, 0
+    if sizing_policy in ("none", 0):
+        # the display-ratio round trip (gst_video_calculate_display_ratio, :330-352) is the identity at 1/1
+        return pad_w, pad_h, 0, 0
+    g1, g2 = gcd(src_w, src_h), gcd(pad_w, pad_h)
+    num, den = src_w // g1, src_h // g1
+    if (num, den) == (pad_w // g2, pad_h // g2):
+        return pad_w, pad_h, 0, 0
+    sh = pad_w * den // num                     # gst_util_uint64_scale_int (pad_width, den, num)
+    if sh == 0:
+        return 0, 0, 0, 0
+    # gst_video_center_rect (gstvideosink.c:122-164), scaling: doubles, then truncation to int
+    src_ratio, dst_ratio = pad_w / sh, pad_w / pad_h
+    if src_ratio > dst_ratio:
+        w, h = pad_w, int(pad_w / src_ratio)
+        return w, h, 0, (pad_h - h) // 2
+    if src_ratio < dst_ratio:
+        w, h = int(pad_h * src_ratio), pad_h
+        return w, h, (pad_w - w) // 2, 0
+    return pad_w, pad_h, 0, 0
+
+
 class CudaCompositorPad:
     """GstCompositorPad.  `width`/`height` are the pad properties (compositor.c:190-196): the size the
     pad's picture takes in the output.  With `in_info` the pad is a GstVideoAggregatorConvertPad: its
@@ -33,7 +68,15 @@ class CudaCompositorPad:
     DEFAULT options — cubic b = c = 1/3 (video-converter.c:791, video-resampler.c:63-64), i.e. exactly
     cudavideoconvertscale method=mitchell — before blending."""
 
-    def __init__(self, width, height, stride=None, xpos=0, ypos=0, alpha=1.0, operator=Operator.OVER, in_info=None):
+    def __init__(self, width, height, stride=None, xpos=0, ypos=0, alpha=1.0, operator=Operator.OVER, in_info=None,
+                 sizing_policy="none"):
+        # sizing-policy (compositor.c:714): "keep-aspect-ratio" shrinks a converting pad's picture inside width x height
+        # so that the source's display aspect ratio survives, centred by x_offset / y_offset
+        self.x_offset = self.y_offset = 0
+        self.sizing_policy = sizing_policy
+        if in_info is not None:
+            width, height, self.x_offset, self.y_offset = pad_output_size(in_info.width, in_info.height, width, height,
+                                                                          sizing_policy)
         self.width, self.height = width, height
         self.stride = stride or width * 4
         self.xpos, self.ypos, self.alpha, self.operator = xpos, ypos, alpha, Operator(operator)
@@ -92,7 +135,7 @@ class CudaCompositor:
             keep.append(info)
             arr[i].data = _ptr(p.frame)
             arr[i].info = info.c
-            arr[i].xpos, arr[i].ypos, arr[i].alpha, arr[i].op = p.xpos, p.ypos, p.alpha, int(p.operator)
+            arr[i].xpos, arr[i].ypos, arr[i].alpha, arr[i].op = p.xpos + p.x_offset, p.ypos + p.y_offset, p.alpha, int(p.operator)
         check(lib.b200_comp_blend_yuv(self._h, _ptr(outbuf), C.byref(out_info.c), int(self.background), arr, len(pads),
                                       _stream(stream)), "b200_comp_blend_yuv")
 
@@ -105,7 +148,7 @@ class CudaCompositor:
         for i, p in enumerate(pads):
             arr[i].data = _ptr(p._prepare_frame(self.format, self.device, stream))
             arr[i].width, arr[i].height, arr[i].stride = p.width, p.height, p.stride
-            arr[i].xpos, arr[i].ypos, arr[i].alpha, arr[i].op = p.xpos, p.ypos, p.alpha, int(p.operator)
+            arr[i].xpos, arr[i].ypos, arr[i].alpha, arr[i].op = p.xpos + p.x_offset, p.ypos + p.y_offset, p.alpha, int(p.operator)
         check(lib.b200_comp_blend(self._h, _ptr(outbuf), out_stride or self.width * 4, int(self.background),
                                   arr, len(pads), _stream(stream)), "b200_comp_blend")
 

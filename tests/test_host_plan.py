@@ -327,3 +327,28 @@ def test_remaining_element_properties_are_accepted_at_their_defaults():
         assert e.value.status == -2
     with pytest.raises(TypeError):
         g.CudaVideoConvertScale(no_such_property=1)
+
+
+def test_compositor_pad_sizing_policy():
+    """_mixer_pad_get_output_size (compositor.c:289-417) at pixel aspect ratio 1/1"""
+    from gstreamer_b200.compositor import pad_output_size, CudaCompositorPad
+    import gstreamer_b200 as g
+    assert pad_output_size(1920, 1080, 0, 0) == (1920, 1080, 0, 0)                       # unset: unscaled
+    assert pad_output_size(1920, 1080, 640, 640) == (640, 640, 0, 0)                     # policy none: stretched
+    assert pad_output_size(1920, 1080, 640, 640, "keep-aspect-ratio") == (640, 360, 0, 140)
+    assert pad_output_size(640, 480, 1920, 1080, "keep-aspect-ratio") == (1440, 1080, 240, 0)
+    assert pad_output_size(1920, 1080, 1280, 720, "keep-aspect-ratio") == (1280, 720, 0, 0)
+    assert pad_output_size(1000, 3, 10, 100, "keep-aspect-ratio") == (0, 0, 0, 0)        # rounds to an empty picture
+    assert pad_output_size(100, 100, 0, 50, zero_size_is_unscaled=False) == (0, 0, 0, 0)
+    pad = CudaCompositorPad(640, 640, xpos=10, ypos=20, in_info=g.VideoInfo(23, 1920, 1080), sizing_policy="keep-aspect-ratio")
+    assert (pad.width, pad.height, pad.x_offset, pad.y_offset, pad.stride) == (640, 360, 0, 140, 2560)
+
+
+def test_audioresample_remaining_properties():
+    import gstreamer_b200 as g
+    from gstreamer_b200.audio import CudaAudioResample
+    CudaAudioResample(cuda_device_id=-1, resample_method="kaiser", sinc_filter_auto_threshold=1).set_caps(48000, 44100, 2)
+    for kw in ({"resample_method": "linear"}, {"sinc_filter_mode": "full"}, {"sinc_filter_interpolation": "linear"}):
+        with pytest.raises(g.B200Error) as e:
+            CudaAudioResample(cuda_device_id=-1, **kw).set_caps(48000, 44100, 2)
+        assert e.value.status == -2
