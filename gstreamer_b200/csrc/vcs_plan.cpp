@@ -587,6 +587,17 @@ int build_planes (VcsPlan * p, const FilterSpec & f)
 // convert_scale_planes rows (video-converter.c:8879-8896): 4-byte pixels through gst_video_scaler_2d with the element's
 // method, the stepping 2-tap horizontal scaler (video_scale_h_2tap_4u8), every byte - alpha or padding included - a
 // channel.  vcs_planes_kernel with ne = 4.
+// memory byte index of the A (or padding), R, G, B component of a packed 4-byte format
+static void rgb_component_bytes (int format, int pos[4])
+{
+  switch (format) {
+    case B200_VIDEO_FORMAT_BGRA: case B200_VIDEO_FORMAT_BGRx: pos[0] = 3; pos[1] = 2; pos[2] = 1; pos[3] = 0; break;
+    case B200_VIDEO_FORMAT_RGBA: case B200_VIDEO_FORMAT_RGBx: pos[0] = 3; pos[1] = 0; pos[2] = 1; pos[3] = 2; break;
+    case B200_VIDEO_FORMAT_ABGR: case B200_VIDEO_FORMAT_xBGR: pos[0] = 0; pos[1] = 3; pos[2] = 2; pos[3] = 1; break;
+    default: pos[0] = 0; pos[1] = 1; pos[2] = 2; pos[3] = 3; break;          // ARGB / xRGB
+  }
+}
+
 static int build_rgb_same_plan (VcsPlan * p)
 {
   const b200_video_info *in = &p->in, *out = &p->out;
@@ -598,12 +609,26 @@ static int build_rgb_same_plan (VcsPlan * p)
   PlanePlan & q = p->planes[0];
   q = PlanePlan ();
   q.src_plane = 0; q.iw = iw; q.ih = ih; q.ow = ow; q.oh = oh; q.ne = 4;
+  // another byte order (BGRA -> RGBA ...) has no table row: the reference's chain runs - byte-shuffle unpack, the same
+  // 4-byte-pixel scalers, byte-shuffle pack, no matrix and (alpha value 1.0) no alpha stage - so it differs from the
+  // same-format rows only in the pass order rule (chain_scale :1697-1714 instead of gst_video_scaler_2d :1542-1545)
+  // and in where each byte lands; a format's padding byte travels as alpha, like in the reference's unpack
+  const bool cross = in->format != out->format;
+  if (cross) {
+    int pi[4], po[4];
+    rgb_component_bytes (in->format, pi);
+    rgb_component_bytes (out->format, po);
+    unsigned swz = 0;
+    for (int comp = 0; comp < 4; comp++) swz |= (unsigned) pi[comp] << (4 * po[comp]);
+    q.swz = swz == 0x3210u ? 0u : swz;
+  }
   if (iw == ow && ih == oh) { q.mode = PM_COPY; return B200_OK; }
   q.mode = PM_SCALE;
   q.have_h = iw != ow; q.have_v = ih != oh;
   if (q.have_h) scaled_axis (&q.h, f, iw, ow, true, true); else identity_axis (&q.h, iw);
   if (q.have_v) scaled_axis (&q.v, f, ih, oh, false); else identity_axis (&q.v, ih);
-  q.h_first = !(q.have_h && q.have_v) || (int64_t) q.v.offset[oh - 1] <= (int64_t) oh;
+  if (cross) q.h_first = (int64_t) ow * ih <= (int64_t) iw * oh;
+  else q.h_first = !(q.have_h && q.have_v) || (int64_t) q.v.offset[oh - 1] <= (int64_t) oh;
   return B200_OK;
 }
 
@@ -611,10 +636,10 @@ static int build_rgb_in_plan (VcsPlan * p)
 {
   const b200_video_info *in = &p->in, *out = &p->out;
   if (!getenv ("B200_VCS_EXPERIMENTAL")) return B200_ERR_UNSUPPORTED;
-  if (out->format == in->format) return build_rgb_same_plan (p);
+  if (out->format >= B200_VIDEO_FORMAT_RGBx && out->format <= B200_VIDEO_FORMAT_ABGR) return build_rgb_same_plan (p);
   const bool out_pl = out->format == B200_VIDEO_FORMAT_I420 || out->format == B200_VIDEO_FORMAT_YV12;
   const bool out_semi = out->format == B200_VIDEO_FORMAT_NV12 || out->format == B200_VIDEO_FORMAT_NV21;
-  if (!out_pl && !out_semi) return B200_ERR_UNSUPPORTED;           // RGB -> another RGB byte order: not built
+  if (!out_pl && !out_semi) return B200_ERR_UNSUPPORTED;
   if (in->stride[0] < in->width * 4 || (in->stride[0] & 3) || (in->offset[0] & 3)) return B200_ERR_INVALID_ARG;
   const int ocw = (out->width + 1) / 2;
   if (out->stride[0] < out->width) return B200_ERR_INVALID_ARG;

@@ -33,7 +33,8 @@ enum PlaneMode : int { PM_COPY = 0, PM_HALVE_V = 1, PM_HALVE_H = 2, PM_HALVE_HV 
 struct PlanePlan {
   int src_plane = 0;             // plane of the input that feeds this output plane
   int iw = 0, ih = 0, ow = 0, oh = 0;    // in pixels of this plane
-  int ne = 1;                    // bytes per pixel (2 for the interleaved UV plane)
+  int ne = 1;                    // bytes per pixel (2 for the interleaved UV plane, 4 for packed RGB)
+  unsigned swz = 0;              // packed RGB to another byte order: output byte c <- source byte (swz >> 4c) & 3
   int mode = PM_COPY;
   bool have_h = false, have_v = false, h_first = true;
   AxisPlan h, v;

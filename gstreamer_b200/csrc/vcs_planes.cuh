@@ -36,6 +36,7 @@ struct PlaneDev {
   unsigned long long src_off, dst_off;
   int sstride, dstride, iw, ih, ow, oh, ne, mode, h_first;
   int vec4;                      // copy / halve plane whose rows are word (source: double-word for h halving) aligned
+  unsigned swz;                  // 4-byte pixels only: output byte c takes source byte (swz >> 4c) & 3; 0 = same order
   PlaneAxisDev h, v;
 };
 
@@ -87,6 +88,7 @@ vcs_planes_kernel (const PlanesParams P, const VcsBatch frames)
     unsigned o;
     if (Q.mode == PM_COPY) {
       o = __ldg ((const unsigned *) (src + (size_t) wy * Q.sstride) + wx);
+      if (Q.swz) o = __byte_perm (o, 0, Q.swz);                     // another byte order of the same 4-byte pixel
     } else if (Q.mode == PM_HALVE_V) {
       o = avg_ceil4 (__ldg ((const unsigned *) (src + (size_t) (2 * wy) * Q.sstride) + wx),
           __ldg ((const unsigned *) (src + (size_t) (2 * wy + 1) * Q.sstride) + wx));
@@ -110,12 +112,13 @@ vcs_planes_kernel (const PlanesParams P, const VcsBatch frames)
   uint8_t *__restrict__ dst = frames.out[frame] + Q.dst_off;
   const int nes = Q.ne >> 1;                                        // ne is 1, 2 or 4 (shift 0, 1, 2): divide by shifting
   const int x = min (xb, wbytes - 1) >> nes, c = min (xb, wbytes - 1) - (x << nes);
+  const int cs = Q.swz ? (int) ((Q.swz >> (4 * c)) & 3) : c;        // source component feeding output component c
   int v = 0;
   if (Q.mode != PM_SCALE) {
     if (!live) return;
     switch (Q.mode) {
       case PM_COPY:
-        v = src[(size_t) y * Q.sstride + xb];
+        v = src[(size_t) y * Q.sstride + (x << nes) + cs];
         break;
       case PM_HALVE_V:                                             // avgub of the two lines
         v = (src[(size_t) (2 * y) * Q.sstride + xb] + src[(size_t) (2 * y + 1) * Q.sstride + xb] + 1) >> 1;
@@ -165,8 +168,8 @@ vcs_planes_kernel (const PlanesParams P, const VcsBatch frames)
     __syncthreads ();
     if (!live) return;
     auto vcol = [&] (int col) -> int {                             // v-scaled byte of source pixel `col`, component c
-      if (staged) return stage[ty * PL_STAGE_COLS + (col - c0) * Q.ne + c];
-      return vfilter (src + (size_t) V.offset[y] * Q.sstride + col * Q.ne + c, y);
+      if (staged) return stage[ty * PL_STAGE_COLS + (col - c0) * Q.ne + cs];
+      return vfilter (src + (size_t) V.offset[y] * Q.sstride + col * Q.ne + cs, y);
     };
     const int i0 = (int) H.offset[x];
     if (H.mode == PASS_COPY) v = vcol (i0);
@@ -186,13 +189,13 @@ vcs_planes_kernel (const PlanesParams P, const VcsBatch frames)
       // thread (tx, ty) fills column tx of source lines ty, ty + 4, ...
       if (tx < tw)
         for (int r = ty; r < nr; r += PL_TH)
-          stage[r * PL_TW + tx] = (uint8_t) plane_h (Q, src + (size_t) (r0 + r) * Q.sstride, x, c);
+          stage[r * PL_TW + tx] = (uint8_t) plane_h (Q, src + (size_t) (r0 + r) * Q.sstride, x, cs);
     }
     __syncthreads ();
     if (!live) return;
     auto hline = [&] (int line) -> int {                           // h-scaled byte of source line `line` at this thread's column
       if (staged) return stage[(line - r0) * PL_TW + tx];
-      return plane_h (Q, src + (size_t) line * Q.sstride, x, c);
+      return plane_h (Q, src + (size_t) line * Q.sstride, x, cs);
     };
     const int l0 = (int) V.offset[y];
     if (V.mode == PASS_COPY) v = hline (l0);
@@ -224,6 +227,7 @@ inline int prepare_planes (const VcsPlan & p, PlanesState * st)
     d.src_off = p.in.offset[q.src_plane]; d.dst_off = p.out.offset[i];
     d.sstride = p.in.stride[q.src_plane]; d.dstride = p.out.stride[i];
     d.iw = q.iw; d.ih = q.ih; d.ow = q.ow; d.oh = q.oh; d.ne = q.ne; d.mode = q.mode; d.h_first = q.h_first ? 1 : 0;
+    d.swz = q.swz;
     {
       const bool hh = q.mode == PM_HALVE_H || q.mode == PM_HALVE_HV;     // these read 8 source bytes per 4 output bytes
       const int sa = hh ? 7 : 3;

@@ -273,12 +273,12 @@ def test_rgb_input_plan_is_opt_in_and_matches_the_oracle_matrix(monkeypatch):
             d.out_matrix, d.out_range = matrix, rng
             assert ob.oracle().oracle_vcs_matrix_rgb2yuv(C.byref(d), im) == 0
             assert el.matrix().ravel().tolist() == list(im)
-    with pytest.raises(g.B200Error):
-        build(12, 11, 64, 48, 32, 24)                          # RGB -> another RGB byte order: not built
-    # the same format at another size (a compositor's scaled pads): the one-plane scaling rows
+    # the same format at another size (a compositor's scaled pads): the one-plane scaling rows; another byte order: the
+    # matrix-free chain, same kernel with a byte swizzle and the chain's pass-order rule
     for m in range(10):
         for size in [(64, 48, 32, 24), (40, 30, 64, 48), (100, 100, 150, 50), (64, 48, 64, 48)]:
             assert int(build(11, 11, *size, m=m).plan_info().kernel_variant) == 4
+            assert int(build(12, 11, *size, m=m).plan_info().kernel_variant) == 4
 
 
 def test_add_borders_rectangle_and_plan():

@@ -99,17 +99,19 @@ def test_rgb_to_420_batch(cuda_device):
 @pytest.mark.parametrize("method", [0, 1, 3, 4, 9], ids=["nearest", "bilinear", "lanczos", "bilinear2", "mitchell"])
 @pytest.mark.parametrize("size", [(64, 48, 32, 24), (40, 30, 64, 48), (65, 49, 33, 26), (33, 17, 20, 31), (100, 100, 150, 50),
                                   (40, 90, 40, 31), (64, 48, 64, 24), (64, 48, 32, 48), (3, 5, 7, 2), (1, 1, 4, 4),
-                                  (1920, 1080, 640, 360), (640, 360, 1280, 720)], ids=lambda s: "%dx%d-%dx%d" % s)
+                                  (50, 21, 50, 21), (1920, 1080, 640, 360), (640, 360, 1280, 720)], ids=lambda s: "%dx%d-%dx%d" % s)
 def test_rgb_same_format_scaling_matches_oracle(cuda_device, size, method):
     """a compositor's scaled RGBA pads: one plane of 4-byte pixels through vcs_planes_kernel (ne = 4)"""
     import torch
     import gstreamer_b200 as g
     iw, ih, ow, oh = size
-    for fmt in (["BGRA"] if iw * ih > 500_000 else ["BGRA", "RGBA", "ARGB", "xBGR"]):
+    pairs = [("BGRA", "BGRA")] if iw * ih > 500_000 else [("BGRA", "BGRA"), ("RGBA", "RGBA"), ("ARGB", "ARGB"), ("xBGR", "xBGR"),
+                                                            ("BGRA", "RGBA"), ("ARGB", "BGRx"), ("RGBx", "ABGR"), ("xRGB", "BGRA")]
+    for fmt, fmt_out in pairs:                      # same format: one-plane rows; another byte order: matrix-free chain
         frame = rgb_frame(iw, ih, 11)
-        want = ob.oracle_vcs_convert(ob.vcs_desc(iw, ih, ow, oh, method, in_fmt=ob.FMT[fmt], out_fmt=ob.FMT[fmt]), frame)
+        want = ob.oracle_vcs_convert(ob.vcs_desc(iw, ih, ow, oh, method, in_fmt=ob.FMT[fmt], out_fmt=ob.FMT[fmt_out]), frame)
         el = g.CudaVideoConvertScale(method=method, cuda_device_id=0)
-        ii, oi = g.VideoInfo(ob.FMT[fmt], iw, ih), g.VideoInfo(ob.FMT[fmt], ow, oh)
+        ii, oi = g.VideoInfo(ob.FMT[fmt], iw, ih), g.VideoInfo(ob.FMT[fmt_out], ow, oh)
         el.set_info(ii, oi)
         assert int(el.plan_info().kernel_variant) == 4
         dst = torch.full((oi.size,), 0x5A, dtype=torch.uint8, device="cuda")
@@ -117,4 +119,4 @@ def test_rgb_same_format_scaling_matches_oracle(cuda_device, size, method):
         torch.cuda.synchronize()
         got = dst.cpu().numpy()
         bad = np.argwhere(got != want)
-        assert bad.size == 0, f"{fmt}: {len(bad)} bytes differ, first at {bad[:4].ravel().tolist()}"
+        assert bad.size == 0, f"{fmt}->{fmt_out}: {len(bad)} bytes differ, first at {bad[:4].ravel().tolist()}"
