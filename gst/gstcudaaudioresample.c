@@ -26,8 +26,8 @@ static GstStaticPadTemplate ars_sink = GST_STATIC_PAD_TEMPLATE ("sink", GST_PAD_
 static GstStaticPadTemplate ars_src = GST_STATIC_PAD_TEMPLATE ("src", GST_PAD_SRC, GST_PAD_ALWAYS, GST_STATIC_CAPS (ARS_CAPS));
 
 enum { PROP_0, PROP_QUALITY, PROP_DEVICE_ID,
-  /* the stock element's remaining properties (gstaudioresample.c:160-186): installed with the stock defaults so that
-   * existing pipelines load; only the default of each is implemented (set_caps refuses anything else) */
+  /* the stock element's remaining properties (gstaudioresample.c:160-186), stock defaults: kaiser and blackman-nuttall,
+   * every filter mode, cubic table interpolation or none are implemented; the rest fails set_caps */
   PROP_RESAMPLE_METHOD, PROP_SINC_FILTER_MODE, PROP_SINC_FILTER_AUTO_THRESHOLD, PROP_SINC_FILTER_INTERPOLATION
 };
 
@@ -87,11 +87,11 @@ ars_set_caps (GstBaseTransform * trans, GstCaps * incaps, GstCaps * outcaps)
   if (!gst_audio_info_from_caps (&self->in, incaps) || !gst_audio_info_from_caps (&self->out, outcaps))
     return FALSE;
   g_clear_pointer (&self->ars, b200_ars_destroy);
-  if (self->method != GST_AUDIO_RESAMPLER_METHOD_KAISER || self->sinc_filter_mode != GST_AUDIO_RESAMPLER_FILTER_MODE_AUTO ||
-      self->sinc_filter_interpolation != GST_AUDIO_RESAMPLER_FILTER_INTERPOLATION_CUBIC) {
-    GST_ERROR_OBJECT (self, "only resample-method=kaiser, sinc-filter-mode=auto, sinc-filter-interpolation=cubic are implemented");
-    return FALSE;
-  }
+  /* b200_ars_config carries the reference's enum values + 1 (0 = element default); b200_ars_create answers
+   * B200_ERR_UNSUPPORTED for the nearest / linear / cubic methods and for linear table interpolation */
+  cfg.resample_method = self->method + 1;
+  cfg.sinc_filter_mode = self->sinc_filter_mode + 1;
+  cfg.sinc_filter_interpolation = self->sinc_filter_interpolation + 1;
   cfg.in_rate = GST_AUDIO_INFO_RATE (&self->in);
   cfg.out_rate = GST_AUDIO_INFO_RATE (&self->out);
   cfg.channels = GST_AUDIO_INFO_CHANNELS (&self->in);

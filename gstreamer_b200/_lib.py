@@ -56,7 +56,8 @@ class CompPadYuvC(C.Structure):
 
 class ArsConfigC(C.Structure):
     _fields_ = [("in_rate", C.c_int32), ("out_rate", C.c_int32), ("channels", C.c_int32),
-                ("quality", C.c_int32), ("format", C.c_int32), ("reserved", C.c_int32 * 7)]
+                ("quality", C.c_int32), ("format", C.c_int32), ("resample_method", C.c_int32),
+                ("sinc_filter_mode", C.c_int32), ("sinc_filter_interpolation", C.c_int32), ("reserved", C.c_int32 * 4)]
 
 
 class ArsPlanInfoC(C.Structure):

@@ -21,10 +21,14 @@ class AudioFormat:
 
 
 class CudaAudioResample:
-    # the stock element's remaining properties (gstaudioresample.c:153-186) and their defaults: accepted so that existing
-    # pipelines keep working, only the default of each is implemented (set_caps refuses anything else).
-    # sinc-filter-auto-threshold never reaches the reference's resampler anyway (UINT stored, INT read: SURVEY A.10)
+    # the stock element's remaining properties (gstaudioresample.c:153-186) with their nicks.  Implemented: both
+    # windowed-sinc methods, every filter mode, cubic table interpolation or none (what needs no new device code); the
+    # library answers B200_ERR_UNSUPPORTED for nearest / linear / cubic methods and linear table interpolation.
+    # sinc-filter-auto-threshold never reaches the reference's resampler (UINT stored, INT read: SURVEY A.10)
     REST_DEFAULTS = {"resample_method": "kaiser", "sinc_filter_mode": "auto", "sinc_filter_interpolation": "cubic"}
+    METHODS = {"nearest": 1, "linear": 2, "cubic": 3, "blackman-nuttall": 4, "kaiser": 5}
+    FILTER_MODES = {"interpolated": 1, "full": 2, "auto": 3}
+    INTERPOLATIONS = {"none": 1, "linear": 2, "cubic": 3}
 
     def __init__(self, quality=4, cuda_device_id=0, format=AudioFormat.F32LE, sinc_filter_auto_threshold=1048576, **rest):
         unknown = set(rest) - set(self.REST_DEFAULTS)
@@ -41,12 +45,13 @@ class CudaAudioResample:
     # GstBaseTransformClass::set_caps (interleaved samples of self.format)
     def set_caps(self, in_rate, out_rate, channels):
         self._free()
-        for k, v in self.rest.items():
-            if v != self.REST_DEFAULTS[k]:
-                raise _lib.B200Error(-2, f"property {k.replace('_', '-')}={v!r}: only the default is implemented")
+        method = self.METHODS[self.rest["resample_method"]]
+        mode = self.FILTER_MODES[self.rest["sinc_filter_mode"]]
+        interp = self.INTERPOLATIONS[self.rest["sinc_filter_interpolation"]]
         cfg = _lib.ArsConfigC()
         cfg.in_rate, cfg.out_rate, cfg.channels, cfg.quality = in_rate, out_rate, channels, self.quality
         cfg.format = int(self.format)
+        cfg.resample_method, cfg.sinc_filter_mode, cfg.sinc_filter_interpolation = method, mode, interp
         h = C.c_void_p()
         check(lib.b200_ars_create(C.byref(cfg), self.cuda_device_id, C.byref(h)), "b200_ars_create")
         self._h = h

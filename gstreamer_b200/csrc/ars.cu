@@ -59,6 +59,8 @@ struct ArsPlan {
   int samp_inc = 0, samp_frac = 0;
   int n_taps = 0, oversample = 0, n_phases = 0;
   bool full = false;
+  bool blackman = false;         // resample-method=blackman-nuttall (else kaiser)
+  bool interp_none = false;      // FULL mode with sinc-filter-interpolation=none: every phase's taps computed directly
   double cutoff = 0, beta = 0;
   std::vector<float> proto;      // (oversample + 4) x n_taps oversampled prototype
   std::vector<float> phases;     // n_phases x n_taps (FULL mode), all phases precomputed
@@ -165,6 +167,22 @@ static int build_ars_plan (const b200_ars_config & cfg, ArsPlan * p)
   const double dw = 2 * M_PI * q.trbw;
   p->n_taps = (int) ((A - 8.0) / (2.285 * dw)) + 1;
   p->cutoff = fc;
+  // the element's other properties: only what needs no new device code - both windowed-sinc methods, every filter
+  // mode, cubic table interpolation or none
+  if (cfg.resample_method != 0 && cfg.resample_method != B200_ARS_METHOD_KAISER && cfg.resample_method != B200_ARS_METHOD_BLACKMAN_NUTTALL)
+    return B200_ERR_UNSUPPORTED;
+  if (cfg.sinc_filter_mode < 0 || cfg.sinc_filter_mode > B200_ARS_FILTER_MODE_AUTO) return B200_ERR_INVALID_ARG;
+  if (cfg.sinc_filter_interpolation != 0 && cfg.sinc_filter_interpolation != B200_ARS_FILTER_INTERPOLATION_CUBIC &&
+      cfg.sinc_filter_interpolation != B200_ARS_FILTER_INTERPOLATION_NONE)
+    return B200_ERR_UNSUPPORTED;
+  p->blackman = cfg.resample_method == B200_ARS_METHOD_BLACKMAN_NUTTALL;
+  if (p->blackman) {                    // blackman_qualities, audio-resampler.c:81-93; options_set_quality :1299-1305
+    static const struct { int n_taps; double cutoff; } kBlackman[11] = {{8, 0.5}, {16, 0.6}, {24, 0.72}, {32, 0.8},
+      {48, 0.85}, {64, 0.90}, {80, 0.92}, {96, 0.933}, {128, 0.950}, {148, 0.955}, {160, 0.960}};
+    p->n_taps = kBlackman[cfg.quality].n_taps;
+    p->cutoff = kBlackman[cfg.quality].cutoff;
+  }
+  const bool no_interp = cfg.sinc_filter_interpolation == B200_ARS_FILTER_INTERPOLATION_NONE;
   if (p->out_step < p->in_step) {
     p->cutoff = p->cutoff * p->out_step / p->in_step;
     p->n_taps = (int) (((unsigned long long) p->n_taps * p->in_step) / p->out_step);
@@ -172,31 +190,56 @@ static int build_ars_plan (const b200_ars_config & cfg, ArsPlan * p)
   p->n_taps = (p->n_taps + 7) & ~7;
   int over = kOversample[cfg.quality];
   for (int mult = 2; over > 1 && mult * p->out_step < p->in_step; mult *= 2) over >>= 1;
+  if (no_interp) over = 1;              // audio-resampler.c:1141-1143
   p->oversample = over;
   // filter-mode auto with the element's VARIABLE_RATE flag: FULL when the whole phase table is
   // below the (effectively fixed) 1 MiB threshold (audio-resampler.c:1147-1166)
-  p->full = (long long) p->bps * p->n_taps * p->out_step < 1048576;       // bps * n_taps * out_rate, :1153
+  if (cfg.sinc_filter_mode == 0 || cfg.sinc_filter_mode == B200_ARS_FILTER_MODE_AUTO)
+    p->full = (long long) p->bps * p->n_taps * p->out_step < 1048576;     // bps * n_taps * out_rate, :1153
+  else
+    p->full = cfg.sinc_filter_mode == B200_ARS_FILTER_MODE_FULL;
+  // an interpolated table with no interpolation falls back to the default cubic one, at the oversampling of 1 chosen
+  // above (:1167-1170)
+  p->interp_none = p->full && no_interp;
   p->n_phases = p->full ? p->out_step : 0;
 
   const int n = p->n_taps;
   p->proto.assign ((size_t) (over + 4) * n, 0.f);
   if (p->fmt != ARS_F32) p->proto_x.assign ((size_t) (over + 4) * n * p->bps, 0);
   std::vector<double> tmp (n);
-  for (int row = 0; row < over + 4; row++) {
-    const double x0 = -(n / 2) + row / (double) over;
+  // make_taps (audio-resampler.c:287-323): n windowed-sinc values starting at x0, normalised, in float and (other
+  // sample formats) in the samples' own type
+  auto make_row = [&] (double x0, float *rowf, uint8_t *px) {
     double weight = 0.0;
-    for (int i = 0; i < n; i++) {          // get_kaiser_tap, audio-resampler.c:205-215
+    for (int i = 0; i < n; i++) {
       const double x = x0 + i, y = M_PI * x;
       const double s = (y == 0.0 ? p->cutoff : sin (y * p->cutoff) / y);
-      const double w = 2.0 * x / n;
-      tmp[i] = s * bessel_i0 (p->beta * sqrt (fmax (1 - w * w, 0)));
+      if (p->blackman) {                   // get_blackman_nuttall_tap, :192-203
+        const double w = 2.0 * y / n + M_PI;
+        tmp[i] = s * (0.3635819 - 0.4891775 * cos (w) + 0.1365995 * cos (2 * w) - 0.0106411 * cos (3 * w));
+      } else {                             // get_kaiser_tap, :205-215
+        const double w = 2.0 * x / n;
+        tmp[i] = s * bessel_i0 (p->beta * sqrt (fmax (1 - w * w, 0)));
+      }
       weight += tmp[i];
     }
-    for (int i = 0; i < n; i++) p->proto[(size_t) row * n + i] = (float) (tmp[i] / weight);
-    uint8_t *px = p->proto_x.data () + (size_t) row * n * p->bps;
+    if (rowf) for (int i = 0; i < n; i++) rowf[i] = (float) (tmp[i] / weight);
+    if (!px) return;
     if (p->fmt == ARS_S16) convert_taps_int (tmp.data (), (int16_t *) px, weight, n, 15);
     else if (p->fmt == ARS_S32) convert_taps_int (tmp.data (), (int32_t *) px, weight, n, 31);
     else if (p->fmt == ARS_F64) for (int i = 0; i < n; i++) ((double *) px)[i] = tmp[i] / weight;
+  };
+  for (int row = 0; row < over + 4; row++)
+    make_row (-(n / 2) + row / (double) over, &p->proto[(size_t) row * n],
+        p->fmt != ARS_F32 ? p->proto_x.data () + (size_t) row * n * p->bps : nullptr);
+  if (p->interp_none) {
+    // GST_AUDIO_RESAMPLER_FILTER_INTERPOLATION_NONE in FULL mode (get_taps_<type>_full :517-525): x = 1 - n/2 - phase/n_phases
+    if (p->fmt == ARS_F32) p->phases.assign ((size_t) p->n_phases * n, 0.f);
+    else p->phases_x.assign ((size_t) p->n_phases * n * p->bps, 0);
+    for (int ph = 0; ph < p->n_phases; ph++)
+      make_row (1.0 - n / 2 - (double) ph / p->n_phases, p->fmt == ARS_F32 ? &p->phases[(size_t) ph * n] : nullptr,
+          p->fmt != ARS_F32 ? p->phases_x.data () + (size_t) ph * n * p->bps : nullptr);
+    return B200_OK;
   }
   if (p->full && p->fmt != ARS_F32) {
     // every phase (get_taps_<type>_full): interpolate_gint16_cubic_sse2 / interpolate_gint32_cubic_c /

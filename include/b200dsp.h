@@ -235,8 +235,19 @@ typedef struct {
   int32_t in_rate, out_rate, channels;
   int32_t quality;               /* 0..10, element default 4 (gstaudioresample.c:68) */
   int32_t format;                /* B200_AUDIO_FORMAT_*; 0 = F32LE */
-  int32_t reserved[7];
+  /* the element's resample-method / sinc-filter-mode / sinc-filter-interpolation properties (gstaudioresample.c:160-186).
+   * 0 = the element default in each; other values are the reference's enum value + 1 so that a zeroed config is the
+   * default configuration: */
+  int32_t resample_method;       /* 0 or B200_ARS_METHOD_KAISER; B200_ARS_METHOD_BLACKMAN_NUTTALL; the others: unsupported */
+  int32_t sinc_filter_mode;      /* 0 or B200_ARS_FILTER_MODE_AUTO; _INTERPOLATED; _FULL */
+  int32_t sinc_filter_interpolation;     /* 0 or B200_ARS_FILTER_INTERPOLATION_CUBIC; _NONE; _LINEAR: unsupported */
+  int32_t reserved[4];
 } b200_ars_config;
+enum { B200_ARS_METHOD_NEAREST = 1, B200_ARS_METHOD_LINEAR = 2, B200_ARS_METHOD_CUBIC = 3,
+  B200_ARS_METHOD_BLACKMAN_NUTTALL = 4, B200_ARS_METHOD_KAISER = 5 };
+enum { B200_ARS_FILTER_MODE_INTERPOLATED = 1, B200_ARS_FILTER_MODE_FULL = 2, B200_ARS_FILTER_MODE_AUTO = 3 };
+enum { B200_ARS_FILTER_INTERPOLATION_NONE = 1, B200_ARS_FILTER_INTERPOLATION_LINEAR = 2,
+  B200_ARS_FILTER_INTERPOLATION_CUBIC = 3 };
 
 int b200_ars_create (const b200_ars_config * cfg, int device, b200_ars ** handle);
 void b200_ars_destroy (b200_ars * h);

@@ -89,6 +89,8 @@ def oracle():
             o.oracle_ars_new.argtypes = [C.c_int] * 4
             o.oracle_ars_new_fmt.restype = P
             o.oracle_ars_new_fmt.argtypes = [C.c_int] * 5
+            o.oracle_ars_new_opts.restype = P
+            o.oracle_ars_new_opts.argtypes = [C.c_int] * 8
             o.oracle_ars_process_any.restype = C.c_size_t
             o.oracle_ars_process_any.argtypes = [P, P, C.c_size_t, P, C.c_size_t]
             o.oracle_ars_free.argtypes = [P]
@@ -136,6 +138,9 @@ def ref():
             if hasattr(r, "ref_ars_new_fmt"):
                 r.ref_ars_new_fmt.restype = P
                 r.ref_ars_new_fmt.argtypes = [C.c_int] * 5
+            if hasattr(r, "ref_ars_new_opts"):
+                r.ref_ars_new_opts.restype = P
+                r.ref_ars_new_opts.argtypes = [C.c_int] * 8
             r.ref_ars_free.argtypes = [P]
             r.ref_ars_reset.argtypes = [P]
             for n in ("ref_ars_get_out_frames", "ref_ars_get_in_frames"):

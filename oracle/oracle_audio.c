@@ -60,6 +60,7 @@ struct OracleArs
   int channels, in_rate, out_rate;      /* rates after gcd reduction */
   int samp_inc, samp_frac, samp_index, samp_phase, skip;
   int n_taps, oversample, n_phases, full;
+  int method, interp_none;      /* ORACLE_ARS_METHOD_*; sinc-filter-interpolation=none (FULL mode: exact taps per phase) */
   double cutoff, beta;
   int fmt, bps;                 /* ORACLE_AFMT_*, bytes per sample */
   float *table;                 /* (oversample + 4) rows of n_taps, the oversampled prototype (typed by fmt) */
@@ -129,8 +130,13 @@ make_row (const OracleArs * r, void *res, double x)
   for (i = 0; i < n; i++) {
     double xx = x + i, y = M_PI * xx, s, w;
     s = (y == 0.0 ? r->cutoff : sin (y * r->cutoff) / y);
-    w = 2.0 * xx / n;
-    tmp[i] = s * bessel_i0 (r->beta * sqrt (fmax (1 - w * w, 0)));
+    if (r->method == ORACLE_ARS_METHOD_BLACKMAN_NUTTALL) {      /* get_blackman_nuttall_tap, audio-resampler.c:192-203 */
+      w = 2.0 * y / n + M_PI;
+      tmp[i] = s * (0.3635819 - 0.4891775 * cos (w) + 0.1365995 * cos (2 * w) - 0.0106411 * cos (3 * w));
+    } else {                    /* get_kaiser_tap, :205-215 */
+      w = 2.0 * xx / n;
+      tmp[i] = s * bessel_i0 (r->beta * sqrt (fmax (1 - w * w, 0)));
+    }
     weight += tmp[i];
   }
   switch (r->fmt) {
@@ -156,6 +162,17 @@ oracle_ars_new (int in_rate, int out_rate, int channels, int quality)
 OracleArs *
 oracle_ars_new_fmt (int in_rate, int out_rate, int channels, int quality, int fmt)
 {
+  return oracle_ars_new_opts (in_rate, out_rate, channels, quality, fmt, ORACLE_ARS_METHOD_KAISER, ORACLE_ARS_MODE_AUTO,
+      ORACLE_ARS_INTERP_CUBIC);
+}
+
+OracleArs *
+oracle_ars_new_opts (int in_rate, int out_rate, int channels, int quality, int fmt, int method, int filter_mode,
+    int interpolation)
+{
+  /* blackman_qualities (audio-resampler.c:81-93): n_taps, cutoff */
+  static const struct { int n_taps; double cutoff; } blackman_q[11] = { {8, 0.5}, {16, 0.6}, {24, 0.72}, {32, 0.8},
+    {48, 0.85}, {64, 0.90}, {80, 0.92}, {96, 0.933}, {128, 0.950}, {148, 0.955}, {160, 0.960} };
   OracleArs *r;
   double Fc, A, tr_bw, B, dw;
   int g, n, oversample, i;
@@ -163,7 +180,12 @@ oracle_ars_new_fmt (int in_rate, int out_rate, int channels, int quality, int fm
     return NULL;
   if (fmt < 0 || fmt > ORACLE_AFMT_F64)
     return NULL;
+  if ((method != ORACLE_ARS_METHOD_KAISER && method != ORACLE_ARS_METHOD_BLACKMAN_NUTTALL) ||
+      filter_mode < ORACLE_ARS_MODE_INTERPOLATED || filter_mode > ORACLE_ARS_MODE_AUTO ||
+      (interpolation != ORACLE_ARS_INTERP_CUBIC && interpolation != ORACLE_ARS_INTERP_NONE))
+    return NULL;                /* nearest / linear / cubic methods and linear table interpolation: not restated */
   r = calloc (1, sizeof (*r));
+  r->method = method;
   r->channels = channels;
   r->fmt = fmt;
   r->bps = fmt == ORACLE_AFMT_S16 ? 2 : (fmt == ORACLE_AFMT_F64 ? 8 : 4);
@@ -192,6 +214,10 @@ oracle_ars_new_fmt (int in_rate, int out_rate, int channels, int quality, int fm
   r->beta = B;
   r->n_taps = n + 1;
   r->cutoff = Fc;
+  if (method == ORACLE_ARS_METHOD_BLACKMAN_NUTTALL) {   /* options_set_quality :1299-1305 -> calculate_taps :1084-1090 */
+    r->n_taps = blackman_q[quality].n_taps;
+    r->cutoff = blackman_q[quality].cutoff;
+  }
   if (r->out_rate < r->in_rate) {
     r->cutoff = r->cutoff * r->out_rate / r->in_rate;
     r->n_taps = (int) (((unsigned long long) r->n_taps * r->in_rate) / r->out_rate);
@@ -199,7 +225,7 @@ oracle_ars_new_fmt (int in_rate, int out_rate, int channels, int quality, int fm
   r->n_taps = ROUND_UP_8 (r->n_taps);
   /* cubic filter interpolation: oversampling from the quality, halved while the decimation
    * ratio allows it (audio-resampler.c:1119-1140) */
-  {
+  if (interpolation != ORACLE_ARS_INTERP_NONE) {
     int mult = 2;
     oversample = oversample_q[quality];
     while (oversample > 1) {
@@ -208,13 +234,19 @@ oracle_ars_new_fmt (int in_rate, int out_rate, int channels, int quality, int fm
       mult *= 2;
       oversample >>= 1;
     }
-  }
+  } else
+    oversample = 1;             /* :1141-1143 */
   r->oversample = oversample;
   /* filter-mode auto; the element stores the threshold as UINT, the resampler reads it as INT,
    * so the default 1048576 always applies; VARIABLE_RATE is set by the
    * element so the first clause never selects FULL */
-  if (r->bps * r->n_taps * r->out_rate < 1048576)       /* bps * n_taps * out_rate, :1153 */
-    r->full = 1;
+  if (filter_mode == ORACLE_ARS_MODE_AUTO)
+    r->full = r->bps * r->n_taps * r->out_rate < 1048576;       /* bps * n_taps * out_rate, :1153 */
+  else
+    r->full = filter_mode == ORACLE_ARS_MODE_FULL;
+  /* an interpolated table without an interpolation falls back to the default cubic one - with the oversampling of 1
+   * computed above (:1167-1170) */
+  r->interp_none = r->full && interpolation == ORACLE_ARS_INTERP_NONE;
   r->n_phases = r->out_rate;
   r->table = calloc ((size_t) (oversample + 4) * r->n_taps, r->bps);
   for (i = 0; i < oversample + 4; i++)
@@ -271,6 +303,11 @@ static const float *
 phase_taps (OracleArs * r, int phase)
 {
   float *res = r->cache + (size_t) phase * r->n_taps;
+  if (!r->have[phase] && r->interp_none) {
+    /* GST_AUDIO_RESAMPLER_FILTER_INTERPOLATION_NONE (:517-525): the taps of this phase computed directly */
+    make_row (r, res, 1.0 - r->n_taps / 2 - (double) phase / r->n_phases);
+    r->have[phase] = 1;
+  }
   if (!r->have[phase]) {
     int pos = phase * r->oversample, offset = (r->oversample - 1) - pos / r->n_phases;
     int frac = pos % r->n_phases, i, n = r->n_taps;
@@ -421,6 +458,10 @@ phase_taps_any (OracleArs * r, int phase)
 {
   size_t n = r->n_taps;
   char *res = (char *) r->cache + (size_t) phase * n * r->bps;
+  if (!r->have[phase] && r->interp_none) {
+    make_row (r, res, 1.0 - r->n_taps / 2 - (double) phase / r->n_phases);
+    r->have[phase] = 1;
+  }
   if (!r->have[phase]) {
     int pos = phase * r->oversample, offset = (r->oversample - 1) - pos / r->n_phases;
     int frac = pos % r->n_phases;

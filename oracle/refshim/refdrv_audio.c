@@ -22,21 +22,33 @@ ref_ars_new (int in_rate, int out_rate, int channels, int quality)
 
 /* format: GstAudioFormat of the samples the resampler works on — S16, S32, F32 or F64 in native
  * endianness, the formats audioresample hands over unconverted (audio-converter.c:700-727) */
+GstAudioResampler *ref_ars_new_opts (int in_rate, int out_rate, int channels, int quality, int format, int method,
+    int filter_mode, int interpolation);
+
 GstAudioResampler *
 ref_ars_new_fmt (int in_rate, int out_rate, int channels, int quality, int format)
 {
+  return ref_ars_new_opts (in_rate, out_rate, channels, quality, format, GST_AUDIO_RESAMPLER_METHOD_KAISER,
+      GST_AUDIO_RESAMPLER_FILTER_MODE_AUTO, GST_AUDIO_RESAMPLER_FILTER_INTERPOLATION_CUBIC);
+}
+
+/* the element's properties resample-method / sinc-filter-mode / sinc-filter-interpolation as make_options passes them
+ * (gstaudioresample.c:374-396); enum values are the reference's (audio-resampler.h:112-160) */
+GstAudioResampler *
+ref_ars_new_opts (int in_rate, int out_rate, int channels, int quality, int format, int method, int filter_mode,
+    int interpolation)
+{
   GstStructure *options = gst_structure_new_static_str_empty ("resampler-options");
   GstAudioResampler *r;
-  gst_audio_resampler_options_set_quality (GST_AUDIO_RESAMPLER_METHOD_KAISER, quality, in_rate,
-      out_rate, options);
+  gst_audio_resampler_options_set_quality ((GstAudioResamplerMethod) method, quality, in_rate, out_rate, options);
   gst_structure_set_static_str (options,
-      OPT_METHOD, GST_TYPE_AUDIO_RESAMPLER_METHOD, GST_AUDIO_RESAMPLER_METHOD_KAISER,
+      OPT_METHOD, GST_TYPE_AUDIO_RESAMPLER_METHOD, (GstAudioResamplerMethod) method,
       GST_AUDIO_RESAMPLER_OPT_FILTER_MODE, GST_TYPE_AUDIO_RESAMPLER_FILTER_MODE,
-      GST_AUDIO_RESAMPLER_FILTER_MODE_AUTO,
+      (GstAudioResamplerFilterMode) filter_mode,
       GST_AUDIO_RESAMPLER_OPT_FILTER_MODE_THRESHOLD, G_TYPE_UINT, (guint) 1048576,
       GST_AUDIO_RESAMPLER_OPT_FILTER_INTERPOLATION, GST_TYPE_AUDIO_RESAMPLER_FILTER_INTERPOLATION,
-      GST_AUDIO_RESAMPLER_FILTER_INTERPOLATION_CUBIC, NULL);
-  r = gst_audio_resampler_new (GST_AUDIO_RESAMPLER_METHOD_KAISER,
+      (GstAudioResamplerFilterInterpolation) interpolation, NULL);
+  r = gst_audio_resampler_new ((GstAudioResamplerMethod) method,
       GST_AUDIO_RESAMPLER_FLAG_VARIABLE_RATE, (GstAudioFormat) format, channels, in_rate, out_rate,
       options);
   gst_structure_free (options);

@@ -1,0 +1,55 @@
+"""cudaaudioresample with the element's resample-method / sinc-filter-mode / sinc-filter-interpolation properties at
+non-default values (blackman-nuttall window, forced full / interpolated tables, no table interpolation).  Only the host
+side changes (tap tables and the mode decision — checked against the oracle bit for bit in tests/test_host_plan.py); the
+device kernels are the ones the default configuration runs.  Still: written after this round's device budget was
+spent, so skipped unless B200_TEST_EXPERIMENTAL=1.  Run next round:
+  B200_TEST_EXPERIMENTAL=1 python -m pytest tests/test_ars_options_gpu.py -q"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import bindings as ob
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("B200_TEST_EXPERIMENTAL") != "1", reason="opt-in: B200_TEST_EXPERIMENTAL=1")]
+
+M = {"blackman-nuttall": 3, "kaiser": 4}
+MO = {"interpolated": 0, "full": 1, "auto": 2}
+I = {"none": 0, "cubic": 2}
+
+
+@pytest.mark.parametrize("fmt", ["F32", "S16", "S32", "F64"])
+@pytest.mark.parametrize("method,mode,interp", [("blackman-nuttall", "auto", "cubic"), ("blackman-nuttall", "full", "none"),
+                                                ("kaiser", "full", "cubic"), ("kaiser", "full", "none"),
+                                                ("kaiser", "interpolated", "cubic"), ("kaiser", "interpolated", "none"),
+                                                ("blackman-nuttall", "interpolated", "cubic"), ("kaiser", "auto", "none")])
+def test_method_and_filter_mode_properties(cuda_device, fmt, method, mode, interp):
+    import torch
+    from gstreamer_b200.audio import CudaAudioResample
+    ofmt, gfmt, dt, _ = ob.AUDIO_FORMATS[fmt]
+    tdt = {np.float32: torch.float32, np.int16: torch.int16, np.int32: torch.int32, np.float64: torch.float64}[dt]
+    o = ob.oracle()
+    for (a, b, ch, q) in [(48000, 44100, 2, 4), (44100, 48000, 1, 6), (8000, 16000, 2, 0), (96000, 44100, 3, 8), (101, 99, 1, 10)]:
+        ho = o.oracle_ars_new_opts(a, b, ch, q, ofmt, M[method], MO[mode], I[interp])
+        rs = CudaAudioResample(quality=q, format=gfmt, resample_method=method, sinc_filter_mode=mode,
+                               sinc_filter_interpolation=interp)
+        rs.set_caps(a, b, ch)
+        rng = np.random.default_rng(ch + a)
+        for n in [480, 480, 100, 1, 2000, 37, None]:
+            x = None
+            if n is None:
+                n = rs.max_latency
+            else:
+                x = ob.audio_test_signal(rng, n, ch, fmt)
+            cap = int(n * b / a) + 64
+            want = np.zeros((cap, ch), dtype=dt)
+            assert rs.get_out_frames(n) == o.oracle_ars_get_out_frames(ho, n)
+            nw = o.oracle_ars_process_any(ho, x.ctypes.data if x is not None else None, n, want.ctypes.data, cap)
+            out = torch.full((cap * ch,), 7, dtype=tdt, device="cuda")
+            ng = rs.transform(torch.from_numpy(x).cuda() if x is not None else None, n, out, cap)
+            torch.cuda.synchronize()
+            got = out.cpu().numpy().reshape(cap, ch)
+            assert ng == nw and got[:ng].tobytes() == want[:nw].tobytes(), (a, b, ch, q, n)
+            assert (got[ng:] == 7).all()
+        o.oracle_ars_free(ho)

@@ -348,7 +348,36 @@ def test_audioresample_remaining_properties():
     import gstreamer_b200 as g
     from gstreamer_b200.audio import CudaAudioResample
     CudaAudioResample(cuda_device_id=-1, resample_method="kaiser", sinc_filter_auto_threshold=1).set_caps(48000, 44100, 2)
-    for kw in ({"resample_method": "linear"}, {"sinc_filter_mode": "full"}, {"sinc_filter_interpolation": "linear"}):
+    for kw in ({"resample_method": "linear"}, {"resample_method": "nearest"}, {"resample_method": "cubic"},
+               {"sinc_filter_interpolation": "linear"}):
         with pytest.raises(g.B200Error) as e:
             CudaAudioResample(cuda_device_id=-1, **kw).set_caps(48000, 44100, 2)
         assert e.value.status == -2
+
+
+@pytest.mark.parametrize("method,mode,interp", [("blackman-nuttall", "auto", "cubic"), ("blackman-nuttall", "full", "none"),
+                                                ("kaiser", "full", "cubic"), ("kaiser", "full", "none"),
+                                                ("kaiser", "interpolated", "cubic"), ("kaiser", "interpolated", "none"),
+                                                ("blackman-nuttall", "interpolated", "cubic"), ("kaiser", "auto", "none")])
+def test_audio_method_and_filter_mode_plans(method, mode, interp):
+    """host plan == oracle (pinned to the reference for these options) for the filter design, the mode decision and -
+    FULL mode, F32 - every phase's taps bit for bit"""
+    from gstreamer_b200.audio import CudaAudioResample
+    o = ob.oracle()
+    M = {"blackman-nuttall": 3, "kaiser": 4}
+    MO = {"interpolated": 0, "full": 1, "auto": 2}
+    I = {"none": 0, "cubic": 2}
+    for (a, b, q) in [(48000, 44100, 4), (44100, 48000, 6), (8000, 16000, 0), (96000, 44100, 8), (101, 99, 10)]:
+        rs = CudaAudioResample(quality=q, cuda_device_id=-1, resample_method=method, sinc_filter_mode=mode,
+                               sinc_filter_interpolation=interp)
+        rs.set_caps(a, b, 2)
+        pi = rs.plan_info()
+        ho = o.oracle_ars_new_opts(a, b, 2, q, 0, M[method], MO[mode], I[interp])
+        v = [C.c_int() for _ in range(6)]
+        o.oracle_ars_info(ho, *[C.byref(x) for x in v])
+        assert [pi.n_taps, pi.n_phases, pi.in_step, pi.out_step, pi.filter_mode, pi.oversample] == [x.value for x in v]
+        for ph in range(0, pi.n_phases, max(1, pi.n_phases // 50)):
+            t = np.zeros(pi.n_taps, dtype=np.float32)
+            o.oracle_ars_phase_taps(ho, ph, t.ctypes.data)
+            assert np.array_equal(t.view(np.uint32), rs.phase_taps(ph).view(np.uint32)), f"phase {ph}"
+        o.oracle_ars_free(ho)

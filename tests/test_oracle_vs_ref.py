@@ -546,3 +546,39 @@ def test_destination_rectangle_and_borders_match_reference(pair):
             assert False, (iw, ih, W, H, dest, method)
         checked += 1
     assert checked >= 25
+
+
+@pytest.mark.parametrize("fmt", ["F32", "S16", "S32", "F64"])
+@pytest.mark.parametrize("method,mode,interp", [(3, 2, 2), (3, 1, 2), (3, 0, 2), (4, 1, 2), (4, 0, 2), (4, 1, 0), (3, 1, 0),
+                                                (4, 2, 0), (4, 0, 0), (3, 2, 0)])
+def test_audio_method_and_filter_mode_properties(fmt, method, mode, interp):
+    """resample-method kaiser / blackman-nuttall, sinc-filter-mode interpolated / full / auto, sinc-filter-interpolation
+    cubic / none (FULL mode then computes every phase's taps directly; an interpolated table falls back to cubic with an
+    oversampling of 1) — byte-identical output for every sample format"""
+    import ctypes as C
+    ofmt, gfmt, dt, _ = ob.AUDIO_FORMATS[fmt]
+    o, r = ob.oracle(), ob.ref()
+    for (a, b, ch, q) in [(48000, 44100, 2, 4), (44100, 48000, 1, 6), (8000, 16000, 2, 2), (96000, 44100, 1, 8), (44100, 44099, 1, 3)]:
+        ho = o.oracle_ars_new_opts(a, b, ch, q, ofmt, method, mode, interp)
+        hr = r.ref_ars_new_opts(a, b, ch, q, gfmt, method, mode, interp)
+        assert ho and hr
+        io = [C.c_int() for _ in range(6)]
+        ir = [C.c_int() for _ in range(6)]
+        o.oracle_ars_info(ho, *[C.byref(v) for v in io])
+        r.ref_ars_info(hr, *[C.byref(v) for v in ir])
+        assert [v.value for v in io] == [v.value for v in ir], (a, b, q)
+        rng = np.random.default_rng(a + b)
+        for n in [480, 100, 1, 1500, None]:
+            x = None
+            if n is None:
+                n = io[0].value // 2
+            else:
+                x = ob.audio_test_signal(rng, n, ch, fmt)
+            cap = int(n * b / a) + 64
+            o1 = np.zeros((cap, ch), dtype=dt)
+            o2 = o1.copy()
+            n1 = o.oracle_ars_process_any(ho, x.ctypes.data if x is not None else None, n, o1.ctypes.data, cap)
+            n2 = r.ref_ars_process(hr, x.ctypes.data if x is not None else None, n, o2.ctypes.data, cap)
+            assert n1 == n2 and o1[:n1].tobytes() == o2[:n2].tobytes(), (a, b, q, n)
+        o.oracle_ars_free(ho)
+        r.ref_ars_free(hr)

@@ -10,6 +10,8 @@ run() { local name=$1; shift; echo "== $name"; timeout "$1" "${@:2}" > "gpurun_o
 run rgbin 240 python -m pytest tests/test_vcs_rgbin_gpu.py -q -p no:cacheprovider
 # 2. destination rectangle + borders (new vcs_border_kernel around the existing kernels)
 run borders 180 python -m pytest tests/test_vcs_borders_gpu.py -q -p no:cacheprovider
+# 2b. audioresample's method / filter-mode properties (host tables only; the default kernels)
+run arsopts 240 python -m pytest tests/test_ars_options_gpu.py -q -p no:cacheprovider
 # 3. random sweep of the RGB -> 4:2:0 path, every outcome recorded in gpurun_out/cross_check.json
 run rgbsweep 90 python tools/gpu_cross_check.py 60 rgb
 # 4. the regular device suite (the generic kernel and the plan builder changed underneath it)
