@@ -1,0 +1,84 @@
+#!/usr/bin/env python
+"""tests/cudaemu/build_emu.py — TEST INFRASTRUCTURE.
+
+Builds tests/cudaemu/_build/libb200emu.so: the product's convert+scale glue (vcs.cu), its host plan builder and the
+kernels that need neither PTX nor warp shuffles (vcs_generic_kernel, vcs_planes_kernel, vcs_down420_kernel,
+vcs_border_kernel) compiled with g++ against the stand-in runtime in emu/.  The sources are the product's own files,
+patched textually only where CUDA syntax has no C++ spelling:
+    kernel <<<grid, block, smem, stream>>> (args);   ->   b200emu::launch (grid, block, smem, [&] { kernel (args); });
+    extern __shared__ ... smem[];                    ->   uint8_t *smem = b200emu::dyn_smem;
+    __shared__ T x[N];                               ->   static T x[N];
+The library exports the same b200_vcs_* C-ABI; "device pointers" are host pointers.  It exists so that kernel indexing
+and integer arithmetic can be checked against the oracle without a GPU — it is never loaded by gstreamer_b200."""
+import hashlib
+import os
+import re
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+CSRC = os.path.join(ROOT, "gstreamer_b200", "csrc")
+OUT = os.path.join(HERE, "_build")
+LIB = os.path.join(OUT, "libb200emu.so")
+
+LAUNCH = re.compile(r"(\b\w+)\s*<<<(.+?)>>>\s*\(([^;]*)\);")
+
+
+def patch(text):
+    def repl(m):
+        name, cfg, args = m.group(1), m.group(2), m.group(3)
+        parts = [c.strip() for c in cfg.split(",")]
+        assert len(parts) == 4, cfg
+        return f"b200emu::launch ({parts[0]}, {parts[1]}, {parts[2]}, [&] {{ {name} ({args}); }});"
+    text, n = LAUNCH.subn(repl, text)
+    text = re.sub(r"extern __shared__ __align__ \(16\) uint8_t smem\[\];", "uint8_t *smem = b200emu::dyn_smem;", text)
+    text = re.sub(r"(^|\n)(\s*)__shared__ ", r"\1\2static ", text)
+    return text, n
+
+
+def sources():
+    return [os.path.join(CSRC, f) for f in ("vcs.cu", "vcs_planes.cuh", "vcs_kernels.cuh", "vcs_down420.cuh", "common.cu",
+                                            "vcs_plan.cpp", "vcs_plan.h", "vcs_device.h", "common.h")] + \
+        [os.path.join(HERE, "emu", f) for f in sorted(os.listdir(os.path.join(HERE, "emu")))] + [os.path.abspath(__file__)]
+
+
+def digest():
+    h = hashlib.sha256()
+    for s in sources():
+        h.update(open(s, "rb").read())
+    return h.hexdigest()
+
+
+def build(force=False):
+    os.makedirs(OUT, exist_ok=True)
+    stamp = os.path.join(OUT, "stamp")
+    d = digest()
+    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == d:
+        return LIB
+    gen = os.path.join(OUT, "gen")
+    os.makedirs(gen, exist_ok=True)
+    launches = 0
+    for src, dst in (("vcs.cu", "vcs_emu.cpp"), ("vcs_planes.cuh", "vcs_planes.cuh"), ("vcs_kernels.cuh", "vcs_kernels.cuh"),
+                     ("vcs_down420.cuh", "vcs_down420.cuh"), ("common.cu", "common_emu.cpp")):
+        text, n = patch(open(os.path.join(CSRC, src)).read())
+        launches += n
+        open(os.path.join(gen, dst), "w").write(text)
+    assert launches >= 6, f"expected the launch sites of vcs.cu and vcs_planes.cuh, patched {launches}"
+    for f in os.listdir(os.path.join(HERE, "emu")):                # stand-in headers next to the generated sources
+        if f.endswith((".h", ".cuh")):
+            open(os.path.join(gen, f), "w").write(open(os.path.join(HERE, "emu", f)).read())
+    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas", "-DB200_CUDA_EMU=1",
+           "-I", gen, "-I", CSRC, "-o", LIB,
+           os.path.join(gen, "vcs_emu.cpp"), os.path.join(gen, "common_emu.cpp"), os.path.join(CSRC, "vcs_plan.cpp"),
+           os.path.join(HERE, "emu", "emu_runtime.cpp")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout[-4000:] + r.stderr[-8000:])
+        raise RuntimeError("emulation build failed")
+    open(stamp, "w").write(d)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv))

@@ -1,0 +1,101 @@
+// tests/cudaemu/emu/cuda_runtime.h — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// A minimal stand-in for the CUDA runtime and the device execution model so that the SAME kernel sources the product
+// compiles with nvcc (vcs_kernels.cuh, vcs_planes.cuh, vcs_down420.cuh and the glue in vcs.cu) can be compiled with g++
+// and have their indexing and integer arithmetic checked against the oracle on a machine without a GPU.  "Device
+// memory" is host memory; a launch runs the blocks of the grid one after another, each block as real threads with a
+// barrier behind __syncthreads().  Nothing in gstreamer_b200/ loads the library built from this; libb200dsp.so has no
+// CPU fallback.  Kernels that use PTX or warp shuffles (the lanczos2 / light / n-tap fast kernels, the audio and
+// compositor kernels) are not emulated.
+#pragma once
+
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <functional>
+#include <vector>
+
+#define B200_CUDA_EMU 1
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __align__(n) alignas (n)
+
+struct uint3_emu { unsigned x, y, z; };
+struct dim3 {
+  unsigned x, y, z;
+  dim3 (unsigned a = 1, unsigned b = 1, unsigned c = 1) : x (a), y (b), z (c) {}
+};
+struct uint2 { unsigned x, y; };
+struct uint4 { unsigned x, y, z, w; };
+struct int4 { int x, y, z, w; };
+
+extern thread_local uint3_emu threadIdx, blockIdx;
+extern thread_local dim3 blockDim, gridDim;
+
+namespace b200emu {
+extern uint8_t dyn_smem[256 * 1024];
+void barrier ();
+// runs body once per thread of every block of the grid
+void launch (dim3 grid, dim3 block, size_t smem_bytes, const std::function<void ()> & body);
+}
+
+inline void __syncthreads () { b200emu::barrier (); }
+
+using std::max;
+using std::min;
+
+template <typename T> inline T __ldg (const T *p) { return *p; }
+inline unsigned __byte_perm (unsigned a, unsigned b, unsigned s)
+{
+  const unsigned long long v = ((unsigned long long) b << 32) | a;
+  unsigned r = 0;
+  for (int i = 0; i < 4; i++) {
+    const unsigned sel = (s >> (4 * i)) & 0xf;
+    unsigned byte = (unsigned) (v >> (8 * (sel & 7))) & 0xff;
+    if (sel & 8) byte = (byte & 0x80) ? 0xff : 0x00;              // msb replication mode
+    r |= byte << (8 * i);
+  }
+  return r;
+}
+inline unsigned __vavgu4 (unsigned a, unsigned b)
+{
+  unsigned r = 0;
+  for (int i = 0; i < 4; i++) r |= ((((a >> (8 * i)) & 0xff) + ((b >> (8 * i)) & 0xff) + 1) >> 1) << (8 * i);
+  return r;
+}
+
+// ---- runtime API subset -----------------------------------------------------------------------------------------------
+typedef int cudaError_t;
+enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorNoDevice = 100, cudaErrorInsufficientDriver = 35 };
+typedef void *cudaStream_t;
+typedef void *cudaEvent_t;
+enum cudaMemcpyKind { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
+enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaHostAllocPortable = 1 };
+enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaDevAttrMultiProcessorCount = 16 };
+
+inline cudaError_t cudaMalloc (void **p, size_t n) { *p = malloc (n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+inline cudaError_t cudaFree (void *p) { free (p); return cudaSuccess; }
+inline cudaError_t cudaMemcpy (void *d, const void *s, size_t n, cudaMemcpyKind) { memcpy (d, s, n); return cudaSuccess; }
+inline cudaError_t cudaMemcpyAsync (void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy (d, s, n); return cudaSuccess; }
+inline cudaError_t cudaGetLastError () { return cudaSuccess; }
+inline const char *cudaGetErrorName (cudaError_t) { return "emu"; }
+inline const char *cudaGetErrorString (cudaError_t) { return "emu"; }
+inline cudaError_t cudaGetDevice (int *d) { *d = 0; return cudaSuccess; }
+inline cudaError_t cudaSetDevice (int) { return cudaSuccess; }
+inline cudaError_t cudaGetDeviceCount (int *n) { *n = 1; return cudaSuccess; }
+inline cudaError_t cudaDeviceGetAttribute (int *v, int, int) { *v = 148; return cudaSuccess; }
+inline cudaError_t cudaStreamCreateWithFlags (cudaStream_t *s, unsigned) { *s = nullptr; return cudaSuccess; }
+inline cudaError_t cudaStreamDestroy (cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaStreamSynchronize (cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaStreamWaitEvent (cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
+inline cudaError_t cudaEventCreateWithFlags (cudaEvent_t *e, unsigned) { *e = nullptr; return cudaSuccess; }
+inline cudaError_t cudaEventDestroy (cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaEventRecord (cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaHostAlloc (void **p, size_t n, unsigned) { *p = malloc (n); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+inline cudaError_t cudaFreeHost (void *p) { free (p); return cudaSuccess; }
+template <typename F> inline cudaError_t cudaFuncSetAttribute (F, int, int) { return cudaSuccess; }

@@ -1,0 +1,171 @@
+"""Kernel logic without a GPU: the product's own kernel sources (vcs_generic_kernel, vcs_planes_kernel,
+vcs_down420_kernel, vcs_border_kernel) and glue (vcs.cu), compiled for the host against a stand-in CUDA runtime
+(tests/cudaemu: blocks run one after another, threads of a block are real threads, __syncthreads is a barrier), driven
+through the same C-ABI and compared with the oracle.  TEST INFRASTRUCTURE — the product never loads this library and has
+no CPU fallback; the `-m gpu` tests remain the parity tests proper.  What it buys: indexing and integer arithmetic of the
+kernels that use neither PTX nor warp shuffles are checked on every CPU run, including the paths written after the
+round's device budget was spent (packed RGB input, RGB -> RGB, destination rectangle + borders)."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import bindings as ob
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests", "cudaemu"))
+
+RGB = ["BGRA", "RGBA", "ARGB", "ABGR", "BGRx", "RGBx", "xRGB", "xBGR"]
+YUV = ["NV12", "NV21", "I420", "YV12"]
+
+
+@pytest.fixture(scope="module")
+def emu():
+    import build_emu
+    from gstreamer_b200 import _lib
+    lib = C.CDLL(build_emu.build())
+    for name, (res, args) in _lib._SIGS.items():
+        if hasattr(lib, name):
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+    return lib
+
+
+def frame_for(fmt, iw, ih, seed):
+    if fmt in RGB:
+        return np.random.default_rng(seed).integers(0, 256, iw * ih * 4, dtype=np.uint8)
+    return ob.i420_random_frame(iw, ih, seed) if fmt in ("I420", "YV12") else ob.nv12_random_frame(iw, ih, seed)
+
+
+def run(emu, fi, fo, size, method, frame, colorimetry=None, dest=None, border=0xff000000, site=None, out_site=None, force_generic=True):
+    """one conversion through the emulated C-ABI; returns the output frame (filled with 0x5A beforehand)"""
+    from gstreamer_b200 import _lib
+    iw, ih, W, H = size
+    ii, oi = _lib.VideoInfoC(), _lib.VideoInfoC()
+    assert emu.b200_video_info_set_format(C.byref(ii), ob.FMT[fi], iw, ih) == 0
+    assert emu.b200_video_info_set_format(C.byref(oi), ob.FMT[fo], W, H) == 0
+    if site is not None:
+        ii.chroma_site = site
+    if fi in YUV and fo in YUV:                      # what the element's caps fixation does
+        oi.color_matrix, oi.color_range, oi.chroma_site = ii.color_matrix, ii.color_range, ii.chroma_site
+    if out_site is not None:
+        oi.chroma_site = out_site
+    if colorimetry:
+        oi.color_matrix, oi.color_range, oi.chroma_site = colorimetry
+    cfg = _lib.VcsConfigC()
+    emu.b200_vcs_config_init(C.byref(cfg))
+    cfg.method = method
+    if dest:
+        cfg.dest_x, cfg.dest_y, cfg.dest_width, cfg.dest_height = dest
+        cfg.border_argb = border
+    h = C.c_void_p()
+    st = emu.b200_vcs_create(C.byref(ii), C.byref(oi), C.byref(cfg), 0, C.byref(h))
+    assert st == 0, (st, fi, fo, size)
+    try:
+        if force_generic:
+            emu.b200_vcs_set_kernel_variant(h, 0)    # the fast kernels (PTX, shuffles) are not emulated
+        out = np.full(emu.b200_video_info_size(C.byref(oi)), 0x5A, dtype=np.uint8)
+        src = np.ascontiguousarray(frame)
+        assert emu.b200_vcs_convert(h, src.ctypes.data, out.ctypes.data, None) == 0
+    finally:
+        emu.b200_vcs_destroy(h)
+    return out
+
+
+def expected(fi, fo, size, method, frame, colorimetry=None, dest=None, border=0xff000000, site=None, out_site=None):
+    iw, ih, W, H = size
+    d = ob.vcs_desc(iw, ih, W, H, method, in_fmt=ob.FMT[fi], out_fmt=ob.FMT[fo], site=site)
+    if out_site is not None:
+        d.out_chroma_site = out_site
+    if colorimetry:
+        d.out_matrix, d.out_range, d.out_chroma_site = colorimetry
+    if dest:
+        return ob.oracle_vcs_convert_dest(d, frame, dest, border, fill=0x5A)
+    want = np.full(ob.vcs_sizes(d)[1], 0x5A, dtype=np.uint8)
+    assert ob.oracle().oracle_vcs_convert(C.byref(d), np.ascontiguousarray(frame).ctypes.data, want.ctypes.data) == 0
+    return want
+
+
+def check(got, want, tag):
+    bad = np.argwhere(got != want)
+    assert bad.size == 0, f"{tag}: {len(bad)} of {got.size} bytes differ, first at {bad[:5].ravel().tolist()}"
+
+
+SMALL = [(64, 48, 32, 24), (40, 30, 64, 48), (33, 17, 20, 31), (57, 35, 29, 35), (50, 21, 50, 21), (100, 60, 150, 30), (7, 5, 3, 9)]
+
+
+# ---- 1. the emulator itself, on paths the device has already confirmed bit-exact ------------------------------------
+@pytest.mark.parametrize("size", SMALL, ids=lambda s: "%dx%d-%dx%d" % s)
+def test_emulator_agrees_on_device_verified_paths(emu, size):
+    """generic kernel (4:2:0 -> packed RGB), plane kernel (same family) and chain + chroma down-sampling (other family)
+    are bit-exact on a B200 (tests/test_vcs_gpu.py, _planes_gpu, _cross_gpu); the emulated build must say the same"""
+    iw, ih = size[:2]
+    for fi, fo, method in [("NV12", "BGRA", 3), ("I420", "RGBA", 1), ("NV21", "xRGB", 0), ("NV12", "NV12", 1), ("I420", "YV12", 9),
+                           ("NV12", "I420", 3), ("YV12", "NV21", 1), ("I420", "NV12", 0)]:
+        frame = frame_for(fi, iw, ih, 3)
+        for site in (1, 2):
+            got = run(emu, fi, fo, size, method, frame, site=site)
+            check(got, expected(fi, fo, size, method, frame, site=site), f"{fi}->{fo} m{method} site{site}")
+
+
+# ---- 2. paths whose first device run is still pending ------------------------------------------------------------------
+@pytest.mark.parametrize("size", SMALL, ids=lambda s: "%dx%d-%dx%d" % s)
+def test_rgb_to_420(emu, size, monkeypatch):
+    monkeypatch.setenv("B200_VCS_EXPERIMENTAL", "1")
+    iw, ih = size[:2]
+    for k, (fi, fo) in enumerate([("BGRA", "NV12"), ("RGBA", "I420"), ("ARGB", "NV21"), ("ABGR", "YV12"), ("xRGB", "NV12"), ("BGRx", "I420")]):
+        frame = frame_for(fi, iw, ih, 4)
+        method = [1, 3, 0, 9, 4, 5][k]
+        check(run(emu, fi, fo, size, method, frame), expected(fi, fo, size, method, frame), f"{fi}->{fo} m{method}")
+    frame = frame_for("BGRA", iw, ih, 5)
+    for col in [(3, 2, 2), (4, 1, 1), (6, 2, 6), (2, 1, 4), (5, 2, 1)]:
+        check(run(emu, "BGRA", "NV12", size, 3, frame, colorimetry=col), expected("BGRA", "NV12", size, 3, frame, colorimetry=col),
+              f"colorimetry {col}")
+
+
+@pytest.mark.parametrize("size", SMALL + [(64, 48, 64, 24), (64, 48, 32, 48)], ids=lambda s: "%dx%d-%dx%d" % s)
+def test_rgb_to_rgb(emu, size, monkeypatch):
+    monkeypatch.setenv("B200_VCS_EXPERIMENTAL", "1")
+    iw, ih = size[:2]
+    for k, (fi, fo) in enumerate([("BGRA", "BGRA"), ("RGBA", "RGBA"), ("xBGR", "xBGR"), ("BGRA", "RGBA"), ("ARGB", "BGRx"),
+                                  ("RGBx", "ABGR"), ("xRGB", "BGRA")]):
+        frame = frame_for(fi, iw, ih, 6)
+        for method in [[1, 3], [0], [4], [9, 1], [3], [5], [1]][k]:
+            check(run(emu, fi, fo, size, method, frame, force_generic=False), expected(fi, fo, size, method, frame), f"{fi}->{fo} m{method}")
+
+
+@pytest.mark.parametrize("pair", [("NV12", "BGRA"), ("I420", "RGBA"), ("NV12", "NV12"), ("I420", "YV12"), ("NV12", "I420"),
+                                  ("YV12", "NV21"), ("BGRA", "NV12"), ("RGBA", "RGBA"), ("BGRA", "ARGB")], ids=lambda p: "%s-%s" % p)
+def test_destination_rectangle_and_borders(emu, pair, monkeypatch):
+    monkeypatch.setenv("B200_VCS_EXPERIMENTAL", "1")
+    fi, fo = pair
+    rng = np.random.default_rng(9)
+    for t in range(6):
+        iw, ih, W, H = (int(v) for v in rng.integers(2, 64, 4))
+        if t % 2:
+            dest = ob.vcs_borders(iw, ih, W, H)
+        else:
+            dw, dh = int(rng.integers(1, W + 1)), int(rng.integers(1, H + 1))
+            dest = (int(rng.integers(0, W - dw + 1)), int(rng.integers(0, H - dh + 1)), dw, dh)
+        if dest[2] < 1 or dest[3] < 1:
+            continue
+        border = [0xff000000, 0x80ff4020, 0xff10c0f0][t % 3]
+        method = [1, 3, 0, 9][t % 4]
+        frame = frame_for(fi, iw, ih, t)
+        size = (iw, ih, W, H)
+        generic = not (fi in RGB and fo in RGB)
+        got = run(emu, fi, fo, size, method, frame, dest=dest, border=border, force_generic=generic)
+        check(got, expected(fi, fo, size, method, frame, dest=dest, border=border), f"{size} dest {dest} m{method}")
+
+
+def test_odd_height_without_vertical_scaler(emu):
+    """the third launch of the cross-family path (device-verified) — keeps the emulator honest about multi-launch glue"""
+    for size in [(64, 49, 32, 49), (50, 21, 50, 21), (33, 5, 70, 5)]:
+        frame = frame_for("NV12", size[0], size[1], 2)
+        for site, out_site in ((1, 1), (2, 1), (1, 6)):
+            if size[:2] == size[2:] and site == out_site:
+                continue
+            got = run(emu, "NV12", "I420", size, 3, frame, site=site, out_site=out_site)
+            check(got, expected("NV12", "I420", size, 3, frame, site=site, out_site=out_site), f"{size} {site}->{out_site}")
