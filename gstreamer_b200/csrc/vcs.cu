@@ -9,6 +9,7 @@
 #include "vcs_device.h"
 #include "vcs_kernels.cuh"
 #include "vcs_lanczos2.cuh"
+#include "vcs_l2mma.cuh"
 #include "vcs_light.cuh"
 #include "vcs_ntap.cuh"
 #include "vcs_planes.cuh"
@@ -38,6 +39,8 @@ struct b200_vcs {
   Lanczos2Tables l2_tables;
   Lanczos2State l2;
   NtapState ntap;
+  L2mmaTables mma_tables;         // experimental tensor-path variant of the 2:1 kernel (variant 6, opt-in)
+  L2mmaState mma;
   PlanesState planes;
   // 4:2:0 -> other 4:2:0 family: scaled A,Y,U,V scratch images between the two launches
   Down420Dev down;
@@ -93,6 +96,11 @@ int launch_convert (b200_vcs * h, int n, const VcsBatch & batch, cudaStream_t st
     bool aligned = true;                                            // the word-wide halve / copy path needs 8-byte aligned frames
     for (int i = 0; i < n; i++) aligned = aligned && ((((uintptr_t) batch.in[i]) | ((uintptr_t) batch.out[i])) & 7) == 0;
     return launch_planes (h->planes, batch, n, stream, aligned);
+  }
+  if (h->variant == 6 && h->mma.ready) {
+    bool aligned = true;                                            // 64-bit plane loads
+    for (int i = 0; i < n; i++) aligned = aligned && (((uintptr_t) batch.in[i]) & 7) == 0 && (((uintptr_t) batch.out[i]) & 3) == 0;
+    if (aligned) return launch_l2mma (h->dev, h->mma, batch, n, stream);
   }
   if (h->variant == 1 && p.lanczos2_ok)
     return launch_lanczos2 (h->dev, h->l2, batch, n, stream);
@@ -291,6 +299,7 @@ int b200_vcs_create (const b200_video_info * in, const b200_video_info * out,
   if (!h->plan.yuv_out) {
     h->l2_tables = build_lanczos2_tables (h->plan);
     h->plan.lanczos2_ok = h->l2_tables.ok;
+    h->mma_tables = build_l2mma_tables (h->plan);
   }
   const VcsPlan & p = h->plan;
   if (!p.yuv_out && ((p.out.stride[0] & 3) || (p.out.offset[0] & 3))) { delete h; return B200_ERR_UNSUPPORTED; }
@@ -348,6 +357,10 @@ int b200_vcs_create (const b200_video_info * in, const b200_video_info * out,
     cudaError_t e = cudaFuncSetAttribute (vcs_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
         p.smem_bytes);
     if (e != cudaSuccess) { b200_vcs_destroy (h); return cuda_fail (e, "cudaFuncSetAttribute", __FILE__, __LINE__); }
+    if (h->mma_tables.ok) {
+      st = prepare_l2mma (h->mma_tables, &h->mma);
+      if (st != B200_OK) { b200_vcs_destroy (h); return st; }
+    }
     if (p.lanczos2_ok) {
       st = prepare_lanczos2 (h->l2_tables, h->dev, &h->l2);
       if (st != B200_OK) { b200_vcs_destroy (h); return st; }
@@ -362,6 +375,7 @@ int b200_vcs_create (const b200_video_info * in, const b200_video_info * out,
       h->variant = 3;
     }
   }
+  if (h->mma.ready && getenv ("B200_L2_MMA")) h->variant = 6;     // opt-in until it has been measured on a device
   *handle = h;
   return B200_OK;
 }
@@ -374,6 +388,7 @@ void b200_vcs_destroy (b200_vcs * h)
     cudaFree (h->d_hoff); cudaFree (h->d_voff); cudaFree (h->d_hcoef); cudaFree (h->d_vcoef);
     cudaFree (h->d_hsum); cudaFree (h->d_vsum); cudaFree (h->d_cmode);
     cudaFree (h->l2.d_htab); cudaFree (h->l2.d_vtab); cudaFree (h->ntap.d_h); cudaFree (h->ntap.d_v);
+    cudaFree (h->mma.d_bh); cudaFree (h->mma.d_bv);
     free_planes (&h->planes);
     cudaFree (h->d_scratch);
     for (int i = 0; i < b200_vcs::kSlots; i++) {
@@ -454,7 +469,7 @@ int b200_vcs_get_plan_info (const b200_vcs * h, b200_vcs_plan_info * info)
   info->h_first = p.h_first; info->matrix_first = p.matrix_first;
   for (int i = 0; i < 5; i++) info->p[i] = p.p[i];
   info->tile_w = p.tile_w; info->tile_h = p.tile_h; info->smem_bytes = p.smem_bytes;
-  info->kernel_variant = p.yuv_out ? 5 : p.planes_mode ? 4 : (h->variant == 1 && p.lanczos2_ok) ? 1 : (h->variant == 2 && p.light_ok) ? 2 : (h->variant == 3 && p.ntap_ok) ? 3 : 0;
+  info->kernel_variant = p.yuv_out ? 5 : p.planes_mode ? 4 : (h->variant == 6 && h->mma.ready) ? 6 : (h->variant == 1 && p.lanczos2_ok) ? 1 : (h->variant == 2 && p.light_ok) ? 2 : (h->variant == 3 && p.ntap_ok) ? 3 : 0;
   info->n_launches_per_convert = (p.yuv_out ? (p.extra_row ? 3 : 2) : 1) + (p.has_dest && p.fill_border ? 1 : 0);
   return B200_OK;
 }
@@ -493,8 +508,9 @@ int b200_vcs_get_chroma_plan (const b200_vcs * h, uint8_t * mode, size_t len)
 
 int b200_vcs_set_kernel_variant (b200_vcs * h, int variant)
 {
-  if (!h || variant < 0 || variant > 3) return B200_ERR_INVALID_ARG;
+  if (!h || variant < 0 || (variant > 3 && variant != 6)) return B200_ERR_INVALID_ARG;
   if (h->plan.planes_mode || h->plan.yuv_out) return B200_ERR_UNSUPPORTED;   // one kernel only
+  if (variant == 6 && !h->mma.ready) return B200_ERR_UNSUPPORTED;
   if (variant == 3 && !(h->plan.ntap_ok && h->ntap.ready)) return B200_ERR_UNSUPPORTED;
   if (variant == 1 && !h->plan.lanczos2_ok) return B200_ERR_UNSUPPORTED;
   if (variant == 2 && !h->plan.light_ok) return B200_ERR_UNSUPPORTED;

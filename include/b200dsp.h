@@ -167,7 +167,8 @@ typedef struct {
   int32_t tile_w, tile_h;        /* generic kernel output tile */
   int32_t smem_bytes;
   int32_t kernel_variant;        /* 0 = generic tiled, 1 = lanczos 2:1 specialised, 2 = light (copy / 2-tap axes), 3 = n-tap any ratio, 4 = YUV plane scaling,
-                                  * 5 = chain + chroma down-sampling (4:2:0 -> the other 4:2:0 family; 2 launches) */
+                                  * 5 = chain + chroma down-sampling (4:2:0 -> the other 4:2:0 family; 2 launches),
+                                  * 6 = lanczos 2:1 on the integer tensor path (experimental, opt-in: B200_L2_MMA=1 or set_kernel_variant) */
   int32_t n_launches_per_convert;
 } b200_vcs_plan_info;
 int b200_vcs_get_plan_info (const b200_vcs * h, b200_vcs_plan_info * info);
@@ -180,7 +181,7 @@ int b200_vcs_get_taps (const b200_vcs * h, int dir, uint32_t * offsets, int16_t 
 int b200_vcs_get_matrix (const b200_vcs * h, int32_t im[16]);
 /* per input line chroma pairing mode (0 own row, 1 first of pair, 2 second of pair) */
 int b200_vcs_get_chroma_plan (const b200_vcs * h, uint8_t * mode, size_t len);
-/* force a kernel variant (0 generic, 1 specialised if eligible); for A/B tests */
+/* force a kernel variant (0 generic, 1-3 the fast kernels, 6 the tensor-path 2:1 kernel, each if eligible); for A/B tests */
 int b200_vcs_set_kernel_variant (b200_vcs * h, int variant);
 
 /* ------------------------------------------------------------------ compositor */

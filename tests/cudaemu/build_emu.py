@@ -38,7 +38,7 @@ def patch(text):
 
 
 def sources():
-    return [os.path.join(CSRC, f) for f in ("vcs.cu", "vcs_planes.cuh", "vcs_kernels.cuh", "vcs_down420.cuh", "common.cu",
+    return [os.path.join(CSRC, f) for f in ("vcs.cu", "vcs_planes.cuh", "vcs_kernels.cuh", "vcs_down420.cuh", "vcs_l2mma.cuh", "common.cu",
                                             "vcs_plan.cpp", "vcs_plan.h", "vcs_device.h", "common.h")] + \
         [os.path.join(HERE, "emu", f) for f in sorted(os.listdir(os.path.join(HERE, "emu")))] + [os.path.abspath(__file__)]
 
@@ -60,11 +60,11 @@ def build(force=False):
     os.makedirs(gen, exist_ok=True)
     launches = 0
     for src, dst in (("vcs.cu", "vcs_emu.cpp"), ("vcs_planes.cuh", "vcs_planes.cuh"), ("vcs_kernels.cuh", "vcs_kernels.cuh"),
-                     ("vcs_down420.cuh", "vcs_down420.cuh"), ("common.cu", "common_emu.cpp")):
+                     ("vcs_down420.cuh", "vcs_down420.cuh"), ("vcs_l2mma.cuh", "vcs_l2mma.cuh"), ("common.cu", "common_emu.cpp")):
         text, n = patch(open(os.path.join(CSRC, src)).read())
         launches += n
         open(os.path.join(gen, dst), "w").write(text)
-    assert launches >= 6, f"expected the launch sites of vcs.cu and vcs_planes.cuh, patched {launches}"
+    assert launches >= 7, f"expected the launch sites of vcs.cu and vcs_planes.cuh, patched {launches}"
     for f in os.listdir(os.path.join(HERE, "emu")):                # stand-in headers next to the generated sources
         if f.endswith((".h", ".cuh")):
             open(os.path.join(gen, f), "w").write(open(os.path.join(HERE, "emu", f)).read())

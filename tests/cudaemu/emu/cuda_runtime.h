@@ -46,6 +46,14 @@ void launch (dim3 grid, dim3 block, size_t smem_bytes, const std::function<void 
 
 inline void __syncthreads () { b200emu::barrier (); }
 
+namespace b200emu {
+// mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 for the calling thread's warp (warp = 32 consecutive thread ids of
+// the block; every lane must call it).  Fragment layouts as in the PTX ISA: A 16x32 u8 row-major - a0: row g, k 4t..4t+3;
+// a1: row g+8, same k; a2: row g, k 16+4t..; a3: row g+8, k 16+4t.. - B 32x8 s8 column-major - b0: k 4t..4t+3, n g;
+// b1: k 16+4t.., n g - C/D 16x8 s32 - d0: (g, 2t), d1: (g, 2t+1), d2: (g+8, 2t), d3: (g+8, 2t+1); g = lane >> 2, t = lane & 3.
+void warp_mma_u8s8 (int d[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0, unsigned b1, const int c[4]);
+}
+
 using std::max;
 using std::min;
 

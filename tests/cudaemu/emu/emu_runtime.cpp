@@ -37,9 +37,35 @@ struct LiveBarrier {
 };
 
 static LiveBarrier g_sync;
+static LiveBarrier g_warp[64];                 // one per warp of the block
+static unsigned g_wa[64][32][4], g_wb[64][32][2];
 static pthread_barrier_t g_block;
 
 void barrier () { g_sync.wait (); }
+
+void warp_mma_u8s8 (int d[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0, unsigned b1, const int c[4])
+{
+  const unsigned tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+  const unsigned w = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  g_wa[w][lane][0] = a0; g_wa[w][lane][1] = a1; g_wa[w][lane][2] = a2; g_wa[w][lane][3] = a3;
+  g_wb[w][lane][0] = b0; g_wb[w][lane][1] = b1;
+  g_warp[w].wait ();
+  auto A = [&] (unsigned row, unsigned k) -> int {                 // u8
+    const unsigned src = (row & 7) * 4 + ((k & 15) >> 2), reg = (row >> 3) + 2 * (k >> 4);
+    return (int) ((g_wa[w][src][reg] >> (8 * (k & 3))) & 0xff);
+  };
+  auto B = [&] (unsigned k, unsigned n) -> int {                   // s8
+    const unsigned src = n * 4 + ((k & 15) >> 2), reg = k >> 4;
+    return (int) (int8_t) ((g_wb[w][src][reg] >> (8 * (k & 3))) & 0xff);
+  };
+  const unsigned rows[4] = {g, g, g + 8, g + 8}, cols[4] = {2 * t, 2 * t + 1, 2 * t, 2 * t + 1};
+  for (int i = 0; i < 4; i++) {
+    int acc = c[i];
+    for (unsigned k = 0; k < 32; k++) acc += A (rows[i], k) * B (k, cols[i]);
+    d[i] = acc;
+  }
+  g_warp[w].wait ();
+}
 
 struct Job {
   const std::function<void ()> *body;
@@ -77,6 +103,7 @@ void launch (dim3 grid, dim3 block, size_t, const std::function<void ()> & body)
   pthread_attr_setstacksize (&attr, 256 * 1024);
   pthread_barrier_init (&g_block, nullptr, nt);
   g_sync.reset (nt);
+  for (unsigned w = 0; w < 64; w++) g_warp[w].reset (32);
   for (unsigned t = 0; t < nt; t++) {
     jobs[t] = Job {&body, grid, block, t, nt};
     pthread_create (&th[t], &attr, thread_main, &jobs[t]);

@@ -169,3 +169,35 @@ def test_odd_height_without_vertical_scaler(emu):
                 continue
             got = run(emu, "NV12", "I420", size, 3, frame, site=site, out_site=out_site)
             check(got, expected("NV12", "I420", size, 3, frame, site=site, out_site=out_site), f"{size} {site}->{out_site}")
+
+
+# ---- 3. the tensor-path variant of the 2:1 kernel (variant 6, opt-in) ----------------------------------------------------
+@pytest.mark.parametrize("size", [(128, 96, 64, 48), (256, 48, 128, 24), (144, 80, 72, 40), (16, 16, 8, 8), (272, 112, 136, 56)],
+                         ids=lambda s: "%dx%d-%dx%d" % s)
+def test_l2mma_variant(emu, size):
+    """vcs_l2mma_kernel: both FIR passes as u8 x s8 banded matrix products (mma.sync.m16n8k32, emulated from the PTX
+    fragment layouts), staging, packing and the matrix epilogue — against the oracle for every 8-tap method, both
+    semi-planar orders, frame borders on all four sides of every tile"""
+    from gstreamer_b200 import _lib
+    iw, ih, W, H = size
+    for fi, fo, method in [("NV12", "BGRA", 3), ("NV21", "RGBA", 9), ("NV12", "xRGB", 5), ("NV12", "ABGR", 6), ("NV21", "BGRx", 8), ("NV12", "RGBx", 7)]:
+        frame = frame_for(fi, iw, ih, 7)
+        ii, oi = _lib.VideoInfoC(), _lib.VideoInfoC()
+        emu.b200_video_info_set_format(C.byref(ii), ob.FMT[fi], iw, ih)
+        emu.b200_video_info_set_format(C.byref(oi), ob.FMT[fo], W, H)
+        ii.chroma_site = 2                          # h-cosited (the caps default above 576 lines)
+        cfg = _lib.VcsConfigC()
+        emu.b200_vcs_config_init(C.byref(cfg))
+        cfg.method = method
+        h = C.c_void_p()
+        assert emu.b200_vcs_create(C.byref(ii), C.byref(oi), C.byref(cfg), 0, C.byref(h)) == 0
+        try:
+            assert emu.b200_vcs_set_kernel_variant(h, 6) == 0, "not eligible"
+            info = _lib.VcsPlanInfoC()
+            emu.b200_vcs_get_plan_info(h, C.byref(info))
+            assert int(info.kernel_variant) == 6
+            out = np.full(W * H * 4, 0x5A, dtype=np.uint8)
+            assert emu.b200_vcs_convert(h, frame.ctypes.data, out.ctypes.data, None) == 0
+        finally:
+            emu.b200_vcs_destroy(h)
+        check(out, expected(fi, fo, size, method, frame, site=2), f"{fi}->{fo} m{method}")
