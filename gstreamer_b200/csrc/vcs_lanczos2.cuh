@@ -56,9 +56,13 @@ struct Lanczos2Dev {
 // re-associates the mask behind the shift and spends a second LOP3 on it
 __device__ __forceinline__ unsigned xor_and_fe (unsigned a, unsigned b)
 {
+#ifdef B200_CUDA_EMU               // host build of the kernel sources for tests/cudaemu: same function, plain C
+  return (a ^ b) & 0xfefefefeu;
+#else
   unsigned d;
   asm ("lop3.b32 %0, %1, %2, 0xfefefefe, 0x28;" : "=r" (d) : "r" (a), "r" (b));
   return d;
+#endif
 }
 __device__ __forceinline__ unsigned avg_floor4 (unsigned a, unsigned b)
 {
@@ -70,15 +74,24 @@ __device__ __forceinline__ unsigned avg_ceil4 (unsigned a, unsigned b)
 }
 __device__ __forceinline__ int dp4a_u8s8 (unsigned px, int taps, int acc)
 {
+#ifdef B200_CUDA_EMU
+  for (int i = 0; i < 4; i++) acc += (int) ((px >> (8 * i)) & 0xff) * (int) (int8_t) ((unsigned) taps >> (8 * i));
+  return acc;
+#else
   int d;
   asm ("dp4a.u32.s32 %0, %1, %2, %3;" : "=r" (d) : "r" (px), "r" (taps), "r" (acc));
   return d;
+#endif
 }
 __device__ __forceinline__ int prmt_s (unsigned a, unsigned sel)      // prmt.b32: selector msb replicates the sign
 {
+#ifdef B200_CUDA_EMU
+  return (int) __byte_perm (a, 0, sel);
+#else
   int d;
   asm ("prmt.b32 %0, %1, 0, %2;" : "=r" (d) : "r" (a), "r" (sel));
   return d;
+#endif
 }
 // acc >> 6 (arithmetic).  SHF runs at half rate on the ALU pipe; IMAD.HI would be a quarter-rate
 // alternative on sm_100a (profiles/r01_ubench_sm100a.txt), so the plain shift stays.
@@ -86,9 +99,13 @@ __device__ __forceinline__ int sra6 (int acc) { return acc >> 6; }
 // d = { c[15:0], sat_u8(a), sat_u8(b) }  (b in the lowest byte)
 __device__ __forceinline__ unsigned pack_sat2 (int a, int b, unsigned c)
 {
+#ifdef B200_CUDA_EMU
+  return (c << 16) | ((unsigned) min (max (a, 0), 255) << 8) | (unsigned) min (max (b, 0), 255);
+#else
   unsigned d;
   asm ("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r" (d) : "r" (a), "r" (b), "r" (c));
   return d;
+#endif
 }
 
 // 4 outputs from 16 aligned bytes w0..w3: outputs 0,1 read words 0..2, outputs 2,3 words 1..3

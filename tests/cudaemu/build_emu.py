@@ -25,20 +25,38 @@ LIB = os.path.join(OUT, "libb200emu.so")
 LAUNCH = re.compile(r"(\b\w+)\s*<<<(.+?)>>>\s*\(([^;]*)\);")
 
 
+def split_top(s):
+    """split on commas that are not inside <...> or (...)"""
+    parts, depth, cur = [], 0, ""
+    for ch in s:
+        if ch in "<(":
+            depth += 1
+        elif ch in ">)":
+            depth -= 1
+        if ch == "," and depth == 0:
+            parts.append(cur.strip())
+            cur = ""
+        else:
+            cur += ch
+    parts.append(cur.strip())
+    return parts
+
+
 def patch(text):
     def repl(m):
         name, cfg, args = m.group(1), m.group(2), m.group(3)
-        parts = [c.strip() for c in cfg.split(",")]
+        parts = split_top(cfg)
         assert len(parts) == 4, cfg
         return f"b200emu::launch ({parts[0]}, {parts[1]}, {parts[2]}, [&] {{ {name} ({args}); }});"
     text, n = LAUNCH.subn(repl, text)
-    text = re.sub(r"extern __shared__ __align__ \(16\) uint8_t smem\[\];", "uint8_t *smem = b200emu::dyn_smem;", text)
+    text = re.sub(r"extern __shared__ __align__ \(16\) (\w+) (\w+)\[\];", r"\1 *\2 = (\1 *) b200emu::dyn_smem;", text)
     text = re.sub(r"(^|\n)(\s*)__shared__ ", r"\1\2static ", text)
     return text, n
 
 
 def sources():
-    return [os.path.join(CSRC, f) for f in ("vcs.cu", "vcs_planes.cuh", "vcs_kernels.cuh", "vcs_down420.cuh", "vcs_l2mma.cuh", "common.cu",
+    return [os.path.join(CSRC, f) for f in ("vcs.cu", "vcs_planes.cuh", "vcs_kernels.cuh", "vcs_down420.cuh", "vcs_l2mma.cuh", "vcs_lanczos2.cuh", "vcs_light.cuh",
+                                            "vcs_ntap.cuh", "common.cu",
                                             "vcs_plan.cpp", "vcs_plan.h", "vcs_device.h", "common.h")] + \
         [os.path.join(HERE, "emu", f) for f in sorted(os.listdir(os.path.join(HERE, "emu")))] + [os.path.abspath(__file__)]
 
@@ -60,11 +78,12 @@ def build(force=False):
     os.makedirs(gen, exist_ok=True)
     launches = 0
     for src, dst in (("vcs.cu", "vcs_emu.cpp"), ("vcs_planes.cuh", "vcs_planes.cuh"), ("vcs_kernels.cuh", "vcs_kernels.cuh"),
-                     ("vcs_down420.cuh", "vcs_down420.cuh"), ("vcs_l2mma.cuh", "vcs_l2mma.cuh"), ("common.cu", "common_emu.cpp")):
+                     ("vcs_down420.cuh", "vcs_down420.cuh"), ("vcs_l2mma.cuh", "vcs_l2mma.cuh"), ("vcs_lanczos2.cuh", "vcs_lanczos2.cuh"),
+                     ("vcs_light.cuh", "vcs_light.cuh"), ("vcs_ntap.cuh", "vcs_ntap.cuh"), ("common.cu", "common_emu.cpp")):
         text, n = patch(open(os.path.join(CSRC, src)).read())
         launches += n
         open(os.path.join(gen, dst), "w").write(text)
-    assert launches >= 7, f"expected the launch sites of vcs.cu and vcs_planes.cuh, patched {launches}"
+    assert launches >= 10, f"expected the launch sites of vcs.cu and vcs_planes.cuh, patched {launches}"
     for f in os.listdir(os.path.join(HERE, "emu")):                # stand-in headers next to the generated sources
         if f.endswith((".h", ".cuh")):
             open(os.path.join(gen, f), "w").write(open(os.path.join(HERE, "emu", f)).read())

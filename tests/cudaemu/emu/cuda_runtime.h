@@ -52,7 +52,40 @@ namespace b200emu {
 // a1: row g+8, same k; a2: row g, k 16+4t..; a3: row g+8, k 16+4t.. - B 32x8 s8 column-major - b0: k 4t..4t+3, n g;
 // b1: k 16+4t.., n g - C/D 16x8 s32 - d0: (g, 2t), d1: (g, 2t+1), d2: (g+8, 2t), d3: (g+8, 2t+1); g = lane >> 2, t = lane & 3.
 void warp_mma_u8s8 (int d[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0, unsigned b1, const int c[4]);
+// every lane of the calling thread's warp contributes `v`; returns the 32 values (all lanes must call it)
+void warp_gather (unsigned v, unsigned out[32]);
+unsigned lane_id ();
 }
+
+inline unsigned __shfl_sync (unsigned, unsigned v, int src) { unsigned a[32]; b200emu::warp_gather (v, a); return a[src & 31]; }
+inline int __shfl_sync (unsigned m, int v, int src) { return (int) __shfl_sync (m, (unsigned) v, src); }
+inline unsigned __shfl_up_sync (unsigned, unsigned v, unsigned delta)
+{
+  unsigned a[32]; b200emu::warp_gather (v, a);
+  const unsigned l = b200emu::lane_id ();
+  return l >= delta ? a[l - delta] : v;
+}
+inline unsigned __shfl_down_sync (unsigned, unsigned v, unsigned delta)
+{
+  unsigned a[32]; b200emu::warp_gather (v, a);
+  const unsigned l = b200emu::lane_id ();
+  return l + delta < 32 ? a[l + delta] : v;
+}
+inline unsigned __ballot_sync (unsigned, int pred)
+{
+  unsigned a[32], m = 0; b200emu::warp_gather (pred ? 1u : 0u, a);
+  for (int i = 0; i < 32; i++) m |= a[i] << i;
+  return m;
+}
+inline int __popc (unsigned v) { return __builtin_popcount (v); }
+inline unsigned __umulhi (unsigned a, unsigned b) { return (unsigned) (((unsigned long long) a * b) >> 32); }
+inline unsigned __funnelshift_r (unsigned lo, unsigned hi, unsigned sh)
+{
+  return (unsigned) ((((unsigned long long) hi << 32) | lo) >> (sh & 31));
+}
+inline uint4 make_uint4 (unsigned x, unsigned y, unsigned z, unsigned w) { return uint4 {x, y, z, w}; }
+inline uint2 make_uint2 (unsigned x, unsigned y) { return uint2 {x, y}; }
+inline int4 make_int4 (int x, int y, int z, int w) { return int4 {x, y, z, w}; }
 
 using std::max;
 using std::min;

@@ -43,6 +43,23 @@ static pthread_barrier_t g_block;
 
 void barrier () { g_sync.wait (); }
 
+static unsigned g_wx[64][32];
+
+unsigned lane_id ()
+{
+  return (threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z)) & 31;
+}
+
+void warp_gather (unsigned v, unsigned out[32])
+{
+  const unsigned tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+  const unsigned w = tid >> 5, lane = tid & 31;
+  g_wx[w][lane] = v;
+  g_warp[w].wait ();
+  for (int i = 0; i < 32; i++) out[i] = g_wx[w][i];
+  g_warp[w].wait ();
+}
+
 void warp_mma_u8s8 (int d[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0, unsigned b1, const int c[4])
 {
   const unsigned tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);

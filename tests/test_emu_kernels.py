@@ -171,6 +171,43 @@ def test_odd_height_without_vertical_scaler(emu):
             check(got, expected("NV12", "I420", size, 3, frame, site=site, out_site=out_site), f"{size} {site}->{out_site}")
 
 
+# ---- 2b. the fast kernels (device-verified; here as a CPU regression net for future changes to them) -----------------------
+@pytest.mark.parametrize("case", [
+    # (in, out, size, method, expected kernel_variant)
+    ("NV12", "BGRA", (128, 96, 64, 48), 3, 1), ("NV21", "RGBA", (144, 80, 72, 40), 9, 1),          # lanczos2 (exact 2:1, 8 taps)
+    ("NV12", "BGRA", (96, 54, 64, 36), 1, 2), ("I420", "xRGB", (64, 48, 96, 72), 0, 2), ("NV12", "ARGB", (100, 60, 150, 30), 1, 2),
+    ("YV12", "BGRA", (64, 48, 64, 48), 1, 2),                                                       # light (copy / 2-tap axes)
+    ("NV12", "BGRA", (96, 54, 64, 36), 3, 3), ("I420", "RGBA", (64, 48, 96, 72), 9, 3), ("NV21", "ABGR", (120, 66, 40, 22), 5, 3),
+    ("NV12", "BGRA", (100, 60, 150, 30), 3, 3),                                                     # n-tap, both pass orders
+], ids=lambda c: "%s-%s-%dx%d-%dx%d-m%d-v%d" % (c[0], c[1], *c[2], c[3], c[4]))
+def test_fast_kernels(emu, case):
+    """vcs_lanczos2_kernel (warp shuffles), vcs_light_kernel (ballot work lists, 16-bit-lane lerps) and the n-tap kernels
+    (funnel shifts + dp4a) from their own sources: PTX helpers take their plain-C branch (B200_CUDA_EMU), warp collectives
+    are emulated lane by lane"""
+    from gstreamer_b200 import _lib
+    fi, fo, size, method, variant = case
+    iw, ih, W, H = size
+    frame = frame_for(fi, iw, ih, 8)
+    ii, oi = _lib.VideoInfoC(), _lib.VideoInfoC()
+    emu.b200_video_info_set_format(C.byref(ii), ob.FMT[fi], iw, ih)
+    emu.b200_video_info_set_format(C.byref(oi), ob.FMT[fo], W, H)
+    ii.chroma_site = 2
+    cfg = _lib.VcsConfigC()
+    emu.b200_vcs_config_init(C.byref(cfg))
+    cfg.method = method
+    h = C.c_void_p()
+    assert emu.b200_vcs_create(C.byref(ii), C.byref(oi), C.byref(cfg), 0, C.byref(h)) == 0
+    try:
+        info = _lib.VcsPlanInfoC()
+        emu.b200_vcs_get_plan_info(h, C.byref(info))
+        assert int(info.kernel_variant) == variant
+        out = np.full(W * H * 4, 0x5A, dtype=np.uint8)
+        assert emu.b200_vcs_convert(h, frame.ctypes.data, out.ctypes.data, None) == 0
+    finally:
+        emu.b200_vcs_destroy(h)
+    check(out, expected(fi, fo, size, method, frame, site=2), str(case))
+
+
 # ---- 3. the tensor-path variant of the 2:1 kernel (variant 6, opt-in) ----------------------------------------------------
 @pytest.mark.parametrize("size", [(128, 96, 64, 48), (256, 48, 128, 24), (144, 80, 72, 40), (16, 16, 8, 8), (272, 112, 136, 56)],
                          ids=lambda s: "%dx%d-%dx%d" % s)
