@@ -388,7 +388,8 @@ void b200_vcs_destroy (b200_vcs * h)
     cudaFree (h->d_hoff); cudaFree (h->d_voff); cudaFree (h->d_hcoef); cudaFree (h->d_vcoef);
     cudaFree (h->d_hsum); cudaFree (h->d_vsum); cudaFree (h->d_cmode);
     cudaFree (h->l2.d_htab); cudaFree (h->l2.d_vtab); cudaFree (h->ntap.d_h); cudaFree (h->ntap.d_v);
-    cudaFree (h->mma.d_bh); cudaFree (h->mma.d_bv);
+    cudaFree (h->l2.d_htab4); cudaFree (h->l2.d_vtab4); cudaFree (h->l2.d_v4);
+    cudaFree (h->mma.d_bh); cudaFree (h->mma.d_bv); cudaFree (h->mma.d_h4); cudaFree (h->mma.d_v4);
     free_planes (&h->planes);
     cudaFree (h->d_scratch);
     for (int i = 0; i < b200_vcs::kSlots; i++) {

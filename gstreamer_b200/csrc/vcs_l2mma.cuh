@@ -15,7 +15,8 @@
 //  H        a warp owns 8 output columns for all 64 staged lines: A = 16 line-groups x a 32-byte column window
 //           (LDS.64 per fragment half; MMA i of 4 takes line i of every group, so a thread ends up with 4 consecutive
 //           lines of its two groups and packs them into one word), B = the tap band of those 8 columns from a host table
-//           (edge columns simply have other taps there), C preset to the rounding constant 32.  Result words
+//           (edge columns simply have other taps there), C preset to the rounding constant (128: the tables carry the taps times 4, so that the rounded, saturated result is
+//           byte 1 of a saturating 16-bit pack - no shifts).  Result words
 //           [line-group][column] = 4 lines of one column, as in the SIMT kernel.
 //  V        a warp owns 16 columns x 8 output rows: A = columns x 32 staged lines (the words above), B = the vertical tap
 //           band, C = 32; epilogue per pixel = the SIMT kernel's: saturate, mulhi matrix, byte order, store.
@@ -43,6 +44,9 @@ constexpr int LM_SMEM = 3 * 4 * LM_NG * LM_SP + 3 * LM_NG * LM_HP * 4;
 struct L2mmaDev {
   const uint2 *bh;               // [ow/8][32 lanes]: B fragment (b0, b1) of each group of 8 output columns
   const uint2 *bv;               // [oh/8][32 lanes]
+  // per group: 1 = the table carries the taps times 4 (accumulator preset 128, result = byte 1 of a saturating 16-bit
+  // pack, no shifts); 0 = plain taps (preset 32, shift by 6) - groups at a frame border, whose folded taps reach 32
+  const uint8_t *h4, *v4;
 };
 
 // D = A(16x32 u8, row) * B(32x8 s8, col) + c  (mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32); all 4 accumulators
@@ -132,6 +136,8 @@ vcs_l2mma_kernel (const VcsDev P, const L2mmaDev L, const VcsBatch frames)
   // ---------------------------------------------------------------- H phase: warp = 8 output columns, all staged lines
   for (int j = warp; j < LM_TW / 8; j += L2_THREADS / 32) {
     const uint2 B = __ldg (L.bh + (size_t) ((x0 >> 3) + j) * 32 + lane);
+    const bool x4 = __ldg (L.h4 + (x0 >> 3) + j) != 0;              // warp-uniform
+    const int c_init = x4 ? 128 : 32;
 #pragma unroll
     for (int ch = 0; ch < 3; ch++) {
       const uint8_t *base = S + (size_t) ch * 4 * LM_NG * LM_SP + 16 * j + 8 * t;
@@ -140,14 +146,21 @@ vcs_l2mma_kernel (const VcsDev P, const L2mmaDev L, const VcsBatch frames)
       for (int i = 0; i < 4; i++) {
         const uint2 lo = *(const uint2 *) (base + (size_t) (4 * g + i) * LM_SP);
         const uint2 hi = *(const uint2 *) (base + (size_t) (4 * (g + 8) + i) * LM_SP);
-        mma_u8s8 (d[i], lo.x, hi.x, lo.y, hi.y, B.x, B.y, 32);
+        mma_u8s8 (d[i], lo.x, hi.x, lo.y, hi.y, B.x, B.y, c_init);
       }
       // (acc+32)>>6 saturated to u8 (video-orc.orc:2474-2481); byte i of a word = line i of the group
       uint2 wlo, whi;
-      wlo.x = pack_sat2 (sra6 (d[1][0]), sra6 (d[0][0]), pack_sat2 (sra6 (d[3][0]), sra6 (d[2][0]), 0u));
-      wlo.y = pack_sat2 (sra6 (d[1][1]), sra6 (d[0][1]), pack_sat2 (sra6 (d[3][1]), sra6 (d[2][1]), 0u));
-      whi.x = pack_sat2 (sra6 (d[1][2]), sra6 (d[0][2]), pack_sat2 (sra6 (d[3][2]), sra6 (d[2][2]), 0u));
-      whi.y = pack_sat2 (sra6 (d[1][3]), sra6 (d[0][3]), pack_sat2 (sra6 (d[3][3]), sra6 (d[2][3]), 0u));
+      if (x4) {                  // = byte 1 of sat_u16 (4 acc + 128)
+        wlo.x = __byte_perm (pack_sat_u16x2 (d[1][0], d[0][0]), pack_sat_u16x2 (d[3][0], d[2][0]), 0x7531);
+        wlo.y = __byte_perm (pack_sat_u16x2 (d[1][1], d[0][1]), pack_sat_u16x2 (d[3][1], d[2][1]), 0x7531);
+        whi.x = __byte_perm (pack_sat_u16x2 (d[1][2], d[0][2]), pack_sat_u16x2 (d[3][2], d[2][2]), 0x7531);
+        whi.y = __byte_perm (pack_sat_u16x2 (d[1][3], d[0][3]), pack_sat_u16x2 (d[3][3], d[2][3]), 0x7531);
+      } else {
+        wlo.x = pack_sat2 (sra6 (d[1][0]), sra6 (d[0][0]), pack_sat2 (sra6 (d[3][0]), sra6 (d[2][0]), 0u));
+        wlo.y = pack_sat2 (sra6 (d[1][1]), sra6 (d[0][1]), pack_sat2 (sra6 (d[3][1]), sra6 (d[2][1]), 0u));
+        whi.x = pack_sat2 (sra6 (d[1][2]), sra6 (d[0][2]), pack_sat2 (sra6 (d[3][2]), sra6 (d[2][2]), 0u));
+        whi.y = pack_sat2 (sra6 (d[1][3]), sra6 (d[0][3]), pack_sat2 (sra6 (d[3][3]), sra6 (d[2][3]), 0u));
+      }
       unsigned *hs = HS + (size_t) ch * LM_NG * LM_HP + 8 * j + 2 * t;
       *(uint2 *) (hs + (size_t) g * LM_HP) = wlo;
       *(uint2 *) (hs + (size_t) (g + 8) * LM_HP) = whi;
@@ -161,20 +174,22 @@ vcs_l2mma_kernel (const VcsDev P, const L2mmaDev L, const VcsBatch frames)
     const int oyq = oy0 + 8 * q;
     if (oyq >= P.oh) continue;                                   // warp-uniform
     const uint2 B = __ldg (L.bv + (size_t) (oyq >> 3) * 32 + lane);
+    const bool x4 = __ldg (L.v4 + (oyq >> 3)) != 0;                 // warp-uniform
     int d[3][4];
 #pragma unroll
     for (int ch = 0; ch < 3; ch++) {
       const unsigned *hs = HS + (size_t) ch * LM_NG * LM_HP + c0 + g;
       const unsigned a0 = hs[(size_t) (4 * q + t) * LM_HP], a1 = hs[(size_t) (4 * q + t) * LM_HP + 8];
       const unsigned a2 = hs[(size_t) (4 * q + 4 + t) * LM_HP], a3 = hs[(size_t) (4 * q + 4 + t) * LM_HP + 8];
-      mma_u8s8 (d[ch], a0, a1, a2, a3, B.x, B.y, 32);
+      mma_u8s8 (d[ch], a0, a1, a2, a3, B.x, B.y, x4 ? 128 : 32);
     }
 #pragma unroll
     for (int e = 0; e < 4; e++) {
       const int ox = x0 + c0 + g + 8 * (e >> 1), oy = oyq + 2 * t + (e & 1);
       if (ox >= P.ow || oy >= P.oh) continue;
       // saturate the three channels at once, bias by 128 and sign-splat each byte to s16 (video-orc.orc:1634-1688)
-      unsigned yuv = pack_sat2 (d[1][e] >> 6, d[0][e] >> 6, pack_sat2 (0, d[2][e] >> 6, 0u));
+      unsigned yuv = x4 ? __byte_perm (pack_sat_u16x2 (d[1][e], d[0][e]), pack_sat_u16x2 (0, d[2][e]), 0x7531)
+          : pack_sat2 (d[1][e] >> 6, d[0][e] >> 6, pack_sat2 (0, d[2][e] >> 6, 0u));
       yuv ^= 0x00808080u;
       const int wy = prmt_s (yuv, 0x8800u), wu = prmt_s (yuv, 0x9911u), wv = prmt_s (yuv, 0xaa22u);
       const int ty = ((wy * P.p1) >> 16) + 128;
@@ -190,18 +205,25 @@ vcs_l2mma_kernel (const VcsDev P, const L2mmaDev L, const VcsBatch frames)
 // ------------------------------------------------------------------------------------ host side
 struct L2mmaTables {
   std::vector<uint32_t> bh, bv;        // [groups][32 lanes][2]
+  std::vector<uint8_t> h4, v4;         // [groups]: taps stored times 4
   bool ok = false;
 };
 
 // B fragments of one axis: group T covers outputs 8T..8T+7 and the 32 input samples starting at 16T - bias.
 // Fragment element k of lane (g, t), register r, byte b: k = 16r + 4t + b, n = g; the sample k stands for is
 // window[k] (h: the 8-byte interleave that lets a thread fetch its two fragment registers with one LDS.64).
-inline bool pack_axis_l2mma (const AxisPlan & a, int bias, bool interleave8, std::vector<uint32_t> * tab)
+inline bool pack_axis_l2mma (const AxisPlan & a, int bias, bool interleave8, std::vector<uint32_t> * tab,
+    std::vector<uint8_t> * times4)
 {
   if (a.mode != PASS_NTAP || a.n_taps != 8 || a.in_size != 2 * a.out_size || (a.out_size & 7)) return false;
   const int groups = a.out_size / 8;
   tab->assign ((size_t) groups * 64, 0);
+  times4->assign (groups, 1);
   for (int T = 0; T < groups; T++) {
+    for (int j = 8 * T; j < 8 * T + 8; j++)             // taps times 4 must fit s8: not where folded edge taps reach 32
+      for (int k = 0; k < 8; k++)
+        if (4 * a.coef[(size_t) j * 8 + k] < -128 || 4 * a.coef[(size_t) j * 8 + k] > 127) (*times4)[T] = 0;
+    const int scale = (*times4)[T] ? 4 : 1;
     for (int n = 0; n < 8; n++) {
       const int j = 8 * T + n;
       int8_t col[32] = {0};
@@ -212,9 +234,9 @@ inline bool pack_axis_l2mma (const AxisPlan & a, int bias, bool interleave8, std
         if (tap == 0) continue;
         const int pos = (int) a.offset[j] + k - (16 * T - bias);               // window sample index
         if (pos < 0 || pos >= 32 || tap < -128 || tap > 127) return false;
-        col[pos] = (int8_t) tap;
+        col[pos] = (int8_t) (scale * tap);
       }
-      if (255 * mag + 32 > 32767) return false;        // must stay inside the reference's 16-bit accumulator
+      if (255 * mag + 32 > 32767) return false;        // must stay inside the reference's 16-bit accumulator (unscaled taps)
       for (int k = 0; k < 32; k++) {
         // which window sample does fragment element k hold?
         const int w = interleave8 ? 8 * ((k & 15) >> 2) + (k & 3) + ((k >> 4) ? 4 : 0) : k;
@@ -238,14 +260,15 @@ inline L2mmaTables build_l2mma_tables (const VcsPlan & p)
     if (p.chroma_mode[y] != (y == 0 ? 0 : ((y & 1) ? 1 : 2))) return t;
   for (int16_t s : p.h.sum) if (s < 64 || s > 128) return t;      // alpha stays 255 through both passes
   for (int16_t s : p.v.sum) if (s < 64 || s > 128) return t;
-  if (!pack_axis_l2mma (p.h, 8, true, &t.bh)) return t;            // staged columns start 8 pixels left of the tile
-  if (!pack_axis_l2mma (p.v, 3, false, &t.bv)) return t;           // staged lines start at 2*oy0 - 3
+  if (!pack_axis_l2mma (p.h, 8, true, &t.bh, &t.h4)) return t;     // staged columns start 8 pixels left of the tile
+  if (!pack_axis_l2mma (p.v, 3, false, &t.bv, &t.v4)) return t;    // staged lines start at 2*oy0 - 3
   t.ok = true;
   return t;
 }
 
 struct L2mmaState {
   uint32_t *d_bh = nullptr, *d_bv = nullptr;
+  uint8_t *d_h4 = nullptr, *d_v4 = nullptr;
   L2mmaDev dev;
   bool ready = false;
 };
@@ -255,8 +278,11 @@ inline int prepare_l2mma (const L2mmaTables & t, L2mmaState * st)
   int rc;
   if ((rc = upload (&st->d_bh, t.bh.data (), t.bh.size ())) != B200_OK) return rc;
   if ((rc = upload (&st->d_bv, t.bv.data (), t.bv.size ())) != B200_OK) return rc;
+  if ((rc = upload (&st->d_h4, t.h4.data (), t.h4.size ())) != B200_OK) return rc;
+  if ((rc = upload (&st->d_v4, t.v4.data (), t.v4.size ())) != B200_OK) return rc;
   st->dev.bh = (const uint2 *) st->d_bh;
   st->dev.bv = (const uint2 *) st->d_bv;
+  st->dev.h4 = st->d_h4; st->dev.v4 = st->d_v4;
   B200_CUDA_TRY (cudaFuncSetAttribute (vcs_l2mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LM_SMEM));
   st->ready = true;
   return B200_OK;

@@ -49,6 +49,12 @@ struct Lanczos2Dev {
   const int4 *vtab;                    // [oh/4][3]
   const short *hsum, *vsum;            // tap sums (alpha channel)
   int alpha_opaque;                    // every tap sum >= 64: alpha is 255 everywhere
+  // X4 instantiation (opt-in): the same tables with every tap times 4.  With the accumulator preset to 128 the rounded,
+  // saturated FIR output is byte 1 of a saturating 16-bit pack of 4 acc + 128 - one I2IP per two outputs and one PRMT
+  // per four instead of a shift per output.  Folded taps at the frame borders reach 32 (x4 = 128 does not fit s8): edge
+  // tiles keep the plain tables in the H phase, and v4[row group] says which row groups may use vtab4.
+  const int4 *htab4, *vtab4;
+  const uint8_t *v4;
 };
 
 // ---- packed byte helpers -----------------------------------------------------------------
@@ -108,16 +114,29 @@ __device__ __forceinline__ unsigned pack_sat2 (int a, int b, unsigned c)
 #endif
 }
 
+// d = { sat_u16(a), sat_u16(b) }  (b in the low half).  With taps scaled by 4 and the accumulator preset to 128 the
+// rounded, saturated FIR output (acc + 32) >> 6 clamped to [0, 255] is byte 1 of sat_u16 (4 acc + 128): no shift needed
+__device__ __forceinline__ unsigned pack_sat_u16x2 (int a, int b)
+{
+#ifdef B200_CUDA_EMU
+  return ((unsigned) min (max (a, 0), 65535) << 16) | (unsigned) min (max (b, 0), 65535);
+#else
+  unsigned d;
+  asm ("cvt.pack.sat.u16.s32 %0, %1, %2;" : "=r" (d) : "r" (a), "r" (b));
+  return d;
+#endif
+}
+
 // 4 outputs from 16 aligned bytes w0..w3: outputs 0,1 read words 0..2, outputs 2,3 words 1..3
-#define L2_FIR4(o0, o1, o2, o3, w0, w1, w2, w3, T)                                             \
+#define L2_FIR4(o0, o1, o2, o3, w0, w1, w2, w3, T, INIT)                                       \
   do {                                                                                         \
-    o0 = dp4a_u8s8 (w2, T[0].z, dp4a_u8s8 (w1, T[0].y, dp4a_u8s8 (w0, T[0].x, 32)));           \
-    o1 = dp4a_u8s8 (w2, T[1].y, dp4a_u8s8 (w1, T[1].x, dp4a_u8s8 (w0, T[0].w, 32)));           \
-    o2 = dp4a_u8s8 (w3, T[2].x, dp4a_u8s8 (w2, T[1].w, dp4a_u8s8 (w1, T[1].z, 32)));           \
-    o3 = dp4a_u8s8 (w3, T[2].w, dp4a_u8s8 (w2, T[2].z, dp4a_u8s8 (w1, T[2].y, 32)));           \
+    o0 = dp4a_u8s8 (w2, T[0].z, dp4a_u8s8 (w1, T[0].y, dp4a_u8s8 (w0, T[0].x, INIT)));         \
+    o1 = dp4a_u8s8 (w2, T[1].y, dp4a_u8s8 (w1, T[1].x, dp4a_u8s8 (w0, T[0].w, INIT)));         \
+    o2 = dp4a_u8s8 (w3, T[2].x, dp4a_u8s8 (w2, T[1].w, dp4a_u8s8 (w1, T[1].z, INIT)));         \
+    o3 = dp4a_u8s8 (w3, T[2].w, dp4a_u8s8 (w2, T[2].z, dp4a_u8s8 (w1, T[2].y, INIT)));         \
   } while (0)
 
-template <bool ALPHA_OPAQUE, int MINB, int TH, int NWC>
+template <bool ALPHA_OPAQUE, int MINB, int TH, int NWC, bool X4 = false>
 __global__ void __launch_bounds__ (L2_THREADS, MINB)
 vcs_lanczos2_kernel (const VcsDev P, const Lanczos2Dev L, const VcsBatch frames)
 {
@@ -141,15 +160,18 @@ vcs_lanczos2_kernel (const VcsDev P, const Lanczos2Dev L, const VcsBatch frames)
   const bool edge_tile = R0 < 0 || R0 + 4 * L2_NG > P.ih || x0 == 0 || x0 + L2_TW + 4 >= P.ow;
   auto h_phase = [&] (auto edge_tag) {
     constexpr bool EDGE = decltype (edge_tag)::value;
+    constexpr bool H4 = X4 && !EDGE;                             // interior tiles only: no folded taps there
+    constexpr int HINIT = H4 ? 128 : 32;
+    const int4 *__restrict__ htab = H4 ? L.htab4 : L.htab;
   for (int item = warp; item < L2_NG * L2_NWC; item += L2_THREADS / 32) {
     const int g = item / L2_NWC, wc = item - g * L2_NWC;
     const int col0 = x0 + wc * L2_WCOLS + (lane - 1) * 4;        // first of this lane's 4 output columns
     int4 T[3];
     {
       const int grp = EDGE ? min (max (col0 >> 2, 0), (P.ow >> 2) - 1) : (col0 >> 2);
-      T[0] = __ldg (L.htab + grp * 3 + 0);
-      T[1] = __ldg (L.htab + grp * 3 + 1);
-      T[2] = __ldg (L.htab + grp * 3 + 2);
+      T[0] = __ldg (htab + grp * 3 + 0);
+      T[1] = __ldg (htab + grp * 3 + 1);
+      T[2] = __ldg (htab + grp * 3 + 2);
     }
     const int xb = EDGE ? min (max (2 * col0, 0), P.iw - 8) : 2 * col0;   // byte column of the lane's 8 input pixels
     const bool right_edge = EDGE && 2 * col0 + 8 >= P.iw;        // no chroma sample to the right
@@ -192,13 +214,13 @@ vcs_lanczos2_kernel (const VcsDev P, const Lanczos2Dev L, const VcsBatch frames)
 
     // (acc+32)>>6 saturated to u8 (video-orc.orc:2474-2481); four lines of a column go into
     // one word so that the V phase finds its 16 lines in 4 aligned words
+#define L2_PACK4(A, c)                                                                         \
+    (H4 ? __byte_perm (pack_sat_u16x2 (A[1][c], A[0][c]), pack_sat_u16x2 (A[3][c], A[2][c]), 0x7531)              \
+        : pack_sat2 (sra6 (A[1][c]), sra6 (A[0][c]), pack_sat2 (sra6 (A[3][c]), sra6 (A[2][c]), 0u)))
 #define L2_STORE(ch, A)                                                                        \
     do {                                                                                       \
       uint4 o;                                                                                 \
-      o.x = pack_sat2 (sra6 (A[1][0]), sra6 (A[0][0]), pack_sat2 (sra6 (A[3][0]), sra6 (A[2][0]), 0u)); \
-      o.y = pack_sat2 (sra6 (A[1][1]), sra6 (A[0][1]), pack_sat2 (sra6 (A[3][1]), sra6 (A[2][1]), 0u)); \
-      o.z = pack_sat2 (sra6 (A[1][2]), sra6 (A[0][2]), pack_sat2 (sra6 (A[3][2]), sra6 (A[2][2]), 0u)); \
-      o.w = pack_sat2 (sra6 (A[1][3]), sra6 (A[0][3]), pack_sat2 (sra6 (A[3][3]), sra6 (A[2][3]), 0u)); \
+      o.x = L2_PACK4 (A, 0); o.y = L2_PACK4 (A, 1); o.z = L2_PACK4 (A, 2); o.w = L2_PACK4 (A, 3); \
       *(uint4 *) (hs + ((ch) * L2_NG + g) * L2_TWP + wc * 128 + lane * 4) = o;                 \
     } while (0)
 
@@ -206,13 +228,13 @@ vcs_lanczos2_kernel (const VcsDev P, const Lanczos2Dev L, const VcsBatch frames)
 #pragma unroll
     for (int r = 0; r < 4; r++) {
       const unsigned w0 = __shfl_up_sync (0xffffffffu, U[r][1], 1), w3 = __shfl_down_sync (0xffffffffu, U[r][0], 1);
-      L2_FIR4 (acc[r][0], acc[r][1], acc[r][2], acc[r][3], w0, U[r][0], U[r][1], w3, T);
+      L2_FIR4 (acc[r][0], acc[r][1], acc[r][2], acc[r][3], w0, U[r][0], U[r][1], w3, T, HINIT);
     }
     L2_STORE (1, acc);
 #pragma unroll
     for (int r = 0; r < 4; r++) {
       const unsigned w0 = __shfl_up_sync (0xffffffffu, V[r][1], 1), w3 = __shfl_down_sync (0xffffffffu, V[r][0], 1);
-      L2_FIR4 (acc[r][0], acc[r][1], acc[r][2], acc[r][3], w0, V[r][0], V[r][1], w3, T);
+      L2_FIR4 (acc[r][0], acc[r][1], acc[r][2], acc[r][3], w0, V[r][0], V[r][1], w3, T, HINIT);
     }
     L2_STORE (2, acc);
 #pragma unroll
@@ -220,7 +242,7 @@ vcs_lanczos2_kernel (const VcsDev P, const Lanczos2Dev L, const VcsBatch frames)
       const int y = EDGE ? min (max (y0 + r, 0), P.ih - 1) : y0 + r;
       const uint2 yy = __ldg ((const uint2 *) (plane_y + (size_t) y * P.stride_y + xb));
       const unsigned w0 = __shfl_up_sync (0xffffffffu, yy.y, 1), w3 = __shfl_down_sync (0xffffffffu, yy.x, 1);
-      L2_FIR4 (acc[r][0], acc[r][1], acc[r][2], acc[r][3], w0, yy.x, yy.y, w3, T);
+      L2_FIR4 (acc[r][0], acc[r][1], acc[r][2], acc[r][3], w0, yy.x, yy.y, w3, T, HINIT);
     }
     L2_STORE (0, acc);
   }
@@ -234,9 +256,12 @@ vcs_lanczos2_kernel (const VcsDev P, const Lanczos2Dev L, const VcsBatch frames)
     const int oy = oy0 + 4 * q;
     if (oy < P.oh) {
       int4 T[3];
-      T[0] = __ldg (L.vtab + (oy >> 2) * 3 + 0);
-      T[1] = __ldg (L.vtab + (oy >> 2) * 3 + 1);
-      T[2] = __ldg (L.vtab + (oy >> 2) * 3 + 2);
+      const bool v4 = X4 && __ldg (L.v4 + (oy >> 2)) != 0;       // warp-uniform: this row group's taps fit s8 times 4
+      const int4 *__restrict__ vtab = v4 ? L.vtab4 : L.vtab;
+      const int vinit = v4 ? 128 : 32;
+      T[0] = __ldg (vtab + (oy >> 2) * 3 + 0);
+      T[1] = __ldg (vtab + (oy >> 2) * 3 + 1);
+      T[2] = __ldg (vtab + (oy >> 2) * 3 + 2);
       int vs[4] = {64, 64, 64, 64};
       if (!ALPHA_OPAQUE) {
 #pragma unroll
@@ -252,7 +277,7 @@ vcs_lanczos2_kernel (const VcsDev P, const Lanczos2Dev L, const VcsBatch frames)
         for (int ch = 0; ch < 3; ch++) {
           const unsigned *p = hs + (ch * L2_NG + 2 * q) * L2_TWP + sc;
           const unsigned w0 = p[0], w1 = p[L2_TWP], w2 = p[2 * L2_TWP], w3 = p[3 * L2_TWP];
-          L2_FIR4 (a[ch][0], a[ch][1], a[ch][2], a[ch][3], w0, w1, w2, w3, T);
+          L2_FIR4 (a[ch][0], a[ch][1], a[ch][2], a[ch][3], w0, w1, w2, w3, T, vinit);
         }
         int ah = 255;
         if (!ALPHA_OPAQUE) ah = fir_round_u8 ((int) (short) (255 * (int) L.hsum[ox]));
@@ -260,7 +285,8 @@ vcs_lanczos2_kernel (const VcsDev P, const Lanczos2Dev L, const VcsBatch frames)
 #pragma unroll
         for (int i = 0; i < 4; i++) {
           // saturate the three channels at once, bias by 128 and sign-splat each byte to s16
-          unsigned yuv = pack_sat2 (a[1][i] >> 6, a[0][i] >> 6, pack_sat2 (0, a[2][i] >> 6, 0u));
+          unsigned yuv = v4 ? __byte_perm (pack_sat_u16x2 (a[1][i], a[0][i]), pack_sat_u16x2 (0, a[2][i]), 0x7531)
+              : pack_sat2 (a[1][i] >> 6, a[0][i] >> 6, pack_sat2 (0, a[2][i] >> 6, 0u));
           yuv ^= 0x00808080u;
           const int wy = prmt_s (yuv, 0x8800u), wu = prmt_s (yuv, 0x9911u), wv = prmt_s (yuv, 0xaa22u);
           const int ty = ((wy * P.p1) >> 16) + 128;
@@ -283,18 +309,31 @@ struct Lanczos2Tables {
   std::vector<int> htab, vtab;          // 12 words per group
   bool ok = false;
   bool alpha_opaque = false;
+  // X4 instantiation: taps times 4 where they fit s8 (per 4-output group), see Lanczos2Dev
+  std::vector<int> htab4, vtab4;
+  std::vector<uint8_t> h4, v4;
+  bool x4_ok = false;
 };
 
 // Place the taps of 4 consecutive outputs into their 16-sample aligned frame; outputs 0,1 may
 // only touch samples 0..11 and outputs 2,3 samples 4..15.
-inline bool pack_axis_lanczos2 (const AxisPlan & a, int frame_bias, std::vector<int> * tab)
+inline bool pack_axis_lanczos2 (const AxisPlan & a, int frame_bias, std::vector<int> * tab, int scale = 1,
+    std::vector<uint8_t> * fits = nullptr)
 {
   if (a.mode != PASS_NTAP || a.n_taps != 8 || a.in_size != 2 * a.out_size || (a.out_size & 3))
     return false;
   const int groups = a.out_size / 4;
   tab->assign ((size_t) groups * 12, 0);
+  if (fits) fits->assign (groups, 1);
   for (int gidx = 0; gidx < groups; gidx++) {
     const int base = 8 * gidx - frame_bias;
+    if (fits)                                       // a scaled table: groups whose taps do not fit are left zero and flagged
+      for (int j = 4 * gidx; j < 4 * gidx + 4; j++)
+        for (int k = 0; k < 8; k++) {
+          const int v = scale * a.coef[(size_t) j * 8 + k];
+          if (v < -128 || v > 127) (*fits)[gidx] = 0;
+        }
+    if (fits && !(*fits)[gidx]) continue;
     for (int i = 0; i < 4; i++) {
       const int j = 4 * gidx + i;
       int8_t frame[16] = {0};
@@ -303,8 +342,8 @@ inline bool pack_axis_lanczos2 (const AxisPlan & a, int frame_bias, std::vector<
         if (tap == 0) continue;
         const int pos = (int) a.offset[j] + k - base;
         const int lo = i < 2 ? 0 : 4, hi = i < 2 ? 12 : 16;
-        if (pos < lo || pos >= hi || tap < -128 || tap > 127) return false;
-        frame[pos] = (int8_t) tap;
+        if (pos < lo || pos >= hi || scale * tap < -128 || scale * tap > 127) return false;
+        frame[pos] = (int8_t) (scale * tap);
       }
       // 255 * sum(|taps|) + 32 must stay inside the reference's 16-bit accumulator
       int mag = 0;
@@ -335,13 +374,27 @@ inline Lanczos2Tables build_lanczos2_tables (const VcsPlan & p)
   for (int16_t s : p.h.sum) if (s < 64 || s > 128) t.alpha_opaque = false;
   for (int16_t s : p.v.sum) if (s < 64 || s > 128) t.alpha_opaque = false;
   t.ok = true;
+  // X4 tables: usable when every column group OUTSIDE the kernel's edge tiles (the first tile column and the tiles that
+  // reach the right border: x0 == 0 || x0 + TW + 4 >= ow, TW = 120) fits; row groups are flagged one by one
+  if (t.alpha_opaque && pack_axis_lanczos2 (p.h, 4, &t.htab4, 4, &t.h4) && pack_axis_lanczos2 (p.v, 3, &t.vtab4, 4, &t.v4)) {
+    t.x4_ok = true;
+    const int ow = p.out.width, TW = L2_WCOLS;
+    for (size_t grp = 0; grp < t.h4.size (); grp++) {
+      const int x0 = ((int) (4 * grp) / TW) * TW;
+      const bool edge = x0 == 0 || x0 + TW + 4 >= ow;
+      if (!edge && !t.h4[grp]) t.x4_ok = false;
+    }
+  }
   return t;
 }
 
 struct Lanczos2State {
   int4 *d_htab = nullptr, *d_vtab = nullptr;
+  int4 *d_htab4 = nullptr, *d_vtab4 = nullptr;
+  uint8_t *d_v4 = nullptr;
   Lanczos2Dev dev;
   int variant = 0;
+  bool x4 = false;               // launch the X4 instantiation (opt-in: B200_L2_X4=1, until it has been measured)
 };
 
 inline int prepare_lanczos2 (const Lanczos2Tables & t, const VcsDev & d, Lanczos2State * st)
@@ -354,6 +407,16 @@ inline int prepare_lanczos2 (const Lanczos2Tables & t, const VcsDev & d, Lanczos
   st->dev.htab = st->d_htab; st->dev.vtab = st->d_vtab;
   st->dev.hsum = d.h.sum; st->dev.vsum = d.v.sum;
   st->dev.alpha_opaque = t.alpha_opaque;
+  st->dev.htab4 = st->dev.htab; st->dev.vtab4 = st->dev.vtab; st->dev.v4 = nullptr;
+  if (t.x4_ok && getenv ("B200_L2_X4")) {
+    int *h4 = nullptr, *v4 = nullptr;
+    if ((rc = upload (&h4, t.htab4.data (), t.htab4.size ())) != B200_OK) return rc;
+    if ((rc = upload (&v4, t.vtab4.data (), t.vtab4.size ())) != B200_OK) return rc;
+    if ((rc = upload (&st->d_v4, t.v4.data (), t.v4.size ())) != B200_OK) return rc;
+    st->d_htab4 = (int4 *) h4; st->d_vtab4 = (int4 *) v4;
+    st->dev.htab4 = st->d_htab4; st->dev.vtab4 = st->d_vtab4; st->dev.v4 = st->d_v4;
+    st->x4 = true;
+  }
   {
     const char *e = getenv ("B200_L2_VARIANT");      // tuning knob (0..3), see launch_lanczos2
     st->variant = e ? atoi (e) : 3;        // 120x60 tiles, 4 CTAs/SM measured fastest (profiles/)
@@ -364,9 +427,10 @@ inline int prepare_lanczos2 (const Lanczos2Tables & t, const VcsDev & d, Lanczos
 inline int launch_lanczos2 (const VcsDev & d, const Lanczos2State & st, const VcsBatch & batch, int n,
     cudaStream_t stream)
 {
-#define L2_LAUNCH(ALPHA, MINB, TH, NWC)                                                        \
+#define L2_LAUNCH(ALPHA, MINB, TH, NWC) L2_LAUNCH_X (ALPHA, MINB, TH, NWC, false)
+#define L2_LAUNCH_X(ALPHA, MINB, TH, NWC, X4)                                                  \
   do {                                                                                         \
-    auto kern = vcs_lanczos2_kernel<ALPHA, MINB, TH, NWC>;                                     \
+    auto kern = vcs_lanczos2_kernel<ALPHA, MINB, TH, NWC, X4>;                                 \
     static bool attr_done[16] = {false};                                                       \
     int dev = 0; cudaGetDevice (&dev);                                                         \
     if (!attr_done[dev & 15]) {                                                                \
@@ -378,6 +442,7 @@ inline int launch_lanczos2 (const VcsDev & d, const Lanczos2State & st, const Vc
     kern <<<grid, L2_THREADS, L2Shape<TH, NWC>::SMEM, stream>>> (d, st.dev, batch);            \
   } while (0)
   if (!st.dev.alpha_opaque) L2_LAUNCH (false, 3, 32, 2);
+  else if (st.x4) L2_LAUNCH_X (true, 4, 60, 1, true);              // the default shape with taps times 4
   else switch (st.variant) {
     case 1: L2_LAUNCH (true, 4, 32, 2); break;
     case 2: L2_LAUNCH (true, 3, 60, 1); break;
@@ -385,6 +450,7 @@ inline int launch_lanczos2 (const VcsDev & d, const Lanczos2State & st, const Vc
     default: L2_LAUNCH (true, 3, 32, 2); break;
   }
 #undef L2_LAUNCH
+#undef L2_LAUNCH_X
   B200_CUDA_TRY (cudaGetLastError ());
   return B200_OK;
 }

@@ -238,3 +238,33 @@ def test_l2mma_variant(emu, size):
         finally:
             emu.b200_vcs_destroy(h)
         check(out, expected(fi, fo, size, method, frame, site=2), f"{fi}->{fo} m{method}")
+
+
+@pytest.mark.parametrize("size", [(512, 144, 256, 72), (256, 240, 128, 120), (496, 128, 248, 64)], ids=lambda s: "%dx%d-%dx%d" % s)
+def test_lanczos2_x4_variant(emu, size, monkeypatch):
+    """the SIMT 2:1 kernel with its taps times 4 (B200_L2_X4=1): interior tiles and row groups read the scaled tables and
+    take the rounded, saturated output as byte 1 of a saturating 16-bit pack; tiles and row groups at a frame border keep
+    the plain tables — sizes with interior tiles in both directions"""
+    from gstreamer_b200 import _lib
+    monkeypatch.setenv("B200_L2_X4", "1")
+    iw, ih, W, H = size
+    for fi, fo, method in [("NV12", "BGRA", 3), ("NV21", "RGBA", 9)]:
+        frame = frame_for(fi, iw, ih, 12)
+        ii, oi = _lib.VideoInfoC(), _lib.VideoInfoC()
+        emu.b200_video_info_set_format(C.byref(ii), ob.FMT[fi], iw, ih)
+        emu.b200_video_info_set_format(C.byref(oi), ob.FMT[fo], W, H)
+        ii.chroma_site = 2
+        cfg = _lib.VcsConfigC()
+        emu.b200_vcs_config_init(C.byref(cfg))
+        cfg.method = method
+        h = C.c_void_p()
+        assert emu.b200_vcs_create(C.byref(ii), C.byref(oi), C.byref(cfg), 0, C.byref(h)) == 0
+        try:
+            info = _lib.VcsPlanInfoC()
+            emu.b200_vcs_get_plan_info(h, C.byref(info))
+            assert int(info.kernel_variant) == 1
+            out = np.full(W * H * 4, 0x5A, dtype=np.uint8)
+            assert emu.b200_vcs_convert(h, frame.ctypes.data, out.ctypes.data, None) == 0
+        finally:
+            emu.b200_vcs_destroy(h)
+        check(out, expected(fi, fo, size, method, frame, site=2), f"{fi}->{fo} m{method}")

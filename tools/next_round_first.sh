@@ -14,7 +14,9 @@ run borders 180 python -m pytest tests/test_vcs_borders_gpu.py -q -p no:cachepro
 run arsopts 240 python -m pytest tests/test_ars_options_gpu.py -q -p no:cacheprovider
 # 2c. tensor-path variant of the 2:1 kernel: parity, then the headline bench with it (compare with the default line)
 run l2mma 240 python -m pytest tests/test_vcs_l2mma_gpu.py -q -p no:cacheprovider
+B200_L2_X4=1 run l2x4 300 python -m pytest tests/test_vcs_lanczos2_gpu.py -q -p no:cacheprovider
 B200_L2_MMA=1 timeout 300 python bench.py > gpurun_out/nr_bench_l2mma.json 2> gpurun_out/nr_bench_l2mma.err; tail -c 600 gpurun_out/nr_bench_l2mma.json
+B200_L2_X4=1 timeout 300 python bench.py > gpurun_out/nr_bench_x4.json 2> gpurun_out/nr_bench_x4.err; tail -c 600 gpurun_out/nr_bench_x4.json
 timeout 300 python bench.py > gpurun_out/nr_bench_default.json 2> gpurun_out/nr_bench_default.err; tail -c 600 gpurun_out/nr_bench_default.json
 # 3. random sweep of the RGB -> 4:2:0 path, every outcome recorded in gpurun_out/cross_check.json
 run rgbsweep 90 python tools/gpu_cross_check.py 60 rgb
