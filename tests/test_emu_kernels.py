@@ -17,6 +17,8 @@ from oracle import bindings as ob
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests", "cudaemu"))
 
+pytestmark = pytest.mark.timeout(600)           # emulated barriers: a logic error must fail, not hang the CPU suite
+
 RGB = ["BGRA", "RGBA", "ARGB", "ABGR", "BGRx", "RGBx", "xRGB", "xBGR"]
 YUV = ["NV12", "NV21", "I420", "YV12"]
 
