@@ -63,9 +63,13 @@ __device__ __forceinline__ unsigned px_blend (unsigned d, unsigned s, unsigned a
 // d = { c[15:0], sat_u8(a), sat_u8(b) }  (b in the lowest byte): I2IP
 __device__ __forceinline__ unsigned sat_pack2 (unsigned a, unsigned b, unsigned c)
 {
+#ifdef B200_CUDA_EMU               // host build of the kernel sources for tests/cudaemu: same function, plain C
+  return (c << 16) | ((unsigned) min (max ((int) a, 0), 255) << 8) | (unsigned) min (max ((int) b, 0), 255);
+#else
   unsigned d;
   asm ("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r" (d) : "r" (a), "r" (b), "r" (c));
   return d;
+#endif
 }
 
 // compositor_orc_overlay_* (+ _addition): colour = (s*as + d*ad) / (as+ad) with divluw semantics

@@ -22,7 +22,7 @@ CSRC = os.path.join(ROOT, "gstreamer_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libb200emu.so")
 
-LAUNCH = re.compile(r"(\b\w+)\s*<<<(.+?)>>>\s*\(([^;]*)\);")
+LAUNCH = re.compile(r"(\b\w+(?:<[^<>;()]*>)?)\s*<<<(.+?)>>>\s*\(([^;]*)\);")
 
 
 def split_top(s):
@@ -56,7 +56,7 @@ def patch(text):
 
 def sources():
     return [os.path.join(CSRC, f) for f in ("vcs.cu", "vcs_planes.cuh", "vcs_kernels.cuh", "vcs_down420.cuh", "vcs_l2mma.cuh", "vcs_lanczos2.cuh", "vcs_light.cuh",
-                                            "vcs_ntap.cuh", "common.cu",
+                                            "vcs_ntap.cuh", "common.cu", "comp.cu", "ars.cu", "besi0_coeffs.inc",
                                             "vcs_plan.cpp", "vcs_plan.h", "vcs_device.h", "common.h")] + \
         [os.path.join(HERE, "emu", f) for f in sorted(os.listdir(os.path.join(HERE, "emu")))] + [os.path.abspath(__file__)]
 
@@ -79,17 +79,19 @@ def build(force=False):
     launches = 0
     for src, dst in (("vcs.cu", "vcs_emu.cpp"), ("vcs_planes.cuh", "vcs_planes.cuh"), ("vcs_kernels.cuh", "vcs_kernels.cuh"),
                      ("vcs_down420.cuh", "vcs_down420.cuh"), ("vcs_l2mma.cuh", "vcs_l2mma.cuh"), ("vcs_lanczos2.cuh", "vcs_lanczos2.cuh"),
-                     ("vcs_light.cuh", "vcs_light.cuh"), ("vcs_ntap.cuh", "vcs_ntap.cuh"), ("common.cu", "common_emu.cpp")):
+                     ("vcs_light.cuh", "vcs_light.cuh"), ("vcs_ntap.cuh", "vcs_ntap.cuh"), ("common.cu", "common_emu.cpp"),
+                     ("comp.cu", "comp_emu.cpp"), ("ars.cu", "ars_emu.cpp")):
         text, n = patch(open(os.path.join(CSRC, src)).read())
         launches += n
         open(os.path.join(gen, dst), "w").write(text)
-    assert launches >= 10, f"expected the launch sites of vcs.cu and vcs_planes.cuh, patched {launches}"
+    assert launches >= 18, f"expected the launch sites of vcs.cu and vcs_planes.cuh, patched {launches}"
     for f in os.listdir(os.path.join(HERE, "emu")):                # stand-in headers next to the generated sources
         if f.endswith((".h", ".cuh")):
             open(os.path.join(gen, f), "w").write(open(os.path.join(HERE, "emu", f)).read())
-    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas", "-DB200_CUDA_EMU=1",
+    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-Wno-unknown-pragmas", "-DB200_CUDA_EMU=1",
            "-I", gen, "-I", CSRC, "-o", LIB,
-           os.path.join(gen, "vcs_emu.cpp"), os.path.join(gen, "common_emu.cpp"), os.path.join(CSRC, "vcs_plan.cpp"),
+           os.path.join(gen, "vcs_emu.cpp"), os.path.join(gen, "common_emu.cpp"), os.path.join(gen, "comp_emu.cpp"),
+           os.path.join(gen, "ars_emu.cpp"), os.path.join(CSRC, "vcs_plan.cpp"),
            os.path.join(HERE, "emu", "emu_runtime.cpp")]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

@@ -33,6 +33,12 @@ struct dim3 {
 struct uint2 { unsigned x, y; };
 struct uint4 { unsigned x, y, z, w; };
 struct int4 { int x, y, z, w; };
+struct int2 { int x, y; };
+struct float2 { float x, y; };
+struct alignas (16) float4 { float x, y, z, w; };
+struct double2 { double x, y; };
+struct short2 { short x, y; };
+struct short4 { short x, y, z, w; };
 
 extern thread_local uint3_emu threadIdx, blockIdx;
 extern thread_local dim3 blockDim, gridDim;
@@ -83,6 +89,16 @@ inline unsigned __funnelshift_r (unsigned lo, unsigned hi, unsigned sh)
 {
   return (unsigned) ((((unsigned long long) hi << 32) | lo) >> (sh & 31));
 }
+// IEEE single operations, no contraction (the build passes -ffp-contract=off; x86-64 SSE arithmetic rounds each operation)
+inline float __fadd_rn (float a, float b) { volatile float r = a + b; return r; }
+inline float __fsub_rn (float a, float b) { volatile float r = a - b; return r; }
+inline float __fmul_rn (float a, float b) { volatile float r = a * b; return r; }
+inline float __fdiv_rn (float a, float b) { volatile float r = a / b; return r; }
+inline float __int2float_rn (int a) { return (float) a; }
+inline double __dadd_rn (double a, double b) { volatile double r = a + b; return r; }
+inline double __dsub_rn (double a, double b) { volatile double r = a - b; return r; }
+inline double __dmul_rn (double a, double b) { volatile double r = a * b; return r; }
+inline double __ddiv_rn (double a, double b) { volatile double r = a / b; return r; }
 inline uint4 make_uint4 (unsigned x, unsigned y, unsigned z, unsigned w) { return uint4 {x, y, z, w}; }
 inline uint2 make_uint2 (unsigned x, unsigned y) { return uint2 {x, y}; }
 inline int4 make_int4 (int x, int y, int z, int w) { return int4 {x, y, z, w}; }
@@ -122,6 +138,9 @@ enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaDevAttrMultiProcesso
 inline cudaError_t cudaMalloc (void **p, size_t n) { *p = malloc (n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 inline cudaError_t cudaFree (void *p) { free (p); return cudaSuccess; }
 inline cudaError_t cudaMemcpy (void *d, const void *s, size_t n, cudaMemcpyKind) { memcpy (d, s, n); return cudaSuccess; }
+inline cudaError_t cudaMemset (void *d, int v, size_t n) { memset (d, v, n); return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync (void *d, int v, size_t n, cudaStream_t) { memset (d, v, n); return cudaSuccess; }
+inline cudaError_t cudaDeviceSynchronize () { return cudaSuccess; }
 inline cudaError_t cudaMemcpyAsync (void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy (d, s, n); return cudaSuccess; }
 inline cudaError_t cudaGetLastError () { return cudaSuccess; }
 inline const char *cudaGetErrorName (cudaError_t) { return "emu"; }

@@ -270,3 +270,83 @@ def test_lanczos2_x4_variant(emu, size, monkeypatch):
         finally:
             emu.b200_vcs_destroy(h)
         check(out, expected(fi, fo, size, method, frame, site=2), f"{fi}->{fo} m{method}")
+
+
+# ---- 4. compositor and audio resampler sources under the same emulation --------------------------------------------------
+@pytest.mark.parametrize("fmt", ["RGBA", "BGRA", "ARGB", "ABGR"])
+@pytest.mark.parametrize("background", [0, 1, 2, 3])
+def test_compositor_kernel(emu, fmt, background):
+    """comp_kernel (ballot-culled pad list, PRMT blend, reciprocal-multiply overlay) against the oracle"""
+    from gstreamer_b200 import _lib
+    W, H = 96, 64
+    rng = np.random.default_rng(background * 7 + len(fmt))
+    n = 5
+    pads = (_lib.CompPadC * n)()
+    opads = (ob.OraclePad * n)()
+    keep = []
+    for k in range(n):
+        w, h = int(rng.integers(1, 70)), int(rng.integers(1, 50))
+        src = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+        keep.append(src)
+        x, y = int(rng.integers(-30, W)), int(rng.integers(-20, H))
+        a, op = float(rng.choice([1.0, 0.5, 0.25, 0.9])), int(rng.integers(0, 3))
+        pads[k].data, pads[k].width, pads[k].height, pads[k].stride = src.ctypes.data, w, h, w * 4
+        pads[k].xpos, pads[k].ypos, pads[k].alpha, pads[k].op = x, y, a, op
+        opads[k].data, opads[k].width, opads[k].height, opads[k].stride = src.ctypes.data, w, h, w * 4
+        opads[k].xpos, opads[k].ypos, opads[k].alpha, opads[k].op = x, y, a, op
+    want = np.zeros((H, W, 4), dtype=np.uint8)
+    ob.oracle().oracle_compositor(ob.FMT[fmt], want.ctypes.data, W, H, W * 4, background, opads, n)
+    hc = C.c_void_p()
+    assert emu.b200_comp_create(ob.FMT[fmt], W, H, 0, C.byref(hc)) == 0
+    out = np.zeros((H, W, 4), dtype=np.uint8)
+    try:
+        assert emu.b200_comp_blend(hc, out.ctypes.data, W * 4, background, pads, n, None) == 0
+    finally:
+        emu.b200_comp_destroy(hc)
+    check(out.ravel(), want.ravel(), f"{fmt} background {background}")
+
+
+AUDIO_OPTS = [("kaiser", "auto", "cubic"), ("blackman-nuttall", "auto", "cubic"), ("kaiser", "full", "none"),
+              ("kaiser", "interpolated", "cubic"), ("blackman-nuttall", "full", "none"), ("kaiser", "interpolated", "none")]
+
+
+@pytest.mark.parametrize("fmt", ["F32", "S16", "S32", "F64"])
+@pytest.mark.parametrize("opts", AUDIO_OPTS, ids=lambda o: "-".join(o))
+def test_audio_kernels(emu, fmt, opts):
+    """the resampler kernels (tiled F32 / S16, direct S32 / F64, interpolated) with the default configuration and with the
+    element's resample-method / sinc-filter-* properties, bit for bit against the oracle — the first end-to-end check of
+    those option sets through the product's own kernel code"""
+    from gstreamer_b200 import _lib
+    from gstreamer_b200.audio import CudaAudioResample as A
+    method, mode, interp = opts
+    ofmt, gfmt, dt, _ = ob.AUDIO_FORMATS[fmt]
+    o = ob.oracle()
+    M = {"blackman-nuttall": 3, "kaiser": 4}
+    MO = {"interpolated": 0, "full": 1, "auto": 2}
+    I = {"none": 0, "cubic": 2}
+    for (a, b, ch, q) in [(48000, 44100, 2, 4), (44100, 48000, 66, 2) if fmt in ("F32", "S16") else (96000, 44100, 1, 6)]:
+        ho = o.oracle_ars_new_opts(a, b, ch, q, ofmt, M[method], MO[mode], I[interp])
+        cfg = _lib.ArsConfigC()
+        cfg.in_rate, cfg.out_rate, cfg.channels, cfg.quality, cfg.format = a, b, ch, q, gfmt
+        cfg.resample_method, cfg.sinc_filter_mode, cfg.sinc_filter_interpolation = A.METHODS[method], A.FILTER_MODES[mode], A.INTERPOLATIONS[interp]
+        h = C.c_void_p()
+        assert emu.b200_ars_create(C.byref(cfg), 0, C.byref(h)) == 0
+        rng = np.random.default_rng(a + ch)
+        try:
+            for n in [300, 100, 1, None]:
+                x = None
+                if n is None:
+                    n = emu.b200_ars_get_max_latency(h)
+                else:
+                    x = ob.audio_test_signal(rng, n, ch, fmt)
+                cap = int(n * b / a) + 64
+                want = np.zeros((cap, ch), dtype=dt)
+                nw = o.oracle_ars_process_any(ho, x.ctypes.data if x is not None else None, n, want.ctypes.data, cap)
+                got = np.full((cap, ch), 7, dtype=dt)
+                ng = C.c_size_t()
+                assert emu.b200_ars_process(h, x.ctypes.data if x is not None else None, n, got.ctypes.data, cap, C.byref(ng), None) == 0
+                assert ng.value == nw and got[:nw].tobytes() == want[:nw].tobytes(), (a, b, ch, q, n)
+                assert (got[nw:] == 7).all()
+        finally:
+            emu.b200_ars_destroy(h)
+            o.oracle_ars_free(ho)
