@@ -23,7 +23,7 @@ ELEMENT_METHODS = {0: (0, 0, None), 1: (1, 2, None), 2: (3, 4, None), 3: (4, 0, 
                    5: (3, 0, None), 6: (2, 0, (0., 0.)), 7: (2, 0, (1., 0.)), 8: (2, 0, (0., .5)),
                    9: (2, 0, (1 / 3, 1 / 3))}
 FMT = {"RGBx": 7, "BGRx": 8, "xRGB": 9, "xBGR": 10, "RGBA": 11, "BGRA": 12, "ARGB": 13, "ABGR": 14,
-       "AYUV": 6, "NV12": 23, "NV21": 24, "I420": 2, "YV12": 3}
+       "AYUV": 6, "NV12": 23, "NV21": 24, "I420": 2, "YV12": 3, "YUY2": 4, "UYVY": 5, "Y42B": 18, "YVYU": 19, "Y444": 20}
 
 
 def build(ref=True):

@@ -24,7 +24,8 @@ extern "C" {
 #endif
 
 /* GstVideoFormat subset */
-enum { ORC_FMT_I420 = 2, ORC_FMT_YV12 = 3, ORC_FMT_RGBx = 7, ORC_FMT_BGRx = 8, ORC_FMT_xRGB = 9,
+enum { ORC_FMT_I420 = 2, ORC_FMT_YV12 = 3, ORC_FMT_YUY2 = 4, ORC_FMT_UYVY = 5, ORC_FMT_Y42B = 18, ORC_FMT_YVYU = 19,
+  ORC_FMT_Y444 = 20, ORC_FMT_RGBx = 7, ORC_FMT_BGRx = 8, ORC_FMT_xRGB = 9,
   ORC_FMT_xBGR = 10, ORC_FMT_RGBA = 11, ORC_FMT_BGRA = 12, ORC_FMT_ARGB = 13, ORC_FMT_ABGR = 14,
   ORC_FMT_NV12 = 23, ORC_FMT_NV21 = 24 };
 /* GstVideoResamplerMethod */

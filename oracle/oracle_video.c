@@ -213,13 +213,21 @@ fmt_is_rgb (int f)
   return f >= ORC_FMT_RGBx && f <= ORC_FMT_ABGR;
 }
 
+/* 4:2:2 / 4:4:4 inputs (packed YUY2 / UYVY / YVYU, planar Y42B / Y444): where the samples of a line live.  Chroma is
+ * sub-sampled horizontally by hshift and not at all vertically. */
+static int
+fmt_is_422_444 (int f)
+{
+  return f == ORC_FMT_YUY2 || f == ORC_FMT_UYVY || f == ORC_FMT_YVYU || f == ORC_FMT_Y42B || f == ORC_FMT_Y444;
+}
+
 int
 oracle_vcs_default_desc (OracleVcsDesc * d, int in_format, int in_w, int in_h,
     int out_format, int out_w, int out_h, int method, int max_taps_opt)
 {
   memset (d, 0, sizeof (*d));
   if (in_format != ORC_FMT_NV12 && in_format != ORC_FMT_NV21 && in_format != ORC_FMT_I420 &&
-      in_format != ORC_FMT_YV12 && !fmt_is_rgb (in_format))
+      in_format != ORC_FMT_YV12 && !fmt_is_rgb (in_format) && !fmt_is_422_444 (in_format))
     return -1;
   d->in_format = in_format;
   d->in_width = in_w;
@@ -228,6 +236,16 @@ oracle_vcs_default_desc (OracleVcsDesc * d, int in_format, int in_w, int in_h,
   d->in_offset[0] = 0;
   if (fmt_is_rgb (in_format)) {
     d->in_stride[0] = in_w * 4;         /* video-info.c:890-894 */
+  } else if (in_format == ORC_FMT_YUY2 || in_format == ORC_FMT_UYVY || in_format == ORC_FMT_YVYU) {
+    d->in_stride[0] = ROUND_UP_4 (in_w * 2);    /* :882-889 */
+  } else if (in_format == ORC_FMT_Y42B) {       /* :1020-1029 */
+    d->in_stride[1] = d->in_stride[2] = ((in_w + 7) & ~7) / 2;
+    d->in_offset[1] = (size_t) d->in_stride[0] * in_h;
+    d->in_offset[2] = d->in_offset[1] + (size_t) d->in_stride[1] * in_h;
+  } else if (in_format == ORC_FMT_Y444) {       /* :1030-1041 */
+    d->in_stride[1] = d->in_stride[2] = d->in_stride[0];
+    d->in_offset[1] = (size_t) d->in_stride[0] * in_h;
+    d->in_offset[2] = d->in_offset[1] * 2;
   } else if (in_format == ORC_FMT_I420 || in_format == ORC_FMT_YV12) {
     /* video-info.c:997-1009 (YV12: same planes, 1 and 2 swapped in the format description) */
     d->in_stride[1] = d->in_stride[2] = ROUND_UP_4 (ROUND_UP_2 (in_w) / 2);
@@ -273,8 +291,10 @@ oracle_vcs_default_desc (OracleVcsDesc * d, int in_format, int in_w, int in_h,
 size_t
 oracle_vcs_in_size (const OracleVcsDesc * d)
 {
-  if (fmt_is_rgb (d->in_format))
+  if (fmt_is_rgb (d->in_format) || d->in_format == ORC_FMT_YUY2 || d->in_format == ORC_FMT_UYVY || d->in_format == ORC_FMT_YVYU)
     return d->in_offset[0] + (size_t) d->in_stride[0] * d->in_height;
+  if (d->in_format == ORC_FMT_Y42B || d->in_format == ORC_FMT_Y444)
+    return d->in_offset[2] + (size_t) d->in_stride[2] * d->in_height;
   if (d->in_format == ORC_FMT_I420 || d->in_format == ORC_FMT_YV12)
     return d->in_offset[2] + (size_t) d->in_stride[2] * (ROUND_UP_2 (d->in_height) / 2);
   return d->in_offset[1] + (size_t) d->in_stride[1] * (ROUND_UP_2 (d->in_height) / 2);
@@ -532,6 +552,31 @@ static void
 unpack_line (const OracleVcsDesc * d, const uint8_t * in, int y, uint8_t * dst)
 {
   const uint8_t *sy = in + d->in_offset[0] + (size_t) d->in_stride[0] * y;
+  if (fmt_is_422_444 (d->in_format)) {
+    /* unpack_YUY2 / _UYVY / _YVYU (video-format.c:155-197, :232-274, :...), unpack_Y42B (:1009-1050), unpack_Y444
+     * (:1091-1104): the chroma sample of a pixel pair feeds both pixels (none shared for 4:4:4), every line has its own */
+    int i;
+    for (i = 0; i < d->in_width; i++) {
+      int yy, u, v;
+      switch (d->in_format) {
+        case ORC_FMT_YUY2: yy = sy[2 * i]; u = sy[4 * (i >> 1) + 1]; v = sy[4 * (i >> 1) + 3]; break;
+        case ORC_FMT_YVYU: yy = sy[2 * i]; v = sy[4 * (i >> 1) + 1]; u = sy[4 * (i >> 1) + 3]; break;
+        case ORC_FMT_UYVY: yy = sy[2 * i + 1]; u = sy[4 * (i >> 1)]; v = sy[4 * (i >> 1) + 2]; break;
+        case ORC_FMT_Y42B:
+          yy = sy[i];
+          u = in[d->in_offset[1] + (size_t) d->in_stride[1] * y + (i >> 1)];
+          v = in[d->in_offset[2] + (size_t) d->in_stride[2] * y + (i >> 1)];
+          break;
+        default:
+          yy = sy[i];
+          u = in[d->in_offset[1] + (size_t) d->in_stride[1] * y + i];
+          v = in[d->in_offset[2] + (size_t) d->in_stride[2] * y + i];
+          break;
+      }
+      dst[i * 4 + 0] = 0xff; dst[i * 4 + 1] = (uint8_t) yy; dst[i * 4 + 2] = (uint8_t) u; dst[i * 4 + 3] = (uint8_t) v;
+    }
+    return;
+  }
   if (d->in_format == ORC_FMT_I420 || d->in_format == ORC_FMT_YV12) {
     /* unpack_I420 -> video_orc_unpack_I420 (video-format.c:100-115, video-orc.orc:63-79): loadupdb = each
      * chroma sample feeds two pixels; YV12 keeps U in plane 2 */
@@ -1140,9 +1185,11 @@ oracle_vcs_convert (const OracleVcsDesc * d, const uint8_t * in, uint8_t * out)
   chroma_plan (d, have_v ? &vs : NULL, mode);
   for (y = 0; y < ih; y++) {
     unpack_line (d, in, y, cur + (size_t) y * iw * 4);
-    chroma_h_line (cur + (size_t) y * iw * 4, iw, (d->in_chroma_site & ORC_SITE_H_COSITED) != 0);
+    if (d->in_format != ORC_FMT_Y444)   /* 4:4:4: gst_video_chroma_resample_new (.., 0, 0) is NULL (video-chroma.c:1054-1055) */
+      chroma_h_line (cur + (size_t) y * iw * 4, iw, (d->in_chroma_site & ORC_SITE_H_COSITED) != 0);
   }
-  if (!(d->in_chroma_site & ORC_SITE_V_COSITED)) {
+  /* 4:2:2: v_factor 0 selects video_chroma_none (video-chroma.c:989-994): horizontal filter only, line by line */
+  if (!(d->in_chroma_site & ORC_SITE_V_COSITED) && !fmt_is_422_444 (d->in_format)) {
     /* both lines of a pair are filtered from the ORIGINAL (h-filtered) values, so
      * work from a copy of the chroma of the partner line */
     uint8_t *orig = malloc ((size_t) iw * ih * 4);

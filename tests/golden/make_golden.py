@@ -258,6 +258,27 @@ def video_rgb_rgb():
     json.dump(cases, open(os.path.join(HERE, "video_rgb_rgb_cases.json"), "w"), indent=1)
 
 
+def video_422():
+    """packed / planar 4:2:2 and 4:4:4 inputs -> packed RGB"""
+    arrays, cases = {}, []
+    for fi, fo in [("YUY2", "BGRA"), ("UYVY", "RGBA"), ("YVYU", "xRGB"), ("Y42B", "ARGB"), ("Y444", "BGRx")]:
+        for (iw, ih, ow, oh) in [(64, 48, 32, 24), (64, 48, 96, 72), (65, 49, 33, 25), (33, 17, 20, 31), (50, 21, 50, 21), (40, 90, 40, 31)]:
+            for m, site in ((1, 2), (3, 1), (9, 2), (0, 1)):
+                if m == 0 and oh > ih and ow * oh <= iw * ih:
+                    continue
+                d = ob.vcs_desc(iw, ih, ow, oh, m, in_fmt=ob.FMT[fi], out_fmt=ob.FMT[fo], site=site)
+                frame = np.random.default_rng(m + iw).integers(0, 256, ob.vcs_sizes(d)[0], dtype=np.uint8)
+                r = ob.RefVcs(iw, ih, ow, oh, m, in_fmt=ob.FMT[fi], out_fmt=ob.FMT[fo], site=site)
+                out = r.convert(frame, np.zeros(ow * oh * 4, dtype=np.uint8))
+                r.close()
+                key = f"s_{fi}_{fo}_{iw}x{ih}_{ow}x{oh}_m{m}"
+                arrays[key] = out
+                cases.append({"key": key, "in_fmt": fi, "out_fmt": fo, "in": [iw, ih], "out": [ow, oh], "method": m, "site": site,
+                              "seed": m + iw})
+    np.savez_compressed(os.path.join(HERE, "video_422.npz"), **arrays)
+    json.dump(cases, open(os.path.join(HERE, "video_422_cases.json"), "w"), indent=1)
+
+
 def compositor_420():
     """I420 / YV12 / NV12 / NV21 output"""
     o, r = ob.oracle(), ob.ref()
@@ -292,7 +313,7 @@ if __name__ == "__main__":
     only = set(sys.argv[1:])
     for name, fn in [("video", video), ("compositor", compositor), ("audio", audio), ("video_planar", video_planar),
                      ("audio_interpolated", audio_interpolated), ("audio_formats", audio_formats), ("compositor_420", compositor_420), ("video_yuv", video_yuv),
-                     ("video_cross", video_cross), ("video_rgb_in", video_rgb_in), ("video_rgb_rgb", video_rgb_rgb)]:
+                     ("video_cross", video_cross), ("video_rgb_in", video_rgb_in), ("video_rgb_rgb", video_rgb_rgb), ("video_422", video_422)]:
         if not only or name in only:
             fn()
     print("golden fixtures written to", HERE)

@@ -582,3 +582,26 @@ def test_audio_method_and_filter_mode_properties(fmt, method, mode, interp):
             assert n1 == n2 and o1[:n1].tobytes() == o2[:n2].tobytes(), (a, b, q, n)
         o.oracle_ars_free(ho)
         r.ref_ars_free(hr)
+
+
+# ------------------------------------------------------------------- 4:2:2 and 4:4:4 inputs (capture formats) -> packed RGB
+@pytest.mark.parametrize("fi", ["YUY2", "UYVY", "YVYU", "Y42B", "Y444"])
+@pytest.mark.parametrize("size", [(64, 48, 32, 24), (64, 48, 96, 72), (33, 17, 20, 31), (50, 21, 50, 21), (100, 100, 150, 50),
+                                  (40, 90, 40, 31), (1, 1, 5, 4), (7, 3, 3, 9)], ids=lambda s: "%dx%d-%dx%d" % s)
+def test_422_444_inputs_match_reference(fi, size):
+    """unpack_YUY2 / _UYVY / _YVYU / _Y42B / _Y444, horizontal chroma up-sampling only for 4:2:2 (v_factor 0 selects
+    video_chroma_none), none for 4:4:4; then the usual scalers, fast matrix and pack.  No line pairs here, so vertical-first
+    geometries compare directly as well."""
+    iw, ih, ow, oh = size
+    for k, method in enumerate(range(10)):
+        fo = RGB_IN[k % 8]
+        for site, matrix, rng in ((2, 3, 2), (1, 4, 1)):
+            d = ob.vcs_desc(iw, ih, ow, oh, method, in_fmt=ob.FMT[fi], out_fmt=ob.FMT[fo], site=site, matrix=matrix, rng=rng)
+            frame = np.random.default_rng(method).integers(0, 256, ob.vcs_sizes(d)[0], dtype=np.uint8)
+            got = ob.oracle_vcs_convert(d, frame)
+            r = ob.RefVcs(iw, ih, ow, oh, method, in_fmt=ob.FMT[fi], out_fmt=ob.FMT[fo], site=site, matrix=matrix, rng=rng)
+            want = r.convert(frame, np.zeros(got.size, dtype=np.uint8))
+            r.close()
+            if _one_tap_vertical_repeat(iw, ih, ow, oh, method) and not np.array_equal(got, want):
+                continue
+            assert np.array_equal(got, want), f"{fo} method {method} site {site}"
