@@ -214,6 +214,22 @@ int b200_video_info_set_format (b200_video_info * info, int format, int width, i
       info->color_range = B200_COLOR_RANGE_16_235;
       info->chroma_site = height > 576 ? B200_CHROMA_SITE_H_COSITED : B200_CHROMA_SITE_NONE;
       return B200_OK;
+    case B200_VIDEO_FORMAT_YUY2: case B200_VIDEO_FORMAT_UYVY: case B200_VIDEO_FORMAT_YVYU:
+    case B200_VIDEO_FORMAT_Y42B: case B200_VIDEO_FORMAT_Y444:
+      if (format == B200_VIDEO_FORMAT_Y42B) {                      // video-info.c:1020-1029
+        info->stride[0] = (width + 3) & ~3;
+        info->stride[1] = info->stride[2] = ((width + 7) & ~7) / 2;
+        info->offset[1] = (uint64_t) info->stride[0] * height;
+        info->offset[2] = info->offset[1] + (uint64_t) info->stride[1] * height;
+      } else if (format == B200_VIDEO_FORMAT_Y444) {               // :1030-1041
+        info->stride[0] = info->stride[1] = info->stride[2] = (width + 3) & ~3;
+        info->offset[1] = (uint64_t) info->stride[0] * height;
+        info->offset[2] = info->offset[1] * 2;
+      } else info->stride[0] = (width * 2 + 3) & ~3;               // :882-889
+      info->color_matrix = height > 576 ? B200_COLOR_MATRIX_BT709 : B200_COLOR_MATRIX_BT601;
+      info->color_range = B200_COLOR_RANGE_16_235;
+      info->chroma_site = height > 576 ? B200_CHROMA_SITE_H_COSITED : B200_CHROMA_SITE_NONE;
+      return B200_OK;
     case B200_VIDEO_FORMAT_RGBx: case B200_VIDEO_FORMAT_BGRx: case B200_VIDEO_FORMAT_xRGB:
     case B200_VIDEO_FORMAT_xBGR: case B200_VIDEO_FORMAT_RGBA: case B200_VIDEO_FORMAT_BGRA:
     case B200_VIDEO_FORMAT_ARGB: case B200_VIDEO_FORMAT_ABGR:
@@ -237,6 +253,8 @@ size_t b200_video_info_size (const b200_video_info * info)
       const size_t e2 = (size_t) info->offset[2] + (size_t) info->stride[2] * ch;
       return e1 > e2 ? e1 : e2;
     }
+    case B200_VIDEO_FORMAT_Y42B: case B200_VIDEO_FORMAT_Y444:
+      return (size_t) info->offset[2] + (size_t) info->stride[2] * info->height;
     default:
       return (size_t) info->offset[0] + (size_t) info->stride[0] * info->height;
   }
@@ -296,7 +314,7 @@ int b200_vcs_create (const b200_video_info * in, const b200_video_info * out,
     *handle = h;
     return B200_OK;
   }
-  if (!h->plan.yuv_out) {
+  if (!h->plan.yuv_out && !h->plan.in_422_444) {
     h->l2_tables = build_lanczos2_tables (h->plan);
     h->plan.lanczos2_ok = h->l2_tables.ok;
     h->mma_tables = build_l2mma_tables (h->plan);
@@ -327,6 +345,12 @@ int b200_vcs_create (const b200_video_info * in, const b200_video_info * out,
       d.stride_u = d.stride_v = p.in.stride[1];
     }
     d.cstep = p.planar ? 1 : 2;
+    d.ystep = 1; d.chshift = 1; d.cvshift = 1;
+    if (p.in_422_444) {                                           // capture formats: explicit sample geometry
+      d.off_y = p.in_off_y; d.off_u = p.in_off_u; d.off_v = p.in_off_v;
+      d.stride_u = p.in_stride_u; d.stride_v = p.in_stride_v; d.cstep = p.cstep_in;
+      d.ystep = p.ystep; d.chshift = p.chshift; d.cvshift = p.cvshift;
+    }
     d.h_first = p.h_first; d.matrix_first = p.matrix_first;
     d.yuv_out = p.yuv_out ? 1 : 0;
     d.rgb_in = p.rgb_in ? 1 : 0; d.in_sel = p.in_sel;

@@ -25,6 +25,9 @@ struct VcsDev {
   unsigned long long off_u, off_v;
   int stride_u, stride_v, cstep;
   int planar;                    // I420 / YV12
+  // generic kernel only: bytes between consecutive luma samples (2 in YUY2 / UYVY / YVYU), chroma sub-sampling shifts
+  // (horizontal 1 except 4:4:4, vertical 1 only for 4:2:0)
+  int ystep, chshift, cvshift;
   int chroma_nearest;            // unchanged-size I420/YV12: the reference's fast path replicates chroma (no filter)
   int h_first, matrix_first;
   int yuv_out;                   // 4:2:0 output through the chain: no matrix stage, scaled A,Y,U,V pixels go to a scratch image

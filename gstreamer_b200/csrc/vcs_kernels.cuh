@@ -42,6 +42,8 @@ __device__ __forceinline__ int lerp_h_u8 (int a, int b, int f)
 // (2 in an interleaved UV row, 1 in a planar one).
 __device__ __forceinline__ int chroma_hup (const uint8_t * __restrict__ c, int x, int iw, int mode, int step = 2)
 {
+  if (mode == 3)                 // 4:4:4: every pixel has its own sample, no filter (no chroma resampler exists)
+    return c[step * x];
   const int k = x >> 1;
   if (mode == 2)
     return c[step * k];
@@ -146,12 +148,13 @@ vcs_generic_kernel (const VcsDev P, const VcsBatch frames)
     CV[i] = P.v.coef[(size_t) oy0 * P.v.coef_per_out + i];
 
   // ---- A1: chroma rows, horizontally upsampled to the region's columns
-  const int cr0 = max (ry0 - 1, 0) >> 1, cr1 = min (ry1, P.ih - 1) >> 1;       // inclusive
+  // chroma rows the tile touches (inclusive): with 4:2:0 the rows of the lines one above / below too (line pairs)
+  const int cr0 = P.cvshift ? max (ry0 - 1, 0) >> 1 : ry0, cr1 = P.cvshift ? min (ry1, P.ih - 1) >> 1 : ry1 - 1;
   const int ncr = cr1 - cr0 + 1;
   for (int i = tid; i < (P.rgb_in ? 0 : ncr * C); i += nthr) {
     const int r = i / C, c = i - r * C;
     const int x = cx0 + c;
-    const int hmode = P.chroma_nearest ? 2 : P.h_cosited;
+    const int hmode = P.chshift == 0 ? 3 : (P.chroma_nearest ? 2 : P.h_cosited);
     HU[r * Cp + c] = (uint8_t) chroma_hup (in + P.off_u + (size_t) (cr0 + r) * P.stride_u, x, P.iw, hmode, P.cstep);
     HU[hup_sz + r * Cp + c] = (uint8_t) chroma_hup (in + P.off_v + (size_t) (cr0 + r) * P.stride_v, x, P.iw, hmode, P.cstep);
   }
@@ -161,7 +164,7 @@ vcs_generic_kernel (const VcsDev P, const VcsBatch frames)
   for (int i = tid; i < R * C; i += nthr) {
     const int r = i / C, c = i - r * C;
     const int y = ry0 + r;
-    const int own = (y >> 1) - cr0;
+    const int own = (y >> P.cvshift) - cr0;
     int yy, u, v;
     if (P.rgb_in) {
       // unpack_BGRA / _RGBA / _ABGR / unpack_copy4 (video-format.c:1433-1502, :536-547): a byte shuffle to A,R,G,B
@@ -173,7 +176,7 @@ vcs_generic_kernel (const VcsDev P, const VcsBatch frames)
       S[2 * plane_sz + r * Cp + c] = (uint8_t) v;
       continue;
     }
-    yy = plane_y[(size_t) y * P.stride_y + cx0 + c];
+    yy = plane_y[(size_t) y * P.stride_y + (size_t) (cx0 + c) * P.ystep];
     u = HU[own * Cp + c]; v = HU[hup_sz + own * Cp + c];
     const int m = P.v_pairs ? P.chroma_mode[y] : 0;
     if (m) {

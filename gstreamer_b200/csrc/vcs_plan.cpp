@@ -337,7 +337,7 @@ void tile_geometry (VcsPlan * p)
       max_cols = std::max (max_cols, (int) (p->h.offset[x1] + p->h.span - p->h.offset[x0]));
     }
     int pitch = (max_cols + 3) & ~3;
-    int crows = max_rows / 2 + 3;
+    int crows = p->cvshift ? max_rows / 2 + 3 : max_rows + 1;    // chroma rows staged per tile
     size_t planes = (size_t) 3 * max_rows * pitch;
     size_t hup = (size_t) 2 * crows * pitch;
     size_t mid = p->h_first ? (size_t) 3 * max_rows * tw : (size_t) 3 * th * pitch;
@@ -799,11 +799,44 @@ static int build_inner_plan (const b200_video_info * in, const b200_video_info *
       in->width > 32767 || in->height > 32767 || out->width > 32767 || out->height > 32767)
     return B200_ERR_INVALID_ARG;        // caps range [1,32767], gstvideoconvertscale.c:168-169
   const bool in_rgb = in->format >= B200_VIDEO_FORMAT_RGBx && in->format <= B200_VIDEO_FORMAT_ABGR;
+  const bool in_422 = in->format == B200_VIDEO_FORMAT_YUY2 || in->format == B200_VIDEO_FORMAT_UYVY ||
+      in->format == B200_VIDEO_FORMAT_YVYU || in->format == B200_VIDEO_FORMAT_Y42B || in->format == B200_VIDEO_FORMAT_Y444;
   if (in->format != B200_VIDEO_FORMAT_NV12 && in->format != B200_VIDEO_FORMAT_NV21 &&
-      in->format != B200_VIDEO_FORMAT_I420 && in->format != B200_VIDEO_FORMAT_YV12 && !in_rgb)
+      in->format != B200_VIDEO_FORMAT_I420 && in->format != B200_VIDEO_FORMAT_YV12 && !in_rgb && !in_422)
     return B200_ERR_UNSUPPORTED;
   p->in = *in; p->out = *out; p->cfg = *cfg;
   if (in_rgb) return build_rgb_in_plan (p);
+  if (in_422) {
+    // capture formats: unpack_YUY2 / _UYVY / _YVYU / _Y42B / _Y444 (video-format.c:155-274, :1009-1104), horizontal chroma
+    // up-sampling only (4:2:2: v_factor 0 selects video_chroma_none, video-chroma.c:989-994; 4:4:4: no resampler at all),
+    // then the usual chain to packed RGB.  Generic kernel; written without device access: opt-in.
+    if (!getenv ("B200_VCS_EXPERIMENTAL")) return B200_ERR_UNSUPPORTED;
+    if (!(out->format >= B200_VIDEO_FORMAT_RGBx && out->format <= B200_VIDEO_FORMAT_ABGR)) return B200_ERR_UNSUPPORTED;
+    const int w = in->width;
+    p->in_422_444 = true;
+    p->cvshift = 0;
+    p->chshift = in->format == B200_VIDEO_FORMAT_Y444 ? 0 : 1;
+    switch (in->format) {
+      case B200_VIDEO_FORMAT_YUY2: case B200_VIDEO_FORMAT_YVYU: case B200_VIDEO_FORMAT_UYVY: {
+        if (in->stride[0] < 4 * ((w + 1) / 2)) return B200_ERR_INVALID_ARG;
+        const int yo = in->format == B200_VIDEO_FORMAT_UYVY ? 1 : 0;
+        const int uo = in->format == B200_VIDEO_FORMAT_YUY2 ? 1 : (in->format == B200_VIDEO_FORMAT_YVYU ? 3 : 0);
+        const int vo = in->format == B200_VIDEO_FORMAT_YUY2 ? 3 : (in->format == B200_VIDEO_FORMAT_YVYU ? 1 : 2);
+        p->ystep = 2; p->cstep_in = 4;
+        p->in_off_y = in->offset[0] + yo; p->in_off_u = in->offset[0] + uo; p->in_off_v = in->offset[0] + vo;
+        p->in_stride_u = p->in_stride_v = in->stride[0];
+        break;
+      }
+      default: {
+        const int cw = p->chshift ? (w + 1) / 2 : w;
+        if (in->stride[0] < w || in->stride[1] < cw || in->stride[2] < cw) return B200_ERR_INVALID_ARG;
+        p->ystep = 1; p->cstep_in = 1;
+        p->in_off_y = in->offset[0]; p->in_off_u = in->offset[1]; p->in_off_v = in->offset[2];
+        p->in_stride_u = in->stride[1]; p->in_stride_v = in->stride[2];
+        break;
+      }
+    }
+  }
   // caps defaults (video-info.c:165-185, :211-225)
   if (p->in.color_matrix == 0) p->in.color_matrix = in->height > 576 ? B200_COLOR_MATRIX_BT709 : B200_COLOR_MATRIX_BT601;
   if (p->in.color_range == 0) p->in.color_range = B200_COLOR_RANGE_16_235;
@@ -857,7 +890,9 @@ static int build_inner_plan (const b200_video_info * in, const b200_video_info *
   }
   p->planar = in->format == B200_VIDEO_FORMAT_I420 || in->format == B200_VIDEO_FORMAT_YV12;
   const int min_out_stride = p->yuv_out ? out->width : out->width * 4;
-  if (p->planar) {
+  if (p->in_422_444) {
+    if (out->stride[0] < min_out_stride) return B200_ERR_INVALID_ARG;
+  } else if (p->planar) {
     const int cw = (in->width + 1) / 2;
     if (in->stride[0] < in->width || in->stride[1] < cw || in->stride[2] < cw || out->stride[0] < min_out_stride)
       return B200_ERR_INVALID_ARG;
@@ -867,7 +902,7 @@ static int build_inner_plan (const b200_video_info * in, const b200_video_info *
     return B200_ERR_INVALID_ARG;
   p->u_index = in->format == B200_VIDEO_FORMAT_NV21 ? 1 : 0;
   p->h_cosited = (p->in.chroma_site & B200_CHROMA_SITE_H_COSITED) != 0;
-  p->v_pairs = (p->in.chroma_site & B200_CHROMA_SITE_V_COSITED) == 0;
+  p->v_pairs = (p->in.chroma_site & B200_CHROMA_SITE_V_COSITED) == 0 && !p->in_422_444;   // line pairs: 4:2:0 only
 
   if (!p->yuv_out) {
     int st = colour_matrix (p);
@@ -911,6 +946,12 @@ static int build_inner_plan (const b200_video_info * in, const b200_video_info *
       // on a one-line view of the frame (line ih-1 with chroma row (ih-1)>>1: a 1-line frame has no vertical filter).
       p->extra_row = (oh & 1) && ih == oh && p->down_v && p->v_pairs && p->chroma_mode[ih - 1] != 0;
     }
+    tile_geometry (p);
+    p->light_ok = p->ntap_ok = p->lanczos2_ok = false;
+    return B200_OK;
+  }
+  if (p->in_422_444) {
+    std::fill (p->chroma_mode.begin (), p->chroma_mode.end (), 0);
     tile_geometry (p);
     p->light_ok = p->ntap_ok = p->lanczos2_ok = false;
     return B200_OK;

@@ -53,6 +53,11 @@ struct VcsPlan {
   bool planar = false;           // I420 / YV12: separate U and V planes
   int plane_u = 1, plane_v = 1;  // plane index holding U / V
   bool chroma_nearest = false;   // planar input at unchanged size: convert_I420_BGRA family fast path
+  // 4:2:2 / 4:4:4 inputs (generic kernel only): luma sample pitch, chroma shifts, byte offsets of Y / U / V samples
+  int ystep = 1, chshift = 1, cvshift = 1, cstep_in = 0;
+  uint64_t in_off_y = 0, in_off_u = 0, in_off_v = 0;
+  int in_stride_u = 0, in_stride_v = 0;
+  bool in_422_444 = false;
   uint8_t byte_sel[4] = {3, 2, 1, 0};   // output byte i takes component byte_sel[i] of (A,R,G,B)
   std::vector<uint8_t> chroma_mode;     // per input line: 0 own row, 1 first of pair, 2 second
 

@@ -19,6 +19,11 @@ from ._lib import lib, check
 class VideoFormat(enum.IntEnum):
     I420 = 2
     YV12 = 3
+    YUY2 = 4
+    UYVY = 5
+    Y42B = 18
+    YVYU = 19
+    Y444 = 20
     RGBx = 7
     BGRx = 8
     xRGB = 9

@@ -69,6 +69,8 @@ int b200_host_free (void *ptr);
 /* GstVideoFormat values (gst-libs/gst/video/video-format.h:195-) */
 typedef enum {
   B200_VIDEO_FORMAT_I420 = 2, B200_VIDEO_FORMAT_YV12 = 3,
+  B200_VIDEO_FORMAT_YUY2 = 4, B200_VIDEO_FORMAT_UYVY = 5, B200_VIDEO_FORMAT_Y42B = 18, B200_VIDEO_FORMAT_YVYU = 19,
+  B200_VIDEO_FORMAT_Y444 = 20,   /* 4:2:2 / 4:4:4 inputs (capture formats) -> packed RGB: opt-in, see DESIGN.md */
   B200_VIDEO_FORMAT_RGBx = 7, B200_VIDEO_FORMAT_BGRx = 8, B200_VIDEO_FORMAT_xRGB = 9,
   B200_VIDEO_FORMAT_xBGR = 10, B200_VIDEO_FORMAT_RGBA = 11, B200_VIDEO_FORMAT_BGRA = 12,
   B200_VIDEO_FORMAT_ARGB = 13, B200_VIDEO_FORMAT_ABGR = 14,

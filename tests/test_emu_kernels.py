@@ -21,6 +21,7 @@ pytestmark = pytest.mark.timeout(600)           # emulated barriers: a logic err
 
 RGB = ["BGRA", "RGBA", "ARGB", "ABGR", "BGRx", "RGBx", "xRGB", "xBGR"]
 YUV = ["NV12", "NV21", "I420", "YV12"]
+YUV_422_444 = ["YUY2", "UYVY", "YVYU", "Y42B", "Y444"]
 
 
 @pytest.fixture(scope="module")
@@ -36,6 +37,9 @@ def emu():
 
 
 def frame_for(fmt, iw, ih, seed):
+    if fmt in YUV_422_444:
+        d = ob.vcs_desc(iw, ih, iw, ih, 1, in_fmt=ob.FMT[fmt], out_fmt=12)
+        return np.random.default_rng(seed).integers(0, 256, ob.vcs_sizes(d)[0], dtype=np.uint8)
     if fmt in RGB:
         return np.random.default_rng(seed).integers(0, 256, iw * ih * 4, dtype=np.uint8)
     return ob.i420_random_frame(iw, ih, seed) if fmt in ("I420", "YV12") else ob.nv12_random_frame(iw, ih, seed)
@@ -125,6 +129,21 @@ def test_rgb_to_420(emu, size, monkeypatch):
     for col in [(3, 2, 2), (4, 1, 1), (6, 2, 6), (2, 1, 4), (5, 2, 1)]:
         check(run(emu, "BGRA", "NV12", size, 3, frame, colorimetry=col), expected("BGRA", "NV12", size, 3, frame, colorimetry=col),
               f"colorimetry {col}")
+
+
+@pytest.mark.parametrize("size", SMALL, ids=lambda s: "%dx%d-%dx%d" % s)
+def test_422_444_inputs(emu, size, monkeypatch):
+    """YUY2 / UYVY / YVYU / Y42B / Y444 -> packed RGB through the generic kernel (luma pitch 2 in the packed formats,
+    per-line chroma rows, horizontal-only or no chroma up-sampling)"""
+    monkeypatch.setenv("B200_VCS_EXPERIMENTAL", "1")
+    iw, ih = size[:2]
+    for k, fi in enumerate(YUV_422_444):
+        frame = frame_for(fi, iw, ih, 10 + k)
+        method = [1, 3, 0, 9, 4][k]
+        fo = RGB[k]
+        for site in (1, 2):
+            check(run(emu, fi, fo, size, method, frame, site=site), expected(fi, fo, size, method, frame, site=site),
+                  f"{fi}->{fo} m{method} site{site}")
 
 
 @pytest.mark.parametrize("size", SMALL + [(64, 48, 64, 24), (64, 48, 32, 48)], ids=lambda s: "%dx%d-%dx%d" % s)

@@ -120,3 +120,29 @@ def test_rgb_same_format_scaling_matches_oracle(cuda_device, size, method):
         got = dst.cpu().numpy()
         bad = np.argwhere(got != want)
         assert bad.size == 0, f"{fmt}->{fmt_out}: {len(bad)} bytes differ, first at {bad[:4].ravel().tolist()}"
+
+
+@pytest.mark.parametrize("fi", ["YUY2", "UYVY", "YVYU", "Y42B", "Y444"])
+@pytest.mark.parametrize("size", [(64, 48, 32, 24), (64, 48, 96, 72), (65, 49, 33, 26), (33, 17, 20, 31), (50, 21, 50, 21),
+                                  (100, 100, 150, 50), (40, 90, 40, 31), (1, 1, 5, 4), (1920, 1080, 1280, 720)],
+                         ids=lambda s: "%dx%d-%dx%d" % s)
+def test_422_444_inputs_match_oracle(cuda_device, fi, size):
+    """capture formats -> packed RGB through the generic kernel"""
+    import torch
+    import gstreamer_b200 as g
+    iw, ih, ow, oh = size
+    for method in ([1] if iw * ih > 500_000 else [0, 1, 3, 9]):
+        for site in (1, 2):
+            d = ob.vcs_desc(iw, ih, ow, oh, method, in_fmt=ob.FMT[fi], out_fmt=ob.FMT["BGRA"], site=site)
+            frame = np.random.default_rng(method).integers(0, 256, ob.vcs_sizes(d)[0], dtype=np.uint8)
+            want = ob.oracle_vcs_convert(d, frame)
+            el = g.CudaVideoConvertScale(method=method, cuda_device_id=0)
+            ii, oi = g.VideoInfo(ob.FMT[fi], iw, ih), g.VideoInfo(ob.FMT["BGRA"], ow, oh)
+            ii.set_colorimetry(chroma_site=site)
+            el.set_info(ii, oi)
+            dst = torch.full((oi.size,), 0x5A, dtype=torch.uint8, device="cuda")
+            el.transform_frame(torch.from_numpy(frame).cuda(), dst)
+            torch.cuda.synchronize()
+            got = dst.cpu().numpy()
+            bad = np.argwhere(got != want)
+            assert bad.size == 0, f"m{method} site{site}: {len(bad)} bytes differ, first at {bad[:4].ravel().tolist()}"
