@@ -6,7 +6,7 @@ set -u
 mkdir -p gpurun_out
 export B200_TEST_EXPERIMENTAL=1
 run() { local name=$1; shift; echo "== $name"; timeout "$1" "${@:2}" > "gpurun_out/nr_$name.log" 2>&1; echo "rc=$? ($name)"; tail -4 "gpurun_out/nr_$name.log"; }
-# 1. packed RGB -> 4:2:0 and same-format RGB scaling (opt-in product paths: B200_VCS_EXPERIMENTAL is set by the tests)
+# 1. packed RGB -> 4:2:0, RGB -> RGB, 4:2:2 / 4:4:4 inputs (opt-in product paths: B200_VCS_EXPERIMENTAL is set by the tests)
 run rgbin 240 python -m pytest tests/test_vcs_rgbin_gpu.py -q -p no:cacheprovider
 # 2. destination rectangle + borders (new vcs_border_kernel around the existing kernels)
 run borders 180 python -m pytest tests/test_vcs_borders_gpu.py -q -p no:cacheprovider
