@@ -37,9 +37,15 @@ namespace b200 {
 constexpr int LM_TW = 64, LM_TH = 24;          // output tile
 constexpr int LM_NG = 16;                       // line groups of 4 staged lines (2*TH+6 = 54 lines -> 14 used; the MMA's M is 16)
 constexpr int LM_UNITS = (2 * LM_TW + 16) / 8;  // 8-pixel units per staged line (8 halo pixels each side)
-constexpr int LM_SP = 152;                      // staged row pitch in bytes (>= 144; 4*pitch = 96 mod 128: conflict-free LDS.64)
+// staged input bytes: [channel][line of its group i][group pair g][word column w][group g | group g+8], i.e. the two
+// line groups the MMA's rows g and g+8 stand for are interleaved word by word, so that ONE LDS.128 at word column 4j+2t
+// returns a0 (row g, window bytes 8t..8t+3), a1 (row g+8, same bytes), a2 (row g, bytes 8t+4..), a3 (row g+8) - the
+// fragment in the register order the instruction wants (IMMA overwrites its A registers with D: a fresh load per MMA is
+// what it takes anyway)
+constexpr int LM_WP = 40;                       // word columns per staged row (>= 36; row pitch 320 B = 64 mod 128: conflict-free)
+constexpr int LM_PLANE = 4 * 8 * LM_WP * 8;     // bytes per staged channel
 constexpr int LM_HP = LM_TW + 8;                // pitch of the h-scaled words (72: rows 8 banks apart)
-constexpr int LM_SMEM = 3 * 4 * LM_NG * LM_SP + 3 * LM_NG * LM_HP * 4;
+constexpr int LM_SMEM = 3 * LM_PLANE + 3 * LM_NG * LM_HP * 4;
 
 struct L2mmaDev {
   const uint2 *bh;               // [ow/8][32 lanes]: B fragment (b0, b1) of each group of 8 output columns
@@ -52,57 +58,69 @@ struct L2mmaDev {
 // D = A(16x32 u8, row) * B(32x8 s8, col) + c  (mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32); all 4 accumulators
 // start at the same constant
 __device__ __forceinline__ void mma_u8s8 (int (&d)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0,
-    unsigned b1, int c)
+    unsigned b1, const int (&c)[4])
 {
 #ifdef B200_CUDA_EMU
-  const int cc[4] = {c, c, c, c};
-  b200emu::warp_mma_u8s8 (d, a0, a1, a2, a3, b0, b1, cc);
+  b200emu::warp_mma_u8s8 (d, a0, a1, a2, a3, b0, b1, c);
 #else
-  asm volatile ("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+  asm volatile ("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
       : "=r" (d[0]), "=r" (d[1]), "=r" (d[2]), "=r" (d[3])
-      : "r" (a0), "r" (a1), "r" (a2), "r" (a3), "r" (b0), "r" (b1), "r" (c));
+      : "r" (a0), "r" (a1), "r" (a2), "r" (a3), "r" (b0), "r" (b1), "r" (c[0]), "r" (c[1]), "r" (c[2]), "r" (c[3]));
 #endif
 }
 
-__global__ void __launch_bounds__ (L2_THREADS, 3)
-vcs_l2mma_kernel (const VcsDev P, const L2mmaDev L, const VcsBatch frames)
+// the same product with the operand types swapped: A s8 (taps), B u8 (pixels)
+__device__ __forceinline__ void mma_s8u8 (int (&d)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0,
+    unsigned b1, const int (&c)[4])
 {
-  extern __shared__ __align__ (16) uint8_t smem[];
-  uint8_t *S = smem;                                             // [3][4*LM_NG][LM_SP] staged Y, U, V bytes
-  unsigned *HS = (unsigned *) (smem + 3 * 4 * LM_NG * LM_SP);    // [3][LM_NG][LM_HP] words: 4 lines of one h-scaled column
+#ifdef B200_CUDA_EMU
+  b200emu::warp_mma_s8u8 (d, a0, a1, a2, a3, b0, b1, c);
+#else
+  asm volatile ("mma.sync.aligned.m16n8k32.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
+      : "=r" (d[0]), "=r" (d[1]), "=r" (d[2]), "=r" (d[3])
+      : "r" (a0), "r" (a1), "r" (a2), "r" (a3), "r" (b0), "r" (b1), "r" (c[0]), "r" (c[1]), "r" (c[2]), "r" (c[3]));
+#endif
+}
+
+// EDGE = the tile touches a frame border: line / chroma-row / column indices are clamped and the "no chroma sample to the
+// right" case exists; interior tiles run the instantiation without any of it (same split as vcs_lanczos2_kernel).
+template <bool EDGE>
+__device__ __forceinline__ void l2mma_tile (const VcsDev & P, const L2mmaDev & L, const uint8_t *__restrict__ in,
+    uint8_t *__restrict__ out, uint8_t *smem, int x0, int oy0)
+{
+  uint8_t *S = smem;                                             // [3][4][8][LM_WP][2] words, see LM_WP
+  unsigned *HS = (unsigned *) (smem + 3 * LM_PLANE);             // [3][LM_NG][LM_HP] words: 4 lines of one h-scaled column
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const uint8_t *__restrict__ in = frames.in[blockIdx.z];
-  uint8_t *__restrict__ out = frames.out[blockIdx.z];
   const uint8_t *__restrict__ plane_y = in + P.off_y;
   const uint8_t *__restrict__ plane_c = in + P.off_c;
-  const int x0 = blockIdx.x * LM_TW, oy0 = blockIdx.y * LM_TH;
   const int R0 = 2 * oy0 - 3;                                    // first staged line; R0 % 4 == 1
   const int crows = P.ih >> 1;
   const unsigned selU = P.u_index ? 0x7531u : 0x6420u, selV = P.u_index ? 0x6420u : 0x7531u;
 
-  // ---------------------------------------------------------------- stage A
+  // ---------------------------------------------------------------- stage A: Y and full-resolution chroma of the region
   for (int item = tid; item < (LM_NG - 2) * LM_UNITS; item += L2_THREADS) {
     const int lg = item / LM_UNITS, u = item - lg * LM_UNITS;
-    const int xb = min (max (2 * x0 - 8 + 8 * u, 0), P.iw - 8);  // byte column of the unit's 8 input pixels
-    const bool right_edge = xb + 8 >= P.iw;                      // no chroma sample to the right
+    const int xraw = 2 * x0 - 8 + 8 * u;
+    const int xb = EDGE ? min (max (xraw, 0), P.iw - 8) : xraw;  // byte column of the unit's 8 input pixels
+    const bool right_edge = EDGE && xb + 8 >= P.iw;              // no chroma sample to the right
     const int y0 = R0 + 4 * lg;                                  // lines y0..y0+3, y0 % 4 == 1
     const int m2 = (y0 - 1) >> 1;                                // chroma rows m2, m2+1, m2+2
     unsigned ulo[3], uhi[3], vlo[3], vhi[3];
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-      const int cr = min (max (m2 + k, 0), crows - 1);
-      const uint8_t *row = plane_c + (size_t) cr * P.stride_c + xb;
+      const int cr = EDGE ? min (max (m2 + k, 0), crows - 1) : m2 + k;
+      const uint8_t *row = plane_c + (unsigned) cr * (unsigned) P.stride_c + (unsigned) xb;
       const uint2 c = __ldg ((const uint2 *) row);
       const unsigned ue = __byte_perm (c.x, c.y, selU), ve = __byte_perm (c.x, c.y, selV);
       unsigned un, vn;
       if (right_edge) {
         un = __byte_perm (ue, ue, 0x3321);
         vn = __byte_perm (ve, ve, 0x3321);
-      } else {                                                   // the first sample of the next unit
-        const unsigned nu = row[8 + P.u_index], nv = row[8 + (P.u_index ^ 1)];
-        un = __byte_perm (ue, nu, 0x4321);
-        vn = __byte_perm (ve, nv, 0x4321);
+      } else {                                                   // the first sample pair of the next unit
+        const unsigned nx = __ldg ((const unsigned short *) (row + 8));
+        un = __byte_perm (ue, nx, P.u_index ? 0x5321 : 0x4321);
+        vn = __byte_perm (ve, nx, P.u_index ? 0x4321 : 0x5321);
       }
       const unsigned uo = avg_ceil4 (ue, un), vo = avg_ceil4 (ve, vn);        // video-chroma.c:687-699
       ulo[k] = __byte_perm (ue, uo, 0x5140); uhi[k] = __byte_perm (ue, uo, 0x7362);
@@ -121,32 +139,34 @@ vcs_l2mma_kernel (const VcsDev P, const L2mmaDev L, const VcsBatch frames)
       f = avg_floor4 (vlo[1], vlo[2]); V[2].x = avg_ceil4 (vlo[1], f); V[3].x = avg_ceil4 (vlo[2], f);
       f = avg_floor4 (vhi[1], vhi[2]); V[2].y = avg_ceil4 (vhi[1], f); V[3].y = avg_ceil4 (vhi[2], f);
     }
+    unsigned *d = (unsigned *) S + ((lg & 7) * LM_WP + 2 * u) * 2 + (lg >> 3);   // word (line 0, pair lg&7, column 2u, half lg>>3)
+    const uint8_t *py = plane_y + (unsigned) xb;
 #pragma unroll
     for (int r = 0; r < 4; r++) {
-      const int y = min (max (y0 + r, 0), P.ih - 1);
-      const uint2 yy = __ldg ((const uint2 *) (plane_y + (size_t) y * P.stride_y + xb));
-      uint8_t *d = S + (size_t) (4 * lg + r) * LM_SP + 8 * u;
-      *(uint2 *) d = yy;
-      *(uint2 *) (d + 4 * LM_NG * LM_SP) = U[r];
-      *(uint2 *) (d + 2 * 4 * LM_NG * LM_SP) = V[r];
+      const int y = EDGE ? min (max (y0 + r, 0), P.ih - 1) : y0 + r;
+      const uint2 yy = __ldg ((const uint2 *) (py + (unsigned) y * (unsigned) P.stride_y));
+      unsigned *dr = d + r * 8 * LM_WP * 2;
+      dr[0] = yy.x; dr[2] = yy.y;
+      dr[LM_PLANE / 4] = U[r].x; dr[LM_PLANE / 4 + 2] = U[r].y;
+      dr[2 * (LM_PLANE / 4)] = V[r].x; dr[2 * (LM_PLANE / 4) + 2] = V[r].y;
     }
   }
   __syncthreads ();
 
   // ---------------------------------------------------------------- H phase: warp = 8 output columns, all staged lines
   for (int j = warp; j < LM_TW / 8; j += L2_THREADS / 32) {
-    const uint2 B = __ldg (L.bh + (size_t) ((x0 >> 3) + j) * 32 + lane);
+    const uint2 B = __ldg (L.bh + ((x0 >> 3) + j) * 32 + lane);
     const bool x4 = __ldg (L.h4 + (x0 >> 3) + j) != 0;              // warp-uniform
-    const int c_init = x4 ? 128 : 32;
+    const int ci = x4 ? 128 : 32;
+    const int c_init[4] = {ci, ci, ci, ci};
+    const uint4 *frag = (const uint4 *) S + (g * LM_WP + 4 * j + 2 * t) / 2;      // 16 bytes: a0, a1, a2, a3 of line 0
 #pragma unroll
     for (int ch = 0; ch < 3; ch++) {
-      const uint8_t *base = S + (size_t) ch * 4 * LM_NG * LM_SP + 16 * j + 8 * t;
       int d[4][4];                                               // [line of the group][fragment element]
 #pragma unroll
       for (int i = 0; i < 4; i++) {
-        const uint2 lo = *(const uint2 *) (base + (size_t) (4 * g + i) * LM_SP);
-        const uint2 hi = *(const uint2 *) (base + (size_t) (4 * (g + 8) + i) * LM_SP);
-        mma_u8s8 (d[i], lo.x, hi.x, lo.y, hi.y, B.x, B.y, c_init);
+        const uint4 a = frag[(ch * LM_PLANE + i * 8 * LM_WP * 8) / 16];
+        mma_u8s8 (d[i], a.x, a.y, a.z, a.w, B.x, B.y, c_init);
       }
       // (acc+32)>>6 saturated to u8 (video-orc.orc:2474-2481); byte i of a word = line i of the group
       uint2 wlo, whi;
@@ -161,9 +181,9 @@ vcs_l2mma_kernel (const VcsDev P, const L2mmaDev L, const VcsBatch frames)
         whi.x = pack_sat2 (sra6 (d[1][2]), sra6 (d[0][2]), pack_sat2 (sra6 (d[3][2]), sra6 (d[2][2]), 0u));
         whi.y = pack_sat2 (sra6 (d[1][3]), sra6 (d[0][3]), pack_sat2 (sra6 (d[3][3]), sra6 (d[2][3]), 0u));
       }
-      unsigned *hs = HS + (size_t) ch * LM_NG * LM_HP + 8 * j + 2 * t;
-      *(uint2 *) (hs + (size_t) g * LM_HP) = wlo;
-      *(uint2 *) (hs + (size_t) (g + 8) * LM_HP) = whi;
+      unsigned *hs = HS + ch * LM_NG * LM_HP + 8 * j + 2 * t + g * LM_HP;
+      *(uint2 *) hs = wlo;
+      *(uint2 *) (hs + 8 * LM_HP) = whi;
     }
   }
   __syncthreads ();
@@ -173,16 +193,17 @@ vcs_l2mma_kernel (const VcsDev P, const L2mmaDev L, const VcsBatch frames)
     const int q = item / (LM_TW / 16), c0 = (item - q * (LM_TW / 16)) * 16;
     const int oyq = oy0 + 8 * q;
     if (oyq >= P.oh) continue;                                   // warp-uniform
-    const uint2 B = __ldg (L.bv + (size_t) (oyq >> 3) * 32 + lane);
+    const uint2 B = __ldg (L.bv + (oyq >> 3) * 32 + lane);
     const bool x4 = __ldg (L.v4 + (oyq >> 3)) != 0;                 // warp-uniform
+    const int ci = x4 ? 128 : 32;
+    const int c_init[4] = {ci, ci, ci, ci};
     int d[3][4];
 #pragma unroll
     for (int ch = 0; ch < 3; ch++) {
-      const unsigned *hs = HS + (size_t) ch * LM_NG * LM_HP + c0 + g;
-      const unsigned a0 = hs[(size_t) (4 * q + t) * LM_HP], a1 = hs[(size_t) (4 * q + t) * LM_HP + 8];
-      const unsigned a2 = hs[(size_t) (4 * q + 4 + t) * LM_HP], a3 = hs[(size_t) (4 * q + 4 + t) * LM_HP + 8];
-      mma_u8s8 (d[ch], a0, a1, a2, a3, B.x, B.y, x4 ? 128 : 32);
+      const unsigned *hs = HS + ch * LM_NG * LM_HP + c0 + g + (4 * q + t) * LM_HP;
+      mma_u8s8 (d[ch], hs[0], hs[8], hs[4 * LM_HP], hs[4 * LM_HP + 8], B.x, B.y, c_init);
     }
+    uint8_t *orow = out + P.off_out + (unsigned) (oyq + 2 * t) * (unsigned) P.stride_out + (unsigned) (x0 + c0 + g) * 4u;
 #pragma unroll
     for (int e = 0; e < 4; e++) {
       const int ox = x0 + c0 + g + 8 * (e >> 1), oy = oyq + 2 * t + (e & 1);
@@ -197,9 +218,20 @@ vcs_l2mma_kernel (const VcsDev P, const L2mmaDev L, const VcsBatch frames)
       const int b = ty + ((wu * P.p3) >> 16);
       const int gg = ty + ((wu * P.p4) >> 16) + ((wv * P.p5) >> 16);
       const unsigned argb = pack_sat2 (r, 255, pack_sat2 (b, gg, 0u));
-      *(unsigned *) (out + P.off_out + (size_t) oy * P.stride_out + (size_t) ox * 4u) = __byte_perm (argb, 0, P.sel);
+      *(unsigned *) (orow + (e & 1) * P.stride_out + (e >> 1) * 32) = __byte_perm (argb, 0, P.sel);
     }
   }
+}
+
+__global__ void __launch_bounds__ (L2_THREADS, 3)
+vcs_l2mma_kernel (const VcsDev P, const L2mmaDev L, const VcsBatch frames)
+{
+  extern __shared__ __align__ (16) uint8_t smem[];
+  const int x0 = blockIdx.x * LM_TW, oy0 = blockIdx.y * LM_TH;
+  // staged region: lines 2*oy0-3 .. +55 (groups 14, 15 are never written: no tap references them), columns 2*x0-8 .. +143
+  const bool edge = 2 * oy0 - 3 < 0 || 2 * oy0 - 3 + 4 * (LM_NG - 2) > P.ih || x0 == 0 || 2 * x0 - 8 + 8 * LM_UNITS + 8 > P.iw;
+  if (edge) l2mma_tile<true> (P, L, frames.in[blockIdx.z], frames.out[blockIdx.z], smem, x0, oy0);
+  else l2mma_tile<false> (P, L, frames.in[blockIdx.z], frames.out[blockIdx.z], smem, x0, oy0);
 }
 
 // ------------------------------------------------------------------------------------ host side

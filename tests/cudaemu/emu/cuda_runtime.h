@@ -58,6 +58,7 @@ namespace b200emu {
 // a1: row g+8, same k; a2: row g, k 16+4t..; a3: row g+8, k 16+4t.. - B 32x8 s8 column-major - b0: k 4t..4t+3, n g;
 // b1: k 16+4t.., n g - C/D 16x8 s32 - d0: (g, 2t), d1: (g, 2t+1), d2: (g+8, 2t), d3: (g+8, 2t+1); g = lane >> 2, t = lane & 3.
 void warp_mma_u8s8 (int d[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0, unsigned b1, const int c[4]);
+void warp_mma_s8u8 (int d[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0, unsigned b1, const int c[4]);   // A s8, B u8
 // every lane of the calling thread's warp contributes `v`; returns the 32 values (all lanes must call it)
 void warp_gather (unsigned v, unsigned out[32]);
 unsigned lane_id ();

@@ -60,7 +60,21 @@ void warp_gather (unsigned v, unsigned out[32])
   g_warp[w].wait ();
 }
 
+static void warp_mma (int d[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0, unsigned b1, const int c[4],
+    bool a_signed);
+
 void warp_mma_u8s8 (int d[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0, unsigned b1, const int c[4])
+{
+  warp_mma (d, a0, a1, a2, a3, b0, b1, c, false);
+}
+
+void warp_mma_s8u8 (int d[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0, unsigned b1, const int c[4])
+{
+  warp_mma (d, a0, a1, a2, a3, b0, b1, c, true);
+}
+
+static void warp_mma (int d[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0, unsigned b1, const int c[4],
+    bool a_signed)
 {
   const unsigned tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
   const unsigned w = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
@@ -69,11 +83,13 @@ void warp_mma_u8s8 (int d[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3
   g_warp[w].wait ();
   auto A = [&] (unsigned row, unsigned k) -> int {                 // u8
     const unsigned src = (row & 7) * 4 + ((k & 15) >> 2), reg = (row >> 3) + 2 * (k >> 4);
-    return (int) ((g_wa[w][src][reg] >> (8 * (k & 3))) & 0xff);
+    const unsigned v = (g_wa[w][src][reg] >> (8 * (k & 3))) & 0xff;
+    return a_signed ? (int) (int8_t) v : (int) v;
   };
   auto B = [&] (unsigned k, unsigned n) -> int {                   // s8
     const unsigned src = n * 4 + ((k & 15) >> 2), reg = k >> 4;
-    return (int) (int8_t) ((g_wb[w][src][reg] >> (8 * (k & 3))) & 0xff);
+    const unsigned v = (g_wb[w][src][reg] >> (8 * (k & 3))) & 0xff;
+    return a_signed ? (int) v : (int) (int8_t) v;                  // the operand that is not the taps holds u8 pixels
   };
   const unsigned rows[4] = {g, g, g + 8, g + 8}, cols[4] = {2 * t, 2 * t + 1, 2 * t, 2 * t + 1};
   for (int i = 0; i < 4; i++) {
