@@ -63,6 +63,7 @@ def sources():
 
 def digest():
     h = hashlib.sha256()
+    h.update((os.environ.get("B200_EMU_TSAN", "") + "/" + os.environ.get("B200_EMU_DROP_SYNC", "")).encode())
     for s in sources():
         h.update(open(s, "rb").read())
     return h.hexdigest()
@@ -82,6 +83,8 @@ def build(force=False):
                      ("vcs_light.cuh", "vcs_light.cuh"), ("vcs_ntap.cuh", "vcs_ntap.cuh"), ("common.cu", "common_emu.cpp"),
                      ("comp.cu", "comp_emu.cpp"), ("ars.cu", "ars_emu.cpp")):
         text, n = patch(open(os.path.join(CSRC, src)).read())
+        if os.environ.get("B200_EMU_DROP_SYNC") and src == "vcs_kernels.cuh":    # negative control for the race detector
+            text = text.replace("__syncthreads ();", "", 1)
         launches += n
         open(os.path.join(gen, dst), "w").write(text)
     assert launches >= 18, f"expected the launch sites of vcs.cu and vcs_planes.cuh, patched {launches}"
@@ -93,6 +96,8 @@ def build(force=False):
            os.path.join(gen, "vcs_emu.cpp"), os.path.join(gen, "common_emu.cpp"), os.path.join(gen, "comp_emu.cpp"),
            os.path.join(gen, "ars_emu.cpp"), os.path.join(CSRC, "vcs_plan.cpp"),
            os.path.join(HERE, "emu", "emu_runtime.cpp")]
+    if os.environ.get("B200_EMU_TSAN"):              # race detector build: every shared-memory access of the kernels is checked
+        cmd[1:1] = ["-fsanitize=thread"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout[-4000:] + r.stderr[-8000:])
