@@ -155,6 +155,7 @@ __device__ __forceinline__ void l2mma_tile (const VcsDev & P, const L2mmaDev & L
 
   // ---------------------------------------------------------------- H phase: warp = 8 output columns, all staged lines
   for (int j = warp; j < LM_TW / 8; j += L2_THREADS / 32) {
+    if (x0 + 8 * j >= P.ow) continue;                              // partial last tile: no such columns (warp-uniform)
     const uint2 B = __ldg (L.bh + ((x0 >> 3) + j) * 32 + lane);
     const bool x4 = __ldg (L.h4 + (x0 >> 3) + j) != 0;              // warp-uniform
     const int ci = x4 ? 128 : 32;

@@ -44,7 +44,7 @@ extern thread_local uint3_emu threadIdx, blockIdx;
 extern thread_local dim3 blockDim, gridDim;
 
 namespace b200emu {
-extern uint8_t dyn_smem[256 * 1024];
+extern uint8_t *dyn_smem;         // the launch's dynamic shared memory: a heap block of exactly the requested size
 void barrier ();
 // runs body once per thread of every block of the grid
 void launch (dim3 grid, dim3 block, size_t smem_bytes, const std::function<void ()> & body);

@@ -13,7 +13,7 @@ thread_local dim3 blockDim, gridDim;
 
 namespace b200emu {
 
-uint8_t dyn_smem[256 * 1024];
+uint8_t *dyn_smem = nullptr;
 
 struct LiveBarrier {
   std::mutex m;
@@ -126,9 +126,12 @@ static void *thread_main (void *arg)
   return nullptr;
 }
 
-void launch (dim3 grid, dim3 block, size_t, const std::function<void ()> & body)
+void launch (dim3 grid, dim3 block, size_t smem_bytes, const std::function<void ()> & body)
 {
   const unsigned nt = block.x * block.y * block.z;
+  // exactly the requested bytes (rounded to 16): an address sanitizer build then catches a kernel that runs past them
+  uint8_t *smem = (uint8_t *) aligned_alloc (16, std::max<size_t> (16, (smem_bytes + 15) & ~(size_t) 15));
+  dyn_smem = smem;
   std::vector<pthread_t> th (nt);
   std::vector<Job> jobs (nt);
   pthread_attr_t attr;
@@ -144,6 +147,8 @@ void launch (dim3 grid, dim3 block, size_t, const std::function<void ()> & body)
   for (unsigned t = 0; t < nt; t++) pthread_join (th[t], nullptr);
   pthread_barrier_destroy (&g_block);
   pthread_attr_destroy (&attr);
+  dyn_smem = nullptr;
+  free (smem);
 }
 
 }  // namespace b200emu
