@@ -1,0 +1,96 @@
+#!/usr/bin/env python
+"""tools/emu_fuzz.py [seconds] [seed] — randomised differential run of the EMULATED convert+scale kernels (tests/cudaemu:
+the product's kernel sources compiled for the host) against the oracle: random sizes (biased small and odd), methods,
+all format pairs incl. the opt-in ones, chroma sitings, colorimetry, destination rectangles.  TEST INFRASTRUCTURE.
+Meant to be run under the sanitizer builds as well:
+    B200_EMU_ASAN=1 LD_PRELOAD=$(g++ -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0:halt_on_error=0:log_path=/tmp/asan python tools/emu_fuzz.py 300
+"""
+import ctypes as C
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests", "cudaemu"))
+os.environ["B200_VCS_EXPERIMENTAL"] = "1"
+
+from oracle import bindings as ob   # noqa: E402
+import test_emu_kernels as T        # noqa: E402
+
+
+def main():
+    budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
+    rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+    import build_emu
+    from gstreamer_b200 import _lib
+    emu = C.CDLL(build_emu.build())
+    for name, (res, args) in _lib._SIGS.items():
+        if hasattr(emu, name):
+            fn = getattr(emu, name)
+            fn.restype, fn.argtypes = res, args
+    t0, n, bad, kinds = time.time(), 0, 0, {}
+    while time.time() - t0 < budget:
+        big = rng.random() < 0.2
+        hi = 300 if big else 70
+        iw, ih, W, H = (int(v) for v in rng.integers(1, hi, 4))
+        r = rng.random()
+        if r < 0.15:
+            W = iw
+        elif r < 0.3:
+            H = ih
+        elif r < 0.4:
+            W, H = max(1, iw // 2), max(1, ih // 2)
+        method = int(rng.integers(0, 10))
+        kind = str(rng.choice(["yuv-rgb", "yuv-rgb", "same", "cross", "rgb-yuv", "rgb-rgb", "422-rgb"]))
+        if kind == "yuv-rgb":
+            fi, fo = str(rng.choice(T.YUV)), str(rng.choice(T.RGB))
+        elif kind == "same":
+            fi = str(rng.choice(T.YUV))
+            fo = fi if fi in ("NV12", "NV21") else str(rng.choice(["I420", "YV12"]))
+        elif kind == "cross":
+            fi = str(rng.choice(T.YUV))
+            fo = str(rng.choice([f for f in T.YUV if not ((fi in ("I420", "YV12")) == (f in ("I420", "YV12")) and (fi == f or fi in ("I420", "YV12")))]))
+        elif kind == "rgb-yuv":
+            fi, fo = str(rng.choice(T.RGB)), str(rng.choice(T.YUV))
+        elif kind == "rgb-rgb":
+            fi, fo = str(rng.choice(T.RGB)), str(rng.choice(T.RGB))
+        else:
+            fi, fo = str(rng.choice(T.YUV_422_444)), str(rng.choice(T.RGB))
+        site = int(rng.choice([1, 2, 4, 6]))
+        out_site = int(rng.choice([1, 2, 4, 6])) if kind == "cross" else None
+        dest = None
+        if rng.random() < 0.25:
+            dw, dh = int(rng.integers(1, W + 1)), int(rng.integers(1, H + 1))
+            dest = (int(rng.integers(0, W - dw + 1)), int(rng.integers(0, H - dh + 1)), dw, dh)
+        frame = T.frame_for(fi, iw, ih, n)
+        size = (iw, ih, W, H)
+        generic = not (fi in T.RGB and fo in T.RGB) and not (kind == "same")
+        try:
+            kw = dict(site=site if fi not in T.RGB else None, out_site=out_site, dest=dest)
+            want = T.expected(fi, fo, size, method, frame, **kw)
+            got = T.run(emu, fi, fo, size, method, frame, force_generic=False, **kw)
+            if rng.random() < 0.3 and generic:      # the generic kernel on shapes the fast kernels would take
+                got2 = T.run(emu, fi, fo, size, method, frame, force_generic=True, **kw)
+                if not np.array_equal(got2, want):
+                    bad += 1
+                    print("MISMATCH (generic)", kind, fi, fo, size, "m", method, "site", site, out_site, "dest", dest, flush=True)
+        except Exception as e:                      # noqa: BLE001
+            print("ERROR", kind, fi, fo, size, "m", method, "dest", dest, repr(e)[:200], flush=True)
+            bad += 1
+            continue
+        n += 1
+        kinds[kind] = kinds.get(kind, 0) + 1
+        if not np.array_equal(got, want):
+            bad += 1
+            print("MISMATCH", kind, fi, fo, size, "m", method, "site", site, out_site, "dest", dest,
+                  int(np.count_nonzero(got != want)), "of", got.size, flush=True)
+    print(f"emu_fuzz: {n} cases, {bad} problems, {kinds}")
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
