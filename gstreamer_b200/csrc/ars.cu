@@ -94,9 +94,9 @@ __host__ __device__ inline void cubic_coeff_s16 (int num, int denom, int ic[4])
 {
   const int x = (int) (((long long) num << 15) / denom);
   const int x2 = (int) ((unsigned) x * (unsigned) x) >> 15, x3 = (int) ((unsigned) x2 * (unsigned) x) >> 15;
-  const short c0 = (short) ((((x3 - x) << 15) / 6) >> 15);
+  const short c0 = (short) ((((x3 - x) * 32768) / 6) >> 15);      // (a << 15) of the reference, without shifting a negative value
   const short c1 = (short) (x + ((x2 - x3) >> 1));
-  const short c3 = (short) (-(((x << 15) / 3) >> 15) + (x2 >> 1) - (((x3 << 15) / 6) >> 15));
+  const short c3 = (short) (-(((x * 32768) / 3) >> 15) + (x2 >> 1) - (((x3 * 32768) / 6) >> 15));
   ic[0] = c0; ic[1] = c1; ic[3] = c3;
   ic[2] = (short) (32767 - c0 - c1 - c3);
 }
@@ -104,9 +104,9 @@ __host__ __device__ inline void cubic_coeff_s32 (int num, int denom, int ic[4])
 {
   const long long one = (1LL << 31) - 1;
   const long long x = ((long long) num << 31) / denom, x2 = (x * x) >> 31, x3 = (x2 * x) >> 31;
-  ic[0] = (int) ((((x3 - x) << 31) / 6) >> 31);
+  ic[0] = (int) ((((x3 - x) * (1LL << 31)) / 6) >> 31);
   ic[1] = (int) (x + ((x2 - x3) >> 1));
-  ic[3] = (int) (-(((x << 31) / 3) >> 31) + (x2 >> 1) - (((x3 << 31) / 6) >> 31));
+  ic[3] = (int) (-(((x * (1LL << 31)) / 3) >> 31) + (x2 >> 1) - (((x3 * (1LL << 31)) / 6) >> 31));
   ic[2] = (int) (one - ic[0] - ic[1] - ic[3]);
 }
 // make_coeff_gdouble_cubic: float literals promoted to double; no FMA may be formed

@@ -64,7 +64,7 @@ __device__ __forceinline__ int chroma_hup (const uint8_t * __restrict__ c, int x
 // splatbw of the biased byte ub=(x^0x80) read as s16 is (x-128)*256 + ub.
 __device__ __forceinline__ int splat_s16 (int x)
 {
-  return ((x - 128) << 8) + (x ^ 0x80);
+  return (x - 128) * 256 + (x ^ 0x80);
 }
 
 __device__ __forceinline__ void yuv_to_rgb (int y, int u, int v, int p1, int p2, int p3, int p4, int p5,

@@ -63,7 +63,7 @@ def sources():
 
 def digest():
     h = hashlib.sha256()
-    h.update((os.environ.get("B200_EMU_TSAN", "") + "/" + os.environ.get("B200_EMU_DROP_SYNC", "") + "/" + os.environ.get("B200_EMU_ASAN", "")).encode())
+    h.update((os.environ.get("B200_EMU_TSAN", "") + "/" + os.environ.get("B200_EMU_DROP_SYNC", "") + "/" + os.environ.get("B200_EMU_ASAN", "") + "/" + os.environ.get("B200_EMU_UBSAN", "")).encode())
     for s in sources():
         h.update(open(s, "rb").read())
     return h.hexdigest()
@@ -98,6 +98,8 @@ def build(force=False):
            os.path.join(HERE, "emu", "emu_runtime.cpp")]
     if os.environ.get("B200_EMU_ASAN"):              # out-of-bounds accesses of frames, tables and static shared arrays
         cmd[1:1] = ["-fsanitize=address", "-fno-omit-frame-pointer"]
+    if os.environ.get("B200_EMU_UBSAN"):             # misaligned vector accesses (a fault on the device), shifts, overflows
+        cmd[1:1] = ["-fsanitize=undefined"]
     if os.environ.get("B200_EMU_TSAN"):              # race detector build: every shared-memory access of the kernels is checked
         cmd[1:1] = ["-fsanitize=thread"]
     r = subprocess.run(cmd, capture_output=True, text=True)
