@@ -60,9 +60,11 @@ struct ArsPlan {
   int n_taps = 0, oversample = 0, n_phases = 0;
   bool full = false;
   bool blackman = false;         // resample-method=blackman-nuttall (else kaiser)
+  bool linear = false;           // sinc-filter-interpolation=linear: two prototype rows per phase, 11x the oversampling
+  int isize = 4;                 // prototype rows one phase reads (4 cubic, 2 linear)
   bool interp_none = false;      // FULL mode with sinc-filter-interpolation=none: every phase's taps computed directly
   double cutoff = 0, beta = 0;
-  std::vector<float> proto;      // (oversample + 4) x n_taps oversampled prototype
+  std::vector<float> proto;      // (oversample + isize) x n_taps oversampled prototype
   std::vector<float> phases;     // n_phases x n_taps (FULL mode), all phases precomputed
   // other sample formats: the same two tables in the samples' own type
   int fmt = 0, bps = 4;          // ArsFmt, bytes per sample
@@ -168,13 +170,12 @@ static int build_ars_plan (const b200_ars_config & cfg, ArsPlan * p)
   p->n_taps = (int) ((A - 8.0) / (2.285 * dw)) + 1;
   p->cutoff = fc;
   // the element's other properties: only what needs no new device code - both windowed-sinc methods, every filter
-  // mode, cubic table interpolation or none
+  // mode, and every table interpolation
   if (cfg.resample_method != 0 && cfg.resample_method != B200_ARS_METHOD_KAISER && cfg.resample_method != B200_ARS_METHOD_BLACKMAN_NUTTALL)
     return B200_ERR_UNSUPPORTED;
   if (cfg.sinc_filter_mode < 0 || cfg.sinc_filter_mode > B200_ARS_FILTER_MODE_AUTO) return B200_ERR_INVALID_ARG;
-  if (cfg.sinc_filter_interpolation != 0 && cfg.sinc_filter_interpolation != B200_ARS_FILTER_INTERPOLATION_CUBIC &&
-      cfg.sinc_filter_interpolation != B200_ARS_FILTER_INTERPOLATION_NONE)
-    return B200_ERR_UNSUPPORTED;
+  if (cfg.sinc_filter_interpolation < 0 || cfg.sinc_filter_interpolation > B200_ARS_FILTER_INTERPOLATION_CUBIC)
+    return B200_ERR_INVALID_ARG;
   p->blackman = cfg.resample_method == B200_ARS_METHOD_BLACKMAN_NUTTALL;
   if (p->blackman) {                    // blackman_qualities, audio-resampler.c:81-93; options_set_quality :1299-1305
     static const struct { int n_taps; double cutoff; } kBlackman[11] = {{8, 0.5}, {16, 0.6}, {24, 0.72}, {32, 0.8},
@@ -191,6 +192,10 @@ static int build_ars_plan (const b200_ars_config & cfg, ArsPlan * p)
   int over = kOversample[cfg.quality];
   for (int mult = 2; over > 1 && mult * p->out_step < p->in_step; mult *= 2) over >>= 1;
   if (no_interp) over = 1;              // audio-resampler.c:1141-1143
+  p->linear = cfg.sinc_filter_interpolation == B200_ARS_FILTER_INTERPOLATION_LINEAR;
+  if (p->linear) over *= 11;            // :1131-1137
+  p->isize = p->linear ? 2 : 4;         // :1186-1197
+  const int isize = p->isize;
   p->oversample = over;
   // filter-mode auto with the element's VARIABLE_RATE flag: FULL when the whole phase table is
   // below the (effectively fixed) 1 MiB threshold (audio-resampler.c:1147-1166)
@@ -202,10 +207,12 @@ static int build_ars_plan (const b200_ars_config & cfg, ArsPlan * p)
   // above (:1167-1170)
   p->interp_none = p->full && no_interp;
   p->n_phases = p->full ? p->out_step : 0;
+  // the linear blend of the interpolated filter mode runs in device code no device session has checked yet
+  if (p->linear && !p->full && !getenv ("B200_VCS_EXPERIMENTAL")) return B200_ERR_UNSUPPORTED;
 
   const int n = p->n_taps;
-  p->proto.assign ((size_t) (over + 4) * n, 0.f);
-  if (p->fmt != ARS_F32) p->proto_x.assign ((size_t) (over + 4) * n * p->bps, 0);
+  p->proto.assign ((size_t) (over + isize) * n, 0.f);
+  if (p->fmt != ARS_F32) p->proto_x.assign ((size_t) (over + isize) * n * p->bps, 0);
   std::vector<double> tmp (n);
   // make_taps (audio-resampler.c:287-323): n windowed-sinc values starting at x0, normalised, in float and (other
   // sample formats) in the samples' own type
@@ -229,7 +236,7 @@ static int build_ars_plan (const b200_ars_config & cfg, ArsPlan * p)
     else if (p->fmt == ARS_S32) convert_taps_int (tmp.data (), (int32_t *) px, weight, n, 31);
     else if (p->fmt == ARS_F64) for (int i = 0; i < n; i++) ((double *) px)[i] = tmp[i] / weight;
   };
-  for (int row = 0; row < over + 4; row++)
+  for (int row = 0; row < over + isize; row++)
     make_row (-(n / 2) + row / (double) over, &p->proto[(size_t) row * n],
         p->fmt != ARS_F32 ? p->proto_x.data () + (size_t) row * n * p->bps : nullptr);
   if (p->interp_none) {
@@ -249,7 +256,29 @@ static int build_ars_plan (const b200_ars_config & cfg, ArsPlan * p)
       const int pos = ph * over, offset = (over - 1) - pos / p->n_phases, frac = pos % p->n_phases;
       const uint8_t *c0 = p->proto_x.data () + (size_t) offset * n * p->bps;
       uint8_t *res = p->phases_x.data () + (size_t) ph * n * p->bps;
-      if (p->fmt == ARS_S16) {
+      if (p->linear && p->fmt == ARS_S16) {      // interpolate_gint16_linear_sse2 (audio-resampler-x86-sse2.c:267-299)
+        const int x = (int) (((long long) frac << 15) / p->n_phases), y = 32767 - x;   // make_coeff_gint16_linear :325-332
+        const int16_t *a = (const int16_t *) c0, *b = a + n;
+        for (int i = 0; i < n; i++) {
+          const int t = (int) ((unsigned) (a[i] * x) + (unsigned) (b[i] * y) + (1u << 14)) >> 15;
+          ((int16_t *) res)[i] = (int16_t) (t < -32768 ? -32768 : (t > 32767 ? 32767 : t));
+        }
+      } else if (p->linear && p->fmt == ARS_S32) {   // interpolate_gint32_linear_c (audio-resampler.c:375-390); the store truncates
+        const long long x = ((long long) frac << 31) / p->n_phases;
+        const int32_t *a = (const int32_t *) c0, *b = a + n;
+        for (int i = 0; i < n; i++) {
+          const unsigned long long t = (unsigned long long) (((long long) a[i] - (long long) b[i]) * x) +
+              ((unsigned long long) (long long) b[i] << 31);
+          ((int32_t *) res)[i] = (int32_t) (uint32_t) ((long long) (t + (1ULL << 30)) >> 31);
+        }
+      } else if (p->linear) {                    // interpolate_gdouble_linear_sse2 (audio-resampler-x86-sse2.c:344-366)
+        volatile double x = (double) frac / p->n_phases, y = 1.0 - x;
+        const double *a = (const double *) c0, *b = a + n;
+        for (int i = 0; i < n; i++) {
+          volatile double t0 = a[i] * x, t1 = b[i] * y;
+          ((double *) res)[i] = t0 + t1;
+        }
+      } else if (p->fmt == ARS_S16) {
         int ic[4];
         cubic_coeff_s16 (frac, p->n_phases, ic);
         const int16_t *a = (const int16_t *) c0, *b = a + n, *c = b + n, *d = c + n;
@@ -287,9 +316,17 @@ static int build_ars_plan (const b200_ars_config & cfg, ArsPlan * p)
     for (int ph = 0; ph < p->n_phases; ph++) {
       const int pos = ph * over, offset = (over - 1) - pos / p->n_phases, frac = pos % p->n_phases;
       float ic[4];
-      cubic_coeff (frac, p->n_phases, ic);
       const float *c0 = &p->proto[(size_t) offset * n], *c1 = c0 + n, *c2 = c1 + n, *c3 = c2 + n;
       float *res = &p->phases[(size_t) ph * n];
+      if (p->linear) {          // make_coeff_gfloat_linear (:333-340) + interpolate_gfloat_linear_sse: c0*f0 + c1*f1
+        volatile float x = (float) frac / p->n_phases, y = 1.0f - x;
+        for (int i = 0; i < n; i++) {
+          volatile float t0 = c0[i] * x, t1 = c1[i] * y;
+          res[i] = t0 + t1;
+        }
+        continue;
+      }
+      cubic_coeff (frac, p->n_phases, ic);
       for (int i = 0; i < n; i++) {
         volatile float t0 = c0[i] * ic[0], t1 = c1[i] * ic[1], t2 = c2[i] * ic[2], t3 = c3[i] * ic[3];
         volatile float u0 = t0 + t1, u2 = t2 + t3;
@@ -639,6 +676,9 @@ ars_tile_kernel_s16 (const ArsLaunch L, const ArsTile Tl)
 // Warp = one output frame x 32 channels; the prototype rows are warp-uniform LDG.128.
 // Lane sums follow the tap index mod 4 as in the reference; (c0*f0 + c1*f1) + (c2*f2 + c3*f3)
 // per lane, then (l0 + l2) + (l1 + l3).  No FMA anywhere.
+// LIN: sinc-filter-interpolation=linear (get_taps_gfloat_linear + inner_product_gfloat_linear_1_sse,
+// audio-resampler-x86-sse.c:48-74): two rows, blended per lane as (s0 - s1) * x + s1.
+template <bool LIN>
 __global__ void __launch_bounds__ (ARS_THREADS)
 ars_interp_kernel (const ArsLaunch L, const float *__restrict__ table, int oversample)
 {
@@ -659,6 +699,7 @@ ars_interp_kernel (const ArsLaunch L, const float *__restrict__ table, int overs
   const float ic2 = __fsub_rn (__fsub_rn (__fsub_rn (1.0f, ic0), ic1), ic3);
   const float4 *row = (const float4 *) (table + (size_t) offset * L.n_taps);
   const int rstride = L.n_taps >> 2;
+  constexpr int ROWS = LIN ? 2 : 4;
   float acc[4][4];
 #pragma unroll
   for (int k = 0; k < 4; k++)
@@ -678,7 +719,7 @@ ars_interp_kernel (const ArsLaunch L, const float *__restrict__ table, int overs
       xs[l] = v;
     }
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < ROWS; k++) {
       const float4 t = __ldg (row + k * rstride + (i >> 2));
       acc[k][0] = __fadd_rn (acc[k][0], __fmul_rn (xs[0], t.x));
       acc[k][1] = __fadd_rn (acc[k][1], __fmul_rn (xs[1], t.y));
@@ -689,8 +730,11 @@ ars_interp_kernel (const ArsLaunch L, const float *__restrict__ table, int overs
   float t[4];
 #pragma unroll
   for (int l = 0; l < 4; l++)
-    t[l] = __fadd_rn (__fadd_rn (__fmul_rn (acc[0][l], ic0), __fmul_rn (acc[1][l], ic1)),
-        __fadd_rn (__fmul_rn (acc[2][l], ic2), __fmul_rn (acc[3][l], ic3)));
+    if (LIN)                    // make_coeff_gfloat_linear (:333-340): ic[0] = x
+      t[l] = __fadd_rn (__fmul_rn (__fsub_rn (acc[0][l], acc[1][l]), x), acc[1][l]);
+    else
+      t[l] = __fadd_rn (__fadd_rn (__fmul_rn (acc[0][l], ic0), __fmul_rn (acc[1][l], ic1)),
+          __fadd_rn (__fmul_rn (acc[2][l], ic2), __fmul_rn (acc[3][l], ic3)));
   if (live)
     L.out[(size_t) o * L.channels + c] = __fadd_rn (__fadd_rn (t[0], t[2]), __fadd_rn (t[1], t[3]));
 }
@@ -703,11 +747,16 @@ ars_interp_kernel (const ArsLaunch L, const float *__restrict__ table, int overs
 struct ArsLaunchX {
   const void *hist, *in;
   void *out;
-  const void *table;             // FULL: [n_phases][n_taps] taps; interpolated: [oversample + 4][n_taps] prototype
+  const void *table;             // FULL: [n_phases][n_taps] taps; interpolated: [oversample + 4 (2: linear)][n_taps] prototype
   long long hist_frames, avail, out_frames;
   int channels, n_taps, out_step, samp_inc, samp_frac, samp_index, samp_phase;
   int full, oversample;
 };
+// make_coeff_gint16_linear / _gint32_linear (audio-resampler.c:325-332): ic[0] = x, ic[1] = 2^prec - 1 - x
+__device__ __forceinline__ int linear_coeff_int (int frac, int denom, int prec)
+{
+  return (int) (((long long) frac << prec) / denom);
+}
 
 template <typename T>
 __device__ __forceinline__ T ars_sample (const ArsLaunchX & L, long long f, int c)
@@ -718,7 +767,7 @@ __device__ __forceinline__ T ars_sample (const ArsLaunchX & L, long long f, int 
 }
 
 
-template <int FMT>
+template <int FMT, bool LIN>
 __global__ void __launch_bounds__ (ARS_THREADS)
 ars_direct_kernel (const ArsLaunchX L)
 {
@@ -741,6 +790,25 @@ ars_direct_kernel (const ArsLaunchX L)
       unsigned sum = 0;
       for (int i = 0; i < n; i++) sum += (unsigned) ((int) ars_sample<short> (L, idx + i, c) * (int) __ldg (tab + i));
       ((short *) L.out)[(size_t) o * L.channels + c] = (short) sat_s16 ((int) (sum + (1u << 14)) >> 15);
+    } else if (LIN) {             // inner_product_gint16_linear_1_sse2 (audio-resampler-x86-sse2.c:57-108): 32-bit lane l
+      unsigned s[2][4];           // sums the tap pairs (2l, 2l+1) of every eight; each LANE is shifted and multiplied
+#pragma unroll
+      for (int k = 0; k < 2; k++)
+#pragma unroll
+        for (int l = 0; l < 4; l++) s[k][l] = 0;
+      for (int i = 0; i < n; i += 8)
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const int x = ars_sample<short> (L, idx + i + j, c);
+          s[0][j >> 1] += (unsigned) (x * (int) __ldg (tab + i + j));
+          s[1][j >> 1] += (unsigned) (x * (int) __ldg (tab + n + i + j));
+        }
+      const int x = linear_coeff_int (frac, L.out_step, 15), y = 32767 - x;
+      unsigned acc = 0;
+#pragma unroll
+      for (int l = 0; l < 4; l++)
+        acc += (unsigned) ((int) (short) ((int) s[0][l] >> 15) * x) + (unsigned) ((int) (short) ((int) s[1][l] >> 15) * y);
+      ((short *) L.out)[(size_t) o * L.channels + c] = (short) sat_s16 ((int) (acc + (1u << 14)) >> 15);
     } else {                      // inner_product_gint16_cubic_1_sse2
       unsigned s0 = 0, s1 = 0, s2 = 0, s3 = 0;
       for (int i = 0; i < n; i++) {
@@ -763,22 +831,27 @@ ars_direct_kernel (const ArsLaunchX L)
       for (int i = 0; i < n; i++) sum += (unsigned long long) ((long long) ars_sample<int> (L, idx + i, c) * __ldg (tab + i));
       ((int *) L.out)[(size_t) o * L.channels + c] = (int) sat_s32 (((long long) sum + (1 << 30)) >> 31);
     } else {                      // inner_product_gint32_cubic_1_sse41: each 64-bit LANE (even / odd taps) is
-      unsigned long long s[4][2]; // shifted and multiplied before the lanes are added
+      unsigned long long s[4][2]; // shifted and multiplied before the lanes are added; _linear_1_sse41 (:70-112) is the same
+      constexpr int ROWS = LIN ? 2 : 4;   // arithmetic over two rows
 #pragma unroll
       for (int k = 0; k < 4; k++) s[k][0] = s[k][1] = 0;
       for (int i = 0; i < n; i += 2) {
         const long long x0 = ars_sample<int> (L, idx + i, c), x1 = ars_sample<int> (L, idx + i + 1, c);
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
+        for (int k = 0; k < ROWS; k++) {
           s[k][0] += (unsigned long long) (x0 * __ldg (tab + k * n + i));
           s[k][1] += (unsigned long long) (x1 * __ldg (tab + k * n + i + 1));
         }
       }
       int ic[4];
-      cubic_coeff_s32 (frac, L.out_step, ic);
+      if (LIN) {
+        ic[0] = ic[2] = linear_coeff_int (frac, L.out_step, 31);
+        ic[1] = ic[3] = 2147483647 - ic[0];
+      } else
+        cubic_coeff_s32 (frac, L.out_step, ic);
       unsigned long long acc = 0;
 #pragma unroll
-      for (int k = 0; k < 4; k++)
+      for (int k = 0; k < ROWS; k++)
 #pragma unroll
         for (int l = 0; l < 2; l++)
           acc += (unsigned long long) ((long long) (int) (unsigned) (s[k][l] >> 31) * (long long) ic[k]);
@@ -793,6 +866,20 @@ ars_direct_kernel (const ArsLaunchX L)
         s1 = __dadd_rn (s1, __dmul_rn (ars_sample<double> (L, idx + i + 1, c), __ldg (tab + i + 1)));
       }
       ((double *) L.out)[(size_t) o * L.channels + c] = __dadd_rn (s0, s1);
+    } else if (LIN) {             // inner_product_gdouble_linear_1_sse2 (audio-resampler-x86-sse2.c:195-220)
+      double s[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+      for (int i = 0; i < n; i += 2) {
+        const double x0 = ars_sample<double> (L, idx + i, c), x1 = ars_sample<double> (L, idx + i + 1, c);
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+          s[k][0] = __dadd_rn (s[k][0], __dmul_rn (x0, __ldg (tab + k * n + i)));
+          s[k][1] = __dadd_rn (s[k][1], __dmul_rn (x1, __ldg (tab + k * n + i + 1)));
+        }
+      }
+      const double x = __ddiv_rn ((double) frac, (double) L.out_step);      // make_coeff_gdouble_linear: ic[0]
+      const double l0 = __dadd_rn (__dmul_rn (__dsub_rn (s[0][0], s[1][0]), x), s[1][0]);
+      const double l1 = __dadd_rn (__dmul_rn (__dsub_rn (s[0][1], s[1][1]), x), s[1][1]);
+      ((double *) L.out)[(size_t) o * L.channels + c] = __dadd_rn (l0, l1);
     } else {                      // inner_product_gdouble_cubic_1_sse2
       double s[4][2];
 #pragma unroll
@@ -1043,13 +1130,22 @@ int b200_ars_process (b200_ars * h, const void *in_v, size_t in_frames, void *ou
       X.samp_inc = p.samp_inc; X.samp_frac = p.samp_frac; X.samp_index = h->samp_index; X.samp_phase = h->samp_phase;
       X.full = p.full ? 1 : 0; X.oversample = p.oversample;
       const dim3 grid ((unsigned) ((out_frames + ARS_THREADS / 32 - 1) / (ARS_THREADS / 32)), (unsigned) ((p.channels + 31) / 32));
-      if (p.fmt == ARS_S16) ars_direct_kernel<ARS_S16> <<<grid, ARS_THREADS, 0, stream>>> (X);
-      else if (p.fmt == ARS_S32) ars_direct_kernel<ARS_S32> <<<grid, ARS_THREADS, 0, stream>>> (X);
-      else ars_direct_kernel<ARS_F64> <<<grid, ARS_THREADS, 0, stream>>> (X);
+      const bool lin = p.linear && !p.full;
+      if (p.fmt == ARS_S16) {
+        if (lin) ars_direct_kernel<ARS_S16, true> <<<grid, ARS_THREADS, 0, stream>>> (X);
+        else ars_direct_kernel<ARS_S16, false> <<<grid, ARS_THREADS, 0, stream>>> (X);
+      } else if (p.fmt == ARS_S32) {
+        if (lin) ars_direct_kernel<ARS_S32, true> <<<grid, ARS_THREADS, 0, stream>>> (X);
+        else ars_direct_kernel<ARS_S32, false> <<<grid, ARS_THREADS, 0, stream>>> (X);
+      } else {
+        if (lin) ars_direct_kernel<ARS_F64, true> <<<grid, ARS_THREADS, 0, stream>>> (X);
+        else ars_direct_kernel<ARS_F64, false> <<<grid, ARS_THREADS, 0, stream>>> (X);
+      }
     } else if (!p.full) {
       L.no = 0; L.row_pitch = 0; L.wcn = 1;
       const dim3 grid ((unsigned) ((out_frames + ARS_THREADS / 32 - 1) / (ARS_THREADS / 32)), (unsigned) ((p.channels + 31) / 32));
-      ars_interp_kernel <<<grid, ARS_THREADS, 0, stream>>> (L, h->d_proto, p.oversample);
+      if (p.linear) ars_interp_kernel<true> <<<grid, ARS_THREADS, 0, stream>>> (L, h->d_proto, p.oversample);
+      else ars_interp_kernel<false> <<<grid, ARS_THREADS, 0, stream>>> (L, h->d_proto, p.oversample);
     } else {
     const char *env_no = getenv ("B200_ARS_NO"), *env_cpt = getenv ("B200_ARS_CPT");
     int no = env_no ? atoi (env_no) : 32;

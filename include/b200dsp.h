@@ -243,7 +243,7 @@ typedef struct {
    * default configuration: */
   int32_t resample_method;       /* 0 or B200_ARS_METHOD_KAISER; B200_ARS_METHOD_BLACKMAN_NUTTALL; the others: unsupported */
   int32_t sinc_filter_mode;      /* 0 or B200_ARS_FILTER_MODE_AUTO; _INTERPOLATED; _FULL */
-  int32_t sinc_filter_interpolation;     /* 0 or B200_ARS_FILTER_INTERPOLATION_CUBIC; _NONE; _LINEAR: unsupported */
+  int32_t sinc_filter_interpolation;     /* 0 or B200_ARS_FILTER_INTERPOLATION_CUBIC; _NONE; _LINEAR */
   int32_t reserved[4];
 } b200_ars_config;
 enum { B200_ARS_METHOD_NEAREST = 1, B200_ARS_METHOD_LINEAR = 2, B200_ARS_METHOD_CUBIC = 3,

@@ -60,6 +60,7 @@ struct OracleArs
   int channels, in_rate, out_rate;      /* rates after gcd reduction */
   int samp_inc, samp_frac, samp_index, samp_phase, skip;
   int n_taps, oversample, n_phases, full;
+  int linear, isize;            /* sinc-filter-interpolation=linear: two table rows per phase, 11x the oversampling */
   int method, interp_none;      /* ORACLE_ARS_METHOD_*; sinc-filter-interpolation=none (FULL mode: exact taps per phase) */
   double cutoff, beta;
   int fmt, bps;                 /* ORACLE_AFMT_*, bytes per sample */
@@ -182,8 +183,8 @@ oracle_ars_new_opts (int in_rate, int out_rate, int channels, int quality, int f
     return NULL;
   if ((method != ORACLE_ARS_METHOD_KAISER && method != ORACLE_ARS_METHOD_BLACKMAN_NUTTALL) ||
       filter_mode < ORACLE_ARS_MODE_INTERPOLATED || filter_mode > ORACLE_ARS_MODE_AUTO ||
-      (interpolation != ORACLE_ARS_INTERP_CUBIC && interpolation != ORACLE_ARS_INTERP_NONE))
-    return NULL;                /* nearest / linear / cubic methods and linear table interpolation: not restated */
+      interpolation < ORACLE_ARS_INTERP_NONE || interpolation > ORACLE_ARS_INTERP_CUBIC)
+    return NULL;                /* nearest / linear / cubic methods: not restated */
   r = calloc (1, sizeof (*r));
   r->method = method;
   r->channels = channels;
@@ -234,9 +235,13 @@ oracle_ars_new_opts (int in_rate, int out_rate, int channels, int quality, int f
       mult *= 2;
       oversample >>= 1;
     }
+    if (interpolation == ORACLE_ARS_INTERP_LINEAR)
+      oversample *= 11;         /* :1131-1137 */
   } else
     oversample = 1;             /* :1141-1143 */
   r->oversample = oversample;
+  r->linear = interpolation == ORACLE_ARS_INTERP_LINEAR;
+  r->isize = r->linear ? 2 : 4; /* :1186-1197 */
   /* filter-mode auto; the element stores the threshold as UINT, the resampler reads it as INT,
    * so the default 1048576 always applies; VARIABLE_RATE is set by the
    * element so the first clause never selects FULL */
@@ -248,8 +253,8 @@ oracle_ars_new_opts (int in_rate, int out_rate, int channels, int quality, int f
    * computed above (:1167-1170) */
   r->interp_none = r->full && interpolation == ORACLE_ARS_INTERP_NONE;
   r->n_phases = r->out_rate;
-  r->table = calloc ((size_t) (oversample + 4) * r->n_taps, r->bps);
-  for (i = 0; i < oversample + 4; i++)
+  r->table = calloc ((size_t) (oversample + r->isize) * r->n_taps, r->bps);
+  for (i = 0; i < oversample + r->isize; i++)
     make_row (r, (char *) r->table + (size_t) i * r->n_taps * r->bps, -(r->n_taps / 2) + i / (double) oversample);
   if (r->full) {
     r->cache = calloc ((size_t) r->n_phases * r->n_taps, r->bps);
@@ -298,6 +303,15 @@ cubic_coeff (int num, int denom, float ic[4])
   ic[2] = (float) 1.0 - ic[0] - ic[1] - ic[3];
 }
 
+/* make_coeff_gfloat_linear, audio-resampler.c:333-340 */
+static void
+linear_coeff (int num, int denom, float ic[4])
+{
+  float x = (float) num / denom;
+  ic[0] = ic[2] = x;
+  ic[1] = ic[3] = (float) 1.0 - x;
+}
+
 /* taps of one phase in FULL mode, built lazily like get_taps_gfloat_full() */
 static const float *
 phase_taps (OracleArs * r, int phase)
@@ -313,6 +327,15 @@ phase_taps (OracleArs * r, int phase)
     int frac = pos % r->n_phases, i, n = r->n_taps;
     const float *c0 = r->table + (size_t) offset * n, *c1 = c0 + n, *c2 = c1 + n, *c3 = c2 + n;
     float ic[4];
+    if (r->linear) {            /* interpolate_gfloat_linear_sse (audio-resampler-x86-sse.c:113-137): c0*f0 + c1*f1 */
+      linear_coeff (frac, r->n_phases, ic);
+      for (i = 0; i < n; i++) {
+        float t0 = c0[i] * ic[0], t1 = c1[i] * ic[1];
+        res[i] = t0 + t1;
+      }
+      r->have[phase] = 1;
+      return res;
+    }
     cubic_coeff (frac, r->n_phases, ic);
     for (i = 0; i < n; i++) {
       /* interpolate_gfloat_cubic_sse: (c0*f0 + c1*f1) + (c2*f2 + c3*f3) */
@@ -409,6 +432,28 @@ dot_cubic (const float *a, const float *c0, int stride, int len, const float ic[
   return (s[0][0] + s[0][2]) + (s[0][1] + s[0][3]);
 }
 
+/* inner_product_gfloat_linear_1_sse (audio-resampler-x86-sse.c:48-74): four lane sums per row, blended per lane as
+ * (s0 - s1) * ic[0] + s1 */
+static float
+dot_linear (const float *a, const float *c0, int stride, int len, const float ic[4])
+{
+  float s[2][4];
+  int i, l, k;
+  memset (s, 0, sizeof (s));
+  for (i = 0; i < len; i += 4)
+    for (k = 0; k < 2; k++)
+      for (l = 0; l < 4; l++) {
+        float p = a[i + l] * c0[(size_t) k * stride + i + l];
+        s[k][l] = s[k][l] + p;
+      }
+  for (l = 0; l < 4; l++) {
+    float d = s[0][l] - s[1][l];
+    d = d * ic[0];
+    s[0][l] = d + s[1][l];
+  }
+  return (s[0][0] + s[0][2]) + (s[0][1] + s[0][3]);
+}
+
 /* ---- S16 / S32 / F64 (audio-resampler.c macros + audio-resampler-x86-sse2.c / -sse41.c, the
  * implementations an x86 build selects, audio-resampler-x86.h:29-70) --------------------------- */
 
@@ -441,6 +486,24 @@ cubic_coeff_int (int num, int denom, int prec, int64_t ic[4])
   ic[2] = (int32_t) (one - ic[0] - ic[1] - ic[3]);
 }
 
+/* make_coeff_gint16_linear / _gint32_linear (audio-resampler.c:325-332) */
+static void
+linear_coeff_int (int num, int denom, int prec, int64_t ic[4])
+{
+  int64_t x = ((int64_t) num << prec) / denom;
+  ic[0] = ic[2] = x;
+  ic[1] = ic[3] = (((int64_t) 1 << prec) - 1) - x;
+}
+
+/* make_coeff_gdouble_linear (:333-340) */
+static void
+linear_coeff_f64 (int num, int denom, double ic[4])
+{
+  double x = (double) num / denom;
+  ic[0] = ic[2] = x;
+  ic[1] = ic[3] = (double) 1.0 - x;
+}
+
 /* make_coeff_gdouble_cubic: the literals are float constants promoted to double */
 static void
 cubic_coeff_f64 (int num, int denom, double ic[4])
@@ -467,7 +530,32 @@ phase_taps_any (OracleArs * r, int phase)
     int frac = pos % r->n_phases;
     size_t i;
     const char *c0 = (const char *) r->table + (size_t) offset * n * r->bps;
-    if (r->fmt == ORACLE_AFMT_S16) {    /* interpolate_gint16_cubic_sse2: 32-bit sums, +2^14, >>15, packs */
+    if (r->linear && r->fmt == ORACLE_AFMT_S16) {       /* interpolate_gint16_linear_sse2 (audio-resampler-x86-sse2.c:267-299) */
+      const int16_t *a = (const int16_t *) c0, *b = a + n;
+      int64_t ic[4];
+      linear_coeff_int (frac, r->n_phases, 15, ic);
+      for (i = 0; i < n; i++) {
+        int32_t t = (int32_t) ((uint32_t) (a[i] * (int32_t) ic[0]) + (uint32_t) (b[i] * (int32_t) ic[1]) + (1u << 14));
+        ((int16_t *) res)[i] = (int16_t) sat64 (t >> 15, -32768, 32767);
+      }
+    } else if (r->linear && r->fmt == ORACLE_AFMT_S32) {        /* interpolate_gint32_linear_c (audio-resampler.c:375-390) */
+      const int32_t *a = (const int32_t *) c0, *b = a + n;
+      int64_t ic[4];
+      linear_coeff_int (frac, r->n_phases, 31, ic);
+      for (i = 0; i < n; i++) {
+        /* (c0 - c1) * x + (c1 << 31), in 64 bits; the store truncates */
+        uint64_t t = (uint64_t) (((int64_t) a[i] - (int64_t) b[i]) * ic[0]) + ((uint64_t) (int64_t) b[i] << 31);
+        ((int32_t *) res)[i] = (int32_t) (uint32_t) ((int64_t) (t + ((uint64_t) 1 << 30)) >> 31);
+      }
+    } else if (r->linear) {     /* interpolate_gdouble_linear_sse2 (audio-resampler-x86-sse2.c:344-366) */
+      const double *a = (const double *) c0, *b = a + n;
+      double ic[4];
+      linear_coeff_f64 (frac, r->n_phases, ic);
+      for (i = 0; i < n; i++) {
+        double t0 = a[i] * ic[0], t1 = b[i] * ic[1];
+        ((double *) res)[i] = t0 + t1;
+      }
+    } else if (r->fmt == ORACLE_AFMT_S16) {    /* interpolate_gint16_cubic_sse2: 32-bit sums, +2^14, >>15, packs */
       const int16_t *a = (const int16_t *) c0, *b = a + n, *c = b + n, *d = c + n;
       int64_t ic[4];
       cubic_coeff_int (frac, r->n_phases, 15, ic);
@@ -514,6 +602,23 @@ resample_one_any (OracleArs * r, const void *a, int phase, void *o)
       for (i = 0; i < n; i++)
         sum += (uint32_t) (x[i] * (int32_t) t[i]);
       *(int16_t *) o = (int16_t) sat64 ((int32_t) (sum + (1u << 14)) >> 15, -32768, 32767);
+    } else if (r->linear) {     /* get_taps_gint16_linear + inner_product_gint16_linear_1_sse2 (audio-resampler-x86-sse2.c:57-108) */
+      int pos = phase * r->oversample, offset = (r->oversample - 1) - pos / r->out_rate;
+      const int16_t *c = (const int16_t *) r->table + (size_t) offset * n;
+      int64_t ic[4];
+      uint32_t s[2][4], acc = 0;
+      int l;
+      linear_coeff_int (pos % r->out_rate, r->out_rate, 15, ic);
+      memset (s, 0, sizeof (s));
+      /* pmaddwd: 32-bit lane l sums the tap pairs (2l, 2l+1) of every group of eight */
+      for (k = 0; k < 2; k++)
+        for (i = 0; i < n; i++)
+          s[k][(i >> 1) & 3] += (uint32_t) (x[i] * (int32_t) c[(size_t) k * n + i]);
+      /* every LANE: srai 15, then pmaddwd of its low 16 bits with the coefficient, before the lanes meet */
+      for (k = 0; k < 2; k++)
+        for (l = 0; l < 4; l++)
+          acc += (uint32_t) ((int32_t) (int16_t) ((int32_t) s[k][l] >> 15) * (int32_t) (int16_t) ic[k]);
+      *(int16_t *) o = (int16_t) sat64 ((int32_t) (acc + (1u << 14)) >> 15, -32768, 32767);
     } else {                    /* get_taps_gint16_cubic + inner_product_gint16_cubic_1_sse2 */
       int pos = phase * r->oversample, offset = (r->oversample - 1) - pos / r->out_rate;
       const int16_t *c = (const int16_t *) r->table + (size_t) offset * n;
@@ -536,20 +641,24 @@ resample_one_any (OracleArs * r, const void *a, int phase, void *o)
       for (i = 0; i < n; i++)
         sum += (uint64_t) ((int64_t) x[i] * t[i]);
       *(int32_t *) o = (int32_t) sat64 (((int64_t) sum + (1 << 30)) >> 31, lo, hi);
-    } else {                    /* inner_product_gint32_cubic_1_sse41 */
+    } else {                    /* inner_product_gint32_cubic_1_sse41 / _linear_1_sse41 (audio-resampler-x86-sse41.c:70-112): the
+                                 * same lane arithmetic over four or two table rows */
       int pos = phase * r->oversample, offset = (r->oversample - 1) - pos / r->out_rate;
       const int32_t *c = (const int32_t *) r->table + (size_t) offset * n;
       int64_t ic[4];
       uint64_t s[4][2], acc = 0;
       int l;
-      cubic_coeff_int (pos % r->out_rate, r->out_rate, 31, ic);
+      if (r->linear)
+        linear_coeff_int (pos % r->out_rate, r->out_rate, 31, ic);
+      else
+        cubic_coeff_int (pos % r->out_rate, r->out_rate, 31, ic);
       memset (s, 0, sizeof (s));
       /* two 64-bit lanes per row: pmuldq of (a0,a1 | a2,a3) pairs puts even taps in lane 0, odd taps in lane 1 */
-      for (k = 0; k < 4; k++)
+      for (k = 0; k < r->isize; k++)
         for (i = 0; i < n; i++)
           s[k][i & 1] += (uint64_t) ((int64_t) x[i] * c[(size_t) k * n + i]);
       /* each LANE is shifted (srli 31) and multiplied (pmuldq: low 32 bits, signed) before the lanes meet */
-      for (k = 0; k < 4; k++)
+      for (k = 0; k < r->isize; k++)
         for (l = 0; l < 2; l++)
           acc += (uint64_t) ((int64_t) (int32_t) (uint32_t) (s[k][l] >> 31) * (int64_t) (int32_t) ic[k]);
       *(int32_t *) o = (int32_t) sat64 (((int64_t) acc + (1 << 30)) >> 31, lo, hi);
@@ -565,6 +674,24 @@ resample_one_any (OracleArs * r, const void *a, int phase, void *o)
         s1 = s1 + p1;
       }
       *(double *) o = s0 + s1;
+    } else if (r->linear) {     /* inner_product_gdouble_linear_1_sse2 (audio-resampler-x86-sse2.c:195-220) */
+      int pos = phase * r->oversample, offset = (r->oversample - 1) - pos / r->out_rate;
+      const double *c = (const double *) r->table + (size_t) offset * n;
+      double ic[4], s[2][2], l[2];
+      linear_coeff_f64 (pos % r->out_rate, r->out_rate, ic);
+      memset (s, 0, sizeof (s));
+      for (i = 0; i < n; i += 2)
+        for (k = 0; k < 2; k++) {
+          double p0 = x[i] * c[(size_t) k * n + i], p1 = x[i + 1] * c[(size_t) k * n + i + 1];
+          s[k][0] = s[k][0] + p0;
+          s[k][1] = s[k][1] + p1;
+        }
+      for (i = 0; i < 2; i++) {
+        double d = s[0][i] - s[1][i];
+        d = d * ic[0];
+        l[i] = d + s[1][i];
+      }
+      *(double *) o = l[0] + l[1];
     } else {                    /* inner_product_gdouble_cubic_1_sse2 */
       int pos = phase * r->oversample, offset = (r->oversample - 1) - pos / r->out_rate;
       const double *c = (const double *) r->table + (size_t) offset * n;
@@ -703,9 +830,14 @@ oracle_ars_process (OracleArs * r, const float *in, size_t in_frames, float *out
       } else {                  /* get_taps_gfloat_cubic, :567-600 */
         int pos = samp_phase * r->oversample, offset = (r->oversample - 1) - pos / r->out_rate;
         float ic[4];
+        if (r->linear) {        /* get_taps_gfloat_linear */
+          linear_coeff (pos % r->out_rate, r->out_rate, ic);
+          out[di * ch + c] = dot_linear (ipp, r->table + (size_t) offset * r->n_taps, r->n_taps, r->n_taps, ic);
+        } else {
         cubic_coeff (pos % r->out_rate, r->out_rate, ic);
         out[di * ch + c] = dot_cubic (ipp, r->table + (size_t) offset * r->n_taps, r->n_taps,
             r->n_taps, ic);
+        }
       }
       samp_index += r->samp_inc;
       samp_phase += r->samp_frac;

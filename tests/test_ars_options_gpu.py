@@ -1,7 +1,8 @@
 """cudaaudioresample with the element's resample-method / sinc-filter-mode / sinc-filter-interpolation properties at
-non-default values (blackman-nuttall window, forced full / interpolated tables, no table interpolation).  Only the host
-side changes (tap tables and the mode decision — checked against the oracle bit for bit in tests/test_host_plan.py); the
-device kernels are the ones the default configuration runs.  Still: written after this round's device budget was
+non-default values (blackman-nuttall window, forced full / interpolated tables, linear or no table interpolation).  Only the
+host side changes (tap tables and the mode decision — checked against the oracle bit for bit in tests/test_host_plan.py) and
+the device kernels are the ones the default configuration runs — except for linear interpolation in the interpolated filter
+mode, whose two-row blend is new device code (emulation-checked; the product gates it behind B200_VCS_EXPERIMENTAL).  Still: written after this round's device budget was
 spent, so skipped unless B200_TEST_EXPERIMENTAL=1.  Run next round:
   B200_TEST_EXPERIMENTAL=1 python -m pytest tests/test_ars_options_gpu.py -q"""
 import os
@@ -16,15 +17,18 @@ pytestmark = [pytest.mark.gpu,
 
 M = {"blackman-nuttall": 3, "kaiser": 4}
 MO = {"interpolated": 0, "full": 1, "auto": 2}
-I = {"none": 0, "cubic": 2}
+I = {"none": 0, "linear": 1, "cubic": 2}
 
 
 @pytest.mark.parametrize("fmt", ["F32", "S16", "S32", "F64"])
 @pytest.mark.parametrize("method,mode,interp", [("blackman-nuttall", "auto", "cubic"), ("blackman-nuttall", "full", "none"),
                                                 ("kaiser", "full", "cubic"), ("kaiser", "full", "none"),
                                                 ("kaiser", "interpolated", "cubic"), ("kaiser", "interpolated", "none"),
-                                                ("blackman-nuttall", "interpolated", "cubic"), ("kaiser", "auto", "none")])
-def test_method_and_filter_mode_properties(cuda_device, fmt, method, mode, interp):
+                                                ("blackman-nuttall", "interpolated", "cubic"), ("kaiser", "auto", "none"),
+                                                ("kaiser", "full", "linear"), ("kaiser", "interpolated", "linear"),
+                                                ("blackman-nuttall", "auto", "linear")])
+def test_method_and_filter_mode_properties(cuda_device, fmt, method, mode, interp, monkeypatch):
+    monkeypatch.setenv("B200_VCS_EXPERIMENTAL", "1")
     import torch
     from gstreamer_b200.audio import CudaAudioResample
     ofmt, gfmt, dt, _ = ob.AUDIO_FORMATS[fmt]

@@ -326,12 +326,13 @@ def test_compositor_kernel(emu, fmt, background):
 
 
 AUDIO_OPTS = [("kaiser", "auto", "cubic"), ("blackman-nuttall", "auto", "cubic"), ("kaiser", "full", "none"),
-              ("kaiser", "interpolated", "cubic"), ("blackman-nuttall", "full", "none"), ("kaiser", "interpolated", "none")]
+              ("kaiser", "interpolated", "cubic"), ("blackman-nuttall", "full", "none"), ("kaiser", "interpolated", "none"),
+              ("kaiser", "full", "linear"), ("kaiser", "interpolated", "linear"), ("blackman-nuttall", "interpolated", "linear")]
 
 
 @pytest.mark.parametrize("fmt", ["F32", "S16", "S32", "F64"])
 @pytest.mark.parametrize("opts", AUDIO_OPTS, ids=lambda o: "-".join(o))
-def test_audio_kernels(emu, fmt, opts):
+def test_audio_kernels(emu, fmt, opts, monkeypatch):
     """the resampler kernels (tiled F32 / S16, direct S32 / F64, interpolated) with the default configuration and with the
     element's resample-method / sinc-filter-* properties, bit for bit against the oracle — the first end-to-end check of
     those option sets through the product's own kernel code"""
@@ -342,7 +343,8 @@ def test_audio_kernels(emu, fmt, opts):
     o = ob.oracle()
     M = {"blackman-nuttall": 3, "kaiser": 4}
     MO = {"interpolated": 0, "full": 1, "auto": 2}
-    I = {"none": 0, "cubic": 2}
+    I = {"none": 0, "linear": 1, "cubic": 2}
+    monkeypatch.setenv("B200_VCS_EXPERIMENTAL", "1")          # the linear blend of the interpolated mode is opt-in
     for (a, b, ch, q) in [(48000, 44100, 2, 4), (44100, 48000, 66, 2) if fmt in ("F32", "S16") else (96000, 44100, 1, 6)]:
         ho = o.oracle_ars_new_opts(a, b, ch, q, ofmt, M[method], MO[mode], I[interp])
         cfg = _lib.ArsConfigC()

@@ -344,12 +344,15 @@ def test_compositor_pad_sizing_policy():
     assert (pad.width, pad.height, pad.x_offset, pad.y_offset, pad.stride) == (640, 360, 0, 140, 2560)
 
 
-def test_audioresample_remaining_properties():
+def test_audioresample_remaining_properties(monkeypatch):
     import gstreamer_b200 as g
+    monkeypatch.delenv("B200_VCS_EXPERIMENTAL", raising=False)
     from gstreamer_b200.audio import CudaAudioResample
     CudaAudioResample(cuda_device_id=-1, resample_method="kaiser", sinc_filter_auto_threshold=1).set_caps(48000, 44100, 2)
+    # linear table interpolation: FULL mode is host work only; the interpolated mode's blend is opt-in device code
+    CudaAudioResample(cuda_device_id=-1, sinc_filter_interpolation="linear").set_caps(48000, 44100, 2)
     for kw in ({"resample_method": "linear"}, {"resample_method": "nearest"}, {"resample_method": "cubic"},
-               {"sinc_filter_interpolation": "linear"}):
+               {"sinc_filter_interpolation": "linear", "sinc_filter_mode": "interpolated"}):
         with pytest.raises(g.B200Error) as e:
             CudaAudioResample(cuda_device_id=-1, **kw).set_caps(48000, 44100, 2)
         assert e.value.status == -2
@@ -358,15 +361,19 @@ def test_audioresample_remaining_properties():
 @pytest.mark.parametrize("method,mode,interp", [("blackman-nuttall", "auto", "cubic"), ("blackman-nuttall", "full", "none"),
                                                 ("kaiser", "full", "cubic"), ("kaiser", "full", "none"),
                                                 ("kaiser", "interpolated", "cubic"), ("kaiser", "interpolated", "none"),
-                                                ("blackman-nuttall", "interpolated", "cubic"), ("kaiser", "auto", "none")])
-def test_audio_method_and_filter_mode_plans(method, mode, interp):
+                                                ("blackman-nuttall", "interpolated", "cubic"), ("kaiser", "auto", "none"),
+                                                ("kaiser", "full", "linear"), ("blackman-nuttall", "auto", "linear"),
+                                                ("kaiser", "interpolated", "linear")])
+def test_audio_method_and_filter_mode_plans(method, mode, interp, monkeypatch):
     """host plan == oracle (pinned to the reference for these options) for the filter design, the mode decision and -
     FULL mode, F32 - every phase's taps bit for bit"""
     from gstreamer_b200.audio import CudaAudioResample
     o = ob.oracle()
     M = {"blackman-nuttall": 3, "kaiser": 4}
     MO = {"interpolated": 0, "full": 1, "auto": 2}
-    I = {"none": 0, "cubic": 2}
+    I = {"none": 0, "linear": 1, "cubic": 2}
+    if (mode, interp) == ("interpolated", "linear"):
+        monkeypatch.setenv("B200_VCS_EXPERIMENTAL", "1")
     for (a, b, q) in [(48000, 44100, 4), (44100, 48000, 6), (8000, 16000, 0), (96000, 44100, 8), (101, 99, 10)]:
         rs = CudaAudioResample(quality=q, cuda_device_id=-1, resample_method=method, sinc_filter_mode=mode,
                                sinc_filter_interpolation=interp)

@@ -550,10 +550,11 @@ def test_destination_rectangle_and_borders_match_reference(pair):
 
 @pytest.mark.parametrize("fmt", ["F32", "S16", "S32", "F64"])
 @pytest.mark.parametrize("method,mode,interp", [(3, 2, 2), (3, 1, 2), (3, 0, 2), (4, 1, 2), (4, 0, 2), (4, 1, 0), (3, 1, 0),
-                                                (4, 2, 0), (4, 0, 0), (3, 2, 0)])
+                                                (4, 2, 0), (4, 0, 0), (3, 2, 0),
+                                                (4, 2, 1), (4, 1, 1), (4, 0, 1), (3, 1, 1), (3, 0, 1)])
 def test_audio_method_and_filter_mode_properties(fmt, method, mode, interp):
     """resample-method kaiser / blackman-nuttall, sinc-filter-mode interpolated / full / auto, sinc-filter-interpolation
-    cubic / none (FULL mode then computes every phase's taps directly; an interpolated table falls back to cubic with an
+    cubic / linear (two table rows per phase, 11x the oversampling) / none (FULL mode then computes every phase's taps directly; an interpolated table falls back to cubic with an
     oversampling of 1) — byte-identical output for every sample format"""
     import ctypes as C
     ofmt, gfmt, dt, _ = ob.AUDIO_FORMATS[fmt]
