@@ -124,8 +124,9 @@ enum { ORACLE_AFMT_F32 = 0, ORACLE_AFMT_S16 = 1, ORACLE_AFMT_S32 = 2, ORACLE_AFM
 OracleArs *oracle_ars_new_fmt (int in_rate, int out_rate, int channels, int quality, int fmt);
 /* the element's resample-method / sinc-filter-mode / sinc-filter-interpolation properties (gstaudioresample.c:160-186,
  * make_options :374-396); values are the reference's enums (audio-resampler.h:104-106, :138-140, :169-178).  Restated:
- * kaiser and blackman-nuttall, every filter mode, every table interpolation. */
-enum { ORACLE_ARS_METHOD_BLACKMAN_NUTTALL = 3, ORACLE_ARS_METHOD_KAISER = 4 };
+ * every method, every filter mode, every table interpolation. */
+enum { ORACLE_ARS_METHOD_NEAREST = 0, ORACLE_ARS_METHOD_LINEAR = 1, ORACLE_ARS_METHOD_CUBIC = 2,
+  ORACLE_ARS_METHOD_BLACKMAN_NUTTALL = 3, ORACLE_ARS_METHOD_KAISER = 4 };
 enum { ORACLE_ARS_MODE_INTERPOLATED = 0, ORACLE_ARS_MODE_FULL = 1, ORACLE_ARS_MODE_AUTO = 2 };
 enum { ORACLE_ARS_INTERP_NONE = 0, ORACLE_ARS_INTERP_LINEAR = 1, ORACLE_ARS_INTERP_CUBIC = 2 };
 OracleArs *oracle_ars_new_opts (int in_rate, int out_rate, int channels, int quality, int fmt, int method,

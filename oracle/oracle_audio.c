@@ -131,7 +131,18 @@ make_row (const OracleArs * r, void *res, double x)
   for (i = 0; i < n; i++) {
     double xx = x + i, y = M_PI * xx, s, w;
     s = (y == 0.0 ? r->cutoff : sin (y * r->cutoff) / y);
-    if (r->method == ORACLE_ARS_METHOD_BLACKMAN_NUTTALL) {      /* get_blackman_nuttall_tap, audio-resampler.c:192-203 */
+    if (r->method == ORACLE_ARS_METHOD_LINEAR) {        /* get_linear_tap, audio-resampler.c:163-168 */
+      tmp[i] = ((n + 1) & ~1) / 2 - fabs (xx);
+    } else if (r->method == ORACLE_ARS_METHOD_CUBIC) {  /* get_cubic_tap :170-190 with the default b = 1, c = 0 (:97-98) */
+      const double b = 1.0, c = 0.0;
+      double a = fabs (xx * 4.0) / n, a2 = a * a, a3 = a2 * a;
+      if (a <= 1.0)
+        tmp[i] = ((12.0 - 9.0 * b - 6.0 * c) * a3 + (-18.0 + 12.0 * b + 6.0 * c) * a2 + (6.0 - 2.0 * b)) / 6.0;
+      else if (a <= 2.0)
+        tmp[i] = ((-b - 6.0 * c) * a3 + (6.0 * b + 30.0 * c) * a2 + (-12.0 * b - 48.0 * c) * a + (8.0 * b + 24.0 * c)) / 6.0;
+      else
+        tmp[i] = 0.0;
+    } else if (r->method == ORACLE_ARS_METHOD_BLACKMAN_NUTTALL) {      /* get_blackman_nuttall_tap, audio-resampler.c:192-203 */
       w = 2.0 * y / n + M_PI;
       tmp[i] = s * (0.3635819 - 0.4891775 * cos (w) + 0.1365995 * cos (2 * w) - 0.0106411 * cos (3 * w));
     } else {                    /* get_kaiser_tap, :205-215 */
@@ -181,10 +192,10 @@ oracle_ars_new_opts (int in_rate, int out_rate, int channels, int quality, int f
     return NULL;
   if (fmt < 0 || fmt > ORACLE_AFMT_F64)
     return NULL;
-  if ((method != ORACLE_ARS_METHOD_KAISER && method != ORACLE_ARS_METHOD_BLACKMAN_NUTTALL) ||
+  if (method < ORACLE_ARS_METHOD_NEAREST || method > ORACLE_ARS_METHOD_KAISER ||
       filter_mode < ORACLE_ARS_MODE_INTERPOLATED || filter_mode > ORACLE_ARS_MODE_AUTO ||
       interpolation < ORACLE_ARS_INTERP_NONE || interpolation > ORACLE_ARS_INTERP_CUBIC)
-    return NULL;                /* nearest / linear / cubic methods: not restated */
+    return NULL;
   r = calloc (1, sizeof (*r));
   r->method = method;
   r->channels = channels;
@@ -219,11 +230,20 @@ oracle_ars_new_opts (int in_rate, int out_rate, int channels, int quality, int f
     r->n_taps = blackman_q[quality].n_taps;
     r->cutoff = blackman_q[quality].cutoff;
   }
-  if (r->out_rate < r->in_rate) {
+  /* the methods without a sinc table (resampler_calculate_taps :1070-1117): 2 taps (nearest: never scaled), 2 (linear),
+   * 4 (cubic; options_set_quality :1286-1297); no rounding up to 8 - the SIMD inner products run into the 16 zero taps
+   * every table row ends with (TAPS_OVERREAD :34, :979), which changes no sum; FULL mode, no table interpolation */
+  if (method <= ORACLE_ARS_METHOD_CUBIC) {
+    r->n_taps = method == ORACLE_ARS_METHOD_CUBIC ? 4 : 2;
+    filter_mode = ORACLE_ARS_MODE_FULL;
+    interpolation = ORACLE_ARS_INTERP_NONE;
+  }
+  if (r->out_rate < r->in_rate && method != ORACLE_ARS_METHOD_NEAREST) {
     r->cutoff = r->cutoff * r->out_rate / r->in_rate;
     r->n_taps = (int) (((unsigned long long) r->n_taps * r->in_rate) / r->out_rate);
   }
-  r->n_taps = ROUND_UP_8 (r->n_taps);
+  if (method > ORACLE_ARS_METHOD_CUBIC)
+    r->n_taps = ROUND_UP_8 (r->n_taps);
   /* cubic filter interpolation: oversampling from the quality, halved while the decimation
    * ratio allows it (audio-resampler.c:1119-1140) */
   if (interpolation != ORACLE_ARS_INTERP_NONE) {
@@ -363,7 +383,7 @@ oracle_ars_info (OracleArs * r, int *n_taps, int *n_phases, int *in_step, int *o
     int *filter_mode, int *oversample)
 {
   *n_taps = r->n_taps;
-  *n_phases = r->full ? r->n_phases : 0;  /* only the FULL mode sets n_phases (audio-resampler.c:1173-1178) */
+  *n_phases = r->full && r->method != ORACLE_ARS_METHOD_NEAREST ? r->n_phases : 0;  /* only the FULL mode sets n_phases (audio-resampler.c:1173-1178) */
   *in_step = r->in_rate;
   *out_step = r->out_rate;
   *filter_mode = r->full ? 1 : 0;       /* GST_AUDIO_RESAMPLER_FILTER_MODE_{INTERPOLATED=0,FULL=1} */
@@ -403,7 +423,7 @@ dot_full (const float *a, const float *b, int len)
   float s[4] = { 0, 0, 0, 0 };
   int i, l;
   for (i = 0; i < len; i += 4)
-    for (l = 0; l < 4; l++) {
+    for (l = 0; l < 4 && i + l < len; l++) {    /* a tap count off the lane width ends in the row's zero taps */
       float p = a[i + l] * b[i + l];
       s[l] = s[l] + p;
     }
@@ -594,6 +614,10 @@ static void
 resample_one_any (OracleArs * r, const void *a, int phase, void *o)
 {
   int n = r->n_taps, i, k;
+  if (r->method == ORACLE_ARS_METHOD_NEAREST) {   /* inner_product_<type>_nearest_1_c (audio-resampler.c:602-612): *o = *a */
+    memcpy (o, a, r->bps);
+    return;
+  }
   if (r->fmt == ORACLE_AFMT_S16) {
     const int16_t *x = a;
     if (r->full) {              /* inner_product_gint16_full_1_sse2 */
@@ -669,7 +693,7 @@ resample_one_any (OracleArs * r, const void *a, int phase, void *o)
       const double *t = phase_taps_any (r, phase);
       double s0 = 0, s1 = 0;
       for (i = 0; i < n; i += 2) {
-        double p0 = x[i] * t[i], p1 = x[i + 1] * t[i + 1];
+        double p0 = x[i] * t[i], p1 = i + 1 < n ? x[i + 1] * t[i + 1] : 0.0;
         s0 = s0 + p0;
         s1 = s1 + p1;
       }
@@ -825,7 +849,9 @@ oracle_ars_process (OracleArs * r, const float *in, size_t in_frames, float *out
     samp_phase = r->samp_phase;
     for (di = 0; di < out_frames; di++) {
       const float *ipp = ip + samp_index;
-      if (r->full) {
+      if (r->method == ORACLE_ARS_METHOD_NEAREST) {       /* inner_product_gfloat_nearest_1_c */
+        out[di * ch + c] = ipp[0];
+      } else if (r->full) {
         out[di * ch + c] = dot_full (ipp, phase_taps (r, samp_phase), r->n_taps);
       } else {                  /* get_taps_gfloat_cubic, :567-600 */
         int pos = samp_phase * r->oversample, offset = (r->oversample - 1) - pos / r->out_rate;

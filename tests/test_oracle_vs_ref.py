@@ -551,7 +551,8 @@ def test_destination_rectangle_and_borders_match_reference(pair):
 @pytest.mark.parametrize("fmt", ["F32", "S16", "S32", "F64"])
 @pytest.mark.parametrize("method,mode,interp", [(3, 2, 2), (3, 1, 2), (3, 0, 2), (4, 1, 2), (4, 0, 2), (4, 1, 0), (3, 1, 0),
                                                 (4, 2, 0), (4, 0, 0), (3, 2, 0),
-                                                (4, 2, 1), (4, 1, 1), (4, 0, 1), (3, 1, 1), (3, 0, 1)])
+                                                (4, 2, 1), (4, 1, 1), (4, 0, 1), (3, 1, 1), (3, 0, 1),
+                                                (0, 2, 2), (1, 2, 2), (2, 2, 2), (1, 0, 1), (2, 1, 0)])
 def test_audio_method_and_filter_mode_properties(fmt, method, mode, interp):
     """resample-method kaiser / blackman-nuttall, sinc-filter-mode interpolated / full / auto, sinc-filter-interpolation
     cubic / linear (two table rows per phase, 11x the oversampling) / none (FULL mode then computes every phase's taps directly; an interpolated table falls back to cubic with an
@@ -559,7 +560,8 @@ def test_audio_method_and_filter_mode_properties(fmt, method, mode, interp):
     import ctypes as C
     ofmt, gfmt, dt, _ = ob.AUDIO_FORMATS[fmt]
     o, r = ob.oracle(), ob.ref()
-    for (a, b, ch, q) in [(48000, 44100, 2, 4), (44100, 48000, 1, 6), (8000, 16000, 2, 2), (96000, 44100, 1, 8), (44100, 44099, 1, 3)]:
+    for (a, b, ch, q) in [(48000, 44100, 2, 4), (44100, 48000, 1, 6), (8000, 16000, 2, 2), (96000, 44100, 1, 8), (44100, 44099, 1, 3),
+                          (3, 2, 1, 5), (48000, 8000, 2, 1)]:
         ho = o.oracle_ars_new_opts(a, b, ch, q, ofmt, method, mode, interp)
         hr = r.ref_ars_new_opts(a, b, ch, q, gfmt, method, mode, interp)
         assert ho and hr
