@@ -60,6 +60,7 @@ struct ArsPlan {
   int n_taps = 0, oversample = 0, n_phases = 0;
   bool full = false;
   bool blackman = false;         // resample-method=blackman-nuttall (else kaiser)
+  int small = 0;                 // resample-method nearest (1) / linear (2) / cubic (3): a few taps, no sinc table, FULL mode
   bool linear = false;           // sinc-filter-interpolation=linear: two prototype rows per phase, 11x the oversampling
   int isize = 4;                 // prototype rows one phase reads (4 cubic, 2 linear)
   bool interp_none = false;      // FULL mode with sinc-filter-interpolation=none: every phase's taps computed directly
@@ -171,8 +172,12 @@ static int build_ars_plan (const b200_ars_config & cfg, ArsPlan * p)
   p->cutoff = fc;
   // the element's other properties: only what needs no new device code - both windowed-sinc methods, every filter
   // mode, and every table interpolation
-  if (cfg.resample_method != 0 && cfg.resample_method != B200_ARS_METHOD_KAISER && cfg.resample_method != B200_ARS_METHOD_BLACKMAN_NUTTALL)
-    return B200_ERR_UNSUPPORTED;
+  if (cfg.resample_method < 0 || cfg.resample_method > B200_ARS_METHOD_KAISER) return B200_ERR_INVALID_ARG;
+  // nearest / linear / cubic run in their own small kernel, which no device session has checked yet
+  if (cfg.resample_method >= B200_ARS_METHOD_NEAREST && cfg.resample_method <= B200_ARS_METHOD_CUBIC) {
+    if (!getenv ("B200_VCS_EXPERIMENTAL")) return B200_ERR_UNSUPPORTED;
+    p->small = cfg.resample_method;
+  }
   if (cfg.sinc_filter_mode < 0 || cfg.sinc_filter_mode > B200_ARS_FILTER_MODE_AUTO) return B200_ERR_INVALID_ARG;
   if (cfg.sinc_filter_interpolation < 0 || cfg.sinc_filter_interpolation > B200_ARS_FILTER_INTERPOLATION_CUBIC)
     return B200_ERR_INVALID_ARG;
@@ -183,23 +188,28 @@ static int build_ars_plan (const b200_ars_config & cfg, ArsPlan * p)
     p->n_taps = kBlackman[cfg.quality].n_taps;
     p->cutoff = kBlackman[cfg.quality].cutoff;
   }
-  const bool no_interp = cfg.sinc_filter_interpolation == B200_ARS_FILTER_INTERPOLATION_NONE;
-  if (p->out_step < p->in_step) {
+  // the methods without a sinc table (resampler_calculate_taps :1070-1117): 2 taps (nearest, never scaled), 2 (linear),
+  // 4 (cubic, options_set_quality :1286-1297), not rounded up to 8; FULL mode with no table interpolation
+  if (p->small) p->n_taps = p->small == B200_ARS_METHOD_CUBIC ? 4 : 2;
+  const bool no_interp = p->small || cfg.sinc_filter_interpolation == B200_ARS_FILTER_INTERPOLATION_NONE;
+  if (p->out_step < p->in_step && p->small != B200_ARS_METHOD_NEAREST) {
     p->cutoff = p->cutoff * p->out_step / p->in_step;
     p->n_taps = (int) (((unsigned long long) p->n_taps * p->in_step) / p->out_step);
   }
-  p->n_taps = (p->n_taps + 7) & ~7;
+  if (!p->small) p->n_taps = (p->n_taps + 7) & ~7;
   int over = kOversample[cfg.quality];
   for (int mult = 2; over > 1 && mult * p->out_step < p->in_step; mult *= 2) over >>= 1;
   if (no_interp) over = 1;              // audio-resampler.c:1141-1143
-  p->linear = cfg.sinc_filter_interpolation == B200_ARS_FILTER_INTERPOLATION_LINEAR;
+  p->linear = !p->small && cfg.sinc_filter_interpolation == B200_ARS_FILTER_INTERPOLATION_LINEAR;
   if (p->linear) over *= 11;            // :1131-1137
   p->isize = p->linear ? 2 : 4;         // :1186-1197
   const int isize = p->isize;
   p->oversample = over;
   // filter-mode auto with the element's VARIABLE_RATE flag: FULL when the whole phase table is
   // below the (effectively fixed) 1 MiB threshold (audio-resampler.c:1147-1166)
-  if (cfg.sinc_filter_mode == 0 || cfg.sinc_filter_mode == B200_ARS_FILTER_MODE_AUTO)
+  if (p->small)
+    p->full = true;
+  else if (cfg.sinc_filter_mode == 0 || cfg.sinc_filter_mode == B200_ARS_FILTER_MODE_AUTO)
     p->full = (long long) p->bps * p->n_taps * p->out_step < 1048576;     // bps * n_taps * out_rate, :1153
   else
     p->full = cfg.sinc_filter_mode == B200_ARS_FILTER_MODE_FULL;
@@ -221,7 +231,14 @@ static int build_ars_plan (const b200_ars_config & cfg, ArsPlan * p)
     for (int i = 0; i < n; i++) {
       const double x = x0 + i, y = M_PI * x;
       const double s = (y == 0.0 ? p->cutoff : sin (y * p->cutoff) / y);
-      if (p->blackman) {                   // get_blackman_nuttall_tap, :192-203
+      if (p->small == B200_ARS_METHOD_LINEAR) {            // get_linear_tap, :163-168
+        tmp[i] = ((n + 1) & ~1) / 2 - fabs (x);
+      } else if (p->small == B200_ARS_METHOD_CUBIC) {      // get_cubic_tap :170-190, b = 1, c = 0 (:97-98)
+        const double b = 1.0, c = 0.0, a = fabs (x * 4.0) / n, a2 = a * a, a3 = a2 * a;
+        if (a <= 1.0) tmp[i] = ((12.0 - 9.0 * b - 6.0 * c) * a3 + (-18.0 + 12.0 * b + 6.0 * c) * a2 + (6.0 - 2.0 * b)) / 6.0;
+        else if (a <= 2.0) tmp[i] = ((-b - 6.0 * c) * a3 + (6.0 * b + 30.0 * c) * a2 + (-12.0 * b - 48.0 * c) * a + (8.0 * b + 24.0 * c)) / 6.0;
+        else tmp[i] = 0.0;
+      } else if (p->blackman) {            // get_blackman_nuttall_tap, :192-203
         const double w = 2.0 * y / n + M_PI;
         tmp[i] = s * (0.3635819 - 0.4891775 * cos (w) + 0.1365995 * cos (2 * w) - 0.0106411 * cos (3 * w));
       } else {                             // get_kaiser_tap, :205-215
@@ -239,6 +256,13 @@ static int build_ars_plan (const b200_ars_config & cfg, ArsPlan * p)
   for (int row = 0; row < over + isize; row++)
     make_row (-(n / 2) + row / (double) over, &p->proto[(size_t) row * n],
         p->fmt != ARS_F32 ? p->proto_x.data () + (size_t) row * n * p->bps : nullptr);
+  if (p->small == B200_ARS_METHOD_NEAREST) {
+    // no taps at all (make_taps :294-295, n_phases stays 0): one zero row so that the tables are never empty
+    p->n_phases = 0;
+    if (p->fmt == ARS_F32) p->phases.assign ((size_t) n, 0.f);
+    else p->phases_x.assign ((size_t) n * p->bps, 0);
+    return B200_OK;
+  }
   if (p->interp_none) {
     // GST_AUDIO_RESAMPLER_FILTER_INTERPOLATION_NONE in FULL mode (get_taps_<type>_full :517-525): x = 1 - n/2 - phase/n_phases
     if (p->fmt == ARS_F32) p->phases.assign ((size_t) p->n_phases * n, 0.f);
@@ -909,6 +933,58 @@ ars_direct_kernel (const ArsLaunchX L)
   }
 }
 
+// resample-method nearest / linear / cubic: a handful of taps per output (2, 4, or those scaled by the decimation
+// ratio; any count, odd ones included), FULL mode.  The reference's SIMD inner products run past n_taps into the zero
+// taps every table row ends with (TAPS_OVERREAD, audio-resampler.c:34), which changes no sum, so the lanes here simply
+// stop at n_taps: F32 four lanes by tap index mod 4 and (l0 + l2) + (l1 + l3) (inner_product_gfloat_full_1_sse), F64 two
+// lanes by parity, the integer sums exact.  Nearest copies the first sample of the window
+// (inner_product_<type>_nearest_1_c :602-612).  Warp = one output frame x 32 channels.
+template <int FMT>
+__global__ void __launch_bounds__ (ARS_THREADS)
+ars_small_kernel (const ArsLaunchX L, int nearest)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long o = (long long) blockIdx.x * (ARS_THREADS / 32) + warp;
+  if (o >= L.out_frames) return;
+  const int c = blockIdx.y * 32 + lane;
+  if (c >= L.channels) return;
+  const long long t0 = (long long) L.samp_phase + o * L.samp_frac;
+  const long long idx = (long long) L.samp_index + o * L.samp_inc + t0 / L.out_step;
+  const int phase = (int) (t0 % L.out_step), n = L.n_taps;
+  const size_t at = (size_t) o * L.channels + c, row0 = (size_t) phase * n;
+  if (FMT == ARS_S16) {
+    if (nearest) { ((short *) L.out)[at] = ars_sample<short> (L, idx, c); return; }
+    const short *tab = (const short *) L.table + row0;
+    unsigned sum = 0;
+    for (int i = 0; i < n; i++) sum += (unsigned) ((int) ars_sample<short> (L, idx + i, c) * (int) __ldg (tab + i));
+    ((short *) L.out)[at] = (short) sat_s16 ((int) (sum + (1u << 14)) >> 15);
+  } else if (FMT == ARS_S32) {
+    if (nearest) { ((int *) L.out)[at] = ars_sample<int> (L, idx, c); return; }
+    const int *tab = (const int *) L.table + row0;
+    unsigned long long sum = 0;
+    for (int i = 0; i < n; i++) sum += (unsigned long long) ((long long) ars_sample<int> (L, idx + i, c) * __ldg (tab + i));
+    ((int *) L.out)[at] = (int) sat_s32 (((long long) sum + (1 << 30)) >> 31);
+  } else if (FMT == ARS_F64) {
+    if (nearest) { ((double *) L.out)[at] = ars_sample<double> (L, idx, c); return; }
+    const double *tab = (const double *) L.table + row0;
+    double s0 = 0.0, s1 = 0.0;
+    for (int i = 0; i < n; i += 2) {
+      s0 = __dadd_rn (s0, __dmul_rn (ars_sample<double> (L, idx + i, c), __ldg (tab + i)));
+      if (i + 1 < n) s1 = __dadd_rn (s1, __dmul_rn (ars_sample<double> (L, idx + i + 1, c), __ldg (tab + i + 1)));
+    }
+    ((double *) L.out)[at] = __dadd_rn (s0, s1);
+  } else {
+    if (nearest) { ((float *) L.out)[at] = ars_sample<float> (L, idx, c); return; }
+    const float *tab = (const float *) L.table + row0;
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int i = 0; i < n; i += 4)
+#pragma unroll
+      for (int l = 0; l < 4; l++)
+        if (i + l < n) s[l] = __fadd_rn (s[l], __fmul_rn (ars_sample<float> (L, idx + i + l, c), __ldg (tab + i + l)));
+    ((float *) L.out)[at] = __fadd_rn (__fadd_rn (s[0], s[2]), __fadd_rn (s[1], s[3]));
+  }
+}
+
 // new history = frames [first, first+keep) of the (old history ++ input) stream, any sample width
 template <typename T>
 __global__ void ars_history_kernel_x (T *dst, const T *hist, const T *in, long long hist_frames,
@@ -1102,8 +1178,23 @@ int b200_ars_process (b200_ars * h, const void *in_v, size_t in_frames, void *ou
     L.row_pitch = (p.n_taps + 4 + 3) & ~3;
     L.wcn = (p.channels + 31) / 32; if (L.wcn > 8) L.wcn = 8;
     while (8 % L.wcn) L.wcn++;                                   // 1, 2, 4 or 8 warps across channels
-    bool s16_tiled = false;
-    if (p.fmt == ARS_S16 && p.full && p.channels >= 64 && !getenv ("B200_ARS_GENERIC")) {
+    bool s16_tiled = false;           // ... or the small-method kernel: launched already
+    if (p.small) {
+      ArsLaunchX X;
+      X.hist = h->d_hist[h->cur]; X.in = in_v; X.out = out_v;
+      X.table = p.fmt == ARS_F32 ? (const void *) h->d_phases : (const void *) h->d_table_x;
+      X.hist_frames = (long long) hist; X.avail = (long long) avail; X.out_frames = (long long) out_frames;
+      X.channels = p.channels; X.n_taps = p.n_taps; X.out_step = p.out_step;
+      X.samp_inc = p.samp_inc; X.samp_frac = p.samp_frac; X.samp_index = h->samp_index; X.samp_phase = h->samp_phase;
+      X.full = 1; X.oversample = 1;
+      const int nearest = p.small == B200_ARS_METHOD_NEAREST;
+      const dim3 grid ((unsigned) ((out_frames + ARS_THREADS / 32 - 1) / (ARS_THREADS / 32)), (unsigned) ((p.channels + 31) / 32));
+      if (p.fmt == ARS_S16) ars_small_kernel<ARS_S16> <<<grid, ARS_THREADS, 0, stream>>> (X, nearest);
+      else if (p.fmt == ARS_S32) ars_small_kernel<ARS_S32> <<<grid, ARS_THREADS, 0, stream>>> (X, nearest);
+      else if (p.fmt == ARS_F64) ars_small_kernel<ARS_F64> <<<grid, ARS_THREADS, 0, stream>>> (X, nearest);
+      else ars_small_kernel<ARS_F32> <<<grid, ARS_THREADS, 0, stream>>> (X, nearest);
+      s16_tiled = true;
+    } else if (p.fmt == ARS_S16 && p.full && p.channels >= 64 && !getenv ("B200_ARS_GENERIC")) {
       // tiled S16 kernel: same tile geometry as the F32 one (4-byte staged samples and taps)
       const int cb = p.channels >= 128 ? 128 : 64, no = 32;
       ArsTile tl;

@@ -241,7 +241,7 @@ typedef struct {
   /* the element's resample-method / sinc-filter-mode / sinc-filter-interpolation properties (gstaudioresample.c:160-186).
    * 0 = the element default in each; other values are the reference's enum value + 1 so that a zeroed config is the
    * default configuration: */
-  int32_t resample_method;       /* 0 or B200_ARS_METHOD_KAISER; B200_ARS_METHOD_BLACKMAN_NUTTALL; the others: unsupported */
+  int32_t resample_method;       /* 0 or B200_ARS_METHOD_KAISER; any B200_ARS_METHOD_* */
   int32_t sinc_filter_mode;      /* 0 or B200_ARS_FILTER_MODE_AUTO; _INTERPOLATED; _FULL */
   int32_t sinc_filter_interpolation;     /* 0 or B200_ARS_FILTER_INTERPOLATION_CUBIC; _NONE; _LINEAR */
   int32_t reserved[4];

@@ -1,5 +1,6 @@
 """cudaaudioresample with the element's resample-method / sinc-filter-mode / sinc-filter-interpolation properties at
-non-default values (blackman-nuttall window, forced full / interpolated tables, linear or no table interpolation).  Only the
+non-default values (blackman-nuttall window, forced full / interpolated tables, linear or no table interpolation, and the
+nearest / linear / cubic methods, which have their own small kernel).  Only the
 host side changes (tap tables and the mode decision — checked against the oracle bit for bit in tests/test_host_plan.py) and
 the device kernels are the ones the default configuration runs — except for linear interpolation in the interpolated filter
 mode, whose two-row blend is new device code (emulation-checked; the product gates it behind B200_VCS_EXPERIMENTAL).  Still: written after this round's device budget was
@@ -15,7 +16,7 @@ from oracle import bindings as ob
 pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(os.environ.get("B200_TEST_EXPERIMENTAL") != "1", reason="opt-in: B200_TEST_EXPERIMENTAL=1")]
 
-M = {"blackman-nuttall": 3, "kaiser": 4}
+M = {"nearest": 0, "linear": 1, "cubic": 2, "blackman-nuttall": 3, "kaiser": 4}
 MO = {"interpolated": 0, "full": 1, "auto": 2}
 I = {"none": 0, "linear": 1, "cubic": 2}
 
@@ -26,7 +27,8 @@ I = {"none": 0, "linear": 1, "cubic": 2}
                                                 ("kaiser", "interpolated", "cubic"), ("kaiser", "interpolated", "none"),
                                                 ("blackman-nuttall", "interpolated", "cubic"), ("kaiser", "auto", "none"),
                                                 ("kaiser", "full", "linear"), ("kaiser", "interpolated", "linear"),
-                                                ("blackman-nuttall", "auto", "linear")])
+                                                ("blackman-nuttall", "auto", "linear"),
+                                                ("nearest", "auto", "cubic"), ("linear", "auto", "cubic"), ("cubic", "auto", "cubic")])
 def test_method_and_filter_mode_properties(cuda_device, fmt, method, mode, interp, monkeypatch):
     monkeypatch.setenv("B200_VCS_EXPERIMENTAL", "1")
     import torch
@@ -34,7 +36,8 @@ def test_method_and_filter_mode_properties(cuda_device, fmt, method, mode, inter
     ofmt, gfmt, dt, _ = ob.AUDIO_FORMATS[fmt]
     tdt = {np.float32: torch.float32, np.int16: torch.int16, np.int32: torch.int32, np.float64: torch.float64}[dt]
     o = ob.oracle()
-    for (a, b, ch, q) in [(48000, 44100, 2, 4), (44100, 48000, 1, 6), (8000, 16000, 2, 0), (96000, 44100, 3, 8), (101, 99, 1, 10)]:
+    for (a, b, ch, q) in [(48000, 44100, 2, 4), (44100, 48000, 1, 6), (8000, 16000, 2, 0), (96000, 44100, 3, 8), (101, 99, 1, 10),
+                          (3, 2, 3, 5), (48000, 8000, 40, 1)]:
         ho = o.oracle_ars_new_opts(a, b, ch, q, ofmt, M[method], MO[mode], I[interp])
         rs = CudaAudioResample(quality=q, format=gfmt, resample_method=method, sinc_filter_mode=mode,
                                sinc_filter_interpolation=interp)

@@ -327,7 +327,8 @@ def test_compositor_kernel(emu, fmt, background):
 
 AUDIO_OPTS = [("kaiser", "auto", "cubic"), ("blackman-nuttall", "auto", "cubic"), ("kaiser", "full", "none"),
               ("kaiser", "interpolated", "cubic"), ("blackman-nuttall", "full", "none"), ("kaiser", "interpolated", "none"),
-              ("kaiser", "full", "linear"), ("kaiser", "interpolated", "linear"), ("blackman-nuttall", "interpolated", "linear")]
+              ("kaiser", "full", "linear"), ("kaiser", "interpolated", "linear"), ("blackman-nuttall", "interpolated", "linear"),
+              ("nearest", "auto", "cubic"), ("linear", "auto", "cubic"), ("cubic", "auto", "cubic")]
 
 
 @pytest.mark.parametrize("fmt", ["F32", "S16", "S32", "F64"])
@@ -341,11 +342,14 @@ def test_audio_kernels(emu, fmt, opts, monkeypatch):
     method, mode, interp = opts
     ofmt, gfmt, dt, _ = ob.AUDIO_FORMATS[fmt]
     o = ob.oracle()
-    M = {"blackman-nuttall": 3, "kaiser": 4}
+    M = {"nearest": 0, "linear": 1, "cubic": 2, "blackman-nuttall": 3, "kaiser": 4}
     MO = {"interpolated": 0, "full": 1, "auto": 2}
     I = {"none": 0, "linear": 1, "cubic": 2}
     monkeypatch.setenv("B200_VCS_EXPERIMENTAL", "1")          # the linear blend of the interpolated mode is opt-in
-    for (a, b, ch, q) in [(48000, 44100, 2, 4), (44100, 48000, 66, 2) if fmt in ("F32", "S16") else (96000, 44100, 1, 6)]:
+    rates = [(48000, 44100, 2, 4), (44100, 48000, 66, 2) if fmt in ("F32", "S16") else (96000, 44100, 1, 6)]
+    if M[method] < 3:                                         # tap counts off the lane widths: 3, 12; and the 96k -> 44.1k pair
+        rates += [(3, 2, 3, 5), (48000, 8000, 2, 1), (96000, 44100, 1, 6)]
+    for (a, b, ch, q) in rates:
         ho = o.oracle_ars_new_opts(a, b, ch, q, ofmt, M[method], MO[mode], I[interp])
         cfg = _lib.ArsConfigC()
         cfg.in_rate, cfg.out_rate, cfg.channels, cfg.quality, cfg.format = a, b, ch, q, gfmt

@@ -363,18 +363,21 @@ def test_audioresample_remaining_properties(monkeypatch):
                                                 ("kaiser", "interpolated", "cubic"), ("kaiser", "interpolated", "none"),
                                                 ("blackman-nuttall", "interpolated", "cubic"), ("kaiser", "auto", "none"),
                                                 ("kaiser", "full", "linear"), ("blackman-nuttall", "auto", "linear"),
-                                                ("kaiser", "interpolated", "linear")])
+                                                ("kaiser", "interpolated", "linear"),
+                                                ("nearest", "auto", "cubic"), ("linear", "auto", "cubic"),
+                                                ("cubic", "interpolated", "linear")])
 def test_audio_method_and_filter_mode_plans(method, mode, interp, monkeypatch):
     """host plan == oracle (pinned to the reference for these options) for the filter design, the mode decision and -
     FULL mode, F32 - every phase's taps bit for bit"""
     from gstreamer_b200.audio import CudaAudioResample
     o = ob.oracle()
-    M = {"blackman-nuttall": 3, "kaiser": 4}
+    M = {"nearest": 0, "linear": 1, "cubic": 2, "blackman-nuttall": 3, "kaiser": 4}
     MO = {"interpolated": 0, "full": 1, "auto": 2}
     I = {"none": 0, "linear": 1, "cubic": 2}
-    if (mode, interp) == ("interpolated", "linear"):
+    if (mode, interp) == ("interpolated", "linear") or M[method] < 3:
         monkeypatch.setenv("B200_VCS_EXPERIMENTAL", "1")
-    for (a, b, q) in [(48000, 44100, 4), (44100, 48000, 6), (8000, 16000, 0), (96000, 44100, 8), (101, 99, 10)]:
+    for (a, b, q) in [(48000, 44100, 4), (44100, 48000, 6), (8000, 16000, 0), (96000, 44100, 8), (101, 99, 10), (3, 2, 5),
+                      (48000, 8000, 1)]:
         rs = CudaAudioResample(quality=q, cuda_device_id=-1, resample_method=method, sinc_filter_mode=mode,
                                sinc_filter_interpolation=interp)
         rs.set_caps(a, b, 2)
