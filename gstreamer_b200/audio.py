@@ -10,7 +10,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import lib, check
+from ._lib import lib, check, B200Error
 from .video import _ptr, _stream
 
 
@@ -42,11 +42,18 @@ class CudaAudioResample:
         self.format = format
         self.cuda_device_id = cuda_device_id
         self._h = None
+        self.passthrough = False
         self.in_rate = self.out_rate = self.channels = None
 
     # GstBaseTransformClass::set_caps (interleaved samples of self.format)
     def set_caps(self, in_rate, out_rate, channels):
         self._free()
+        # gst_audio_resample_set_caps: equal rates put the base transform in pass-through mode (buffers are forwarded
+        # untouched and transform() is never called)
+        self.passthrough = in_rate == out_rate
+        if self.passthrough:
+            self.in_rate, self.out_rate, self.channels = in_rate, out_rate, channels
+            return True
         method = self.METHODS[self.rest["resample_method"]]
         mode = self.FILTER_MODES[self.rest["sinc_filter_mode"]]
         interp = self.INTERPOLATIONS[self.rest["sinc_filter_interpolation"]]
@@ -72,6 +79,8 @@ class CudaAudioResample:
 
     # GstBaseTransformClass::transform — device buffers, F32 interleaved; inbuf None = drain zeros
     def transform(self, inbuf, in_frames, outbuf, out_capacity, stream=None):
+        if self._h is None:
+            raise B200Error(-1, "transform() in pass-through mode (equal rates): the buffer is forwarded as it is")
         n = C.c_size_t()
         check(lib.b200_ars_process(self._h, _ptr(inbuf), in_frames, _ptr(outbuf), out_capacity, C.byref(n),
                                    _stream(stream)), "b200_ars_process")

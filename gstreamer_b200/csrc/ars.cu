@@ -60,6 +60,7 @@ struct ArsPlan {
   int n_taps = 0, oversample = 0, n_phases = 0;
   bool full = false;
   bool blackman = false;         // resample-method=blackman-nuttall (else kaiser)
+  bool copy = false;             // equal rates: the reference selects its nearest functions (setup_functions :1019-1020)
   int small = 0;                 // resample-method nearest (1) / linear (2) / cubic (3): a few taps, no sinc table, FULL mode
   bool linear = false;           // sinc-filter-interpolation=linear: two prototype rows per phase, 11x the oversampling
   int isize = 4;                 // prototype rows one phase reads (4 cubic, 2 linear)
@@ -178,6 +179,10 @@ static int build_ars_plan (const b200_ars_config & cfg, ArsPlan * p)
     if (!getenv ("B200_VCS_EXPERIMENTAL")) return B200_ERR_UNSUPPORTED;
     p->small = cfg.resample_method;
   }
+  // equal rates (the element itself goes pass-through, gstaudioresample.c set_caps): every output is the first sample of
+  // its window, through the same small kernel
+  p->copy = p->in_step == p->out_step;
+  if (p->copy && !getenv ("B200_VCS_EXPERIMENTAL")) return B200_ERR_UNSUPPORTED;
   if (cfg.sinc_filter_mode < 0 || cfg.sinc_filter_mode > B200_ARS_FILTER_MODE_AUTO) return B200_ERR_INVALID_ARG;
   if (cfg.sinc_filter_interpolation < 0 || cfg.sinc_filter_interpolation > B200_ARS_FILTER_INTERPOLATION_CUBIC)
     return B200_ERR_INVALID_ARG;
@@ -1179,7 +1184,7 @@ int b200_ars_process (b200_ars * h, const void *in_v, size_t in_frames, void *ou
     L.wcn = (p.channels + 31) / 32; if (L.wcn > 8) L.wcn = 8;
     while (8 % L.wcn) L.wcn++;                                   // 1, 2, 4 or 8 warps across channels
     bool s16_tiled = false;           // ... or the small-method kernel: launched already
-    if (p.small) {
+    if (p.small || p.copy) {
       ArsLaunchX X;
       X.hist = h->d_hist[h->cur]; X.in = in_v; X.out = out_v;
       X.table = p.fmt == ARS_F32 ? (const void *) h->d_phases : (const void *) h->d_table_x;
@@ -1187,7 +1192,7 @@ int b200_ars_process (b200_ars * h, const void *in_v, size_t in_frames, void *ou
       X.channels = p.channels; X.n_taps = p.n_taps; X.out_step = p.out_step;
       X.samp_inc = p.samp_inc; X.samp_frac = p.samp_frac; X.samp_index = h->samp_index; X.samp_phase = h->samp_phase;
       X.full = 1; X.oversample = 1;
-      const int nearest = p.small == B200_ARS_METHOD_NEAREST;
+      const int nearest = p.small == B200_ARS_METHOD_NEAREST || p.copy;
       const dim3 grid ((unsigned) ((out_frames + ARS_THREADS / 32 - 1) / (ARS_THREADS / 32)), (unsigned) ((p.channels + 31) / 32));
       if (p.fmt == ARS_S16) ars_small_kernel<ARS_S16> <<<grid, ARS_THREADS, 0, stream>>> (X, nearest);
       else if (p.fmt == ARS_S32) ars_small_kernel<ARS_S32> <<<grid, ARS_THREADS, 0, stream>>> (X, nearest);

@@ -60,6 +60,7 @@ struct OracleArs
   int channels, in_rate, out_rate;      /* rates after gcd reduction */
   int samp_inc, samp_frac, samp_index, samp_phase, skip;
   int n_taps, oversample, n_phases, full;
+  int copy;                     /* nearest method, or equal rates (setup_functions, audio-resampler.c:1019-1020): *o = *a */
   int linear, isize;            /* sinc-filter-interpolation=linear: two table rows per phase, 11x the oversampling */
   int method, interp_none;      /* ORACLE_ARS_METHOD_*; sinc-filter-interpolation=none (FULL mode: exact taps per phase) */
   double cutoff, beta;
@@ -205,6 +206,7 @@ oracle_ars_new_opts (int in_rate, int out_rate, int channels, int quality, int f
   g = gcd_ (in_rate, out_rate);
   r->in_rate = in_rate / g;
   r->out_rate = out_rate / g;
+  r->copy = method == ORACLE_ARS_METHOD_NEAREST || r->in_rate == r->out_rate;
   r->samp_inc = r->in_rate / r->out_rate;
   r->samp_frac = r->in_rate % r->out_rate;
 
@@ -614,7 +616,7 @@ static void
 resample_one_any (OracleArs * r, const void *a, int phase, void *o)
 {
   int n = r->n_taps, i, k;
-  if (r->method == ORACLE_ARS_METHOD_NEAREST) {   /* inner_product_<type>_nearest_1_c (audio-resampler.c:602-612): *o = *a */
+  if (r->copy) {                /* inner_product_<type>_nearest_1_c (audio-resampler.c:602-612): *o = *a */
     memcpy (o, a, r->bps);
     return;
   }
@@ -849,7 +851,7 @@ oracle_ars_process (OracleArs * r, const float *in, size_t in_frames, float *out
     samp_phase = r->samp_phase;
     for (di = 0; di < out_frames; di++) {
       const float *ipp = ip + samp_index;
-      if (r->method == ORACLE_ARS_METHOD_NEAREST) {       /* inner_product_gfloat_nearest_1_c */
+      if (r->copy) {            /* inner_product_gfloat_nearest_1_c */
         out[di * ch + c] = ipp[0];
       } else if (r->full) {
         out[di * ch + c] = dot_full (ipp, phase_taps (r, samp_phase), r->n_taps);

@@ -349,6 +349,8 @@ def test_audio_kernels(emu, fmt, opts, monkeypatch):
     rates = [(48000, 44100, 2, 4), (44100, 48000, 66, 2) if fmt in ("F32", "S16") else (96000, 44100, 1, 6)]
     if M[method] < 3:                                         # tap counts off the lane widths: 3, 12; and the 96k -> 44.1k pair
         rates += [(3, 2, 3, 5), (48000, 8000, 2, 1), (96000, 44100, 1, 6)]
+    if opts == AUDIO_OPTS[0]:
+        rates += [(44100, 44100, 3, 4)]                       # equal rates: gst_audio_resampler's nearest functions
     for (a, b, ch, q) in rates:
         ho = o.oracle_ars_new_opts(a, b, ch, q, ofmt, M[method], MO[mode], I[interp])
         cfg = _lib.ArsConfigC()

@@ -349,6 +349,17 @@ def test_audioresample_remaining_properties(monkeypatch):
     monkeypatch.delenv("B200_VCS_EXPERIMENTAL", raising=False)
     from gstreamer_b200.audio import CudaAudioResample
     CudaAudioResample(cuda_device_id=-1, resample_method="kaiser", sinc_filter_auto_threshold=1).set_caps(48000, 44100, 2)
+    # equal rates: pass-through like the element (no resampler behind it); the library itself follows gst_audio_resampler
+    # (every output = the first sample of its window) in opt-in device code
+    rs = CudaAudioResample(cuda_device_id=-1)
+    rs.set_caps(44100, 44100, 2)
+    assert rs.passthrough
+    with pytest.raises(g.B200Error):
+        rs.transform(None, 10, None, 10)
+    from gstreamer_b200 import _lib
+    cfg, h = _lib.ArsConfigC(), C.c_void_p()
+    cfg.in_rate, cfg.out_rate, cfg.channels, cfg.quality = 48000, 48000, 2, 4
+    assert g.lib.b200_ars_create(C.byref(cfg), -1, C.byref(h)) == -2
     # linear table interpolation: FULL mode is host work only; the interpolated mode's blend is opt-in device code
     CudaAudioResample(cuda_device_id=-1, sinc_filter_interpolation="linear").set_caps(48000, 44100, 2)
     for kw in ({"resample_method": "linear"}, {"resample_method": "nearest"}, {"resample_method": "cubic"},

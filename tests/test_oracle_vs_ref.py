@@ -561,7 +561,7 @@ def test_audio_method_and_filter_mode_properties(fmt, method, mode, interp):
     ofmt, gfmt, dt, _ = ob.AUDIO_FORMATS[fmt]
     o, r = ob.oracle(), ob.ref()
     for (a, b, ch, q) in [(48000, 44100, 2, 4), (44100, 48000, 1, 6), (8000, 16000, 2, 2), (96000, 44100, 1, 8), (44100, 44099, 1, 3),
-                          (3, 2, 1, 5), (48000, 8000, 2, 1)]:
+                          (3, 2, 1, 5), (48000, 8000, 2, 1), (44100, 44100, 2, 4)]:   # equal rates: the nearest functions
         ho = o.oracle_ars_new_opts(a, b, ch, q, ofmt, method, mode, interp)
         hr = r.ref_ars_new_opts(a, b, ch, q, gfmt, method, mode, interp)
         assert ho and hr
