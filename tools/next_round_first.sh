@@ -10,7 +10,8 @@ run() { local name=$1; shift; echo "== $name"; timeout "$1" "${@:2}" > "gpurun_o
 run rgbin 240 python -m pytest tests/test_vcs_rgbin_gpu.py -q -p no:cacheprovider
 # 2. destination rectangle + borders (new vcs_border_kernel around the existing kernels)
 run borders 180 python -m pytest tests/test_vcs_borders_gpu.py -q -p no:cacheprovider
-# 2b. audioresample's method / filter-mode properties (host tables only; the default kernels)
+# 2b. audioresample's method / filter-mode / interpolation properties (mostly host tables in front of the default kernels; new
+#     device code: the two-row linear blend of the interpolated mode and ars_small_kernel for nearest / linear / cubic)
 run arsopts 240 python -m pytest tests/test_ars_options_gpu.py -q -p no:cacheprovider
 # 2c. tensor-path variant of the 2:1 kernel: parity, then the headline bench with it (compare with the default line)
 run l2mma 240 python -m pytest tests/test_vcs_l2mma_gpu.py -q -p no:cacheprovider
