@@ -22,6 +22,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <new>
+#include <algorithm>
 #include <vector>
 
 #include "besi0_coeffs.inc"
@@ -1172,6 +1173,7 @@ int b200_ars_process (b200_ars * h, const void *in_v, size_t in_frames, void *ou
   const size_t hist = h->samples_avail, avail = hist + in_frames;
   const size_t need = (size_t) p.n_taps + h->samp_index;
   size_t consumed = 0;
+  long long moved_from = 0;       // the absolute sample index the reference's buffers are shifted down by (macros.h:91-93)
   int new_phase = h->samp_phase;
   if (avail >= need && out_frames > 0) {
     ArsLaunch L;
@@ -1282,6 +1284,7 @@ int b200_ars_process (b200_ars * h, const void *in_v, size_t in_frames, void *ou
     const long long end_index = (long long) h->samp_index + (long long) out_frames * p.samp_inc + t / p.out_step;
     new_phase = (int) (t % p.out_step);
     consumed = (size_t) (end_index - h->samp_index);
+    moved_from = end_index;
     h->samp_index = 0;
     h->samp_phase = new_phase;
   }
@@ -1294,22 +1297,33 @@ int b200_ars_process (b200_ars * h, const void *in_v, size_t in_frames, void *ou
   const int nxt = h->cur ^ 1;
   int st = ars_ensure_hist (h, nxt, keep);
   if (st != B200_OK) return st;
-  if (keep) {
-    const long long n = (long long) keep * p.channels;
+  // The reference shifts its buffers down by the ABSOLUTE final sample index but counts what is left from the index it
+  // started at (consumed = final - initial, :1790-1804).  The two differ only after a skip (nearest method while
+  // decimating: the next window starts beyond the data), and then the last `initial` of the kept samples are not the
+  // stream's tail but whatever the shift left in place: the frames at those same buffer positions.  Part 1 = frames
+  // [moved_from, ...) -> position 0, part 2 = frames [n1, keep) staying where they were (empty without a skip).
+  (void) first;
+  const size_t n1 = (long long) avail > moved_from ? std::min (keep, (size_t) ((long long) avail - moved_from)) : 0;
+  auto copy_hist = [&] (size_t dst_frame, long long from, size_t count) {
+    if (!count) return;
+    const long long n = (long long) count * p.channels;
     const int blocks = (int) ((n + 255) / 256 > 1184 ? 1184 : (n + 255) / 256);
+    const size_t off = dst_frame * p.channels;
     if (p.bps == 2)
-      ars_history_kernel_x<unsigned short> <<<blocks, 256, 0, stream>>> ((unsigned short *) h->d_hist[nxt],
-          (const unsigned short *) h->d_hist[h->cur], (const unsigned short *) in_v, (long long) hist, (long long) first,
-          (long long) keep, p.channels);
+      ars_history_kernel_x<unsigned short> <<<blocks, 256, 0, stream>>> ((unsigned short *) h->d_hist[nxt] + off,
+          (const unsigned short *) h->d_hist[h->cur], (const unsigned short *) in_v, (long long) hist, from,
+          (long long) count, p.channels);
     else if (p.bps == 8)
-      ars_history_kernel_x<unsigned long long> <<<blocks, 256, 0, stream>>> ((unsigned long long *) h->d_hist[nxt],
+      ars_history_kernel_x<unsigned long long> <<<blocks, 256, 0, stream>>> ((unsigned long long *) h->d_hist[nxt] + off,
           (const unsigned long long *) h->d_hist[h->cur], (const unsigned long long *) in_v, (long long) hist,
-          (long long) first, (long long) keep, p.channels);
+          from, (long long) count, p.channels);
     else
-      ars_history_kernel <<<blocks, 256, 0, stream>>> (h->d_hist[nxt], h->d_hist[h->cur], in, (long long) hist,
-          (long long) first, (long long) keep, p.channels);
-    B200_CUDA_TRY (cudaGetLastError ());
-  }
+      ars_history_kernel <<<blocks, 256, 0, stream>>> (h->d_hist[nxt] + off, h->d_hist[h->cur], in, (long long) hist,
+          from, (long long) count, p.channels);
+  };
+  copy_hist (0, moved_from, n1);
+  copy_hist (n1, (long long) n1, keep - n1);
+  if (keep) B200_CUDA_TRY (cudaGetLastError ());
   h->cur = nxt;
   h->samples_avail = keep;
   return B200_OK;

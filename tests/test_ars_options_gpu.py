@@ -60,3 +60,30 @@ def test_method_and_filter_mode_properties(cuda_device, fmt, method, mode, inter
             assert ng == nw and got[:ng].tobytes() == want[:nw].tobytes(), (a, b, ch, q, n)
             assert (got[ng:] == 7).all()
         o.oracle_ars_free(ho)
+
+
+@pytest.mark.parametrize("fmt", ["F32", "S16", "F64"])
+def test_nearest_decimation_skip_quirk(cuda_device, fmt, monkeypatch):
+    """tests/test_oracle_vs_ref.py::test_audio_nearest_decimation_skip_quirk on the device"""
+    import torch
+    from gstreamer_b200.audio import CudaAudioResample
+    monkeypatch.setenv("B200_VCS_EXPERIMENTAL", "1")
+    ofmt, gfmt, dt, _ = ob.AUDIO_FORMATS[fmt]
+    tdt = {np.float32: torch.float32, np.int16: torch.int16, np.int32: torch.int32, np.float64: torch.float64}[dt]
+    o = ob.oracle()
+    for (a, b, ch) in [(48000, 11025, 3), (96000, 8000, 1), (400, 3, 2)]:
+        for seed in range(3):
+            rng = np.random.default_rng(seed)
+            ho = o.oracle_ars_new_opts(a, b, ch, 4, ofmt, 0, 2, 2)
+            rs = CudaAudioResample(quality=4, format=gfmt, resample_method="nearest")
+            rs.set_caps(a, b, ch)
+            for n in [int(v) for v in rng.choice([1, 2, 7, 37, 100, 160, 480], 6)]:
+                x = ob.audio_test_signal(rng, n, ch, fmt)
+                cap = int(n * b / a) + 64
+                want = np.full((cap, ch), 7, dtype=dt)
+                nw = o.oracle_ars_process_any(ho, x.ctypes.data, n, want.ctypes.data, cap)
+                out = torch.full((cap * ch,), 7, dtype=tdt, device="cuda")
+                ng = rs.transform(torch.from_numpy(x).cuda(), n, out, cap)
+                torch.cuda.synchronize()
+                assert ng == nw and out.cpu().numpy().tobytes() == want.tobytes(), (a, b, ch, seed, n)
+            o.oracle_ars_free(ho)

@@ -325,6 +325,37 @@ def test_compositor_kernel(emu, fmt, background):
     check(out.ravel(), want.ravel(), f"{fmt} background {background}")
 
 
+@pytest.mark.parametrize("fmt", ["F32", "S16", "F64"])
+def test_audio_nearest_decimation_skip_quirk(emu, fmt, monkeypatch):
+    """the product's history after a skip (tests/test_oracle_vs_ref.py::test_audio_nearest_decimation_skip_quirk): part of what
+    the reference keeps is what its buffer shift left in place, not the stream's tail"""
+    from gstreamer_b200 import _lib
+    monkeypatch.setenv("B200_VCS_EXPERIMENTAL", "1")
+    ofmt, gfmt, dt, _ = ob.AUDIO_FORMATS[fmt]
+    o = ob.oracle()
+    for (a, b, ch) in [(48000, 11025, 3), (96000, 8000, 1), (400, 3, 2)]:
+        for seed in range(3):
+            rng = np.random.default_rng(seed)
+            ho = o.oracle_ars_new_opts(a, b, ch, 4, ofmt, 0, 2, 2)
+            cfg = _lib.ArsConfigC()
+            cfg.in_rate, cfg.out_rate, cfg.channels, cfg.quality, cfg.format, cfg.resample_method = a, b, ch, 4, gfmt, 1
+            h = C.c_void_p()
+            assert emu.b200_ars_create(C.byref(cfg), 0, C.byref(h)) == 0
+            try:
+                for n in [int(v) for v in rng.choice([1, 2, 7, 37, 100, 160, 480], 6)]:
+                    x = ob.audio_test_signal(rng, n, ch, fmt)
+                    cap = int(n * b / a) + 64
+                    want = np.full((cap, ch), 7, dtype=dt)
+                    got = want.copy()
+                    nw = o.oracle_ars_process_any(ho, x.ctypes.data, n, want.ctypes.data, cap)
+                    ng = C.c_size_t()
+                    assert emu.b200_ars_process(h, x.ctypes.data, n, got.ctypes.data, cap, C.byref(ng), None) == 0
+                    assert ng.value == nw and got.tobytes() == want.tobytes(), (a, b, ch, seed, n)
+            finally:
+                emu.b200_ars_destroy(h)
+                o.oracle_ars_free(ho)
+
+
 AUDIO_OPTS = [("kaiser", "auto", "cubic"), ("blackman-nuttall", "auto", "cubic"), ("kaiser", "full", "none"),
               ("kaiser", "interpolated", "cubic"), ("blackman-nuttall", "full", "none"), ("kaiser", "interpolated", "none"),
               ("kaiser", "full", "linear"), ("kaiser", "interpolated", "linear"), ("blackman-nuttall", "interpolated", "linear"),

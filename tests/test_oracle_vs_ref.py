@@ -587,6 +587,31 @@ def test_audio_method_and_filter_mode_properties(fmt, method, mode, interp):
         r.ref_ars_free(hr)
 
 
+@pytest.mark.parametrize("fmt", ["F32", "S16", "F64"])
+def test_audio_nearest_decimation_skip_quirk(fmt):
+    """nearest method while decimating: the next window can start beyond the data, gst_audio_resampler_resample then sets
+    `skip` (:1796-1803), adds it to samp_index on EVERY later call (:1762, never cleared), and after such a call shifts its
+    buffers by the absolute final index while counting the rest from the start index - so the tail of what it keeps is
+    whatever the shift left in place.  The oracle keeps the same buffers and reproduces all of it."""
+    ofmt, gfmt, dt, _ = ob.AUDIO_FORMATS[fmt]
+    o, r = ob.oracle(), ob.ref()
+    for (a, b, ch) in [(48000, 11025, 3), (48000, 8000, 2), (96000, 8000, 1), (400, 3, 2)]:
+        for seed in range(4):
+            rng = np.random.default_rng(seed)
+            ho = o.oracle_ars_new_opts(a, b, ch, 4, ofmt, 0, 2, 2)
+            hr = r.ref_ars_new_opts(a, b, ch, 4, gfmt, 0, 2, 2)
+            for n in [int(v) for v in rng.choice([1, 2, 7, 37, 100, 160, 480], 6)]:
+                x = ob.audio_test_signal(rng, n, ch, fmt)
+                cap = int(n * b / a) + 64
+                o1 = np.full((cap, ch), 7, dtype=dt)
+                o2 = o1.copy()
+                n1 = o.oracle_ars_process_any(ho, x.ctypes.data, n, o1.ctypes.data, cap)
+                n2 = r.ref_ars_process(hr, x.ctypes.data, n, o2.ctypes.data, cap)
+                assert n1 == n2 and o1.tobytes() == o2.tobytes(), (a, b, ch, seed, n)
+            o.oracle_ars_free(ho)
+            r.ref_ars_free(hr)
+
+
 # ------------------------------------------------------------------- 4:2:2 and 4:4:4 inputs (capture formats) -> packed RGB
 @pytest.mark.parametrize("fi", ["YUY2", "UYVY", "YVYU", "Y42B", "Y444"])
 @pytest.mark.parametrize("size", [(64, 48, 32, 24), (64, 48, 96, 72), (33, 17, 20, 31), (50, 21, 50, 21), (100, 100, 150, 50),
