@@ -85,20 +85,21 @@ def main():
             else:
                 x = ob.audio_test_signal(rng, nb, ch, fmt)
             cap = int(nb * b / a) + 64
-            want = np.zeros((cap, ch), dtype=dt)
+            # every buffer starts from the same fill: after a skip the reference can report frames it never writes
+            want = np.full((cap, ch), 7, dtype=dt)
             px = x.ctypes.data if x is not None else None
             nw = o.oracle_ars_process_any(ho, px, nb, want.ctypes.data, cap)
             if hr:
-                w2 = np.zeros((cap, ch), dtype=dt)
+                w2 = np.full((cap, ch), 7, dtype=dt)
                 n2 = r.ref_ars_process(hr, px, nb, w2.ctypes.data, cap)
-                if n2 != nw or w2[:n2].tobytes() != want[:nw].tobytes():
+                if n2 != nw or w2.tobytes() != want.tobytes():
                     print("ORACLE != REF", desc, nb, flush=True)
                     bad += 1
                     break
             got = np.full((cap, ch), 7, dtype=dt)
             ng = C.c_size_t()
             st = emu.b200_ars_process(h, px, nb, got.ctypes.data, cap, C.byref(ng), None)
-            if st != 0 or ng.value != nw or got[:nw].tobytes() != want[:nw].tobytes() or not (got[nw:] == 7).all():
+            if st != 0 or ng.value != nw or got.tobytes() != want.tobytes():
                 print("EMU != ORACLE", st, desc, nb, ng.value, nw, flush=True)
                 bad += 1
                 break
