@@ -325,6 +325,45 @@ def test_compositor_kernel(emu, fmt, background):
     check(out.ravel(), want.ravel(), f"{fmt} background {background}")
 
 
+@pytest.mark.parametrize("fmt", [2, 3, 23, 24], ids=["I420", "YV12", "NV12", "NV21"])
+def test_compositor_420_kernel(emu, fmt):
+    """the 4:2:0 compositor (b200_comp_blend_yuv: per-plane blend, pad positions rounded up to even, ceil(w/2) chroma
+    samples) against the oracle: random layouts, both ranges, every background, one trial beyond a launch chunk of pads"""
+    from gstreamer_b200 import _lib
+    o = ob.oracle()
+    rng = np.random.default_rng(fmt)
+    for trial in range(8):
+        W, H, bg, rg = int(rng.integers(1, 120)), int(rng.integers(1, 90)), int(rng.integers(0, 4)), int(rng.integers(0, 2))
+        n = int(rng.integers(0, 6)) if trial % 4 else 30
+        oi = _lib.VideoInfoC()
+        assert emu.b200_video_info_set_format(C.byref(oi), fmt, W, H) == 0
+        oi.color_range = 2 if rg else 1
+        opads = (ob.OraclePad * max(n, 1))()
+        pads = (_lib.CompPadYuvC * max(n, 1))()
+        keep = []
+        for i in range(n):
+            w, h = int(rng.integers(1, 80)), int(rng.integers(1, 60))
+            a = rng.integers(0, 256, o.oracle_compositor_yuv_size(fmt, w, h), dtype=np.uint8)
+            keep.append(a)
+            x, y = int(rng.integers(-40, W + 5)), int(rng.integers(-40, H + 5))
+            al, op = float(rng.choice([0.0, 0.3, 0.5, 0.999, 1.0, 0.004])), int(rng.integers(0, 3))
+            opads[i].data, opads[i].width, opads[i].height, opads[i].stride = a.ctypes.data, w, h, 0
+            opads[i].xpos, opads[i].ypos, opads[i].alpha, opads[i].op = x, y, al, op
+            assert emu.b200_video_info_set_format(C.byref(pads[i].info), fmt, w, h) == 0
+            pads[i].data, pads[i].xpos, pads[i].ypos, pads[i].alpha, pads[i].op = a.ctypes.data, x, y, al, op
+        sz = o.oracle_compositor_yuv_size(fmt, W, H)
+        want = np.zeros(sz, dtype=np.uint8)
+        assert o.oracle_compositor_yuv(fmt, want.ctypes.data, W, H, bg, rg, opads, n) == 0
+        hc = C.c_void_p()
+        assert emu.b200_comp_create(fmt, W, H, 0, C.byref(hc)) == 0
+        out = np.zeros(sz, dtype=np.uint8)
+        try:
+            assert emu.b200_comp_blend_yuv(hc, out.ctypes.data, C.byref(oi), bg, pads, n, None) == 0
+        finally:
+            emu.b200_comp_destroy(hc)
+        check(out, want, f"fmt {fmt} trial {trial} {W}x{H} bg {bg} range {rg} pads {n}")
+
+
 @pytest.mark.parametrize("fmt", ["F32", "S16", "F64"])
 def test_audio_nearest_decimation_skip_quirk(emu, fmt, monkeypatch):
     """the product's history after a skip (tests/test_oracle_vs_ref.py::test_audio_nearest_decimation_skip_quirk): part of what
