@@ -97,9 +97,16 @@ ars_set_caps (GstBaseTransform * trans, GstCaps * incaps, GstCaps * outcaps)
   cfg.channels = GST_AUDIO_INFO_CHANNELS (&self->in);
   cfg.quality = self->quality;
   cfg.format = GST_AUDIO_INFO_FORMAT (&self->in);       /* B200_AUDIO_FORMAT_* are GstAudioFormat values */
+  /* equal rates: pass-through, no resampler behind the element (gst_audio_resample_set_caps does the same with
+   * gst_base_transform_set_passthrough) */
+  if (cfg.in_rate == cfg.out_rate) {
+    gst_base_transform_set_passthrough (trans, TRUE);
+    ars_reset_position (self);
+    return TRUE;
+  }
   if (b200_ars_create (&cfg, self->device_id, &self->ars) != B200_OK)
     return FALSE;
-  gst_base_transform_set_passthrough (trans, cfg.in_rate == cfg.out_rate);
+  gst_base_transform_set_passthrough (trans, FALSE);
   ars_reset_position (self);
   return TRUE;
 }
@@ -121,6 +128,10 @@ ars_transform_size (GstBaseTransform * trans, GstPadDirection direction, GstCaps
   GstCudaAudioResample *self = (GstCudaAudioResample *) trans;
   const gsize bpf = GST_AUDIO_INFO_BPF (&self->in);
   gsize frames = size / bpf;
+  if (gst_base_transform_is_passthrough (trans)) {
+    *othersize = size;
+    return TRUE;
+  }
   if (!self->ars)
     return FALSE;
   frames = direction == GST_PAD_SINK ? b200_ars_get_out_frames (self->ars, frames)
