@@ -124,7 +124,15 @@ ref_compositor_yuv (int format, guint8 * dst, int width, int height, int backgro
     case 1: fill_color (&out, 0, height, range_16_235 ? 16 : 0, 128, 128); break;
     case 2: fill_color (&out, 0, height, range_16_235 ? 235 : 255, 128, 128); break;
     default:
-      memset (dst, 0, out.info.size);   /* every plane row zeroed; overlay == blend for these formats */
+      /* the element's own loop is a static function (_draw_background, compositor.c:1640-1670): the visible bytes of
+       * every plane row are zeroed, the stride padding is left alone; overlay == blend for these formats */
+      for (p = 0; p < (int) GST_VIDEO_INFO_N_PLANES (&out.info); p++) {
+        gint comp[GST_VIDEO_MAX_COMPONENTS], row;
+        gst_video_format_info_component (out.info.finfo, p, comp);
+        for (row = 0; row < GST_VIDEO_FRAME_COMP_HEIGHT (&out, comp[0]); row++)
+          memset ((guint8 *) out.data[p] + (gsize) row * GST_VIDEO_FRAME_PLANE_STRIDE (&out, p), 0,
+              GST_VIDEO_FRAME_COMP_WIDTH (&out, comp[0]) * GST_VIDEO_FRAME_COMP_PSTRIDE (&out, comp[0]));
+      }
       break;
   }
   for (i = 0; i < n_pads; i++) {
