@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """tools/emu_fuzz.py [seconds] [seed] — randomised differential run of the EMULATED convert+scale kernels (tests/cudaemu:
 the product's kernel sources compiled for the host) against the oracle: random sizes (biased small and odd), methods,
-all format pairs incl. the opt-in ones, chroma sitings, colorimetry, destination rectangles.  TEST INFRASTRUCTURE.
+all format pairs incl. the opt-in ones, chroma sitings, colorimetry, destination rectangles; where the reference build
+(oracle/_ref) is present, half of the cases also compare the oracle with the reference's own converter, leaving out the
+reference's two known defect classes.  TEST INFRASTRUCTURE.
 Meant to be run under the sanitizer builds as well:
     B200_EMU_ASAN=1 LD_PRELOAD=$(g++ -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0:halt_on_error=0:log_path=/tmp/asan python tools/emu_fuzz.py 300
 """
@@ -33,6 +35,12 @@ def main():
             fn = getattr(emu, name)
             fn.restype, fn.argtypes = res, args
     t0, n, bad, kinds = time.time(), 0, 0, {}
+    n_ref = n_defect = 0
+    try:
+        ob.ref()
+        ref_ok = True
+    except Exception:                               # noqa: BLE001  (oracle/_ref absent: the GPU box)
+        ref_ok = False
     while time.time() - t0 < budget:
         big = rng.random() < 0.2
         hi = 300 if big else 70
@@ -72,6 +80,28 @@ def main():
         try:
             kw = dict(site=site if fi not in T.RGB else None, out_site=out_site, dest=dest)
             want = T.expected(fi, fo, size, method, frame, **kw)
+            if ref_ok and rng.random() < 0.5:       # ... and the oracle itself against the reference build
+                rkw = {}
+                if fi not in T.RGB:
+                    rkw["site"] = site
+                if fi not in T.RGB and fo not in T.RGB:
+                    d0 = ob.vcs_desc(iw, ih, W, H, method, in_fmt=ob.FMT[fi], out_fmt=ob.FMT[fo], site=site)
+                    rkw.update(matrix=d0.in_matrix, out_matrix=d0.in_matrix, out_site=site if out_site is None else out_site)
+                if dest:
+                    rkw.update(dest=dest, border_argb=0xff000000)
+                rv = ob.RefVcs(iw, ih, W, H, method, in_fmt=ob.FMT[fi], out_fmt=ob.FMT[fo], **rkw)
+                ref_out = rv.convert(frame, np.full(want.size, 0x5A, dtype=np.uint8))
+                rv.close()
+                n_ref += 1
+                if not np.array_equal(ref_out, want):
+                    dw, dh = (dest[2], dest[3]) if dest else (W, H)
+                    vfirst = ih != dh and (iw == dw or dw * ih > iw * dh)
+                    if not (fi in T.RGB and fo in T.RGB) and (vfirst or (method == 0 or ih == 1) and dh > ih):
+                        n_defect += 1               # the two reference defect classes, not reproduced
+                    else:
+                        bad += 1
+                        print("ORACLE != REF", kind, fi, fo, size, "m", method, "site", site, out_site, "dest", dest,
+                              int(np.count_nonzero(ref_out != want)), "of", want.size, flush=True)
             got = T.run(emu, fi, fo, size, method, frame, force_generic=False, **kw)
             if rng.random() < 0.3 and generic:      # the generic kernel on shapes the fast kernels would take
                 got2 = T.run(emu, fi, fo, size, method, frame, force_generic=True, **kw)
@@ -88,7 +118,8 @@ def main():
             bad += 1
             print("MISMATCH", kind, fi, fo, size, "m", method, "site", site, out_site, "dest", dest,
                   int(np.count_nonzero(got != want)), "of", got.size, flush=True)
-    print(f"emu_fuzz: {n} cases, {bad} problems, {kinds}")
+    print(f"emu_fuzz: {n} cases, {bad} problems, {kinds}; oracle vs reference build on {n_ref} of them "
+          f"({n_defect} in the reference's two known defect classes)")
     return 1 if bad else 0
 
 
