@@ -447,3 +447,16 @@ def test_audio_kernels(emu, fmt, opts, monkeypatch):
         finally:
             emu.b200_ars_destroy(h)
             o.oracle_ars_free(ho)
+
+
+# ---- 5. the randomised three-way runs (tools/emu_fuzz*.py) keep working: a few seconds of each -------------------------
+@pytest.mark.parametrize("tool", ["emu_fuzz.py", "emu_fuzz_audio.py", "emu_fuzz_comp.py"])
+def test_random_run_tools(emu, tool):
+    """reference build (when present) vs oracle vs emulated kernels on random configurations; the long runs are recorded
+    in profiles/r01_race_check.txt"""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "tools", tool), "6", "4"], capture_output=True, text=True, timeout=300)
+    last = p.stdout.strip().splitlines()[-1] if p.stdout.strip() else ""
+    assert p.returncode == 0 and (" 0 problems" in last or " 0 mismatches" in last), (p.stdout[-600:], p.stderr[-600:])
