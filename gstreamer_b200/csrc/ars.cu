@@ -259,6 +259,9 @@ static int build_ars_plan (const b200_ars_config & cfg, ArsPlan * p)
     else if (p->fmt == ARS_S32) convert_taps_int (tmp.data (), (int32_t *) px, weight, n, 31);
     else if (p->fmt == ARS_F64) for (int i = 0; i < n; i++) ((double *) px)[i] = tmp[i] / weight;
   };
+  // (the reference builds this table only with a table interpolation, :1181-1201; the small methods have none, and
+  // their tap shapes can sum to zero on rows nobody would read)
+  if (!p->small)
   for (int row = 0; row < over + isize; row++)
     make_row (-(n / 2) + row / (double) over, &p->proto[(size_t) row * n],
         p->fmt != ARS_F32 ? p->proto_x.data () + (size_t) row * n * p->bps : nullptr);

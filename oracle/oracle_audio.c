@@ -276,7 +276,7 @@ oracle_ars_new_opts (int in_rate, int out_rate, int channels, int quality, int f
   r->interp_none = r->full && interpolation == ORACLE_ARS_INTERP_NONE;
   r->n_phases = r->out_rate;
   r->table = calloc ((size_t) (oversample + r->isize) * r->n_taps, r->bps);
-  for (i = 0; i < oversample + r->isize; i++)
+  for (i = 0; i < oversample + r->isize && method > ORACLE_ARS_METHOD_CUBIC; i++)     /* no table without a table interpolation (:1181-1201) */
     make_row (r, (char *) r->table + (size_t) i * r->n_taps * r->bps, -(r->n_taps / 2) + i / (double) oversample);
   if (r->full) {
     r->cache = calloc ((size_t) r->n_phases * r->n_taps, r->bps);

@@ -70,7 +70,16 @@ def digest():
 
 
 def build(force=False):
+    # one builder at a time (pytest-xdist workers all arrive here after a source change); the others wait and then find
+    # the stamp up to date
+    import fcntl
     os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, "lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        return _build_locked(force)
+
+
+def _build_locked(force):
     stamp = os.path.join(OUT, "stamp")
     d = digest()
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == d:
@@ -92,7 +101,7 @@ def build(force=False):
         if f.endswith((".h", ".cuh")):
             open(os.path.join(gen, f), "w").write(open(os.path.join(HERE, "emu", f)).read())
     cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-Wno-unknown-pragmas", "-DB200_CUDA_EMU=1",
-           "-I", gen, "-I", CSRC, "-o", LIB,
+           "-I", gen, "-I", CSRC, "-o", LIB + ".tmp",
            os.path.join(gen, "vcs_emu.cpp"), os.path.join(gen, "common_emu.cpp"), os.path.join(gen, "comp_emu.cpp"),
            os.path.join(gen, "ars_emu.cpp"), os.path.join(CSRC, "vcs_plan.cpp"),
            os.path.join(HERE, "emu", "emu_runtime.cpp")]
@@ -106,6 +115,7 @@ def build(force=False):
     if r.returncode != 0:
         sys.stderr.write(r.stdout[-4000:] + r.stderr[-8000:])
         raise RuntimeError("emulation build failed")
+    os.replace(LIB + ".tmp", LIB)                     # never write into a library another process has mapped
     open(stamp, "w").write(d)
     return LIB
 
