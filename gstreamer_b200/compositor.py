@@ -95,7 +95,7 @@ class CudaCompositorPad:
         import torch
         from .video import CudaVideoConvertScale, VideoInfo, VideoScaleMethod
         if self._conv is None:
-            self._conv = CudaVideoConvertScale(method=VideoScaleMethod.MITCHELL, cuda_device_id=device)
+            self._conv = CudaVideoConvertScale(add_borders=False, method=VideoScaleMethod.MITCHELL, cuda_device_id=device)
             self._out_info = VideoInfo(out_format, self.width, self.height)
             self._conv.set_info(self.in_info, self._out_info)
             self._converted = torch.empty(self._out_info.size, dtype=torch.uint8, device=f"cuda:{device}")

@@ -175,15 +175,12 @@ static int build_ars_plan (const b200_ars_config & cfg, ArsPlan * p)
   // the element's other properties: only what needs no new device code - both windowed-sinc methods, every filter
   // mode, and every table interpolation
   if (cfg.resample_method < 0 || cfg.resample_method > B200_ARS_METHOD_KAISER) return B200_ERR_INVALID_ARG;
-  // nearest / linear / cubic run in their own small kernel, which no device session has checked yet
-  if (cfg.resample_method >= B200_ARS_METHOD_NEAREST && cfg.resample_method <= B200_ARS_METHOD_CUBIC) {
-    if (!getenv ("B200_VCS_EXPERIMENTAL")) return B200_ERR_UNSUPPORTED;
+  // nearest / linear / cubic run in their own small kernel (ars_small_kernel)
+  if (cfg.resample_method >= B200_ARS_METHOD_NEAREST && cfg.resample_method <= B200_ARS_METHOD_CUBIC)
     p->small = cfg.resample_method;
-  }
   // equal rates (the element itself goes pass-through, gstaudioresample.c set_caps): every output is the first sample of
   // its window, through the same small kernel
   p->copy = p->in_step == p->out_step;
-  if (p->copy && !getenv ("B200_VCS_EXPERIMENTAL")) return B200_ERR_UNSUPPORTED;
   if (cfg.sinc_filter_mode < 0 || cfg.sinc_filter_mode > B200_ARS_FILTER_MODE_AUTO) return B200_ERR_INVALID_ARG;
   if (cfg.sinc_filter_interpolation < 0 || cfg.sinc_filter_interpolation > B200_ARS_FILTER_INTERPOLATION_CUBIC)
     return B200_ERR_INVALID_ARG;
@@ -223,8 +220,6 @@ static int build_ars_plan (const b200_ars_config & cfg, ArsPlan * p)
   // above (:1167-1170)
   p->interp_none = p->full && no_interp;
   p->n_phases = p->full ? p->out_step : 0;
-  // the linear blend of the interpolated filter mode runs in device code no device session has checked yet
-  if (p->linear && !p->full && !getenv ("B200_VCS_EXPERIMENTAL")) return B200_ERR_UNSUPPORTED;
 
   const int n = p->n_taps;
   p->proto.assign ((size_t) (over + isize) * n, 0.f);
@@ -1052,17 +1047,20 @@ static int ars_reset_state (b200_ars * h, cudaStream_t stream)
   return B200_OK;
 }
 
-static int ars_ensure_hist (b200_ars * h, int which, size_t frames)
+// `stream` is the stream the next writers / readers of the buffer run on: the clear is ordered there, not on the legacy
+// default stream (a cudaStreamNonBlocking user stream is not ordered against that one)
+static int ars_ensure_hist (b200_ars * h, int which, size_t frames, cudaStream_t stream)
 {
   if (h->hist_cap[which] >= frames) return B200_OK;
   size_t cap = frames + (size_t) h->plan.n_taps;
   float *n = nullptr;
   const size_t bps = (size_t) h->plan.bps;                        // the buffers hold samples of the plan's format
   B200_CUDA_TRY (cudaMalloc ((void **) &n, cap * h->plan.channels * bps));
-  B200_CUDA_TRY (cudaMemset (n, 0, cap * h->plan.channels * bps));
+  B200_CUDA_TRY (cudaMemsetAsync (n, 0, cap * h->plan.channels * bps, stream));
   if (h->d_hist[which]) {
     if (which == h->cur && h->samples_avail)
-      B200_CUDA_TRY (cudaMemcpy (n, h->d_hist[which], h->samples_avail * h->plan.channels * bps, cudaMemcpyDeviceToDevice));
+      B200_CUDA_TRY (cudaMemcpyAsync (n, h->d_hist[which], h->samples_avail * h->plan.channels * bps, cudaMemcpyDeviceToDevice, stream));
+    B200_CUDA_TRY (cudaStreamSynchronize (stream));                 // the old buffer is released below
     cudaFree (h->d_hist[which]);
   }
   h->d_hist[which] = n;
@@ -1095,9 +1093,10 @@ int b200_ars_create (const b200_ars_config * cfg, int device, b200_ars ** handle
     } else
       st = h->plan.full ? upload (&h->d_phases, h->plan.phases.data (), h->plan.phases.size ())
                         : upload (&h->d_proto, h->plan.proto.data (), h->plan.proto.size ());
-    if (st != B200_OK ||
-        (st = ars_ensure_hist (h, 0, (size_t) h->plan.n_taps)) != B200_OK ||
-        (st = ars_ensure_hist (h, 1, (size_t) h->plan.n_taps)) != B200_OK) {
+    if (st == B200_OK) st = ars_ensure_hist (h, 0, (size_t) h->plan.n_taps, nullptr);
+    if (st == B200_OK) st = ars_ensure_hist (h, 1, (size_t) h->plan.n_taps, nullptr);
+    if (st == B200_OK && cudaDeviceSynchronize () != cudaSuccess) st = B200_ERR_CUDA;   // clears done before any user stream
+    if (st != B200_OK) {
       b200_ars_destroy (h);
       return st;
     }
@@ -1130,8 +1129,13 @@ int b200_ars_reset (b200_ars * h)
   if (!h) return B200_ERR_INVALID_ARG;
   if (h->device >= 0) {
     DeviceGuard g (h->device);
+    // flush / discont: wait for whatever stream the caller last processed on, clear, and wait for the clear - the next
+    // process() may come on a non-blocking stream that the legacy stream does not order
     B200_CUDA_TRY (cudaDeviceSynchronize ());
-    return ars_reset_state (h, nullptr);
+    int st = ars_reset_state (h, nullptr);
+    if (st != B200_OK) return st;
+    B200_CUDA_TRY (cudaStreamSynchronize (nullptr));
+    return B200_OK;
   }
   return ars_reset_state (h, nullptr);
 }
@@ -1298,7 +1302,7 @@ int b200_ars_process (b200_ars * h, const void *in_v, size_t in_frames, void *ou
     else { first = avail; keep = 0; h->skip = (int) (consumed - avail); }
   }
   const int nxt = h->cur ^ 1;
-  int st = ars_ensure_hist (h, nxt, keep);
+  int st = ars_ensure_hist (h, nxt, keep, stream);
   if (st != B200_OK) return st;
   // The reference shifts its buffers down by the ABSOLUTE final sample index but counts what is left from the index it
   // started at (consumed = final - initial, :1790-1804).  The two differ only after a skip (nearest method while

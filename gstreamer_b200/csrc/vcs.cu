@@ -378,9 +378,7 @@ int b200_vcs_create (const b200_video_info * in, const b200_video_info * out,
       return st;
     }
     d.chroma_mode = h->d_cmode;
-    cudaError_t e = cudaFuncSetAttribute (vcs_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-        p.smem_bytes);
-    if (e != cudaSuccess) { b200_vcs_destroy (h); return cuda_fail (e, "cudaFuncSetAttribute", __FILE__, __LINE__); }
+    if ((st = allow_max_dyn_smem (vcs_generic_kernel)) != B200_OK) { b200_vcs_destroy (h); return st; }
     if (h->mma_tables.ok) {
       st = prepare_l2mma (h->mma_tables, &h->mma);
       if (st != B200_OK) { b200_vcs_destroy (h); return st; }
@@ -390,8 +388,7 @@ int b200_vcs_create (const b200_video_info * in, const b200_video_info * out,
       if (st != B200_OK) { b200_vcs_destroy (h); return st; }
       h->variant = 1;
     } else if (p.light_ok) {
-      e = cudaFuncSetAttribute (light_kernel_for (p), cudaFuncAttributeMaxDynamicSharedMemorySize, p.light_smem);
-      if (e != cudaSuccess) { b200_vcs_destroy (h); return cuda_fail (e, "cudaFuncSetAttribute", __FILE__, __LINE__); }
+      if ((st = allow_max_dyn_smem (light_kernel_for (p))) != B200_OK) { b200_vcs_destroy (h); return st; }
       h->variant = 2;
     } else if (p.ntap_ok) {
       st = prepare_ntap (p, &h->ntap);
@@ -399,7 +396,8 @@ int b200_vcs_create (const b200_video_info * in, const b200_video_info * out,
       h->variant = 3;
     }
   }
-  if (h->mma.ready && getenv ("B200_L2_MMA")) h->variant = 6;     // opt-in until it has been measured on a device
+  // variant 6 (mma.sync formulation of the 2:1 kernel) measured 12.7 us/frame against 8.4 for the SIMT kernel
+  // (profiles/r02_first_bench_l2mma.json): kept selectable through b200_vcs_set_kernel_variant for cross-checks only
   *handle = h;
   return B200_OK;
 }

@@ -394,7 +394,7 @@ struct Lanczos2State {
   uint8_t *d_v4 = nullptr;
   Lanczos2Dev dev;
   int variant = 0;
-  bool x4 = false;               // launch the X4 instantiation (opt-in: B200_L2_X4=1, until it has been measured)
+  bool x4 = false;               // launch the X4 instantiation (whenever the tables allow it)
 };
 
 inline int prepare_lanczos2 (const Lanczos2Tables & t, const VcsDev & d, Lanczos2State * st)
@@ -408,7 +408,8 @@ inline int prepare_lanczos2 (const Lanczos2Tables & t, const VcsDev & d, Lanczos
   st->dev.hsum = d.h.sum; st->dev.vsum = d.v.sum;
   st->dev.alpha_opaque = t.alpha_opaque;
   st->dev.htab4 = st->dev.htab; st->dev.vtab4 = st->dev.vtab; st->dev.v4 = nullptr;
-  if (t.x4_ok && getenv ("B200_L2_X4")) {
+  const char *x4e = getenv ("B200_L2_X4");        // tuning knob: "0" keeps the plain tables
+  if (t.x4_ok && !(x4e && x4e[0] == '0')) {      // measured 0.8 % faster than the plain tables (profiles/r02_first_bench_x4.json)
     int *h4 = nullptr, *v4 = nullptr;
     if ((rc = upload (&h4, t.htab4.data (), t.htab4.size ())) != B200_OK) return rc;
     if ((rc = upload (&v4, t.vtab4.data (), t.vtab4.size ())) != B200_OK) return rc;

@@ -363,7 +363,7 @@ inline int prepare_ntap (const VcsPlan & p, NtapState * st)
   int s;
   if ((s = upload (&st->d_h, p.h_packed.data (), p.h_packed.size ())) != B200_OK) return s;
   if ((s = upload (&st->d_v, p.v_packed.data (), p.v_packed.size ())) != B200_OK) return s;
-  B200_CUDA_TRY (cudaFuncSetAttribute (ntap_kernel_for (p), cudaFuncAttributeMaxDynamicSharedMemorySize, p.ntap_smem));
+  if ((s = allow_max_dyn_smem (ntap_kernel_for (p))) != B200_OK) return s;
   st->ready = true;
   return B200_OK;
 }

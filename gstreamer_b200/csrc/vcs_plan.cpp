@@ -635,7 +635,6 @@ static int build_rgb_same_plan (VcsPlan * p)
 static int build_rgb_in_plan (VcsPlan * p)
 {
   const b200_video_info *in = &p->in, *out = &p->out;
-  if (!getenv ("B200_VCS_EXPERIMENTAL")) return B200_ERR_UNSUPPORTED;
   if (out->format >= B200_VIDEO_FORMAT_RGBx && out->format <= B200_VIDEO_FORMAT_ABGR) return build_rgb_same_plan (p);
   const bool out_pl = out->format == B200_VIDEO_FORMAT_I420 || out->format == B200_VIDEO_FORMAT_YV12;
   const bool out_semi = out->format == B200_VIDEO_FORMAT_NV12 || out->format == B200_VIDEO_FORMAT_NV21;
@@ -809,8 +808,7 @@ static int build_inner_plan (const b200_video_info * in, const b200_video_info *
   if (in_422) {
     // capture formats: unpack_YUY2 / _UYVY / _YVYU / _Y42B / _Y444 (video-format.c:155-274, :1009-1104), horizontal chroma
     // up-sampling only (4:2:2: v_factor 0 selects video_chroma_none, video-chroma.c:989-994; 4:4:4: no resampler at all),
-    // then the usual chain to packed RGB.  Generic kernel; written without device access: opt-in.
-    if (!getenv ("B200_VCS_EXPERIMENTAL")) return B200_ERR_UNSUPPORTED;
+    // then the usual chain to packed RGB.  Generic kernel (device-verified: tests/test_vcs_rgbin_gpu.py).
     if (!(out->format >= B200_VIDEO_FORMAT_RGBx && out->format <= B200_VIDEO_FORMAT_ABGR)) return B200_ERR_UNSUPPORTED;
     const int w = in->width;
     p->in_422_444 = true;

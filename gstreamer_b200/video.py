@@ -192,14 +192,14 @@ class CudaVideoConvertScale:
                      "primaries_mode": "none", "converter_config": None}
 
     def __init__(self, method=VideoScaleMethod.BILINEAR, envelope=2.0, sharpness=1.0, sharpen=0.0,
-                 cuda_device_id=0, add_borders=False, n_threads=1, **rest):
+                 cuda_device_id=0, add_borders=True, n_threads=1, **rest):
         unknown = set(rest) - set(self.REST_DEFAULTS)
         if unknown:
             raise TypeError(f"no such property: {sorted(unknown)}")
         self.n_threads = n_threads
         self.rest = dict(self.REST_DEFAULTS, **rest)
-        # add-borders: TRUE in the stock element (DEFAULT_PROP_ADD_BORDERS, gstvideoconvertscale.c:131); this mirror keeps
-        # it FALSE until the border path has run on a device, so the converter-level parity tests stay border-free
+        # add-borders: TRUE like the stock element (DEFAULT_PROP_ADD_BORDERS, gstvideoconvertscale.c:131); the converter-level
+        # parity tests pass add_borders=False (= gst_video_converter_new without a destination rectangle)
         self.add_borders = add_borders
         self.borders_w = self.borders_h = 0
         self.method = VideoScaleMethod(method)

@@ -24,7 +24,10 @@ def _have_gpu():
 def pytest_collection_modifyitems(config, items):
     from oracle import bindings
     have_ref = bindings.have_ref()
+    have_gpu = _have_gpu() or os.environ.get("B200_REQUIRE_GPU") == "1"   # on the device box a missing GPU must fail loudly
     for item in items:
+        if "gpu" in item.keywords and not have_gpu:
+            item.add_marker(pytest.mark.skip(reason="no CUDA device visible (gpu tests run on the B200 box)"))
         if "ref" in item.keywords and not have_ref:
             item.add_marker(pytest.mark.skip(reason="oracle/_ref/libgstref.so not built"))
 

@@ -134,7 +134,7 @@ typedef void *cudaStream_t;
 typedef void *cudaEvent_t;
 enum cudaMemcpyKind { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
 enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaHostAllocPortable = 1 };
-enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaDevAttrMultiProcessorCount = 16 };
+enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaDevAttrMultiProcessorCount = 16, cudaDevAttrMaxSharedMemoryPerBlockOptin = 97 };
 
 inline cudaError_t cudaMalloc (void **p, size_t n) { *p = malloc (n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 inline cudaError_t cudaFree (void *p) { free (p); return cudaSuccess; }
@@ -149,7 +149,7 @@ inline const char *cudaGetErrorString (cudaError_t) { return "emu"; }
 inline cudaError_t cudaGetDevice (int *d) { *d = 0; return cudaSuccess; }
 inline cudaError_t cudaSetDevice (int) { return cudaSuccess; }
 inline cudaError_t cudaGetDeviceCount (int *n) { *n = 1; return cudaSuccess; }
-inline cudaError_t cudaDeviceGetAttribute (int *v, int, int) { *v = 148; return cudaSuccess; }
+inline cudaError_t cudaDeviceGetAttribute (int *v, int a, int) { *v = a == cudaDevAttrMaxSharedMemoryPerBlockOptin ? 232448 : 148; return cudaSuccess; }
 inline cudaError_t cudaStreamCreateWithFlags (cudaStream_t *s, unsigned) { *s = nullptr; return cudaSuccess; }
 inline cudaError_t cudaStreamDestroy (cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaStreamSynchronize (cudaStream_t) { return cudaSuccess; }

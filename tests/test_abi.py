@@ -39,7 +39,7 @@ def test_no_cpu_fallback_without_device():
     """device = -1 builds the host plan only; every compute entry point must refuse"""
     import gstreamer_b200 as g
     from gstreamer_b200.audio import CudaAudioResample
-    el = g.CudaVideoConvertScale(method=3, cuda_device_id=-1)
+    el = g.CudaVideoConvertScale(add_borders=False, method=3, cuda_device_id=-1)
     el.set_info(g.VideoInfo(23, 64, 48), g.VideoInfo(12, 32, 24))
     buf = np.zeros(64 * 48 * 2, dtype=np.uint8)
     with pytest.raises(g.B200Error) as e:

@@ -13,8 +13,7 @@ import pytest
 
 from oracle import bindings as ob
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("B200_TEST_EXPERIMENTAL") != "1", reason="opt-in: B200_TEST_EXPERIMENTAL=1")]
+pytestmark = [pytest.mark.gpu]
 
 M = {"nearest": 0, "linear": 1, "cubic": 2, "blackman-nuttall": 3, "kaiser": 4}
 MO = {"interpolated": 0, "full": 1, "auto": 2}

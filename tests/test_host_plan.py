@@ -35,7 +35,7 @@ def _oracle_taps(method, insz, outsz, prec):
 def test_tap_tables_and_order(size, method):
     import gstreamer_b200 as g
     iw, ih, ow, oh = size
-    el = g.CudaVideoConvertScale(method=method, cuda_device_id=-1)
+    el = g.CudaVideoConvertScale(add_borders=False, method=method, cuda_device_id=-1)
     el.set_info(g.VideoInfo(23, iw, ih), g.VideoInfo(12, ow, oh))
     pi = el.plan_info()
     for d, (a, b) in enumerate([(iw, ow), (ih, oh)]):
@@ -69,7 +69,7 @@ def test_tap_tables_and_order(size, method):
 @pytest.mark.parametrize("matrix,rng", [(2, 1), (2, 2), (3, 1), (3, 2), (4, 1), (4, 2), (5, 2), (6, 1), (6, 2)])
 def test_matrix_all_colorimetries(matrix, rng):
     import gstreamer_b200 as g
-    el = g.CudaVideoConvertScale(method=3, cuda_device_id=-1)
+    el = g.CudaVideoConvertScale(add_borders=False, method=3, cuda_device_id=-1)
     el.set_info(g.VideoInfo(23, 64, 48).set_colorimetry(matrix=matrix, range=rng), g.VideoInfo(12, 32, 24))
     d = ob.vcs_desc(64, 48, 32, 24, 3, matrix=matrix, rng=rng)
     p = (C.c_int * 5)()
@@ -80,12 +80,12 @@ def test_matrix_all_colorimetries(matrix, rng):
 
 def test_chroma_plan_standard_and_skipping():
     import gstreamer_b200 as g
-    el = g.CudaVideoConvertScale(method=3, cuda_device_id=-1)
+    el = g.CudaVideoConvertScale(add_borders=False, method=3, cuda_device_id=-1)
     el.set_info(g.VideoInfo(23, 64, 48), g.VideoInfo(12, 32, 24))
     m = el.chroma_plan()
     assert m[0] == 0 and (m[1::2] == 1).all() and (m[2::2] == 2).all()
     # nearest 2:1 skips lines: a requested even line opens its own pair
-    el = g.CudaVideoConvertScale(method=0, cuda_device_id=-1)
+    el = g.CudaVideoConvertScale(add_borders=False, method=0, cuda_device_id=-1)
     el.set_info(g.VideoInfo(23, 640, 480), g.VideoInfo(12, 320, 240))
     off, _ = el.taps(1)
     m = el.chroma_plan()
@@ -97,7 +97,7 @@ def test_specialised_kernel_eligibility():
     import gstreamer_b200 as g
 
     def eligible(iw, ih, ow, oh, method, site=2, **kw):
-        el = g.CudaVideoConvertScale(method=method, cuda_device_id=-1)
+        el = g.CudaVideoConvertScale(add_borders=False, method=method, cuda_device_id=-1)
         ii = g.VideoInfo(23, iw, ih).set_colorimetry(chroma_site=site)
         if "stride" in kw:
             ii.set_layout([kw["stride"], kw["stride"]], [0, kw["stride"] * ih])
@@ -170,7 +170,7 @@ def test_fast_kernel_selection_sweep():
             ow, oh = int(rng.integers(1, 2000)), int(rng.integers(1, 1200))
         m = int(rng.integers(0, 10))
         fmt = int(rng.choice([23, 24, 2, 3]))
-        el = g.CudaVideoConvertScale(method=m, cuda_device_id=-1)
+        el = g.CudaVideoConvertScale(add_borders=False, method=m, cuda_device_id=-1)
         el.set_info(g.VideoInfo(fmt, iw, ih), g.VideoInfo(12, ow, oh))
         v = int(el.plan_info().kernel_variant)
         counts[v] = counts.get(v, 0) + 1
@@ -189,7 +189,7 @@ def test_cross_family_420_plan():
     import gstreamer_b200 as g
 
     def build(fi, fo, iw, ih, ow, oh, m=1, matrix=None, site=None, out_site=None):
-        el = g.CudaVideoConvertScale(method=m, cuda_device_id=-1)
+        el = g.CudaVideoConvertScale(add_borders=False, method=m, cuda_device_id=-1)
         ii, oi = g.VideoInfo(fi, iw, ih), g.VideoInfo(fo, ow, oh)
         if site is not None:
             ii.set_colorimetry(chroma_site=site)
@@ -223,7 +223,7 @@ def test_transfer_colorimetry_from_input():
     import gstreamer_b200 as g
     ii, oi = g.VideoInfo(23, 1920, 1080), g.VideoInfo(2, 854, 480)
     assert (oi.c.color_matrix, oi.c.chroma_site) == (4, 1)
-    el = g.CudaVideoConvertScale(method=1, cuda_device_id=-1)
+    el = g.CudaVideoConvertScale(add_borders=False, method=1, cuda_device_id=-1)
     with pytest.raises(g.B200Error):
         el.set_info(ii, oi)
     g.transfer_colorimetry_from_input(ii, oi)
@@ -235,26 +235,21 @@ def test_transfer_colorimetry_from_input():
     assert rgb.c.color_matrix == 1
 
 
-def test_rgb_input_plan_is_opt_in_and_matches_the_oracle_matrix(monkeypatch):
-    """packed RGB -> 4:2:0 (generic kernel + chroma down-sampling, written without device access): refused unless
-    B200_VCS_EXPERIMENTAL is set; with it the host plan carries the same x256 RGB -> YUV matrix as the oracle for
+def test_rgb_input_plan_matches_the_oracle_matrix(monkeypatch):
+    """packed RGB -> 4:2:0 (generic kernel + chroma down-sampling; device-verified in tests/test_vcs_rgbin_gpu.py):
+    the host plan carries the same x256 RGB -> YUV matrix as the oracle for
     every output colorimetry, sits the matrix between the shrinking and the growing scalers, and never needs the
     odd-height third launch"""
     import gstreamer_b200 as g
 
     def build(fi, fo, iw, ih, ow, oh, m=1, **out_colorimetry):
-        el = g.CudaVideoConvertScale(method=m, cuda_device_id=-1)
+        el = g.CudaVideoConvertScale(add_borders=False, method=m, cuda_device_id=-1)
         ii, oi = g.VideoInfo(fi, iw, ih), g.VideoInfo(fo, ow, oh)
         if out_colorimetry:
             oi.set_colorimetry(**out_colorimetry)
         el.set_info(ii, oi)
         return el
 
-    monkeypatch.delenv("B200_VCS_EXPERIMENTAL", raising=False)
-    with pytest.raises(g.B200Error) as e:
-        build(12, 23, 64, 48, 32, 24)
-    assert e.value.status == -2
-    monkeypatch.setenv("B200_VCS_EXPERIMENTAL", "1")
     im = (C.c_int * 16)()
     for fi in (7, 8, 9, 10, 11, 12, 13, 14):
         for fo in (2, 3, 23, 24):
@@ -319,14 +314,14 @@ def test_add_borders_rectangle_and_plan():
 def test_remaining_element_properties_are_accepted_at_their_defaults():
     import gstreamer_b200 as g
     ii, oi = g.VideoInfo(23, 64, 48), g.VideoInfo(12, 32, 24)
-    g.CudaVideoConvertScale(cuda_device_id=-1, n_threads=8, dither="none", chroma_resampler="linear", alpha_value=1.0).set_info(ii, oi)
+    g.CudaVideoConvertScale(add_borders=False, cuda_device_id=-1, n_threads=8, dither="none", chroma_resampler="linear", alpha_value=1.0).set_info(ii, oi)
     for kw in ({"chroma_resampler": "cubic"}, {"alpha_mode": "set"}, {"alpha_value": 0.5}, {"gamma_mode": "remap"},
                {"primaries_mode": "fast"}, {"matrix_mode": "none"}, {"chroma_mode": "none"}, {"dither_quantization": 4}):
         with pytest.raises(g.B200Error) as e:
-            g.CudaVideoConvertScale(cuda_device_id=-1, **kw).set_info(ii, oi)
+            g.CudaVideoConvertScale(add_borders=False, cuda_device_id=-1, **kw).set_info(ii, oi)
         assert e.value.status == -2
     with pytest.raises(TypeError):
-        g.CudaVideoConvertScale(no_such_property=1)
+        g.CudaVideoConvertScale(add_borders=False, no_such_property=1)
 
 
 def test_compositor_pad_sizing_policy():
@@ -359,14 +354,13 @@ def test_audioresample_remaining_properties(monkeypatch):
     from gstreamer_b200 import _lib
     cfg, h = _lib.ArsConfigC(), C.c_void_p()
     cfg.in_rate, cfg.out_rate, cfg.channels, cfg.quality = 48000, 48000, 2, 4
-    assert g.lib.b200_ars_create(C.byref(cfg), -1, C.byref(h)) == -2
-    # linear table interpolation: FULL mode is host work only; the interpolated mode's blend is opt-in device code
+    assert g.lib.b200_ars_create(C.byref(cfg), -1, C.byref(h)) == 0     # the library follows gst_audio_resampler (copy kernel)
+    g.lib.b200_ars_destroy(h)
+    # every method / table interpolation / filter mode builds a plan (device-verified in tests/test_ars_options_gpu.py)
     CudaAudioResample(cuda_device_id=-1, sinc_filter_interpolation="linear").set_caps(48000, 44100, 2)
     for kw in ({"resample_method": "linear"}, {"resample_method": "nearest"}, {"resample_method": "cubic"},
                {"sinc_filter_interpolation": "linear", "sinc_filter_mode": "interpolated"}):
-        with pytest.raises(g.B200Error) as e:
-            CudaAudioResample(cuda_device_id=-1, **kw).set_caps(48000, 44100, 2)
-        assert e.value.status == -2
+        CudaAudioResample(cuda_device_id=-1, **kw).set_caps(48000, 44100, 2)
 
 
 @pytest.mark.parametrize("method,mode,interp", [("blackman-nuttall", "auto", "cubic"), ("blackman-nuttall", "full", "none"),

@@ -13,8 +13,7 @@ import pytest
 
 from oracle import bindings as ob
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("B200_TEST_EXPERIMENTAL") != "1", reason="opt-in: B200_TEST_EXPERIMENTAL=1")]
+pytestmark = [pytest.mark.gpu]
 
 PAIRS = [("NV12", "BGRA"), ("I420", "RGBA"), ("NV12", "NV12"), ("I420", "YV12"), ("NV12", "I420"), ("YV12", "NV21")]
 

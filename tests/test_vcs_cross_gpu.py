@@ -36,7 +36,7 @@ def convert(size, method, frame, pair, site, out_site, batch=1):
     import torch
     import gstreamer_b200 as g
     iw, ih, ow, oh = size
-    el = g.CudaVideoConvertScale(method=method, cuda_device_id=0)
+    el = g.CudaVideoConvertScale(add_borders=False, method=method, cuda_device_id=0)
     ii, oi = g.VideoInfo(ob.FMT[pair[0]], iw, ih), g.VideoInfo(ob.FMT[pair[1]], ow, oh)
     ii.set_colorimetry(chroma_site=site)
     oi.set_colorimetry(matrix=ii.c.color_matrix, chroma_site=out_site)      # what the element's caps fixation does
@@ -96,7 +96,7 @@ def test_cross_family_batch(cuda_device):
 
 def test_cross_family_refusals(cuda_device):
     import gstreamer_b200 as g
-    el = g.CudaVideoConvertScale(method=1)
+    el = g.CudaVideoConvertScale(add_borders=False, method=1)
     ii, oi = g.VideoInfo(23, 64, 48), g.VideoInfo(2, 32, 24)
     oi.set_colorimetry(matrix=3 if ii.c.color_matrix == 4 else 4)           # a matrix stage: not built
     with pytest.raises(g.B200Error):
@@ -119,7 +119,7 @@ def test_cross_family_odd_height_without_vertical_scaler(cuda_device, size):
             want = expected(size, method, frame, pair, site, out_site)
             (got,), oi = convert(size, method, frame, pair, site, out_site)
             assert not planes_equal(got, want, oi, ow, oh, False), (method, site, out_site)
-    el = g.CudaVideoConvertScale(method=1)
+    el = g.CudaVideoConvertScale(add_borders=False, method=1)
     ii, oi = g.VideoInfo(23, 64, 49), g.VideoInfo(2, 32, 49)
     g.transfer_colorimetry_from_input(ii, oi)
     el.set_info(ii, oi)

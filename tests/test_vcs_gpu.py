@@ -26,7 +26,7 @@ def _run_gpu(iw, ih, ow, oh, method, frame, in_fmt=23, out_fmt=12, site=None, ma
              batch=1):
     import torch
     import gstreamer_b200 as g
-    el = g.CudaVideoConvertScale(method=method, cuda_device_id=0)
+    el = g.CudaVideoConvertScale(add_borders=False, method=method, cuda_device_id=0)
     ii = g.VideoInfo(in_fmt, iw, ih)
     ii.set_colorimetry(matrix=matrix, range=rng, chroma_site=site)
     oi = g.VideoInfo(out_fmt, ow, oh)
@@ -116,7 +116,7 @@ def test_custom_strides_and_offsets(cuda_device):
     padded[256 + pitch * ih:].reshape(ih // 2, pitch)[:, :st] = uv
     ii = g.VideoInfo(23, iw, ih).set_layout([pitch, pitch], [256, 256 + pitch * ih])
     oi = g.VideoInfo(12, ow, oh).set_layout([opitch], [64])
-    el = g.CudaVideoConvertScale(method=3)
+    el = g.CudaVideoConvertScale(add_borders=False, method=3)
     el.set_info(ii, oi)
     src = torch.from_numpy(padded).cuda()
     dst = torch.full((64 + opitch * oh,), 0x5A, dtype=torch.uint8, device="cuda")
@@ -134,7 +134,7 @@ def test_host_path_round_trip(cuda_device):
     import gstreamer_b200 as g
     iw, ih, ow, oh = 640, 360, 320, 180
     d = ob.vcs_desc(iw, ih, ow, oh, 3)
-    el = g.CudaVideoConvertScale(method=3)
+    el = g.CudaVideoConvertScale(add_borders=False, method=3)
     ii, oi = g.VideoInfo(23, iw, ih), g.VideoInfo(12, ow, oh)
     el.set_info(ii, oi)
     n = 9
@@ -181,3 +181,29 @@ def test_linearity_of_luma_steps_full_size(cuda_device):
     d = ob.vcs_desc(iw, strip_h, ow, strip_h // 2, 3, site=2, matrix=3, rng=2)
     want = ob.oracle_vcs_convert(d, strip).reshape(strip_h // 2, ow, 4)
     assert np.array_equal(got[4:56], want[4:56])
+
+
+@pytest.mark.parametrize("variant", [0, 2, 3])
+def test_two_handles_share_a_kernel(cuda_device, variant):
+    """The dynamic shared-memory limit is an attribute of the kernel FUNCTION: a second handle with a smaller footprint
+    must not lower it under the first one (two converters in one process, a compositor's per-pad converters)."""
+    import torch
+    import gstreamer_b200 as g
+    method = 1 if variant == 2 else 3
+    big, small = (1920, 1080, 1280, 720), (64, 48, 32, 24)
+
+    def make(size):
+        el = g.CudaVideoConvertScale(add_borders=False, method=method, cuda_device_id=0)
+        ii, oi = g.VideoInfo(23, size[0], size[1]), g.VideoInfo(12, size[2], size[3])
+        el.set_info(ii, oi)
+        el.set_kernel_variant(variant)
+        return el, ii, oi
+
+    a, ii, oi = make(big)
+    b, _, _ = make(small)          # created after, smaller tiles: used to shrink the shared attribute
+    frame = ob.nv12_random_frame(big[0], big[1], seed=11)
+    want = ob.oracle_vcs_convert(ob.vcs_desc(*big, method), frame)
+    dst = torch.full((oi.size,), 0xA5, dtype=torch.uint8, device="cuda")
+    a.transform_frame(torch.from_numpy(frame).cuda(), dst)
+    torch.cuda.synchronize()
+    assert np.array_equal(dst.cpu().numpy(), want)

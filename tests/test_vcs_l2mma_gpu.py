@@ -9,8 +9,7 @@ import pytest
 
 from oracle import bindings as ob
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("B200_TEST_EXPERIMENTAL") != "1", reason="opt-in: B200_TEST_EXPERIMENTAL=1")]
+pytestmark = [pytest.mark.gpu]
 
 SIZES = [(16, 16), (64, 48), (256, 144), (496, 272), (1920, 1088), (3840, 2160)]   # output sizes must be multiples of 8
 METHODS = [3, 5, 6, 7, 8, 9]
@@ -19,7 +18,7 @@ METHODS = [3, 5, 6, 7, 8, 9]
 def convert(iw, ih, method, frame, in_fmt=23, out_fmt=12, matrix=None, rng=None, batch=1):
     import torch
     import gstreamer_b200 as g
-    el = g.CudaVideoConvertScale(method=method)
+    el = g.CudaVideoConvertScale(add_borders=False, method=method)
     ii = g.VideoInfo(in_fmt, iw, ih).set_colorimetry(chroma_site=2, matrix=matrix, range=rng)
     oi = g.VideoInfo(out_fmt, iw // 2, ih // 2)
     el.set_info(ii, oi)

@@ -14,7 +14,7 @@ METHODS = [3, 5, 6, 7, 8, 9]          # every element method that yields 8 taps 
 def _convert(iw, ih, method, frame, variant, in_fmt=23, out_fmt=12, matrix=None, rng=None):
     import torch
     import gstreamer_b200 as g
-    el = g.CudaVideoConvertScale(method=method)
+    el = g.CudaVideoConvertScale(add_borders=False, method=method)
     ii = g.VideoInfo(in_fmt, iw, ih).set_colorimetry(chroma_site=2, matrix=matrix, range=rng)
     oi = g.VideoInfo(out_fmt, iw // 2, ih // 2)
     el.set_info(ii, oi)

@@ -19,7 +19,7 @@ SIZES = [
 def _convert(iw, ih, ow, oh, method, frame, variant=None, in_fmt=23, out_fmt=12, site=None, matrix=None, rng=None):
     import torch
     import gstreamer_b200 as g
-    el = g.CudaVideoConvertScale(method=method, cuda_device_id=0)
+    el = g.CudaVideoConvertScale(add_borders=False, method=method, cuda_device_id=0)
     ii = g.VideoInfo(in_fmt, iw, ih)
     ii.set_colorimetry(matrix=matrix, range=rng, chroma_site=site)
     oi = g.VideoInfo(out_fmt, ow, oh)
@@ -83,7 +83,7 @@ def test_light_pitched_layout(cuda_device):
     padded[256 + pitch * ih:].reshape(ih // 2, pitch)[:, :st] = frame[st * ih:].reshape(ih // 2, st)
     ii = g.VideoInfo(23, iw, ih).set_layout([pitch, pitch], [256, 256 + pitch * ih])
     oi = g.VideoInfo(12, ow, oh).set_layout([opitch], [64])
-    el = g.CudaVideoConvertScale(method=1)
+    el = g.CudaVideoConvertScale(add_borders=False, method=1)
     el.set_info(ii, oi)
     assert int(el.plan_info().kernel_variant) == 2
     dst = torch.full((64 + opitch * oh,), 0x77, dtype=torch.uint8, device="cuda")
@@ -108,7 +108,7 @@ def test_light_unaligned_layout_falls_back(cuda_device):
     padded[pitch * ih:].reshape(ih // 2, pitch)[:, :iw] = frame[st * ih:].reshape(ih // 2, st)[:, :iw]
     ii = g.VideoInfo(23, iw, ih).set_layout([pitch, pitch], [0, pitch * ih])
     oi = g.VideoInfo(12, ow, oh)
-    el = g.CudaVideoConvertScale(method=1)
+    el = g.CudaVideoConvertScale(add_borders=False, method=1)
     el.set_info(ii, oi)
     assert int(el.plan_info().kernel_variant) == 0
     dst = torch.zeros(oi.size, dtype=torch.uint8, device="cuda")
@@ -123,7 +123,7 @@ def test_light_batch(cuda_device):
     iw, ih, ow, oh = 1920, 1080, 1280, 720
     frames = [ob.nv12_smpte_like_frame(iw, ih, s) for s in range(3)]
     d = ob.vcs_desc(iw, ih, ow, oh, 1)
-    el = g.CudaVideoConvertScale(method=1)
+    el = g.CudaVideoConvertScale(add_borders=False, method=1)
     ii, oi = g.VideoInfo(23, iw, ih), g.VideoInfo(12, ow, oh)
     el.set_info(ii, oi)
     src = [torch.from_numpy(f).cuda() for f in frames]

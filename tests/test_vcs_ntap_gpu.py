@@ -19,7 +19,7 @@ METHODS = [2, 3, 4, 5, 6, 7, 8, 9]      # every n-tap method of GstVideoScaleMet
 def _convert(iw, ih, ow, oh, method, frame, variant=None, in_fmt=23, out_fmt=12, site=None, matrix=None, rng=None):
     import torch
     import gstreamer_b200 as g
-    el = g.CudaVideoConvertScale(method=method, cuda_device_id=0)
+    el = g.CudaVideoConvertScale(add_borders=False, method=method, cuda_device_id=0)
     ii = g.VideoInfo(in_fmt, iw, ih)
     ii.set_colorimetry(matrix=matrix, range=rng, chroma_site=site)
     oi = g.VideoInfo(out_fmt, ow, oh)
@@ -100,7 +100,7 @@ def test_ntap_batch_full_size(cuda_device):
     iw, ih, ow, oh = 3840, 2160, 1280, 720
     frames = [ob.nv12_random_frame(iw, ih, s) for s in range(2)]
     d = ob.vcs_desc(iw, ih, ow, oh, 3)
-    el = g.CudaVideoConvertScale(method=3)
+    el = g.CudaVideoConvertScale(add_borders=False, method=3)
     ii, oi = g.VideoInfo(23, iw, ih), g.VideoInfo(12, ow, oh)
     el.set_info(ii, oi)
     assert int(el.plan_info().kernel_variant) == 3

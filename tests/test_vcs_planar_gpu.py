@@ -16,7 +16,7 @@ def _convert(iw, ih, ow, oh, method, frame, in_fmt, variant=None, out_fmt=12, si
              layout=None):
     import torch
     import gstreamer_b200 as g
-    el = g.CudaVideoConvertScale(method=method, cuda_device_id=0)
+    el = g.CudaVideoConvertScale(add_borders=False, method=method, cuda_device_id=0)
     ii = g.VideoInfo(in_fmt, iw, ih)
     ii.set_colorimetry(matrix=matrix, range=rng, chroma_site=site)
     if layout:

@@ -18,7 +18,7 @@ PAIRS = [("NV12", "NV12"), ("NV21", "NV21"), ("I420", "I420"), ("YV12", "YV12"),
 def _convert(iw, ih, ow, oh, method, frame, in_fmt, out_fmt, batch=1):
     import torch
     import gstreamer_b200 as g
-    el = g.CudaVideoConvertScale(method=method, cuda_device_id=0)
+    el = g.CudaVideoConvertScale(add_borders=False, method=method, cuda_device_id=0)
     ii, oi = g.VideoInfo(in_fmt, iw, ih), g.VideoInfo(out_fmt, ow, oh)
     el.set_info(ii, oi)
     assert int(el.plan_info().kernel_variant) == 4

@@ -13,8 +13,7 @@ import pytest
 
 from oracle import bindings as ob
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("B200_TEST_EXPERIMENTAL") != "1", reason="opt-in: B200_TEST_EXPERIMENTAL=1")]
+pytestmark = [pytest.mark.gpu]
 
 RGB_IN = ["BGRA", "RGBA", "ARGB", "ABGR", "BGRx", "RGBx", "xRGB", "xBGR"]
 YUV_OUT = ["NV12", "I420", "NV21", "YV12"]
@@ -36,7 +35,7 @@ def convert(size, method, frame, fi, fo, colorimetry=None, batch=1):
     import torch
     import gstreamer_b200 as g
     iw, ih, ow, oh = size
-    el = g.CudaVideoConvertScale(method=method, cuda_device_id=0)
+    el = g.CudaVideoConvertScale(add_borders=False, method=method, cuda_device_id=0)
     ii, oi = g.VideoInfo(ob.FMT[fi], iw, ih), g.VideoInfo(ob.FMT[fo], ow, oh)
     if colorimetry:
         oi.set_colorimetry(matrix=colorimetry[0], range=colorimetry[1], chroma_site=colorimetry[2])
@@ -110,7 +109,7 @@ def test_rgb_same_format_scaling_matches_oracle(cuda_device, size, method):
     for fmt, fmt_out in pairs:                      # same format: one-plane rows; another byte order: matrix-free chain
         frame = rgb_frame(iw, ih, 11)
         want = ob.oracle_vcs_convert(ob.vcs_desc(iw, ih, ow, oh, method, in_fmt=ob.FMT[fmt], out_fmt=ob.FMT[fmt_out]), frame)
-        el = g.CudaVideoConvertScale(method=method, cuda_device_id=0)
+        el = g.CudaVideoConvertScale(add_borders=False, method=method, cuda_device_id=0)
         ii, oi = g.VideoInfo(ob.FMT[fmt], iw, ih), g.VideoInfo(ob.FMT[fmt_out], ow, oh)
         el.set_info(ii, oi)
         assert int(el.plan_info().kernel_variant) == 4
@@ -136,7 +135,7 @@ def test_422_444_inputs_match_oracle(cuda_device, fi, size):
             d = ob.vcs_desc(iw, ih, ow, oh, method, in_fmt=ob.FMT[fi], out_fmt=ob.FMT["BGRA"], site=site)
             frame = np.random.default_rng(method).integers(0, 256, ob.vcs_sizes(d)[0], dtype=np.uint8)
             want = ob.oracle_vcs_convert(d, frame)
-            el = g.CudaVideoConvertScale(method=method, cuda_device_id=0)
+            el = g.CudaVideoConvertScale(add_borders=False, method=method, cuda_device_id=0)
             ii, oi = g.VideoInfo(ob.FMT[fi], iw, ih), g.VideoInfo(ob.FMT["BGRA"], ow, oh)
             ii.set_colorimetry(chroma_site=site)
             el.set_info(ii, oi)

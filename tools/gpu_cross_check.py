@@ -114,7 +114,7 @@ def main():
     # 3. timing: 1080p -> 720p NV12 -> I420 lanczos, 16 frames per launch pair
     try:
         size, pair = (1920, 1080, 1280, 720), ("NV12", "I420")
-        el = g.CudaVideoConvertScale(method=3, cuda_device_id=0)
+        el = g.CudaVideoConvertScale(add_borders=False, method=3, cuda_device_id=0)
         ii, oi = g.VideoInfo(23, 1920, 1080), g.VideoInfo(2, 1280, 720)
         oi.set_colorimetry(matrix=ii.c.color_matrix, chroma_site=ii.c.chroma_site)
         el.set_info(ii, oi)

@@ -39,7 +39,7 @@ def main():
         d = ob.vcs_desc(iw, ih, ow, oh, m, in_fmt=fi, out_fmt=fo, site=site, matrix=mat, rng=rg)
         d.out_chroma_site = out_site
         want = ob.oracle_vcs_convert(d, frame)
-        el = g.CudaVideoConvertScale(method=m)
+        el = g.CudaVideoConvertScale(add_borders=False, method=m)
         ii = g.VideoInfo(fi, iw, ih)
         ii.set_colorimetry(matrix=mat, range=rg, chroma_site=site)
         oi = g.VideoInfo(fo, ow, oh)
