@@ -80,6 +80,8 @@ _SIGS = {
     "b200_device_count": (C.c_int, []),
     "b200_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_P)]),
     "b200_host_free": (C.c_int, [_P]),
+    "b200_host_alloc_near": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(_P)]),
+    "b200_device_numa_node": (C.c_int, [C.c_int]),
     "b200_video_info_set_format": (C.c_int, [C.POINTER(VideoInfoC), C.c_int, C.c_int, C.c_int]),
     "b200_video_info_size": (C.c_size_t, [C.POINTER(VideoInfoC)]),
     "b200_vcs_config_init": (None, [C.POINTER(VcsConfigC)]),
@@ -89,6 +91,7 @@ _SIGS = {
     "b200_vcs_convert": (C.c_int, [_P, _P, _P, _P]),
     "b200_vcs_convert_batch": (C.c_int, [_P, C.c_int, C.POINTER(_P), C.POINTER(_P), _P]),
     "b200_vcs_convert_host": (C.c_int, [_P, C.c_int, C.POINTER(_P), C.POINTER(_P)]),
+    "b200_vcs_copy_probe": (C.c_int, [_P, C.c_int, C.POINTER(_P), C.POINTER(_P)]),
     "b200_vcs_get_plan_info": (C.c_int, [_P, C.POINTER(VcsPlanInfoC)]),
     "b200_vcs_get_taps": (C.c_int, [_P, C.c_int, _P, _P, C.c_size_t, C.c_size_t]),
     "b200_vcs_get_matrix": (C.c_int, [_P, _P]),

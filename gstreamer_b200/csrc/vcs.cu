@@ -31,11 +31,12 @@ struct b200_vcs {
   int16_t *d_hcoef = nullptr, *d_vcoef = nullptr, *d_hsum = nullptr, *d_vsum = nullptr;
   uint8_t *d_cmode = nullptr;
   // host<->device pipeline for system-memory peers
-  static const int kSlots = 4;
+  static const int kSlots = 4, kChunk = 4;
   uint8_t *slot_in[kSlots] = {nullptr}, *slot_out[kSlots] = {nullptr};
   cudaStream_t s_h2d = nullptr, s_run = nullptr, s_d2h = nullptr;
   cudaEvent_t ev_in[kSlots] = {nullptr}, ev_run[kSlots] = {nullptr}, ev_out[kSlots] = {nullptr};
   bool pipeline_ready = false;
+  int slot_frames = 0;            // frames each slot holds (one kernel launch per slot-full)
   Lanczos2Tables l2_tables;
   Lanczos2State l2;
   NtapState ntap;
@@ -158,22 +159,33 @@ int launch_convert (b200_vcs * h, int n, const VcsBatch & batch, cudaStream_t st
   return B200_OK;
 }
 
-int ensure_pipeline (b200_vcs * h)
+int ensure_pipeline (b200_vcs * h, int chunk)
 {
-  if (h->pipeline_ready) return B200_OK;
+  if (h->pipeline_ready && chunk <= h->slot_frames) return B200_OK;
   h->in_bytes = frame_bytes (h->plan.in);
   h->out_bytes = frame_bytes (h->plan.frame_out);
-  B200_CUDA_TRY (cudaStreamCreateWithFlags (&h->s_h2d, cudaStreamNonBlocking));
-  B200_CUDA_TRY (cudaStreamCreateWithFlags (&h->s_run, cudaStreamNonBlocking));
-  B200_CUDA_TRY (cudaStreamCreateWithFlags (&h->s_d2h, cudaStreamNonBlocking));
-  for (int i = 0; i < b200_vcs::kSlots; i++) {
-    B200_CUDA_TRY (cudaMalloc ((void **) &h->slot_in[i], h->in_bytes));
-    B200_CUDA_TRY (cudaMalloc ((void **) &h->slot_out[i], h->out_bytes));
-    B200_CUDA_TRY (cudaEventCreateWithFlags (&h->ev_in[i], cudaEventDisableTiming));
-    B200_CUDA_TRY (cudaEventCreateWithFlags (&h->ev_run[i], cudaEventDisableTiming));
-    B200_CUDA_TRY (cudaEventCreateWithFlags (&h->ev_out[i], cudaEventDisableTiming));
+  if (!h->pipeline_ready) {
+    B200_CUDA_TRY (cudaStreamCreateWithFlags (&h->s_h2d, cudaStreamNonBlocking));
+    B200_CUDA_TRY (cudaStreamCreateWithFlags (&h->s_run, cudaStreamNonBlocking));
+    B200_CUDA_TRY (cudaStreamCreateWithFlags (&h->s_d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < b200_vcs::kSlots; i++) {
+      B200_CUDA_TRY (cudaEventCreateWithFlags (&h->ev_in[i], cudaEventDisableTiming));
+      B200_CUDA_TRY (cudaEventCreateWithFlags (&h->ev_run[i], cudaEventDisableTiming));
+      B200_CUDA_TRY (cudaEventCreateWithFlags (&h->ev_out[i], cudaEventDisableTiming));
+    }
+    h->pipeline_ready = true;
   }
-  h->pipeline_ready = true;
+  // (re)size the slots: each holds `chunk` frames, so that one kernel launch and one event triple serve a whole chunk
+  for (int i = 0; i < b200_vcs::kSlots; i++) {
+    B200_CUDA_TRY (cudaFree (h->slot_in[i])); h->slot_in[i] = nullptr;       // cudaFree waits for work still using it
+    B200_CUDA_TRY (cudaFree (h->slot_out[i])); h->slot_out[i] = nullptr;
+  }
+  h->slot_frames = 0;
+  for (int i = 0; i < b200_vcs::kSlots; i++) {
+    B200_CUDA_TRY (cudaMalloc ((void **) &h->slot_in[i], h->in_bytes * chunk));
+    B200_CUDA_TRY (cudaMalloc ((void **) &h->slot_out[i], h->out_bytes * chunk));
+  }
+  h->slot_frames = chunk;
   return B200_OK;
 }
 
@@ -452,32 +464,60 @@ int b200_vcs_convert_host (b200_vcs * h, int n, const void *const *in_host, void
 {
   if (!h || !in_host || !out_host || n < 1) return B200_ERR_INVALID_ARG;
   if (h->device < 0) return B200_ERR_NO_DEVICE;
+  for (int i = 0; i < n; i++) if (!in_host[i] || !out_host[i]) return B200_ERR_INVALID_ARG;
   DeviceGuard g (h->device);
   if (!g.ok) return B200_ERR_CUDA;
-  int st = ensure_pipeline (h);
-  if (st != B200_OK) return st;
-  // three-stage software pipeline over kSlots device frame pairs: the upload of frame
-  // i+1 and the download of frame i-1 overlap the kernel of frame i (copy engines run
-  // beside the SMs).  Slot reuse is fenced by the download event of its previous user.
+  // Three-stage software pipeline over kSlots device slots of `chunk` frames: the upload of chunk c+1 and the download
+  // of chunk c-1 overlap the kernel of chunk c (the copy engines run beside the SMs).  One kernel launch and one event
+  // triple per chunk, not per frame; with few frames the chunk shrinks so that all three stages still overlap.
   const int K = b200_vcs::kSlots;
-  for (int i = 0; i < n; i++) {
-    const int s = i % K;
-    if (!in_host[i] || !out_host[i]) return B200_ERR_INVALID_ARG;
-    if (i >= K) {
+  // measured: 16 frames in chunks of 4 lose 14 % to pipeline fill / drain against single frames
+  const int chunk = n >= 16 * b200_vcs::kChunk ? b200_vcs::kChunk : (n >= 32 ? 2 : 1);
+  int st = ensure_pipeline (h, chunk);
+  if (st != B200_OK) return st;
+  int c = 0;
+  for (int i0 = 0; i0 < n; i0 += chunk, c++) {
+    const int s = c % K, m = min (chunk, n - i0);
+    if (c >= K) {
       B200_CUDA_TRY (cudaStreamWaitEvent (h->s_h2d, h->ev_run[s], 0));   // input slot consumed
       B200_CUDA_TRY (cudaStreamWaitEvent (h->s_run, h->ev_out[s], 0));   // output slot drained
     }
-    B200_CUDA_TRY (cudaMemcpyAsync (h->slot_in[s], in_host[i], h->in_bytes, cudaMemcpyHostToDevice, h->s_h2d));
+    VcsBatch b;
+    for (int j = 0; j < m; j++) {
+      b.in[j] = h->slot_in[s] + (size_t) j * h->in_bytes; b.out[j] = h->slot_out[s] + (size_t) j * h->out_bytes;
+      B200_CUDA_TRY (cudaMemcpyAsync ((void *) b.in[j], in_host[i0 + j], h->in_bytes, cudaMemcpyHostToDevice, h->s_h2d));
+    }
     B200_CUDA_TRY (cudaEventRecord (h->ev_in[s], h->s_h2d));
     B200_CUDA_TRY (cudaStreamWaitEvent (h->s_run, h->ev_in[s], 0));
-    VcsBatch b;
-    b.in[0] = h->slot_in[s]; b.out[0] = h->slot_out[s];
-    if ((st = launch (h, 1, b, h->s_run)) != B200_OK) return st;
+    if ((st = launch (h, m, b, h->s_run)) != B200_OK) return st;
     B200_CUDA_TRY (cudaEventRecord (h->ev_run[s], h->s_run));
     B200_CUDA_TRY (cudaStreamWaitEvent (h->s_d2h, h->ev_run[s], 0));
-    B200_CUDA_TRY (cudaMemcpyAsync (out_host[i], h->slot_out[s], h->out_bytes, cudaMemcpyDeviceToHost, h->s_d2h));
+    for (int j = 0; j < m; j++)
+      B200_CUDA_TRY (cudaMemcpyAsync (out_host[i0 + j], b.out[j], h->out_bytes, cudaMemcpyDeviceToHost, h->s_d2h));
     B200_CUDA_TRY (cudaEventRecord (h->ev_out[s], h->s_d2h));
   }
+  B200_CUDA_TRY (cudaStreamSynchronize (h->s_d2h));
+  return B200_OK;
+}
+
+int b200_vcs_copy_probe (b200_vcs * h, int n, const void *const *in_host, void *const *out_host)
+{
+  // the copies of b200_vcs_convert_host without the kernels: H2D of every input on one stream, D2H of every output
+  // (whatever the slots hold) on another, both directions in flight together - the link's ceiling for this call
+  if (!h || !in_host || !out_host || n < 1) return B200_ERR_INVALID_ARG;
+  if (h->device < 0) return B200_ERR_NO_DEVICE;
+  DeviceGuard g (h->device);
+  if (!g.ok) return B200_ERR_CUDA;
+  int st = ensure_pipeline (h, max (h->slot_frames, 1));
+  if (st != B200_OK) return st;
+  const int K = b200_vcs::kSlots, chunk = h->slot_frames;
+  for (int i = 0; i < n; i++) {
+    const int s = (i / chunk) % K, j = i % chunk;
+    if (!in_host[i] || !out_host[i]) return B200_ERR_INVALID_ARG;
+    B200_CUDA_TRY (cudaMemcpyAsync (h->slot_in[s] + (size_t) j * h->in_bytes, in_host[i], h->in_bytes, cudaMemcpyHostToDevice, h->s_h2d));
+    B200_CUDA_TRY (cudaMemcpyAsync (out_host[i], h->slot_out[s] + (size_t) j * h->out_bytes, h->out_bytes, cudaMemcpyDeviceToHost, h->s_d2h));
+  }
+  B200_CUDA_TRY (cudaStreamSynchronize (h->s_h2d));
   B200_CUDA_TRY (cudaStreamSynchronize (h->s_d2h));
   return B200_OK;
 }

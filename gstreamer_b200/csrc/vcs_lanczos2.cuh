@@ -130,13 +130,17 @@ __device__ __forceinline__ unsigned pack_sat_u16x2 (int a, int b)
 // 4 outputs from 16 aligned bytes w0..w3: outputs 0,1 read words 0..2, outputs 2,3 words 1..3
 #define L2_FIR4(o0, o1, o2, o3, w0, w1, w2, w3, T, INIT)                                       \
   do {                                                                                         \
+    if (ABL & L2_FIR_BIT) { o0 = (w0) + T[0].x; o1 = (w1) + T[1].x; o2 = (w2) + T[2].x; o3 = (w3) + INIT; break; } \
     o0 = dp4a_u8s8 (w2, T[0].z, dp4a_u8s8 (w1, T[0].y, dp4a_u8s8 (w0, T[0].x, INIT)));         \
     o1 = dp4a_u8s8 (w2, T[1].y, dp4a_u8s8 (w1, T[1].x, dp4a_u8s8 (w0, T[0].w, INIT)));         \
     o2 = dp4a_u8s8 (w3, T[2].x, dp4a_u8s8 (w2, T[1].w, dp4a_u8s8 (w1, T[1].z, INIT)));         \
     o3 = dp4a_u8s8 (w3, T[2].w, dp4a_u8s8 (w2, T[2].z, dp4a_u8s8 (w1, T[2].y, INIT)));         \
   } while (0)
 
-template <bool ALPHA_OPAQUE, int MINB, int TH, int NWC, bool X4 = false>
+// ABL != 0: NON-PARITY ablation builds for tools/l2lab.cu (which stage costs what, measured instead of counted); the
+// product only ever instantiates ABL = 0.  Bits: 1 no chroma preparation, 2 no H FIR, 4 no V phase, 8 no H phase,
+// 16 no matrix, 32 no V FIR.
+template <bool ALPHA_OPAQUE, int MINB, int TH, int NWC, bool X4 = false, int ABL = 0>
 __global__ void __launch_bounds__ (L2_THREADS, MINB)
 vcs_lanczos2_kernel (const VcsDev P, const Lanczos2Dev L, const VcsBatch frames)
 {
@@ -158,8 +162,10 @@ vcs_lanczos2_kernel (const VcsDev P, const Lanczos2Dev L, const VcsBatch frames)
   // Tiles that touch no frame border skip every clamp (line / chroma-row / column indices and the
   // "no chroma sample to the right" fix-up): warp-uniform choice between two instantiations.
   const bool edge_tile = R0 < 0 || R0 + 4 * L2_NG > P.ih || x0 == 0 || x0 + L2_TW + 4 >= P.ow;
+#define L2_FIR_BIT 2
   auto h_phase = [&] (auto edge_tag) {
     constexpr bool EDGE = decltype (edge_tag)::value;
+    if (ABL & 8) return;
     constexpr bool H4 = X4 && !EDGE;                             // interior tiles only: no folded taps there
     constexpr int HINIT = H4 ? 128 : 32;
     const int4 *__restrict__ htab = H4 ? L.htab4 : L.htab;
@@ -180,10 +186,14 @@ vcs_lanczos2_kernel (const VcsDev P, const Lanczos2Dev L, const VcsBatch frames)
 
     // chroma: three rows, de-interleave, cosited h up-sample (video-chroma.c:687-699)
     unsigned ulo[3], uhi[3], vlo[3], vhi[3];
+    // interior tiles: one 64-bit address per plane and item, then row-to-row steps (the per-row index form costs a
+    // 64-bit multiply-add per load)
+    const uint8_t *pc = plane_c + (ptrdiff_t) m2 * P.stride_c + xb;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
       const int cr = EDGE ? min (max (m2 + k, 0), crows - 1) : m2 + k;
-      const uint2 c = __ldg ((const uint2 *) (plane_c + (size_t) cr * P.stride_c + xb));
+      const uint2 c = __ldg ((const uint2 *) (EDGE ? plane_c + (size_t) cr * P.stride_c + xb : pc));
+      pc += P.stride_c;
       const unsigned ue = __byte_perm (c.x, c.y, selU), ve = __byte_perm (c.x, c.y, selV);
       unsigned un = __shfl_down_sync (0xffffffffu, ue, 1), vn = __shfl_down_sync (0xffffffffu, ve, 1);
       if (EDGE) {
@@ -193,14 +203,19 @@ vcs_lanczos2_kernel (const VcsDev P, const Lanczos2Dev L, const VcsBatch frames)
         un = __byte_perm (ue, un, 0x4321);
         vn = __byte_perm (ve, vn, 0x4321);
       }
-      const unsigned uo = avg_ceil4 (ue, un), vo = avg_ceil4 (ve, vn);
+      const unsigned uo = (ABL & 1) ? un : avg_ceil4 (ue, un), vo = (ABL & 1) ? vn : avg_ceil4 (ve, vn);
       ulo[k] = __byte_perm (ue, uo, 0x5140); uhi[k] = __byte_perm (ue, uo, 0x7362);
       vlo[k] = __byte_perm (ve, vo, 0x5140); vhi[k] = __byte_perm (ve, vo, 0x7362);
     }
     // vertical pairs (4m+1,4m+2) on rows (a,b) and (4m+3,4m+4) on rows (b,c):
     // (3x+y+2)>>2 == avg_ceil (x, avg_floor (x,y))   (video-orc.orc:2705-2735)
     unsigned U[4][2], V[4][2];
-    {
+    if (ABL & 1) {
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        U[r][0] = ulo[(r + 1) >> 1]; U[r][1] = uhi[(r + 1) >> 1]; V[r][0] = vlo[(r + 1) >> 1]; V[r][1] = vhi[(r + 1) >> 1];
+      }
+    } else {
       unsigned f;
       f = avg_floor4 (ulo[0], ulo[1]); U[0][0] = avg_ceil4 (ulo[0], f); U[1][0] = avg_ceil4 (ulo[1], f);
       f = avg_floor4 (uhi[0], uhi[1]); U[0][1] = avg_ceil4 (uhi[0], f); U[1][1] = avg_ceil4 (uhi[1], f);
@@ -237,10 +252,12 @@ vcs_lanczos2_kernel (const VcsDev P, const Lanczos2Dev L, const VcsBatch frames)
       L2_FIR4 (acc[r][0], acc[r][1], acc[r][2], acc[r][3], w0, V[r][0], V[r][1], w3, T, HINIT);
     }
     L2_STORE (2, acc);
+    const uint8_t *py = plane_y + (ptrdiff_t) y0 * P.stride_y + xb;
 #pragma unroll
     for (int r = 0; r < 4; r++) {
       const int y = EDGE ? min (max (y0 + r, 0), P.ih - 1) : y0 + r;
-      const uint2 yy = __ldg ((const uint2 *) (plane_y + (size_t) y * P.stride_y + xb));
+      const uint2 yy = __ldg ((const uint2 *) (EDGE ? plane_y + (size_t) y * P.stride_y + xb : py));
+      py += P.stride_y;
       const unsigned w0 = __shfl_up_sync (0xffffffffu, yy.y, 1), w3 = __shfl_down_sync (0xffffffffu, yy.x, 1);
       L2_FIR4 (acc[r][0], acc[r][1], acc[r][2], acc[r][3], w0, yy.x, yy.y, w3, T, HINIT);
     }
@@ -248,30 +265,39 @@ vcs_lanczos2_kernel (const VcsDev P, const Lanczos2Dev L, const VcsBatch frames)
   }
   };
   if (edge_tile) h_phase (std::true_type {}); else h_phase (std::false_type {});
+#undef L2_FIR_BIT
+#define L2_FIR_BIT 32
   __syncthreads ();
+  if (ABL & 4) return;
 
   // ---------------------------------------------------------------- V phase
-  // a warp owns output rows oy0+4q .. +3 for all columns of the tile
-  for (int q = warp; q < L2_TH / 4; q += L2_THREADS / 32) {
+  // a warp owns output rows oy0+4q .. +3 for all columns of the tile.  The taps-times-4 choice is warp-uniform and taken
+  // as a BRANCH between two instantiations (as predicates both variants' packs would issue for every pixel); the column
+  // loop is unrolled so that the four row pointers are formed once per row group and every store offset is an immediate.
+  auto v_rows = [&] (auto v4_tag, int q) {
+    constexpr bool V4 = decltype (v4_tag)::value;
     const int oy = oy0 + 4 * q;
-    if (oy < P.oh) {
-      int4 T[3];
-      const bool v4 = X4 && __ldg (L.v4 + (oy >> 2)) != 0;       // warp-uniform: this row group's taps fit s8 times 4
-      const int4 *__restrict__ vtab = v4 ? L.vtab4 : L.vtab;
-      const int vinit = v4 ? 128 : 32;
-      T[0] = __ldg (vtab + (oy >> 2) * 3 + 0);
-      T[1] = __ldg (vtab + (oy >> 2) * 3 + 1);
-      T[2] = __ldg (vtab + (oy >> 2) * 3 + 2);
-      int vs[4] = {64, 64, 64, 64};
-      if (!ALPHA_OPAQUE) {
+    int4 T[3];
+    const int4 *__restrict__ vtab = V4 ? L.vtab4 : L.vtab;
+    constexpr int vinit = V4 ? 128 : 32;
+    T[0] = __ldg (vtab + (oy >> 2) * 3 + 0);
+    T[1] = __ldg (vtab + (oy >> 2) * 3 + 1);
+    T[2] = __ldg (vtab + (oy >> 2) * 3 + 2);
+    int vs[4] = {64, 64, 64, 64};
+    if (!ALPHA_OPAQUE) {
 #pragma unroll
-        for (int i = 0; i < 4; i++) vs[i] = L.vsum[min (oy + i, P.oh - 1)];
-      }
-      uint8_t *row0 = out + P.off_out + (size_t) oy * P.stride_out;   // oh % 4 == 0: all 4 rows exist
-      for (int c = lane; c < L2_TW; c += 32) {
-        const int ox = x0 + c;
-        if (ox >= P.ow) break;
-        const int sc = c + 4 + (c / L2_WCOLS) * (128 - L2_WCOLS);           // smem column of this output column
+      for (int i = 0; i < 4; i++) vs[i] = L.vsum[min (oy + i, P.oh - 1)];
+    }
+    uint8_t *rowp[4];                                            // oh % 4 == 0: all 4 rows exist
+    rowp[0] = out + P.off_out + (size_t) oy * P.stride_out + (size_t) (x0 + lane) * 4u;
+#pragma unroll
+    for (int i = 1; i < 4; i++) rowp[i] = rowp[i - 1] + P.stride_out;
+#pragma unroll
+    for (int k = 0; k < (L2_TW + 31) / 32; k++) {
+      const int c = lane + 32 * k;
+      const int ox = x0 + c;
+      if ((32 * k + 32 <= L2_TW || c < L2_TW) && ox < P.ow) {
+        const int sc = c + 4 + (L2_NWC == 1 ? 0 : (c / L2_WCOLS) * (128 - L2_WCOLS));   // smem column of this output column
         int a[3][4];
 #pragma unroll
         for (int ch = 0; ch < 3; ch++) {
@@ -281,11 +307,10 @@ vcs_lanczos2_kernel (const VcsDev P, const Lanczos2Dev L, const VcsBatch frames)
         }
         int ah = 255;
         if (!ALPHA_OPAQUE) ah = fir_round_u8 ((int) (short) (255 * (int) L.hsum[ox]));
-        uint8_t *dst = row0 + (unsigned) ox * 4u;
 #pragma unroll
         for (int i = 0; i < 4; i++) {
           // saturate the three channels at once, bias by 128 and sign-splat each byte to s16
-          unsigned yuv = v4 ? __byte_perm (pack_sat_u16x2 (a[1][i], a[0][i]), pack_sat_u16x2 (0, a[2][i]), 0x7531)
+          unsigned yuv = V4 ? __byte_perm (pack_sat_u16x2 (a[1][i], a[0][i]), pack_sat_u16x2 (0, a[2][i]), 0x7531)
               : pack_sat2 (a[1][i] >> 6, a[0][i] >> 6, pack_sat2 (0, a[2][i] >> 6, 0u));
           yuv ^= 0x00808080u;
           const int wy = prmt_s (yuv, 0x8800u), wu = prmt_s (yuv, 0x9911u), wv = prmt_s (yuv, 0xaa22u);
@@ -296,12 +321,20 @@ vcs_lanczos2_kernel (const VcsDev P, const Lanczos2Dev L, const VcsBatch frames)
           int al = 255;
           if (!ALPHA_OPAQUE) al = fir_round_u8 ((int) (short) (ah * vs[i]));
           // ARGB bytes in one word, then the output format's byte order
-          const unsigned argb = pack_sat2 (r, al, pack_sat2 (b, gg, 0u));
-          *(unsigned *) (dst + (size_t) i * P.stride_out) = __byte_perm (argb, 0, P.sel);
+          const unsigned argb = (ABL & 16) ? yuv : pack_sat2 (r, al, pack_sat2 (b, gg, 0u));
+          *(unsigned *) (rowp[i] + 128 * k) = __byte_perm (argb, 0, P.sel);
         }
       }
     }
+  };
+  for (int q = warp; q < L2_TH / 4; q += L2_THREADS / 32) {
+    const int oy = oy0 + 4 * q;
+    if (oy < P.oh) {
+      if (X4 && __ldg (L.v4 + (oy >> 2)) != 0) v_rows (std::true_type {}, q);     // this row group's taps fit s8 times 4
+      else v_rows (std::false_type {}, q);
+    }
   }
+#undef L2_FIR_BIT
 }
 
 // ------------------------------------------------------------------------------------ host side

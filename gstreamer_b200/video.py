@@ -155,9 +155,12 @@ def transfer_colorimetry_from_input(in_info, out_info):
 class PinnedBuffer:
     """Page-locked host staging buffer (b200_host_alloc), exposed as a numpy uint8 array."""
 
-    def __init__(self, nbytes):
+    def __init__(self, nbytes, device=None):
         p = C.c_void_p()
-        check(lib.b200_host_alloc(nbytes, C.byref(p)), "b200_host_alloc")
+        if device is None:
+            check(lib.b200_host_alloc(nbytes, C.byref(p)), "b200_host_alloc")
+        else:                   # on the NUMA node that device hangs off
+            check(lib.b200_host_alloc_near(device, nbytes, C.byref(p)), "b200_host_alloc_near")
         self.ptr = p.value
         self.nbytes = nbytes
         self.array = np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(self.ptr))
@@ -262,6 +265,13 @@ class CudaVideoConvertScale:
         ins = (C.c_void_p * n)(*[_ptr(f) for f in in_frames])
         outs = (C.c_void_p * n)(*[_ptr(f) for f in out_frames])
         check(lib.b200_vcs_convert_host(self._h, n, ins, outs), "b200_vcs_convert_host")
+
+    def copy_probe(self, in_frames, out_frames):
+        """the copies of transform_host_frames without the kernels (b200_vcs_copy_probe): the link's ceiling"""
+        n = len(in_frames)
+        ins = (C.c_void_p * n)(*[_ptr(f) for f in in_frames])
+        outs = (C.c_void_p * n)(*[_ptr(f) for f in out_frames])
+        check(lib.b200_vcs_copy_probe(self._h, n, ins, outs), "b200_vcs_copy_probe")
 
     # ---- introspection -------------------------------------------------------------
     def plan_info(self):

@@ -62,8 +62,13 @@ int b200_device_count (void);
 
 /* pinned host staging memory (what a GstCudaBufferPool-style pool hands upstream
  * so H2D/D2H can be asynchronous; gst-plugins-bad/gst-libs/gst/cuda/gstcudamemory.cpp:446-522) */
-int b200_host_alloc (size_t size, void **ptr);
+int b200_host_alloc (size_t size, void **ptr);            /* near the calling thread's current device */
 int b200_host_free (void *ptr);
+/* the same, placed on the NUMA node `device` hangs off (mbind before first touch, then cudaHostRegister): with one
+ * pipeline per GPU on a multi-socket host the staging buffers must not cross the socket interconnect.
+ * b200_device_numa_node: that node from sysfs, -1 if unknown. */
+int b200_host_alloc_near (int device, size_t size, void **ptr);
+int b200_device_numa_node (int device);
 
 /* ------------------------------------------------------------------ video types */
 /* GstVideoFormat values (gst-libs/gst/video/video-format.h:195-) */
@@ -159,6 +164,9 @@ int b200_vcs_convert_batch (b200_vcs * h, int n, const void *const *in_frames,
  * b200_host_alloc (pinned) for the copies to overlap. */
 int b200_vcs_convert_host (b200_vcs * h, int n, const void *const *in_host,
     void *const *out_host);
+/* diagnostic: the host<->device copies of b200_vcs_convert_host alone (both directions in flight, no kernel; the
+ * outputs receive whatever the device slots hold).  Timed by the caller it is the link's ceiling for the same call. */
+int b200_vcs_copy_probe (b200_vcs * h, int n, const void *const *in_host, void *const *out_host);
 
 /* plan introspection (tests, debugging, gst-inspect style dumps) */
 typedef struct {
