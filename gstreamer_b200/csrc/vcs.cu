@@ -10,6 +10,9 @@
 #include "vcs_kernels.cuh"
 #include "vcs_lanczos2.cuh"
 #include "vcs_l2mma.cuh"
+#ifndef B200_CUDA_EMU
+#include "vcs_l2tc.cuh"          // tcgen05 / TMEM: no host emulation
+#endif
 #include "vcs_light.cuh"
 #include "vcs_ntap.cuh"
 #include "vcs_planes.cuh"
@@ -42,6 +45,10 @@ struct b200_vcs {
   NtapState ntap;
   L2mmaTables mma_tables;         // experimental tensor-path variant of the 2:1 kernel (variant 6, opt-in)
   L2mmaState mma;
+#ifndef B200_CUDA_EMU
+  L2tcTables tc_tables;           // tcgen05 formulation of the 2:1 kernel (variant 7)
+  L2tcState tc;
+#endif
   PlanesState planes;
   // 4:2:0 -> other 4:2:0 family: scaled A,Y,U,V scratch images between the two launches
   Down420Dev down;
@@ -103,6 +110,14 @@ int launch_convert (b200_vcs * h, int n, const VcsBatch & batch, cudaStream_t st
     for (int i = 0; i < n; i++) aligned = aligned && (((uintptr_t) batch.in[i]) & 7) == 0 && (((uintptr_t) batch.out[i]) & 3) == 0;
     if (aligned) return launch_l2mma (h->dev, h->mma, batch, n, stream);
   }
+#ifndef B200_CUDA_EMU
+  if (h->variant == 7 && h->tc.ready) {
+    bool aligned = true;                                            // 16-byte cp.async of the luma rows
+    for (int i = 0; i < n; i++) aligned = aligned && (((uintptr_t) batch.in[i]) & 15) == 0 && (((uintptr_t) batch.out[i]) & 3) == 0;
+    if (aligned) return launch_l2tc (h->dev, h->tc, batch, n, stream);
+    if (p.lanczos2_ok) return launch_lanczos2 (h->dev, h->l2, batch, n, stream);
+  }
+#endif
   if (h->variant == 1 && p.lanczos2_ok)
     return launch_lanczos2 (h->dev, h->l2, batch, n, stream);
   if (h->variant == 2 && p.light_ok) {
@@ -330,6 +345,9 @@ int b200_vcs_create (const b200_video_info * in, const b200_video_info * out,
     h->l2_tables = build_lanczos2_tables (h->plan);
     h->plan.lanczos2_ok = h->l2_tables.ok;
     h->mma_tables = build_l2mma_tables (h->plan);
+#ifndef B200_CUDA_EMU
+    h->tc_tables = build_l2tc_tables (h->plan, h->l2_tables);
+#endif
   }
   const VcsPlan & p = h->plan;
   if (!p.yuv_out && ((p.out.stride[0] & 3) || (p.out.offset[0] & 3))) { delete h; return B200_ERR_UNSUPPORTED; }
@@ -399,6 +417,10 @@ int b200_vcs_create (const b200_video_info * in, const b200_video_info * out,
       st = prepare_lanczos2 (h->l2_tables, h->dev, &h->l2);
       if (st != B200_OK) { b200_vcs_destroy (h); return st; }
       h->variant = 1;
+#ifndef B200_CUDA_EMU
+      if ((st = prepare_l2tc (h->tc_tables, &h->tc)) != B200_OK) { b200_vcs_destroy (h); return st; }
+      { const char *e = getenv ("B200_L2_TC"); if (e && e[0] == '1' && h->tc.ready) h->variant = 7; }   // tuning knob
+#endif
     } else if (p.light_ok) {
       if ((st = allow_max_dyn_smem (light_kernel_for (p))) != B200_OK) { b200_vcs_destroy (h); return st; }
       h->variant = 2;
@@ -424,6 +446,9 @@ void b200_vcs_destroy (b200_vcs * h)
     cudaFree (h->l2.d_htab); cudaFree (h->l2.d_vtab); cudaFree (h->ntap.d_h); cudaFree (h->ntap.d_v);
     cudaFree (h->l2.d_htab4); cudaFree (h->l2.d_vtab4); cudaFree (h->l2.d_v4);
     cudaFree (h->mma.d_bh); cudaFree (h->mma.d_bv); cudaFree (h->mma.d_h4); cudaFree (h->mma.d_v4);
+#ifndef B200_CUDA_EMU
+    cudaFree (h->tc.d_band); cudaFree (h->tc.d_vband); cudaFree (h->tc.d_hx4); cudaFree (h->tc.d_vx4);
+#endif
     free_planes (&h->planes);
     cudaFree (h->d_scratch);
     for (int i = 0; i < b200_vcs::kSlots; i++) {
@@ -532,7 +557,7 @@ int b200_vcs_get_plan_info (const b200_vcs * h, b200_vcs_plan_info * info)
   info->h_first = p.h_first; info->matrix_first = p.matrix_first;
   for (int i = 0; i < 5; i++) info->p[i] = p.p[i];
   info->tile_w = p.tile_w; info->tile_h = p.tile_h; info->smem_bytes = p.smem_bytes;
-  info->kernel_variant = p.yuv_out ? 5 : p.planes_mode ? 4 : (h->variant == 6 && h->mma.ready) ? 6 : (h->variant == 1 && p.lanczos2_ok) ? 1 : (h->variant == 2 && p.light_ok) ? 2 : (h->variant == 3 && p.ntap_ok) ? 3 : 0;
+  info->kernel_variant = p.yuv_out ? 5 : p.planes_mode ? 4 : h->variant == 7 ? 7 : (h->variant == 6 && h->mma.ready) ? 6 : (h->variant == 1 && p.lanczos2_ok) ? 1 : (h->variant == 2 && p.light_ok) ? 2 : (h->variant == 3 && p.ntap_ok) ? 3 : 0;
   info->n_launches_per_convert = (p.yuv_out ? (p.extra_row ? 3 : 2) : 1) + (p.has_dest && p.fill_border ? 1 : 0);
   return B200_OK;
 }
@@ -571,9 +596,14 @@ int b200_vcs_get_chroma_plan (const b200_vcs * h, uint8_t * mode, size_t len)
 
 int b200_vcs_set_kernel_variant (b200_vcs * h, int variant)
 {
-  if (!h || variant < 0 || (variant > 3 && variant != 6)) return B200_ERR_INVALID_ARG;
+  if (!h || variant < 0 || (variant > 3 && variant != 6 && variant != 7)) return B200_ERR_INVALID_ARG;
   if (h->plan.planes_mode || h->plan.yuv_out) return B200_ERR_UNSUPPORTED;   // one kernel only
   if (variant == 6 && !h->mma.ready) return B200_ERR_UNSUPPORTED;
+#ifndef B200_CUDA_EMU
+  if (variant == 7 && !h->tc.ready) return B200_ERR_UNSUPPORTED;
+#else
+  if (variant == 7) return B200_ERR_UNSUPPORTED;
+#endif
   if (variant == 3 && !(h->plan.ntap_ok && h->ntap.ready)) return B200_ERR_UNSUPPORTED;
   if (variant == 1 && !h->plan.lanczos2_ok) return B200_ERR_UNSUPPORTED;
   if (variant == 2 && !h->plan.light_ok) return B200_ERR_UNSUPPORTED;

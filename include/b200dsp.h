@@ -178,7 +178,9 @@ typedef struct {
   int32_t smem_bytes;
   int32_t kernel_variant;        /* 0 = generic tiled, 1 = lanczos 2:1 specialised, 2 = light (copy / 2-tap axes), 3 = n-tap any ratio, 4 = YUV plane scaling,
                                   * 5 = chain + chroma down-sampling (4:2:0 -> the other 4:2:0 family; 2 launches),
-                                  * 6 = lanczos 2:1 on the integer tensor path (experimental, opt-in: B200_L2_MMA=1 or set_kernel_variant) */
+                                  * 6 = lanczos 2:1 with mma.sync FIRs (cross-check only: set_kernel_variant; measured slower),
+                                  * 7 = lanczos 2:1 with both FIR passes as tcgen05.mma.kind::i8 banded products, accumulators in TMEM
+                                  *     (bit-exact; set_kernel_variant(7) or B200_L2_TC=1 - not the default) */
   int32_t n_launches_per_convert;
 } b200_vcs_plan_info;
 int b200_vcs_get_plan_info (const b200_vcs * h, b200_vcs_plan_info * info);

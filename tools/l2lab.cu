@@ -19,6 +19,7 @@
 #include "../gstreamer_b200/csrc/vcs_device.h"
 #include "../gstreamer_b200/csrc/vcs_kernels.cuh"
 #include "../gstreamer_b200/csrc/vcs_lanczos2.cuh"
+#include "../gstreamer_b200/csrc/vcs_l2tc.cuh"
 #ifdef L2LAB_EXTRA
 #include L2LAB_EXTRA
 #endif
@@ -48,7 +49,46 @@ struct Lab {
   uint8_t *in[RING], *out[RING];
   size_t in_bytes, out_bytes;
   std::vector<uint8_t> ref;      // output of frame 0 from the reference instantiation
+  L2tcTables tct;
+  L2tcState tc;
 };
+
+void launch_tc (Lab & L, const VcsBatch & b, cudaStream_t s)
+{
+  if (launch_l2tc (L.dev, L.tc, b, Lab::PER, s) != B200_OK) { printf ("launch_l2tc failed: %s\n", b200_last_cuda_error ()); exit (1); }
+}
+
+// H pass of the tensor kernel in isolation: raw accumulators of tile 0 (frame 0, strip 0, row tile 0) against a plain
+// CPU evaluation of the same banded product for the luma plane
+int tc_debug (Lab & L)
+{
+  unsigned *d_dbg; const size_t n = 3 * 128 * 64;
+  CK (cudaMalloc ((void **) &d_dbg, n * 4)); CK (cudaMemset (d_dbg, 0xee, n * 4));
+  VcsBatch b; b.in[0] = L.in[0]; b.out[0] = L.out[0];
+  if (launch_l2tc (L.dev, L.tc, b, 1, 0, d_dbg, 1) != B200_OK) { printf ("launch failed: %s\n", b200_last_cuda_error ()); return 1; }
+  cudaError_t e = cudaDeviceSynchronize ();
+  if (e != cudaSuccess) { printf ("kernel error: %s\n", cudaGetErrorString (e)); return 1; }
+  std::vector<unsigned> dbg (n); std::vector<uint8_t> frame (L.in_bytes);
+  CK (cudaMemcpy (dbg.data (), d_dbg, n * 4, cudaMemcpyDeviceToHost));
+  CK (cudaMemcpy (frame.data (), L.in[0], L.in_bytes, cudaMemcpyDeviceToHost));
+  const VcsPlan & p = L.plan;
+  const int scale = L.tct.hx4[0] ? 4 : 1, rnd = L.tct.hx4[0] ? 128 : 32;
+  long bad = 0, checked = 0;
+  for (int j = 0; j < 128; j++)
+    for (int li = 3; li < 62; li++) {                  // lines 0..2 are above the frame in row tile 0
+      const int y = li - 3;
+      int acc = rnd;
+      for (int k = 0; k < 8; k++)
+        acc += scale * p.h.coef[(size_t) j * 8 + k] * frame[p.in.offset[0] + (size_t) y * p.in.stride[0] + p.h.offset[j] + k];
+      const int got = (int) dbg[(0 * 128 + j) * 64 + li];
+      checked++;
+      if (got != acc) { if (bad < 8) printf ("  Y mismatch col %d line %d: got %d want %d\n", j, li, got, acc); bad++; }
+    }
+  printf ("tc_debug: H pass luma accumulators of tile 0: %ld of %ld differ (x4 %d)\n", bad, checked, (int) L.tct.hx4[0]);
+  printf ("  sample U accumulators col 5: %d %d %d %d\n", (int) dbg[(128 + 5) * 64 + 10], (int) dbg[(128 + 5) * 64 + 11], (int) dbg[(128 + 5) * 64 + 12], (int) dbg[(128 + 5) * 64 + 13]);
+  cudaFree (d_dbg);
+  return bad != 0;
+}
 
 typedef void (*launch_fn) (Lab & L, const VcsBatch & b, cudaStream_t s);
 
@@ -98,10 +138,15 @@ int main (int argc, char **argv)
     fill_random <<<592, 256>>> (L.in[i], L.in_bytes, 1234567u * (i + 1));
   }
   CK (cudaDeviceSynchronize ());
+  L.tct = build_l2tc_tables (L.plan, L.tab);
+  if (!L.tct.ok) { printf ("tensor tables not eligible\n"); return 1; }
+  if (prepare_l2tc (L.tct, &L.tc) != B200_OK) { printf ("prepare_l2tc failed\n"); return 1; }
+  if (!strcmp (filter, "tcdbg")) return tc_debug (L);
 
   std::vector<Variant> vs = {
     {"ref_x4_default", launch_l2<4, 60, 1, true, 0>, true},
     {"plain_tables", launch_l2<4, 60, 1, false, 0>, true},
+    {"tcgen05_both_passes", launch_tc, true},
     {"abl1_no_chroma_prep", launch_l2<4, 60, 1, true, 1>, false},
     {"abl2_no_hfir", launch_l2<4, 60, 1, true, 2>, false},
     {"abl3_no_chroma_no_hfir", launch_l2<4, 60, 1, true, 3>, false},
