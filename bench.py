@@ -33,7 +33,10 @@ ALG_BYTES_PER_FRAME = 12_441_600 + 8_294_400
 IN_PIX_PER_FRAME = IW * IH
 FRAMES_PER_STEP = 32
 RING = 64
-WORKLOAD = "3840x2160 NV12 -> 1920x1080 BGRA, lanczos (8-tap), cudavideoconvertscale"
+WORKLOAD = "3840x2160 NV12 -> 1920x1080 BGRA, lanczos (8-tap), videoconvertscale semantics"
+METRIC = "4K NV12->BGRA+lanczos->1080p throughput"
+REF_NOTE = ("oracle/_ref: the reference's own video-converter.c compiled here, ORC C backups (no liborc SIMD JIT), n-threads = all "
+            "cores but the converter caps its task count at rows/200 (about 10 effective threads for 4K -> 1080p)")
 
 
 def measured_peak():
@@ -145,7 +148,7 @@ def cpu_baseline(seconds=10.0, threads=None):
         conv = ob.RefVcs(IW, IH, OW, OH, METHOD, n_threads=cores)
         out = np.zeros(OW * OH * 4, dtype=np.uint8)
         run = lambda f: conv.convert(f, out)
-        impl = "oracle/_ref: reference video-converter.c + ORC C backups (no liborc SIMD JIT)"
+        impl = REF_NOTE
     else:
         kind = "port"
         cores = 1
@@ -171,35 +174,69 @@ def run_reference(args):
     from oracle import bindings as ob
     import numpy as np
     cores = os.cpu_count() or 1
-    per_step = 4
-    frames = [ob.nv12_random_frame(IW, IH, s) for s in range(per_step)]
+    per_step = FRAMES_PER_STEP
+    frames = [ob.nv12_random_frame(IW, IH, s) for s in range(4)]
     if ob.have_ref():
         kind = "reference"
         conv = ob.RefVcs(IW, IH, OW, OH, METHOD, n_threads=cores)
         out = np.zeros(OW * OH * 4, dtype=np.uint8)
         run = lambda f: conv.convert(f, out)
+        note = REF_NOTE
     else:
         kind, cores = "port", 1
         d = ob.vcs_desc(IW, IH, OW, OH, METHOD)
         run = lambda f: ob.oracle_vcs_convert(d, f)
-    for _ in range(args.warmup):
-        for f in frames:
-            run(f)
+        note = "oracle port (scalar C, 1 thread)"
+    for _ in range(min(args.warmup, 3)):
+        for k in range(4):
+            run(frames[k])
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        for f in frames:
-            run(f)
+        for k in range(per_step):
+            run(frames[k % 4])
     dt = time.perf_counter() - t0
     val = args.steps * per_step * IN_PIX_PER_FRAME / dt / 1e6
-    line = {"impl": "reference", "metric": "4K NV12->BGRA+lanczos->1080p throughput", "value": val,
+    line = {"impl": "reference", "metric": METRIC, "value": val,
             "unit": "Mpix/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD + " (CPU videoconvertscale path)", "frames_per_step": per_step},
+            "config": {"workload": WORKLOAD, "frames_per_step": per_step},
             "cpu_baseline": {"value": val, "unit": "Mpix/s", "cores": cores, "kind": kind,
-                             "sample": f"{args.steps}x{per_step} frames, n-threads={cores}"},
+                             "sample": f"{args.steps} steps x {per_step} frames; {note}"},
             "e2e": {"value": val, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def run_extras(steps):
+    """the other BASELINE configs on this GPU (kernel-resident, CUDA events): C1 element default, C4 both backgrounds, C5"""
+    import bench_extra as bx
+    bx.QUIET = True
+    a = argparse.Namespace(steps=steps, seconds=20, background=0, no_cpu=True, variant=-1)
+    out = {}
+
+    def slim(d, key="us_per_frame"):
+        r = d["roofline"]
+        e = {"us": d.get(key), "alg_bytes": r.get("alg_bytes_per_launch"), "achieved_gbs": r["achieved"], "frac": r["frac"],
+             "config": d["config"]}
+        if "achieved_gflops" in r:
+            e["achieved_gflops_non_fma"] = r["achieved_gflops"]
+        return e
+    try:
+        d = bx.bench_c1(a)
+        d["us_per_frame"] = d["us_per_frame"]
+        e = slim(d); e["alg_bytes"] = d["roofline"]["alg_bytes_per_launch"] // 64; e["kernel_variant"] = d["kernel_variant"]
+        out["c1"] = e
+        a.background = 0
+        out["c4_checker"] = slim(bx.bench_c4(a))
+        a.background = 3
+        out["c4_transparent"] = slim(bx.bench_c4(a))
+        a.steps = max(3, steps // 4)
+        d = bx.bench_c5(a)
+        d["us_per_frame"] = d["ms_per_buffer"] * 1e3
+        out["c5"] = slim(d)
+    except Exception as e:          # an extra must never take the headline line down
+        out["error"] = repr(e)
+    return out
 
 
 def run_ours(args):
@@ -210,6 +247,7 @@ def run_ours(args):
 
     from gstreamer_b200 import multi
     rank, world, local = multi.rank_info()
+    numa = multi.bind_to_gpu_numa(local)          # before any staging memory exists
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     dist = multi.init("nccl", device=dev)
@@ -218,6 +256,7 @@ def run_ours(args):
     ii, oi = g.VideoInfo(g.VideoFormat.NV12, IW, IH), g.VideoInfo(g.VideoFormat.BGRA, OW, OH)
     el.set_info(ii, oi)
     pinfo = el.plan_info()
+    kname = {1: "vcs_lanczos2_kernel", 7: "vcs_l2tc_kernel"}.get(int(pinfo.kernel_variant), "vcs_generic_kernel")
 
     # ring of distinct frames resident in HBM
     base = [torch.from_numpy(ob.nv12_random_frame(IW, IH, multi.stream_seed(rank, s))).to(dev) for s in range(4)]
@@ -261,33 +300,66 @@ def run_ours(args):
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- e2e: host frames through the C-ABI (pinned staging, copies inside the timed region)
-    e2e_frames = 16
-    hin = [g.PinnedBuffer(ii.size) for _ in range(e2e_frames)]
-    hout = [g.PinnedBuffer(oi.size) for _ in range(e2e_frames)]
+    # ---- sustained: the same launches back to back for >= 2 s (an issue-bound kernel follows the SM clock, and the
+    # clock under a seconds-long load is not the burst clock)
+    sustained = None
+    if not profiling and args.sustained_seconds > 0:
+        n_sus = max(50, int(args.sustained_seconds * 1e3 / max(ms / args.steps, 1e-3)))
+        barrier()
+        s2 = ClockSampler(local)
+        if rank == 0:
+            s2.start()
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for i in range(n_sus):
+                step(i)
+            e1.record(stream)
+        barrier()
+        sus_ms = e0.elapsed_time(e1)
+        c2 = s2.stop() if rank == 0 else None
+        sus_ms, = multi.reduce_max(dist, [sus_ms], device=dev)
+        sustained = {"launches": n_sus, "seconds": sus_ms * 1e-3,
+                     "value": n_sus * FRAMES_PER_STEP * world * IN_PIX_PER_FRAME / (sus_ms * 1e-3) / 1e6, "unit": "Mpix/s",
+                     "us_per_launch": sus_ms * 1e3 / n_sus, "clocks": c2}
+
+    # ---- e2e: host frames through the C-ABI (pinned staging next to the GPU, copies inside the timed region)
+    e2e_frames = 32
+    hin = [g.PinnedBuffer(ii.size, device=local) for _ in range(e2e_frames)]
+    hout = [g.PinnedBuffer(oi.size, device=local) for _ in range(e2e_frames)]
     for k, b in enumerate(hin):
-        b.array[:] = ob.nv12_random_frame(IW, IH, 77 + k)
+        b.array[:] = ob.nv12_random_frame(IW, IH, 77 + k % 4)
+        b.array[:: 4099] += k
     inp, outp = [b.ptr for b in hin], [b.ptr for b in hout]
     for _ in range(max(1, min(args.warmup, 3))):
         el.transform_host_frames(inp, outp)
     barrier()
-    e2e_steps = max(3, min(args.steps, 20))
+    e2e_steps = max(3, min(args.steps, 10))
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         el.transform_host_frames(inp, outp)     # returns when every output is back in host memory
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     checksum = int(hout[0].array[:4096].sum())
+    # the link's ceiling for the same call: the same copies on the same buffers without the kernels
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        el.copy_probe(inp, outp)
+    torch.cuda.synchronize()
+    probe_s = time.perf_counter() - t0
 
-    ms, e2e_s = multi.reduce_max(dist, [ms, e2e_s], device=dev)    # slowest rank defines the job
+    ms, e2e_s, probe_s = multi.reduce_max(dist, [ms, e2e_s, probe_s], device=dev)    # slowest rank defines the job
+    extras = run_extras(10) if (rank == 0 and world == 1 and not args.no_extras and not profiling) else None
     if rank == 0:
         frames = args.steps * FRAMES_PER_STEP * world
         value = frames * IN_PIX_PER_FRAME / (ms * 1e-3) / 1e6
         peak, peak_src = measured_peak()
         achieved = args.steps * FRAMES_PER_STEP * ALG_BYTES_PER_FRAME / (ms * 1e-3) / 1e9   # per GPU
         e2e_val = e2e_steps * e2e_frames * world * IN_PIX_PER_FRAME / e2e_s / 1e6
+        ceil_val = e2e_steps * e2e_frames * world * IN_PIX_PER_FRAME / probe_s / 1e6
+        traffic = ncu_traffic(kname, FRAMES_PER_STEP)
         line = {
-            "metric": "4K NV12->BGRA+lanczos->1080p throughput", "value": value, "unit": "Mpix/s",
+            "metric": METRIC, "value": value, "unit": "Mpix/s",
             "frames_per_s": frames / (ms * 1e-3),
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
@@ -295,20 +367,34 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "frames_per_step": FRAMES_PER_STEP, "ring_frames": RING,
                        "l2": "inputs larger than L2 (ring %.0f MB in + %.0f MB out)" %
                              (RING * ii.size / 1e6, RING * oi.size / 1e6),
-                       "kernel_variant": int(pinfo.kernel_variant), "parallelism": f"streams{world}"},
+                       "kernel_variant": int(pinfo.kernel_variant), "parallelism": f"streams{world}", "numa": numa},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak,
-                         "traffic": ncu_traffic("vcs_lanczos2_kernel", FRAMES_PER_STEP) if pinfo.kernel_variant == 1 else None,
-                         "peak_source": peak_src,
-                         "kernel": "vcs_lanczos2_kernel" if pinfo.kernel_variant == 1 else "vcs_generic_kernel",
+                         "traffic": traffic,
+                         "traffic_source": "dram__bytes_read+write of the committed ncu --set full capture (profiles/traffic.json), not measured in this run",
+                         "peak_source": peak_src, "kernel": kname,
                          "alg_bytes_per_launch": FRAMES_PER_STEP * ALG_BYTES_PER_FRAME,
                          "us_per_launch": ms * 1e3 / args.steps},
+            "sustained": sustained,
             "e2e": {"value": e2e_val, "unit": "Mpix/s", "h2d_bytes_per_step": e2e_frames * ii.size,
                     "d2h_bytes_per_step": e2e_frames * oi.size, "frames_per_step": e2e_frames,
-                    "steps": e2e_steps, "checksum": checksum},
+                    "steps": e2e_steps, "checksum": checksum,
+                    "copy_ceiling": {"value": ceil_val, "unit": "Mpix/s", "frac_of_ceiling": e2e_val / ceil_val,
+                                     "what": "the same H2D || D2H copies on the same pinned buffers without the kernels (b200_vcs_copy_probe)"},
+                    "staging": "b200_host_alloc_near: mbind to the GPU's NUMA node, then cudaHostRegister"},
             "gpu_launches": args.steps * pinfo.n_launches_per_convert,
             "clocks": clocks,
         }
+        if extras is not None:
+            line["extra"] = extras
+        if world == 1 and not profiling and not args.no_extras:
+            # the reference's GPU path for the same conversion: its CUDA converter kernel (texture-bilinear, float
+            # matrix - different arithmetic, so a speed reference only), compiled from the reference's own source
+            gb = ob.run_refcuda_bench()
+            if gb is not None and "us_per_frame" in gb:
+                gb.update({"value": gb["mpix_per_s_in"], "unit": "Mpix/s", "frac": gb["achieved_gbs"] / peak,
+                           "note": "reference cudaconvertscale kernel, bilinear texture sampling: not bit-exact with videoconvertscale"})
+            line["gpu_baseline"] = gb
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
         print(json.dumps(line), flush=True)
@@ -324,6 +410,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the C1 / C4 / C5 block of the line")
+    ap.add_argument("--sustained-seconds", type=float, default=2.5)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -15,6 +15,15 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 
+QUIET = False      # bench.py imports these benches and embeds their results instead of printing them
+
+
+def emit(d):
+    if not QUIET:
+        print(json.dumps(d), flush=True)
+    return d
+
+
 def peak():
     try:
         return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
@@ -72,13 +81,13 @@ def bench_c1(args):
                        "sample": f"{n} frames, video-converter.c + ORC C backups, n-threads=1 (element default)"}
             else:
                 cpu["all_cores"] = {"value": fps, "cores": threads}
-    print(json.dumps({"config": "C1 cudavideoconvertscale 1920x1080 NV12 -> 1280x720 BGRA bilinear",
+    return emit({"config": "C1 cudavideoconvertscale 1920x1080 NV12 -> 1280x720 BGRA bilinear",
                       "kernel_variant": int(el.plan_info().kernel_variant),
                       "frames_per_s": per * 1e3 / ms, "us_per_frame": ms * 1e3 / per,
                       "mpix_per_s_in": per * IW * IH / (ms * 1e-3) / 1e6,
                       "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak(), "unit": "GB/s",
                                    "frac": alg / (ms * 1e-3) / 1e9 / peak(), "alg_bytes_per_launch": alg},
-                      "cpu_baseline": cpu}), flush=True)
+                      "cpu_baseline": cpu})
 
 
 def bench_ntap(args):
@@ -233,11 +242,11 @@ def bench_c4(args):
             n += 1
         cpu = {"value": n / (time.perf_counter() - t0), "unit": "frames/s", "cores": 1, "kind": "reference",
                "sample": f"{n} frames, blend.c + ORC C backups, single thread"}
-    print(json.dumps({"config": "C4 cudacompositor 16x1080p RGBA -> 4K RGBA", "background": args.background,
+    return emit({"config": "C4 cudacompositor 16x1080p RGBA -> 4K RGBA", "background": args.background,
                       "frames_per_s": 1e3 / ms, "us_per_frame": ms * 1e3,
                       "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak(), "unit": "GB/s",
                                    "frac": alg / (ms * 1e-3) / 1e9 / peak(), "alg_bytes_per_launch": alg},
-                      "cpu_baseline": cpu}), flush=True)
+                      "cpu_baseline": cpu})
 
 
 def bench_c5(args):
@@ -286,14 +295,14 @@ def bench_c5(args):
         cpu = {"value": k * n * ch / dt / 1e6, "unit": "Msamples/s (input)", "cores": 1, "kind": "reference",
                "sample": f"{k} x 0.5 s buffers, audio-resampler.c SSE inner product, single thread"}
         r.ref_ars_free(h)
-    print(json.dumps({"config": f"C5 cudaaudioresample 48k->44.1k F32 256ch, {args.seconds} s buffer",
+    return emit({"config": f"C5 cudaaudioresample 48k->44.1k F32 256ch, {args.seconds} s buffer",
                       "msamples_per_s_in": frames * ch / (ms * 1e-3) / 1e6, "ms_per_buffer": ms,
                       "realtime_factor": args.seconds / (ms * 1e-3),
                       "roofline": {"bound": "fp32-issue (no FMA allowed for bit-exactness), then hbm",
                                    "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak(), "unit": "GB/s",
                                    "frac": alg / (ms * 1e-3) / 1e9 / peak(),
                                    "achieved_gflops": flops / (ms * 1e-3) / 1e9, "alg_bytes_per_launch": alg},
-                      "cpu_baseline": cpu}), flush=True)
+                      "cpu_baseline": cpu})
 
 
 if __name__ == "__main__":

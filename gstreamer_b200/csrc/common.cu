@@ -104,10 +104,12 @@ int b200_host_alloc_near (int device, size_t size, void **ptr)
     B200_CUDA_TRY (cudaHostAlloc (ptr, size, cudaHostAllocPortable));
     return B200_OK;
   }
-  const size_t page = (size_t) sysconf (_SC_PAGESIZE);
+  // 2 MB granules + MADV_HUGEPAGE: transparent huge pages where the host allows them (fewer, larger DMA mappings)
+  const size_t page = (size_t) 2 << 20;
   const size_t bytes = (size + page - 1) / page * page;
   void *p = mmap (nullptr, bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
   if (p == MAP_FAILED) return B200_ERR_NOMEM;
+  (void) madvise (p, bytes, MADV_HUGEPAGE);
   unsigned long mask[16] = {0};
   mask[node / (8 * sizeof (unsigned long))] = 1ul << (node % (8 * sizeof (unsigned long)));
   // MPOL_BIND = 2; a kernel without NUMA support fails here and the pages simply follow the default policy

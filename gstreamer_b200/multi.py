@@ -51,3 +51,57 @@ def whole_job_throughput(units_per_rank, world, seconds_max):
     """weak scaling: every rank processes the same number of units; the job's rate is all units
     over the slowest rank's time"""
     return units_per_rank * world / seconds_max
+
+
+def gpu_numa_cpus(local_gpu):
+    """(numa node, cpu list) the GPU hangs off, from sysfs (nvidia-smi topo prints the same affinity); (None, []) if unknown"""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        idx = local_gpu
+        ids = [v for v in vis.split(",") if v.strip()]
+        if ids and local_gpu < len(ids) and ids[local_gpu].strip().isdigit():
+            idx = int(ids[local_gpu])
+        pci = nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(idx)).busId
+        pci = pci.decode() if isinstance(pci, bytes) else pci
+        pci = pci.lower()
+        if len(pci.split(":")[0]) == 8:          # NVML prints an 8-digit domain, sysfs a 4-digit one
+            pci = pci[4:]
+        base = "/sys/bus/pci/devices/" + pci
+        node = int(open(base + "/numa_node").read())
+        cpus = _parse_cpulist(open(base + "/local_cpulist").read())
+        return (node if node >= 0 else None), cpus
+    except Exception:
+        return None, []
+
+
+def _parse_cpulist(text):
+    out = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        out.extend(range(int(a), int(b or a) + 1))
+    return out
+
+
+def bind_to_gpu_numa(local_gpu):
+    """Pin this process (one pipeline per GPU) to the cores next to its GPU, BEFORE any staging memory is allocated or
+    touched: one pipeline per GPU on a two-socket host otherwise pushes half of the H2D / D2H bytes across the socket
+    interconnect (round 1: per-GPU H2D fell from 49 to 22 GB/s at 8 pipelines).  Returns what it did, for the bench line."""
+    node, cpus = gpu_numa_cpus(local_gpu)
+    if not cpus:
+        return {"numa_node": node, "bound": False}
+    try:
+        os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "bound": True, "cpus": len(cpus)}
+    except Exception as e:          # cgroup cpuset narrower than the GPU's local list
+        try:
+            allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+            if allowed:
+                os.sched_setaffinity(0, allowed)
+                return {"numa_node": node, "bound": True, "cpus": len(allowed)}
+        except Exception:
+            pass
+        return {"numa_node": node, "bound": False, "error": str(e)}

@@ -31,6 +31,23 @@ def build(ref=True):
     subprocess.check_call(["make", "-s", "-C", _HERE, "oracle"])
     if ref and os.path.exists("/root/reference/subprojects/gst-plugins-base"):
         subprocess.check_call(["make", "-s", "-C", _HERE, "ref"])
+        # the reference's CUDA converter kernel as bench.py's gpu_baseline (needs nvcc; a missing compiler is not fatal)
+        subprocess.call(["make", "-s", "-C", _HERE, "refcuda"])
+
+
+REFCUDA_BENCH = os.path.join(_HERE, "_ref", "refcuda_bench")
+
+
+def run_refcuda_bench(reps=20, timeout=120):
+    """runs the reference's own CUDA converter kernel (oracle/_ref/refcuda_bench) on the bench shape; None if absent"""
+    import json
+    if not os.path.exists(REFCUDA_BENCH):
+        return None
+    try:
+        out = subprocess.run([REFCUDA_BENCH, str(reps)], capture_output=True, text=True, timeout=timeout)
+        return json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception as e:
+        return {"error": repr(e)}
 
 
 class RS(C.Structure):
