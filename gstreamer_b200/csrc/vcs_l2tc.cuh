@@ -157,12 +157,81 @@ __device__ __forceinline__ unsigned tc_pack4 (int a0, int a1, int a2, int a3)
 }
 
 // ---- the kernel ------------------------------------------------------------------------------------------------------
-// Persistent CTAs (two per SM: 2 x 256 TMEM columns, 2 x 102 KB shared memory) walk the tile list strip by strip, so the
-// 40 KB band is loaded once per strip change.  Per tile: stage Y by cp.async and the prepared chroma by SIMT -> 30 MMAs
-// (3 channels x (9 K steps + rounding)) -> H epilogue (TMEM -> packed bytes -> V operand) -> 9 MMAs -> V epilogue
-// (TMEM -> saturate -> matrix -> coalesced stores).  While one CTA waits for its MMAs the SM's other CTA computes.
+// One persistent CTA per SM, warp-specialised (the canonical sm_100 pipeline, with SIMT stages where a GEMM has TMA):
+//
+//   warps 0-7   PRODUCERS   stage tile k+1: Y by cp.async, prepared chroma by SIMT, tap bands -> planes[k&1]
+//   warps 8-15  CONSUMERS   tile k: H epilogue (TMEM -> bytes -> V operand), V epilogue (TMEM -> matrix -> stores)
+//   warp 16     MMA ISSUER  one lane: H pass of tile k+1 (30 MMAs), then V pass of tile k (9 MMAs)
+//
+// mbarriers:  full[2] (producers -> issuer: planes staged), empty[2] (commit of the H pass: planes free again),
+// dh_full[2] / dh_empty[2] (H accumulators of the two TMEM buffers), hs_full (consumers -> issuer: V operand written),
+// dv_full (commit of the V pass).  TMEM: 2 x 192 columns for the H pass, 96 for the V pass.
+constexpr int TC_PROD_WARPS = 8, TC_CONS_WARPS = 8;
+constexpr int TC_THREADS2 = 32 * (TC_PROD_WARPS + TC_CONS_WARPS + 1);
+constexpr int TC_VB_RING = 4;
+constexpr int TC2_OFF_BAND = 0;
+constexpr int TC2_OFF_ONES = TC2_OFF_BAND + TC_BAND_BYTES;
+constexpr int TC2_OFF_VB = TC2_OFF_ONES + TC_ONES_BYTES;
+constexpr int TC2_OFF_IMG = TC2_OFF_VB + TC_VB_RING * TC_VB_BYTES;      // 2 buffers x 3 planes
+constexpr int TC2_OFF_HS = TC2_OFF_IMG + 2 * 3 * TC_IMG_BYTES;
+constexpr int TC2_OFF_BAR = TC2_OFF_HS + 3 * TC_HS_BYTES;
+constexpr int TC2_SMEM = TC2_OFF_BAR + 128;
+constexpr int TC2_TMEM_COLS = 512;
+constexpr int TC2_DV_COL = 2 * 3 * TC_N;                                // 384: the V accumulators
+enum { TCB_FULL0 = 0, TCB_FULL1, TCB_EMPTY0, TCB_EMPTY1, TCB_DHF0, TCB_DHF1, TCB_DHE0, TCB_DHE1, TCB_HSF, TCB_DVF, TCB_COUNT };
+
+__device__ __forceinline__ void tc_bar_wait_guard (uint32_t bar, uint32_t parity)
+{
+#ifndef B200_CUDA_EMU
+  uint32_t ok, spins = 0;
+  do {
+    asm volatile ("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r" (ok) : "r" (bar), "r" (parity) : "memory");
+    if (!ok && ++spins > (1u << 26)) __trap ();                  // a lost arrival must fail loudly, not hang the device
+  } while (!ok);
+#endif
+}
+__device__ __forceinline__ bool tc_bar_test (uint32_t bar, uint32_t parity)
+{
+#ifndef B200_CUDA_EMU
+  uint32_t ok;
+  asm volatile ("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r" (ok) : "r" (bar), "r" (parity) : "memory");
+  return ok != 0;
+#else
+  return true;
+#endif
+}
+__device__ __forceinline__ void tc_bar_arrive (uint32_t bar)
+{
+#ifndef B200_CUDA_EMU
+  asm volatile ("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r" (bar) : "memory");
+#endif
+}
+
+template <bool X4>
+__device__ __forceinline__ void tc_v_rows (const VcsDev & P, const int (&a)[3][16], uint8_t *dst, int rows, unsigned *dbg_row)
+{
+#pragma unroll
+  for (int i = 0; i < 14; i++) {
+    if (i < rows) {
+      unsigned yuv = X4 ? __byte_perm (pack_sat_u16x2 (a[1][i], a[0][i]), pack_sat_u16x2 (0, a[2][i]), 0x7531)
+          : pack_sat2 (a[1][i] >> 6, a[0][i] >> 6, pack_sat2 (0, a[2][i] >> 6, 0u));
+      yuv ^= 0x00808080u;
+      const int wy = prmt_s (yuv, 0x8800u), wu = prmt_s (yuv, 0x9911u), wv = prmt_s (yuv, 0xaa22u);
+      const int ty = ((wy * P.p1) >> 16) + 128;
+      const int r = ty + ((wv * P.p2) >> 16);
+      const int b = ty + ((wu * P.p3) >> 16);
+      const int gg = ty + ((wu * P.p4) >> 16) + ((wv * P.p5) >> 16);
+      const unsigned argb = pack_sat2 (r, 255, pack_sat2 (b, gg, 0u));
+      *(unsigned *) dst = __byte_perm (argb, 0, P.sel);
+    }
+    dst += P.stride_out;
+  }
+}
+
 template <int DBG>
-__global__ void __launch_bounds__ (TC_THREADS, 2)
+__global__ void __launch_bounds__ (TC_THREADS2, 1)
 vcs_l2tc_kernel (const VcsDev P, const L2tcDev L, const VcsBatch frames, int n_frames, unsigned *dbg)
 {
 #ifndef B200_CUDA_EMU
@@ -170,146 +239,171 @@ vcs_l2tc_kernel (const VcsDev P, const L2tcDev L, const VcsBatch frames, int n_f
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync (0xffffffffu, tid >> 5, 0);
   const uint32_t s_base = tc_smem_u32 (sm);
-  const uint32_t s_band = s_base + TC_OFF_BAND, s_ones = s_base + TC_OFF_ONES, s_vb = s_base + TC_OFF_VB,
-      s_img = s_base + TC_OFF_IMG, s_bar = s_base + TC_OFF_BAR, s_tptr = s_base + TC_OFF_BAR + 8;
+  const uint32_t s_band = s_base + TC2_OFF_BAND, s_ones = s_base + TC2_OFF_ONES, s_vb = s_base + TC2_OFF_VB,
+      s_img = s_base + TC2_OFF_IMG, s_hs = s_base + TC2_OFF_HS, s_bar = s_base + TC2_OFF_BAR, s_tptr = s_bar + 8 * TCB_COUNT;
+  auto bar = [&] (int i) { return s_bar + 8u * (uint32_t) i; };
 
-  // one-time setup: mbarrier, TMEM, the block of ones
   if (tid == 0) {
-    asm volatile ("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r" (s_bar) : "memory");
+    const int counts[TCB_COUNT] = {TC_PROD_WARPS, TC_PROD_WARPS, 1, 1, 1, 1, TC_CONS_WARPS, TC_CONS_WARPS, TC_CONS_WARPS, 1};
+    for (int i = 0; i < TCB_COUNT; i++)
+      asm volatile ("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r" (bar (i)), "r" (counts[i]) : "memory");
     asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) {
-    asm volatile ("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r" (s_tptr), "r" (TC_TMEM_COLS) : "memory");
+  if (warp == TC_PROD_WARPS + TC_CONS_WARPS) {
+    asm volatile ("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r" (s_tptr), "r" (TC2_TMEM_COLS) : "memory");
     asm volatile ("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int i = tid; i < TC_ONES_BYTES / 16; i += TC_THREADS)
-    *(uint4 *) (sm + TC_OFF_ONES + 16 * i) = make_uint4 (0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
+  for (int i = tid; i < TC_ONES_BYTES / 16; i += TC_THREADS2)
+    *(uint4 *) (sm + TC2_OFF_ONES + 16 * i) = make_uint4 (0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
+  tc_fence_async_smem ();
   tc_fence_before ();
   __syncthreads ();
   tc_fence_after ();
-  const uint32_t tmem = *(volatile uint32_t *) (sm + TC_OFF_BAR + 8);
+  const uint32_t tmem = *(volatile uint32_t *) (sm + TC2_OFF_BAR + 8 * TCB_COUNT);
 
   const int per_strip = n_frames * L.row_tiles;
   const int n_tiles = L.strips * per_strip;
-  int cur_strip = -1;
-  uint32_t parity = 0;
-  const int crows = P.ih >> 1;
-  const unsigned selU = P.u_index ? 0x7531u : 0x6420u, selV = P.u_index ? 0x6420u : 0x7531u;
-  constexpr uint32_t IDESC_H = tc_idesc (1, 0, TC_N, 128), IDESC_V = tc_idesc (0, 1, TC_VROWS, 128);
+  const int my_tiles = blockIdx.x < n_tiles ? (n_tiles - 1 - (int) blockIdx.x) / (int) gridDim.x + 1 : 0;
+  auto tile_of = [&] (int k, int & strip, int & f, int & rt) {
+    const int t = blockIdx.x + k * gridDim.x;
+    strip = t / per_strip;
+    const int rem = t - strip * per_strip;
+    f = rem / L.row_tiles; rt = rem - f * L.row_tiles;
+  };
 
-  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-    const int strip = t / per_strip, rem = t - strip * per_strip;
-    const int f = rem / L.row_tiles, rt = rem - f * L.row_tiles;
-    const uint8_t *__restrict__ in = frames.in[f];
-    uint8_t *__restrict__ out = frames.out[f];
-    const uint8_t *__restrict__ plane_y = in + P.off_y;
-    const uint8_t *__restrict__ plane_c = in + P.off_c;
-    const int x0 = strip * TC_TW, oy0 = rt * TC_TH;
-    const int X0 = 2 * x0 - TC_X_LEAD;                             // input column of staged byte 0
-    const int R0 = 2 * oy0 - 3;                                    // input line of staged line 0 (R0 % 4 == 1)
-
-    // ------------------------------------------------------------ stage: band (on a strip change), V band, Y
-    if (strip != cur_strip) {
-      const uint8_t *src = L.band + (size_t) strip * TC_BAND_BYTES;
-      for (int i = tid; i < TC_BAND_BYTES / 16; i += TC_THREADS) tc_cp16 (s_band + 16 * i, src + 16 * i);
-      cur_strip = strip;
-    }
-    if (tid < TC_VB_BYTES / 16) tc_cp16 (s_vb + 16 * tid, L.vband + (size_t) rt * TC_VB_BYTES + 16 * tid);
-    for (int i = tid; i < (2 * TC_TH + 6) * TC_CHUNKS; i += TC_THREADS) {
-      const int li = i / TC_CHUNKS, c = i - li * TC_CHUNKS;
-      const int y = R0 + li, x = X0 + 16 * c;
-      if (y >= 0 && y < P.ih && x >= 0 && x + 16 <= P.iw)
-        tc_cp16 (s_img + c * TC_IMG_LBO + (li >> 3) * 128 + (li & 7) * 16, plane_y + (size_t) y * P.stride_y + x);
-    }
-
-    // ------------------------------------------------------------ stage: chroma (SIMT): 4 lines x 8 pixels per item
-    // item = (line group g, 8-pixel slot): three chroma rows -> de-interleave -> co-sited h up-sampling -> the two line
-    // pairs (3a+b+2)>>2 -> full-resolution U and V bytes straight into the MMA operand layout
-    {
-      uint8_t *img_u = sm + TC_OFF_IMG + TC_IMG_BYTES, *img_v = img_u + TC_IMG_BYTES;
-      constexpr int SLOTS = 2 * TC_CHUNKS - 2;                     // slots 1 .. 34 carry taps (13 .. 274)
-      for (int item = tid; item < (TC_N / 4) * SLOTS; item += TC_THREADS) {
-        const int g = item / SLOTS, slot = item - g * SLOTS + 1;
-        const int x = X0 + 8 * slot;                               // first of this item's 8 input pixels (multiple of 8)
-        if (x < 0 || x >= P.iw) continue;
-        const bool right_edge = x + 8 >= P.iw;                     // no chroma sample to the right
-        const int y0 = R0 + 4 * g, m2 = (y0 - 1) >> 1;
-        unsigned ulo[3], uhi[3], vlo[3], vhi[3];
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-          const int cr = min (max (m2 + k, 0), crows - 1);
-          const uint8_t *row = plane_c + (size_t) cr * P.stride_c + x;
-          const uint2 c = __ldg ((const uint2 *) row);
-          const unsigned nx = right_edge ? 0u : (unsigned) __ldg ((const unsigned short *) (row + 8));
-          const unsigned ue = __byte_perm (c.x, c.y, selU), ve = __byte_perm (c.x, c.y, selV);
-          const unsigned un = right_edge ? __byte_perm (ue, ue, 0x3321) : __byte_perm (ue, nx, P.u_index ? 0x5321 : 0x4321);
-          const unsigned vn = right_edge ? __byte_perm (ve, ve, 0x3321) : __byte_perm (ve, nx, P.u_index ? 0x4321 : 0x5321);
-          const unsigned uo = avg_ceil4 (ue, un), vo = avg_ceil4 (ve, vn);
-          ulo[k] = __byte_perm (ue, uo, 0x5140); uhi[k] = __byte_perm (ue, uo, 0x7362);
-          vlo[k] = __byte_perm (ve, vo, 0x5140); vhi[k] = __byte_perm (ve, vo, 0x7362);
-        }
-        uint2 U[4], V[4];
-        {
-          unsigned q;
-          q = avg_floor4 (ulo[0], ulo[1]); U[0].x = avg_ceil4 (ulo[0], q); U[1].x = avg_ceil4 (ulo[1], q);
-          q = avg_floor4 (uhi[0], uhi[1]); U[0].y = avg_ceil4 (uhi[0], q); U[1].y = avg_ceil4 (uhi[1], q);
-          q = avg_floor4 (ulo[1], ulo[2]); U[2].x = avg_ceil4 (ulo[1], q); U[3].x = avg_ceil4 (ulo[2], q);
-          q = avg_floor4 (uhi[1], uhi[2]); U[2].y = avg_ceil4 (uhi[1], q); U[3].y = avg_ceil4 (uhi[2], q);
-          q = avg_floor4 (vlo[0], vlo[1]); V[0].x = avg_ceil4 (vlo[0], q); V[1].x = avg_ceil4 (vlo[1], q);
-          q = avg_floor4 (vhi[0], vhi[1]); V[0].y = avg_ceil4 (vhi[0], q); V[1].y = avg_ceil4 (vhi[1], q);
-          q = avg_floor4 (vlo[1], vlo[2]); V[2].x = avg_ceil4 (vlo[1], q); V[3].x = avg_ceil4 (vlo[2], q);
-          q = avg_floor4 (vhi[1], vhi[2]); V[2].y = avg_ceil4 (vhi[1], q); V[3].y = avg_ceil4 (vhi[2], q);
-        }
-        const int off = (slot >> 1) * TC_IMG_LBO + (g >> 1) * 128 + (g & 1) * 64 + (slot & 1) * 8;   // line 4g + r: + 16 r
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-          *(uint2 *) (img_u + off + 16 * r) = U[r];
-          *(uint2 *) (img_v + off + 16 * r) = V[r];
+  if (warp < TC_PROD_WARPS) {
+    // ================================================================ PRODUCERS
+    const int crows = P.ih >> 1;
+    const unsigned selU = P.u_index ? 0x7531u : 0x6420u, selV = P.u_index ? 0x6420u : 0x7531u;
+    const unsigned nselU = P.u_index ? 0x5321u : 0x4321u, nselV = P.u_index ? 0x4321u : 0x5321u;
+    int prev_strip = -1;
+    for (int k = 0; k < my_tiles; k++) {
+      int strip, f, rt;
+      tile_of (k, strip, f, rt);
+      const int buf = k & 1, use = k >> 1;
+      if (use > 0) tc_bar_wait_guard (bar (TCB_EMPTY0 + buf), (use - 1) & 1);          // H pass of tile k-2 has read these planes
+      if (strip != prev_strip) {
+        // the band is single-buffered: the H pass of tile k-1 must have finished with the old one
+        if (k > 0) tc_bar_wait_guard (bar (TCB_EMPTY0 + (buf ^ 1)), ((k - 1) >> 1) & 1);
+        const uint8_t *src = L.band + (size_t) strip * TC_BAND_BYTES;
+        for (int i = tid; i < TC_BAND_BYTES / 16; i += 32 * TC_PROD_WARPS) tc_cp16 (s_band + 16 * i, src + 16 * i);
+        prev_strip = strip;
+      }
+      const uint8_t *__restrict__ in = frames.in[f];
+      const uint8_t *__restrict__ plane_y = in + P.off_y;
+      const uint8_t *__restrict__ plane_c = in + P.off_c;
+      const int x0 = strip * TC_TW, oy0 = rt * TC_TH;
+      const int X0 = 2 * x0 - TC_X_LEAD, R0 = 2 * oy0 - 3;
+      const uint32_t img = s_img + buf * 3 * TC_IMG_BYTES;
+      uint8_t *img_u = sm + TC2_OFF_IMG + buf * 3 * TC_IMG_BYTES + TC_IMG_BYTES, *img_v = img_u + TC_IMG_BYTES;
+      if (tid < TC_VB_BYTES / 16)
+        tc_cp16 (s_vb + (k % TC_VB_RING) * TC_VB_BYTES + 16 * tid, L.vband + (size_t) rt * TC_VB_BYTES + 16 * tid);
+      // Y: a warp takes lines w, w + 8, ...; lanes 0..17 one 16-byte chunk each
+      {
+        const int x = X0 + 16 * lane;
+        const bool xin = lane < TC_CHUNKS && x >= 0 && x + 16 <= P.iw;
+        const uint8_t *src = plane_y + (ptrdiff_t) (R0 + warp) * P.stride_y + x;
+        const ptrdiff_t step = (ptrdiff_t) TC_PROD_WARPS * P.stride_y;
+        for (int li = warp; li < 2 * TC_TH + 6; li += TC_PROD_WARPS, src += step) {
+          const int y = R0 + li;
+          if (xin && y >= 0 && y < P.ih) tc_cp16 (img + lane * TC_IMG_LBO + (li >> 3) * 128 + (li & 7) * 16, src);
         }
       }
+      // chroma: item = (line group g, 8-pixel slot); units of 32 items, the odd unit rotates over the warps.  All raw
+      // chroma of a warp's (at most 3) units is requested before the first byte-SIMD instruction needs any of it.
+      {
+        constexpr int SLOTS = 2 * TC_CHUNKS - 2, ITEMS = (TC_N / 4) * SLOTS, UNITS = (ITEMS + 31) / 32;
+        constexpr int MAXU = (UNITS + TC_PROD_WARPS - 1) / TC_PROD_WARPS;
+        const int u0 = (warp + k) % TC_PROD_WARPS;
+        uint2 raw[MAXU][3];
+        unsigned nxt[MAXU][3];
+        int offs[MAXU];
+        bool redge[MAXU];
+#pragma unroll
+        for (int j = 0; j < MAXU; j++) {
+          const int item = 32 * (u0 + j * TC_PROD_WARPS) + lane;
+          offs[j] = -1; redge[j] = false;
+          if (u0 + j * TC_PROD_WARPS < UNITS && item < ITEMS) {
+            const int g = item / SLOTS, slot = item - g * SLOTS + 1;
+            const int x = X0 + 8 * slot;
+            if (x >= 0 && x < P.iw) {
+              redge[j] = x + 8 >= P.iw;
+              const int m2 = (R0 + 4 * g - 1) >> 1;
+              offs[j] = (slot >> 1) * TC_IMG_LBO + (g >> 1) * 128 + (g & 1) * 64 + (slot & 1) * 8;   // line 4g + r: + 16 r
+#pragma unroll
+              for (int kk = 0; kk < 3; kk++) {
+                const int cr = min (max (m2 + kk, 0), crows - 1);
+                const uint8_t *row = plane_c + (size_t) cr * P.stride_c + x;
+                raw[j][kk] = __ldg ((const uint2 *) row);
+                nxt[j][kk] = redge[j] ? 0u : (unsigned) __ldg ((const unsigned short *) (row + 8));
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < MAXU; j++) {
+          if (offs[j] < 0) continue;
+          unsigned ulo[3], uhi[3], vlo[3], vhi[3];
+#pragma unroll
+          for (int kk = 0; kk < 3; kk++) {
+            const uint2 c = raw[j][kk];
+            const unsigned ue = __byte_perm (c.x, c.y, selU), ve = __byte_perm (c.x, c.y, selV);
+            const unsigned un = redge[j] ? __byte_perm (ue, ue, 0x3321) : __byte_perm (ue, nxt[j][kk], nselU);
+            const unsigned vn = redge[j] ? __byte_perm (ve, ve, 0x3321) : __byte_perm (ve, nxt[j][kk], nselV);
+            const unsigned uo = avg_ceil4 (ue, un), vo = avg_ceil4 (ve, vn);
+            ulo[kk] = __byte_perm (ue, uo, 0x5140); uhi[kk] = __byte_perm (ue, uo, 0x7362);
+            vlo[kk] = __byte_perm (ve, vo, 0x5140); vhi[kk] = __byte_perm (ve, vo, 0x7362);
+          }
+          uint2 U[4], V[4];
+          {
+            unsigned q;
+            q = avg_floor4 (ulo[0], ulo[1]); U[0].x = avg_ceil4 (ulo[0], q); U[1].x = avg_ceil4 (ulo[1], q);
+            q = avg_floor4 (uhi[0], uhi[1]); U[0].y = avg_ceil4 (uhi[0], q); U[1].y = avg_ceil4 (uhi[1], q);
+            q = avg_floor4 (ulo[1], ulo[2]); U[2].x = avg_ceil4 (ulo[1], q); U[3].x = avg_ceil4 (ulo[2], q);
+            q = avg_floor4 (uhi[1], uhi[2]); U[2].y = avg_ceil4 (uhi[1], q); U[3].y = avg_ceil4 (uhi[2], q);
+            q = avg_floor4 (vlo[0], vlo[1]); V[0].x = avg_ceil4 (vlo[0], q); V[1].x = avg_ceil4 (vlo[1], q);
+            q = avg_floor4 (vhi[0], vhi[1]); V[0].y = avg_ceil4 (vhi[0], q); V[1].y = avg_ceil4 (vhi[1], q);
+            q = avg_floor4 (vlo[1], vlo[2]); V[2].x = avg_ceil4 (vlo[1], q); V[3].x = avg_ceil4 (vlo[2], q);
+            q = avg_floor4 (vhi[1], vhi[2]); V[2].y = avg_ceil4 (vhi[1], q); V[3].y = avg_ceil4 (vhi[2], q);
+          }
+#pragma unroll
+          for (int r = 0; r < 4; r++) {
+            *(uint2 *) (img_u + offs[j] + 16 * r) = U[r];
+            *(uint2 *) (img_v + offs[j] + 16 * r) = V[r];
+          }
+        }
+      }
+      tc_cp_wait ();
+      tc_fence_async_smem ();
+      __syncwarp ();
+      if (lane == 0) tc_bar_arrive (bar (TCB_FULL0 + buf));
     }
-    tc_cp_wait ();
-    tc_fence_async_smem ();
-    tc_fence_before ();
-    __syncthreads ();
-
-    // ------------------------------------------------------------ H pass: 3 channels x (9 K steps + rounding step)
-    if (tid == 0) {
+  } else if (warp < TC_PROD_WARPS + TC_CONS_WARPS) {
+    // ================================================================ CONSUMERS
+    const int cw = warp - TC_PROD_WARPS, qd = cw & 3, hf = cw >> 2;
+    const int col = 32 * qd + lane;
+    const uint32_t lane_base = tmem + ((uint32_t) (32 * qd) << 16);
+    for (int k = 0; k < my_tiles; k++) {
+      int strip, f, rt;
+      tile_of (k, strip, f, rt);
+      const int acc = k & 1, use = k >> 1;
+      // ---------------- H epilogue: 32 lines of one column per thread and channel
+      tc_bar_wait_guard (bar (TCB_DHF0 + acc), use & 1);
       tc_fence_after ();
-#pragma unroll 1
-      for (int ch = 0; ch < 3; ch++) {
-        const uint32_t img = s_img + ch * TC_IMG_BYTES;
-#pragma unroll 1
-        for (int s = 0; s < TC_CHUNKS / 2 + 1; s++) {
-          const uint64_t a = tc_desc (s_band + 2 * s * TC_BAND_LBO, TC_BAND_LBO, 128);
-          const uint64_t b = s < TC_CHUNKS / 2 ? tc_desc (img + 2 * s * TC_IMG_LBO, TC_IMG_LBO, 128) : tc_desc (s_ones, TC_BAND_LBO, 128);
-          tc_mma (tmem + ch * TC_N, a, b, IDESC_H, s > 0);
-        }
-      }
-      tc_commit (s_bar);
-    }
-    tc_bar_wait (s_bar, parity);
-    parity ^= 1;
-    tc_fence_after ();
-
-    // ------------------------------------------------------------ H epilogue: column = TMEM lane; 32 lines per warp half
-    {
-      const int qd = warp & 3, hf = warp >> 2;
-      const int col = 32 * qd + lane;
-      const bool x4 = __ldg (L.hx4 + strip) != 0;
+      const bool hx4 = __ldg (L.hx4 + strip) != 0;
 #pragma unroll 1
       for (int ch = 0; ch < 3; ch++) {
         int v[32];
-        const uint32_t ta = tmem + ((uint32_t) (32 * qd) << 16) + ch * TC_N + 32 * hf;
+        const uint32_t ta = lane_base + acc * 3 * TC_N + ch * TC_N + 32 * hf;
         TC_LD16 (v, ta);
         TC_LD16 ((v + 16), (ta + 16));
         tc_ld_wait ();
-        if (DBG == 1 && dbg && t == 0) {
+        if (DBG == 1 && dbg && blockIdx.x == 0 && k == 0) {
 #pragma unroll
           for (int i = 0; i < 32; i++) dbg[(ch * 128 + col) * 64 + 32 * hf + i] = (unsigned) v[i];
         }
         uint4 w0, w1;
-        if (x4) {
+        if (hx4) {
           w0.x = tc_pack4<true> (v[0], v[1], v[2], v[3]); w0.y = tc_pack4<true> (v[4], v[5], v[6], v[7]);
           w0.z = tc_pack4<true> (v[8], v[9], v[10], v[11]); w0.w = tc_pack4<true> (v[12], v[13], v[14], v[15]);
           w1.x = tc_pack4<true> (v[16], v[17], v[18], v[19]); w1.y = tc_pack4<true> (v[20], v[21], v[22], v[23]);
@@ -320,77 +414,91 @@ vcs_l2tc_kernel (const VcsDev P, const L2tcDev L, const VcsBatch frames, int n_f
           w1.x = tc_pack4<false> (v[16], v[17], v[18], v[19]); w1.y = tc_pack4<false> (v[20], v[21], v[22], v[23]);
           w1.z = tc_pack4<false> (v[24], v[25], v[26], v[27]); w1.w = tc_pack4<false> (v[28], v[29], v[30], v[31]);
         }
-        // V operand: row = output column, K = line: chunk (line / 16) at LBO, 16 bytes per row inside a chunk
-        uint8_t *hs = sm + TC_OFF_IMG + ch * TC_HS_BYTES + (2 * hf) * TC_HS_LBO + col * 16;
+        uint8_t *hs = sm + TC2_OFF_HS + ch * TC_HS_BYTES + (2 * hf) * TC_HS_LBO + col * 16;
         *(uint4 *) hs = w0;
         *(uint4 *) (hs + TC_HS_LBO) = w1;
       }
+      tc_fence_before ();
+      tc_fence_async_smem ();
+      __syncwarp ();
+      if (lane == 0) { tc_bar_arrive (bar (TCB_DHE0 + acc)); tc_bar_arrive (bar (TCB_HSF)); }
+      // ---------------- V epilogue: 14 rows of one column per thread
+      tc_bar_wait_guard (bar (TCB_DVF), k & 1);
+      tc_fence_after ();
+      {
+        const int x0 = strip * TC_TW, oy0 = rt * TC_TH, ox = x0 + col, r0 = 14 * hf;
+        int a[3][16];
+        const uint32_t ta = lane_base + TC2_DV_COL + r0;
+        TC_LD16 (a[0], ta);
+        TC_LD16 (a[1], (ta + TC_VROWS));
+        TC_LD16 (a[2], (ta + 2 * TC_VROWS));
+        tc_ld_wait ();
+        tc_fence_before ();                                        // the next V pass may overwrite the accumulators once hs_full comes
+        const int rows = min (min (TC_TH, P.oh - oy0) - r0, 14);
+        if (ox < P.ow && rows > 0) {
+          uint8_t *dst = frames.out[f] + P.off_out + (size_t) (oy0 + r0) * P.stride_out + (size_t) ox * 4u;
+          if (__ldg (L.vx4 + rt) != 0) tc_v_rows<true> (P, a, dst, rows, nullptr);
+          else tc_v_rows<false> (P, a, dst, rows, nullptr);
+        }
+      }
     }
-    tc_fence_async_smem ();
-    tc_fence_before ();
-    __syncthreads ();
-
-    // ------------------------------------------------------------ V pass: 3 channels x (2 K steps + rounding step)
-    if (tid == 0) {
+  } else if (lane == 0) {
+    // ================================================================ MMA ISSUER (one lane)
+    constexpr uint32_t IDESC_H = tc_idesc (1, 0, TC_N, 128), IDESC_V = tc_idesc (0, 1, TC_VROWS, 128);
+    // Both passes are issued from one lane in whatever order their inputs become ready: the H pass of tile k+1 must not
+    // wait behind the V pass of tile k (that one waits for the consumers), nor the other way round (the H pass waits for
+    // the producers).  The H pass runs at most one tile ahead (two TMEM / plane buffers).
+    auto issue_h = [&] (int k) {
+      const int buf = k & 1;
       tc_fence_after ();
 #pragma unroll 1
       for (int ch = 0; ch < 3; ch++) {
-        const uint32_t hs = s_img + ch * TC_HS_BYTES;
+        const uint32_t img = s_img + (buf * 3 + ch) * TC_IMG_BYTES;
+#pragma unroll 1
+        for (int s = 0; s < TC_CHUNKS / 2 + 1; s++) {
+          const uint64_t a = tc_desc (s_band + 2 * s * TC_BAND_LBO, TC_BAND_LBO, 128);
+          const uint64_t b = s < TC_CHUNKS / 2 ? tc_desc (img + 2 * s * TC_IMG_LBO, TC_IMG_LBO, 128) : tc_desc (s_ones, TC_BAND_LBO, 128);
+          tc_mma (tmem + buf * 3 * TC_N + ch * TC_N, a, b, IDESC_H, s > 0);
+        }
+      }
+      tc_commit (bar (TCB_EMPTY0 + buf));
+      tc_commit (bar (TCB_DHF0 + buf));
+    };
+    auto issue_v = [&] (int k) {
+      tc_fence_after ();
+      const uint32_t vb = s_vb + (k % TC_VB_RING) * TC_VB_BYTES;
+#pragma unroll 1
+      for (int ch = 0; ch < 3; ch++) {
+        const uint32_t hs = s_hs + ch * TC_HS_BYTES;
 #pragma unroll 1
         for (int s = 0; s < TC_N / 32 + 1; s++) {
           const uint64_t a = s < TC_N / 32 ? tc_desc (hs + 2 * s * TC_HS_LBO, TC_HS_LBO, 128) : tc_desc (s_ones, TC_BAND_LBO, 128);
-          const uint64_t b = tc_desc (s_vb + 2 * s * TC_VB_LBO, TC_VB_LBO, 128);
-          tc_mma (tmem + ch * TC_VROWS, a, b, IDESC_V, s > 0);
+          const uint64_t b = tc_desc (vb + 2 * s * TC_VB_LBO, TC_VB_LBO, 128);
+          tc_mma (tmem + TC2_DV_COL + ch * TC_VROWS, a, b, IDESC_V, s > 0);
         }
       }
-      tc_commit (s_bar);
-    }
-    tc_bar_wait (s_bar, parity);
-    parity ^= 1;
-    tc_fence_after ();
-
-    // ------------------------------------------------------------ V epilogue: 16 rows of one column per thread
-    {
-      const int qd = warp & 3, hf = warp >> 2;
-      const int col = 32 * qd + lane, ox = x0 + col;
-      const int r0 = 16 * hf;
-      const bool x4 = __ldg (L.vx4 + rt) != 0;
-      int a[3][16];
-      const uint32_t ta = tmem + ((uint32_t) (32 * qd) << 16) + r0;
-      TC_LD16 (a[0], ta);
-      TC_LD16 (a[1], (ta + TC_VROWS));
-      TC_LD16 (a[2], (ta + 2 * TC_VROWS));
-      tc_ld_wait ();
-      const int rows = min (min (TC_TH, P.oh - oy0) - r0, 16);
-      if (ox < P.ow) {
-        uint8_t *dst = out + P.off_out + (size_t) (oy0 + r0) * P.stride_out + (size_t) ox * 4u;
-#pragma unroll
-        for (int i = 0; i < 16; i++) {
-          if (i < rows) {
-            unsigned yuv = x4 ? __byte_perm (pack_sat_u16x2 (a[1][i], a[0][i]), pack_sat_u16x2 (0, a[2][i]), 0x7531)
-                : pack_sat2 (a[1][i] >> 6, a[0][i] >> 6, pack_sat2 (0, a[2][i] >> 6, 0u));
-            if (DBG == 2 && dbg && t == 0) dbg[(r0 + i) * 128 + col] = yuv;
-            yuv ^= 0x00808080u;
-            const int wy = prmt_s (yuv, 0x8800u), wu = prmt_s (yuv, 0x9911u), wv = prmt_s (yuv, 0xaa22u);
-            const int ty = ((wy * P.p1) >> 16) + 128;
-            const int r = ty + ((wv * P.p2) >> 16);
-            const int b = ty + ((wu * P.p3) >> 16);
-            const int gg = ty + ((wu * P.p4) >> 16) + ((wv * P.p5) >> 16);
-            const unsigned argb = pack_sat2 (r, 255, pack_sat2 (b, gg, 0u));
-            *(unsigned *) dst = __byte_perm (argb, 0, P.sel);
-          }
-          dst += P.stride_out;
+      tc_commit (bar (TCB_DVF));
+    };
+    int nh = 0, nv = 0;
+    uint32_t idle = 0;
+    while (nv < my_tiles) {
+      bool progressed = false;
+      if (nh < my_tiles && nh <= nv + 1) {
+        const int buf = nh & 1, use = nh >> 1;
+        if (tc_bar_test (bar (TCB_FULL0 + buf), use & 1) && (use == 0 || tc_bar_test (bar (TCB_DHE0 + buf), (use - 1) & 1))) {
+          issue_h (nh); nh++; progressed = true;
         }
       }
+      if (nv < nh && tc_bar_test (bar (TCB_HSF), nv & 1)) { issue_v (nv); nv++; progressed = true; }
+      if (progressed) idle = 0;
+      else if (++idle > (1u << 27)) __trap ();
     }
-    tc_fence_before ();
-    __syncthreads ();                                              // TMEM and the staged planes are free again
-    tc_fence_after ();
   }
 
+  tc_fence_before ();
   __syncthreads ();
-  if (warp == 0)
-    asm volatile ("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r" (tmem), "r" (TC_TMEM_COLS) : "memory");
+  if (warp == TC_PROD_WARPS + TC_CONS_WARPS)
+    asm volatile ("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r" (tmem), "r" (TC2_TMEM_COLS) : "memory");
 #endif
 }
 
@@ -482,20 +590,20 @@ inline int launch_l2tc (const VcsDev & d, const L2tcState & st, const VcsBatch &
   int dev = 0;
   B200_CUDA_TRY (cudaGetDevice (&dev));
   const int tiles = st.dev.strips * st.dev.row_tiles * n;
-  const int grid = min (tiles, 2 * sm_count (dev));
+  const int grid = min (tiles, sm_count (dev));
   if (dbg_mode == 1) {
     if ((rc = allow_max_dyn_smem (vcs_l2tc_kernel<1>)) != B200_OK) return rc;
-    vcs_l2tc_kernel<1> <<<grid, TC_THREADS, TC_SMEM, stream>>> (d, st.dev, batch, n, dbg);
+    vcs_l2tc_kernel<1> <<<grid, TC_THREADS2, TC2_SMEM, stream>>> (d, st.dev, batch, n, dbg);
   } else if (dbg_mode == 2) {
     if ((rc = allow_max_dyn_smem (vcs_l2tc_kernel<2>)) != B200_OK) return rc;
-    vcs_l2tc_kernel<2> <<<grid, TC_THREADS, TC_SMEM, stream>>> (d, st.dev, batch, n, dbg);
+    vcs_l2tc_kernel<2> <<<grid, TC_THREADS2, TC2_SMEM, stream>>> (d, st.dev, batch, n, dbg);
   } else {
     static bool attr_done[16] = {false};
     if (!attr_done[dev & 15]) {
       if ((rc = allow_max_dyn_smem (vcs_l2tc_kernel<0>)) != B200_OK) return rc;
       attr_done[dev & 15] = true;
     }
-    vcs_l2tc_kernel<0> <<<grid, TC_THREADS, TC_SMEM, stream>>> (d, st.dev, batch, n, nullptr);
+    vcs_l2tc_kernel<0> <<<grid, TC_THREADS2, TC2_SMEM, stream>>> (d, st.dev, batch, n, nullptr);
   }
   B200_CUDA_TRY (cudaGetLastError ());
   return B200_OK;
