@@ -4,15 +4,15 @@
  * (gst-plugins-base/gst/audioresample/gstaudioresample.c:68, :144-228), same framing rules —
  * output length from the resampler before processing (:763-769), zero-length outputs dropped
  * (:879-882), reset on flush/discont (:462, :907-915), drain with silence on EOS (:590-662),
- * timestamps from running sample counters (:846-866).  The FIR runs on the GPU through
- * b200_ars_process(); audio buffers are system memory, so the element stages them through
- * pinned buffers and one CUDA stream.
+ * timestamps from running sample counters (:846-866).  Audio buffers are system memory: the FIR runs on the GPU
+ * through b200_ars_process_host_submit / _wait, i.e. the LIBRARY owns the device staging ring (sized in the caps'
+ * bytes per frame, allocated on the element's device under its own device guard) and the three side streams; the
+ * element holds no CUDA state of its own.
  *
  * NOT compiled in the development image (no GLib/GStreamer there); see INTEGRATION.md.
  */
 #include <gst/base/gstbasetransform.h>
 #include <gst/audio/audio.h>
-#include <cuda_runtime_api.h>
 
 #include "gstb200elements.h"
 
@@ -39,9 +39,6 @@ typedef struct
   guint sinc_filter_auto_threshold;
   GstAudioInfo in, out;
   b200_ars *ars;
-  cudaStream_t stream;
-  float *d_in, *d_out;           /* device staging */
-  gsize d_in_frames, d_out_frames;
   /* running position (gstaudioresample.c:846-866) */
   GstClockTime t0;
   guint64 in_offset0, out_offset0, samples_in, samples_out;
@@ -58,25 +55,6 @@ ars_reset_position (GstCudaAudioResample * self)
   self->need_discont = TRUE;
   if (self->ars)
     b200_ars_reset (self->ars);
-}
-
-static gboolean
-ars_ensure_staging (GstCudaAudioResample * self, gsize in_frames, gsize out_frames)
-{
-  const gsize ch = GST_AUDIO_INFO_CHANNELS (&self->in);
-  if (in_frames > self->d_in_frames) {
-    cudaFree (self->d_in);
-    if (cudaMalloc ((void **) &self->d_in, in_frames * ch * sizeof (float)) != cudaSuccess)
-      return FALSE;
-    self->d_in_frames = in_frames;
-  }
-  if (out_frames > self->d_out_frames) {
-    cudaFree (self->d_out);
-    if (cudaMalloc ((void **) &self->d_out, out_frames * ch * sizeof (float)) != cudaSuccess)
-      return FALSE;
-    self->d_out_frames = out_frames;
-  }
-  return TRUE;
 }
 
 static gboolean
@@ -157,23 +135,23 @@ ars_transform (GstBaseTransform * trans, GstBuffer * inbuf, GstBuffer * outbuf)
     self->out_offset0 = gst_util_uint64_scale_int_round (self->in_offset0, GST_AUDIO_INFO_RATE (&self->out),
         GST_AUDIO_INFO_RATE (&self->in));
   }
-  gst_buffer_map (inbuf, &imap, GST_MAP_READ);
+  if (!gst_buffer_map (inbuf, &imap, GST_MAP_READ))
+    return GST_FLOW_ERROR;
   in_frames = imap.size / bpf;
   out_frames = b200_ars_get_out_frames (self->ars, in_frames);
-  if (!ars_ensure_staging (self, in_frames, MAX (out_frames, 1))) {
+  if (!gst_buffer_map (outbuf, &omap, GST_MAP_WRITE)) {
     gst_buffer_unmap (inbuf, &imap);
     return GST_FLOW_ERROR;
   }
-  gst_buffer_map (outbuf, &omap, GST_MAP_WRITE);
-  cudaMemcpyAsync (self->d_in, imap.data, in_frames * bpf, cudaMemcpyHostToDevice, self->stream);
-  st = b200_ars_process (self->ars, GST_BUFFER_FLAG_IS_SET (inbuf, GST_BUFFER_FLAG_GAP) ? NULL : self->d_in,
-      in_frames, self->d_out, out_frames, &got, self->stream);
-  if (st == B200_OK && got)
-    cudaMemcpyAsync (omap.data, self->d_out, got * bpf, cudaMemcpyDeviceToHost, self->stream);
-  cudaStreamSynchronize (self->stream);
+  /* upload -> FIR -> download on the library's streams; GstBaseTransform hands the output on when we return, so this
+   * buffer has to be complete: one wait per buffer, no device-wide synchronisation */
+  st = b200_ars_process_host_submit (self->ars, GST_BUFFER_FLAG_IS_SET (inbuf, GST_BUFFER_FLAG_GAP) ? NULL : imap.data,
+      in_frames, omap.data, MIN (out_frames, omap.size / bpf), &got);
+  if (st == B200_OK)
+    st = b200_ars_process_host_wait (self->ars, 0);
   gst_buffer_unmap (outbuf, &omap);
   gst_buffer_unmap (inbuf, &imap);
-  GST_B200_FLOW_FROM_STATUS (self, st, "b200_ars_process");
+  GST_B200_FLOW_FROM_STATUS (self, st, "b200_ars_process_host");
 
   gst_buffer_set_size (outbuf, got * bpf);             /* :763-769 */
   GST_BUFFER_PTS (outbuf) = self->t0 + gst_util_uint64_scale_int_round (self->samples_out, GST_SECOND,
@@ -204,17 +182,20 @@ ars_push_drain (GstCudaAudioResample * self)
     return;
   in_frames = b200_ars_get_max_latency (self->ars);
   out_frames = b200_ars_get_out_frames (self->ars, in_frames);
-  if (out_frames == 0 || !ars_ensure_staging (self, 1, out_frames))
+  if (out_frames == 0)
     return;
   outbuf = gst_buffer_new_and_alloc (out_frames * bpf);
-  if (b200_ars_process (self->ars, NULL, in_frames, self->d_out, out_frames, &got, self->stream) != B200_OK || !got) {
+  if (!gst_buffer_map (outbuf, &omap, GST_MAP_WRITE)) {
     gst_buffer_unref (outbuf);
     return;
   }
-  gst_buffer_map (outbuf, &omap, GST_MAP_WRITE);
-  cudaMemcpyAsync (omap.data, self->d_out, got * bpf, cudaMemcpyDeviceToHost, self->stream);
-  cudaStreamSynchronize (self->stream);
+  if (b200_ars_process_host (self->ars, NULL, in_frames, omap.data, out_frames, &got) != B200_OK)
+    got = 0;
   gst_buffer_unmap (outbuf, &omap);
+  if (!got) {
+    gst_buffer_unref (outbuf);
+    return;
+  }
   gst_buffer_set_size (outbuf, got * bpf);
   GST_BUFFER_PTS (outbuf) = self->t0 + gst_util_uint64_scale_int_round (self->samples_out, GST_SECOND,
       GST_AUDIO_INFO_RATE (&self->out));
@@ -239,24 +220,15 @@ static gboolean
 ars_start (GstBaseTransform * trans)
 {
   GstCudaAudioResample *self = (GstCudaAudioResample *) trans;
-  if (b200_device_count () <= 0)
-    return FALSE;
-  cudaSetDevice (self->device_id);
-  return cudaStreamCreateWithFlags (&self->stream, cudaStreamNonBlocking) == cudaSuccess;
+  (void) self;
+  return b200_device_count () > 0;                      /* no CPU fallback: refuse to start without a device */
 }
 
 static gboolean
 ars_stop (GstBaseTransform * trans)
 {
   GstCudaAudioResample *self = (GstCudaAudioResample *) trans;
-  g_clear_pointer (&self->ars, b200_ars_destroy);
-  cudaFree (self->d_in);
-  cudaFree (self->d_out);
-  self->d_in = self->d_out = NULL;
-  self->d_in_frames = self->d_out_frames = 0;
-  if (self->stream)
-    cudaStreamDestroy (self->stream);
-  self->stream = NULL;
+  g_clear_pointer (&self->ars, b200_ars_destroy);     /* frees the staging ring and the streams with it */
   return TRUE;
 }
 

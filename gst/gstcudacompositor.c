@@ -17,8 +17,10 @@ GST_DEBUG_CATEGORY_STATIC (cuda_comp_debug);
 #define GST_CAT_DEFAULT cuda_comp_debug
 
 #define COMP_FORMATS "{ RGBA, BGRA, ARGB, ABGR, I420, YV12, NV12, NV21 }"
-#define COMP_CAPS "video/x-raw(" GST_CAPS_FEATURE_MEMORY_CUDA_MEMORY "), format = (string) " COMP_FORMATS \
+#define COMP_FIELDS "format = (string) " COMP_FORMATS \
     ", width = (int) [ 1, 32767 ], height = (int) [ 1, 32767 ], framerate = (fraction) [ 0/1, max ]"
+/* device memory preferred; system memory (packed RGB) goes through b200_comp_blend_host */
+#define COMP_CAPS "video/x-raw(" GST_CAPS_FEATURE_MEMORY_CUDA_MEMORY "), " COMP_FIELDS "; video/x-raw, " COMP_FIELDS
 
 static GstStaticPadTemplate comp_src = GST_STATIC_PAD_TEMPLATE ("src", GST_PAD_SRC, GST_PAD_ALWAYS,
     GST_STATIC_CAPS (COMP_CAPS));
@@ -228,7 +230,8 @@ comp_aggregate_frames (GstVideoAggregator * vagg, GstBuffer * outbuf)
     self->comp_h = GST_VIDEO_INFO_HEIGHT (oinfo);
     self->comp_fmt = GST_VIDEO_INFO_FORMAT (oinfo);
   }
-  if (!gst_video_frame_map (&out_frame, (GstVideoInfo *) oinfo, outbuf, GST_MAP_WRITE | GST_MAP_CUDA))
+  const gboolean on_device = gst_is_cuda_memory (gst_buffer_peek_memory (outbuf, 0));
+  if (!gst_video_frame_map (&out_frame, (GstVideoInfo *) oinfo, outbuf, on_device ? (GST_MAP_WRITE | GST_MAP_CUDA) : GST_MAP_WRITE))
     return GST_FLOW_ERROR;
 
   /* sink pads in z-order (the aggregator keeps element->sinkpads sorted by zorder);
@@ -261,6 +264,17 @@ comp_aggregate_frames (GstVideoAggregator * vagg, GstBuffer * outbuf)
   GST_OBJECT_UNLOCK (vagg);
 
   gst_cuda_context_push (self->context);
+  if (!on_device) {
+    /* system-memory peers (packed RGB): prepared frames and the output are host memory; the library stages them through
+     * its own device ring - upload, one blend pass, download */
+    st = GST_VIDEO_INFO_IS_YUV (oinfo) ? B200_ERR_UNSUPPORTED
+        : b200_comp_blend_host (self->comp, GST_VIDEO_FRAME_PLANE_DATA (&out_frame, 0),
+        GST_VIDEO_FRAME_PLANE_STRIDE (&out_frame, 0), self->background, pads, n);
+    gst_cuda_context_pop (NULL);
+    gst_video_frame_unmap (&out_frame);
+    GST_B200_FLOW_FROM_STATUS (self, st, "b200_comp_blend_host");
+    return GST_FLOW_OK;
+  }
   if (GST_VIDEO_INFO_IS_YUV (oinfo)) {
     /* 4:2:0 output: plane layouts travel as b200_video_info, offsets relative to plane 0 */
     b200_comp_pad_yuv ypads[B200_COMP_MAX_PADS];

@@ -8,7 +8,8 @@
  * sharing, stream selection, allocation queries) follows the stock CUDA converter
  * gst-plugins-bad/sys/nvcodec/gstcudaconvertscale.c:1483-1587 and gstcudabasetransform.c.
  *
- * NOT compiled in the development image (no GLib/GStreamer there); see INTEGRATION.md.
+ * NOT built in the development image (no GLib/GStreamer there); `make -C gst/check` runs the sources through
+ * gcc -fsyntax-only against declarations restated from the reference headers (gst/check/), see INTEGRATION.md.
  */
 #include <gst/base/gstbasetransform.h>
 #include <gst/cuda/gstcuda.h>
@@ -24,13 +25,17 @@ GST_DEBUG_CATEGORY_STATIC (cuda_vcs_debug);
  * (transfer_colorimetry_from_input, gstvideoconvertscale.c:1335-1427) - b200_vcs_create refuses a YUV -> YUV
  * matrix change with B200_ERR_UNSUPPORTED */
 #define SRC_FORMATS "{ BGRA, RGBA, ARGB, ABGR, BGRx, RGBx, xRGB, xBGR, NV12, NV21, I420, YV12 }"
-#define CUDA_CAPS(f) "video/x-raw(" GST_CAPS_FEATURE_MEMORY_CUDA_MEMORY "), format = (string) " f \
+#define RAW_FIELDS(f) "format = (string) " f \
     ", width = (int) [ 1, 32767 ], height = (int) [ 1, 32767 ], framerate = (fraction) [ 0/1, max ]"
+/* device memory first (zero copy between CUDA elements), then plain system memory: in that case transform() hands the
+ * mapped host frames to b200_vcs_convert_host(), whose pinned-slot pipeline does the H2D / D2H - the element drops in
+ * for videoconvertscale without cudaupload / cudadownload around it */
+#define BOTH_CAPS(f) "video/x-raw(" GST_CAPS_FEATURE_MEMORY_CUDA_MEMORY "), " RAW_FIELDS (f) "; video/x-raw, " RAW_FIELDS (f)
 
 static GstStaticPadTemplate sink_tmpl = GST_STATIC_PAD_TEMPLATE ("sink", GST_PAD_SINK, GST_PAD_ALWAYS,
-    GST_STATIC_CAPS (CUDA_CAPS (SINK_FORMATS)));
+    GST_STATIC_CAPS (BOTH_CAPS (SINK_FORMATS)));
 static GstStaticPadTemplate src_tmpl = GST_STATIC_PAD_TEMPLATE ("src", GST_PAD_SRC, GST_PAD_ALWAYS,
-    GST_STATIC_CAPS (CUDA_CAPS (SRC_FORMATS)));
+    GST_STATIC_CAPS (BOTH_CAPS (SRC_FORMATS)));
 
 enum { PROP_0, PROP_METHOD, PROP_ENVELOPE, PROP_SHARPNESS, PROP_SHARPEN, PROP_ADD_BORDERS, PROP_DEVICE_ID,
   /* the stock element's remaining properties (gstvideoconvertscale.c:326-391): installed so that existing pipelines keep
@@ -167,7 +172,10 @@ static gboolean
 vcs_stop (GstBaseTransform * trans)
 {
   GstCudaVideoConvertScale *self = (GstCudaVideoConvertScale *) trans;
-  g_clear_pointer (&self->vcs, b200_vcs_destroy);
+  if (self->vcs && self->context && gst_cuda_context_push (self->context)) {
+    g_clear_pointer (&self->vcs, b200_vcs_destroy);    /* frees device tables: in the context that owns them */
+    gst_cuda_context_pop (NULL);
+  }
   gst_clear_cuda_stream (&self->stream);
   gst_clear_object (&self->context);
   return TRUE;
@@ -300,8 +308,13 @@ vcs_rebuild (GstCudaVideoConvertScale * self)
   GST_OBJECT_UNLOCK (self);
   gst_b200_video_info_from_gst (&in, &self->in_info);
   gst_b200_video_info_from_gst (&out, &self->out_info);
+  /* every b200 call runs with the element's GstCudaContext current: the library's runtime-API allocations (tap tables,
+   * staging slots) must live in the context the frames live in (gstcudacontext.cpp:417 creates a non-primary one) */
+  if (!self->context || !gst_cuda_context_push (self->context))
+    return FALSE;
   g_clear_pointer (&self->vcs, b200_vcs_destroy);
   st = b200_vcs_create (&in, &out, &cfg, self->device_id, &self->vcs);
+  gst_cuda_context_pop (NULL);
   if (st != B200_OK) {
     GST_ERROR_OBJECT (self, "b200_vcs_create: %s", b200_strerror (st));
     return FALSE;                                      /* -> not negotiated */
@@ -329,12 +342,29 @@ vcs_transform (GstBaseTransform * trans, GstBuffer * inbuf, GstBuffer * outbuf)
   GstCudaStream *in_stream, *out_stream, *use;
   int st;
 
-  if (!gst_is_cuda_memory (in_mem) || !gst_is_cuda_memory (out_mem)) {
-    GST_ERROR_OBJECT (self, "buffers are not CUDA memory");
-    return GST_FLOW_ERROR;
-  }
   if (self->config_changed && !vcs_rebuild (self))
     return GST_FLOW_NOT_NEGOTIATED;
+  if (!gst_is_cuda_memory (in_mem) || !gst_is_cuda_memory (out_mem)) {
+    /* system-memory peers: plain maps (a GstCudaMemory on one side maps through its own staging) and the library's
+     * host entry point: upload, kernel and download pipelined over its device slots */
+    const void *src;
+    void *dst;
+    if (!gst_video_frame_map (&in_frame, &self->in_info, inbuf, GST_MAP_READ))
+      return GST_FLOW_ERROR;
+    if (!gst_video_frame_map (&out_frame, &self->out_info, outbuf, GST_MAP_WRITE)) {
+      gst_video_frame_unmap (&in_frame);
+      return GST_FLOW_ERROR;
+    }
+    src = GST_VIDEO_FRAME_PLANE_DATA (&in_frame, 0);
+    dst = GST_VIDEO_FRAME_PLANE_DATA (&out_frame, 0);
+    gst_cuda_context_push (self->context);
+    st = b200_vcs_convert_host (self->vcs, 1, &src, &dst);
+    gst_cuda_context_pop (NULL);
+    gst_video_frame_unmap (&out_frame);
+    gst_video_frame_unmap (&in_frame);
+    GST_B200_FLOW_FROM_STATUS (self, st, "b200_vcs_convert_host");
+    return GST_FLOW_OK;
+  }
 
   in_stream = gst_cuda_memory_get_stream (GST_CUDA_MEMORY_CAST (in_mem));
   out_stream = gst_cuda_memory_get_stream (GST_CUDA_MEMORY_CAST (out_mem));
@@ -366,6 +396,46 @@ vcs_transform (GstBaseTransform * trans, GstBuffer * inbuf, GstBuffer * outbuf)
 }
 
 static gboolean
+vcs_caps_are_cuda (GstCaps * caps)
+{
+  GstCapsFeatures *f = caps && gst_caps_get_size (caps) ? gst_caps_get_features (caps, 0) : NULL;
+  return f && gst_caps_features_contains (f, GST_CAPS_FEATURE_MEMORY_CUDA_MEMORY);
+}
+
+/* propose_allocation (pattern: GstVideoFilter, gst-libs/gst/video/gstvideofilter.c:56-115): offer upstream a pool for
+ * our sink caps - a GstCudaBufferPool for CUDA caps, a plain video pool for system memory - and GstVideoMeta, so that
+ * strides other than the default reach transform() through the frame map */
+static gboolean
+vcs_propose_allocation (GstBaseTransform * trans, GstQuery * decide_query, GstQuery * query)
+{
+  GstCudaVideoConvertScale *self = (GstCudaVideoConvertScale *) trans;
+  GstCaps *caps;
+  GstVideoInfo info;
+  GstBufferPool *pool;
+  GstStructure *config;
+  gboolean need_pool;
+  if (decide_query == NULL)                              /* pass-through: let the query travel */
+    return GST_BASE_TRANSFORM_CLASS (gst_cuda_video_convert_scale_parent_class)->propose_allocation (trans, decide_query, query);
+  gst_query_parse_allocation (query, &caps, &need_pool);
+  if (caps == NULL || !gst_video_info_from_caps (&info, caps))
+    return FALSE;
+  if (need_pool) {
+    pool = vcs_caps_are_cuda (caps) && self->context ? gst_cuda_buffer_pool_new (self->context) : gst_video_buffer_pool_new ();
+    config = gst_buffer_pool_get_config (pool);
+    gst_buffer_pool_config_set_params (config, caps, GST_VIDEO_INFO_SIZE (&info), 0, 0);
+    gst_buffer_pool_config_add_option (config, GST_BUFFER_POOL_OPTION_VIDEO_META);
+    if (!gst_buffer_pool_set_config (pool, config)) {
+      gst_object_unref (pool);
+      return FALSE;
+    }
+    gst_query_add_allocation_pool (query, pool, GST_VIDEO_INFO_SIZE (&info), 0, 0);
+    gst_object_unref (pool);
+  }
+  gst_query_add_allocation_meta (query, GST_VIDEO_META_API_TYPE, NULL);
+  return TRUE;
+}
+
+static gboolean
 vcs_decide_allocation (GstBaseTransform * trans, GstQuery * query)
 {
   GstCudaVideoConvertScale *self = (GstCudaVideoConvertScale *) trans;
@@ -374,6 +444,8 @@ vcs_decide_allocation (GstBaseTransform * trans, GstQuery * query)
   GstStructure *config;
   guint size = GST_VIDEO_INFO_SIZE (&self->out_info), min = 0, max = 0;
   gst_query_parse_allocation (query, &caps, NULL);
+  if (!vcs_caps_are_cuda (caps))                        /* system-memory downstream: the base class picks its pool */
+    return GST_BASE_TRANSFORM_CLASS (gst_cuda_video_convert_scale_parent_class)->decide_allocation (trans, query);
   if (gst_query_get_n_allocation_pools (query) > 0)
     gst_query_parse_nth_allocation_pool (query, 0, &pool, &size, &min, &max);
   if (pool && !GST_IS_CUDA_BUFFER_POOL (pool))
@@ -458,6 +530,7 @@ gst_cuda_video_convert_scale_class_init (GstCudaVideoConvertScaleClass * klass)
   trans->fixate_caps = vcs_fixate_caps;
   trans->set_caps = vcs_set_caps;
   trans->transform = vcs_transform;
+  trans->propose_allocation = vcs_propose_allocation;
   trans->decide_allocation = vcs_decide_allocation;
   GST_DEBUG_CATEGORY_INIT (cuda_vcs_debug, "cudavideoconvertscale", 0, "B200 convert + scale");
 }

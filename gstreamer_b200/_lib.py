@@ -100,6 +100,9 @@ _SIGS = {
     "b200_comp_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
     "b200_comp_destroy": (None, [_P]),
     "b200_comp_blend": (C.c_int, [_P, _P, C.c_int32, C.c_int, C.POINTER(CompPadC), C.c_int, _P]),
+    "b200_comp_blend_host_submit": (C.c_int, [_P, _P, C.c_int32, C.c_int, C.POINTER(CompPadC), C.c_int]),
+    "b200_comp_blend_host_wait": (C.c_int, [_P, C.c_int]),
+    "b200_comp_blend_host": (C.c_int, [_P, _P, C.c_int32, C.c_int, C.POINTER(CompPadC), C.c_int]),
     "b200_comp_blend_yuv": (C.c_int, [_P, _P, C.POINTER(VideoInfoC), C.c_int, C.POINTER(CompPadYuvC), C.c_int, _P]),
     "b200_ars_create": (C.c_int, [C.POINTER(ArsConfigC), C.c_int, C.POINTER(_P)]),
     "b200_ars_destroy": (None, [_P]),
@@ -108,6 +111,9 @@ _SIGS = {
     "b200_ars_get_in_frames": (C.c_size_t, [_P, C.c_size_t]),
     "b200_ars_get_max_latency": (C.c_size_t, [_P]),
     "b200_ars_process": (C.c_int, [_P, _P, C.c_size_t, _P, C.c_size_t, C.POINTER(C.c_size_t), _P]),
+    "b200_ars_process_host_submit": (C.c_int, [_P, _P, C.c_size_t, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "b200_ars_process_host_wait": (C.c_int, [_P, C.c_int]),
+    "b200_ars_process_host": (C.c_int, [_P, _P, C.c_size_t, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "b200_ars_get_plan_info": (C.c_int, [_P, C.POINTER(ArsPlanInfoC)]),
     "b200_ars_get_phase_taps": (C.c_int, [_P, C.c_int, _P, C.c_size_t]),
 }

@@ -86,6 +86,17 @@ class CudaAudioResample:
                                    _stream(stream)), "b200_ars_process")
         return n.value
 
+    # system-memory peers: host buffers in, host buffers out (pinned ring + side streams inside the library)
+    def transform_host(self, in_ptr, in_frames, out_ptr, out_capacity, wait=True):
+        """wait=False: queued (b200_ars_process_host_submit); host_wait(k) later returns when all but the k latest are done"""
+        n = C.c_size_t()
+        fn = lib.b200_ars_process_host if wait else lib.b200_ars_process_host_submit
+        check(fn(self._h, in_ptr, in_frames, out_ptr, out_capacity, C.byref(n)), "b200_ars_process_host")
+        return n.value
+
+    def host_wait(self, keep_in_flight=0):
+        check(lib.b200_ars_process_host_wait(self._h, keep_in_flight), "b200_ars_process_host_wait")
+
     def reset(self):
         check(lib.b200_ars_reset(self._h), "b200_ars_reset")
 

@@ -152,6 +152,20 @@ class CudaCompositor:
         check(lib.b200_comp_blend(self._h, _ptr(outbuf), out_stride or self.width * 4, int(self.background),
                                   arr, len(pads), _stream(stream)), "b200_comp_blend")
 
+    # system-memory peers: pad frames and the output are HOST buffers (addresses); see b200_comp_blend_host_submit
+    def aggregate_host_frames(self, out_ptr, pad_ptrs, out_stride=None, wait=True):
+        pads = [p for p in self.sinkpads]
+        arr = (_lib.CompPadC * max(len(pads), 1))()
+        for i, (p, ptr) in enumerate(zip(pads, pad_ptrs)):
+            arr[i].data = ptr
+            arr[i].width, arr[i].height, arr[i].stride = p.width, p.height, p.stride
+            arr[i].xpos, arr[i].ypos, arr[i].alpha, arr[i].op = p.xpos + p.x_offset, p.ypos + p.y_offset, p.alpha, int(p.operator)
+        fn = lib.b200_comp_blend_host if wait else lib.b200_comp_blend_host_submit
+        check(fn(self._h, out_ptr, out_stride or self.width * 4, int(self.background), arr, len(pads)), "b200_comp_blend_host")
+
+    def host_wait(self, keep_in_flight=0):
+        check(lib.b200_comp_blend_host_wait(self._h, keep_in_flight), "b200_comp_blend_host_wait")
+
     def __del__(self):
         try:
             if self._h:

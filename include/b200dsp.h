@@ -223,6 +223,18 @@ void b200_comp_destroy (b200_comp * h);
 int b200_comp_blend (b200_comp * h, void *dst, int32_t dst_stride, int background,
     const b200_comp_pad * pads, int n_pads, void *cuda_stream);
 
+/* System-memory peers (what GstVideoAggregator hands a compositor without cudaupload in front): pads[].data are HOST
+ * pointers (pinned by b200_host_alloc for the copies to be asynchronous), dst_host receives the frame.
+ * _submit queues upload -> blend -> download on the handle's own three streams over a ring of 3 device slots and
+ * returns at once; _wait (h, k) returns when all but the k most recent submissions are complete in host memory
+ * (k = 1: push frame n-1 downstream while frame n is in flight - no per-buffer device synchronisation);
+ * b200_comp_blend_host = _submit + _wait (h, 0).  Host buffers of a submission must stay untouched until it completed. */
+int b200_comp_blend_host_submit (b200_comp * h, void *dst_host, int32_t dst_stride, int background,
+    const b200_comp_pad * pads, int n_pads);
+int b200_comp_blend_host_wait (b200_comp * h, int keep_in_flight);
+int b200_comp_blend_host (b200_comp * h, void *dst_host, int32_t dst_stride, int background,
+    const b200_comp_pad * pads, int n_pads);
+
 /* 4:2:0 output (I420, YV12, NV12, NV21 given to b200_comp_create): blend.c PLANAR_YUV_BLEND / NV_YUV_BLEND.
  * Every pad frame has the OUTPUT's format (the aggregator converts pads that differ);
  * plane strides / offsets of the destination and of every pad come from their b200_video_info. */
@@ -274,6 +286,17 @@ size_t b200_ars_get_max_latency (b200_ars * h);
  * Consumes all in_frames, writes b200_ars_get_out_frames() frames, asynchronous on cuda_stream. */
 int b200_ars_process (b200_ars * h, const void *in, size_t in_frames, void *out,
     size_t out_capacity_frames, size_t * out_frames, void *cuda_stream);
+/* System-memory peers (an audioresample between system-memory elements): in_host / out_host are HOST buffers (pinned by
+ * b200_host_alloc for the copies to be asynchronous).  _submit queues upload -> resample -> download on the handle's own
+ * three streams over a ring of 3 device slots, returns the frame count at once (it only depends on the stream position);
+ * _wait (h, k) returns when all but the k most recent submissions are complete in host memory (k = 1: push buffer n-1
+ * while buffer n is in flight); b200_ars_process_host = _submit + _wait (h, 0).  Do not mix with b200_ars_process on
+ * another stream without synchronising: the history lives on the handle. */
+int b200_ars_process_host_submit (b200_ars * h, const void *in_host, size_t in_frames, void *out_host,
+    size_t out_capacity_frames, size_t * out_frames);
+int b200_ars_process_host_wait (b200_ars * h, int keep_in_flight);
+int b200_ars_process_host (b200_ars * h, const void *in_host, size_t in_frames, void *out_host,
+    size_t out_capacity_frames, size_t * out_frames);
 typedef struct { int32_t n_taps, n_phases, in_step, out_step, filter_mode, oversample; } b200_ars_plan_info;
 int b200_ars_get_plan_info (const b200_ars * h, b200_ars_plan_info * info);
 int b200_ars_get_phase_taps (const b200_ars * h, int phase, float *taps, size_t len);

@@ -157,6 +157,7 @@ inline cudaError_t cudaStreamWaitEvent (cudaStream_t, cudaEvent_t, unsigned) { r
 inline cudaError_t cudaEventCreateWithFlags (cudaEvent_t *e, unsigned) { *e = nullptr; return cudaSuccess; }
 inline cudaError_t cudaEventDestroy (cudaEvent_t) { return cudaSuccess; }
 inline cudaError_t cudaEventRecord (cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaEventSynchronize (cudaEvent_t) { return cudaSuccess; }
 inline cudaError_t cudaHostAlloc (void **p, size_t n, unsigned) { *p = malloc (n); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 inline cudaError_t cudaFreeHost (void *p) { free (p); return cudaSuccess; }
 inline cudaError_t cudaHostRegister (void *, size_t, unsigned) { return cudaSuccess; }
