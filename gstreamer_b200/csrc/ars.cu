@@ -481,7 +481,32 @@ ars_full_kernel (const ArsLaunch L)
 struct ArsTile {
   int win;                       // staged frames per CTA (multiple of 4)
   int nch;                       // chunks per output group (upper bound, fixed stride of the tap table)
+  // chunk-major taps of every possible 4-output group, laid out on the host once per plan (F32 only):
+  // qtab[((a * out_step + phase) * nch + chunk) * RQ + r], a = (first window sample of the group) mod 4, phase = its filter
+  // phase.  A CTA copies the rows of its groups instead of gathering taps one by one with bounds tests.
+  const float4 *qtab;
 };
+
+// host side of the layout above; nch as computed at launch (ars_tile_geometry)
+static void ars_build_qtab (const ArsPlan & p, int nch, std::vector<float> * out)
+{
+  const int RQ = 4;
+  out->assign ((size_t) 4 * p.out_step * nch * RQ * 4, 0.f);
+  for (int a = 0; a < 4; a++)
+    for (int ph = 0; ph < p.out_step; ph++)
+      for (int r = 0; r < RQ; r++) {
+        const long long t = (long long) ph + (long long) r * p.samp_frac;
+        const int delta = (int) ((long long) r * p.samp_inc + t / p.out_step), phase = (int) (t % p.out_step);
+        const float *src = &p.phases[(size_t) phase * p.n_taps];
+        for (int chunk = 0; chunk < nch; chunk++) {
+          float *dst = &(*out)[((((size_t) a * p.out_step + ph) * nch + chunk) * RQ + r) * 4];
+          for (int k = 0; k < 4; k++) {
+            const int tap = 4 * chunk + k - (a + delta);
+            dst[k] = (tap >= 0 && tap < p.n_taps) ? src[tap] : 0.f;
+          }
+        }
+      }
+}
 
 template <int CB, int CPT>
 __global__ void __launch_bounds__ (ARS_THREADS)
@@ -510,29 +535,31 @@ ars_tile_kernel (const ArsLaunch L, const ArsTile Tl)
   }
   // stage the input window row by row (one warp per frame, coalesced)
   const int c_base = blockIdx.y * CB;
+  // CB == 128 with whole, 16-byte aligned channel blocks: a lane moves 4 channels of a frame (LDG.128 -> STS.128)
+  const bool vec = CB == 128 && (L.channels & 3) == 0 && c_base + CB <= L.channels &&
+      ((((uintptr_t) L.hist) | ((uintptr_t) L.in)) & 15) == 0;
   for (int fr = warp; fr < Tl.win; fr += ARS_THREADS / 32) {
     const long long f = f0 + fr;
     const float *src = nullptr;
     if (f < L.hist_frames) src = L.hist + f * L.channels;
     else if (f < L.avail && L.in) src = L.in + (f - L.hist_frames) * L.channels;
+    if (vec) {
+      *(float4 *) (xin + fr * CB + 4 * lane) = src ? __ldg ((const float4 *) (src + c_base) + lane) : make_float4 (0.f, 0.f, 0.f, 0.f);
+    } else {
 #pragma unroll
-    for (int c = lane; c < CB; c += 32)
-      xin[fr * CB + c] = (src && c_base + c < L.channels) ? __ldg (src + c_base + c) : 0.f;
+      for (int c = lane; c < CB; c += 32)
+        xin[fr * CB + c] = (src && c_base + c < L.channels) ? __ldg (src + c_base + c) : 0.f;
+    }
   }
   __syncthreads ();
-  // chunk-major tap table
-  for (int i = threadIdx.x; i < nq * Tl.nch * RQ; i += ARS_THREADS) {
-    const int r = i % RQ, chunk = (i / RQ) % Tl.nch, q = i / (RQ * Tl.nch);
-    const int j = q * RQ + r;
-    const int s_min = s_rel[q * RQ] & ~3;
-    const int k0 = s_min + 4 * chunk - s_rel[j];
-    const float *src = L.phases + (size_t) s_phase[j] * L.n_taps;
-    float4 t;
-    t.x = (k0 + 0 >= 0 && k0 + 0 < L.n_taps) ? __ldg (src + k0 + 0) : 0.f;
-    t.y = (k0 + 1 >= 0 && k0 + 1 < L.n_taps) ? __ldg (src + k0 + 1) : 0.f;
-    t.z = (k0 + 2 >= 0 && k0 + 2 < L.n_taps) ? __ldg (src + k0 + 2) : 0.f;
-    t.w = (k0 + 3 >= 0 && k0 + 3 < L.n_taps) ? __ldg (src + k0 + 3) : 0.f;
-    qt[i] = t;
+  // chunk-major tap table: the rows of this CTA's output groups, copied from the plan's pre-laid table
+  {
+    const int row = Tl.nch * RQ;                                  // float4 per group
+    const int e = threadIdx.x & 127, qq = threadIdx.x >> 7;       // two groups per pass, up to 128 float4 each
+    for (int q = qq; q < nq; q += ARS_THREADS / 128) {
+      const float4 *src = Tl.qtab + ((size_t) (s_rel[q * RQ] & 3) * L.out_step + s_phase[q * RQ]) * row;
+      for (int i = e; i < row; i += 128) qt[q * row + i] = __ldg (src + i);
+    }
   }
   __syncthreads ();
 
@@ -605,6 +632,146 @@ __device__ __forceinline__ long long sat_s32 (long long v) { return v < -2147483
 // S16 samples through the same tiling: the window is staged widened to 32 bits, taps likewise; the sums are
 // integers (wrapping 32 bit like the SSE2 pmaddwd path), so no lane structure has to be kept —
 // inner_product_gint16_full_1_sse2 (audio-resampler-x86-sse2.c:29-56): sum, + 2^14, >> 15, saturate.
+// ---- ars_pipe_kernel: the tile kernel as a persistent, double-buffered pipeline ------------------------------------------
+// Profile of ars_tile_kernel on the C5 shape (profiles/r02_ars_*): 57 % of the stall samples sit in the prologue (window and
+// tap rows travelling from L2 to shared memory) although it is 16 % of the instructions - two CTAs per SM cannot hide it.
+// Here one CTA per SM (16 warps) walks its tiles (64 outputs x 128 channels) with TWO staging buffers: while the warps
+// multiply tile k, cp.async fills the window and the tap rows of tile k+1 (zero fill for silence / missing frames through
+// the src-size operand).  With registers no longer shared between CTAs a thread owns 4 adjacent channels x 4 outputs:
+// one LDS.128 of samples and one broadcast LDS.128 of taps feed 32 FMUL + 32 FADD.  Arithmetic and its order are those of
+// ars_tile_kernel (four partial sums by tap index mod 4, (l0 + l2) + (l1 + l3), no FMA): bit-identical output.
+constexpr int ARS_PIPE_THREADS = 512, ARS_PIPE_NO = 64, ARS_PIPE_CB = 128;
+
+__device__ __forceinline__ void ars_cp16 (void *dst_smem, const void *src, bool real)
+{
+#ifndef B200_CUDA_EMU
+  const unsigned d = (unsigned) __cvta_generic_to_shared (dst_smem);
+  const int bytes = real ? 16 : 0;                                // src-size 0: the 16 bytes are written as zeros
+  asm volatile ("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r" (d), "l" (src), "r" (bytes) : "memory");
+#else
+  if (real) *(float4 *) dst_smem = *(const float4 *) src; else *(float4 *) dst_smem = make_float4 (0.f, 0.f, 0.f, 0.f);
+#endif
+}
+
+__global__ void __launch_bounds__ (ARS_PIPE_THREADS, 1)
+ars_pipe_kernel (const ArsLaunch L, const ArsTile Tl, int n_fb, int n_cb)
+{
+  extern __shared__ __align__ (16) float sm[];
+  constexpr int RQ = ARS_RQ, NO = ARS_PIPE_NO, CB = ARS_PIPE_CB, NQ = NO / RQ;
+  const int row = Tl.nch * RQ;                                    // float4 per output group in the tap table
+  const size_t qt_floats = (size_t) NQ * row * 4, xin_floats = (size_t) Tl.win * CB;
+  float *base[2] = {sm, sm + qt_floats + xin_floats};
+  __shared__ int s_rel[3][NO], s_phase[3][NO];                    // positions run two tiles ahead, off the critical path
+  __shared__ long long s_f0[3];
+  const int lane = threadIdx.x & 31;
+  const int warp = __shfl_sync (0xffffffffu, (int) (threadIdx.x >> 5), 0);
+  const int n_tiles = n_fb * n_cb;
+
+  auto positions = [&] (int t, int b) {                           // threads < NO: where tile t's outputs sit in the stream (b: slot of 3)
+    if (threadIdx.x < NO) {
+      const long long o0 = (long long) (t / n_cb) * NO;
+      const int n_out = (int) min ((long long) NO, L.out_frames - o0);
+      long long f0; int ph0;
+      ars_position (L, o0, f0, ph0);
+      f0 &= ~3LL;
+      long long idx; int phase;
+      ars_position (L, o0 + min ((int) threadIdx.x, n_out - 1), idx, phase);
+      s_rel[b][threadIdx.x] = (int) (idx - f0);
+      s_phase[b][threadIdx.x] = phase;
+      if (threadIdx.x == 0) s_f0[b] = f0;
+    }
+  };
+  auto prefetch = [&] (int t, int b, int ps) {                    // all threads: cp.async of tile t into buffer b; ps: its position slot
+    float4 *qt = (float4 *) base[b];
+    float *xin = base[b] + qt_floats;
+    const long long f0 = s_f0[ps];
+    const int c_base = (t % n_cb) * CB;
+    for (int fr = warp; fr < Tl.win; fr += ARS_PIPE_THREADS / 32) {
+      const long long f = f0 + fr;
+      const float *src = nullptr;
+      if (f < L.hist_frames) src = L.hist + f * L.channels;
+      else if (f < L.avail && L.in) src = L.in + (f - L.hist_frames) * L.channels;
+      ars_cp16 (xin + fr * CB + 4 * lane, src ? (const void *) (src + c_base + 4 * lane) : (const void *) Tl.qtab, src != nullptr);
+    }
+    const int e = threadIdx.x & 127, qq = threadIdx.x >> 7;
+    for (int q = qq; q < NQ; q += ARS_PIPE_THREADS / 128) {
+      const float4 *src = Tl.qtab + ((size_t) (s_rel[ps][q * RQ] & 3) * L.out_step + s_phase[ps][q * RQ]) * row;
+      for (int i = e; i < row; i += 128) ars_cp16 (qt + q * row + i, src + i, true);
+    }
+#ifndef B200_CUDA_EMU
+    asm volatile ("cp.async.commit_group;" ::: "memory");
+#endif
+  };
+
+  int t = blockIdx.x, b = 0, ps = 0;                              // ps: position slot of tile t (k mod 3)
+  if (t < n_tiles) positions (t, 0);
+  if (t + (int) gridDim.x < n_tiles) positions (t + gridDim.x, 1);
+  __syncthreads ();
+  if (t < n_tiles) prefetch (t, 0, 0);
+  for (; t < n_tiles; t += gridDim.x, b ^= 1, ps = (ps + 1) % 3) {
+    const int tn = t + gridDim.x, tnn = tn + gridDim.x;
+#ifndef B200_CUDA_EMU
+    asm volatile ("cp.async.wait_group 0;" ::: "memory");
+#endif
+    __syncthreads ();                                             // tile t staged; positions of tile t+1 visible (written an iteration ago)
+    if (tn < n_tiles) prefetch (tn, b ^ 1, (ps + 1) % 3);
+    if (tnn < n_tiles) positions (tnn, (ps + 2) % 3);             // overlaps this tile's arithmetic
+
+    const float4 *qt = (const float4 *) base[b];
+    const float *xin = base[b] + qt_floats;
+    const long long o0 = (long long) (t / n_cb) * NO;
+    const int n_out = (int) min ((long long) NO, L.out_frames - o0);
+    const int nq = (n_out + RQ - 1) / RQ;
+    const int c = (t % n_cb) * CB + 4 * lane;
+    for (int q = warp; q < nq; q += ARS_PIPE_THREADS / 32) {
+      float acc[4][RQ][4];
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+#pragma unroll
+        for (int r = 0; r < RQ; r++)
+#pragma unroll
+          for (int k = 0; k < 4; k++) acc[u][r][k] = 0.f;
+      const int s_min = s_rel[ps][q * RQ] & ~3;
+      const int s_max = (s_rel[ps][min (q * RQ + RQ - 1, n_out - 1)] + L.n_taps + 3) & ~3;
+      const int nch = (s_max - s_min) >> 2;
+      const float *xp = xin + s_min * CB + 4 * lane;
+      const float4 *tp = qt + (size_t) q * row;
+#pragma unroll 2
+      for (int ch = 0; ch < nch; ch++, xp += 4 * CB, tp += RQ) {
+        float x[4][4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const float4 v = *(const float4 *) (xp + k * CB);
+          x[0][k] = v.x; x[1][k] = v.y; x[2][k] = v.z; x[3][k] = v.w;
+        }
+#pragma unroll
+        for (int r = 0; r < RQ; r++) {
+          const float4 tq = tp[r];
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            acc[u][r][0] = __fadd_rn (acc[u][r][0], __fmul_rn (x[u][0], tq.x));
+            acc[u][r][1] = __fadd_rn (acc[u][r][1], __fmul_rn (x[u][1], tq.y));
+            acc[u][r][2] = __fadd_rn (acc[u][r][2], __fmul_rn (x[u][2], tq.z));
+            acc[u][r][3] = __fadd_rn (acc[u][r][3], __fmul_rn (x[u][3], tq.w));
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < RQ; r++) {
+        if (q * RQ + r < n_out) {
+          float4 o;
+          o.x = __fadd_rn (__fadd_rn (acc[0][r][0], acc[0][r][2]), __fadd_rn (acc[0][r][1], acc[0][r][3]));
+          o.y = __fadd_rn (__fadd_rn (acc[1][r][0], acc[1][r][2]), __fadd_rn (acc[1][r][1], acc[1][r][3]));
+          o.z = __fadd_rn (__fadd_rn (acc[2][r][0], acc[2][r][2]), __fadd_rn (acc[2][r][1], acc[2][r][3]));
+          o.w = __fadd_rn (__fadd_rn (acc[3][r][0], acc[3][r][2]), __fadd_rn (acc[3][r][1], acc[3][r][3]));
+          *(float4 *) (L.out + (size_t) (o0 + q * RQ + r) * L.channels + c) = o;
+        }
+      }
+    }
+    __syncthreads ();                                             // buffer b and its positions are free for tile t + 2
+  }
+}
+
 template <int CB>
 __global__ void __launch_bounds__ (ARS_THREADS)
 ars_tile_kernel_s16 (const ArsLaunch L, const ArsTile Tl)
@@ -1028,6 +1195,8 @@ struct b200_ars {
   ArsPlan plan;
   int device = -1;
   float *d_phases = nullptr;
+  float *d_qtab = nullptr;       // chunk-major taps of every 4-output group (F32, FULL mode): see ArsTile::qtab
+  int qtab_nch = 0;
   float *d_proto = nullptr;      // interpolated mode: the oversampled prototype rows
   void *d_table_x = nullptr;     // other sample formats: phase taps (FULL) or prototype rows, in the samples' type
   float *d_hist[2] = {nullptr, nullptr};
@@ -1103,6 +1272,16 @@ int b200_ars_create (const b200_ars_config * cfg, int device, b200_ars ** handle
     } else
       st = h->plan.full ? upload (&h->d_phases, h->plan.phases.data (), h->plan.phases.size ())
                         : upload (&h->d_proto, h->plan.proto.data (), h->plan.proto.size ());
+    if (st == B200_OK && h->plan.fmt == ARS_F32 && h->plan.full && !h->plan.small && !h->plan.copy) {
+      // tap rows of every (alignment, phase) group for the tile kernel; bounded by the FULL-mode threshold
+      // (bps * n_taps * out_rate < 1 MiB  =>  at most 16 x that in this layout)
+      const ArsPlan & q = h->plan;
+      const long long spread = ((long long) (ARS_RQ - 1) * q.in_step + q.out_step - 1) / q.out_step + 1;
+      h->qtab_nch = (int) ((spread + q.n_taps + 3 + 3) / 4 + 1);
+      std::vector<float> tab;
+      ars_build_qtab (q, h->qtab_nch, &tab);
+      st = upload (&h->d_qtab, tab.data (), tab.size ());
+    }
     if (st == B200_OK) st = ars_ensure_hist (h, 0, (size_t) h->plan.n_taps, nullptr);
     if (st == B200_OK) st = ars_ensure_hist (h, 1, (size_t) h->plan.n_taps, nullptr);
     if (st == B200_OK && cudaDeviceSynchronize () != cudaSuccess) st = B200_ERR_CUDA;   // clears done before any user stream
@@ -1111,6 +1290,7 @@ int b200_ars_create (const b200_ars_config * cfg, int device, b200_ars ** handle
       return st;
     }
     cudaFuncSetAttribute (ars_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    if ((st = allow_max_dyn_smem (ars_pipe_kernel)) != B200_OK) { b200_ars_destroy (h); return st; }
     cudaFuncSetAttribute (ars_tile_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ARS_TILE_SMEM);
     cudaFuncSetAttribute (ars_tile_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ARS_TILE_SMEM);
     cudaFuncSetAttribute (ars_tile_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ARS_TILE_SMEM);
@@ -1129,7 +1309,7 @@ void b200_ars_destroy (b200_ars * h)
   if (!h) return;
   if (h->device >= 0) {
     DeviceGuard g (h->device);
-    cudaFree (h->d_phases); cudaFree (h->d_proto); cudaFree (h->d_table_x); cudaFree (h->d_hist[0]); cudaFree (h->d_hist[1]);
+    cudaFree (h->d_phases); cudaFree (h->d_qtab); cudaFree (h->d_proto); cudaFree (h->d_table_x); cudaFree (h->d_hist[0]); cudaFree (h->d_hist[1]);
     if (h->s_h2d) {
       cudaStreamSynchronize (h->s_d2h);
       for (int i = 0; i < b200_ars::kSlots; i++) {
@@ -1231,7 +1411,7 @@ int b200_ars_process (b200_ars * h, const void *in_v, size_t in_frames, void *ou
     } else if (p.fmt == ARS_S16 && p.full && p.channels >= 64 && !getenv ("B200_ARS_GENERIC")) {
       // tiled S16 kernel: same tile geometry as the F32 one (4-byte staged samples and taps)
       const int cb = p.channels >= 128 ? 128 : 64, no = 32;
-      ArsTile tl;
+      ArsTile tl = ArsTile ();
       const long long span = ((long long) no * p.in_step + p.out_step - 1) / p.out_step + 8 + p.n_taps;
       tl.win = (int) ((span + 3) & ~3LL);
       const long long spread = ((long long) (ARS_RQ - 1) * p.in_step + p.out_step - 1) / p.out_step + 1;
@@ -1273,14 +1453,15 @@ int b200_ars_process (b200_ars * h, const void *in_v, size_t in_frames, void *ou
       else ars_interp_kernel<false> <<<grid, ARS_THREADS, 0, stream>>> (L, h->d_proto, p.oversample);
     } else {
     const char *env_no = getenv ("B200_ARS_NO"), *env_cpt = getenv ("B200_ARS_CPT");
-    int no = env_no ? atoi (env_no) : 32;
+    int no = env_no ? atoi (env_no) : 32;                        // measured best for the non-persistent tile kernel (3 CTAs / SM)
     if (no < ARS_RQ || no > 64 || (no & (no - 1))) no = 32;      // s_rel/s_phase hold 64 outputs
     while (no > ARS_RQ && (size_t) no * L.row_pitch * sizeof (float) > 96 * 1024) no >>= 1;
     if ((size_t) no * L.row_pitch * sizeof (float) > 160 * 1024) return B200_ERR_UNSUPPORTED;
     L.no = no;
     // fast path when the CTA's input window fits in shared memory next to the chunk-major taps
-    ArsTile tl;
-    const int cb = 32 * (L.wcn > 4 ? 4 : L.wcn);
+    ArsTile tl = ArsTile ();
+    int cb = 32 * (L.wcn > 4 ? 4 : L.wcn);
+    { const char *e = getenv ("B200_ARS_CB"); if (e && (atoi (e) == 64 || atoi (e) == 32) && atoi (e) < cb) cb = atoi (e); }   // tuning knob
     // channels per thread: 2 measured best on B200 (C5: 2.01 ms vs 2.44 ms for 1 and 2.57 ms for 4)
     int cpt = cb >= 64 ? 2 : 1;
     if (env_cpt && (atoi (env_cpt) == 1 || (atoi (env_cpt) == 4 && cb >= 128))) cpt = atoi (env_cpt);
@@ -1290,9 +1471,29 @@ int b200_ars_process (b200_ars * h, const void *in_v, size_t in_frames, void *ou
       tl.win = (int) ((span + 3) & ~3LL);
       const long long spread = ((long long) (ARS_RQ - 1) * p.in_step + p.out_step - 1) / p.out_step + 1;
       tl.nch = (int) ((spread + p.n_taps + 3 + 3) / 4 + 1);
+      tl.qtab = (const float4 *) h->d_qtab;
     }
     const size_t smem_tile = ((size_t) (no / ARS_RQ) * tl.nch * ARS_RQ * 4 + (size_t) tl.win * cb) * sizeof (float);
-    if (smem_tile <= (size_t) ARS_TILE_SMEM && !getenv ("B200_ARS_GENERIC")) {
+    // the persistent pipeline: whole 128-channel blocks, 16-byte aligned streams, both buffers in shared memory
+    bool piped = false;
+    if (h->d_qtab && tl.nch == h->qtab_nch && (p.channels % ARS_PIPE_CB) == 0 && !getenv ("B200_ARS_GENERIC") && !getenv ("B200_ARS_NOPIPE") &&
+        ((((uintptr_t) L.hist) | ((uintptr_t) L.in) | ((uintptr_t) L.out)) & 15) == 0) {
+      ArsTile tp = tl;
+      const long long span = ((long long) ARS_PIPE_NO * p.in_step + p.out_step - 1) / p.out_step + 8 + p.n_taps;
+      tp.win = (int) ((span + 3) & ~3LL);
+      const size_t smem_pipe = 2 * ((size_t) (ARS_PIPE_NO / ARS_RQ) * tp.nch * ARS_RQ * 4 + (size_t) tp.win * ARS_PIPE_CB) * sizeof (float);
+      int optin = 0;
+      cudaDeviceGetAttribute (&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
+      if (smem_pipe + 2048 <= (size_t) optin) {
+        L.no = ARS_PIPE_NO;
+        const int n_fb = (int) ((out_frames + ARS_PIPE_NO - 1) / ARS_PIPE_NO), n_cb = p.channels / ARS_PIPE_CB;
+        const int grid = (int) std::min ((long long) n_fb * n_cb, (long long) sm_count (h->device));
+        ars_pipe_kernel <<<grid, ARS_PIPE_THREADS, smem_pipe, stream>>> (L, tp, n_fb, n_cb);
+        piped = true;
+      }
+    }
+    if (piped) {
+    } else if (smem_tile <= (size_t) ARS_TILE_SMEM && h->d_qtab && tl.nch == h->qtab_nch && !getenv ("B200_ARS_GENERIC")) {
       const dim3 grid ((unsigned) ((out_frames + no - 1) / no), (unsigned) ((p.channels + cb - 1) / cb));
       if (cb == 128 && cpt == 4) ars_tile_kernel<128, 4> <<<grid, ARS_THREADS, smem_tile, stream>>> (L, tl);
       else if (cb == 128 && cpt == 2) ars_tile_kernel<128, 2> <<<grid, ARS_THREADS, smem_tile, stream>>> (L, tl);

@@ -41,7 +41,9 @@ int allow_max_dyn_smem (F fn)
   int dev = 0, optin = 0;
   B200_CUDA_TRY (cudaGetDevice (&dev));
   B200_CUDA_TRY (cudaDeviceGetAttribute (&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  B200_CUDA_TRY (cudaFuncSetAttribute (fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  cudaFuncAttributes fa;
+  B200_CUDA_TRY (cudaFuncGetAttributes (&fa, fn));               // static shared memory counts against the same limit
+  B200_CUDA_TRY (cudaFuncSetAttribute (fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int) fa.sharedSizeBytes));
   return B200_OK;
 }
 

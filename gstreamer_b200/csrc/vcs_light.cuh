@@ -31,8 +31,9 @@ namespace b200 {
 
 struct LightDev {
   int tw, th, max_rows, cp;      // tile size, shared-memory rows, words per staged input row
-  int t_words;                   // words of the intermediate tile (max_rows x tw, or th x cp when vertical runs first)
+  int t_words;                   // words of the intermediate tile (th x cp when vertical runs first, else none)
   int h_first;
+  int std_pairs;                 // every input line consumed in order with the standard 4:2:0 pairing: fast stage A
 };
 
 constexpr int LIGHT_THREADS = 256;
@@ -273,8 +274,94 @@ __device__ __forceinline__ void vcs_unpack_stage (const VcsDev & P, const uint8_
   if (P.planar) run (std::true_type {}); else run (std::false_type {});
 }
 
+// ---- stage A, fast form ----------------------------------------------------------------------------------------------
+// Interleaved chroma (NV12 / NV21), co-sited horizontally, every line of the tile consumed in order (standard pairing:
+// line 0 alone, then (1,2), (3,4) ... each pair on two chroma rows with swapped 3:1 weights).  No work list, no per-item
+// entry: an item is (line pair q, 8 pixels) - four chroma samples of two rows, one LDG.64 each plus the next sample for the
+// last odd pixel, two LDG.64 of luma - and leaves as four STS.128 of {Y,U,V,-} pixels.  Frame edges need no other path:
+// chroma rows are clamped (line 0 and the last line then see the same row twice and 3c + c reproduces the unfiltered
+// sample), the last odd pixel replicates (video_chroma_up_h2_cs_u8, video-chroma.c:687-699), columns left of the tile's
+// first staged word or right of the frame are simply not stored.
+template <bool MFIRST>
+__device__ __forceinline__ void vcs_unpack_fast_cs (const VcsDev & P, const uint8_t *__restrict__ in, int cxa, int cx1,
+    int ry0, int R, unsigned *S, int pitch)
+{
+  const uint8_t *__restrict__ plane_y = in + P.off_y, *__restrict__ plane_c = in + P.off_c;
+  const unsigned selU = P.u_index ? 0x7531u : 0x6420u, selV = P.u_index ? 0x6420u : 0x7531u;
+  const unsigned nselU = P.u_index ? 0x5321u : 0x4321u, nselV = P.u_index ? 0x4321u : 0x5321u;
+  const int xs = cxa & ~7;                                        // 8-byte aligned loads
+  const int n8 = (min (cx1, P.iw) - xs + 7) >> 3;                 // 8-pixel items per line pair
+  const int q0 = (ry0 + 1) >> 1, nq = ((ry0 + R) >> 1) - q0 + 1;  // pairs (2q-1, 2q) touching rows ry0 .. ry0+R-1
+  const int crows = (P.ih + 1) >> 1, total = nq * n8;
+  const unsigned magic = 0xffffffffu / (unsigned) n8 + 1u;
+  for (int item = threadIdx.x; item < total; item += blockDim.x) {
+    const int qi = n8 > 1 ? (int) __umulhi ((unsigned) item, magic) : item;
+    const int j = item - qi * n8, q = q0 + qi;
+    const int x = xs + 8 * j;
+    const bool right_edge = x + 8 >= P.iw;                        // no chroma sample to the right of this item
+    // at the frame's right edge an odd pixel is averaged with its right neighbour only if that pixel is not the last one
+    // (x_odd < iw - 1): byte i of the neighbour word is sample i + 1 for i <= lim, else sample i itself
+    const int lim = (P.iw - 3 - x) >> 1;
+    const unsigned esel = 0x3210u + (lim >= 0 ? 0x1u : 0u) + (lim >= 1 ? 0x10u : 0u) + (lim >= 2 ? 0x100u : 0u);
+    const int ra = min (max (q - 1, 0), crows - 1), rb = min (q, crows - 1);
+    const uint8_t *pa = plane_c + (size_t) ra * P.stride_c + x, *pb = plane_c + (size_t) rb * P.stride_c + x;
+    const uint2 ca = __ldg ((const uint2 *) pa), cb = __ldg ((const uint2 *) pb);
+    const unsigned na = right_edge ? 0u : (unsigned) __ldg ((const unsigned short *) (pa + 8));
+    const unsigned nb = right_edge ? 0u : (unsigned) __ldg ((const unsigned short *) (pb + 8));
+    const int ya = 2 * q - 1, yb = 2 * q;                         // the pair's lines; ya == -1 for q == 0
+    const bool sa = ya >= ry0 && ya < ry0 + R, sb = yb >= ry0 && yb < ry0 + R && yb < P.ih;
+    uint2 y0 = make_uint2 (0u, 0u), y1 = make_uint2 (0u, 0u);
+    if (sa) y0 = __ldg ((const uint2 *) (plane_y + (size_t) ya * P.stride_y + x));
+    if (sb) y1 = __ldg ((const uint2 *) (plane_y + (size_t) yb * P.stride_y + x));
+    // co-sited h up-sampling of both rows: even pixel = c[k], odd pixel = (c[k] + c[k+1] + 1) >> 1
+    unsigned alo[2], ahi[2], blo[2], bhi[2];                      // [U, V] x 8 full-resolution samples (lo = pixels 0..3)
+    {
+      const unsigned ue = __byte_perm (ca.x, ca.y, selU), ve = __byte_perm (ca.x, ca.y, selV);
+      const unsigned un = right_edge ? __byte_perm (ue, ue, esel) : __byte_perm (ue, na, nselU);
+      const unsigned vn = right_edge ? __byte_perm (ve, ve, esel) : __byte_perm (ve, na, nselV);
+      const unsigned uo = avg_ceil4 (ue, un), vo = avg_ceil4 (ve, vn);
+      alo[0] = __byte_perm (ue, uo, 0x5140); ahi[0] = __byte_perm (ue, uo, 0x7362);
+      alo[1] = __byte_perm (ve, vo, 0x5140); ahi[1] = __byte_perm (ve, vo, 0x7362);
+    }
+    {
+      const unsigned ue = __byte_perm (cb.x, cb.y, selU), ve = __byte_perm (cb.x, cb.y, selV);
+      const unsigned un = right_edge ? __byte_perm (ue, ue, esel) : __byte_perm (ue, nb, nselU);
+      const unsigned vn = right_edge ? __byte_perm (ve, ve, esel) : __byte_perm (ve, nb, nselV);
+      const unsigned uo = avg_ceil4 (ue, un), vo = avg_ceil4 (ve, vn);
+      blo[0] = __byte_perm (ue, uo, 0x5140); bhi[0] = __byte_perm (ue, uo, 0x7362);
+      blo[1] = __byte_perm (ve, vo, 0x5140); bhi[1] = __byte_perm (ve, vo, 0x7362);
+    }
+    // the pair: line 2q-1 = (3a + b + 2) >> 2, line 2q = (a + 3b + 2) >> 2   (video_chroma_up_v2_u8)
+    unsigned u0[2], v0[2], u1[2], v1[2];                          // [pixels 0..3, pixels 4..7]
+    {
+      unsigned f;
+      f = avg_floor4 (alo[0], blo[0]); u0[0] = avg_ceil4 (alo[0], f); u1[0] = avg_ceil4 (blo[0], f);
+      f = avg_floor4 (ahi[0], bhi[0]); u0[1] = avg_ceil4 (ahi[0], f); u1[1] = avg_ceil4 (bhi[0], f);
+      f = avg_floor4 (alo[1], blo[1]); v0[0] = avg_ceil4 (alo[1], f); v1[0] = avg_ceil4 (blo[1], f);
+      f = avg_floor4 (ahi[1], bhi[1]); v0[1] = avg_ceil4 (ahi[1], f); v1[1] = avg_ceil4 (bhi[1], f);
+    }
+    auto store4 = [&] (int row, int col, unsigned yw, unsigned u, unsigned v) {
+      if (col < 0 || col + cxa >= cx1) return;                    // left of the tile's first staged word / right of its last column
+      const unsigned yu01 = __byte_perm (yw, u, 0x5140), yu23 = __byte_perm (yw, u, 0x7362);
+      uint4 px;
+      px.x = __byte_perm (yu01, v, 0x4410);
+      px.y = __byte_perm (yu01, v, 0x5532);
+      px.z = __byte_perm (yu23, v, 0x6610);
+      px.w = __byte_perm (yu23, v, 0x7732);
+      if (MFIRST) {
+        px.x = light_matrix (px.x, P); px.y = light_matrix (px.y, P);
+        px.z = light_matrix (px.z, P); px.w = light_matrix (px.w, P);
+      }
+      *(uint4 *) (S + row * pitch + col) = px;
+    };
+    const int col = x - cxa;
+    if (sa) { store4 (ya - ry0, col, y0.x, u0[0], v0[0]); store4 (ya - ry0, col + 4, y0.y, u0[1], v0[1]); }
+    if (sb) { store4 (yb - ry0, col, y1.x, u1[0], v1[0]); store4 (yb - ry0, col + 4, y1.y, u1[1], v1[1]); }
+  }
+}
+
 template <int HM, int VM, bool MFIRST, bool COSITED>
-__global__ void __launch_bounds__ (LIGHT_THREADS, 3)
+__global__ void __launch_bounds__ (LIGHT_THREADS, 4)
 vcs_light_kernel (const VcsDev P, const LightDev G, const VcsBatch frames)
 {
   extern __shared__ __align__ (16) unsigned lsm[];
@@ -298,39 +385,49 @@ vcs_light_kernel (const VcsDev P, const LightDev G, const VcsBatch frames)
     const int oy = oy0 + tid - 32;
     vtab[tid - 32] = (P.v.offset[oy] - (unsigned) ry0) | (VM == 2 ? (unsigned) (int) P.v.coef[oy] << 16 : 0u);
   }
-  vcs_unpack_worklist (P, ry0, R, ent, G.max_rows);
-  __syncthreads ();
-  vcs_unpack_stage<MFIRST, COSITED, 0> (P, plane_y, in, cxa, ng, ent, (int) ent[G.max_rows].x, S, G.cp, 0);
+  if (COSITED && G.std_pairs) {                                   // warp-uniform: a property of the plan
+    vcs_unpack_fast_cs<MFIRST> (P, in, cxa, cx1, ry0, R, S, G.cp);
+  } else {
+    vcs_unpack_worklist (P, ry0, R, ent, G.max_rows);
+    __syncthreads ();
+    vcs_unpack_stage<MFIRST, COSITED, 0> (P, plane_y, in, cxa, ng, ent, (int) ent[G.max_rows].x, S, G.cp, 0);
+  }
   __syncthreads ();
 
   const int tx = tid & 127, rph = tid >> 7;                      // tw <= 128, two row phases
   if (G.h_first) {
-    // -------------------------------------------------------------- B: horizontal pass
-    // a thread keeps one output column: its source column and fraction live in registers
+    // -------------------------------------------------------------- B + C fused: a thread owns one output column and walks
+    // half of the tile's output rows top to bottom.  The h-lerped value of its column is kept in registers for the two
+    // source rows of the current output row; the next output row re-uses them when its source rows repeat (always for an
+    // up-scale, every other row at 1.5:1) - no intermediate tile, no second barrier.  Rounding is unchanged: the h pass
+    // rounds to 8 bits before the v pass sees it (video-scaler.c:609-618, :846-879).
     if (tx < tw) {
       const int base = (int) P.h.offset[ox0 + tx] - cxa;
       unsigned f = 0;
       if (HM == 2) f = (unsigned) (int) P.h.coef[ox0 + tx];
-      for (int r = rph; r < R; r += LIGHT_THREADS / 128) {
-        const unsigned a = S[r * G.cp + base];
-        unsigned d = a;
-        if (HM == 2) d = light_lerp (a, S[r * G.cp + base + 1], 256u - f, f, 0u);
-        T[r * G.tw + tx] = d;
-      }
-    }
-    __syncthreads ();
-
-    // -------------------------------------------------------------- C: vertical pass, matrix, pack
-    if (tx < tw) {
-      uint8_t *dst = out + P.off_out + (size_t) (oy0 + rph) * P.stride_out + (size_t) (ox0 + tx) * 4u;
-      const size_t dstep = (size_t) P.stride_out * (LIGHT_THREADS / 128);
-      for (int ty = rph; ty < th; ty += LIGHT_THREADS / 128, dst += dstep) {
+      const unsigned *col = S + base;
+      auto hrow = [&] (int r) {
+        const unsigned a = col[r * G.cp];
+        return HM == 2 ? light_lerp (a, col[r * G.cp + 1], 256u - f, f, 0u) : a;
+      };
+      const int half = (th + 1) >> 1, t0 = rph * half, t1 = min (th, t0 + half);
+      uint8_t *dst = out + P.off_out + (size_t) (oy0 + t0) * P.stride_out + (size_t) (ox0 + tx) * 4u;
+      int ca = -2;                                                // source row of va (vb = row ca + 1)
+      unsigned va = 0, vb = 0;
+      for (int ty = t0; ty < t1; ty++, dst += P.stride_out) {
         const unsigned vo = vtab[ty];                             // row offset inside the tile | weight << 16
-        const unsigned *t = T + (vo & 0xffffu) * G.tw + tx;
-        unsigned d = t[0];
+        const int a = (int) (vo & 0xffffu);
+        unsigned d;
         if (VM == 2) {
+          if (a != ca) {                                          // warp-uniform: every lane has the same output row
+            if (a == ca + 1) va = vb; else va = hrow (a);
+            vb = hrow (a + 1);
+            ca = a;
+          }
           const unsigned p = vo >> 16;
-          d = light_lerp (d, t[G.tw], 256u - p, p, 0x00800080u);
+          d = light_lerp (va, vb, 256u - p, p, 0x00800080u);
+        } else {
+          d = hrow (a);
         }
         if (!MFIRST) d = light_matrix (d, P);
         else d |= 0x000000ffu;                                    // alpha passes every 2-tap/copy stage as 255
@@ -390,7 +487,9 @@ inline int launch_light (const VcsDev & dev, const VcsPlan & p, const VcsBatch &
   LightDev g;
   g.tw = p.light_tw; g.th = p.light_th; g.max_rows = p.light_rows; g.cp = p.light_cp;
   g.h_first = p.h_first ? 1 : 0;
-  g.t_words = p.h_first ? p.light_rows * p.light_tw : p.light_th * p.light_cp;
+  g.std_pairs = p.light_std_pairs ? 1 : 0;
+  for (int i = 0; i < n; i++) if (((uintptr_t) batch.in[i]) & 7) g.std_pairs = 0;     // the fast stage A loads 64 bits at a time
+  g.t_words = p.h_first ? 0 : p.light_th * p.light_cp;
   dim3 grid ((p.out.width + g.tw - 1) / g.tw, (p.out.height + g.th - 1) / g.th, n);
   fn <<<grid, LIGHT_THREADS, p.light_smem, stream>>> (dev, g, batch);
   B200_CUDA_TRY (cudaGetLastError ());

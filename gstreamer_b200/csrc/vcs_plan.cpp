@@ -401,11 +401,21 @@ void light_geometry (VcsPlan * p)
       max_cols = std::max (max_cols, c1 - c0);
     }
     const int cp = max_cols + 4;                                  // +4 words: rows start on distinct banks
-    const size_t t_words = p->h_first ? (size_t) max_rows * tw : (size_t) th * cp;
+    const size_t t_words = p->h_first ? 0 : (size_t) th * cp;     // horizontal first: the two passes are fused, no intermediate tile
     const size_t total = ((size_t) max_rows * cp + t_words + 4 * (size_t) max_rows + 4 + th) * 4;   // S, T, work list, v table
     if (total <= (env_th ? 200 : 96) * 1024) {
       p->light_ok = true; p->light_tw = tw; p->light_th = th; p->light_rows = max_rows; p->light_cp = cp;
       p->light_smem = (int) total;
+      // fast stage A: NV12 / NV21, real chroma filtering, every line's chroma_mode the standard one (all lines pulled in
+      // order), 64-bit loads possible (8-byte aligned rows; a last item may read up to 7 bytes past the width: inside the
+      // row's stride, or - last row - inside the frame because a chroma plane follows the luma plane and the chroma rows
+      // themselves are as wide as the luma rows)
+      bool std_pairs = !p->planar && !p->chroma_nearest && p->v_pairs && !p->in_422_444 && !p->rgb_in &&
+          !(p->in.stride[0] & 7) && !(p->in.stride[1] & 7) && !(p->in.offset[0] & 7) && !(p->in.offset[1] & 7) &&
+          p->in.stride[0] >= ((p->in.width + 7) & ~7) && p->in.stride[1] >= ((p->in.width + 7) & ~7) && !(p->in.height & 1);
+      for (int y = 0; std_pairs && y < p->in.height; y++)
+        if (p->chroma_mode[y] != (y == 0 ? 0 : ((y & 1) ? 1 : 2))) std_pairs = false;
+      p->light_std_pairs = std_pairs;
       return;
     }
   }

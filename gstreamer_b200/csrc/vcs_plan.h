@@ -106,6 +106,7 @@ struct VcsPlan {
   // "light" kernel (both axes copy or 2-tap, horizontal first): tile geometry
   bool light_ok = false;
   int light_tw = 128, light_th = 16, light_rows = 0, light_cp = 0, light_smem = 0;
+  bool light_std_pairs = false;          // standard in-order 4:2:0 pairing, interleaved chroma, 8-byte aligned planes: fast stage A
 };
 
 // builds everything that does not need a device; returns b200_status

@@ -102,6 +102,7 @@ inline double __dmul_rn (double a, double b) { volatile double r = a * b; return
 inline double __ddiv_rn (double a, double b) { volatile double r = a / b; return r; }
 inline uint4 make_uint4 (unsigned x, unsigned y, unsigned z, unsigned w) { return uint4 {x, y, z, w}; }
 inline uint2 make_uint2 (unsigned x, unsigned y) { return uint2 {x, y}; }
+inline float4 make_float4 (float x, float y, float z, float w) { return float4 {x, y, z, w}; }
 inline int4 make_int4 (int x, int y, int z, int w) { return int4 {x, y, z, w}; }
 
 using std::max;
@@ -164,3 +165,5 @@ inline cudaError_t cudaHostRegister (void *, size_t, unsigned) { return cudaSucc
 inline cudaError_t cudaHostUnregister (void *) { return cudaSuccess; }
 inline cudaError_t cudaDeviceGetPCIBusId (char *b, int n, int) { if (n > 0) b[0] = 0; return cudaErrorNoDevice; }
 template <typename F> inline cudaError_t cudaFuncSetAttribute (F, int, int) { return cudaSuccess; }
+struct cudaFuncAttributes { size_t sharedSizeBytes = 0; };
+template <typename F> inline cudaError_t cudaFuncGetAttributes (cudaFuncAttributes *a, F) { a->sharedSizeBytes = 0; return cudaSuccess; }

@@ -198,6 +198,9 @@ def test_odd_height_without_vertical_scaler(emu):
     ("NV12", "BGRA", (128, 96, 64, 48), 3, 1), ("NV21", "RGBA", (144, 80, 72, 40), 9, 1),          # lanczos2 (exact 2:1, 8 taps)
     ("NV12", "BGRA", (96, 54, 64, 36), 1, 2), ("I420", "xRGB", (64, 48, 96, 72), 0, 2), ("NV12", "ARGB", (100, 60, 150, 30), 1, 2),
     ("YV12", "BGRA", (64, 48, 64, 48), 1, 2),                                                       # light (copy / 2-tap axes)
+    ("NV12", "BGRA", (200, 120, 133, 80), 1, 2), ("NV21", "RGBA", (648, 360, 427, 240), 1, 2),      # light, fast stage A: several tiles,
+    ("NV12", "xBGR", (136, 72, 200, 100), 1, 2), ("NV12", "BGRA", (264, 10, 100, 33), 0, 2),        # edges, up-scale, nearest
+    ("NV21", "RGBA", (166, 256, 490, 272), 1, 2), ("NV12", "BGRA", (162, 20, 81, 10), 1, 2),        # width % 8 != 0: last odd pixel
     ("NV12", "BGRA", (96, 54, 64, 36), 3, 3), ("I420", "RGBA", (64, 48, 96, 72), 9, 3), ("NV21", "ABGR", (120, 66, 40, 22), 5, 3),
     ("NV12", "BGRA", (100, 60, 150, 30), 3, 3),                                                     # n-tap, both pass orders
 ], ids=lambda c: "%s-%s-%dx%d-%dx%d-m%d-v%d" % (c[0], c[1], *c[2], c[3], c[4]))
@@ -421,6 +424,8 @@ def test_audio_kernels(emu, fmt, opts, monkeypatch):
         rates += [(3, 2, 3, 5), (48000, 8000, 2, 1), (96000, 44100, 1, 6)]
     if opts == AUDIO_OPTS[0]:
         rates += [(44100, 44100, 3, 4)]                       # equal rates: gst_audio_resampler's nearest functions
+        if fmt == "F32":
+            rates += [(48000, 44100, 128, 4), (44100, 48000, 256, 2)]   # whole 128-channel blocks: the persistent pipelined kernel
     for (a, b, ch, q) in rates:
         ho = o.oracle_ars_new_opts(a, b, ch, q, ofmt, M[method], MO[mode], I[interp])
         cfg = _lib.ArsConfigC()
