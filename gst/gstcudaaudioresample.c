@@ -62,8 +62,23 @@ ars_set_caps (GstBaseTransform * trans, GstCaps * incaps, GstCaps * outcaps)
 {
   GstCudaAudioResample *self = (GstCudaAudioResample *) trans;
   b200_ars_config cfg = { 0, };
-  if (!gst_audio_info_from_caps (&self->in, incaps) || !gst_audio_info_from_caps (&self->out, outcaps))
+  GstAudioInfo in, out;
+  if (!gst_audio_info_from_caps (&in, incaps) || !gst_audio_info_from_caps (&out, outcaps))
     return FALSE;
+  /* gst_audio_resample_update_state (gstaudioresample.c:398-437): same sample format and channel count on a live
+   * resampler is a RATE CHANGE - the converter is updated, history and phase survive (b200_ars_update); anything else
+   * builds a new resampler */
+  if (self->ars && GST_AUDIO_INFO_FORMAT (&in) == GST_AUDIO_INFO_FORMAT (&self->in) &&
+      GST_AUDIO_INFO_CHANNELS (&in) == GST_AUDIO_INFO_CHANNELS (&self->in) &&
+      GST_AUDIO_INFO_RATE (&in) != GST_AUDIO_INFO_RATE (&out)) {
+    if (b200_ars_update (self->ars, GST_AUDIO_INFO_RATE (&in), GST_AUDIO_INFO_RATE (&out)) != B200_OK)
+      return FALSE;
+    self->in = in;
+    self->out = out;
+    return TRUE;
+  }
+  self->in = in;
+  self->out = out;
   g_clear_pointer (&self->ars, b200_ars_destroy);
   /* b200_ars_config carries the reference's enum values + 1 (0 = element default); b200_ars_create answers
    * B200_ERR_UNSUPPORTED for what is still opt-in (B200_VCS_EXPERIMENTAL): the nearest / linear / cubic methods */

@@ -107,6 +107,7 @@ _SIGS = {
     "b200_ars_create": (C.c_int, [C.POINTER(ArsConfigC), C.c_int, C.POINTER(_P)]),
     "b200_ars_destroy": (None, [_P]),
     "b200_ars_reset": (C.c_int, [_P]),
+    "b200_ars_update": (C.c_int, [_P, C.c_int, C.c_int]),
     "b200_ars_get_out_frames": (C.c_size_t, [_P, C.c_size_t]),
     "b200_ars_get_in_frames": (C.c_size_t, [_P, C.c_size_t]),
     "b200_ars_get_max_latency": (C.c_size_t, [_P]),

@@ -47,6 +47,12 @@ class CudaAudioResample:
 
     # GstBaseTransformClass::set_caps (interleaved samples of self.format)
     def set_caps(self, in_rate, out_rate, channels):
+        # gst_audio_resample_update_state (gstaudioresample.c:398-437): same format and channel count on a live resampler
+        # = a rate change, the converter is UPDATED (history and phase survive); anything else builds a new one
+        if self._h is not None and channels == getattr(self, "channels", None) and in_rate != out_rate:
+            self.update_rates(in_rate, out_rate)
+            self.in_rate, self.out_rate = in_rate, out_rate
+            return True
         self._free()
         # gst_audio_resample_set_caps: equal rates put the base transform in pass-through mode (buffers are forwarded
         # untouched and transform() is never called)
@@ -99,6 +105,10 @@ class CudaAudioResample:
 
     def reset(self):
         check(lib.b200_ars_reset(self._h), "b200_ars_reset")
+
+    def update_rates(self, in_rate, out_rate):
+        """new caps with the same format / channels on a live stream (gst_audio_resample_update_state): keeps history"""
+        check(lib.b200_ars_update(self._h, in_rate, out_rate), "b200_ars_update")
 
     def plan_info(self):
         info = _lib.ArsPlanInfoC()

@@ -146,7 +146,9 @@ static void cubic_coeff (int num, int denom, float ic[4])
   ic[2] = (float) 1.0 - ic[0] - ic[1] - ic[3];
 }
 
-static int build_ars_plan (const b200_ars_config & cfg, ArsPlan * p)
+// forced_div > 0: the divisor gst_audio_resampler_update () settled on (a rate change keeps the common divisor only as far
+// as the rescaled phase allows, audio-resampler.c:1525-1551); 0: the plain gcd of a fresh resampler
+static int build_ars_plan (const b200_ars_config & cfg, ArsPlan * p, int forced_div = 0)
 {
   if (cfg.in_rate <= 0 || cfg.out_rate <= 0 || cfg.channels <= 0 || cfg.quality < 0 || cfg.quality > 10)
     return B200_ERR_INVALID_ARG;
@@ -160,6 +162,7 @@ static int build_ars_plan (const b200_ars_config & cfg, ArsPlan * p)
   p->channels = cfg.channels;
   int a = cfg.in_rate, b = cfg.out_rate;
   while (b) { int t = a; a = b; b = t % b; }
+  if (forced_div > 0) a = forced_div;
   p->in_step = cfg.in_rate / a;
   p->out_step = cfg.out_rate / a;
   p->samp_inc = p->in_step / p->out_step;
@@ -1194,6 +1197,7 @@ using namespace b200;
 struct b200_ars {
   ArsPlan plan;
   int device = -1;
+  b200_ars_config cfg;           // as created / last updated (b200_ars_update re-designs the filter from it)
   float *d_phases = nullptr;
   float *d_qtab = nullptr;       // chunk-major taps of every 4-output group (F32, FULL mode): see ArsTile::qtab
   int qtab_nch = 0;
@@ -1247,6 +1251,34 @@ static int ars_ensure_hist (b200_ars * h, int which, size_t frames, cudaStream_t
   return B200_OK;
 }
 
+// the plan's tables on the device (the current device is the handle's): phase taps or prototype rows, and for the F32 tile
+// kernels the pre-laid chunk-major rows
+static int ars_upload_tables (b200_ars * h)
+{
+  int st;
+  cudaFree (h->d_phases); cudaFree (h->d_qtab); cudaFree (h->d_proto); cudaFree (h->d_table_x);
+  h->d_phases = h->d_qtab = h->d_proto = nullptr; h->d_table_x = nullptr; h->qtab_nch = 0;
+  if (h->plan.fmt != ARS_F32) {
+    const std::vector<uint8_t> & t = h->plan.full ? h->plan.phases_x : h->plan.proto_x;
+    uint8_t *d = nullptr;
+    st = upload (&d, t.data (), t.size ());
+    h->d_table_x = d;
+  } else
+    st = h->plan.full ? upload (&h->d_phases, h->plan.phases.data (), h->plan.phases.size ())
+                      : upload (&h->d_proto, h->plan.proto.data (), h->plan.proto.size ());
+  if (st == B200_OK && h->plan.fmt == ARS_F32 && h->plan.full && !h->plan.small && !h->plan.copy) {
+    // tap rows of every (alignment, phase) group for the tile kernels; bounded by the FULL-mode threshold
+    // (bps * n_taps * out_rate < 1 MiB  =>  at most 16 x that in this layout)
+    const ArsPlan & q = h->plan;
+    const long long spread = ((long long) (ARS_RQ - 1) * q.in_step + q.out_step - 1) / q.out_step + 1;
+    h->qtab_nch = (int) ((spread + q.n_taps + 3 + 3) / 4 + 1);
+    std::vector<float> tab;
+    ars_build_qtab (q, h->qtab_nch, &tab);
+    st = upload (&h->d_qtab, tab.data (), tab.size ());
+  }
+  return st;
+}
+
 extern "C" {
 
 int b200_ars_create (const b200_ars_config * cfg, int device, b200_ars ** handle)
@@ -1255,6 +1287,7 @@ int b200_ars_create (const b200_ars_config * cfg, int device, b200_ars ** handle
   *handle = nullptr;
   b200_ars *h = new (std::nothrow) b200_ars ();
   if (!h) return B200_ERR_NOMEM;
+  h->cfg = *cfg;
   int st = build_ars_plan (*cfg, &h->plan);
   if (st != B200_OK) { delete h; return st; }
   h->device = device;
@@ -1264,24 +1297,7 @@ int b200_ars_create (const b200_ars_config * cfg, int device, b200_ars ** handle
     if (n <= 0) { delete h; return n < 0 ? n : B200_ERR_NO_DEVICE; }
     if (device >= n) { delete h; return B200_ERR_INVALID_ARG; }
     DeviceGuard g (device);
-    if (h->plan.fmt != ARS_F32) {
-      const std::vector<uint8_t> & t = h->plan.full ? h->plan.phases_x : h->plan.proto_x;
-      uint8_t *d = nullptr;
-      st = upload (&d, t.data (), t.size ());
-      h->d_table_x = d;
-    } else
-      st = h->plan.full ? upload (&h->d_phases, h->plan.phases.data (), h->plan.phases.size ())
-                        : upload (&h->d_proto, h->plan.proto.data (), h->plan.proto.size ());
-    if (st == B200_OK && h->plan.fmt == ARS_F32 && h->plan.full && !h->plan.small && !h->plan.copy) {
-      // tap rows of every (alignment, phase) group for the tile kernel; bounded by the FULL-mode threshold
-      // (bps * n_taps * out_rate < 1 MiB  =>  at most 16 x that in this layout)
-      const ArsPlan & q = h->plan;
-      const long long spread = ((long long) (ARS_RQ - 1) * q.in_step + q.out_step - 1) / q.out_step + 1;
-      h->qtab_nch = (int) ((spread + q.n_taps + 3 + 3) / 4 + 1);
-      std::vector<float> tab;
-      ars_build_qtab (q, h->qtab_nch, &tab);
-      st = upload (&h->d_qtab, tab.data (), tab.size ());
-    }
+    st = ars_upload_tables (h);
     if (st == B200_OK) st = ars_ensure_hist (h, 0, (size_t) h->plan.n_taps, nullptr);
     if (st == B200_OK) st = ars_ensure_hist (h, 1, (size_t) h->plan.n_taps, nullptr);
     if (st == B200_OK && cudaDeviceSynchronize () != cudaSuccess) st = B200_ERR_CUDA;   // clears done before any user stream
@@ -1338,6 +1354,73 @@ int b200_ars_reset (b200_ars * h)
     return B200_OK;
   }
   return ars_reset_state (h, nullptr);
+}
+
+// gst_audio_resampler_update () as the element drives it (gst_audio_resample_update_state, gstaudioresample.c:398-437:
+// new rates AND a fresh option bag -> the filter is re-designed): the phase is rescaled to the new output rate, the rates'
+// common divisor is reduced only while the phase error stays below DEFAULT_OPT_MAX_PHASE_ERROR 0.1
+// (audio-resampler.c:1517-1551), and when the tap count changes the history moves by half the difference (:1572-1603) -
+// shrinking drops the oldest samples, growing leaves the oldest ones in place twice.  The stream position survives.
+int b200_ars_update (b200_ars * h, int in_rate, int out_rate)
+{
+  if (!h) return B200_ERR_INVALID_ARG;
+  if (in_rate <= 0) in_rate = h->plan.in_step;                     // "0 = unchanged" means the REDUCED rate, like the reference
+  if (out_rate <= 0) out_rate = h->plan.out_step;
+  long long sp = (long long) ((unsigned long long) h->samp_phase * (unsigned long long) out_rate / (unsigned long long) h->plan.out_step);
+  int a = in_rate, b = out_rate;
+  while (b) { int t = a; a = b; b = t % b; }
+  int g = a;
+  while (g > 1) {
+    const double ph1 = (double) sp / out_rate, ph2 = (double) (sp / g) / (out_rate / g);
+    if (fabs (ph1 - ph2) < 0.1) break;
+    int factor = 2;
+    while (g % factor != 0) factor++;
+    g /= factor;
+  }
+  b200_ars_config cfg = h->cfg;
+  cfg.in_rate = in_rate; cfg.out_rate = out_rate;
+  ArsPlan np;
+  int st = build_ars_plan (cfg, &np, g);
+  if (st != B200_OK) return st;
+  const int old_taps = h->plan.n_taps;
+  const int diff = (np.n_taps - old_taps) / 2;
+  if (h->device >= 0) {
+    DeviceGuard dg (h->device);
+    if (!dg.ok) return B200_ERR_CUDA;
+    B200_CUDA_TRY (cudaDeviceSynchronize ());                      // kernels of the old filter still read its tables
+    if (diff != 0) {
+      // history into the other buffer, shifted (samp_index is 0 between calls: process () compacts)
+      const size_t bpf = (size_t) np.channels * np.bps;
+      const size_t avail = h->samples_avail;
+      const long long new_avail = (long long) avail + diff;
+      const int nxt = h->cur ^ 1;
+      ArsPlan keep = h->plan;
+      h->plan = np;                                                // ars_ensure_hist sizes with the new tap count
+      st = ars_ensure_hist (h, nxt, (size_t) std::max (new_avail, (long long) avail) + 1, nullptr);
+      if (st != B200_OK) { h->plan = keep; return st; }
+      const uint8_t *src = (const uint8_t *) h->d_hist[h->cur];
+      uint8_t *dst = (uint8_t *) h->d_hist[nxt];
+      if (diff < 0) {
+        if (new_avail > 0)
+          B200_CUDA_TRY (cudaMemcpy (dst, src + (size_t) (-diff) * bpf, (size_t) new_avail * bpf, cudaMemcpyDeviceToDevice));
+      } else {
+        const size_t lead = std::min ((size_t) diff, avail);      // "just leave the old samples in there"
+        if (lead) B200_CUDA_TRY (cudaMemcpy (dst, src, lead * bpf, cudaMemcpyDeviceToDevice));
+        if (avail) B200_CUDA_TRY (cudaMemcpy (dst + (size_t) diff * bpf, src, avail * bpf, cudaMemcpyDeviceToDevice));
+      }
+      h->cur = nxt;
+      h->samples_avail = (size_t) std::max (new_avail, 0LL);
+    } else
+      h->plan = np;
+    if ((st = ars_upload_tables (h)) != B200_OK) return st;
+    B200_CUDA_TRY (cudaDeviceSynchronize ());
+  } else {
+    h->plan = np;
+    h->samples_avail = (size_t) std::max ((long long) h->samples_avail + diff, 0LL);
+  }
+  h->cfg = cfg;
+  h->samp_phase = (int) (sp / g);
+  return B200_OK;
 }
 
 size_t b200_ars_get_out_frames (b200_ars * h, size_t in_frames)

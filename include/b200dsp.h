@@ -278,6 +278,10 @@ int b200_ars_create (const b200_ars_config * cfg, int device, b200_ars ** handle
 void b200_ars_destroy (b200_ars * h);
 /* discard history (flush / discont), gst_audio_resampler_reset */
 int b200_ars_reset (b200_ars * h);
+/* rate change on a live stream (gst_audio_resampler_update as audioresample drives it, audio-resampler.c:1503): the filter
+ * is re-designed for the new rates, the phase is rescaled, the history follows the tap count - no samples are lost and no
+ * reset happens.  A rate <= 0 keeps the current one.  Synchronises the device (rate changes are rare events). */
+int b200_ars_update (b200_ars * h, int in_rate, int out_rate);
 /* frames the next process() call will produce for in_frames of input */
 size_t b200_ars_get_out_frames (b200_ars * h, size_t in_frames);
 size_t b200_ars_get_in_frames (b200_ars * h, size_t out_frames);

@@ -112,6 +112,8 @@ def oracle():
             o.oracle_ars_process_any.argtypes = [P, P, C.c_size_t, P, C.c_size_t]
             o.oracle_ars_free.argtypes = [P]
             o.oracle_ars_reset.argtypes = [P]
+            if hasattr(o, "oracle_ars_update"):
+                o.oracle_ars_update.argtypes = [P, C.c_int, C.c_int]
             for n in ("oracle_ars_get_out_frames", "oracle_ars_get_in_frames"):
                 getattr(o, n).restype = C.c_size_t
                 getattr(o, n).argtypes = [P, C.c_size_t]
@@ -160,6 +162,8 @@ def ref():
                 r.ref_ars_new_opts.argtypes = [C.c_int] * 8
             r.ref_ars_free.argtypes = [P]
             r.ref_ars_reset.argtypes = [P]
+            if hasattr(r, "ref_ars_update"):
+                r.ref_ars_update.argtypes = [P] + [C.c_int] * 6
             for n in ("ref_ars_get_out_frames", "ref_ars_get_in_frames"):
                 getattr(r, n).restype = C.c_size_t
                 getattr(r, n).argtypes = [P, C.c_size_t]

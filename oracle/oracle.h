@@ -135,6 +135,8 @@ OracleArs *oracle_ars_new_opts (int in_rate, int out_rate, int channels, int qua
 size_t oracle_ars_process_any (OracleArs * r, const void *in, size_t in_frames, void *out, size_t out_capacity);
 void oracle_ars_free (OracleArs * r);
 void oracle_ars_reset (OracleArs * r);
+/* rate change on a live stream (gst_audio_resampler_update with the element's fresh option bag, audio-resampler.c:1503) */
+int oracle_ars_update (OracleArs * r, int in_rate, int out_rate);
 size_t oracle_ars_get_out_frames (OracleArs * r, size_t in_frames);
 size_t oracle_ars_get_in_frames (OracleArs * r, size_t out_frames);
 size_t oracle_ars_max_latency (OracleArs * r);

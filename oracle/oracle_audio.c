@@ -63,6 +63,8 @@ struct OracleArs
   int copy;                     /* nearest method, or equal rates (setup_functions, audio-resampler.c:1019-1020): *o = *a */
   int linear, isize;            /* sinc-filter-interpolation=linear: two table rows per phase, 11x the oversampling */
   int method, interp_none;      /* ORACLE_ARS_METHOD_*; sinc-filter-interpolation=none (FULL mode: exact taps per phase) */
+  int quality, opt_filter_mode, opt_interpolation;      /* the option bag, kept for oracle_ars_update () */
+  int raw_down;                 /* out_rate < in_rate on the UN-reduced rates (options_set_quality sees those) */
   double cutoff, beta;
   int fmt, bps;                 /* ORACLE_AFMT_*, bytes per sample */
   float *table;                 /* (oversample + 4) rows of n_taps, the oversampled prototype (typed by fmt) */
@@ -166,54 +168,24 @@ make_row (const OracleArs * r, void *res, double x)
   free (tmp);
 }
 
-OracleArs *
-oracle_ars_new (int in_rate, int out_rate, int channels, int quality)
+/* resampler_calculate_taps () with the element's option bag (audio-resampler.c:1064-1215), on the handle's current
+ * (reduced) rates; called from the constructor and from oracle_ars_update () */
+static void
+ars_configure (OracleArs * r)
 {
-  return oracle_ars_new_fmt (in_rate, out_rate, channels, quality, ORACLE_AFMT_F32);
-}
-
-OracleArs *
-oracle_ars_new_fmt (int in_rate, int out_rate, int channels, int quality, int fmt)
-{
-  return oracle_ars_new_opts (in_rate, out_rate, channels, quality, fmt, ORACLE_ARS_METHOD_KAISER, ORACLE_ARS_MODE_AUTO,
-      ORACLE_ARS_INTERP_CUBIC);
-}
-
-OracleArs *
-oracle_ars_new_opts (int in_rate, int out_rate, int channels, int quality, int fmt, int method, int filter_mode,
-    int interpolation)
-{
-  /* blackman_qualities (audio-resampler.c:81-93): n_taps, cutoff */
   static const struct { int n_taps; double cutoff; } blackman_q[11] = { {8, 0.5}, {16, 0.6}, {24, 0.72}, {32, 0.8},
     {48, 0.85}, {64, 0.90}, {80, 0.92}, {96, 0.933}, {128, 0.950}, {148, 0.955}, {160, 0.960} };
-  OracleArs *r;
   double Fc, A, tr_bw, B, dw;
-  int g, n, oversample, i;
-  if (in_rate <= 0 || out_rate <= 0 || channels <= 0 || quality < 0 || quality > 10)
-    return NULL;
-  if (fmt < 0 || fmt > ORACLE_AFMT_F64)
-    return NULL;
-  if (method < ORACLE_ARS_METHOD_NEAREST || method > ORACLE_ARS_METHOD_KAISER ||
-      filter_mode < ORACLE_ARS_MODE_INTERPOLATED || filter_mode > ORACLE_ARS_MODE_AUTO ||
-      interpolation < ORACLE_ARS_INTERP_NONE || interpolation > ORACLE_ARS_INTERP_CUBIC)
-    return NULL;
-  r = calloc (1, sizeof (*r));
-  r->method = method;
-  r->channels = channels;
-  r->fmt = fmt;
-  r->bps = fmt == ORACLE_AFMT_S16 ? 2 : (fmt == ORACLE_AFMT_F64 ? 8 : 4);
-  /* update(): first call runs with options == NULL: max_error 0.1, samp_phase 0 -> plain gcd */
-  g = gcd_ (in_rate, out_rate);
-  r->in_rate = in_rate / g;
-  r->out_rate = out_rate / g;
+  int n, oversample, i;
+  const int quality = r->quality, method = r->method;
+  int filter_mode = r->opt_filter_mode, interpolation = r->opt_interpolation;
+  free (r->table); free (r->cache); free (r->have);
+  r->table = r->cache = NULL; r->have = NULL;
   r->copy = method == ORACLE_ARS_METHOD_NEAREST || r->in_rate == r->out_rate;
-  r->samp_inc = r->in_rate / r->out_rate;
-  r->samp_frac = r->in_rate % r->out_rate;
-
   /* options_set_quality(kaiser) then calculate_kaiser_params: the option values override the
    * DEFAULT_QUALITY row */
   Fc = kaiser_q[quality].cutoff;
-  if (out_rate < in_rate)
+  if (r->raw_down)
     Fc *= kaiser_q[quality].down;
   A = kaiser_q[quality].atten;
   tr_bw = kaiser_q[quality].trbw;
@@ -282,6 +254,49 @@ oracle_ars_new_opts (int in_rate, int out_rate, int channels, int quality, int f
     r->cache = calloc ((size_t) r->n_phases * r->n_taps, r->bps);
     r->have = calloc (r->n_phases, 1);
   }
+}
+
+OracleArs *
+oracle_ars_new (int in_rate, int out_rate, int channels, int quality)
+{
+  return oracle_ars_new_fmt (in_rate, out_rate, channels, quality, ORACLE_AFMT_F32);
+}
+
+OracleArs *
+oracle_ars_new_fmt (int in_rate, int out_rate, int channels, int quality, int fmt)
+{
+  return oracle_ars_new_opts (in_rate, out_rate, channels, quality, fmt, ORACLE_ARS_METHOD_KAISER, ORACLE_ARS_MODE_AUTO,
+      ORACLE_ARS_INTERP_CUBIC);
+}
+
+OracleArs *
+oracle_ars_new_opts (int in_rate, int out_rate, int channels, int quality, int fmt, int method, int filter_mode,
+    int interpolation)
+{
+  OracleArs *r;
+  int g;
+  if (in_rate <= 0 || out_rate <= 0 || channels <= 0 || quality < 0 || quality > 10)
+    return NULL;
+  if (fmt < 0 || fmt > ORACLE_AFMT_F64)
+    return NULL;
+  if (method < ORACLE_ARS_METHOD_NEAREST || method > ORACLE_ARS_METHOD_KAISER ||
+      filter_mode < ORACLE_ARS_MODE_INTERPOLATED || filter_mode > ORACLE_ARS_MODE_AUTO ||
+      interpolation < ORACLE_ARS_INTERP_NONE || interpolation > ORACLE_ARS_INTERP_CUBIC)
+    return NULL;
+  r = calloc (1, sizeof (*r));
+  r->method = method;
+  r->channels = channels;
+  r->fmt = fmt;
+  r->bps = fmt == ORACLE_AFMT_S16 ? 2 : (fmt == ORACLE_AFMT_F64 ? 8 : 4);
+  /* update(): first call runs with options == NULL: max_error 0.1, samp_phase 0 -> plain gcd */
+  g = gcd_ (in_rate, out_rate);
+  r->in_rate = in_rate / g;
+  r->out_rate = out_rate / g;
+  r->samp_inc = r->in_rate / r->out_rate;
+  r->samp_frac = r->in_rate % r->out_rate;
+  r->quality = quality; r->opt_filter_mode = filter_mode; r->opt_interpolation = interpolation;
+  r->raw_down = out_rate < in_rate;
+  ars_configure (r);
   r->sbuf = calloc (channels, sizeof (float *));
   oracle_ars_reset (r);
   return r;
@@ -312,6 +327,67 @@ oracle_ars_reset (OracleArs * r)
   r->samp_index = 0;
   r->samples_avail = r->n_taps / 2 - 1;
   /* note: samp_phase and skip are left alone, exactly like gst_audio_resampler_reset() */
+}
+
+/* gst_audio_resampler_update () as the element drives it (gst_audio_resample_update_state -> gst_audio_converter_update_config,
+ * gstaudioresample.c:398-437, audio-converter.c:349-375): new rates AND a fresh option bag, so the filter is re-designed;
+ * the stream position survives: the phase is rescaled, the common divisor of the rates is reduced only as far as the phase
+ * error stays below 0.1 (DEFAULT_OPT_MAX_PHASE_ERROR), and the history moves by half the change of the tap count
+ * (audio-resampler.c:1503-1615).  in_rate / out_rate <= 0 keep the old value - of the REDUCED rates, like the reference. */
+int
+oracle_ars_update (OracleArs * r, int in_rate, int out_rate)
+{
+  int g, samp_phase, old_n_taps = r->n_taps, c;
+  if (in_rate <= 0)
+    in_rate = r->in_rate;
+  if (out_rate <= 0)
+    out_rate = r->out_rate;
+  samp_phase = (int) (((unsigned long long) r->samp_phase * (unsigned long long) out_rate) / (unsigned long long) r->out_rate);
+  g = gcd_ (in_rate, out_rate);
+  while (g > 1) {
+    double ph1 = (double) samp_phase / out_rate;
+    double ph2 = (double) (samp_phase / g) / (out_rate / g);
+    int factor = 2;
+    if (fabs (ph1 - ph2) < 0.1)
+      break;
+    while (g % factor != 0)
+      factor++;
+    g /= factor;
+  }
+  r->raw_down = out_rate < in_rate;
+  r->samp_phase = samp_phase / g;
+  r->in_rate = in_rate / g;
+  r->out_rate = out_rate / g;
+  r->samp_inc = r->in_rate / r->out_rate;
+  r->samp_frac = r->in_rate % r->out_rate;
+  ars_configure (r);
+  if (old_n_taps > 0 && old_n_taps != r->n_taps) {
+    const int diff = (r->n_taps - old_n_taps) / 2, bps = r->bps;
+    size_t need = (size_t) r->n_taps;                              /* get_sample_bufs (resampler, n_taps) */
+    long long bytes = (long long) r->samples_avail * bps, soff = (long long) r->samp_index * bps, doff = soff;
+    if (need < r->samp_index + r->samples_avail + (size_t) (diff > 0 ? diff : 0))
+      need = r->samp_index + r->samples_avail + (size_t) (diff > 0 ? diff : 0);   /* the reference would write past its buffer */
+    if (r->samples_len < need) {
+      for (c = 0; c < r->channels; c++) {
+        char *n = calloc (need, bps);
+        if (r->sbuf[c])
+          memcpy (n, r->sbuf[c], r->samples_avail * bps);
+        free (r->sbuf[c]);
+        r->sbuf[c] = (float *) n;
+      }
+      r->samples_len = need;
+    }
+    if (diff < 0) {
+      soff += (long long) -diff * bps;
+      bytes -= (long long) -diff * bps;
+    } else
+      doff += (long long) diff * bps;
+    if (bytes > 0)
+      for (c = 0; c < r->channels; c++)
+        memmove ((char *) r->sbuf[c] + doff, (char *) r->sbuf[c] + soff, (size_t) bytes);
+    r->samples_avail += diff;
+  }
+  return 0;
 }
 
 static void

@@ -55,6 +55,27 @@ ref_ars_new_opts (int in_rate, int out_rate, int channels, int quality, int form
   return r;
 }
 
+/* the element's rate change: gst_audio_resample_update_state () builds a fresh option bag with make_options () for the
+ * new rates and hands both to gst_audio_converter_update_config () -> gst_audio_resampler_update ()
+ * (gstaudioresample.c:398-437, audio-converter.c:349-375) */
+int
+ref_ars_update (GstAudioResampler * r, int in_rate, int out_rate, int quality, int method, int filter_mode, int interpolation)
+{
+  GstStructure *options = gst_structure_new_static_str_empty ("resampler-options");
+  gboolean ok;
+  gst_audio_resampler_options_set_quality ((GstAudioResamplerMethod) method, quality, in_rate, out_rate, options);
+  gst_structure_set_static_str (options,
+      OPT_METHOD, GST_TYPE_AUDIO_RESAMPLER_METHOD, (GstAudioResamplerMethod) method,
+      GST_AUDIO_RESAMPLER_OPT_FILTER_MODE, GST_TYPE_AUDIO_RESAMPLER_FILTER_MODE,
+      (GstAudioResamplerFilterMode) filter_mode,
+      GST_AUDIO_RESAMPLER_OPT_FILTER_MODE_THRESHOLD, G_TYPE_UINT, (guint) 1048576,
+      GST_AUDIO_RESAMPLER_OPT_FILTER_INTERPOLATION, GST_TYPE_AUDIO_RESAMPLER_FILTER_INTERPOLATION,
+      (GstAudioResamplerFilterInterpolation) interpolation, NULL);
+  ok = gst_audio_resampler_update (r, in_rate, out_rate, options);
+  gst_structure_free (options);
+  return ok ? 0 : -1;
+}
+
 void ref_ars_free (GstAudioResampler * r) { gst_audio_resampler_free (r); }
 void ref_ars_reset (GstAudioResampler * r) { gst_audio_resampler_reset (r); }
 size_t ref_ars_get_out_frames (GstAudioResampler * r, size_t n) { return gst_audio_resampler_get_out_frames (r, n); }

@@ -182,3 +182,50 @@ def test_sample_formats(cuda_device, fmt, cfg):
         assert ng == nw and got[:ng].tobytes() == want[:nw].tobytes()
         assert (got[ng:] == 7).all()
     o.oracle_ars_free(ho)
+
+
+RATE_WALKS = [
+    (2, 4, "F32LE", [(48000, 44100), (48000, 96000), (48000, 32000), (44100, 48000)]),
+    (3, 6, "F32LE", [(48000, 44100), (48000, 44101), (48001, 44100), (8000, 7999)]),       # FULL <-> interpolated filter mode
+    (128, 4, "F32LE", [(48000, 44100), (47999, 44100), (48000, 44100)]),                   # the pipelined kernel, clock-drift steps
+    (2, 4, "S16LE", [(44100, 48000), (44100, 8000), (44100, 96000)]),
+    (1, 4, "S32LE", [(44100, 48000), (22050, 48000)]),
+    (2, 10, "F64LE", [(44100, 48000), (44100, 16000)]),
+]
+
+
+@pytest.mark.parametrize("walk", RATE_WALKS, ids=lambda w: "%dch-q%d-%s-%s" % (w[0], w[1], w[2], "_".join("%d-%d" % p for p in w[3])))
+def test_rate_update_keeps_the_stream(cuda_device, walk):
+    """b200_ars_update == gst_audio_resampler_update as the element drives it: rates change on a live stream, phase and
+    history survive, output byte-identical with the oracle (pinned to the reference build in tests/test_oracle_vs_ref.py)"""
+    import torch
+    from gstreamer_b200.audio import CudaAudioResample, AudioFormat
+    ch, q, fmt_name, pairs = walk
+    fmt = getattr(AudioFormat, fmt_name)
+    key = {"F32LE": "F32", "S16LE": "S16", "S32LE": "S32", "F64LE": "F64"}[fmt_name]
+    ofmt, _, dt, _ = ob.AUDIO_FORMATS[key]
+    o = ob.oracle()
+    a, b = pairs[0]
+    ho = o.oracle_ars_new_fmt(a, b, ch, q, ofmt)
+    rs = CudaAudioResample(quality=q, format=fmt)
+    rs.set_caps(a, b, ch)
+    rng = np.random.default_rng(a + b + ch)
+    tdt = {np.float32: torch.float32, np.int16: torch.int16, np.int32: torch.int32, np.float64: torch.float64}[dt]
+    try:
+        for k, (a, b) in enumerate(pairs):
+            if k:
+                assert o.oracle_ars_update(ho, a, b) == 0
+                rs.set_caps(a, b, ch)                      # same format and channels: the mirror updates, like the element
+            for n in [int(v) for v in rng.choice([1, 7, 160, 481, 1000], 4)]:
+                x = ob.audio_test_signal(rng, n, ch, key)
+                cap = int(n * b / a) + 64
+                want = np.zeros((cap, ch), dtype=dt)
+                nw = o.oracle_ars_process_any(ho, x.ctypes.data, n, want.ctypes.data, cap)
+                out = torch.zeros(cap * ch, dtype=tdt, device="cuda")
+                assert rs.get_out_frames(n) == nw
+                ng = rs.transform(torch.from_numpy(x).cuda().reshape(-1), n, out, cap)
+                torch.cuda.synchronize()
+                got = out.cpu().numpy().reshape(cap, ch)
+                assert ng == nw and got[:nw].tobytes() == want[:nw].tobytes(), (k, a, b, n)
+    finally:
+        o.oracle_ars_free(ho)

@@ -633,3 +633,57 @@ def test_422_444_inputs_match_reference(fi, size):
             if _one_tap_vertical_repeat(iw, ih, ow, oh, method) and not np.array_equal(got, want):
                 continue
             assert np.array_equal(got, want), f"{fo} method {method} site {site}"
+
+
+# ---- variable rate: gst_audio_resampler_update on a live stream (audio-resampler.c:1503-1615) -------------------------------
+RATE_WALKS = [
+    # (channels, quality, [(in, out), ...]): every pair after the first arrives through update() with a fresh option bag
+    (2, 4, [(48000, 44100), (48000, 48000 * 2), (48000, 32000), (44100, 48000)]),
+    (1, 4, [(44100, 48000), (44100, 44100 * 3 // 2), (44100, 8000), (44100, 96000)]),      # tap count changes both ways
+    (3, 6, [(48000, 44100), (48000, 44101), (48001, 44100), (8000, 7999)]),                # FULL <-> interpolated, odd rates
+    (2, 0, [(96000, 8000), (96000, 44100), (32000, 48000)]),
+    (2, 10, [(44100, 48000), (22050, 48000), (44100, 16000)]),
+    (5, 4, [(48000, 44100), (47999, 44100), (48000, 44100), (48000, 44099)]),              # clock-drift sized steps
+]
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize("fmt", ["F32", "S16", "S32", "F64"])
+@pytest.mark.parametrize("walk", RATE_WALKS, ids=lambda w: "%dch-q%d-%s" % (w[0], w[1], "_".join("%d-%d" % p for p in w[2])))
+def test_audio_rate_update_matches_reference(fmt, walk):
+    """The element's rate change (gst_audio_resample_update_state -> gst_audio_resampler_update with a fresh option bag):
+    the phase is rescaled, the divisor of the rates follows the phase-error rule, the filter is re-designed and the
+    history moves by half the tap-count change - byte-identical output with the reference build across every change,
+    with the stream cut into uneven buffers around them"""
+    import ctypes as C
+    ch, q, pairs = walk
+    ofmt, gfmt, dt, _ = ob.AUDIO_FORMATS[fmt]
+    o, r = ob.oracle(), ob.ref()
+    a, b = pairs[0]
+    ho, hr = o.oracle_ars_new_fmt(a, b, ch, q, ofmt), r.ref_ars_new_fmt(a, b, ch, q, gfmt)
+    rng = np.random.default_rng(a * 7 + b + ch)
+    try:
+        for k, (a, b) in enumerate(pairs):
+            if k:
+                assert o.oracle_ars_update(ho, a, b) == 0
+                assert r.ref_ars_update(hr, a, b, q, 4, 2, 2) == 0      # kaiser, filter-mode auto, cubic interpolation
+                io = [C.c_int() for _ in range(6)]
+                ir = [C.c_int() for _ in range(6)]
+                o.oracle_ars_info(ho, *[C.byref(v) for v in io])
+                r.ref_ars_info(hr, *[C.byref(v) for v in ir])
+                vo, vr = [v.value for v in io], [v.value for v in ir]
+                if vr[4] == 0:          # interpolated mode: the reference leaves the FULL-mode phase count of before in place
+                    vo[1] = vr[1] = 0
+                assert vo == vr, (a, b)
+            for n in [int(v) for v in rng.choice([1, 7, 160, 481, 1000], 4)]:
+                x = ob.audio_test_signal(rng, n, ch, fmt)
+                cap = int(n * b / a) + 64
+                o1 = np.zeros((cap, ch), dtype=dt)
+                o2 = o1.copy()
+                assert o.oracle_ars_get_out_frames(ho, n) == r.ref_ars_get_out_frames(hr, n)
+                n1 = o.oracle_ars_process_any(ho, x.ctypes.data, n, o1.ctypes.data, cap)
+                n2 = r.ref_ars_process(hr, x.ctypes.data, n, o2.ctypes.data, cap)
+                assert n1 == n2 and o1[:n1].tobytes() == o2[:n2].tobytes(), (k, a, b, n)
+    finally:
+        o.oracle_ars_free(ho)
+        r.ref_ars_free(hr)
