@@ -1361,6 +1361,9 @@ int b200_ars_reset (b200_ars * h)
 // common divisor is reduced only while the phase error stays below DEFAULT_OPT_MAX_PHASE_ERROR 0.1
 // (audio-resampler.c:1517-1551), and when the tap count changes the history moves by half the difference (:1572-1603) -
 // shrinking drops the oldest samples, growing leaves the oldest ones in place twice.  The stream position survives.
+// One corner is NOT the reference's: when the tap count grows by more than twice the kept history, the reference's
+// "old samples left in place" (its FIXME, :1597-1599) are leftover bytes of earlier calls in its sample buffer; the
+// product has zeros there.
 int b200_ars_update (b200_ars * h, int in_rate, int out_rate)
 {
   if (!h) return B200_ERR_INVALID_ARG;

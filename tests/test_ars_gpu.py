@@ -188,7 +188,7 @@ RATE_WALKS = [
     (2, 4, "F32LE", [(48000, 44100), (48000, 96000), (48000, 32000), (44100, 48000)]),
     (3, 6, "F32LE", [(48000, 44100), (48000, 44101), (48001, 44100), (8000, 7999)]),       # FULL <-> interpolated filter mode
     (128, 4, "F32LE", [(48000, 44100), (47999, 44100), (48000, 44100)]),                   # the pipelined kernel, clock-drift steps
-    (2, 4, "S16LE", [(44100, 48000), (44100, 8000), (44100, 96000)]),
+    (2, 4, "S16LE", [(44100, 48000), (44100, 32000), (44100, 96000)]),
     (1, 4, "S32LE", [(44100, 48000), (22050, 48000)]),
     (2, 10, "F64LE", [(44100, 48000), (44100, 16000)]),
 ]
@@ -197,7 +197,9 @@ RATE_WALKS = [
 @pytest.mark.parametrize("walk", RATE_WALKS, ids=lambda w: "%dch-q%d-%s-%s" % (w[0], w[1], w[2], "_".join("%d-%d" % p for p in w[3])))
 def test_rate_update_keeps_the_stream(cuda_device, walk):
     """b200_ars_update == gst_audio_resampler_update as the element drives it: rates change on a live stream, phase and
-    history survive, output byte-identical with the oracle (pinned to the reference build in tests/test_oracle_vs_ref.py)"""
+    history survive, output byte-identical with the oracle (pinned to the reference build in tests/test_oracle_vs_ref.py).
+    Walks keep the tap count's growth within the kept history: beyond it the reference reads whatever its sample buffer
+    still holds from earlier calls (its own FIXME, audio-resampler.c:1597-1599) where the product has zeros - DESIGN.md."""
     import torch
     from gstreamer_b200.audio import CudaAudioResample, AudioFormat
     ch, q, fmt_name, pairs = walk
@@ -218,7 +220,7 @@ def test_rate_update_keeps_the_stream(cuda_device, walk):
                 rs.set_caps(a, b, ch)                      # same format and channels: the mirror updates, like the element
             for n in [int(v) for v in rng.choice([1, 7, 160, 481, 1000], 4)]:
                 x = ob.audio_test_signal(rng, n, ch, key)
-                cap = int(n * b / a) + 64
+                cap = int(o.oracle_ars_get_out_frames(ho, n)) + 64       # after a shrinking filter the surplus history plays out too
                 want = np.zeros((cap, ch), dtype=dt)
                 nw = o.oracle_ars_process_any(ho, x.ctypes.data, n, want.ctypes.data, cap)
                 out = torch.zeros(cap * ch, dtype=tdt, device="cuda")

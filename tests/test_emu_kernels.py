@@ -493,7 +493,7 @@ def test_audio_rate_update(emu, fmt):
                     assert emu.b200_ars_update(h, a, b) == 0
                 for n in [int(v) for v in rng.choice([1, 7, 160, 481], 3)]:
                     x = ob.audio_test_signal(rng, n, ch, fmt)
-                    cap = int(n * b / a) + 64
+                    cap = int(o.oracle_ars_get_out_frames(ho, n)) + 64
                     want = np.zeros((cap, ch), dtype=dt)
                     got = want.copy()
                     nw = o.oracle_ars_process_any(ho, x.ctypes.data, n, want.ctypes.data, cap)
