@@ -34,12 +34,12 @@ def convert(iw, ih, method, frame, in_fmt=23, out_fmt=12, matrix=None, rng=None,
     return [d.cpu().numpy() for d in dst]
 
 
-@pytest.mark.parametrize("size", SIZES, ids=lambda s: "%dx%d" % s)
-@pytest.mark.parametrize("method", METHODS)
+TC_CASES = [(s, m) for m in METHODS for s in SIZES if not (s[0] * s[1] > 2_000_000 and m not in (3, 9))]   # large: lanczos, mitchell
+
+
+@pytest.mark.parametrize("size,method", TC_CASES, ids=lambda v: "%dx%d" % v if isinstance(v, tuple) else str(v))
 def test_matches_oracle(cuda_device, size, method):
     iw, ih = size
-    if iw * ih > 2_000_000 and method not in (3, 9):
-        pytest.skip("large shape: lanczos and mitchell only")
     frame = ob.nv12_random_frame(iw, ih, seed=iw + method)
     want = ob.oracle_vcs_convert(ob.vcs_desc(iw, ih, iw // 2, ih // 2, method, site=2), frame)
     got = convert(iw, ih, method, frame)[0]
