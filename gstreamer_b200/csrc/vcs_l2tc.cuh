@@ -70,6 +70,7 @@ struct L2tcDev {
   const uint8_t *vband;         // [row tiles][TC_VB_BYTES]
   const uint8_t *hx4, *vx4;     // per strip / row tile: taps are stored times 4 (rounding 128, result in byte 1)
   int strips, row_tiles;
+  unsigned magic_rt;            // 2^32 / row_tiles + 1: t / row_tiles == umulhi (t, magic) for the tile counts that occur
 };
 
 // ---- PTX wrappers (sm_100a) -----------------------------------------------------------------------------------------
@@ -187,7 +188,10 @@ __device__ __forceinline__ void tc_bar_wait_guard (uint32_t bar, uint32_t parity
   do {
     asm volatile ("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
         : "=r" (ok) : "r" (bar), "r" (parity) : "memory");
-    if (!ok && ++spins > (1u << 26)) __trap ();                  // a lost arrival must fail loudly, not hang the device
+    if (!ok) {
+      __nanosleep (40);                                           // a waiting warp should not compete for issue slots
+      if (++spins > (1u << 24)) __trap ();                        // a lost arrival must fail loudly, not hang the device
+    }
   } while (!ok);
 #endif
 }
@@ -209,12 +213,12 @@ __device__ __forceinline__ void tc_bar_arrive (uint32_t bar)
 #endif
 }
 
-template <bool X4>
-__device__ __forceinline__ void tc_v_rows (const VcsDev & P, const int (&a)[3][16], uint8_t *dst, int rows, unsigned *dbg_row)
+template <bool X4, bool FULL>
+__device__ __forceinline__ void tc_v_rows (const VcsDev & P, const int (&a)[3][16], uint8_t *dst, int rows)
 {
 #pragma unroll
   for (int i = 0; i < 14; i++) {
-    if (i < rows) {
+    if (FULL || i < rows) {
       unsigned yuv = X4 ? __byte_perm (pack_sat_u16x2 (a[1][i], a[0][i]), pack_sat_u16x2 (0, a[2][i]), 0x7531)
           : pack_sat2 (a[1][i] >> 6, a[0][i] >> 6, pack_sat2 (0, a[2][i] >> 6, 0u));
       yuv ^= 0x00808080u;
@@ -264,11 +268,15 @@ vcs_l2tc_kernel (const VcsDev P, const L2tcDev L, const VcsBatch frames, int n_f
   const int per_strip = n_frames * L.row_tiles;
   const int n_tiles = L.strips * per_strip;
   const int my_tiles = blockIdx.x < n_tiles ? (n_tiles - 1 - (int) blockIdx.x) / (int) gridDim.x + 1 : 0;
+  const unsigned magic_ps = 0xffffffffu / (unsigned) per_strip + 1u;    // tiles < 2^16 * ... : exact for t < 2^32 / per_strip
   auto tile_of = [&] (int k, int & strip, int & f, int & rt) {
-    const int t = blockIdx.x + k * gridDim.x;
-    strip = t / per_strip;
-    const int rem = t - strip * per_strip;
-    f = rem / L.row_tiles; rt = rem - f * L.row_tiles;
+    const unsigned t = blockIdx.x + (unsigned) k * gridDim.x;
+    strip = (int) __umulhi (t, magic_ps);
+    if ((unsigned) (strip + 1) * (unsigned) per_strip <= t) strip++;          // the reciprocals round down at most one short
+    const unsigned rem = t - (unsigned) strip * (unsigned) per_strip;
+    f = (int) __umulhi (rem, L.magic_rt);
+    if ((unsigned) (f + 1) * (unsigned) L.row_tiles <= rem) f++;
+    rt = (int) (rem - (unsigned) f * (unsigned) L.row_tiles);
   };
 
   if (warp < TC_PROD_WARPS) {
@@ -315,6 +323,8 @@ vcs_l2tc_kernel (const VcsDev P, const L2tcDev L, const VcsBatch frames, int n_f
         constexpr int SLOTS = 2 * TC_CHUNKS - 2, ITEMS = (TC_N / 4) * SLOTS, UNITS = (ITEMS + 31) / 32;
         constexpr int MAXU = (UNITS + TC_PROD_WARPS - 1) / TC_PROD_WARPS;
         const int u0 = (warp + k) % TC_PROD_WARPS;
+        // tiles that touch no frame border: no row clamps, no right-edge replication, no column tests
+        const bool interior = R0 >= 1 && R0 + 4 * (TC_N / 4) + 2 <= P.ih && X0 >= 0 && X0 + 16 * TC_CHUNKS + 8 <= P.iw;
         uint2 raw[MAXU][3];
         unsigned nxt[MAXU][3];
         int offs[MAXU];
@@ -326,7 +336,15 @@ vcs_l2tc_kernel (const VcsDev P, const L2tcDev L, const VcsBatch frames, int n_f
           if (u0 + j * TC_PROD_WARPS < UNITS && item < ITEMS) {
             const int g = item / SLOTS, slot = item - g * SLOTS + 1;
             const int x = X0 + 8 * slot;
-            if (x >= 0 && x < P.iw) {
+            if (interior) {
+              offs[j] = (slot >> 1) * TC_IMG_LBO + (g >> 1) * 128 + (g & 1) * 64 + (slot & 1) * 8;
+              const uint8_t *row = plane_c + (ptrdiff_t) (oy0 - 2 + 2 * g) * P.stride_c + x;    // (R0 + 4g - 1) >> 1 == oy0 - 2 + 2g
+#pragma unroll
+              for (int kk = 0; kk < 3; kk++, row += P.stride_c) {
+                raw[j][kk] = __ldg ((const uint2 *) row);
+                nxt[j][kk] = (unsigned) __ldg ((const unsigned short *) (row + 8));
+              }
+            } else if (x >= 0 && x < P.iw) {
               redge[j] = x + 8 >= P.iw;
               const int m2 = (R0 + 4 * g - 1) >> 1;
               offs[j] = (slot >> 1) * TC_IMG_LBO + (g >> 1) * 128 + (g & 1) * 64 + (slot & 1) * 8;   // line 4g + r: + 16 r
@@ -437,8 +455,9 @@ vcs_l2tc_kernel (const VcsDev P, const L2tcDev L, const VcsBatch frames, int n_f
         const int rows = min (min (TC_TH, P.oh - oy0) - r0, 14);
         if (ox < P.ow && rows > 0) {
           uint8_t *dst = frames.out[f] + P.off_out + (size_t) (oy0 + r0) * P.stride_out + (size_t) ox * 4u;
-          if (__ldg (L.vx4 + rt) != 0) tc_v_rows<true> (P, a, dst, rows, nullptr);
-          else tc_v_rows<false> (P, a, dst, rows, nullptr);
+          const bool vx4 = __ldg (L.vx4 + rt) != 0;              // warp-uniform: branches, not predicates
+          if (rows == 14) { if (vx4) tc_v_rows<true, true> (P, a, dst, 14); else tc_v_rows<false, true> (P, a, dst, 14); }
+          else { if (vx4) tc_v_rows<true, false> (P, a, dst, rows); else tc_v_rows<false, false> (P, a, dst, rows); }
         }
       }
     }
@@ -448,48 +467,53 @@ vcs_l2tc_kernel (const VcsDev P, const L2tcDev L, const VcsBatch frames, int n_f
     // Both passes are issued from one lane in whatever order their inputs become ready: the H pass of tile k+1 must not
     // wait behind the V pass of tile k (that one waits for the consumers), nor the other way round (the H pass waits for
     // the producers).  The H pass runs at most one tile ahead (two TMEM / plane buffers).
-    auto issue_h = [&] (int k) {
+    // descriptors differ only in their start-address field (bits 0..13, units of 16 bytes): base descriptor + offset
+    const uint64_t d_band = tc_desc (s_band, TC_BAND_LBO, 128), d_ones = tc_desc (s_ones, TC_BAND_LBO, 128);
+    const uint64_t d_img = tc_desc (s_img, TC_IMG_LBO, 128), d_hs = tc_desc (s_hs, TC_HS_LBO, 128);
+    const uint64_t d_vb = tc_desc (s_vb, TC_VB_LBO, 128);
+    auto issue_h_ch = [&] (int k, int ch) {                       // one channel of the H pass: 9 K steps + the rounding step
       const int buf = k & 1;
-      tc_fence_after ();
-#pragma unroll 1
-      for (int ch = 0; ch < 3; ch++) {
-        const uint32_t img = s_img + (buf * 3 + ch) * TC_IMG_BYTES;
-#pragma unroll 1
-        for (int s = 0; s < TC_CHUNKS / 2 + 1; s++) {
-          const uint64_t a = tc_desc (s_band + 2 * s * TC_BAND_LBO, TC_BAND_LBO, 128);
-          const uint64_t b = s < TC_CHUNKS / 2 ? tc_desc (img + 2 * s * TC_IMG_LBO, TC_IMG_LBO, 128) : tc_desc (s_ones, TC_BAND_LBO, 128);
-          tc_mma (tmem + buf * 3 * TC_N + ch * TC_N, a, b, IDESC_H, s > 0);
-        }
+      const uint64_t img = d_img + (uint64_t) (((buf * 3 + ch) * TC_IMG_BYTES) >> 4);
+      const uint32_t acc = tmem + buf * 3 * TC_N + ch * TC_N;
+#pragma unroll
+      for (int s = 0; s < TC_CHUNKS / 2; s++)
+        tc_mma (acc, d_band + (uint64_t) ((2 * s * TC_BAND_LBO) >> 4), img + (uint64_t) ((2 * s * TC_IMG_LBO) >> 4), IDESC_H, s > 0);
+      tc_mma (acc, d_band + (uint64_t) ((TC_CHUNKS * TC_BAND_LBO) >> 4), d_ones, IDESC_H, 1);
+      if (ch == 2) {
+        tc_commit (bar (TCB_EMPTY0 + buf));
+        tc_commit (bar (TCB_DHF0 + buf));
       }
-      tc_commit (bar (TCB_EMPTY0 + buf));
-      tc_commit (bar (TCB_DHF0 + buf));
     };
     auto issue_v = [&] (int k) {
       tc_fence_after ();
-      const uint32_t vb = s_vb + (k % TC_VB_RING) * TC_VB_BYTES;
-#pragma unroll 1
+      const uint64_t vb = d_vb + (uint64_t) (((k % TC_VB_RING) * TC_VB_BYTES) >> 4);
+#pragma unroll
       for (int ch = 0; ch < 3; ch++) {
-        const uint32_t hs = s_hs + ch * TC_HS_BYTES;
-#pragma unroll 1
-        for (int s = 0; s < TC_N / 32 + 1; s++) {
-          const uint64_t a = s < TC_N / 32 ? tc_desc (hs + 2 * s * TC_HS_LBO, TC_HS_LBO, 128) : tc_desc (s_ones, TC_BAND_LBO, 128);
-          const uint64_t b = tc_desc (vb + 2 * s * TC_VB_LBO, TC_VB_LBO, 128);
-          tc_mma (tmem + TC2_DV_COL + ch * TC_VROWS, a, b, IDESC_V, s > 0);
-        }
+        const uint64_t hs = d_hs + (uint64_t) ((ch * TC_HS_BYTES) >> 4);
+        const uint32_t acc = tmem + TC2_DV_COL + ch * TC_VROWS;
+#pragma unroll
+        for (int s = 0; s < TC_N / 32; s++)
+          tc_mma (acc, hs + (uint64_t) ((2 * s * TC_HS_LBO) >> 4), vb + (uint64_t) ((2 * s * TC_VB_LBO) >> 4), IDESC_V, s > 0);
+        tc_mma (acc, d_ones, vb + (uint64_t) ((2 * (TC_N / 32) * TC_VB_LBO) >> 4), IDESC_V, 1);
       }
       tc_commit (bar (TCB_DVF));
     };
-    int nh = 0, nv = 0;
+    // The tensor pipe runs its MMAs in issue order, so the short V pass (consumers wait for it) is looked at between the
+    // three channel-sized bites of the long H pass instead of after all of it.
+    int nh = 0, hch = 0, nv = 0;                                  // hch: channels of H pass nh already issued
     uint32_t idle = 0;
     while (nv < my_tiles) {
       bool progressed = false;
+      if (nv < nh && tc_bar_test (bar (TCB_HSF), nv & 1)) { issue_v (nv); nv++; progressed = true; }
       if (nh < my_tiles && nh <= nv + 1) {
         const int buf = nh & 1, use = nh >> 1;
-        if (tc_bar_test (bar (TCB_FULL0 + buf), use & 1) && (use == 0 || tc_bar_test (bar (TCB_DHE0 + buf), (use - 1) & 1))) {
-          issue_h (nh); nh++; progressed = true;
+        if (hch > 0 || (tc_bar_test (bar (TCB_FULL0 + buf), use & 1) && (use == 0 || tc_bar_test (bar (TCB_DHE0 + buf), (use - 1) & 1)))) {
+          if (hch == 0) tc_fence_after ();
+          issue_h_ch (nh, hch);
+          if (++hch == 3) { hch = 0; nh++; }
+          progressed = true;
         }
       }
-      if (nv < nh && tc_bar_test (bar (TCB_HSF), nv & 1)) { issue_v (nv); nv++; progressed = true; }
       if (progressed) idle = 0;
       else if (++idle > (1u << 27)) __trap ();
     }
@@ -579,6 +603,7 @@ inline int prepare_l2tc (const L2tcTables & t, L2tcState * st)
   if ((rc = upload (&st->d_vx4, t.vx4.data (), t.vx4.size ())) != B200_OK) return rc;
   st->dev.band = st->d_band; st->dev.vband = st->d_vband; st->dev.hx4 = st->d_hx4; st->dev.vx4 = st->d_vx4;
   st->dev.strips = t.strips; st->dev.row_tiles = t.row_tiles;
+  st->dev.magic_rt = 0xffffffffu / (unsigned) t.row_tiles + 1u;
   st->ready = true;
   return B200_OK;
 }
