@@ -282,9 +282,10 @@ __device__ __forceinline__ void vcs_unpack_stage (const VcsDev & P, const uint8_
 // chroma rows are clamped (line 0 and the last line then see the same row twice and 3c + c reproduces the unfiltered
 // sample), the last odd pixel replicates (video_chroma_up_h2_cs_u8, video-chroma.c:687-699), columns left of the tile's
 // first staged word or right of the frame are simply not stored.
-template <bool MFIRST>
+// LAYOUT as in vcs_unpack_stage (0: packed pixels; 1 / 2: the byte planes of the n-tap kernels, matrix-last only).
+template <bool MFIRST, int LAYOUT = 0>
 __device__ __forceinline__ void vcs_unpack_fast_cs (const VcsDev & P, const uint8_t *__restrict__ in, int cxa, int cx1,
-    int ry0, int R, unsigned *S, int pitch)
+    int ry0, int R, unsigned *S, int pitch, int plane_words = 0)
 {
   const uint8_t *__restrict__ plane_y = in + P.off_y, *__restrict__ plane_c = in + P.off_c;
   const unsigned selU = P.u_index ? 0x7531u : 0x6420u, selV = P.u_index ? 0x6420u : 0x7531u;
@@ -342,6 +343,13 @@ __device__ __forceinline__ void vcs_unpack_fast_cs (const VcsDev & P, const uint
     }
     auto store4 = [&] (int row, int col, unsigned yw, unsigned u, unsigned v) {
       if (col < 0 || col + cxa >= cx1) return;                    // left of the tile's first staged word / right of its last column
+      if (LAYOUT != 0) {                                          // byte planes: one word of 4 pixels per channel
+        const int j = col >> 2;
+        unsigned *d = LAYOUT == 2 ? S + ((row >> 2) * 3 * pitch + j) * 4 + (row & 3) : S + row * pitch + j;
+        const int cstep = LAYOUT == 2 ? pitch * 4 : plane_words;
+        d[0] = yw; d[cstep] = u; d[2 * cstep] = v;
+        return;
+      }
       const unsigned yu01 = __byte_perm (yw, u, 0x5140), yu23 = __byte_perm (yw, u, 0x7362);
       uint4 px;
       px.x = __byte_perm (yu01, v, 0x4410);

@@ -33,6 +33,7 @@ struct NtapDev {
   int ntw_h, ntw_v;              // packed tap words per output column / row
   const int *h_packed, *v_packed;
   int alpha_opaque;
+  int std_pairs;                 // fast stage A (vcs_unpack_fast_cs) applies
 };
 
 constexpr int NTAP_THREADS = 256;
@@ -72,10 +73,14 @@ vcs_ntap_kernel (const VcsDev P, const NtapDev G, const VcsBatch frames)
   if (tid < th) vrow[tid] = P.v.offset[oy0 + tid] - (unsigned) ry0;
 
   // ---------------------------------------------------------------- A: unpack + chroma up-sample
-  vcs_unpack_worklist (P, ry0, R, ent, G.rows);
-  __syncthreads ();
-  vcs_unpack_stage<MFIRST, COSITED, 2> (P, plane_y, in, cxa, ng, ent, (int) ent[G.rows].x, (unsigned *) S4,
-      G.pitch, 0);
+  if (COSITED && !MFIRST && G.std_pairs) {                        // warp-uniform: a property of the plan
+    vcs_unpack_fast_cs<false, 2> (P, in, cxa, cx1, ry0, R, (unsigned *) S4, G.pitch, 0);
+  } else {
+    vcs_unpack_worklist (P, ry0, R, ent, G.rows);
+    __syncthreads ();
+    vcs_unpack_stage<MFIRST, COSITED, 2> (P, plane_y, in, cxa, ng, ent, (int) ent[G.rows].x, (unsigned *) S4,
+        G.pitch, 0);
+  }
   __syncthreads ();
 
   // ---------------------------------------------------------------- B: horizontal pass
@@ -225,9 +230,13 @@ vcs_ntap_vfirst_kernel (const VcsDev P, const NtapDev G, const VcsBatch frames)
     for (int i = tid; i < th * P.v.n_taps; i += NTAP_THREADS) TV[i] = (int) P.v.coef[(size_t) oy0 * P.v.n_taps + i];
   if (tid < th) vrow[tid] = P.v.offset[oy0 + tid] - (unsigned) ry0;
 
-  vcs_unpack_worklist (P, ry0, R, ent, G.rows);
-  __syncthreads ();
-  vcs_unpack_stage<MFIRST, COSITED, 1> (P, plane_y, in, cxa, ng, ent, (int) ent[G.rows].x, S, G.pitch, plane_words);
+  if (COSITED && !MFIRST && G.std_pairs) {
+    vcs_unpack_fast_cs<false, 1> (P, in, cxa, cx1, ry0, R, S, G.pitch, plane_words);
+  } else {
+    vcs_unpack_worklist (P, ry0, R, ent, G.rows);
+    __syncthreads ();
+    vcs_unpack_stage<MFIRST, COSITED, 1> (P, plane_y, in, cxa, ng, ent, (int) ent[G.rows].x, S, G.pitch, plane_words);
+  }
   __syncthreads ();
 
   // ---------------------------------------------------------------- B': vertical pass
@@ -377,6 +386,8 @@ inline int launch_ntap (const VcsDev & dev, const VcsPlan & p, const NtapState &
   g.tw = p.ntap_tw; g.th = p.ntap_th; g.rows = p.ntap_rows; g.pitch = p.ntap_pitch;
   g.ntw_h = p.ntw_h; g.ntw_v = p.ntw_v; g.h_packed = st.d_h; g.v_packed = st.d_v;
   g.alpha_opaque = p.ntap_alpha_opaque ? 1 : 0;
+  g.std_pairs = p.light_std_pairs ? 1 : 0;
+  for (int i = 0; i < n; i++) if (((uintptr_t) batch.in[i]) & 7) g.std_pairs = 0;     // the fast stage A loads 64 bits at a time
   dim3 grid ((p.out.width + g.tw - 1) / g.tw, (p.out.height + g.th - 1) / g.th, n);
   fn <<<grid, NTAP_THREADS, p.ntap_smem, stream>>> (dev, g, batch);
   B200_CUDA_TRY (cudaGetLastError ());

@@ -376,6 +376,20 @@ bool fast_layout_ok (const VcsPlan * p)
   return (int64_t) p->in.stride[1] * p->in.height < (1ll << 31);
 }
 
+// fast stage A of the light and n-tap kernels (vcs_unpack_fast_cs): NV12 / NV21, real chroma filtering, every line's
+// chroma_mode the standard one (all lines pulled in order), 64-bit loads possible (8-byte aligned rows; a last item may
+// read up to 7 bytes past the width: inside the row's stride)
+void std_pairs_check (VcsPlan * p)
+{
+  bool std_pairs = !p->planar && !p->chroma_nearest && p->v_pairs && !p->in_422_444 && !p->rgb_in && !p->yuv_out && !p->planes_mode &&
+      !(p->in.stride[0] & 7) && !(p->in.stride[1] & 7) && !(p->in.offset[0] & 7) && !(p->in.offset[1] & 7) &&
+      p->in.stride[0] >= ((p->in.width + 7) & ~7) && p->in.stride[1] >= ((p->in.width + 7) & ~7) && !(p->in.height & 1) &&
+      (int) p->chroma_mode.size () >= p->in.height;
+  for (int y = 0; std_pairs && y < p->in.height; y++)
+    if (p->chroma_mode[y] != (y == 0 ? 0 : ((y & 1) ? 1 : 2))) std_pairs = false;
+  p->light_std_pairs = std_pairs;
+}
+
 void light_geometry (VcsPlan * p)
 {
   p->light_ok = false;
@@ -406,16 +420,7 @@ void light_geometry (VcsPlan * p)
     if (total <= (env_th ? 200 : 96) * 1024) {
       p->light_ok = true; p->light_tw = tw; p->light_th = th; p->light_rows = max_rows; p->light_cp = cp;
       p->light_smem = (int) total;
-      // fast stage A: NV12 / NV21, real chroma filtering, every line's chroma_mode the standard one (all lines pulled in
-      // order), 64-bit loads possible (8-byte aligned rows; a last item may read up to 7 bytes past the width: inside the
-      // row's stride, or - last row - inside the frame because a chroma plane follows the luma plane and the chroma rows
-      // themselves are as wide as the luma rows)
-      bool std_pairs = !p->planar && !p->chroma_nearest && p->v_pairs && !p->in_422_444 && !p->rgb_in &&
-          !(p->in.stride[0] & 7) && !(p->in.stride[1] & 7) && !(p->in.offset[0] & 7) && !(p->in.offset[1] & 7) &&
-          p->in.stride[0] >= ((p->in.width + 7) & ~7) && p->in.stride[1] >= ((p->in.width + 7) & ~7) && !(p->in.height & 1);
-      for (int y = 0; std_pairs && y < p->in.height; y++)
-        if (p->chroma_mode[y] != (y == 0 ? 0 : ((y & 1) ? 1 : 2))) std_pairs = false;
-      p->light_std_pairs = std_pairs;
+
       return;
     }
   }
@@ -965,6 +970,7 @@ static int build_inner_plan (const b200_video_info * in, const b200_video_info *
     return B200_OK;
   }
   tile_geometry (p);
+  std_pairs_check (p);
   light_geometry (p);
   ntap_geometry (p);
   validate_fast_geometry (p);

@@ -203,6 +203,8 @@ def test_odd_height_without_vertical_scaler(emu):
     ("NV21", "RGBA", (166, 256, 490, 272), 1, 2), ("NV12", "BGRA", (162, 20, 81, 10), 1, 2),        # width % 8 != 0: last odd pixel
     ("NV12", "BGRA", (96, 54, 64, 36), 3, 3), ("I420", "RGBA", (64, 48, 96, 72), 9, 3), ("NV21", "ABGR", (120, 66, 40, 22), 5, 3),
     ("NV12", "BGRA", (100, 60, 150, 30), 3, 3),                                                     # n-tap, both pass orders
+    ("NV12", "BGRA", (648, 360, 427, 240), 3, 3), ("NV21", "RGBA", (166, 256, 100, 150), 3, 3),     # n-tap, fast stage A: several
+    ("NV12", "xRGB", (200, 120, 300, 90), 9, 3), ("NV12", "BGRA", (264, 40, 100, 33), 5, 3),        # tiles, edges, odd widths, v-first
 ], ids=lambda c: "%s-%s-%dx%d-%dx%d-m%d-v%d" % (c[0], c[1], *c[2], c[3], c[4]))
 def test_fast_kernels(emu, case):
     """vcs_lanczos2_kernel (warp shuffles), vcs_light_kernel (ballot work lists, 16-bit-lane lerps) and the n-tap kernels
