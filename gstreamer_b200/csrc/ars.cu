@@ -657,7 +657,7 @@ __device__ __forceinline__ void ars_cp16 (void *dst_smem, const void *src, bool 
 }
 
 __global__ void __launch_bounds__ (ARS_PIPE_THREADS, 1)
-ars_pipe_kernel (const ArsLaunch L, const ArsTile Tl, int n_fb, int n_cb)
+ars_pipe_kernel_v1 (const ArsLaunch L, const ArsTile Tl, int n_fb, int n_cb)
 {
   extern __shared__ __align__ (16) float sm[];
   constexpr int RQ = ARS_RQ, NO = ARS_PIPE_NO, CB = ARS_PIPE_CB, NQ = NO / RQ;
@@ -772,6 +772,228 @@ ars_pipe_kernel (const ArsLaunch L, const ArsTile Tl, int n_fb, int n_cb)
       }
     }
     __syncthreads ();                                             // buffer b and its positions are free for tile t + 2
+  }
+}
+
+// ---- ars_pipe_kernel (second form): bulk copies + mbarriers, no CTA-wide barrier in the steady state ----------------------
+// Profile of the cp.async form above (profiles/r02_ars_pipe_ncu.txt): 3580 instructions per thread and tile of which 2560
+// are the FIR; ~280 were cp.async issue + its address arithmetic (4800 16-byte copies per tile), the two __syncthreads per
+// tile cost 0.47 stalled warps per issue, and the stage pointers selected from a two-entry array made the inner loop's
+// loads generic (LD.E.128) instead of LDS.128.  Here a window row (CB channels of one frame, 512 contiguous bytes) and a
+// tap row (one 4-output group, nch * 64 bytes) each travel as ONE cp.async.bulk issued by one lane (166 per tile instead
+// of 6080 cp.async), completion is counted by an mbarrier per stage (full[2]), and the stage is handed back through a
+// second one (empty[2]) on which only the four producing warps ever wait - the other twelve go from tile to tile without
+// meeting anybody.  Frames outside the stream (silence, start-up) are zero rows written by the producing lane itself.
+// Arithmetic, its order and the staged layout are unchanged: bit-identical output.
+struct alignas (16) ArsBar { unsigned long long w[2]; };         // w[0]: the mbarrier object (the emulated build uses all 16 bytes)
+constexpr int ARS_PIPE_PROD = 4;                                  // producing warps (one per scheduler)
+
+#ifdef B200_CUDA_EMU
+}  // namespace b200 (reopened below)
+#include <mutex>
+#include <thread>
+namespace b200 {
+static std::mutex g_emu_bar_mu;
+struct EmuBar { int count, pending, tx, phase; };
+static_assert (sizeof (EmuBar) == sizeof (ArsBar), "emulated barrier must fit");
+static inline void emu_bar_check (EmuBar *e) { if (e->pending == 0 && e->tx == 0) { e->phase ^= 1; e->pending = e->count; } }
+#endif
+
+__device__ __forceinline__ void ars_bar_init (ArsBar *bar, unsigned count)
+{
+#ifndef B200_CUDA_EMU
+  asm volatile ("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r" ((unsigned) __cvta_generic_to_shared (bar)), "r" (count) : "memory");
+#else
+  EmuBar *e = (EmuBar *) bar; e->count = e->pending = (int) count; e->tx = 0; e->phase = 0;
+#endif
+}
+__device__ __forceinline__ void ars_bar_arrive (ArsBar *bar)
+{
+#ifndef B200_CUDA_EMU
+  asm volatile ("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r" ((unsigned) __cvta_generic_to_shared (bar)) : "memory");
+#else
+  std::lock_guard<std::mutex> l (g_emu_bar_mu); EmuBar *e = (EmuBar *) bar; e->pending--; emu_bar_check (e);
+#endif
+}
+__device__ __forceinline__ void ars_bar_arrive_tx (ArsBar *bar, unsigned bytes)
+{
+#ifndef B200_CUDA_EMU
+  asm volatile ("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r" ((unsigned) __cvta_generic_to_shared (bar)), "r" (bytes) : "memory");
+#else
+  std::lock_guard<std::mutex> l (g_emu_bar_mu); EmuBar *e = (EmuBar *) bar; e->tx += (int) bytes; e->pending--; emu_bar_check (e);
+#endif
+}
+// waits until the phase of the given parity has completed; a lost arrival must fail loudly, not hang the device
+__device__ __forceinline__ void ars_bar_wait (ArsBar *bar, unsigned parity)
+{
+#ifndef B200_CUDA_EMU
+  const unsigned a = (unsigned) __cvta_generic_to_shared (bar);
+  unsigned spins = 0;
+  for (;;) {
+    unsigned ok;
+    asm volatile ("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r" (ok) : "r" (a), "r" (parity) : "memory");
+    if (ok) break;
+    if (++spins > (1u << 22)) __trap ();
+  }
+#else
+  for (;;) {
+    { std::lock_guard<std::mutex> l (g_emu_bar_mu); if ((unsigned) ((EmuBar *) bar)->phase != parity) break; }
+    std::this_thread::yield ();
+  }
+#endif
+}
+// one contiguous global -> shared copy (16-byte aligned, size a multiple of 16) whose bytes count on `bar`
+__device__ __forceinline__ void ars_bulk_g2s (void *dst_smem, const void *src, unsigned bytes, ArsBar *bar)
+{
+#ifndef B200_CUDA_EMU
+  asm volatile ("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      :: "r" ((unsigned) __cvta_generic_to_shared (dst_smem)), "l" (src), "r" (bytes), "r" ((unsigned) __cvta_generic_to_shared (bar)) : "memory");
+#else
+  memcpy (dst_smem, src, bytes);
+  std::lock_guard<std::mutex> l (g_emu_bar_mu); EmuBar *e = (EmuBar *) bar; e->tx -= (int) bytes; emu_bar_check (e);
+#endif
+}
+__device__ __forceinline__ void ars_warp_sync ()
+{
+#ifndef B200_CUDA_EMU
+  __syncwarp ();
+#else
+  (void) __shfl_sync (0xffffffffu, 0u, 0);                        // the emulated shuffle is a warp barrier
+#endif
+}
+
+__global__ void __launch_bounds__ (ARS_PIPE_THREADS, 1)
+ars_pipe_kernel (const ArsLaunch L, const ArsTile Tl, int n_fb, int n_cb)
+{
+  extern __shared__ __align__ (16) float sm[];
+  constexpr int RQ = ARS_RQ, NO = ARS_PIPE_NO, CB = ARS_PIPE_CB, NQ = NO / RQ, NW = ARS_PIPE_THREADS / 32;
+  const int row = Tl.nch * RQ;                                    // float4 per output group in the tap table
+  const unsigned qt_floats = (unsigned) NQ * row * 4, stage_floats = qt_floats + (unsigned) Tl.win * CB;
+  __shared__ ArsBar s_full[2], s_empty[2];
+  __shared__ int s_rel[2][NO];
+  const int lane = threadIdx.x & 31;
+  const int warp = __shfl_sync (0xffffffffu, (int) (threadIdx.x >> 5), 0);
+  const int n_tiles = n_fb * n_cb;
+  if (threadIdx.x == 0) {
+    ars_bar_init (&s_full[0], ARS_PIPE_PROD); ars_bar_init (&s_full[1], ARS_PIPE_PROD);
+    ars_bar_init (&s_empty[0], NW); ars_bar_init (&s_empty[1], NW);
+#ifndef B200_CUDA_EMU
+    asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
+  }
+  __syncthreads ();
+
+  // producing warps: positions of tile t's outputs, one bulk copy per tap row and per window row into stage b
+  auto produce = [&] (int t, int b) {
+    float *stage = sm + (size_t) b * stage_floats;
+    float4 *qt = (float4 *) stage;
+    float *xin = stage + qt_floats;
+    const int fb = t / n_cb, c_base = (t - fb * n_cb) * CB;
+    const long long o0 = (long long) fb * NO;
+    const int n_out = (int) min ((long long) NO, L.out_frames - o0);
+    long long f0; int ph0;
+    ars_position (L, o0, f0, ph0);
+    f0 &= ~3LL;
+#ifndef B200_CUDA_EMU
+    asm volatile ("fence.proxy.async.shared::cta;" ::: "memory");  // zero rows written two tiles ago vs this tile's bulk writes
+#endif
+    unsigned tx = 0;
+    if (lane < NO / ARS_PIPE_PROD) {
+      const int j = warp * (NO / ARS_PIPE_PROD) + lane;
+      long long idx; int phase;
+      ars_position (L, o0 + min (j, n_out - 1), idx, phase);
+      const int rel = (int) (idx - f0);
+      s_rel[b][j] = rel;
+      if ((j & (RQ - 1)) == 0) {
+        const float4 *src = Tl.qtab + ((size_t) (rel & 3) * L.out_step + phase) * row;
+        ars_bulk_g2s (qt + (size_t) (j / RQ) * row, src, (unsigned) row * 16u, &s_full[b]);
+        tx += (unsigned) row * 16u;
+      }
+    }
+    for (int fr = warp * 32 + lane; fr < Tl.win; fr += 32 * ARS_PIPE_PROD) {
+      const long long f = f0 + fr;
+      const float *src = nullptr;
+      if (f < L.hist_frames) src = L.hist + f * L.channels;
+      else if (f < L.avail && L.in) src = L.in + (f - L.hist_frames) * L.channels;
+      float *dst = xin + (size_t) fr * CB;
+      if (src) { ars_bulk_g2s (dst, src + c_base, CB * 4u, &s_full[b]); tx += CB * 4u; }
+      else {
+#pragma unroll 4
+        for (int i = 0; i < CB / 4; i++) ((float4 *) dst)[i] = make_float4 (0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) tx += __shfl_down_sync (0xffffffffu, tx, d);
+    ars_warp_sync ();                                             // the lanes' s_rel entries and zero rows before lane 0's release
+    if (lane == 0) ars_bar_arrive_tx (&s_full[b], tx);
+  };
+
+  int t = blockIdx.x, k = 0;
+  if (warp < ARS_PIPE_PROD && t < n_tiles) produce (t, 0);
+  for (; t < n_tiles; t += gridDim.x, k++) {
+    const int b = k & 1, tn = t + gridDim.x;
+    if (warp < ARS_PIPE_PROD && tn < n_tiles) {
+      if (k >= 1) ars_bar_wait (&s_empty[b ^ 1], (unsigned) ((k - 1) >> 1) & 1u);   // every warp is done with tile k - 1
+      produce (tn, b ^ 1);
+    }
+    ars_bar_wait (&s_full[b], (unsigned) (k >> 1) & 1u);
+
+    const float4 *qt = (const float4 *) (sm + (size_t) b * stage_floats);
+    const float *xin = sm + (size_t) b * stage_floats + qt_floats;
+    const int fb = t / n_cb;
+    const long long o0 = (long long) fb * NO;
+    const int n_out = (int) min ((long long) NO, L.out_frames - o0);
+    const int nq = (n_out + RQ - 1) / RQ;
+    const int c = (t - fb * n_cb) * CB + 4 * lane;
+    for (int q = warp; q < nq; q += NW) {
+      float acc[4][RQ][4];
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+#pragma unroll
+        for (int r = 0; r < RQ; r++)
+#pragma unroll
+          for (int kk = 0; kk < 4; kk++) acc[u][r][kk] = 0.f;
+      const int s_min = s_rel[b][q * RQ] & ~3;
+      const int s_max = (s_rel[b][min (q * RQ + RQ - 1, n_out - 1)] + L.n_taps + 3) & ~3;
+      const int nch = (s_max - s_min) >> 2;
+      const float *xp = xin + s_min * CB + 4 * lane;
+      const float4 *tp = qt + (size_t) q * row;
+#pragma unroll 2
+      for (int ch = 0; ch < nch; ch++, xp += 4 * CB, tp += RQ) {
+        float x[4][4];
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) {
+          const float4 v = *(const float4 *) (xp + kk * CB);
+          x[0][kk] = v.x; x[1][kk] = v.y; x[2][kk] = v.z; x[3][kk] = v.w;
+        }
+#pragma unroll
+        for (int r = 0; r < RQ; r++) {
+          const float4 tq = tp[r];
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            acc[u][r][0] = __fadd_rn (acc[u][r][0], __fmul_rn (x[u][0], tq.x));
+            acc[u][r][1] = __fadd_rn (acc[u][r][1], __fmul_rn (x[u][1], tq.y));
+            acc[u][r][2] = __fadd_rn (acc[u][r][2], __fmul_rn (x[u][2], tq.z));
+            acc[u][r][3] = __fadd_rn (acc[u][r][3], __fmul_rn (x[u][3], tq.w));
+          }
+        }
+      }
+      float *op = L.out + (size_t) (o0 + q * RQ) * L.channels + c;
+#pragma unroll
+      for (int r = 0; r < RQ; r++) {
+        if (q * RQ + r < n_out) {
+          float4 o;
+          o.x = __fadd_rn (__fadd_rn (acc[0][r][0], acc[0][r][2]), __fadd_rn (acc[0][r][1], acc[0][r][3]));
+          o.y = __fadd_rn (__fadd_rn (acc[1][r][0], acc[1][r][2]), __fadd_rn (acc[1][r][1], acc[1][r][3]));
+          o.z = __fadd_rn (__fadd_rn (acc[2][r][0], acc[2][r][2]), __fadd_rn (acc[2][r][1], acc[2][r][3]));
+          o.w = __fadd_rn (__fadd_rn (acc[3][r][0], acc[3][r][2]), __fadd_rn (acc[3][r][1], acc[3][r][3]));
+          *(float4 *) (op + (size_t) r * L.channels) = o;
+        }
+      }
+    }
+    ars_warp_sync ();
+    if (lane == 0) ars_bar_arrive (&s_empty[b]);                  // this warp no longer reads stage b
   }
 }
 
@@ -1307,6 +1529,7 @@ int b200_ars_create (const b200_ars_config * cfg, int device, b200_ars ** handle
     }
     cudaFuncSetAttribute (ars_full_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     if ((st = allow_max_dyn_smem (ars_pipe_kernel)) != B200_OK) { b200_ars_destroy (h); return st; }
+    if ((st = allow_max_dyn_smem (ars_pipe_kernel_v1)) != B200_OK) { b200_ars_destroy (h); return st; }
     cudaFuncSetAttribute (ars_tile_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ARS_TILE_SMEM);
     cudaFuncSetAttribute (ars_tile_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ARS_TILE_SMEM);
     cudaFuncSetAttribute (ars_tile_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ARS_TILE_SMEM);
@@ -1573,8 +1796,11 @@ int b200_ars_process (b200_ars * h, const void *in_v, size_t in_frames, void *ou
       if (smem_pipe + 2048 <= (size_t) optin) {
         L.no = ARS_PIPE_NO;
         const int n_fb = (int) ((out_frames + ARS_PIPE_NO - 1) / ARS_PIPE_NO), n_cb = p.channels / ARS_PIPE_CB;
-        const int grid = (int) std::min ((long long) n_fb * n_cb, (long long) sm_count (h->device));
-        ars_pipe_kernel <<<grid, ARS_PIPE_THREADS, smem_pipe, stream>>> (L, tp, n_fb, n_cb);
+        int grid = (int) std::min ((long long) n_fb * n_cb, (long long) sm_count (h->device));
+        { const char *e = getenv ("B200_ARS_GRID"); if (e && atoi (e) > 0) grid = std::min (grid, atoi (e)); }   // tuning / test knob: persistent CTAs
+        static const bool v1 = getenv ("B200_ARS_PIPE_V1") != nullptr;   // A/B knob: the cp.async form
+        if (v1) ars_pipe_kernel_v1 <<<grid, ARS_PIPE_THREADS, smem_pipe, stream>>> (L, tp, n_fb, n_cb);
+        else ars_pipe_kernel <<<grid, ARS_PIPE_THREADS, smem_pipe, stream>>> (L, tp, n_fb, n_cb);
         piped = true;
       }
     }

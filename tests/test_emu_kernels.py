@@ -456,6 +456,41 @@ def test_audio_kernels(emu, fmt, opts, monkeypatch):
             o.oracle_ars_free(ho)
 
 
+def test_audio_pipeline_many_tiles_per_cta(emu, monkeypatch):
+    """ars_pipe_kernel's stage hand-over (full / empty barriers, two stages): B200_ARS_GRID=2 makes each persistent CTA walk
+    a dozen tiles, with start-up zeros, a silent call (no input pointer) and a last partial tile"""
+    from gstreamer_b200 import _lib
+    monkeypatch.setenv("B200_ARS_GRID", "2")
+    ofmt, gfmt, dt, _ = ob.AUDIO_FORMATS["F32"]
+    o = ob.oracle()
+    for (a, b, ch, grid) in [(48000, 44100, 256, "2"), (44100, 48000, 128, "3"), (48000, 44100, 128, "1")]:
+        monkeypatch.setenv("B200_ARS_GRID", grid)
+        ho = o.oracle_ars_new_fmt(a, b, ch, 4, ofmt)
+        cfg = _lib.ArsConfigC()
+        cfg.in_rate, cfg.out_rate, cfg.channels, cfg.quality, cfg.format = a, b, ch, 4, gfmt
+        h = C.c_void_p()
+        assert emu.b200_ars_create(C.byref(cfg), 0, C.byref(h)) == 0
+        rng = np.random.default_rng(ch + a)
+        try:
+            for n in [700, 333, None, 90]:
+                x = None
+                if n is None:
+                    n = 200
+                else:
+                    x = ob.audio_test_signal(rng, n, ch, "F32")
+                cap = int(n * b / a) + 64
+                want = np.zeros((cap, ch), dtype=dt)
+                nw = o.oracle_ars_process_any(ho, x.ctypes.data if x is not None else None, n, want.ctypes.data, cap)
+                got = np.full((cap, ch), 7, dtype=dt)
+                ng = C.c_size_t()
+                assert emu.b200_ars_process(h, x.ctypes.data if x is not None else None, n, got.ctypes.data, cap, C.byref(ng), None) == 0
+                assert ng.value == nw and got[:nw].tobytes() == want[:nw].tobytes(), (a, b, ch, n)
+                assert (got[nw:] == 7).all()
+        finally:
+            emu.b200_ars_destroy(h)
+            o.oracle_ars_free(ho)
+
+
 # ---- 5. the randomised three-way runs (tools/emu_fuzz*.py) keep working: a few seconds of each -------------------------
 @pytest.mark.parametrize("tool", ["emu_fuzz.py", "emu_fuzz_audio.py", "emu_fuzz_comp.py"])
 def test_random_run_tools(emu, tool):
