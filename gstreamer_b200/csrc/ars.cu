@@ -17,6 +17,9 @@
 // Tap rows are staged per CTA in shared memory pre-shifted to the window alignment of each
 // output so that all tap loads are aligned 128-bit broadcasts.
 #include "common.h"
+#ifndef B200_CUDA_EMU
+#include <cuda.h>            // CUtensorMap types only: the encoder is fetched through cudaGetDriverEntryPoint
+#endif
 
 #include <math.h>
 #include <stdlib.h>
@@ -854,6 +857,18 @@ __device__ __forceinline__ void ars_bulk_g2s (void *dst_smem, const void *src, u
   std::lock_guard<std::mutex> l (g_emu_bar_mu); EmuBar *e = (EmuBar *) bar; e->tx -= (int) bytes; emu_bar_check (e);
 #endif
 }
+// CUtensorMap as an opaque 128-byte kernel parameter (the emulated build has no driver types)
+struct alignas (64) ArsTensorMap { unsigned long long opaque[16]; };
+__device__ __forceinline__ void ars_tensor_g2s (void *dst_smem, const ArsTensorMap *tm, int c0, int c1, ArsBar *bar)
+{
+#ifndef B200_CUDA_EMU
+  asm volatile ("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      :: "r" ((unsigned) __cvta_generic_to_shared (dst_smem)), "l" (tm), "r" (c0), "r" (c1),
+         "r" ((unsigned) __cvta_generic_to_shared (bar)) : "memory");
+#else
+  (void) dst_smem; (void) tm; (void) c0; (void) c1; (void) bar;   // never taken: the emulated launch passes use_tm = 0
+#endif
+}
 __device__ __forceinline__ void ars_warp_sync ()
 {
 #ifndef B200_CUDA_EMU
@@ -864,9 +879,9 @@ __device__ __forceinline__ void ars_warp_sync ()
 }
 
 __global__ void __launch_bounds__ (ARS_PIPE_THREADS, 1)
-ars_pipe_kernel (const ArsLaunch L, const ArsTile Tl, int n_fb, int n_cb)
+ars_pipe_kernel (const ArsLaunch L, const ArsTile Tl, int n_fb, int n_cb, const __grid_constant__ ArsTensorMap tm_in, int use_tm)
 {
-  extern __shared__ __align__ (16) float sm[];
+  extern __shared__ __align__ (128) float smp[];
   constexpr int RQ = ARS_RQ, NO = ARS_PIPE_NO, CB = ARS_PIPE_CB, NQ = NO / RQ, NW = ARS_PIPE_THREADS / 32;
   const int row = Tl.nch * RQ;                                    // float4 per output group in the tap table
   const unsigned qt_floats = (unsigned) NQ * row * 4, stage_floats = qt_floats + (unsigned) Tl.win * CB;
@@ -886,7 +901,7 @@ ars_pipe_kernel (const ArsLaunch L, const ArsTile Tl, int n_fb, int n_cb)
 
   // producing warps: positions of tile t's outputs, one bulk copy per tap row and per window row into stage b
   auto produce = [&] (int t, int b) {
-    float *stage = sm + (size_t) b * stage_floats;
+    float *stage = smp + (size_t) b * stage_floats;
     float4 *qt = (float4 *) stage;
     float *xin = stage + qt_floats;
     const int fb = t / n_cb, c_base = (t - fb * n_cb) * CB;
@@ -911,7 +926,18 @@ ars_pipe_kernel (const ArsLaunch L, const ArsTile Tl, int n_fb, int n_cb)
         tx += (unsigned) row * 16u;
       }
     }
-    for (int fr = warp * 32 + lane; fr < Tl.win; fr += 32 * ARS_PIPE_PROD) {
+    // a window that lies in the caller's input (every tile but the first few) is ONE tensor copy: box = CB channels x win
+    // frames, rows past the end of the input arrive as zeros (out-of-bounds fill) like the missing frames of the row path.
+    // (Divergent lanes issuing a bulk copy each are serialised through the uniform datapath: the row path below costs the
+    // producing warps ~40 copies each and made them the tile's stragglers - measured 1.77 ms against 1.72 for cp.async.)
+    const bool tensor = use_tm && f0 >= L.hist_frames;
+    if (tensor) {
+      if (warp == 0 && lane == 0) {
+        ars_tensor_g2s (xin, &tm_in, c_base, (int) (f0 - L.hist_frames), &s_full[b]);
+        tx += (unsigned) Tl.win * CB * 4u;
+      }
+    } else
+    for (int fr = warp + ARS_PIPE_PROD * lane; fr < Tl.win; fr += 32 * ARS_PIPE_PROD) {
       const long long f = f0 + fr;
       const float *src = nullptr;
       if (f < L.hist_frames) src = L.hist + f * L.channels;
@@ -939,8 +965,8 @@ ars_pipe_kernel (const ArsLaunch L, const ArsTile Tl, int n_fb, int n_cb)
     }
     ars_bar_wait (&s_full[b], (unsigned) (k >> 1) & 1u);
 
-    const float4 *qt = (const float4 *) (sm + (size_t) b * stage_floats);
-    const float *xin = sm + (size_t) b * stage_floats + qt_floats;
+    const float4 *qt = (const float4 *) (smp + (size_t) b * stage_floats);
+    const float *xin = smp + (size_t) b * stage_floats + qt_floats;
     const int fb = t / n_cb;
     const long long o0 = (long long) fb * NO;
     const int n_out = (int) min ((long long) NO, L.out_frames - o0);
@@ -1416,6 +1442,35 @@ __global__ void ars_history_kernel (float *dst, const float *hist, const float *
 
 using namespace b200;
 
+// Tensor map of the caller's input for the pipelined kernel's window copies: 2-D [frames][channels] F32, box = cb channels x
+// win frames, out-of-bounds rows read as zeros.  Encoded on the host per call (the input pointer changes with every buffer;
+// cuTensorMapEncodeTiled is pure CPU work) through the driver entry point - the library does not link libcuda.
+// Returns 1 when the map is usable.
+#ifndef B200_CUDA_EMU
+static_assert (sizeof (ArsTensorMap) == sizeof (CUtensorMap), "CUtensorMap is 128 bytes");
+typedef CUresult (*ars_encode_fn) (CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int ars_encode_window_map (ArsTensorMap *tm, const float *in, unsigned long long in_frames, int channels, int cb, int win)
+{
+  static ars_encode_fn fn = [] () -> ars_encode_fn {
+    void *f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint ("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+    return (ars_encode_fn) f;
+  } ();
+  static const bool off = getenv ("B200_ARS_NO_TENSORMAP") != nullptr;       // A/B knob: row-wise bulk copies only
+  if (!fn || off || !in || in_frames == 0 || win > 256 || cb > 256 || (((uintptr_t) in) & 15) || (channels & 3)) return 0;
+  const cuuint64_t gdim[2] = {(cuuint64_t) channels, (cuuint64_t) in_frames};
+  const cuuint64_t gstride[1] = {(cuuint64_t) channels * sizeof (float)};
+  const cuuint32_t box[2] = {(cuuint32_t) cb, (cuuint32_t) win}, estr[2] = {1, 1};
+  const CUresult r = fn ((CUtensorMap *) tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *) in, gdim, gstride, box, estr,
+      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+#else
+static int ars_encode_window_map (ArsTensorMap *, const float *, unsigned long long, int, int, int) { return 0; }
+#endif
+
 struct b200_ars {
   ArsPlan plan;
   int device = -1;
@@ -1800,7 +1855,11 @@ int b200_ars_process (b200_ars * h, const void *in_v, size_t in_frames, void *ou
         { const char *e = getenv ("B200_ARS_GRID"); if (e && atoi (e) > 0) grid = std::min (grid, atoi (e)); }   // tuning / test knob: persistent CTAs
         static const bool v1 = getenv ("B200_ARS_PIPE_V1") != nullptr;   // A/B knob: the cp.async form
         if (v1) ars_pipe_kernel_v1 <<<grid, ARS_PIPE_THREADS, smem_pipe, stream>>> (L, tp, n_fb, n_cb);
-        else ars_pipe_kernel <<<grid, ARS_PIPE_THREADS, smem_pipe, stream>>> (L, tp, n_fb, n_cb);
+        else {
+          ArsTensorMap tm = ArsTensorMap ();
+          const int use_tm = ars_encode_window_map (&tm, L.in, (unsigned long long) in_frames, p.channels, ARS_PIPE_CB, tp.win);
+          ars_pipe_kernel <<<grid, ARS_PIPE_THREADS, smem_pipe, stream>>> (L, tp, n_fb, n_cb, tm, use_tm);
+        }
         piped = true;
       }
     }

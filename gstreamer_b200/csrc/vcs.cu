@@ -9,6 +9,7 @@
 #include "vcs_device.h"
 #include "vcs_kernels.cuh"
 #include "vcs_lanczos2.cuh"
+#include "vcs_lanczos2_v2.cuh"
 #include "vcs_l2mma.cuh"
 #ifndef B200_CUDA_EMU
 #include "vcs_l2tc.cuh"          // tcgen05 / TMEM: no host emulation
@@ -42,6 +43,8 @@ struct b200_vcs {
   int slot_frames = 0;            // frames each slot holds (one kernel launch per slot-full)
   Lanczos2Tables l2_tables;
   Lanczos2State l2;
+  Lanczos2V2Tables l2v2_tables;      // second form of the headline kernel (vcs_lanczos2_v2.cuh) where the plan allows it
+  Lanczos2V2State l2v2;
   NtapState ntap;
   L2mmaTables mma_tables;         // experimental tensor-path variant of the 2:1 kernel (variant 6, opt-in)
   L2mmaState mma;
@@ -118,8 +121,10 @@ int launch_convert (b200_vcs * h, int n, const VcsBatch & batch, cudaStream_t st
     if (p.lanczos2_ok) return launch_lanczos2 (h->dev, h->l2, batch, n, stream);
   }
 #endif
-  if (h->variant == 1 && p.lanczos2_ok)
+  if (h->variant == 1 && p.lanczos2_ok) {
+    if (h->l2v2.ready && h->l2.x4) return launch_lanczos2_v2 (h->dev, h->l2, h->l2v2, batch, n, stream);
     return launch_lanczos2 (h->dev, h->l2, batch, n, stream);
+  }
   if (h->variant == 2 && p.light_ok) {
     // 32-bit plane loads: the frame itself must be word aligned (device allocations always are)
     bool aligned = true;
@@ -344,6 +349,7 @@ int b200_vcs_create (const b200_video_info * in, const b200_video_info * out,
   if (!h->plan.yuv_out && !h->plan.in_422_444) {
     h->l2_tables = build_lanczos2_tables (h->plan);
     h->plan.lanczos2_ok = h->l2_tables.ok;
+    h->l2v2_tables = build_lanczos2_v2_tables (h->plan, h->l2_tables);
     h->mma_tables = build_l2mma_tables (h->plan);
 #ifndef B200_CUDA_EMU
     h->tc_tables = build_l2tc_tables (h->plan, h->l2_tables);
@@ -417,6 +423,9 @@ int b200_vcs_create (const b200_video_info * in, const b200_video_info * out,
       st = prepare_lanczos2 (h->l2_tables, h->dev, &h->l2);
       if (st != B200_OK) { b200_vcs_destroy (h); return st; }
       h->variant = 1;
+      if (h->l2v2_tables.ok && !getenv ("B200_L2_V1")) {            // tuning knob: B200_L2_V1 keeps the first form
+        if ((st = prepare_lanczos2_v2 (h->l2v2_tables, &h->l2v2)) != B200_OK) { b200_vcs_destroy (h); return st; }
+      }
 #ifndef B200_CUDA_EMU
       if ((st = prepare_l2tc (h->tc_tables, &h->tc)) != B200_OK) { b200_vcs_destroy (h); return st; }
       { const char *e = getenv ("B200_L2_TC"); if (e && e[0] == '1' && h->tc.ready) h->variant = 7; }   // tuning knob
@@ -444,7 +453,7 @@ void b200_vcs_destroy (b200_vcs * h)
     cudaFree (h->d_hoff); cudaFree (h->d_voff); cudaFree (h->d_hcoef); cudaFree (h->d_vcoef);
     cudaFree (h->d_hsum); cudaFree (h->d_vsum); cudaFree (h->d_cmode);
     cudaFree (h->l2.d_htab); cudaFree (h->l2.d_vtab); cudaFree (h->ntap.d_h); cudaFree (h->ntap.d_v);
-    cudaFree (h->l2.d_htab4); cudaFree (h->l2.d_vtab4); cudaFree (h->l2.d_v4);
+    cudaFree (h->l2.d_htab4); cudaFree (h->l2.d_vtab4); cudaFree (h->l2.d_v4); cudaFree (h->l2v2.d_vkind);
     cudaFree (h->mma.d_bh); cudaFree (h->mma.d_bv); cudaFree (h->mma.d_h4); cudaFree (h->mma.d_v4);
 #ifndef B200_CUDA_EMU
     cudaFree (h->tc.d_band); cudaFree (h->tc.d_vband); cudaFree (h->tc.d_hx4); cudaFree (h->tc.d_vx4);

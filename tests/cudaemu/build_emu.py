@@ -49,7 +49,7 @@ def patch(text):
         assert len(parts) == 4, cfg
         return f"b200emu::launch ({parts[0]}, {parts[1]}, {parts[2]}, [&] {{ {name} ({args}); }});"
     text, n = LAUNCH.subn(repl, text)
-    text = re.sub(r"extern __shared__ __align__ \(16\) (\w+) (\w+)\[\];", r"\1 *\2 = (\1 *) b200emu::dyn_smem;", text)
+    text = re.sub(r"extern __shared__ __align__ \((?:16|128)\) (\w+) (\w+)\[\];", r"\1 *\2 = (\1 *) b200emu::dyn_smem;", text)
     text = re.sub(r"(^|\n)(\s*)__shared__ ", r"\1\2static ", text)
     return text, n
 

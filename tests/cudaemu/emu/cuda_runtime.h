@@ -23,6 +23,7 @@
 #define __host__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
+#define __grid_constant__
 #define __align__(n) alignas (n)
 
 struct uint3_emu { unsigned x, y, z; };
