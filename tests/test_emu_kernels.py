@@ -296,6 +296,35 @@ def test_lanczos2_x4_variant(emu, size, monkeypatch):
         check(out, expected(fi, fo, size, method, frame, site=2), f"{fi}->{fo} m{method}")
 
 
+@pytest.mark.parametrize("size", [(512, 248, 256, 124), (752, 376, 376, 188)], ids=lambda s: "%dx%d-%dx%d" % s)
+def test_lanczos2_v2_interior_tiles(emu, size):
+    """vcs_lanczos2_v2_kernel (the default for plans with uniform interior taps): sizes with tiles that touch no frame border
+    in either direction, so the constant-tap H path on the shifted chroma grid, the prefetching item loop and all three row
+    group kinds of the V phase run; byte orders with a compile-time selector (BGRA, RGBA) and with the run-time one"""
+    from gstreamer_b200 import _lib
+    iw, ih, W, H = size
+    for fi, fo, method in [("NV12", "BGRA", 3), ("NV21", "RGBA", 9), ("NV12", "ARGB", 5), ("NV21", "xBGR", 3)]:
+        frame = frame_for(fi, iw, ih, 21)
+        ii, oi = _lib.VideoInfoC(), _lib.VideoInfoC()
+        emu.b200_video_info_set_format(C.byref(ii), ob.FMT[fi], iw, ih)
+        emu.b200_video_info_set_format(C.byref(oi), ob.FMT[fo], W, H)
+        ii.chroma_site = 2
+        cfg = _lib.VcsConfigC()
+        emu.b200_vcs_config_init(C.byref(cfg))
+        cfg.method = method
+        h = C.c_void_p()
+        assert emu.b200_vcs_create(C.byref(ii), C.byref(oi), C.byref(cfg), 0, C.byref(h)) == 0
+        try:
+            info = _lib.VcsPlanInfoC()
+            emu.b200_vcs_get_plan_info(h, C.byref(info))
+            assert int(info.kernel_variant) == 1
+            out = np.full(W * H * 4, 0x5A, dtype=np.uint8)
+            assert emu.b200_vcs_convert(h, frame.ctypes.data, out.ctypes.data, None) == 0
+        finally:
+            emu.b200_vcs_destroy(h)
+        check(out, expected(fi, fo, size, method, frame, site=2), f"{fi}->{fo} m{method}")
+
+
 # ---- 4. compositor and audio resampler sources under the same emulation --------------------------------------------------
 @pytest.mark.parametrize("fmt", ["RGBA", "BGRA", "ARGB", "ABGR"])
 @pytest.mark.parametrize("background", [0, 1, 2, 3])

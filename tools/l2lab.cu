@@ -19,6 +19,7 @@
 #include "../gstreamer_b200/csrc/vcs_device.h"
 #include "../gstreamer_b200/csrc/vcs_kernels.cuh"
 #include "../gstreamer_b200/csrc/vcs_lanczos2.cuh"
+#include "../gstreamer_b200/csrc/vcs_lanczos2_v2.cuh"
 #include "../gstreamer_b200/csrc/vcs_l2tc.cuh"
 #ifdef L2LAB_EXTRA
 #include L2LAB_EXTRA
@@ -51,6 +52,8 @@ struct Lab {
   std::vector<uint8_t> ref;      // output of frame 0 from the reference instantiation
   L2tcTables tct;
   L2tcState tc;
+  Lanczos2V2Tables v2t;
+  Lanczos2V2State v2;
 };
 
 void launch_tc (Lab & L, const VcsBatch & b, cudaStream_t s)
@@ -91,6 +94,13 @@ int tc_debug (Lab & L)
 }
 
 typedef void (*launch_fn) (Lab & L, const VcsBatch & b, cudaStream_t s);
+
+template <int SEL, bool PF>
+void launch_v2 (Lab & L, const VcsBatch & b, cudaStream_t s)
+{
+  if (launch_lanczos2_v2_sel<SEL, PF> (L.dev, L.st, L.v2, b, Lab::PER, s) != B200_OK) { printf ("launch_v2 failed: %s\n", b200_last_cuda_error ()); exit (1); }
+}
+
 
 template <int MINB, int TH, int NWC, bool X4, int ABL>
 void launch_l2 (Lab & L, const VcsBatch & b, cudaStream_t s)
@@ -142,10 +152,15 @@ int main (int argc, char **argv)
   if (!L.tct.ok) { printf ("tensor tables not eligible\n"); return 1; }
   if (prepare_l2tc (L.tct, &L.tc) != B200_OK) { printf ("prepare_l2tc failed\n"); return 1; }
   if (!strcmp (filter, "tcdbg")) return tc_debug (L);
+  L.v2t = build_lanczos2_v2_tables (L.plan, L.tab);
+  if (!L.v2t.ok || prepare_lanczos2_v2 (L.v2t, &L.v2) != B200_OK) { printf ("v2 tables not eligible\n"); return 1; }
 
   std::vector<Variant> vs = {
     {"ref_x4_default", launch_l2<4, 60, 1, true, 0>, true},
     {"plain_tables", launch_l2<4, 60, 1, false, 0>, true},
+    {"v2_bgra_prefetch", launch_v2<0x0123, true>, true},
+    {"v2_bgra_noprefetch", launch_v2<0x0123, false>, true},
+    {"v2_runtime_sel_prefetch", launch_v2<-1, true>, true},
     {"tcgen05_both_passes", launch_tc, true},
     {"abl1_no_chroma_prep", launch_l2<4, 60, 1, true, 1>, false},
     {"abl2_no_hfir", launch_l2<4, 60, 1, true, 2>, false},
