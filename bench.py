@@ -256,7 +256,8 @@ def run_ours(args):
     ii, oi = g.VideoInfo(g.VideoFormat.NV12, IW, IH), g.VideoInfo(g.VideoFormat.BGRA, OW, OH)
     el.set_info(ii, oi)
     pinfo = el.plan_info()
-    kname = {1: "vcs_lanczos2_kernel", 7: "vcs_l2tc_kernel"}.get(int(pinfo.kernel_variant), "vcs_generic_kernel")
+    from gstreamer_b200 import _lib as _b200lib
+    kname = _b200lib.lib.b200_vcs_kernel_name(el._h).decode()
 
     # ring of distinct frames resident in HBM
     base = [torch.from_numpy(ob.nv12_random_frame(IW, IH, multi.stream_seed(rank, s))).to(dev) for s in range(4)]

@@ -97,6 +97,7 @@ _SIGS = {
     "b200_vcs_get_matrix": (C.c_int, [_P, _P]),
     "b200_vcs_get_chroma_plan": (C.c_int, [_P, _P, C.c_size_t]),
     "b200_vcs_set_kernel_variant": (C.c_int, [_P, C.c_int]),
+    "b200_vcs_kernel_name": (C.c_char_p, [_P]),
     "b200_comp_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
     "b200_comp_destroy": (None, [_P]),
     "b200_comp_blend": (C.c_int, [_P, _P, C.c_int32, C.c_int, C.POINTER(CompPadC), C.c_int, _P]),

@@ -620,4 +620,19 @@ int b200_vcs_set_kernel_variant (b200_vcs * h, int variant)
   return B200_OK;
 }
 
+const char *b200_vcs_kernel_name (const b200_vcs * h)
+{
+  if (!h) return "";
+  const VcsPlan & p = h->plan;
+  if (p.planes_mode) return "vcs_planes_kernel";
+  if (h->variant == 6 && h->mma.ready) return "vcs_l2mma_kernel";
+#ifndef B200_CUDA_EMU
+  if (h->variant == 7 && h->tc.ready) return "vcs_l2tc_kernel";
+#endif
+  if ((h->variant == 1 || h->variant == 7) && p.lanczos2_ok) return (h->l2v2.ready && h->l2.x4) ? "vcs_lanczos2_v2_kernel" : "vcs_lanczos2_kernel";
+  if (h->variant == 2 && p.light_ok) return "vcs_light_kernel";
+  if (h->variant == 3 && p.ntap_ok) return "vcs_ntap_kernel";
+  return "vcs_generic_kernel";
+}
+
 }  // extern "C"

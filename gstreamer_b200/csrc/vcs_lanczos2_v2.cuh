@@ -62,14 +62,16 @@ __device__ __forceinline__ unsigned pack_sat_s16x2 (int a, int b)     // { sat_s
   } while (0)
 
 // SEL: the output format's byte selector (VcsDev::sel) when known at compile time, -1: applied with a PRMT per pixel.
-// PF: prefetch the next H item's loads.
-template <int MINB, int SEL, bool PF>
-__global__ void __launch_bounds__ (L2_THREADS, MINB)
+// PF: 1 the next H item's loads are issued before this item's arithmetic, 2 only its chroma rows, 0 neither.
+// TH x NT: output rows per tile and threads per CTA (60 x 256 at 4 CTAs per SM, or 124 x 512 at 2: 256 of 254 filtered lines used
+// instead of 128 of 126).
+template <int MINB, int SEL, int PF, int TH = 60, int NT = L2_THREADS>
+__global__ void __launch_bounds__ (NT, MINB)
 vcs_lanczos2_v2_kernel (const VcsDev P, const Lanczos2Dev L, const Lanczos2V2Dev K, const VcsBatch frames)
 {
-  constexpr int TH = 60, NWC = 1;
+  constexpr int NWC = 1, NWARP = NT / 32;
   constexpr int L2_NG = L2Shape<TH, NWC>::NG, L2_TW = L2Shape<TH, NWC>::TW, L2_TWP = L2Shape<TH, NWC>::TWP;
-  static_assert (L2_NG % (2 * (L2_THREADS / 32)) == 0, "the prefetching loop walks two items per turn");
+
   extern __shared__ __align__ (16) unsigned hs[];                // [3][L2_NG][L2_TWP] words
   const int lane = threadIdx.x & 31;
   const int warp = __shfl_sync (0xffffffffu, (int) (threadIdx.x >> 5), 0);
@@ -83,7 +85,12 @@ vcs_lanczos2_v2_kernel (const VcsDev P, const Lanczos2Dev L, const Lanczos2V2Dev
   const unsigned selU = P.u_index ? 0x7531u : 0x6420u, selV = P.u_index ? 0x6420u : 0x7531u;
 
   // ---------------------------------------------------------------- H phase
-  const bool edge_tile = R0 < 0 || R0 + 4 * L2_NG > P.ih || x0 == 0 || x0 + L2_TW + 4 >= P.ow;
+  // line groups this tile's rows need (the frame's last tile row may be short)
+  const int ng = min (L2_NG, (2 * min (TH, P.oh - oy0) + 6 + 3) >> 2);
+  // tiles at the left / right frame border take the table path (folded taps, clamped columns); tiles that only reach the top or
+  // bottom border keep the constant taps and clamp their line / chroma-row indices
+  const bool edge_tile = x0 == 0 || x0 + L2_TW + 4 >= P.ow;
+  const bool edge_rows = R0 < 0 || R0 + 4 * ng > P.ih;
   struct Raw { uint2 c[3]; uint2 y[4]; };
 
 #define L2_PACK4X(A, c) __byte_perm (pack_sat_u16x2 (A[1][c], A[0][c]), pack_sat_u16x2 (A[3][c], A[2][c]), 0x7531)
@@ -107,7 +114,7 @@ vcs_lanczos2_v2_kernel (const VcsDev P, const Lanczos2Dev L, const Lanczos2V2Dev
   if (edge_tile) {
     // tiles at a frame border: clamped lines / chroma rows / columns, per-column tap tables (folded taps do not fit times 4)
     const int4 *__restrict__ htab = L.htab;
-    for (int item = warp; item < L2_NG; item += L2_THREADS / 32) {
+    for (int item = warp; item < ng; item += NWARP) {
       const int g = item;
       const int col0 = x0 + (lane - 1) * 4;
       int4 T[3];
@@ -159,20 +166,35 @@ vcs_lanczos2_v2_kernel (const VcsDev P, const Lanczos2Dev L, const Lanczos2V2Dev
   } else {
     // interior tiles: uniform taps times 4 from the constant bank, chroma on the shifted grid, loads one item ahead
     const int xb = 2 * (x0 + (lane - 1) * 4);                    // byte column of the lane's 8 input pixels
-    auto h_load = [&] (int g, Raw & R) {
-      const int y0 = R0 + 4 * g, m2 = (y0 - 1) >> 1;
-      const uint8_t *pc = plane_c + (ptrdiff_t) m2 * P.stride_c + xb;
-      const uint8_t *py = plane_y + (ptrdiff_t) y0 * P.stride_y + xb;
+    auto h_load_c = [&] (auto clamp_tag, int g, uint2 (&c)[3]) {
+      const int m2 = (R0 + 4 * g - 1) >> 1;
+      if (decltype (clamp_tag)::value) {
 #pragma unroll
-      for (int k = 0; k < 3; k++) { R.c[k] = __ldg ((const uint2 *) pc); pc += P.stride_c; }
+        for (int k = 0; k < 3; k++)
+          c[k] = __ldg ((const uint2 *) (plane_c + (size_t) min (max (m2 + k, 0), crows - 1) * P.stride_c + xb));
+      } else {
+        const uint8_t *pc = plane_c + (ptrdiff_t) m2 * P.stride_c + xb;
 #pragma unroll
-      for (int r = 0; r < 4; r++) { R.y[r] = __ldg ((const uint2 *) py); py += P.stride_y; }
+        for (int k = 0; k < 3; k++) { c[k] = __ldg ((const uint2 *) pc); pc += P.stride_c; }
+      }
     };
-    auto h_item = [&] (int g, const Raw & R) {
+    auto h_load_y = [&] (auto clamp_tag, int g, uint2 (&y)[4]) {
+      const int y0 = R0 + 4 * g;
+      if (decltype (clamp_tag)::value) {
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+          y[r] = __ldg ((const uint2 *) (plane_y + (size_t) min (max (y0 + r, 0), P.ih - 1) * P.stride_y + xb));
+      } else {
+        const uint8_t *py = plane_y + (ptrdiff_t) y0 * P.stride_y + xb;
+#pragma unroll
+        for (int r = 0; r < 4; r++) { y[r] = __ldg ((const uint2 *) py); py += P.stride_y; }
+      }
+    };
+    auto h_item = [&] (int g, const uint2 (&rc)[3], const uint2 (&ry)[4]) {
       unsigned ulo[3], uhi[3], vlo[3], vhi[3];                   // [o0 e1 o1 e2], [o2 e3 o3 e4]: pixels 8L+1 .. 8L+8
 #pragma unroll
       for (int k = 0; k < 3; k++) {
-        const unsigned ue = __byte_perm (R.c[k].x, R.c[k].y, selU), ve = __byte_perm (R.c[k].x, R.c[k].y, selV);
+        const unsigned ue = __byte_perm (rc[k].x, rc[k].y, selU), ve = __byte_perm (rc[k].x, rc[k].y, selV);
         unsigned un = __shfl_down_sync (0xffffffffu, ue, 1), vn = __shfl_down_sync (0xffffffffu, ve, 1);
         un = __byte_perm (ue, un, 0x4321);
         vn = __byte_perm (ve, vn, 0x4321);
@@ -198,28 +220,43 @@ vcs_lanczos2_v2_kernel (const VcsDev P, const Lanczos2Dev L, const Lanczos2V2Dev
       L2_STOREV (2, acc, L2_PACK4X);
 #pragma unroll
       for (int r = 0; r < 4; r++) {
-        const unsigned w0 = __shfl_up_sync (0xffffffffu, R.y[r].y, 1), w3 = __shfl_down_sync (0xffffffffu, R.y[r].x, 1);
-        L2_FIR4K (acc[r][0], acc[r][1], acc[r][2], acc[r][3], w0, R.y[r].x, R.y[r].y, w3, K.hy, 128, false);
+        const unsigned w0 = __shfl_up_sync (0xffffffffu, ry[r].y, 1), w3 = __shfl_down_sync (0xffffffffu, ry[r].x, 1);
+        L2_FIR4K (acc[r][0], acc[r][1], acc[r][2], acc[r][3], w0, ry[r].x, ry[r].y, w3, K.hy, 128, false);
       }
       L2_STOREV (0, acc, L2_PACK4X);
     };
-    constexpr int NWARP = L2_THREADS / 32;
-    if (PF) {
-      Raw ra, rb;
-      h_load (warp, ra);
-      for (int g = warp; g < L2_NG; g += 2 * NWARP) {
-        h_load (g + NWARP, rb);
-        h_item (g, ra);
-        if (g + 2 * NWARP < L2_NG) h_load (g + 2 * NWARP, ra);
-        h_item (g + NWARP, rb);
+    auto h_run = [&] (auto clamp_tag) {
+      if (PF == 1) {                                             // all seven loads one item ahead
+        Raw ra, rb;
+        if (warp < ng) { h_load_c (clamp_tag, warp, ra.c); h_load_y (clamp_tag, warp, ra.y); }
+        for (int g = warp; g < ng; g += 2 * NWARP) {             // ng < L2_NG in the frame's last, short tile row
+          if (g + NWARP < ng) { h_load_c (clamp_tag, g + NWARP, rb.c); h_load_y (clamp_tag, g + NWARP, rb.y); }
+          h_item (g, ra.c, ra.y);
+          if (g + 2 * NWARP < ng) { h_load_c (clamp_tag, g + 2 * NWARP, ra.c); h_load_y (clamp_tag, g + 2 * NWARP, ra.y); }
+          if (g + NWARP < ng) h_item (g + NWARP, rb.c, rb.y);
+        }
+      } else if (PF == 2) {                                      // the chroma rows (needed first) one item ahead
+        uint2 ca[3], cb[3], y[4];
+        if (warp < ng) h_load_c (clamp_tag, warp, ca);
+        for (int g = warp; g < ng; g += 2 * NWARP) {
+          h_load_y (clamp_tag, g, y);
+          if (g + NWARP < ng) h_load_c (clamp_tag, g + NWARP, cb);
+          h_item (g, ca, y);
+          if (g + NWARP < ng) {
+            h_load_y (clamp_tag, g + NWARP, y);
+            if (g + 2 * NWARP < ng) h_load_c (clamp_tag, g + 2 * NWARP, ca);
+            h_item (g + NWARP, cb, y);
+          }
+        }
+      } else {
+        for (int g = warp; g < ng; g += NWARP) {
+          Raw r;
+          h_load_c (clamp_tag, g, r.c); h_load_y (clamp_tag, g, r.y);
+          h_item (g, r.c, r.y);
+        }
       }
-    } else {
-      for (int g = warp; g < L2_NG; g += NWARP) {
-        Raw r;
-        h_load (g, r);
-        h_item (g, r);
-      }
-    }
+    };
+    if (edge_rows) h_run (std::true_type {}); else h_run (std::false_type {});
   }
   __syncthreads ();
 
@@ -287,7 +324,7 @@ vcs_lanczos2_v2_kernel (const VcsDev P, const Lanczos2Dev L, const Lanczos2V2Dev
       }
     }
   };
-  for (int q = warp; q < TH / 4; q += L2_THREADS / 32) {
+  for (int q = warp; q < TH / 4; q += NWARP) {
     const int oy = oy0 + 4 * q;
     if (oy < P.oh) {
       const int kind = __ldg (K.vkind + (oy >> 2));
@@ -359,19 +396,19 @@ inline int prepare_lanczos2_v2 (const Lanczos2V2Tables & t, Lanczos2V2State * st
   return B200_OK;
 }
 
-template <int SEL, bool PF>
+template <int SEL, int PF, int MINB = 4, int TH = 60, int NT = L2_THREADS>
 inline int launch_lanczos2_v2_sel (const VcsDev & d, const Lanczos2State & st, const Lanczos2V2State & v2, const VcsBatch & batch,
     int n, cudaStream_t stream)
 {
-  auto kern = vcs_lanczos2_v2_kernel<4, SEL, PF>;
+  auto kern = vcs_lanczos2_v2_kernel<MINB, SEL, PF, TH, NT>;
   static bool attr_done[16] = {false};
   int dev = 0; cudaGetDevice (&dev);
   if (!attr_done[dev & 15]) {
-    B200_CUDA_TRY (cudaFuncSetAttribute (kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L2Shape<60, 1>::SMEM));
+    B200_CUDA_TRY (cudaFuncSetAttribute (kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L2Shape<TH, 1>::SMEM));
     attr_done[dev & 15] = true;
   }
-  dim3 grid ((d.ow + L2Shape<60, 1>::TW - 1) / L2Shape<60, 1>::TW, (d.oh + 59) / 60, n);
-  kern <<<grid, L2_THREADS, L2Shape<60, 1>::SMEM, stream>>> (d, st.dev, v2.dev, batch);
+  dim3 grid ((d.ow + L2Shape<TH, 1>::TW - 1) / L2Shape<TH, 1>::TW, (d.oh + TH - 1) / TH, n);
+  kern <<<grid, NT, L2Shape<TH, 1>::SMEM, stream>>> (d, st.dev, v2.dev, batch);
   B200_CUDA_TRY (cudaGetLastError ());
   return B200_OK;
 }
@@ -380,9 +417,10 @@ inline int launch_lanczos2_v2 (const VcsDev & d, const Lanczos2State & st, const
     cudaStream_t stream)
 {
   switch (d.sel) {
-    case 0x0123u: return launch_lanczos2_v2_sel<0x0123, true> (d, st, v2, batch, n, stream);   // BGRA / BGRx
-    case 0x0321u: return launch_lanczos2_v2_sel<0x0321, true> (d, st, v2, batch, n, stream);   // RGBA / RGBx
-    default: return launch_lanczos2_v2_sel<-1, true> (d, st, v2, batch, n, stream);
+    // (prefetching the next item's loads measured slower: 6.87 against 6.56 us/frame, profiles/r02_l2_v2_lab.txt)
+    case 0x0123u: return launch_lanczos2_v2_sel<0x0123, 0> (d, st, v2, batch, n, stream);   // BGRA / BGRx
+    case 0x0321u: return launch_lanczos2_v2_sel<0x0321, 0> (d, st, v2, batch, n, stream);   // RGBA / RGBx
+    default: return launch_lanczos2_v2_sel<-1, 0> (d, st, v2, batch, n, stream);
   }
 }
 

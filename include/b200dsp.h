@@ -195,6 +195,8 @@ int b200_vcs_get_matrix (const b200_vcs * h, int32_t im[16]);
 int b200_vcs_get_chroma_plan (const b200_vcs * h, uint8_t * mode, size_t len);
 /* force a kernel variant (0 generic, 1-3 the fast kernels, 6 the tensor-path 2:1 kernel, each if eligible); for A/B tests */
 int b200_vcs_set_kernel_variant (b200_vcs * h, int variant);
+/* name of the __global__ function b200_vcs_convert launches for this handle (what a profiler's launch list shows) */
+const char *b200_vcs_kernel_name (const b200_vcs * h);
 
 /* ------------------------------------------------------------------ compositor */
 typedef enum { B200_COMP_BG_CHECKER = 0, B200_COMP_BG_BLACK = 1, B200_COMP_BG_WHITE = 2,

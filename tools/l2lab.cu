@@ -95,10 +95,10 @@ int tc_debug (Lab & L)
 
 typedef void (*launch_fn) (Lab & L, const VcsBatch & b, cudaStream_t s);
 
-template <int SEL, bool PF>
+template <int SEL, int PF, int MINB = 4, int TH = 60, int NT = 256>
 void launch_v2 (Lab & L, const VcsBatch & b, cudaStream_t s)
 {
-  if (launch_lanczos2_v2_sel<SEL, PF> (L.dev, L.st, L.v2, b, Lab::PER, s) != B200_OK) { printf ("launch_v2 failed: %s\n", b200_last_cuda_error ()); exit (1); }
+  if (launch_lanczos2_v2_sel<SEL, PF, MINB, TH, NT> (L.dev, L.st, L.v2, b, Lab::PER, s) != B200_OK) { printf ("launch_v2 failed: %s\n", b200_last_cuda_error ()); exit (1); }
 }
 
 
@@ -158,9 +158,10 @@ int main (int argc, char **argv)
   std::vector<Variant> vs = {
     {"ref_x4_default", launch_l2<4, 60, 1, true, 0>, true},
     {"plain_tables", launch_l2<4, 60, 1, false, 0>, true},
-    {"v2_bgra_prefetch", launch_v2<0x0123, true>, true},
-    {"v2_bgra_noprefetch", launch_v2<0x0123, false>, true},
-    {"v2_runtime_sel_prefetch", launch_v2<-1, true>, true},
+    {"v2_bgra", launch_v2<0x0123, 0>, true},
+    {"v2_bgra_prefetch_all", launch_v2<0x0123, 1>, true},
+    {"v2_bgra_prefetch_chroma", launch_v2<0x0123, 2>, true},
+    {"v2_runtime_sel", launch_v2<-1, 0>, true},
     {"tcgen05_both_passes", launch_tc, true},
     {"abl1_no_chroma_prep", launch_l2<4, 60, 1, true, 1>, false},
     {"abl2_no_hfir", launch_l2<4, 60, 1, true, 2>, false},
