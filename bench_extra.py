@@ -130,10 +130,15 @@ def bench_planes(args):
     import torch
     import gstreamer_b200 as g
     from oracle import bindings as ob
-    for (fmt, IW, IH, OW, OH, m) in [(23, 3840, 2160, 1920, 1080, 1), (23, 3840, 2160, 1920, 1080, 3),
-                                     (2, 1920, 1080, 1280, 720, 3), (23, 1920, 1080, 1280, 720, 1)]:
+    # (input format, output format, ...): 23 NV12, 2 I420; a differing pair is the cross-family chain (two launches)
+    for (fmt, fmt_o, IW, IH, OW, OH, m) in [(23, 23, 3840, 2160, 1920, 1080, 1), (23, 23, 3840, 2160, 1920, 1080, 3),
+                                            (2, 2, 1920, 1080, 1280, 720, 3), (23, 23, 1920, 1080, 1280, 720, 1),
+                                            (23, 2, 3840, 2160, 1920, 1080, 3), (23, 2, 1920, 1080, 1280, 720, 1)]:
         el = g.CudaVideoConvertScale(method=m)
-        ii, oi = g.VideoInfo(fmt, IW, IH), g.VideoInfo(fmt, OW, OH)
+        ii, oi = g.VideoInfo(fmt, IW, IH), g.VideoInfo(fmt_o, OW, OH)
+        if fmt != fmt_o:                              # what the element's caps fixation does for YUV -> YUV
+            from gstreamer_b200.video import transfer_colorimetry_from_input
+            transfer_colorimetry_from_input(ii, oi)
         el.set_info(ii, oi)
         per = 32
         gen = ob.i420_random_frame if fmt in (2, 3) else ob.nv12_random_frame
@@ -154,7 +159,7 @@ def bench_planes(args):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / args.steps
         alg = per * (ii.size + oi.size)
-        print(json.dumps({"config": f"{g.VideoFormat(fmt).name} {IW}x{IH} -> {g.VideoFormat(fmt).name} {OW}x{OH} method {m}",
+        print(json.dumps({"config": f"{g.VideoFormat(fmt).name} {IW}x{IH} -> {g.VideoFormat(fmt_o).name} {OW}x{OH} method {m}",
                           "kernel_variant": int(el.plan_info().kernel_variant), "us_per_frame": ms * 1e3 / per,
                           "frames_per_s": per * 1e3 / ms,
                           "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak(), "unit": "GB/s",

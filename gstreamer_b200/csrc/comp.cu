@@ -212,43 +212,26 @@ comp_kernel (const CompParams P)
 #pragma unroll
     for (int i = 0; i < 4; i++) d[i] = i < n ? dp[i] : 0u;
   }
-  // z-order walk with the NEXT covering pad's pixels already in flight while the current pad is blended (the blends of
-  // one output pixel are a dependent chain: without this every pad costs a full memory latency per thread, profile r01:
-  // 6.3 warps per issue waiting for loads).  kind: 0 this group is outside the pad, 1 wholly inside (one LDG.128 or four
-  // LDG.32), 2 the pad's left / right edge cuts the group (per-pixel path, loaded in place).
-  auto classify = [&] (int k) -> int {
+  // (fetching the next covering pad's pixels while the current one is blended was measured and dropped: 56.7 against 48.5 us
+  //  per C4 frame - 40 registers instead of 32 cost more occupancy than the overlap returned, profiles/r02_comp_prefetch.txt)
+  for (int k = 0; k < count; k++) {
     const CompTilePad & p = s_pads[k];
-    if (!p.full && (y < p.y0 || y >= p.y1 || x0 >= p.x1 || x0 + n <= p.x0)) return 0;
-    return (n == 4 && (p.full || (x0 >= p.x0 && x0 + 4 <= p.x1))) ? 1 : 2;
-  };
-  auto fetch4 = [&] (int k, unsigned (&s)[4]) {
-    const CompTilePad & p = s_pads[k];
+    const int full = p.full;
+    if (!full && (y < p.y0 || y >= p.y1 || x0 >= p.x1 || x0 + n <= p.x0)) continue;
     const unsigned *sp = (const unsigned *) (p.data + (long long) y * p.stride) + x0;
-    if ((((size_t) sp) & 15) == 0) {
-      const uint4 v = __ldg ((const uint4 *) sp);
-      s[0] = v.x; s[1] = v.y; s[2] = v.z; s[3] = v.w;
-    } else {
-#pragma unroll
-      for (int i = 0; i < 4; i++) s[i] = __ldg (sp + i);
-    }
-  };
-  int k = 0, kind_n = 0;
-  unsigned sn[4] = {0u, 0u, 0u, 0u};
-  while (k < count && (kind_n = classify (k)) == 0) k++;
-  if (k < count && kind_n == 1) fetch4 (k, sn);
-  while (k < count) {
-    const int kc = k, kind = kind_n;
-    unsigned s[4] = {sn[0], sn[1], sn[2], sn[3]};
-    k++;
-    while (k < count && (kind_n = classify (k)) == 0) k++;
-    if (k < count && kind_n == 1) fetch4 (k, sn);
-    const CompTilePad & p = s_pads[kc];
     const int mode = p.mode;
     const unsigned s_alpha = (unsigned) p.s_alpha;
-    if (kind == 1) {
+    if (n == 4 && (full || (x0 >= p.x0 && x0 + 4 <= p.x1))) {     // whole group inside the pad
+      unsigned s[4];
+      if ((((size_t) sp) & 15) == 0) {
+        const uint4 v = __ldg ((const uint4 *) sp);
+        s[0] = v.x; s[1] = v.y; s[2] = v.z; s[3] = v.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; i++) s[i] = __ldg (sp + i);
+      }
       apply_pad4 (d, s, mode, s_alpha, shift, alpha_mask, s_recip);
     } else {
-      const unsigned *sp = (const unsigned *) (p.data + (long long) y * p.stride) + x0;
 #pragma unroll
       for (int i = 0; i < 4; i++)
         if (i < n && x0 + i >= p.x0 && x0 + i < p.x1)

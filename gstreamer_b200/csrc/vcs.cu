@@ -125,13 +125,13 @@ int launch_convert (b200_vcs * h, int n, const VcsBatch & batch, cudaStream_t st
     if (h->l2v2.ready && h->l2.x4) return launch_lanczos2_v2 (h->dev, h->l2, h->l2v2, batch, n, stream);
     return launch_lanczos2 (h->dev, h->l2, batch, n, stream);
   }
-  if (h->variant == 2 && p.light_ok) {
+  if (h->variant == 2 && p.light_ok && !p.yuv_out) {
     // 32-bit plane loads: the frame itself must be word aligned (device allocations always are)
     bool aligned = true;
     for (int i = 0; i < n; i++) aligned = aligned && (((uintptr_t) batch.in[i]) & 3) == 0;
     if (aligned) return launch_light (h->dev, p, batch, n, stream);
   }
-  if (h->variant == 3 && p.ntap_ok) {
+  if (h->variant == 3 && p.ntap_ok && !p.yuv_out) {
     bool aligned = true;
     for (int i = 0; i < n; i++) aligned = aligned && (((uintptr_t) batch.in[i]) & 3) == 0;
     if (aligned) return launch_ntap (h->dev, p, h->ntap, batch, n, stream);
@@ -154,8 +154,20 @@ int launch_convert (b200_vcs * h, int n, const VcsBatch & batch, cudaStream_t st
       mid.in[i] = batch.in[i]; mid.out[i] = h->d_scratch + frame * i;
       fin.scratch[i] = mid.out[i]; fin.out[i] = batch.out[i];
     }
-    vcs_generic_kernel <<<grid, 256, p.smem_bytes, stream>>> (h->dev, mid);
-    B200_CUDA_TRY (cudaGetLastError ());
+    // the chain up to the scaled pixels: the light / n-tap kernels (matrix stage off) where the plan allows, else the generic one
+    bool word_aligned = true;
+    for (int i = 0; i < n; i++) word_aligned = word_aligned && (((uintptr_t) batch.in[i]) & 3) == 0;
+    static const bool slow_chain = getenv ("B200_CROSS_GENERIC") != nullptr;     // A/B knob
+    if (!slow_chain && word_aligned && h->variant == 2 && p.light_ok) {
+      const int s = launch_light (h->dev, p, mid, n, stream);
+      if (s != B200_OK) return s;
+    } else if (!slow_chain && word_aligned && h->variant == 3 && p.ntap_ok && h->ntap.ready) {
+      const int s = launch_ntap (h->dev, p, h->ntap, mid, n, stream);
+      if (s != B200_OK) return s;
+    } else {
+      vcs_generic_kernel <<<grid, 256, p.smem_bytes, stream>>> (h->dev, mid);
+      B200_CUDA_TRY (cudaGetLastError ());
+    }
     if (p.extra_row) {
       // scratch row `oh`: the chain over a one-line view of the frame (its last line, chroma row unfiltered vertically)
       VcsDev x = h->dev;
@@ -624,7 +636,10 @@ const char *b200_vcs_kernel_name (const b200_vcs * h)
 {
   if (!h) return "";
   const VcsPlan & p = h->plan;
-  if (p.planes_mode) return "vcs_planes_kernel";
+  if (p.planes_mode) {
+    for (int i = 0; i < p.n_planes; i++) if (h->planes.fast[i].ok) return h->planes.fast[i].vfirst ? "vcs_planes_fast_vfirst_kernel" : "vcs_planes_fast_kernel";
+    return "vcs_planes_kernel";
+  }
   if (h->variant == 6 && h->mma.ready) return "vcs_l2mma_kernel";
 #ifndef B200_CUDA_EMU
   if (h->variant == 7 && h->tc.ready) return "vcs_l2tc_kernel";

@@ -28,7 +28,7 @@
 namespace b200 {
 
 struct Lanczos2V2Dev {
-  int hy[12], hc[12], vv[12];          // uniform taps times 4 in the L2_FIR4 word order (luma frame, chroma frame, vertical)
+  int hy[6], hc[6], vv[6];             // uniform taps times 4: first half of an L2_FIR4 table row (luma frame, chroma frame, vertical)
   const uint8_t *vkind;                // per row group: 2 uniform (vv), 1 table times 4, 0 plain table
 };
 
@@ -43,15 +43,17 @@ __device__ __forceinline__ unsigned pack_sat_s16x2 (int a, int b)     // { sat_s
 #endif
 }
 
-// constants K[12] in the word order of an L2_FIR4 table row; Z: words 2 and 8 are zero (windows on the 0/2/4/6 byte grid)
+// constants K[6]: the first half of an L2_FIR4 table row - with one set of taps for every output the second half (outputs 2, 3
+// on words 1..3) repeats the first (outputs 0, 1 on words 0..2), which the host verifies; Z: word 2 is zero (windows on the
+// 0/2/4/6 byte grid)
 #define L2_FIR4K(o0, o1, o2, o3, w0, w1, w2, w3, K, INIT, Z)                                    \
   do {                                                                                         \
     o0 = dp4a_u8s8 (w1, K[1], dp4a_u8s8 (w0, K[0], INIT));                                     \
     if (!(Z)) o0 = dp4a_u8s8 (w2, K[2], o0);                                                   \
     o1 = dp4a_u8s8 (w2, K[5], dp4a_u8s8 (w1, K[4], dp4a_u8s8 (w0, K[3], INIT)));               \
-    o2 = dp4a_u8s8 (w2, K[7], dp4a_u8s8 (w1, K[6], INIT));                                     \
-    if (!(Z)) o2 = dp4a_u8s8 (w3, K[8], o2);                                                   \
-    o3 = dp4a_u8s8 (w3, K[11], dp4a_u8s8 (w2, K[10], dp4a_u8s8 (w1, K[9], INIT)));             \
+    o2 = dp4a_u8s8 (w2, K[1], dp4a_u8s8 (w1, K[0], INIT));                                     \
+    if (!(Z)) o2 = dp4a_u8s8 (w3, K[2], o2);                                                   \
+    o3 = dp4a_u8s8 (w3, K[5], dp4a_u8s8 (w2, K[4], dp4a_u8s8 (w1, K[3], INIT)));               \
   } while (0)
 #define L2_FIR4T(o0, o1, o2, o3, w0, w1, w2, w3, T, INIT)                                      \
   do {                                                                                         \
@@ -342,7 +344,7 @@ vcs_lanczos2_v2_kernel (const VcsDev P, const Lanczos2Dev L, const Lanczos2V2Dev
 // ------------------------------------------------------------------------------------ host side
 struct Lanczos2V2Tables {
   bool ok = false;
-  int hy[12], hc[12], vv[12];
+  int hy[6], hc[6], vv[6];
   std::vector<uint8_t> vkind;
 };
 
@@ -356,7 +358,9 @@ inline Lanczos2V2Tables build_lanczos2_v2_tables (const VcsPlan & p, const Lancz
   if (!pack_axis_lanczos2 (p.h, 3, &hc4, 4, &hcfits)) return r;  // the chroma frame: windows on the 0/2/4/6 byte grid
   const int groups = p.out.width / 4, ow = p.out.width, TW = L2_WCOLS;
   const int gm = groups / 2;
-  if (!t.h4[gm] || !hcfits[gm] || hc4[(size_t) gm * 12 + 2] != 0 || hc4[(size_t) gm * 12 + 8] != 0) return r;
+  if (!t.h4[gm] || !hcfits[gm] || hc4[(size_t) gm * 12 + 2] != 0) return r;
+  for (int w = 0; w < 6; w++)                                    // outputs 2, 3 = outputs 0, 1 one word further
+    if (t.htab4[(size_t) gm * 12 + w] != t.htab4[(size_t) gm * 12 + 6 + w] || hc4[(size_t) gm * 12 + w] != hc4[(size_t) gm * 12 + 6 + w]) return r;
   for (int x0 = TW; x0 + TW + 4 < ow; x0 += TW)                  // interior tile columns (the kernel's edge_tile test)
     for (int g = x0 / 4 - 1; g <= (x0 + TW) / 4; g++) {
       if (g < 0 || g >= groups || !t.h4[g] || !hcfits[g]) return r;
@@ -364,7 +368,8 @@ inline Lanczos2V2Tables build_lanczos2_v2_tables (const VcsPlan & p, const Lancz
         if (t.htab4[(size_t) g * 12 + w] != t.htab4[(size_t) gm * 12 + w] || hc4[(size_t) g * 12 + w] != hc4[(size_t) gm * 12 + w]) return r;
     }
   const int vgroups = p.out.height / 4, vm = vgroups / 2;
-  const bool vuni = t.v4[vm] && t.vtab4[(size_t) vm * 12 + 2] == 0 && t.vtab4[(size_t) vm * 12 + 8] == 0;
+  bool vuni = t.v4[vm] && t.vtab4[(size_t) vm * 12 + 2] == 0;
+  for (int w = 0; w < 6; w++) vuni = vuni && t.vtab4[(size_t) vm * 12 + w] == t.vtab4[(size_t) vm * 12 + 6 + w];
   r.vkind.assign (vgroups, 0);
   for (int g = 0; g < vgroups; g++) {
     if (!t.v4[g]) continue;
@@ -373,7 +378,7 @@ inline Lanczos2V2Tables build_lanczos2_v2_tables (const VcsPlan & p, const Lancz
     for (int w = 0; w < 12 && same; w++) same = t.vtab4[(size_t) g * 12 + w] == t.vtab4[(size_t) vm * 12 + w];
     if (same) r.vkind[g] = 2;
   }
-  for (int w = 0; w < 12; w++) {
+  for (int w = 0; w < 6; w++) {
     r.hy[w] = t.htab4[(size_t) gm * 12 + w]; r.hc[w] = hc4[(size_t) gm * 12 + w]; r.vv[w] = t.vtab4[(size_t) vm * 12 + w];
   }
   r.ok = true;
@@ -390,7 +395,7 @@ inline int prepare_lanczos2_v2 (const Lanczos2V2Tables & t, Lanczos2V2State * st
 {
   int rc;
   if ((rc = upload (&st->d_vkind, t.vkind.data (), t.vkind.size ())) != B200_OK) return rc;
-  for (int w = 0; w < 12; w++) { st->dev.hy[w] = t.hy[w]; st->dev.hc[w] = t.hc[w]; st->dev.vv[w] = t.vv[w]; }
+  for (int w = 0; w < 6; w++) { st->dev.hy[w] = t.hy[w]; st->dev.hc[w] = t.hc[w]; st->dev.vv[w] = t.vv[w]; }
   st->dev.vkind = st->d_vkind;
   st->ready = true;
   return B200_OK;

@@ -41,6 +41,7 @@ constexpr int LIGHT_THREADS = 256;
 // {Y,U,V,-} -> {A,R,G,B} word (A = 255): video_orc_convert_AYUV_ARGB on one pixel
 __device__ __forceinline__ unsigned light_matrix (unsigned yuv, const VcsDev & P)
 {
+  if (P.yuv_out) return __byte_perm (yuv, 0x000000ffu, 0x2104);   // 4:2:0 output: no matrix, {A = 255, Y, U, V} for the down-sampler
   yuv ^= 0x00808080u;
   const int wy = prmt_s (yuv, 0x8800u), wu = prmt_s (yuv, 0x9911u), wv = prmt_s (yuv, 0xaa22u);
   const int ty = ((wy * P.p1) >> 16) + 128;

@@ -381,7 +381,7 @@ bool fast_layout_ok (const VcsPlan * p)
 // read up to 7 bytes past the width: inside the row's stride)
 void std_pairs_check (VcsPlan * p)
 {
-  bool std_pairs = !p->planar && !p->chroma_nearest && p->v_pairs && !p->in_422_444 && !p->rgb_in && !p->yuv_out && !p->planes_mode &&
+  bool std_pairs = !p->planar && !p->chroma_nearest && p->v_pairs && !p->in_422_444 && !p->rgb_in && !p->planes_mode &&
       !(p->in.stride[0] & 7) && !(p->in.stride[1] & 7) && !(p->in.offset[0] & 7) && !(p->in.offset[1] & 7) &&
       p->in.stride[0] >= ((p->in.width + 7) & ~7) && p->in.stride[1] >= ((p->in.width + 7) & ~7) && !(p->in.height & 1) &&
       (int) p->chroma_mode.size () >= p->in.height;
@@ -961,6 +961,14 @@ static int build_inner_plan (const b200_video_info * in, const b200_video_info *
     }
     tile_geometry (p);
     p->light_ok = p->ntap_ok = p->lanczos2_ok = false;
+    if (!p->rgb_in && !p->in_422_444 && !p->has_dest) {
+      // 4:2:0 in: the first launch (the chain up to the scaled A,Y,U,V pixels) may run the light / n-tap kernels with their
+      // matrix stage switched off (VcsDev::yuv_out) instead of the generic kernel
+      std_pairs_check (p);
+      light_geometry (p);
+      ntap_geometry (p);
+      validate_fast_geometry (p);
+    }
     return B200_OK;
   }
   if (p->in_422_444) {

@@ -23,6 +23,7 @@
 #include "vcs_kernels.cuh"
 #include "vcs_lanczos2.cuh"      // packed-byte averages
 #include "vcs_plan.h"
+#include "vcs_planes_fast.cuh"   // the word-wide kernel most PM_SCALE planes take
 
 namespace b200 {
 
@@ -210,10 +211,41 @@ vcs_planes_kernel (const PlanesParams P, const VcsBatch frames)
   dst[(size_t) y * Q.dstride + xb] = (uint8_t) v;
 }
 
+// copy / halve planes with word-aligned rows on their own: one thread = one output word, the grid exactly the plane's words
+// (inside vcs_planes_kernel these modes ran on the byte kernel's grid with its register footprint: 10.6 us for the luma plane of
+// a 4K -> 1080p NV12 frame, 1 TB/s).  Same arithmetic as the vec4 branch above (video_orc_planar_chroma_*, avgub).
+__global__ void __launch_bounds__ (256)
+vcs_planes_vec_kernel (const PlaneDev Q, const VcsBatch frames)
+{
+  const int wpr = (Q.ow * Q.ne) >> 2;                              // words per output row
+  const int wx = blockIdx.x * 64 + (threadIdx.x & 63), wy = blockIdx.y * 4 + (threadIdx.x >> 6);
+  if (wx >= wpr || wy >= Q.oh) return;
+  const uint8_t *__restrict__ src = frames.in[blockIdx.z] + Q.src_off;
+  uint8_t *__restrict__ dst = frames.out[blockIdx.z] + Q.dst_off;
+  unsigned o;
+  if (Q.mode == PM_COPY) {
+    o = __ldg ((const unsigned *) (src + (size_t) wy * Q.sstride) + wx);
+    if (Q.swz) o = __byte_perm (o, 0, Q.swz);
+  } else if (Q.mode == PM_HALVE_V) {
+    o = avg_ceil4 (__ldg ((const unsigned *) (src + (size_t) (2 * wy) * Q.sstride) + wx),
+        __ldg ((const unsigned *) (src + (size_t) (2 * wy + 1) * Q.sstride) + wx));
+  } else if (Q.mode == PM_HALVE_H) {
+    const uint2 a = __ldg ((const uint2 *) (src + (size_t) wy * Q.sstride) + wx);
+    o = avg_ceil4 (__byte_perm (a.x, a.y, 0x6420), __byte_perm (a.x, a.y, 0x7531));
+  } else {                                                         // PM_HALVE_HV: lines first, then the byte pairs
+    const uint2 a = __ldg ((const uint2 *) (src + (size_t) (2 * wy) * Q.sstride) + wx);
+    const uint2 b = __ldg ((const uint2 *) (src + (size_t) (2 * wy + 1) * Q.sstride) + wx);
+    const unsigned t = avg_ceil4 (a.x, b.x), u = avg_ceil4 (a.y, b.y);
+    o = avg_ceil4 (__byte_perm (t, u, 0x6420), __byte_perm (t, u, 0x7531));
+  }
+  *((unsigned *) (dst + (size_t) wy * Q.dstride) + wx) = o;
+}
+
 struct PlanesState {
   uint32_t *d_off[3][2] = {{nullptr}};
   int16_t *d_coef[3][2] = {{nullptr}};
   PlanesParams params;
+  PlaneFastState fast[3];        // planes that run vcs_planes_fast_kernel instead (fast[i].ok)
   bool ready = false;
 };
 
@@ -235,6 +267,15 @@ inline int prepare_planes (const VcsPlan & p, PlanesState * st)
           (d.src_off & sa) == 0;
     }
     if (q.mode != PM_SCALE) continue;
+    {
+      static const bool slow = getenv ("B200_PLANES_SLOW") != nullptr;     // A/B knob: the byte-wise kernel for every plane
+      std::vector<int32_t> hp, vp;
+      const bool okf = !slow && plan_plane_fast (q, d.sstride, d.src_off, d.dstride, d.dst_off, &st->fast[i], &hp, &vp);
+      if (okf) {
+        const int s = prepare_plane_fast (q, hp, vp, &st->fast[i]);
+        if (s != B200_OK) return s;
+      }
+    }
     const AxisPlan *ax[2] = {&q.h, &q.v};
     PlaneAxisDev *dv[2] = {&d.h, &d.v};
     for (int a = 0; a < 2; a++) {
@@ -253,11 +294,28 @@ inline void free_planes (PlanesState * st)
 {
   for (int i = 0; i < 3; i++)
     for (int a = 0; a < 2; a++) { cudaFree (st->d_off[i][a]); cudaFree (st->d_coef[i][a]); }
+  for (int i = 0; i < 3; i++) free_plane_fast (&st->fast[i]);
 }
 
 inline int launch_planes (const PlanesState & st, const VcsBatch & batch, int n, cudaStream_t stream, bool aligned)
 {
-  PlanesParams P = st.params;
+  // planes with a word-wide plan run their own launch (32-bit source loads: word-aligned frames, which `aligned` implies)
+  PlanesParams P;
+  memset (&P, 0, sizeof (P));
+  for (int i = 0; i < st.params.n_planes; i++) {
+    const PlaneDev & q = st.params.pl[i];
+    if (st.fast[i].ok && aligned) {
+      const int s = launch_plane_fast (st.fast[i], batch, n, stream);
+      if (s != B200_OK) return s;
+    } else if (aligned && q.vec4 && q.mode != PM_SCALE && q.mode != PM_DOUBLE) {
+      const dim3 grid ((((q.ow * q.ne) >> 2) + 63) / 64, (q.oh + 3) / 4, n);
+      vcs_planes_vec_kernel <<<grid, 256, 0, stream>>> (q, batch);
+      B200_CUDA_TRY (cudaGetLastError ());
+    } else {
+      P.pl[P.n_planes++] = st.params.pl[i];
+    }
+  }
+  if (P.n_planes == 0) return B200_OK;
   if (!aligned)
     for (int i = 0; i < P.n_planes; i++) P.pl[i].vec4 = 0;
   int wmax = 0, hmax = 0;

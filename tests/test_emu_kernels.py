@@ -192,6 +192,19 @@ def test_odd_height_without_vertical_scaler(emu):
             check(got, expected("NV12", "I420", size, 3, frame, site=site, out_site=out_site), f"{size} {site}->{out_site}")
 
 
+@pytest.mark.parametrize("size", [(400, 300, 150, 100), (160, 90, 300, 200), (262, 146, 131, 73), (129, 67, 200, 67), (96, 200, 96, 75),
+                                  (514, 130, 258, 66), (70, 40, 35, 20)], ids=lambda s: "%dx%d-%dx%d" % s)
+def test_planes_fast_kernel(emu, size, monkeypatch):
+    """vcs_planes_fast_kernel (the word-wide plane scaler): 1- and 2-byte planes, every pass-mode pair (nearest, bilinear,
+    n-tap in either direction), several tiles per plane, odd widths whose last word overhangs the line; and the byte-wise
+    kernel (B200_PLANES_SLOW) must agree with the same oracle"""
+    iw, ih = size[:2]
+    for fi, fo in [("NV12", "NV12"), ("I420", "I420"), ("NV21", "NV21"), ("I420", "YV12")]:
+        frame = frame_for(fi, iw, ih, 5)
+        for method in (0, 1, 3, 9, 4):
+            check(run(emu, fi, fo, size, method, frame), expected(fi, fo, size, method, frame), f"{fi}->{fo} m{method}")
+
+
 # ---- 2b. the fast kernels (device-verified; here as a CPU regression net for future changes to them) -----------------------
 @pytest.mark.parametrize("case", [
     # (in, out, size, method, expected kernel_variant)
