@@ -186,7 +186,8 @@ vcs_planes_fast_kernel (const PlaneFastDev Q, const VcsBatch frames)
 //     first line, 4 IDP.4A; the four results leave as one word of 4 PIXELS in T[row][column word] - the natural layout for
 //  C' the horizontal pass: a thread owns one output byte (or U,V pair): funnel shift to the window's first pixel, IDP.4A / lerp /
 //     byte select on the v-scaled row, one store, lanes on consecutive columns.
-template <int HM, int VM, int NC>
+// NTW > 0: every n-tap axis of the plane uses exactly NTW packed tap words (straight-line FIRs); 0: run-time loops
+template <int HM, int VM, int NC, int NTW = 0>
 __global__ void __launch_bounds__ (PLF_THREADS, 2)
 vcs_planes_fast_vfirst_kernel (const PlaneFastDev Q, const VcsBatch frames)
 {
@@ -219,8 +220,9 @@ vcs_planes_fast_vfirst_kernel (const PlaneFastDev Q, const VcsBatch frames)
   // ---------------------------------------------------------------- A': stage, transposed
   const int RG = (R + 3) >> 2;
   const int last_word = Q.sstride - 4;
+  const unsigned magic = 0xffffffffu / (unsigned) ng + 1u;       // i / ng by multiplication: exact for i, ng < 2^16 (a tile has a few thousand items)
   for (int i = tid; i < RG * ng; i += PLF_THREADS) {
-    const int g = i / ng, j = i - g * ng;
+    const int g = ng > 1 ? (int) __umulhi ((unsigned) i, magic) : i, j = i - g * ng;
     unsigned w[NC][4];
 #pragma unroll
     for (int l = 0; l < 4; l++) {
@@ -247,7 +249,7 @@ vcs_planes_fast_vfirst_kernel (const PlaneFastDev Q, const VcsBatch frames)
 
   // ---------------------------------------------------------------- B': vertical pass
   for (int i = tid; i < th * ng; i += PLF_THREADS) {
-    const int ty = i / ng, j = i - ty * ng;
+    const int ty = ng > 1 ? (int) __umulhi ((unsigned) i, magic) : i, j = i - ty * ng;
     const int rb = (int) vrow[ty];
     const int sh = (rb & 3) * 8;
 #pragma unroll
@@ -259,8 +261,8 @@ vcs_planes_fast_vfirst_kernel (const PlaneFastDev Q, const VcsBatch frames)
         int acc[4] = {32, 32, 32, 32};
         uint4 lo = sp[0];
         const int *taps = TV + ty * Q.ntw_v;
-#pragma unroll 2
-        for (int k = 0; k < Q.ntw_v; k++) {
+#pragma unroll
+        for (int k = 0; k < (NTW > 0 ? NTW : Q.ntw_v); k++) {
           const int t = taps[k];
           const uint4 hi = sp[(k + 1) * gstep];
           acc[0] = dp4a_u8s8 (__funnelshift_r (lo.x, hi.x, sh), t, acc[0]);
@@ -305,8 +307,8 @@ vcs_planes_fast_vfirst_kernel (const PlaneFastDev Q, const VcsBatch frames)
           int acc = 32;
           unsigned lo = tp[0];
           const int *taps = TH + tx * Q.ntw_h;
-#pragma unroll 2
-          for (int k = 0; k < Q.ntw_h; k++) {
+#pragma unroll
+          for (int k = 0; k < (NTW > 0 ? NTW : Q.ntw_h); k++) {
             const unsigned hi = tp[k + 1];
             acc = dp4a_u8s8 (__funnelshift_r (lo, hi, sh), taps[k], acc);
             lo = hi;
@@ -331,6 +333,7 @@ struct PlaneFastState {
   PlaneFastDev dev;
   int hm = 0, vm = 0, nc = 0;
   bool vfirst = false;
+  int ntw = 0;                   // the n-tap axes' common tap-word count (0: they differ, run-time loops)
   size_t smem = 0;
   uint32_t *d_hoff = nullptr, *d_voff = nullptr;
   int16_t *d_hcoef = nullptr, *d_vcoef = nullptr;
@@ -339,10 +342,12 @@ struct PlaneFastState {
 
 typedef void (*plane_fast_fn) (const PlaneFastDev, const VcsBatch);
 
-inline plane_fast_fn plane_fast_kernel_for (int hm, int vm, int nc, bool vfirst)
+inline plane_fast_fn plane_fast_kernel_for (int hm, int vm, int nc, bool vfirst, int ntw = 0)
 {
 #define PLF_PICK(H, V)                                                                         \
   if (hm == H && vm == V) {                                                                    \
+    if (vfirst && ntw == 2 && (H == 3 || V == 3)) return nc == 1 ? vcs_planes_fast_vfirst_kernel<H, V, 1, 2> : vcs_planes_fast_vfirst_kernel<H, V, 2, 2>;   \
+    if (vfirst && ntw == 1 && (H == 3 || V == 3)) return nc == 1 ? vcs_planes_fast_vfirst_kernel<H, V, 1, 1> : vcs_planes_fast_vfirst_kernel<H, V, 2, 1>;   \
     if (vfirst) return nc == 1 ? vcs_planes_fast_vfirst_kernel<H, V, 1> : vcs_planes_fast_vfirst_kernel<H, V, 2>;   \
     return nc == 1 ? vcs_planes_fast_kernel<H, V, 1> : vcs_planes_fast_kernel<H, V, 2>;       \
   }
@@ -439,6 +444,7 @@ inline bool plan_plane_fast (const PlanePlan & q, int sstride, unsigned long lon
   d.iw = q.iw; d.ih = q.ih; d.ow = q.ow; d.oh = q.oh;
   d.ntw_h = ntw_h; d.ntw_v = ntw_v; d.hspan = hspan; d.vspan = vspan;
   st->hm = H.mode; st->vm = V.mode; st->nc = q.ne; st->vfirst = !q.h_first;
+  st->ntw = (H.mode == PASS_NTAP && V.mode == PASS_NTAP) ? (ntw_h == ntw_v ? ntw_h : 0) : (H.mode == PASS_NTAP ? ntw_h : ntw_v);
   st->ok = true;
   return true;
 }
@@ -454,7 +460,7 @@ inline int prepare_plane_fast (const PlanePlan & q, const std::vector<int32_t> &
   if ((s = upload (&st->d_vp, vp.data (), vp.size ())) != B200_OK) return s;
   st->dev.hoff = st->d_hoff; st->dev.voff = st->d_voff; st->dev.hcoef = st->d_hcoef; st->dev.vcoef = st->d_vcoef;
   st->dev.h_packed = st->d_hp; st->dev.v_packed = st->d_vp;
-  return allow_max_dyn_smem (plane_fast_kernel_for (st->hm, st->vm, st->nc, st->vfirst));
+  return allow_max_dyn_smem (plane_fast_kernel_for (st->hm, st->vm, st->nc, st->vfirst, st->ntw));
 }
 
 inline void free_plane_fast (PlaneFastState * st)
@@ -464,7 +470,7 @@ inline void free_plane_fast (PlaneFastState * st)
 
 inline int launch_plane_fast (const PlaneFastState & st, const VcsBatch & batch, int n, cudaStream_t stream)
 {
-  plane_fast_fn fn = plane_fast_kernel_for (st.hm, st.vm, st.nc, st.vfirst);
+  plane_fast_fn fn = plane_fast_kernel_for (st.hm, st.vm, st.nc, st.vfirst, st.ntw);
   if (!fn) return B200_ERR_STATE;
   const dim3 grid ((st.dev.ow + st.dev.tw - 1) / st.dev.tw, (st.dev.oh + st.dev.th - 1) / st.dev.th, n);
   fn <<<grid, PLF_THREADS, st.smem, stream>>> (st.dev, batch);
