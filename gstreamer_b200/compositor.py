@@ -120,7 +120,9 @@ class CudaCompositor:
         self.sinkpads.append(pad)
         return pad
 
-    YUV_FORMATS = (VideoFormat.I420, VideoFormat.YV12, VideoFormat.NV12, VideoFormat.NV21)
+    YUV_FORMATS = (VideoFormat.I420, VideoFormat.YV12, VideoFormat.NV12, VideoFormat.NV21, VideoFormat.Y444, VideoFormat.Y42B,
+                   VideoFormat.I420_10LE, VideoFormat.I420_12LE, VideoFormat.I422_10LE, VideoFormat.I422_12LE,
+                   VideoFormat.Y444_10LE, VideoFormat.Y444_12LE, VideoFormat.Y444_16LE)
 
     def _aggregate_yuv(self, outbuf, out_info, stream):
         """4:2:0 output: every pad frame has the output's format (blend.c PLANAR_YUV_BLEND / NV_YUV_BLEND);

@@ -261,8 +261,9 @@ struct CompYuvRect {
   const uint8_t *src;            // offset so that src + y*stride + x is the source byte of PLANE byte (x,y)
   int stride;
   int x0, x1, y0, y1;            // plane-byte rectangle
-  int alpha;                     // 0..255 blend, 256 = copy
+  int alpha;                     // 0 .. 2^nbits - 1 blend, CY_COPY = copy
 };
+constexpr int CY_COPY = 0x10000;
 
 struct CompYuvParams {
   uint8_t *dst[3];
@@ -270,6 +271,7 @@ struct CompYuvParams {
   int bg_mode[3];                // 0 checker (luma), 1 constant, -1 keep destination (continuation chunk)
   int bg_value[3];
   int n_planes, n_pads;
+  int es, nbits;                 // bytes per sample (1, or 2: little-endian 10 / 12 / 16-bit planes), significant bits
   CompYuvRect pads[CY_MAX_PADS][3];
 };
 
@@ -282,12 +284,14 @@ comp_yuv_kernel (const CompYuvParams P)
   uint8_t *dp = P.dst[z] + (size_t) y * P.stride[z] + x;
   const int n = min (4, P.wbytes[z] - x);
   const bool vec = n == 4 && (((size_t) dp) & 3) == 0;
+  const bool wide = P.es == 2;                                     // two 16-bit samples per word
   unsigned d;
-  if (P.bg_mode[z] == 0) {                                         // fill_checker_*: 8x8 squares of 80 / 160
-    const unsigned v = ((y >> 3) ^ (x >> 3)) & 1 ? 160u : 80u;     // x % 4 == 0: the 4 bytes share a square
-    d = v * 0x01010101u;
+  if (P.bg_mode[z] == 0) {                                         // fill_checker_*: 8x8 squares of 80 / 160 (<< nbits - 8)
+    const int px = wide ? x >> 1 : x;                              // x % 4 == 0: the word's samples share a square
+    const unsigned v = (((y >> 3) ^ (px >> 3)) & 1 ? 160u : 80u) << (P.nbits - 8);
+    d = wide ? v * 0x00010001u : v * 0x01010101u;
   } else if (P.bg_mode[z] == 1) {
-    d = (unsigned) P.bg_value[z] * 0x01010101u;
+    d = (unsigned) P.bg_value[z] * (wide ? 0x00010001u : 0x01010101u);
   } else if (vec) {
     d = *(const unsigned *) dp;
   } else {
@@ -306,7 +310,14 @@ comp_yuv_kernel (const CompYuvParams P)
         m |= 0xffu << (8 * i);
       }
     unsigned v = s;
-    if (r.alpha < 256) {                                           // (d*(256-a) + s*a) >> 8 on two 16-bit lanes
+    if (r.alpha != CY_COPY && wide) {
+      // compositor_orc_blend_u10 / _u12 / _u16 (compositororc.orc:38-100): ((d << n) + (s - d) * a) >> n in wrapping 32-bit
+      // arithmetic with a logical shift, then signed-to-unsigned-word saturation
+      const unsigned a = (unsigned) r.alpha;
+      const unsigned d0 = d & 0xffffu, d1 = d >> 16, s0 = s & 0xffffu, s1 = s >> 16;
+      const int r0 = (int) (((d0 << P.nbits) + (s0 - d0) * a) >> P.nbits), r1 = (int) (((d1 << P.nbits) + (s1 - d1) * a) >> P.nbits);
+      v = (unsigned) min (max (r0, 0), 65535) | ((unsigned) min (max (r1, 0), 65535) << 16);
+    } else if (r.alpha != CY_COPY) {                               // (d*(256-a) + s*a) >> 8 on two 16-bit lanes
       const unsigned a = (unsigned) r.alpha, ia = 256u - a;
       const unsigned lo = (d & 0x00ff00ffu) * ia + (s & 0x00ff00ffu) * a;
       const unsigned hi = __byte_perm (d, 0, 0x4341) * ia + __byte_perm (s, 0, 0x4341) * a;
@@ -353,7 +364,11 @@ int b200_comp_create (int out_format, int width, int height, int device, b200_co
     case B200_VIDEO_FORMAT_BGRA: case B200_VIDEO_FORMAT_RGBA: shift = 24; break;
     case B200_VIDEO_FORMAT_ARGB: case B200_VIDEO_FORMAT_ABGR: shift = 0; break;
     case B200_VIDEO_FORMAT_I420: case B200_VIDEO_FORMAT_YV12: case B200_VIDEO_FORMAT_NV12: case B200_VIDEO_FORMAT_NV21:
-      shift = -1; break;                                           // 4:2:0 output: b200_comp_blend_yuv
+    case B200_VIDEO_FORMAT_Y444: case B200_VIDEO_FORMAT_Y42B:
+    case B200_VIDEO_FORMAT_I420_10LE: case B200_VIDEO_FORMAT_I420_12LE: case B200_VIDEO_FORMAT_I422_10LE:
+    case B200_VIDEO_FORMAT_I422_12LE: case B200_VIDEO_FORMAT_Y444_10LE: case B200_VIDEO_FORMAT_Y444_12LE:
+    case B200_VIDEO_FORMAT_Y444_16LE:
+      shift = -1; break;                                           // planar / semi-planar YUV output: b200_comp_blend_yuv
     default: return B200_ERR_UNSUPPORTED;
   }
   if (device >= 0) {
@@ -449,26 +464,47 @@ int b200_comp_blend_yuv (b200_comp * h, void *dst, const b200_video_info * di, i
   if (h->device < 0) return B200_ERR_NO_DEVICE;
   DeviceGuard g (h->device);
   if (!g.ok) return B200_ERR_CUDA;
-  const bool semi = h->format == B200_VIDEO_FORMAT_NV12 || h->format == B200_VIDEO_FORMAT_NV21;
+  // the format's PLANAR_YUV_BLEND / NV_YUV_BLEND instantiation (blend.c:591-646, :1386): chroma sub-sampling shifts, the
+  // x_round / y_round of the position, bytes per sample and depth
+  bool semi = false;
+  int ws = 1, hs = 1, xr = 2, yr = 2, es = 1, nbits = 8;
+  switch (h->format) {
+    case B200_VIDEO_FORMAT_NV12: case B200_VIDEO_FORMAT_NV21: semi = true; break;
+    case B200_VIDEO_FORMAT_I420: case B200_VIDEO_FORMAT_YV12: break;
+    case B200_VIDEO_FORMAT_Y444: ws = hs = 0; xr = yr = 1; break;
+    case B200_VIDEO_FORMAT_Y42B: hs = 0; yr = 1; break;
+    case B200_VIDEO_FORMAT_I420_10LE: es = 2; nbits = 10; break;
+    case B200_VIDEO_FORMAT_I420_12LE: es = 2; nbits = 12; break;
+    case B200_VIDEO_FORMAT_I422_10LE: es = 2; nbits = 10; hs = 0; yr = 1; break;
+    case B200_VIDEO_FORMAT_I422_12LE: es = 2; nbits = 12; hs = 0; yr = 1; break;
+    case B200_VIDEO_FORMAT_Y444_10LE: es = 2; nbits = 10; ws = hs = 0; xr = yr = 1; break;
+    case B200_VIDEO_FORMAT_Y444_12LE: es = 2; nbits = 12; ws = hs = 0; xr = yr = 1; break;
+    case B200_VIDEO_FORMAT_Y444_16LE: es = 2; nbits = 16; ws = hs = 0; xr = yr = 1; break;
+    default: return B200_ERR_STATE;
+  }
   const int W = h->width, H = h->height, n_planes = semi ? 2 : 3;
-  auto half_up = [] (int v) { return -((-v) >> 1); };              // GST_VIDEO_FORMAT_INFO_SCALE_WIDTH / _HEIGHT, 2x sub-sampling
+  auto sub = [] (int v, int sh) { return -((-v) >> sh); };         // GST_VIDEO_FORMAT_INFO_SCALE_WIDTH / _HEIGHT (round up)
   CompYuvParams P;
   memset (&P, 0, sizeof (P));
-  P.n_planes = n_planes;
+  P.n_planes = n_planes; P.es = es; P.nbits = nbits;
   for (int p = 0; p < n_planes; p++) {
     P.dst[p] = (uint8_t *) dst + di->offset[p];
     P.stride[p] = di->stride[p];
-    P.wbytes[p] = p == 0 ? W : (semi ? 2 * half_up (W) : half_up (W));
-    P.rows[p] = p == 0 ? H : half_up (H);
+    P.wbytes[p] = (p == 0 ? W : (semi ? 2 * sub (W, ws) : sub (W, ws))) * es;
+    P.rows[p] = p == 0 ? H : sub (H, hs);
     if (P.stride[p] < P.wbytes[p]) return B200_ERR_INVALID_ARG;
-    // _draw_background (compositor.c:1619-1675): checker = luma squares + 0x80 chroma; black / white from the
-    // range offsets (compositor.c:1131-1149); transparent = zeroed planes (and overlay == blend)
+    if (es == 2 && ((P.stride[p] & 1) || (di->offset[p] & 1))) return B200_ERR_INVALID_ARG;
+    // _draw_background (compositor.c:1619-1675): checker = luma squares + mid-grey chroma; black / white from the range
+    // offsets at the format's depth (compositor.c:1131-1149, gst_video_color_range_offsets video-color.c:204-252: 16-235 ->
+    // 16 << (n - 8) .. 235 << (n - 8); 0-255 -> 0 .. 2^n - 1; chroma 1 << (n - 1)); transparent = zeroed planes
     const bool full_range = di->color_range == B200_COLOR_RANGE_0_255;
-    if (background == B200_COMP_BG_CHECKER) { P.bg_mode[p] = p == 0 ? 0 : 1; P.bg_value[p] = 0x80; }
+    const int mid = 1 << (nbits - 1);
+    if (background == B200_COMP_BG_CHECKER) { P.bg_mode[p] = p == 0 ? 0 : 1; P.bg_value[p] = mid; }
     else if (background == B200_COMP_BG_TRANSPARENT) { P.bg_mode[p] = 1; P.bg_value[p] = 0; }
     else {
       P.bg_mode[p] = 1;
-      P.bg_value[p] = p ? 128 : (background == B200_COMP_BG_BLACK ? (full_range ? 0 : 16) : (full_range ? 255 : 235));
+      P.bg_value[p] = p ? mid : (background == B200_COMP_BG_BLACK ? (full_range ? 0 : 16 << (nbits - 8))
+                                                                  : (full_range ? (1 << nbits) - 1 : 235 << (nbits - 8)));
     }
   }
   unsigned gx = 0, gy = 0;
@@ -486,14 +522,15 @@ int b200_comp_blend_yuv (b200_comp * h, void *dst, const b200_video_info * di, i
     for (int p = 0; p < n_planes; p++) P.bg_mode[p] = -1;           // later chunks continue from the destination
     return B200_OK;
   };
+  const int range = (1 << nbits) - 1;
   for (int i = 0; i < n_pads; i++) {
     const b200_comp_pad_yuv & pad = pads[i];
     if (pad.info.format != h->format || pad.info.width < 1 || pad.info.height < 1 || !pad.data) return B200_ERR_INVALID_ARG;
     double alpha = pad.alpha;
     if (pad.op == B200_COMP_OP_SOURCE) alpha = 1.0;                // _blend_*: source mode copies
     if (alpha == 0.0) continue;
-    // blend_<format> (blend.c:284-340 / :1418-1470): position rounded up to even, clip against the frame
-    int xpos = (pad.xpos + 1) & ~1, ypos = (pad.ypos + 1) & ~1, xoffset = 0, yoffset = 0;
+    // blend_<format> (blend.c:284-340 / :1418-1470): position rounded UP to the format's grid, clip against the frame
+    int xpos = (pad.xpos + xr - 1) & ~(xr - 1), ypos = (pad.ypos + yr - 1) & ~(yr - 1), xoffset = 0, yoffset = 0;
     int bw = pad.info.width, bh = pad.info.height;
     if (xpos < 0) { xoffset = -xpos; bw -= -xpos; xpos = 0; }
     if (ypos < 0) { yoffset = -ypos; bh -= -ypos; ypos = 0; }
@@ -501,17 +538,19 @@ int b200_comp_blend_yuv (b200_comp * h, void *dst, const b200_video_info * di, i
     if (xpos + bw > W) bw = W - xpos;
     if (ypos + bh > H) bh = H - ypos;
     if (bw <= 0 || bh <= 0) continue;
-    int b_alpha = 256;
-    if (alpha != 1.0) { b_alpha = (int) (alpha * 255); b_alpha = b_alpha < 0 ? 0 : (b_alpha > 255 ? 255 : b_alpha); }
+    int b_alpha = CY_COPY;
+    if (alpha != 1.0) { b_alpha = (int) (alpha * range); b_alpha = b_alpha < 0 ? 0 : (b_alpha > range ? range : b_alpha); }
     if (P.n_pads == CY_MAX_PADS) { int st = flush (); if (st != B200_OK) return st; }
-    const int cw = half_up (bw), ch = half_up (bh);
-    const int cxpos = xpos ? half_up (xpos) : 0, cypos = ypos >> 1, cxoff = xoffset ? half_up (xoffset) : 0, cyoff = yoffset >> 1;
+    // chroma: widths and x positions by SCALE_WIDTH (round up), rows by a plain shift (blend.c:371-376)
+    const int cw = sub (bw, ws), ch = sub (bh, hs);
+    const int cxpos = xpos ? sub (xpos, ws) : 0, cypos = ypos >> hs, cxoff = xoffset ? sub (xoffset, ws) : 0, cyoff = yoffset >> hs;
     for (int p = 0; p < n_planes; p++) {
       CompYuvRect & r = P.pads[P.n_pads][p];
-      const int mul = (p && semi) ? 2 : 1;
-      const int px = p ? mul * cxpos : xpos, py = p ? cypos : ypos, sx = p ? mul * cxoff : xoffset, sy = p ? cyoff : yoffset;
-      const int w = p ? mul * cw : bw, hgt = p ? ch : bh;
+      const int mul = ((p && semi) ? 2 : 1) * es;                   // plane bytes per (chroma) sample position
+      const int px = p ? mul * cxpos : es * xpos, py = p ? cypos : ypos, sx = p ? mul * cxoff : es * xoffset, sy = p ? cyoff : yoffset;
+      const int w = p ? mul * cw : es * bw, hgt = p ? ch : bh;
       r.stride = pad.info.stride[p];
+      if (es == 2 && ((r.stride & 1) || (pad.info.offset[p] & 1) || (((uintptr_t) pad.data) & 1))) return B200_ERR_INVALID_ARG;
       r.x0 = px; r.x1 = px + w; r.y0 = py; r.y1 = py + hgt; r.alpha = b_alpha;
       r.src = (const uint8_t *) pad.data + pad.info.offset[p] + (long long) (sy - py) * r.stride + (sx - px);
     }

@@ -280,6 +280,27 @@ int b200_video_info_set_format (b200_video_info * info, int format, int width, i
       info->stride[0] = width * 4;      // video-info.c:890-894
       info->color_matrix = B200_COLOR_MATRIX_RGB; info->color_range = B200_COLOR_RANGE_0_255;
       return B200_OK;
+    case B200_VIDEO_FORMAT_I420_10LE: case B200_VIDEO_FORMAT_I420_12LE:       // video-info.c:1142-1156
+    case B200_VIDEO_FORMAT_I422_10LE: case B200_VIDEO_FORMAT_I422_12LE: {     // :1157-1169
+      const bool is420 = format == B200_VIDEO_FORMAT_I420_10LE || format == B200_VIDEO_FORMAT_I420_12LE;
+      const int hh = (height + 1) & ~1;
+      info->stride[0] = (width * 2 + 3) & ~3;
+      info->stride[1] = info->stride[2] = (width + 3) & ~3;
+      info->offset[1] = (uint64_t) info->stride[0] * hh;
+      info->offset[2] = info->offset[1] + (uint64_t) info->stride[1] * (is420 ? hh / 2 : hh);
+      info->color_matrix = height > 576 ? B200_COLOR_MATRIX_BT709 : B200_COLOR_MATRIX_BT601;
+      info->color_range = B200_COLOR_RANGE_16_235;
+      info->chroma_site = height > 576 ? B200_CHROMA_SITE_H_COSITED : B200_CHROMA_SITE_NONE;
+      return B200_OK;
+    }
+    case B200_VIDEO_FORMAT_Y444_10LE: case B200_VIDEO_FORMAT_Y444_12LE: case B200_VIDEO_FORMAT_Y444_16LE:   // :1170-1188
+      info->stride[0] = info->stride[1] = info->stride[2] = (width * 2 + 3) & ~3;
+      info->offset[1] = (uint64_t) info->stride[0] * height;
+      info->offset[2] = info->offset[1] * 2;
+      info->color_matrix = height > 576 ? B200_COLOR_MATRIX_BT709 : B200_COLOR_MATRIX_BT601;
+      info->color_range = B200_COLOR_RANGE_16_235;
+      info->chroma_site = height > 576 ? B200_CHROMA_SITE_H_COSITED : B200_CHROMA_SITE_NONE;
+      return B200_OK;
     default:
       return B200_ERR_UNSUPPORTED;
   }
@@ -298,7 +319,12 @@ size_t b200_video_info_size (const b200_video_info * info)
       return e1 > e2 ? e1 : e2;
     }
     case B200_VIDEO_FORMAT_Y42B: case B200_VIDEO_FORMAT_Y444:
+    case B200_VIDEO_FORMAT_Y444_10LE: case B200_VIDEO_FORMAT_Y444_12LE: case B200_VIDEO_FORMAT_Y444_16LE:
       return (size_t) info->offset[2] + (size_t) info->stride[2] * info->height;
+    case B200_VIDEO_FORMAT_I420_10LE: case B200_VIDEO_FORMAT_I420_12LE:
+      return (size_t) info->offset[2] + (size_t) info->stride[2] * (((info->height + 1) & ~1) / 2);
+    case B200_VIDEO_FORMAT_I422_10LE: case B200_VIDEO_FORMAT_I422_12LE:
+      return (size_t) info->offset[2] + (size_t) info->stride[2] * ((info->height + 1) & ~1);
     default:
       return (size_t) info->offset[0] + (size_t) info->stride[0] * info->height;
   }

@@ -33,6 +33,14 @@ class VideoFormat(enum.IntEnum):
     ARGB = 13
     ABGR = 14
     NV12 = 23
+    # compositor formats only (planar, little endian, 10 / 12 / 16 bits)
+    I420_10LE = 43
+    I422_10LE = 45
+    Y444_10LE = 47
+    I420_12LE = 73
+    I422_12LE = 75
+    Y444_12LE = 77
+    Y444_16LE = 88
     NV21 = 24
 
 

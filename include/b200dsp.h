@@ -79,7 +79,12 @@ typedef enum {
   B200_VIDEO_FORMAT_RGBx = 7, B200_VIDEO_FORMAT_BGRx = 8, B200_VIDEO_FORMAT_xRGB = 9,
   B200_VIDEO_FORMAT_xBGR = 10, B200_VIDEO_FORMAT_RGBA = 11, B200_VIDEO_FORMAT_BGRA = 12,
   B200_VIDEO_FORMAT_ARGB = 13, B200_VIDEO_FORMAT_ABGR = 14,
-  B200_VIDEO_FORMAT_NV12 = 23, B200_VIDEO_FORMAT_NV21 = 24
+  B200_VIDEO_FORMAT_NV12 = 23, B200_VIDEO_FORMAT_NV21 = 24,
+  /* compositor formats only (blend.c PLANAR_YUV_BLEND at 10 / 12 / 16 bits, little endian; Y444 and Y42B above are
+   * compositor formats too) */
+  B200_VIDEO_FORMAT_I420_10LE = 43, B200_VIDEO_FORMAT_I422_10LE = 45, B200_VIDEO_FORMAT_Y444_10LE = 47,
+  B200_VIDEO_FORMAT_I420_12LE = 73, B200_VIDEO_FORMAT_I422_12LE = 75, B200_VIDEO_FORMAT_Y444_12LE = 77,
+  B200_VIDEO_FORMAT_Y444_16LE = 88
 } b200_video_format;
 
 /* GstVideoScaleMethod of the element (gst/videoconvertscale/gstvideoconvertscale.h:59-71) */

@@ -27,7 +27,10 @@ extern "C" {
 enum { ORC_FMT_I420 = 2, ORC_FMT_YV12 = 3, ORC_FMT_YUY2 = 4, ORC_FMT_UYVY = 5, ORC_FMT_Y42B = 18, ORC_FMT_YVYU = 19,
   ORC_FMT_Y444 = 20, ORC_FMT_RGBx = 7, ORC_FMT_BGRx = 8, ORC_FMT_xRGB = 9,
   ORC_FMT_xBGR = 10, ORC_FMT_RGBA = 11, ORC_FMT_BGRA = 12, ORC_FMT_ARGB = 13, ORC_FMT_ABGR = 14,
-  ORC_FMT_NV12 = 23, ORC_FMT_NV21 = 24 };
+  ORC_FMT_NV12 = 23, ORC_FMT_NV21 = 24,
+  /* compositor outputs only (planar high bit depth, little endian; GstVideoFormat values) */
+  ORC_FMT_I420_10LE = 43, ORC_FMT_I422_10LE = 45, ORC_FMT_Y444_10LE = 47, ORC_FMT_I420_12LE = 73, ORC_FMT_I422_12LE = 75,
+  ORC_FMT_Y444_12LE = 77, ORC_FMT_Y444_16LE = 88 };
 /* GstVideoResamplerMethod */
 enum { ORC_RS_NEAREST = 0, ORC_RS_LINEAR = 1, ORC_RS_CUBIC = 2, ORC_RS_SINC = 3, ORC_RS_LANCZOS = 4 };
 /* GstVideoColorMatrix / Range / ChromaSite */

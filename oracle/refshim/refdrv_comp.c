@@ -112,6 +112,17 @@ ref_compositor_yuv (int format, guint8 * dst, int width, int height, int backgro
     case GST_VIDEO_FORMAT_NV21:
       blend = gst_compositor_blend_nv21; fill_checker = gst_compositor_fill_checker_nv21; fill_color = gst_compositor_fill_color_nv21;
       break;
+    case GST_VIDEO_FORMAT_Y444:
+      blend = gst_compositor_blend_y444; fill_checker = gst_compositor_fill_checker_y444; fill_color = gst_compositor_fill_color_y444;
+      break;
+    case GST_VIDEO_FORMAT_Y42B:
+      blend = gst_compositor_blend_y42b; fill_checker = gst_compositor_fill_checker_y42b; fill_color = gst_compositor_fill_color_y42b;
+      break;
+#define HIGH(fmt, name) case GST_VIDEO_FORMAT_##fmt: \
+      blend = gst_compositor_blend_##name; fill_checker = gst_compositor_fill_checker_##name; fill_color = gst_compositor_fill_color_##name; break;
+    HIGH (I420_10LE, i420_10le) HIGH (I420_12LE, i420_12le) HIGH (I422_10LE, i422_10le) HIGH (I422_12LE, i422_12le)
+    HIGH (Y444_10LE, y444_10le) HIGH (Y444_12LE, y444_12le) HIGH (Y444_16LE, y444_16le)
+#undef HIGH
     default:
       return -1;
   }
@@ -121,8 +132,14 @@ ref_compositor_yuv (int format, guint8 * dst, int width, int height, int backgro
     out.data[p] = dst + out.info.offset[p];
   switch (background) {
     case 0: fill_checker (&out, 0, height); break;
-    case 1: fill_color (&out, 0, height, range_16_235 ? 16 : 0, 128, 128); break;
-    case 2: fill_color (&out, 0, height, range_16_235 ? 235 : 255, 128, 128); break;
+    case 1: case 2: {
+      /* compositor.c:1131-1149: black / white from the reference's own range offsets at the format's depth */
+      gint offset[GST_VIDEO_MAX_COMPONENTS], scale[GST_VIDEO_MAX_COMPONENTS];
+      gst_video_color_range_offsets (range_16_235 ? GST_VIDEO_COLOR_RANGE_16_235 : GST_VIDEO_COLOR_RANGE_0_255, out.info.finfo,
+          offset, scale);
+      fill_color (&out, 0, height, background == 1 ? offset[0] : scale[0] + offset[0], offset[1], offset[2]);
+      break;
+    }
     default:
       /* the element's own loop is a static function (_draw_background, compositor.c:1640-1670): the visible bytes of
        * every plane row are zeroed, the stride padding is left alone; overlay == blend for these formats */

@@ -107,10 +107,13 @@ def test_convert_pads(cuda_device):
     assert np.array_equal(out.cpu().numpy().reshape(H, W, 4), want)
 
 
-@pytest.mark.parametrize("fmt", [2, 3, 23, 24], ids=["I420", "YV12", "NV12", "NV21"])
+@pytest.mark.parametrize("fmt", [2, 3, 23, 24, 20, 18, 43, 73, 45, 75, 47, 77, 88],
+                         ids=["I420", "YV12", "NV12", "NV21", "Y444", "Y42B", "I420_10LE", "I420_12LE", "I422_10LE", "I422_12LE", "Y444_10LE",
+                              "Y444_12LE", "Y444_16LE"])
 def test_420_output_random_layouts(cuda_device, fmt):
-    """4:2:0 output and pads: every plane byte equals the oracle's (random sizes, positions, alphas, operators,
-    backgrounds, both ranges; more pads than one launch chunk in some trials)"""
+    """planar / semi-planar YUV output and pads (4:2:0, 4:2:2, 4:4:4; 8 bits and little-endian 10 / 12 / 16 bits): every plane
+    byte equals the oracle's (random sizes, positions, alphas, operators, backgrounds, both ranges; more pads than one launch
+    chunk in some trials)"""
     import torch
     import gstreamer_b200 as g
     from gstreamer_b200.compositor import CudaCompositor

@@ -372,10 +372,16 @@ def test_compositor_kernel(emu, fmt, background):
     check(out.ravel(), want.ravel(), f"{fmt} background {background}")
 
 
-@pytest.mark.parametrize("fmt", [2, 3, 23, 24], ids=["I420", "YV12", "NV12", "NV21"])
+COMP_YUV_FORMATS = [2, 3, 23, 24, 20, 18, 43, 73, 45, 75, 47, 77, 88]
+COMP_YUV_IDS = ["I420", "YV12", "NV12", "NV21", "Y444", "Y42B", "I420_10LE", "I420_12LE", "I422_10LE", "I422_12LE", "Y444_10LE", "Y444_12LE",
+                "Y444_16LE"]
+
+
+@pytest.mark.parametrize("fmt", COMP_YUV_FORMATS, ids=COMP_YUV_IDS)
 def test_compositor_420_kernel(emu, fmt):
-    """the 4:2:0 compositor (b200_comp_blend_yuv: per-plane blend, pad positions rounded up to even, ceil(w/2) chroma
-    samples) against the oracle: random layouts, both ranges, every background, one trial beyond a launch chunk of pads"""
+    """the planar / semi-planar YUV compositor (b200_comp_blend_yuv: per-plane blend, pad positions rounded up to the format's
+    grid, round-up chroma rectangles; 8-bit and little-endian 10 / 12 / 16-bit samples) against the oracle: random layouts,
+    both ranges, every background, one trial beyond a launch chunk of pads"""
     from gstreamer_b200 import _lib
     o = ob.oracle()
     rng = np.random.default_rng(fmt)

@@ -266,6 +266,36 @@ def test_compositor_420_matches_reference():
         assert np.array_equal(d1, d2), f"trial {trial}"
 
 
+@pytest.mark.parametrize("fmt", [20, 18, 43, 73, 45, 75, 47, 77, 88], ids=["Y444", "Y42B", "I420_10LE", "I420_12LE", "I422_10LE", "I422_12LE",
+                                                                         "Y444_10LE", "Y444_12LE", "Y444_16LE"])
+def test_compositor_planar_444_422_and_high_depth_match_reference(fmt):
+    """the other PLANAR_YUV_BLEND instantiations (blend.c:596-646): Y444 / Y42B at 8 bits, the little-endian 10 / 12 / 16-bit
+    I420 / I422 / Y444 families with compositor_orc_blend_u10 / _u12 / _u16 (32-bit wrapping arithmetic), their x / y
+    rounding, chroma rectangles, checker / black / white / transparent backgrounds at the format's depth - random layouts
+    with samples over the whole 16-bit range (the reference does not mask them either), byte-identical frames"""
+    o, r = ob.oracle(), ob.ref()
+    rng = np.random.default_rng(100 + fmt)
+    for trial in range(120):
+        W, H, bg, rg = int(rng.integers(1, 90)), int(rng.integers(1, 70)), int(rng.integers(0, 4)), int(rng.integers(0, 2))
+        n = int(rng.integers(0, 5))
+        pads = (ob.OraclePad * max(n, 1))()
+        keep = []
+        for i in range(n):
+            w, h = int(rng.integers(1, 60)), int(rng.integers(1, 50))
+            a = rng.integers(0, 256, o.oracle_compositor_yuv_size(fmt, w, h), dtype=np.uint8)
+            keep.append(a)
+            pads[i].data, pads[i].width, pads[i].height, pads[i].stride = a.ctypes.data, w, h, 0
+            pads[i].xpos, pads[i].ypos = int(rng.integers(-30, W + 5)), int(rng.integers(-30, H + 5))
+            pads[i].alpha, pads[i].op = float(rng.choice([0.0, 0.3, 0.5, 0.999, 1.0, 0.004, 0.00002])), int(rng.integers(0, 3))
+        sz = o.oracle_compositor_yuv_size(fmt, W, H)
+        assert sz > 0
+        d1 = np.full(sz, 0xA5, dtype=np.uint8)          # stride padding must stay untouched in both
+        d2 = d1.copy()
+        assert r.ref_compositor_yuv(fmt, d1.ctypes.data, W, H, bg, rg, pads, n) == 0
+        assert o.oracle_compositor_yuv(fmt, d2.ctypes.data, W, H, bg, rg, pads, n) == 0
+        assert np.array_equal(d1, d2), f"trial {trial}: {int((d1 != d2).sum())} bytes differ, first at {int(np.argmax(d1 != d2))}"
+
+
 YUV_PAIRS = [("NV12", "NV12"), ("NV21", "NV21"), ("I420", "I420"), ("YV12", "YV12"), ("I420", "YV12"), ("YV12", "I420")]
 YUV_SIZES = [(64, 48, 32, 24), (64, 48, 128, 96), (64, 48, 40, 30), (64, 48, 100, 70), (65, 49, 33, 25), (33, 17, 20, 9),
              (64, 48, 64, 24), (64, 48, 32, 48), (64, 48, 64, 96), (64, 48, 128, 48), (640, 480, 320, 240), (320, 240, 640, 480),
