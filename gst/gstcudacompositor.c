@@ -16,7 +16,10 @@
 GST_DEBUG_CATEGORY_STATIC (cuda_comp_debug);
 #define GST_CAT_DEFAULT cuda_comp_debug
 
-#define COMP_FORMATS "{ RGBA, BGRA, ARGB, ABGR, I420, YV12, NV12, NV21 }"
+/* Y444 / Y42B and the little-endian 10 / 12 / 16-bit planar formats blend pads that already have the aggregator's format
+ * (blend.c:596-646); convert pads (b200_vcs) exist for the 8-bit 4:2:0 and packed RGB formats */
+#define COMP_FORMATS "{ RGBA, BGRA, ARGB, ABGR, I420, YV12, NV12, NV21, Y444, Y42B, I420_10LE, I420_12LE, " \
+    "I422_10LE, I422_12LE, Y444_10LE, Y444_12LE, Y444_16LE }"
 #define COMP_FIELDS "format = (string) " COMP_FORMATS \
     ", width = (int) [ 1, 32767 ], height = (int) [ 1, 32767 ], framerate = (fraction) [ 0/1, max ]"
 /* device memory preferred; system memory (packed RGB) goes through b200_comp_blend_host */
@@ -265,10 +268,22 @@ comp_aggregate_frames (GstVideoAggregator * vagg, GstBuffer * outbuf)
 
   gst_cuda_context_push (self->context);
   if (!on_device) {
-    /* system-memory peers (packed RGB): prepared frames and the output are host memory; the library stages them through
+    /* system-memory peers: prepared frames and the output are host memory; the library stages them through
      * its own device ring - upload, one blend pass, download */
-    st = GST_VIDEO_INFO_IS_YUV (oinfo) ? B200_ERR_UNSUPPORTED
-        : b200_comp_blend_host (self->comp, GST_VIDEO_FRAME_PLANE_DATA (&out_frame, 0),
+    if (GST_VIDEO_INFO_IS_YUV (oinfo)) {
+      b200_comp_pad_yuv ypads[B200_COMP_MAX_PADS];
+      b200_video_info di;
+      gint i;
+      gst_b200_video_info_from_gst (&di, &out_frame.info);
+      for (i = 0; i < n; i++) {
+        ypads[i].data = GST_VIDEO_FRAME_PLANE_DATA (mapped[i], 0);
+        gst_b200_video_info_from_gst (&ypads[i].info, &mapped[i]->info);
+        ypads[i].xpos = pads[i].xpos; ypads[i].ypos = pads[i].ypos;
+        ypads[i].alpha = pads[i].alpha; ypads[i].op = pads[i].op; ypads[i].reserved = 0;
+      }
+      st = b200_comp_blend_yuv_host (self->comp, GST_VIDEO_FRAME_PLANE_DATA (&out_frame, 0), &di, self->background, ypads, n);
+    } else
+    st = b200_comp_blend_host (self->comp, GST_VIDEO_FRAME_PLANE_DATA (&out_frame, 0),
         GST_VIDEO_FRAME_PLANE_STRIDE (&out_frame, 0), self->background, pads, n);
     gst_cuda_context_pop (NULL);
     gst_video_frame_unmap (&out_frame);

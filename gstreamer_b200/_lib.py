@@ -103,6 +103,8 @@ _SIGS = {
     "b200_comp_blend": (C.c_int, [_P, _P, C.c_int32, C.c_int, C.POINTER(CompPadC), C.c_int, _P]),
     "b200_comp_blend_host_submit": (C.c_int, [_P, _P, C.c_int32, C.c_int, C.POINTER(CompPadC), C.c_int]),
     "b200_comp_blend_host_wait": (C.c_int, [_P, C.c_int]),
+    "b200_comp_blend_yuv_host_submit": (C.c_int, [_P, _P, C.POINTER(VideoInfoC), C.c_int, C.POINTER(CompPadYuvC), C.c_int]),
+    "b200_comp_blend_yuv_host": (C.c_int, [_P, _P, C.POINTER(VideoInfoC), C.c_int, C.POINTER(CompPadYuvC), C.c_int]),
     "b200_comp_blend_host": (C.c_int, [_P, _P, C.c_int32, C.c_int, C.POINTER(CompPadC), C.c_int]),
     "b200_comp_blend_yuv": (C.c_int, [_P, _P, C.POINTER(VideoInfoC), C.c_int, C.POINTER(CompPadYuvC), C.c_int, _P]),
     "b200_ars_create": (C.c_int, [C.POINTER(ArsConfigC), C.c_int, C.POINTER(_P)]),

@@ -165,6 +165,22 @@ class CudaCompositor:
         fn = lib.b200_comp_blend_host if wait else lib.b200_comp_blend_host_submit
         check(fn(self._h, out_ptr, out_stride or self.width * 4, int(self.background), arr, len(pads)), "b200_comp_blend_host")
 
+    def aggregate_host_frames_yuv(self, out_ptr, pad_ptrs, out_info=None, wait=True):
+        """system-memory peers of a planar / semi-planar YUV compositor (b200_comp_blend_yuv_host[_submit])"""
+        from .video import VideoInfo
+        out_info = out_info or VideoInfo(self.format, self.width, self.height)
+        pads = [p for p in self.sinkpads]
+        arr = (_lib.CompPadYuvC * max(len(pads), 1))()
+        keep = []
+        for i, (p, ptr) in enumerate(zip(pads, pad_ptrs)):
+            info = p.in_info or VideoInfo(self.format, p.width, p.height)
+            keep.append(info)
+            arr[i].data = ptr
+            arr[i].info = info.c
+            arr[i].xpos, arr[i].ypos, arr[i].alpha, arr[i].op = p.xpos + p.x_offset, p.ypos + p.y_offset, p.alpha, int(p.operator)
+        fn = lib.b200_comp_blend_yuv_host if wait else lib.b200_comp_blend_yuv_host_submit
+        check(fn(self._h, out_ptr, C.byref(out_info.c), int(self.background), arr, len(pads)), "b200_comp_blend_yuv_host")
+
     def host_wait(self, keep_in_flight=0):
         check(lib.b200_comp_blend_host_wait(self._h, keep_in_flight), "b200_comp_blend_host_wait")
 

@@ -653,4 +653,71 @@ int b200_comp_blend_host (b200_comp * h, void *dst_host, int32_t dst_stride, int
   return b200_comp_blend_host_wait (h, 0);
 }
 
+// planar / semi-planar YUV output from host memory: the same ring of device slots and streams as b200_comp_blend_host_submit;
+// every pad frame and the destination travel as whole frames (b200_video_info_size bytes, the caller's plane layout)
+int b200_comp_blend_yuv_host_submit (b200_comp * h, void *dst_host, const b200_video_info * di, int background,
+    const b200_comp_pad_yuv * pads, int n_pads)
+{
+  if (!h || !dst_host || !di || n_pads < 0 || n_pads > B200_COMP_MAX_PADS || (n_pads && !pads)) return B200_ERR_INVALID_ARG;
+  if (h->alpha_shift >= 0) return B200_ERR_STATE;
+  if (h->device < 0) return B200_ERR_NO_DEVICE;
+  DeviceGuard g (h->device);
+  if (!g.ok) return B200_ERR_CUDA;
+  int st = comp_host_ready (h);
+  if (st != B200_OK) return st;
+  CompHostSlot & sl = h->slot[h->submitted % b200_comp::kSlots];
+  size_t need = 0, off[B200_COMP_MAX_PADS], bytes[B200_COMP_MAX_PADS];
+  for (int i = 0; i < n_pads; i++) {
+    if (!pads[i].data || pads[i].info.width < 1 || pads[i].info.height < 1) return B200_ERR_INVALID_ARG;
+    bytes[i] = b200_video_info_size (&pads[i].info);
+    off[i] = need;
+    need += (bytes[i] + 255) & ~(size_t) 255;
+  }
+  const size_t dst_bytes = b200_video_info_size (di);
+  if (sl.used) {
+    B200_CUDA_TRY (cudaStreamWaitEvent (h->s_h2d, sl.ev_run, 0));
+    B200_CUDA_TRY (cudaStreamWaitEvent (h->s_run, sl.ev_out, 0));
+  }
+  if (need > sl.pads_cap) {
+    if (sl.used) B200_CUDA_TRY (cudaEventSynchronize (sl.ev_run));
+    B200_CUDA_TRY (cudaFree (sl.d_pads)); sl.d_pads = nullptr; sl.pads_cap = 0;
+    B200_CUDA_TRY (cudaMalloc ((void **) &sl.d_pads, need));
+    sl.pads_cap = need;
+  }
+  if (dst_bytes > sl.dst_cap) {
+    if (sl.used) B200_CUDA_TRY (cudaEventSynchronize (sl.ev_out));
+    B200_CUDA_TRY (cudaFree (sl.d_dst)); sl.d_dst = nullptr; sl.dst_cap = 0;
+    B200_CUDA_TRY (cudaMalloc ((void **) &sl.d_dst, dst_bytes));
+    sl.dst_cap = dst_bytes;
+  }
+  b200_comp_pad_yuv dev_pads[B200_COMP_MAX_PADS];
+  for (int i = 0; i < n_pads; i++) {
+    dev_pads[i] = pads[i];
+    dev_pads[i].data = sl.d_pads + off[i];
+    if (pads[i].alpha == 0.0 && pads[i].op != B200_COMP_OP_SOURCE) continue;        // never read by the blend
+    B200_CUDA_TRY (cudaMemcpyAsync (sl.d_pads + off[i], pads[i].data, bytes[i], cudaMemcpyHostToDevice, h->s_h2d));
+  }
+  B200_CUDA_TRY (cudaEventRecord (sl.ev_in, h->s_h2d));
+  B200_CUDA_TRY (cudaStreamWaitEvent (h->s_run, sl.ev_in, 0));
+  // the blend writes the visible bytes of every plane row only; the rows' stride padding must come back as the caller had it
+  // (the reference never touches it), so the destination travels up first
+  B200_CUDA_TRY (cudaMemcpyAsync (sl.d_dst, dst_host, dst_bytes, cudaMemcpyHostToDevice, h->s_run));
+  if ((st = b200_comp_blend_yuv (h, sl.d_dst, di, background, dev_pads, n_pads, h->s_run)) != B200_OK) return st;
+  B200_CUDA_TRY (cudaEventRecord (sl.ev_run, h->s_run));
+  B200_CUDA_TRY (cudaStreamWaitEvent (h->s_d2h, sl.ev_run, 0));
+  B200_CUDA_TRY (cudaMemcpyAsync (dst_host, sl.d_dst, dst_bytes, cudaMemcpyDeviceToHost, h->s_d2h));
+  B200_CUDA_TRY (cudaEventRecord (sl.ev_out, h->s_d2h));
+  sl.used = true;
+  h->submitted++;
+  return B200_OK;
+}
+
+int b200_comp_blend_yuv_host (b200_comp * h, void *dst_host, const b200_video_info * di, int background,
+    const b200_comp_pad_yuv * pads, int n_pads)
+{
+  int st = b200_comp_blend_yuv_host_submit (h, dst_host, di, background, pads, n_pads);
+  if (st != B200_OK) return st;
+  return b200_comp_blend_host_wait (h, 0);
+}
+
 }  // extern "C"

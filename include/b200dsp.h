@@ -256,6 +256,13 @@ typedef struct {
 /* dst_info->color_range picks the black / white background levels (16..235 unless B200_COLOR_RANGE_0_255) */
 int b200_comp_blend_yuv (b200_comp * h, void *dst, const b200_video_info * dst_info, int background,
     const b200_comp_pad_yuv * pads, int n_pads, void *cuda_stream);
+/* system-memory peers of the YUV compositor: pad frames and the destination are HOST buffers laid out as their
+ * b200_video_info says (b200_video_info_size bytes each); same device ring, streams and _wait as b200_comp_blend_host_submit
+ * (gstcudamemorycopy.c's role folded into the element).  The destination's stride padding is preserved. */
+int b200_comp_blend_yuv_host_submit (b200_comp * h, void *dst_host, const b200_video_info * dst_info, int background,
+    const b200_comp_pad_yuv * pads, int n_pads);
+int b200_comp_blend_yuv_host (b200_comp * h, void *dst_host, const b200_video_info * dst_info, int background,
+    const b200_comp_pad_yuv * pads, int n_pads);
 
 /* ------------------------------------------------------------------ audio resampler */
 typedef struct b200_ars b200_ars;

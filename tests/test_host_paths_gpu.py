@@ -9,6 +9,41 @@ from oracle import bindings as ob
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("fmt", [23, 2, 20, 45, 88], ids=["NV12", "I420", "Y444", "I422_10LE", "Y444_16LE"])
+def test_compositor_yuv_host_frames_pipelined(cuda_device, fmt):
+    """b200_comp_blend_yuv_host_submit / _wait: planar / semi-planar YUV pads and destination in pinned host memory, more
+    submissions than ring slots, the destination's stride padding comes back untouched"""
+    import gstreamer_b200 as g
+    from gstreamer_b200.compositor import CudaCompositor
+    o = ob.oracle()
+    W, H, bg = 322, 201, 2
+    rng = np.random.default_rng(fmt)
+    specs = [(161, 120, -10, 5, 1.0, 1), (200, 91, 100, 60, 0.5, 1), (64, 64, 250, 150, 0.7, 2), (50, 40, 10, 150, 0.0, 1)]
+    comp = CudaCompositor(fmt, W, H, bg)
+    for (w, h, x, y, a, op) in specs:
+        comp.request_pad(w, h, xpos=x, ypos=y, alpha=a, operator=op)
+    sz = o.oracle_compositor_yuv_size(fmt, W, H)
+    outs, wants, keep = [], [], []
+    for n in range(6):
+        bufs = [g.PinnedBuffer(o.oracle_compositor_yuv_size(fmt, w, h)) for (w, h, *_r) in specs]
+        opads = (ob.OraclePad * len(specs))()
+        for k, ((w, h, x, y, a, op), b) in enumerate(zip(specs, bufs)):
+            b.array[:] = rng.integers(0, 256, b.array.size, dtype=np.uint8)
+            p = opads[k]
+            p.data, p.width, p.height, p.stride, p.xpos, p.ypos, p.alpha, p.op = b.ptr, w, h, 0, x, y, a, op
+        want = np.full(sz, 0x33, dtype=np.uint8)
+        assert o.oracle_compositor_yuv(fmt, want.ctypes.data, W, H, bg, 1, opads, len(specs)) == 0
+        out = g.PinnedBuffer(sz)
+        out.array[:] = 0x33
+        comp.aggregate_host_frames_yuv(out.ptr, [b.ptr for b in bufs], wait=False)
+        comp.host_wait(keep_in_flight=1)
+        if n > 0:
+            assert np.array_equal(outs[-1].array, wants[-1]), f"frame {n - 1}"
+        keep.append(bufs); outs.append(out); wants.append(want)
+    comp.host_wait(0)
+    assert np.array_equal(outs[-1].array, wants[-1])
+
+
 def test_compositor_host_frames_pipelined(cuda_device):
     import gstreamer_b200 as g
     from gstreamer_b200.compositor import CudaCompositor
