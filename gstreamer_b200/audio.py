@@ -131,26 +131,3 @@ class CudaAudioResample:
             self._free()
         except Exception:
             pass
-
-
-def smoke():
-    import torch
-    from oracle import bindings as ob
-    o = ob.oracle()
-    ch, n = 8, 480
-    rs = CudaAudioResample(quality=4)
-    rs.set_caps(48000, 44100, ch)
-    ho = o.oracle_ars_new(48000, 44100, ch, 4)
-    rng = np.random.default_rng(1)
-    for _ in range(3):
-        x = rng.standard_normal((n, ch)).astype(np.float32)
-        want = np.zeros((n, ch), dtype=np.float32)
-        nw = o.oracle_ars_process(ho, x.ctypes.data, n, want.ctypes.data, n)
-        out = torch.zeros(n * ch, dtype=torch.float32, device="cuda")
-        ng = rs.transform(torch.from_numpy(x).cuda(), n, out, n)
-        torch.cuda.synchronize()
-        got = out.cpu().numpy().reshape(n, ch)
-        assert ng == nw and np.array_equal(got[:ng].view(np.uint32), want[:nw].view(np.uint32)), \
-            "cudaaudioresample differs from the oracle"
-    o.oracle_ars_free(ho)
-    print("smoke: cudaaudioresample 48k->44.1k 8ch: bit-exact vs oracle")

@@ -191,27 +191,3 @@ class CudaCompositor:
                 self._h = None
         except Exception:
             pass
-
-
-def smoke():
-    import numpy as np
-    import torch
-    from oracle import bindings as ob
-    W, H = 96, 64
-    rng = np.random.default_rng(5)
-    comp = CudaCompositor(VideoFormat.RGBA, W, H, Background.CHECKER)
-    opads = (ob.OraclePad * 3)()
-    keep = []
-    for k, (x, y, a) in enumerate([(-8, 4, 1.0), (30, 20, 0.5), (60, -10, 0.7)]):
-        src = rng.integers(0, 256, (40, 48, 4), dtype=np.uint8)
-        keep.append(src)
-        comp.request_pad(48, 40, xpos=x, ypos=y, alpha=a).set_frame(torch.from_numpy(src).cuda())
-        opads[k].data, opads[k].width, opads[k].height, opads[k].stride = src.ctypes.data, 48, 40, 192
-        opads[k].xpos, opads[k].ypos, opads[k].alpha, opads[k].op = x, y, a, 1
-    want = np.zeros((H, W, 4), dtype=np.uint8)
-    ob.oracle().oracle_compositor(int(VideoFormat.RGBA), want.ctypes.data, W, H, W * 4, 0, opads, 3)
-    out = torch.zeros(H * W * 4, dtype=torch.uint8, device="cuda")
-    comp.aggregate_frames(out)
-    torch.cuda.synchronize()
-    assert np.array_equal(out.cpu().numpy().reshape(H, W, 4), want), "cudacompositor differs from the oracle"
-    print("smoke: cudacompositor 3 pads -> 96x64 RGBA: bit-exact vs oracle")

@@ -19,6 +19,7 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #include "common.h"
 #include "vcs_device.h"
@@ -396,11 +397,15 @@ inline bool plan_plane_fast (const PlanePlan & q, int sstride, unsigned long lon
   const int hspan = H.mode == PASS_NTAP ? H.n_taps : (H.mode == PASS_2TAP ? 2 : 1);
   const int vspan = V.mode == PASS_NTAP ? V.n_taps : (V.mode == PASS_2TAP ? 2 : 1);
   const int ow = q.ow, oh = q.oh;
-  static const int shapes[][2] = {{128, 32}, {128, 16}, {64, 32}, {128, 8}, {64, 16}, {32, 32}, {64, 8}, {32, 16},
+  static const int shapes[][2] = {{128, 64}, {128, 32}, {128, 16}, {64, 32}, {128, 8}, {64, 16}, {32, 32}, {64, 8}, {32, 16},
                                   {64, 4}, {32, 8}, {32, 4}};
   double best = 0; bool found = false;
+  const char *env_shape = getenv ("B200_PLF_SHAPE");               // tuning aid: "tw,th"
+  int etw = 0, eth = 0;
+  if (env_shape && sscanf (env_shape, "%d,%d", &etw, &eth) != 2) etw = eth = 0;
   for (auto & sh : shapes) {
     const int tw = sh[0], th = sh[1];
+    if (etw && (tw != etw || th != eth)) continue;
     if (th > 16 && oh < 2 * th) continue;
     int max_rows = 0, max_cols = 0;
     bool ok = true;
