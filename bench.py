@@ -208,7 +208,8 @@ def run_reference(args):
 
 
 def run_extras(steps):
-    """the other BASELINE configs on this GPU (kernel-resident, CUDA events): C1 element default, C4 both backgrounds, C5"""
+    """the other BASELINE configs on this GPU (kernel-resident, CUDA events): C1 element default, C4 both backgrounds, C5;
+    and the YUV -> YUV scaling cases of bench_extra.py --only planes"""
     import bench_extra as bx
     bx.QUIET = True
     a = argparse.Namespace(steps=steps, seconds=20, background=0, no_cpu=True, variant=-1)
@@ -234,6 +235,13 @@ def run_extras(steps):
         d = bx.bench_c5(a)
         d["us_per_frame"] = d["ms_per_buffer"] * 1e3
         out["c5"] = slim(d)
+        # the transcoding-ladder cases (not BASELINE configs): YUV -> YUV plane scaling and the cross-family chain
+        a.steps = max(3, steps // 2)
+        ladder = []
+        for d in bx.bench_planes(a):
+            e = slim(d); e["alg_bytes"] = d["roofline"]["alg_bytes_per_launch"] // 32; e["kernel_variant"] = d["kernel_variant"]
+            ladder.append(e)
+        out["yuv_ladder"] = ladder
     except Exception as e:          # an extra must never take the headline line down
         out["error"] = repr(e)
     return out

@@ -131,6 +131,7 @@ def bench_planes(args):
     import gstreamer_b200 as g
     from oracle import bindings as ob
     # (input format, output format, ...): 23 NV12, 2 I420; a differing pair is the cross-family chain (two launches)
+    results = []
     for (fmt, fmt_o, IW, IH, OW, OH, m) in [(23, 23, 3840, 2160, 1920, 1080, 1), (23, 23, 3840, 2160, 1920, 1080, 3),
                                             (2, 2, 1920, 1080, 1280, 720, 3), (23, 23, 1920, 1080, 1280, 720, 1),
                                             (23, 2, 3840, 2160, 1920, 1080, 3), (23, 2, 1920, 1080, 1280, 720, 1)]:
@@ -159,11 +160,13 @@ def bench_planes(args):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / args.steps
         alg = per * (ii.size + oi.size)
-        print(json.dumps({"config": f"{g.VideoFormat(fmt).name} {IW}x{IH} -> {g.VideoFormat(fmt_o).name} {OW}x{OH} method {m}",
-                          "kernel_variant": int(el.plan_info().kernel_variant), "us_per_frame": ms * 1e3 / per,
-                          "frames_per_s": per * 1e3 / ms,
-                          "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak(), "unit": "GB/s",
-                                       "frac": alg / (ms * 1e-3) / 1e9 / peak()}}), flush=True)
+        results.append(emit({"config": f"{g.VideoFormat(fmt).name} {IW}x{IH} -> {g.VideoFormat(fmt_o).name} {OW}x{OH} method {m}",
+                             "kernel_variant": int(el.plan_info().kernel_variant), "us_per_frame": ms * 1e3 / per,
+                             "frames_per_s": per * 1e3 / ms,
+                             "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak(), "unit": "GB/s",
+                                          "frac": alg / (ms * 1e-3) / 1e9 / peak(), "alg_bytes_per_launch": alg}}))
+        del rin, rout, base
+    return results
 
 
 def bench_audio_formats(args):

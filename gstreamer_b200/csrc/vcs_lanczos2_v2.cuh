@@ -326,6 +326,12 @@ vcs_lanczos2_v2_kernel (const VcsDev P, const Lanczos2Dev L, const Lanczos2V2Dev
       }
     }
   };
+  // Two more things were built, measured or checked, and dropped (profiles/r02_l2_v2_lab.txt): (1) packing the 24 left-over
+  // columns of the tile's 15 row groups into 12 full warp passes instead of 15 three-quarter-full ones - the packed passes'
+  // per-lane row pointers and indices cost more than the three passes saved (6.52 against 6.46 us/frame); (2) running the
+  // left / right border tiles on the constant taps over edge-REPLICATED samples - the reference folds its edge taps in
+  // double precision BEFORE quantising them, so the folded integer taps are not the uniform integer taps summed over the
+  // replicated positions (column 1 of the bench shape: -3 8 28 28 7 -3 -1 against -4 8 28 28 8 -3 -1): not bit-exact.
   for (int q = warp; q < TH / 4; q += NWARP) {
     const int oy = oy0 + 4 * q;
     if (oy < P.oh) {
