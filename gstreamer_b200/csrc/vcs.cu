@@ -118,12 +118,12 @@ int launch_convert (b200_vcs * h, int n, const VcsBatch & batch, cudaStream_t st
     bool aligned = true;                                            // 16-byte cp.async of the luma rows
     for (int i = 0; i < n; i++) aligned = aligned && (((uintptr_t) batch.in[i]) & 15) == 0 && (((uintptr_t) batch.out[i]) & 3) == 0;
     if (aligned) return launch_l2tc (h->dev, h->tc, batch, n, stream);
-    if (p.lanczos2_ok) return launch_lanczos2 (h->dev, h->l2, batch, n, stream);
+    if (p.lanczos2_ok && !p.planar) return launch_lanczos2 (h->dev, h->l2, batch, n, stream);
   }
 #endif
   if (h->variant == 1 && p.lanczos2_ok) {
     if (h->l2v2.ready && h->l2.x4) return launch_lanczos2_v2 (h->dev, h->l2, h->l2v2, batch, n, stream);
-    return launch_lanczos2 (h->dev, h->l2, batch, n, stream);
+    if (!p.planar) return launch_lanczos2 (h->dev, h->l2, batch, n, stream);
   }
   if (h->variant == 2 && p.light_ok && !p.yuv_out) {
     // 32-bit plane loads: the frame itself must be word aligned (device allocations always are)
@@ -386,8 +386,9 @@ int b200_vcs_create (const b200_video_info * in, const b200_video_info * out,
   }
   if (!h->plan.yuv_out && !h->plan.in_422_444) {
     h->l2_tables = build_lanczos2_tables (h->plan);
-    h->plan.lanczos2_ok = h->l2_tables.ok;
     h->l2v2_tables = build_lanczos2_v2_tables (h->plan, h->l2_tables);
+    // planar (I420 / YV12) input exists in the second form of the kernel only
+    h->plan.lanczos2_ok = h->l2_tables.ok && (!h->plan.planar || (h->l2v2_tables.ok && !getenv ("B200_L2_V1") && !getenv ("B200_L2_X4")));
     h->mma_tables = build_l2mma_tables (h->plan);
 #ifndef B200_CUDA_EMU
     h->tc_tables = build_l2tc_tables (h->plan, h->l2_tables);

@@ -539,7 +539,7 @@ inline size_t tc_pos (int row, int k, int lbo) { return (size_t) (k >> 4) * lbo 
 inline L2tcTables build_l2tc_tables (const VcsPlan & p, const Lanczos2Tables & l2)
 {
   L2tcTables t;
-  if (!l2.ok || !l2.alpha_opaque) return t;                        // same eligibility as the SIMT 2:1 kernel, opaque alpha only
+  if (!l2.ok || !l2.alpha_opaque || p.planar) return t;           // same eligibility as the SIMT 2:1 kernel, opaque alpha, semi-planar only
   if ((p.in.width & 15) || (p.in.stride[0] & 15) || (p.in.stride[1] & 15) || (p.in.offset[0] & 15) || (p.in.offset[1] & 15)) return t;
   const int ow = p.out.width, oh = p.out.height, iw = p.in.width, ih = p.in.height;
   t.strips = (ow + TC_TW - 1) / TC_TW; t.row_tiles = (oh + TC_TH - 1) / TC_TH;

@@ -396,8 +396,11 @@ inline bool pack_axis_lanczos2 (const AxisPlan & a, int frame_bias, std::vector<
 inline Lanczos2Tables build_lanczos2_tables (const VcsPlan & p)
 {
   Lanczos2Tables t;
-  if (!p.h_first || p.matrix_first || !p.h_cosited || !p.v_pairs || p.planar) return t;
-  if ((p.in.stride[0] & 7) || (p.in.stride[1] & 7) || (p.in.offset[0] & 7) || (p.in.offset[1] & 7)) return t;
+  if (!p.h_first || p.matrix_first || !p.h_cosited || !p.v_pairs || p.chroma_nearest) return t;
+  if (p.planar) {                                 // I420 / YV12: only the second form of the kernel reads separate U and V planes (32-bit loads)
+    if ((p.in.stride[0] & 7) || (p.in.offset[0] & 7)) return t;
+    for (int k = 1; k <= 2; k++) if ((p.in.stride[k] & 3) || (p.in.offset[k] & 3) || p.in.stride[k] < (p.in.width >> 1)) return t;
+  } else if ((p.in.stride[0] & 7) || (p.in.stride[1] & 7) || (p.in.offset[0] & 7) || (p.in.offset[1] & 7)) return t;
   if ((p.in.width & 7) || (p.in.height & 1)) return t;
   for (int y = 0; y < p.in.height; y++)       // every line consumed in order: standard pairing
     if (p.chroma_mode[y] != (y == 0 ? 0 : ((y & 1) ? 1 : 2))) return t;

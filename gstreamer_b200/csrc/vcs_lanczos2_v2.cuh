@@ -65,9 +65,10 @@ __device__ __forceinline__ unsigned pack_sat_s16x2 (int a, int b)     // { sat_s
 
 // SEL: the output format's byte selector (VcsDev::sel) when known at compile time, -1: applied with a PRMT per pixel.
 // PF: 1 the next H item's loads are issued before this item's arithmetic, 2 only its chroma rows, 0 neither.
+// PLANAR: I420 / YV12 input - a chroma row is one 32-bit word from each of the U and V planes (already de-interleaved).
 // TH x NT: output rows per tile and threads per CTA (60 x 256 at 4 CTAs per SM, or 124 x 512 at 2: 256 of 254 filtered lines used
 // instead of 128 of 126).
-template <int MINB, int SEL, int PF, int TH = 60, int NT = L2_THREADS>
+template <int MINB, int SEL, int PF, int TH = 60, int NT = L2_THREADS, bool PLANAR = false>
 __global__ void __launch_bounds__ (NT, MINB)
 vcs_lanczos2_v2_kernel (const VcsDev P, const Lanczos2Dev L, const Lanczos2V2Dev K, const VcsBatch frames)
 {
@@ -81,6 +82,7 @@ vcs_lanczos2_v2_kernel (const VcsDev P, const Lanczos2Dev L, const Lanczos2V2Dev
   uint8_t *__restrict__ out = frames.out[blockIdx.z];
   const uint8_t *__restrict__ plane_y = in + P.off_y;
   const uint8_t *__restrict__ plane_c = in + P.off_c;
+  const uint8_t *__restrict__ plane_u = in + P.off_u, *__restrict__ plane_v = in + P.off_v;   // PLANAR
   const int x0 = blockIdx.x * L2_TW, oy0 = blockIdx.y * TH;
   const int R0 = 2 * oy0 - 3;                                    // first input line of the tile
   const int crows = P.ih >> 1;
@@ -131,8 +133,14 @@ vcs_lanczos2_v2_kernel (const VcsDev P, const Lanczos2Dev L, const Lanczos2V2Dev
 #pragma unroll
       for (int k = 0; k < 3; k++) {
         const int cr = min (max (m2 + k, 0), crows - 1);
-        const uint2 c = __ldg ((const uint2 *) (plane_c + (size_t) cr * P.stride_c + xb));
-        const unsigned ue = __byte_perm (c.x, c.y, selU), ve = __byte_perm (c.x, c.y, selV);
+        unsigned ue, ve;
+        if (PLANAR) {
+          ue = __ldg ((const unsigned *) (plane_u + (size_t) cr * P.stride_u + (xb >> 1)));
+          ve = __ldg ((const unsigned *) (plane_v + (size_t) cr * P.stride_v + (xb >> 1)));
+        } else {
+          const uint2 c = __ldg ((const uint2 *) (plane_c + (size_t) cr * P.stride_c + xb));
+          ue = __byte_perm (c.x, c.y, selU); ve = __byte_perm (c.x, c.y, selV);
+        }
         unsigned un = __shfl_down_sync (0xffffffffu, ue, 1), vn = __shfl_down_sync (0xffffffffu, ve, 1);
         un = right_edge ? __byte_perm (ue, ue, 0x3321) : __byte_perm (ue, un, 0x4321);
         vn = right_edge ? __byte_perm (ve, ve, 0x3321) : __byte_perm (ve, vn, 0x4321);
@@ -170,7 +178,14 @@ vcs_lanczos2_v2_kernel (const VcsDev P, const Lanczos2Dev L, const Lanczos2V2Dev
     const int xb = 2 * (x0 + (lane - 1) * 4);                    // byte column of the lane's 8 input pixels
     auto h_load_c = [&] (auto clamp_tag, int g, uint2 (&c)[3]) {
       const int m2 = (R0 + 4 * g - 1) >> 1;
-      if (decltype (clamp_tag)::value) {
+      if (PLANAR) {                                              // c[k].x = 4 U samples, c[k].y = 4 V samples
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          const int cr = decltype (clamp_tag)::value ? min (max (m2 + k, 0), crows - 1) : m2 + k;
+          c[k].x = __ldg ((const unsigned *) (plane_u + (ptrdiff_t) cr * P.stride_u + (xb >> 1)));
+          c[k].y = __ldg ((const unsigned *) (plane_v + (ptrdiff_t) cr * P.stride_v + (xb >> 1)));
+        }
+      } else if (decltype (clamp_tag)::value) {
 #pragma unroll
         for (int k = 0; k < 3; k++)
           c[k] = __ldg ((const uint2 *) (plane_c + (size_t) min (max (m2 + k, 0), crows - 1) * P.stride_c + xb));
@@ -196,7 +211,7 @@ vcs_lanczos2_v2_kernel (const VcsDev P, const Lanczos2Dev L, const Lanczos2V2Dev
       unsigned ulo[3], uhi[3], vlo[3], vhi[3];                   // [o0 e1 o1 e2], [o2 e3 o3 e4]: pixels 8L+1 .. 8L+8
 #pragma unroll
       for (int k = 0; k < 3; k++) {
-        const unsigned ue = __byte_perm (rc[k].x, rc[k].y, selU), ve = __byte_perm (rc[k].x, rc[k].y, selV);
+        const unsigned ue = PLANAR ? rc[k].x : __byte_perm (rc[k].x, rc[k].y, selU), ve = PLANAR ? rc[k].y : __byte_perm (rc[k].x, rc[k].y, selV);
         unsigned un = __shfl_down_sync (0xffffffffu, ue, 1), vn = __shfl_down_sync (0xffffffffu, ve, 1);
         un = __byte_perm (ue, un, 0x4321);
         vn = __byte_perm (ve, vn, 0x4321);
@@ -407,11 +422,11 @@ inline int prepare_lanczos2_v2 (const Lanczos2V2Tables & t, Lanczos2V2State * st
   return B200_OK;
 }
 
-template <int SEL, int PF, int MINB = 4, int TH = 60, int NT = L2_THREADS>
+template <int SEL, int PF, int MINB = 4, int TH = 60, int NT = L2_THREADS, bool PLANAR = false>
 inline int launch_lanczos2_v2_sel (const VcsDev & d, const Lanczos2State & st, const Lanczos2V2State & v2, const VcsBatch & batch,
     int n, cudaStream_t stream)
 {
-  auto kern = vcs_lanczos2_v2_kernel<MINB, SEL, PF, TH, NT>;
+  auto kern = vcs_lanczos2_v2_kernel<MINB, SEL, PF, TH, NT, PLANAR>;
   static bool attr_done[16] = {false};
   int dev = 0; cudaGetDevice (&dev);
   if (!attr_done[dev & 15]) {
@@ -427,6 +442,13 @@ inline int launch_lanczos2_v2_sel (const VcsDev & d, const Lanczos2State & st, c
 inline int launch_lanczos2_v2 (const VcsDev & d, const Lanczos2State & st, const Lanczos2V2State & v2, const VcsBatch & batch, int n,
     cudaStream_t stream)
 {
+  if (d.planar) {                                 // I420 / YV12 input
+    switch (d.sel) {
+      case 0x0123u: return launch_lanczos2_v2_sel<0x0123, 0, 4, 60, L2_THREADS, true> (d, st, v2, batch, n, stream);
+      case 0x0321u: return launch_lanczos2_v2_sel<0x0321, 0, 4, 60, L2_THREADS, true> (d, st, v2, batch, n, stream);
+      default: return launch_lanczos2_v2_sel<-1, 0, 4, 60, L2_THREADS, true> (d, st, v2, batch, n, stream);
+    }
+  }
   switch (d.sel) {
     // (prefetching the next item's loads measured slower: 6.87 against 6.56 us/frame, profiles/r02_l2_v2_lab.txt)
     case 0x0123u: return launch_lanczos2_v2_sel<0x0123, 0> (d, st, v2, batch, n, stream);   // BGRA / BGRx

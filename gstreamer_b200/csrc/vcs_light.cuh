@@ -284,13 +284,14 @@ __device__ __forceinline__ void vcs_unpack_stage (const VcsDev & P, const uint8_
 // sample), the last odd pixel replicates (video_chroma_up_h2_cs_u8, video-chroma.c:687-699), columns left of the tile's
 // first staged word or right of the frame are simply not stored.
 // LAYOUT as in vcs_unpack_stage (0: packed pixels; 1 / 2: the byte planes of the n-tap kernels, matrix-last only).
-template <bool MFIRST, int LAYOUT = 0>
-__device__ __forceinline__ void vcs_unpack_fast_cs (const VcsDev & P, const uint8_t *__restrict__ in, int cxa, int cx1,
+template <bool MFIRST, int LAYOUT = 0, bool PLANAR = false>
+__device__ __forceinline__ void vcs_unpack_fast_cs_impl (const VcsDev & P, const uint8_t *__restrict__ in, int cxa, int cx1,
     int ry0, int R, unsigned *S, int pitch, int plane_words = 0)
 {
   const uint8_t *__restrict__ plane_y = in + P.off_y, *__restrict__ plane_c = in + P.off_c;
   const unsigned selU = P.u_index ? 0x7531u : 0x6420u, selV = P.u_index ? 0x6420u : 0x7531u;
-  const unsigned nselU = P.u_index ? 0x5321u : 0x4321u, nselV = P.u_index ? 0x4321u : 0x5321u;
+  // {samples 1..3 of this word, the next sample}: byte 0 of a planar next-sample load, or the U / V byte of the next interleaved pair
+  const unsigned sel_nu = (!PLANAR && P.u_index) ? 0x5321u : 0x4321u, sel_nv = (!PLANAR && !P.u_index) ? 0x5321u : 0x4321u;
   const int xs = cxa & ~7;                                        // 8-byte aligned loads
   const int n8 = (min (cx1, P.iw) - xs + 7) >> 3;                 // 8-pixel items per line pair
   const int q0 = (ry0 + 1) >> 1, nq = ((ry0 + R) >> 1) - q0 + 1;  // pairs (2q-1, 2q) touching rows ry0 .. ry0+R-1
@@ -306,10 +307,24 @@ __device__ __forceinline__ void vcs_unpack_fast_cs (const VcsDev & P, const uint
     const int lim = (P.iw - 3 - x) >> 1;
     const unsigned esel = 0x3210u + (lim >= 0 ? 0x1u : 0u) + (lim >= 1 ? 0x10u : 0u) + (lim >= 2 ? 0x100u : 0u);
     const int ra = min (max (q - 1, 0), crows - 1), rb = min (q, crows - 1);
-    const uint8_t *pa = plane_c + (size_t) ra * P.stride_c + x, *pb = plane_c + (size_t) rb * P.stride_c + x;
-    const uint2 ca = __ldg ((const uint2 *) pa), cb = __ldg ((const uint2 *) pb);
-    const unsigned na = right_edge ? 0u : (unsigned) __ldg ((const unsigned short *) (pa + 8));
-    const unsigned nb = right_edge ? 0u : (unsigned) __ldg ((const unsigned short *) (pb + 8));
+    // chroma rows a, b as de-interleaved words: {U, V} x 4 samples, and the next sample of each for the last odd pixel
+    unsigned uea, vea, ueb, veb, una, vna, unb, vnb;
+    if (PLANAR) {                                                 // I420 / YV12: separate planes, 32-bit loads (x / 2 is a multiple of 4)
+      const uint8_t *ua = in + P.off_u + (size_t) ra * P.stride_u + (x >> 1), *ub = in + P.off_u + (size_t) rb * P.stride_u + (x >> 1);
+      const uint8_t *va = in + P.off_v + (size_t) ra * P.stride_v + (x >> 1), *vb = in + P.off_v + (size_t) rb * P.stride_v + (x >> 1);
+      uea = __ldg ((const unsigned *) ua); ueb = __ldg ((const unsigned *) ub);
+      vea = __ldg ((const unsigned *) va); veb = __ldg ((const unsigned *) vb);
+      una = right_edge ? 0u : (unsigned) __ldg (ua + 4); unb = right_edge ? 0u : (unsigned) __ldg (ub + 4);
+      vna = right_edge ? 0u : (unsigned) __ldg (va + 4); vnb = right_edge ? 0u : (unsigned) __ldg (vb + 4);
+    } else {
+      const uint8_t *pa = plane_c + (size_t) ra * P.stride_c + x, *pb = plane_c + (size_t) rb * P.stride_c + x;
+      const uint2 ca = __ldg ((const uint2 *) pa), cb = __ldg ((const uint2 *) pb);
+      const unsigned na = right_edge ? 0u : (unsigned) __ldg ((const unsigned short *) (pa + 8));
+      const unsigned nb = right_edge ? 0u : (unsigned) __ldg ((const unsigned short *) (pb + 8));
+      uea = __byte_perm (ca.x, ca.y, selU); vea = __byte_perm (ca.x, ca.y, selV);
+      ueb = __byte_perm (cb.x, cb.y, selU); veb = __byte_perm (cb.x, cb.y, selV);
+      una = vna = na; unb = vnb = nb;                             // the next pair: its U / V byte is picked by sel_nu / sel_nv
+    }
     const int ya = 2 * q - 1, yb = 2 * q;                         // the pair's lines; ya == -1 for q == 0
     const bool sa = ya >= ry0 && ya < ry0 + R, sb = yb >= ry0 && yb < ry0 + R && yb < P.ih;
     uint2 y0 = make_uint2 (0u, 0u), y1 = make_uint2 (0u, 0u);
@@ -318,17 +333,17 @@ __device__ __forceinline__ void vcs_unpack_fast_cs (const VcsDev & P, const uint
     // co-sited h up-sampling of both rows: even pixel = c[k], odd pixel = (c[k] + c[k+1] + 1) >> 1
     unsigned alo[2], ahi[2], blo[2], bhi[2];                      // [U, V] x 8 full-resolution samples (lo = pixels 0..3)
     {
-      const unsigned ue = __byte_perm (ca.x, ca.y, selU), ve = __byte_perm (ca.x, ca.y, selV);
-      const unsigned un = right_edge ? __byte_perm (ue, ue, esel) : __byte_perm (ue, na, nselU);
-      const unsigned vn = right_edge ? __byte_perm (ve, ve, esel) : __byte_perm (ve, na, nselV);
+      const unsigned ue = uea, ve = vea;
+      const unsigned un = right_edge ? __byte_perm (ue, ue, esel) : __byte_perm (ue, una, sel_nu);
+      const unsigned vn = right_edge ? __byte_perm (ve, ve, esel) : __byte_perm (ve, vna, sel_nv);
       const unsigned uo = avg_ceil4 (ue, un), vo = avg_ceil4 (ve, vn);
       alo[0] = __byte_perm (ue, uo, 0x5140); ahi[0] = __byte_perm (ue, uo, 0x7362);
       alo[1] = __byte_perm (ve, vo, 0x5140); ahi[1] = __byte_perm (ve, vo, 0x7362);
     }
     {
-      const unsigned ue = __byte_perm (cb.x, cb.y, selU), ve = __byte_perm (cb.x, cb.y, selV);
-      const unsigned un = right_edge ? __byte_perm (ue, ue, esel) : __byte_perm (ue, nb, nselU);
-      const unsigned vn = right_edge ? __byte_perm (ve, ve, esel) : __byte_perm (ve, nb, nselV);
+      const unsigned ue = ueb, ve = veb;
+      const unsigned un = right_edge ? __byte_perm (ue, ue, esel) : __byte_perm (ue, unb, sel_nu);
+      const unsigned vn = right_edge ? __byte_perm (ve, ve, esel) : __byte_perm (ve, vnb, sel_nv);
       const unsigned uo = avg_ceil4 (ue, un), vo = avg_ceil4 (ve, vn);
       blo[0] = __byte_perm (ue, uo, 0x5140); bhi[0] = __byte_perm (ue, uo, 0x7362);
       blo[1] = __byte_perm (ve, vo, 0x5140); bhi[1] = __byte_perm (ve, vo, 0x7362);
@@ -367,6 +382,15 @@ __device__ __forceinline__ void vcs_unpack_fast_cs (const VcsDev & P, const uint
     if (sa) { store4 (ya - ry0, col, y0.x, u0[0], v0[0]); store4 (ya - ry0, col + 4, y0.y, u0[1], v0[1]); }
     if (sb) { store4 (yb - ry0, col, y1.x, u1[0], v1[0]); store4 (yb - ry0, col + 4, y1.y, u1[1], v1[1]); }
   }
+}
+
+// semi-planar (NV12 / NV21) or planar (I420 / YV12) chroma: a property of the plan, two instantiations of the stage
+template <bool MFIRST, int LAYOUT = 0>
+__device__ __forceinline__ void vcs_unpack_fast_cs (const VcsDev & P, const uint8_t *__restrict__ in, int cxa, int cx1,
+    int ry0, int R, unsigned *S, int pitch, int plane_words = 0)
+{
+  if (P.planar) vcs_unpack_fast_cs_impl<MFIRST, LAYOUT, true> (P, in, cxa, cx1, ry0, R, S, pitch, plane_words);
+  else vcs_unpack_fast_cs_impl<MFIRST, LAYOUT, false> (P, in, cxa, cx1, ry0, R, S, pitch, plane_words);
 }
 
 template <int HM, int VM, bool MFIRST, bool COSITED>

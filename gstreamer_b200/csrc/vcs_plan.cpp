@@ -381,10 +381,14 @@ bool fast_layout_ok (const VcsPlan * p)
 // read up to 7 bytes past the width: inside the row's stride)
 void std_pairs_check (VcsPlan * p)
 {
-  bool std_pairs = !p->planar && !p->chroma_nearest && p->v_pairs && !p->in_422_444 && !p->rgb_in && !p->planes_mode &&
-      !(p->in.stride[0] & 7) && !(p->in.stride[1] & 7) && !(p->in.offset[0] & 7) && !(p->in.offset[1] & 7) &&
-      p->in.stride[0] >= ((p->in.width + 7) & ~7) && p->in.stride[1] >= ((p->in.width + 7) & ~7) && !(p->in.height & 1) &&
+  bool std_pairs = !p->chroma_nearest && p->v_pairs && !p->in_422_444 && !p->rgb_in && !p->planes_mode &&
+      !(p->in.stride[0] & 7) && !(p->in.offset[0] & 7) && p->in.stride[0] >= ((p->in.width + 7) & ~7) && !(p->in.height & 1) &&
       (int) p->chroma_mode.size () >= p->in.height;
+  if (p->planar)                                  // I420 / YV12: 32-bit loads of 4 samples + the next one from each chroma plane
+    for (int k = 1; k <= 2; k++)
+      std_pairs = std_pairs && !(p->in.stride[k] & 3) && !(p->in.offset[k] & 3) && p->in.stride[k] >= ((((p->in.width + 7) & ~7) >> 1));
+  else
+    std_pairs = std_pairs && !(p->in.stride[1] & 7) && !(p->in.offset[1] & 7) && p->in.stride[1] >= ((p->in.width + 7) & ~7);
   for (int y = 0; std_pairs && y < p->in.height; y++)
     if (p->chroma_mode[y] != (y == 0 ? 0 : ((y & 1) ? 1 : 2))) std_pairs = false;
   p->light_std_pairs = std_pairs;

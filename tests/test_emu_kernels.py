@@ -316,7 +316,8 @@ def test_lanczos2_v2_interior_tiles(emu, size):
     group kinds of the V phase run; byte orders with a compile-time selector (BGRA, RGBA) and with the run-time one"""
     from gstreamer_b200 import _lib
     iw, ih, W, H = size
-    for fi, fo, method in [("NV12", "BGRA", 3), ("NV21", "RGBA", 9), ("NV12", "ARGB", 5), ("NV21", "xBGR", 3)]:
+    for fi, fo, method in [("NV12", "BGRA", 3), ("NV21", "RGBA", 9), ("NV12", "ARGB", 5), ("NV21", "xBGR", 3), ("I420", "BGRA", 3),
+                           ("YV12", "RGBA", 7), ("I420", "ABGR", 9)]:     # planar input: the kernel's PLANAR instantiation
         frame = frame_for(fi, iw, ih, 21)
         ii, oi = _lib.VideoInfoC(), _lib.VideoInfoC()
         emu.b200_video_info_set_format(C.byref(ii), ob.FMT[fi], iw, ih)

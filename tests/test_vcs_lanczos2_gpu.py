@@ -63,6 +63,27 @@ def test_specialised_formats(cuda_device, in_fmt, out_fmt):
     assert np.array_equal(got, want), _explain(got, want, iw // 2)
 
 
+@pytest.mark.parametrize("in_fmt", ["I420", "YV12"])
+@pytest.mark.parametrize("size,method,out_fmt", [((64, 48), 9, "RGBA"), ((488, 264), 3, "BGRA"), ((496, 280), 6, "ARGB"),
+                                                 ((1000, 520), 3, "xBGR"), ((1928, 1096), 3, "BGRA"), ((3840, 2160), 3, "BGRA")],
+                         ids=lambda v: "%dx%d" % v if isinstance(v, tuple) else str(v))
+def test_planar_input_runs_the_second_form(cuda_device, in_fmt, size, method, out_fmt):
+    """I420 / YV12 input on the exact-2:1 kernel (vcs_lanczos2_v2_kernel<PLANAR>): separate U and V planes with their own
+    strides, every tile class (left / right border table path, top / bottom clamped rows, interior), byte orders with and
+    without a compile-time selector - against the oracle"""
+    import gstreamer_b200 as g
+    from gstreamer_b200 import _lib
+    iw, ih = size
+    d = ob.vcs_desc(iw, ih, iw // 2, ih // 2, method, in_fmt=ob.FMT[in_fmt], out_fmt=ob.FMT[out_fmt], site=2)
+    frame = ob.i420_random_frame(iw, ih, seed=iw + method)
+    want = ob.oracle_vcs_convert(d, frame)
+    got = _convert(iw, ih, method, frame, 1, in_fmt=ob.FMT[in_fmt], out_fmt=ob.FMT[out_fmt])
+    assert np.array_equal(got, want), _explain(got, want, iw // 2)
+    el = g.CudaVideoConvertScale(add_borders=False, method=method)
+    el.set_info(g.VideoInfo(ob.FMT[in_fmt], iw, ih).set_colorimetry(chroma_site=2), g.VideoInfo(ob.FMT[out_fmt], iw // 2, ih // 2))
+    assert _lib.lib.b200_vcs_kernel_name(el._h) == b"vcs_lanczos2_v2_kernel"
+
+
 def test_specialised_equals_generic_on_structured_content(cuda_device):
     iw, ih = 3840, 2160
     frame = ob.nv12_smpte_like_frame(iw, ih, 4)
