@@ -121,7 +121,7 @@ int launch_convert (b200_vcs * h, int n, const VcsBatch & batch, cudaStream_t st
     if (p.lanczos2_ok && !p.planar) return launch_lanczos2 (h->dev, h->l2, batch, n, stream);
   }
 #endif
-  if (h->variant == 1 && p.lanczos2_ok) {
+  if (h->variant == 1 && p.lanczos2_ok && !p.yuv_out) {
     if (h->l2v2.ready && h->l2.x4) return launch_lanczos2_v2 (h->dev, h->l2, h->l2v2, batch, n, stream);
     if (!p.planar) return launch_lanczos2 (h->dev, h->l2, batch, n, stream);
   }
@@ -158,7 +158,12 @@ int launch_convert (b200_vcs * h, int n, const VcsBatch & batch, cudaStream_t st
     bool word_aligned = true;
     for (int i = 0; i < n; i++) word_aligned = word_aligned && (((uintptr_t) batch.in[i]) & 3) == 0;
     static const bool slow_chain = getenv ("B200_CROSS_GENERIC") != nullptr;     // A/B knob
-    if (!slow_chain && word_aligned && h->variant == 2 && p.light_ok) {
+    bool dword_aligned = true;
+    for (int i = 0; i < n; i++) dword_aligned = dword_aligned && (((uintptr_t) batch.in[i]) & 7) == 0;
+    if (!slow_chain && dword_aligned && h->variant == 1 && p.lanczos2_ok && h->l2v2.ready && h->l2.x4) {
+      const int s = launch_lanczos2_v2 (h->dev, h->l2, h->l2v2, mid, n, stream);      // exact 2:1, 8 taps: the headline kernel without its matrix
+      if (s != B200_OK) return s;
+    } else if (!slow_chain && word_aligned && h->variant == 2 && p.light_ok) {
       const int s = launch_light (h->dev, p, mid, n, stream);
       if (s != B200_OK) return s;
     } else if (!slow_chain && word_aligned && h->variant == 3 && p.ntap_ok && h->ntap.ready) {
@@ -383,6 +388,12 @@ int b200_vcs_create (const b200_video_info * in, const b200_video_info * out,
     }
     *handle = h;
     return B200_OK;
+  }
+  if (h->plan.yuv_out && !h->plan.rgb_in && !h->plan.in_422_444 && !h->plan.has_dest) {
+    // the chain's first launch may be the second form of the exact-2:1 kernel with its matrix stage off
+    h->l2_tables = build_lanczos2_tables (h->plan);
+    h->l2v2_tables = build_lanczos2_v2_tables (h->plan, h->l2_tables);
+    h->plan.lanczos2_ok = h->l2_tables.ok && h->l2v2_tables.ok && !getenv ("B200_L2_V1") && !getenv ("B200_L2_X4") && !getenv ("B200_CROSS_GENERIC");
   }
   if (!h->plan.yuv_out && !h->plan.in_422_444) {
     h->l2_tables = build_lanczos2_tables (h->plan);

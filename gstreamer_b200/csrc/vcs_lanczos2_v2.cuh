@@ -66,9 +66,10 @@ __device__ __forceinline__ unsigned pack_sat_s16x2 (int a, int b)     // { sat_s
 // SEL: the output format's byte selector (VcsDev::sel) when known at compile time, -1: applied with a PRMT per pixel.
 // PF: 1 the next H item's loads are issued before this item's arithmetic, 2 only its chroma rows, 0 neither.
 // PLANAR: I420 / YV12 input - a chroma row is one 32-bit word from each of the U and V planes (already de-interleaved).
+// YUVOUT: 4:2:0 output through the chain (VcsDev::yuv_out): no matrix stage, {255, Y, U, V} pixels for vcs_down420_kernel.
 // TH x NT: output rows per tile and threads per CTA (60 x 256 at 4 CTAs per SM, or 124 x 512 at 2: 256 of 254 filtered lines used
 // instead of 128 of 126).
-template <int MINB, int SEL, int PF, int TH = 60, int NT = L2_THREADS, bool PLANAR = false>
+template <int MINB, int SEL, int PF, int TH = 60, int NT = L2_THREADS, bool PLANAR = false, bool YUVOUT = false>
 __global__ void __launch_bounds__ (NT, MINB)
 vcs_lanczos2_v2_kernel (const VcsDev P, const Lanczos2Dev L, const Lanczos2V2Dev K, const VcsBatch frames)
 {
@@ -313,6 +314,17 @@ vcs_lanczos2_v2_kernel (const VcsDev P, const Lanczos2Dev L, const Lanczos2V2Dev
         if (KIND) { pv[0] = pack_sat_s16x2 (a[2][1], a[2][0]); pv[1] = pack_sat_s16x2 (a[2][3], a[2][2]); }
 #pragma unroll
         for (int i = 0; i < 4; i++) {
+          if (YUVOUT) {                                            // the scaled samples themselves: undo the -128 bias of the packs
+            unsigned px;
+            if (KIND) {
+              const unsigned pyu = pack_sat_s16x2 (a[1][i], a[0][i]);
+              px = (__byte_perm (pyu, pv[i >> 1], (i & 1) ? 0x7310u : 0x5310u) ^ 0x80808000u) | 0xffu;
+            } else {
+              px = __byte_perm (pack_sat2 (a[1][i] >> 6, a[0][i] >> 6, pack_sat2 (0, a[2][i] >> 6, 0u)), 0x000000ffu, 0x2104);
+            }
+            *(unsigned *) (rowp[i] + 128 * k) = px;
+            continue;
+          }
           int wy, wu, wv;
           if (KIND) {
             // byte 1 of sat_s16 (4 acc + 128 - 32768) = clamp ((acc + 32) >> 6, 0, 255) - 128: the biased sample, sign-splat to s16
@@ -422,11 +434,11 @@ inline int prepare_lanczos2_v2 (const Lanczos2V2Tables & t, Lanczos2V2State * st
   return B200_OK;
 }
 
-template <int SEL, int PF, int MINB = 4, int TH = 60, int NT = L2_THREADS, bool PLANAR = false>
+template <int SEL, int PF, int MINB = 4, int TH = 60, int NT = L2_THREADS, bool PLANAR = false, bool YUVOUT = false>
 inline int launch_lanczos2_v2_sel (const VcsDev & d, const Lanczos2State & st, const Lanczos2V2State & v2, const VcsBatch & batch,
     int n, cudaStream_t stream)
 {
-  auto kern = vcs_lanczos2_v2_kernel<MINB, SEL, PF, TH, NT, PLANAR>;
+  auto kern = vcs_lanczos2_v2_kernel<MINB, SEL, PF, TH, NT, PLANAR, YUVOUT>;
   static bool attr_done[16] = {false};
   int dev = 0; cudaGetDevice (&dev);
   if (!attr_done[dev & 15]) {
@@ -442,6 +454,9 @@ inline int launch_lanczos2_v2_sel (const VcsDev & d, const Lanczos2State & st, c
 inline int launch_lanczos2_v2 (const VcsDev & d, const Lanczos2State & st, const Lanczos2V2State & v2, const VcsBatch & batch, int n,
     cudaStream_t stream)
 {
+  if (d.yuv_out)                                  // the cross-family chain's first launch: scaled {255, Y, U, V} pixels, no matrix
+    return d.planar ? launch_lanczos2_v2_sel<-1, 0, 4, 60, L2_THREADS, true, true> (d, st, v2, batch, n, stream)
+                    : launch_lanczos2_v2_sel<-1, 0, 4, 60, L2_THREADS, false, true> (d, st, v2, batch, n, stream);
   if (d.planar) {                                 // I420 / YV12 input
     switch (d.sel) {
       case 0x0123u: return launch_lanczos2_v2_sel<0x0123, 0, 4, 60, L2_THREADS, true> (d, st, v2, batch, n, stream);

@@ -339,6 +339,17 @@ def test_lanczos2_v2_interior_tiles(emu, size):
         check(out, expected(fi, fo, size, method, frame, site=2), f"{fi}->{fo} m{method}")
 
 
+def test_lanczos2_v2_as_first_launch_of_the_cross_family_chain(emu):
+    """exact 2:1 with 8 taps into the OTHER 4:2:0 family: launch 1 is vcs_lanczos2_v2_kernel<YUVOUT> ({255, Y, U, V} pixels, no
+    matrix), launch 2 the chroma down-sampler - interior, border and clamped-row tiles, semi-planar and planar inputs"""
+    size = (512, 248, 256, 124)
+    for fi, fo, method in [("NV12", "I420", 3), ("I420", "NV12", 3), ("NV21", "YV12", 9), ("YV12", "NV21", 6), ("NV12", "NV21", 3)]:
+        frame = frame_for(fi, size[0], size[1], 31)
+        for site in (2, 3):                          # h-cosited sites: the kernel's chroma up-sampler
+            got = run(emu, fi, fo, size, method, frame, site=site)
+            check(got, expected(fi, fo, size, method, frame, site=site), f"{fi}->{fo} m{method} site{site}")
+
+
 # ---- 4. compositor and audio resampler sources under the same emulation --------------------------------------------------
 @pytest.mark.parametrize("fmt", ["RGBA", "BGRA", "ARGB", "ABGR"])
 @pytest.mark.parametrize("background", [0, 1, 2, 3])
