@@ -514,6 +514,29 @@ static void ars_build_qtab (const ArsPlan & p, int nch, std::vector<float> * out
       }
 }
 
+// the same layout with the S16 resampler's integer taps widened to 32 bits (phases_x holds them as int16, [phase][n_taps])
+static void ars_build_qtab_s16 (const ArsPlan & p, int nch, std::vector<float> * out)
+{
+  const int RQ = 4;
+  out->assign ((size_t) 4 * p.out_step * nch * RQ * 4, 0.f);
+  const int16_t *phases = (const int16_t *) p.phases_x.data ();
+  int32_t *o = (int32_t *) out->data ();
+  for (int a = 0; a < 4; a++)
+    for (int ph = 0; ph < p.out_step; ph++)
+      for (int r = 0; r < RQ; r++) {
+        const long long t = (long long) ph + (long long) r * p.samp_frac;
+        const int delta = (int) ((long long) r * p.samp_inc + t / p.out_step), phase = (int) (t % p.out_step);
+        const int16_t *src = phases + (size_t) phase * p.n_taps;
+        for (int chunk = 0; chunk < nch; chunk++) {
+          int32_t *dst = o + ((((size_t) a * p.out_step + ph) * nch + chunk) * RQ + r) * 4;
+          for (int k = 0; k < 4; k++) {
+            const int tap = 4 * chunk + k - (a + delta);
+            dst[k] = (tap >= 0 && tap < p.n_taps) ? (int32_t) src[tap] : 0;
+          }
+        }
+      }
+}
+
 template <int CB, int CPT>
 __global__ void __launch_bounds__ (ARS_THREADS)
 ars_tile_kernel (const ArsLaunch L, const ArsTile Tl)
@@ -1023,6 +1046,169 @@ ars_pipe_kernel (const ArsLaunch L, const ArsTile Tl, int n_fb, int n_cb, const 
   }
 }
 
+// sign-extending byte permute: the 16-bit sample in the low (0x9910) or high (0xbb32) half of a word as an int
+__device__ __forceinline__ int prmt_s16 (unsigned v, unsigned sel)
+{
+#ifdef B200_CUDA_EMU
+  return sel == 0x9910u ? (int) (short) (v & 0xffffu) : (int) (short) (v >> 16);
+#else
+  int d;
+  asm ("prmt.b32 %0, %1, 0, %2;" : "=r" (d) : "r" (v), "r" (sel));
+  return d;
+#endif
+}
+
+// ---- ars_pipe_kernel_s16: the same pipeline for S16 streams ----------------------------------------------------------------
+// The window travels as raw 16-bit samples (one tensor copy of half the bytes), the tap rows as 32-bit ints in the F32 kernel's
+// chunk-major layout (host: ars_build_qtab_s16); a thread owns 4 channels x 4 outputs: per frame position one LDS.64 of samples
+// (4 sign-extending PRMT) and per output one broadcast LDS.128 of taps feed 16 IMAD - the IMADs (half rate) bound it exactly
+// where FMUL + FADD bound the F32 kernel.  Sums wrap in 32 bits, + 2^14, >> 15, saturate: byte-identical to ars_tile_kernel_s16.
+__global__ void __launch_bounds__ (ARS_PIPE_THREADS, 1)
+ars_pipe_kernel_s16 (const ArsLaunch L, const ArsTile Tl, int n_fb, int n_cb, const __grid_constant__ ArsTensorMap tm_in, int use_tm)
+{
+  extern __shared__ __align__ (128) float smp[];
+  constexpr int RQ = ARS_RQ, NO = ARS_PIPE_NO, CB = ARS_PIPE_CB, NQ = NO / RQ, NW = ARS_PIPE_THREADS / 32;
+  const int row = Tl.nch * RQ;                                    // float4 per output group in the tap table
+  // a stage = the tap rows (32-bit ints, the layout of the F32 kernel) + the window as RAW 16-bit samples (half a float each)
+  const unsigned qt_floats = (unsigned) NQ * row * 4, stage_floats = qt_floats + (unsigned) Tl.win * CB / 2;
+  const short *hist16 = (const short *) L.hist, *in16 = (const short *) L.in;
+  short *out16 = (short *) L.out;
+  __shared__ ArsBar s_full[2], s_empty[2];
+  __shared__ int s_rel[2][NO];
+  const int lane = threadIdx.x & 31;
+  const int warp = __shfl_sync (0xffffffffu, (int) (threadIdx.x >> 5), 0);
+  const int n_tiles = n_fb * n_cb;
+  if (threadIdx.x == 0) {
+    ars_bar_init (&s_full[0], ARS_PIPE_PROD); ars_bar_init (&s_full[1], ARS_PIPE_PROD);
+    ars_bar_init (&s_empty[0], NW); ars_bar_init (&s_empty[1], NW);
+#ifndef B200_CUDA_EMU
+    asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
+  }
+  __syncthreads ();
+
+  // producing warps: positions of tile t's outputs, one bulk copy per tap row and per window row into stage b
+  auto produce = [&] (int t, int b) {
+    float *stage = smp + (size_t) b * stage_floats;
+    float4 *qt = (float4 *) stage;
+    float *xin = stage + qt_floats;
+    const int fb = t / n_cb, c_base = (t - fb * n_cb) * CB;
+    const long long o0 = (long long) fb * NO;
+    const int n_out = (int) min ((long long) NO, L.out_frames - o0);
+    long long f0; int ph0;
+    ars_position (L, o0, f0, ph0);
+    f0 &= ~3LL;
+#ifndef B200_CUDA_EMU
+    asm volatile ("fence.proxy.async.shared::cta;" ::: "memory");  // zero rows written two tiles ago vs this tile's bulk writes
+#endif
+    unsigned tx = 0;
+    if (lane < NO / ARS_PIPE_PROD) {
+      const int j = warp * (NO / ARS_PIPE_PROD) + lane;
+      long long idx; int phase;
+      ars_position (L, o0 + min (j, n_out - 1), idx, phase);
+      const int rel = (int) (idx - f0);
+      s_rel[b][j] = rel;
+      if ((j & (RQ - 1)) == 0) {
+        const float4 *src = Tl.qtab + ((size_t) (rel & 3) * L.out_step + phase) * row;
+        ars_bulk_g2s (qt + (size_t) (j / RQ) * row, src, (unsigned) row * 16u, &s_full[b]);
+        tx += (unsigned) row * 16u;
+      }
+    }
+    // a window that lies in the caller's input (every tile but the first few) is ONE tensor copy: box = CB channels x win
+    // frames, rows past the end of the input arrive as zeros (out-of-bounds fill) like the missing frames of the row path.
+    // (Divergent lanes issuing a bulk copy each are serialised through the uniform datapath: the row path below costs the
+    // producing warps ~40 copies each and made them the tile's stragglers - measured 1.77 ms against 1.72 for cp.async.)
+    const bool tensor = use_tm && f0 >= L.hist_frames;
+    if (tensor) {
+      if (warp == 0 && lane == 0) {
+        ars_tensor_g2s (xin, &tm_in, c_base, (int) (f0 - L.hist_frames), &s_full[b]);
+        tx += (unsigned) Tl.win * CB * 2u;
+      }
+    } else
+    for (int fr = warp + ARS_PIPE_PROD * lane; fr < Tl.win; fr += 32 * ARS_PIPE_PROD) {
+      const long long f = f0 + fr;
+      const short *src = nullptr;
+      if (f < L.hist_frames) src = hist16 + f * L.channels;
+      else if (f < L.avail && in16) src = in16 + (f - L.hist_frames) * L.channels;
+      float *dst = xin + (size_t) fr * (CB / 2);
+      if (src) { ars_bulk_g2s (dst, src + c_base, CB * 2u, &s_full[b]); tx += CB * 2u; }
+      else {
+#pragma unroll 4
+        for (int i = 0; i < CB / 8; i++) ((float4 *) dst)[i] = make_float4 (0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) tx += __shfl_down_sync (0xffffffffu, tx, d);
+    ars_warp_sync ();                                             // the lanes' s_rel entries and zero rows before lane 0's release
+    if (lane == 0) ars_bar_arrive_tx (&s_full[b], tx);
+  };
+
+  int t = blockIdx.x, k = 0;
+  if (warp < ARS_PIPE_PROD && t < n_tiles) produce (t, 0);
+  for (; t < n_tiles; t += gridDim.x, k++) {
+    const int b = k & 1, tn = t + gridDim.x;
+    if (warp < ARS_PIPE_PROD && tn < n_tiles) {
+      if (k >= 1) ars_bar_wait (&s_empty[b ^ 1], (unsigned) ((k - 1) >> 1) & 1u);   // every warp is done with tile k - 1
+      produce (tn, b ^ 1);
+    }
+    ars_bar_wait (&s_full[b], (unsigned) (k >> 1) & 1u);
+
+    const int4 *qt = (const int4 *) (smp + (size_t) b * stage_floats);
+    const short *xin = (const short *) (smp + (size_t) b * stage_floats + qt_floats);
+    const int fb = t / n_cb;
+    const long long o0 = (long long) fb * NO;
+    const int n_out = (int) min ((long long) NO, L.out_frames - o0);
+    const int nq = (n_out + RQ - 1) / RQ;
+    const int c = (t - fb * n_cb) * CB + 4 * lane;
+    for (int q = warp; q < nq; q += NW) {
+      // integer sums wrap in 32 bits like the SSE2 pmaddwd path (inner_product_gint16_full_1_sse2, audio-resampler-x86-sse2.c:29-56):
+      // no lane structure to keep, one accumulator per (channel, output)
+      unsigned acc[4][RQ];
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+#pragma unroll
+        for (int r = 0; r < RQ; r++) acc[u][r] = 0u;
+      const int s_min = s_rel[b][q * RQ] & ~3;
+      const int s_max = (s_rel[b][min (q * RQ + RQ - 1, n_out - 1)] + L.n_taps + 3) & ~3;
+      const int nch = (s_max - s_min) >> 2;
+      const short *xp = xin + s_min * CB + 4 * lane;
+      const int4 *tp = qt + (size_t) q * row;
+#pragma unroll 2
+      for (int ch = 0; ch < nch; ch++, xp += 4 * CB, tp += RQ) {
+        int x[4][4];
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) {
+          const uint2 v = *(const uint2 *) (xp + kk * CB);           // 4 adjacent channels of one frame, 16 bits each
+          x[0][kk] = prmt_s16 (v.x, 0x9910u); x[1][kk] = prmt_s16 (v.x, 0xbb32u);
+          x[2][kk] = prmt_s16 (v.y, 0x9910u); x[3][kk] = prmt_s16 (v.y, 0xbb32u);
+        }
+#pragma unroll
+        for (int r = 0; r < RQ; r++) {
+          const int4 tq = tp[r];
+#pragma unroll
+          for (int u = 0; u < 4; u++)
+            acc[u][r] += (unsigned) (x[u][0] * tq.x) + (unsigned) (x[u][1] * tq.y) + (unsigned) (x[u][2] * tq.z) + (unsigned) (x[u][3] * tq.w);
+        }
+      }
+      short *op = out16 + (size_t) (o0 + q * RQ) * L.channels + c;
+#pragma unroll
+      for (int r = 0; r < RQ; r++) {
+        if (q * RQ + r < n_out) {
+          // + 2^14, >> 15, saturate (audio-resampler-x86-sse2.c:48-54)
+          const int v0 = sat_s16 ((int) (acc[0][r] + (1u << 14)) >> 15), v1 = sat_s16 ((int) (acc[1][r] + (1u << 14)) >> 15);
+          const int v2 = sat_s16 ((int) (acc[2][r] + (1u << 14)) >> 15), v3 = sat_s16 ((int) (acc[3][r] + (1u << 14)) >> 15);
+          uint2 o;
+          o.x = ((unsigned) v0 & 0xffffu) | ((unsigned) v1 << 16);
+          o.y = ((unsigned) v2 & 0xffffu) | ((unsigned) v3 << 16);
+          *(uint2 *) (op + (size_t) r * L.channels) = o;
+        }
+      }
+    }
+    ars_warp_sync ();
+    if (lane == 0) ars_bar_arrive (&s_empty[b]);                  // this warp no longer reads stage b
+  }
+}
+
 template <int CB>
 __global__ void __launch_bounds__ (ARS_THREADS)
 ars_tile_kernel_s16 (const ArsLaunch L, const ArsTile Tl)
@@ -1450,7 +1636,7 @@ using namespace b200;
 static_assert (sizeof (ArsTensorMap) == sizeof (CUtensorMap), "CUtensorMap is 128 bytes");
 typedef CUresult (*ars_encode_fn) (CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
     const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static int ars_encode_window_map (ArsTensorMap *tm, const float *in, unsigned long long in_frames, int channels, int cb, int win)
+static int ars_encode_window_map (ArsTensorMap *tm, const void *in, unsigned long long in_frames, int channels, int cb, int win, int elem_bytes = 4)
 {
   static ars_encode_fn fn = [] () -> ars_encode_fn {
     void *f = nullptr;
@@ -1461,14 +1647,15 @@ static int ars_encode_window_map (ArsTensorMap *tm, const float *in, unsigned lo
   static const bool off = getenv ("B200_ARS_NO_TENSORMAP") != nullptr;       // A/B knob: row-wise bulk copies only
   if (!fn || off || !in || in_frames == 0 || win > 256 || cb > 256 || (((uintptr_t) in) & 15) || (channels & 3)) return 0;
   const cuuint64_t gdim[2] = {(cuuint64_t) channels, (cuuint64_t) in_frames};
-  const cuuint64_t gstride[1] = {(cuuint64_t) channels * sizeof (float)};
+  const cuuint64_t gstride[1] = {(cuuint64_t) channels * (cuuint64_t) elem_bytes};
   const cuuint32_t box[2] = {(cuuint32_t) cb, (cuuint32_t) win}, estr[2] = {1, 1};
-  const CUresult r = fn ((CUtensorMap *) tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *) in, gdim, gstride, box, estr,
+  if (((cuuint64_t) channels * (cuuint64_t) elem_bytes) & 15) return 0;
+  const CUresult r = fn ((CUtensorMap *) tm, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *) in, gdim, gstride, box, estr,
       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 #else
-static int ars_encode_window_map (ArsTensorMap *, const float *, unsigned long long, int, int, int) { return 0; }
+static int ars_encode_window_map (ArsTensorMap *, const void *, unsigned long long, int, int, int, int = 4) { return 0; }
 #endif
 
 struct b200_ars {
@@ -1543,6 +1730,16 @@ static int ars_upload_tables (b200_ars * h)
   } else
     st = h->plan.full ? upload (&h->d_phases, h->plan.phases.data (), h->plan.phases.size ())
                       : upload (&h->d_proto, h->plan.proto.data (), h->plan.proto.size ());
+  if (st == B200_OK && h->plan.fmt == ARS_S16 && h->plan.full && !h->plan.small && !h->plan.copy && (h->plan.channels % ARS_PIPE_CB) == 0 &&
+      h->plan.phases_x.size () == (size_t) h->plan.out_step * h->plan.n_taps * 2) {
+    // the pipelined S16 kernel's tap rows (32-bit ints in the F32 layout)
+    const ArsPlan & q = h->plan;
+    const long long spread = ((long long) (ARS_RQ - 1) * q.in_step + q.out_step - 1) / q.out_step + 1;
+    h->qtab_nch = (int) ((spread + q.n_taps + 3 + 3) / 4 + 1);
+    std::vector<float> tab;
+    ars_build_qtab_s16 (q, h->qtab_nch, &tab);
+    st = upload (&h->d_qtab, tab.data (), tab.size ());
+  }
   if (st == B200_OK && h->plan.fmt == ARS_F32 && h->plan.full && !h->plan.small && !h->plan.copy) {
     // tap rows of every (alignment, phase) group for the tile kernels; bounded by the FULL-mode threshold
     // (bps * n_taps * out_rate < 1 MiB  =>  at most 16 x that in this layout)
@@ -1554,6 +1751,36 @@ static int ars_upload_tables (b200_ars * h)
     st = upload (&h->d_qtab, tab.data (), tab.size ());
   }
   return st;
+}
+
+// the pipelined S16 kernel (whole 128-channel blocks, 16-byte aligned streams); false: not applicable, take the tile kernel
+static bool ars_launch_pipe_s16 (b200_ars * h, ArsLaunch & L, size_t in_frames, size_t out_frames, cudaStream_t stream)
+{
+  const ArsPlan & p = h->plan;
+  ArsTile tp = ArsTile ();
+  const long long spread = ((long long) (ARS_RQ - 1) * p.in_step + p.out_step - 1) / p.out_step + 1;
+  tp.nch = (int) ((spread + p.n_taps + 3 + 3) / 4 + 1);
+  if (tp.nch != h->qtab_nch) return false;
+  const long long span = ((long long) ARS_PIPE_NO * p.in_step + p.out_step - 1) / p.out_step + 8 + p.n_taps;
+  tp.win = (int) ((span + 3) & ~3LL);
+  tp.qtab = (const float4 *) h->d_qtab;
+  const size_t smem_pipe = 2 * ((size_t) (ARS_PIPE_NO / ARS_RQ) * tp.nch * ARS_RQ * 4 * sizeof (float) + (size_t) tp.win * ARS_PIPE_CB * 2);
+  int optin = 0;
+  cudaDeviceGetAttribute (&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
+  if (smem_pipe + 2048 > (size_t) optin) return false;
+  static bool attr_done[16] = {false};
+  if (!attr_done[h->device & 15]) {
+    if (allow_max_dyn_smem (ars_pipe_kernel_s16) != B200_OK) return false;
+    attr_done[h->device & 15] = true;
+  }
+  L.no = ARS_PIPE_NO;
+  const int n_fb = (int) ((out_frames + ARS_PIPE_NO - 1) / ARS_PIPE_NO), n_cb = p.channels / ARS_PIPE_CB;
+  int grid = (int) std::min ((long long) n_fb * n_cb, (long long) sm_count (h->device));
+  { const char *e = getenv ("B200_ARS_GRID"); if (e && atoi (e) > 0) grid = std::min (grid, atoi (e)); }
+  ArsTensorMap tm = ArsTensorMap ();
+  const int use_tm = ars_encode_window_map (&tm, L.in, (unsigned long long) in_frames, p.channels, ARS_PIPE_CB, tp.win, 2);
+  ars_pipe_kernel_s16 <<<grid, ARS_PIPE_THREADS, smem_pipe, stream>>> (L, tp, n_fb, n_cb, tm, use_tm);
+  return true;
 }
 
 extern "C" {
@@ -1771,6 +1998,10 @@ int b200_ars_process (b200_ars * h, const void *in_v, size_t in_frames, void *ou
       else if (p.fmt == ARS_S32) ars_small_kernel<ARS_S32> <<<grid, ARS_THREADS, 0, stream>>> (X, nearest);
       else if (p.fmt == ARS_F64) ars_small_kernel<ARS_F64> <<<grid, ARS_THREADS, 0, stream>>> (X, nearest);
       else ars_small_kernel<ARS_F32> <<<grid, ARS_THREADS, 0, stream>>> (X, nearest);
+      s16_tiled = true;
+    } else if (p.fmt == ARS_S16 && p.full && h->d_qtab && (p.channels % ARS_PIPE_CB) == 0 && !getenv ("B200_ARS_GENERIC") &&
+        !getenv ("B200_ARS_NOPIPE") && ((((uintptr_t) L.hist) | ((uintptr_t) L.in) | ((uintptr_t) L.out)) & 15) == 0 &&
+        ars_launch_pipe_s16 (h, L, in_frames, out_frames, stream)) {
       s16_tiled = true;
     } else if (p.fmt == ARS_S16 && p.full && p.channels >= 64 && !getenv ("B200_ARS_GENERIC")) {
       // tiled S16 kernel: same tile geometry as the F32 one (4-byte staged samples and taps)

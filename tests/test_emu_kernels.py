@@ -486,8 +486,8 @@ def test_audio_kernels(emu, fmt, opts, monkeypatch):
         rates += [(3, 2, 3, 5), (48000, 8000, 2, 1), (96000, 44100, 1, 6)]
     if opts == AUDIO_OPTS[0]:
         rates += [(44100, 44100, 3, 4)]                       # equal rates: gst_audio_resampler's nearest functions
-        if fmt == "F32":
-            rates += [(48000, 44100, 128, 4), (44100, 48000, 256, 2)]   # whole 128-channel blocks: the persistent pipelined kernel
+        if fmt in ("F32", "S16"):
+            rates += [(48000, 44100, 128, 4), (44100, 48000, 256, 2)]   # whole 128-channel blocks: the persistent pipelined kernels
     for (a, b, ch, q) in rates:
         ho = o.oracle_ars_new_opts(a, b, ch, q, ofmt, M[method], MO[mode], I[interp])
         cfg = _lib.ArsConfigC()
@@ -516,12 +516,13 @@ def test_audio_kernels(emu, fmt, opts, monkeypatch):
             o.oracle_ars_free(ho)
 
 
-def test_audio_pipeline_many_tiles_per_cta(emu, monkeypatch):
+@pytest.mark.parametrize("fmt", ["F32", "S16"])
+def test_audio_pipeline_many_tiles_per_cta(emu, monkeypatch, fmt):
     """ars_pipe_kernel's stage hand-over (full / empty barriers, two stages): B200_ARS_GRID=2 makes each persistent CTA walk
     a dozen tiles, with start-up zeros, a silent call (no input pointer) and a last partial tile"""
     from gstreamer_b200 import _lib
     monkeypatch.setenv("B200_ARS_GRID", "2")
-    ofmt, gfmt, dt, _ = ob.AUDIO_FORMATS["F32"]
+    ofmt, gfmt, dt, _ = ob.AUDIO_FORMATS[fmt]
     o = ob.oracle()
     for (a, b, ch, grid) in [(48000, 44100, 256, "2"), (44100, 48000, 128, "3"), (48000, 44100, 128, "1")]:
         monkeypatch.setenv("B200_ARS_GRID", grid)
@@ -537,7 +538,7 @@ def test_audio_pipeline_many_tiles_per_cta(emu, monkeypatch):
                 if n is None:
                     n = 200
                 else:
-                    x = ob.audio_test_signal(rng, n, ch, "F32")
+                    x = ob.audio_test_signal(rng, n, ch, fmt)
                 cap = int(n * b / a) + 64
                 want = np.zeros((cap, ch), dtype=dt)
                 nw = o.oracle_ars_process_any(ho, x.ctypes.data if x is not None else None, n, want.ctypes.data, cap)
