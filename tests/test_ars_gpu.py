@@ -146,6 +146,41 @@ def test_interpolated_filter_mode(cuda_device, cfg):
     _stream_through(a, b, ch, q, [480, 480, 100, 1, 2000, 37], seed=ch)
 
 
+@pytest.mark.parametrize("grid", ["3", "16"])
+@pytest.mark.parametrize("fmt", ["F32", "S16"])
+def test_pipeline_many_tiles_per_cta(cuda_device, monkeypatch, fmt, grid):
+    """the persistent pipelines (ars_pipe_kernel, ars_pipe_kernel_s16) with FEWER CTAs than tiles (B200_ARS_GRID): every CTA walks
+    dozens of tiles through its two stages - full / empty barrier phases, the tensor-copy path and the row path of the tiles that
+    touch the history, a last partial tile - byte-identical to the oracle over several buffers"""
+    import torch
+    from gstreamer_b200.audio import CudaAudioResample
+    monkeypatch.setenv("B200_ARS_GRID", grid)
+    a, b, ch, q = 48000, 44100, 256, 4
+    ofmt, gfmt, dt, _ = ob.AUDIO_FORMATS[fmt]
+    o = ob.oracle()
+    ho = o.oracle_ars_new_fmt(a, b, ch, q, ofmt)
+    rs = CudaAudioResample(quality=q, format=gfmt)
+    rs.set_caps(a, b, ch)
+    rng = np.random.default_rng(int(grid))
+    tdt = {np.float32: torch.float32, np.int16: torch.int16}[dt]
+    for n in [4800, 7001, 480, None]:
+        x = None
+        if n is None:
+            n = rs.max_latency
+        else:
+            x = ob.audio_test_signal(rng, n, ch, fmt)
+        cap = int(n * b / a) + 64
+        want = np.zeros((cap, ch), dtype=dt)
+        nw = o.oracle_ars_process_any(ho, x.ctypes.data if x is not None else None, n, want.ctypes.data, cap)
+        out = torch.full((cap * ch,), 7, dtype=tdt, device="cuda")
+        ng = rs.transform(torch.from_numpy(x).cuda() if x is not None else None, n, out, cap)
+        torch.cuda.synchronize()
+        got = out.cpu().numpy().reshape(cap, ch)
+        assert ng == nw and got[:ng].tobytes() == want[:nw].tobytes(), (fmt, grid, n)
+        assert (got[ng:] == 7).all()
+    o.oracle_ars_free(ho)
+
+
 @pytest.mark.parametrize("cfg", [(48000, 44100, 2, 4), (44100, 48000, 3, 4), (8000, 16000, 1, 4), (48000, 24000, 40, 4),
                                  (101, 99, 1, 4), (44100, 8000, 2, 10), (96000, 8000, 1, 7), (12345, 54321, 2, 4),
                                  (44100, 48001, 2, 4), (48000, 44101, 1, 6), (7999, 48000, 3, 10),
