@@ -134,7 +134,9 @@ def bench_planes(args):
     results = []
     for (fmt, fmt_o, IW, IH, OW, OH, m) in [(23, 23, 3840, 2160, 1920, 1080, 1), (23, 23, 3840, 2160, 1920, 1080, 3),
                                             (2, 2, 1920, 1080, 1280, 720, 3), (23, 23, 1920, 1080, 1280, 720, 1),
-                                            (23, 2, 3840, 2160, 1920, 1080, 3), (23, 2, 1920, 1080, 1280, 720, 1)]:
+                                            (23, 2, 3840, 2160, 1920, 1080, 3), (23, 2, 1920, 1080, 1280, 720, 1),
+                                            (12, 12, 3840, 2160, 1920, 1080, 1), (12, 11, 3840, 2160, 1920, 1080, 3),
+                                            (12, 12, 1920, 1080, 1280, 720, 3)]:      # 12 BGRA, 11 RGBA: 4-byte pixels
         el = g.CudaVideoConvertScale(method=m)
         ii, oi = g.VideoInfo(fmt, IW, IH), g.VideoInfo(fmt_o, OW, OH)
         if fmt != fmt_o:                              # what the element's caps fixation does for YUV -> YUV
@@ -142,7 +144,11 @@ def bench_planes(args):
             transfer_colorimetry_from_input(ii, oi)
         el.set_info(ii, oi)
         per = 32
-        gen = ob.i420_random_frame if fmt in (2, 3) else ob.nv12_random_frame
+        if fmt in (11, 12):
+            import numpy as np
+            gen = lambda w, h, seed: np.random.default_rng(seed).integers(0, 256, w * h * 4, dtype=np.uint8)
+        else:
+            gen = ob.i420_random_frame if fmt in (2, 3) else ob.nv12_random_frame
         base = [torch.from_numpy(gen(IW, IH, s)).cuda() for s in range(2)]
         rin = [base[k % 2].clone() for k in range(2 * per)]
         rout = [torch.empty(oi.size, dtype=torch.uint8, device="cuda") for _ in range(2 * per)]

@@ -18,6 +18,7 @@
 #include "vcs_ntap.cuh"
 #include "vcs_planes.cuh"
 #include "vcs_down420.cuh"
+#include "vcs_rgb420.cuh"
 
 #include <string.h>
 #include <new>
@@ -58,6 +59,11 @@ struct b200_vcs {
   BorderDev border;               // destination rectangle: what to fill around it
   uint8_t *d_scratch = nullptr;
   int scratch_frames = 0;
+  size_t scratch_frame_bytes = 0;
+  // packed RGB -> 4:2:0 at an unchanged or shrinking size: [word-wide scaler on 4-byte pixels ->] matrix + down-sample + pack
+  Rgb420Dev rgb420;
+  bool rgb420_ok = false, rgb420_scaled = false;
+  PlaneFastState rgb420_scaler;
   size_t in_bytes = 0, out_bytes = 0;
 };
 
@@ -81,6 +87,47 @@ int upload_axis (const AxisPlan & a, uint32_t **off, int16_t **coef, int16_t **s
 }
 
 int launch_convert (b200_vcs * h, int n, const VcsBatch & batch, cudaStream_t stream);
+
+// packed RGB -> 4:2:0 with every scaler in front of the matrix (the frame does not grow) and no destination rectangle:
+// vcs_rgb420.cuh.  Leaves rgb420_ok false (the generic chain runs) for what the fast kernels decline.
+int prepare_rgb420 (b200_vcs * h)
+{
+  const VcsPlan & p = h->plan;
+  h->rgb420_ok = false;
+  if (!p.rgb_in || !p.yuv_out || p.matrix_first || p.has_dest || getenv ("B200_RGB420_GENERIC")) return B200_OK;
+  Rgb420Dev & r = h->rgb420;
+  memset (&r, 0, sizeof (r));
+  const int pos_r = p.in_sel & 0xf, pos_g = (p.in_sel >> 4) & 0xf, pos_b = (p.in_sel >> 8) & 0xf;
+  for (int i = 0; i < 3; i++) {
+    if (!rgb420_split_row (p.m_rgb2yuv[i], pos_r, pos_g, pos_b, &r.ca[i], &r.cb[i])) return B200_OK;
+    r.off[i] = p.m_rgb2yuv[i][3];
+  }
+  const Down420Dev & q = h->down;
+  r.ow = q.ow; r.oh = q.oh; r.hmode = q.hmode; r.vavg = q.vavg;
+  r.stride_y = q.stride_y; r.stride_u = q.stride_u; r.stride_v = q.stride_v; r.cstep = q.cstep;
+  r.off_y = q.off_y; r.off_u = q.off_u; r.off_v = q.off_v;
+  const unsigned long long cbase = q.cstep == 2 ? std::min (q.off_u, q.off_v) : (q.off_u | q.off_v);
+  r.wvec = ((q.stride_y | q.stride_u | q.stride_v) & 3) == 0 && ((q.off_y | cbase) & 3) == 0;
+  h->rgb420_scaled = p.h.scaling || p.v.scaling;
+  if (!h->rgb420_scaled) {
+    r.sstride = p.in.stride[0]; r.soff = p.in.offset[0];
+    r.svec = (r.sstride & 15) == 0 && (r.soff & 15) == 0;
+  } else {
+    PlanePlan pl;
+    pl.src_plane = 0; pl.iw = p.in.width; pl.ih = p.in.height; pl.ow = p.out.width; pl.oh = p.out.height;
+    pl.ne = 4; pl.swz = 0; pl.mode = PM_SCALE;
+    pl.have_h = p.h.scaling; pl.have_v = p.v.scaling; pl.h_first = p.h_first;
+    pl.h = p.h; pl.v = p.v;
+    const int sstride = (p.out.width * 4 + 15) & ~15;
+    std::vector<int32_t> hp, vp;
+    if (!plan_plane_fast (pl, p.in.stride[0], p.in.offset[0], sstride, 0, &h->rgb420_scaler, &hp, &vp)) return B200_OK;
+    const int st = prepare_plane_fast (pl, hp, vp, &h->rgb420_scaler);
+    if (st != B200_OK) return st;
+    r.sstride = sstride; r.soff = 0; r.svec = 1;
+  }
+  h->rgb420_ok = true;
+  return B200_OK;
+}
 
 int launch (b200_vcs * h, int n, const VcsBatch & batch, cudaStream_t stream)
 {
@@ -139,14 +186,41 @@ int launch_convert (b200_vcs * h, int n, const VcsBatch & batch, cudaStream_t st
   dim3 grid ((p.out.width + p.tile_w - 1) / p.tile_w, (p.out.height + p.tile_h - 1) / p.tile_h, n);
   if (p.rgb_in)                                                    // packed pixels are read with 32-bit loads
     for (int i = 0; i < n; i++) if (((uintptr_t) batch.in[i]) & 3) return B200_ERR_INVALID_ARG;
+  if (p.yuv_out && h->rgb420_ok) {
+    Rgb420Dev r = h->rgb420;
+    Rgb420Batch fin;
+    for (int i = 0; i < n; i++) {
+      fin.out[i] = batch.out[i];
+      if (((uintptr_t) batch.out[i]) & 3) r.wvec = 0;
+    }
+    if (h->rgb420_scaled) {
+      const size_t frame = (size_t) r.sstride * p.out.height;
+      if (n > h->scratch_frames || frame != h->scratch_frame_bytes) {
+        B200_CUDA_TRY (cudaFree (h->d_scratch));                    // synchronises with launches still reading it
+        h->d_scratch = nullptr; h->scratch_frames = 0;
+        B200_CUDA_TRY (cudaMalloc ((void **) &h->d_scratch, frame * n));
+        h->scratch_frames = n; h->scratch_frame_bytes = frame;
+      }
+      VcsBatch mid;
+      for (int i = 0; i < n; i++) { mid.in[i] = batch.in[i]; mid.out[i] = h->d_scratch + frame * i; fin.src[i] = mid.out[i]; }
+      const int s = launch_plane_fast (h->rgb420_scaler, mid, n, stream);
+      if (s != B200_OK) return s;
+    } else {
+      for (int i = 0; i < n; i++) {
+        fin.src[i] = batch.in[i];
+        if (((uintptr_t) batch.in[i]) & 15) r.svec = 0;
+      }
+    }
+    return launch_rgb420 (r, fin, n, stream);
+  }
   if (p.yuv_out) {
     // launch 1 writes the scaled pixels of every frame to its scratch image, launch 2 down-samples and packs
     const size_t frame = (size_t) h->down.stride_s * (p.out.height + (p.extra_row ? 1 : 0));
-    if (n > h->scratch_frames) {
+    if (n > h->scratch_frames || frame != h->scratch_frame_bytes) {
       B200_CUDA_TRY (cudaFree (h->d_scratch));                      // synchronises with launches still reading it
       h->d_scratch = nullptr; h->scratch_frames = 0;
       B200_CUDA_TRY (cudaMalloc ((void **) &h->d_scratch, frame * n));
-      h->scratch_frames = n;
+      h->scratch_frames = n; h->scratch_frame_bytes = frame;
     }
     VcsBatch mid;
     Down420Batch fin;
@@ -452,6 +526,7 @@ int b200_vcs_create (const b200_video_info * in, const b200_video_info * out,
       q.cstep = p.out_cstep;
       q.off_u = p.out.offset[p.out_plane_u] + (p.out_cstep == 2 ? p.out_u_index : 0);
       q.off_v = p.out.offset[p.out_plane_v] + (p.out_cstep == 2 ? (p.out_u_index ^ 1) : 0);
+      if ((st = prepare_rgb420 (h)) != B200_OK) { b200_vcs_destroy (h); return st; }
     }
     d.p1 = p.p[0]; d.p2 = p.p[1]; d.p3 = p.p[2]; d.p4 = p.p[3]; d.p5 = p.p[4];
     d.sel = p.byte_sel[0] | (p.byte_sel[1] << 4) | (p.byte_sel[2] << 8) | (p.byte_sel[3] << 12);
@@ -617,7 +692,7 @@ int b200_vcs_get_plan_info (const b200_vcs * h, b200_vcs_plan_info * info)
   for (int i = 0; i < 5; i++) info->p[i] = p.p[i];
   info->tile_w = p.tile_w; info->tile_h = p.tile_h; info->smem_bytes = p.smem_bytes;
   info->kernel_variant = p.yuv_out ? 5 : p.planes_mode ? 4 : h->variant == 7 ? 7 : (h->variant == 6 && h->mma.ready) ? 6 : (h->variant == 1 && p.lanczos2_ok) ? 1 : (h->variant == 2 && p.light_ok) ? 2 : (h->variant == 3 && p.ntap_ok) ? 3 : 0;
-  info->n_launches_per_convert = (p.yuv_out ? (p.extra_row ? 3 : 2) : 1) + (p.has_dest && p.fill_border ? 1 : 0);
+  info->n_launches_per_convert = (h->rgb420_ok ? (h->rgb420_scaled ? 2 : 1) : p.yuv_out ? (p.extra_row ? 3 : 2) : 1) + (p.has_dest && p.fill_border ? 1 : 0);
   return B200_OK;
 }
 

@@ -36,6 +36,7 @@ struct PlaneFastDev {
   int tw, th, rows, pitch;       // tile (output pixels x rows), staged source lines (multiple of 4), word columns per staged line
   int ntw_h, ntw_v;              // packed tap words per output column / row (n-tap axes)
   int hspan, vspan;
+  unsigned swz;                  // 4-byte pixels: output byte c takes component (swz >> 4c) & 3; 0 = same order
   const uint32_t *hoff, *voff;   // first source pixel / line of each output column / row
   const int16_t *hcoef, *vcoef;  // 2-tap axes: the fraction / the weight of the second line
   const int *h_packed, *v_packed;
@@ -87,11 +88,20 @@ vcs_planes_fast_kernel (const PlaneFastDev Q, const VcsBatch frames)
       const uint8_t *line = src + (size_t) min (ry0 + 4 * g + l, Q.ih - 1) * Q.sstride;
       if (NC == 1) {
         w[0][l] = __ldg ((const unsigned *) (line + min (cxa + 4 * j, last_word)));
-      } else {
+      } else if (NC == 2) {
         const unsigned a = __ldg ((const unsigned *) (line + min ((cxa + 4 * j) * 2, last_word)));
         const unsigned b = __ldg ((const unsigned *) (line + min ((cxa + 4 * j) * 2 + 4, last_word)));
         w[0][l] = __byte_perm (a, b, 0x6420);
-        w[NC - 1][l] = __byte_perm (a, b, 0x7531);
+        w[1 % NC][l] = __byte_perm (a, b, 0x7531);
+      } else {                                                     // 4-byte pixels: 4 pixels -> one word per component
+        const unsigned p0 = __ldg ((const unsigned *) (line + min ((cxa + 4 * j) * 4, last_word)));
+        const unsigned p1 = __ldg ((const unsigned *) (line + min ((cxa + 4 * j) * 4 + 4, last_word)));
+        const unsigned p2 = __ldg ((const unsigned *) (line + min ((cxa + 4 * j) * 4 + 8, last_word)));
+        const unsigned p3 = __ldg ((const unsigned *) (line + min ((cxa + 4 * j) * 4 + 12, last_word)));
+        const unsigned a01 = __byte_perm (p0, p1, 0x5140), a23 = __byte_perm (p2, p3, 0x5140);   // c0 c0' c1 c1' of pixels (0,1) / (2,3)
+        const unsigned b01 = __byte_perm (p0, p1, 0x7362), b23 = __byte_perm (p2, p3, 0x7362);   // c2 c2' c3 c3'
+        w[0][l] = __byte_perm (a01, a23, 0x5410); w[1 % NC][l] = __byte_perm (a01, a23, 0x7632);
+        w[2 % NC][l] = __byte_perm (b01, b23, 0x5410); w[3 % NC][l] = __byte_perm (b01, b23, 0x7632);
       }
     }
 #pragma unroll
@@ -175,7 +185,11 @@ vcs_planes_fast_kernel (const PlaneFastDev Q, const VcsBatch frames)
         }
       }
       if (NC == 1) *dp = (uint8_t) v[0];
-      else *(unsigned short *) dp = (unsigned short) ((unsigned) v[0] | ((unsigned) v[NC - 1] << 8));
+      else if (NC == 2) *(unsigned short *) dp = (unsigned short) ((unsigned) v[0] | ((unsigned) v[1 % NC] << 8));
+      else {                                                       // 4-byte pixel, optionally in another byte order (PlaneFastDev::swz)
+        const unsigned px = (unsigned) v[0] | ((unsigned) v[1 % NC] << 8) | ((unsigned) v[2 % NC] << 16) | ((unsigned) v[3 % NC] << 24);
+        *(unsigned *) dp = Q.swz ? __byte_perm (px, 0, Q.swz) : px;
+      }
     }
   }
 }
@@ -230,11 +244,20 @@ vcs_planes_fast_vfirst_kernel (const PlaneFastDev Q, const VcsBatch frames)
       const uint8_t *line = src + (size_t) min (ry0 + 4 * g + l, Q.ih - 1) * Q.sstride;
       if (NC == 1) {
         w[0][l] = __ldg ((const unsigned *) (line + min (cxa + 4 * j, last_word)));
-      } else {
+      } else if (NC == 2) {
         const unsigned a = __ldg ((const unsigned *) (line + min ((cxa + 4 * j) * 2, last_word)));
         const unsigned b = __ldg ((const unsigned *) (line + min ((cxa + 4 * j) * 2 + 4, last_word)));
         w[0][l] = __byte_perm (a, b, 0x6420);
-        w[NC - 1][l] = __byte_perm (a, b, 0x7531);
+        w[1 % NC][l] = __byte_perm (a, b, 0x7531);
+      } else {                                                     // 4-byte pixels: 4 pixels -> one word per component
+        const unsigned p0 = __ldg ((const unsigned *) (line + min ((cxa + 4 * j) * 4, last_word)));
+        const unsigned p1 = __ldg ((const unsigned *) (line + min ((cxa + 4 * j) * 4 + 4, last_word)));
+        const unsigned p2 = __ldg ((const unsigned *) (line + min ((cxa + 4 * j) * 4 + 8, last_word)));
+        const unsigned p3 = __ldg ((const unsigned *) (line + min ((cxa + 4 * j) * 4 + 12, last_word)));
+        const unsigned a01 = __byte_perm (p0, p1, 0x5140), a23 = __byte_perm (p2, p3, 0x5140);   // c0 c0' c1 c1' of pixels (0,1) / (2,3)
+        const unsigned b01 = __byte_perm (p0, p1, 0x7362), b23 = __byte_perm (p2, p3, 0x7362);   // c2 c2' c3 c3'
+        w[0][l] = __byte_perm (a01, a23, 0x5410); w[1 % NC][l] = __byte_perm (a01, a23, 0x7632);
+        w[2 % NC][l] = __byte_perm (b01, b23, 0x5410); w[3 % NC][l] = __byte_perm (b01, b23, 0x7632);
       }
     }
 #pragma unroll
@@ -323,7 +346,11 @@ vcs_planes_fast_vfirst_kernel (const PlaneFastDev Q, const VcsBatch frames)
         }
       }
       if (NC == 1) *dp = (uint8_t) v[0];
-      else *(unsigned short *) dp = (unsigned short) ((unsigned) v[0] | ((unsigned) v[NC - 1] << 8));
+      else if (NC == 2) *(unsigned short *) dp = (unsigned short) ((unsigned) v[0] | ((unsigned) v[1 % NC] << 8));
+      else {                                                       // 4-byte pixel, optionally in another byte order (PlaneFastDev::swz)
+        const unsigned px = (unsigned) v[0] | ((unsigned) v[1 % NC] << 8) | ((unsigned) v[2 % NC] << 16) | ((unsigned) v[3 % NC] << 24);
+        *(unsigned *) dp = Q.swz ? __byte_perm (px, 0, Q.swz) : px;
+      }
     }
   }
 }
@@ -347,6 +374,7 @@ inline plane_fast_fn plane_fast_kernel_for (int hm, int vm, int nc, bool vfirst,
 {
 #define PLF_PICK(H, V)                                                                         \
   if (hm == H && vm == V) {                                                                    \
+    if (nc == 4) return vfirst ? vcs_planes_fast_vfirst_kernel<H, V, 4> : vcs_planes_fast_kernel<H, V, 4>;   \
     if (vfirst && ntw == 2 && (H == 3 || V == 3)) return nc == 1 ? vcs_planes_fast_vfirst_kernel<H, V, 1, 2> : vcs_planes_fast_vfirst_kernel<H, V, 2, 2>;   \
     if (vfirst && ntw == 1 && (H == 3 || V == 3)) return nc == 1 ? vcs_planes_fast_vfirst_kernel<H, V, 1, 1> : vcs_planes_fast_vfirst_kernel<H, V, 2, 1>;   \
     if (vfirst) return nc == 1 ? vcs_planes_fast_vfirst_kernel<H, V, 1> : vcs_planes_fast_vfirst_kernel<H, V, 2>;   \
@@ -385,9 +413,10 @@ inline bool plan_plane_fast (const PlanePlan & q, int sstride, unsigned long lon
     PlaneFastState * st, std::vector<int32_t> * hp, std::vector<int32_t> * vp)
 {
   st->ok = false;
-  if (q.mode != PM_SCALE || (q.ne != 1 && q.ne != 2) || q.swz) return false;
+  if (q.mode != PM_SCALE || (q.ne != 1 && q.ne != 2 && q.ne != 4) || (q.swz && q.ne != 4)) return false;
   if ((sstride & 3) || (src_off & 3) || sstride < 4) return false;
   if (q.ne == 2 && ((dstride & 1) || (dst_off & 1))) return false;
+  if (q.ne == 4 && ((dstride & 3) || (dst_off & 3))) return false;
   const AxisPlan & H = q.h, & V = q.v;
   if (H.mode < 1 || H.mode > 3 || V.mode < 1 || V.mode > 3) return false;
   int ntw_h = 0, ntw_v = 0;
@@ -447,7 +476,7 @@ inline bool plan_plane_fast (const PlanePlan & q, int sstride, unsigned long lon
   PlaneFastDev & d = st->dev;
   d.src_off = src_off; d.dst_off = dst_off; d.sstride = sstride; d.dstride = dstride;
   d.iw = q.iw; d.ih = q.ih; d.ow = q.ow; d.oh = q.oh;
-  d.ntw_h = ntw_h; d.ntw_v = ntw_v; d.hspan = hspan; d.vspan = vspan;
+  d.ntw_h = ntw_h; d.ntw_v = ntw_v; d.hspan = hspan; d.vspan = vspan; d.swz = q.swz;
   st->hm = H.mode; st->vm = V.mode; st->nc = q.ne; st->vfirst = !q.h_first;
   st->ntw = (H.mode == PASS_NTAP && V.mode == PASS_NTAP) ? (ntw_h == ntw_v ? ntw_h : 0) : (H.mode == PASS_NTAP ? ntw_h : ntw_v);
   st->ok = true;

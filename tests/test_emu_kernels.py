@@ -602,3 +602,15 @@ def test_audio_rate_update(emu, fmt):
         finally:
             emu.b200_ars_destroy(h)
             o.oracle_ars_free(ho)
+
+
+@pytest.mark.parametrize("size", [(400, 300, 150, 100), (160, 90, 300, 200), (262, 146, 131, 73), (129, 67, 200, 67), (96, 200, 96, 75),
+                                  (70, 40, 35, 20)], ids=lambda s: "%dx%d-%dx%d" % s)
+def test_planes_fast_kernel_packed_rgb(emu, size):
+    """the word-wide plane scaler on 4-byte pixels (packed RGB -> packed RGB of the same or another byte order): stage A
+    de-interleaves 4 pixels into one word per component, the store re-packs (and re-orders) them"""
+    iw, ih = size[:2]
+    for k, (fi, fo) in enumerate([("BGRA", "BGRA"), ("RGBA", "BGRA"), ("xRGB", "RGBA"), ("ARGB", "ABGR")]):
+        frame = frame_for(fi, iw, ih, 11 + k)
+        for method in [(1, 3), (0, 9), (4, 1), (3,)][k]:
+            check(run(emu, fi, fo, size, method, frame, force_generic=False), expected(fi, fo, size, method, frame), f"{fi}->{fo} m{method}")

@@ -3,9 +3,8 @@ generic chain: unpack to ARGB, the scalers that shrink, the RGB -> YUV table mat
 video-converter.c:1178-1200), the scalers that grow, chroma down-sampling, 4:2:0 pack.  Product: vcs_generic_kernel
 (packed-pixel input stage, matrix between the passes) into scratch A,Y,U,V images, then vcs_down420_kernel.
 
-Written after this round's device budget was spent: the path is opt-in in the product (B200_VCS_EXPERIMENTAL) and these
-tests are skipped unless B200_TEST_EXPERIMENTAL=1, so that an unconfirmed kernel cannot take the suite down.
-First thing to run next round:  B200_TEST_EXPERIMENTAL=1 python -m pytest tests/test_vcs_rgbin_gpu.py -q"""
+Packed RGB -> packed RGB takes the plane-scaling fast path (convert_scale_planes): vcs_planes_fast_kernel on 4-byte
+pixels where the shape is eligible, the byte-wise vcs_planes_kernel otherwise."""
 import os
 
 import numpy as np
@@ -20,11 +19,6 @@ YUV_OUT = ["NV12", "I420", "NV21", "YV12"]
 SIZES = [(64, 48, 32, 24), (64, 48, 96, 72), (65, 49, 33, 26), (33, 17, 20, 31), (50, 21, 50, 21), (57, 35, 29, 35),
          (100, 100, 150, 50), (40, 90, 40, 31), (17, 9, 64, 31), (2, 2, 1, 1), (1, 1, 5, 4), (640, 480, 320, 240),
          (1920, 1080, 1280, 720), (1280, 720, 1920, 1080)]
-
-
-@pytest.fixture(autouse=True)
-def _opt_in(monkeypatch):
-    monkeypatch.setenv("B200_VCS_EXPERIMENTAL", "1")
 
 
 def rgb_frame(iw, ih, seed):
@@ -99,13 +93,15 @@ def test_rgb_to_420_batch(cuda_device):
 @pytest.mark.parametrize("method", [0, 1, 3, 4, 9], ids=["nearest", "bilinear", "lanczos", "bilinear2", "mitchell"])
 @pytest.mark.parametrize("size", [(64, 48, 32, 24), (40, 30, 64, 48), (65, 49, 33, 26), (33, 17, 20, 31), (100, 100, 150, 50),
                                   (40, 90, 40, 31), (64, 48, 64, 24), (64, 48, 32, 48), (3, 5, 7, 2), (1, 1, 4, 4),
-                                  (50, 21, 50, 21), (1920, 1080, 640, 360), (640, 360, 1280, 720)], ids=lambda s: "%dx%d-%dx%d" % s)
+                                  (50, 21, 50, 21), (1920, 1080, 640, 360), (640, 360, 1280, 720), (1918, 1080, 1279, 721),
+                                  (402, 300, 150, 100)], ids=lambda s: "%dx%d-%dx%d" % s)
 def test_rgb_same_format_scaling_matches_oracle(cuda_device, size, method):
-    """a compositor's scaled RGBA pads: one plane of 4-byte pixels through vcs_planes_kernel (ne = 4)"""
+    """a compositor's scaled RGBA pads: one plane of 4-byte pixels through vcs_planes_fast_kernel (NC = 4; the byte order
+    change is one PRMT at the store) or, for shapes it declines, the byte-wise vcs_planes_kernel (ne = 4)"""
     import torch
     import gstreamer_b200 as g
     iw, ih, ow, oh = size
-    pairs = [("BGRA", "BGRA")] if iw * ih > 500_000 else [("BGRA", "BGRA"), ("RGBA", "RGBA"), ("ARGB", "ARGB"), ("xBGR", "xBGR"),
+    pairs = [("BGRA", "BGRA"), ("xRGB", "BGRA")] if iw * ih > 500_000 else [("BGRA", "BGRA"), ("RGBA", "RGBA"), ("ARGB", "ARGB"), ("xBGR", "xBGR"),
                                                             ("BGRA", "RGBA"), ("ARGB", "BGRx"), ("RGBx", "ABGR"), ("xRGB", "BGRA")]
     for fmt, fmt_out in pairs:                      # same format: one-plane rows; another byte order: matrix-free chain
         frame = rgb_frame(iw, ih, 11)
