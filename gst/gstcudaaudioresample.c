@@ -80,8 +80,7 @@ ars_set_caps (GstBaseTransform * trans, GstCaps * incaps, GstCaps * outcaps)
   self->in = in;
   self->out = out;
   g_clear_pointer (&self->ars, b200_ars_destroy);
-  /* b200_ars_config carries the reference's enum values + 1 (0 = element default); b200_ars_create answers
-   * B200_ERR_UNSUPPORTED for what is still opt-in (B200_VCS_EXPERIMENTAL): the nearest / linear / cubic methods */
+  /* b200_ars_config carries the reference's enum values + 1 (0 = element default) */
   cfg.resample_method = self->method + 1;
   cfg.sinc_filter_mode = self->sinc_filter_mode + 1;
   cfg.sinc_filter_interpolation = self->sinc_filter_interpolation + 1;

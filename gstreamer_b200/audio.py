@@ -22,10 +22,8 @@ class AudioFormat:
 
 class CudaAudioResample:
     # the stock element's remaining properties (gstaudioresample.c:153-186) with their nicks.  Implemented: both
-    # windowed-sinc methods, every filter mode, every table interpolation, and the nearest / linear / cubic methods.  Two
-    # of those run device code written after the last device session — linear interpolation in the interpolated filter
-    # mode, and the small kernel of the nearest / linear / cubic methods — and answer B200_ERR_UNSUPPORTED unless
-    # B200_VCS_EXPERIMENTAL is set.
+    # windowed-sinc methods, every filter mode, every table interpolation, and the nearest / linear / cubic methods
+    # (device-verified: tests/test_ars_options_gpu.py).
     # sinc-filter-auto-threshold never reaches the reference's resampler (UINT stored, INT read: SURVEY A.10)
     REST_DEFAULTS = {"resample_method": "kaiser", "sinc_filter_mode": "auto", "sinc_filter_interpolation": "cubic"}
     METHODS = {"nearest": 1, "linear": 2, "cubic": 3, "blackman-nuttall": 4, "kaiser": 5}

@@ -584,6 +584,7 @@ void b200_vcs_destroy (b200_vcs * h)
     cudaFree (h->tc.d_band); cudaFree (h->tc.d_vband); cudaFree (h->tc.d_hx4); cudaFree (h->tc.d_vx4);
 #endif
     free_planes (&h->planes);
+    free_plane_fast (&h->rgb420_scaler);
     cudaFree (h->d_scratch);
     for (int i = 0; i < b200_vcs::kSlots; i++) {
       cudaFree (h->slot_in[i]); cudaFree (h->slot_out[i]);
@@ -753,6 +754,7 @@ const char *b200_vcs_kernel_name (const b200_vcs * h)
     for (int i = 0; i < p.n_planes; i++) if (h->planes.fast[i].ok) return h->planes.fast[i].vfirst ? "vcs_planes_fast_vfirst_kernel" : "vcs_planes_fast_kernel";
     return "vcs_planes_kernel";
   }
+  if (h->rgb420_ok) return "vcs_rgb420_kernel";
   if (h->variant == 6 && h->mma.ready) return "vcs_l2mma_kernel";
 #ifndef B200_CUDA_EMU
   if (h->variant == 7 && h->tc.ready) return "vcs_l2tc_kernel";

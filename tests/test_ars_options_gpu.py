@@ -3,9 +3,7 @@ non-default values (blackman-nuttall window, forced full / interpolated tables, 
 nearest / linear / cubic methods, which have their own small kernel).  Only the
 host side changes (tap tables and the mode decision — checked against the oracle bit for bit in tests/test_host_plan.py) and
 the device kernels are the ones the default configuration runs — except for linear interpolation in the interpolated filter
-mode, whose two-row blend is new device code (emulation-checked; the product gates it behind B200_VCS_EXPERIMENTAL).  Still: written after this round's device budget was
-spent, so skipped unless B200_TEST_EXPERIMENTAL=1.  Run next round:
-  B200_TEST_EXPERIMENTAL=1 python -m pytest tests/test_ars_options_gpu.py -q"""
+mode, whose two-row blend is its own device code."""
 import os
 
 import numpy as np
@@ -29,7 +27,6 @@ I = {"none": 0, "linear": 1, "cubic": 2}
                                                 ("blackman-nuttall", "auto", "linear"),
                                                 ("nearest", "auto", "cubic"), ("linear", "auto", "cubic"), ("cubic", "auto", "cubic")])
 def test_method_and_filter_mode_properties(cuda_device, fmt, method, mode, interp, monkeypatch):
-    monkeypatch.setenv("B200_VCS_EXPERIMENTAL", "1")
     import torch
     from gstreamer_b200.audio import CudaAudioResample
     ofmt, gfmt, dt, _ = ob.AUDIO_FORMATS[fmt]
@@ -66,7 +63,6 @@ def test_nearest_decimation_skip_quirk(cuda_device, fmt, monkeypatch):
     """tests/test_oracle_vs_ref.py::test_audio_nearest_decimation_skip_quirk on the device"""
     import torch
     from gstreamer_b200.audio import CudaAudioResample
-    monkeypatch.setenv("B200_VCS_EXPERIMENTAL", "1")
     ofmt, gfmt, dt, _ = ob.AUDIO_FORMATS[fmt]
     tdt = {np.float32: torch.float32, np.int16: torch.int16, np.int32: torch.int32, np.float64: torch.float64}[dt]
     o = ob.oracle()

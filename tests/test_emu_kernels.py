@@ -116,10 +116,9 @@ def test_emulator_agrees_on_device_verified_paths(emu, size):
             check(got, expected(fi, fo, size, method, frame, site=site), f"{fi}->{fo} m{method} site{site}")
 
 
-# ---- 2. paths whose first device run is still pending ------------------------------------------------------------------
+# ---- 2. the remaining converter paths (device-verified since: tests/test_vcs_rgbin_gpu.py) ------------------------------------
 @pytest.mark.parametrize("size", SMALL, ids=lambda s: "%dx%d-%dx%d" % s)
 def test_rgb_to_420(emu, size, monkeypatch):
-    monkeypatch.setenv("B200_VCS_EXPERIMENTAL", "1")
     iw, ih = size[:2]
     for k, (fi, fo) in enumerate([("BGRA", "NV12"), ("RGBA", "I420"), ("ARGB", "NV21"), ("ABGR", "YV12"), ("xRGB", "NV12"), ("BGRx", "I420")]):
         frame = frame_for(fi, iw, ih, 4)
@@ -135,7 +134,6 @@ def test_rgb_to_420(emu, size, monkeypatch):
 def test_422_444_inputs(emu, size, monkeypatch):
     """YUY2 / UYVY / YVYU / Y42B / Y444 -> packed RGB through the generic kernel (luma pitch 2 in the packed formats,
     per-line chroma rows, horizontal-only or no chroma up-sampling)"""
-    monkeypatch.setenv("B200_VCS_EXPERIMENTAL", "1")
     iw, ih = size[:2]
     for k, fi in enumerate(YUV_422_444):
         frame = frame_for(fi, iw, ih, 10 + k)
@@ -148,7 +146,6 @@ def test_422_444_inputs(emu, size, monkeypatch):
 
 @pytest.mark.parametrize("size", SMALL + [(64, 48, 64, 24), (64, 48, 32, 48)], ids=lambda s: "%dx%d-%dx%d" % s)
 def test_rgb_to_rgb(emu, size, monkeypatch):
-    monkeypatch.setenv("B200_VCS_EXPERIMENTAL", "1")
     iw, ih = size[:2]
     for k, (fi, fo) in enumerate([("BGRA", "BGRA"), ("RGBA", "RGBA"), ("xBGR", "xBGR"), ("BGRA", "RGBA"), ("ARGB", "BGRx"),
                                   ("RGBx", "ABGR"), ("xRGB", "BGRA")]):
@@ -160,7 +157,6 @@ def test_rgb_to_rgb(emu, size, monkeypatch):
 @pytest.mark.parametrize("pair", [("NV12", "BGRA"), ("I420", "RGBA"), ("NV12", "NV12"), ("I420", "YV12"), ("NV12", "I420"),
                                   ("YV12", "NV21"), ("BGRA", "NV12"), ("RGBA", "RGBA"), ("BGRA", "ARGB")], ids=lambda p: "%s-%s" % p)
 def test_destination_rectangle_and_borders(emu, pair, monkeypatch):
-    monkeypatch.setenv("B200_VCS_EXPERIMENTAL", "1")
     fi, fo = pair
     rng = np.random.default_rng(9)
     for t in range(6):
@@ -434,7 +430,6 @@ def test_audio_nearest_decimation_skip_quirk(emu, fmt, monkeypatch):
     """the product's history after a skip (tests/test_oracle_vs_ref.py::test_audio_nearest_decimation_skip_quirk): part of what
     the reference keeps is what its buffer shift left in place, not the stream's tail"""
     from gstreamer_b200 import _lib
-    monkeypatch.setenv("B200_VCS_EXPERIMENTAL", "1")
     ofmt, gfmt, dt, _ = ob.AUDIO_FORMATS[fmt]
     o = ob.oracle()
     for (a, b, ch) in [(48000, 11025, 3), (96000, 8000, 1), (400, 3, 2)]:
@@ -480,7 +475,6 @@ def test_audio_kernels(emu, fmt, opts, monkeypatch):
     M = {"nearest": 0, "linear": 1, "cubic": 2, "blackman-nuttall": 3, "kaiser": 4}
     MO = {"interpolated": 0, "full": 1, "auto": 2}
     I = {"none": 0, "linear": 1, "cubic": 2}
-    monkeypatch.setenv("B200_VCS_EXPERIMENTAL", "1")          # the linear blend of the interpolated mode is opt-in
     rates = [(48000, 44100, 2, 4), (44100, 48000, 66, 2) if fmt in ("F32", "S16") else (96000, 44100, 1, 6)]
     if M[method] < 3:                                         # tap counts off the lane widths: 3, 12; and the 96k -> 44.1k pair
         rates += [(3, 2, 3, 5), (48000, 8000, 2, 1), (96000, 44100, 1, 6)]
@@ -614,3 +608,36 @@ def test_planes_fast_kernel_packed_rgb(emu, size):
         frame = frame_for(fi, iw, ih, 11 + k)
         for method in [(1, 3), (0, 9), (4, 1), (3,)][k]:
             check(run(emu, fi, fo, size, method, frame, force_generic=False), expected(fi, fo, size, method, frame), f"{fi}->{fo} m{method}")
+
+
+@pytest.mark.parametrize("size", [(64, 48, 64, 48), (50, 21, 50, 21), (33, 17, 33, 17), (1, 1, 1, 1), (2, 2, 2, 2), (7, 5, 7, 5), (16, 2, 16, 2),
+                                  (400, 300, 150, 100), (262, 146, 131, 73), (129, 67, 100, 67), (96, 200, 96, 75), (100, 60, 150, 30),
+                                  (70, 40, 35, 20), (41, 23, 17, 9)], ids=lambda s: "%dx%d-%dx%d" % s)
+def test_rgb_to_420_fast_kernels(emu, size, monkeypatch):
+    """vcs_rgb420_kernel (matrix + chroma down-sampling + pack; alone at an unchanged size, behind the word-wide scaler on
+    4-byte pixels where the frame shrinks): every input byte order, both output layouts, co-sited and centred chroma
+    sites, full and video range; the generic chain (B200_RGB420_GENERIC) must agree with the same oracle"""
+    from gstreamer_b200 import _lib
+    iw, ih, W, H = size
+    ii, oi = _lib.VideoInfoC(), _lib.VideoInfoC()
+    emu.b200_video_info_set_format(C.byref(ii), ob.FMT["BGRA"], iw, ih)
+    emu.b200_video_info_set_format(C.byref(oi), ob.FMT["NV12"], W, H)
+    cfg = _lib.VcsConfigC()
+    emu.b200_vcs_config_init(C.byref(cfg))
+    cfg.method = 1
+    h = C.c_void_p()
+    assert emu.b200_vcs_create(C.byref(ii), C.byref(oi), C.byref(cfg), 0, C.byref(h)) == 0
+    emu.b200_vcs_kernel_name.restype = C.c_char_p
+    name = emu.b200_vcs_kernel_name(h).decode()
+    emu.b200_vcs_destroy(h)
+    assert name == "vcs_rgb420_kernel" or min(W, H) < 8, name
+    for k, (fi, fo) in enumerate([("BGRA", "NV12"), ("RGBA", "I420"), ("ARGB", "NV21"), ("ABGR", "YV12"), ("xRGB", "NV12"), ("BGRx", "I420")]):
+        frame = frame_for(fi, iw, ih, 40 + k)
+        for method in [(1, 3), (3,), (0, 9), (4,), (1,), (5,)][k]:
+            check(run(emu, fi, fo, size, method, frame), expected(fi, fo, size, method, frame), f"{fi}->{fo} m{method}")
+    frame = frame_for("BGRA", iw, ih, 5)
+    for col in [(3, 2, 2), (4, 1, 1), (6, 2, 6), (2, 1, 4), (5, 2, 1), (3, 1, 3)]:          # (matrix, range, chroma site)
+        check(run(emu, "BGRA", "NV12", size, 1, frame, colorimetry=col), expected("BGRA", "NV12", size, 1, frame, colorimetry=col),
+              f"colorimetry {col}")
+    monkeypatch.setenv("B200_RGB420_GENERIC", "1")
+    check(run(emu, "BGRA", "NV12", size, 1, frame), expected("BGRA", "NV12", size, 1, frame), "generic chain")

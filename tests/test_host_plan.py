@@ -341,7 +341,6 @@ def test_compositor_pad_sizing_policy():
 
 def test_audioresample_remaining_properties(monkeypatch):
     import gstreamer_b200 as g
-    monkeypatch.delenv("B200_VCS_EXPERIMENTAL", raising=False)
     from gstreamer_b200.audio import CudaAudioResample
     CudaAudioResample(cuda_device_id=-1, resample_method="kaiser", sinc_filter_auto_threshold=1).set_caps(48000, 44100, 2)
     # equal rates: pass-through like the element (no resampler behind it); the library itself follows gst_audio_resampler
@@ -379,8 +378,6 @@ def test_audio_method_and_filter_mode_plans(method, mode, interp, monkeypatch):
     M = {"nearest": 0, "linear": 1, "cubic": 2, "blackman-nuttall": 3, "kaiser": 4}
     MO = {"interpolated": 0, "full": 1, "auto": 2}
     I = {"none": 0, "linear": 1, "cubic": 2}
-    if (mode, interp) == ("interpolated", "linear") or M[method] < 3:
-        monkeypatch.setenv("B200_VCS_EXPERIMENTAL", "1")
     for (a, b, q) in [(48000, 44100, 4), (44100, 48000, 6), (8000, 16000, 0), (96000, 44100, 8), (101, 99, 10), (3, 2, 5),
                       (48000, 8000, 1)]:
         rs = CudaAudioResample(quality=q, cuda_device_id=-1, resample_method=method, sinc_filter_mode=mode,

@@ -1,10 +1,7 @@
 """Destination rectangle + border fill (the element's add-borders; GST_VIDEO_CONVERTER_OPT_DEST_*): the input is scaled
 into a rectangle of the output frame by the ordinary kernels (the plan describes the rectangle: same strides, shifted
 plane origins) and vcs_border_kernel fills the rest with the border colour (setup_borderline / convert_fill_border,
-video-converter.c:2189-2258, :7190-7300).
-
-Written after this round's device budget was spent: skipped unless B200_TEST_EXPERIMENTAL=1 (the feature itself is only
-active when a rectangle is configured).  Run next round:  B200_TEST_EXPERIMENTAL=1 python -m pytest tests/test_vcs_borders_gpu.py -q"""
+video-converter.c:2189-2258, :7190-7300)."""
 import ctypes as C
 import os
 

@@ -1,7 +1,6 @@
 """vcs_l2mma_kernel (kernel_variant 6): the 2:1 / 8-tap kernel with both FIR passes on the integer tensor path
-(mma.sync.m16n8k32 u8 x s8).  Bit-exact under emulation (tests/test_emu_kernels.py); its first device run — and the
-measurement that decides whether it replaces the SIMT kernel — is pending, so these tests are skipped unless
-B200_TEST_EXPERIMENTAL=1.  Run next round:  B200_TEST_EXPERIMENTAL=1 python -m pytest tests/test_vcs_l2mma_gpu.py -q"""
+(mma.sync.m16n8k32 u8 x s8).  Bit-exact under emulation (tests/test_emu_kernels.py) and on the device; slower than the SIMT kernel
+(DESIGN.md), so it stays an opt-in variant."""
 import os
 
 import numpy as np

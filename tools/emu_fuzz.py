@@ -18,7 +18,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, os.path.join(ROOT, "tests", "cudaemu"))
-os.environ["B200_VCS_EXPERIMENTAL"] = "1"
 
 from oracle import bindings as ob   # noqa: E402
 import test_emu_kernels as T        # noqa: E402

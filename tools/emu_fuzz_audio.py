@@ -14,7 +14,6 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests", "cudaemu"))
-os.environ["B200_VCS_EXPERIMENTAL"] = "1"
 
 from oracle import bindings as ob   # noqa: E402
 

@@ -16,9 +16,7 @@ import numpy as np   # noqa: E402
 
 
 def rgb_mode(budget, t_start, out, flush):
-    """random packed RGB -> 4:2:0 configurations (B200_VCS_EXPERIMENTAL path)"""
-    os.environ["B200_VCS_EXPERIMENTAL"] = "1"
-    os.environ["B200_TEST_EXPERIMENTAL"] = "1"
+    """random packed RGB -> 4:2:0 configurations"""
     import test_vcs_rgbin_gpu as R
     import test_vcs_cross_gpu as T
     rng = np.random.default_rng(2)
