@@ -237,11 +237,12 @@ def run_extras(steps):
         out["c5"] = slim(d)
         # the transcoding-ladder cases (not BASELINE configs): YUV -> YUV plane scaling and the cross-family chain
         a.steps = max(3, steps // 2)
-        ladder = []
+        ladder, rgb = [], []
         for d in bx.bench_planes(a):
             e = slim(d); e["alg_bytes"] = d["roofline"]["alg_bytes_per_launch"] // 32; e["kernel_variant"] = d["kernel_variant"]
-            ladder.append(e)
+            (rgb if d["config"].startswith(("BGRA", "RGBA")) else ladder).append(e)
         out["yuv_ladder"] = ladder
+        out["rgb_paths"] = rgb          # packed RGB -> packed RGB scaling, packed RGB -> 4:2:0 (compositor output -> encoder input)
     except Exception as e:          # an extra must never take the headline line down
         out["error"] = repr(e)
     return out

@@ -139,7 +139,7 @@ def bench_planes(args):
                                             (12, 12, 1920, 1080, 1280, 720, 3),       # 12 BGRA, 11 RGBA: 4-byte pixels
                                             (12, 23, 1920, 1080, 1920, 1080, 1), (12, 23, 3840, 2160, 3840, 2160, 1),
                                             (12, 23, 3840, 2160, 1920, 1080, 1), (12, 23, 3840, 2160, 1920, 1080, 3),
-                                            (11, 2, 1920, 1080, 1280, 720, 3)]:       # compositor output -> encoder input
+                                            (11, 2, 1920, 1080, 1280, 720, 3), (12, 23, 1280, 720, 1920, 1080, 1)]:   # compositor output -> encoder input
         el = g.CudaVideoConvertScale(method=m)
         ii, oi = g.VideoInfo(fmt, IW, IH), g.VideoInfo(fmt_o, OW, OH)
         if fmt != fmt_o and fmt not in (11, 12):      # what the element's caps fixation does for YUV -> YUV

@@ -62,7 +62,8 @@ struct b200_vcs {
   size_t scratch_frame_bytes = 0;
   // packed RGB -> 4:2:0 at an unchanged or shrinking size: [word-wide scaler on 4-byte pixels ->] matrix + down-sample + pack
   Rgb420Dev rgb420;
-  bool rgb420_ok = false, rgb420_scaled = false;
+  Rgb2AyuvDev rgb2ayuv;           // the frame grows: the matrix runs first, on its own
+  bool rgb420_ok = false, rgb420_scaled = false, rgb420_matrix_first = false;
   PlaneFastState rgb420_scaler;
   size_t in_bytes = 0, out_bytes = 0;
 };
@@ -94,7 +95,7 @@ int prepare_rgb420 (b200_vcs * h)
 {
   const VcsPlan & p = h->plan;
   h->rgb420_ok = false;
-  if (!p.rgb_in || !p.yuv_out || p.matrix_first || p.has_dest || getenv ("B200_RGB420_GENERIC")) return B200_OK;
+  if (!p.rgb_in || !p.yuv_out || getenv ("B200_RGB420_GENERIC")) return B200_OK;
   Rgb420Dev & r = h->rgb420;
   memset (&r, 0, sizeof (r));
   const int pos_r = p.in_sel & 0xf, pos_g = (p.in_sel >> 4) & 0xf, pos_b = (p.in_sel >> 8) & 0xf;
@@ -109,6 +110,7 @@ int prepare_rgb420 (b200_vcs * h)
   const unsigned long long cbase = q.cstep == 2 ? std::min (q.off_u, q.off_v) : (q.off_u | q.off_v);
   r.wvec = ((q.stride_y | q.stride_u | q.stride_v) & 3) == 0 && ((q.off_y | cbase) & 3) == 0;
   h->rgb420_scaled = p.h.scaling || p.v.scaling;
+  h->rgb420_matrix_first = p.matrix_first && h->rgb420_scaled;
   if (!h->rgb420_scaled) {
     r.sstride = p.in.stride[0]; r.soff = p.in.offset[0];
     r.svec = (r.sstride & 15) == 0 && (r.soff & 15) == 0;
@@ -120,7 +122,17 @@ int prepare_rgb420 (b200_vcs * h)
     pl.h = p.h; pl.v = p.v;
     const int sstride = (p.out.width * 4 + 15) & ~15;
     std::vector<int32_t> hp, vp;
-    if (!plan_plane_fast (pl, p.in.stride[0], p.in.offset[0], sstride, 0, &h->rgb420_scaler, &hp, &vp)) return B200_OK;
+    int in_stride = p.in.stride[0];
+    unsigned long long in_off = p.in.offset[0];
+    if (h->rgb420_matrix_first) {                                   // the scaler reads the A,Y,U,V image of vcs_rgb2ayuv_kernel
+      Rgb2AyuvDev & m = h->rgb2ayuv;
+      memset (&m, 0, sizeof (m));
+      m.w = p.in.width; m.h = p.in.height; m.sstride = p.in.stride[0]; m.soff = p.in.offset[0];
+      m.dstride = (p.in.width * 4 + 15) & ~15;
+      for (int i = 0; i < 3; i++) { m.ca[i] = r.ca[i]; m.cb[i] = r.cb[i]; m.off[i] = r.off[i]; }
+      in_stride = m.dstride; in_off = 0;
+    }
+    if (!plan_plane_fast (pl, in_stride, in_off, sstride, 0, &h->rgb420_scaler, &hp, &vp)) return B200_OK;
     const int st = prepare_plane_fast (pl, hp, vp, &h->rgb420_scaler);
     if (st != B200_OK) return st;
     r.sstride = sstride; r.soff = 0; r.svec = 1;
@@ -194,7 +206,9 @@ int launch_convert (b200_vcs * h, int n, const VcsBatch & batch, cudaStream_t st
       if (((uintptr_t) batch.out[i]) & 3) r.wvec = 0;
     }
     if (h->rgb420_scaled) {
-      const size_t frame = (size_t) r.sstride * p.out.height;
+      const size_t scaled = (size_t) r.sstride * p.out.height;
+      const size_t pre = h->rgb420_matrix_first ? (size_t) h->rgb2ayuv.dstride * p.in.height : 0;
+      const size_t frame = scaled + pre;
       if (n > h->scratch_frames || frame != h->scratch_frame_bytes) {
         B200_CUDA_TRY (cudaFree (h->d_scratch));                    // synchronises with launches still reading it
         h->d_scratch = nullptr; h->scratch_frames = 0;
@@ -203,8 +217,15 @@ int launch_convert (b200_vcs * h, int n, const VcsBatch & batch, cudaStream_t st
       }
       VcsBatch mid;
       for (int i = 0; i < n; i++) { mid.in[i] = batch.in[i]; mid.out[i] = h->d_scratch + frame * i; fin.src[i] = mid.out[i]; }
+      if (h->rgb420_matrix_first) {
+        Rgb420Batch pre_b;
+        for (int i = 0; i < n; i++) { pre_b.src[i] = batch.in[i]; pre_b.out[i] = h->d_scratch + frame * i + scaled; mid.in[i] = pre_b.out[i]; }
+        const int s0 = launch_rgb2ayuv (h->rgb2ayuv, pre_b, n, stream);
+        if (s0 != B200_OK) return s0;
+      }
       const int s = launch_plane_fast (h->rgb420_scaler, mid, n, stream);
       if (s != B200_OK) return s;
+      return launch_rgb420 (r, fin, n, stream, !h->rgb420_matrix_first);
     } else {
       for (int i = 0; i < n; i++) {
         fin.src[i] = batch.in[i];
@@ -693,7 +714,7 @@ int b200_vcs_get_plan_info (const b200_vcs * h, b200_vcs_plan_info * info)
   for (int i = 0; i < 5; i++) info->p[i] = p.p[i];
   info->tile_w = p.tile_w; info->tile_h = p.tile_h; info->smem_bytes = p.smem_bytes;
   info->kernel_variant = p.yuv_out ? 5 : p.planes_mode ? 4 : h->variant == 7 ? 7 : (h->variant == 6 && h->mma.ready) ? 6 : (h->variant == 1 && p.lanczos2_ok) ? 1 : (h->variant == 2 && p.light_ok) ? 2 : (h->variant == 3 && p.ntap_ok) ? 3 : 0;
-  info->n_launches_per_convert = (h->rgb420_ok ? (h->rgb420_scaled ? 2 : 1) : p.yuv_out ? (p.extra_row ? 3 : 2) : 1) + (p.has_dest && p.fill_border ? 1 : 0);
+  info->n_launches_per_convert = (h->rgb420_ok ? (h->rgb420_matrix_first ? 3 : h->rgb420_scaled ? 2 : 1) : p.yuv_out ? (p.extra_row ? 3 : 2) : 1) + (p.has_dest && p.fill_border ? 1 : 0);
   return B200_OK;
 }
 

@@ -44,8 +44,23 @@ struct PlaneFastDev {
 
 constexpr int PLF_THREADS = 256;
 
-// HM / VM: PassMode of the axis (1 copy / nearest, 2 two taps, 3 n taps); NC: bytes per pixel (1, or 2 for interleaved UV)
-template <int HM, int VM, int NC>
+// the NC words of one pixel column (one per component) as a single shared-memory access
+template <int NC> __device__ __forceinline__ void plf_ld (const unsigned *p, unsigned (&v)[NC])
+{
+  if (NC == 4) { const uint4 q = *(const uint4 *) p; v[0] = q.x; v[1 % NC] = q.y; v[2 % NC] = q.z; v[3 % NC] = q.w; }
+  else if (NC == 2) { const uint2 q = *(const uint2 *) p; v[0] = q.x; v[1 % NC] = q.y; }
+  else v[0] = p[0];
+}
+template <int NC> __device__ __forceinline__ void plf_st (unsigned *p, const unsigned (&v)[NC])
+{
+  if (NC == 4) *(uint4 *) p = make_uint4 (v[0], v[1 % NC], v[2 % NC], v[3 % NC]);
+  else if (NC == 2) *(uint2 *) p = make_uint2 (v[0], v[1 % NC]);
+  else p[0] = v[0];
+}
+
+// HM / VM: PassMode of the axis (1 copy / nearest, 2 two taps, 3 n taps); NC: bytes per pixel (1, 2 for interleaved UV, 4 for
+// packed RGB); NTW > 0: every n-tap axis uses exactly NTW packed tap words (straight-line FIRs), 0: run-time loops
+template <int HM, int VM, int NC, int NTW = 0>
 __global__ void __launch_bounds__ (PLF_THREADS, 2)
 vcs_planes_fast_kernel (const PlaneFastDev Q, const VcsBatch frames)
 {
@@ -115,6 +130,7 @@ vcs_planes_fast_kernel (const PlaneFastDev Q, const VcsBatch frames)
     const int base = (int) Q.hoff[ox0 + tx] - cxa;
     const int wi = base >> 2, sh = (base & 3) * 8;
     for (int g = ph; g < RG; g += nph) {
+      unsigned oc[NC];
 #pragma unroll
       for (int c = 0; c < NC; c++) {
         const uint4 *sp = S4 + (g * NC + c) * Q.pitch + wi;
@@ -123,8 +139,8 @@ vcs_planes_fast_kernel (const PlaneFastDev Q, const VcsBatch frames)
           int acc[4] = {32, 32, 32, 32};
           uint4 lo = sp[0];
           const int *taps = TH + tx * Q.ntw_h;
-#pragma unroll 2
-          for (int k = 0; k < Q.ntw_h; k++) {
+#pragma unroll (NTW > 0 ? NTW : 2)
+          for (int k = 0; k < (NTW > 0 ? NTW : Q.ntw_h); k++) {
             const int t = taps[k];
             const uint4 hi = sp[k + 1];
             acc[0] = dp4a_u8s8 (__funnelshift_r (lo.x, hi.x, sh), t, acc[0]);
@@ -148,8 +164,9 @@ vcs_planes_fast_kernel (const PlaneFastDev Q, const VcsBatch frames)
           const uint4 a = sp[0];
           o = __byte_perm (__byte_perm (a.x, a.y, s01), __byte_perm (a.z, a.w, s01), 0x5410);
         }
-        T[(g * Q.tw + tx) * NC + c] = o;
+        oc[c] = o;
       }
+      plf_st<NC> (T + (g * Q.tw + tx) * NC, oc);
     }
   }
   __syncthreads ();
@@ -163,26 +180,36 @@ vcs_planes_fast_kernel (const PlaneFastDev Q, const VcsBatch frames)
       const int rb = (int) vrow[ty];
       const int sh = (rb & 3) * 8;
       int v[NC];
+      const unsigned *tp = T + ((rb >> 2) * Q.tw + tx) * NC;
+      unsigned lo[NC];
+      plf_ld<NC> (tp, lo);
+      if (VM == 3) {
+        int acc[NC];
 #pragma unroll
-      for (int c = 0; c < NC; c++) {
-        const unsigned *tp = T + ((rb >> 2) * Q.tw + tx) * NC + c;
-        if (VM == 3) {
-          int acc = 32;
-          unsigned lo = tp[0];
-          const int *taps = TV + ty * Q.ntw_v;
-#pragma unroll 2
-          for (int k = 0; k < Q.ntw_v; k++) {
-            const unsigned hi = tp[(k + 1) * gs];
-            acc = dp4a_u8s8 (__funnelshift_r (lo, hi, sh), taps[k], acc);
-            lo = hi;
-          }
-          v[c] = min (max (acc >> 6, 0), 255);
-        } else if (VM == 2) {
-          const unsigned w = __funnelshift_r (tp[0], tp[gs], sh);
-          v[c] = lerp_v_u8 ((int) (w & 0xffu), (int) ((w >> 8) & 0xffu), TV[ty]);
-        } else {
-          v[c] = (int) ((tp[0] >> sh) & 0xffu);
+        for (int c = 0; c < NC; c++) acc[c] = 32;
+        const int *taps = TV + ty * Q.ntw_v;
+#pragma unroll (NTW > 0 ? NTW : 2)
+        for (int k = 0; k < (NTW > 0 ? NTW : Q.ntw_v); k++) {
+          unsigned hi[NC];
+          plf_ld<NC> (tp + (k + 1) * gs, hi);
+          const int t = taps[k];
+#pragma unroll
+          for (int c = 0; c < NC; c++) { acc[c] = dp4a_u8s8 (__funnelshift_r (lo[c], hi[c], sh), t, acc[c]); lo[c] = hi[c]; }
         }
+#pragma unroll
+        for (int c = 0; c < NC; c++) v[c] = min (max (acc[c] >> 6, 0), 255);
+      } else if (VM == 2) {
+        unsigned hi[NC];
+        plf_ld<NC> (tp + gs, hi);
+        const int wt = TV[ty];
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+          const unsigned w = __funnelshift_r (lo[c], hi[c], sh);
+          v[c] = lerp_v_u8 ((int) (w & 0xffu), (int) ((w >> 8) & 0xffu), wt);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < NC; c++) v[c] = (int) ((lo[c] >> sh) & 0xffu);
       }
       if (NC == 1) *dp = (uint8_t) v[0];
       else if (NC == 2) *(unsigned short *) dp = (unsigned short) ((unsigned) v[0] | ((unsigned) v[1 % NC] << 8));
@@ -374,6 +401,10 @@ inline plane_fast_fn plane_fast_kernel_for (int hm, int vm, int nc, bool vfirst,
 {
 #define PLF_PICK(H, V)                                                                         \
   if (hm == H && vm == V) {                                                                    \
+    if (nc == 4 && vfirst && ntw == 2 && (H == 3 || V == 3)) return vcs_planes_fast_vfirst_kernel<H, V, 4, 2>;   \
+    if (nc == 4 && !vfirst && ntw == 2 && (H == 3 || V == 3)) return vcs_planes_fast_kernel<H, V, 4, 2>;   \
+    if (nc == 4 && !vfirst && ntw == 1 && (H == 3 || V == 3)) return vcs_planes_fast_kernel<H, V, 4, 1>;   \
+    if (nc != 4 && !vfirst && ntw == 1 && (H == 3 || V == 3)) return nc == 1 ? vcs_planes_fast_kernel<H, V, 1, 1> : vcs_planes_fast_kernel<H, V, 2, 1>;   \
     if (nc == 4) return vfirst ? vcs_planes_fast_vfirst_kernel<H, V, 4> : vcs_planes_fast_kernel<H, V, 4>;   \
     if (vfirst && ntw == 2 && (H == 3 || V == 3)) return nc == 1 ? vcs_planes_fast_vfirst_kernel<H, V, 1, 2> : vcs_planes_fast_vfirst_kernel<H, V, 2, 2>;   \
     if (vfirst && ntw == 1 && (H == 3 || V == 3)) return nc == 1 ? vcs_planes_fast_vfirst_kernel<H, V, 1, 1> : vcs_planes_fast_vfirst_kernel<H, V, 2, 1>;   \

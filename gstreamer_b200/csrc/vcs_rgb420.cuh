@@ -13,6 +13,9 @@
 // alpha / padding byte's coefficient 0), the vertical pair average, the horizontal filter of the output's chroma site
 // (arithmetic of vcs_down420.cuh, whose header cites the reference's filters), word-wide stores.
 // HBM bound: 8 bytes read and 3 bytes written per chroma sample's 2 x 2 block.
+// When the frame grows the chain runs the matrix FIRST (chain_scale puts the scalers behind it): vcs_rgb2ayuv_kernel
+// (one pixel per thread, the same dot products) leaves A,Y,U,V pixels in a scratch image, the word-wide scaler grows
+// them, and this kernel's MATRIX = false form only down-samples and packs.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -63,6 +66,7 @@ struct Rgb420Line {
   unsigned um, vm;               // chroma of the pixel left of the block (co-sited filter), in byte 0
 };
 
+template <bool MATRIX>
 __device__ __forceinline__ void rgb420_line (const Rgb420Dev & P, const uint8_t * __restrict__ row, int x0, bool full, bool left, Rgb420Line & L)
 {
   unsigned px[8];
@@ -76,9 +80,14 @@ __device__ __forceinline__ void rgb420_line (const Rgb420Dev & P, const uint8_t 
   L.y[0] = L.y[1] = L.u[0] = L.u[1] = L.v[0] = L.v[1] = 0;
 #pragma unroll
   for (int i = 0; i < 8; i++) {
-    const unsigned yy = (unsigned) (rgb420_dot (px[i], P.ca[0], P.cb[0], P.off[0]) >> 8) & 0xff;
-    const unsigned uu = (unsigned) (rgb420_dot (px[i], P.ca[1], P.cb[1], P.off[1]) >> 8) & 0xff;
-    const unsigned vv = (unsigned) (rgb420_dot (px[i], P.ca[2], P.cb[2], P.off[2]) >> 8) & 0xff;
+    unsigned yy, uu, vv;
+    if (MATRIX) {
+      yy = (unsigned) (rgb420_dot (px[i], P.ca[0], P.cb[0], P.off[0]) >> 8) & 0xff;
+      uu = (unsigned) (rgb420_dot (px[i], P.ca[1], P.cb[1], P.off[1]) >> 8) & 0xff;
+      vv = (unsigned) (rgb420_dot (px[i], P.ca[2], P.cb[2], P.off[2]) >> 8) & 0xff;
+    } else {                                                        // A,Y,U,V pixels of vcs_rgb2ayuv_kernel
+      yy = (px[i] >> 8) & 0xff; uu = (px[i] >> 16) & 0xff; vv = px[i] >> 24;
+    }
     L.y[i >> 2] |= yy << (8 * (i & 3));
     L.u[i >> 2] |= uu << (8 * (i & 3));
     L.v[i >> 2] |= vv << (8 * (i & 3));
@@ -86,8 +95,12 @@ __device__ __forceinline__ void rgb420_line (const Rgb420Dev & P, const uint8_t 
   L.um = L.vm = 0;
   if (left) {
     const unsigned pm = __ldg ((const unsigned *) row + (x0 - 1));
-    L.um = (unsigned) (rgb420_dot (pm, P.ca[1], P.cb[1], P.off[1]) >> 8) & 0xff;
-    L.vm = (unsigned) (rgb420_dot (pm, P.ca[2], P.cb[2], P.off[2]) >> 8) & 0xff;
+    if (MATRIX) {
+      L.um = (unsigned) (rgb420_dot (pm, P.ca[1], P.cb[1], P.off[1]) >> 8) & 0xff;
+      L.vm = (unsigned) (rgb420_dot (pm, P.ca[2], P.cb[2], P.off[2]) >> 8) & 0xff;
+    } else {
+      L.um = (pm >> 16) & 0xff; L.vm = pm >> 24;
+    }
   }
 }
 
@@ -115,6 +128,7 @@ __device__ __forceinline__ unsigned rgb420_down_h (const Rgb420Dev & P, const un
   return o;
 }
 
+template <bool MATRIX>
 __global__ void __launch_bounds__ (256)
 vcs_rgb420_kernel (const Rgb420Dev P, const Rgb420Batch frames)
 {
@@ -129,8 +143,8 @@ vcs_rgb420_kernel (const Rgb420Dev P, const Rgb420Batch frames)
   const bool left = P.hmode == DOWN_H_COSITED && x0 > 0;
 
   Rgb420Line A, B;
-  rgb420_line (P, s + (size_t) y0 * P.sstride, x0, full, left, A);
-  if (two_rows) rgb420_line (P, s + (size_t) (y0 + 1) * P.sstride, x0, full, left, B);
+  rgb420_line<MATRIX> (P, s + (size_t) y0 * P.sstride, x0, full, left, A);
+  if (two_rows) rgb420_line<MATRIX> (P, s + (size_t) (y0 + 1) * P.sstride, x0, full, left, B);
   else B = A;                                                       // odd height: the pair's second line is the last line itself
 
   // luma: every pixel of both lines
@@ -186,11 +200,41 @@ inline bool rgb420_split_row (const int row[4], int pos_r, int pos_g, int pos_b,
   return true;
 }
 
-inline int launch_rgb420 (const Rgb420Dev & d, const Rgb420Batch & batch, int n, cudaStream_t stream)
+// the matrix alone: packed RGB pixels -> A,Y,U,V pixels (bytes 0..3) of the same size, one pixel per thread
+struct Rgb2AyuvDev {
+  int w, h;
+  int sstride, dstride;          // bytes
+  unsigned long long soff;
+  unsigned ca[3], cb[3];
+  int off[3];
+};
+
+__global__ void __launch_bounds__ (256)
+vcs_rgb2ayuv_kernel (const Rgb2AyuvDev P, const Rgb420Batch frames)
+{
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= P.w) return;
+  const unsigned px = __ldg ((const unsigned *) (frames.src[blockIdx.z] + P.soff + (size_t) y * P.sstride) + x);
+  const unsigned yy = (unsigned) (rgb420_dot (px, P.ca[0], P.cb[0], P.off[0]) >> 8) & 0xff;
+  const unsigned uu = (unsigned) (rgb420_dot (px, P.ca[1], P.cb[1], P.off[1]) >> 8) & 0xff;
+  const unsigned vv = (unsigned) (rgb420_dot (px, P.ca[2], P.cb[2], P.off[2]) >> 8) & 0xff;
+  ((unsigned *) (frames.out[blockIdx.z] + (size_t) y * P.dstride))[x] = 0xffu | (yy << 8) | (uu << 16) | (vv << 24);
+}
+
+inline int launch_rgb2ayuv (const Rgb2AyuvDev & d, const Rgb420Batch & batch, int n, cudaStream_t stream)
+{
+  dim3 grid ((d.w + 255) / 256, d.h, n);
+  vcs_rgb2ayuv_kernel <<<grid, 256, 0, stream>>> (d, batch);
+  B200_CUDA_TRY (cudaGetLastError ());
+  return B200_OK;
+}
+
+inline int launch_rgb420 (const Rgb420Dev & d, const Rgb420Batch & batch, int n, cudaStream_t stream, bool matrix = true)
 {
   const int cw = (d.ow + 1) / 2, chh = (d.oh + 1) / 2, cb = (cw + 3) / 4;
   dim3 blk (32, 8), grid ((cb + 31) / 32, (chh + 7) / 8, n);
-  vcs_rgb420_kernel <<<grid, blk, 0, stream>>> (d, batch);
+  if (matrix) vcs_rgb420_kernel<true> <<<grid, blk, 0, stream>>> (d, batch);
+  else vcs_rgb420_kernel<false> <<<grid, blk, 0, stream>>> (d, batch);
   B200_CUDA_TRY (cudaGetLastError ());
   return B200_OK;
 }

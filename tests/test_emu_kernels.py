@@ -612,10 +612,12 @@ def test_planes_fast_kernel_packed_rgb(emu, size):
 
 @pytest.mark.parametrize("size", [(64, 48, 64, 48), (50, 21, 50, 21), (33, 17, 33, 17), (1, 1, 1, 1), (2, 2, 2, 2), (7, 5, 7, 5), (16, 2, 16, 2),
                                   (400, 300, 150, 100), (262, 146, 131, 73), (129, 67, 100, 67), (96, 200, 96, 75), (100, 60, 150, 30),
-                                  (70, 40, 35, 20), (41, 23, 17, 9)], ids=lambda s: "%dx%d-%dx%d" % s)
+                                  (70, 40, 35, 20), (41, 23, 17, 9),
+                                  (40, 30, 64, 48), (160, 90, 300, 200), (33, 17, 50, 31), (129, 67, 200, 67), (96, 75, 96, 200),
+                                  (60, 100, 150, 60)], ids=lambda s: "%dx%d-%dx%d" % s)
 def test_rgb_to_420_fast_kernels(emu, size, monkeypatch):
     """vcs_rgb420_kernel (matrix + chroma down-sampling + pack; alone at an unchanged size, behind the word-wide scaler on
-    4-byte pixels where the frame shrinks): every input byte order, both output layouts, co-sited and centred chroma
+    4-byte pixels where the frame shrinks, behind vcs_rgb2ayuv_kernel + that scaler where it grows): every input byte order, both output layouts, co-sited and centred chroma
     sites, full and video range; the generic chain (B200_RGB420_GENERIC) must agree with the same oracle"""
     from gstreamer_b200 import _lib
     iw, ih, W, H = size
@@ -641,3 +643,18 @@ def test_rgb_to_420_fast_kernels(emu, size, monkeypatch):
               f"colorimetry {col}")
     monkeypatch.setenv("B200_RGB420_GENERIC", "1")
     check(run(emu, "BGRA", "NV12", size, 1, frame), expected("BGRA", "NV12", size, 1, frame), "generic chain")
+
+
+@pytest.mark.parametrize("case", [((200, 120), (320, 240), (31, 17, 200, 120)), ((200, 120), (320, 240), (40, 20, 100, 60)),
+                                  ((100, 60), (321, 201), (11, 3, 299, 180)), ((160, 90), (160, 200), (0, 55, 160, 90)),
+                                  ((64, 64), (200, 100), (51, 1, 97, 99))], ids=lambda c: "%dx%d-in-%dx%d" % (c[0] + c[1]))
+def test_rgb_to_420_fast_kernels_destination_rectangle(emu, case):
+    """the same kernels writing into a destination rectangle of the output frame (odd origins and sizes included: the plan
+    shifts the plane origins, the kernels fall back from word stores to byte stores where the rectangle is unaligned)"""
+    (iw, ih), (W, H), dest = case
+    for k, (fi, fo) in enumerate([("BGRA", "NV12"), ("RGBA", "I420"), ("xRGB", "NV21"), ("ABGR", "YV12")]):
+        frame = frame_for(fi, iw, ih, 70 + k)
+        method = [1, 3, 0, 9][k]
+        size = (iw, ih, W, H)
+        got = run(emu, fi, fo, size, method, frame, dest=dest, border=0xff204080)
+        check(got, expected(fi, fo, size, method, frame, dest=dest, border=0xff204080), f"{fi}->{fo} m{method} dest {dest}")

@@ -30,6 +30,6 @@ t[kname] = entry
 json.dump(t, open('profiles/traffic.json', 'w'), indent=1)
 PY
 # SASS opcode histogram of the default headline instantiation
-cuobjdump -sass -fun '_ZN4b20022vcs_lanczos2_v2_kernelILi4ELi291ELi0ELi60ELi256EEEvNS_6VcsDevENS_11Lanczos2DevENS_13Lanczos2V2DevENS_8VcsBatchE' gstreamer_b200/libb200dsp.so 2>/dev/null \
+cuobjdump -sass -fun '_ZN4b20022vcs_lanczos2_v2_kernelILi4ELi291ELi0ELi60ELi256ELb0ELb0EEEvNS_6VcsDevENS_11Lanczos2DevENS_13Lanczos2V2DevENS_8VcsBatchE' gstreamer_b200/libb200dsp.so 2>/dev/null \
   | grep -o "^\s*/\*[0-9a-f]*\*/\s*[A-Z0-9_.]*" | awk '{print $2}' | sed 's/\..*//' | grep -v '^$' | sort | uniq -c | sort -rn > profiles/${P}_lanczos2_sass_histogram.txt
 ls -la profiles | grep ${P}
