@@ -115,6 +115,7 @@ GstFlowReturn gst_pad_push (GstPad * pad, GstBuffer * buffer);
 typedef enum { GST_CAPS_INTERSECT_ZIG_ZAG, GST_CAPS_INTERSECT_FIRST } GstCapsIntersectMode;
 GstCaps *gst_static_pad_template_get_caps (GstStaticPadTemplate * templ);
 GstCaps *gst_caps_new_empty (void); GstCaps *gst_caps_copy (const GstCaps * caps); void gst_caps_unref (GstCaps * caps);
+GstCaps *gst_caps_from_string (const gchar * string);   /* gstcaps.h:570 */
 guint gst_caps_get_size (const GstCaps * caps); GstStructure *gst_caps_get_structure (const GstCaps * caps, guint index);
 GstCapsFeatures *gst_caps_get_features (const GstCaps * caps, guint index);
 gboolean gst_caps_features_contains (const GstCapsFeatures * features, const gchar * feature);

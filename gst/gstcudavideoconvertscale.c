@@ -19,12 +19,17 @@
 GST_DEBUG_CATEGORY_STATIC (cuda_vcs_debug);
 #define GST_CAT_DEFAULT cuda_vcs_debug
 
-#define SINK_FORMATS "{ NV12, NV21, I420, YV12 }"
+/* what b200_vcs_create accepts: 4:2:0 in -> 4:2:0 or packed RGB; packed RGB in -> packed RGB (scaling, byte order) or
+ * 4:2:0 (the encoder-feeding direction); the capture formats (packed 4:2:2, Y42B, Y444) -> packed RGB */
+#define YUV420_FORMATS "NV12, NV21, I420, YV12"
+#define RGB_FORMATS "BGRA, RGBA, ARGB, ABGR, BGRx, RGBx, xRGB, xBGR"
+#define CAPTURE_FORMATS "YUY2, UYVY, YVYU, Y42B, Y444"
+#define SINK_FORMATS "{ " YUV420_FORMATS ", " RGB_FORMATS ", " CAPTURE_FORMATS " }"
 /* YUV outputs: the same family (NV12->NV12, NV21->NV21, I420/YV12 -> I420/YV12) scales plane by plane, the other
  * 4:2:0 pairs run the chain with chroma down-sampling; fixate_caps must carry the input colorimetry over
  * (transfer_colorimetry_from_input, gstvideoconvertscale.c:1335-1427) - b200_vcs_create refuses a YUV -> YUV
  * matrix change with B200_ERR_UNSUPPORTED */
-#define SRC_FORMATS "{ BGRA, RGBA, ARGB, ABGR, BGRx, RGBx, xRGB, xBGR, NV12, NV21, I420, YV12 }"
+#define SRC_FORMATS "{ " RGB_FORMATS ", " YUV420_FORMATS " }"
 #define RAW_FIELDS(f) "format = (string) " f \
     ", width = (int) [ 1, 32767 ], height = (int) [ 1, 32767 ], framerate = (fraction) [ 0/1, max ]"
 /* device memory first (zero copy between CUDA elements), then plain system memory: in that case transform() hands the
@@ -191,20 +196,45 @@ vcs_query (GstBaseTransform * trans, GstPadDirection direction, GstQuery * query
   return GST_BASE_TRANSFORM_CLASS (gst_cuda_video_convert_scale_parent_class)->query (trans, direction, query);
 }
 
-/* caps on the other pad: any supported format of the other direction, any size in range,
- * colorimetry/chroma-site dropped (gstvideoconvertscale.c:703-748) */
+/* 0: 4:2:0, 1: packed RGB, 2: capture format, -1: not a fixed format name of ours */
+static gint
+vcs_format_class (const GstStructure * st)
+{
+  const gchar *f = gst_structure_get_string (st, "format");
+  if (!f)
+    return -1;
+  if (strstr (YUV420_FORMATS, f))
+    return 0;
+  if (strstr (RGB_FORMATS, f))
+    return 1;
+  if (strstr (CAPTURE_FORMATS, f))
+    return 2;
+  return -1;
+}
+
+/* caps on the other pad: the formats b200_vcs_create pairs with this one (every format of the other direction when
+ * the structure does not name a single format), any size in range, colorimetry/chroma-site dropped
+ * (gstvideoconvertscale.c:703-748) */
 static GstCaps *
 vcs_transform_caps (GstBaseTransform * trans, GstPadDirection direction, GstCaps * caps, GstCaps * filter)
 {
   GstCaps *tmpl, *res;
   guint i, n;
+  (void) trans;
   tmpl = gst_static_pad_template_get_caps (direction == GST_PAD_SINK ? &src_tmpl : &sink_tmpl);
   res = gst_caps_new_empty ();
   n = gst_caps_get_size (caps);
   for (i = 0; i < n; i++) {
     GstStructure *in = gst_caps_get_structure (caps, i);
-    GstCaps *one = gst_caps_copy (tmpl);
+    GstCaps *one;
     const GValue *fr = gst_structure_get_value (in, "framerate");
+    const gint cls = vcs_format_class (in);
+    if (direction == GST_PAD_SINK && cls == 2)      /* capture formats convert to packed RGB only */
+      one = gst_caps_from_string (BOTH_CAPS ("{ " RGB_FORMATS " }"));
+    else if (direction == GST_PAD_SRC && cls == 0)  /* a 4:2:0 output comes from 4:2:0 or packed RGB */
+      one = gst_caps_from_string (BOTH_CAPS ("{ " YUV420_FORMATS ", " RGB_FORMATS " }"));
+    else
+      one = gst_caps_copy (tmpl);
     if (fr)
       gst_caps_set_value (one, "framerate", fr);       /* framerate and interlace-mode pass through */
     gst_caps_append (res, one);
