@@ -240,9 +240,9 @@ def run_extras(steps):
         ladder, rgb = [], []
         for d in bx.bench_planes(a):
             e = slim(d); e["alg_bytes"] = d["roofline"]["alg_bytes_per_launch"] // 32; e["kernel_variant"] = d["kernel_variant"]
-            (rgb if d["config"].startswith(("BGRA", "RGBA")) else ladder).append(e)
+            (rgb if d["config"].startswith(("BGRA", "RGBA", "YUY2", "UYVY")) else ladder).append(e)
         out["yuv_ladder"] = ladder
-        out["rgb_paths"] = rgb          # packed RGB -> packed RGB scaling, packed RGB -> 4:2:0 (compositor output -> encoder input)
+        out["rgb_paths"] = rgb          # packed RGB -> packed RGB scaling, packed RGB / packed 4:2:2 -> 4:2:0 (compositor / capture -> encoder)
     except Exception as e:          # an extra must never take the headline line down
         out["error"] = repr(e)
     return out

@@ -139,17 +139,18 @@ def bench_planes(args):
                                             (12, 12, 1920, 1080, 1280, 720, 3),       # 12 BGRA, 11 RGBA: 4-byte pixels
                                             (12, 23, 1920, 1080, 1920, 1080, 1), (12, 23, 3840, 2160, 3840, 2160, 1),
                                             (12, 23, 3840, 2160, 1920, 1080, 1), (12, 23, 3840, 2160, 1920, 1080, 3),
-                                            (11, 2, 1920, 1080, 1280, 720, 3), (12, 23, 1280, 720, 1920, 1080, 1)]:   # compositor output -> encoder input
+                                            (11, 2, 1920, 1080, 1280, 720, 3), (12, 23, 1280, 720, 1920, 1080, 1),      # compositor output -> encoder input
+                                            (4, 2, 1920, 1080, 1920, 1080, 1), (4, 23, 1920, 1080, 1920, 1080, 1)]:   # capture (YUY2) -> encoder input
         el = g.CudaVideoConvertScale(method=m)
         ii, oi = g.VideoInfo(fmt, IW, IH), g.VideoInfo(fmt_o, OW, OH)
-        if fmt != fmt_o and fmt not in (11, 12):      # what the element's caps fixation does for YUV -> YUV
+        if fmt != fmt_o:                              # what the element's caps fixation does for YUV -> YUV
             from gstreamer_b200.video import transfer_colorimetry_from_input
             transfer_colorimetry_from_input(ii, oi)
         el.set_info(ii, oi)
         per = 32
-        if fmt in (11, 12):
+        if fmt in (11, 12, 4, 5):
             import numpy as np
-            gen = lambda w, h, seed: np.random.default_rng(seed).integers(0, 256, w * h * 4, dtype=np.uint8)
+            gen = lambda w, h, seed, nbytes=ii.size: np.random.default_rng(seed).integers(0, 256, nbytes, dtype=np.uint8)
         else:
             gen = ob.i420_random_frame if fmt in (2, 3) else ob.nv12_random_frame
         base = [torch.from_numpy(gen(IW, IH, s)).cuda() for s in range(2)]

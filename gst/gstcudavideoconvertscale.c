@@ -20,10 +20,12 @@ GST_DEBUG_CATEGORY_STATIC (cuda_vcs_debug);
 #define GST_CAT_DEFAULT cuda_vcs_debug
 
 /* what b200_vcs_create accepts: 4:2:0 in -> 4:2:0 or packed RGB; packed RGB in -> packed RGB (scaling, byte order) or
- * 4:2:0 (the encoder-feeding direction); the capture formats (packed 4:2:2, Y42B, Y444) -> packed RGB */
+ * 4:2:0 (the encoder-feeding direction); packed 4:2:2 (capture) -> packed RGB or 4:2:0; planar Y42B / Y444 -> packed RGB */
 #define YUV420_FORMATS "NV12, NV21, I420, YV12"
 #define RGB_FORMATS "BGRA, RGBA, ARGB, ABGR, BGRx, RGBx, xRGB, xBGR"
-#define CAPTURE_FORMATS "YUY2, UYVY, YVYU, Y42B, Y444"
+#define PACKED422_FORMATS "YUY2, UYVY, YVYU"
+#define PLANAR4XX_FORMATS "Y42B, Y444"
+#define CAPTURE_FORMATS PACKED422_FORMATS ", " PLANAR4XX_FORMATS
 #define SINK_FORMATS "{ " YUV420_FORMATS ", " RGB_FORMATS ", " CAPTURE_FORMATS " }"
 /* YUV outputs: the same family (NV12->NV12, NV21->NV21, I420/YV12 -> I420/YV12) scales plane by plane, the other
  * 4:2:0 pairs run the chain with chroma down-sampling; fixate_caps must carry the input colorimetry over
@@ -196,7 +198,7 @@ vcs_query (GstBaseTransform * trans, GstPadDirection direction, GstQuery * query
   return GST_BASE_TRANSFORM_CLASS (gst_cuda_video_convert_scale_parent_class)->query (trans, direction, query);
 }
 
-/* 0: 4:2:0, 1: packed RGB, 2: capture format, -1: not a fixed format name of ours */
+/* 0: 4:2:0, 1: packed RGB, 2: planar 4:2:2 / 4:4:4, 3: packed 4:2:2, -1: not a fixed format name of ours */
 static gint
 vcs_format_class (const GstStructure * st)
 {
@@ -207,8 +209,10 @@ vcs_format_class (const GstStructure * st)
     return 0;
   if (strstr (RGB_FORMATS, f))
     return 1;
-  if (strstr (CAPTURE_FORMATS, f))
+  if (strstr (PLANAR4XX_FORMATS, f))
     return 2;
+  if (strstr (PACKED422_FORMATS, f))
+    return 3;
   return -1;
 }
 
@@ -229,10 +233,10 @@ vcs_transform_caps (GstBaseTransform * trans, GstPadDirection direction, GstCaps
     GstCaps *one;
     const GValue *fr = gst_structure_get_value (in, "framerate");
     const gint cls = vcs_format_class (in);
-    if (direction == GST_PAD_SINK && cls == 2)      /* capture formats convert to packed RGB only */
+    if (direction == GST_PAD_SINK && cls == 2)      /* Y42B / Y444 convert to packed RGB only */
       one = gst_caps_from_string (BOTH_CAPS ("{ " RGB_FORMATS " }"));
-    else if (direction == GST_PAD_SRC && cls == 0)  /* a 4:2:0 output comes from 4:2:0 or packed RGB */
-      one = gst_caps_from_string (BOTH_CAPS ("{ " YUV420_FORMATS ", " RGB_FORMATS " }"));
+    else if (direction == GST_PAD_SRC && cls == 0)  /* a 4:2:0 output comes from 4:2:0, packed RGB or packed 4:2:2 */
+      one = gst_caps_from_string (BOTH_CAPS ("{ " YUV420_FORMATS ", " RGB_FORMATS ", " PACKED422_FORMATS " }"));
     else
       one = gst_caps_copy (tmpl);
     if (fr)
@@ -265,7 +269,10 @@ vcs_transfer_colorimetry (GstCaps * in_caps, GstCaps * out_caps)
     return;
   if (!gst_structure_has_field (out, "colorimetry") && (v = gst_structure_get_value (in, "colorimetry")))
     gst_structure_set_value (out, "colorimetry", v);
-  if (!gst_structure_has_field (out, "chroma-site") && (v = gst_structure_get_value (in, "chroma-site")))
+  /* the chroma-site travels only across an unchanged sub-sampling (subsampling_unchanged, gstvideoconvertscale.c:1411-1424):
+   * a packed 4:2:2 input leaves a 4:2:0 output the default site of its own size */
+  if (vcs_format_class (in) == vcs_format_class (out) && !gst_structure_has_field (out, "chroma-site") &&
+      (v = gst_structure_get_value (in, "chroma-site")))
     gst_structure_set_value (out, "chroma-site", v);
 }
 

@@ -19,6 +19,7 @@
 #include "vcs_planes.cuh"
 #include "vcs_down420.cuh"
 #include "vcs_rgb420.cuh"
+#include "vcs_yuy2_420.cuh"
 
 #include <string.h>
 #include <new>
@@ -63,8 +64,11 @@ struct b200_vcs {
   // packed RGB -> 4:2:0 at an unchanged or shrinking size: [word-wide scaler on 4-byte pixels ->] matrix + down-sample + pack
   Rgb420Dev rgb420;
   Rgb2AyuvDev rgb2ayuv;           // the frame grows: the matrix runs first, on its own
-  bool rgb420_ok = false, rgb420_scaled = false, rgb420_matrix_first = false;
+  Yuy2AyuvDev yuy2ayuv;           // packed 4:2:2 input: unpack + horizontal chroma up-sampling, on its own
+  bool rgb420_ok = false, rgb420_scaled = false;
+  int rgb420_pre = 0;             // 0: none, 1: vcs_rgb2ayuv_kernel, 2: vcs_yuy2_ayuv_kernel
   PlaneFastState rgb420_scaler;
+  Yuy2Dev yuy2;                   // YUY2 / UYVY -> I420 / YV12 at an unchanged size (plan.yuy2_420)
   size_t in_bytes = 0, out_bytes = 0;
 };
 
@@ -95,14 +99,17 @@ int prepare_rgb420 (b200_vcs * h)
 {
   const VcsPlan & p = h->plan;
   h->rgb420_ok = false;
-  if (!p.rgb_in || !p.yuv_out || getenv ("B200_RGB420_GENERIC")) return B200_OK;
+  const bool packed422 = p.in_422_444 && p.ystep == 2;            // YUY2 / UYVY / YVYU
+  if (!(p.rgb_in || packed422) || !p.yuv_out || p.yuy2_420 || getenv ("B200_RGB420_GENERIC")) return B200_OK;
   Rgb420Dev & r = h->rgb420;
   memset (&r, 0, sizeof (r));
-  const int pos_r = p.in_sel & 0xf, pos_g = (p.in_sel >> 4) & 0xf, pos_b = (p.in_sel >> 8) & 0xf;
-  for (int i = 0; i < 3; i++) {
-    if (!rgb420_split_row (p.m_rgb2yuv[i], pos_r, pos_g, pos_b, &r.ca[i], &r.cb[i])) return B200_OK;
-    r.off[i] = p.m_rgb2yuv[i][3];
-  }
+  if (p.rgb_in) {
+    const int pos_r = p.in_sel & 0xf, pos_g = (p.in_sel >> 4) & 0xf, pos_b = (p.in_sel >> 8) & 0xf;
+    for (int i = 0; i < 3; i++) {
+      if (!rgb420_split_row (p.m_rgb2yuv[i], pos_r, pos_g, pos_b, &r.ca[i], &r.cb[i])) return B200_OK;
+      r.off[i] = p.m_rgb2yuv[i][3];
+    }
+  } else if ((p.in.stride[0] & 3) || (p.in.offset[0] & 3)) return B200_OK;      // pixel pairs are read as words
   const Down420Dev & q = h->down;
   r.ow = q.ow; r.oh = q.oh; r.hmode = q.hmode; r.vavg = q.vavg;
   r.stride_y = q.stride_y; r.stride_u = q.stride_u; r.stride_v = q.stride_v; r.cstep = q.cstep;
@@ -110,9 +117,30 @@ int prepare_rgb420 (b200_vcs * h)
   const unsigned long long cbase = q.cstep == 2 ? std::min (q.off_u, q.off_v) : (q.off_u | q.off_v);
   r.wvec = ((q.stride_y | q.stride_u | q.stride_v) & 3) == 0 && ((q.off_y | cbase) & 3) == 0;
   h->rgb420_scaled = p.h.scaling || p.v.scaling;
-  h->rgb420_matrix_first = p.matrix_first && h->rgb420_scaled;
+  // a kernel of its own in front of the scalers: the RGB -> YUV matrix when the frame grows (chain_scale puts the
+  // scalers behind it), unpack + horizontal chroma up-sampling for packed 4:2:2
+  h->rgb420_pre = packed422 ? 2 : (p.matrix_first && h->rgb420_scaled) ? 1 : 0;
+  int in_stride = p.in.stride[0];
+  unsigned long long in_off = p.in.offset[0];
+  if (h->rgb420_pre) {
+    const int dstride = (p.in.width * 4 + 15) & ~15;
+    if (h->rgb420_pre == 1) {
+      Rgb2AyuvDev & m = h->rgb2ayuv;
+      memset (&m, 0, sizeof (m));
+      m.w = p.in.width; m.h = p.in.height; m.sstride = p.in.stride[0]; m.soff = p.in.offset[0]; m.dstride = dstride;
+      for (int i = 0; i < 3; i++) { m.ca[i] = r.ca[i]; m.cb[i] = r.cb[i]; m.off[i] = r.off[i]; }
+    } else {
+      Yuy2AyuvDev & m = h->yuy2ayuv;
+      memset (&m, 0, sizeof (m));
+      m.w = p.in.width; m.h = p.in.height; m.sstride = p.in.stride[0]; m.soff = p.in.offset[0]; m.dstride = dstride;
+      // byte positions inside a pixel-pair word, from the plan's sample offsets (YUY2: Y0 U Y1 V; UYVY: U Y0 V Y1; YVYU: Y0 V Y1 U)
+      m.ypos = (int) (p.in_off_y - p.in.offset[0]); m.upos = (int) (p.in_off_u - p.in.offset[0]); m.vpos = (int) (p.in_off_v - p.in.offset[0]);
+      m.cosited = p.h_cosited ? 1 : 0;
+    }
+    in_stride = dstride; in_off = 0;
+  }
   if (!h->rgb420_scaled) {
-    r.sstride = p.in.stride[0]; r.soff = p.in.offset[0];
+    r.sstride = in_stride; r.soff = in_off;
     r.svec = (r.sstride & 15) == 0 && (r.soff & 15) == 0;
   } else {
     PlanePlan pl;
@@ -122,16 +150,6 @@ int prepare_rgb420 (b200_vcs * h)
     pl.h = p.h; pl.v = p.v;
     const int sstride = (p.out.width * 4 + 15) & ~15;
     std::vector<int32_t> hp, vp;
-    int in_stride = p.in.stride[0];
-    unsigned long long in_off = p.in.offset[0];
-    if (h->rgb420_matrix_first) {                                   // the scaler reads the A,Y,U,V image of vcs_rgb2ayuv_kernel
-      Rgb2AyuvDev & m = h->rgb2ayuv;
-      memset (&m, 0, sizeof (m));
-      m.w = p.in.width; m.h = p.in.height; m.sstride = p.in.stride[0]; m.soff = p.in.offset[0];
-      m.dstride = (p.in.width * 4 + 15) & ~15;
-      for (int i = 0; i < 3; i++) { m.ca[i] = r.ca[i]; m.cb[i] = r.cb[i]; m.off[i] = r.off[i]; }
-      in_stride = m.dstride; in_off = 0;
-    }
     if (!plan_plane_fast (pl, in_stride, in_off, sstride, 0, &h->rgb420_scaler, &hp, &vp)) return B200_OK;
     const int st = prepare_plane_fast (pl, hp, vp, &h->rgb420_scaler);
     if (st != B200_OK) return st;
@@ -198,6 +216,18 @@ int launch_convert (b200_vcs * h, int n, const VcsBatch & batch, cudaStream_t st
   dim3 grid ((p.out.width + p.tile_w - 1) / p.tile_w, (p.out.height + p.tile_h - 1) / p.tile_h, n);
   if (p.rgb_in)                                                    // packed pixels are read with 32-bit loads
     for (int i = 0; i < n; i++) if (((uintptr_t) batch.in[i]) & 3) return B200_ERR_INVALID_ARG;
+  if (p.yuy2_420) {
+    Yuy2Dev y = h->yuy2;
+    Yuy2Batch b;
+    for (int i = 0; i < n; i++) {
+      b.src[i] = batch.in[i]; b.out[i] = batch.out[i];
+      const uintptr_t a = (uintptr_t) batch.in[i];
+      if ((a & 15) && y.svec > 1) y.svec = 1;
+      if (a & 3) y.svec = 0;
+      if (((uintptr_t) batch.out[i]) & 3) y.wvec = 0;
+    }
+    return launch_yuy2_420 (y, b, n, stream);
+  }
   if (p.yuv_out && h->rgb420_ok) {
     Rgb420Dev r = h->rgb420;
     Rgb420Batch fin;
@@ -205,34 +235,36 @@ int launch_convert (b200_vcs * h, int n, const VcsBatch & batch, cudaStream_t st
       fin.out[i] = batch.out[i];
       if (((uintptr_t) batch.out[i]) & 3) r.wvec = 0;
     }
+    const int pre = h->rgb420_pre;
+    const int pre_stride = pre == 1 ? h->rgb2ayuv.dstride : pre == 2 ? h->yuy2ayuv.dstride : 0;
+    const size_t pre_bytes = (size_t) pre_stride * p.in.height;
+    const size_t scaled_bytes = h->rgb420_scaled ? (size_t) r.sstride * p.out.height : 0;
+    const size_t frame = pre_bytes + scaled_bytes;
+    if (frame && (n > h->scratch_frames || frame != h->scratch_frame_bytes)) {
+      B200_CUDA_TRY (cudaFree (h->d_scratch));                      // synchronises with launches still reading it
+      h->d_scratch = nullptr; h->scratch_frames = 0;
+      B200_CUDA_TRY (cudaMalloc ((void **) &h->d_scratch, frame * n));
+      h->scratch_frames = n; h->scratch_frame_bytes = frame;
+    }
+    VcsBatch mid;                                                   // the scaler's view: in = the pre kernel's image or the frame
+    for (int i = 0; i < n; i++) mid.in[i] = batch.in[i];
+    if (pre) {
+      Rgb420Batch pre_b;
+      for (int i = 0; i < n; i++) { pre_b.src[i] = batch.in[i]; pre_b.out[i] = h->d_scratch + frame * i + scaled_bytes; mid.in[i] = pre_b.out[i]; }
+      const int s0 = pre == 1 ? launch_rgb2ayuv (h->rgb2ayuv, pre_b, n, stream) : launch_yuy2_ayuv (h->yuy2ayuv, pre_b, n, stream);
+      if (s0 != B200_OK) return s0;
+    }
     if (h->rgb420_scaled) {
-      const size_t scaled = (size_t) r.sstride * p.out.height;
-      const size_t pre = h->rgb420_matrix_first ? (size_t) h->rgb2ayuv.dstride * p.in.height : 0;
-      const size_t frame = scaled + pre;
-      if (n > h->scratch_frames || frame != h->scratch_frame_bytes) {
-        B200_CUDA_TRY (cudaFree (h->d_scratch));                    // synchronises with launches still reading it
-        h->d_scratch = nullptr; h->scratch_frames = 0;
-        B200_CUDA_TRY (cudaMalloc ((void **) &h->d_scratch, frame * n));
-        h->scratch_frames = n; h->scratch_frame_bytes = frame;
-      }
-      VcsBatch mid;
-      for (int i = 0; i < n; i++) { mid.in[i] = batch.in[i]; mid.out[i] = h->d_scratch + frame * i; fin.src[i] = mid.out[i]; }
-      if (h->rgb420_matrix_first) {
-        Rgb420Batch pre_b;
-        for (int i = 0; i < n; i++) { pre_b.src[i] = batch.in[i]; pre_b.out[i] = h->d_scratch + frame * i + scaled; mid.in[i] = pre_b.out[i]; }
-        const int s0 = launch_rgb2ayuv (h->rgb2ayuv, pre_b, n, stream);
-        if (s0 != B200_OK) return s0;
-      }
-      const int s = launch_plane_fast (h->rgb420_scaler, mid, n, stream);
-      if (s != B200_OK) return s;
-      return launch_rgb420 (r, fin, n, stream, !h->rgb420_matrix_first);
+      for (int i = 0; i < n; i++) { mid.out[i] = h->d_scratch + frame * i; fin.src[i] = mid.out[i]; }
+      const int s1 = launch_plane_fast (h->rgb420_scaler, mid, n, stream);
+      if (s1 != B200_OK) return s1;
     } else {
       for (int i = 0; i < n; i++) {
-        fin.src[i] = batch.in[i];
-        if (((uintptr_t) batch.in[i]) & 15) r.svec = 0;
+        fin.src[i] = mid.in[i];
+        if (((uintptr_t) mid.in[i]) & 15) r.svec = 0;
       }
     }
-    return launch_rgb420 (r, fin, n, stream);
+    return launch_rgb420 (r, fin, n, stream, pre == 0);
   }
   if (p.yuv_out) {
     // launch 1 writes the scaled pixels of every frame to its scratch image, launch 2 down-samples and packs
@@ -548,6 +580,17 @@ int b200_vcs_create (const b200_video_info * in, const b200_video_info * out,
       q.off_u = p.out.offset[p.out_plane_u] + (p.out_cstep == 2 ? p.out_u_index : 0);
       q.off_v = p.out.offset[p.out_plane_v] + (p.out_cstep == 2 ? (p.out_u_index ^ 1) : 0);
       if ((st = prepare_rgb420 (h)) != B200_OK) { b200_vcs_destroy (h); return st; }
+      if (p.yuy2_420) {
+        Yuy2Dev & y = h->yuy2;
+        memset (&y, 0, sizeof (y));
+        const bool uyvy = p.in.format == B200_VIDEO_FORMAT_UYVY;
+        y.w = p.in.width; y.h = p.in.height; y.sstride = p.in.stride[0]; y.soff = p.in.offset[0];
+        y.sel_y = uyvy ? 0x7531 : 0x6420; y.sel_c = uyvy ? 0x6420 : 0x7531;
+        y.svec = ((y.sstride | y.soff) & 15) == 0 ? 2 : (((y.sstride | y.soff) & 3) == 0 ? 1 : 0);
+        y.stride_y = q.stride_y; y.stride_u = q.stride_u; y.stride_v = q.stride_v;
+        y.off_y = q.off_y; y.off_u = q.off_u; y.off_v = q.off_v;
+        y.wvec = ((q.stride_y | q.stride_u | q.stride_v) & 3) == 0 && ((q.off_y | q.off_u | q.off_v) & 3) == 0;
+      }
     }
     d.p1 = p.p[0]; d.p2 = p.p[1]; d.p3 = p.p[2]; d.p4 = p.p[3]; d.p5 = p.p[4];
     d.sel = p.byte_sel[0] | (p.byte_sel[1] << 4) | (p.byte_sel[2] << 8) | (p.byte_sel[3] << 12);
@@ -714,7 +757,7 @@ int b200_vcs_get_plan_info (const b200_vcs * h, b200_vcs_plan_info * info)
   for (int i = 0; i < 5; i++) info->p[i] = p.p[i];
   info->tile_w = p.tile_w; info->tile_h = p.tile_h; info->smem_bytes = p.smem_bytes;
   info->kernel_variant = p.yuv_out ? 5 : p.planes_mode ? 4 : h->variant == 7 ? 7 : (h->variant == 6 && h->mma.ready) ? 6 : (h->variant == 1 && p.lanczos2_ok) ? 1 : (h->variant == 2 && p.light_ok) ? 2 : (h->variant == 3 && p.ntap_ok) ? 3 : 0;
-  info->n_launches_per_convert = (h->rgb420_ok ? (h->rgb420_matrix_first ? 3 : h->rgb420_scaled ? 2 : 1) : p.yuv_out ? (p.extra_row ? 3 : 2) : 1) + (p.has_dest && p.fill_border ? 1 : 0);
+  info->n_launches_per_convert = (p.yuy2_420 ? 1 : h->rgb420_ok ? (1 + (h->rgb420_pre ? 1 : 0) + (h->rgb420_scaled ? 1 : 0)) : p.yuv_out ? (p.extra_row ? 3 : 2) : 1) + (p.has_dest && p.fill_border ? 1 : 0);
   return B200_OK;
 }
 
@@ -775,7 +818,8 @@ const char *b200_vcs_kernel_name (const b200_vcs * h)
     for (int i = 0; i < p.n_planes; i++) if (h->planes.fast[i].ok) return h->planes.fast[i].vfirst ? "vcs_planes_fast_vfirst_kernel" : "vcs_planes_fast_kernel";
     return "vcs_planes_kernel";
   }
-  if (h->rgb420_ok) return "vcs_rgb420_kernel";
+  if (p.yuy2_420) return "vcs_yuy2_420_kernel";
+  if (h->rgb420_ok) return h->rgb420_pre == 2 ? "vcs_yuy2_ayuv_kernel" : "vcs_rgb420_kernel";
   if (h->variant == 6 && h->mma.ready) return "vcs_l2mma_kernel";
 #ifndef B200_CUDA_EMU
   if (h->variant == 7 && h->tc.ready) return "vcs_l2tc_kernel";

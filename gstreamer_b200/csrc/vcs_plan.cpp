@@ -798,6 +798,9 @@ int build_vcs_plan (const b200_video_info * in, const b200_video_info * out,
     if (inner.color_range == 0) inner.color_range = B200_COLOR_RANGE_16_235;
     if (inner.chroma_site == 0) inner.chroma_site = out->height > 576 ? B200_CHROMA_SITE_H_COSITED : B200_CHROMA_SITE_NONE;
   }
+  const bool in_422p = in->format == B200_VIDEO_FORMAT_YUY2 || in->format == B200_VIDEO_FORMAT_UYVY || in->format == B200_VIDEO_FORMAT_YVYU;
+  if (yuv && in_422p && inner.chroma_site == 0)
+    inner.chroma_site = out->height > 576 ? B200_CHROMA_SITE_H_COSITED : B200_CHROMA_SITE_NONE;
   // video_converter_compute_resample (:2850-2895) compares the input with the whole output frame
   const bool forced = in->width != out->width || in->height != out->height;
   int st = build_inner_plan (in, &inner, cfg, p, forced);
@@ -828,7 +831,14 @@ static int build_inner_plan (const b200_video_info * in, const b200_video_info *
     // capture formats: unpack_YUY2 / _UYVY / _YVYU / _Y42B / _Y444 (video-format.c:155-274, :1009-1104), horizontal chroma
     // up-sampling only (4:2:2: v_factor 0 selects video_chroma_none, video-chroma.c:989-994; 4:4:4: no resampler at all),
     // then the usual chain to packed RGB.  Generic kernel (device-verified: tests/test_vcs_rgbin_gpu.py).
-    if (!(out->format >= B200_VIDEO_FORMAT_RGBx && out->format <= B200_VIDEO_FORMAT_ABGR)) return B200_ERR_UNSUPPORTED;
+    // Packed 4:2:2 (YUY2 / UYVY / YVYU) also converts to 4:2:0 (capture -> encoder): the chain closed by chroma
+    // down-sampling, or the table rows YUY2 / UYVY -> I420 / YV12 at an unchanged size (yuy2_420 below).  Planar
+    // 4:2:2 / 4:4:4 -> 4:2:0 are plane-scaling table rows of the reference: not built.
+    const bool out_rgb = out->format >= B200_VIDEO_FORMAT_RGBx && out->format <= B200_VIDEO_FORMAT_ABGR;
+    const bool out_420 = out->format == B200_VIDEO_FORMAT_I420 || out->format == B200_VIDEO_FORMAT_YV12 ||
+        out->format == B200_VIDEO_FORMAT_NV12 || out->format == B200_VIDEO_FORMAT_NV21;
+    const bool in_packed = in->format == B200_VIDEO_FORMAT_YUY2 || in->format == B200_VIDEO_FORMAT_UYVY || in->format == B200_VIDEO_FORMAT_YVYU;
+    if (!out_rgb && !(out_420 && in_packed)) return B200_ERR_UNSUPPORTED;
     const int w = in->width;
     p->in_422_444 = true;
     p->cvshift = 0;
@@ -884,7 +894,10 @@ static int build_inner_plan (const b200_video_info * in, const b200_video_info *
     // (video-orc.orc:2079-2133 vs video-converter.c:1136-1176): refused.  The element's caps fixation carries the
     // input colorimetry over to a YUV output (gstvideoconvertscale.c:1335-1427), so equal is the negotiated case.
     if (p->out.color_matrix != 0 && p->out.color_matrix != p->in.color_matrix) return B200_ERR_UNSUPPORTED;
-    if (p->out.chroma_site == 0) p->out.chroma_site = p->in.chroma_site;
+    // a changing sub-sampling (4:2:2 in) does not carry the input's chroma-site over (gstvideoconvertscale.c:1411-1424):
+    // the output keeps the default of its size
+    if (p->out.chroma_site == 0)
+      p->out.chroma_site = !p->in_422_444 ? p->in.chroma_site : (out->height > 576 ? B200_CHROMA_SITE_H_COSITED : B200_CHROMA_SITE_NONE);
     if (out->stride[0] < out->width) return B200_ERR_INVALID_ARG;
     if (out_pl) {
       if (out->stride[1] < ocw || out->stride[2] < ocw) return B200_ERR_INVALID_ARG;
@@ -944,10 +957,17 @@ static int build_inner_plan (const b200_video_info * in, const b200_video_info *
     p->v_pairs = false;
     std::fill (p->chroma_mode.begin (), p->chroma_mode.end (), 0);
   }
+  if (p->yuv_out && p->in_422_444) {
+    const bool out_pl = out->format == B200_VIDEO_FORMAT_I420 || out->format == B200_VIDEO_FORMAT_YV12;
+    // table rows YUY2 / UYVY -> I420 / YV12 (video-converter.c:8493-8507; a border rectangle disables them, :8993)
+    p->yuy2_420 = (in->format == B200_VIDEO_FORMAT_YUY2 || in->format == B200_VIDEO_FORMAT_UYVY) && out_pl &&
+        iw == ow && ih == oh && !resample_forced;
+    if (p->yuy2_420 && out->stride[0] < 2 * ((ow + 1) / 2)) return B200_ERR_INVALID_ARG;   // whole pairs of luma per line
+  }
   if (p->yuv_out) {
     // video_converter_compute_resample (video-converter.c:2850-2895): chroma resamplers exist on BOTH sides as soon
     // as the size or the site differs (the sub-sampling is 4:2:0 on both), on neither otherwise
-    const bool resample = iw != ow || ih != oh || p->out.chroma_site != p->in.chroma_site || resample_forced;
+    const bool resample = iw != ow || ih != oh || p->out.chroma_site != p->in.chroma_site || resample_forced || p->in_422_444;
     if (!resample) {
       p->chroma_nearest = true; p->v_pairs = false;
       std::fill (p->chroma_mode.begin (), p->chroma_mode.end (), 0);

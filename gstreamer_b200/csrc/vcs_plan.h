@@ -58,6 +58,7 @@ struct VcsPlan {
   uint64_t in_off_y = 0, in_off_u = 0, in_off_v = 0;
   int in_stride_u = 0, in_stride_v = 0;
   bool in_422_444 = false;
+  bool yuy2_420 = false;         // YUY2 / UYVY -> I420 / YV12 at an unchanged size: the reference's table row (vcs_yuy2_420.cuh)
   uint8_t byte_sel[4] = {3, 2, 1, 0};   // output byte i takes component byte_sel[i] of (A,R,G,B)
   std::vector<uint8_t> chroma_mode;     // per input line: 0 own row, 1 first of pair, 2 second
 

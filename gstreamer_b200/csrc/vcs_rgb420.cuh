@@ -229,6 +229,50 @@ inline int launch_rgb2ayuv (const Rgb2AyuvDev & d, const Rgb420Batch & batch, in
   return B200_OK;
 }
 
+// packed 4:2:2 (YUY2 / UYVY / YVYU) -> A,Y,U,V pixels of the same size: unpack (each pair's chroma sample feeds both pixels,
+// video-format.c:155-274) + the 4:2:2 horizontal chroma up-sampler of the input's site, one pixel per thread.
+//   co-sited  video_chroma_up_h2_cs_u8 (video-chroma.c:687-699): odd pixels x <= w - 2 take (c[k] + c[k+1] + 1) >> 1
+//   centred   video_chroma_up_h2_u8 (:309-327): pixel 0 keeps c[0]; odd x <= w - 2: (3 c[k] + c[k+1] + 2) >> 2;
+//             even x >= 2: (c[k-1] + 3 c[k] + 2) >> 2; a last odd pixel x = w - 1 keeps c[k]        (k = x >> 1)
+struct Yuy2AyuvDev {
+  int w, h;
+  int sstride, dstride;
+  unsigned long long soff;
+  int ypos, upos, vpos;          // byte of Y0, U, V inside a pixel pair's word (Y1 = ypos + 2)
+  int cosited;
+};
+
+__global__ void __launch_bounds__ (256)
+vcs_yuy2_ayuv_kernel (const Yuy2AyuvDev P, const Rgb420Batch frames)
+{
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= P.w) return;
+  const unsigned *row = (const unsigned *) (frames.src[blockIdx.z] + P.soff + (size_t) y * P.sstride);
+  const int k = x >> 1, np = (P.w + 1) >> 1;
+  const unsigned own = __ldg (row + k);
+  const unsigned yy = (own >> (8 * (P.ypos + 2 * (x & 1)))) & 0xff;
+  unsigned u = (own >> (8 * P.upos)) & 0xff, v = (own >> (8 * P.vpos)) & 0xff;
+  if ((x & 1) && x < P.w - 1) {                                    // odd pixel with a pair to its right
+    const unsigned nb = __ldg (row + min (k + 1, np - 1));
+    const unsigned un = (nb >> (8 * P.upos)) & 0xff, vn = (nb >> (8 * P.vpos)) & 0xff;
+    if (P.cosited) { u = (u + un + 1) >> 1; v = (v + vn + 1) >> 1; }
+    else { u = (3 * u + un + 2) >> 2; v = (3 * v + vn + 2) >> 2; }
+  } else if (!(x & 1) && x >= 2 && !P.cosited) {                   // even pixel behind another pair (centred site only)
+    const unsigned nb = __ldg (row + (k - 1));
+    const unsigned up = (nb >> (8 * P.upos)) & 0xff, vp = (nb >> (8 * P.vpos)) & 0xff;
+    u = (up + 3 * u + 2) >> 2; v = (vp + 3 * v + 2) >> 2;
+  }
+  ((unsigned *) (frames.out[blockIdx.z] + (size_t) y * P.dstride))[x] = 0xffu | (yy << 8) | (u << 16) | (v << 24);
+}
+
+inline int launch_yuy2_ayuv (const Yuy2AyuvDev & d, const Rgb420Batch & batch, int n, cudaStream_t stream)
+{
+  dim3 grid ((d.w + 255) / 256, d.h, n);
+  vcs_yuy2_ayuv_kernel <<<grid, 256, 0, stream>>> (d, batch);
+  B200_CUDA_TRY (cudaGetLastError ());
+  return B200_OK;
+}
+
 inline int launch_rgb420 (const Rgb420Dev & d, const Rgb420Batch & batch, int n, cudaStream_t stream, bool matrix = true)
 {
   const int cw = (d.ow + 1) / 2, chh = (d.oh + 1) / 2, cb = (cw + 3) / 4;

@@ -146,6 +146,7 @@ class VideoInfo:
 
 
 _YUV_420 = (VideoFormat.I420, VideoFormat.YV12, VideoFormat.NV12, VideoFormat.NV21)
+_YUV_422_PACKED = (VideoFormat.YUY2, VideoFormat.UYVY, VideoFormat.YVYU)
 
 
 def transfer_colorimetry_from_input(in_info, out_info):
@@ -157,6 +158,10 @@ def transfer_colorimetry_from_input(in_info, out_info):
         out_info.c.color_matrix = in_info.c.color_matrix
         out_info.c.color_range = in_info.c.color_range
         out_info.c.chroma_site = in_info.c.chroma_site
+    elif in_info.format in _YUV_422_PACKED and out_info.format in _YUV_420:
+        # the sub-sampling changes: colorimetry carried over, chroma-site left to the output's own default (:1411-1424)
+        out_info.c.color_matrix = in_info.c.color_matrix
+        out_info.c.color_range = in_info.c.color_range
     return out_info
 
 
@@ -286,6 +291,10 @@ class CudaVideoConvertScale:
         info = _lib.VcsPlanInfoC()
         check(lib.b200_vcs_get_plan_info(self._h, C.byref(info)))
         return info
+
+    def kernel_name(self):
+        """the kernel (the first one of a multi-launch path) this plan runs: b200_vcs_kernel_name"""
+        return lib.b200_vcs_kernel_name(self._h).decode()
 
     def matrix(self):
         im = (C.c_int32 * 16)()

@@ -1084,6 +1084,39 @@ convert_planes (const OracleVcsDesc * d, const uint8_t * in, uint8_t * out)
   return 0;
 }
 
+/* table rows YUY2 / UYVY -> I420 / YV12 (video-converter.c:8493-8507: unchanged size, same matrix; range and chroma-site are
+ * not looked at): convert_YUY2_I420 / convert_UYVY_I420 (:3954-4028, :4913-4986) -> video_orc_convert_YUY2_I420 /
+ * _UYVY_I420 (video-orc.orc:716-744, :781-809): per line pair the luma of both lines is copied - (width + 1) / 2 PAIRS, so an
+ * odd width writes one byte of row padding - and each chroma sample is avgub of the pair's two lines, no horizontal filter.
+ * A last odd line goes through unpack + pack_planar_420 (video-format.c:117-148): its own chroma, even pixels. */
+static int
+convert_yuy2_i420 (const OracleVcsDesc * d, const uint8_t * in, uint8_t * out)
+{
+  const int w = d->in_width, h = d->in_height, h2 = h & ~1, np = (w + 1) / 2;
+  const int yo = d->in_format == ORC_FMT_UYVY ? 1 : 0, uo = d->in_format == ORC_FMT_UYVY ? 0 : 1, vo = uo + 2;
+  const int pu = d->out_format == ORC_FMT_YV12 ? 2 : 1, pv = 3 - pu;
+  int y, i;
+  for (y = 0; y < h2; y += 2) {
+    const uint8_t *s1 = in + d->in_offset[0] + (size_t) d->in_stride[0] * y, *s2 = s1 + d->in_stride[0];
+    uint8_t *y1 = out + d->out_offset[0] + (size_t) d->out_stride[0] * y, *y2 = y1 + d->out_stride[0];
+    uint8_t *du = out + d->out_offset[pu] + (size_t) d->out_stride[pu] * (y >> 1);
+    uint8_t *dv = out + d->out_offset[pv] + (size_t) d->out_stride[pv] * (y >> 1);
+    for (i = 0; i < np; i++) {
+      y1[2 * i] = s1[4 * i + yo]; y1[2 * i + 1] = s1[4 * i + yo + 2];
+      y2[2 * i] = s2[4 * i + yo]; y2[2 * i + 1] = s2[4 * i + yo + 2];
+      du[i] = AVGUB (s1[4 * i + uo], s2[4 * i + uo]);
+      dv[i] = AVGUB (s1[4 * i + vo], s2[4 * i + vo]);
+    }
+  }
+  if (h2 != h) {
+    uint8_t *line = malloc ((size_t) w * 4);
+    unpack_line (d, in, h - 1, line);
+    pack_line_420 (d, line, out, h - 1);
+    free (line);
+  }
+  return 0;
+}
+
 int
 oracle_vcs_convert (const OracleVcsDesc * d, const uint8_t * in, uint8_t * out)
 {
@@ -1121,6 +1154,9 @@ oracle_vcs_convert (const OracleVcsDesc * d, const uint8_t * in, uint8_t * out)
     if ((in_planar && out_planar) || ((d->out_format == ORC_FMT_NV12 || d->out_format == ORC_FMT_NV21) &&
             d->in_format == d->out_format))
       return convert_planes (d, in, out);
+    if ((d->in_format == ORC_FMT_Y42B || d->in_format == ORC_FMT_Y444) && (out_planar || d->out_format == ORC_FMT_NV12 ||
+            d->out_format == ORC_FMT_NV21))
+      return -1;                /* planar 4:2:2 / 4:4:4 -> planar 4:2:0 are plane-scaling table rows: not restated */
     if (out_planar || d->out_format == ORC_FMT_NV12 || d->out_format == ORC_FMT_NV21) {
       /* the other 4:2:0 pairs (NV12 <-> I420, NV12 <-> NV21 ...) have no table row: generic chain, with
        * chain_downsample (video-converter.c:2018-2032) and the 4:2:0 pack functions at its end.  chain_convert
@@ -1131,9 +1167,17 @@ oracle_vcs_convert (const OracleVcsDesc * d, const uint8_t * in, uint8_t * out)
         return -1;
       yuv_out = 1;
       out_site = d->out_chroma_site ? d->out_chroma_site : d->in_chroma_site;
+      if (fmt_is_422_444 (d->in_format)) {
+        /* packed 4:2:2 (capture) -> 4:2:0 (encoder): the sub-sampling changes, so the element's fixation does not carry
+         * the input's chroma-site over (gstvideoconvertscale.c:1411-1424): the output keeps the default of its size */
+        if (!d->out_chroma_site)
+          out_site = oh > 576 ? ORC_SITE_H_COSITED : ORC_SITE_NONE;
+        if ((d->in_format == ORC_FMT_YUY2 || d->in_format == ORC_FMT_UYVY) && out_planar && iw == ow && ih == oh)
+          return convert_yuy2_i420 (d, in, out);
+      }
     }
   }
-  if (yuv_out && !rgb_in && iw == ow && ih == oh && out_site == d->in_chroma_site && !d->force_resample) {
+  if (yuv_out && !rgb_in && !fmt_is_422_444 (d->in_format) && iw == ow && ih == oh && out_site == d->in_chroma_site && !d->force_resample) {
     /* video_converter_compute_resample (:2850-2895): same sub-sampling, site and size -> no chroma resampler
      * on either side; unpack replicates every chroma sample and pack reads it back */
     uint8_t *line = malloc ((size_t) iw * 4);

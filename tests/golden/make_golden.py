@@ -279,6 +279,28 @@ def video_422():
     json.dump(cases, open(os.path.join(HERE, "video_422_cases.json"), "w"), indent=1)
 
 
+def video_422_420():
+    """packed 4:2:2 -> 4:2:0 (capture -> encoder): the YUY2 / UYVY -> I420 / YV12 table rows at an unchanged size, the chain otherwise;
+    output chroma-site = the default of the output size (the element's fixation across a sub-sampling change)"""
+    arrays, cases = {}, []
+    for fi, fo in [("YUY2", "I420"), ("UYVY", "YV12"), ("YVYU", "I420"), ("YUY2", "NV12"), ("UYVY", "NV21")]:
+        for (iw, ih, ow, oh) in [(64, 48, 64, 48), (33, 17, 33, 17), (50, 21, 50, 21), (64, 48, 32, 24), (64, 48, 96, 72), (33, 17, 20, 31)]:
+            for m, site in ((1, 2), (3, 1), (9, 2)):
+                d = ob.vcs_desc(iw, ih, ow, oh, m, in_fmt=ob.FMT[fi], out_fmt=ob.FMT[fo], site=site)
+                frame = np.random.default_rng(m + iw).integers(0, 256, ob.vcs_sizes(d)[0], dtype=np.uint8)
+                out_site = 2 if oh > 576 else 1
+                r = ob.RefVcs(iw, ih, ow, oh, m, in_fmt=ob.FMT[fi], out_fmt=ob.FMT[fo], site=site, matrix=d.in_matrix,
+                              out_matrix=d.in_matrix, out_site=out_site)
+                out = r.convert(frame, np.zeros(ob.vcs_sizes(d)[1], dtype=np.uint8))
+                r.close()
+                key = f"t_{fi}_{fo}_{iw}x{ih}_{ow}x{oh}_m{m}"
+                arrays[key] = out
+                cases.append({"key": key, "in_fmt": fi, "out_fmt": fo, "in": [iw, ih], "out": [ow, oh], "method": m, "site": site,
+                              "seed": m + iw})
+    np.savez_compressed(os.path.join(HERE, "video_422_420.npz"), **arrays)
+    json.dump(cases, open(os.path.join(HERE, "video_422_420_cases.json"), "w"), indent=1)
+
+
 def compositor_420():
     """I420 / YV12 / NV12 / NV21 output"""
     o, r = ob.oracle(), ob.ref()
@@ -313,7 +335,7 @@ if __name__ == "__main__":
     only = set(sys.argv[1:])
     for name, fn in [("video", video), ("compositor", compositor), ("audio", audio), ("video_planar", video_planar),
                      ("audio_interpolated", audio_interpolated), ("audio_formats", audio_formats), ("compositor_420", compositor_420), ("video_yuv", video_yuv),
-                     ("video_cross", video_cross), ("video_rgb_in", video_rgb_in), ("video_rgb_rgb", video_rgb_rgb), ("video_422", video_422)]:
+                     ("video_cross", video_cross), ("video_rgb_in", video_rgb_in), ("video_rgb_rgb", video_rgb_rgb), ("video_422", video_422), ("video_422_420", video_422_420)]:
         if not only or name in only:
             fn()
     print("golden fixtures written to", HERE)

@@ -56,6 +56,8 @@ def run(emu, fi, fo, size, method, frame, colorimetry=None, dest=None, border=0x
         ii.chroma_site = site
     if fi in YUV and fo in YUV:                      # what the element's caps fixation does
         oi.color_matrix, oi.color_range, oi.chroma_site = ii.color_matrix, ii.color_range, ii.chroma_site
+    if fi in YUV_422_444 and fo in YUV:              # ... across a sub-sampling change: the site stays the output's own
+        oi.color_matrix, oi.color_range = ii.color_matrix, ii.color_range
     if out_site is not None:
         oi.chroma_site = out_site
     if colorimetry:
@@ -658,3 +660,28 @@ def test_rgb_to_420_fast_kernels_destination_rectangle(emu, case):
         size = (iw, ih, W, H)
         got = run(emu, fi, fo, size, method, frame, dest=dest, border=0xff204080)
         check(got, expected(fi, fo, size, method, frame, dest=dest, border=0xff204080), f"{fi}->{fo} m{method} dest {dest}")
+
+
+@pytest.mark.parametrize("size", [(64, 48, 64, 48), (50, 21, 50, 21), (33, 17, 33, 17), (1, 1, 1, 1), (2, 3, 2, 3), (130, 34, 130, 34),
+                                  (64, 48, 32, 24), (40, 30, 64, 48), (33, 17, 20, 31), (100, 60, 150, 30), (57, 35, 29, 35)],
+                         ids=lambda s: "%dx%d-%dx%d" % s)
+def test_packed_422_to_420(emu, size):
+    """capture -> encoder: YUY2 / UYVY -> I420 / YV12 at an unchanged size is the table row (vcs_yuy2_420_kernel: luma copy in
+    whole pairs, avgub of the line pair's chroma); every other pair or size runs the chain with the output size's default
+    chroma site: vcs_yuy2_ayuv_kernel (unpack + horizontal chroma up-sampling), the word-wide scaler on the A,Y,U,V pixels,
+    vcs_rgb420_kernel<MATRIX = false> (down-sample + pack) - and the generic kernels (B200_RGB420_GENERIC) must agree"""
+    import os
+    iw, ih, W, H = size
+    for k, (fi, fo) in enumerate([("YUY2", "I420"), ("UYVY", "YV12"), ("UYVY", "I420"), ("YVYU", "I420"), ("YUY2", "NV12"),
+                                  ("UYVY", "NV21"), ("YVYU", "YV12")]):
+        frame = frame_for(fi, iw, ih, 90 + k)
+        for method in [(1, 3), (0,), (9,), (4,), (1, 5), (3,), (1,)][k]:
+            for site in (1, 2):
+                want = expected(fi, fo, size, method, frame, site=site)
+                check(run(emu, fi, fo, size, method, frame, site=site), want, f"{fi}->{fo} m{method} site{site}")
+                if k in (3, 4):
+                    os.environ["B200_RGB420_GENERIC"] = "1"
+                    try:
+                        check(run(emu, fi, fo, size, method, frame, site=site), want, f"generic {fi}->{fo} m{method} site{site}")
+                    finally:
+                        del os.environ["B200_RGB420_GENERIC"]

@@ -214,3 +214,13 @@ def test_video_422_444_inputs(case):
     d = ob.vcs_desc(iw, ih, ow, oh, m, in_fmt=ob.FMT[case["in_fmt"]], out_fmt=ob.FMT[case["out_fmt"]], site=case["site"])
     frame = np.random.default_rng(case["seed"]).integers(0, 256, ob.vcs_sizes(d)[0], dtype=np.uint8)
     assert np.array_equal(ob.oracle_vcs_convert(d, frame), gold)
+
+
+@pytest.mark.parametrize("case", json.load(open(os.path.join(G, "video_422_420_cases.json"))), ids=lambda c: c["key"])
+def test_video_packed_422_to_420(case):
+    """capture -> encoder: the YUY2 / UYVY -> I420 / YV12 table rows and the chain, outputs of the reference itself"""
+    gold = np.load(os.path.join(G, "video_422_420.npz"))[case["key"]]
+    (iw, ih), (ow, oh), m = case["in"], case["out"], case["method"]
+    d = ob.vcs_desc(iw, ih, ow, oh, m, in_fmt=ob.FMT[case["in_fmt"]], out_fmt=ob.FMT[case["out_fmt"]], site=case["site"])
+    frame = np.random.default_rng(case["seed"]).integers(0, 256, ob.vcs_sizes(d)[0], dtype=np.uint8)
+    assert np.array_equal(ob.oracle_vcs_convert(d, frame), gold)

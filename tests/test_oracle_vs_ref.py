@@ -717,3 +717,34 @@ def test_audio_rate_update_matches_reference(fmt, walk):
     finally:
         o.oracle_ars_free(ho)
         r.ref_ars_free(hr)
+
+
+# ------------------------------------------------------------------- packed 4:2:2 (capture) -> 4:2:0 (encoder input)
+@pytest.mark.ref
+@pytest.mark.parametrize("fi", ["YUY2", "UYVY", "YVYU"])
+@pytest.mark.parametrize("fo", ["I420", "YV12", "NV12", "NV21"])
+@pytest.mark.parametrize("size", [(64, 48, 64, 48), (50, 21, 50, 21), (33, 17, 33, 17), (1, 1, 1, 1), (2, 3, 2, 3), (64, 48, 32, 24),
+                                  (64, 48, 96, 72), (33, 17, 20, 31), (100, 100, 150, 50), (40, 90, 40, 31), (57, 35, 29, 35),
+                                  (7, 3, 3, 9)], ids=lambda s: "%dx%d-%dx%d" % s)
+def test_packed_422_to_420_matches_reference(fi, fo, size):
+    """YUY2 / UYVY -> I420 / YV12 at an unchanged size: the table rows convert_YUY2_I420 / convert_UYVY_I420 (luma copy,
+    avgub of the line pair's chroma); every other pair or size: the chain - unpack, horizontal chroma up-sampling, scalers,
+    chroma down-sampling with the OUTPUT size's default site (the fixation does not carry the site across a
+    sub-sampling change), 4:2:0 pack"""
+    iw, ih, ow, oh = size
+    for method in range(10):
+        for site in (1, 2):
+            out_site = 2 if oh > 576 else 1
+            d = ob.vcs_desc(iw, ih, ow, oh, method, in_fmt=ob.FMT[fi], out_fmt=ob.FMT[fo], site=site)
+            d.out_chroma_site = out_site
+            frame = np.random.default_rng(method + 10 * site).integers(0, 256, ob.vcs_sizes(d)[0], dtype=np.uint8)
+            got = ob.oracle_vcs_convert(d, frame)
+            r = ob.RefVcs(iw, ih, ow, oh, method, in_fmt=ob.FMT[fi], out_fmt=ob.FMT[fo], site=site, matrix=d.in_matrix,
+                          out_matrix=d.in_matrix, out_site=out_site)
+            want = r.convert(frame, np.full(got.size, 0, dtype=np.uint8))
+            r.close()
+            if not np.array_equal(got, want):
+                if _one_tap_vertical_inplace(ih, oh, method) or _one_tap_vertical_repeat(iw, ih, ow, oh, method):
+                    continue
+                bad = np.argwhere(got != want).ravel()
+                assert False, f"method {method} site {site}: {len(bad)} bytes differ, first {bad[:6].tolist()}"

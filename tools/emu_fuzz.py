@@ -23,6 +23,9 @@ from oracle import bindings as ob   # noqa: E402
 import test_emu_kernels as T        # noqa: E402
 
 
+ONLY = [k for k in os.environ.get("B200_FUZZ_KINDS", "").split(",") if k]      # e.g. B200_FUZZ_KINDS=422-420,rgb-yuv
+
+
 def main():
     budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
     rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
@@ -52,7 +55,7 @@ def main():
         elif r < 0.4:
             W, H = max(1, iw // 2), max(1, ih // 2)
         method = int(rng.integers(0, 10))
-        kind = str(rng.choice(["yuv-rgb", "yuv-rgb", "same", "cross", "rgb-yuv", "rgb-rgb", "422-rgb"]))
+        kind = str(rng.choice(ONLY or ["yuv-rgb", "yuv-rgb", "same", "cross", "rgb-yuv", "rgb-rgb", "422-rgb", "422-420"]))
         if kind == "yuv-rgb":
             fi, fo = str(rng.choice(T.YUV)), str(rng.choice(T.RGB))
         elif kind == "same":
@@ -65,10 +68,16 @@ def main():
             fi, fo = str(rng.choice(T.RGB)), str(rng.choice(T.YUV))
         elif kind == "rgb-rgb":
             fi, fo = str(rng.choice(T.RGB)), str(rng.choice(T.RGB))
+        elif kind == "422-420":                     # capture -> encoder: table rows at an unchanged size, the chain otherwise
+            fi, fo = str(rng.choice(["YUY2", "UYVY", "YVYU"])), str(rng.choice(T.YUV))
+            if rng.random() < 0.3:
+                W, H = iw, ih
         else:
             fi, fo = str(rng.choice(T.YUV_422_444)), str(rng.choice(T.RGB))
         site = int(rng.choice([1, 2, 4, 6]))
         out_site = int(rng.choice([1, 2, 4, 6])) if kind == "cross" else None
+        if kind == "422-420":                       # the output keeps the default site of its own (frame) size
+            out_site = 2 if H > 576 else 1
         dest = None
         if rng.random() < 0.25:
             dw, dh = int(rng.integers(1, W + 1)), int(rng.integers(1, H + 1))
