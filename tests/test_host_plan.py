@@ -393,3 +393,40 @@ def test_audio_method_and_filter_mode_plans(method, mode, interp, monkeypatch):
             o.oracle_ars_phase_taps(ho, ph, t.ctypes.data)
             assert np.array_equal(t.view(np.uint32), rs.phase_taps(ph).view(np.uint32)), f"phase {ph}"
         o.oracle_ars_free(ho)
+
+
+def test_packed_422_to_420_plan():
+    """capture -> encoder: YUY2 / UYVY -> I420 / YV12 at an unchanged size is the reference's table row (one launch,
+    vcs_yuy2_420_kernel); any other pair or size the chain; a border rectangle disables the table row; the output keeps
+    the chroma-site default of its own size (the fixation does not carry it across a sub-sampling change); planar
+    4:2:2 / 4:4:4 -> 4:2:0 is not built"""
+    import gstreamer_b200 as g
+    from gstreamer_b200.video import transfer_colorimetry_from_input
+
+    def build(fi, fo, iw, ih, ow, oh, m=1, site=None, **cfg):
+        el = g.CudaVideoConvertScale(add_borders=False, method=m, cuda_device_id=-1, **cfg)
+        ii, oi = g.VideoInfo(fi, iw, ih), g.VideoInfo(fo, ow, oh)
+        if site is not None:
+            ii.set_colorimetry(chroma_site=site)
+        transfer_colorimetry_from_input(ii, oi)
+        el.set_info(ii, oi)
+        return el, ii, oi
+
+    YUY2, UYVY, YVYU, Y42B, Y444, I420, YV12, NV12 = 4, 5, 19, 18, 20, 2, 3, 23
+    for fi in (YUY2, UYVY):
+        for fo in (I420, YV12):
+            el, _, _ = build(fi, fo, 640, 480, 640, 480)
+            assert el.kernel_name() == "vcs_yuy2_420_kernel" and int(el.plan_info().n_launches_per_convert) == 1
+            el, _, _ = build(fi, fo, 33, 17, 33, 17, m=3)
+            assert el.kernel_name() == "vcs_yuy2_420_kernel"
+    for fi, fo, size in [(YVYU, I420, (640, 480, 640, 480)), (YUY2, NV12, (640, 480, 640, 480)), (YUY2, I420, (640, 480, 320, 240)),
+                         (UYVY, YV12, (64, 48, 96, 72))]:
+        el, _, _ = build(fi, fo, *size)
+        assert el.kernel_name() != "vcs_yuy2_420_kernel" and int(el.plan_info().kernel_variant) == 5
+    # sub-sampling changes: matrix / range travel, the site does not (1080p input site 2 -> 480p output default 1)
+    _, ii, oi = build(YUY2, I420, 1920, 1080, 854, 480)
+    assert (oi.c.color_matrix, oi.c.color_range) == (ii.c.color_matrix, ii.c.color_range) and oi.c.chroma_site == 1
+    for fi in (Y42B, Y444):
+        with pytest.raises(g.B200Error):
+            build(fi, I420, 64, 48, 64, 48)
+    build(Y42B, 12, 64, 48, 64, 48)                              # ... but still convert to packed RGB
