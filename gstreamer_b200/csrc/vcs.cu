@@ -228,7 +228,10 @@ int launch_convert (b200_vcs * h, int n, const VcsBatch & batch, cudaStream_t st
     }
     return launch_yuy2_420 (y, b, n, stream);
   }
-  if (p.yuv_out && h->rgb420_ok) {
+  bool pairs_aligned = true;                                        // vcs_yuy2_ayuv_kernel reads pixel pairs as words
+  if (h->rgb420_pre == 2)
+    for (int i = 0; i < n; i++) pairs_aligned = pairs_aligned && (((uintptr_t) batch.in[i]) & 3) == 0;
+  if (p.yuv_out && h->rgb420_ok && pairs_aligned) {
     Rgb420Dev r = h->rgb420;
     Rgb420Batch fin;
     for (int i = 0; i < n; i++) {

@@ -685,3 +685,18 @@ def test_packed_422_to_420(emu, size):
                         check(run(emu, fi, fo, size, method, frame, site=site), want, f"generic {fi}->{fo} m{method} site{site}")
                     finally:
                         del os.environ["B200_RGB420_GENERIC"]
+
+
+def test_packed_422_to_420_unaligned_frame(emu):
+    """a frame that does not start on a 4-byte boundary: the table-row kernel falls back to byte loads, the chain to the
+    generic kernels (vcs_yuy2_ayuv_kernel reads pixel pairs as words)"""
+    for fi, fo, size in [("YUY2", "I420", (50, 22, 50, 22)), ("UYVY", "NV12", (50, 22, 50, 22)), ("YUY2", "NV21", (64, 48, 32, 24))]:
+        frame = frame_for(fi, size[0], size[1], 3)
+        want = expected(fi, fo, size, 1, frame, site=1)
+        for shift in (1, 2):
+            buf = np.zeros(frame.size + 8, dtype=np.uint8)
+            off = (-buf.ctypes.data) % 4 + shift
+            view = buf[off:off + frame.size]
+            view[:] = frame
+            assert view.ctypes.data % 4 == shift
+            check(run(emu, fi, fo, size, 1, view, site=1), want, f"{fi}->{fo} shift {shift}")
