@@ -145,6 +145,12 @@ void b200_vcs_config_init (b200_vcs_config * cfg);
 typedef struct b200_vcs b200_vcs;
 
 /* Build the per-caps plan (tap tables, matrix, chroma pairing, tiling) and upload it.
+ * Format pairs (anything else: B200_ERR_UNSUPPORTED):
+ *   NV12 / NV21 / I420 / YV12      -> the eight 4-byte RGB orders, or NV12 / NV21 / I420 / YV12
+ *   the eight 4-byte RGB orders    -> the eight 4-byte RGB orders, or NV12 / NV21 / I420 / YV12
+ *   YUY2 / UYVY / YVYU             -> the eight 4-byte RGB orders, or NV12 / NV21 / I420 / YV12
+ *   Y42B / Y444                    -> the eight 4-byte RGB orders
+ * A YUV -> YUV pair must name the same colour matrix on both sides (what the element's caps fixation produces).
  * device >= 0: CUDA device ordinal (the element's cuda-device-id property,
  * gst-plugins-bad/sys/nvcodec/gstcudabasetransform.c:89-90).
  * device == -1: host-side plan only (no CUDA calls; convert() then fails with

@@ -647,14 +647,16 @@ def test_rgb_to_420_fast_kernels(emu, size, monkeypatch):
     check(run(emu, "BGRA", "NV12", size, 1, frame), expected("BGRA", "NV12", size, 1, frame), "generic chain")
 
 
-@pytest.mark.parametrize("case", [((200, 120), (320, 240), (31, 17, 200, 120)), ((200, 120), (320, 240), (40, 20, 100, 60)),
-                                  ((100, 60), (321, 201), (11, 3, 299, 180)), ((160, 90), (160, 200), (0, 55, 160, 90)),
-                                  ((64, 64), (200, 100), (51, 1, 97, 99))], ids=lambda c: "%dx%d-in-%dx%d" % (c[0] + c[1]))
+@pytest.mark.parametrize("case", [((100, 60), (160, 120), (31, 17, 100, 60)), ((200, 120), (320, 240), (40, 20, 100, 60)),
+                                  ((100, 60), (161, 101), (11, 3, 139, 90)), ((160, 90), (160, 200), (0, 55, 160, 90)),
+                                  ((64, 64), (200, 100), (51, 1, 97, 99))], ids=lambda c: "%dx%d-in-%dx%d-%d" % (c[0] + c[1] + c[2][:1]))
 def test_rgb_to_420_fast_kernels_destination_rectangle(emu, case):
     """the same kernels writing into a destination rectangle of the output frame (odd origins and sizes included: the plan
     shifts the plane origins, the kernels fall back from word stores to byte stores where the rectangle is unaligned)"""
     (iw, ih), (W, H), dest = case
-    for k, (fi, fo) in enumerate([("BGRA", "NV12"), ("RGBA", "I420"), ("xRGB", "NV21"), ("ABGR", "YV12")]):
+    pairs = [("BGRA", "NV12"), ("RGBA", "I420"), ("xRGB", "NV21"), ("ABGR", "YV12")]
+    for k in ((0, 1) if (dest[0] & 1) else (2, 3)):            # two of the four pairs per case keep the CPU suite short
+        fi, fo = pairs[k]
         frame = frame_for(fi, iw, ih, 70 + k)
         method = [1, 3, 0, 9][k]
         size = (iw, ih, W, H)
