@@ -556,7 +556,7 @@ void validate_fast_geometry (VcsPlan * p)
   }
 }
 
-// setup_scale (video-converter.c:8092-8245) for same-family 4:2:0 in/out: what each output plane does
+// setup_scale (video-converter.c:8092-8245) for planar in/out (4:2:0 same family; Y42B / Y444 -> I420 / YV12): what each output plane does
 int build_planes (VcsPlan * p, const FilterSpec & f)
 {
   const bool semi = p->out.format == B200_VIDEO_FORMAT_NV12 || p->out.format == B200_VIDEO_FORMAT_NV21;
@@ -566,8 +566,12 @@ int build_planes (VcsPlan * p, const FilterSpec & f)
   for (int i = 0; i < p->n_planes; i++) {
     PlanePlan & q = p->planes[i];
     q = PlanePlan ();
-    q.src_plane = (!semi && i > 0 && p->in.format != p->out.format) ? 3 - i : i;   // I420 <-> YV12 swap U and V
-    q.iw = i ? (iw + 1) / 2 : iw; q.ih = i ? (ih + 1) / 2 : ih;
+    // exactly one side YV12: U and V planes swap (the source plane is the one holding the same component)
+    q.src_plane = (!semi && i > 0 && (p->in.format == B200_VIDEO_FORMAT_YV12) != (p->out.format == B200_VIDEO_FORMAT_YV12)) ? 3 - i : i;
+    // chroma plane size of the input: 4:2:0 halves both directions, Y42B the width only, Y444 neither
+    const int in_wsub = p->in.format == B200_VIDEO_FORMAT_Y444 ? 0 : 1;
+    const int in_hsub = (p->in.format == B200_VIDEO_FORMAT_Y444 || p->in.format == B200_VIDEO_FORMAT_Y42B) ? 0 : 1;
+    q.iw = i ? (iw + in_wsub) >> in_wsub : iw; q.ih = i ? (ih + in_hsub) >> in_hsub : ih;
     q.ow = i ? (ow + 1) / 2 : ow; q.oh = i ? (oh + 1) / 2 : oh;
     q.ne = (semi && i == 1) ? 2 : 1;
     if (p->in.stride[q.src_plane] < q.iw * q.ne || p->out.stride[i] < q.ow * q.ne) return B200_ERR_INVALID_ARG;
@@ -838,6 +842,15 @@ static int build_inner_plan (const b200_video_info * in, const b200_video_info *
     const bool out_420 = out->format == B200_VIDEO_FORMAT_I420 || out->format == B200_VIDEO_FORMAT_YV12 ||
         out->format == B200_VIDEO_FORMAT_NV12 || out->format == B200_VIDEO_FORMAT_NV21;
     const bool in_packed = in->format == B200_VIDEO_FORMAT_YUY2 || in->format == B200_VIDEO_FORMAT_UYVY || in->format == B200_VIDEO_FORMAT_YVYU;
+    const bool out_pl420 = out->format == B200_VIDEO_FORMAT_I420 || out->format == B200_VIDEO_FORMAT_YV12;
+    if (!in_packed && out_pl420) {
+      // planar 4:2:2 / 4:4:4 -> planar 4:2:0: plane-scaling table rows like I420 -> I420 (video-converter.c:8607-8628; the
+      // same colour matrix on both sides, :8989 - what the element's fixation produces): no chain, no chroma siting
+      if (p->in.color_matrix == 0) p->in.color_matrix = in->height > 576 ? B200_COLOR_MATRIX_BT709 : B200_COLOR_MATRIX_BT601;
+      if (p->out.color_matrix != 0 && p->out.color_matrix != p->in.color_matrix) return B200_ERR_UNSUPPORTED;
+      if (in->stride[0] < in->width || out->stride[0] < out->width) return B200_ERR_INVALID_ARG;
+      return build_planes (p, filter_from_method (*cfg));
+    }
     if (!out_rgb && !(out_420 && in_packed)) return B200_ERR_UNSUPPORTED;
     const int w = in->width;
     p->in_422_444 = true;

@@ -158,7 +158,7 @@ def transfer_colorimetry_from_input(in_info, out_info):
         out_info.c.color_matrix = in_info.c.color_matrix
         out_info.c.color_range = in_info.c.color_range
         out_info.c.chroma_site = in_info.c.chroma_site
-    elif in_info.format in _YUV_422_PACKED and out_info.format in _YUV_420:
+    elif in_info.format in _YUV_422_PACKED + (VideoFormat.Y42B, VideoFormat.Y444) and out_info.format in _YUV_420:
         # the sub-sampling changes: colorimetry carried over, chroma-site left to the output's own default (:1411-1424)
         out_info.c.color_matrix = in_info.c.color_matrix
         out_info.c.color_range = in_info.c.color_range

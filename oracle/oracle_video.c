@@ -1022,15 +1022,17 @@ convert_planes (const OracleVcsDesc * d, const uint8_t * in, uint8_t * out)
      * one holding the same component (fsplane) */
     int sp = i;
     int pw, ph, qw, qh, ne = (semi && i == 1) ? 2 : 1, x, y;
+    /* chroma plane size of the INPUT: 4:2:0 halves both directions, Y42B the width only, Y444 neither */
+    const int in_wsub = d->in_format == ORC_FMT_Y444 ? 0 : 1, in_hsub = (d->in_format == ORC_FMT_Y444 || d->in_format == ORC_FMT_Y42B) ? 0 : 1;
     const uint8_t *s;
     uint8_t *dp;
     int ss, ds, method;
     OracleResamplerOpts rs = d->rs;
     Scaler hs, vs;
     int need_h = 0, need_v = 0;
-    if (!semi && i > 0 && d->in_format != d->out_format)
-      sp = 3 - i;               /* I420 <-> YV12: U and V planes swap */
-    pw = i ? (iw + 1) / 2 : iw; ph = i ? (ih + 1) / 2 : ih;
+    if (!semi && i > 0 && (d->in_format == ORC_FMT_YV12) != (d->out_format == ORC_FMT_YV12))
+      sp = 3 - i;               /* exactly one side is YV12: U and V planes swap */
+    pw = i ? (iw + in_wsub) >> in_wsub : iw; ph = i ? (ih + in_hsub) >> in_hsub : ih;
     qw = i ? (ow + 1) / 2 : ow; qh = i ? (oh + 1) / 2 : oh;
     s = in + d->in_offset[sp]; ss = d->in_stride[sp];
     dp = out + d->out_offset[i]; ds = d->out_stride[i];
@@ -1154,9 +1156,15 @@ oracle_vcs_convert (const OracleVcsDesc * d, const uint8_t * in, uint8_t * out)
     if ((in_planar && out_planar) || ((d->out_format == ORC_FMT_NV12 || d->out_format == ORC_FMT_NV21) &&
             d->in_format == d->out_format))
       return convert_planes (d, in, out);
-    if ((d->in_format == ORC_FMT_Y42B || d->in_format == ORC_FMT_Y444) && (out_planar || d->out_format == ORC_FMT_NV12 ||
-            d->out_format == ORC_FMT_NV21))
-      return -1;                /* planar 4:2:2 / 4:4:4 -> planar 4:2:0 are plane-scaling table rows: not restated */
+    if ((d->in_format == ORC_FMT_Y42B || d->in_format == ORC_FMT_Y444) && out_planar) {
+      /* planar 4:2:2 / 4:4:4 -> planar 4:2:0: plane-scaling table rows like I420 -> I420 (video-converter.c:8607-8628,
+       * same colour matrix required, :8989): every output plane is scaled from the plane holding the same component */
+      if (d->out_matrix && d->out_matrix != d->in_matrix)
+        return -1;
+      return convert_planes (d, in, out);
+    }
+    if ((d->in_format == ORC_FMT_Y42B || d->in_format == ORC_FMT_Y444) && (d->out_format == ORC_FMT_NV12 || d->out_format == ORC_FMT_NV21))
+      return -1;                /* the chain: not restated */
     if (out_planar || d->out_format == ORC_FMT_NV12 || d->out_format == ORC_FMT_NV21) {
       /* the other 4:2:0 pairs (NV12 <-> I420, NV12 <-> NV21 ...) have no table row: generic chain, with
        * chain_downsample (video-converter.c:2018-2032) and the 4:2:0 pack functions at its end.  chain_convert

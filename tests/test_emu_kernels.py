@@ -702,3 +702,16 @@ def test_packed_422_to_420_unaligned_frame(emu):
             view[:] = frame
             assert view.ctypes.data % 4 == shift
             check(run(emu, fi, fo, size, 1, view, site=1), want, f"{fi}->{fo} shift {shift}")
+
+
+@pytest.mark.parametrize("size", [(64, 48, 64, 48), (50, 21, 50, 21), (33, 17, 33, 17), (2, 3, 2, 3), (64, 48, 32, 24), (40, 30, 64, 48),
+                                  (33, 17, 20, 31), (100, 60, 150, 30), (64, 48, 64, 24), (64, 48, 128, 96), (262, 146, 131, 73)],
+                         ids=lambda s: "%dx%d-%dx%d" % s)
+def test_planar_422_444_to_420(emu, size):
+    """Y42B / Y444 -> I420 / YV12: the reference's plane-scaling rows - every output plane from the plane holding the same
+    component, chroma planes with their own geometry (4:2:2 -> 4:2:0 at an unchanged size is the line-pair average of
+    convert_plane_v_halve, 4:4:4 -> 4:2:0 the 2 x 2 one); plane kernels unchanged, only their geometry is new"""
+    for k, (fi, fo) in enumerate([("Y42B", "I420"), ("Y444", "YV12"), ("Y42B", "YV12"), ("Y444", "I420")]):
+        frame = frame_for(fi, size[0], size[1], 120 + k)
+        for method in [(1, 3), (0, 9), (4,), (1, 5)][k]:
+            check(run(emu, fi, fo, size, method, frame, force_generic=False), expected(fi, fo, size, method, frame), f"{fi}->{fo} m{method}")

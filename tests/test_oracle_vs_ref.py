@@ -748,3 +748,26 @@ def test_packed_422_to_420_matches_reference(fi, fo, size):
                     continue
                 bad = np.argwhere(got != want).ravel()
                 assert False, f"method {method} site {site}: {len(bad)} bytes differ, first {bad[:6].tolist()}"
+
+
+# ------------------------------------------------------------------- planar 4:2:2 / 4:4:4 -> planar 4:2:0 (plane-scaling table rows)
+@pytest.mark.ref
+@pytest.mark.parametrize("fi", ["Y42B", "Y444"])
+@pytest.mark.parametrize("fo", ["I420", "YV12"])
+@pytest.mark.parametrize("size", [(64, 48, 64, 48), (50, 21, 50, 21), (33, 17, 33, 17), (1, 1, 1, 1), (2, 3, 2, 3), (64, 48, 32, 24),
+                                  (64, 48, 96, 72), (33, 17, 20, 31), (100, 100, 150, 50), (40, 90, 40, 31), (7, 3, 3, 9),
+                                  (64, 48, 64, 24), (64, 48, 128, 96), (64, 48, 32, 48)], ids=lambda s: "%dx%d-%dx%d" % s)
+def test_planar_422_444_to_420_matches_reference(fi, fo, size):
+    """convert_scale_planes rows Y42B / Y444 -> I420 / YV12 (video-converter.c:8607-8628): every output plane scaled from the
+    plane holding the same component with the chroma resampler method, halving / doubling special cases included; all ten
+    element methods, byte-identical (no defect class on this route: no chain, no in-place filters)"""
+    iw, ih, ow, oh = size
+    for method in range(10):
+        d = ob.vcs_desc(iw, ih, ow, oh, method, in_fmt=ob.FMT[fi], out_fmt=ob.FMT[fo], site=2)
+        frame = np.random.default_rng(method).integers(0, 256, ob.vcs_sizes(d)[0], dtype=np.uint8)
+        got = ob.oracle_vcs_convert(d, frame)
+        r = ob.RefVcs(iw, ih, ow, oh, method, in_fmt=ob.FMT[fi], out_fmt=ob.FMT[fo], site=2, matrix=d.in_matrix, out_matrix=d.in_matrix,
+                      out_site=1)
+        want = r.convert(frame, np.zeros(got.size, dtype=np.uint8))
+        r.close()
+        assert np.array_equal(got, want), f"method {method}"
