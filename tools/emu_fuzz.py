@@ -55,7 +55,7 @@ def main():
         elif r < 0.4:
             W, H = max(1, iw // 2), max(1, ih // 2)
         method = int(rng.integers(0, 10))
-        kind = str(rng.choice(ONLY or ["yuv-rgb", "yuv-rgb", "same", "cross", "rgb-yuv", "rgb-rgb", "422-rgb", "422-420"]))
+        kind = str(rng.choice(ONLY or ["yuv-rgb", "yuv-rgb", "same", "cross", "rgb-yuv", "rgb-rgb", "422-rgb", "422-420", "4xx-420"]))
         if kind == "yuv-rgb":
             fi, fo = str(rng.choice(T.YUV)), str(rng.choice(T.RGB))
         elif kind == "same":
@@ -72,6 +72,10 @@ def main():
             fi, fo = str(rng.choice(["YUY2", "UYVY", "YVYU"])), str(rng.choice(T.YUV))
             if rng.random() < 0.3:
                 W, H = iw, ih
+        elif kind == "4xx-420":                     # planar 4:2:2 / 4:4:4 -> planar 4:2:0: plane-scaling rows
+            fi, fo = str(rng.choice(["Y42B", "Y444"])), str(rng.choice(["I420", "YV12"]))
+            if rng.random() < 0.3:
+                W, H = iw, ih
         else:
             fi, fo = str(rng.choice(T.YUV_422_444)), str(rng.choice(T.RGB))
         site = int(rng.choice([1, 2, 4, 6]))
@@ -84,7 +88,7 @@ def main():
             dest = (int(rng.integers(0, W - dw + 1)), int(rng.integers(0, H - dh + 1)), dw, dh)
         frame = T.frame_for(fi, iw, ih, n)
         size = (iw, ih, W, H)
-        generic = not (fi in T.RGB and fo in T.RGB) and not (kind == "same")
+        generic = not (fi in T.RGB and fo in T.RGB) and kind not in ("same", "4xx-420")
         try:
             kw = dict(site=site if fi not in T.RGB else None, out_site=out_site, dest=dest)
             want = T.expected(fi, fo, size, method, frame, **kw)
