@@ -19,9 +19,8 @@
 GST_DEBUG_CATEGORY_STATIC (cuda_vcs_debug);
 #define GST_CAT_DEFAULT cuda_vcs_debug
 
-/* what b200_vcs_create accepts: 4:2:0 in -> 4:2:0 or packed RGB; packed RGB in -> packed RGB (scaling, byte order) or
- * 4:2:0 (the encoder-feeding direction); packed 4:2:2 (capture) -> packed RGB or 4:2:0; planar Y42B / Y444 -> packed RGB or
- * I420 / YV12 */
+/* what b200_vcs_create accepts: every sink format to every src format - 4:2:0, packed RGB, packed 4:2:2 (capture) and planar
+ * Y42B / Y444 in; packed RGB (scaling, byte order) or 4:2:0 (the encoder-feeding direction) out */
 #define YUV420_FORMATS "NV12, NV21, I420, YV12"
 #define RGB_FORMATS "BGRA, RGBA, ARGB, ABGR, BGRx, RGBx, xRGB, xBGR"
 #define PACKED422_FORMATS "YUY2, UYVY, YVYU"
@@ -217,8 +216,7 @@ vcs_format_class (const GstStructure * st)
   return -1;
 }
 
-/* caps on the other pad: the formats b200_vcs_create pairs with this one (every format of the other direction when
- * the structure does not name a single format), any size in range, colorimetry/chroma-site dropped
+/* caps on the other pad: every format of the other direction, any size in range, colorimetry/chroma-site dropped
  * (gstvideoconvertscale.c:703-748) */
 static GstCaps *
 vcs_transform_caps (GstBaseTransform * trans, GstPadDirection direction, GstCaps * caps, GstCaps * filter)
@@ -231,20 +229,8 @@ vcs_transform_caps (GstBaseTransform * trans, GstPadDirection direction, GstCaps
   n = gst_caps_get_size (caps);
   for (i = 0; i < n; i++) {
     GstStructure *in = gst_caps_get_structure (caps, i);
-    GstCaps *one;
+    GstCaps *one = gst_caps_copy (tmpl);            /* every sink format converts to every src format */
     const GValue *fr = gst_structure_get_value (in, "framerate");
-    const gint cls = vcs_format_class (in);
-    if (direction == GST_PAD_SINK && cls == 2)      /* Y42B / Y444 convert to packed RGB or planar 4:2:0 (plane scaling) */
-      one = gst_caps_from_string (BOTH_CAPS ("{ " RGB_FORMATS ", I420, YV12 }"));
-    else if (direction == GST_PAD_SRC && cls == 0) {        /* a 4:2:0 output comes from 4:2:0, packed RGB or packed 4:2:2 ... */
-      const gchar *f = gst_structure_get_string (in, "format");
-      if (f && f[0] != 'N')                         /* ... the planar ones (I420, YV12) also from Y42B / Y444 */
-        one = gst_caps_from_string (BOTH_CAPS (SINK_FORMATS));
-      else
-        one = gst_caps_from_string (BOTH_CAPS ("{ " YUV420_FORMATS ", " RGB_FORMATS ", " PACKED422_FORMATS " }"));
-    }
-    else
-      one = gst_caps_copy (tmpl);
     if (fr)
       gst_caps_set_value (one, "framerate", fr);       /* framerate and interlace-mode pass through */
     gst_caps_append (res, one);

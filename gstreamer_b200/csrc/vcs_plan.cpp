@@ -837,7 +837,7 @@ static int build_inner_plan (const b200_video_info * in, const b200_video_info *
     // then the usual chain to packed RGB.  Generic kernel (device-verified: tests/test_vcs_rgbin_gpu.py).
     // Packed 4:2:2 (YUY2 / UYVY / YVYU) also converts to 4:2:0 (capture -> encoder): the chain closed by chroma
     // down-sampling, or the table rows YUY2 / UYVY -> I420 / YV12 at an unchanged size (yuy2_420 below).  Planar
-    // 4:2:2 / 4:4:4 -> 4:2:0 are plane-scaling table rows of the reference: not built.
+    // 4:2:2 / 4:4:4 -> planar 4:2:0 are plane-scaling table rows, -> semi-planar 4:2:0 the chain again.
     const bool out_rgb = out->format >= B200_VIDEO_FORMAT_RGBx && out->format <= B200_VIDEO_FORMAT_ABGR;
     const bool out_420 = out->format == B200_VIDEO_FORMAT_I420 || out->format == B200_VIDEO_FORMAT_YV12 ||
         out->format == B200_VIDEO_FORMAT_NV12 || out->format == B200_VIDEO_FORMAT_NV21;
@@ -851,7 +851,8 @@ static int build_inner_plan (const b200_video_info * in, const b200_video_info *
       if (in->stride[0] < in->width || out->stride[0] < out->width) return B200_ERR_INVALID_ARG;
       return build_planes (p, filter_from_method (*cfg));
     }
-    if (!out_rgb && !(out_420 && in_packed)) return B200_ERR_UNSUPPORTED;
+    // (planar 4:2:2 / 4:4:4 -> NV12 / NV21 has no table row: the chain, like the packed inputs)
+    if (!out_rgb && !out_420) return B200_ERR_UNSUPPORTED;
     const int w = in->width;
     p->in_422_444 = true;
     p->cvshift = 0;

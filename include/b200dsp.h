@@ -149,7 +149,7 @@ typedef struct b200_vcs b200_vcs;
  *   NV12 / NV21 / I420 / YV12      -> the eight 4-byte RGB orders, or NV12 / NV21 / I420 / YV12
  *   the eight 4-byte RGB orders    -> the eight 4-byte RGB orders, or NV12 / NV21 / I420 / YV12
  *   YUY2 / UYVY / YVYU             -> the eight 4-byte RGB orders, or NV12 / NV21 / I420 / YV12
- *   Y42B / Y444                    -> the eight 4-byte RGB orders, or I420 / YV12
+ *   Y42B / Y444                    -> the eight 4-byte RGB orders, or NV12 / NV21 / I420 / YV12
  * A YUV -> YUV pair must name the same colour matrix on both sides (what the element's caps fixation produces).
  * device >= 0: CUDA device ordinal (the element's cuda-device-id property,
  * gst-plugins-bad/sys/nvcodec/gstcudabasetransform.c:89-90).

@@ -1163,8 +1163,6 @@ oracle_vcs_convert (const OracleVcsDesc * d, const uint8_t * in, uint8_t * out)
         return -1;
       return convert_planes (d, in, out);
     }
-    if ((d->in_format == ORC_FMT_Y42B || d->in_format == ORC_FMT_Y444) && (d->out_format == ORC_FMT_NV12 || d->out_format == ORC_FMT_NV21))
-      return -1;                /* the chain: not restated */
     if (out_planar || d->out_format == ORC_FMT_NV12 || d->out_format == ORC_FMT_NV21) {
       /* the other 4:2:0 pairs (NV12 <-> I420, NV12 <-> NV21 ...) have no table row: generic chain, with
        * chain_downsample (video-converter.c:2018-2032) and the 4:2:0 pack functions at its end.  chain_convert
@@ -1176,7 +1174,8 @@ oracle_vcs_convert (const OracleVcsDesc * d, const uint8_t * in, uint8_t * out)
       yuv_out = 1;
       out_site = d->out_chroma_site ? d->out_chroma_site : d->in_chroma_site;
       if (fmt_is_422_444 (d->in_format)) {
-        /* packed 4:2:2 (capture) -> 4:2:0 (encoder): the sub-sampling changes, so the element's fixation does not carry
+        /* 4:2:2 / 4:4:4 -> 4:2:0 through the chain (packed inputs; planar ones to the semi-planar outputs - their planar
+         * outputs were plane-scaling rows above): the sub-sampling changes, so the element's fixation does not carry
          * the input's chroma-site over (gstvideoconvertscale.c:1411-1424): the output keeps the default of its size */
         if (!d->out_chroma_site)
           out_site = oh > 576 ? ORC_SITE_H_COSITED : ORC_SITE_NONE;
@@ -1318,7 +1317,8 @@ scale_passes:
     if ((oh & 1) && !have_v && !(out_site & ORC_SITE_V_COSITED) && !rgb_in) {   /* RGB: the clamped line IS the last line */
       uint8_t *one = malloc ((size_t) iw * 4);
       unpack_line (d, in, ih - 1, one);
-      chroma_h_line (one, iw, (d->in_chroma_site & ORC_SITE_H_COSITED) != 0);
+      if (d->in_format != ORC_FMT_Y444)     /* 4:4:4 has no up-sampler: the clamped request is the last line as unpacked */
+        chroma_h_line (one, iw, (d->in_chroma_site & ORC_SITE_H_COSITED) != 0);
       if (have_h) {
         extra = malloc ((size_t) ow * 4);
         hscale_image (&hs, one, iw, extra, ow, 1);

@@ -284,7 +284,8 @@ def video_422_420():
     output chroma-site = the default of the output size (the element's fixation across a sub-sampling change)"""
     arrays, cases = {}, []
     for fi, fo in [("YUY2", "I420"), ("UYVY", "YV12"), ("YVYU", "I420"), ("YUY2", "NV12"), ("UYVY", "NV21"),
-                   ("Y42B", "I420"), ("Y444", "YV12")]:         # the last two: planar -> planar plane-scaling rows
+                   ("Y42B", "I420"), ("Y444", "YV12"),          # planar -> planar: plane-scaling rows
+                   ("Y42B", "NV12"), ("Y444", "NV21")]:         # planar -> semi-planar: the chain
         for (iw, ih, ow, oh) in [(64, 48, 64, 48), (33, 17, 33, 17), (50, 21, 50, 21), (64, 48, 32, 24), (64, 48, 96, 72), (33, 17, 20, 31)]:
             for m, site in ((1, 2), (3, 1), (9, 2)):
                 d = ob.vcs_desc(iw, ih, ow, oh, m, in_fmt=ob.FMT[fi], out_fmt=ob.FMT[fo], site=site)

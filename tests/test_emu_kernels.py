@@ -715,3 +715,16 @@ def test_planar_422_444_to_420(emu, size):
         frame = frame_for(fi, size[0], size[1], 120 + k)
         for method in [(1, 3), (0, 9), (4,), (1, 5)][k]:
             check(run(emu, fi, fo, size, method, frame, force_generic=False), expected(fi, fo, size, method, frame), f"{fi}->{fo} m{method}")
+
+
+@pytest.mark.parametrize("size", [(64, 48, 64, 48), (50, 21, 50, 21), (33, 17, 33, 17), (2, 3, 2, 3), (64, 48, 32, 24), (40, 30, 64, 48),
+                                  (33, 17, 20, 31), (100, 60, 150, 30), (57, 35, 29, 35)], ids=lambda s: "%dx%d-%dx%d" % s)
+def test_planar_422_444_to_semi_planar_420(emu, size):
+    """Y42B / Y444 -> NV12 / NV21: no table row, the chain (generic kernel with the planar 4:2:2 / 4:4:4 input stage, matrix
+    off, then vcs_down420_kernel); 4:4:4 has no up-sampler at all - the odd-height corner reads the last line as unpacked"""
+    for k, (fi, fo) in enumerate([("Y42B", "NV12"), ("Y444", "NV21"), ("Y444", "NV12"), ("Y42B", "NV21")]):
+        frame = frame_for(fi, size[0], size[1], 140 + k)
+        for method in [(1, 3), (0, 9), (1,), (4,)][k]:
+            for site in (1, 2):
+                check(run(emu, fi, fo, size, method, frame, site=site), expected(fi, fo, size, method, frame, site=site),
+                      f"{fi}->{fo} m{method} site{site}")

@@ -426,14 +426,13 @@ def test_packed_422_to_420_plan():
     # sub-sampling changes: matrix / range travel, the site does not (1080p input site 2 -> 480p output default 1)
     _, ii, oi = build(YUY2, I420, 1920, 1080, 854, 480)
     assert (oi.c.color_matrix, oi.c.color_range) == (ii.c.color_matrix, ii.c.color_range) and oi.c.chroma_site == 1
-    # planar 4:2:2 / 4:4:4 -> planar 4:2:0: the reference's plane-scaling rows (kernel_variant 4); semi-planar outputs would be its
-    # chain: not built
+    # planar 4:2:2 / 4:4:4 -> planar 4:2:0: the reference's plane-scaling rows (kernel_variant 4)
     for fi in (Y42B, Y444):
         for fo in (I420, YV12):
             el, _, _ = build(fi, fo, 64, 48, 64, 48)
             assert int(el.plan_info().kernel_variant) == 4
             el, _, _ = build(fi, fo, 64, 48, 40, 30, m=3)
             assert int(el.plan_info().kernel_variant) == 4
-        with pytest.raises(g.B200Error):
-            build(fi, NV12, 64, 48, 64, 48)
+        el, _, oi = build(fi, NV12, 64, 48, 64, 48)                # semi-planar outputs: the chain (kernel_variant 5)
+        assert int(el.plan_info().kernel_variant) == 5 and oi.c.chroma_site == 1
     build(Y42B, 12, 64, 48, 64, 48)                              # ... and to packed RGB as before

@@ -771,3 +771,27 @@ def test_planar_422_444_to_420_matches_reference(fi, fo, size):
         want = r.convert(frame, np.zeros(got.size, dtype=np.uint8))
         r.close()
         assert np.array_equal(got, want), f"method {method}"
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize("fi", ["Y42B", "Y444"])
+@pytest.mark.parametrize("fo", ["NV12", "NV21"])
+@pytest.mark.parametrize("size", [(64, 48, 64, 48), (50, 21, 50, 21), (33, 17, 33, 17), (1, 1, 1, 1), (2, 3, 2, 3), (64, 48, 32, 24),
+                                  (64, 48, 96, 72), (33, 17, 20, 31), (100, 100, 150, 50), (40, 90, 40, 31), (7, 3, 3, 9),
+                                  (57, 35, 29, 35), (40, 33, 57, 33)], ids=lambda s: "%dx%d-%dx%d" % s)
+def test_planar_422_444_to_semi_planar_420_matches_reference(fi, fo, size):
+    """Y42B / Y444 -> NV12 / NV21: no table row, the chain (4:2:2: horizontal up-sampler; 4:4:4: none - an odd height at an
+    unchanged size then reads the last line as unpacked), chroma down-sampling with the output size's default site"""
+    iw, ih, ow, oh = size
+    for method in range(10):
+        for site in (1, 2):
+            d = ob.vcs_desc(iw, ih, ow, oh, method, in_fmt=ob.FMT[fi], out_fmt=ob.FMT[fo], site=site)
+            d.out_chroma_site = 1
+            frame = np.random.default_rng(method).integers(0, 256, ob.vcs_sizes(d)[0], dtype=np.uint8)
+            got = ob.oracle_vcs_convert(d, frame)
+            r = ob.RefVcs(iw, ih, ow, oh, method, in_fmt=ob.FMT[fi], out_fmt=ob.FMT[fo], site=site, matrix=d.in_matrix,
+                          out_matrix=d.in_matrix, out_site=1)
+            want = r.convert(frame, np.zeros(got.size, dtype=np.uint8))
+            r.close()
+            if not np.array_equal(got, want):
+                assert _one_tap_vertical_inplace(ih, oh, method), f"method {method} site {site}"

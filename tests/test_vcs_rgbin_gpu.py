@@ -186,13 +186,14 @@ def test_packed_422_to_420_matches_oracle(cuda_device, pair, size):
             assert not bad, f"m{method} site{site}: " + "; ".join(bad)
 
 
-@pytest.mark.parametrize("pair", [("Y42B", "I420"), ("Y444", "YV12"), ("Y42B", "YV12"), ("Y444", "I420")], ids=lambda p: "%s-%s" % p)
+@pytest.mark.parametrize("pair", [("Y42B", "I420"), ("Y444", "YV12"), ("Y42B", "YV12"), ("Y444", "I420"), ("Y42B", "NV12"), ("Y444", "NV21")],
+                         ids=lambda p: "%s-%s" % p)
 @pytest.mark.parametrize("size", [(64, 48, 64, 48), (50, 21, 50, 21), (33, 17, 33, 17), (2, 3, 2, 3), (64, 48, 32, 24), (64, 48, 96, 72),
                                   (33, 17, 20, 31), (100, 100, 150, 50), (64, 48, 64, 24), (64, 48, 128, 96), (1920, 1080, 1920, 1080),
                                   (1920, 1080, 1280, 720)], ids=lambda s: "%dx%d-%dx%d" % s)
 def test_planar_422_444_to_420_matches_oracle(cuda_device, pair, size):
     """Y42B / Y444 -> I420 / YV12: the reference's plane-scaling rows on the plane kernels (kernel_variant 4), chroma planes
-    with the input format's own geometry"""
+    with the input format's own geometry; -> NV12 / NV21: the chain (kernel_variant 5: generic kernel + vcs_down420_kernel)"""
     import torch
     import gstreamer_b200 as g
     from gstreamer_b200.video import transfer_colorimetry_from_input
@@ -207,9 +208,10 @@ def test_planar_422_444_to_420_matches_oracle(cuda_device, pair, size):
         ii, oi = g.VideoInfo(ob.FMT[fi], iw, ih), g.VideoInfo(ob.FMT[fo], ow, oh)
         transfer_colorimetry_from_input(ii, oi)
         el.set_info(ii, oi)
-        assert int(el.plan_info().kernel_variant) == 4
+        semi = fo in ("NV12", "NV21")
+        assert int(el.plan_info().kernel_variant) == (5 if semi else 4)
         dst = torch.full((oi.size,), 0x5A, dtype=torch.uint8, device="cuda")
         el.transform_frame(torch.from_numpy(frame).cuda(), dst)
         torch.cuda.synchronize()
-        bad = planes_equal(dst.cpu().numpy(), want, oi, ow, oh, False)
+        bad = planes_equal(dst.cpu().numpy(), want, oi, ow, oh, semi)
         assert not bad, f"m{method}: " + "; ".join(bad)

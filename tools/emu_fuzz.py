@@ -73,14 +73,14 @@ def main():
             if rng.random() < 0.3:
                 W, H = iw, ih
         elif kind == "4xx-420":                     # planar 4:2:2 / 4:4:4 -> planar 4:2:0: plane-scaling rows
-            fi, fo = str(rng.choice(["Y42B", "Y444"])), str(rng.choice(["I420", "YV12"]))
+            fi, fo = str(rng.choice(["Y42B", "Y444"])), str(rng.choice(T.YUV))    # ... to NV12 / NV21: the chain
             if rng.random() < 0.3:
                 W, H = iw, ih
         else:
             fi, fo = str(rng.choice(T.YUV_422_444)), str(rng.choice(T.RGB))
         site = int(rng.choice([1, 2, 4, 6]))
         out_site = int(rng.choice([1, 2, 4, 6])) if kind == "cross" else None
-        if kind == "422-420":                       # the output keeps the default site of its own (frame) size
+        if kind == "422-420" or (kind == "4xx-420" and fo in ("NV12", "NV21")):   # the output keeps the default site of its own (frame) size
             out_site = 2 if H > 576 else 1
         dest = None
         if rng.random() < 0.25:
